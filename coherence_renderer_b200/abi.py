@@ -1,0 +1,241 @@
+"""ctypes binding of include/coherence_b200.h (the drop-in C ABI).
+
+Loading fails loudly if the library has not been built; creating a context fails loudly
+without a CUDA device.  Nothing in this module computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcoherence_b200.so")
+
+COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH = 0, 1, 2, 3, 4
+COH_NONZERO, COH_EVENODD = 0, 1
+COH_FILL_PLAIN, COH_FILL_AXIAL, COH_FILL_RADIAL = 0, 1, 2
+COH_FILL_EXT_S, COH_FILL_EXT_E = 1, 2
+COH_RENDER_RECORD_U = 1
+
+
+class CohObject(C.Structure):
+    """struct coh_object (include/coherence_b200.h)."""
+
+    _fields_ = [
+        ("kind", C.c_int32), ("winding", C.c_int32), ("first", C.c_int32), ("count", C.c_int32),
+        ("fill_kind", C.c_int32), ("colour0", C.c_uint32), ("colour1", C.c_uint32), ("fill_flags", C.c_int32),
+        ("pretrans", C.c_int32), ("dx", C.c_int32), ("dy", C.c_int32), ("bounds", C.c_int32 * 4),
+        ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("reserved", C.c_int32), ("id", C.c_int64),
+        ("fparam", C.c_double * 6), ("brush_opacity", C.c_double), ("brush_radius", C.c_double),
+    ]
+
+
+# every symbol include/coherence_b200.h declares (checked by tests/test_abi_symbols.py)
+SYMBOLS = [
+    "coh_init", "coh_shutdown", "coh_last_error", "coh_device_name", "coh_stream", "coh_launch_count",
+    "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_polygon_opacity",
+    "coh_polygon_sprite", "coh_shape_box", "coh_shape_import", "coh_shape_export_size", "coh_shape_export",
+    "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
+    "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
+    "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_uncovered", "coh_sync",
+    "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888",
+]
+
+_lib = None
+
+
+class CohError(RuntimeError):
+    """The OCaml stub raises `Failure msg` for these (reference convention: failwith)."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CohError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)"
+            )
+        L = C.CDLL(LIB_PATH)
+        L.coh_last_error.restype = C.c_char_p
+        L.coh_last_error.argtypes = [C.c_void_p]
+        L.coh_stream.restype = C.c_void_p
+        L.coh_stream.argtypes = [C.c_void_p]
+        L.coh_fb_device_ptr.restype = C.c_void_p
+        L.coh_fb_device_ptr.argtypes = [C.c_void_p]
+        L.coh_launch_count.restype = C.c_int64
+        L.coh_launch_count.argtypes = [C.c_void_p]
+        L.coh_rgba8_of_colour.restype = C.c_uint32
+        L.coh_colour_of_rgba8.restype = C.c_int32
+        _lib = L
+    return _lib
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Context:
+    """One GPU, one scanline band (coh_init / coh_shutdown)."""
+
+    def __init__(self, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().coh_init(device, C.byref(self._h))
+        if rc != 0:
+            raise CohError(lib().coh_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().coh_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise CohError(lib().coh_last_error(self._h).decode())
+
+    # -- info
+    def device_name(self):
+        b = C.create_string_buffer(256)
+        self._chk(lib().coh_device_name(self._h, b, 256))
+        return b.value.decode()
+
+    def stream(self):
+        return lib().coh_stream(self._h)
+
+    def launch_count(self):
+        return lib().coh_launch_count(self._h)
+
+    def sync(self):
+        self._chk(lib().coh_sync(self._h))
+
+    # -- shapes
+    def shape_import(self, flat):
+        a = np.ascontiguousarray(flat, dtype=np.int32)
+        h = C.c_uint64()
+        self._chk(lib().coh_shape_import(self._h, _i32p(a), C.c_int64(len(a)), C.byref(h)))
+        return h.value
+
+    def shape_export(self, h):
+        n = C.c_int64()
+        self._chk(lib().coh_shape_export_size(self._h, C.c_uint64(h), C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.int32)
+        m = C.c_int64()
+        self._chk(lib().coh_shape_export(self._h, C.c_uint64(h), _i32p(out), C.c_int64(n.value), C.byref(m)))
+        return out[: m.value]
+
+    def shape_free(self, h):
+        if h:
+            self._chk(lib().coh_shape_free(self._h, C.c_uint64(h)))
+
+    def shape_box(self, x, y, w, h):
+        o = C.c_uint64()
+        self._chk(lib().coh_shape_box(self._h, x, y, w, h, C.byref(o)))
+        return o.value
+
+    def shape_bounds(self, h):
+        box = (C.c_int32 * 4)()
+        isnull = C.c_int32()
+        self._chk(lib().coh_shape_bounds(self._h, C.c_uint64(h), box, C.byref(isnull)))
+        return None if isnull.value else tuple(box)
+
+    def shape_card(self, h):
+        n = C.c_int64()
+        self._chk(lib().coh_shape_card(self._h, C.c_uint64(h), C.byref(n)))
+        return n.value
+
+    def _binop(self, fn, a, b):
+        o = C.c_uint64()
+        self._chk(fn(self._h, C.c_uint64(a), C.c_uint64(b), C.byref(o)))
+        return o.value
+
+    def shape_union(self, a, b):
+        return self._binop(lib().coh_shape_union, a, b)
+
+    def shape_difference(self, a, b):
+        return self._binop(lib().coh_shape_difference, a, b)
+
+    def shape_intersection(self, a, b):
+        return self._binop(lib().coh_shape_intersection, a, b)
+
+    def _unop(self, fn, a, m, n):
+        o = C.c_uint64()
+        self._chk(fn(self._h, C.c_uint64(a), m, n, C.byref(o)))
+        return o.value
+
+    def shape_translate(self, a, dx, dy):
+        return self._unop(lib().coh_shape_translate, a, dx, dy)
+
+    def shape_bloat(self, a, m, n):
+        return self._unop(lib().coh_shape_bloat, a, m, n)
+
+    def shape_erode(self, a, m, n):
+        return self._unop(lib().coh_shape_erode, a, m, n)
+
+    # -- polygon
+    def shapeminshape_of_edgelist(self, edges, winding):
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
+        s, m = C.c_uint64(), C.c_uint64()
+        self._chk(lib().coh_shapeminshape_of_edgelist(self._h, _i32p(e), len(e), winding, C.byref(s), C.byref(m)))
+        return s.value, m.value
+
+    def polygon_opacity(self, edges, winding, shp):
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
+        cap = self.shape_card(shp)
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        n = C.c_int64()
+        self._chk(lib().coh_polygon_opacity(self._h, _i32p(e), len(e), winding, C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    def polygon_sprite(self, fill_obj, edges, winding, shp):
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
+        cap = self.shape_card(shp)
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = C.c_int64()
+        self._chk(lib().coh_polygon_sprite(self._h, C.byref(fill_obj), _i32p(e), len(e), winding, C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    # -- scenes / rendering
+    def scene_create(self, objs, n_background, edges, points):
+        """objs: ctypes array of CohObject (scene objects then n_background background objects)."""
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
+        p = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+        h = C.c_uint64()
+        self._chk(lib().coh_scene_create(self._h, objs, len(objs), n_background, _i32p(e), len(e), _i32p(p), len(p), C.byref(h)))
+        return h.value
+
+    def scene_free(self, h):
+        if h:
+            self._chk(lib().coh_scene_free(self._h, C.c_uint64(h)))
+
+    def fb_configure(self, width, height, band_y0=0, band_y1=None):
+        self._chk(lib().coh_fb_configure(self._h, width, height, band_y0, height if band_y1 is None else band_y1))
+        self._wh = (width, height)
+
+    def render_frame(self, scene, update, flags=0):
+        ux, uy, uw, uh = update
+        self._chk(lib().coh_render_frame(self._h, C.c_uint64(scene), ux, uy, uw, uh, flags))
+
+    def render_uncovered(self):
+        o = C.c_uint64()
+        self._chk(lib().coh_render_uncovered(self._h, C.byref(o)))
+        return o.value
+
+    def fb_device_ptr(self):
+        return lib().coh_fb_device_ptr(self._h)
+
+    def fb_read_rgba(self, x, y, w, h, out=None):
+        if out is None:
+            out = np.zeros((h, w), dtype=np.uint32)
+        self._chk(lib().coh_fb_read_rgba(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def fb_read_rgb888(self, x, y, w, h):
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        self._chk(lib().coh_fb_read_rgb888(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out

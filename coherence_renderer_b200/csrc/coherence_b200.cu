@@ -1,0 +1,812 @@
+// coherence_b200.cu — C ABI (include/coherence_b200.h) over the sm_100a kernels.
+// Host glue only: buffer management, launches, error reporting.  No CPU fallback: every
+// compute entry point needs a live CUDA context and fails loudly otherwise.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../../include/coherence_b200.h"
+#include "kernels.cuh"
+
+using namespace coh;
+
+// ---------------------------------------------------------------------------------------
+struct DevShape {
+  int y0 = 0, n_rows = 0;       // rows y0 .. y0+n_rows-1 (row lists may be empty)
+  int* row_ptr = nullptr;       // device, n_rows+1
+  int2* spans = nullptr;        // device
+  int n_spans = 0;
+  long long card = 0;           // pixels
+  int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;  // tight bounds (valid if n_spans > 0)
+};
+struct DevScene {
+  int n_objs = 0, n_leaves = 0, n_edges = 0, n_points = 0;
+  ObjRec* objs = nullptr;
+  int* leaves = nullptr;
+  EdgeRec* edges = nullptr;
+  int2* points = nullptr;
+  uint8_t* stamps = nullptr;
+  std::vector<ObjRec> h_objs;
+  size_t items_total = 0;
+  int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
+};
+
+struct coh_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  AATable* d_aa = nullptr;
+  int* d_error = nullptr;
+  int* h_error = nullptr;  // pinned
+  // framebuffer
+  Frame fr{0, 0, 0, 0, 0, 0};
+  uint32_t* fb = nullptr;
+  uint32_t* u_out = nullptr;   // bit-frame of `u` after the scene pass
+  bool have_u = false;
+  // binning scratch
+  int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
+  int* cell_items = nullptr; size_t cell_items_cap = 0;
+  int* h_total = nullptr;  // pinned
+};
+
+static std::string g_init_err;
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char b_[512];                                                                           \
+      snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                          \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+#define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+#define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) q--; return q; }
+
+// AA table (polygon.ml:616-651): maintable via exp on the host once; prefix sums per scaled row.
+static void build_aa_table(AATable& t) {
+  int M[32][32];
+  for (int x = 1; x <= 32; x++)
+    for (int y = 1; y <= 32; y++) {
+      double xp = ((double)(x - 1) * 6.) / 31. - 3., yp = ((double)(y - 1) * 6.) / 31. - 3.;
+      M[x - 1][y - 1] = (int)(exp(-((xp * xp + yp * yp) / 2.0)) * 255.);
+    }
+  long total = 0;
+  for (int j = 0; j < 32; j++) {
+    t.prefix[j][0] = 0;
+    for (int i = 0; i < 32; i++) { t.prefix[j][i + 1] = t.prefix[j][i] + M[i][j]; total += M[i][j]; }
+  }
+  t.volume = (int)((total * 256) / 255);
+}
+
+extern "C" {
+
+const char* coh_last_error(coh_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+int coh_init(int device, coh_ctx** out) {
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_init_err = std::string("coh_init: no CUDA device available (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return 1;
+  }
+  coh_ctx* ctx = new coh_ctx();
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t err) { g_init_err = std::string(what) + ": " + cudaGetErrorString(err); delete ctx; return 1; };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  AATable t; build_aa_table(t);
+  if ((e = cudaMalloc(&ctx->d_aa, sizeof(AATable))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpy(ctx->d_aa, &t, sizeof t, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+  if ((e = cudaMalloc(&ctx->d_error, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemset(ctx->d_error, 0, sizeof(int));
+  if ((e = cudaMallocHost(&ctx->h_error, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&ctx->h_total, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
+  *out = ctx;
+  return 0;
+}
+
+int coh_shutdown(coh_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_aa); cudaFree(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
+  cudaFree(ctx->fb); cudaFree(ctx->u_out);
+  cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+int coh_device_name(coh_ctx* ctx, char* buf, int cap) {
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, ctx->device));
+  snprintf(buf, cap, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
+  return 0;
+}
+void* coh_stream(coh_ctx* ctx) { return (void*)ctx->stream; }
+int64_t coh_launch_count(coh_ctx* ctx) { return ctx->launches; }
+static int check_error_flag(coh_ctx* ctx, const char* what);
+int coh_sync(coh_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  return check_error_flag(ctx, "coh_sync");  // synchronises the stream and reports deferred kernel-side failures
+}
+
+// ---- colour codec: colour.ml:99-172 (host-side pure functions for the OCaml boundary) ----
+int32_t coh_colour_of_rgba8(uint32_t w) {
+  int r8 = w & 255, g8 = (w >> 8) & 255, b8 = (w >> 16) & 255, a8 = w >> 24;
+  int r = r8 >> 1, g = g8 >> 1, b = b8 >> 1, a = a8 >> 1;
+  int rl = r8 & 1, gl = g8 & 1, bl = b8 & 1, al = a8 & 1;
+  auto cat = [](int p, int q, int s, int t) { return (p << 21) | (q << 14) | (s << 7) | t; };
+  if (r != a && g != a && b != a)
+    return (rl << 29) | (gl << 28) | (bl ? (al ? cat(r, g, b, a) : cat(r, g, a, b)) : (al ? cat(r, a, b, g) : cat(a, g, b, r)));
+  int tail = r == a ? cat(0, g, b, a) : g == a ? cat(0, r, b, a) : cat(0, r, g, a);
+  return (1 << 30) | (rl << 29) | (gl << 28) | (bl << 27) | (al << 26) | ((r == a) << 25) | ((g == a) << 24) | ((b == a) << 23) | tail;
+}
+uint32_t coh_rgba8_of_colour(int32_t c) {
+  int r = 0, g = 0, b = 0, a = 0, rl = (c >> 29) & 1, gl = (c >> 28) & 1, bl = 0, al = 0;
+  int c3 = (c >> 21) & 127, c2 = (c >> 14) & 127, c1 = (c >> 7) & 127, c0 = c & 127;
+  if (!(c & (1 << 30))) {
+    int m;  // index of the maximum, colour.ml:86-96
+    if (c3 > c2) m = (c1 > c0) ? (c3 > c1 ? 0 : 2) : (c3 > c0 ? 0 : 3);
+    else m = (c1 > c0) ? (c2 > c1 ? 1 : 2) : (c2 > c0 ? 1 : 3);
+    switch (m) {
+      case 3: bl = 1; al = 1; r = c3; g = c2; b = c1; a = c0; break;
+      case 2: bl = 1; al = 0; r = c3; g = c2; a = c1; b = c0; break;
+      case 1: bl = 0; al = 1; r = c3; a = c2; b = c1; g = c0; break;
+      default: bl = 0; al = 0; a = c3; g = c2; b = c1; r = c0; break;
+    }
+  } else {
+    bl = (c >> 27) & 1; al = (c >> 26) & 1; a = c0;
+    if (c & (1 << 25)) { r = a; g = c2; b = c1; }
+    else if (c & (1 << 24)) { g = a; r = c2; b = c1; }
+    else { b = a; r = c2; g = c1; }
+  }
+  return (uint32_t)((r << 1) | rl) | ((uint32_t)((g << 1) | gl) << 8) | ((uint32_t)((b << 1) | bl) << 16) | ((uint32_t)((a << 1) | al) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// Shapes
+// ---------------------------------------------------------------------------------------
+static void free_shape(DevShape* s) {
+  if (!s) return;
+  cudaFree(s->row_ptr); cudaFree(s->spans);
+  delete s;
+}
+int coh_shape_free(coh_ctx* ctx, coh_shape_t h) {
+  CK(cudaSetDevice(ctx->device));
+  free_shape((DevShape*)h);
+  return 0;
+}
+
+// Bit-frame [n_rows][nw] (device) -> span set.  Consumes nothing; returns 0 handle for the empty set.
+static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_rows, int wx0, int nw, coh_shape_t* out) {
+  *out = 0;
+  if (n_rows <= 0 || nw <= 0) return 0;
+  int* counts = nullptr; int* ptr = nullptr; unsigned long long* d_card = nullptr;
+  CK(cudaMalloc(&counts, sizeof(int) * n_rows));
+  CK(cudaMalloc(&ptr, sizeof(int) * (n_rows + 1)));
+  CK(cudaMalloc(&d_card, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_card, 0, sizeof(unsigned long long), ctx->stream));
+  k_count_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, counts, d_card); LAUNCHED();
+  k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(counts, ptr, n_rows); LAUNCHED();
+  std::vector<int> h_ptr(n_rows + 1);
+  unsigned long long card = 0;
+  CK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int) * (n_rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&card, d_card, sizeof card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(counts); cudaFree(d_card);
+  int total = h_ptr[n_rows];
+  if (total == 0) { cudaFree(ptr); return 0; }
+  // trim empty rows at both ends so that y0 / n_rows are tight
+  int first = 0, last = n_rows - 1;
+  while (h_ptr[first + 1] == h_ptr[first]) first++;
+  while (h_ptr[last + 1] == h_ptr[last]) last--;
+  DevShape* s = new DevShape();
+  s->n_spans = total; s->card = (long long)card;
+  CK(cudaMalloc(&s->spans, sizeof(int2) * total));
+  k_fill_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, wx0, ptr, s->spans); LAUNCHED();
+  s->y0 = y0 + first; s->n_rows = last - first + 1;
+  CK(cudaMalloc(&s->row_ptr, sizeof(int) * (s->n_rows + 1)));
+  CK(cudaMemcpyAsync(s->row_ptr, ptr + first, sizeof(int) * (s->n_rows + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+  // bounds: x extremes need the spans; take them from a host copy (export path, not hot)
+  std::vector<int2> h_spans(total);
+  CK(cudaMemcpyAsync(h_spans.data(), s->spans, sizeof(int2) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ptr);
+  s->by0 = s->y0; s->by1 = s->y0 + s->n_rows - 1; s->bx0 = INT32_MAX; s->bx1 = INT32_MIN;
+  for (int r = first; r <= last; r++) {
+    if (h_ptr[r + 1] > h_ptr[r]) {
+      s->bx0 = std::min(s->bx0, h_spans[h_ptr[r]].x);
+      const int2& l = h_spans[h_ptr[r + 1] - 1];
+      s->bx1 = std::max(s->bx1, l.x + l.y - 1);
+    }
+  }
+  *out = (coh_shape_t)s;
+  return 0;
+}
+// span set -> freshly allocated bit-frame covering rows [y0, y0+n_rows) and words from pixel wx0
+static int bits_from_shape(coh_ctx* ctx, const DevShape* s, int y0, int n_rows, int wx0, int nw, uint32_t** out) {
+  uint32_t* bits = nullptr;
+  CK(cudaMalloc(&bits, sizeof(uint32_t) * (size_t)n_rows * nw));
+  CK(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)n_rows * nw, ctx->stream));
+  if (s && s->n_spans > 0) {
+    k_spans_to_bits<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, s->y0, s->n_rows, y0, n_rows, wx0, nw, bits);
+    LAUNCHED();
+  }
+  *out = bits;
+  return 0;
+}
+
+int coh_shape_box(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (w == 0 && h == 0) return 0;                       // sprite.ml:463
+  if (w < 0 || h < 0) FAIL("Sprite.box: negative argument.");  // sprite.ml:464
+  if (w == 0 || h == 0) return 0;
+  std::vector<int> flat;
+  for (int r = 0; r < h; r++) { flat.push_back(y + r); flat.push_back(1); flat.push_back(x); flat.push_back(w); }
+  return coh_shape_import(ctx, flat.data(), (int64_t)flat.size(), out);
+}
+int coh_shape_import(coh_ctx* ctx, const int32_t* flat, int64_t n, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (n == 0) return 0;
+  // validate canonical form (sprite.ml:201-239) while building the CSR
+  std::vector<int> ys; std::vector<int> cnt; std::vector<int2> spans;
+  int64_t i = 0; long long card = 0;
+  int bx0 = INT32_MAX, bx1 = INT32_MIN;
+  while (i < n) {
+    if (i + 2 > n) FAIL("shape import: truncated row header");
+    int y = flat[i], k = flat[i + 1]; i += 2;
+    if (k <= 0) FAIL("shape import: malformed shape (empty spanline)");
+    if (!ys.empty() && y <= ys.back()) FAIL("shape import: malformed shape (rows not increasing)");
+    if (i + 2 * (int64_t)k > n) FAIL("shape import: truncated spans");
+    for (int q = 0; q < k; q++, i += 2) {
+      int x = flat[i], l = flat[i + 1];
+      if (l <= 0) FAIL("shape import: malformed shape (span length)");
+      if (q && x <= spans.back().x + spans.back().y) FAIL("shape import: malformed shape (spans overlap or abut)");
+      spans.push_back(make_int2(x, l)); card += l;
+      bx0 = std::min(bx0, x); bx1 = std::max(bx1, x + l - 1);
+    }
+    ys.push_back(y); cnt.push_back(k);
+  }
+  DevShape* s = new DevShape();
+  s->y0 = ys.front(); s->n_rows = ys.back() - ys.front() + 1;
+  std::vector<int> ptr(s->n_rows + 1, 0);
+  for (size_t r = 0; r < ys.size(); r++) ptr[ys[r] - s->y0 + 1] = cnt[r];
+  for (int r = 0; r < s->n_rows; r++) ptr[r + 1] += ptr[r];
+  s->n_spans = (int)spans.size(); s->card = card;
+  s->bx0 = bx0; s->bx1 = bx1; s->by0 = ys.front(); s->by1 = ys.back();
+  CK(cudaMalloc(&s->row_ptr, sizeof(int) * ptr.size()));
+  CK(cudaMalloc(&s->spans, sizeof(int2) * spans.size()));
+  CK(cudaMemcpyAsync(s->row_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(s->spans, spans.data(), sizeof(int2) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = (coh_shape_t)s;
+  return 0;
+}
+static int download_shape(coh_ctx* ctx, const DevShape* s, std::vector<int>& ptr, std::vector<int2>& spans) {
+  ptr.resize(s->n_rows + 1); spans.resize(s->n_spans);
+  CK(cudaMemcpyAsync(ptr.data(), s->row_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(spans.data(), s->spans, sizeof(int2) * spans.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int coh_shape_export_size(coh_ctx* ctx, coh_shape_t h, int64_t* n) {
+  CK(cudaSetDevice(ctx->device));
+  *n = 0;
+  if (!h) return 0;
+  DevShape* s = (DevShape*)h;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  int64_t rows = 0;
+  for (int r = 0; r < s->n_rows; r++) rows += ptr[r + 1] > ptr[r];
+  *n = 2 * rows + 2 * (int64_t)s->n_spans;
+  return 0;
+}
+int coh_shape_export(coh_ctx* ctx, coh_shape_t h, int32_t* flat, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!h) return 0;
+  DevShape* s = (DevShape*)h;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  int64_t k = 0;
+  for (int r = 0; r < s->n_rows; r++) {
+    int c = ptr[r + 1] - ptr[r];
+    if (!c) continue;
+    if (k + 2 + 2 * c > cap) FAIL("coh_shape_export: buffer too small");
+    flat[k++] = s->y0 + r; flat[k++] = c;
+    for (int q = ptr[r]; q < ptr[r + 1]; q++) { flat[k++] = spans[q].x; flat[k++] = spans[q].y; }
+  }
+  *n_out = k;
+  return 0;
+}
+int coh_shape_bounds(coh_ctx* ctx, coh_shape_t h, int32_t box[4], int32_t* is_null) {
+  (void)ctx;
+  DevShape* s = (DevShape*)h;
+  *is_null = !s;
+  if (s) { box[0] = s->bx0; box[1] = s->by0; box[2] = s->bx1; box[3] = s->by1; }
+  return 0;
+}
+int coh_shape_card(coh_ctx* ctx, coh_shape_t h, int64_t* n) {
+  (void)ctx;
+  *n = h ? ((DevShape*)h)->card : 0;
+  return 0;
+}
+
+// Binary set algebra through bit-frames over the union bounding box (K3).
+static int shape_binop(coh_ctx* ctx, coh_shape_t ha, coh_shape_t hb, int op, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  DevShape* a = (DevShape*)ha; DevShape* b = (DevShape*)hb;
+  if (!a && !b) return 0;
+  if (!a && op != 0) return 0;       // {} - b = {} ; {} & b = {}
+  if (!b && op == 2) return 0;
+  int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+  for (DevShape* s : {a, b}) if (s) { x0 = std::min(x0, s->bx0); x1 = std::max(x1, s->bx1); y0 = std::min(y0, s->by0); y1 = std::max(y1, s->by1); }
+  int wx0 = floordiv(x0, 32) * 32, nw = (x1 - wx0) / 32 + 1, n_rows = y1 - y0 + 1;
+  uint32_t *ba = nullptr, *bb = nullptr;
+  if (bits_from_shape(ctx, a, y0, n_rows, wx0, nw, &ba)) return 1;
+  if (bits_from_shape(ctx, b, y0, n_rows, wx0, nw, &bb)) return 1;
+  size_t n = (size_t)n_rows * nw;
+  k_bitop<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ba, bb, ba, n, op); LAUNCHED();
+  int rc = shape_from_bits(ctx, ba, y0, n_rows, wx0, nw, out);
+  cudaFree(ba); cudaFree(bb);
+  return rc;
+}
+int coh_shape_union(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out) { return shape_binop(ctx, a, b, 0, out); }
+int coh_shape_difference(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out) { return shape_binop(ctx, a, b, 1, out); }
+int coh_shape_intersection(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out) { return shape_binop(ctx, a, b, 2, out); }
+
+int coh_shape_translate(coh_ctx* ctx, coh_shape_t h, int32_t dx, int32_t dy, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (!h) return 0;
+  DevShape* s = (DevShape*)h;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  for (auto& sp : spans) sp.x += dx;
+  DevShape* t = new DevShape(*s);
+  t->y0 += dy; t->bx0 += dx; t->bx1 += dx; t->by0 += dy; t->by1 += dy;
+  CK(cudaMalloc(&t->row_ptr, sizeof(int) * ptr.size()));
+  CK(cudaMalloc(&t->spans, sizeof(int2) * spans.size()));
+  CK(cudaMemcpyAsync(t->row_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(t->spans, spans.data(), sizeof(int2) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = (coh_shape_t)t;
+  return 0;
+}
+static int bloat_impl(coh_ctx* ctx, const DevShape* s, int x0, int y0, int x1, int y1, int m, int n, bool complement_in_box,
+                      coh_shape_t* out) {
+  // frame = box [x0..x1] x [y0..y1] grown by (m, n) on every side
+  int fx0 = x0 - m, fy0 = y0 - n, fx1 = x1 + m, fy1 = y1 + n;
+  int wx0 = floordiv(fx0, 32) * 32, nw = (fx1 - wx0) / 32 + 1, n_rows = fy1 - fy0 + 1;
+  uint32_t *in = nullptr, *tmp = nullptr;
+  if (bits_from_shape(ctx, s, fy0, n_rows, wx0, nw, &in)) return 1;
+  CK(cudaMalloc(&tmp, sizeof(uint32_t) * (size_t)n_rows * nw));
+  size_t nwords = (size_t)n_rows * nw;
+  if (complement_in_box) {
+    // erode (sprite.ml:1867-1877): inverse = enclosing - shp, bloated, then shp - bloated
+    uint32_t* box = nullptr;
+    CK(cudaMalloc(&box, sizeof(uint32_t) * nwords));
+    dim3 g(cdiv(nw, 128), n_rows);
+    k_fill_box_bits<<<g, 128, 0, ctx->stream>>>(box, n_rows, nw, wx0, fy0, fx0, fy0, fx1, fy1); LAUNCHED();
+    k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(box, in, box, nwords, 1); LAUNCHED();  // inverse
+    k_dilate<<<g, 128, 0, ctx->stream>>>(box, tmp, n_rows, nw, m, n); LAUNCHED();
+    k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(in, tmp, tmp, nwords, 1); LAUNCHED();    // shp - bloated
+    cudaFree(box);
+  } else {
+    dim3 g(cdiv(nw, 128), n_rows);
+    k_dilate<<<g, 128, 0, ctx->stream>>>(in, tmp, n_rows, nw, m, n); LAUNCHED();
+  }
+  int rc = shape_from_bits(ctx, tmp, fy0, n_rows, wx0, nw, out);
+  cudaFree(in); cudaFree(tmp);
+  return rc;
+}
+int coh_shape_bloat(coh_ctx* ctx, coh_shape_t h, int32_t m, int32_t n, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (!h) return 0;
+  if (m < 0 || n < 0) FAIL("Sprite.bloat: negative radius");
+  DevShape* s = (DevShape*)h;
+  return bloat_impl(ctx, s, s->bx0, s->by0, s->bx1, s->by1, m, n, false, out);
+}
+int coh_shape_erode(coh_ctx* ctx, coh_shape_t h, int32_t m, int32_t n, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (!h) return 0;
+  if (m < 0 || n < 0) FAIL("Sprite.erode: negative radius");
+  DevShape* s = (DevShape*)h;
+  return bloat_impl(ctx, s, s->bx0, s->by0, s->bx1, s->by1, m, n, true, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// Polygon
+// ---------------------------------------------------------------------------------------
+struct EdgeBox { int xmin, xmax, ymin, ymax; };
+static EdgeBox edge_bounds(const int32_t* e, int n) {
+  EdgeBox b{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+  for (int i = 0; i < n; i++) {
+    b.xmin = std::min(b.xmin, std::min(e[4 * i], e[4 * i + 2])); b.xmax = std::max(b.xmax, std::max(e[4 * i], e[4 * i + 2]));
+    b.ymin = std::min(b.ymin, std::min(e[4 * i + 1], e[4 * i + 3])); b.ymax = std::max(b.ymax, std::max(e[4 * i + 1], e[4 * i + 3]));
+  }
+  return b;
+}
+// Conservative pixel box of the shape of an edge list: a row y is touched iff its band
+// [32y-47, 32y+16] meets [ymin, ymax]; columns from the widened coverage (polygon.ml:444-453)
+// plus two pixels of slack: band crossings are rounded by truncation toward zero and the
+// bottom crossing of a doubly clipped edge restarts from the rounded top crossing
+// (polygon.ml:365-379), so a crossing can leave the edge's x range by up to 3 sub-bins, and
+// pix_of_sub itself truncates toward zero on negative sub-bins.
+static void shape_pixel_box(const EdgeBox& b, int& px0, int& py0, int& px1, int& py1) {
+  py0 = floordiv(b.ymin - 16 + 31, 32);   // smallest y with 32y+16 >= ymin
+  py1 = floordiv(b.ymax + 47, 32);        // largest y with 32y-47 <= ymax
+  px0 = floordiv(b.xmin - 16, 32) - 2;
+  px1 = floordiv(b.xmax + 16 + 31, 32) + 2;
+}
+static int upload_edges(coh_ctx* ctx, const int32_t* edges, int n, EdgeRec** out) {
+  int4* raw = nullptr;
+  CK(cudaMalloc(&raw, sizeof(int4) * std::max(n, 1)));
+  CK(cudaMalloc(out, sizeof(EdgeRec) * std::max(n, 1)));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(raw, edges, sizeof(int4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_prep_edges<<<cdiv(n, 256), 256, 0, ctx->stream>>>(raw, *out, n); LAUNCHED();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(raw);
+  return 0;
+}
+static int check_error_flag(coh_ctx* ctx, const char* what) {
+  CK(cudaMemcpyAsync(ctx->h_error, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_error) {
+    cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
+    ctx->err = std::string(what) + ": an object has more than " + std::to_string(COH_MAXX) + " band crossings in one row (COH_MAXX)";
+    return 1;
+  }
+  return 0;
+}
+
+int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
+                                  coh_shape_t* shape, coh_shape_t* minshape) {
+  CK(cudaSetDevice(ctx->device));
+  *shape = 0; *minshape = 0;
+  if (n_edges <= 0) return 0;  // polygon.ml:584: NullShape, NullShape
+  if (winding != COH_NONZERO && winding != COH_EVENODD) FAIL("bad winding rule");
+  EdgeBox eb = edge_bounds(edges, n_edges);
+  int px0, py0, px1, py1; shape_pixel_box(eb, px0, py0, px1, py1);
+  int wx0 = floordiv(px0, 32) * 32, nw = (px1 - wx0) / 32 + 1, n_rows = py1 - py0 + 1;
+  EdgeRec* d_edges = nullptr;
+  if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
+  size_t nwords = (size_t)n_rows * nw;
+  uint32_t *S = nullptr, *C = nullptr;
+  CK(cudaMalloc(&S, sizeof(uint32_t) * nwords)); CK(cudaMalloc(&C, sizeof(uint32_t) * nwords));
+  CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  k_scan_rows<<<cdiv(n_rows, 64), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
+  int rc = check_error_flag(ctx, "coh_shapeminshape_of_edgelist");
+  if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
+  if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
+  if (!rc) rc = shape_from_bits(ctx, C, py0, n_rows, wx0, nw, minshape);
+  cudaFree(S); cudaFree(C); cudaFree(d_edges);
+  return rc;
+}
+
+// dense AA opacity bytes over the bit-frame of `shp`, then gathered in span order
+static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges, int winding, const DevShape* s,
+                                 uint8_t** dense, int* wx0_out, int* nw_out) {
+  int wx0 = floordiv(s->bx0, 32) * 32, nw = (s->bx1 - wx0) / 32 + 1;
+  uint32_t* Q = nullptr;
+  if (bits_from_shape(ctx, s, s->y0, s->n_rows, wx0, nw, &Q)) return 1;
+  EdgeRec* d_edges = nullptr;
+  if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
+  CK(cudaMalloc(dense, (size_t)s->n_rows * nw * 32));
+  CK(cudaMemsetAsync(*dense, 0, (size_t)s->n_rows * nw * 32, ctx->stream));
+  dim3 g(cdiv(nw, 8), s->n_rows);
+  k_aa_rows<<<g, 256, 0, ctx->stream>>>(d_edges, n_edges, winding, Q, s->y0, s->n_rows, wx0, nw, ctx->d_aa, *dense, ctx->d_error); LAUNCHED();
+  int rc = check_error_flag(ctx, "coh_polygon_opacity");
+  cudaFree(Q); cudaFree(d_edges);
+  *wx0_out = wx0; *nw_out = nw;
+  return rc;
+}
+int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding, coh_shape_t shp,
+                        uint8_t* out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!shp) return 0;
+  DevShape* s = (DevShape*)shp;
+  if (s->card > cap) FAIL("coh_polygon_opacity: buffer too small");
+  uint8_t* dense = nullptr; int wx0, nw;
+  if (n_edges <= 0) { memset(out, 0, (size_t)s->card); *n_out = s->card; return 0; }  // empty scaled shape: coverage 0
+  if (polygon_opacity_dense(ctx, edges, n_edges, winding, s, &dense, &wx0, &nw)) return 1;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  std::vector<uint8_t> h((size_t)s->n_rows * nw * 32);
+  CK(cudaMemcpyAsync(h.data(), dense, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dense);
+  int64_t k = 0;
+  for (int r = 0; r < s->n_rows; r++)
+    for (int q = ptr[r]; q < ptr[r + 1]; q++)
+      for (int i = 0; i < spans[q].y; i++) out[k++] = h[(size_t)r * nw * 32 + (spans[q].x + i - wx0)];
+  *n_out = k;
+  return 0;
+}
+int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edges, int32_t n_edges, int32_t winding,
+                       coh_shape_t shp, uint32_t* out, int64_t cap, int64_t* n_out) {
+  // polygon.ml:729-746: per span, colour = dissolve (fillsingle x_spanstart y) opacity.  The fill is
+  // evaluated by the same device routine as the walker through a one-object render of `shp`'s spans;
+  // here the opacity comes from the AA kernel and the (cheap, per-span) fill lookup runs on the host
+  // side of the ABI only for this export entry point.
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!shp) return 0;
+  DevShape* s = (DevShape*)shp;
+  if (s->card > cap) FAIL("coh_polygon_sprite: buffer too small");
+  std::vector<uint8_t> op((size_t)s->card);
+  int64_t n = 0;
+  if (coh_polygon_opacity(ctx, edges, n_edges, winding, shp, op.data(), s->card, &n)) return 1;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  FillRec f; f.kind = fill->fill_kind; f.c0 = fill->colour0; f.c1 = fill->colour1; f.flags = fill->fill_flags;
+  for (int i = 0; i < 6; i++) f.p[i] = fill->fparam[i];
+  int64_t k = 0;
+  for (int r = 0; r < s->n_rows; r++)
+    for (int q = ptr[r]; q < ptr[r + 1]; q++) {
+      uint32_t c = fill_lookup(f, spans[q].x, s->y0 + r);
+      for (int i = 0; i < spans[q].y; i++, k++) out[k] = px_dissolve(c, op[k]);
+    }
+  *n_out = k;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scenes and rendering
+// ---------------------------------------------------------------------------------------
+int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
+  CK(cudaSetDevice(ctx->device));
+  DevScene* s = (DevScene*)h;
+  if (!s) return 0;
+  cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
+  delete s;
+  return 0;
+}
+
+// brush.ml:60-92: alpha of the Gaussian stamp of white at `opacity`.
+static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out) {
+  int intopacity = (int)(opacity * 255.), intr = (int)ceil(radius);
+  int size = 2 * intr + 1;
+  r_out = intr;
+  size_t base = out.size();
+  out.resize(base + (size_t)size * size);
+  uint32_t white = 0xFFFFFFFFu;
+  uint32_t c1 = px_dissolve(white, intopacity);
+  for (int y = 0; y < size; y++)
+    for (int x = 0; x < size; x++) {
+      double xp = (double)(x - intr), yp = (double)(y - intr), rr = radius / 2.;
+      double v = 255. * exp(-((xp / rr) * (xp / rr) + (yp / rr) * (yp / rr)));
+      int vi = (int)(v * 1.);
+      out[base + (size_t)y * size + x] = (uint8_t)(px_dissolve(c1, vi) >> 24);
+    }
+}
+
+int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32_t n_background, const int32_t* edges,
+                     int32_t n_edges, const int32_t* points, int32_t n_points, coh_scene_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (n_objs < 0 || n_background < 0 || n_background > n_objs) FAIL("scene: bad object counts");
+  // The scene list and the (pages @ background) list are each wrapped in an implicit root group:
+  // render_frame renders them separately over the same update and composites the two results
+  // with `over` (render.ml:1357-1365), which is exactly what two sibling groups do in one walk.
+  std::vector<ObjRec> recs;
+  std::vector<int> leaves;
+  std::vector<uint8_t> stamps;
+  std::vector<int> open;  // indices (into recs) of open groups
+  ObjRec root; memset(&root, 0, sizeof root);
+  root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
+  recs.push_back(root); open.push_back(0);
+  for (int i = 0; i < n_objs; i++) {
+    if (i == n_objs - n_background) {
+      if (open.size() != 1) FAIL("scene: unterminated group");
+      root.flags = OF_ROOT_BACKGROUND;
+      recs.push_back(root); open[0] = (int)recs.size() - 1;
+    }
+    const coh_object& c = objs[i];
+    if (c.kind == COH_OBJ_GROUP_END) {
+      if (open.size() <= 1) FAIL("scene: GROUP_END without GROUP_BEGIN");
+      open.pop_back();
+      continue;
+    }
+    ObjRec o; memset(&o, 0, sizeof o);
+    o.pretrans = c.pretrans; o.dx = c.dx; o.dy = c.dy;
+    if (c.pretrans < -1 || c.pretrans > 255) FAIL("scene: pretrans out of range");
+    o.depth = (int)open.size();
+    if (o.depth > MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
+    for (int d = 0; d < o.depth; d++) o.anc[d] = open[d];
+    o.fill.kind = c.fill_kind; o.fill.c0 = c.colour0; o.fill.c1 = c.colour1; o.fill.flags = c.fill_flags;
+    for (int k = 0; k < 6; k++) o.fill.p[k] = c.fparam[k];
+    switch (c.kind) {
+      case COH_OBJ_GROUP_BEGIN:
+        o.kind = K_GROUP;
+        if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
+        recs.push_back(o); open.push_back((int)recs.size() - 1);
+        continue;
+      case COH_OBJ_PATH: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
+        o.kind = K_PATH; o.winding = c.winding; o.aa_winding = c.winding; o.first = c.first; o.count = c.count;
+        if (c.count == 0) continue;  // NullShape: nothing to draw
+        EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+        shape_pixel_box(eb, o.bx0, o.by0, o.bx1, o.by1);
+        break;
+      }
+      case COH_OBJ_PRIMITIVE:
+        o.kind = K_PRIM; o.fill.kind = 0;
+        if (c.prim_null) continue;
+        for (int k = 0; k < 4; k++) o.prim[k] = c.prim[k];
+        if (c.prim[2] < c.prim[0] || c.prim[3] < c.prim[1]) FAIL("scene: primitive with negative extent");
+        o.bx0 = c.prim[0]; o.by0 = c.prim[1]; o.bx1 = c.prim[2]; o.by1 = c.prim[3];
+        break;
+      case COH_OBJ_BRUSH: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_points) FAIL("scene: point range out of bounds");
+        if (!(c.brush_radius >= 0.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range");
+        o.kind = K_BRUSH; o.first = c.first; o.count = c.count;
+        if (c.count == 0) continue;
+        o.stamp_off = (int)stamps.size();
+        brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r);
+        int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+        for (int k = 0; k < c.count; k++) {
+          int px = points[2 * ((size_t)c.first + k)], py = points[2 * ((size_t)c.first + k) + 1];
+          x0 = std::min(x0, px); x1 = std::max(x1, px); y0 = std::min(y0, py); y1 = std::max(y1, py);
+        }
+        o.bx0 = x0 - o.brush_r; o.bx1 = x1 + o.brush_r; o.by0 = y0 - o.brush_r; o.by1 = y1 + o.brush_r;
+        break;
+      }
+      default: FAIL("scene: unknown object kind");
+    }
+    o.bx0 += o.dx; o.bx1 += o.dx; o.by0 += o.dy; o.by1 += o.dy;
+    recs.push_back(o);
+    leaves.push_back((int)recs.size() - 1);
+  }
+  if (open.size() != 1) FAIL("scene: unterminated group");
+  DevScene* s = new DevScene();
+  s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
+  s->h_objs = recs;
+  CK(cudaMalloc(&s->objs, sizeof(ObjRec) * recs.size()));
+  CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMalloc(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
+  if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaves, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
+  CK(cudaMalloc(&s->points, sizeof(int2) * std::max(n_points, 1)));
+  if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMalloc(&s->stamps, std::max<size_t>(stamps.size(), 1)));
+  if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = (coh_scene_t)s;
+  return 0;
+}
+
+int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1) {
+  CK(cudaSetDevice(ctx->device));
+  if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
+  if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
+  if (width != ctx->fr.W || height != ctx->fr.H) {
+    cudaFree(ctx->fb); cudaFree(ctx->u_out); ctx->fb = nullptr; ctx->u_out = nullptr;
+    CK(cudaMalloc(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
+    CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
+    CK(cudaMalloc(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
+  }
+  ctx->fr.W = width; ctx->fr.H = height; ctx->fr.band_y0 = band_y0; ctx->fr.band_y1 = band_y1;
+  ctx->fr.tiles_x = cdiv(width, 32); ctx->fr.cells_y = cdiv(height, CELL_H);
+  ctx->have_u = false;
+  return 0;
+}
+
+// One pass (scene or background) of render_frame over the band.
+static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh, bool write_clear, bool record_u) {
+  const Frame& fr = ctx->fr;
+  if (fr.band_y1 <= fr.band_y0 || uw <= 0 || uh <= 0) return 0;
+  int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
+  int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
+  if (n_cells > ctx->n_cells_cap) {
+    cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off);
+    CK(cudaMalloc(&ctx->cell_counts, sizeof(int) * n_cells));
+    CK(cudaMalloc(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
+    ctx->n_cells_cap = n_cells;
+  }
+  // K1: count, scan, fill
+  int bin_blocks = cdiv(n_cells * 32, 256);
+  k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
+  k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
+  // capacity of the item pool: the exact total is a pure function of the object boxes and the
+  // frame geometry, so it is computed on the host (once per scene and geometry) — no device
+  // round trip inside a frame.
+  if (s->items_for_W != fr.W || s->items_for_H != fr.H || s->items_for_y0 != fr.band_y0 || s->items_for_y1 != fr.band_y1) {
+    size_t tot = 0;
+    for (const ObjRec& o : s->h_objs) {
+      if (o.kind == K_GROUP) continue;
+      int cx0 = std::max(o.bx0 >> 5, 0), cx1 = std::min(o.bx1 >> 5, fr.tiles_x - 1);
+      int cy0 = std::max(floordiv(o.by0, CELL_H), cell_row0), cy1 = std::min(floordiv(o.by1, CELL_H), cell_row1);
+      if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+    }
+    s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1;
+  }
+  size_t total = s->items_total;
+  if (total > ctx->cell_items_cap) {
+    cudaFree(ctx->cell_items);
+    size_t cap = total + total / 2 + 1024;
+    CK(cudaMalloc(&ctx->cell_items, sizeof(int) * cap));
+    ctx->cell_items_cap = cap;
+  }
+  k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items); LAUNCHED();
+  WalkParams P;
+  P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
+  P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
+  P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
+  P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
+  P.write_clear = write_clear ? 1 : 0;
+  dim3 grid(cdiv(fr.tiles_x, 8), fr.band_y1 - fr.band_y0);
+  k_walk<<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+  return 0;
+}
+
+// Merge the objects of `scene` and `background` into one walk: the reference renders the two
+// lists separately over the same update and composites the results with `over`
+// (render.ml:1357-1365); a pixel of the background is only visible where the scene pass left
+// `u`, so one front-to-back walk over [Group scene; Group background] gives the same pixels.
+int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh, int32_t flags) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_render_frame: call coh_fb_configure first");
+  if (uw < 0 || uh < 0) FAIL("Sprite.box: negative argument.");
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_render_frame: null scene");
+  bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
+  if (render_pass(ctx, s, ux, uy, uw, uh, true, record_u)) return 1;
+  ctx->have_u = record_u;
+  return 0;
+}
+int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (!ctx->have_u) FAIL("coh_render_uncovered: no frame rendered");
+  const Frame& fr = ctx->fr;
+  int n_rows = fr.band_y1 - fr.band_y0;
+  return shape_from_bits(ctx, ctx->u_out + (size_t)fr.band_y0 * fr.tiles_x, fr.band_y0, n_rows, 0, fr.tiles_x, out);
+}
+void* coh_fb_device_ptr(coh_ctx* ctx) { return ctx->fb; }
+int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_fb_read_rgba: no framebuffer");
+  if (x < 0 || y < 0 || w < 0 || h < 0 || x + w > ctx->fr.W || y + h > ctx->fr.H) FAIL("coh_fb_read_rgba: rectangle outside the framebuffer");
+  if (w == 0 || h == 0) return 0;
+  CK(cudaMemcpy2DAsync(out, (size_t)w * 4, ctx->fb + (size_t)y * ctx->fr.W + x, (size_t)ctx->fr.W * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_fb_read_rgb888: no framebuffer");
+  if (x < 0 || y < 0 || w < 0 || h < 0 || x + w > ctx->fr.W || y + h > ctx->fr.H) FAIL("coh_fb_read_rgb888: rectangle outside the framebuffer");
+  if (w == 0 || h == 0) return 0;
+  uint8_t* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)w * h * 3));
+  dim3 g(cdiv(w, 128), h);
+  k_rgb888<<<g, 128, 0, ctx->stream>>>(ctx->fb, ctx->fr.W, x, y, w, h, d); LAUNCHED();
+  CK(cudaMemcpyAsync(out, d, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// device_types.cuh — records shared by the kernels and the C-ABI host glue.
+#pragma once
+#include <stdint.h>
+#include "raster_core.cuh"
+
+namespace coh {
+
+constexpr int TILE_W = 32;       // pixels per tile word (one warp lane per pixel)
+constexpr int CELL_H = 16;       // rows per binning cell
+constexpr int MAX_DEPTH = 6;     // nested Group depth (incl. the implicit scene / background groups)
+constexpr int AA_WORDS = 17;     // (32 + 2) * 16 scaled columns of one tile = 544 bits
+
+enum { K_PATH = 0, K_PRIM = 1, K_GROUP = 2, K_BRUSH = 4 };
+enum { OF_ROOT_SCENE = 1, OF_ROOT_BACKGROUND = 2 };
+
+// One record per leaf object or group, device resident (96 bytes + fill).
+struct ObjRec {
+  int kind;
+  int winding;      // shape winding rule (polygon.ml:588-591)
+  int aa_winding;   // sprite winding rule (render.ml:1018 uses EvenOdd for stroked paths)
+  int first, count; // edges (PATH) or stamp points (BRUSH)
+  int pretrans;     // -1 or 0..255
+  int dx, dy;       // alias translation (pixels)
+  int bx0, by0, bx1, by1;  // conservative pixel bbox of the shape in DEVICE space (alias applied)
+  int prim[4];      // PRIM: inclusive box in the object's own frame
+  int depth;        // number of enclosing groups (>= 1: implicit root group)
+  int anc[MAX_DEPTH];  // enclosing group object indices, outermost first
+  int flags;
+  int brush_r;      // BRUSH: (w-1)/2
+  int stamp_off;    // BRUSH: offset of the (2r+1)^2 alpha stamp in the stamp pool
+  int pad;
+  FillRec fill;
+};
+
+struct Frame {
+  int W, H;            // framebuffer size in pixels
+  int band_y0, band_y1;  // rows rendered by this context
+  int tiles_x;         // ceil(W / 32)
+  int cells_y;         // ceil(H / CELL_H)
+};
+
+}  // namespace coh

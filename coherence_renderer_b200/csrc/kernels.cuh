@@ -1,0 +1,464 @@
+// kernels.cuh — hand-written sm_100a kernels of the raster hot path.
+//
+//   k_prep_edges      int32 edges -> EdgeRec (x0in/x1in/ymin/ymax, FP64 gradient, direction)
+//   k_bin_count/fill  K1: per-cell (32 px x 16 rows) front-to-back object lists (ballot compaction)
+//   k_walk            K2+K4+K5 fused: one warp per (pixel row, 32-pixel tile) walks its cell list
+//                     front to back; scan-converts each candidate object's row into 32-bit
+//                     shape/coverage words, prunes with the covered-so-far word `u`, evaluates the
+//                     correlated-matte AA only for still-visible edge pixels, composites with
+//                     8-bit premultiplied `over`, and subtracts newly opaque pixels from `u`.
+//                     The row of RGBA8 is written once, 128 B per warp, fully coalesced.
+//   k_scan_rows       K2 stand-alone: shape + coverage bit-rows of one edge list (export path)
+//   k_aa_rows         K4 stand-alone: AA opacity bytes for the pixels of a bit-frame
+//   bit-frame kernels K3: span sets <-> bit-frames, AND/OR/ANDNOT, dilation
+//
+// Design notes are in DESIGN.md.  No tensor cores: this is integer/bit work with a few FP64
+// crossings per (edge,row); the relevant roofline is HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include "device_types.cuh"
+
+namespace coh {
+
+// ------------------------------------------------------------------------------------
+__global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 e = in[i];  // x0, y0, x1, y1
+  out[i] = make_edge(e.x, e.y, e.z, e.w);
+}
+
+// ------------------------------------------------------------------------------------
+// K1 binning.  One warp per cell scans the leaf objects in index order (= front to back),
+// 32 at a time; ballot + popc give each overlapping object its slot, so every list comes
+// out already sorted and the two passes (count / fill) are identical apart from the store.
+// ------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void k_bin(const ObjRec* __restrict__ objs, const int* __restrict__ leaves, int n_leaves, Frame fr,
+                      int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
+                      int* __restrict__ items) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n_cells) return;
+  int cx = warp % fr.tiles_x, cy = cell_row0 + warp / fr.tiles_x;
+  int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1;
+  int y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
+  int base = FILL ? offsets[warp] : 0;
+  int n = 0;
+  for (int b = 0; b < n_leaves; b += 32) {
+    int li = b + lane;
+    bool hit = false;
+    int idx = -1;
+    if (li < n_leaves) {
+      idx = leaves[li];
+      const ObjRec& o = objs[idx];
+      hit = !(o.bx0 > x1 || o.bx1 < x0 || o.by0 > y1 || o.by1 < y0);
+    }
+    unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (FILL && hit) items[base + n + __popc(m & ((1u << lane) - 1u))] = idx;
+    n += __popc(m);
+  }
+  if (!FILL && lane == 0) counts[warp] = n;
+}
+
+// Exclusive scan of n ints by a single block (n is the number of cells: tens of thousands).
+__global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, s, d); if (lane >= d) s += t; }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int prefix = carry + (wid ? warp_sums[wid - 1] : 0);
+    if (i < n) out[i] = prefix + x - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------
+// The fused walker.
+// ------------------------------------------------------------------------------------
+struct WalkParams {
+  const ObjRec* objs;
+  const EdgeRec* edges;
+  const int2* points;          // brush stamp centres (object frame), list order
+  const uint8_t* stamps;       // brush alpha stamps
+  const int* cell_off;         // per cell [first, last) into cell_items
+  const int* cell_items;
+  const AATable* aa;
+  Frame fr;
+  int cell_row0;               // first cell row covered by cell_off
+  int ux0, uy0, ux1, uy1;      // update box, inclusive
+  const uint32_t* u_init;      // optional update set as a bit-frame (fr.H x fr.tiles_x words), else box
+  uint32_t* u_out;             // optional: `u` after the scene pass (same layout)
+  uint32_t* fb;                // RGBA8 framebuffer, fr.W x fr.H
+  int* error_flag;             // set to 1 when an object overflows COH_MAXX crossings
+  int write_clear;             // write clear pixels of the update too (1) or only touched pixels
+};
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
+
+// AA opacity of the visible edge pixels `edge` (bit b = pixel xx0 + b of row yy, object
+// frame) of one polygon.  Lane j scan-converts scaled row 16*yy - 32 + j of the x16 edge
+// list (polygon.ml:673-692) into its private 544-bit row in shared memory; then for every
+// edge pixel the 32 lanes each weigh their row's 32-column window and the warp reduces.
+// Returns the opacity of pixel `lane` (undefined where edge bit is 0).
+__device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, int n_edges, int winding, int xx0, int yy,
+                                       uint32_t edge, uint32_t* aa_bits /*32*AA_WORDS, warp private*/,
+                                       const int* __restrict__ prefix /*[32][33] shared*/, int volume, int lane,
+                                       bool& ok) {
+  uint32_t* row = aa_bits + lane * AA_WORDS;
+#pragma unroll
+  for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
+  SinkMem sink;
+  sink.wx0 = 16 * xx0 - 32; sink.nwords = AA_WORDS; sink.stride = 1; sink.S = row; sink.C = nullptr;
+  ok = scan_row(edges, n_edges, 16, 16 * yy - 32 + lane, winding, true, sink);
+  __syncwarp();
+  int opacity = 0;
+  const int* prow = prefix + lane * 33;
+  uint32_t e = edge;
+  while (e) {
+    int b = __ffs((int)e) - 1;
+    e &= e - 1;
+    uint32_t lo = row[b >> 1], hi = row[(b >> 1) + 1];
+    uint32_t m = (b & 1) ? ((lo >> 16) | (hi << 16)) : lo;
+    int tot = warp_sum(aa_row_sum(prow, m));
+    if (lane == b) opacity = aa_opacity(tot, volume);
+  }
+  __syncwarp();
+  return opacity;
+}
+
+__global__ void __launch_bounds__(256) k_walk(WalkParams P) {
+  __shared__ int s_prefix[32 * 33];
+  __shared__ uint32_t s_aa[8][32 * AA_WORDS];
+  __shared__ uint32_t s_acc[8][MAX_DEPTH][32];
+  __shared__ uint32_t s_u[8][MAX_DEPTH];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
+  __syncthreads();
+  const int volume = P.aa->volume;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x * 8 + wid;
+  const int y = P.fr.band_y0 + blockIdx.y;
+  if (tile >= P.fr.tiles_x || y >= P.fr.band_y1) return;
+  const int tx0 = tile * TILE_W;
+
+  // initial covered-so-far complement `u` for this word of the row
+  uint32_t u;
+  if (P.u_init) u = P.u_init[(size_t)y * P.fr.tiles_x + tile];
+  else u = (y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
+  if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
+  const uint32_t u_update = u;
+  if (P.u_out && lane == 0) P.u_out[(size_t)y * P.fr.tiles_x + tile] = u;  // nothing covered yet
+  if (u == 0u) return;
+
+  uint32_t acc = 0u;       // accumulator of the current nesting level, this lane's pixel
+  int depth = 0;           // open groups
+  int open_grp[MAX_DEPTH];
+  bool bad = false;
+
+  const int cell = (y / CELL_H - P.cell_row0) * P.fr.tiles_x + tile;
+  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+
+  auto pop_group = [&]() {
+    // close the innermost group: its accumulated sprite goes under the parent accumulator
+    // (render.ml:1294 caf over opaque a s; 1295-1298 PreTrans), newly opaque pixels leave the
+    // parent's u (render.ml:1308).
+    int g = open_grp[depth - 1];
+    int pt = P.objs[g].pretrans;
+    int gflags = P.objs[g].flags;
+    uint32_t s = acc;
+    if (pt >= 0) s = px_dissolve(s, pt);
+    uint32_t pa = s_acc[wid][depth - 1][lane];
+    uint32_t pu = s_u[wid][depth - 1];
+    uint32_t r = px_over(pa, s);
+    uint32_t opq = __ballot_sync(0xFFFFFFFFu, (r >> 24) == 255u);
+    acc = r;
+    u = pu & ~opq;
+    depth--;
+    if ((gflags & OF_ROOT_SCENE) && P.u_out) {
+      if (lane == 0) P.u_out[(size_t)y * P.fr.tiles_x + tile] = u;
+    }
+  };
+  auto push_group = [&](int g) {
+    s_acc[wid][depth][lane] = acc;
+    if (lane == 0) s_u[wid][depth] = u;
+    __syncwarp();
+    open_grp[depth] = g;
+    depth++;
+    acc = 0u;
+  };
+
+  for (int base = it0; base < it1; base += 32) {
+    // ---- lane-parallel scan conversion of up to 32 candidate objects for this row word ----
+    int idx = base + lane < it1 ? P.cell_items[base + lane] : -1;
+    uint32_t S = 0u, C = 0u;
+    if (idx >= 0) {
+      const ObjRec& o = P.objs[idx];
+      if (!(o.by0 > y || o.by1 < y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
+        const int yy = y - o.dy, xx0 = tx0 - o.dx;
+        if (o.kind == K_PRIM) {
+          if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
+        } else if (o.kind == K_PATH) {
+          Sink32 sink; sink.wx0 = xx0; sink.S = 0u; sink.C = 0u;
+          if (!scan_row(P.edges + o.first, o.count, 1, yy, o.winding, false, sink)) bad = true;
+          S = sink.S; C = sink.C;
+        } else if (o.kind == K_BRUSH) {
+          // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
+          const int r = o.brush_r;
+          for (int k = 0; k < o.count; k++) {
+            int2 p = P.points[o.first + k];
+            if (p.y - r <= yy && yy <= p.y + r) S |= interval_mask32(xx0, p.x - r, p.x + r);
+          }
+          C = S;
+        }
+      }
+    }
+    unsigned cand = __ballot_sync(0xFFFFFFFFu, (S & u) != 0u);
+    // ---- sequential front-to-back composite of the candidates ----
+    while (cand) {
+      const int k = __ffs((int)cand) - 1;
+      cand &= cand - 1;
+      const uint32_t Sk = __shfl_sync(0xFFFFFFFFu, S, k);
+      const uint32_t Ck = __shfl_sync(0xFFFFFFFFu, C, k);
+      const int ik = __shfl_sync(0xFFFFFFFFu, idx, k);
+      const ObjRec& o = P.objs[ik];
+      // group transitions: close groups that do not enclose this object, open the ones that do
+      int common = 0;
+      while (common < depth && common < o.depth && open_grp[common] == o.anc[common]) common++;
+      while (depth > common) pop_group();
+      while (depth < o.depth) push_group(o.anc[depth]);
+      const uint32_t vis = Sk & u;
+      if (vis == 0u) continue;
+      const uint32_t M = Sk & ~Ck;          // minshape word (polygon.ml:526)
+      const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
+      const int yy = y - o.dy, xx0 = tx0 - o.dx;
+      int opacity = 255;
+      if (edge) {
+        if (o.kind == K_PATH) {
+          bool ok;
+          opacity = aa_tile(P.edges + o.first, o.count, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
+          if (!ok) bad = true;
+        } else if (o.kind == K_BRUSH) {
+          // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
+          const int r = o.brush_r, w = 2 * r + 1;
+          const int px = xx0 + lane;
+          uint32_t a = 0u;
+          if ((edge >> lane) & 1u) {
+            for (int q = 0; q < o.count; q++) {
+              int2 p = P.points[o.first + q];
+              int ddx = px - p.x, ddy = yy - p.y;
+              if (ddx >= -r && ddx <= r && ddy >= -r && ddy <= r)
+                a = alpha_over(a, P.stamps[o.stamp_off + (ddy + r) * w + (ddx + r)]);
+            }
+          }
+          opacity = (int)a;
+        }
+      }
+      bool mine = (vis >> lane) & 1u;
+      if (mine) {
+        const bool is_edge = (edge >> lane) & 1u;
+        uint32_t col;
+        if (o.kind == K_PRIM || o.fill.kind == 0) col = o.fill.c0;
+        else if (!is_edge || o.kind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
+        else {
+          // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span
+          // (run of `edge` bits; a run continuing into the previous tile is cut at the tile — DESIGN.md)
+          uint32_t below = ~edge & ((1u << lane) - 1u);
+          int start = below ? (32 - __clz((int)below)) : 0;
+          col = fill_lookup(o.fill, xx0 + start, yy);
+        }
+        if (is_edge) col = px_dissolve(col, opacity);
+        if (o.pretrans >= 0) col = px_dissolve(col, o.pretrans);
+        acc = px_over(acc, col);
+      }
+      const uint32_t opq = __ballot_sync(0xFFFFFFFFu, mine && (acc >> 24) == 255u);
+      u &= ~opq;  // u' = u --- f  (render.ml:1308)
+    }
+  }
+  while (depth > 0) pop_group();
+  if (bad) *P.error_flag = 1;
+  const int x = tx0 + lane;
+  if ((u_update >> lane) & 1u) {
+    if (P.write_clear || acc != 0u) P.fb[(size_t)y * P.fr.W + x] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K2 stand-alone (export path): one thread per pixel row of one edge list writes the
+// shape and coverage bit-rows into global bit-frames of `nw` words per row.
+// ------------------------------------------------------------------------------------
+__global__ void k_scan_rows(const EdgeRec* __restrict__ edges, int n_edges, int winding, int y0, int n_rows,
+                            int wx0, int nw, uint32_t* __restrict__ S, uint32_t* __restrict__ C, int* error_flag) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  SinkMem sink;
+  sink.wx0 = wx0; sink.nwords = nw; sink.stride = 1;
+  sink.S = S + (size_t)r * nw; sink.C = C + (size_t)r * nw;
+  if (!scan_row(edges, n_edges, 1, y0 + r, winding, false, sink)) *error_flag = 1;
+}
+
+// ------------------------------------------------------------------------------------
+// K4 stand-alone (export path): AA opacity for every set pixel of a bit-frame `Q`
+// (rows y0.., nw words per row starting at pixel wx0).  One warp per (row, word).
+// Output: dense bytes out[r][nw*32].
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_aa_rows(const EdgeRec* __restrict__ edges, int n_edges, int winding,
+                                                 const uint32_t* __restrict__ Q, int y0, int n_rows, int wx0, int nw,
+                                                 const AATable* __restrict__ aa, uint8_t* __restrict__ out, int* error_flag) {
+  __shared__ int s_prefix[32 * 33];
+  __shared__ uint32_t s_aa[8][32 * AA_WORDS];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&aa->prefix[0][0])[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int w = blockIdx.x * 8 + wid, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  uint32_t q = Q[(size_t)r * nw + w];
+  if (!q) return;
+  bool ok;
+  int op = aa_tile(edges, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_prefix, aa->volume, lane, ok);
+  if (!ok) *error_flag = 1;
+  if ((q >> lane) & 1u) out[((size_t)r * nw + w) * 32 + lane] = (uint8_t)op;
+}
+
+// ------------------------------------------------------------------------------------
+// K3: span sets <-> bit-frames and word-wise set algebra.
+// A device span set is CSR: rows y0 .. y0+n_rows-1, row_ptr[n_rows+1], spans (x, len).
+// ------------------------------------------------------------------------------------
+__global__ void k_spans_to_bits(const int* __restrict__ row_ptr, const int2* __restrict__ spans, int src_y0,
+                                int src_rows, int y0, int n_rows, int wx0, int nw, uint32_t* __restrict__ bits) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;  // destination row
+  if (r >= n_rows) return;
+  int sr = y0 + r - src_y0;
+  if (sr < 0 || sr >= src_rows) return;
+  uint32_t* row = bits + (size_t)r * nw;
+  for (int k = row_ptr[sr]; k < row_ptr[sr + 1]; k++) {
+    int2 s = spans[k];
+    or_interval(row, 1, nw, wx0, s.x, s.x + s.y - 1);
+  }
+}
+// op: 0 OR, 1 ANDNOT (a & ~b), 2 AND
+__global__ void k_bitop(const uint32_t* a, const uint32_t* b, uint32_t* out,
+                        size_t n, int op) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = a[i], y = b[i];
+  out[i] = op == 0 ? (x | y) : op == 1 ? (x & ~y) : (x & y);
+}
+// Dilation by (2m+1) x (2n+1) (Sprite.bloat, sprite.ml:1749-1864) on a bit-frame that
+// already has a margin of m pixels / n rows around the set.  One thread per word.
+__global__ void k_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n_rows, int nw, int m, int n) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  uint32_t acc = 0u;
+  for (int rr = max(0, r - n); rr <= min(n_rows - 1, r + n); rr++) {
+    const uint32_t* row = in + (size_t)rr * nw;
+    // OR of the row shifted by -m..+m pixels, gathered for this word
+    for (int s = -m; s <= m; s++) {
+      // bit i of result word w comes from pixel 32w + i - s
+      int q = 32 * w - s;            // source pixel of bit 0
+      int qw = q >> 5, qb = q & 31;  // arithmetic shift: floor
+      uint32_t lo = (qw >= 0 && qw < nw) ? row[qw] : 0u;
+      uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
+      acc |= qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
+    }
+  }
+  out[(size_t)r * nw + w] = acc;
+}
+// Run extraction: count the maximal runs of every row (thread per row), then fill.
+__global__ void k_count_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int* __restrict__ counts,
+                             unsigned long long* __restrict__ card) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t* row = bits + (size_t)r * nw;
+  int n = 0; uint32_t carry = 0u; unsigned long long px = 0;
+  for (int w = 0; w < nw; w++) {
+    uint32_t v = row[w];
+    n += __popc(v & ~((v << 1) | carry));
+    px += __popc(v);
+    carry = v >> 31;
+  }
+  counts[r] = n;
+  if (card && px) atomicAdd(card, px);
+}
+__global__ void k_fill_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int wx0,
+                            const int* __restrict__ row_ptr, int2* __restrict__ spans) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t* row = bits + (size_t)r * nw;
+  int k = row_ptr[r];
+  int start = 0; bool in = false;
+  for (int w = 0; w < nw; w++) {
+    uint32_t v = row[w];
+    int base = wx0 + 32 * w;
+    int pos = 0;
+    while (pos < 32) {
+      if (!in) {
+        uint32_t rest = pos ? (v >> pos) : v;
+        if (!rest) break;
+        pos += __ffs((int)rest) - 1;
+        start = base + pos; in = true;
+      } else {
+        uint32_t rest = ~(pos ? (v >> pos) : v);
+        if (pos) rest &= (0xFFFFFFFFu >> pos);  // bits shifted in from above are not pixels
+        if (!rest) { pos = 32; break; }
+        pos += __ffs((int)rest) - 1;
+        spans[k++] = make_int2(start, base + pos - start);
+        in = false;
+      }
+    }
+  }
+  if (in) spans[k++] = make_int2(start, wx0 + 32 * nw - start);
+}
+// Box-shaped bit-frame (Sprite.box) or clear.
+__global__ void k_fill_box_bits(uint32_t* __restrict__ bits, int n_rows, int nw, int wx0, int y0, int bx0, int by0,
+                                int bx1, int by1) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  int y = y0 + r;
+  bits[(size_t)r * nw + w] = (y >= by0 && y <= by1) ? interval_mask32(wx0 + 32 * w, bx0, bx1) : 0u;
+}
+// RGB888 export of a framebuffer rectangle (wxgui.ml:417-424 plot_sprite byte layout).
+__global__ void k_rgb888(const uint32_t* __restrict__ fb, int W, int x0, int y0, int w, int h, uint8_t* __restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  uint32_t c = fb[(size_t)(y0 + y) * W + x0 + x];
+  uint8_t* p = out + ((size_t)y * w + x) * 3;
+  p[0] = c & 255u; p[1] = (c >> 8) & 255u; p[2] = (c >> 16) & 255u;
+}
+// Gather dense per-pixel values in canonical span order: thread per row.
+template <class T>
+__global__ void k_gather_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,
+                               const long long* __restrict__ px_off, int n_rows, int wx0, int nw,
+                               const T* __restrict__ dense, T* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  long long o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    int2 s = spans[k];
+    for (int i = 0; i < s.y; i++) out[o++] = dense[(size_t)r * nw * 32 + (s.x + i - wx0)];
+  }
+}
+
+}  // namespace coh

@@ -1,0 +1,354 @@
+// raster_core.cuh — the per-row arithmetic of the B200 raster hot path.
+//
+// Everything here is written from the specification in SURVEY.md Appendix A (itself a
+// restatement of /root/reference/{coord,colour,polygon,fill}.ml) and is shaped for the
+// GPU: a row band of one object is evaluated by ONE lane into bit-rows (one bit per
+// pixel) instead of the reference's sorted span lists, because a canonical span list is
+// just the run-length view of a pixel set and set algebra on bit-rows is word-wise
+// AND/OR/ANDNOT.  Span lists only exist at the C-ABI boundary and in the HBM-resident
+// cache (see spans.cuh).
+//
+// The functions are __host__ __device__ so that tests/ can compile this header with g++
+// and drive the very same row arithmetic on the CPU against the oracle (no GPU in the
+// build container).  The product library only ever calls them from kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define COH_HD __host__ __device__ __forceinline__
+#else
+#define COH_HD inline
+#endif
+
+namespace coh {
+
+// ---------------------------------------------------------------------------------
+// FP64 with the reference's rounding: OCaml floats are IEEE binary64 with one rounding
+// per operation and no fused multiply-add (SURVEY.md §7 "hard parts").
+// ---------------------------------------------------------------------------------
+COH_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b; return r;
+#endif
+}
+COH_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b; return r;
+#endif
+}
+COH_HD double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  volatile double r = a / b; return r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------
+// Coord (coord.ml:23-47).  Integer division truncates toward zero, as in OCaml.
+// ---------------------------------------------------------------------------------
+COH_HD int pix_of_sub(int n) { return (n + 31) / 32; }
+COH_HD int imin(int a, int b) { return a < b ? a : b; }
+COH_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------------
+// Colour on decoded RGBA8 words r | g<<8 | b<<16 | a<<24 (colour.ml:287-365).  The
+// 31-bit codec of the reference is lossless on premultiplied values, so operating on
+// the decoded channels gives identical results; the codec lives at the ABI boundary.
+// ---------------------------------------------------------------------------------
+COH_HD uint32_t div255(uint32_t i) { return (i + (i >> 8) + 1) >> 8; }  // colour.ml:287
+COH_HD uint32_t px_alpha(uint32_t c) { return c >> 24; }
+COH_HD uint32_t px_dissolve(uint32_t c, int delta) {  // colour.ml:291-304
+  if (delta == 0) return 0u;
+  if (delta == 255) return c;
+  uint32_t d = (uint32_t)delta;
+  uint32_t r = div255((c & 255u) * d), g = div255(((c >> 8) & 255u) * d);
+  uint32_t b = div255(((c >> 16) & 255u) * d), a = div255((c >> 24) * d);
+  return r | (g << 8) | (b << 16) | (a << 24);
+}
+COH_HD uint32_t prelerp(uint32_t p, uint32_t q, uint32_t a) {  // colour.ml:310-311
+  uint32_t t = a * p + 128u;
+  return p + q - (((t >> 8) + t) >> 8);
+}
+// colour.ml:314-328: `over a b`, a nearer the viewer.
+COH_HD uint32_t px_over(uint32_t a, uint32_t b) {
+  uint32_t aa = a >> 24;
+  if (aa == 0) return b;
+  if (aa == 255) return a;
+  uint32_t r = prelerp(b & 255u, a & 255u, aa);
+  uint32_t g = prelerp((b >> 8) & 255u, (a >> 8) & 255u, aa);
+  uint32_t bl = prelerp((b >> 16) & 255u, (a >> 16) & 255u, aa);
+  uint32_t al = prelerp(b >> 24, aa, aa);
+  return r | (g << 8) | (bl << 16) | (al << 24);
+}
+// colour.ml:332-336 on the alpha channel alone (brush stamping only reads alpha back).
+COH_HD uint32_t alpha_over(uint32_t aa, uint32_t ab) {
+  if (aa == 0) return ab;
+  if (aa == 255) return aa;
+  return prelerp(ab, aa, aa);
+}
+COH_HD uint32_t px_plus(uint32_t a, uint32_t b) { return a + b; }  // colour.ml:339-352 (no channel overflows by contract)
+COH_HD uint32_t px_dissolve_between(uint32_t a, uint32_t b, int alpha) {  // colour.ml:355-361
+  if (alpha == 0) return b;
+  if (alpha == 255) return a;
+  return px_plus(px_dissolve(a, alpha), px_dissolve(b, 255 - alpha));
+}
+
+// ---------------------------------------------------------------------------------
+// Prepared edge (one per input edge, built once by k_prep_edges).
+// polygon.ml:235-240 (x0in/x1in/ymin/ymax), 532-535 (gradient), 326-328 (direction).
+// ---------------------------------------------------------------------------------
+struct EdgeRec {
+  int x0in, x1in, ymin, ymax;  // sub-bins; x0in is the x at the ymin end
+  double g;                    // float (x1in - x0in) /. float (ymax - ymin), 0 when horizontal
+  int dir;                     // +1 if y1 > y0 (A) else -1 (C)
+  int pad;
+};
+COH_HD EdgeRec make_edge(int x0, int y0, int x1, int y1) {
+  EdgeRec e;
+  if (y0 > y1) { e.x0in = x1; e.x1in = x0; }
+  else if (y1 > y0) { e.x0in = x0; e.x1in = x1; }
+  else { e.x0in = imin(x0, x1); e.x1in = imax(x0, x1); }
+  e.ymin = imin(y0, y1); e.ymax = imax(y0, y1);
+  int denom = e.ymax - e.ymin;
+  e.g = denom == 0 ? 0.0 : ddiv((double)(e.x1in - e.x0in), (double)denom);
+  e.dir = y1 > y0 ? 1 : -1;
+  e.pad = 0;
+  return e;
+}
+// polygon.ml:347-348: toint (float x0 +. g *. (float (y - ymin) +. 0.25) +. 0.5)
+COH_HD int crossing_x(int x0, double g, int dy) {
+  return (int)dadd(dadd((double)x0, dmul(g, dadd((double)dy, 0.25))), 0.5);
+}
+
+// ---------------------------------------------------------------------------------
+// Bit-rows.  A bit-row covers pixels [wx0, wx0 + 32*NW); bit i of word w is pixel
+// wx0 + 32*w + i.
+// ---------------------------------------------------------------------------------
+template <int NW>
+struct BitRow {
+  uint32_t w[NW];
+  COH_HD void clear() {
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = 0u;
+  }
+};
+// OR pixel interval [a, b] (inclusive, absolute pixel coords) into a bit-row stored at
+// `bits` with stride `stride` words between consecutive words (stride lets 32 lanes
+// keep private rows in shared memory without bank conflicts).
+COH_HD void or_interval(uint32_t* bits, int stride, int nwords, int wx0, int a, int b) {
+  a -= wx0; b -= wx0;
+  int nb = nwords * 32;
+  if (b < 0 || a >= nb) return;
+  if (a < 0) a = 0;
+  if (b > nb - 1) b = nb - 1;
+  if (a > b) return;
+  int wa = a >> 5, wb = b >> 5;
+  uint32_t ma = 0xFFFFFFFFu << (a & 31), mb = 0xFFFFFFFFu >> (31 - (b & 31));
+  if (wa == wb) { bits[wa * stride] |= (ma & mb); return; }
+  bits[wa * stride] |= ma;
+  for (int w = wa + 1; w < wb; w++) bits[w * stride] = 0xFFFFFFFFu;
+  bits[wb * stride] |= mb;
+}
+// single-word variant returning the mask
+COH_HD uint32_t interval_mask32(int wx0, int a, int b) {
+  a -= wx0; b -= wx0;
+  if (b < 0 || a > 31) return 0u;
+  if (a < 0) a = 0;
+  if (b > 31) b = 31;
+  if (a > b) return 0u;
+  return (0xFFFFFFFFu << a) & (0xFFFFFFFFu >> (31 - b));
+}
+
+// ---------------------------------------------------------------------------------
+// Row scan (polygon.ml:332-528 for one row band).
+//
+// For pixel row `y` of the edge list scaled by `s` (1: shape/minshape; 16: the x16
+// super-sampled shape of polygon.ml:673-692) compute
+//     T ∪ B  = winding spans of the top / bottom band crossings,
+//     C      = coverage spans of the clipped "middle" pieces,
+// and hand every interval to the sink: sink.span(a, b) for T/B spans, sink.cover(a, b)
+// for C spans (pixel coordinates, inclusive).  shape_row = T∪B∪C, minshape_row =
+// shape_row − C (polygon.ml:520-528); the union/fuse of the reference's span lists is
+// the OR of the bit-rows, and ties between equal crossings cannot change the pixel set
+// (SURVEY.md §3.2), so crossings are ranked by (pos, list index).
+//
+// MAXX bounds the crossings kept per list in lane-private storage; on overflow the
+// function returns false and the caller reports the object as too complex (loudly).
+// ---------------------------------------------------------------------------------
+#ifndef COH_MAXX
+#define COH_MAXX 24
+#endif
+
+struct CrossList {
+  int v[COH_MAXX];  // (pos << 1) | (dir > 0)
+  int n;
+};
+
+template <class Sink>
+COH_HD void winding_spans(const CrossList& L, int winding, bool aa, Sink& sink) {
+  int n = L.n < COH_MAXX ? L.n : COH_MAXX;
+  for (int i = 0; i < n; i++) {
+    int vi = L.v[i];
+    int pi = vi >> 1;
+    // rank / running winding count of crossing i in the (pos, index) order, and its successor
+    int cnt = 0, rank = 0;
+    int succ = 0x7FFFFFFF; bool has = false;
+    for (int j = 0; j < n; j++) {
+      int vj = L.v[j];
+      int pj = vj >> 1;
+      bool before_or_self = (pj < pi) || (pj == pi && j <= i);
+      if (before_or_self) { cnt += (vj & 1) ? 1 : -1; rank += (j != i); }
+      else { if (pj < succ) succ = pj; has = true; }
+    }
+    if (!has) continue;  // the last crossing has no successor (polygon.ml:484, 458)
+    bool emit = winding == 0 ? (cnt != 0) : ((rank & 1) == 0);
+    if (!emit) continue;
+    int a = aa ? pix_of_sub(pi) : pix_of_sub(pi - 16);
+    int b = aa ? pix_of_sub(succ) : pix_of_sub(succ + 16);
+    sink.span(a, b);
+  }
+}
+
+// Edge coordinates are scaled by s and translated by (ox, oy) sub-bins AFTER scaling
+// (integer-pixel aliases: ox = 32*dx*s would be wrong for s=16 rows, so callers pass the
+// row/window already moved into the object's own frame and use ox = oy = 0).
+template <class Sink>
+COH_HD bool scan_row(const EdgeRec* __restrict__ edges, int n_edges, int s, int y, int winding, bool aa, Sink& sink) {
+  const int top = 32 * y - 47;  // polygon.ml:539: left_of_pix y - halfips
+  const int bot = top + 63;     // polygon.ml:540
+  CrossList tops, bots;
+  tops.n = 0; bots.n = 0;
+  for (int i = 0; i < n_edges; i++) {
+    const EdgeRec e = edges[i];
+    const int ymin = e.ymin * s, ymax = e.ymax * s;
+    if (ymin > bot || ymax < top) continue;  // polygon.ml:338
+    const int x0 = e.x0in * s, x1 = e.x1in * s;
+    int lo, hi;
+    if (ymin == ymax || (ymin >= top && ymax <= bot)) {  // polygon.ml:340-343
+      lo = imin(x0, x1); hi = imax(x0, x1);
+    } else if (ymin >= top) {  // just bottom clipping, polygon.ml:345-353
+      int xb = crossing_x(x0, e.g, bot - ymin);
+      lo = imin(x0, xb); hi = imax(x0, xb);
+      if (bots.n < COH_MAXX) bots.v[bots.n] = (xb << 1) | (e.dir > 0);
+      bots.n++;
+    } else if (ymax <= bot) {  // just top clipping, polygon.ml:355-364
+      int xt = crossing_x(x0, e.g, top - 1 - ymin);
+      lo = imin(xt, x1); hi = imax(xt, x1);
+      if (tops.n < COH_MAXX) tops.v[tops.n] = (xt << 1) | (e.dir > 0);
+      tops.n++;
+    } else {  // clip both: bottom crossing restarts from the rounded top crossing, polygon.ml:365-385
+      int xt = crossing_x(x0, e.g, top - 1 - ymin);
+      int xb = crossing_x(xt, e.g, bot - top);
+      lo = imin(xt, xb); hi = imax(xt, xb);
+      if (tops.n < COH_MAXX) tops.v[tops.n] = (xt << 1) | (e.dir > 0);
+      tops.n++;
+      if (bots.n < COH_MAXX) bots.v[bots.n] = (xb << 1) | (e.dir > 0);
+      bots.n++;
+    }
+    sink.cover(pix_of_sub(lo - 16), pix_of_sub(hi + 16));  // polygon.ml:444-453
+  }
+  if (tops.n > COH_MAXX || bots.n > COH_MAXX) return false;
+  winding_spans(tops, winding, aa, sink);
+  winding_spans(bots, winding, aa, sink);
+  return true;
+}
+
+// Sinks -----------------------------------------------------------------------------
+// One 32-pixel word, registers only (pixel rows of the tile walker).
+struct Sink32 {
+  int wx0;
+  uint32_t S, C;
+  COH_HD void span(int a, int b) { S |= interval_mask32(wx0, a, b); }
+  COH_HD void cover(int a, int b) { uint32_t m = interval_mask32(wx0, a, b); S |= m; C |= m; }
+};
+// Multi-word rows in memory (export kernels, AA rows).  C may be null (AA needs only S).
+struct SinkMem {
+  int wx0, nwords, stride;
+  uint32_t* S;
+  uint32_t* C;
+  COH_HD void span(int a, int b) { or_interval(S, stride, nwords, wx0, a, b); }
+  COH_HD void cover(int a, int b) {
+    or_interval(S, stride, nwords, wx0, a, b);
+    if (C) or_interval(C, stride, nwords, wx0, a, b);
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// Antialiasing (polygon.ml:616-705).  AA_PREFIX[j][k] = sum_{i<k} maintable[i][j]; the
+// coverage of scaled row j inside a pixel's 32-wide window with occupancy mask m is the
+// sum over the runs of m of AA_PREFIX[j][end+1] - AA_PREFIX[j][start].
+// ---------------------------------------------------------------------------------
+struct AATable {
+  int prefix[32][33];
+  int volume;  // polygon.ml:646-647
+};
+COH_HD int aa_row_sum(const int* prefix_row /*33 ints*/, uint32_t m) {
+  int sum = 0;
+  while (m) {
+#if defined(__CUDA_ARCH__)
+    int s = __ffs((int)m) - 1;
+#else
+    int s = __builtin_ctz(m);
+#endif
+    uint32_t t = ~(m >> s);  // zeros where the run continues (bits above 31-s read as 1)
+#if defined(__CUDA_ARCH__)
+    int l = t ? (__ffs((int)t) - 1) : (32 - s);
+#else
+    int l = t ? __builtin_ctz(t) : (32 - s);
+#endif
+    if (l > 32 - s) l = 32 - s;
+    sum += prefix_row[s + l] - prefix_row[s];
+    uint32_t run = (l >= 32) ? 0xFFFFFFFFu : (((1u << l) - 1u) << s);
+    m &= ~run;
+  }
+  return sum;
+}
+COH_HD int aa_opacity(int table_sum, int volume) {  // polygon.ml:650-651 with cov = 256 * sum
+  return (256 * table_sum + volume / 2) / volume;
+}
+
+// ---------------------------------------------------------------------------------
+// Fills (fill.ml:62-140) evaluated per pixel.
+// ---------------------------------------------------------------------------------
+struct FillRec {
+  int kind;            // 0 plain, 1 axial, 2 radial
+  uint32_t c0, c1;     // RGBA8 premultiplied
+  int flags;           // bit0 ext_s, bit1 ext_e
+  double p[6];
+};
+COH_HD double dsqr(double v) { return dmul(v, v); }
+COH_HD uint32_t fill_lookup(const FillRec& f, int xi, int yi) {
+  if (f.kind == 0) return f.c0;
+  double x = (double)xi, y = (double)yi;
+  if (f.kind == 1) {  // fill.ml:77-93
+    double x0 = f.p[0], y0 = f.p[1], x1 = f.p[2], y1 = f.p[3];
+    if (x1 == x0 && y1 == y0) return 0u;
+    double bottom = dadd(dsqr(dadd(x1, -x0)), dsqr(dadd(y1, -y0)));
+    double xp = ddiv(dadd(dmul(dadd(x1, -x0), dadd(x, -x0)), dmul(dadd(y1, -y0), dadd(y, -y0))), bottom);
+    if (xp < 0.) return (f.flags & 1) ? f.c0 : 0u;
+    if (xp > 1.) return (f.flags & 2) ? f.c1 : 0u;
+    return px_dissolve_between(f.c0, f.c1, 255 - (int)dmul(xp, 255.));
+  }
+  // radial, fill.ml:112-127
+#if defined(__CUDA_ARCH__)
+#define COH_SQRT(v) __dsqrt_rn(v)
+#else
+#define COH_SQRT(v) __builtin_sqrt(v)
+#endif
+  double r = COH_SQRT(dadd(dsqr(dadd(f.p[0], -f.p[2])), dsqr(dadd(f.p[1], -f.p[3]))));
+  double r2 = COH_SQRT(dadd(dsqr(dadd(f.p[0], -f.p[4])), dsqr(dadd(f.p[1], -f.p[5]))));
+  double diff = dadd(r2, -r);
+  double d = COH_SQRT(dadd(dsqr(dadd(f.p[0], -x)), dsqr(dadd(f.p[1], -y))));
+  if (d > r2) return (f.flags & 2) ? f.c1 : 0u;
+  if (d < r) return (f.flags & 1) ? f.c0 : 0u;
+  if (diff == 0.) return f.c0;
+  double t = ddiv(dadd(d, -r), diff);
+  return px_dissolve_between(f.c0, f.c1, 255 - (int)dmul(t, 255.));
+}
+
+}  // namespace coh

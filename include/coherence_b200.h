@@ -1,0 +1,151 @@
+/* coherence_b200.h — C ABI of the B200-native Coherence raster hot path.
+ *
+ * This is the drop-in boundary: OCaml `external` stubs (ocaml/coherence_stubs.c, see
+ * INTEGRATION.md) bind exactly these entry points behind the reference's own module
+ * signatures.  There is no FFI in the reference today; each entry point names the
+ * OCaml interface it replaces (file:line in /root/reference).
+ *
+ * Conventions
+ *  - plain C, `extern "C"`, caller-owned contiguous buffers (OCaml Bigarray.Array1
+ *    c_layout), opaque 64-bit handles for device-resident objects.
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    available from coh_last_error().  The OCaml stub raises `Failure msg`
+ *    (reference convention: failwith, 98 sites; e.g. sprite.ml:463, render.ml:1274).
+ *  - colours cross the boundary as RGBA8 words r | g<<8 | b<<16 | a<<24,
+ *    premultiplied (r,g,b <= a), the decoded form of the reference's 31-bit
+ *    `Colour.colour` (colour.ml:66-244); coh_colour_* convert.
+ *  - geometry crosses the boundary AFTER the affine transform, as integer edges in
+ *    sub-pixel bins (Coord.sub_of_float, coord.ml:47): int32 {x0, y0, x1, y1}.
+ *  - span sets ("shapes", sprite.ml:46-54) are exported in canonical order as
+ *    int32 records: for every non-empty row in increasing y:  y, nspans, then nspans
+ *    pairs (x, len).  Rows group into the reference's vspans by consecutive y.
+ *  - there is NO CPU fallback: every compute entry point fails with an error if no
+ *    CUDA device is usable.
+ */
+#ifndef COHERENCE_B200_H
+#define COHERENCE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct coh_ctx coh_ctx;
+typedef uint64_t coh_shape_t; /* device-resident span set; 0 == Sprite.NullShape */
+typedef uint64_t coh_scene_t; /* device-resident scene */
+
+/* ---- scene description (render.ml:19-75 `renderobject`, flattened depth-first) ---- */
+enum {
+  COH_OBJ_PATH = 0,        /* Basic (fill, Path p), edges = Polygon.edgelist_of_path      */
+  COH_OBJ_PRIMITIVE = 1,   /* Primitive (colour, HLine|VLine|Rectangle), render.ml:556-586 */
+  COH_OBJ_GROUP_BEGIN = 2, /* Group scene ... */
+  COH_OBJ_GROUP_END = 3,   /* ... end of the innermost open group                          */
+  COH_OBJ_BRUSH = 4        /* Basic (fill, Brushstroke ((opacity, Gaussian r), path))      */
+};
+enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
+enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
+enum { COH_FILL_EXT_S = 1, COH_FILL_EXT_E = 2 };
+
+typedef struct coh_object {
+  int32_t kind;        /* COH_OBJ_* */
+  int32_t winding;     /* COH_NONZERO / COH_EVENODD (PATH) */
+  int32_t first;       /* PATH: first edge; BRUSH: first point */
+  int32_t count;       /* PATH: number of edges; BRUSH: number of points */
+  int32_t fill_kind;   /* COH_FILL_* */
+  uint32_t colour0;    /* plain colour / gradient start `cs`; PRIMITIVE colour (RGBA8 premultiplied) */
+  uint32_t colour1;    /* gradient end `ce` */
+  int32_t fill_flags;  /* COH_FILL_EXT_S | COH_FILL_EXT_E */
+  int32_t pretrans;    /* -1: Over; 0..255: PreTrans (v, Over) with toint (v *. 255.) (render.ml:1295-1298) */
+  int32_t dx, dy;      /* integer pixel translation alias (Cache.addtranslation, cache.ml:423-436) */
+  int32_t bounds[4];   /* bounds_of_basicshape xmin,xmax,ymin,ymax (render.ml:377-437); used for the
+                          trivial reject of render.ml:1270-1279 only where it is row-local */
+  int32_t prim[4];     /* PRIMITIVE: inclusive pixel box x0,y0,x1,y1 (toint of the float rectangle) */
+  int32_t prim_null;   /* PRIMITIVE: 1 for a zero-length HLine/VLine (NullShape) */
+  int32_t reserved;
+  int64_t id;          /* cache key (Id.idset); < 0: fresh id each render, never cached */
+  double fparam[6];    /* AXIAL: x0,y0,x1,y1;  RADIAL: cx,cy, px,py, p'x,p'y (fill.ml:77,112) */
+  double brush_opacity; /* BRUSH: opacity in 0..1 */
+  double brush_radius;  /* BRUSH: Gaussian radius */
+} coh_object;
+
+/* ---- lifecycle ---- */
+/* One context owns one GPU and one horizontal band of scanlines [band_y0, band_y1).
+ * device < 0 selects the current device.  Fails when no CUDA device is present. */
+int coh_init(int device, coh_ctx** out);
+int coh_shutdown(coh_ctx* ctx);
+const char* coh_last_error(coh_ctx* ctx); /* ctx may be NULL for init errors */
+int coh_device_name(coh_ctx* ctx, char* buf, int cap);
+/* the CUDA stream every kernel of this context is launched on (for event timing) */
+void* coh_stream(coh_ctx* ctx);
+/* number of kernel launches issued by this context since creation */
+int64_t coh_launch_count(coh_ctx* ctx);
+
+/* ---- colour codec (colour.ml:99-172 colour_of_rgba / rgba_of_colour) ---- */
+int32_t coh_colour_of_rgba8(uint32_t rgba8);
+uint32_t coh_rgba8_of_colour(int32_t colour);
+
+/* ---- Polygon (polygon.mli:44-59) ---- */
+/* Polygon.shapeminshape_of_unsorted_edgelist edges winding  (polygon.ml:608-609):
+ * scan-converts one edge list into (shape, minshape), both device resident. */
+int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
+                                  coh_shape_t* shape, coh_shape_t* minshape);
+/* Antialiased coverage of Polygon.polygon_sprite_edgelist (polygon.ml:694-746) without
+ * the fill: opacity 0..255 for every pixel of `shp`, in canonical span order. */
+int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
+                        coh_shape_t shp, uint8_t* opacity_out, int64_t cap, int64_t* n_out);
+/* Polygon.polygon_sprite_edgelist fill shp edges winding (polygon.ml:729-746): RGBA8 per
+ * pixel of `shp` in canonical span order.  `fill` uses the fill_* / colour* / fparam fields. */
+int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edges, int32_t n_edges,
+                       int32_t winding, coh_shape_t shp, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+
+/* ---- Sprite span-set algebra (sprite.mli:83-136,173-175) ---- */
+int coh_shape_box(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, coh_shape_t* out); /* Sprite.box, sprite.ml:462 */
+int coh_shape_import(coh_ctx* ctx, const int32_t* flat, int64_t n, coh_shape_t* out);
+int coh_shape_export_size(coh_ctx* ctx, coh_shape_t s, int64_t* n_int32);
+int coh_shape_export(coh_ctx* ctx, coh_shape_t s, int32_t* flat, int64_t cap, int64_t* n_out);
+int coh_shape_bounds(coh_ctx* ctx, coh_shape_t s, int32_t box[4], int32_t* is_null); /* x0,y0,x1,y1 (boxshape, sprite.ml:542) */
+int coh_shape_card(coh_ctx* ctx, coh_shape_t s, int64_t* npixels);
+int coh_shape_free(coh_ctx* ctx, coh_shape_t s);
+int coh_shape_union(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out);        /* `|||` sprite.ml:1275 */
+int coh_shape_difference(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out);   /* `---` sprite.ml:1483 */
+int coh_shape_intersection(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out); /* `&&&` sprite.ml:1623 */
+int coh_shape_translate(coh_ctx* ctx, coh_shape_t a, int32_t dx, int32_t dy, coh_shape_t* out); /* sprite.ml:476 */
+int coh_shape_bloat(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1857 */
+int coh_shape_erode(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1867 */
+
+/* ---- Render (render.mli:211-217) ---- */
+/* Upload a scene (flattened object list, head = front-most) with its edge and brush
+ * point pools.  Edges: int32[n_edges][4] = x0,y0,x1,y1 sub-bins.  Points: int32[n][2].
+ * The LAST n_background objects are render_frame's (view.pages @ view.background) list
+ * (render.ml:1364), the others its scene list (render.ml:1357-1363). */
+int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32_t n_background,
+                     const int32_t* edges, int32_t n_edges, const int32_t* points, int32_t n_points,
+                     coh_scene_t* out);
+int coh_scene_free(coh_ctx* ctx, coh_scene_t s);
+/* Size of the device framebuffer (RGBA8, W x H, pixel (0,0) first) and the scanline band
+ * [band_y0, band_y1) this context renders; rows outside the band are left untouched. */
+int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1);
+/* Render.render_frame lmo view update (render.ml:1345-1365) with update = Sprite.box ux uy uw uh:
+ * scene pass over (pages @ background) pass, composited front to back with hidden-surface
+ * set subtraction, into the device framebuffer.  Pixels of the update box not reached by
+ * any object become clear (0).  Asynchronous on coh_stream(); Render.render_simple_scene
+ * (render.ml:1368-1370) is the same call on a scene created with n_background = 0. */
+enum { COH_RENDER_RECORD_U = 1 };
+int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh,
+                     int32_t flags);
+/* The covered-so-far set: export `u` as it stands after the scene pass of the last frame
+ * rendered with COH_RENDER_RECORD_U (the set-subtraction artefact of render.ml:1308:
+ * update minus every pixel the scene pass made opaque), as a device shape. */
+int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out);
+/* Wait for the context's stream and report deferred kernel-side failures. */
+int coh_sync(coh_ctx* ctx);
+/* Device pointer of the framebuffer (band gather by NCCL / peer copies happens on these). */
+void* coh_fb_device_ptr(coh_ctx* ctx);
+/* Copy a rectangle of the framebuffer to host memory: RGBA8, or the RGB888 layout that
+ * Wxgui.plot_sprite writes (wxgui.ml:417-424, premultiplied r,g,b bytes, no alpha). */
+int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COHERENCE_B200_H */

@@ -1,0 +1,132 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (never linked into the product library).
+// CPU restatement of the reference's brush strokes.  Follows
+// /root/reference/brush.ml:14-27 (types, sizeof_brush), 60-92 (g, drawround), 102-122
+// (stamp), 126-130 (points_of_brushstroke), 135-173 (shape), 176-222 (sprite) and
+// /root/reference/polygon.ml:143-218 (points_on_path).
+// PARITY UNPINNED (no reference tests / golden vectors exist).
+#pragma once
+#include <cmath>
+#include "polygon.hpp"
+#include "sprite.hpp"
+namespace oracle {
+
+// A path as the reference's Pdfgraphics.path restricted to what the rasteriser reads:
+// subpaths of segments; a segment is Straight(p1,p2) or Bezier(p1..p4).
+struct Segment { bool bezier; Pt p[4]; };
+typedef std::vector<Segment> Subpath;
+typedef std::vector<Subpath> Path;
+
+// polygon.ml:143-218.  Beziers are flattened at curve_accuracy; flattened pieces of
+// one segment are prepended as a block (segment order reversed, pieces forward).
+inline double straightlength(Pt a, Pt b) {
+  auto sq = [](double x) { return x * x; };
+  return std::sqrt(sq(b.first - a.first) + sq(b.second - a.second));
+}
+inline std::vector<Pt> points_on_path(double sep, const Path& path) {
+  std::vector<Pt> points;
+  for (const Subpath& sub : path) {
+    std::vector<std::pair<Pt, Pt>> segs;  // head of the reference list = segs.front()
+    for (const Segment& s : sub) {
+      if (!s.bezier) segs.insert(segs.begin(), {s.p[0], s.p[1]});
+      else {
+        std::vector<std::pair<Pt, Pt>> e;
+        bezier_subdivide(curve_accuracy, s.p[0], s.p[1], s.p[2], s.p[3], e);
+        segs.insert(segs.begin(), e.begin(), e.end());
+      }
+    }
+    // takelength (polygon.ml:173-184): walk `sep` along the list, splitting a segment
+    size_t i = 0;
+    while (i < segs.size()) {
+      double want = sep;
+      bool found = false;
+      while (i < segs.size()) {
+        double l = straightlength(segs[i].first, segs[i].second);
+        if (want <= l) {
+          // splitat (polygon.ml:151-160)
+          ORACLE_ASSERT(l > 0., "splitat: zero length");
+          double prop = want / l;
+          Pt p1 = segs[i].first, p2 = segs[i].second;
+          Pt p(p1.first * (1. - prop) + p2.first * prop, p1.second * (1. - prop) + p2.second * prop);
+          points.push_back(p);
+          if (p == p2) i++; else segs[i].first = p;
+          found = true;
+          break;
+        }
+        want -= l; i++;
+      }
+      if (!found) break;
+    }
+  }
+  return points;  // the reference conses then reverses: emission order
+}
+
+struct BrushStroke {
+  double opacity = 1.0, radius = 1.0;       // (opacity, Gaussian radius)
+  std::vector<std::pair<int, int>> points;  // toint(x+0.5), toint(y+0.5), in list order (brush.ml:172,196-199)
+  int bw() const { return (int)std::ceil(radius) * 2 + 1; }  // brush.ml:25-28
+};
+inline std::vector<std::pair<int, int>> round_points(const std::vector<Pt>& pts) {
+  std::vector<std::pair<int, int>> o;
+  for (auto& p : pts) o.push_back({(int)(p.first + 0.5), (int)(p.second + 0.5)});
+  return o;
+}
+// brush.ml:60-92: the (2*intr+1)^2 Gaussian stamp of `colour`.
+inline std::vector<colour> drawround(double radius, double opacity, colour col, int& size) {
+  ORACLE_ASSERT(radius >= 0., "drawround: radius");
+  ORACLE_ASSERT(opacity >= 0. && opacity <= 1., "drawround: opacity");
+  int intopacity = (int)(opacity * 255.), intr = (int)std::ceil(radius);
+  size = intr * 2 + 1;
+  std::vector<colour> brush((size_t)size * size);
+  auto sq = [](double x) { return x * x; };
+  for (int x = 1; x <= size; x++)
+    for (int y = 1; y <= size; y++) {
+      int xp = x - intr - 1, yp = y - intr - 1;
+      double r = radius / 2.;
+      double v = 255. * std::exp(-(sq((double)xp / r) + sq((double)yp / r)));
+      int vi = (int)(v * 1.);
+      ORACLE_ASSERT(vi >= 0 && vi <= 255, "drawround: v'");
+      brush[(size_t)(y - 1) * size + (x - 1)] = dissolve(dissolve(col, intopacity), vi);
+    }
+  return brush;
+}
+// brush.ml:135-173
+inline Shape shape_of_brushstroke(const BrushStroke& b) {
+  std::vector<std::pair<int, int>> pts = b.points;
+  std::stable_sort(pts.begin(), pts.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& c) {
+    return a.second != c.second ? a.second < c.second : a.first < c.first;
+  });
+  Shape s;
+  for (auto& p : pts) {
+    if (s.rows.empty() || s.rows.back().y != p.second) s.rows.push_back({p.second, {}});
+    Spanline& l = s.rows.back().spans;
+    if (!l.empty() && l.back().x + l.back().len - 1 == p.first) continue;          // duplicate point
+    if (!l.empty() && l.back().x + l.back().len == p.first) l.back().len++;        // abutting
+    else l.push_back({p.first, 1});
+  }
+  int r = (b.bw() - 1) / 2;
+  return bloat(r, r, s);
+}
+// brush.ml:176-222
+inline Sprite sprite_of_brushstroke(const BrushStroke& b, const Fill& fill, const Shape& shp) {
+  Sprite none;
+  if (shp.null()) return none;
+  int r = (b.bw() - 1) / 2;
+  Shape bloated = bloat(r, r, shp);
+  Shape twice = bloat(r, r, bloated);
+  Box bb; shape_bounds(twice, bb);
+  Canvas canvas(bb.x0, bb.y0, bb.x1 - bb.x0 + 1, bb.y1 - bb.y0 + 1, clear_colour());
+  int size;
+  std::vector<colour> brush = drawround(b.radius, b.opacity, mkcol(255, 255, 255), size);
+  for (auto& p : b.points) {
+    if (!point_in_shape(bloated, p.first, p.second)) continue;
+    for (int by = 0; by < size; by++)
+      for (int bx = 0; bx < size; bx++) {
+        colour& c = canvas.at(p.first - r + bx, p.second - r + by);
+        c = alpha_over(c, brush[(size_t)by * size + bx]);
+      }
+  }
+  return map_shape(shp, [&](int x, int y, int l, colour* out) {
+    for (int k = 0; k < l; k++) out[k] = dissolve(fill.fillsingle(x + k, y), alpha_of_colour(canvas.at(x + k, y)));
+  });
+}
+}  // namespace oracle

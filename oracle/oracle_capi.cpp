@@ -1,0 +1,282 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  C entry points (ctypes) over the CPU restatement
+// of the reference.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load this library; the product library never does.
+// PARITY UNPINNED (no reference tests / golden vectors exist; OCaml cannot be built here).
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "../include/coherence_b200.h"
+#include "render.hpp"
+
+using namespace oracle;
+
+static thread_local std::string g_err;
+#define ORC_TRY try {
+#define ORC_CATCH } catch (const std::exception& e) { g_err = e.what(); return 1; } return 0;
+
+static std::vector<Edge> edges_from(const int32_t* e, int n) {
+  std::vector<Edge> v((size_t)n);
+  for (int i = 0; i < n; i++) v[i] = Edge{e[4 * i], e[4 * i + 2], e[4 * i + 1], e[4 * i + 3]};  // x0,y0,x1,y1 -> {x0,x1,y0,y1}
+  return v;
+}
+static int32_t* dup_ints(const std::vector<int>& v) {
+  int32_t* p = (int32_t*)std::malloc(sizeof(int32_t) * (v.size() + 1));
+  if (!v.empty()) std::memcpy(p, v.data(), sizeof(int32_t) * v.size());
+  return p;
+}
+static Fill fill_from(const coh_object& o) {
+  Fill f;
+  f.kind = (Fill::Kind)o.fill_kind;
+  f.c0 = colour_of_rgba8(o.colour0); f.c1 = colour_of_rgba8(o.colour1);
+  for (int i = 0; i < 6; i++) f.p[i] = o.fparam[i];
+  f.ext_s = o.fill_flags & COH_FILL_EXT_S; f.ext_e = o.fill_flags & COH_FILL_EXT_E;
+  return f;
+}
+// Rebuild the object tree from the flattened list.  An alias (dx,dy) is applied the way
+// the reference's cache would serve it: the ORIGINAL geometry's shape/sprite translated
+// by whole pixels (cache.ml:380-385,400-405) == rasterising the edges moved by 32*d sub-bins.
+static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, const int32_t* points) {
+  std::vector<Scene> stack(1);
+  std::vector<Obj> open;
+  for (int i = 0; i < n; i++) {
+    const coh_object& c = objs[i];
+    Obj o;
+    o.id = c.id; o.pretrans = c.pretrans;
+    for (int k = 0; k < 4; k++) o.bounds[k] = c.bounds[k];
+    o.has_bounds = !(c.bounds[0] == 0 && c.bounds[1] == 0 && c.bounds[2] == 0 && c.bounds[3] == 0);
+    switch (c.kind) {
+      case COH_OBJ_PATH: {
+        o.kind = Obj::Path; o.fill = fill_from(c); o.winding = (Winding)c.winding;
+        o.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
+        for (Edge& e : o.edges) { e.x0 += 32 * c.dx; e.x1 += 32 * c.dx; e.y0 += 32 * c.dy; e.y1 += 32 * c.dy; }
+        sort_edgelist_maxy_rev(o.edges);
+        stack.back().push_back(std::move(o));
+        break;
+      }
+      case COH_OBJ_PRIMITIVE: {
+        o.kind = Obj::Primitive; o.prim_colour = colour_of_rgba8(c.colour0); o.prim_null = c.prim_null;
+        for (int k = 0; k < 4; k++) o.prim[k] = c.prim[k];
+        stack.back().push_back(std::move(o));
+        break;
+      }
+      case COH_OBJ_BRUSH: {
+        o.kind = Obj::Brush; o.fill = fill_from(c);
+        o.stroke.opacity = c.brush_opacity; o.stroke.radius = c.brush_radius;
+        for (int k = 0; k < c.count; k++)
+          o.stroke.points.push_back({points[2 * ((size_t)c.first + k)] + c.dx, points[2 * ((size_t)c.first + k) + 1] + c.dy});
+        stack.back().push_back(std::move(o));
+        break;
+      }
+      case COH_OBJ_GROUP_BEGIN: {
+        o.kind = Obj::Group;
+        open.push_back(std::move(o)); stack.emplace_back();
+        break;
+      }
+      case COH_OBJ_GROUP_END: {
+        if (open.empty()) throw std::runtime_error("scene: GROUP_END without GROUP_BEGIN");
+        Obj g = std::move(open.back()); open.pop_back();
+        g.children = std::move(stack.back()); stack.pop_back();
+        if (g.children.empty()) throw std::runtime_error("Empty groups aren't allowed");  // render.ml:317
+        stack.back().push_back(std::move(g));
+        break;
+      }
+      default: throw std::runtime_error("scene: unknown object kind");
+    }
+  }
+  if (!open.empty()) throw std::runtime_error("scene: unterminated group");
+  return stack[0];
+}
+static void sprite_to_dense(const Sprite& s, int ux, int uy, int uw, int uh, uint32_t* out) {
+  for (auto& r : s.rows) {
+    if (r.y < uy || r.y >= uy + uh) continue;
+    int off = 0;
+    for (auto& sp : r.spans) {
+      for (int k = 0; k < sp.len; k++) {
+        int x = sp.x + k;
+        if (x >= ux && x < ux + uw) out[(size_t)(r.y - uy) * uw + (x - ux)] = rgba8_of_colour(r.px[off + k]);
+      }
+      off += sp.len;
+    }
+  }
+}
+
+extern "C" {
+const char* orc_last_error() { return g_err.c_str(); }
+void orc_free(void* p) { std::free(p); }
+
+int32_t orc_colour_of_rgba8(uint32_t w) { return colour_of_rgba8(w); }
+uint32_t orc_rgba8_of_colour(int32_t c) { return rgba8_of_colour(c); }
+int32_t orc_colour_of_rgba(int r, int g, int b, int a) { return colour_of_rgba(r, g, b, a); }
+int orc_div255(int i) { return div255(i); }
+// op: 0 over, 1 alpha_over, 2 pd_plus, 3 dissolve(a, delta=b), 4 dissolve_between(a,b,alpha=c), 5 monochrome(a)
+int orc_colour_op(int op, uint32_t a, uint32_t b, int c, uint32_t* out) {
+  ORC_TRY
+  colour ca = colour_of_rgba8(a), cb = colour_of_rgba8(b), r;
+  switch (op) {
+    case 0: r = over(ca, cb); break;
+    case 1: r = alpha_over(ca, cb); break;
+    case 2: r = pd_plus(ca, cb); break;
+    case 3: r = dissolve(ca, (int)b); break;
+    case 4: r = dissolve_between(ca, cb, c); break;
+    case 5: r = monochrome(ca); break;
+    default: throw std::runtime_error("orc_colour_op: bad op");
+  }
+  *out = rgba8_of_colour(r);
+  ORC_CATCH
+}
+int orc_sub_of_float(double f) { return sub_of_float(f); }
+int orc_pix_of_sub(int n) { return pix_of_sub(n); }
+
+// AA tables: maintable (32*32 ints, [x][y]) and volume.
+int orc_aa_tables(int32_t* maintable, int32_t* volume) {
+  const AATables& T = aa_tables();
+  for (int x = 0; x < 32; x++) for (int y = 0; y < 32; y++) maintable[x * 32 + y] = T.maintable[x][y];
+  *volume = T.volume;
+  return 0;
+}
+
+// Polygon.shapeminshape_of_unsorted_edgelist: returns two malloc'd flat shapes.
+int orc_shapeminshape(const int32_t* edges, int n, int winding, int32_t** shp, int64_t* nshp, int32_t** minshp, int64_t* nmin) {
+  ORC_TRY
+  Shape s, m;
+  shapeminshape_of_unsorted_edgelist(edges_from(edges, n), (Winding)winding, s, m);
+  if (!shapecheck(s) || !shapecheck(m)) throw std::runtime_error("shapeminshape: malformed output");
+  auto a = shape_to_flat(s), b = shape_to_flat(m);
+  *shp = dup_ints(a); *nshp = (int64_t)a.size(); *minshp = dup_ints(b); *nmin = (int64_t)b.size();
+  ORC_CATCH
+}
+// The x16 scaled shape of polygon.ml:673-692 (debug / cross-check artefact).
+int orc_scaled_shape(const int32_t* edges, int n, int winding, int32_t** shp, int64_t* nshp) {
+  ORC_TRY
+  std::vector<Edge> es = edges_from(edges, n);
+  sort_edgelist_maxy_rev(es);
+  auto a = shape_to_flat(mk_scaled_shape((Winding)winding, es));
+  *shp = dup_ints(a); *nshp = (int64_t)a.size();
+  ORC_CATCH
+}
+// AA opacity for every pixel of `shape` (flat), span order.
+int orc_polygon_opacity(const int32_t* edges, int n, int winding, const int32_t* shape, int64_t nshape, uint8_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  std::vector<Edge> es = edges_from(edges, n);
+  sort_edgelist_maxy_rev(es);
+  Shape scaled = mk_scaled_shape((Winding)winding, es);
+  Shape shp = shape_from_flat(shape, (int)nshape);
+  int64_t k = 0;
+  for (auto& r : shp.rows) for (auto& sp : r.spans) for (int i = 0; i < sp.len; i++) {
+    if (k >= cap) throw std::runtime_error("orc_polygon_opacity: buffer too small");
+    out[k++] = (uint8_t)pixel_opacity(scaled, sp.x + i, r.y);
+  }
+  *nout = k;
+  ORC_CATCH
+}
+// Polygon.polygon_sprite_edgelist: RGBA8 per pixel of shape, span order.
+int orc_polygon_sprite(const coh_object* fill, const int32_t* edges, int n, int winding, const int32_t* shape, int64_t nshape, uint32_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  std::vector<Edge> es = edges_from(edges, n);
+  sort_edgelist_maxy_rev(es);
+  Sprite s = Renderer::polygon_sprite_edgelist(fill_from(*fill), shape_from_flat(shape, (int)nshape), es, (Winding)winding);
+  int64_t k = 0;
+  for (auto& r : s.rows) for (colour c : r.px) {
+    if (k >= cap) throw std::runtime_error("orc_polygon_sprite: buffer too small");
+    out[k++] = rgba8_of_colour(c);
+  }
+  *nout = k;
+  ORC_CATCH
+}
+// op: 0 union 1 difference 2 intersection
+int orc_shape_op(int op, const int32_t* a, int64_t na, const int32_t* b, int64_t nb, int32_t** out, int64_t* nout) {
+  ORC_TRY
+  Shape A = shape_from_flat(a, (int)na), B = shape_from_flat(b, (int)nb), R;
+  if (!shapecheck(A) || !shapecheck(B)) throw std::runtime_error("shape op: malformed input");
+  R = op == 0 ? shape_union(A, B) : op == 1 ? shape_difference(A, B) : shape_intersection(A, B);
+  if (!shapecheck(R)) throw std::runtime_error("shape op: malformed output");
+  auto f = shape_to_flat(R); *out = dup_ints(f); *nout = (int64_t)f.size();
+  ORC_CATCH
+}
+// op: 0 bloat m n, 1 erode m n, 2 translate dx dy
+int orc_shape_unary(int op, const int32_t* a, int64_t na, int m, int n, int32_t** out, int64_t* nout) {
+  ORC_TRY
+  Shape A = shape_from_flat(a, (int)na), R;
+  R = op == 0 ? bloat(m, n, A) : op == 1 ? erode(m, n, A) : translate_shape(m, n, A);
+  if (!shapecheck(R)) throw std::runtime_error("shape unary: malformed output");
+  auto f = shape_to_flat(R); *out = dup_ints(f); *nout = (int64_t)f.size();
+  ORC_CATCH
+}
+
+// Render.render_frame over update = Sprite.box ux uy uw uh.  `out` is a dense uw*uh RGBA8
+// image (0 where the result sprite has no pixel).  If u_out != NULL it receives the flat
+// shape of the covered-so-far complement `u` after the scene pass.
+// flags bit0: disable the bbox trivial reject.  usecache: Cache.usecache.
+int orc_render_frame(const coh_object* objs, int n_scene, int n_background, const int32_t* edges, const int32_t* points,
+                     int ux, int uy, int uw, int uh, int flags, int usecache, uint32_t* out, int32_t** u_out, int64_t* nu_out) {
+  ORC_TRY
+  Scene scene = build_scene(objs, n_scene, edges, points);
+  Scene bg = build_scene(objs + n_scene, n_background, edges, points);
+  Renderer R; R.bbox_reject = !(flags & 1); R.cache.usecache = usecache != 0;
+  Shape update = shape_box(ux, uy, uw, uh);
+  std::memset(out, 0, sizeof(uint32_t) * (size_t)uw * uh);
+  Shape u1 = update; Sprite a1; R.render_scene(u1, a1, scene, false);
+  Sprite res = a1;
+  if (n_background > 0) {
+    Shape u2 = update; Sprite a2; R.render_scene(u2, a2, bg, true);
+    res = caf(over, opaque, a1, a2).first;
+  }
+  sprite_to_dense(res, ux, uy, uw, uh, out);
+  if (u_out) { auto f = shape_to_flat(u1); *u_out = dup_ints(f); *nu_out = (int64_t)f.size(); }
+  ORC_CATCH
+}
+
+// Persistent renderer for the cached / animated configurations (C4): keeps Cache between frames.
+void* orc_renderer_new(int usecache) { Renderer* r = new Renderer(); r->cache.usecache = usecache != 0; return r; }
+void orc_renderer_free(void* r) { delete (Renderer*)r; }
+int orc_renderer_addtranslation(void* r, int64_t id, int64_t target, int dx, int dy) {
+  ((Renderer*)r)->cache.addtranslation(id, target, dx, dy); return 0;
+}
+int orc_renderer_frame(void* rp, const coh_object* objs, int n_scene, int n_background, const int32_t* edges, const int32_t* points,
+                       const int32_t* update_flat, int64_t n_update, int ox, int oy, int ow, int oh, uint32_t* out) {
+  ORC_TRY
+  Renderer& R = *(Renderer*)rp;
+  Scene scene = build_scene(objs, n_scene, edges, points);
+  Scene bg = build_scene(objs + n_scene, n_background, edges, points);
+  Shape update = shape_from_flat(update_flat, (int)n_update);
+  Sprite res = R.render_frame(scene, bg, update);
+  sprite_to_dense(res, ox, oy, ow, oh, out);
+  ORC_CATCH
+}
+
+// Host-side geometry helpers restated from polygon.ml (used to cross-check the product's
+// own host-side flattening): bezier flattening and points_on_path.
+int orc_flatten_bezier(const double* p8, double eps, double** out, int64_t* nseg) {
+  ORC_TRY
+  std::vector<std::pair<Pt, Pt>> e;
+  bezier_subdivide(eps, Pt(p8[0], p8[1]), Pt(p8[2], p8[3]), Pt(p8[4], p8[5]), Pt(p8[6], p8[7]), e);
+  double* o = (double*)std::malloc(sizeof(double) * 4 * (e.size() + 1));
+  for (size_t i = 0; i < e.size(); i++) { o[4 * i] = e[i].first.first; o[4 * i + 1] = e[i].first.second; o[4 * i + 2] = e[i].second.first; o[4 * i + 3] = e[i].second.second; }
+  *out = o; *nseg = (int64_t)e.size();
+  ORC_CATCH
+}
+// segs: nseg records of 9 doubles: kind (0 straight, 1 bezier), then 4 points (straight uses 2).
+// One subpath.  Returns rounded integer points (brush.ml:172).
+int orc_points_on_path(const double* segs, int nseg, double sep, int32_t** out, int64_t* npts) {
+  ORC_TRY
+  Subpath sub;
+  for (int i = 0; i < nseg; i++) {
+    Segment s; s.bezier = segs[9 * i] != 0.;
+    for (int k = 0; k < 4; k++) s.p[k] = Pt(segs[9 * i + 1 + 2 * k], segs[9 * i + 2 + 2 * k]);
+    sub.push_back(s);
+  }
+  auto pts = round_points(points_on_path(sep, Path{sub}));
+  std::vector<int> f;
+  for (auto& p : pts) { f.push_back(p.first); f.push_back(p.second); }
+  *out = dup_ints(f); *npts = (int64_t)pts.size();
+  ORC_CATCH
+}
+int orc_brush_stamp(double radius, double opacity, uint8_t* alpha_out, int cap, int* size_out) {
+  ORC_TRY
+  int size; auto b = drawround(radius, opacity, mkcol(255, 255, 255), size);
+  if (size * size > cap) throw std::runtime_error("orc_brush_stamp: buffer too small");
+  for (int i = 0; i < size * size; i++) alpha_out[i] = (uint8_t)alpha_of_colour(b[i]);
+  *size_out = size;
+  ORC_CATCH
+}
+}  // extern "C"

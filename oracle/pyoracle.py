@@ -1,0 +1,194 @@
+"""ctypes binding of the ORACLE (CPU restatement of the reference renderer).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+PARITY UNPINNED: the reference has no tests or golden vectors and cannot be built here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_last_error.restype = C.c_char_p
+        _LIB.orc_rgba8_of_colour.restype = C.c_uint32
+        _LIB.orc_renderer_new.restype = C.c_void_p
+    return _LIB
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _chk(rc):
+    if rc != 0:
+        raise OracleError(lib().orc_last_error().decode())
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a, t=C.c_int32):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _take(p, n):
+    out = np.ctypeslib.as_array(p, shape=(max(int(n), 1),))[: int(n)].copy()
+    lib().orc_free(p)
+    return out
+
+
+def colour_of_rgba8(w):
+    return lib().orc_colour_of_rgba8(C.c_uint32(w))
+
+
+def rgba8_of_colour(c):
+    return lib().orc_rgba8_of_colour(C.c_int32(c))
+
+
+def colour_of_rgba(r, g, b, a):
+    return lib().orc_colour_of_rgba(r, g, b, a)
+
+
+def colour_op(op, a, b=0, c=0):
+    ops = {"over": 0, "alpha_over": 1, "pd_plus": 2, "dissolve": 3, "dissolve_between": 4, "monochrome": 5}
+    out = C.c_uint32()
+    _chk(lib().orc_colour_op(ops[op], C.c_uint32(a), C.c_uint32(b), c, C.byref(out)))
+    return out.value
+
+
+def div255(i):
+    return lib().orc_div255(i)
+
+
+def sub_of_float(f):
+    return lib().orc_sub_of_float(C.c_double(f))
+
+
+def pix_of_sub(n):
+    return lib().orc_pix_of_sub(n)
+
+
+def aa_tables():
+    t = np.zeros(32 * 32, dtype=np.int32)
+    v = C.c_int32()
+    lib().orc_aa_tables(_ptr(t), C.byref(v))
+    return t.reshape(32, 32), v.value
+
+
+def shapeminshape(edges, winding):
+    e = _i32(edges).reshape(-1, 4)
+    ps, pm = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+    ns, nm = C.c_int64(), C.c_int64()
+    _chk(lib().orc_shapeminshape(_ptr(e), len(e), winding, C.byref(ps), C.byref(ns), C.byref(pm), C.byref(nm)))
+    return _take(ps, ns.value), _take(pm, nm.value)
+
+
+def scaled_shape(edges, winding):
+    e = _i32(edges).reshape(-1, 4)
+    ps, ns = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_scaled_shape(_ptr(e), len(e), winding, C.byref(ps), C.byref(ns)))
+    return _take(ps, ns.value)
+
+
+def shape_card(flat):
+    n, i, flat = 0, 0, np.asarray(flat)
+    while i < len(flat):
+        k = int(flat[i + 1])
+        n += int(flat[i + 3 : i + 2 + 2 * k : 2].sum())
+        i += 2 + 2 * k
+    return n
+
+
+def polygon_opacity(edges, winding, shape_flat):
+    e = _i32(edges).reshape(-1, 4)
+    s = _i32(shape_flat)
+    cap = shape_card(s)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    n = C.c_int64()
+    _chk(lib().orc_polygon_opacity(_ptr(e), len(e), winding, _ptr(s), C.c_int64(len(s)), _ptr(out, C.c_uint8), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]
+
+
+def polygon_sprite(fill_obj, edges, winding, shape_flat):
+    e = _i32(edges).reshape(-1, 4)
+    s = _i32(shape_flat)
+    cap = shape_card(s)
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_int64()
+    _chk(lib().orc_polygon_sprite(C.byref(fill_obj), _ptr(e), len(e), winding, _ptr(s), C.c_int64(len(s)), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]
+
+
+def shape_op(op, a, b):
+    ops = {"union": 0, "difference": 1, "intersection": 2}
+    a, b = _i32(a), _i32(b)
+    p, n = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_shape_op(ops[op], _ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b)), C.byref(p), C.byref(n)))
+    return _take(p, n.value)
+
+
+def shape_unary(op, a, m, n_):
+    ops = {"bloat": 0, "erode": 1, "translate": 2}
+    a = _i32(a)
+    p, n = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_shape_unary(ops[op], _ptr(a), C.c_int64(len(a)), m, n_, C.byref(p), C.byref(n)))
+    return _take(p, n.value)
+
+
+def render_frame(objs, n_scene, n_background, edges, points, update, bbox_reject=True, usecache=False, want_u=False):
+    """objs: ctypes array of coh_object (scene objects then background objects)."""
+    ux, uy, uw, uh = update
+    e = _i32(edges).reshape(-1, 4)
+    p = _i32(points).reshape(-1, 2)
+    out = np.zeros((uh, uw), dtype=np.uint32)
+    pu, nu = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(
+        lib().orc_render_frame(
+            objs, n_scene, n_background, _ptr(e), _ptr(p), ux, uy, uw, uh, 0 if bbox_reject else 1, 1 if usecache else 0,
+            _ptr(out, C.c_uint32), C.byref(pu) if want_u else None, C.byref(nu) if want_u else None,
+        )
+    )
+    if want_u:
+        return out, _take(pu, nu.value)
+    return out
+
+
+def flatten_bezier(p8, eps=0.2):
+    a = np.ascontiguousarray(p8, dtype=np.float64).reshape(8)
+    p, n = C.POINTER(C.c_double)(), C.c_int64()
+    _chk(lib().orc_flatten_bezier(_ptr(a, C.c_double), C.c_double(eps), C.byref(p), C.byref(n)))
+    out = np.ctypeslib.as_array(p, shape=(max(n.value, 1) * 4,))[: n.value * 4].copy().reshape(-1, 4)
+    lib().orc_free(p)
+    return out
+
+
+def points_on_path(segs, sep):
+    a = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 9)
+    p, n = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_points_on_path(_ptr(a, C.c_double), len(a), C.c_double(sep), C.byref(p), C.byref(n)))
+    return _take(p, n.value * 2).reshape(-1, 2)
+
+
+def brush_stamp(radius, opacity):
+    out = np.zeros(101 * 101, dtype=np.uint8)
+    size = C.c_int()
+    _chk(lib().orc_brush_stamp(C.c_double(radius), C.c_double(opacity), _ptr(out, C.c_uint8), len(out), C.byref(size)))
+    s = size.value
+    return out[: s * s].reshape(s, s)

@@ -1,0 +1,277 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (never linked into the product library).
+// CPU restatement of the reference's scene renderer: per-object shapes, the
+// min/max-shape split, the partial-sprite cache and the front-to-back loop with
+// hidden-surface set subtraction.  Follows /root/reference/render.ml:19-75 (scene
+// types), 469-594 (shape_of_basicshape), 984-1078 (sprite_of_basicshape), 1134-1242
+// (spriteof), 1268-1335 (renderobj, render_scene), 1345-1370 (render_frame,
+// render_simple_scene), 1376-1400 (dirty regions) and /root/reference/cache.ml:57-436.
+// Transforms are applied before this boundary: geometry arrives as
+// integer sub-bin edges, so no camlpdf arithmetic is involved.
+// PARITY UNPINNED (no reference tests / golden vectors exist).
+#pragma once
+#include <map>
+#include <memory>
+#include "brush.hpp"
+#include "convolve.hpp"
+#include "polygon.hpp"
+#include "sprite.hpp"
+namespace oracle {
+
+struct Obj;
+typedef std::vector<Obj> Scene;
+
+struct Obj {
+  enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4 } kind = Path;
+  long id = -1;              // < 0: a fresh id per render (Id.new_ids ()), never cached
+  int pretrans = -1;         // -1: Over; else PreTrans(v, Over) with delta = toint (v *. 255.)
+  int bounds[4] = {0, 0, 0, 0};  // bounds_of_basicshape: xmin, xmax, ymin, ymax (render.ml:377-437)
+  bool has_bounds = false;
+  // Path
+  Fill fill;
+  std::vector<Edge> edges;   // sorted by sort_edgelist_maxy_rev
+  Winding winding = NonZero;
+  // Primitive (render.ml:556-586): inclusive integer box; prim_null for zero-length lines
+  colour prim_colour = 0;
+  int prim[4] = {0, 0, 0, 0};  // x0, y0, x1, y1 inclusive
+  bool prim_null = false;
+  // Group
+  Scene children;
+  // Brush
+  BrushStroke stroke;
+  // Convolved (kernel, child geometry = children[0])
+  Kernel kernel;
+};
+
+// ---- cache.ml restated: shapes and partial sprites keyed by id, integer-translation
+// aliases.  Eviction order in the reference follows Hashtbl.iter (unspecified); the
+// cache never changes a rendered value, only the work done, so a simple byte budget
+// with "drop sprites first, then shapes" stands in for drophalf (cache.ml:242-271).
+struct Cache {
+  struct Entry {
+    bool alias = false; int dx = 0, dy = 0; long target = 0;
+    bool has_shape = false; Shape shape, minshape;
+    bool has_sprite = false; Sprite sprite; Shape pshape;
+  };
+  bool usecache = false;
+  std::map<long, Entry> tab;
+  long shphit = 0, shpmis = 0, sprhit = 0, sprmis = 0;
+  void clear() { tab.clear(); }
+  bool getshape(long id, Shape& s, Shape& m) {  // cache.ml:370-387
+    if (!usecache || id < 0) return false;
+    auto it = tab.find(id);
+    if (it == tab.end()) { shpmis++; return false; }
+    Entry& e = it->second;
+    if (e.alias) {
+      Shape s0, m0;
+      if (!getshape(e.target, s0, m0)) return false;
+      s = translate_shape(e.dx, e.dy, s0); m = translate_shape(e.dx, e.dy, m0);
+      return true;
+    }
+    if (!e.has_shape) { shpmis++; return false; }
+    shphit++; s = e.shape; m = e.minshape; return true;
+  }
+  void addshape(long id, const Shape& s, const Shape& m) {  // cache.ml:280-324
+    if (!usecache || id < 0) return;
+    auto it = tab.find(id);
+    if (it != tab.end() && it->second.alias) { id = it->second.target; it = tab.find(id); }
+    if (it != tab.end() && it->second.has_shape) return;
+    Entry& e = tab[id];
+    e.has_shape = true; e.shape = s; e.minshape = m;
+  }
+  bool getsprite(long id, Sprite& spr, Shape& pshape) {  // cache.ml:390-407
+    if (!usecache || id < 0) return false;
+    auto it = tab.find(id);
+    if (it == tab.end()) { sprmis++; return false; }
+    Entry& e = it->second;
+    if (e.alias) {
+      Sprite s0; Shape p0;
+      if (!getsprite(e.target, s0, p0)) return false;
+      spr = translate_sprite(e.dx, e.dy, s0); pshape = translate_shape(e.dx, e.dy, p0);
+      return true;
+    }
+    if (!e.has_sprite) { sprmis++; return false; }
+    sprhit++; spr = e.sprite; pshape = e.pshape; return true;
+  }
+  void addsprite(long id, const Sprite& spr, const Shape& pshape) {  // cache.ml:328-367
+    if (!usecache || id < 0) return;
+    auto it = tab.find(id);
+    if (it != tab.end() && it->second.alias) {
+      int dx = it->second.dx, dy = it->second.dy; long t = it->second.target;
+      Entry& e = tab[t];
+      e.has_sprite = true; e.sprite = translate_sprite(-dx, -dy, spr); e.pshape = translate_shape(-dx, -dy, pshape);
+      return;
+    }
+    Entry& e = tab[id];
+    e.has_sprite = true; e.sprite = spr; e.pshape = pshape;
+  }
+  void addtranslation(long id, long target, int dx, int dy) {  // cache.ml:423-436
+    if (!usecache) return;
+    auto it = tab.find(target);
+    if (it == tab.end()) return;
+    Entry e; e.alias = true;
+    if (it->second.alias) { e.dx = dx + it->second.dx; e.dy = dy + it->second.dy; e.target = it->second.target; }
+    else { e.dx = dx; e.dy = dy; e.target = target; }
+    tab[id] = e;
+  }
+};
+
+struct Renderer {
+  Cache cache;
+  bool bbox_reject = true;   // render.ml:1270-1279 trivial reject on bounds
+  // optional trace of the covered-so-far sets: u after each renderobj at top level
+  std::vector<Shape>* trace_u = nullptr;
+
+  // render.ml:469-594
+  void shape_of_basicshape(const Obj& o, Shape& shp, Shape& minshp) {
+    switch (o.kind) {
+      case Obj::Group: {
+        if (cache.getshape(o.id, shp, minshp)) return;
+        shp = Shape(); minshp = Shape();
+        for (const Obj& c : o.children) {  // members get fresh ids (render.ml:483)
+          Shape s, m; shape_of_basicshape(c, s, m);
+          shp = shape_union(shp, s);
+        }
+        cache.addshape(o.id, shp, minshp);  // group minshape is always null (render.ml:494)
+        return;
+      }
+      case Obj::Path: {
+        if (cache.getshape(o.id, shp, minshp)) return;
+        shapeminshape_of_edgelist(o.edges, o.winding, false, shp, minshp);
+        cache.addshape(o.id, shp, minshp);
+        return;
+      }
+      case Obj::Brush: {
+        if (cache.getshape(o.id, shp, minshp)) return;
+        shp = shape_of_brushstroke(o.stroke); minshp = Shape();  // brush.ml:135-173
+        cache.addshape(o.id, shp, minshp);
+        return;
+      }
+      case Obj::Convolved: {  // render.ml:536-555 (cache switched off while computing)
+        if (cache.getshape(o.id, shp, minshp)) return;
+        int r = radius_of_kernel(o.kernel);
+        bool saved = cache.usecache; cache.usecache = false;
+        const Obj& child = o.children.at(0);
+        Shape cs, cm; shape_of_basicshape(child, cs, cm);
+        shp = bloat(r, r, cs);
+        if (findfill_fancy(child)) minshp = Shape(); else minshp = erode(r, r, cm);
+        cache.usecache = saved;
+        cache.addshape(o.id, shp, minshp);
+        return;
+      }
+      case Obj::Primitive: {
+        shp = Shape();
+        if (!o.prim_null) shp = shape_box(o.prim[0], o.prim[1], o.prim[2] - o.prim[0] + 1, o.prim[3] - o.prim[1] + 1);
+        minshp = shp;
+        return;
+      }
+    }
+  }
+  static bool findfill_fancy(const Obj& o) {  // render.ml `findfill`
+    if (o.kind == Obj::Group) return true;
+    if (o.kind == Obj::Convolved) return findfill_fancy(o.children.at(0));
+    return o.fill.fancy();
+  }
+
+  // polygon.ml:729-746 — AA sprite of a polygon inside `shp`.  Quirk kept: the fill
+  // is sampled at the span's first x for every pixel of the span (polygon.ml:736).
+  static Sprite polygon_sprite_edgelist(const Fill& f, const Shape& shp, const std::vector<Edge>& edges, Winding w) {
+    Shape scaled = mk_scaled_shape(w, edges);
+    return map_shape(shp, [&](int x, int y, int l, colour* out) {
+      for (int k = 0; k < l; k++) {
+        int opacity = pixel_opacity(scaled, x + k, y);
+        out[k] = dissolve(f.fillsingle(x, y), opacity);
+      }
+    });
+  }
+
+  // render.ml:984-1078
+  Sprite sprite_of_basicshape(const Obj& o, const Shape& shp) {
+    switch (o.kind) {
+      case Obj::Group: {
+        Sprite a; Shape u = shp;
+        render_scene(u, a, o.children, true);
+        return a;
+      }
+      case Obj::Path: return polygon_sprite_edgelist(o.fill, shp, o.edges, o.winding);
+      case Obj::Brush: return sprite_of_brushstroke(o.stroke, o.fill, shp);
+      case Obj::Convolved: {  // render.ml:1023-1052: always the "fancy" route
+        int r = radius_of_kernel(o.kernel);
+        Shape shp2 = bloat(r, r, shp);
+        Sprite raster = sprite_of_basicshape(o.children.at(0), shp2);
+        return portion(convolve_sprite(o.kernel, raster), shp);
+      }
+      default: throw std::runtime_error("Internal inconsistency: Should already have been rendered");
+    }
+  }
+
+  // render.ml:1134-1242 (non-filter objects)
+  Sprite spriteof(const Obj& o, const Shape& shp) {
+    Sprite cached; Shape pshape;
+    cache.getsprite(o.id, cached, pshape);
+    Shape shptorender = shape_difference(shp, pshape);
+    if (shptorender.null()) return portion(cached, shp);
+    Sprite rendered;
+    if (o.kind == Obj::Primitive) {
+      Shape s, m; shape_of_basicshape(o, s, m);
+      rendered = fillshape(shape_intersection(shptorender, s), Fill::plain(o.prim_colour));
+    } else {
+      Shape s, m; shape_of_basicshape(o, s, m);
+      Shape maxshape = shape_difference(s, m);
+      Sprite maxbit = sprite_of_basicshape(o, shape_intersection(shptorender, maxshape));
+      Sprite minbit = fillshape(shape_intersection(m, shptorender), o.fill);
+      rendered = caf(nocover, opaque, minbit, maxbit).first;
+    }
+    Sprite newwhole = caf(nocover, opaque, cached, rendered).first;
+    Shape pshape2 = shape_of_sprite(newwhole);
+    if (o.kind != Obj::Primitive) cache.addsprite(o.id, newwhole, pshape2);
+    return portion(newwhole, shape_intersection(shp, pshape2));
+  }
+
+  // render.ml:1268-1308
+  void renderobj(const Obj& o, Shape& u, Sprite& a) {
+    if (bbox_reject && o.has_bounds) {
+      Box ub; shape_bounds(u, ub);
+      // Pdfutil.box_overlap on inclusive integer boxes
+      if (o.bounds[0] > ub.x1 || o.bounds[1] < ub.x0 || o.bounds[2] > ub.y1 || o.bounds[3] < ub.y0) return;
+    }
+    Shape r, rm; shape_of_basicshape(o, r, rm);
+    Shape r2 = shape_intersection(r, u);
+    if (r2.null()) return;
+    Sprite s = spriteof(o, r2);
+    if (o.pretrans >= 0) {
+      int d = o.pretrans;
+      s = sprite_map([d](colour c) { return dissolve(c, d); }, s);
+    }
+    auto res = caf(over, opaque, a, s);
+    a = std::move(res.first);
+    u = shape_difference(u, res.second);
+  }
+  // render.ml:1310-1335
+  void render_scene(Shape& u, Sprite& a, const Scene& objs, bool nested) {
+    for (const Obj& o : objs) {
+      if (u.null()) return;
+      renderobj(o, u, a);
+      if (!nested && trace_u) trace_u->push_back(u);
+    }
+  }
+  // render.ml:1345-1365 — scene pass and background pass over the same update.
+  Sprite render_frame(const Scene& scene, const Scene& background, const Shape& update) {
+    Shape u1 = update; Sprite a1; render_scene(u1, a1, scene, false);
+    Shape u2 = update; Sprite a2; render_scene(u2, a2, background, true);
+    return caf(over, opaque, a1, a2).first;
+  }
+  // render.ml:1368-1370
+  Sprite render_simple_scene(const Scene& scene, const Shape& shape) {
+    Shape u = shape; Sprite a; render_scene(u, a, scene, false);
+    return a;
+  }
+};
+
+// render.ml:1376-1400 — dirty region of a moved object (o = old, n = new shapes).
+inline Shape plaindirty(const Shape& shp_o, const Shape& min_o, const Shape& shp_n, const Shape& min_n, const Shape& u) {
+  return shape_intersection(shape_union(shape_difference(shp_o, min_n), shape_difference(shp_n, min_o)), u);
+}
+inline Shape alldirty(const Shape& shp_o, const Shape& shp_n, const Shape& u) {
+  return shape_intersection(shape_union(shp_o, shp_n), u);
+}
+}  // namespace oracle

@@ -1,0 +1,115 @@
+// TEST HARNESS ONLY.  Compiles the product's row arithmetic (raster_core.cuh, the code the
+// CUDA kernels execute per lane) with g++ so that the build container — which has no GPU —
+// can check it against the oracle on thousands of inputs.  Never part of the product
+// library and never a fallback: the C ABI in libcoherence_b200.so has no CPU path.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cmath>
+#include "../../coherence_renderer_b200/csrc/raster_core.cuh"
+
+using namespace coh;
+
+static int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) q--; return q; }
+
+static void runs_to_flat(const std::vector<uint32_t>& bits, int y0, int n_rows, int wx0, int nw, std::vector<int>& flat) {
+  for (int r = 0; r < n_rows; r++) {
+    std::vector<int> sp;
+    int start = 0; bool in = false;
+    for (int i = 0; i < nw * 32; i++) {
+      bool b = (bits[(size_t)r * nw + (i >> 5)] >> (i & 31)) & 1u;
+      if (b && !in) { start = i; in = true; }
+      if (!b && in) { sp.push_back(wx0 + start); sp.push_back(i - start); in = false; }
+    }
+    if (in) { sp.push_back(wx0 + start); sp.push_back(nw * 32 - start); }
+    if (!sp.empty()) { flat.push_back(y0 + r); flat.push_back((int)sp.size() / 2); flat.insert(flat.end(), sp.begin(), sp.end()); }
+  }
+}
+
+extern "C" {
+void emul_free(void* p) { std::free(p); }
+
+// shape and minshape of an edge list through scan_row + bit-rows (what k_scan_rows does)
+int emul_shapeminshape(const int32_t* edges, int n, int winding, int32_t** shp, int64_t* nshp, int32_t** mshp, int64_t* nm) {
+  std::vector<EdgeRec> es;
+  int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+  for (int i = 0; i < n; i++) {
+    es.push_back(make_edge(edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]));
+    xmin = std::min(xmin, std::min(edges[4 * i], edges[4 * i + 2])); xmax = std::max(xmax, std::max(edges[4 * i], edges[4 * i + 2]));
+    ymin = std::min(ymin, std::min(edges[4 * i + 1], edges[4 * i + 3])); ymax = std::max(ymax, std::max(edges[4 * i + 1], edges[4 * i + 3]));
+  }
+  std::vector<int> fs, fm;
+  bool ok = true;
+  if (n > 0) {
+    int py0 = floordiv(ymin - 16 + 31, 32), py1 = floordiv(ymax + 47, 32);
+    int px0 = floordiv(xmin - 16, 32) - 2, px1 = floordiv(xmax + 16 + 31, 32) + 2;
+    // two rows / 64 columns of extra margin: the test asserts nothing lands outside the product's box
+    int y0 = py0 - 2, n_rows = py1 - py0 + 5;
+    int wx0 = floordiv(px0, 32) * 32 - 32, nw = (px1 - wx0) / 32 + 2;
+    std::vector<uint32_t> S((size_t)n_rows * nw, 0u), C((size_t)n_rows * nw, 0u);
+    for (int r = 0; r < n_rows; r++) {
+      SinkMem sink; sink.wx0 = wx0; sink.nwords = nw; sink.stride = 1; sink.S = &S[(size_t)r * nw]; sink.C = &C[(size_t)r * nw];
+      ok = scan_row(es.data(), n, 1, y0 + r, winding, false, sink) && ok;
+    }
+    // margin must be empty (shape_pixel_box of the product is conservative)
+    for (int r = 0; r < n_rows; r++) for (int w = 0; w < nw; w++) {
+      bool inside_rows = (y0 + r >= py0 && y0 + r <= py1);
+      uint32_t v = S[(size_t)r * nw + w];
+      if (!inside_rows && v) return 3;
+      for (int b = 0; b < 32; b++) if ((v >> b) & 1u) { int x = wx0 + 32 * w + b; if (x < px0 || x > px1) return 4; }
+    }
+    std::vector<uint32_t> M(S.size());
+    for (size_t i = 0; i < S.size(); i++) M[i] = S[i] & ~C[i];
+    runs_to_flat(S, y0, n_rows, wx0, nw, fs);
+    runs_to_flat(M, y0, n_rows, wx0, nw, fm);
+  }
+  *shp = (int32_t*)std::malloc(sizeof(int32_t) * (fs.size() + 1)); std::memcpy(*shp, fs.data(), sizeof(int32_t) * fs.size()); *nshp = (int64_t)fs.size();
+  *mshp = (int32_t*)std::malloc(sizeof(int32_t) * (fm.size() + 1)); std::memcpy(*mshp, fm.data(), sizeof(int32_t) * fm.size()); *nm = (int64_t)fm.size();
+  return ok ? 0 : 2;
+}
+
+static AATable g_aa; static bool g_aa_init = false;
+static void init_aa() {
+  if (g_aa_init) return;
+  int M[32][32];
+  for (int x = 1; x <= 32; x++) for (int y = 1; y <= 32; y++) {
+    double xp = ((double)(x - 1) * 6.) / 31. - 3., yp = ((double)(y - 1) * 6.) / 31. - 3.;
+    M[x - 1][y - 1] = (int)(std::exp(-((xp * xp + yp * yp) / 2.0)) * 255.);
+  }
+  long total = 0;
+  for (int j = 0; j < 32; j++) { g_aa.prefix[j][0] = 0; for (int i = 0; i < 32; i++) { g_aa.prefix[j][i + 1] = g_aa.prefix[j][i] + M[i][j]; total += M[i][j]; } }
+  g_aa.volume = (int)((total * 256) / 255);
+  g_aa_init = true;
+}
+// AA opacity of pixels (x0.., y) for a 32-pixel word, the way aa_tile does it (lane j = scaled row j)
+int emul_opacity_word(const int32_t* edges, int n, int winding, int x0, int y, uint8_t* out32) {
+  init_aa();
+  std::vector<EdgeRec> es;
+  for (int i = 0; i < n; i++) es.push_back(make_edge(edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]));
+  uint32_t rows[32][17];
+  std::memset(rows, 0, sizeof rows);
+  bool ok = true;
+  for (int j = 0; j < 32; j++) {
+    SinkMem sink; sink.wx0 = 16 * x0 - 32; sink.nwords = 17; sink.stride = 1; sink.S = rows[j]; sink.C = nullptr;
+    ok = scan_row(es.data(), n, 16, 16 * y - 32 + j, winding, true, sink) && ok;
+  }
+  for (int b = 0; b < 32; b++) {
+    int tot = 0;
+    for (int j = 0; j < 32; j++) {
+      uint32_t lo = rows[j][b >> 1], hi = rows[j][(b >> 1) + 1];
+      uint32_t m = (b & 1) ? ((lo >> 16) | (hi << 16)) : lo;
+      tot += aa_row_sum(g_aa.prefix[j], m);
+    }
+    out32[b] = (uint8_t)aa_opacity(tot, g_aa.volume);
+  }
+  return ok ? 0 : 2;
+}
+uint32_t emul_over(uint32_t a, uint32_t b) { return px_over(a, b); }
+uint32_t emul_dissolve(uint32_t c, int d) { return px_dissolve(c, d); }
+uint32_t emul_dissolve_between(uint32_t a, uint32_t b, int alpha) { return px_dissolve_between(a, b, alpha); }
+uint32_t emul_alpha_over(uint32_t a, uint32_t b) { return alpha_over(a, b); }
+uint32_t emul_fill(int kind, uint32_t c0, uint32_t c1, int flags, const double* p, int x, int y) {
+  FillRec f; f.kind = kind; f.c0 = c0; f.c1 = c1; f.flags = flags; for (int i = 0; i < 6; i++) f.p[i] = p[i];
+  return fill_lookup(f, x, y);
+}
+}
