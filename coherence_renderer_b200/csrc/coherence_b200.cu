@@ -29,7 +29,10 @@ struct DevScene {
   EdgeRec* edges = nullptr;
   int2* points = nullptr;
   uint8_t* stamps = nullptr;
+  int* rowedge_ptr = nullptr;   // K1 edge binning (CSR over (path object, pixel row))
+  int* rowedge_idx = nullptr;
   std::vector<ObjRec> h_objs;
+  bool has_fancy = false;    // some path has a gradient / radial fill
   size_t items_total = 0;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
 };
@@ -51,6 +54,15 @@ struct coh_ctx {
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* h_total = nullptr;  // pinned
+  // cross-tile carry for fancy fills
+  int* ticket = nullptr; int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
+  size_t carry_slots = 0; int epoch = 0;
+  bool own_stream = true, own_fb = true;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // bin start, walk start, walk end, spare
+  double walk_ms_sum = 0, bin_ms_sum = 0; long timed_frames = 0;
+  bool ev_pending = false;
 };
 
 static std::string g_init_err;
@@ -121,9 +133,12 @@ int coh_shutdown(coh_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_aa); cudaFree(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
-  cudaFree(ctx->fb); cudaFree(ctx->u_out);
+  if (ctx->own_fb) cudaFree(ctx->fb);
+  cudaFree(ctx->u_out);
   cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
-  cudaStreamDestroy(ctx->stream);
+  cudaFree(ctx->ticket); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
   return 0;
 }
@@ -134,6 +149,38 @@ int coh_device_name(coh_ctx* ctx, char* buf, int cap) {
   return 0;
 }
 void* coh_stream(coh_ctx* ctx) { return (void*)ctx->stream; }
+int coh_set_stream(coh_ctx* ctx, void* stream) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)stream; ctx->own_stream = false;
+  return 0;
+}
+static int drain_timing(coh_ctx* ctx) {
+  if (!ctx->ev_pending) return 0;
+  CK(cudaEventSynchronize(ctx->ev[2]));
+  float a = 0, b = 0;
+  CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+  CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+  ctx->bin_ms_sum += a; ctx->walk_ms_sum += b; ctx->timed_frames++;
+  ctx->ev_pending = false;
+  return 0;
+}
+int coh_set_timing(coh_ctx* ctx, int32_t on) {
+  CK(cudaSetDevice(ctx->device));
+  if (drain_timing(ctx)) return 1;
+  if (on && !ctx->ev[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->ev[i]));
+  ctx->timing = on != 0; ctx->walk_ms_sum = 0; ctx->bin_ms_sum = 0; ctx->timed_frames = 0;
+  return 0;
+}
+int coh_get_timing(coh_ctx* ctx, double* walk_ms_avg, double* bin_ms_avg, int64_t* frames) {
+  CK(cudaSetDevice(ctx->device));
+  if (drain_timing(ctx)) return 1;
+  *frames = ctx->timed_frames;
+  *walk_ms_avg = ctx->timed_frames ? ctx->walk_ms_sum / ctx->timed_frames : 0.;
+  *bin_ms_avg = ctx->timed_frames ? ctx->bin_ms_sum / ctx->timed_frames : 0.;
+  return 0;
+}
 int64_t coh_launch_count(coh_ctx* ctx) { return ctx->launches; }
 static int check_error_flag(coh_ctx* ctx, const char* what);
 int coh_sync(coh_ctx* ctx) {
@@ -472,7 +519,7 @@ static int check_error_flag(coh_ctx* ctx, const char* what) {
   CK(cudaStreamSynchronize(ctx->stream));
   if (*ctx->h_error) {
     cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
-    ctx->err = std::string(what) + ": an object has more than " + std::to_string(COH_MAXX) + " band crossings in one row (COH_MAXX)";
+    ctx->err = std::string(what) + ": an object has more than " + std::to_string(COH_MAXX) + " band crossings inside one tile window of a row (COH_MAXX), or more than " + std::to_string(CARRY_CAP) + " fancy-fill edge runs cross one tile border (CARRY_CAP)";
     return 1;
   }
   return 0;
@@ -494,7 +541,7 @@ int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_
   CK(cudaMalloc(&S, sizeof(uint32_t) * nwords)); CK(cudaMalloc(&C, sizeof(uint32_t) * nwords));
   CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
   CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
-  k_scan_rows<<<cdiv(n_rows, 64), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
+  k_scan_rows<<<dim3(cdiv(n_rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
   int rc = check_error_flag(ctx, "coh_shapeminshape_of_edgelist");
   if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
   if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
@@ -579,6 +626,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
   cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
+  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx);
   delete s;
   return 0;
 }
@@ -613,6 +661,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<int> leaves;
   std::vector<uint8_t> stamps;
   std::vector<int> open;  // indices (into recs) of open groups
+  std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
+  long long total_rows = 0;
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
   recs.push_back(root); open.push_back(0);
@@ -649,6 +699,14 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         if (c.count == 0) continue;  // NullShape: nothing to draw
         EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
         shape_pixel_box(eb, o.bx0, o.by0, o.bx1, o.by1);
+        // rows with a candidate edge list: extended band [32y-67, 32y+16] meets [ymin, ymax]
+        o.ry0 = floordiv(eb.ymin - 16 + 31, 32); o.ry1 = floordiv(eb.ymax + 67, 32);
+        if (total_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
+        o.row_base = (int)total_rows; total_rows += o.ry1 - o.ry0 + 1;
+        for (int k = 0; k < c.count; k++) {
+          if (edge_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share edges");
+          edge_obj[(size_t)c.first + k] = (int)recs.size();
+        }
         break;
       }
       case COH_OBJ_PRIMITIVE:
@@ -683,6 +741,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   DevScene* s = new DevScene();
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->h_objs = recs;
+  for (const ObjRec& o : recs) if (o.kind == K_PATH && o.fill.kind != 0) s->has_fancy = true;
   CK(cudaMalloc(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
@@ -692,17 +751,46 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&s->stamps, std::max<size_t>(stamps.size(), 1)));
   if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  // K1 edge binning: count -> scan -> fill
+  {
+    int* d_edge_obj = nullptr; int* d_counts = nullptr;
+    size_t slots = (size_t)std::max<long long>(total_rows, 1);
+    CK(cudaMalloc(&d_edge_obj, sizeof(int) * edge_obj.size()));
+    CK(cudaMemcpyAsync(d_edge_obj, edge_obj.data(), sizeof(int) * edge_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&d_counts, sizeof(int) * slots));
+    CK(cudaMalloc(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
+    if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, s->rowedge_ptr, (int)slots); LAUNCHED();
+    int total = 0;
+    CK(cudaMemcpyAsync(&total, s->rowedge_ptr + slots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMalloc(&s->rowedge_idx, sizeof(int) * (size_t)std::max(total, 1)));
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
+    if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_edge_obj); cudaFree(d_counts);
+  }
   *out = (coh_scene_t)s;
   return 0;
 }
 
+int coh_fb_attach(coh_ctx* ctx, void* device_rgba8) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fr.W) FAIL("coh_fb_attach: call coh_fb_configure first");
+  if (drain_timing(ctx)) return 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_fb) cudaFree(ctx->fb);
+  ctx->fb = (uint32_t*)device_rgba8; ctx->own_fb = false;
+  return 0;
+}
 int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1) {
   CK(cudaSetDevice(ctx->device));
   if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
   if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
   if (width != ctx->fr.W || height != ctx->fr.H) {
-    cudaFree(ctx->fb); cudaFree(ctx->u_out); ctx->fb = nullptr; ctx->u_out = nullptr;
+    if (ctx->own_fb) cudaFree(ctx->fb);
+    cudaFree(ctx->u_out); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->own_fb = true;
     CK(cudaMalloc(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
     CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
     CK(cudaMalloc(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
@@ -725,6 +813,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
     CK(cudaMalloc(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
     ctx->n_cells_cap = n_cells;
   }
+  if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   // K1: count, scan, fill
   int bin_blocks = cdiv(n_cells * 32, 256);
   k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
@@ -752,12 +841,33 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items); LAUNCHED();
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
+  P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx;
   P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
   dim3 grid(cdiv(fr.tiles_x, 8), fr.band_y1 - fr.band_y0);
-  k_walk<<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  P.ticket = nullptr; P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
+  if (s->has_fancy) {
+    size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
+    if (slots > ctx->carry_slots) {
+      cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
+      CK(cudaMalloc(&ctx->carry_done, sizeof(int) * slots));
+      CK(cudaMalloc(&ctx->carry_cnt, sizeof(int) * slots));
+      CK(cudaMalloc(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
+      CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
+      ctx->carry_slots = slots;
+    }
+    if (!ctx->ticket) CK(cudaMalloc(&ctx->ticket, sizeof(int)));
+    CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(int), ctx->stream));
+    P.ticket = ctx->ticket; P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
+    P.epoch = ++ctx->epoch;
+    k_walk<true><<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+  } else {
+    k_walk<false><<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+  }
+  if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
   return 0;
 }
 

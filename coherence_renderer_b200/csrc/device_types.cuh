@@ -28,6 +28,8 @@ struct ObjRec {
   int flags;
   int brush_r;      // BRUSH: (w-1)/2
   int stamp_off;    // BRUSH: offset of the (2r+1)^2 alpha stamp in the stamp pool
+  int ry0, ry1;     // PATH: pixel rows (object frame) that have a candidate edge list
+  int row_base;     // PATH: first slot of this object in the row-edge CSR
   int pad;
   FillRec fill;
 };

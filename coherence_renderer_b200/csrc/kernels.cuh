@@ -29,6 +29,35 @@ __global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------
+// K1 edge binning (the reference's active-edge bookkeeping, polygon.ml:541-547): for every
+// path object and every pixel row it can touch, the list of candidate edges.  A row's
+// candidates are the edges whose y range meets the row's extended band [32y-67, 32y+16]:
+// the shape band [32y-47, 32y+16] (polygon.ml:539-540) united with the bands of the 32
+// super-sampled rows 16y-32 .. 16y-1 of its AA window (polygon.ml:694-700).
+// Built once per scene: count (atomics) -> exclusive scan -> fill (atomic cursors).  The
+// order inside a list is irrelevant: ties between crossings cannot change the pixel set.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int floordiv32(int a) { return a >> 5; }               // floor(a / 32)
+__device__ __forceinline__ int ceildiv32(int a) { return (a + 31) >> 5; }         // ceil(a / 32)
+template <bool FILL>
+__global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restrict__ edge_obj, int n_edges,
+                           const ObjRec* __restrict__ objs, int* __restrict__ counts, const int* __restrict__ ptr,
+                           int* __restrict__ idx) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int oi = edge_obj[e];
+  if (oi < 0) return;
+  const EdgeRec ed = edges[e];
+  const int row_base = objs[oi].row_base, ry0 = objs[oi].ry0;
+  int ylo = ceildiv32(ed.ymin - 16), yhi = floordiv32(ed.ymax + 67);
+  for (int y = ylo; y <= yhi; y++) {
+    int slot = row_base + y - ry0;
+    int k = atomicAdd(&counts[slot], 1);
+    if (FILL) idx[ptr[slot] + k] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // K1 binning.  One warp per cell scans the leaf objects in index order (= front to back),
 // 32 at a time; ballot + popc give each overlapping object its slot, so every list comes
 // out already sorted and the two passes (count / fill) are identical apart from the store.
@@ -98,6 +127,8 @@ __global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ o
 struct WalkParams {
   const ObjRec* objs;
   const EdgeRec* edges;
+  const int* rowedge_ptr;      // K1 edge binning: per (path object, pixel row) candidate edge lists (CSR)
+  const int* rowedge_idx;
   const int2* points;          // brush stamp centres (object frame), list order
   const uint8_t* stamps;       // brush alpha stamps
   const int* cell_off;         // per cell [first, last) into cell_items
@@ -111,7 +142,18 @@ struct WalkParams {
   uint32_t* fb;                // RGBA8 framebuffer, fr.W x fr.H
   int* error_flag;             // set to 1 when an object overflows COH_MAXX crossings
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
+  // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
+  // x of its span (polygon.ml:736) and a span may begin in a tile further left.  Every tile
+  // publishes, per fancy object whose visible edge run touches its right border, where that run
+  // began; the tile to its right looks it up.  Tiles are handed out by an atomic ticket in
+  // row-major order, so the tile waited on has always started (decoupled look-back).
+  int* ticket;
+  int* carry_done;             // per (band row, tile): == epoch when the tile has finished
+  int* carry_cnt;              // per (band row, tile): number of published entries
+  int2* carry_ent;             // per (band row, tile): CARRY_CAP entries (object index, start x)
+  int epoch;
 };
+constexpr int CARRY_CAP = 8;
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
@@ -124,8 +166,9 @@ __device__ __forceinline__ int warp_sum(int v) {
 // list (polygon.ml:673-692) into its private 544-bit row in shared memory; then for every
 // edge pixel the 32 lanes each weigh their row's 32-column window and the warp reduces.
 // Returns the opacity of pixel `lane` (undefined where edge bit is 0).
-__device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, int n_edges, int winding, int xx0, int yy,
-                                       uint32_t edge, uint32_t* aa_bits /*32*AA_WORDS, warp private*/,
+__device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand,
+                                       int winding, int xx0, int yy, uint32_t edge,
+                                       uint32_t* aa_bits /*32*AA_WORDS, warp private*/,
                                        const int* __restrict__ prefix /*[32][33] shared*/, int volume, int lane,
                                        bool& ok) {
   uint32_t* row = aa_bits + lane * AA_WORDS;
@@ -133,7 +176,7 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, int n_
   for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
   SinkMem sink;
   sink.wx0 = 16 * xx0 - 32; sink.nwords = AA_WORDS; sink.stride = 1; sink.S = row; sink.C = nullptr;
-  ok = scan_row(edges, n_edges, 16, 16 * yy - 32 + lane, winding, true, sink);
+  ok = scan_row(edges, idx, n_cand, 16, 16 * yy - 32 + lane, winding, true, sink.wx0, sink.wx0 + 32 * AA_WORDS - 1, sink);
   __syncwarp();
   int opacity = 0;
   const int* prow = prefix + lane * 33;
@@ -150,19 +193,33 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, int n_
   return opacity;
 }
 
+template <bool CARRY>
 __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
   __shared__ uint32_t s_acc[8][MAX_DEPTH][32];
   __shared__ uint32_t s_u[8][MAX_DEPTH];
+  __shared__ int s_ticket;
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
+  if (CARRY && threadIdx.x == 0) s_ticket = atomicAdd(P.ticket, 1);
   __syncthreads();
   const int volume = P.aa->volume;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int tile = blockIdx.x * 8 + wid;
-  const int y = P.fr.band_y0 + blockIdx.y;
+  int bx = blockIdx.x, by = blockIdx.y;
+  if (CARRY) { bx = s_ticket % gridDim.x; by = s_ticket / gridDim.x; }
+  const int tile = bx * 8 + wid;
+  const int y = P.fr.band_y0 + by;
   if (tile >= P.fr.tiles_x || y >= P.fr.band_y1) return;
   const int tx0 = tile * TILE_W;
+  const size_t slot = (size_t)by * P.fr.tiles_x + tile;
+  int n_carry = 0;
+  auto publish_done = [&]() {
+    if (CARRY && lane == 0) {
+      P.carry_cnt[slot] = n_carry < CARRY_CAP ? n_carry : CARRY_CAP;
+      __threadfence();
+      atomicExch(P.carry_done + slot, P.epoch);
+    }
+  };
 
   // initial covered-so-far complement `u` for this word of the row
   uint32_t u;
@@ -171,7 +228,7 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
   const uint32_t u_update = u;
   if (P.u_out && lane == 0) P.u_out[(size_t)y * P.fr.tiles_x + tile] = u;  // nothing covered yet
-  if (u == 0u) return;
+  if (u == 0u) { publish_done(); return; }
 
   uint32_t acc = 0u;       // accumulator of the current nesting level, this lane's pixel
   int depth = 0;           // open groups
@@ -221,9 +278,13 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
         if (o.kind == K_PRIM) {
           if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
         } else if (o.kind == K_PATH) {
-          Sink32 sink; sink.wx0 = xx0; sink.S = 0u; sink.C = 0u;
-          if (!scan_row(P.edges + o.first, o.count, 1, yy, o.winding, false, sink)) bad = true;
-          S = sink.S; C = sink.C;
+          if (yy >= o.ry0 && yy <= o.ry1) {
+            const int slot = o.row_base + yy - o.ry0;
+            const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+            Sink32 sink; sink.wx0 = xx0; sink.S = 0u; sink.C = 0u;
+            if (!scan_row(P.edges, P.rowedge_idx + a, b - a, 1, yy, o.winding, false, xx0, xx0 + 31, sink)) bad = true;
+            S = sink.S; C = sink.C;
+          }
         } else if (o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
           const int r = o.brush_r;
@@ -258,7 +319,9 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
       if (edge) {
         if (o.kind == K_PATH) {
           bool ok;
-          opacity = aa_tile(P.edges + o.first, o.count, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
+          const int slot = o.row_base + yy - o.ry0;
+          const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+          opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
           if (!ok) bad = true;
         } else if (o.kind == K_BRUSH) {
           // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
@@ -276,6 +339,26 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
           opacity = (int)a;
         }
       }
+      int lead_start = xx0;  // object-frame x where the run containing bit 0 begins
+      if (CARRY && edge && o.kind == K_PATH && o.fill.kind != 0) {
+        if ((edge & 1u) && tile > 0) {
+          const volatile int* done = P.carry_done + slot - 1;
+          while (*done != P.epoch) __nanosleep(32);
+          __threadfence();
+          const int cnt = P.carry_cnt[slot - 1];
+          for (int q = 0; q < cnt; q++) {
+            int2 e = P.carry_ent[(slot - 1) * CARRY_CAP + q];
+            if (e.x == ik) lead_start = e.y - o.dx;
+          }
+        }
+        if (edge >> 31) {
+          const uint32_t nz = ~edge;
+          const int tstart = nz ? (xx0 + 32 - __clz((int)nz)) : lead_start;
+          if (lane == 0 && n_carry < CARRY_CAP) P.carry_ent[slot * CARRY_CAP + n_carry] = make_int2(ik, tstart + o.dx);
+          n_carry++;
+          if (n_carry > CARRY_CAP) bad = true;
+        }
+      }
       bool mine = (vis >> lane) & 1u;
       if (mine) {
         const bool is_edge = (edge >> lane) & 1u;
@@ -283,11 +366,11 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
         if (o.kind == K_PRIM || o.fill.kind == 0) col = o.fill.c0;
         else if (!is_edge || o.kind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
         else {
-          // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span
-          // (run of `edge` bits; a run continuing into the previous tile is cut at the tile — DESIGN.md)
+          // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
+          // of `edge` bits); a run that reaches bit 0 may have begun in a tile further left.
           uint32_t below = ~edge & ((1u << lane) - 1u);
-          int start = below ? (32 - __clz((int)below)) : 0;
-          col = fill_lookup(o.fill, xx0 + start, yy);
+          int start = below ? (xx0 + 32 - __clz((int)below)) : lead_start;
+          col = fill_lookup(o.fill, start, yy);
         }
         if (is_edge) col = px_dissolve(col, opacity);
         if (o.pretrans >= 0) col = px_dissolve(col, o.pretrans);
@@ -298,6 +381,7 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
     }
   }
   while (depth > 0) pop_group();
+  publish_done();
   if (bad) *P.error_flag = 1;
   const int x = tx0 + lane;
   if ((u_update >> lane) & 1u) {
@@ -309,14 +393,17 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
 // K2 stand-alone (export path): one thread per pixel row of one edge list writes the
 // shape and coverage bit-rows into global bit-frames of `nw` words per row.
 // ------------------------------------------------------------------------------------
+constexpr int SCAN_CHUNK_WORDS = 8;  // one thread scans a 256-pixel window of one row
 __global__ void k_scan_rows(const EdgeRec* __restrict__ edges, int n_edges, int winding, int y0, int n_rows,
                             int wx0, int nw, uint32_t* __restrict__ S, uint32_t* __restrict__ C, int* error_flag) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
+  int w0 = blockIdx.y * SCAN_CHUNK_WORDS;
+  if (r >= n_rows || w0 >= nw) return;
   SinkMem sink;
-  sink.wx0 = wx0; sink.nwords = nw; sink.stride = 1;
-  sink.S = S + (size_t)r * nw; sink.C = C + (size_t)r * nw;
-  if (!scan_row(edges, n_edges, 1, y0 + r, winding, false, sink)) *error_flag = 1;
+  sink.wx0 = wx0 + 32 * w0; sink.nwords = min(SCAN_CHUNK_WORDS, nw - w0); sink.stride = 1;
+  sink.S = S + (size_t)r * nw + w0; sink.C = C + (size_t)r * nw + w0;
+  if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink))
+    *error_flag = 1;
 }
 
 // ------------------------------------------------------------------------------------
@@ -337,7 +424,7 @@ __global__ void __launch_bounds__(256) k_aa_rows(const EdgeRec* __restrict__ edg
   uint32_t q = Q[(size_t)r * nw + w];
   if (!q) return;
   bool ok;
-  int op = aa_tile(edges, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_prefix, aa->volume, lane, ok);
+  int op = aa_tile(edges, nullptr, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_prefix, aa->volume, lane, ok);
   if (!ok) *error_flag = 1;
   if ((q >> lane) & 1u) out[((size_t)r * nw + w) * 32 + lane] = (uint8_t)op;
 }

@@ -165,66 +165,103 @@ COH_HD uint32_t interval_mask32(int wx0, int a, int b) {
 }
 
 // ---------------------------------------------------------------------------------
-// Row scan (polygon.ml:332-528 for one row band).
+// Row scan (polygon.ml:332-528 for one row band), restricted to a pixel window.
 //
 // For pixel row `y` of the edge list scaled by `s` (1: shape/minshape; 16: the x16
-// super-sampled shape of polygon.ml:673-692) compute
+// super-sampled shape of polygon.ml:673-692) compute, inside the window [wlo, whi],
 //     T ∪ B  = winding spans of the top / bottom band crossings,
 //     C      = coverage spans of the clipped "middle" pieces,
 // and hand every interval to the sink: sink.span(a, b) for T/B spans, sink.cover(a, b)
-// for C spans (pixel coordinates, inclusive).  shape_row = T∪B∪C, minshape_row =
-// shape_row − C (polygon.ml:520-528); the union/fuse of the reference's span lists is
-// the OR of the bit-rows, and ties between equal crossings cannot change the pixel set
-// (SURVEY.md §3.2), so crossings are ranked by (pos, list index).
+// for C spans (pixel coordinates, inclusive; the sink clips to its own storage).
+// shape_row = T∪B∪C, minshape_row = shape_row − C (polygon.ml:520-528); the union/fuse
+// of the reference's span lists is the OR of the bit-rows, and ties between equal
+// crossings cannot change the pixel set, so crossings are ranked by
+// (pos, list index).
 //
-// MAXX bounds the crossings kept per list in lane-private storage; on overflow the
-// function returns false and the caller reports the object as too complex (loudly).
+// Windowed winding.  Sorted by position the crossings of a band split into those whose
+// pixel reach ends left of the window, those that touch it, and those beyond it.  Only
+// the middle group needs ordering.  The left group contributes its winding sum (and its
+// parity) and acts as ONE predecessor for the first crossing that is not left; the right
+// group only matters as "there is a successor", which clips to the window end.  So a
+// lane keeps at most the crossings that touch its window (one or two for a 32-pixel
+// tile) however complex the object is.
+//
+// MAXX bounds the crossings kept per list; on overflow the function returns false and
+// the caller reports the object as too complex for the window (loudly).
 // ---------------------------------------------------------------------------------
 #ifndef COH_MAXX
-#define COH_MAXX 24
+#define COH_MAXX 16
 #endif
 
 struct CrossList {
-  int v[COH_MAXX];  // (pos << 1) | (dir > 0)
+  int v[COH_MAXX];  // (pos << 1) | (dir > 0), crossings touching the window
   int n;
+  int cnt_left;     // sum of directions of the crossings left of the window
+  int n_left;       // how many there are
+  bool has_right;   // a crossing lies beyond the window
+  COH_HD void init() { n = 0; cnt_left = 0; n_left = 0; has_right = false; }
+  // reach of a crossing at p: [pix(p-16), pix(p+16)] (pixel spans are widened by half a
+  // pixel, polygon.ml:458-459,490-491) or [pix(p), pix(p)] for the AA variant (469-479,498-512)
+  COH_HD void add(int p, int dir, bool aa, int wlo, int whi) {
+    int rhi = aa ? pix_of_sub(p) : pix_of_sub(p + 16);
+    int rlo = aa ? rhi : pix_of_sub(p - 16);
+    if (rhi < wlo) { cnt_left += dir; n_left++; }
+    else if (rlo > whi) has_right = true;
+    else { if (n < COH_MAXX) v[n] = (p << 1) | (dir > 0); n++; }
+  }
 };
 
 template <class Sink>
-COH_HD void winding_spans(const CrossList& L, int winding, bool aa, Sink& sink) {
-  int n = L.n < COH_MAXX ? L.n : COH_MAXX;
+COH_HD void winding_spans(const CrossList& L, int winding, bool aa, int wlo, int whi, Sink& sink) {
+  const int n = L.n < COH_MAXX ? L.n : COH_MAXX;
+  // the left group as one predecessor: its span runs from left of the window to the first
+  // crossing that is not left
+  if (L.n_left > 0 && (n > 0 || L.has_right)) {
+    bool emit = winding == 0 ? (L.cnt_left != 0) : ((L.n_left & 1) == 1);
+    if (emit) {
+      int b = whi;
+      if (n > 0) {
+        int first = L.v[0] >> 1;
+        for (int j = 1; j < n; j++) { int pj = L.v[j] >> 1; if (pj < first) first = pj; }
+        b = aa ? pix_of_sub(first) : pix_of_sub(first + 16);
+      }
+      sink.span(wlo, b);
+    }
+  }
   for (int i = 0; i < n; i++) {
-    int vi = L.v[i];
-    int pi = vi >> 1;
+    const int vi = L.v[i];
+    const int pi = vi >> 1;
     // rank / running winding count of crossing i in the (pos, index) order, and its successor
-    int cnt = 0, rank = 0;
+    int cnt = L.cnt_left, rank = L.n_left;
     int succ = 0x7FFFFFFF; bool has = false;
     for (int j = 0; j < n; j++) {
-      int vj = L.v[j];
-      int pj = vj >> 1;
-      bool before_or_self = (pj < pi) || (pj == pi && j <= i);
+      const int vj = L.v[j];
+      const int pj = vj >> 1;
+      const bool before_or_self = (pj < pi) || (pj == pi && j <= i);
       if (before_or_self) { cnt += (vj & 1) ? 1 : -1; rank += (j != i); }
       else { if (pj < succ) succ = pj; has = true; }
     }
-    if (!has) continue;  // the last crossing has no successor (polygon.ml:484, 458)
-    bool emit = winding == 0 ? (cnt != 0) : ((rank & 1) == 0);
+    if (!has && !L.has_right) continue;  // the last crossing has no successor (polygon.ml:484, 458)
+    const bool emit = winding == 0 ? (cnt != 0) : ((rank & 1) == 0);
     if (!emit) continue;
-    int a = aa ? pix_of_sub(pi) : pix_of_sub(pi - 16);
-    int b = aa ? pix_of_sub(succ) : pix_of_sub(succ + 16);
+    const int a = aa ? pix_of_sub(pi) : pix_of_sub(pi - 16);
+    const int b = has ? (aa ? pix_of_sub(succ) : pix_of_sub(succ + 16)) : whi;
     sink.span(a, b);
   }
 }
 
-// Edge coordinates are scaled by s and translated by (ox, oy) sub-bins AFTER scaling
-// (integer-pixel aliases: ox = 32*dx*s would be wrong for s=16 rows, so callers pass the
-// row/window already moved into the object's own frame and use ox = oy = 0).
+// `idx` (optional) lists the candidate edges of this row (K1 edge binning): any superset
+// of the edges whose y range meets the band gives the same result, since every edge is
+// re-tested against the band here.
 template <class Sink>
-COH_HD bool scan_row(const EdgeRec* __restrict__ edges, int n_edges, int s, int y, int winding, bool aa, Sink& sink) {
+COH_HD bool scan_row(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int s, int y,
+                     int winding, bool aa, int wlo, int whi, Sink& sink) {
   const int top = 32 * y - 47;  // polygon.ml:539: left_of_pix y - halfips
   const int bot = top + 63;     // polygon.ml:540
   CrossList tops, bots;
-  tops.n = 0; bots.n = 0;
-  for (int i = 0; i < n_edges; i++) {
-    const EdgeRec e = edges[i];
+  tops.init(); bots.init();
+  for (int i = 0; i < n_cand; i++) {
+    const EdgeRec e = edges[idx ? idx[i] : i];
     const int ymin = e.ymin * s, ymax = e.ymax * s;
     if (ymin > bot || ymax < top) continue;  // polygon.ml:338
     const int x0 = e.x0in * s, x1 = e.x1in * s;
@@ -234,27 +271,24 @@ COH_HD bool scan_row(const EdgeRec* __restrict__ edges, int n_edges, int s, int 
     } else if (ymin >= top) {  // just bottom clipping, polygon.ml:345-353
       int xb = crossing_x(x0, e.g, bot - ymin);
       lo = imin(x0, xb); hi = imax(x0, xb);
-      if (bots.n < COH_MAXX) bots.v[bots.n] = (xb << 1) | (e.dir > 0);
-      bots.n++;
+      bots.add(xb, e.dir, aa, wlo, whi);
     } else if (ymax <= bot) {  // just top clipping, polygon.ml:355-364
       int xt = crossing_x(x0, e.g, top - 1 - ymin);
       lo = imin(xt, x1); hi = imax(xt, x1);
-      if (tops.n < COH_MAXX) tops.v[tops.n] = (xt << 1) | (e.dir > 0);
-      tops.n++;
+      tops.add(xt, e.dir, aa, wlo, whi);
     } else {  // clip both: bottom crossing restarts from the rounded top crossing, polygon.ml:365-385
       int xt = crossing_x(x0, e.g, top - 1 - ymin);
       int xb = crossing_x(xt, e.g, bot - top);
       lo = imin(xt, xb); hi = imax(xt, xb);
-      if (tops.n < COH_MAXX) tops.v[tops.n] = (xt << 1) | (e.dir > 0);
-      tops.n++;
-      if (bots.n < COH_MAXX) bots.v[bots.n] = (xb << 1) | (e.dir > 0);
-      bots.n++;
+      tops.add(xt, e.dir, aa, wlo, whi);
+      bots.add(xb, e.dir, aa, wlo, whi);
     }
-    sink.cover(pix_of_sub(lo - 16), pix_of_sub(hi + 16));  // polygon.ml:444-453
+    const int ca = pix_of_sub(lo - 16), cb = pix_of_sub(hi + 16);  // polygon.ml:444-453
+    if (cb >= wlo && ca <= whi) sink.cover(ca, cb);
   }
   if (tops.n > COH_MAXX || bots.n > COH_MAXX) return false;
-  winding_spans(tops, winding, aa, sink);
-  winding_spans(bots, winding, aa, sink);
+  winding_spans(tops, winding, aa, wlo, whi, sink);
+  winding_spans(bots, winding, aa, wlo, whi, sink);
   return true;
 }
 

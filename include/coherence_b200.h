@@ -76,8 +76,14 @@ const char* coh_last_error(coh_ctx* ctx); /* ctx may be NULL for init errors */
 int coh_device_name(coh_ctx* ctx, char* buf, int cap);
 /* the CUDA stream every kernel of this context is launched on (for event timing) */
 void* coh_stream(coh_ctx* ctx);
+/* run on a caller-owned CUDA stream instead (e.g. the one a collective library uses) */
+int coh_set_stream(coh_ctx* ctx, void* cuda_stream);
 /* number of kernel launches issued by this context since creation */
 int64_t coh_launch_count(coh_ctx* ctx);
+/* per-kernel timing with CUDA events on the launching stream: average duration of the fused
+ * walker kernel and of the binning kernels over the frames rendered since it was switched on */
+int coh_set_timing(coh_ctx* ctx, int32_t on);
+int coh_get_timing(coh_ctx* ctx, double* walk_ms_avg, double* bin_ms_avg, int64_t* frames);
 
 /* ---- colour codec (colour.ml:99-172 colour_of_rgba / rgba_of_colour) ---- */
 int32_t coh_colour_of_rgba8(uint32_t rgba8);
@@ -124,6 +130,9 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t s);
 /* Size of the device framebuffer (RGBA8, W x H, pixel (0,0) first) and the scanline band
  * [band_y0, band_y1) this context renders; rows outside the band are left untouched. */
 int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1);
+/* Render into a caller-owned device buffer of W*H RGBA8 words instead (band gather by NCCL
+ * happens on buffers the collective library knows). */
+int coh_fb_attach(coh_ctx* ctx, void* device_rgba8);
 /* Render.render_frame lmo view update (render.ml:1345-1365) with update = Sprite.box ux uy uw uh:
  * scene pass over (pages @ background) pass, composited front to back with hidden-surface
  * set subtraction, into the device framebuffer.  Pixels of the update box not reached by

@@ -30,7 +30,8 @@ extern "C" {
 void emul_free(void* p) { std::free(p); }
 
 // shape and minshape of an edge list through scan_row + bit-rows (what k_scan_rows does)
-int emul_shapeminshape(const int32_t* edges, int n, int winding, int32_t** shp, int64_t* nshp, int32_t** mshp, int64_t* nm) {
+// chunk_words: width (in 32-pixel words) of the windows each scan_row call covers; 0 = the whole row
+int emul_shapeminshape(const int32_t* edges, int n, int winding, int chunk_words, int32_t** shp, int64_t* nshp, int32_t** mshp, int64_t* nm) {
   std::vector<EdgeRec> es;
   int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
   for (int i = 0; i < n; i++) {
@@ -47,10 +48,13 @@ int emul_shapeminshape(const int32_t* edges, int n, int winding, int32_t** shp, 
     int y0 = py0 - 2, n_rows = py1 - py0 + 5;
     int wx0 = floordiv(px0, 32) * 32 - 32, nw = (px1 - wx0) / 32 + 2;
     std::vector<uint32_t> S((size_t)n_rows * nw, 0u), C((size_t)n_rows * nw, 0u);
-    for (int r = 0; r < n_rows; r++) {
-      SinkMem sink; sink.wx0 = wx0; sink.nwords = nw; sink.stride = 1; sink.S = &S[(size_t)r * nw]; sink.C = &C[(size_t)r * nw];
-      ok = scan_row(es.data(), n, 1, y0 + r, winding, false, sink) && ok;
-    }
+    int cw = chunk_words > 0 ? chunk_words : nw;
+    for (int r = 0; r < n_rows; r++)
+      for (int w0 = 0; w0 < nw; w0 += cw) {
+        SinkMem sink; sink.wx0 = wx0 + 32 * w0; sink.nwords = std::min(cw, nw - w0); sink.stride = 1;
+        sink.S = &S[(size_t)r * nw + w0]; sink.C = &C[(size_t)r * nw + w0];
+        ok = scan_row(es.data(), nullptr, n, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink) && ok;
+      }
     // margin must be empty (shape_pixel_box of the product is conservative)
     for (int r = 0; r < n_rows; r++) for (int w = 0; w < nw; w++) {
       bool inside_rows = (y0 + r >= py0 && y0 + r <= py1);
@@ -91,7 +95,7 @@ int emul_opacity_word(const int32_t* edges, int n, int winding, int x0, int y, u
   bool ok = true;
   for (int j = 0; j < 32; j++) {
     SinkMem sink; sink.wx0 = 16 * x0 - 32; sink.nwords = 17; sink.stride = 1; sink.S = rows[j]; sink.C = nullptr;
-    ok = scan_row(es.data(), n, 16, 16 * y - 32 + j, winding, true, sink) && ok;
+    ok = scan_row(es.data(), nullptr, n, 16, 16 * y - 32 + j, winding, true, sink.wx0, sink.wx0 + 32 * 17 - 1, sink) && ok;
   }
   for (int b = 0; b < 32; b++) {
     int tot = 0;

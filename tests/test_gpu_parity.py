@@ -1,0 +1,214 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle.
+Bit-exact for span sets and integer coverage; RGBA within 1 LSB (north_star), and in fact
+asserted bit-exact for plain fills."""
+import random
+
+import numpy as np
+import pytest
+
+from coherence_renderer_b200 import abi, scene as S
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _max_lsb(a, b):
+    return int(np.abs(a.view(np.uint8).astype(int) - b.view(np.uint8).astype(int)).max())
+
+
+def test_shapeminshape_random_polygons(ctx, oracle):
+    rng = random.Random(11)
+    for it in range(150):
+        edges = util.random_polygon_edges(rng)
+        w = rng.randint(0, 1)
+        ref_s, ref_m = oracle.shapeminshape(edges, w)
+        hs, hm = ctx.shapeminshape_of_edgelist(edges, w)
+        got_s, got_m = ctx.shape_export(hs), ctx.shape_export(hm)
+        assert np.array_equal(got_s, ref_s), f"shape differs (case {it})"
+        assert np.array_equal(got_m, ref_m), f"minshape differs (case {it})"
+        assert ctx.shape_card(hs) == oracle.shape_card(ref_s)
+        ctx.shape_free(hs)
+        ctx.shape_free(hm)
+
+
+def test_polygon_opacity_random(ctx, oracle):
+    rng = random.Random(12)
+    for it in range(40):
+        edges = util.random_polygon_edges(rng, rmax=80.0)
+        w = rng.randint(0, 1)
+        ref_s, ref_m = oracle.shapeminshape(edges, w)
+        if len(ref_s) == 0:
+            continue
+        maxshape = oracle.shape_op("difference", ref_s, ref_m)
+        hs = ctx.shape_import(maxshape)
+        got = ctx.polygon_opacity(edges, w, hs)
+        ref = oracle.polygon_opacity(edges, w, maxshape)
+        assert np.array_equal(got, ref), f"AA opacity differs (case {it})"
+        ctx.shape_free(hs)
+
+
+def test_shape_algebra(ctx, oracle):
+    rng = random.Random(13)
+    for it in range(25):
+        a, b = util.random_shape_flat(rng), util.random_shape_flat(rng, x0=20, y0=-10)
+        ha, hb = ctx.shape_import(a), ctx.shape_import(b)
+        assert np.array_equal(ctx.shape_export(ha), a)
+        for name, fn in (("union", ctx.shape_union), ("difference", ctx.shape_difference), ("intersection", ctx.shape_intersection)):
+            h = fn(ha, hb)
+            assert np.array_equal(ctx.shape_export(h), oracle.shape_op(name, a, b)), name
+            ctx.shape_free(h)
+        m, n = rng.randint(0, 6), rng.randint(0, 6)
+        h = ctx.shape_bloat(ha, m, n)
+        assert np.array_equal(ctx.shape_export(h), oracle.shape_unary("bloat", a, m, n))
+        ctx.shape_free(h)
+        h = ctx.shape_erode(ha, m, n)
+        assert np.array_equal(ctx.shape_export(h), oracle.shape_unary("erode", a, m, n))
+        ctx.shape_free(h)
+        h = ctx.shape_translate(ha, 7, -3)
+        assert np.array_equal(ctx.shape_export(h), oracle.shape_unary("translate", a, 7, -3))
+        ctx.shape_free(h)
+        ctx.shape_free(ha)
+        ctx.shape_free(hb)
+    assert ctx.shape_box(0, 0, 0, 0) == 0
+    with pytest.raises(abi.CohError):
+        ctx.shape_box(0, 0, -1, 3)
+
+
+def _render_both(ctx, oracle, b, W, H, update=None):
+    update = update or (0, 0, W, H)
+    objs, n, nbg, edges, points = b.arrays()
+    ref, ref_u = oracle.render_frame(objs, n - nbg, nbg, edges, points, update, want_u=True)
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, update, abi.COH_RENDER_RECORD_U)
+    ctx.sync()
+    got = ctx.fb_read_rgba(update[0], update[1], update[2], update[3])
+    hu = ctx.render_uncovered()
+    got_u = ctx.shape_export(hu)
+    ctx.shape_free(hu)
+    ctx.scene_free(sc)
+    return got, ref, got_u, ref_u
+
+
+def test_lion_c1_frame(ctx, oracle):
+    """C1: the lion at the prototype's 1280x1024 canvas."""
+    W, H = 1280, 1024
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, S.lion_scene(W, H, 3.0), W, H)
+    assert np.array_equal(got_u, ref_u), "covered-so-far span set differs"
+    assert _max_lsb(got, ref) == 0
+
+
+def test_lion_small_update_box(ctx, oracle):
+    W, H = 640, 480
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, S.lion_scene(W, H, 1.4), W, H, update=(201, 77, 263, 301))
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_random_layered_polygons(ctx, oracle):
+    """C3-style: translucent and opaque random polygons, front to back."""
+    W, H = 512, 384
+    for seed in (1, 2, 3):
+        b = S.random_scene(W, H, 120, seed=seed, brush_fraction=0.0)
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u), f"u differs (seed {seed})"
+        assert _max_lsb(got, ref) == 0, f"RGBA differs (seed {seed})"
+
+
+def test_groups_and_pretrans(ctx, oracle):
+    W, H = 256, 200
+    b = S.SceneBuilder()
+    b.polygon([(20.3, 20.1), (120.7, 30.2), (60.2, 150.9)], S.Fill.plain(S.dissolve(S.rgba8(200, 30, 30), 180)))
+    b.group_begin(pretrans=140)
+    b.polygon([(40.0, 40.0), (200.5, 60.5), (90.0, 180.0)], S.Fill.plain(S.rgba8(10, 200, 40)))
+    b.polygon([(10.0, 100.0), (240.0, 90.0), (200.0, 190.0), (30.0, 170.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 0, 255), 100)), pretrans=200)
+    b.group_begin()
+    b.rectangle(S.rgba8(255, 255, 0), 100.0, 20.0, 180.0, 120.0, pretrans=90)
+    b.group_end()
+    b.group_end()
+    b.polygon([(0.0, 0.0), (255.0, 0.0), (255.0, 199.0), (0.0, 199.0)], S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 60)))
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_fancy_fills(ctx, oracle):
+    W, H = 200, 160
+    b = S.SceneBuilder()
+    grad = S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 0, 255), 128))
+    rad = S.Fill.radial((100.0, 80.0), (100.0, 90.0), (160.0, 80.0), True, True, S.rgba8(255, 255, 0), S.rgba8(0, 80, 0))
+    b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0), (40.0, 120.0)], grad)
+    b.polygon([(10.0, 10.0), (190.0, 12.0), (180.0, 150.0), (15.0, 140.0)], rad)
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    # AA pixels of fancy fills sample the fill at their span start (polygon.ml:736) even when the span
+    # began several 32-pixel tiles to the left: the walker's cross-tile carry makes this exact.
+    assert _max_lsb(got, ref) == 0
+
+
+def test_fancy_fill_long_shallow_edges(ctx, oracle):
+    """Edge runs hundreds of pixels long (nearly horizontal edges) under a gradient whose alpha varies."""
+    W, H = 700, 120
+    b = S.SceneBuilder()
+    g1 = S.Fill.gradient((0.0, 0.0), (700.0, 0.0), True, True, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 255, 0), 90))
+    g2 = S.Fill.gradient((50.0, 10.0), (650.0, 100.0), False, False, S.dissolve(S.rgba8(0, 0, 255), 200), S.rgba8(255, 255, 0))
+    b.polygon([(5.2, 20.3), (690.7, 23.9), (680.1, 70.2), (15.5, 66.6)], g1)
+    b.polygon([(20.0, 10.0), (660.0, 14.5), (600.0, 110.0), (100.0, 104.0)], g2, pretrans=200)
+    b.polygon([(2.0, 50.0), (698.0, 52.0), (698.0, 58.0), (2.0, 57.0)], S.Fill.plain(S.rgba8(0, 0, 0)))
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_brush_strokes(ctx, oracle):
+    W, H = 320, 240
+    b = S.SceneBuilder()
+    b.brush(0.8, 6.0, [[("C", (30.0, 200.0), (100.0, 10.0), (220.0, 230.0), (290.0, 40.0))]], S.Fill.plain(S.rgba8(20, 20, 120)))
+    b.brush(1.0, 3.0, [[("L", (10.0, 10.0), (300.0, 60.0))]], S.Fill.plain(S.dissolve(S.rgba8(200, 0, 0), 200)))
+    b.polygon([(60.0, 60.0), (260.0, 80.0), (160.0, 220.0)], S.Fill.plain(S.rgba8(240, 200, 60)))
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_rgb888_export(ctx):
+    W, H = 96, 64
+    b = S.SceneBuilder()
+    b.rectangle(S.rgba8(10, 20, 30), 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, edges, points = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    rgb = ctx.fb_read_rgb888(3, 5, 40, 20)
+    assert rgb.shape == (20, 40, 3) and (rgb == np.array([10, 20, 30], dtype=np.uint8)).all()
+    ctx.scene_free(sc)
+
+
+def test_band_partition_equals_whole_frame(ctx, oracle):
+    """§8e: rendering N bands separately and concatenating equals the single-band frame."""
+    W, H = 640, 480
+    b = S.lion_scene(W, H, 1.4)
+    objs, n, nbg, edges, points = b.arrays()
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.fb_configure(W, H)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    whole = ctx.fb_read_rgba(0, 0, W, H).copy()
+    parts = []
+    for k in range(3):
+        y0, y1 = k * H // 3, (k + 1) * H // 3
+        ctx.fb_configure(W, H, y0, y1)
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        parts.append(ctx.fb_read_rgba(0, y0, W, y1 - y0).copy())
+    assert np.array_equal(np.concatenate(parts, axis=0), whole)
+    ctx.scene_free(sc)
