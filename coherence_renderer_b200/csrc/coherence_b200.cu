@@ -846,7 +846,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
-  dim3 grid(cdiv(fr.tiles_x, 8), fr.band_y1 - fr.band_y0);
+  dim3 grid(cdiv(fr.tiles_x, WALK_WARPS), cell_row1 - cell_row0 + 1);
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   P.ticket = nullptr; P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
   if (s->has_fancy) {

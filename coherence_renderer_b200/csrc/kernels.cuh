@@ -193,12 +193,20 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
   return opacity;
 }
 
+constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
+constexpr int NC = 32 / CELL_H;          // candidate objects scan-converted per pass
+constexpr unsigned ROWMASK = (CELL_H >= 32) ? 0xFFFFFFFFu : ((1u << CELL_H) - 1u);
+
+// One warp owns one cell: TILE_W = 32 pixel columns (lane = column when compositing) by
+// CELL_H rows.  Scan conversion runs lane-parallel over (candidate object, row) pairs; the
+// front-to-back composite then visits, object by object, only the rows where the object
+// still has pixels inside the covered-so-far complement `u` (one 32-bit word per row, held
+// by lane r and its NC-1 mirror lanes).
 template <bool CARRY>
-__global__ void __launch_bounds__(256) k_walk(WalkParams P) {
+__global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
   __shared__ int s_prefix[32 * 33];
-  __shared__ uint32_t s_aa[8][32 * AA_WORDS];
-  __shared__ uint32_t s_acc[8][MAX_DEPTH][32];
-  __shared__ uint32_t s_u[8][MAX_DEPTH];
+  __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
+  __shared__ uint32_t s_acc[WALK_WARPS][CELL_H][32];
   __shared__ int s_ticket;
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
   if (CARRY && threadIdx.x == 0) s_ticket = atomicAdd(P.ticket, 1);
@@ -207,74 +215,90 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int bx = blockIdx.x, by = blockIdx.y;
   if (CARRY) { bx = s_ticket % gridDim.x; by = s_ticket / gridDim.x; }
-  const int tile = bx * 8 + wid;
-  const int y = P.fr.band_y0 + by;
-  if (tile >= P.fr.tiles_x || y >= P.fr.band_y1) return;
+  const int tile = bx * WALK_WARPS + wid;
+  if (tile >= P.fr.tiles_x) return;
   const int tx0 = tile * TILE_W;
-  const size_t slot = (size_t)by * P.fr.tiles_x + tile;
-  int n_carry = 0;
+  const int y0 = (P.cell_row0 + by) * CELL_H;
+  const int r_lane = lane % CELL_H, c_lane = lane / CELL_H;
+  const int my_y = y0 + r_lane;                      // the row whose `u` this lane mirrors
+  const bool row_in_band = my_y >= P.fr.band_y0 && my_y < P.fr.band_y1;
+  const size_t my_slot = (size_t)(my_y - P.fr.band_y0) * P.fr.tiles_x + tile;  // carry slot of (row, tile)
+  int n_carry = 0;                                   // published carry entries of my row (mirrored)
+
+  // initial covered-so-far complement `u` of my row's word
+  uint32_t u = 0u;
+  if (row_in_band) {
+    if (P.u_init) u = P.u_init[(size_t)my_y * P.fr.tiles_x + tile];
+    else u = (my_y >= P.uy0 && my_y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
+    if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
+  }
+  const uint32_t u_update = u;
+  if (P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = u;  // nothing covered yet
   auto publish_done = [&]() {
-    if (CARRY && lane == 0) {
-      P.carry_cnt[slot] = n_carry < CARRY_CAP ? n_carry : CARRY_CAP;
+    if (CARRY && row_in_band && c_lane == 0) {
+      P.carry_cnt[my_slot] = n_carry < CARRY_CAP ? n_carry : CARRY_CAP;
       __threadfence();
-      atomicExch(P.carry_done + slot, P.epoch);
+      atomicExch(P.carry_done + my_slot, P.epoch);
     }
   };
+  if (__ballot_sync(0xFFFFFFFFu, u != 0u) == 0u) { publish_done(); return; }
 
-  // initial covered-so-far complement `u` for this word of the row
-  uint32_t u;
-  if (P.u_init) u = P.u_init[(size_t)y * P.fr.tiles_x + tile];
-  else u = (y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
-  if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
-  const uint32_t u_update = u;
-  if (P.u_out && lane == 0) P.u_out[(size_t)y * P.fr.tiles_x + tile] = u;  // nothing covered yet
-  if (u == 0u) { publish_done(); return; }
-
-  uint32_t acc = 0u;       // accumulator of the current nesting level, this lane's pixel
-  int depth = 0;           // open groups
+#pragma unroll
+  for (int r = 0; r < CELL_H; r++) s_acc[wid][r][lane] = 0u;   // accumulator of the current nesting level
+  __syncwarp();
+  int depth = 0;                       // open groups
+  int hit_level = -1;                  // outermost open group that dissolves its sprite (PreTrans), or -1
   int open_grp[MAX_DEPTH];
+  uint32_t stk_u[MAX_DEPTH];           // parents' `u` of my row
+  uint32_t stk_acc[MAX_DEPTH][CELL_H]; // parents' accumulators of my column (local memory; touched on push/pop only)
   bool bad = false;
 
-  const int cell = (y / CELL_H - P.cell_row0) * P.fr.tiles_x + tile;
+  const int cell = by * P.fr.tiles_x + tile;
   const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
 
   auto pop_group = [&]() {
     // close the innermost group: its accumulated sprite goes under the parent accumulator
     // (render.ml:1294 caf over opaque a s; 1295-1298 PreTrans), newly opaque pixels leave the
     // parent's u (render.ml:1308).
-    int g = open_grp[depth - 1];
-    int pt = P.objs[g].pretrans;
-    int gflags = P.objs[g].flags;
-    uint32_t s = acc;
-    if (pt >= 0) s = px_dissolve(s, pt);
-    uint32_t pa = s_acc[wid][depth - 1][lane];
-    uint32_t pu = s_u[wid][depth - 1];
-    uint32_t r = px_over(pa, s);
-    uint32_t opq = __ballot_sync(0xFFFFFFFFu, (r >> 24) == 255u);
-    acc = r;
-    u = pu & ~opq;
-    depth--;
-    if ((gflags & OF_ROOT_SCENE) && P.u_out) {
-      if (lane == 0) P.u_out[(size_t)y * P.fr.tiles_x + tile] = u;
+    const int g = open_grp[depth - 1];
+    const int pt = P.objs[g].pretrans;
+    const int gflags = P.objs[g].flags;
+    const uint32_t pu = stk_u[depth - 1];
+    for (int r = 0; r < CELL_H; r++) {
+      uint32_t sp = s_acc[wid][r][lane];
+      const uint32_t pa = stk_acc[depth - 1][r];
+      if (pt >= 0) sp = px_dissolve(sp, pt);
+      const uint32_t res = px_over(pa, sp);
+      const uint32_t opq = __ballot_sync(0xFFFFFFFFu, (res >> 24) == 255u);
+      s_acc[wid][r][lane] = res;
+      if (r_lane == r) u = pu & ~opq;
     }
+    depth--;
+    if (hit_level >= depth) hit_level = -1;
+    if ((gflags & OF_ROOT_SCENE) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = u;
   };
   auto push_group = [&](int g) {
-    s_acc[wid][depth][lane] = acc;
-    if (lane == 0) s_u[wid][depth] = u;
-    __syncwarp();
+    for (int r = 0; r < CELL_H; r++) { stk_acc[depth][r] = s_acc[wid][r][lane]; s_acc[wid][r][lane] = 0u; }
+    stk_u[depth] = u;
     open_grp[depth] = g;
+    // A group composited with PreTrans (v < 1) gives pixels back to its parent's `u` when it
+    // closes (an opaque member pixel is no longer opaque once dissolved), so while such a group
+    // is open, candidates are pre-selected against the u saved outside the outermost one.
+    const int pt = P.objs[g].pretrans;
+    if (hit_level < 0 && pt >= 0 && pt < 255) hit_level = depth;
     depth++;
-    acc = 0u;
   };
 
-  for (int base = it0; base < it1; base += 32) {
-    // ---- lane-parallel scan conversion of up to 32 candidate objects for this row word ----
-    int idx = base + lane < it1 ? P.cell_items[base + lane] : -1;
+  for (int base = it0; base < it1; base += NC) {
+    // ---- lane-parallel scan conversion: lane (c, r) evaluates row y0+r of candidate c ----
+    const int ci = base + c_lane;
+    const int idx = ci < it1 ? P.cell_items[ci] : -1;
     uint32_t S = 0u, C = 0u;
-    if (idx >= 0) {
+    const uint32_t u_hit = hit_level >= 0 ? stk_u[hit_level] : u;  // superset of every later u of my row
+    if (idx >= 0 && u_hit != 0u) {
       const ObjRec& o = P.objs[idx];
-      if (!(o.by0 > y || o.by1 < y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
-        const int yy = y - o.dy, xx0 = tx0 - o.dx;
+      if (!(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
+        const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
         if (o.kind == K_PRIM) {
           if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
         } else if (o.kind == K_PATH) {
@@ -287,105 +311,120 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
           }
         } else if (o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
-          const int r = o.brush_r;
+          const int br = o.brush_r;
           for (int k = 0; k < o.count; k++) {
             int2 p = P.points[o.first + k];
-            if (p.y - r <= yy && yy <= p.y + r) S |= interval_mask32(xx0, p.x - r, p.x + r);
+            if (p.y - br <= yy && yy <= p.y + br) S |= interval_mask32(xx0, p.x - br, p.x + br);
           }
           C = S;
         }
       }
     }
-    unsigned cand = __ballot_sync(0xFFFFFFFFu, (S & u) != 0u);
-    // ---- sequential front-to-back composite of the candidates ----
-    while (cand) {
-      const int k = __ffs((int)cand) - 1;
-      cand &= cand - 1;
-      const uint32_t Sk = __shfl_sync(0xFFFFFFFFu, S, k);
-      const uint32_t Ck = __shfl_sync(0xFFFFFFFFu, C, k);
-      const int ik = __shfl_sync(0xFFFFFFFFu, idx, k);
+    const unsigned hits = __ballot_sync(0xFFFFFFFFu, (S & u_hit) != 0u);
+    if (hits == 0u) continue;
+    // ---- sequential front-to-back composite of the candidates that still show ----
+    for (int cc = 0; cc < NC; cc++) {
+      unsigned rows = (hits >> (cc * CELL_H)) & ROWMASK;
+      if (rows == 0u) continue;
+      const int ik = __shfl_sync(0xFFFFFFFFu, idx, cc * CELL_H);
       const ObjRec& o = P.objs[ik];
       // group transitions: close groups that do not enclose this object, open the ones that do
       int common = 0;
       while (common < depth && common < o.depth && open_grp[common] == o.anc[common]) common++;
       while (depth > common) pop_group();
       while (depth < o.depth) push_group(o.anc[depth]);
-      const uint32_t vis = Sk & u;
-      if (vis == 0u) continue;
-      const uint32_t M = Sk & ~Ck;          // minshape word (polygon.ml:526)
-      const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
-      const int yy = y - o.dy, xx0 = tx0 - o.dx;
-      int opacity = 255;
-      if (edge) {
-        if (o.kind == K_PATH) {
-          bool ok;
-          const int slot = o.row_base + yy - o.ry0;
-          const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
-          opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
-          if (!ok) bad = true;
-        } else if (o.kind == K_BRUSH) {
-          // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
-          const int r = o.brush_r, w = 2 * r + 1;
-          const int px = xx0 + lane;
-          uint32_t a = 0u;
-          if ((edge >> lane) & 1u) {
-            for (int q = 0; q < o.count; q++) {
-              int2 p = P.points[o.first + q];
-              int ddx = px - p.x, ddy = yy - p.y;
-              if (ddx >= -r && ddx <= r && ddy >= -r && ddy <= r)
-                a = alpha_over(a, P.stamps[o.stamp_off + (ddy + r) * w + (ddx + r)]);
+      const int okind = o.kind, fkind = o.fill.kind, pretrans = o.pretrans, odx = o.dx, ody = o.dy;
+      const uint32_t c0 = o.fill.c0;
+      while (rows) {
+        const int r = __ffs((int)rows) - 1;
+        rows &= rows - 1;
+        const uint32_t Sk = __shfl_sync(0xFFFFFFFFu, S, cc * CELL_H + r);
+        const uint32_t Ck = __shfl_sync(0xFFFFFFFFu, C, cc * CELL_H + r);
+        const uint32_t ur = __shfl_sync(0xFFFFFFFFu, u, r);
+        const uint32_t vis = Sk & ur;
+        if (vis == 0u) continue;
+        const uint32_t M = Sk & ~Ck;          // minshape word (polygon.ml:526)
+        const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
+        const int yy = y0 + r - ody, xx0 = tx0 - odx;
+        int opacity = 255;
+        if (edge) {
+          if (okind == K_PATH) {
+            bool ok;
+            const int slot = o.row_base + yy - o.ry0;
+            const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+            opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
+            if (!ok) bad = true;
+          } else if (okind == K_BRUSH) {
+            // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
+            const int br = o.brush_r, w = 2 * br + 1;
+            const int px = xx0 + lane;
+            uint32_t al = 0u;
+            if ((edge >> lane) & 1u) {
+              for (int q = 0; q < o.count; q++) {
+                int2 p = P.points[o.first + q];
+                int ddx = px - p.x, ddy = yy - p.y;
+                if (ddx >= -br && ddx <= br && ddy >= -br && ddy <= br)
+                  al = alpha_over(al, P.stamps[o.stamp_off + (ddy + br) * w + (ddx + br)]);
+              }
+            }
+            opacity = (int)al;
+          }
+        }
+        int lead_start = xx0;  // object-frame x where the run containing bit 0 begins
+        if (CARRY && edge && okind == K_PATH && fkind != 0) {
+          const size_t slot = (size_t)(y0 + r - P.fr.band_y0) * P.fr.tiles_x + tile;
+          if ((edge & 1u) && tile > 0) {
+            const volatile int* done = P.carry_done + slot - 1;
+            while (*done != P.epoch) __nanosleep(32);
+            __threadfence();
+            const int cnt = P.carry_cnt[slot - 1];
+            for (int q = 0; q < cnt; q++) {
+              int2 e = P.carry_ent[(slot - 1) * CARRY_CAP + q];
+              if (e.x == ik) lead_start = e.y - odx;
             }
           }
-          opacity = (int)a;
-        }
-      }
-      int lead_start = xx0;  // object-frame x where the run containing bit 0 begins
-      if (CARRY && edge && o.kind == K_PATH && o.fill.kind != 0) {
-        if ((edge & 1u) && tile > 0) {
-          const volatile int* done = P.carry_done + slot - 1;
-          while (*done != P.epoch) __nanosleep(32);
-          __threadfence();
-          const int cnt = P.carry_cnt[slot - 1];
-          for (int q = 0; q < cnt; q++) {
-            int2 e = P.carry_ent[(slot - 1) * CARRY_CAP + q];
-            if (e.x == ik) lead_start = e.y - o.dx;
+          if (edge >> 31) {
+            const uint32_t nz = ~edge;
+            const int tstart = nz ? (xx0 + 32 - __clz((int)nz)) : lead_start;
+            const int nc = __shfl_sync(0xFFFFFFFFu, n_carry, r);
+            if (lane == 0 && nc < CARRY_CAP) P.carry_ent[slot * CARRY_CAP + nc] = make_int2(ik, tstart + odx);
+            if (r_lane == r) n_carry++;
+            if (nc + 1 > CARRY_CAP) bad = true;
           }
         }
-        if (edge >> 31) {
-          const uint32_t nz = ~edge;
-          const int tstart = nz ? (xx0 + 32 - __clz((int)nz)) : lead_start;
-          if (lane == 0 && n_carry < CARRY_CAP) P.carry_ent[slot * CARRY_CAP + n_carry] = make_int2(ik, tstart + o.dx);
-          n_carry++;
-          if (n_carry > CARRY_CAP) bad = true;
+        const bool mine = (vis >> lane) & 1u;
+        uint32_t acc = s_acc[wid][r][lane];
+        if (mine) {
+          const bool is_edge = (edge >> lane) & 1u;
+          uint32_t col;
+          if (okind == K_PRIM || fkind == 0) col = c0;
+          else if (!is_edge || okind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
+          else {
+            // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
+            // of `edge` bits); a run that reaches bit 0 may have begun in a tile further left.
+            uint32_t below = ~edge & ((1u << lane) - 1u);
+            int start = below ? (xx0 + 32 - __clz((int)below)) : lead_start;
+            col = fill_lookup(o.fill, start, yy);
+          }
+          if (is_edge) col = px_dissolve(col, opacity);
+          if (pretrans >= 0) col = px_dissolve(col, pretrans);
+          acc = px_over(acc, col);
+          s_acc[wid][r][lane] = acc;
         }
+        const uint32_t opq = __ballot_sync(0xFFFFFFFFu, mine && (acc >> 24) == 255u);
+        if (r_lane == r) u &= ~opq;  // u' = u --- f  (render.ml:1308)
       }
-      bool mine = (vis >> lane) & 1u;
-      if (mine) {
-        const bool is_edge = (edge >> lane) & 1u;
-        uint32_t col;
-        if (o.kind == K_PRIM || o.fill.kind == 0) col = o.fill.c0;
-        else if (!is_edge || o.kind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
-        else {
-          // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
-          // of `edge` bits); a run that reaches bit 0 may have begun in a tile further left.
-          uint32_t below = ~edge & ((1u << lane) - 1u);
-          int start = below ? (xx0 + 32 - __clz((int)below)) : lead_start;
-          col = fill_lookup(o.fill, start, yy);
-        }
-        if (is_edge) col = px_dissolve(col, opacity);
-        if (o.pretrans >= 0) col = px_dissolve(col, o.pretrans);
-        acc = px_over(acc, col);
-      }
-      const uint32_t opq = __ballot_sync(0xFFFFFFFFu, mine && (acc >> 24) == 255u);
-      u &= ~opq;  // u' = u --- f  (render.ml:1308)
     }
   }
   while (depth > 0) pop_group();
   publish_done();
   if (bad) *P.error_flag = 1;
-  const int x = tx0 + lane;
-  if ((u_update >> lane) & 1u) {
-    if (P.write_clear || acc != 0u) P.fb[(size_t)y * P.fr.W + x] = acc;
+  for (int r = 0; r < CELL_H; r++) {
+    const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);
+    if ((uu >> lane) & 1u) {
+      const uint32_t acc = s_acc[wid][r][lane];
+      if (P.write_clear || acc != 0u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = acc;
+    }
   }
 }
 

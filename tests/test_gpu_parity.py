@@ -212,3 +212,21 @@ def test_band_partition_equals_whole_frame(ctx, oracle):
         parts.append(ctx.fb_read_rgba(0, y0, W, y1 - y0).copy())
     assert np.array_equal(np.concatenate(parts, axis=0), whole)
     ctx.scene_free(sc)
+
+
+def test_pretrans_group_returns_pixels_to_u(ctx, oracle):
+    """A PreTrans group with opaque members gives its pixels back to the parent's u when it closes;
+    many objects follow so that several scan passes start while the group is open."""
+    W, H = 160, 96
+    b = S.SceneBuilder()
+    b.group_begin(pretrans=120)
+    for i in range(7):
+        b.polygon([(10.0 + 9 * i, 8.0), (150.0 - 5 * i, 14.0 + 3 * i), (140.0, 88.0 - 4 * i), (12.0 + 3 * i, 80.0)], S.Fill.plain(S.rgba8(30 * i, 255 - 30 * i, 90)))
+    b.group_end()
+    for i in range(9):
+        b.polygon([(5.0 + 11 * i, 5.0 + 2 * i), (60.0 + 11 * i, 9.0), (70.0 + 9 * i, 90.0), (8.0 + 10 * i, 70.0)], S.Fill.plain(S.dissolve(S.rgba8(200, 20 * i, 255 - 20 * i), 255 if i % 2 else 150)))
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
