@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcoherence_b200.so")
+LIB_PATH = os.environ.get("COH_LIB_PATH", os.path.join(_HERE, "libcoherence_b200.so"))  # override: kernel-variant experiments
 
 COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH = 0, 1, 2, 3, 4
 COH_NONZERO, COH_EVENODD = 0, 1

@@ -32,7 +32,8 @@ struct DevScene {
   int* rowedge_ptr = nullptr;   // K1 edge binning (CSR over (path object, pixel row))
   int* rowedge_idx = nullptr;
   std::vector<ObjRec> h_objs;
-  bool has_fancy = false;    // some path has a gradient / radial fill
+  bool has_fancy = false;    // some object has a gradient / radial fill
+  bool has_brush = false;
   size_t items_total = 0;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
 };
@@ -55,7 +56,8 @@ struct coh_ctx {
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* h_total = nullptr;  // pinned
   // cross-tile carry for fancy fills
-  int* ticket = nullptr; int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
+  int* queue = nullptr; int* order_hist = nullptr; int* cell_order = nullptr; int n_sms = 0;
+  int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
   size_t carry_slots = 0; int epoch = 0;
   bool own_stream = true, own_fb = true;
   // optional per-kernel timing (CUDA events on the launching stream)
@@ -136,7 +138,7 @@ int coh_shutdown(coh_ctx* ctx) {
   if (ctx->own_fb) cudaFree(ctx->fb);
   cudaFree(ctx->u_out);
   cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
-  cudaFree(ctx->ticket); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
+  cudaFree(ctx->queue); cudaFree(ctx->order_hist); cudaFree(ctx->cell_order); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -741,7 +743,10 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   DevScene* s = new DevScene();
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->h_objs = recs;
-  for (const ObjRec& o : recs) if (o.kind == K_PATH && o.fill.kind != 0) s->has_fancy = true;
+  for (const ObjRec& o : recs) {
+    if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
+    if (o.kind == K_BRUSH) s->has_brush = true;
+  }
   CK(cudaMalloc(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
@@ -808,16 +813,27 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
   if (n_cells > ctx->n_cells_cap) {
-    cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off);
+    cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_order);
     CK(cudaMalloc(&ctx->cell_counts, sizeof(int) * n_cells));
     CK(cudaMalloc(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
+    CK(cudaMalloc(&ctx->cell_order, sizeof(int) * n_cells));
     ctx->n_cells_cap = n_cells;
   }
+  if (!ctx->queue) {
+    CK(cudaMalloc(&ctx->queue, sizeof(int)));
+    CK(cudaMalloc(&ctx->order_hist, sizeof(int) * 2 * ORDER_BINS));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->n_sms = prop.multiProcessorCount;
+  }
+  const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
+  CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * 2 * ORDER_BINS, ctx->stream));
+  CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
   if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   // K1: count, scan, fill
   int bin_blocks = cdiv(n_cells * 32, 256);
-  k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
+  k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
   k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
+  if (ordered) { k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED(); }
   // capacity of the item pool: the exact total is a pure function of the object boxes and the
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
@@ -838,7 +854,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
     CK(cudaMalloc(&ctx->cell_items, sizeof(int) * cap));
     ctx->cell_items_cap = cap;
   }
-  k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items); LAUNCHED();
+  k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx;
@@ -846,9 +862,11 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
-  dim3 grid(cdiv(fr.tiles_x, WALK_WARPS), cell_row1 - cell_row0 + 1);
+  // persistent grid: exactly one resident wave
+  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells, WALK_WARPS));
+  P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.n_cells = n_cells;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  P.ticket = nullptr; P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
+  P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
   if (s->has_fancy) {
     size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
     if (slots > ctx->carry_slots) {
@@ -859,13 +877,15 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
       CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
       ctx->carry_slots = slots;
     }
-    if (!ctx->ticket) CK(cudaMalloc(&ctx->ticket, sizeof(int)));
-    CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(int), ctx->stream));
-    P.ticket = ctx->ticket; P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
+    P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
     P.epoch = ++ctx->epoch;
-    k_walk<true><<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+    if (s->has_brush) k_walk<true, true><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    else k_walk<true, false><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    LAUNCHED();
   } else {
-    k_walk<false><<<grid, 256, 0, ctx->stream>>>(P); LAUNCHED();
+    if (s->has_brush) k_walk<false, true><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    else k_walk<false, false><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    LAUNCHED();
   }
   if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
   return 0;
@@ -895,6 +915,15 @@ int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out) {
   return shape_from_bits(ctx, ctx->u_out + (size_t)fr.band_y0 * fr.tiles_x, fr.band_y0, n_rows, 0, fr.tiles_x, out);
 }
 void* coh_fb_device_ptr(coh_ctx* ctx) { return ctx->fb; }
+#ifdef COH_PHASE_PROFILE
+int coh_phase_cycles(coh_ctx* ctx, unsigned long long* out8, int reset) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z)); }
+  return 0;
+}
+#endif
 int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->fb) FAIL("coh_fb_read_rgba: no framebuffer");

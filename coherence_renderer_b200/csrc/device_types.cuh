@@ -6,7 +6,10 @@
 namespace coh {
 
 constexpr int TILE_W = 32;       // pixels per tile word (one warp lane per pixel)
-constexpr int CELL_H = 16;       // rows per binning cell
+#ifndef COH_CELL_H
+#define COH_CELL_H 16
+#endif
+constexpr int CELL_H = COH_CELL_H;  // rows per cell (power of two <= 32)
 constexpr int MAX_DEPTH = 6;     // nested Group depth (incl. the implicit scene / background groups)
 constexpr int AA_WORDS = 17;     // (32 + 2) * 16 scaled columns of one tile = 544 bits
 

@@ -62,10 +62,15 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
 // 32 at a time; ballot + popc give each overlapping object its slot, so every list comes
 // out already sorted and the two passes (count / fill) are identical apart from the store.
 // ------------------------------------------------------------------------------------
+// The same kernels also build the walker's work order: cells sorted by descending list length
+// (256-bin counting sort: histogram in the count pass, scatter in the fill pass), so that the
+// persistent walker warps take the heavy cells first and the tail of the launch is light.
+constexpr int ORDER_BINS = 256;
 template <bool FILL>
 __global__ void k_bin(const ObjRec* __restrict__ objs, const int* __restrict__ leaves, int n_leaves, Frame fr,
                       int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
-                      int* __restrict__ items) {
+                      int* __restrict__ items, int* __restrict__ hist /*[2*ORDER_BINS]: starts, cursors*/,
+                      int* __restrict__ order) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_cells) return;
@@ -87,7 +92,22 @@ __global__ void k_bin(const ObjRec* __restrict__ objs, const int* __restrict__ l
     if (FILL && hit) items[base + n + __popc(m & ((1u << lane) - 1u))] = idx;
     n += __popc(m);
   }
-  if (!FILL && lane == 0) counts[warp] = n;
+  if (lane == 0) {
+    const int bin = ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1);  // bin 0 = longest lists
+    if (!FILL) { counts[warp] = n; atomicAdd(&hist[bin], 1); }
+    else if (order) order[hist[bin] + atomicAdd(&hist[ORDER_BINS + bin], 1)] = warp;
+  }
+}
+// exclusive scan of the histogram in place (one warp)
+__global__ void k_order_scan(int* __restrict__ hist) {
+  int lane = threadIdx.x, carry = 0;
+  for (int base = 0; base < ORDER_BINS; base += 32) {
+    int v = hist[base + lane], x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
+    hist[base + lane] = carry + x - v;
+    carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+  }
 }
 
 // Exclusive scan of n ints by a single block (n is the number of cells: tens of thousands).
@@ -145,9 +165,12 @@ struct WalkParams {
   // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
   // x of its span (polygon.ml:736) and a span may begin in a tile further left.  Every tile
   // publishes, per fancy object whose visible edge run touches its right border, where that run
-  // began; the tile to its right looks it up.  Tiles are handed out by an atomic ticket in
-  // row-major order, so the tile waited on has always started (decoupled look-back).
-  int* ticket;
+  // began; the tile to its right looks it up.  With fancy fills cells are taken from the queue
+  // in row-major order, so the cell waited on has always been started by a resident warp
+  // (decoupled look-back).
+  int* queue;                  // work queue head: persistent warps take cells with atomicAdd
+  const int* order;            // q-th cell to process (heavy first), or null for row-major order
+  int n_cells;
   int* carry_done;             // per (band row, tile): == epoch when the tile has finished
   int* carry_cnt;              // per (band row, tile): number of published entries
   int2* carry_ent;             // per (band row, tile): CARRY_CAP entries (object index, start x)
@@ -155,6 +178,17 @@ struct WalkParams {
 };
 constexpr int CARRY_CAP = 8;
 
+// Optional phase timing (tools only; -DCOH_PHASE_PROFILE): cycles per phase summed over warps.
+#ifdef COH_PHASE_PROFILE
+__device__ unsigned long long g_phase_cycles[16];
+#define PH_DECL long long ph_t = clock64(); long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
+#define PH_MARK(i) { long long t_ = clock64(); ph_acc[i] += t_ - ph_t; ph_t = t_; }
+#define PH_FLUSH() { if (lane == 0) { for (int i_ = 0; i_ < 6; i_++) atomicAdd(&g_phase_cycles[i_], (unsigned long long)ph_acc[i_]); } }
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_FLUSH()
+#endif
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
@@ -166,34 +200,124 @@ __device__ __forceinline__ int warp_sum(int v) {
 // list (polygon.ml:673-692) into its private 544-bit row in shared memory; then for every
 // edge pixel the 32 lanes each weigh their row's 32-column window and the warp reduces.
 // Returns the opacity of pixel `lane` (undefined where edge bit is 0).
+// Staged edge of the AA scan: scaled coordinates plus where it lies relative to the window.
+struct StagedEdge { int x0, x1, ymin, ymax; double g; int dir, side; };
+constexpr int STAGE_WORDS = sizeof(StagedEdge) / 4;
 __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand,
-                                       int winding, int xx0, int yy, uint32_t edge,
-                                       uint32_t* aa_bits /*32*AA_WORDS, warp private*/,
-                                       const int* __restrict__ prefix /*[32][33] shared*/, int volume, int lane,
-                                       bool& ok) {
+                                    int winding, int xx0, int yy, uint32_t edge,
+                                    uint32_t* aa_bits /*32*AA_WORDS, warp private*/,
+                                    StagedEdge* stage /*32, warp private*/,
+                                    const int* __restrict__ prefix /*[32][33] shared*/, int volume, int lane,
+                                    bool& ok) {
+#ifdef COH_PHASE_PROFILE
+  long long t0_ = clock64();
+#endif
   uint32_t* row = aa_bits + lane * AA_WORDS;
-#pragma unroll
-  for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
   SinkMem sink;
   sink.wx0 = 16 * xx0 - 32; sink.nwords = AA_WORDS; sink.stride = 1; sink.S = row; sink.C = nullptr;
-  ok = scan_row(edges, idx, n_cand, 16, 16 * yy - 32 + lane, winding, true, sink.wx0, sink.wx0 + 32 * AA_WORDS - 1, sink);
+  const int wlo = sink.wx0, whi = sink.wx0 + 32 * AA_WORDS - 1;
+  // Fast path: the crossings of this lane's row stay in registers (a row of a 34-pixel window is
+  // touched by one or two edges); if any lane needs more, the whole warp redoes the row with the
+  // general lists in local memory.
+  constexpr int FAST_X = 3;
+  ScanStateT<FAST_X, true> fst;
+  SinkRow fsink; fsink.wx0 = wlo; fsink.nwords = AA_WORDS; fsink.S = row;
+#pragma unroll
+  for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
+  scan_begin(fst, 16 * yy - 32 + lane, true, wlo, whi);
+  // The candidate edges are the same for all 32 super-sampled rows: lane i fetches and scales
+  // candidate i once (one parallel round trip to L2 instead of a dependent chain per lane) and
+  // classifies it against the window; then every lane walks the staged copies in shared memory.
+  for (int base = 0; base < n_cand; base += 32) {
+    const int i = base + lane;
+    if (i < n_cand) {
+      const EdgeRec e = edges[idx ? idx[i] : i];
+      StagedEdge se;
+      se.x0 = e.x0in * 16; se.x1 = e.x1in * 16; se.ymin = e.ymin * 16; se.ymax = e.ymax * 16;
+      se.g = e.g; se.dir = e.dir; se.side = edge_side(se.x0, se.x1, wlo, whi);
+      stage[lane] = se;
+    }
+    __syncwarp();
+#ifdef COH_PHASE_PROFILE
+    if (lane == 0) atomicAdd(&g_phase_cycles[12], (unsigned long long)(clock64() - t0_));
+#endif
+    const int cnt = min(32, n_cand - base);
+    for (int k = 0; k < cnt; k++) {
+      const StagedEdge se = stage[k];
+      scan_edge(fst, se.x0, se.x1, se.ymin, se.ymax, se.g, se.dir, se.side, fsink);
+    }
+    __syncwarp();
+  }
+#ifdef COH_PHASE_PROFILE
+  if (lane == 0) atomicAdd(&g_phase_cycles[13], (unsigned long long)(clock64() - t0_));
+#endif
+  bool fast = scan_finish(fst, winding, fsink);
+  fast = __all_sync(0xFFFFFFFFu, fast);
+#ifdef COH_PHASE_PROFILE
+  if (lane == 0) atomicAdd(&g_phase_cycles[14], (unsigned long long)(clock64() - t0_));
+#endif
+  ok = true;
   __syncwarp();
-  int opacity = 0;
+  if (!fast) {
+    // general path (rare): redo the row with unbounded-ish lists into shared-memory bit-rows
+#pragma unroll
+    for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
+    ScanState st;
+    scan_begin(st, 16 * yy - 32 + lane, true, wlo, whi);
+    for (int i = 0; i < n_cand; i++) {
+      const EdgeRec e = edges[idx ? idx[i] : i];
+      const int x0 = e.x0in * 16, x1 = e.x1in * 16;
+      scan_edge(st, x0, x1, e.ymin * 16, e.ymax * 16, e.g, e.dir, edge_side(x0, x1, wlo, whi), sink);
+    }
+    ok = scan_finish(st, winding, sink);
+    __syncwarp();
+  }
+#ifdef COH_PHASE_PROFILE
+  long long t1_ = clock64();
+  if (lane == 0) { atomicAdd(&g_phase_cycles[6], (unsigned long long)(t1_ - t0_)); atomicAdd(&g_phase_cycles[8], 1ull); atomicAdd(&g_phase_cycles[9], (unsigned long long)n_cand); atomicAdd(&g_phase_cycles[10], (unsigned long long)__popc(edge)); atomicAdd(&g_phase_cycles[11], fast ? 0ull : 1ull); }
+#endif
+  int mytot = 0;
   const int* prow = prefix + lane * 33;
   uint32_t e = edge;
+  // Four edge pixels per iteration: a pixel's table sum is at most 42120 < 2^16, so two pixels
+  // share one 32-bit register through the butterfly reduction, and two such registers are
+  // reduced side by side (independent shuffles pipeline).
   while (e) {
-    int b = __ffs((int)e) - 1;
-    e &= e - 1;
-    uint32_t lo = row[b >> 1], hi = row[(b >> 1) + 1];
-    uint32_t m = (b & 1) ? ((lo >> 16) | (hi << 16)) : lo;
-    int tot = warp_sum(aa_row_sum(prow, m));
-    if (lane == b) opacity = aa_opacity(tot, volume);
+    int b[4];
+    int part[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      b[k] = e ? (__ffs((int)e) - 1) : -1;
+      e &= e - 1;   // 0 & anything stays 0
+      part[k] = 0;
+      if (b[k] >= 0) {
+        const uint32_t lo = row[b[k] >> 1], hi = row[(b[k] >> 1) + 1];
+        const uint32_t m = (b[k] & 1) ? ((lo >> 16) | (hi << 16)) : lo;
+        part[k] = aa_row_sum(prow, m);
+      }
+    }
+    int p01 = part[0] | (part[1] << 16), p23 = part[2] | (part[3] << 16);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      p01 += __shfl_xor_sync(0xFFFFFFFFu, p01, d);
+      p23 += __shfl_xor_sync(0xFFFFFFFFu, p23, d);
+    }
+    mytot = (lane == b[0]) ? (p01 & 0xFFFF) : mytot;
+    mytot = (lane == b[1]) ? ((p01 >> 16) & 0xFFFF) : mytot;
+    mytot = (lane == b[2]) ? (p23 & 0xFFFF) : mytot;
+    mytot = (lane == b[3]) ? ((p23 >> 16) & 0xFFFF) : mytot;
   }
   __syncwarp();
-  return opacity;
+#ifdef COH_PHASE_PROFILE
+  if (lane == 0) { atomicAdd(&g_phase_cycles[7], (unsigned long long)(clock64() - t1_)); }
+#endif
+  return aa_opacity(mytot, volume);  // one division per lane, after the loop
 }
 
 constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
+#ifndef WALK_MIN_CTAS
+#define WALK_MIN_CTAS 3
+#endif
 constexpr int NC = 32 / CELL_H;          // candidate objects scan-converted per pass
 constexpr unsigned ROWMASK = (CELL_H >= 32) ? 0xFFFFFFFFu : ((1u << CELL_H) - 1u);
 
@@ -202,21 +326,13 @@ constexpr unsigned ROWMASK = (CELL_H >= 32) ? 0xFFFFFFFFu : ((1u << CELL_H) - 1u
 // front-to-back composite then visits, object by object, only the rows where the object
 // still has pixels inside the covered-so-far complement `u` (one 32-bit word per row, held
 // by lane r and its NC-1 mirror lanes).
-template <bool CARRY>
-__global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
-  __shared__ int s_prefix[32 * 33];
-  __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
-  __shared__ uint32_t s_acc[WALK_WARPS][CELL_H][32];
-  __shared__ int s_ticket;
-  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
-  if (CARRY && threadIdx.x == 0) s_ticket = atomicAdd(P.ticket, 1);
-  __syncthreads();
-  const int volume = P.aa->volume;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int bx = blockIdx.x, by = blockIdx.y;
-  if (CARRY) { bx = s_ticket % gridDim.x; by = s_ticket / gridDim.x; }
-  const int tile = bx * WALK_WARPS + wid;
-  if (tile >= P.fr.tiles_x) return;
+// CARRY: the scene has fancy (gradient / radial) fills -> fill evaluation and the cross-tile carry
+// are compiled in.  BRUSH: the scene has brush strokes.  Plain polygon scenes get the small kernel.
+template <bool CARRY, bool BRUSH>
+__device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int lane,
+                                          uint32_t* __restrict__ aa_bits, StagedEdge* __restrict__ stage,
+                                          uint32_t (*__restrict__ acc_rows)[32],
+                                          const int* __restrict__ s_prefix, const int volume) {
   const int tx0 = tile * TILE_W;
   const int y0 = (P.cell_row0 + by) * CELL_H;
   const int r_lane = lane % CELL_H, c_lane = lane / CELL_H;
@@ -244,7 +360,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
   if (__ballot_sync(0xFFFFFFFFu, u != 0u) == 0u) { publish_done(); return; }
 
 #pragma unroll
-  for (int r = 0; r < CELL_H; r++) s_acc[wid][r][lane] = 0u;   // accumulator of the current nesting level
+  for (int r = 0; r < CELL_H; r++) acc_rows[r][lane] = 0u;   // accumulator of the current nesting level
   __syncwarp();
   int depth = 0;                       // open groups
   int hit_level = -1;                  // outermost open group that dissolves its sprite (PreTrans), or -1
@@ -253,6 +369,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
   uint32_t stk_acc[MAX_DEPTH][CELL_H]; // parents' accumulators of my column (local memory; touched on push/pop only)
   bool bad = false;
 
+  PH_DECL
   const int cell = by * P.fr.tiles_x + tile;
   const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
 
@@ -264,13 +381,14 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
     const int pt = P.objs[g].pretrans;
     const int gflags = P.objs[g].flags;
     const uint32_t pu = stk_u[depth - 1];
+#pragma unroll 1
     for (int r = 0; r < CELL_H; r++) {
-      uint32_t sp = s_acc[wid][r][lane];
+      uint32_t sp = acc_rows[r][lane];
       const uint32_t pa = stk_acc[depth - 1][r];
       if (pt >= 0) sp = px_dissolve(sp, pt);
       const uint32_t res = px_over(pa, sp);
       const uint32_t opq = __ballot_sync(0xFFFFFFFFu, (res >> 24) == 255u);
-      s_acc[wid][r][lane] = res;
+      acc_rows[r][lane] = res;
       if (r_lane == r) u = pu & ~opq;
     }
     depth--;
@@ -278,7 +396,8 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
     if ((gflags & OF_ROOT_SCENE) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = u;
   };
   auto push_group = [&](int g) {
-    for (int r = 0; r < CELL_H; r++) { stk_acc[depth][r] = s_acc[wid][r][lane]; s_acc[wid][r][lane] = 0u; }
+#pragma unroll 1
+    for (int r = 0; r < CELL_H; r++) { stk_acc[depth][r] = acc_rows[r][lane]; acc_rows[r][lane] = 0u; }
     stk_u[depth] = u;
     open_grp[depth] = g;
     // A group composited with PreTrans (v < 1) gives pixels back to its parent's `u` when it
@@ -289,7 +408,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
     depth++;
   };
 
-  for (int base = it0; base < it1; base += NC) {
+  // the loop runs one extra, empty pass whose only effect is to close every open group
+  // (keeps a single inlined copy of the group push/pop code: the kernel must fit the I-cache)
+  for (int base = it0;; base += NC) {
+    const bool closing = base >= it1;
+    PH_MARK(0)  // other / loop overhead
     // ---- lane-parallel scan conversion: lane (c, r) evaluates row y0+r of candidate c ----
     const int ci = base + c_lane;
     const int idx = ci < it1 ? P.cell_items[ci] : -1;
@@ -309,7 +432,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
             if (!scan_row(P.edges, P.rowedge_idx + a, b - a, 1, yy, o.winding, false, xx0, xx0 + 31, sink)) bad = true;
             S = sink.S; C = sink.C;
           }
-        } else if (o.kind == K_BRUSH) {
+        } else if (BRUSH && o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
           const int br = o.brush_r;
           for (int k = 0; k < o.count; k++) {
@@ -320,21 +443,26 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
         }
       }
     }
+    PH_MARK(1)  // scan
     const unsigned hits = __ballot_sync(0xFFFFFFFFu, (S & u_hit) != 0u);
-    if (hits == 0u) continue;
+    if (hits == 0u && !closing) continue;
     // ---- sequential front-to-back composite of the candidates that still show ----
     for (int cc = 0; cc < NC; cc++) {
       unsigned rows = (hits >> (cc * CELL_H)) & ROWMASK;
-      if (rows == 0u) continue;
-      const int ik = __shfl_sync(0xFFFFFFFFu, idx, cc * CELL_H);
+      if (rows == 0u && !(closing && cc == 0)) continue;
+      const int ik = closing ? 0 : __shfl_sync(0xFFFFFFFFu, idx, cc * CELL_H);
       const ObjRec& o = P.objs[ik];
+      PH_MARK(0)
       // group transitions: close groups that do not enclose this object, open the ones that do
+      const int odepth = closing ? 0 : o.depth;
       int common = 0;
-      while (common < depth && common < o.depth && open_grp[common] == o.anc[common]) common++;
+      while (common < depth && common < odepth && open_grp[common] == o.anc[common]) common++;
       while (depth > common) pop_group();
-      while (depth < o.depth) push_group(o.anc[depth]);
+      if (closing) break;
+      while (depth < odepth) push_group(o.anc[depth]);
       const int okind = o.kind, fkind = o.fill.kind, pretrans = o.pretrans, odx = o.dx, ody = o.dy;
       const uint32_t c0 = o.fill.c0;
+      PH_MARK(2)  // transitions
       while (rows) {
         const int r = __ffs((int)rows) - 1;
         rows &= rows - 1;
@@ -347,14 +475,15 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
         const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
         const int yy = y0 + r - ody, xx0 = tx0 - odx;
         int opacity = 255;
+        PH_MARK(3)  // row setup
         if (edge) {
           if (okind == K_PATH) {
             bool ok;
             const int slot = o.row_base + yy - o.ry0;
             const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
-            opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, s_aa[wid], s_prefix, volume, lane, ok);
+            opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, aa_bits, stage, s_prefix, volume, lane, ok);
             if (!ok) bad = true;
-          } else if (okind == K_BRUSH) {
+          } else if (BRUSH && okind == K_BRUSH) {
             // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
             const int br = o.brush_r, w = 2 * br + 1;
             const int px = xx0 + lane;
@@ -370,6 +499,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
             opacity = (int)al;
           }
         }
+        PH_MARK(4)  // AA
         int lead_start = xx0;  // object-frame x where the run containing bit 0 begins
         if (CARRY && edge && okind == K_PATH && fkind != 0) {
           const size_t slot = (size_t)(y0 + r - P.fr.band_y0) * P.fr.tiles_x + tile;
@@ -393,11 +523,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
           }
         }
         const bool mine = (vis >> lane) & 1u;
-        uint32_t acc = s_acc[wid][r][lane];
+        uint32_t acc = acc_rows[r][lane];
         if (mine) {
           const bool is_edge = (edge >> lane) & 1u;
           uint32_t col;
-          if (okind == K_PRIM || fkind == 0) col = c0;
+          if (!CARRY || okind == K_PRIM || fkind == 0) col = c0;
           else if (!is_edge || okind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
           else {
             // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
@@ -409,22 +539,50 @@ __global__ void __launch_bounds__(WALK_WARPS * 32) k_walk(WalkParams P) {
           if (is_edge) col = px_dissolve(col, opacity);
           if (pretrans >= 0) col = px_dissolve(col, pretrans);
           acc = px_over(acc, col);
-          s_acc[wid][r][lane] = acc;
+          acc_rows[r][lane] = acc;
         }
         const uint32_t opq = __ballot_sync(0xFFFFFFFFu, mine && (acc >> 24) == 255u);
+        PH_MARK(5)  // composite
         if (r_lane == r) u &= ~opq;  // u' = u --- f  (render.ml:1308)
       }
     }
+    if (closing) break;
   }
-  while (depth > 0) pop_group();
+  PH_MARK(2)
   publish_done();
   if (bad) *P.error_flag = 1;
+#pragma unroll 1
   for (int r = 0; r < CELL_H; r++) {
     const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);
     if ((uu >> lane) & 1u) {
-      const uint32_t acc = s_acc[wid][r][lane];
+      const uint32_t acc = acc_rows[r][lane];
       if (P.write_clear || acc != 0u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = acc;
     }
+  }
+  PH_MARK(0)
+  PH_FLUSH()
+}
+
+// Persistent launch: every warp keeps taking cells from the queue (heavy cells first) until it
+// is empty; the grid is sized to fill the GPU exactly once (WALK_MIN_CTAS CTAs per SM).
+template <bool CARRY, bool BRUSH>
+__global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
+  __shared__ int s_prefix[32 * 33];
+  __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
+  __shared__ uint32_t s_acc[WALK_WARPS][CELL_H][32];
+  __shared__ StagedEdge s_stage[WALK_WARPS][32];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
+  __syncthreads();
+  const int volume = P.aa->volume;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(P.queue, 1);
+    q = __shfl_sync(0xFFFFFFFFu, q, 0);
+    if (q >= P.n_cells) break;
+    const int cell = P.order ? P.order[q] : q;
+    walk_cell<CARRY, BRUSH>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    __syncwarp();
   }
 }
 
@@ -455,6 +613,7 @@ __global__ void __launch_bounds__(256) k_aa_rows(const EdgeRec* __restrict__ edg
                                                  const AATable* __restrict__ aa, uint8_t* __restrict__ out, int* error_flag) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
+  __shared__ StagedEdge s_stage[8][32];
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&aa->prefix[0][0])[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -463,7 +622,7 @@ __global__ void __launch_bounds__(256) k_aa_rows(const EdgeRec* __restrict__ edg
   uint32_t q = Q[(size_t)r * nw + w];
   if (!q) return;
   bool ok;
-  int op = aa_tile(edges, nullptr, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_prefix, aa->volume, lane, ok);
+  int op = aa_tile(edges, nullptr, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_stage[wid], s_prefix, aa->volume, lane, ok);
   if (!ok) *error_flag = 1;
   if ((q >> lane) & 1u) out[((size_t)r * nw + w) * 32 + lane] = (uint8_t)op;
 }

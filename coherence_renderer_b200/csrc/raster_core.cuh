@@ -16,8 +16,12 @@
 
 #if defined(__CUDACC__)
 #define COH_HD __host__ __device__ __forceinline__
+// big, cold or many-call-site routines stay out of line: the fused walker must fit the
+// instruction cache (a 135 KB kernel stalled 37 % of its issue slots on instruction fetch)
+#define COH_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define COH_HD inline
+#define COH_HD_NOINLINE inline
 #endif
 
 namespace coh {
@@ -140,7 +144,7 @@ struct BitRow {
 // OR pixel interval [a, b] (inclusive, absolute pixel coords) into a bit-row stored at
 // `bits` with stride `stride` words between consecutive words (stride lets 32 lanes
 // keep private rows in shared memory without bank conflicts).
-COH_HD void or_interval(uint32_t* bits, int stride, int nwords, int wx0, int a, int b) {
+COH_HD_NOINLINE void or_interval(uint32_t* bits, int stride, int nwords, int wx0, int a, int b) {
   a -= wx0; b -= wx0;
   int nb = nwords * 32;
   if (b < 0 || a >= nb) return;
@@ -193,8 +197,12 @@ COH_HD uint32_t interval_mask32(int wx0, int a, int b) {
 #define COH_MAXX 16
 #endif
 
-struct CrossList {
-  int v[COH_MAXX];  // (pos << 1) | (dir > 0), crossings touching the window
+// CAP = COH_MAXX: general list (dynamically indexed, lives in local memory).
+// Small CAP with REG = true: every access is a fully unrolled compare-select, so the list stays
+// in registers; callers check `n > CAP` and fall back to the general list (warp-uniformly).
+template <int CAP, bool REG>
+struct CrossListT {
+  int v[CAP];  // (pos << 1) | (dir > 0), crossings touching the window
   int n;
   int cnt_left;     // sum of directions of the crossings left of the window
   int n_left;       // how many there are
@@ -202,18 +210,34 @@ struct CrossList {
   COH_HD void init() { n = 0; cnt_left = 0; n_left = 0; has_right = false; }
   // reach of a crossing at p: [pix(p-16), pix(p+16)] (pixel spans are widened by half a
   // pixel, polygon.ml:458-459,490-491) or [pix(p), pix(p)] for the AA variant (469-479,498-512)
-  COH_HD void add(int p, int dir, bool aa, int wlo, int whi) {
-    int rhi = aa ? pix_of_sub(p) : pix_of_sub(p + 16);
-    int rlo = aa ? rhi : pix_of_sub(p - 16);
-    if (rhi < wlo) { cnt_left += dir; n_left++; }
-    else if (rlo > whi) has_right = true;
-    else { if (n < COH_MAXX) v[n] = (p << 1) | (dir > 0); n++; }
+  COH_HD void add(bool pred, int p, int dir, bool aa, int wlo, int whi) {
+    // branch-free: the 32 lanes of an AA scan sit on different rows and would otherwise diverge
+    const int rhi = aa ? pix_of_sub(p) : pix_of_sub(p + 16);
+    const int rlo = aa ? rhi : pix_of_sub(p - 16);
+    const bool left = pred && rhi < wlo, right = pred && rlo > whi, inside = pred && !(rhi < wlo) && !(rlo > whi);
+    cnt_left += left ? dir : 0;
+    n_left += left ? 1 : 0;
+    has_right = has_right || right;
+    const int val = (p << 1) | (dir > 0);
+    if (REG) {
+#pragma unroll
+      for (int k = 0; k < CAP; k++) v[k] = (inside && n == k) ? val : v[k];
+    } else if (inside && n < CAP) v[n] = val;
+    n += inside ? 1 : 0;
+  }
+  COH_HD int get(int i) const {
+    if (!REG) return v[i];
+    int r = v[0];
+#pragma unroll
+    for (int k = 1; k < CAP; k++) r = (i == k) ? v[k] : r;
+    return r;
   }
 };
+typedef CrossListT<COH_MAXX, false> CrossList;
 
-template <class Sink>
-COH_HD void winding_spans(const CrossList& L, int winding, bool aa, int wlo, int whi, Sink& sink) {
-  const int n = L.n < COH_MAXX ? L.n : COH_MAXX;
+template <int CAP, bool REG, class Sink>
+COH_HD void winding_spans_impl(const CrossListT<CAP, REG>& L, int winding, bool aa, int wlo, int whi, Sink& sink) {
+  const int n = L.n < CAP ? L.n : CAP;
   // the left group as one predecessor: its span runs from left of the window to the first
   // crossing that is not left
   if (L.n_left > 0 && (n > 0 || L.has_right)) {
@@ -222,74 +246,144 @@ COH_HD void winding_spans(const CrossList& L, int winding, bool aa, int wlo, int
       int b = whi;
       if (n > 0) {
         int first = L.v[0] >> 1;
-        for (int j = 1; j < n; j++) { int pj = L.v[j] >> 1; if (pj < first) first = pj; }
+        if (REG) {
+#pragma unroll
+          for (int j = 1; j < CAP; j++) { int pj = L.v[j] >> 1; if (j < n && pj < first) first = pj; }
+        } else {
+          for (int j = 1; j < n; j++) { int pj = L.v[j] >> 1; if (pj < first) first = pj; }
+        }
         b = aa ? pix_of_sub(first) : pix_of_sub(first + 16);
       }
       sink.span(wlo, b);
     }
   }
-  for (int i = 0; i < n; i++) {
-    const int vi = L.v[i];
+  auto one = [&](int i) {
+    const int vi = REG ? L.v[i] : L.get(i);
     const int pi = vi >> 1;
     // rank / running winding count of crossing i in the (pos, index) order, and its successor
     int cnt = L.cnt_left, rank = L.n_left;
     int succ = 0x7FFFFFFF; bool has = false;
-    for (int j = 0; j < n; j++) {
+    auto cmp = [&](int j) {
       const int vj = L.v[j];
       const int pj = vj >> 1;
       const bool before_or_self = (pj < pi) || (pj == pi && j <= i);
       if (before_or_self) { cnt += (vj & 1) ? 1 : -1; rank += (j != i); }
       else { if (pj < succ) succ = pj; has = true; }
+    };
+    if (REG) {
+#pragma unroll
+      for (int j = 0; j < CAP; j++) if (j < n) cmp(j);
+    } else {
+      for (int j = 0; j < n; j++) cmp(j);
     }
-    if (!has && !L.has_right) continue;  // the last crossing has no successor (polygon.ml:484, 458)
+    if (!has && !L.has_right) return;  // the last crossing has no successor (polygon.ml:484, 458)
     const bool emit = winding == 0 ? (cnt != 0) : ((rank & 1) == 0);
-    if (!emit) continue;
+    if (!emit) return;
     const int a = aa ? pix_of_sub(pi) : pix_of_sub(pi - 16);
     const int b = has ? (aa ? pix_of_sub(succ) : pix_of_sub(succ + 16)) : whi;
     sink.span(a, b);
+  };
+  if (REG) {
+#pragma unroll
+    for (int i = 0; i < CAP; i++) if (i < n) one(i);
+  } else {
+    for (int i = 0; i < n; i++) one(i);
   }
+}
+template <class Sink>
+COH_HD_NOINLINE void winding_spans(const CrossList& L, int winding, bool aa, int wlo, int whi, Sink& sink) {
+  winding_spans_impl(L, winding, aa, wlo, whi, sink);
+}
+template <int CAP, class Sink>
+COH_HD void winding_spans(const CrossListT<CAP, true>& L, int winding, bool aa, int wlo, int whi, Sink& sink) {
+  winding_spans_impl(L, winding, aa, wlo, whi, sink);
+}
+
+// The scan of one row band is split into begin / per-edge / finish so that callers can feed
+// edges from wherever they keep them (global memory lists, or a shared-memory stage filled
+// cooperatively by a warp).
+template <int CAP, bool REG>
+struct ScanStateT {
+  CrossListT<CAP, REG> tops, bots;
+  int top, bot;     // band of the row in (scaled) sub-bins, polygon.ml:539-540
+  int wlo, whi;     // window in (scaled) pixels
+  bool aa;
+  COH_HD bool overflow() const { return tops.n > CAP || bots.n > CAP; }
+};
+typedef ScanStateT<COH_MAXX, false> ScanState;
+template <class State>
+COH_HD void scan_begin(State& st, int y, bool aa, int wlo, int whi) {
+  st.top = 32 * y - 47;  // left_of_pix y - halfips
+  st.bot = st.top + 63;
+  st.wlo = wlo; st.whi = whi; st.aa = aa;
+  st.tops.init(); st.bots.init();
+}
+// Where an edge with (scaled) x extremes x0, x1 lies relative to a window: 1 = entirely left,
+// 2 = entirely right, 0 = may touch it.  "Entirely" includes the few sub-bins a rounded
+// crossing can leave the edge's x range by and the half-pixel widening of spans and coverage.
+COH_HD int edge_side(int x0, int x1, int wlo, int whi) {
+  const int exlo = imin(x0, x1) - 4, exhi = imax(x0, x1) + 4;
+  if (pix_of_sub(exhi + 16) < wlo) return 1;
+  if (pix_of_sub(exlo - 16) > whi) return 2;
+  return 0;
+}
+// One edge, coordinates already scaled (polygon.ml:332-388, 444-453).  Written without
+// data-dependent branches apart from the (warp-uniform) `side` test: the four clipping cases of
+// the reference differ only in which crossings exist and which end points bound the middle piece.
+template <class State, class Sink>
+COH_HD void scan_edge(State& st, int x0, int x1, int ymin, int ymax, double g, int dir, int side, Sink& sink) {
+  const int top = st.top, bot = st.bot;
+  const bool active = !(ymin > bot || ymax < top);                                   // polygon.ml:338
+  const bool middle_only = ymin == ymax || (ymin >= top && ymax <= bot);             // polygon.ml:340-343
+  const bool cross_top = active && !middle_only && ymin < top;   // contributes a top crossing
+  const bool cross_bot = active && !middle_only && ymax > bot;   // contributes a bottom crossing
+  // An edge entirely to one side of the window needs no arithmetic: its crossings only count as
+  // "left of the window" or "beyond it", and its coverage is outside.
+  if (side == 1) {
+    st.tops.cnt_left += cross_top ? dir : 0; st.tops.n_left += cross_top ? 1 : 0;
+    st.bots.cnt_left += cross_bot ? dir : 0; st.bots.n_left += cross_bot ? 1 : 0;
+    return;
+  }
+  if (side == 2) {
+    st.tops.has_right = st.tops.has_right || cross_top;
+    st.bots.has_right = st.bots.has_right || cross_bot;
+    return;
+  }
+  // top crossing (polygon.ml:355-364), then the bottom crossing, which restarts from the rounded
+  // top crossing when the edge is clipped at both ends (polygon.ml:365-385) and from x0 otherwise
+  const int xt = crossing_x(x0, g, top - 1 - ymin);
+  const int xs = cross_top ? xt : x0;
+  const int xb = crossing_x(xs, g, cross_top ? (bot - top) : (bot - ymin));
+  st.tops.add(cross_top, xt, dir, st.aa, st.wlo, st.whi);
+  st.bots.add(cross_bot, xb, dir, st.aa, st.wlo, st.whi);
+  // the clipped middle piece runs from (cross_top ? xt : x0) to (cross_bot ? xb : x1)
+  const int pe = cross_bot ? xb : x1;
+  const int lo = imin(xs, pe), hi = imax(xs, pe);
+  const int ca = pix_of_sub(lo - 16), cb = pix_of_sub(hi + 16);  // polygon.ml:444-453
+  if (active && cb >= st.wlo && ca <= st.whi) sink.cover(ca, cb);
+}
+template <class State, class Sink>
+COH_HD bool scan_finish(const State& st, int winding, Sink& sink) {
+  if (st.overflow()) return false;
+  winding_spans(st.tops, winding, st.aa, st.wlo, st.whi, sink);
+  winding_spans(st.bots, winding, st.aa, st.wlo, st.whi, sink);
+  return true;
 }
 
 // `idx` (optional) lists the candidate edges of this row (K1 edge binning): any superset
 // of the edges whose y range meets the band gives the same result, since every edge is
 // re-tested against the band here.
 template <class Sink>
-COH_HD bool scan_row(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int s, int y,
-                     int winding, bool aa, int wlo, int whi, Sink& sink) {
-  const int top = 32 * y - 47;  // polygon.ml:539: left_of_pix y - halfips
-  const int bot = top + 63;     // polygon.ml:540
-  CrossList tops, bots;
-  tops.init(); bots.init();
+COH_HD_NOINLINE bool scan_row(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int s, int y,
+                              int winding, bool aa, int wlo, int whi, Sink& sink) {
+  ScanState st;
+  scan_begin(st, y, aa, wlo, whi);
   for (int i = 0; i < n_cand; i++) {
     const EdgeRec e = edges[idx ? idx[i] : i];
-    const int ymin = e.ymin * s, ymax = e.ymax * s;
-    if (ymin > bot || ymax < top) continue;  // polygon.ml:338
     const int x0 = e.x0in * s, x1 = e.x1in * s;
-    int lo, hi;
-    if (ymin == ymax || (ymin >= top && ymax <= bot)) {  // polygon.ml:340-343
-      lo = imin(x0, x1); hi = imax(x0, x1);
-    } else if (ymin >= top) {  // just bottom clipping, polygon.ml:345-353
-      int xb = crossing_x(x0, e.g, bot - ymin);
-      lo = imin(x0, xb); hi = imax(x0, xb);
-      bots.add(xb, e.dir, aa, wlo, whi);
-    } else if (ymax <= bot) {  // just top clipping, polygon.ml:355-364
-      int xt = crossing_x(x0, e.g, top - 1 - ymin);
-      lo = imin(xt, x1); hi = imax(xt, x1);
-      tops.add(xt, e.dir, aa, wlo, whi);
-    } else {  // clip both: bottom crossing restarts from the rounded top crossing, polygon.ml:365-385
-      int xt = crossing_x(x0, e.g, top - 1 - ymin);
-      int xb = crossing_x(xt, e.g, bot - top);
-      lo = imin(xt, xb); hi = imax(xt, xb);
-      tops.add(xt, e.dir, aa, wlo, whi);
-      bots.add(xb, e.dir, aa, wlo, whi);
-    }
-    const int ca = pix_of_sub(lo - 16), cb = pix_of_sub(hi + 16);  // polygon.ml:444-453
-    if (cb >= wlo && ca <= whi) sink.cover(ca, cb);
+    scan_edge(st, x0, x1, e.ymin * s, e.ymax * s, e.g, e.dir, edge_side(x0, x1, wlo, whi), sink);
   }
-  if (tops.n > COH_MAXX || bots.n > COH_MAXX) return false;
-  winding_spans(tops, winding, aa, wlo, whi, sink);
-  winding_spans(bots, winding, aa, wlo, whi, sink);
-  return true;
+  return scan_finish(st, winding, sink);
 }
 
 // Sinks -----------------------------------------------------------------------------
@@ -299,6 +393,56 @@ struct Sink32 {
   uint32_t S, C;
   COH_HD void span(int a, int b) { S |= interval_mask32(wx0, a, b); }
   COH_HD void cover(int a, int b) { uint32_t m = interval_mask32(wx0, a, b); S |= m; C |= m; }
+};
+// A handful of intervals kept in registers (AA fast path): intervals are clipped to the
+// window on insertion; `over` is set when more than K were produced.
+template <int K>
+struct SinkRegs {
+  int wlo, whi;
+  int a[K], b[K];
+  int n;
+  bool over;
+  COH_HD void init(int lo, int hi) { wlo = lo; whi = hi; n = 0; over = false; }
+  COH_HD void put(int x, int y) {
+    if (x < wlo) x = wlo;
+    if (y > whi) y = whi;
+    if (x > y) return;
+#pragma unroll
+    for (int k = 0; k < K; k++) if (n == k) { a[k] = x; b[k] = y; }
+    if (n >= K) over = true;
+    n++;
+  }
+  COH_HD void span(int x, int y) { put(x, y); }
+  COH_HD void cover(int x, int y) { put(x, y); }
+  // occupancy of the 32 pixels starting at wx0
+  COH_HD uint32_t mask32(int wx0) const {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int k = 0; k < K; k++) if (k < n) m |= interval_mask32(wx0, a[k], b[k]);
+    return m;
+  }
+};
+// Multi-word row with inlined stores (the AA rows of the walker live in shared memory; keeping
+// this inline lets the compiler emit shared-memory stores instead of generic ones).
+struct SinkRow {
+  int wx0, nwords;
+  uint32_t* S;
+  COH_HD void put(int a, int b) {
+    a -= wx0; b -= wx0;
+    const int nb = nwords * 32;
+    if (b < 0 || a >= nb) return;
+    if (a < 0) a = 0;
+    if (b > nb - 1) b = nb - 1;
+    if (a > b) return;
+    const int wa = a >> 5, wb = b >> 5;
+    const uint32_t ma = 0xFFFFFFFFu << (a & 31), mb = 0xFFFFFFFFu >> (31 - (b & 31));
+    if (wa == wb) { S[wa] |= (ma & mb); return; }
+    S[wa] |= ma;
+    for (int w = wa + 1; w < wb; w++) S[w] = 0xFFFFFFFFu;
+    S[wb] |= mb;
+  }
+  COH_HD void span(int a, int b) { put(a, b); }
+  COH_HD void cover(int a, int b) { put(a, b); }
 };
 // Multi-word rows in memory (export kernels, AA rows).  C may be null (AA needs only S).
 struct SinkMem {
@@ -356,7 +500,7 @@ struct FillRec {
   double p[6];
 };
 COH_HD double dsqr(double v) { return dmul(v, v); }
-COH_HD uint32_t fill_lookup(const FillRec& f, int xi, int yi) {
+COH_HD_NOINLINE uint32_t fill_lookup(const FillRec& f, int xi, int yi) {
   if (f.kind == 0) return f.c0;
   double x = (double)xi, y = (double)yi;
   if (f.kind == 1) {  // fill.ml:77-93

@@ -108,6 +108,38 @@ int emul_opacity_word(const int32_t* edges, int n, int winding, int x0, int y, u
   }
   return ok ? 0 : 2;
 }
+// The register fast path of aa_tile (ScanStateT<3,true> into SinkRow) with its fallback.
+// Returns 0 (fast), 1 (fallback used) or -1 on overflow of the general path.
+int emul_opacity_word_fast(const int32_t* edges, int n, int winding, int x0, int y, uint8_t* out32) {
+  init_aa();
+  std::vector<EdgeRec> es;
+  for (int i = 0; i < n; i++) es.push_back(make_edge(edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]));
+  const int wlo = 16 * x0 - 32, whi = wlo + 32 * 17 - 1;
+  bool all_fast = true;
+  uint32_t rows[32][17];
+  std::memset(rows, 0, sizeof rows);
+  for (int j = 0; j < 32; j++) {
+    ScanStateT<3, true> st; SinkRow sk; sk.wx0 = wlo; sk.nwords = 17; sk.S = rows[j];
+    scan_begin(st, 16 * y - 32 + j, true, wlo, whi);
+    for (int i = 0; i < n; i++) {
+      const EdgeRec& e = es[i];
+      int ex0 = e.x0in * 16, ex1 = e.x1in * 16;
+      scan_edge(st, ex0, ex1, e.ymin * 16, e.ymax * 16, e.g, e.dir, edge_side(ex0, ex1, wlo, whi), sk);
+    }
+    all_fast = scan_finish(st, winding, sk) && all_fast;
+  }
+  if (!all_fast) { int rc = emul_opacity_word(edges, n, winding, x0, y, out32); return rc ? -1 : 1; }
+  for (int b = 0; b < 32; b++) {
+    int tot = 0;
+    for (int j = 0; j < 32; j++) {
+      uint32_t lo = rows[j][b >> 1], hi = rows[j][(b >> 1) + 1];
+      uint32_t m = (b & 1) ? ((lo >> 16) | (hi << 16)) : lo;
+      tot += aa_row_sum(g_aa.prefix[j], m);
+    }
+    out32[b] = (uint8_t)aa_opacity(tot, g_aa.volume);
+  }
+  return 0;
+}
 uint32_t emul_over(uint32_t a, uint32_t b) { return px_over(a, b); }
 uint32_t emul_dissolve(uint32_t c, int d) { return px_dissolve(c, d); }
 uint32_t emul_dissolve_between(uint32_t a, uint32_t b, int alpha) { return px_dissolve_between(a, b, alpha); }
