@@ -149,7 +149,9 @@ def run_ours(args):
     N = world
     objs, n, nbg, edges, points = build_scene()
     n_edges, n_objs = len(edges), n
-    y0, y1 = rank * HEIGHT // N, (rank + 1) * HEIGHT // N
+    from coherence_renderer_b200 import bands
+
+    y0, y1 = bands.band_rows(HEIGHT, N, rank)
 
     ctx = abi.Context(local)
     stream = torch.cuda.current_stream()
@@ -158,8 +160,6 @@ def run_ours(args):
     fb = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
     ctx.fb_attach(fb.data_ptr())
     full = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if N > 1 else None
-    rows = [(k * HEIGHT // N, (k + 1) * HEIGHT // N) for k in range(N)]
-    equal = len({b - a for a, b in rows}) == 1
     scene_h = ctx.scene_create(objs, nbg, edges, points)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     update = (0, 0, WIDTH, HEIGHT)
@@ -167,12 +167,7 @@ def run_ours(args):
     def frame():
         ctx.render_frame(scene_h, update)
         if N > 1:
-            strip = fb[y0:y1]
-            if equal:
-                dist.all_gather_into_tensor(full, strip)
-            else:
-                outs = [full[a:b] for a, b in rows]
-                dist.all_gather(outs, strip)
+            bands.gather_strips(dist, fb[y0:y1], full, HEIGHT, N)
 
     def barrier():
         if N > 1:
