@@ -40,6 +40,7 @@ SYMBOLS = [
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888",
+    "coh_host_edgelist_of_subpath", "coh_host_brush_points",
 ]
 
 _lib = None
@@ -68,6 +69,8 @@ def lib():
         L.coh_launch_count.argtypes = [C.c_void_p]
         L.coh_rgba8_of_colour.restype = C.c_uint32
         L.coh_colour_of_rgba8.restype = C.c_int32
+        L.coh_host_edgelist_of_subpath.restype = C.c_int64
+        L.coh_host_brush_points.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -254,3 +257,35 @@ class Context:
         out = np.zeros((h, w, 3), dtype=np.uint8)
         self._chk(lib().coh_fb_read_rgb888(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
+
+
+def _seg_records(segs):
+    rec = np.zeros((len(segs), 9), dtype=np.float64)
+    for i, s in enumerate(segs):
+        rec[i, 0] = 0.0 if s[0] == "L" else 1.0
+        for k, p in enumerate(s[1:]):
+            rec[i, 1 + 2 * k], rec[i, 2 + 2 * k] = p
+    return rec
+
+
+def host_edgelist_of_subpath(segs):
+    """Polygon.edgelist_of_path for one subpath through the library's host-side geometry."""
+    rec = _seg_records(segs)
+    cap = 64 * len(segs) + 64
+    while True:
+        out = np.zeros((cap, 4), dtype=np.int32)
+        n = lib().coh_host_edgelist_of_subpath(rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), _i32p(out), C.c_int64(cap))
+        if n <= cap:
+            return out[:n]
+        cap = int(n)
+
+
+def host_brush_points(segs, radius):
+    rec = _seg_records(segs)
+    cap = 4096
+    while True:
+        out = np.zeros((cap, 2), dtype=np.int32)
+        n = lib().coh_host_brush_points(rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), C.c_double(radius), _i32p(out), C.c_int64(cap))
+        if n <= cap:
+            return out[:n]
+        cap = int(n)

@@ -26,11 +26,13 @@ struct DevScene {
   int n_objs = 0, n_leaves = 0, n_edges = 0, n_points = 0;
   ObjRec* objs = nullptr;
   int* leaves = nullptr;
+  int4* leaf_box = nullptr;     // conservative device-space pixel box per leaf (binning reads these, coalesced)
   EdgeRec* edges = nullptr;
   int2* points = nullptr;
   uint8_t* stamps = nullptr;
   int* rowedge_ptr = nullptr;   // K1 edge binning (CSR over (path object, pixel row))
   int* rowedge_idx = nullptr;
+  int2* brush_ranges = nullptr; // per (stroke, row): [first, last] stamp index reaching the row
   std::vector<ObjRec> h_objs;
   bool has_fancy = false;    // some object has a gradient / radial fill
   bool has_brush = false;
@@ -627,8 +629,8 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   CK(cudaSetDevice(ctx->device));
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
-  cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
-  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx);
+  cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->leaf_box); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
+  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx); cudaFree(s->brush_ranges);
   delete s;
   return 0;
 }
@@ -664,7 +666,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<uint8_t> stamps;
   std::vector<int> open;  // indices (into recs) of open groups
   std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
-  long long total_rows = 0;
+  std::vector<int> point_obj((size_t)std::max(n_points, 1), -1);  // owning brush object of every point
+  long long total_rows = 0, total_brush_rows = 0;
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
   recs.push_back(root); open.push_back(0);
@@ -731,6 +734,13 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           x0 = std::min(x0, px); x1 = std::max(x1, px); y0 = std::min(y0, py); y1 = std::max(y1, py);
         }
         o.bx0 = x0 - o.brush_r; o.bx1 = x1 + o.brush_r; o.by0 = y0 - o.brush_r; o.by1 = y1 + o.brush_r;
+        o.ry0 = o.by0; o.ry1 = o.by1;   // object-frame rows (the alias offset is added to the box below)
+        if (total_brush_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many brush rows");
+        o.row_base = (int)total_brush_rows; total_brush_rows += o.ry1 - o.ry0 + 1;
+        for (int k = 0; k < c.count; k++) {
+          if (point_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share brush points");
+          point_obj[(size_t)c.first + k] = (int)recs.size();
+        }
         break;
       }
       default: FAIL("scene: unknown object kind");
@@ -751,6 +761,10 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
   if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaves, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int4> boxes(leaves.size());
+  for (size_t i = 0; i < leaves.size(); i++) { const ObjRec& o = recs[leaves[i]]; boxes[i] = make_int4(o.bx0, o.by0, o.bx1, o.by1); }
+  CK(cudaMalloc(&s->leaf_box, sizeof(int4) * std::max<size_t>(leaves.size(), 1)));
+  if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaf_box, boxes.data(), sizeof(int4) * boxes.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
   CK(cudaMalloc(&s->points, sizeof(int2) * std::max(n_points, 1)));
   if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
@@ -775,6 +789,17 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_edge_obj); cudaFree(d_counts);
+  }
+  if (total_brush_rows > 0) {
+    int* d_point_obj = nullptr;
+    CK(cudaMalloc(&d_point_obj, sizeof(int) * point_obj.size()));
+    CK(cudaMemcpyAsync(d_point_obj, point_obj.data(), sizeof(int) * point_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
+    std::vector<int2> init((size_t)total_brush_rows, make_int2(INT32_MAX, -1));
+    CK(cudaMemcpyAsync(s->brush_ranges, init.data(), sizeof(int2) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_brush_rows<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_point_obj);
   }
   *out = (coh_scene_t)s;
   return 0;
@@ -829,11 +854,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * 2 * ORDER_BINS, ctx->stream));
   CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
   if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
-  // K1: count, scan, fill
-  int bin_blocks = cdiv(n_cells * 32, 256);
-  k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
-  k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
-  if (ordered) { k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED(); }
+  // K1: count, scan, fill.  Small scenes: warp per cell scanning all leaves (lists come out sorted,
+  // no atomics).  Large scenes: warp per leaf over the cells it covers + per-cell sort.
+  const bool big = s->n_leaves > 1024;
   // capacity of the item pool: the exact total is a pure function of the object boxes and the
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
@@ -847,17 +870,36 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
     }
     s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1;
   }
-  size_t total = s->items_total;
-  if (total > ctx->cell_items_cap) {
+  const size_t total = s->items_total;
+  const size_t need = big ? 2 * total : total;  // the sort of very long lists stages through the upper half
+  if (need > ctx->cell_items_cap) {
     cudaFree(ctx->cell_items);
-    size_t cap = total + total / 2 + 1024;
+    size_t cap = need + need / 2 + 1024;
     CK(cudaMalloc(&ctx->cell_items, sizeof(int) * cap));
     ctx->cell_items_cap = cap;
   }
-  k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->objs, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+  if (!big) {
+    const int bin_blocks = cdiv(n_cells * 32, 256);
+    k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
+    if (ordered) { k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED(); }
+    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+  } else {
+    const int obj_blocks = cdiv(s->n_leaves * 32, 256);
+    CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
+    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
+    if (ordered) {
+      k_bin_hist<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(ctx->cell_counts, n_cells, ctx->order_hist); LAUNCHED();
+      k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED();
+    }
+    CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
+    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, ctx->cell_off, ctx->cell_items); LAUNCHED();
+    k_bin_sort<<<cdiv(n_cells * 32, 128), 128, 0, ctx->stream>>>(ctx->cell_off, ctx->cell_items, ctx->cell_items + total, n_cells, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+  }
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
-  P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx;
+  P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;

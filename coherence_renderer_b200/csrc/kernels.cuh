@@ -57,6 +57,25 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
   }
 }
 
+// K1 for brush strokes: for every (stroke, pixel row) the range [imin, imax] of stamp indices (list
+// order) whose footprint reaches the row.  Stamps are sampled along the path, so the stamps that
+// reach a row are (nearly) consecutive; walking the range in order keeps the reference's stamping
+// order (brush.ml:207-212) and makes the per-row / per-pixel cost independent of the stroke length.
+__global__ void k_brush_rows(const int2* __restrict__ points, const int* __restrict__ point_obj, int n_points,
+                             const ObjRec* __restrict__ objs, int2* __restrict__ ranges) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const int oi = point_obj[i];
+  if (oi < 0) return;
+  const ObjRec& o = objs[oi];
+  const int k = i - o.first, py = points[i].y, r = o.brush_r;
+  for (int y = py - r; y <= py + r; y++) {
+    int2* e = ranges + o.row_base + (y - o.ry0);
+    atomicMin(&e->x, k);
+    atomicMax(&e->y, k);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // K1 binning.  One warp per cell scans the leaf objects in index order (= front to back),
 // 32 at a time; ballot + popc give each overlapping object its slot, so every list comes
@@ -67,7 +86,7 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
 // persistent walker warps take the heavy cells first and the tail of the launch is light.
 constexpr int ORDER_BINS = 256;
 template <bool FILL>
-__global__ void k_bin(const ObjRec* __restrict__ objs, const int* __restrict__ leaves, int n_leaves, Frame fr,
+__global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/, const int* __restrict__ leaves, int n_leaves, Frame fr,
                       int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
                       int* __restrict__ items, int* __restrict__ hist /*[2*ORDER_BINS]: starts, cursors*/,
                       int* __restrict__ order) {
@@ -85,8 +104,8 @@ __global__ void k_bin(const ObjRec* __restrict__ objs, const int* __restrict__ l
     int idx = -1;
     if (li < n_leaves) {
       idx = leaves[li];
-      const ObjRec& o = objs[idx];
-      hit = !(o.bx0 > x1 || o.bx1 < x0 || o.by0 > y1 || o.by1 < y0);
+      const int4 bb = leaf_box[li];
+      hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
     }
     unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
     if (FILL && hit) items[base + n + __popc(m & ((1u << lane) - 1u))] = idx;
@@ -110,35 +129,87 @@ __global__ void k_order_scan(int* __restrict__ hist) {
   }
 }
 
-// Exclusive scan of n ints by a single block (n is the number of cells: tens of thousands).
+// ------------------------------------------------------------------------------------
+// K1 binning for large scenes (object-parallel): one warp per leaf walks the cells its box
+// covers, lanes over cells.  Pass 1 counts (atomics), pass 2 scatters with atomic cursors, then
+// k_bin_sort restores front-to-back order inside every cell (rank sort: leaf indices are unique)
+// and emits the heavy-first cell order.  Cost is O(sum of covered cells), not O(cells x leaves).
+// ------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void k_bin_obj(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr,
+                          int cell_row0, int cell_row1, int* __restrict__ counts, const int* __restrict__ offsets,
+                          int* __restrict__ items) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_leaves) return;
+  const int4 bb = leaf_box[warp];
+  const int cx0 = max(bb.x >> 5, 0), cx1 = min(bb.z >> 5, fr.tiles_x - 1);
+  const int cy0 = max(bb.y / CELL_H - (bb.y < 0 ? 1 : 0), cell_row0), cy1 = min(bb.w < 0 ? -1 : bb.w / CELL_H, cell_row1);
+  if (cx1 < cx0 || cy1 < cy0) return;
+  const int nx = cx1 - cx0 + 1, n = nx * (cy1 - cy0 + 1);
+  const int idx = leaves[warp];
+  for (int k = lane; k < n; k += 32) {
+    const int cell = (cy0 + k / nx - cell_row0) * fr.tiles_x + cx0 + k % nx;
+    const int pos = atomicAdd(&counts[cell], 1);
+    if (FILL) items[offsets[cell] + pos] = idx;
+  }
+}
+// histogram of list lengths (for the heavy-first order), one thread per cell
+__global__ void k_bin_hist(const int* __restrict__ counts, int n_cells, int* __restrict__ hist) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  int n = counts[c];
+  atomicAdd(&hist[ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1)], 1);
+}
+// one warp per cell: rank sort of its list (ascending leaf index) + heavy-first order scatter
+constexpr int SORT_SMEM = 1024;  // list entries staged in shared memory per warp
+__global__ void __launch_bounds__(128) k_bin_sort(const int* __restrict__ offsets, int* __restrict__ items,
+                                                  int* __restrict__ tmp, int n_cells, int* __restrict__ hist,
+                                                  int* __restrict__ order) {
+  __shared__ int s_list[4][SORT_SMEM];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (warp >= n_cells) return;
+  const int a = offsets[warp], n = offsets[warp + 1] - a;
+  if (lane == 0 && order) {
+    const int bin = ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1);
+    order[hist[bin] + atomicAdd(&hist[ORDER_BINS + bin], 1)] = warp;
+  }
+  if (n <= 1) return;
+  const bool in_smem = n <= SORT_SMEM;
+  int* src = in_smem ? s_list[wid] : (tmp + a);
+  for (int i = lane; i < n; i += 32) src[i] = items[a + i];
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int v = src[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += src[j] < v;
+    items[a + rank] = v;
+  }
+}
+
+// Exclusive scan of n ints by a single block of 1024 threads: each thread sums a contiguous
+// chunk, one block-wide scan of the 1024 partial sums, then each thread rescans its chunk.
 __global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
   __shared__ int warp_sums[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int chunk = (n + blockDim.x - 1) / blockDim.x;
+  const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
+  int sum = 0;
+  for (int i = lo; i < hi; i++) sum += in[i];
+  int x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += v; }
+  if (lane == 31) warp_sums[wid] = x;
   __syncthreads();
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int v = i < n ? in[i] : 0;
-    int x = v;
+  if (wid == 0) {
+    int s2 = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      int s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, s, d); if (lane >= d) s += t; }
-      warp_sums[lane] = s;
-    }
-    __syncthreads();
-    int prefix = carry + (wid ? warp_sums[wid - 1] : 0);
-    if (i < n) out[i] = prefix + x - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
-    __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, s2, d); if (lane >= d) s2 += v; }
+    warp_sums[lane] = s2;
   }
-  if (threadIdx.x == 0) out[n] = carry;
+  __syncthreads();
+  int run = (wid ? warp_sums[wid - 1] : 0) + x - sum;  // exclusive prefix of this thread's chunk
+  for (int i = lo; i < hi; i++) { int v = in[i]; out[i] = run; run += v; }
+  if (t == blockDim.x - 1) out[n] = warp_sums[(blockDim.x >> 5) - 1];
 }
 
 // ------------------------------------------------------------------------------------
@@ -150,6 +221,7 @@ struct WalkParams {
   const int* rowedge_ptr;      // K1 edge binning: per (path object, pixel row) candidate edge lists (CSR)
   const int* rowedge_idx;
   const int2* points;          // brush stamp centres (object frame), list order
+  const int2* brush_ranges;    // per (stroke, row): first / last stamp index reaching the row
   const uint8_t* stamps;       // brush alpha stamps
   const int* cell_off;         // per cell [first, last) into cell_items
   const int* cell_items;
@@ -435,9 +507,12 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         } else if (BRUSH && o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
           const int br = o.brush_r;
-          for (int k = 0; k < o.count; k++) {
-            int2 p = P.points[o.first + k];
-            if (p.y - br <= yy && yy <= p.y + br) S |= interval_mask32(xx0, p.x - br, p.x + br);
+          if (yy >= o.ry0 && yy <= o.ry1) {
+            const int2 rg = P.brush_ranges[o.row_base + yy - o.ry0];
+            for (int k = rg.x; k <= rg.y; k++) {
+              int2 p = P.points[o.first + k];
+              if (p.y - br <= yy && yy <= p.y + br) S |= interval_mask32(xx0, p.x - br, p.x + br);
+            }
           }
           C = S;
         }
@@ -489,7 +564,8 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             const int px = xx0 + lane;
             uint32_t al = 0u;
             if ((edge >> lane) & 1u) {
-              for (int q = 0; q < o.count; q++) {
+              const int2 rg = P.brush_ranges[o.row_base + yy - o.ry0];
+              for (int q = rg.x; q <= rg.y; q++) {
                 int2 p = P.points[o.first + q];
                 int ddx = px - p.x, ddy = yy - p.y;
                 if (ddx >= -br && ddx <= br && ddy >= -br && ddy <= br)

@@ -202,6 +202,7 @@ class SceneBuilder:
 
     def __init__(self):
         self.objs, self.edges, self.points = [], [], []
+        self._n_edges = self._n_points = 0
         self.n_background = 0
         self._in_background = False
 
@@ -220,22 +221,28 @@ class SceneBuilder:
     def path_edges(self, edges, fill, winding=COH_NONZERO, bounds=None, **kw):
         """Basic (fill, Path p) with p already flattened to integer sub-bin edges."""
         o = self._obj(COH_OBJ_PATH, **kw)
-        o.winding, o.first, o.count = winding, len(self.edges), len(edges)
-        self.edges.extend([list(map(int, e)) for e in edges])
+        e = np.asarray(edges, dtype=np.int32).reshape(-1, 4)
+        o.winding, o.first, o.count = winding, self._n_edges, len(e)
+        self.edges.append(e)
+        self._n_edges += len(e)
         fill.apply(o)
-        if bounds is None and len(edges):
-            xs = [pix_of_sub(v) for e in edges for v in (e[0], e[2])]
-            ys = [pix_of_sub(v) for e in edges for v in (e[1], e[3])]
-            bounds = (min(xs), max(xs), min(ys), max(ys))
+        if bounds is None and len(e):
+            # bounds_polygon (polygon.ml:405-440): pix_of_float of every end point = pix_of_sub of the edge ends
+            t = e.astype(np.int64) + 31
+            pix = np.where(t >= 0, t // 32, -((-t) // 32))  # truncating division (coord.ml:44)
+            bounds = (int(pix[:, [0, 2]].min()), int(pix[:, [0, 2]].max()), int(pix[:, [1, 3]].min()), int(pix[:, [1, 3]].max()))
         if bounds:
             for i in range(4):
                 o.bounds[i] = bounds[i]
         return o
 
     def path(self, subpaths, fill, winding=COH_NONZERO, **kw):
-        """subpaths: list of segment lists (device-space floats)."""
-        pairs = [pq for segs in subpaths for pq in flatten_segments(segs)]
-        return self.path_edges(edges_of_float_segments(pairs), fill, winding, **kw)
+        """subpaths: list of segment lists (device-space floats); flattened by the library's host-side
+        geometry (Polygon.edgelist_of_path)."""
+        from . import abi
+
+        parts = [abi.host_edgelist_of_subpath(segs) for segs in subpaths]
+        return self.path_edges(np.concatenate(parts) if parts else np.zeros((0, 4), np.int32), fill, winding, **kw)
 
     def polygon(self, points, fill, winding=COH_NONZERO, **kw):
         return self.path([polygon_segments(points)], fill, winding, **kw)
@@ -274,10 +281,14 @@ class SceneBuilder:
 
     def brush(self, opacity, radius, subpaths, fill, **kw):
         """Basic (fill, Brushstroke ((opacity, Gaussian radius), path))."""
+        from . import abi
+
         o = self._obj(COH_OBJ_BRUSH, **kw)
-        pts = brush_points(radius, subpaths)
-        o.first, o.count = len(self.points), len(pts)
-        self.points.extend(pts)
+        parts = [abi.host_brush_points(segs, radius) for segs in subpaths]
+        pts = np.concatenate(parts) if parts else np.zeros((0, 2), np.int32)
+        o.first, o.count = self._n_points, len(pts)
+        self.points.append(pts)
+        self._n_points += len(pts)
         o.brush_opacity, o.brush_radius = float(opacity), float(radius)
         fill.apply(o)
         return o
@@ -290,8 +301,8 @@ class SceneBuilder:
 
     def arrays(self):
         arr = (CohObject * max(len(self.objs), 1))(*self.objs)
-        e = np.array(self.edges, dtype=np.int32).reshape(-1, 4)
-        p = np.array(self.points, dtype=np.int32).reshape(-1, 2)
+        e = np.concatenate(self.edges).reshape(-1, 4) if self.edges else np.zeros((0, 4), np.int32)
+        p = np.concatenate(self.points).reshape(-1, 2) if self.points else np.zeros((0, 2), np.int32)
         return arr, len(self.objs), self.n_background, e, p
 
 

@@ -154,6 +154,15 @@ void* coh_fb_device_ptr(coh_ctx* ctx);
 int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
 
+/* ---- host-side geometry preparation (CPU; the step before the raster path) ----
+ * A path segment record is 9 doubles: kind (0 straight, 1 cubic bezier) then up to four points.
+ * Polygon.edgelist_of_path for one subpath (polygon.ml:119-127, 262-287; Coord.sub_of_float):
+ * returns the number of edges and writes min(n, cap) of them as int32 x0,y0,x1,y1. */
+int64_t coh_host_edgelist_of_subpath(const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap);
+/* Brush.points_of_brushstroke for one subpath, rounded as in brush.ml:172 (polygon.ml:143-218):
+ * returns the number of stamp centres and writes min(n, cap) of them as int32 x,y in list order. */
+int64_t coh_host_brush_points(const double* segs, int32_t n_segs, double radius, int32_t* points_out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -230,3 +230,43 @@ def test_pretrans_group_returns_pixels_to_u(ctx, oracle):
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
     assert np.array_equal(got_u, ref_u)
     assert _max_lsb(got, ref) == 0
+
+
+def test_large_random_scene_object_parallel_binning(ctx, oracle):
+    """> 1024 leaves: K1 switches to warp-per-leaf binning + per-cell sort; brush strokes use their
+    per-row stamp ranges.  C3-style scene (polygons and brush strokes, translucent and opaque)."""
+    W, H = 1024, 768
+    b = S.random_scene(W, H, 1500, seed=7)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_translation_alias_equals_translated_edges(ctx, oracle):
+    """Cache.addtranslation (cache.ml:423-436): an alias (dx, dy) serves the cached shape/sprite translated by
+    whole pixels, i.e. exactly the original edges moved by 32*d sub-bins."""
+    W, H = 400, 300
+    pts = [(60.3, 40.2), (180.9, 70.1), (150.0, 200.7), (40.0, 160.0)]
+    for dx, dy in ((37, 21), (-45, -30), (0, 64)):
+        b = S.SceneBuilder()
+        b.polygon(pts, S.Fill.plain(S.dissolve(S.rgba8(30, 90, 200), 200)), dx=dx, dy=dy)
+        b.brush(0.9, 5.0, [[("C", (20.0, 250.0), (120.0, 20.0), (260.0, 280.0), (380.0, 60.0))]], S.Fill.plain(S.rgba8(200, 40, 40)), dx=dx, dy=dy)
+        b.begin_background()
+        b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+        # and the same picture as moving the integer edges themselves by 32 sub-bins per pixel (moving the
+        # FLOAT path first is not equivalent: sub_of_float (f + d) may round differently, SURVEY.md App. B)
+        poly_only = S.SceneBuilder()
+        o = poly_only.polygon(pts, S.Fill.plain(S.dissolve(S.rgba8(30, 90, 200), 200)), dx=dx, dy=dy)
+        objs, n, nbg, edges, points = poly_only.arrays()
+        b2 = S.SceneBuilder()
+        b2.path_edges(edges + np.array([32 * dx, 32 * dy, 32 * dx, 32 * dy], dtype=np.int32), S.Fill.plain(S.dissolve(S.rgba8(30, 90, 200), 200)))
+        objs2, n2, nbg2, edges2, points2 = b2.arrays()
+        ref2 = oracle.render_frame(objs2, n2 - nbg2, nbg2, edges2, points2, (0, 0, W, H))
+        ctx.fb_configure(W, H)
+        sc = ctx.scene_create(objs, nbg, edges, points)
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        assert np.array_equal(ctx.fb_read_rgba(0, 0, W, H), ref2)
+        ctx.scene_free(sc)
