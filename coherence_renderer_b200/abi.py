@@ -38,9 +38,11 @@ SYMBOLS = [
     "coh_polygon_sprite", "coh_shape_box", "coh_shape_import", "coh_shape_export_size", "coh_shape_export",
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
-    "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_uncovered", "coh_sync",
+    "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
+    "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
+    "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_object_shape",
 ]
 
 _lib = None
@@ -238,6 +240,44 @@ class Context:
     def render_frame(self, scene, update, flags=0):
         ux, uy, uw, uh = update
         self._chk(lib().coh_render_frame(self._h, C.c_uint64(scene), ux, uy, uw, uh, flags))
+
+    def render_frame_shape(self, scene, update_shape, flags=0):
+        self._chk(lib().coh_render_frame_shape(self._h, C.c_uint64(scene), C.c_uint64(update_shape), flags))
+
+    def scene_translate_object(self, scene, obj_index, dx, dy):
+        self._chk(lib().coh_scene_translate_object(self._h, C.c_uint64(scene), obj_index, dx, dy))
+
+    def scene_object_shape(self, scene, obj_index):
+        s, m = C.c_uint64(), C.c_uint64()
+        self._chk(lib().coh_scene_object_shape(self._h, C.c_uint64(scene), obj_index, C.byref(s), C.byref(m)))
+        return s.value, m.value
+
+    def dirty_region(self, shp_o, min_o, shp_n, min_n, u, plain):
+        o = C.c_uint64()
+        self._chk(lib().coh_dirty_region(self._h, C.c_uint64(shp_o), C.c_uint64(min_o), C.c_uint64(shp_n), C.c_uint64(min_n), C.c_uint64(u), 1 if plain else 0, C.byref(o)))
+        return o.value
+
+    def cache_configure(self, usecache=True, max_bytes=0):
+        self._chk(lib().coh_cache_configure(self._h, 1 if usecache else 0, C.c_int64(max_bytes)))
+
+    def cache_clear(self):
+        self._chk(lib().coh_cache_clear(self._h))
+
+    def cache_stats(self):
+        out = (C.c_int64 * 4)()
+        self._chk(lib().coh_cache_stats(self._h, out))
+        return {"shape_hits": out[0], "shape_misses": out[1], "bytes": out[2], "entries": out[3]}
+
+    def cache_addshape(self, oid, shape, minshape):
+        self._chk(lib().coh_cache_addshape(self._h, C.c_int64(oid), C.c_uint64(shape), C.c_uint64(minshape)))
+
+    def cache_getshape(self, oid):
+        s, m, f = C.c_uint64(), C.c_uint64(), C.c_int32()
+        self._chk(lib().coh_cache_getshape(self._h, C.c_int64(oid), C.byref(s), C.byref(m), C.byref(f)))
+        return (s.value, m.value) if f.value else None
+
+    def cache_addtranslation(self, oid, target, dx, dy):
+        self._chk(lib().coh_cache_addtranslation(self._h, C.c_int64(oid), C.c_int64(target), dx, dy))
 
     def render_uncovered(self):
         o = C.c_uint64()

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/coherence_b200.h"
@@ -34,10 +35,21 @@ struct DevScene {
   int* rowedge_idx = nullptr;
   int2* brush_ranges = nullptr; // per (stroke, row): [first, last] stamp index reaching the row
   std::vector<ObjRec> h_objs;
+  std::vector<int64_t> ids;      // cache key (Id.idset) of every record
+  std::vector<int> rec_of_abi;   // record index of every object of the ABI array (-1: GROUP_END / dropped)
+  std::vector<int> group_last;   // for group records: last record index inside the group
   bool has_fancy = false;    // some object has a gradient / radial fill
   bool has_brush = false;
   size_t items_total = 0;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
+};
+
+// Cache (cache.ml:57-83): entries keyed by object id hold device-resident span sets
+// (shape, minshape); an alias entry refers to another id with an integer translation.
+struct CacheEntry {
+  bool alias = false; int dx = 0, dy = 0; int64_t target = 0;
+  DevShape* shape = nullptr; DevShape* minshape = nullptr; bool has = false;
+  size_t bytes = 0; uint64_t lastused = 0;
 };
 
 struct coh_ctx {
@@ -52,6 +64,8 @@ struct coh_ctx {
   Frame fr{0, 0, 0, 0, 0, 0};
   uint32_t* fb = nullptr;
   uint32_t* u_out = nullptr;   // bit-frame of `u` after the scene pass
+  uint32_t* u_init = nullptr;  // bit-frame of an arbitrary update shape
+  bool use_u_init = false;
   bool have_u = false;
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
@@ -62,6 +76,10 @@ struct coh_ctx {
   int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
   size_t carry_slots = 0; int epoch = 0;
   bool own_stream = true, own_fb = true;
+  // coherence cache (HBM-resident span sets)
+  std::map<int64_t, CacheEntry> cache;
+  bool usecache = true; size_t cache_max = 50u * 1024u * 1024u, cache_size = 0; uint64_t cache_timer = 0;  // cache.ml:72-73
+  int64_t shphit = 0, shpmis = 0;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // bin start, walk start, walk end, spare
@@ -132,13 +150,15 @@ int coh_init(int device, coh_ctx** out) {
   return 0;
 }
 
+int coh_cache_clear(coh_ctx* ctx);
 int coh_shutdown(coh_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  coh_cache_clear(ctx);
   cudaFree(ctx->d_aa); cudaFree(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) cudaFree(ctx->fb);
-  cudaFree(ctx->u_out);
+  cudaFree(ctx->u_out); cudaFree(ctx->u_init);
   cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
   cudaFree(ctx->queue); cudaFree(ctx->order_hist); cudaFree(ctx->cell_order); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -425,16 +445,12 @@ int coh_shape_translate(coh_ctx* ctx, coh_shape_t h, int32_t dx, int32_t dy, coh
   *out = 0;
   if (!h) return 0;
   DevShape* s = (DevShape*)h;
-  std::vector<int> ptr; std::vector<int2> spans;
-  if (download_shape(ctx, s, ptr, spans)) return 1;
-  for (auto& sp : spans) sp.x += dx;
   DevShape* t = new DevShape(*s);
   t->y0 += dy; t->bx0 += dx; t->bx1 += dx; t->by0 += dy; t->by1 += dy;
-  CK(cudaMalloc(&t->row_ptr, sizeof(int) * ptr.size()));
-  CK(cudaMalloc(&t->spans, sizeof(int2) * spans.size()));
-  CK(cudaMemcpyAsync(t->row_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(t->spans, spans.data(), sizeof(int2) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMalloc(&t->row_ptr, sizeof(int) * (s->n_rows + 1)));
+  CK(cudaMalloc(&t->spans, sizeof(int2) * s->n_spans));
+  CK(cudaMemcpyAsync(t->row_ptr, s->row_ptr, sizeof(int) * (s->n_rows + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+  k_translate_spans<<<cdiv(s->n_spans, 256), 256, 0, ctx->stream>>>(s->spans, t->spans, s->n_spans, dx); LAUNCHED();
   *out = (coh_shape_t)t;
   return 0;
 }
@@ -529,6 +545,23 @@ static int check_error_flag(coh_ctx* ctx, const char* what) {
   return 0;
 }
 
+// scan-convert device-resident prepared edges inside a pixel box into (shape, minshape) span sets
+static int shapes_from_device_edges(coh_ctx* ctx, const EdgeRec* d_edges, int n_edges, int winding, int px0, int py0,
+                                    int px1, int py1, coh_shape_t* shape, coh_shape_t* minshape, const char* who) {
+  int wx0 = floordiv(px0, 32) * 32, nw = (px1 - wx0) / 32 + 1, n_rows = py1 - py0 + 1;
+  size_t nwords = (size_t)n_rows * nw;
+  uint32_t *S = nullptr, *C = nullptr;
+  CK(cudaMalloc(&S, sizeof(uint32_t) * nwords)); CK(cudaMalloc(&C, sizeof(uint32_t) * nwords));
+  CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  k_scan_rows<<<dim3(cdiv(n_rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
+  int rc = check_error_flag(ctx, who);
+  if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
+  if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
+  if (!rc) rc = shape_from_bits(ctx, C, py0, n_rows, wx0, nw, minshape);
+  cudaFree(S); cudaFree(C);
+  return rc;
+}
 int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
                                   coh_shape_t* shape, coh_shape_t* minshape) {
   CK(cudaSetDevice(ctx->device));
@@ -537,20 +570,10 @@ int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_
   if (winding != COH_NONZERO && winding != COH_EVENODD) FAIL("bad winding rule");
   EdgeBox eb = edge_bounds(edges, n_edges);
   int px0, py0, px1, py1; shape_pixel_box(eb, px0, py0, px1, py1);
-  int wx0 = floordiv(px0, 32) * 32, nw = (px1 - wx0) / 32 + 1, n_rows = py1 - py0 + 1;
   EdgeRec* d_edges = nullptr;
   if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
-  size_t nwords = (size_t)n_rows * nw;
-  uint32_t *S = nullptr, *C = nullptr;
-  CK(cudaMalloc(&S, sizeof(uint32_t) * nwords)); CK(cudaMalloc(&C, sizeof(uint32_t) * nwords));
-  CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
-  CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
-  k_scan_rows<<<dim3(cdiv(n_rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
-  int rc = check_error_flag(ctx, "coh_shapeminshape_of_edgelist");
-  if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
-  if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
-  if (!rc) rc = shape_from_bits(ctx, C, py0, n_rows, wx0, nw, minshape);
-  cudaFree(S); cudaFree(C); cudaFree(d_edges);
+  int rc = shapes_from_device_edges(ctx, d_edges, n_edges, winding, px0, py0, px1, py1, shape, minshape, "coh_shapeminshape_of_edgelist");
+  cudaFree(d_edges);
   return rc;
 }
 
@@ -671,6 +694,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
   recs.push_back(root); open.push_back(0);
+  std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
+  std::vector<int> group_last;
+  std::vector<int64_t> ids;
   for (int i = 0; i < n_objs; i++) {
     if (i == n_objs - n_background) {
       if (open.size() != 1) FAIL("scene: unterminated group");
@@ -680,6 +706,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     const coh_object& c = objs[i];
     if (c.kind == COH_OBJ_GROUP_END) {
       if (open.size() <= 1) FAIL("scene: GROUP_END without GROUP_BEGIN");
+      group_last.resize(recs.size(), -1);
+      group_last[open.back()] = (int)recs.size() - 1;
       open.pop_back();
       continue;
     }
@@ -696,6 +724,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
         recs.push_back(o); open.push_back((int)recs.size() - 1);
+        rec_of_abi[i] = (int)recs.size() - 1;
+        ids.resize(recs.size(), -1); ids.back() = c.id;
         continue;
       case COH_OBJ_PATH: {
         if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
@@ -747,12 +777,17 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     }
     o.bx0 += o.dx; o.bx1 += o.dx; o.by0 += o.dy; o.by1 += o.dy;
     recs.push_back(o);
+    rec_of_abi[i] = (int)recs.size() - 1;
+    ids.resize(recs.size(), -1); ids.back() = c.id;
     leaves.push_back((int)recs.size() - 1);
   }
   if (open.size() != 1) FAIL("scene: unterminated group");
   DevScene* s = new DevScene();
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->h_objs = recs;
+  group_last.resize(recs.size(), -1);
+  ids.resize(recs.size(), -1);
+  s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH) s->has_brush = true;
@@ -820,7 +855,7 @@ int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y
   if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
   if (width != ctx->fr.W || height != ctx->fr.H) {
     if (ctx->own_fb) cudaFree(ctx->fb);
-    cudaFree(ctx->u_out); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->own_fb = true;
+    cudaFree(ctx->u_out); cudaFree(ctx->u_init); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->u_init = nullptr; ctx->own_fb = true;
     CK(cudaMalloc(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
     CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
     CK(cudaMalloc(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
@@ -902,7 +937,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
-  P.u_init = nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
+  P.u_init = ctx->use_u_init ? ctx->u_init : nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
   // persistent grid: exactly one resident wave
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells, WALK_WARPS));
@@ -947,6 +982,200 @@ int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, in
   if (render_pass(ctx, s, ux, uy, uw, uh, true, record_u)) return 1;
   ctx->have_u = record_u;
   return 0;
+}
+// ---------------------------------------------------------------------------------------
+// Cache (cache.mli:32-48): span sets resident in HBM, keyed by id
+// ---------------------------------------------------------------------------------------
+static size_t shape_bytes(const DevShape* s) { return s ? sizeof(int) * (s->n_rows + 1) + sizeof(int2) * (size_t)s->n_spans : 0; }
+static DevShape* clone_shape(coh_ctx* ctx, const DevShape* s, int dx, int dy) {
+  if (!s) return nullptr;
+  coh_shape_t out = 0;
+  if (coh_shape_translate(ctx, (coh_shape_t)s, dx, dy, &out)) return nullptr;
+  return (DevShape*)out;
+}
+static void cache_drop(coh_ctx* ctx, std::map<int64_t, CacheEntry>::iterator it) {
+  ctx->cache_size -= it->second.bytes;
+  free_shape(it->second.shape); free_shape(it->second.minshape);
+  ctx->cache.erase(it);
+}
+static void cache_drophalf(coh_ctx* ctx) {  // cache.ml:242-271 (eviction order: least recently used first)
+  size_t target = ctx->cache_size / 2;
+  while (ctx->cache_size > target) {
+    auto victim = ctx->cache.end();
+    for (auto it = ctx->cache.begin(); it != ctx->cache.end(); ++it)
+      if (!it->second.alias && it->second.has && (victim == ctx->cache.end() || it->second.lastused < victim->second.lastused)) victim = it;
+    if (victim == ctx->cache.end()) break;
+    const int64_t vid = victim->first;
+    cache_drop(ctx, victim);
+    for (auto it = ctx->cache.begin(); it != ctx->cache.end();)  // aliases go with their parent (cache.ml:119-127)
+      if (it->second.alias && it->second.target == vid) it = ctx->cache.erase(it); else ++it;
+  }
+}
+int coh_cache_clear(coh_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  while (!ctx->cache.empty()) cache_drop(ctx, ctx->cache.begin());
+  ctx->cache_size = 0;
+  return 0;
+}
+int coh_cache_configure(coh_ctx* ctx, int32_t usecache, int64_t max_bytes) {  // Cache.usecache, Cache.setsize
+  ctx->usecache = usecache != 0;
+  if (max_bytes > 0) { ctx->cache_max = (size_t)max_bytes; while (ctx->cache_size > ctx->cache_max) cache_drophalf(ctx); }
+  return 0;
+}
+int coh_cache_stats(coh_ctx* ctx, int64_t out[4]) {  // cache.ml:24-38
+  out[0] = ctx->shphit; out[1] = ctx->shpmis; out[2] = (int64_t)ctx->cache_size; out[3] = (int64_t)ctx->cache.size();
+  return 0;
+}
+// Cache.addshape idset shp minshp (cache.ml:280-324): copies are kept; an existing shape is not replaced
+int coh_cache_addshape(coh_ctx* ctx, int64_t id, coh_shape_t shape, coh_shape_t minshape) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->usecache || id < 0) return 0;
+  size_t bytes = shape_bytes((DevShape*)shape) + shape_bytes((DevShape*)minshape);
+  if (bytes > ctx->cache_max / 2) return 0;
+  if (ctx->cache_size + bytes > ctx->cache_max) cache_drophalf(ctx);
+  auto it = ctx->cache.find(id);
+  int dx = 0, dy = 0;
+  if (it != ctx->cache.end() && it->second.alias) { dx = it->second.dx; dy = it->second.dy; id = it->second.target; it = ctx->cache.find(id); }
+  if (it != ctx->cache.end() && it->second.has) return 0;
+  CacheEntry& e = ctx->cache[id];
+  e.shape = clone_shape(ctx, (DevShape*)shape, -dx, -dy); e.minshape = clone_shape(ctx, (DevShape*)minshape, -dx, -dy);
+  e.has = true; e.bytes = bytes; e.lastused = ++ctx->cache_timer;
+  ctx->cache_size += bytes;
+  return 0;
+}
+// Cache.getshape idset (cache.ml:370-387): fresh handles (translated through aliases); found = 0 on a miss
+int coh_cache_getshape(coh_ctx* ctx, int64_t id, coh_shape_t* shape, coh_shape_t* minshape, int32_t* found) {
+  CK(cudaSetDevice(ctx->device));
+  *shape = 0; *minshape = 0; *found = 0;
+  if (!ctx->usecache || id < 0) return 0;
+  auto it = ctx->cache.find(id);
+  int dx = 0, dy = 0;
+  if (it != ctx->cache.end() && it->second.alias) { dx = it->second.dx; dy = it->second.dy; it = ctx->cache.find(it->second.target); }
+  if (it == ctx->cache.end() || !it->second.has) { ctx->shpmis++; return 0; }
+  ctx->shphit++; it->second.lastused = ++ctx->cache_timer;
+  *shape = (coh_shape_t)clone_shape(ctx, it->second.shape, dx, dy);
+  *minshape = (coh_shape_t)clone_shape(ctx, it->second.minshape, dx, dy);
+  *found = 1;
+  return 0;
+}
+// Cache.addtranslation idset target dx dy (cache.ml:423-436)
+int coh_cache_addtranslation(coh_ctx* ctx, int64_t id, int64_t target, int32_t dx, int32_t dy) {
+  if (!ctx->usecache) return 0;
+  ctx->cache_timer++;
+  auto it = ctx->cache.find(target);
+  if (it == ctx->cache.end()) return 0;  // not in the cache, so can't add a translation
+  CacheEntry e; e.alias = true;
+  if (it->second.alias) { e.dx = dx + it->second.dx; e.dy = dy + it->second.dy; e.target = it->second.target; }
+  else { e.dx = dx; e.dy = dy; e.target = target; }
+  ctx->cache[id] = e;
+  return 0;
+}
+// Render.shape_of_basicshape obj (render.ml:469-594) for the obj_index-th object of a scene, through
+// the cache: the entry is keyed by the object's id and holds the shape of the UNTRANSLATED geometry;
+// the object's alias offset is applied on the way out (cache.ml:380-385).
+static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape, coh_shape_t* minshape) {
+  const ObjRec& o = s->h_objs[r];
+  *shape = 0; *minshape = 0;
+  const int64_t id = s->ids[r];
+  int32_t found = 0;
+  coh_shape_t cs = 0, cm = 0;
+  if (coh_cache_getshape(ctx, id, &cs, &cm, &found)) return 1;
+  if (!found) {
+    if (o.kind == K_PATH) {
+      if (shapes_from_device_edges(ctx, s->edges + o.first, o.count, o.winding, o.bx0 - o.dx, o.by0 - o.dy, o.bx1 - o.dx, o.by1 - o.dy, &cs, &cm, "coh_scene_object_shape")) return 1;
+    } else if (o.kind == K_PRIM) {
+      if (coh_shape_box(ctx, o.prim[0], o.prim[1], o.prim[2] - o.prim[0] + 1, o.prim[3] - o.prim[1] + 1, &cs)) return 1;
+      if (coh_shape_translate(ctx, cs, 0, 0, &cm)) return 1;
+    } else if (o.kind == K_GROUP) {
+      // union of the members' shapes, minshape null (render.ml:476-496); members are not cached (fresh ids)
+      for (int k = r + 1; k <= s->group_last[r]; k++) {
+        if (s->h_objs[k].depth != o.depth + 1) continue;  // direct children only (nested groups recurse)
+        coh_shape_t ms = 0, mm = 0, un = 0;
+        if (object_shape_rec(ctx, s, k, &ms, &mm)) return 1;
+        if (coh_shape_union(ctx, cs, ms, &un)) return 1;
+        coh_shape_free(ctx, cs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
+        cs = un;
+      }
+      // members already carry their own alias offsets: the group's entry is stored untranslated
+      *shape = cs; *minshape = 0;
+      return 0;
+    } else FAIL("coh_scene_object_shape: unsupported object kind");
+    if (coh_cache_addshape(ctx, id, cs, cm)) return 1;
+  }
+  // apply the alias offset
+  if (o.dx || o.dy) {
+    coh_shape_t ts = 0, tm = 0;
+    if (coh_shape_translate(ctx, cs, o.dx, o.dy, &ts) || coh_shape_translate(ctx, cm, o.dx, o.dy, &tm)) return 1;
+    coh_shape_free(ctx, cs); coh_shape_free(ctx, cm);
+    cs = ts; cm = tm;
+  }
+  *shape = cs; *minshape = cm;
+  return 0;
+}
+int coh_scene_object_shape(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, coh_shape_t* shape, coh_shape_t* minshape) {
+  CK(cudaSetDevice(ctx->device));
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_scene_object_shape: null scene");
+  if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_object_shape: no such object");
+  return object_shape_rec(ctx, s, s->rec_of_abi[obj_index], shape, minshape);
+}
+// Render.plaindirty / alldirty (render.ml:1376-1391): ((shp_o - minshp_n) ∪ (shp_n - minshp_o)) ∩ u,
+// or (shp_o ∪ shp_n) ∩ u when `plain` is 0.
+int coh_dirty_region(coh_ctx* ctx, coh_shape_t shp_o, coh_shape_t min_o, coh_shape_t shp_n, coh_shape_t min_n,
+                     coh_shape_t u, int32_t plain, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  coh_shape_t a = 0, b = 0, c = 0;
+  if (plain) {
+    if (coh_shape_difference(ctx, shp_o, min_n, &a) || coh_shape_difference(ctx, shp_n, min_o, &b)) return 1;
+    if (coh_shape_union(ctx, a, b, &c)) return 1;
+    coh_shape_free(ctx, a); coh_shape_free(ctx, b);
+  } else {
+    if (coh_shape_union(ctx, shp_o, shp_n, &c)) return 1;
+  }
+  int rc = coh_shape_intersection(ctx, c, u, out);
+  coh_shape_free(ctx, c);
+  return rc;
+}
+
+// Render.translate_renderobject dx dy obj (render.ml:259-271): the object (or every member of the
+// group) becomes an alias of its former self moved by whole pixels; only the alias offsets and the
+// boxes the binning reads change, nothing is re-uploaded.
+int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy) {
+  CK(cudaSetDevice(ctx->device));
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_scene_translate_object: null scene");
+  if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_translate_object: no such object");
+  const int r = s->rec_of_abi[obj_index];
+  const int last = s->h_objs[r].kind == K_GROUP ? s->group_last[r] : r;
+  for (int k = r; k <= last; k++) {
+    ObjRec& o = s->h_objs[k];
+    if (o.kind == K_GROUP) continue;
+    o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
+  }
+  s->items_for_W = -1;  // the item-pool bound depends on the boxes
+  if (s->n_leaves > 0) { k_move_leaves<<<cdiv(s->n_leaves, 256), 256, 0, ctx->stream>>>(s->objs, s->leaf_box, s->leaves, s->n_leaves, r, last, dx, dy); LAUNCHED(); }
+  return 0;
+}
+// Render.render_frame over an arbitrary update shape (the dirty region of engine.ml:224-252).
+int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, int32_t flags) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_render_frame_shape: call coh_fb_configure first");
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_render_frame_shape: null scene");
+  DevShape* us = (DevShape*)update;
+  ctx->have_u = false;
+  if (!us) return 0;  // NullShape: nothing to render (render.ml:1321-1322)
+  const Frame& fr = ctx->fr;
+  if (!ctx->u_init) CK(cudaMalloc(&ctx->u_init, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H));
+  CK(cudaMemsetAsync(ctx->u_init, 0, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H, ctx->stream));
+  k_spans_to_bits<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(us->row_ptr, us->spans, us->y0, us->n_rows, 0, fr.H, 0, fr.tiles_x, ctx->u_init); LAUNCHED();
+  bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
+  ctx->use_u_init = true;
+  int rc = render_pass(ctx, s, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1, true, record_u);
+  ctx->use_u_init = false;
+  ctx->have_u = record_u && !rc;
+  return rc;
 }
 int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out) {
   CK(cudaSetDevice(ctx->device));

@@ -792,6 +792,24 @@ __global__ void k_fill_runs(const uint32_t* __restrict__ bits, int n_rows, int n
   }
   if (in) spans[k++] = make_int2(start, wx0 + 32 * nw - start);
 }
+// Sprite.translate_shape (sprite.ml:470-484) on a device span set: spans move by dx (rows move by
+// changing y0 on the host side).
+__global__ void k_translate_spans(const int2* __restrict__ in, int2* __restrict__ out, int n, int dx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { int2 s = in[i]; out[i] = make_int2(s.x + dx, s.y); }
+}
+// Per-object alias offsets changed in place (Render.translate_renderobject -> Cache.addtranslation):
+// shift the device-space boxes the binning reads.  delta = new offset - old offset.
+__global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf_box, const int* __restrict__ leaves,
+                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy) {
+  int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n_leaves) return;
+  int oi = leaves[li];
+  if (oi < first_obj || oi > last_obj) return;
+  ObjRec& o = objs[oi];
+  o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy;
+  leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
+}
 // Box-shaped bit-frame (Sprite.box) or clear.
 __global__ void k_fill_box_bits(uint32_t* __restrict__ bits, int n_rows, int nw, int wx0, int y0, int bx0, int by0,
                                 int bx1, int by1) {

@@ -118,6 +118,17 @@ int coh_shape_translate(coh_ctx* ctx, coh_shape_t a, int32_t dx, int32_t dy, coh
 int coh_shape_bloat(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1857 */
 int coh_shape_erode(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1867 */
 
+/* ---- Cache (cache.mli:32-48): span sets resident in HBM, keyed by Id.idset ---- */
+int coh_cache_configure(coh_ctx* ctx, int32_t usecache, int64_t max_bytes); /* Cache.usecache / setsize (default 50 MiB, cache.ml:73) */
+int coh_cache_clear(coh_ctx* ctx);                                           /* Cache.clear */
+int coh_cache_stats(coh_ctx* ctx, int64_t out[4]);                           /* shape hits, misses, bytes, entries (cache.ml:24-38) */
+int coh_cache_addshape(coh_ctx* ctx, int64_t id, coh_shape_t shape, coh_shape_t minshape); /* Cache.addshape: copies kept, cache.ml:280 */
+int coh_cache_getshape(coh_ctx* ctx, int64_t id, coh_shape_t* shape, coh_shape_t* minshape, int32_t* found); /* Cache.getshape, cache.ml:370 */
+int coh_cache_addtranslation(coh_ctx* ctx, int64_t id, int64_t target, int32_t dx, int32_t dy); /* cache.ml:423 */
+/* Render.plaindirty (plain != 0) / alldirty (render.ml:1376-1391) */
+int coh_dirty_region(coh_ctx* ctx, coh_shape_t shp_o, coh_shape_t minshp_o, coh_shape_t shp_n, coh_shape_t minshp_n,
+                     coh_shape_t u, int32_t plain, coh_shape_t* out);
+
 /* ---- Render (render.mli:211-217) ---- */
 /* Upload a scene (flattened object list, head = front-most) with its edge and brush
  * point pools.  Edges: int32[n_edges][4] = x0,y0,x1,y1 sub-bins.  Points: int32[n][2].
@@ -141,6 +152,17 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8);
 enum { COH_RENDER_RECORD_U = 1 };
 int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh,
                      int32_t flags);
+/* Render.render_frame over an arbitrary update shape — the dirty region that engine.ml:224-252
+ * (force_update) passes after a change; pixels outside the shape keep their previous value. */
+int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, int32_t flags);
+/* Render.translate_renderobject dx dy obj (render.ml:259-271) on the obj_index-th object of the
+ * array given to coh_scene_create (a GROUP_BEGIN index moves every member): the object becomes an
+ * integer-pixel alias of itself (Cache.addtranslation); offsets accumulate. */
+int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy);
+/* Render.shape_of_basicshape (render.ml:469-594) of the obj_index-th object (Path, Primitive or Group),
+ * through the cache: entries are keyed by the object's id and hold the untranslated geometry's span
+ * sets; the object's alias offset is applied on the way out (cache.ml:380-385). */
+int coh_scene_object_shape(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, coh_shape_t* shape, coh_shape_t* minshape);
 /* The covered-so-far set: export `u` as it stands after the scene pass of the last frame
  * rendered with COH_RENDER_RECORD_U (the set-subtraction artefact of render.ml:1308:
  * update minus every pixel the scene pass made opaque), as a device shape. */

@@ -33,22 +33,21 @@ static Fill fill_from(const coh_object& o) {
   return f;
 }
 // Rebuild the object tree from the flattened list.  An alias (dx,dy) is applied the way
-// the reference's cache would serve it: the ORIGINAL geometry's shape/sprite translated
-// by whole pixels (cache.ml:380-385,400-405) == rasterising the edges moved by 32*d sub-bins.
+// the reference's cache serves it: the ORIGINAL geometry's shape/sprite translated by whole
+// pixels (cache.ml:380-385,400-405) — see Obj::dx in render.hpp.
 static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, const int32_t* points) {
   std::vector<Scene> stack(1);
   std::vector<Obj> open;
   for (int i = 0; i < n; i++) {
     const coh_object& c = objs[i];
     Obj o;
-    o.id = c.id; o.pretrans = c.pretrans;
+    o.id = c.id; o.pretrans = c.pretrans; o.dx = c.dx; o.dy = c.dy;
     for (int k = 0; k < 4; k++) o.bounds[k] = c.bounds[k];
     o.has_bounds = !(c.bounds[0] == 0 && c.bounds[1] == 0 && c.bounds[2] == 0 && c.bounds[3] == 0);
     switch (c.kind) {
       case COH_OBJ_PATH: {
         o.kind = Obj::Path; o.fill = fill_from(c); o.winding = (Winding)c.winding;
         o.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
-        for (Edge& e : o.edges) { e.x0 += 32 * c.dx; e.x1 += 32 * c.dx; e.y0 += 32 * c.dy; e.y1 += 32 * c.dy; }
         sort_edgelist_maxy_rev(o.edges);
         stack.back().push_back(std::move(o));
         break;
@@ -63,7 +62,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         o.kind = Obj::Brush; o.fill = fill_from(c);
         o.stroke.opacity = c.brush_opacity; o.stroke.radius = c.brush_radius;
         for (int k = 0; k < c.count; k++)
-          o.stroke.points.push_back({points[2 * ((size_t)c.first + k)] + c.dx, points[2 * ((size_t)c.first + k) + 1] + c.dy});
+          o.stroke.points.push_back({points[2 * ((size_t)c.first + k)], points[2 * ((size_t)c.first + k) + 1]});
         stack.back().push_back(std::move(o));
         break;
       }

@@ -24,6 +24,12 @@ struct Obj {
   enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4 } kind = Path;
   long id = -1;              // < 0: a fresh id per render (Id.new_ids ()), never cached
   int pretrans = -1;         // -1: Over; else PreTrans(v, Over) with delta = toint (v *. 255.)
+  // Integer-pixel alias (Render.translate_renderobject -> Cache.addtranslation, render.ml:259-271,
+  // cache.ml:423-436): shape and sprite are those of the geometry at its ORIGINAL position,
+  // translated (cache.ml:380-385, 400-405).  This is not the same as rasterising moved edges where
+  // coordinates go negative (pix_of_sub and toint truncate toward zero), so the alias is modelled
+  // the way the cache serves it.
+  int dx = 0, dy = 0;
   int bounds[4] = {0, 0, 0, 0};  // bounds_of_basicshape: xmin, xmax, ymin, ymax (render.ml:377-437)
   bool has_bounds = false;
   // Path
@@ -121,8 +127,12 @@ struct Renderer {
   // optional trace of the covered-so-far sets: u after each renderobj at top level
   std::vector<Shape>* trace_u = nullptr;
 
-  // render.ml:469-594
+  // render.ml:469-594 (+ alias translation as served by the cache)
   void shape_of_basicshape(const Obj& o, Shape& shp, Shape& minshp) {
+    shape_of_basicshape0(o, shp, minshp);
+    if (o.dx || o.dy) { shp = translate_shape(o.dx, o.dy, shp); minshp = translate_shape(o.dx, o.dy, minshp); }
+  }
+  void shape_of_basicshape0(const Obj& o, Shape& shp, Shape& minshp) {
     switch (o.kind) {
       case Obj::Group: {
         if (cache.getshape(o.id, shp, minshp)) return;
@@ -184,8 +194,12 @@ struct Renderer {
     });
   }
 
-  // render.ml:984-1078
+  // render.ml:984-1078 (+ alias translation as served by the cache)
   Sprite sprite_of_basicshape(const Obj& o, const Shape& shp) {
+    if (o.dx || o.dy) return translate_sprite(o.dx, o.dy, sprite_of_basicshape0(o, translate_shape(-o.dx, -o.dy, shp)));
+    return sprite_of_basicshape0(o, shp);
+  }
+  Sprite sprite_of_basicshape0(const Obj& o, const Shape& shp) {
     switch (o.kind) {
       case Obj::Group: {
         Sprite a; Shape u = shp;
@@ -207,7 +221,9 @@ struct Renderer {
   // render.ml:1134-1242 (non-filter objects)
   Sprite spriteof(const Obj& o, const Shape& shp) {
     Sprite cached; Shape pshape;
-    cache.getsprite(o.id, cached, pshape);
+    if (cache.getsprite(o.id, cached, pshape) && (o.dx || o.dy)) {  // entries hold the untranslated geometry's sprite
+      cached = translate_sprite(o.dx, o.dy, cached); pshape = translate_shape(o.dx, o.dy, pshape);
+    }
     Shape shptorender = shape_difference(shp, pshape);
     if (shptorender.null()) return portion(cached, shp);
     Sprite rendered;
@@ -218,12 +234,12 @@ struct Renderer {
       Shape s, m; shape_of_basicshape(o, s, m);
       Shape maxshape = shape_difference(s, m);
       Sprite maxbit = sprite_of_basicshape(o, shape_intersection(shptorender, maxshape));
-      Sprite minbit = fillshape(shape_intersection(m, shptorender), o.fill);
+      Sprite minbit = translate_sprite(o.dx, o.dy, fillshape(translate_shape(-o.dx, -o.dy, shape_intersection(m, shptorender)), o.fill));
       rendered = caf(nocover, opaque, minbit, maxbit).first;
     }
     Sprite newwhole = caf(nocover, opaque, cached, rendered).first;
     Shape pshape2 = shape_of_sprite(newwhole);
-    if (o.kind != Obj::Primitive) cache.addsprite(o.id, newwhole, pshape2);
+    if (o.kind != Obj::Primitive) cache.addsprite(o.id, translate_sprite(-o.dx, -o.dy, newwhole), translate_shape(-o.dx, -o.dy, pshape2));
     return portion(newwhole, shape_intersection(shp, pshape2));
   }
 
@@ -232,7 +248,7 @@ struct Renderer {
     if (bbox_reject && o.has_bounds) {
       Box ub; shape_bounds(u, ub);
       // Pdfutil.box_overlap on inclusive integer boxes
-      if (o.bounds[0] > ub.x1 || o.bounds[1] < ub.x0 || o.bounds[2] > ub.y1 || o.bounds[3] < ub.y0) return;
+      if (o.bounds[0] + o.dx > ub.x1 || o.bounds[1] + o.dx < ub.x0 || o.bounds[2] + o.dy > ub.y1 || o.bounds[3] + o.dy < ub.y0) return;
     }
     Shape r, rm; shape_of_basicshape(o, r, rm);
     Shape r2 = shape_intersection(r, u);

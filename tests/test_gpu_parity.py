@@ -255,8 +255,12 @@ def test_translation_alias_equals_translated_edges(ctx, oracle):
         b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
         got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
         assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
-        # and the same picture as moving the integer edges themselves by 32 sub-bins per pixel (moving the
-        # FLOAT path first is not equivalent: sub_of_float (f + d) may round differently)
+        # and, while every coordinate stays positive, the same picture as moving the integer edges themselves
+        # by 32 sub-bins per pixel.  (Moving the FLOAT path is not equivalent — sub_of_float (f + d) may round
+        # differently, SURVEY.md App. B — and neither is moving edges into negative coordinates, where
+        # pix_of_sub and toint truncate toward zero: the alias keeps the ORIGINAL position's rounding.)
+        if dx < 0 or dy < 0:
+            continue
         poly_only = S.SceneBuilder()
         o = poly_only.polygon(pts, S.Fill.plain(S.dissolve(S.rgba8(30, 90, 200), 200)), dx=dx, dy=dy)
         objs, n, nbg, edges, points = poly_only.arrays()
@@ -270,3 +274,80 @@ def test_translation_alias_equals_translated_edges(ctx, oracle):
         ctx.sync()
         assert np.array_equal(ctx.fb_read_rgba(0, 0, W, H), ref2)
         ctx.scene_free(sc)
+
+
+def test_drag_sequence_dirty_regions_and_cache(ctx, oracle):
+    """C4 in miniature: an object is dragged by integer pixels; every frame re-renders only
+    the dirty region plaindirty = ((shp_o - minshp_n) ∪ (shp_n - minshp_o)) ∩ u computed from cached,
+    HBM-resident span sets, and the framebuffer must equal a full render of the moved scene."""
+    W, H = 480, 360
+    b = S.random_scene(W, H, 60, seed=11, brush_fraction=0.0, background=False)
+    mover = b.polygon([(100.2, 80.1), (220.5, 100.9), (200.0, 230.3), (90.0, 200.0)], S.Fill.plain(S.rgba8(250, 220, 30)), oid=7)
+    mover_index = len(b.objs) - 1
+    for i in range(25):  # objects behind the mover
+        x, y = 30.0 + 16 * i, 20.0 + 11 * i
+        b.polygon([(x, y), (x + 90.5, y + 10.2), (x + 70.1, y + 95.5), (x - 5.0, y + 60.0)], S.Fill.plain(S.dissolve(S.rgba8(20 * i % 255, 200, 255 - 9 * i), 255 if i % 3 else 170)), oid=100 + i)
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, edges, points = b.arrays()
+    ctx.cache_clear()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    master = ctx.shape_box(0, 0, W, H)
+    mo = objs[mover_index]
+    medges = edges[mo.first : mo.first + mo.count]
+    tx = ty = 0
+    for step, (dx, dy) in enumerate([(3, 2), (5, -1), (-7, 4), (0, 9), (12, 12), (-30, -20)]):
+        so, mno = ctx.scene_object_shape(sc, mover_index)
+        ctx.scene_translate_object(sc, mover_index, dx, dy)
+        tx, ty = tx + dx, ty + dy
+        sn, mnn = ctx.scene_object_shape(sc, mover_index)
+        # the new shape is the cached one translated — equal to scan-converting the moved integer edges
+        ref_sn, ref_mn = oracle.shapeminshape(medges + np.array([32 * tx, 32 * ty, 32 * tx, 32 * ty], dtype=np.int32), mo.winding)
+        assert np.array_equal(ctx.shape_export(sn), ref_sn) and np.array_equal(ctx.shape_export(mnn), ref_mn)
+        dirty = ctx.dirty_region(so, mno, sn, mnn, master, plain=True)
+        ref_so, ref_mo = oracle.shapeminshape(medges + np.array([32 * (tx - dx), 32 * (ty - dy)] * 2, dtype=np.int32), mo.winding)
+        box = util.flat_of_rows([(y, [(0, W)]) for y in range(H)])
+        ref_dirty = oracle.shape_op("intersection", oracle.shape_op("union", oracle.shape_op("difference", ref_so, ref_mn), oracle.shape_op("difference", ref_sn, ref_mo)), box)
+        assert np.array_equal(ctx.shape_export(dirty), ref_dirty), f"dirty region differs at step {step}"
+        ctx.render_frame_shape(sc, dirty)
+        ctx.sync()
+        got = ctx.fb_read_rgba(0, 0, W, H)
+        objs[mover_index].dx, objs[mover_index].dy = tx, ty
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert _max_lsb(got, ref) == 0, f"frame differs after incremental update {step}"
+        for h in (so, mno, sn, mnn, dirty):
+            ctx.shape_free(h)
+    st = ctx.cache_stats()
+    assert st["shape_hits"] >= 11 and st["shape_misses"] == 1 and st["entries"] == 1 and st["bytes"] > 0
+    ctx.shape_free(master)
+    ctx.scene_free(sc)
+
+
+def test_update_shape_with_holes(ctx, oracle):
+    """render_frame over a non-rectangular update (rows with several spans): only those pixels change."""
+    W, H = 256, 192
+    b = S.lion_scene(W, H, 0.55)
+    objs, n, nbg, edges, points = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    blank = S.SceneBuilder()
+    blank.rectangle(S.rgba8(1, 2, 3), 0.0, 0.0, float(W), float(H))
+    bo, bn, bnbg, be, bp = blank.arrays()
+    sc0 = ctx.scene_create(bo, bnbg, be, bp)
+    ctx.render_frame(sc0, (0, 0, W, H))
+    rows = [(y, [(10 + (y % 7), 40), (70, 3), (100 + y % 5, 90 - y % 11)]) for y in range(20, 170) if y % 9]
+    upd = util.flat_of_rows(rows)
+    hu = ctx.shape_import(upd)
+    ctx.render_frame_shape(sc, hu)
+    ctx.sync()
+    got = ctx.fb_read_rgba(0, 0, W, H)
+    full = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H), bbox_reject=False)
+    mask = util.bitmap_of_flat(upd, 0, 0, W, H)
+    assert np.array_equal(got[mask], full[mask])
+    assert (got[~mask] == S.rgba8(1, 2, 3)).all()
+    ctx.shape_free(hu)
+    ctx.scene_free(sc)
+    ctx.scene_free(sc0)
