@@ -16,6 +16,7 @@ COH_NONZERO, COH_EVENODD = 0, 1
 COH_FILL_PLAIN, COH_FILL_AXIAL, COH_FILL_RADIAL = 0, 1, 2
 COH_FILL_EXT_S, COH_FILL_EXT_E = 1, 2
 COH_RENDER_RECORD_U = 1
+COH_CONV_UNIT, COH_CONV_GAUSSIAN = 1, 2
 
 
 class CohObject(C.Structure):
@@ -25,7 +26,7 @@ class CohObject(C.Structure):
         ("kind", C.c_int32), ("winding", C.c_int32), ("first", C.c_int32), ("count", C.c_int32),
         ("fill_kind", C.c_int32), ("colour0", C.c_uint32), ("colour1", C.c_uint32), ("fill_flags", C.c_int32),
         ("pretrans", C.c_int32), ("dx", C.c_int32), ("dy", C.c_int32), ("bounds", C.c_int32 * 4),
-        ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("reserved", C.c_int32), ("id", C.c_int64),
+        ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("convolve", C.c_int32), ("id", C.c_int64),
         ("fparam", C.c_double * 6), ("brush_opacity", C.c_double), ("brush_radius", C.c_double),
     ]
 

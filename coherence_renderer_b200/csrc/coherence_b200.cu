@@ -34,6 +34,8 @@ struct DevScene {
   int* rowedge_ptr = nullptr;   // K1 edge binning (CSR over (path object, pixel row))
   int* rowedge_idx = nullptr;
   int2* brush_ranges = nullptr; // per (stroke, row): [first, last] stamp index reaching the row
+  uint32_t* conv_bits = nullptr; // Convolved objects: shape / minshape bit-rows
+  uint32_t* conv_px = nullptr;   // Convolved objects: pre-convolved canvases
   std::vector<ObjRec> h_objs;
   std::vector<int64_t> ids;      // cache key (Id.idset) of every record
   std::vector<int> rec_of_abi;   // record index of every object of the ABI array (-1: GROUP_END / dropped)
@@ -653,7 +655,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
   cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->leaf_box); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
-  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx); cudaFree(s->brush_ranges);
+  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx); cudaFree(s->brush_ranges); cudaFree(s->conv_bits); cudaFree(s->conv_px);
   delete s;
   return 0;
 }
@@ -690,6 +692,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<int> open;  // indices (into recs) of open groups
   std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
   std::vector<int> point_obj((size_t)std::max(n_points, 1), -1);  // owning brush object of every point
+  struct ConvItem { int rec, kind, r; };
+  std::vector<ConvItem> conv_list;
+  size_t conv_words = 0, conv_pixels = 0;
   long long total_rows = 0, total_brush_rows = 0;
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
@@ -732,8 +737,24 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
         o.kind = K_PATH; o.winding = c.winding; o.aa_winding = c.winding; o.first = c.first; o.count = c.count;
         if (c.count == 0) continue;  // NullShape: nothing to draw
+        if (c.convolve) {
+          const int ck = c.convolve & 255, cr = c.convolve >> 8;
+          if ((ck != COH_CONV_UNIT && ck != COH_CONV_GAUSSIAN) || cr <= 0 || cr > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");  // convolve.ml:37-51 Invalid_argument
+          if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: Convolved objects with fancy fills are not supported yet");
+          o.kind = K_CONV;
+          conv_list.push_back({(int)recs.size(), ck, cr});
+        }
         EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
         shape_pixel_box(eb, o.bx0, o.by0, o.bx1, o.by1);
+        if (o.kind == K_CONV) {  // the convolved object reaches r pixels further; its canvas another r (X-pass inputs)
+          const int cr = c.convolve >> 8;
+          o.cv_x0 = floordiv(o.bx0 - 2 * cr, 32) * 32; o.cv_y0 = o.by0 - 2 * cr;
+          o.cv_nw = (o.bx1 + 2 * cr - o.cv_x0) / 32 + 1; o.cv_h = o.by1 + 2 * cr - o.cv_y0 + 1;
+          o.bx0 -= cr; o.bx1 += cr; o.by0 -= cr; o.by1 += cr;
+          o.cv_bits = (int)conv_words; conv_words += 2 * (size_t)o.cv_nw * o.cv_h;
+          o.cv_px = (int)conv_pixels; conv_pixels += (size_t)o.cv_nw * 32 * o.cv_h;
+          if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull) FAIL("scene: Convolved canvases too large");
+        }
         // rows with a candidate edge list: extended band [32y-67, 32y+16] meets [ymin, ymax]
         o.ry0 = floordiv(eb.ymin - 16 + 31, 32); o.ry1 = floordiv(eb.ymax + 67, 32);
         if (total_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
@@ -790,7 +811,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
-    if (o.kind == K_BRUSH) s->has_brush = true;
+    if (o.kind == K_BRUSH || o.kind == K_CONV) s->has_brush = true;
   }
   CK(cudaMalloc(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -824,6 +845,50 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_edge_obj); cudaFree(d_counts);
+  }
+  // Convolved objects (render.ml:1023-1052): AA-rasterise the whole (twice bloated) box of the child,
+  // X pass, Y pass; keep the shape / minshape bit-rows and the convolved canvas resident.
+  if (!conv_list.empty()) {
+    CK(cudaMalloc(&s->conv_bits, sizeof(uint32_t) * conv_words));
+    CK(cudaMalloc(&s->conv_px, sizeof(uint32_t) * conv_pixels));
+    for (const ConvItem& ci : conv_list) {
+      const ObjRec& o = recs[ci.rec];
+      const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;
+      const size_t nwords = (size_t)nw * h, npx = (size_t)w * h;
+      uint32_t *S = nullptr, *C = nullptr, *T = nullptr, *Q = nullptr, *A = nullptr, *X = nullptr; uint8_t* op = nullptr; int* d_taps = nullptr;
+      CK(cudaMalloc(&S, 4 * nwords)); CK(cudaMalloc(&C, 4 * nwords)); CK(cudaMalloc(&T, 4 * nwords)); CK(cudaMalloc(&Q, 4 * nwords));
+      CK(cudaMalloc(&A, 4 * npx)); CK(cudaMalloc(&X, 4 * npx)); CK(cudaMalloc(&op, npx));
+      CK(cudaMemsetAsync(S, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(C, 0, 4 * nwords, ctx->stream));
+      CK(cudaMemsetAsync(op, 0, npx, ctx->stream));
+      const EdgeRec* ed = s->edges + o.first;
+      k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, o.count, o.winding, o.cv_y0, h, o.cv_x0, nw, S, C, ctx->d_error); LAUNCHED();
+      uint32_t* convS = s->conv_bits + o.cv_bits; uint32_t* convM = convS + nwords;
+      dim3 g(cdiv(nw, 128), h);
+      k_dilate<<<g, 128, 0, ctx->stream>>>(S, convS, h, nw, ci.r, ci.r); LAUNCHED();                  // shape = bloat r r (shape g)
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED();  // C := minshape g
+      k_fill_words<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(Q, nwords, 0xFFFFFFFFu); LAUNCHED();
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(Q, C, T, nwords, 1); LAUNCHED();  // T := frame - minshape
+      k_dilate<<<g, 128, 0, ctx->stream>>>(T, S, h, nw, ci.r, ci.r); LAUNCHED();                       // S := bloat (frame - minshape)
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(C, S, convM, nwords, 1); LAUNCHED();  // minshape = erode r r (minshape g)
+      k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, o.count, o.aa_winding, Q, o.cv_y0, h, o.cv_x0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+      k_raster_plain<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(op, A, npx, o.fill.c0); LAUNCHED();
+      std::vector<int> taps; int total = 0;
+      if (ci.kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+        for (int i = -ci.r; i <= ci.r; i++) {
+          double xr = (double)i / (double)ci.r, yr = 0. / (double)ci.r;
+          double gg = exp(-(xr * xr + yr * yr)) / 2.;
+          int v = (int)((double)(4 * ci.r * ci.r) * gg + 0.5);
+          taps.push_back(v); total += v;
+        }
+        CK(cudaMalloc(&d_taps, sizeof(int) * taps.size()));
+        CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      dim3 gp(cdiv(w, 128), h);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, ci.r, ci.kind, d_taps, total, 0); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, s->conv_px + o.cv_px, w, h, ci.r, ci.kind, d_taps, total, 1); LAUNCHED();
+      if (check_error_flag(ctx, "coh_scene_create (Convolved object)")) return 1;
+      cudaFree(S); cudaFree(C); cudaFree(T); cudaFree(Q); cudaFree(A); cudaFree(X); cudaFree(op); cudaFree(d_taps);
+    }
   }
   if (total_brush_rows > 0) {
     int* d_point_obj = nullptr;
@@ -935,6 +1000,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
+  P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
   P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = ctx->use_u_init ? ctx->u_init : nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;

@@ -222,6 +222,8 @@ struct WalkParams {
   const int* rowedge_idx;
   const int2* points;          // brush stamp centres (object frame), list order
   const int2* brush_ranges;    // per (stroke, row): first / last stamp index reaching the row
+  const uint32_t* conv_bits;   // Convolved objects: shape / minshape bit-rows
+  const uint32_t* conv_px;     // Convolved objects: pre-convolved RGBA8 canvases
   const uint8_t* stamps;       // brush alpha stamps
   const int* cell_off;         // per cell [first, last) into cell_items
   const int* cell_items;
@@ -386,6 +388,13 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
   return aa_opacity(mytot, volume);  // one division per lane, after the loop
 }
 
+// 32 bits of a bit-row starting at an arbitrary bit offset (zeros outside the row)
+__device__ __forceinline__ uint32_t conv_load_bits32(const uint32_t* __restrict__ row, int nw, int bitoff) {
+  const int qw = bitoff >> 5, qb = bitoff & 31;
+  const uint32_t lo = (qw >= 0 && qw < nw) ? row[qw] : 0u;
+  const uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
+  return qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
+}
 constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 3
@@ -504,6 +513,14 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             if (!scan_row(P.edges, P.rowedge_idx + a, b - a, 1, yy, o.winding, false, xx0, xx0 + 31, sink)) bad = true;
             S = sink.S; C = sink.C;
           }
+        } else if (BRUSH && o.kind == K_CONV) {
+          // Convolved (k, g): shape = bloat r r (shape g), minshape = erode r r (minshape g) (render.ml:536-555),
+          // both precomputed as bit-rows; C is chosen so that S & ~C is the minshape word
+          if (yy >= o.cv_y0 && yy < o.cv_y0 + o.cv_h) {
+            const uint32_t* rowS = P.conv_bits + o.cv_bits + (size_t)(yy - o.cv_y0) * o.cv_nw;
+            S = conv_load_bits32(rowS, o.cv_nw, xx0 - o.cv_x0);
+            C = S & ~conv_load_bits32(rowS + (size_t)o.cv_h * o.cv_nw, o.cv_nw, xx0 - o.cv_x0);
+          }
         } else if (BRUSH && o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
           const int br = o.brush_r;
@@ -603,7 +620,9 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         if (mine) {
           const bool is_edge = (edge >> lane) & 1u;
           uint32_t col;
-          if (!CARRY || okind == K_PRIM || fkind == 0) col = c0;
+          if (BRUSH && okind == K_CONV && is_edge)  // the convolved sprite, cropped to the visible max-shape (render.ml:1052)
+            col = P.conv_px[(size_t)o.cv_px + (size_t)(yy - o.cv_y0) * (o.cv_nw * 32) + (xx0 + lane - o.cv_x0)];
+          else if (!CARRY || okind == K_PRIM || fkind == 0) col = c0;
           else if (!is_edge || okind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
           else {
             // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
@@ -612,7 +631,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             int start = below ? (xx0 + 32 - __clz((int)below)) : lead_start;
             col = fill_lookup(o.fill, start, yy);
           }
-          if (is_edge) col = px_dissolve(col, opacity);
+          if (is_edge && !(BRUSH && okind == K_CONV)) col = px_dissolve(col, opacity);
           if (pretrans >= 0) col = px_dissolve(col, pretrans);
           acc = px_over(acc, col);
           acc_rows[r][lane] = acc;
@@ -809,6 +828,45 @@ __global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf
   ObjRec& o = objs[oi];
   o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy;
   leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
+}
+// ------------------------------------------------------------------------------------
+// K6 convolve (convolve.ml:115-232) on dense RGBA8 canvases [h][w]; pixels outside the canvas
+// read as clear, like the 2r border of Sprite.flatten_sprite (convolve.ml:247).  One pass per
+// launch (horizontal, then vertical on the re-quantised result): integer sums, truncating
+// division, r,g clamped to alpha for XY kernels (the blue clamp of the reference is a no-op,
+// convolve.ml:118), plain division for the unit kernel (161-204).
+// ------------------------------------------------------------------------------------
+__global__ void k_conv_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int w, int h, int r,
+                            int kind /*1 unit, 2 xy*/, const int* __restrict__ taps, int total, int vertical) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  int tr = 0, tg = 0, tb = 0, ta = 0;
+  for (int q = -r; q <= r; q++) {
+    int xx = vertical ? x : x + q, yy = vertical ? y + q : y;
+    uint32_t c = (xx >= 0 && xx < w && yy >= 0 && yy < h) ? in[(size_t)yy * w + xx] : 0u;
+    int k = kind == 2 ? taps[q + r] : 1;
+    tr += (int)(c & 255u) * k; tg += (int)((c >> 8) & 255u) * k; tb += (int)((c >> 16) & 255u) * k; ta += (int)(c >> 24) * k;
+  }
+  int d = kind == 2 ? total : (2 * r + 1);
+  tr /= d; tg /= d; tb /= d; ta /= d;
+  if (kind == 2) { tr = min(ta, tr); tg = min(ta, tg); }
+  out[(size_t)y * w + x] = (uint32_t)tr | ((uint32_t)tg << 8) | ((uint32_t)tb << 16) | ((uint32_t)ta << 24);
+}
+// AA raster of a plain-filled polygon from dense opacity bytes: dissolve fill opacity (polygon.ml:733-738)
+__global__ void k_raster_plain(const uint8_t* __restrict__ opacity, uint32_t* __restrict__ out, size_t n, uint32_t colour) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = px_dissolve(colour, opacity[i]);
+}
+__global__ void k_fill_words(uint32_t* __restrict__ p, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// 32 bits of a bit-row starting at an arbitrary bit offset (zeros outside the row)
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t* __restrict__ row, int nw, int bitoff) {
+  const int qw = bitoff >> 5, qb = bitoff & 31;
+  const uint32_t lo = (qw >= 0 && qw < nw) ? row[qw] : 0u;
+  const uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
+  return qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
 }
 // Box-shaped bit-frame (Sprite.box) or clear.
 __global__ void k_fill_box_bits(uint32_t* __restrict__ bits, int n_rows, int nw, int wx0, int y0, int bx0, int by0,

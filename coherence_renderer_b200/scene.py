@@ -206,9 +206,13 @@ class SceneBuilder:
         self.n_background = 0
         self._in_background = False
 
-    def _obj(self, kind, pretrans=None, oid=-1, dx=0, dy=0):
+    def _obj(self, kind, pretrans=None, oid=-1, dx=0, dy=0, convolve=None):
+        """convolve = ("unit" | "gaussian", r): Convolved (Convolve.mkunit r | mkgaussian r, this geometry)."""
         o = CohObject()
         o.kind, o.pretrans, o.id, o.dx, o.dy = kind, (-1 if pretrans is None else pretrans), oid, dx, dy
+        if convolve is not None:
+            assert kind == COH_OBJ_PATH and convolve[1] > 0
+            o.convolve = {"unit": 1, "gaussian": 2}[convolve[0]] | (int(convolve[1]) << 8)
         self.objs.append(o)
         if self._in_background:
             self.n_background += 1

@@ -44,6 +44,7 @@ enum {
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
 enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
 enum { COH_FILL_EXT_S = 1, COH_FILL_EXT_E = 2 };
+enum { COH_CONV_UNIT = 1, COH_CONV_GAUSSIAN = 2 };  /* convolve.ml:19-22,37-70 (UnitKernel r / XYKernel from mkgaussian r) */
 
 typedef struct coh_object {
   int32_t kind;        /* COH_OBJ_* */
@@ -60,7 +61,8 @@ typedef struct coh_object {
                           trivial reject of render.ml:1270-1279 only where it is row-local */
   int32_t prim[4];     /* PRIMITIVE: inclusive pixel box x0,y0,x1,y1 (toint of the float rectangle) */
   int32_t prim_null;   /* PRIMITIVE: 1 for a zero-length HLine/VLine (NullShape) */
-  int32_t reserved;
+  int32_t convolve;    /* PATH: 0, or Convolved (kernel, Basic (fill, Path p)) (render.ml:63, 1023-1052):
+                          COH_CONV_UNIT | r << 8  = Convolve.mkunit r,  COH_CONV_GAUSSIAN | r << 8 = Convolve.mkgaussian r */
   int64_t id;          /* cache key (Id.idset); < 0: fresh id each render, never cached */
   double fparam[6];    /* AXIAL: x0,y0,x1,y1;  RADIAL: cx,cy, px,py, p'x,p'y (fill.ml:77,112) */
   double brush_opacity; /* BRUSH: opacity in 0..1 */

@@ -49,6 +49,17 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         o.kind = Obj::Path; o.fill = fill_from(c); o.winding = (Winding)c.winding;
         o.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
         sort_edgelist_maxy_rev(o.edges);
+        if (c.convolve) {  // Convolved (kernel, Basic (fill, Path p)): the path becomes the child
+          Obj outer;
+          outer.kind = Obj::Convolved; outer.id = c.id; outer.pretrans = c.pretrans; outer.dx = c.dx; outer.dy = c.dy;
+          outer.fill = o.fill;
+          int r = c.convolve >> 8;
+          outer.kernel = (c.convolve & 255) == COH_CONV_UNIT ? mkunit(r) : mkgaussian(r);
+          o.id = -1; o.pretrans = -1; o.dx = o.dy = 0; o.has_bounds = false;
+          outer.children.push_back(std::move(o));
+          stack.back().push_back(std::move(outer));
+          break;
+        }
         stack.back().push_back(std::move(o));
         break;
       }

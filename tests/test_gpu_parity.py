@@ -351,3 +351,20 @@ def test_update_shape_with_holes(ctx, oracle):
     ctx.shape_free(hu)
     ctx.scene_free(sc)
     ctx.scene_free(sc0)
+
+
+def test_convolved_objects(ctx, oracle):
+    """Convolved (kernel, Basic (plain fill, Path)) — the page-shadow construct of engine.ml:85-88: shape =
+    bloat r r, minshape = erode r r, sprite = AA raster of the bloated region, X pass, Y pass, cropped
+    (render.ml:536-555, 1023-1052; convolve.ml:115-258)."""
+    W, H = 320, 240
+    for kern in (("gaussian", 4), ("unit", 3), ("gaussian", 7)):
+        b = S.SceneBuilder()
+        b.polygon([(120.3, 40.2), (250.9, 90.1), (150.0, 200.7)], S.Fill.plain(S.dissolve(S.rgba8(250, 180, 20), 220)))
+        b.polygon([(50.0, 40.0), (200.0, 45.5), (190.5, 160.0), (60.0, 150.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 0, 0), 120)), convolve=kern, pretrans=230)
+        b.polygon([(20.0, 100.0), (300.0, 110.0), (280.0, 230.0), (30.0, 220.0)], S.Fill.plain(S.rgba8(40, 160, 90)), convolve=("unit", 2), dx=-3, dy=5)
+        b.begin_background()
+        b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u), kern
+        assert _max_lsb(got, ref) == 0, kern
