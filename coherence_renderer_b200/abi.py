@@ -43,7 +43,7 @@ SYMBOLS = [
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
-    "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_object_shape",
+    "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_object_shape", "coh_convolve_sprite",
 ]
 
 _lib = None
@@ -220,6 +220,18 @@ class Context:
         n = C.c_int64()
         self._chk(lib().coh_polygon_sprite(self._h, C.byref(fill_obj), _i32p(e), len(e), winding, C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
         return out[: n.value]
+
+    def convolve_sprite(self, kernel, r, shape, rgba):
+        """Convolve.convolve_sprite (mkunit r | mkgaussian r): returns (shape handle of the result, rgba per pixel)."""
+        kind = {"unit": COH_CONV_UNIT, "gaussian": COH_CONV_GAUSSIAN}[kernel]
+        src = np.ascontiguousarray(rgba, dtype=np.uint32)
+        bl = self.shape_bloat(shape, r, r)
+        cap = self.shape_card(bl)
+        self.shape_free(bl)
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        o, n = C.c_uint64(), C.c_int64()
+        self._chk(lib().coh_convolve_sprite(self._h, kind, r, C.c_uint64(shape), src.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(o), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return o.value, out[: n.value]
 
     # -- scenes / rendering
     def scene_create(self, objs, n_background, edges, points):

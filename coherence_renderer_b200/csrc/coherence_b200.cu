@@ -648,6 +648,74 @@ int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edge
 }
 
 // ---------------------------------------------------------------------------------------
+// Convolve (convolve.mli:28-40)
+// ---------------------------------------------------------------------------------------
+static int conv_taps(coh_ctx* ctx, int kind, int r, int** d_taps, int* total) {
+  *d_taps = nullptr; *total = 0;
+  if (kind != COH_CONV_GAUSSIAN) return 0;
+  std::vector<int> taps;
+  for (int i = -r; i <= r; i++) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+    double xr = (double)i / (double)r, yr = 0. / (double)r;
+    int v = (int)((double)(4 * r * r) * (exp(-(xr * xr + yr * yr)) / 2.) + 0.5);
+    taps.push_back(v); *total += v;
+  }
+  CK(cudaMalloc(d_taps, sizeof(int) * taps.size()));
+  CK(cudaMemcpyAsync(*d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+static int shape_pixel_offsets(coh_ctx* ctx, const DevShape* s, std::vector<long long>& off) {
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  off.assign(s->n_rows + 1, 0);
+  for (int r = 0; r < s->n_rows; r++) { long long n = 0; for (int q = ptr[r]; q < ptr[r + 1]; q++) n += spans[q].y; off[r + 1] = off[r] + n; }
+  return 0;
+}
+// Convolve.convolve_sprite kernel sprite (convolve.ml:239-258): the sprite is (shape, one RGBA8 per pixel in
+// span order); the result lives on bloat r r (shape) and is returned the same way.
+int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_t shape, const uint32_t* rgba_in,
+                        coh_shape_t* out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *out_shape = 0; *n_out = 0;
+  if ((kernel_kind != COH_CONV_UNIT && kernel_kind != COH_CONV_GAUSSIAN) || r <= 0) FAIL("Convolve.mkunit / Convolve.mkxy: Invalid_argument");
+  if (!shape) return 0;  // NullSprite -> NullSprite
+  DevShape* s = (DevShape*)shape;
+  coh_shape_t R = 0;
+  if (coh_shape_bloat(ctx, shape, r, r, &R)) return 1;
+  DevShape* rs = (DevShape*)R;
+  if (rs->card > cap) { coh_shape_free(ctx, R); FAIL("coh_convolve_sprite: buffer too small"); }
+  // canvas = bounding box grown by 2r (Sprite.flatten_sprite border, convolve.ml:247)
+  const int x0 = s->bx0 - 2 * r, y0 = s->by0 - 2 * r, w = s->bx1 - s->bx0 + 1 + 4 * r, h = s->by1 - s->by0 + 1 + 4 * r;
+  const size_t npx = (size_t)w * h;
+  uint32_t *A = nullptr, *X = nullptr, *d_in = nullptr, *d_out = nullptr; long long* d_off = nullptr; int* d_taps = nullptr; int total = 0;
+  std::vector<long long> off;
+  if (shape_pixel_offsets(ctx, s, off)) return 1;
+  CK(cudaMalloc(&A, 4 * npx)); CK(cudaMalloc(&X, 4 * npx));
+  CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
+  CK(cudaMalloc(&d_in, 4 * (size_t)std::max<long long>(s->card, 1))); CK(cudaMalloc(&d_off, sizeof(long long) * off.size()));
+  CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_scatter_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, s->y0 - y0, x0, w, d_in, A); LAUNCHED();
+  if (conv_taps(ctx, kernel_kind, r, &d_taps, &total)) return 1;
+  dim3 gp(cdiv(w, 128), h);
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, r, kernel_kind, d_taps, total, 0); LAUNCHED();
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, A, w, h, r, kernel_kind, d_taps, total, 1); LAUNCHED();
+  // pick the result up on R (Sprite.pickup)
+  std::vector<long long> roff;
+  if (shape_pixel_offsets(ctx, rs, roff)) return 1;
+  long long* d_roff = nullptr;
+  CK(cudaMalloc(&d_roff, sizeof(long long) * roff.size())); CK(cudaMalloc(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
+  CK(cudaMemcpyAsync(d_roff, roff.data(), sizeof(long long) * roff.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // k_gather_spans indexes dense rows from the shape's first row: pass the canvas rows starting at R's first row
+  k_gather_spans<uint32_t><<<cdiv(rs->n_rows, 128), 128, 0, ctx->stream>>>(rs->row_ptr, rs->spans, d_roff, rs->n_rows, x0, w, A + (size_t)(rs->y0 - y0) * w, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)rs->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(A); cudaFree(X); cudaFree(d_in); cudaFree(d_out); cudaFree(d_off); cudaFree(d_roff); cudaFree(d_taps);
+  *out_shape = R; *n_out = rs->card;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Scenes and rendering
 // ---------------------------------------------------------------------------------------
 int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {

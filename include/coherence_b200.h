@@ -120,6 +120,13 @@ int coh_shape_translate(coh_ctx* ctx, coh_shape_t a, int32_t dx, int32_t dy, coh
 int coh_shape_bloat(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1857 */
 int coh_shape_erode(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1867 */
 
+/* ---- Convolve (convolve.mli:28-40) ----
+ * Convolve.convolve_sprite kernel sprite (convolve.ml:239-258) with kernel = mkunit r / mkgaussian r.  A sprite
+ * crosses the boundary as its shape plus one RGBA8 word per pixel in canonical span order; the result
+ * lives on bloat r r (shape) (returned in *out_shape) and is written the same way. */
+int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_t shape, const uint32_t* rgba_in,
+                        coh_shape_t* out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+
 /* ---- Cache (cache.mli:32-48): span sets resident in HBM, keyed by Id.idset ---- */
 int coh_cache_configure(coh_ctx* ctx, int32_t usecache, int64_t max_bytes); /* Cache.usecache / setsize (default 50 MiB, cache.ml:73) */
 int coh_cache_clear(coh_ctx* ctx);                                           /* Cache.clear */

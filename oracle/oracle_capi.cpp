@@ -236,6 +236,26 @@ int orc_render_frame(const coh_object* objs, int n_scene, int n_background, cons
   ORC_CATCH
 }
 
+// Convolve.convolve_sprite (kind 1 = mkunit r, 2 = mkgaussian r): sprite = flat shape + RGBA8 per pixel.
+int orc_convolve_sprite(int kind, int r, const int32_t* shape, int64_t nshape, const uint32_t* rgba, int32_t** out_shape, int64_t* n_out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  ORC_TRY
+  Shape shp = shape_from_flat(shape, (int)nshape);
+  Sprite spr;
+  int64_t k = 0;
+  for (auto& row : shp.rows) {
+    SpriteRow sr; sr.y = row.y; sr.spans = row.spans;
+    for (auto& sp : row.spans) for (int i = 0; i < sp.len; i++) sr.px.push_back(colour_of_rgba8(rgba[k++]));
+    spr.rows.push_back(std::move(sr));
+  }
+  Sprite res = convolve_sprite(kind == 1 ? mkunit(r) : mkgaussian(r), spr);
+  auto f = shape_to_flat(shape_of_sprite(res));
+  *out_shape = dup_ints(f); *n_out_shape = (int64_t)f.size();
+  int64_t n = 0;
+  for (auto& row : res.rows) for (colour c : row.px) { if (n >= cap) throw std::runtime_error("orc_convolve_sprite: buffer too small"); rgba_out[n++] = rgba8_of_colour(c); }
+  *n_out = n;
+  ORC_CATCH
+}
+
 // Persistent renderer for the cached / animated configurations (C4): keeps Cache between frames.
 void* orc_renderer_new(int usecache) { Renderer* r = new Renderer(); r->cache.usecache = usecache != 0; return r; }
 void orc_renderer_free(void* r) { delete (Renderer*)r; }

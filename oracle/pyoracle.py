@@ -170,6 +170,16 @@ def render_frame(objs, n_scene, n_background, edges, points, update, bbox_reject
     return out
 
 
+def convolve_sprite(kernel, r, shape_flat, rgba):
+    s = _i32(shape_flat)
+    src = np.ascontiguousarray(rgba, dtype=np.uint32)
+    cap = shape_card(shape_unary("bloat", s, r, r))
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    ps, ns, n = C.POINTER(C.c_int32)(), C.c_int64(), C.c_int64()
+    _chk(lib().orc_convolve_sprite({"unit": 1, "gaussian": 2}[kernel], r, _ptr(s), C.c_int64(len(s)), _ptr(src, C.c_uint32), C.byref(ps), C.byref(ns), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return _take(ps, ns.value), out[: n.value]
+
+
 def flatten_bezier(p8, eps=0.2):
     a = np.ascontiguousarray(p8, dtype=np.float64).reshape(8)
     p, n = C.POINTER(C.c_double)(), C.c_int64()

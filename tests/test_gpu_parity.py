@@ -368,3 +368,22 @@ def test_convolved_objects(ctx, oracle):
         got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
         assert np.array_equal(got_u, ref_u), kern
         assert _max_lsb(got, ref) == 0, kern
+
+
+def test_convolve_sprite(ctx, oracle):
+    """Convolve.convolve_sprite on arbitrary sprites (random canonical shapes, random premultiplied colours)."""
+    rng = random.Random(41)
+    for kern, r in (("gaussian", 3), ("unit", 2), ("gaussian", 5), ("unit", 6)):
+        shp = util.random_shape_flat(rng, x0=-10, y0=5, w=140, h=70, density=0.5)
+        n = oracle.shape_card(shp)
+        a = np.array([rng.randint(0, 255) for _ in range(n)], dtype=np.uint32)
+        rgba = np.array([(rng.randint(0, int(v)) | (rng.randint(0, int(v)) << 8) | (rng.randint(0, int(v)) << 16) | (int(v) << 24)) for v in a], dtype=np.uint32)
+        ref_shape, ref_px = oracle.convolve_sprite(kern, r, shp, rgba)
+        h = ctx.shape_import(shp)
+        ho, got_px = ctx.convolve_sprite(kern, r, h, rgba)
+        assert np.array_equal(ctx.shape_export(ho), ref_shape)
+        assert np.array_equal(got_px, ref_px), (kern, r)
+        ctx.shape_free(h)
+        ctx.shape_free(ho)
+    with pytest.raises(abi.CohError):
+        ctx.convolve_sprite("unit", 0, 0, np.zeros(0, np.uint32))
