@@ -274,6 +274,23 @@ __device__ __forceinline__ int warp_sum(int v) {
 // list (polygon.ml:673-692) into its private 544-bit row in shared memory; then for every
 // edge pixel the 32 lanes each weigh their row's 32-column window and the warp reduces.
 // Returns the opacity of pixel `lane` (undefined where edge bit is 0).
+// General (rare) path of the AA scan: this lane's super-sampled row with the 16-entry lists in local
+// memory, written into its 544-bit shared-memory row.  Out of line: it must not bloat the hot path.
+__device__ __noinline__ bool aa_rows_general(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand,
+                                             int winding, int yy, int lane, uint32_t* row, int wlo, int whi) {
+  for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
+  SinkMem sink; sink.wx0 = wlo; sink.nwords = AA_WORDS; sink.stride = 1; sink.S = row; sink.C = nullptr;
+  ScanState st;
+  scan_begin(st, 16 * yy - 32 + lane, true, wlo, whi);
+  for (int i = 0; i < n_cand; i++) {
+    const EdgeRec e = edges[idx ? idx[i] : i];
+    const int x0 = e.x0in * 16, x1 = e.x1in * 16;
+    scan_edge(st, x0, x1, e.ymin * 16, e.ymax * 16, e.g, e.dir, edge_side(x0, x1, wlo, whi), sink);
+  }
+  const bool ok = scan_finish(st, winding, sink);
+  __syncwarp();
+  return ok;
+}
 // Staged edge of the AA scan: scaled coordinates plus where it lies relative to the window.
 struct StagedEdge { int x0, x1, ymin, ymax; double g; int dir, side; };
 constexpr int STAGE_WORDS = sizeof(StagedEdge) / 4;
@@ -287,15 +304,13 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
   long long t0_ = clock64();
 #endif
   uint32_t* row = aa_bits + lane * AA_WORDS;
-  SinkMem sink;
-  sink.wx0 = 16 * xx0 - 32; sink.nwords = AA_WORDS; sink.stride = 1; sink.S = row; sink.C = nullptr;
-  const int wlo = sink.wx0, whi = sink.wx0 + 32 * AA_WORDS - 1;
+  const int wlo = 16 * xx0 - 32, whi = wlo + 32 * AA_WORDS - 1;
   // Fast path: the crossings of this lane's row stay in registers (a row of a 34-pixel window is
   // touched by one or two edges); if any lane needs more, the whole warp redoes the row with the
   // general lists in local memory.
   constexpr int FAST_X = 3;
   ScanStateT<FAST_X, true> fst;
-  SinkRow fsink; fsink.wx0 = wlo; fsink.nwords = AA_WORDS; fsink.S = row;
+  SinkRow fsink; fsink.wx0 = wlo; fsink.nwords = AA_WORDS; fsink.saddr = (uint32_t)__cvta_generic_to_shared(row);
 #pragma unroll
   for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
   scan_begin(fst, 16 * yy - 32 + lane, true, wlo, whi);
@@ -332,20 +347,7 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
 #endif
   ok = true;
   __syncwarp();
-  if (!fast) {
-    // general path (rare): redo the row with unbounded-ish lists into shared-memory bit-rows
-#pragma unroll
-    for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
-    ScanState st;
-    scan_begin(st, 16 * yy - 32 + lane, true, wlo, whi);
-    for (int i = 0; i < n_cand; i++) {
-      const EdgeRec e = edges[idx ? idx[i] : i];
-      const int x0 = e.x0in * 16, x1 = e.x1in * 16;
-      scan_edge(st, x0, x1, e.ymin * 16, e.ymax * 16, e.g, e.dir, edge_side(x0, x1, wlo, whi), sink);
-    }
-    ok = scan_finish(st, winding, sink);
-    __syncwarp();
-  }
+  if (!fast) ok = aa_rows_general(edges, idx, n_cand, winding, yy, lane, row, wlo, whi);
 #ifdef COH_PHASE_PROFILE
   long long t1_ = clock64();
   if (lane == 0) { atomicAdd(&g_phase_cycles[6], (unsigned long long)(t1_ - t0_)); atomicAdd(&g_phase_cycles[8], 1ull); atomicAdd(&g_phase_cycles[9], (unsigned long long)n_cand); atomicAdd(&g_phase_cycles[10], (unsigned long long)__popc(edge)); atomicAdd(&g_phase_cycles[11], fast ? 0ull : 1ull); }
@@ -388,6 +390,23 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
   return aa_opacity(mytot, volume);  // one division per lane, after the loop
 }
 
+// Shape (S) and coverage (C) words of one pixel row of one path object inside a 32-pixel window.
+// Crossings stay in registers (3 per list); a row with more takes the general lists.
+__device__ __noinline__ uint2 scan_row_word(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand,
+                                            int yy, int winding, int xx0, bool& ok) {
+  ScanStateT<3, true> st;
+  Sink32 sink; sink.wx0 = xx0; sink.S = 0u; sink.C = 0u;
+  scan_begin(st, yy, false, xx0, xx0 + 31);
+  for (int i = 0; i < n_cand; i++) {
+    const EdgeRec e = edges[idx[i]];
+    scan_edge(st, e.x0in, e.x1in, e.ymin, e.ymax, e.g, e.dir, edge_side(e.x0in, e.x1in, xx0, xx0 + 31), sink);
+  }
+  if (!scan_finish(st, winding, sink)) {
+    sink.S = 0u; sink.C = 0u;
+    if (!scan_row(edges, idx, n_cand, 1, yy, winding, false, xx0, xx0 + 31, sink)) ok = false;
+  }
+  return make_uint2(sink.S, sink.C);
+}
 // 32 bits of a bit-row starting at an arbitrary bit offset (zeros outside the row)
 __device__ __forceinline__ uint32_t conv_load_bits32(const uint32_t* __restrict__ row, int nw, int bitoff) {
   const int qw = bitoff >> 5, qb = bitoff & 31;
@@ -509,9 +528,10 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
           if (yy >= o.ry0 && yy <= o.ry1) {
             const int slot = o.row_base + yy - o.ry0;
             const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
-            Sink32 sink; sink.wx0 = xx0; sink.S = 0u; sink.C = 0u;
-            if (!scan_row(P.edges, P.rowedge_idx + a, b - a, 1, yy, o.winding, false, xx0, xx0 + 31, sink)) bad = true;
-            S = sink.S; C = sink.C;
+            bool ok = true;
+            const uint2 sc = scan_row_word(P.edges, P.rowedge_idx + a, b - a, yy, o.winding, xx0, ok);
+            if (!ok) bad = true;
+            S = sc.x; C = sc.y;
           }
         } else if (BRUSH && o.kind == K_CONV) {
           // Convolved (k, g): shape = bloat r r (shape g), minshape = erode r r (minshape g) (render.ml:536-555),

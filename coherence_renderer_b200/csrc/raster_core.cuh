@@ -245,49 +245,36 @@ COH_HD void winding_spans_impl(const CrossListT<CAP, REG>& L, int winding, bool 
     if (emit) {
       int b = whi;
       if (n > 0) {
-        int first = L.v[0] >> 1;
-        if (REG) {
-#pragma unroll
-          for (int j = 1; j < CAP; j++) { int pj = L.v[j] >> 1; if (j < n && pj < first) first = pj; }
-        } else {
-          for (int j = 1; j < n; j++) { int pj = L.v[j] >> 1; if (pj < first) first = pj; }
-        }
+        int first = L.get(0) >> 1;
+        for (int j = 1; j < n; j++) { int pj = L.get(j) >> 1; if (pj < first) first = pj; }
         b = aa ? pix_of_sub(first) : pix_of_sub(first + 16);
       }
       sink.span(wlo, b);
     }
   }
-  auto one = [&](int i) {
-    const int vi = REG ? L.v[i] : L.get(i);
+  // (register lists are read through get(): compare-select chains, loops stay rolled to keep the
+  // walker's code small enough for the instruction cache)
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const int vi = L.get(i);
     const int pi = vi >> 1;
     // rank / running winding count of crossing i in the (pos, index) order, and its successor
     int cnt = L.cnt_left, rank = L.n_left;
     int succ = 0x7FFFFFFF; bool has = false;
-    auto cmp = [&](int j) {
-      const int vj = L.v[j];
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      const int vj = L.get(j);
       const int pj = vj >> 1;
       const bool before_or_self = (pj < pi) || (pj == pi && j <= i);
       if (before_or_self) { cnt += (vj & 1) ? 1 : -1; rank += (j != i); }
       else { if (pj < succ) succ = pj; has = true; }
-    };
-    if (REG) {
-#pragma unroll
-      for (int j = 0; j < CAP; j++) if (j < n) cmp(j);
-    } else {
-      for (int j = 0; j < n; j++) cmp(j);
     }
-    if (!has && !L.has_right) return;  // the last crossing has no successor (polygon.ml:484, 458)
+    if (!has && !L.has_right) continue;  // the last crossing has no successor (polygon.ml:484, 458)
     const bool emit = winding == 0 ? (cnt != 0) : ((rank & 1) == 0);
-    if (!emit) return;
+    if (!emit) continue;
     const int a = aa ? pix_of_sub(pi) : pix_of_sub(pi - 16);
     const int b = has ? (aa ? pix_of_sub(succ) : pix_of_sub(succ + 16)) : whi;
     sink.span(a, b);
-  };
-  if (REG) {
-#pragma unroll
-    for (int i = 0; i < CAP; i++) if (i < n) one(i);
-  } else {
-    for (int i = 0; i < n; i++) one(i);
   }
 }
 template <class Sink>
@@ -422,12 +409,42 @@ struct SinkRegs {
     return m;
   }
 };
-// Multi-word row with inlined stores (the AA rows of the walker live in shared memory; keeping
-// this inline lets the compiler emit shared-memory stores instead of generic ones).
+// Multi-word row in SHARED memory (the AA rows of the walker), addressed by its 32-bit shared-window
+// address so that one out-of-line routine serves every call site with ld/st.shared (a generic
+// pointer would cost generic loads/stores, inlining it five times cost 465 instructions of I-cache).
+#if defined(__CUDACC__)
+__device__ __noinline__ void smem_row_put(uint32_t saddr, int nwords, int wx0, int a, int b) {
+  a -= wx0; b -= wx0;
+  const int nb = nwords * 32;
+  if (b < 0 || a >= nb) return;
+  if (a < 0) a = 0;
+  if (b > nb - 1) b = nb - 1;
+  if (a > b) return;
+  const int wa = a >> 5, wb = b >> 5;
+  const uint32_t ma = 0xFFFFFFFFu << (a & 31), mb = 0xFFFFFFFFu >> (31 - (b & 31));
+  uint32_t v;
+  if (wa == wb) {
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + 4 * wa));
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + 4 * wa), "r"(v | (ma & mb)));
+    return;
+  }
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + 4 * wa));
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + 4 * wa), "r"(v | ma));
+  for (int w = wa + 1; w < wb; w++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + 4 * w), "r"(0xFFFFFFFFu));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + 4 * wb));
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + 4 * wb), "r"(v | mb));
+}
 struct SinkRow {
   int wx0, nwords;
+  uint32_t saddr;  // shared-window address of the row
+  __device__ __forceinline__ void span(int a, int b) { smem_row_put(saddr, nwords, wx0, a, b); }
+  __device__ __forceinline__ void cover(int a, int b) { smem_row_put(saddr, nwords, wx0, a, b); }
+};
+#else
+struct SinkRow {  // host build of the same sink (tests/host_emul)
+  int wx0, nwords;
   uint32_t* S;
-  COH_HD void put(int a, int b) {
+  void put(int a, int b) {
     a -= wx0; b -= wx0;
     const int nb = nwords * 32;
     if (b < 0 || a >= nb) return;
@@ -441,9 +458,10 @@ struct SinkRow {
     for (int w = wa + 1; w < wb; w++) S[w] = 0xFFFFFFFFu;
     S[wb] |= mb;
   }
-  COH_HD void span(int a, int b) { put(a, b); }
-  COH_HD void cover(int a, int b) { put(a, b); }
+  void span(int a, int b) { put(a, b); }
+  void cover(int a, int b) { put(a, b); }
 };
+#endif
 // Multi-word rows in memory (export kernels, AA rows).  C may be null (AA needs only S).
 struct SinkMem {
   int wx0, nwords, stride;
