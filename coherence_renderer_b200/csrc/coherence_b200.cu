@@ -1074,7 +1074,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.u_init = ctx->use_u_init ? ctx->u_init : nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
   // persistent grid: exactly one resident wave
-  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells, WALK_WARPS));
+  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * WALK_SUB, WALK_WARPS));
   P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.n_cells = n_cells;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
@@ -1321,6 +1321,12 @@ int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out) {
 }
 void* coh_fb_device_ptr(coh_ctx* ctx) { return ctx->fb; }
 #ifdef COH_PHASE_PROFILE
+int coh_cell_cycles(coh_ctx* ctx, unsigned int* out, int n) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyFromSymbol(out, g_cell_cycles, sizeof(unsigned int) * n));
+  return 0;
+}
 int coh_phase_cycles(coh_ctx* ctx, unsigned long long* out8, int reset) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));

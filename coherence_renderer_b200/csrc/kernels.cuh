@@ -255,6 +255,7 @@ constexpr int CARRY_CAP = 8;
 // Optional phase timing (tools only; -DCOH_PHASE_PROFILE): cycles per phase summed over warps.
 #ifdef COH_PHASE_PROFILE
 __device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned int g_cell_cycles[1 << 20];
 #define PH_DECL long long ph_t = clock64(); long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
 #define PH_MARK(i) { long long t_ = clock64(); ph_acc[i] += t_ - ph_t; ph_t = t_; }
 #define PH_FLUSH() { if (lane == 0) { for (int i_ = 0; i_ < 6; i_++) atomicAdd(&g_phase_cycles[i_], (unsigned long long)ph_acc[i_]); } }
@@ -418,24 +419,32 @@ constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 3
 #endif
-constexpr int NC = 32 / CELL_H;          // candidate objects scan-converted per pass
-constexpr unsigned ROWMASK = (CELL_H >= 32) ? 0xFFFFFFFFu : ((1u << CELL_H) - 1u);
+// A cell list (32 px x CELL_H rows) is shared by CELL_H / WALK_H walker work items of WALK_H rows
+// each: the heaviest cell bounds the kernel's critical path, so the unit of work is kept small while
+// the binning stays coarse.
+#ifndef COH_WALK_H
+#define COH_WALK_H 4
+#endif
+constexpr int WALK_H = COH_WALK_H;       // rows per walker work item (power of two, divides CELL_H)
+constexpr int WALK_SUB = CELL_H / WALK_H;
+constexpr int NC = 32 / WALK_H;          // candidate objects scan-converted per pass
+constexpr unsigned ROWMASK = (WALK_H >= 32) ? 0xFFFFFFFFu : ((1u << WALK_H) - 1u);
 
 // One warp owns one cell: TILE_W = 32 pixel columns (lane = column when compositing) by
-// CELL_H rows.  Scan conversion runs lane-parallel over (candidate object, row) pairs; the
+// WALK_H rows.  Scan conversion runs lane-parallel over (candidate object, row) pairs; the
 // front-to-back composite then visits, object by object, only the rows where the object
 // still has pixels inside the covered-so-far complement `u` (one 32-bit word per row, held
 // by lane r and its NC-1 mirror lanes).
 // CARRY: the scene has fancy (gradient / radial) fills -> fill evaluation and the cross-tile carry
 // are compiled in.  BRUSH: the scene has brush strokes.  Plain polygon scenes get the small kernel.
 template <bool CARRY, bool BRUSH>
-__device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int lane,
+__device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int sub, const int lane,
                                           uint32_t* __restrict__ aa_bits, StagedEdge* __restrict__ stage,
                                           uint32_t (*__restrict__ acc_rows)[32],
                                           const int* __restrict__ s_prefix, const int volume) {
   const int tx0 = tile * TILE_W;
-  const int y0 = (P.cell_row0 + by) * CELL_H;
-  const int r_lane = lane % CELL_H, c_lane = lane / CELL_H;
+  const int y0 = (P.cell_row0 + by) * CELL_H + sub * WALK_H;
+  const int r_lane = lane % WALK_H, c_lane = lane / WALK_H;
   const int my_y = y0 + r_lane;                      // the row whose `u` this lane mirrors
   const bool row_in_band = my_y >= P.fr.band_y0 && my_y < P.fr.band_y1;
   const size_t my_slot = (size_t)(my_y - P.fr.band_y0) * P.fr.tiles_x + tile;  // carry slot of (row, tile)
@@ -460,13 +469,13 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   if (__ballot_sync(0xFFFFFFFFu, u != 0u) == 0u) { publish_done(); return; }
 
 #pragma unroll
-  for (int r = 0; r < CELL_H; r++) acc_rows[r][lane] = 0u;   // accumulator of the current nesting level
+  for (int r = 0; r < WALK_H; r++) acc_rows[r][lane] = 0u;   // accumulator of the current nesting level
   __syncwarp();
   int depth = 0;                       // open groups
   int hit_level = -1;                  // outermost open group that dissolves its sprite (PreTrans), or -1
   int open_grp[MAX_DEPTH];
   uint32_t stk_u[MAX_DEPTH];           // parents' `u` of my row
-  uint32_t stk_acc[MAX_DEPTH][CELL_H]; // parents' accumulators of my column (local memory; touched on push/pop only)
+  uint32_t stk_acc[MAX_DEPTH][WALK_H]; // parents' accumulators of my column (local memory; touched on push/pop only)
   bool bad = false;
 
   PH_DECL
@@ -482,7 +491,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     const int gflags = P.objs[g].flags;
     const uint32_t pu = stk_u[depth - 1];
 #pragma unroll 1
-    for (int r = 0; r < CELL_H; r++) {
+    for (int r = 0; r < WALK_H; r++) {
       uint32_t sp = acc_rows[r][lane];
       const uint32_t pa = stk_acc[depth - 1][r];
       if (pt >= 0) sp = px_dissolve(sp, pt);
@@ -497,7 +506,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   };
   auto push_group = [&](int g) {
 #pragma unroll 1
-    for (int r = 0; r < CELL_H; r++) { stk_acc[depth][r] = acc_rows[r][lane]; acc_rows[r][lane] = 0u; }
+    for (int r = 0; r < WALK_H; r++) { stk_acc[depth][r] = acc_rows[r][lane]; acc_rows[r][lane] = 0u; }
     stk_u[depth] = u;
     open_grp[depth] = g;
     // A group composited with PreTrans (v < 1) gives pixels back to its parent's `u` when it
@@ -560,9 +569,9 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     if (hits == 0u && !closing) continue;
     // ---- sequential front-to-back composite of the candidates that still show ----
     for (int cc = 0; cc < NC; cc++) {
-      unsigned rows = (hits >> (cc * CELL_H)) & ROWMASK;
+      unsigned rows = (hits >> (cc * WALK_H)) & ROWMASK;
       if (rows == 0u && !(closing && cc == 0)) continue;
-      const int ik = closing ? 0 : __shfl_sync(0xFFFFFFFFu, idx, cc * CELL_H);
+      const int ik = closing ? 0 : __shfl_sync(0xFFFFFFFFu, idx, cc * WALK_H);
       const ObjRec& o = P.objs[ik];
       PH_MARK(0)
       // group transitions: close groups that do not enclose this object, open the ones that do
@@ -578,8 +587,8 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
       while (rows) {
         const int r = __ffs((int)rows) - 1;
         rows &= rows - 1;
-        const uint32_t Sk = __shfl_sync(0xFFFFFFFFu, S, cc * CELL_H + r);
-        const uint32_t Ck = __shfl_sync(0xFFFFFFFFu, C, cc * CELL_H + r);
+        const uint32_t Sk = __shfl_sync(0xFFFFFFFFu, S, cc * WALK_H + r);
+        const uint32_t Ck = __shfl_sync(0xFFFFFFFFu, C, cc * WALK_H + r);
         const uint32_t ur = __shfl_sync(0xFFFFFFFFu, u, r);
         const uint32_t vis = Sk & ur;
         if (vis == 0u) continue;
@@ -667,7 +676,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   publish_done();
   if (bad) *P.error_flag = 1;
 #pragma unroll 1
-  for (int r = 0; r < CELL_H; r++) {
+  for (int r = 0; r < WALK_H; r++) {
     const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);
     if ((uu >> lane) & 1u) {
       const uint32_t acc = acc_rows[r][lane];
@@ -684,7 +693,7 @@ template <bool CARRY, bool BRUSH>
 __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
-  __shared__ uint32_t s_acc[WALK_WARPS][CELL_H][32];
+  __shared__ uint32_t s_acc[WALK_WARPS][WALK_H][32];
   __shared__ StagedEdge s_stage[WALK_WARPS][32];
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
   __syncthreads();
@@ -694,10 +703,17 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
     int q = 0;
     if (lane == 0) q = atomicAdd(P.queue, 1);
     q = __shfl_sync(0xFFFFFFFFu, q, 0);
-    if (q >= P.n_cells) break;
-    const int cell = P.order ? P.order[q] : q;
-    walk_cell<CARRY, BRUSH>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    if (q >= P.n_cells * WALK_SUB) break;
+    const int cell = P.order ? P.order[q / WALK_SUB] : q / WALK_SUB;
+    const int sub = q % WALK_SUB;
+#ifdef COH_PHASE_PROFILE
+    long long tc0_ = clock64();
+#endif
+    walk_cell<CARRY, BRUSH>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
     __syncwarp();
+#ifdef COH_PHASE_PROFILE
+    if (lane == 0 && cell < (1 << 20)) g_cell_cycles[cell] = (unsigned int)(clock64() - tc0_);
+#endif
   }
 }
 

@@ -19,3 +19,9 @@ print("total warp-cycles/frame (M):", tot / N / 1e6)
 print("  AA scaled scan %.1f M, AA pixel loop %.1f M" % (buf[6]/N/1e6, buf[7]/N/1e6))
 print("  AA calls/frame %.0f, candidates/call %.2f, edge px/call %.2f, cycles/call scan %.0f, fallbacks/frame %.0f" % (buf[8]/N, buf[9]/max(buf[8],1), buf[10]/max(buf[8],1), buf[6]/max(buf[8],1), buf[11]/N))
 print("  per call (cumulative cycles): staged-load %.0f, edge loop %.0f, finish %.0f" % (buf[12]/max(buf[8],1), buf[13]/max(buf[8],1), buf[14]/max(buf[8],1)))
+import numpy as np
+ncell = 120 * 135
+cc = np.zeros(ncell, dtype=np.uint32)
+abi.lib().coh_cell_cycles(ctx._h, cc.ctypes.data_as(C.POINTER(C.c_uint)), ncell)
+cs = np.sort(cc)[::-1]
+print("per-cell cycles: max %d, top10 %s, p99 %d, median %d, sum %.1f M" % (cs[0], cs[:10].tolist(), cs[ncell // 100], cs[ncell // 2], cc.sum() / 1e6))
