@@ -162,7 +162,7 @@ int coh_shutdown(coh_ctx* ctx) {
   if (ctx->own_fb) cudaFree(ctx->fb);
   cudaFree(ctx->u_out); cudaFree(ctx->u_init);
   cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
-  cudaFree(ctx->queue); cudaFree(ctx->order_hist); cudaFree(ctx->cell_order); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
+  cudaFree(ctx->order_hist); cudaFree(ctx->cell_order); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -1013,14 +1013,13 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
     ctx->n_cells_cap = n_cells;
   }
   if (!ctx->queue) {
-    CK(cudaMalloc(&ctx->queue, sizeof(int)));
-    CK(cudaMalloc(&ctx->order_hist, sizeof(int) * 2 * ORDER_BINS));
+    CK(cudaMalloc(&ctx->order_hist, sizeof(int) * (2 * ORDER_BINS + 1)));  // histogram, cursors, work-queue head
+    ctx->queue = ctx->order_hist + 2 * ORDER_BINS;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->n_sms = prop.multiProcessorCount;
   }
   const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
-  CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * 2 * ORDER_BINS, ctx->stream));
-  CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * (2 * ORDER_BINS + 1), ctx->stream));
   if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   // K1: count, scan, fill.  Small scenes: warp per cell scanning all leaves (lists come out sorted,
   // no atomics).  Large scenes: warp per leaf over the cells it covers + per-cell sort.
@@ -1049,8 +1048,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   if (!big) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
-    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
-    if (ordered) { k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED(); }
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr); LAUNCHED();
     k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   } else {
     const int obj_blocks = cdiv(s->n_leaves * 32, 256);

@@ -20,6 +20,8 @@
 
 namespace coh {
 
+constexpr int ORDER_BINS = 256;  // bins of the heavy-first cell order (counting sort by list length)
+
 // ------------------------------------------------------------------------------------
 __global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +86,6 @@ __global__ void k_brush_rows(const int2* __restrict__ points, const int* __restr
 // The same kernels also build the walker's work order: cells sorted by descending list length
 // (256-bin counting sort: histogram in the count pass, scatter in the fill pass), so that the
 // persistent walker warps take the heavy cells first and the tail of the launch is light.
-constexpr int ORDER_BINS = 256;
 template <bool FILL>
 __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/, const int* __restrict__ leaves, int n_leaves, Frame fr,
                       int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
@@ -188,9 +189,19 @@ __global__ void __launch_bounds__(128) k_bin_sort(const int* __restrict__ offset
 
 // Exclusive scan of n ints by a single block of 1024 threads: each thread sums a contiguous
 // chunk, one block-wide scan of the 1024 partial sums, then each thread rescans its chunk.
-__global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
+__global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ hist = nullptr) {
   __shared__ int warp_sums[32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (hist && wid == 31) {  // the heavy-first order's 256-bin histogram is scanned by the last warp on the side
+    int carry = 0;
+    for (int base = 0; base < ORDER_BINS; base += 32) {
+      int v = hist[base + lane], x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += u; }
+      hist[base + lane] = carry + x - v;
+      carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+    }
+  }
   const int chunk = (n + blockDim.x - 1) / blockDim.x;
   const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
   int sum = 0;
@@ -468,6 +479,31 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   };
   if (__ballot_sync(0xFFFFFFFFu, u != 0u) == 0u) { publish_done(); return; }
 
+  const int cell = by * P.fr.tiles_x + tile;
+  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+  // Fast path: the only object reaching this item is an opaque primitive that covers all of it
+  // (typically the background rectangle): the rows are just that colour.
+  if (it1 - it0 == 1) {
+    const ObjRec& o = P.objs[P.cell_items[it0]];
+    bool simple = o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && P.objs[o.anc[0]].pretrans < 0;
+    if (simple) {
+      const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
+      const uint32_t m = (yy >= o.prim[1] && yy <= o.prim[3]) ? interval_mask32(xx0, o.prim[0], o.prim[2]) : 0u;
+      if (__all_sync(0xFFFFFFFFu, (u & ~m) == 0u)) {
+        const uint32_t c0 = o.fill.c0;
+        const bool scene_root = (P.objs[o.anc[0]].flags & OF_ROOT_SCENE) != 0;
+        if (scene_root && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = 0u;
+        publish_done();
+#pragma unroll 1
+        for (int r = 0; r < WALK_H; r++) {
+          const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u, r);
+          if ((uu >> lane) & 1u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = c0;
+        }
+        return;
+      }
+    }
+  }
+
 #pragma unroll
   for (int r = 0; r < WALK_H; r++) acc_rows[r][lane] = 0u;   // accumulator of the current nesting level
   __syncwarp();
@@ -479,8 +515,6 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   bool bad = false;
 
   PH_DECL
-  const int cell = by * P.fr.tiles_x + tile;
-  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
 
   auto pop_group = [&]() {
     // close the innermost group: its accumulated sprite goes under the parent accumulator
