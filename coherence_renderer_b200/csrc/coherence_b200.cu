@@ -102,6 +102,10 @@ static std::string g_init_err;
     }                                                                                         \
   } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+// Device memory comes from the stream-ordered pool (cudaMallocAsync): allocation and release are
+// ordered on the context's stream and cost microseconds instead of a device-wide synchronisation.
+#define DMALLOC(ptr, bytes) cudaMallocAsync((void**)(ptr), (bytes), ctx->stream)
+#define DFREE(ptr) do { if (ptr) cudaFreeAsync((void*)(ptr), ctx->stream); } while (0)
 #define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -141,11 +145,19 @@ int coh_init(int device, coh_ctx** out) {
   auto bail = [&](const char* what, cudaError_t err) { g_init_err = std::string(what) + ": " + cudaGetErrorString(err); delete ctx; return 1; };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // keep freed blocks in the pool instead of returning them to the driver
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   AATable t; build_aa_table(t);
-  if ((e = cudaMalloc(&ctx->d_aa, sizeof(AATable))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMemcpy(ctx->d_aa, &t, sizeof t, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
-  if ((e = cudaMalloc(&ctx->d_error, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
-  cudaMemset(ctx->d_error, 0, sizeof(int));
+  if ((e = DMALLOC(&ctx->d_aa, sizeof(AATable))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpyAsync(ctx->d_aa, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail("cudaMemcpy", e);
+  if ((e = DMALLOC(&ctx->d_error, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("cudaStreamSynchronize", e);
   if ((e = cudaMallocHost(&ctx->h_error, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&ctx->h_total, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
   *out = ctx;
@@ -158,11 +170,12 @@ int coh_shutdown(coh_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   coh_cache_clear(ctx);
-  cudaFree(ctx->d_aa); cudaFree(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
-  if (ctx->own_fb) cudaFree(ctx->fb);
-  cudaFree(ctx->u_out); cudaFree(ctx->u_init);
-  cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_items);
-  cudaFree(ctx->order_hist); cudaFree(ctx->cell_order); cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
+  DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
+  if (ctx->own_fb) DFREE(ctx->fb);
+  DFREE(ctx->u_out); DFREE(ctx->u_init);
+  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items);
+  DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -250,14 +263,14 @@ uint32_t coh_rgba8_of_colour(int32_t c) {
 // ---------------------------------------------------------------------------------------
 // Shapes
 // ---------------------------------------------------------------------------------------
-static void free_shape(DevShape* s) {
+static void free_shape(coh_ctx* ctx, DevShape* s) {
   if (!s) return;
-  cudaFree(s->row_ptr); cudaFree(s->spans);
+  DFREE(s->row_ptr); DFREE(s->spans);
   delete s;
 }
 int coh_shape_free(coh_ctx* ctx, coh_shape_t h) {
   CK(cudaSetDevice(ctx->device));
-  free_shape((DevShape*)h);
+  free_shape(ctx, (DevShape*)h);
   return 0;
 }
 
@@ -266,9 +279,9 @@ static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_row
   *out = 0;
   if (n_rows <= 0 || nw <= 0) return 0;
   int* counts = nullptr; int* ptr = nullptr; unsigned long long* d_card = nullptr;
-  CK(cudaMalloc(&counts, sizeof(int) * n_rows));
-  CK(cudaMalloc(&ptr, sizeof(int) * (n_rows + 1)));
-  CK(cudaMalloc(&d_card, sizeof(unsigned long long)));
+  CK(DMALLOC(&counts, sizeof(int) * n_rows));
+  CK(DMALLOC(&ptr, sizeof(int) * (n_rows + 1)));
+  CK(DMALLOC(&d_card, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(d_card, 0, sizeof(unsigned long long), ctx->stream));
   k_count_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, counts, d_card); LAUNCHED();
   k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(counts, ptr, n_rows); LAUNCHED();
@@ -277,25 +290,25 @@ static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_row
   CK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int) * (n_rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&card, d_card, sizeof card, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(counts); cudaFree(d_card);
+  DFREE(counts); DFREE(d_card);
   int total = h_ptr[n_rows];
-  if (total == 0) { cudaFree(ptr); return 0; }
+  if (total == 0) { DFREE(ptr); return 0; }
   // trim empty rows at both ends so that y0 / n_rows are tight
   int first = 0, last = n_rows - 1;
   while (h_ptr[first + 1] == h_ptr[first]) first++;
   while (h_ptr[last + 1] == h_ptr[last]) last--;
   DevShape* s = new DevShape();
   s->n_spans = total; s->card = (long long)card;
-  CK(cudaMalloc(&s->spans, sizeof(int2) * total));
+  CK(DMALLOC(&s->spans, sizeof(int2) * total));
   k_fill_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, wx0, ptr, s->spans); LAUNCHED();
   s->y0 = y0 + first; s->n_rows = last - first + 1;
-  CK(cudaMalloc(&s->row_ptr, sizeof(int) * (s->n_rows + 1)));
+  CK(DMALLOC(&s->row_ptr, sizeof(int) * (s->n_rows + 1)));
   CK(cudaMemcpyAsync(s->row_ptr, ptr + first, sizeof(int) * (s->n_rows + 1), cudaMemcpyDeviceToDevice, ctx->stream));
   // bounds: x extremes need the spans; take them from a host copy (export path, not hot)
   std::vector<int2> h_spans(total);
   CK(cudaMemcpyAsync(h_spans.data(), s->spans, sizeof(int2) * total, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(ptr);
+  DFREE(ptr);
   s->by0 = s->y0; s->by1 = s->y0 + s->n_rows - 1; s->bx0 = INT32_MAX; s->bx1 = INT32_MIN;
   for (int r = first; r <= last; r++) {
     if (h_ptr[r + 1] > h_ptr[r]) {
@@ -310,7 +323,7 @@ static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_row
 // span set -> freshly allocated bit-frame covering rows [y0, y0+n_rows) and words from pixel wx0
 static int bits_from_shape(coh_ctx* ctx, const DevShape* s, int y0, int n_rows, int wx0, int nw, uint32_t** out) {
   uint32_t* bits = nullptr;
-  CK(cudaMalloc(&bits, sizeof(uint32_t) * (size_t)n_rows * nw));
+  CK(DMALLOC(&bits, sizeof(uint32_t) * (size_t)n_rows * nw));
   CK(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)n_rows * nw, ctx->stream));
   if (s && s->n_spans > 0) {
     k_spans_to_bits<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, s->y0, s->n_rows, y0, n_rows, wx0, nw, bits);
@@ -360,8 +373,8 @@ int coh_shape_import(coh_ctx* ctx, const int32_t* flat, int64_t n, coh_shape_t* 
   for (int r = 0; r < s->n_rows; r++) ptr[r + 1] += ptr[r];
   s->n_spans = (int)spans.size(); s->card = card;
   s->bx0 = bx0; s->bx1 = bx1; s->by0 = ys.front(); s->by1 = ys.back();
-  CK(cudaMalloc(&s->row_ptr, sizeof(int) * ptr.size()));
-  CK(cudaMalloc(&s->spans, sizeof(int2) * spans.size()));
+  CK(DMALLOC(&s->row_ptr, sizeof(int) * ptr.size()));
+  CK(DMALLOC(&s->spans, sizeof(int2) * spans.size()));
   CK(cudaMemcpyAsync(s->row_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(s->spans, spans.data(), sizeof(int2) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -435,7 +448,7 @@ static int shape_binop(coh_ctx* ctx, coh_shape_t ha, coh_shape_t hb, int op, coh
   size_t n = (size_t)n_rows * nw;
   k_bitop<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ba, bb, ba, n, op); LAUNCHED();
   int rc = shape_from_bits(ctx, ba, y0, n_rows, wx0, nw, out);
-  cudaFree(ba); cudaFree(bb);
+  DFREE(ba); DFREE(bb);
   return rc;
 }
 int coh_shape_union(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, coh_shape_t* out) { return shape_binop(ctx, a, b, 0, out); }
@@ -449,8 +462,8 @@ int coh_shape_translate(coh_ctx* ctx, coh_shape_t h, int32_t dx, int32_t dy, coh
   DevShape* s = (DevShape*)h;
   DevShape* t = new DevShape(*s);
   t->y0 += dy; t->bx0 += dx; t->bx1 += dx; t->by0 += dy; t->by1 += dy;
-  CK(cudaMalloc(&t->row_ptr, sizeof(int) * (s->n_rows + 1)));
-  CK(cudaMalloc(&t->spans, sizeof(int2) * s->n_spans));
+  CK(DMALLOC(&t->row_ptr, sizeof(int) * (s->n_rows + 1)));
+  CK(DMALLOC(&t->spans, sizeof(int2) * s->n_spans));
   CK(cudaMemcpyAsync(t->row_ptr, s->row_ptr, sizeof(int) * (s->n_rows + 1), cudaMemcpyDeviceToDevice, ctx->stream));
   k_translate_spans<<<cdiv(s->n_spans, 256), 256, 0, ctx->stream>>>(s->spans, t->spans, s->n_spans, dx); LAUNCHED();
   *out = (coh_shape_t)t;
@@ -463,24 +476,24 @@ static int bloat_impl(coh_ctx* ctx, const DevShape* s, int x0, int y0, int x1, i
   int wx0 = floordiv(fx0, 32) * 32, nw = (fx1 - wx0) / 32 + 1, n_rows = fy1 - fy0 + 1;
   uint32_t *in = nullptr, *tmp = nullptr;
   if (bits_from_shape(ctx, s, fy0, n_rows, wx0, nw, &in)) return 1;
-  CK(cudaMalloc(&tmp, sizeof(uint32_t) * (size_t)n_rows * nw));
+  CK(DMALLOC(&tmp, sizeof(uint32_t) * (size_t)n_rows * nw));
   size_t nwords = (size_t)n_rows * nw;
   if (complement_in_box) {
     // erode (sprite.ml:1867-1877): inverse = enclosing - shp, bloated, then shp - bloated
     uint32_t* box = nullptr;
-    CK(cudaMalloc(&box, sizeof(uint32_t) * nwords));
+    CK(DMALLOC(&box, sizeof(uint32_t) * nwords));
     dim3 g(cdiv(nw, 128), n_rows);
     k_fill_box_bits<<<g, 128, 0, ctx->stream>>>(box, n_rows, nw, wx0, fy0, fx0, fy0, fx1, fy1); LAUNCHED();
     k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(box, in, box, nwords, 1); LAUNCHED();  // inverse
     k_dilate<<<g, 128, 0, ctx->stream>>>(box, tmp, n_rows, nw, m, n); LAUNCHED();
     k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(in, tmp, tmp, nwords, 1); LAUNCHED();    // shp - bloated
-    cudaFree(box);
+    DFREE(box);
   } else {
     dim3 g(cdiv(nw, 128), n_rows);
     k_dilate<<<g, 128, 0, ctx->stream>>>(in, tmp, n_rows, nw, m, n); LAUNCHED();
   }
   int rc = shape_from_bits(ctx, tmp, fy0, n_rows, wx0, nw, out);
-  cudaFree(in); cudaFree(tmp);
+  DFREE(in); DFREE(tmp);
   return rc;
 }
 int coh_shape_bloat(coh_ctx* ctx, coh_shape_t h, int32_t m, int32_t n, coh_shape_t* out) {
@@ -526,14 +539,14 @@ static void shape_pixel_box(const EdgeBox& b, int& px0, int& py0, int& px1, int&
 }
 static int upload_edges(coh_ctx* ctx, const int32_t* edges, int n, EdgeRec** out) {
   int4* raw = nullptr;
-  CK(cudaMalloc(&raw, sizeof(int4) * std::max(n, 1)));
-  CK(cudaMalloc(out, sizeof(EdgeRec) * std::max(n, 1)));
+  CK(DMALLOC(&raw, sizeof(int4) * std::max(n, 1)));
+  CK(DMALLOC(out, sizeof(EdgeRec) * std::max(n, 1)));
   if (n > 0) {
     CK(cudaMemcpyAsync(raw, edges, sizeof(int4) * n, cudaMemcpyHostToDevice, ctx->stream));
     k_prep_edges<<<cdiv(n, 256), 256, 0, ctx->stream>>>(raw, *out, n); LAUNCHED();
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(raw);
+  DFREE(raw);
   return 0;
 }
 static int check_error_flag(coh_ctx* ctx, const char* what) {
@@ -553,7 +566,7 @@ static int shapes_from_device_edges(coh_ctx* ctx, const EdgeRec* d_edges, int n_
   int wx0 = floordiv(px0, 32) * 32, nw = (px1 - wx0) / 32 + 1, n_rows = py1 - py0 + 1;
   size_t nwords = (size_t)n_rows * nw;
   uint32_t *S = nullptr, *C = nullptr;
-  CK(cudaMalloc(&S, sizeof(uint32_t) * nwords)); CK(cudaMalloc(&C, sizeof(uint32_t) * nwords));
+  CK(DMALLOC(&S, sizeof(uint32_t) * nwords)); CK(DMALLOC(&C, sizeof(uint32_t) * nwords));
   CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
   CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
   k_scan_rows<<<dim3(cdiv(n_rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
@@ -561,7 +574,7 @@ static int shapes_from_device_edges(coh_ctx* ctx, const EdgeRec* d_edges, int n_
   if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
   if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
   if (!rc) rc = shape_from_bits(ctx, C, py0, n_rows, wx0, nw, minshape);
-  cudaFree(S); cudaFree(C);
+  DFREE(S); DFREE(C);
   return rc;
 }
 int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
@@ -575,7 +588,7 @@ int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_
   EdgeRec* d_edges = nullptr;
   if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
   int rc = shapes_from_device_edges(ctx, d_edges, n_edges, winding, px0, py0, px1, py1, shape, minshape, "coh_shapeminshape_of_edgelist");
-  cudaFree(d_edges);
+  DFREE(d_edges);
   return rc;
 }
 
@@ -587,12 +600,12 @@ static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges
   if (bits_from_shape(ctx, s, s->y0, s->n_rows, wx0, nw, &Q)) return 1;
   EdgeRec* d_edges = nullptr;
   if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
-  CK(cudaMalloc(dense, (size_t)s->n_rows * nw * 32));
+  CK(DMALLOC(dense, (size_t)s->n_rows * nw * 32));
   CK(cudaMemsetAsync(*dense, 0, (size_t)s->n_rows * nw * 32, ctx->stream));
   dim3 g(cdiv(nw, 8), s->n_rows);
   k_aa_rows<<<g, 256, 0, ctx->stream>>>(d_edges, n_edges, winding, Q, s->y0, s->n_rows, wx0, nw, ctx->d_aa, *dense, ctx->d_error); LAUNCHED();
   int rc = check_error_flag(ctx, "coh_polygon_opacity");
-  cudaFree(Q); cudaFree(d_edges);
+  DFREE(Q); DFREE(d_edges);
   *wx0_out = wx0; *nw_out = nw;
   return rc;
 }
@@ -611,7 +624,7 @@ int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int
   std::vector<uint8_t> h((size_t)s->n_rows * nw * 32);
   CK(cudaMemcpyAsync(h.data(), dense, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dense);
+  DFREE(dense);
   int64_t k = 0;
   for (int r = 0; r < s->n_rows; r++)
     for (int q = ptr[r]; q < ptr[r + 1]; q++)
@@ -659,7 +672,7 @@ static int conv_taps(coh_ctx* ctx, int kind, int r, int** d_taps, int* total) {
     int v = (int)((double)(4 * r * r) * (exp(-(xr * xr + yr * yr)) / 2.) + 0.5);
     taps.push_back(v); *total += v;
   }
-  CK(cudaMalloc(d_taps, sizeof(int) * taps.size()));
+  CK(DMALLOC(d_taps, sizeof(int) * taps.size()));
   CK(cudaMemcpyAsync(*d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -690,9 +703,9 @@ int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_
   uint32_t *A = nullptr, *X = nullptr, *d_in = nullptr, *d_out = nullptr; long long* d_off = nullptr; int* d_taps = nullptr; int total = 0;
   std::vector<long long> off;
   if (shape_pixel_offsets(ctx, s, off)) return 1;
-  CK(cudaMalloc(&A, 4 * npx)); CK(cudaMalloc(&X, 4 * npx));
+  CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx));
   CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
-  CK(cudaMalloc(&d_in, 4 * (size_t)std::max<long long>(s->card, 1))); CK(cudaMalloc(&d_off, sizeof(long long) * off.size()));
+  CK(DMALLOC(&d_in, 4 * (size_t)std::max<long long>(s->card, 1))); CK(DMALLOC(&d_off, sizeof(long long) * off.size()));
   CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
   k_scatter_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, s->y0 - y0, x0, w, d_in, A); LAUNCHED();
@@ -704,13 +717,13 @@ int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_
   std::vector<long long> roff;
   if (shape_pixel_offsets(ctx, rs, roff)) return 1;
   long long* d_roff = nullptr;
-  CK(cudaMalloc(&d_roff, sizeof(long long) * roff.size())); CK(cudaMalloc(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
+  CK(DMALLOC(&d_roff, sizeof(long long) * roff.size())); CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
   CK(cudaMemcpyAsync(d_roff, roff.data(), sizeof(long long) * roff.size(), cudaMemcpyHostToDevice, ctx->stream));
   // k_gather_spans indexes dense rows from the shape's first row: pass the canvas rows starting at R's first row
   k_gather_spans<uint32_t><<<cdiv(rs->n_rows, 128), 128, 0, ctx->stream>>>(rs->row_ptr, rs->spans, d_roff, rs->n_rows, x0, w, A + (size_t)(rs->y0 - y0) * w, d_out); LAUNCHED();
   CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)rs->card, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(A); cudaFree(X); cudaFree(d_in); cudaFree(d_out); cudaFree(d_off); cudaFree(d_roff); cudaFree(d_taps);
+  DFREE(A); DFREE(X); DFREE(d_in); DFREE(d_out); DFREE(d_off); DFREE(d_roff); DFREE(d_taps);
   *out_shape = R; *n_out = rs->card;
   return 0;
 }
@@ -722,8 +735,8 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   CK(cudaSetDevice(ctx->device));
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
-  cudaFree(s->objs); cudaFree(s->leaves); cudaFree(s->leaf_box); cudaFree(s->edges); cudaFree(s->points); cudaFree(s->stamps);
-  cudaFree(s->rowedge_ptr); cudaFree(s->rowedge_idx); cudaFree(s->brush_ranges); cudaFree(s->conv_bits); cudaFree(s->conv_px);
+  DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
+  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px);
   delete s;
   return 0;
 }
@@ -881,51 +894,51 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH || o.kind == K_CONV) s->has_brush = true;
   }
-  CK(cudaMalloc(&s->objs, sizeof(ObjRec) * recs.size()));
+  CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
+  CK(DMALLOC(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
   if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaves, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
   std::vector<int4> boxes(leaves.size());
   for (size_t i = 0; i < leaves.size(); i++) { const ObjRec& o = recs[leaves[i]]; boxes[i] = make_int4(o.bx0, o.by0, o.bx1, o.by1); }
-  CK(cudaMalloc(&s->leaf_box, sizeof(int4) * std::max<size_t>(leaves.size(), 1)));
+  CK(DMALLOC(&s->leaf_box, sizeof(int4) * std::max<size_t>(leaves.size(), 1)));
   if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaf_box, boxes.data(), sizeof(int4) * boxes.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
-  CK(cudaMalloc(&s->points, sizeof(int2) * std::max(n_points, 1)));
+  CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
   if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&s->stamps, std::max<size_t>(stamps.size(), 1)));
+  CK(DMALLOC(&s->stamps, std::max<size_t>(stamps.size(), 1)));
   if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
   // K1 edge binning: count -> scan -> fill
   {
     int* d_edge_obj = nullptr; int* d_counts = nullptr;
     size_t slots = (size_t)std::max<long long>(total_rows, 1);
-    CK(cudaMalloc(&d_edge_obj, sizeof(int) * edge_obj.size()));
+    CK(DMALLOC(&d_edge_obj, sizeof(int) * edge_obj.size()));
     CK(cudaMemcpyAsync(d_edge_obj, edge_obj.data(), sizeof(int) * edge_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMalloc(&d_counts, sizeof(int) * slots));
-    CK(cudaMalloc(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
+    CK(DMALLOC(&d_counts, sizeof(int) * slots));
+    CK(DMALLOC(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
     if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
     k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, s->rowedge_ptr, (int)slots); LAUNCHED();
     int total = 0;
     CK(cudaMemcpyAsync(&total, s->rowedge_ptr + slots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMalloc(&s->rowedge_idx, sizeof(int) * (size_t)std::max(total, 1)));
+    CK(DMALLOC(&s->rowedge_idx, sizeof(int) * (size_t)std::max(total, 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
     if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_edge_obj); cudaFree(d_counts);
+    DFREE(d_edge_obj); DFREE(d_counts);
   }
   // Convolved objects (render.ml:1023-1052): AA-rasterise the whole (twice bloated) box of the child,
   // X pass, Y pass; keep the shape / minshape bit-rows and the convolved canvas resident.
   if (!conv_list.empty()) {
-    CK(cudaMalloc(&s->conv_bits, sizeof(uint32_t) * conv_words));
-    CK(cudaMalloc(&s->conv_px, sizeof(uint32_t) * conv_pixels));
+    CK(DMALLOC(&s->conv_bits, sizeof(uint32_t) * conv_words));
+    CK(DMALLOC(&s->conv_px, sizeof(uint32_t) * conv_pixels));
     for (const ConvItem& ci : conv_list) {
       const ObjRec& o = recs[ci.rec];
       const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;
       const size_t nwords = (size_t)nw * h, npx = (size_t)w * h;
       uint32_t *S = nullptr, *C = nullptr, *T = nullptr, *Q = nullptr, *A = nullptr, *X = nullptr; uint8_t* op = nullptr; int* d_taps = nullptr;
-      CK(cudaMalloc(&S, 4 * nwords)); CK(cudaMalloc(&C, 4 * nwords)); CK(cudaMalloc(&T, 4 * nwords)); CK(cudaMalloc(&Q, 4 * nwords));
-      CK(cudaMalloc(&A, 4 * npx)); CK(cudaMalloc(&X, 4 * npx)); CK(cudaMalloc(&op, npx));
+      CK(DMALLOC(&S, 4 * nwords)); CK(DMALLOC(&C, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&Q, 4 * nwords));
+      CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx)); CK(DMALLOC(&op, npx));
       CK(cudaMemsetAsync(S, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(C, 0, 4 * nwords, ctx->stream));
       CK(cudaMemsetAsync(op, 0, npx, ctx->stream));
       const EdgeRec* ed = s->edges + o.first;
@@ -948,26 +961,26 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           int v = (int)((double)(4 * ci.r * ci.r) * gg + 0.5);
           taps.push_back(v); total += v;
         }
-        CK(cudaMalloc(&d_taps, sizeof(int) * taps.size()));
+        CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
         CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
       }
       dim3 gp(cdiv(w, 128), h);
       k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, ci.r, ci.kind, d_taps, total, 0); LAUNCHED();
       k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, s->conv_px + o.cv_px, w, h, ci.r, ci.kind, d_taps, total, 1); LAUNCHED();
       if (check_error_flag(ctx, "coh_scene_create (Convolved object)")) return 1;
-      cudaFree(S); cudaFree(C); cudaFree(T); cudaFree(Q); cudaFree(A); cudaFree(X); cudaFree(op); cudaFree(d_taps);
+      DFREE(S); DFREE(C); DFREE(T); DFREE(Q); DFREE(A); DFREE(X); DFREE(op); DFREE(d_taps);
     }
   }
   if (total_brush_rows > 0) {
     int* d_point_obj = nullptr;
-    CK(cudaMalloc(&d_point_obj, sizeof(int) * point_obj.size()));
+    CK(DMALLOC(&d_point_obj, sizeof(int) * point_obj.size()));
     CK(cudaMemcpyAsync(d_point_obj, point_obj.data(), sizeof(int) * point_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMalloc(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
+    CK(DMALLOC(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
     std::vector<int2> init((size_t)total_brush_rows, make_int2(INT32_MAX, -1));
     CK(cudaMemcpyAsync(s->brush_ranges, init.data(), sizeof(int2) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
     k_brush_rows<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_point_obj);
+    DFREE(d_point_obj);
   }
   *out = (coh_scene_t)s;
   return 0;
@@ -978,7 +991,7 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8) {
   if (!ctx->fr.W) FAIL("coh_fb_attach: call coh_fb_configure first");
   if (drain_timing(ctx)) return 1;
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->own_fb) cudaFree(ctx->fb);
+  if (ctx->own_fb) DFREE(ctx->fb);
   ctx->fb = (uint32_t*)device_rgba8; ctx->own_fb = false;
   return 0;
 }
@@ -987,11 +1000,11 @@ int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y
   if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
   if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
   if (width != ctx->fr.W || height != ctx->fr.H) {
-    if (ctx->own_fb) cudaFree(ctx->fb);
-    cudaFree(ctx->u_out); cudaFree(ctx->u_init); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->u_init = nullptr; ctx->own_fb = true;
-    CK(cudaMalloc(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
+    if (ctx->own_fb) DFREE(ctx->fb);
+    DFREE(ctx->u_out); DFREE(ctx->u_init); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->u_init = nullptr; ctx->own_fb = true;
+    CK(DMALLOC(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
     CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
-    CK(cudaMalloc(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
+    CK(DMALLOC(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
   }
   ctx->fr.W = width; ctx->fr.H = height; ctx->fr.band_y0 = band_y0; ctx->fr.band_y1 = band_y1;
   ctx->fr.tiles_x = cdiv(width, 32); ctx->fr.cells_y = cdiv(height, CELL_H);
@@ -1006,14 +1019,14 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
   if (n_cells > ctx->n_cells_cap) {
-    cudaFree(ctx->cell_counts); cudaFree(ctx->cell_off); cudaFree(ctx->cell_order);
-    CK(cudaMalloc(&ctx->cell_counts, sizeof(int) * n_cells));
-    CK(cudaMalloc(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
-    CK(cudaMalloc(&ctx->cell_order, sizeof(int) * n_cells));
+    DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_order);
+    CK(DMALLOC(&ctx->cell_counts, sizeof(int) * n_cells));
+    CK(DMALLOC(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
+    CK(DMALLOC(&ctx->cell_order, sizeof(int) * n_cells));
     ctx->n_cells_cap = n_cells;
   }
   if (!ctx->queue) {
-    CK(cudaMalloc(&ctx->order_hist, sizeof(int) * (2 * ORDER_BINS + 1)));  // histogram, cursors, work-queue head
+    CK(DMALLOC(&ctx->order_hist, sizeof(int) * (2 * ORDER_BINS + 1)));  // histogram, cursors, work-queue head
     ctx->queue = ctx->order_hist + 2 * ORDER_BINS;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->n_sms = prop.multiProcessorCount;
@@ -1040,9 +1053,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   const size_t total = s->items_total;
   const size_t need = big ? 2 * total : total;  // the sort of very long lists stages through the upper half
   if (need > ctx->cell_items_cap) {
-    cudaFree(ctx->cell_items);
+    DFREE(ctx->cell_items);
     size_t cap = need + need / 2 + 1024;
-    CK(cudaMalloc(&ctx->cell_items, sizeof(int) * cap));
+    CK(DMALLOC(&ctx->cell_items, sizeof(int) * cap));
     ctx->cell_items_cap = cap;
   }
   if (!big) {
@@ -1079,10 +1092,10 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   if (s->has_fancy) {
     size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
     if (slots > ctx->carry_slots) {
-      cudaFree(ctx->carry_done); cudaFree(ctx->carry_cnt); cudaFree(ctx->carry_ent);
-      CK(cudaMalloc(&ctx->carry_done, sizeof(int) * slots));
-      CK(cudaMalloc(&ctx->carry_cnt, sizeof(int) * slots));
-      CK(cudaMalloc(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
+      DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+      CK(DMALLOC(&ctx->carry_done, sizeof(int) * slots));
+      CK(DMALLOC(&ctx->carry_cnt, sizeof(int) * slots));
+      CK(DMALLOC(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
       CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
       ctx->carry_slots = slots;
     }
@@ -1127,7 +1140,7 @@ static DevShape* clone_shape(coh_ctx* ctx, const DevShape* s, int dx, int dy) {
 }
 static void cache_drop(coh_ctx* ctx, std::map<int64_t, CacheEntry>::iterator it) {
   ctx->cache_size -= it->second.bytes;
-  free_shape(it->second.shape); free_shape(it->second.minshape);
+  free_shape(ctx, it->second.shape); free_shape(ctx, it->second.minshape);
   ctx->cache.erase(it);
 }
 static void cache_drophalf(coh_ctx* ctx) {  // cache.ml:242-271 (eviction order: least recently used first)
@@ -1299,7 +1312,7 @@ int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, 
   ctx->have_u = false;
   if (!us) return 0;  // NullShape: nothing to render (render.ml:1321-1322)
   const Frame& fr = ctx->fr;
-  if (!ctx->u_init) CK(cudaMalloc(&ctx->u_init, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H));
+  if (!ctx->u_init) CK(DMALLOC(&ctx->u_init, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H));
   CK(cudaMemsetAsync(ctx->u_init, 0, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H, ctx->stream));
   k_spans_to_bits<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(us->row_ptr, us->spans, us->y0, us->n_rows, 0, fr.H, 0, fr.tiles_x, ctx->u_init); LAUNCHED();
   bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
@@ -1348,12 +1361,12 @@ int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h,
   if (x < 0 || y < 0 || w < 0 || h < 0 || x + w > ctx->fr.W || y + h > ctx->fr.H) FAIL("coh_fb_read_rgb888: rectangle outside the framebuffer");
   if (w == 0 || h == 0) return 0;
   uint8_t* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)w * h * 3));
+  CK(DMALLOC(&d, (size_t)w * h * 3));
   dim3 g(cdiv(w, 128), h);
   k_rgb888<<<g, 128, 0, ctx->stream>>>(ctx->fb, ctx->fr.W, x, y, w, h, d); LAUNCHED();
   CK(cudaMemcpyAsync(out, d, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
+  DFREE(d);
   return 0;
 }
 
