@@ -109,7 +109,25 @@ static std::string g_init_err;
 #define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// Exclusive scan of n ints into out[0..n] on the context's stream.  Up to 64 Ki elements every block
+// reduces its own prefix (one launch); beyond that the 1024-element tile sums are scanned recursively.
+static int exclusive_scan(coh_ctx* ctx, const int* in, int* out, int n, int* hist);
 static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) q--; return q; }
+
+static int exclusive_scan(coh_ctx* ctx, const int* in, int* out, int n, int* hist) {
+  const int tiles = std::max(1, cdiv(n, 1024));
+  if (n <= 65536) {
+    k_exclusive_scan<<<tiles, 1024, 0, ctx->stream>>>(in, out, n, hist, nullptr); LAUNCHED();
+    return 0;
+  }
+  int *sums = nullptr, *offs = nullptr;
+  CK(DMALLOC(&sums, sizeof(int) * tiles)); CK(DMALLOC(&offs, sizeof(int) * (tiles + 1)));
+  k_tile_sums<<<tiles, 1024, 0, ctx->stream>>>(in, sums, n); LAUNCHED();
+  if (exclusive_scan(ctx, sums, offs, tiles, nullptr)) return 1;
+  k_exclusive_scan<<<tiles, 1024, 0, ctx->stream>>>(in, out, n, hist, offs); LAUNCHED();
+  DFREE(sums); DFREE(offs);
+  return 0;
+}
 
 // AA table (polygon.ml:616-651): maintable via exp on the host once; prefix sums per scaled row.
 static void build_aa_table(AATable& t) {
@@ -284,7 +302,7 @@ static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_row
   CK(DMALLOC(&d_card, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(d_card, 0, sizeof(unsigned long long), ctx->stream));
   k_count_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, counts, d_card); LAUNCHED();
-  k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(counts, ptr, n_rows); LAUNCHED();
+  if (exclusive_scan(ctx, counts, ptr, n_rows, nullptr)) return 1;
   std::vector<int> h_ptr(n_rows + 1);
   unsigned long long card = 0;
   CK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int) * (n_rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -917,7 +935,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(DMALLOC(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
     if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
-    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, s->rowedge_ptr, (int)slots); LAUNCHED();
+    if (exclusive_scan(ctx, d_counts, s->rowedge_ptr, (int)slots, nullptr)) return 1;
     int total = 0;
     CK(cudaMemcpyAsync(&total, s->rowedge_ptr + slots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1061,13 +1079,13 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   if (!big) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
-    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr); LAUNCHED();
+    if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr)) return 1;
     k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   } else {
     const int obj_blocks = cdiv(s->n_leaves * 32, 256);
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
     k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
-    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(ctx->cell_counts, ctx->cell_off, n_cells); LAUNCHED();
+    if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, nullptr)) return 1;
     if (ordered) {
       k_bin_hist<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(ctx->cell_counts, n_cells, ctx->order_hist); LAUNCHED();
       k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED();
@@ -1084,8 +1102,17 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = ctx->use_u_init ? ctx->u_init : nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0;
-  // persistent grid: exactly one resident wave
-  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * WALK_SUB, WALK_WARPS));
+  // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
+  const int walk_h = big ? 16 : 4;
+  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
+#define LAUNCH_WALK(CARRYV)                                                                                        \
+  do {                                                                                                             \
+    if (walk_h == 4) { if (s->has_brush) k_walk<CARRYV, true, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);    \
+                       else k_walk<CARRYV, false, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P); }              \
+    else { if (s->has_brush) k_walk<CARRYV, true, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);               \
+           else k_walk<CARRYV, false, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P); }                         \
+    LAUNCHED();                                                                                                    \
+  } while (0)
   P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.n_cells = n_cells;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
@@ -1101,13 +1128,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
     }
     P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
     P.epoch = ++ctx->epoch;
-    if (s->has_brush) k_walk<true, true><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    else k_walk<true, false><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    LAUNCHED();
+    LAUNCH_WALK(true);
   } else {
-    if (s->has_brush) k_walk<false, true><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    else k_walk<false, false><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    LAUNCHED();
+    LAUNCH_WALK(false);
   }
   if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
   return 0;

@@ -187,12 +187,37 @@ __global__ void __launch_bounds__(128) k_bin_sort(const int* __restrict__ offset
   }
 }
 
-// Exclusive scan of n ints by a single block of 1024 threads: each thread sums a contiguous
-// chunk, one block-wide scan of the 1024 partial sums, then each thread rescans its chunk.
-__global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ hist = nullptr) {
+// Exclusive scan of n ints (out has n + 1 entries).  Multi-block without inter-block communication:
+// block b first reduces everything in front of its 1024-element tile (coalesced, independent loads —
+// n is tens of thousands, so the redundant reads are cheaper than a second launch or a look-back
+// chain), then scans its tile.  The heavy-first order's 256-bin histogram is scanned on the side by
+// the last warp of block 0.
+__device__ __forceinline__ int block_reduce_1024(int v, int* warp_sums) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if (lane == 0) warp_sums[wid] = v;
+  __syncthreads();
+  int t = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+  __syncthreads();
+  return t;
+}
+// tile_offset (optional): precomputed exclusive prefix of every 1024-element tile (large n, see
+// exclusive_scan() in coherence_b200.cu); without it the block reduces its own prefix.
+__global__ void k_tile_sums(const int* __restrict__ in, int* __restrict__ sums, int n) {
+  __shared__ int warp_sums[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int v = block_reduce_1024(i < n ? in[i] : 0, warp_sums);
+  if (threadIdx.x == 0) sums[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                         int* __restrict__ hist = nullptr,
+                                                         const int* __restrict__ tile_offset = nullptr) {
   __shared__ int warp_sums[32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (hist && wid == 31) {  // the heavy-first order's 256-bin histogram is scanned by the last warp on the side
+  if (hist && blockIdx.x == 0 && wid == 31) {
     int carry = 0;
     for (int base = 0; base < ORDER_BINS; base += 32) {
       int v = hist[base + lane], x = v;
@@ -202,25 +227,31 @@ __global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ o
       carry += __shfl_sync(0xFFFFFFFFu, x, 31);
     }
   }
-  const int chunk = (n + blockDim.x - 1) / blockDim.x;
-  const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
-  int sum = 0;
-  for (int i = lo; i < hi; i++) sum += in[i];
-  int x = sum;
+  const int tile0 = blockIdx.x * 1024;
+  int before = 0;
+  if (tile_offset) before = tile_offset[blockIdx.x];
+  else {
+    for (int i = t; i < tile0; i += 1024) before += in[i];
+    before = block_reduce_1024(before, warp_sums);
+  }
+  const int i = tile0 + t;
+  const int v = i < n ? in[i] : 0;
+  int x = v;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += v; }
+  for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += u; }
   if (lane == 31) warp_sums[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    int s2 = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+    int s2 = warp_sums[lane];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, s2, d); if (lane >= d) s2 += v; }
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xFFFFFFFFu, s2, d); if (lane >= d) s2 += u; }
     warp_sums[lane] = s2;
   }
   __syncthreads();
-  int run = (wid ? warp_sums[wid - 1] : 0) + x - sum;  // exclusive prefix of this thread's chunk
-  for (int i = lo; i < hi; i++) { int v = in[i]; out[i] = run; run += v; }
-  if (t == blockDim.x - 1) out[n] = warp_sums[(blockDim.x >> 5) - 1];
+  const int excl = before + (wid ? warp_sums[wid - 1] : 0) + x - v;
+  if (i < n) out[i] = excl;
+  if (i == n - 1) out[n] = excl + v;
+  if (n == 0 && blockIdx.x == 0 && t == 0) out[0] = 0;
 }
 
 // ------------------------------------------------------------------------------------
@@ -431,16 +462,9 @@ constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 #define WALK_MIN_CTAS 3
 #endif
 // A cell list (32 px x CELL_H rows) is shared by CELL_H / WALK_H walker work items of WALK_H rows
-// each: the heaviest cell bounds the kernel's critical path, so the unit of work is kept small while
-// the binning stays coarse.
-#ifndef COH_WALK_H
-#define COH_WALK_H 4
-#endif
-constexpr int WALK_H = COH_WALK_H;       // rows per walker work item (power of two, divides CELL_H)
-constexpr int WALK_SUB = CELL_H / WALK_H;
-constexpr int NC = 32 / WALK_H;          // candidate objects scan-converted per pass
-constexpr unsigned ROWMASK = (WALK_H >= 32) ? 0xFFFFFFFFu : ((1u << WALK_H) - 1u);
-
+// each: the heaviest work item bounds the kernel's critical path, so for scenes with short lists and
+// heavy antialiasing (the lion) the unit of work is 4 rows; scenes with very long lists (10^5
+// objects) amortise the list walk over all 16 rows.  WALK_H is a template parameter of the walker.
 // One warp owns one cell: TILE_W = 32 pixel columns (lane = column when compositing) by
 // WALK_H rows.  Scan conversion runs lane-parallel over (candidate object, row) pairs; the
 // front-to-back composite then visits, object by object, only the rows where the object
@@ -448,11 +472,13 @@ constexpr unsigned ROWMASK = (WALK_H >= 32) ? 0xFFFFFFFFu : ((1u << WALK_H) - 1u
 // by lane r and its NC-1 mirror lanes).
 // CARRY: the scene has fancy (gradient / radial) fills -> fill evaluation and the cross-tile carry
 // are compiled in.  BRUSH: the scene has brush strokes.  Plain polygon scenes get the small kernel.
-template <bool CARRY, bool BRUSH>
+template <bool CARRY, bool BRUSH, int WALK_H>
 __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int sub, const int lane,
                                           uint32_t* __restrict__ aa_bits, StagedEdge* __restrict__ stage,
                                           uint32_t (*__restrict__ acc_rows)[32],
                                           const int* __restrict__ s_prefix, const int volume) {
+  constexpr int NC = 32 / WALK_H;          // candidate objects scan-converted per pass
+  constexpr unsigned ROWMASK = (WALK_H >= 32) ? 0xFFFFFFFFu : ((1u << WALK_H) - 1u);
   const int tx0 = tile * TILE_W;
   const int y0 = (P.cell_row0 + by) * CELL_H + sub * WALK_H;
   const int r_lane = lane % WALK_H, c_lane = lane / WALK_H;
@@ -723,8 +749,9 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 
 // Persistent launch: every warp keeps taking cells from the queue (heavy cells first) until it
 // is empty; the grid is sized to fill the GPU exactly once (WALK_MIN_CTAS CTAs per SM).
-template <bool CARRY, bool BRUSH>
+template <bool CARRY, bool BRUSH, int WALK_H>
 __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
+  constexpr int WALK_SUB = CELL_H / WALK_H;
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
   __shared__ uint32_t s_acc[WALK_WARPS][WALK_H][32];
@@ -743,7 +770,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
 #endif
-    walk_cell<CARRY, BRUSH>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    walk_cell<CARRY, BRUSH, WALK_H>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
     __syncwarp();
 #ifdef COH_PHASE_PROFILE
     if (lane == 0 && cell < (1 << 20)) g_cell_cycles[cell] = (unsigned int)(clock64() - tc0_);

@@ -1,0 +1,24 @@
+"""Small end-to-end run for compute-sanitizer (memcheck): lion, random scene with brushes, fancy fills,
+Convolved object, shape algebra, update shape."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from coherence_renderer_b200 import abi, scene as S
+ctx = abi.Context(0)
+def run(b, W, H):
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H); sc = ctx.scene_create(objs, nbg, e, p)
+    ctx.render_frame(sc, (0, 0, W, H), abi.COH_RENDER_RECORD_U); ctx.sync()
+    u = ctx.render_uncovered(); ctx.shape_export(u); ctx.shape_free(u)
+    img = ctx.fb_read_rgba(0, 0, W, H); ctx.scene_free(sc); return img
+run(S.lion_scene(333, 257, 0.7), 333, 257)
+run(S.random_scene(300, 200, 1200, seed=3), 300, 200)
+b = S.SceneBuilder()
+b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0), (40.0, 120.0)], S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.rgba8(0, 0, 255)))
+b.polygon([(50.0, 40.0), (150.0, 45.5), (140.5, 120.0)], S.Fill.plain(S.rgba8(0, 0, 0)), convolve=("gaussian", 4))
+b.begin_background(); b.rectangle(S.WHITE, 0.0, 0.0, 200.0, 160.0)
+run(b, 200, 160)
+a = ctx.shape_box(5, 5, 100, 50); c = ctx.shape_box(50, 20, 100, 70)
+for f in (ctx.shape_union, ctx.shape_difference, ctx.shape_intersection): ctx.shape_free(f(a, c))
+ctx.shape_free(ctx.shape_bloat(a, 3, 2)); ctx.shape_free(ctx.shape_erode(a, 3, 2))
+print("sanitize run OK")
