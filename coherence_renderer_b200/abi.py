@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COH_LIB_PATH", os.path.join(_HERE, "libcoherence_b200.so"))  # override: kernel-variant experiments
 
-COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH = 0, 1, 2, 3, 4
+COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH, COH_OBJ_CPG = 0, 1, 2, 3, 4, 5
+COH_CPG_UNION, COH_CPG_INTERSECTION, COH_CPG_SUBTRACTION, COH_CPG_EXCLUSIVEOR = 0, 1, 2, 3
 COH_NONZERO, COH_EVENODD = 0, 1
 COH_FILL_PLAIN, COH_FILL_AXIAL, COH_FILL_RADIAL = 0, 1, 2
 COH_FILL_EXT_S, COH_FILL_EXT_E = 1, 2
@@ -26,8 +27,9 @@ class CohObject(C.Structure):
         ("kind", C.c_int32), ("winding", C.c_int32), ("first", C.c_int32), ("count", C.c_int32),
         ("fill_kind", C.c_int32), ("colour0", C.c_uint32), ("colour1", C.c_uint32), ("fill_flags", C.c_int32),
         ("pretrans", C.c_int32), ("dx", C.c_int32), ("dy", C.c_int32), ("bounds", C.c_int32 * 4),
-        ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("convolve", C.c_int32), ("id", C.c_int64),
+        ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("convolve", C.c_int32), ("sprite_winding", C.c_int32), ("id", C.c_int64),
         ("fparam", C.c_double * 6), ("brush_opacity", C.c_double), ("brush_radius", C.c_double),
+        ("first2", C.c_int32), ("count2", C.c_int32), ("winding2", C.c_int32), ("cpg_op", C.c_int32),
     ]
 
 

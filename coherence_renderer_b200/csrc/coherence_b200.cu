@@ -834,7 +834,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       case COH_OBJ_PATH: {
         if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
         if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
-        o.kind = K_PATH; o.winding = c.winding; o.aa_winding = c.winding; o.first = c.first; o.count = c.count;
+        if (c.sprite_winding < 0 || c.sprite_winding > 2) FAIL("scene: bad sprite winding rule");
+        o.kind = K_PATH; o.winding = c.winding; o.aa_winding = c.sprite_winding ? c.sprite_winding - 1 : c.winding;
+        o.first = c.first; o.count = c.count;
         if (c.count == 0) continue;  // NullShape: nothing to draw
         if (c.convolve) {
           const int ck = c.convolve & 255, cr = c.convolve >> 8;
@@ -862,6 +864,36 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           if (edge_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share edges");
           edge_obj[(size_t)c.first + k] = (int)recs.size();
         }
+        break;
+      }
+      case COH_OBJ_CPG: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.first2 < 0 || c.count2 < 0 || (int64_t)c.first2 + c.count2 > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.first2 < c.first + c.count) FAIL("scene: CPG operand b's edges must follow operand a's");
+        if ((c.winding != COH_NONZERO && c.winding != COH_EVENODD) || (c.winding2 != COH_NONZERO && c.winding2 != COH_EVENODD)) FAIL("scene: bad winding rule");
+        if (c.cpg_op < COH_CPG_UNION || c.cpg_op > COH_CPG_EXCLUSIVEOR) FAIL("scene: bad CPG operator");
+        if (c.convolve) FAIL("scene: Convolved CPG objects are not supported yet");
+        o.kind = K_CPG; o.winding = o.aa_winding = c.winding;
+        o.first = c.first; o.count = c.count; o.b_first = c.first2; o.b_count = c.count2; o.b_opw = c.cpg_op | (c.winding2 << 8);
+        o.bx0 = o.by0 = INT32_MAX; o.bx1 = o.by1 = INT32_MIN;
+        o.ry0 = o.b_ry0 = 0; o.ry1 = o.b_ry1 = -1;   // operands without edges have no rows
+        for (int side = 0; side < 2; side++) {
+          const int f = side ? c.first2 : c.first, n = side ? c.count2 : c.count;
+          if (n == 0) continue;
+          EdgeBox eb = edge_bounds(edges + 4 * (size_t)f, n);
+          int x0, y0, x1, y1;
+          shape_pixel_box(eb, x0, y0, x1, y1);
+          o.bx0 = std::min(o.bx0, x0); o.by0 = std::min(o.by0, y0); o.bx1 = std::max(o.bx1, x1); o.by1 = std::max(o.by1, y1);
+          const int r0 = floordiv(eb.ymin - 16 + 31, 32), r1 = floordiv(eb.ymax + 67, 32);
+          if (total_rows + (r1 - r0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
+          if (side) { o.b_ry0 = r0; o.b_ry1 = r1; o.b_row_base = (int)total_rows; } else { o.ry0 = r0; o.ry1 = r1; o.row_base = (int)total_rows; }
+          total_rows += r1 - r0 + 1;
+          for (int k = 0; k < n; k++) {
+            if (edge_obj[(size_t)f + k] != -1) FAIL("scene: objects may not share edges");
+            edge_obj[(size_t)f + k] = (int)recs.size();
+          }
+        }
+        if (o.bx0 > o.bx1) continue;  // both operands null
         break;
       }
       case COH_OBJ_PRIMITIVE:
@@ -910,7 +942,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
-    if (o.kind == K_BRUSH || o.kind == K_CONV) s->has_brush = true;
+    if (o.kind == K_BRUSH || o.kind == K_CONV || o.kind == K_CPG) s->has_brush = true;
   }
   CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1251,6 +1283,24 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
   if (!found) {
     if (o.kind == K_PATH) {
       if (shapes_from_device_edges(ctx, s->edges + o.first, o.count, o.winding, o.bx0 - o.dx, o.by0 - o.dy, o.bx1 - o.dx, o.by1 - o.dy, &cs, &cm, "coh_scene_object_shape")) return 1;
+    } else if (o.kind == K_CPG) {  // render.ml:508-528
+      coh_shape_t as = 0, am = 0, bs = 0, bm = 0, t0 = 0, t1 = 0;
+      const int x0 = o.bx0 - o.dx, y0 = o.by0 - o.dy, x1 = o.bx1 - o.dx, y1 = o.by1 - o.dy;
+      if (o.count && shapes_from_device_edges(ctx, s->edges + o.first, o.count, o.winding, x0, y0, x1, y1, &as, &am, "coh_scene_object_shape")) return 1;
+      if (o.b_count && shapes_from_device_edges(ctx, s->edges + o.b_first, o.b_count, o.b_opw >> 8, x0, y0, x1, y1, &bs, &bm, "coh_scene_object_shape")) return 1;
+      int rc = 0;
+      switch (o.b_opw & 255) {
+        case COH_CPG_UNION: rc = coh_shape_union(ctx, as, bs, &cs) || coh_shape_union(ctx, am, bm, &cm); break;
+        case COH_CPG_INTERSECTION: rc = coh_shape_intersection(ctx, as, bs, &cs) || coh_shape_intersection(ctx, am, bm, &cm); break;
+        case COH_CPG_SUBTRACTION: rc = coh_shape_difference(ctx, as, bm, &cs) || coh_shape_difference(ctx, am, bs, &cm); break;
+        default:
+          rc = coh_shape_union(ctx, as, bs, &t0) || coh_shape_intersection(ctx, am, bm, &t1) || coh_shape_difference(ctx, t0, t1, &cs);
+          coh_shape_free(ctx, t0); coh_shape_free(ctx, t1); t0 = t1 = 0;
+          rc = rc || coh_shape_difference(ctx, bm, as, &t0) || coh_shape_difference(ctx, am, bs, &t1) || coh_shape_union(ctx, t0, t1, &cm);
+          coh_shape_free(ctx, t0); coh_shape_free(ctx, t1);
+      }
+      coh_shape_free(ctx, as); coh_shape_free(ctx, am); coh_shape_free(ctx, bs); coh_shape_free(ctx, bm);
+      if (rc) return 1;
     } else if (o.kind == K_PRIM) {
       if (coh_shape_box(ctx, o.prim[0], o.prim[1], o.prim[2] - o.prim[0] + 1, o.prim[3] - o.prim[1] + 1, &cs)) return 1;
       if (coh_shape_translate(ctx, cs, 0, 0, &cm)) return 1;

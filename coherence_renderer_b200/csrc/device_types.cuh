@@ -13,7 +13,7 @@ constexpr int CELL_H = COH_CELL_H;  // rows per cell (power of two <= 32)
 constexpr int MAX_DEPTH = 6;     // nested Group depth (incl. the implicit scene / background groups)
 constexpr int AA_WORDS = 17;     // (32 + 2) * 16 scaled columns of one tile = 544 bits
 
-enum { K_PATH = 0, K_PRIM = 1, K_GROUP = 2, K_BRUSH = 4, K_CONV = 5 };
+enum { K_PATH = 0, K_PRIM = 1, K_GROUP = 2, K_BRUSH = 4, K_CONV = 5, K_CPG = 6 };
 enum { OF_ROOT_SCENE = 1, OF_ROOT_BACKGROUND = 2 };
 
 // One record per leaf object or group, device resident (96 bytes + fill).
@@ -33,11 +33,22 @@ struct ObjRec {
   int stamp_off;    // BRUSH: offset of the (2r+1)^2 alpha stamp in the stamp pool
   int ry0, ry1;     // PATH: pixel rows (object frame) that have a candidate edge list
   int row_base;     // PATH: first slot of this object in the row-edge CSR
-  // CONV (Convolved (kernel, Basic (fill, Path))): pre-convolved canvas of the object, object frame
-  int cv_x0, cv_y0; // pixel of bit 0 / first row of the canvas
-  int cv_nw, cv_h;  // 32-pixel words per row, rows
-  int cv_bits;      // offset (words) of the shape bit-rows in the scene's conv bit pool; minshape rows follow
-  int cv_px;        // offset (pixels) of the convolved RGBA8 canvas in the scene's conv pixel pool
+  union {
+    struct {
+      // CONV (Convolved (kernel, Basic (fill, Path))): pre-convolved canvas of the object, object frame
+      int cv_x0, cv_y0; // pixel of bit 0 / first row of the canvas
+      int cv_nw, cv_h;  // 32-pixel words per row, rows
+      int cv_bits;      // offset (words) of the shape bit-rows in the scene's conv bit pool; minshape rows follow
+      int cv_px;        // offset (pixels) of the convolved RGBA8 canvas in the scene's conv pixel pool
+    };
+    struct {
+      // CPG (op, Path a, Path b): operand a uses first / count / winding / ry0 / ry1 / row_base
+      int b_first, b_count;  // edges of operand b
+      int b_ry0, b_ry1;      // rows of operand b that have a candidate edge list
+      int b_row_base;        // first slot of operand b in the row-edge CSR
+      int b_opw;             // op (COH_CPG_*) | winding rule of b << 8
+    };
+  };
   int pad;
   FillRec fill;
 };

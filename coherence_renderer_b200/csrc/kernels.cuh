@@ -50,7 +50,8 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
   int oi = edge_obj[e];
   if (oi < 0) return;
   const EdgeRec ed = edges[e];
-  const int row_base = objs[oi].row_base, ry0 = objs[oi].ry0;
+  int row_base = objs[oi].row_base, ry0 = objs[oi].ry0;
+  if (objs[oi].kind == K_CPG && e >= objs[oi].b_first) { row_base = objs[oi].b_row_base; ry0 = objs[oi].b_ry0; }  // operand b
   int ylo = ceildiv32(ed.ymin - 16), yhi = floordiv32(ed.ymax + 67);
   for (int y = ylo; y <= yhi; y++) {
     int slot = row_base + y - ry0;
@@ -457,6 +458,12 @@ __device__ __forceinline__ uint32_t conv_load_bits32(const uint32_t* __restrict_
   const uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
   return qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
 }
+// out-of-line copy for the rarer object kinds (keeps the polygon walker's code small)
+__device__ __noinline__ int aa_tile_nl(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int winding,
+                                       int xx0, int yy, uint32_t edge, uint32_t* aa_bits, StagedEdge* stage,
+                                       const int* __restrict__ prefix, int volume, int lane, bool& ok) {
+  return aa_tile(edges, idx, n_cand, winding, xx0, yy, edge, aa_bits, stage, prefix, volume, lane, ok);
+}
 constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 #ifndef WALK_MIN_CTAS
 #define WALK_MIN_CTAS 3
@@ -586,6 +593,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     const int ci = base + c_lane;
     const int idx = ci < it1 ? P.cell_items[ci] : -1;
     uint32_t S = 0u, C = 0u;
+    uint32_t gSA = 0u, gMA = 0u, gSB = 0u, gMB = 0u;   // CPG operands: shape / minshape words of a and b
     const uint32_t u_hit = hit_level >= 0 ? stk_u[hit_level] : u;  // superset of every later u of my row
     if (idx >= 0 && u_hit != 0u) {
       const ObjRec& o = P.objs[idx];
@@ -602,6 +610,25 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             if (!ok) bad = true;
             S = sc.x; C = sc.y;
           }
+        } else if (BRUSH && o.kind == K_CPG) {
+          // CPG (op, a, b): shape / minshape are set expressions of the operands' (render.ml:522-528)
+          bool ok = true;
+          if (yy >= o.ry0 && yy <= o.ry1) {
+            const int slot = o.row_base + yy - o.ry0;
+            const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+            const uint2 sc = scan_row_word(P.edges, P.rowedge_idx + a, b - a, yy, o.winding, xx0, ok);
+            gSA = sc.x; gMA = sc.x & ~sc.y;
+          }
+          if (yy >= o.b_ry0 && yy <= o.b_ry1) {
+            const int slot = o.b_row_base + yy - o.b_ry0;
+            const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+            const uint2 sc = scan_row_word(P.edges, P.rowedge_idx + a, b - a, yy, o.b_opw >> 8, xx0, ok);
+            gSB = sc.x; gMB = sc.x & ~sc.y;
+          }
+          if (!ok) bad = true;
+          uint32_t M;
+          cpg_words(o.b_opw & 255, gSA, gMA, gSB, gMB, S, M);
+          C = S & ~M;
         } else if (BRUSH && o.kind == K_CONV) {
           // Convolved (k, g): shape = bloat r r (shape g), minshape = erode r r (minshape g) (render.ml:536-555),
           // both precomputed as bit-rows; C is chosen so that S & ~C is the minshape word
@@ -664,6 +691,30 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
             opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, aa_bits, stage, s_prefix, volume, lane, ok);
             if (!ok) bad = true;
+          } else if (BRUSH && okind == K_CPG) {
+            // sprite_of_cpg (render.ml:867-981): both operands become alpha mattes (255 inside the
+            // minshape, antialiased on the rest of the shape, 0 outside) and are combined per pixel
+            const int src = cc * WALK_H + r;
+            const uint32_t SA = __shfl_sync(0xFFFFFFFFu, gSA, src), MA = __shfl_sync(0xFFFFFFFFu, gMA, src);
+            const uint32_t SB = __shfl_sync(0xFFFFFFFFu, gSB, src), MB = __shfl_sync(0xFFFFFFFFu, gMB, src);
+            const uint32_t XA = edge & SA & ~MA, XB = edge & SB & ~MB;
+            int a = 0, b = 0;
+            bool ok = true;
+            if (XA) {
+              const int slot = o.row_base + yy - o.ry0;
+              const int ea = P.rowedge_ptr[slot], eb = P.rowedge_ptr[slot + 1];
+              a = aa_tile_nl(P.edges, P.rowedge_idx + ea, eb - ea, o.winding, xx0, yy, XA, aa_bits, stage, s_prefix, volume, lane, ok);
+              if (!ok) bad = true;
+            }
+            if (XB) {
+              const int slot = o.b_row_base + yy - o.b_ry0;
+              const int ea = P.rowedge_ptr[slot], eb = P.rowedge_ptr[slot + 1];
+              b = aa_tile_nl(P.edges, P.rowedge_idx + ea, eb - ea, o.b_opw >> 8, xx0, yy, XB, aa_bits, stage, s_prefix, volume, lane, ok);
+              if (!ok) bad = true;
+            }
+            a = ((MA >> lane) & 1u) ? 255 : (((XA >> lane) & 1u) ? a : 0);
+            b = ((MB >> lane) & 1u) ? 255 : (((XB >> lane) & 1u) ? b : 0);
+            opacity = cpg_alpha(o.b_opw & 255, a, b);
           } else if (BRUSH && okind == K_BRUSH) {
             // ordered alpha_over of every stamp covering this pixel (brush.ml:207-212)
             const int br = o.brush_r, w = 2 * br + 1;
@@ -712,7 +763,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
           if (BRUSH && okind == K_CONV && is_edge)  // the convolved sprite, cropped to the visible max-shape (render.ml:1052)
             col = P.conv_px[(size_t)o.cv_px + (size_t)(yy - o.cv_y0) * (o.cv_nw * 32) + (xx0 + lane - o.cv_x0)];
           else if (!CARRY || okind == K_PRIM || fkind == 0) col = c0;
-          else if (!is_edge || okind == K_BRUSH) col = fill_lookup(o.fill, xx0 + lane, yy);
+          else if (!is_edge || okind == K_BRUSH || okind == K_CPG) col = fill_lookup(o.fill, xx0 + lane, yy);  // per-pixel fill (brush.ml / render.ml:975 map_coords)
           else {
             // polygon.ml:736 quirk: AA pixels take the fill at the first x of their span (the run
             // of `edge` bits); a run that reaches bit 0 may have begun in a tile further left.

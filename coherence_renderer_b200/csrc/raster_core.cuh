@@ -508,6 +508,36 @@ COH_HD int aa_opacity(int table_sum, int volume) {  // polygon.ml:650-651 with c
   return (256 * table_sum + volume / 2) / volume;
 }
 
+// ---- constructive planar geometry (render.ml:522-528, 858-981) ----
+// shape / minshape words of CPG (op, a, b) from the operands' words; op: 0 Union, 1 Intersection,
+// 2 Subtraction, 3 ExclusiveOr
+COH_HD void cpg_words(int op, uint32_t SA, uint32_t MA, uint32_t SB, uint32_t MB, uint32_t& S, uint32_t& M) {
+  switch (op) {
+    case 0: S = SA | SB; M = MA | MB; break;
+    case 1: S = SA & SB; M = MA & MB; break;
+    case 2: S = SA & ~MB; M = MA & ~SB; break;
+    default: S = (SA | SB) & ~(MA & MB); M = (MB & ~SA) | (MA & ~SB); break;
+  }
+}
+// Alpha of a CPG pixel from the operands' matte alphas a, b (255 in the minshape, 0 outside the
+// shape).  One expression per operator covers every region the reference splits the sprite into
+// (min/min, min/max, max/min, max/max, a only, b only): e.g. Subtraction's "invert b" over
+// min_a ∩ max_b is max(0, 255 - b).
+COH_HD int cpg_alpha(int op, int a, int b) {
+  switch (op) {
+    case 0: return a + b > 255 ? 255 : a + b;
+    case 1: return a < b ? a : b;
+    case 2: return a - b < 0 ? 0 : a - b;
+    default: {  // eor (render.ml:858-864)
+      const int ia = 255 - a, ib = 255 - b;
+      if (a < 128 && b < 128) return a > b ? a : b;
+      if (a >= 128 && b < 128) return 255 - (ia > b ? ia : b);
+      if (a < 128) return 255 - (a > ib ? a : ib);
+      return ia > ib ? ia : ib;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Fills (fill.ml:62-140) evaluated per pixel.
 // ---------------------------------------------------------------------------------

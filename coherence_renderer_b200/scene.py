@@ -222,6 +222,13 @@ class SceneBuilder:
         """Everything added from here on is render_frame's (pages @ background) list."""
         self._in_background = True
 
+    def stroked_path_edges(self, edges, fill, **kw):
+        """Basic (fill, StrokedPath (p, spec)) with edges = Shapes.strokepath spec p (the stroker itself is host
+        geometry outside this path): shape by NonZero (render.ml:510), sprite by EvenOdd (render.ml:1018)."""
+        o = self.path_edges(edges, fill, COH_NONZERO, **kw)
+        o.sprite_winding = 1 + COH_EVENODD
+        return o
+
     def path_edges(self, edges, fill, winding=COH_NONZERO, bounds=None, **kw):
         """Basic (fill, Path p) with p already flattened to integer sub-bin edges."""
         o = self._obj(COH_OBJ_PATH, **kw)
@@ -294,6 +301,21 @@ class SceneBuilder:
         self.points.append(pts)
         self._n_points += len(pts)
         o.brush_opacity, o.brush_radius = float(opacity), float(radius)
+        fill.apply(o)
+        return o
+
+    def cpg(self, op, subpaths_a, subpaths_b, fill, winding_a=COH_NONZERO, winding_b=COH_NONZERO, **kw):
+        """Basic (fill, CPG (op, Path a, Path b)); op in "union" | "intersection" | "subtraction" | "xor"."""
+        from . import abi
+
+        o = self._obj(abi.COH_OBJ_CPG, **kw)
+        ea = np.concatenate([abi.host_edgelist_of_subpath(sg) for sg in subpaths_a]).reshape(-1, 4)
+        eb = np.concatenate([abi.host_edgelist_of_subpath(sg) for sg in subpaths_b]).reshape(-1, 4)
+        o.first, o.count, o.winding = self._n_edges, len(ea), winding_a
+        o.first2, o.count2, o.winding2 = self._n_edges + len(ea), len(eb), winding_b
+        o.cpg_op = {"union": 0, "intersection": 1, "subtraction": 2, "xor": 3}[op]
+        self.edges.extend([ea, eb])
+        self._n_edges += len(ea) + len(eb)
         fill.apply(o)
         return o
 

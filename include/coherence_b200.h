@@ -39,8 +39,10 @@ enum {
   COH_OBJ_PRIMITIVE = 1,   /* Primitive (colour, HLine|VLine|Rectangle), render.ml:556-586 */
   COH_OBJ_GROUP_BEGIN = 2, /* Group scene ... */
   COH_OBJ_GROUP_END = 3,   /* ... end of the innermost open group                          */
-  COH_OBJ_BRUSH = 4        /* Basic (fill, Brushstroke ((opacity, Gaussian r), path))      */
+  COH_OBJ_BRUSH = 4,       /* Basic (fill, Brushstroke ((opacity, Gaussian r), path))      */
+  COH_OBJ_CPG = 5          /* Basic (fill, CPG (op, Path a, Path b)), render.ml:17-18, 522-528, 867-981 */
 };
+enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH_CPG_EXCLUSIVEOR = 3 };
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
 enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
 enum { COH_FILL_EXT_S = 1, COH_FILL_EXT_E = 2 };
@@ -63,10 +65,17 @@ typedef struct coh_object {
   int32_t prim_null;   /* PRIMITIVE: 1 for a zero-length HLine/VLine (NullShape) */
   int32_t convolve;    /* PATH: 0, or Convolved (kernel, Basic (fill, Path p)) (render.ml:63, 1023-1052):
                           COH_CONV_UNIT | r << 8  = Convolve.mkunit r,  COH_CONV_GAUSSIAN | r << 8 = Convolve.mkgaussian r */
+  int32_t sprite_winding; /* PATH: 0 = the AA sprite uses `winding`; 1 + rule otherwise.  Basic (fill, StrokedPath (p, spec)),
+                          with edges = Shapes.strokepath spec p, takes its shape with NonZero (render.ml:510) but
+                          its sprite with EvenOdd (render.ml:1018): winding = COH_NONZERO, sprite_winding = 1 + COH_EVENODD */
   int64_t id;          /* cache key (Id.idset); < 0: fresh id each render, never cached */
   double fparam[6];    /* AXIAL: x0,y0,x1,y1;  RADIAL: cx,cy, px,py, p'x,p'y (fill.ml:77,112) */
   double brush_opacity; /* BRUSH: opacity in 0..1 */
   double brush_radius;  /* BRUSH: Gaussian radius */
+  int32_t first2;       /* CPG: edges of operand b (operand a uses first / count / winding) */
+  int32_t count2;
+  int32_t winding2;     /* CPG: winding rule of operand b */
+  int32_t cpg_op;       /* CPG: COH_CPG_* */
 } coh_object;
 
 /* ---- lifecycle ---- */

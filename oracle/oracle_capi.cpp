@@ -47,6 +47,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
     switch (c.kind) {
       case COH_OBJ_PATH: {
         o.kind = Obj::Path; o.fill = fill_from(c); o.winding = (Winding)c.winding;
+        o.sprite_winding = c.sprite_winding ? (Winding)(c.sprite_winding - 1) : o.winding;
         o.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
         sort_edgelist_maxy_rev(o.edges);
         if (c.convolve) {  // Convolved (kernel, Basic (fill, Path p)): the path becomes the child
@@ -60,6 +61,18 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
           stack.back().push_back(std::move(outer));
           break;
         }
+        stack.back().push_back(std::move(o));
+        break;
+      }
+      case COH_OBJ_CPG: {
+        o.kind = Obj::CPG; o.fill = fill_from(c); o.cpg_op = c.cpg_op;
+        Obj a, b;
+        a.kind = b.kind = Obj::Path;
+        a.winding = a.sprite_winding = (Winding)c.winding; b.winding = b.sprite_winding = (Winding)c.winding2;
+        a.edges = edges_from(edges + 4 * (size_t)c.first, c.count); b.edges = edges_from(edges + 4 * (size_t)c.first2, c.count2);
+        sort_edgelist_maxy_rev(a.edges); sort_edgelist_maxy_rev(b.edges);
+        o.has_bounds = false;
+        o.children.push_back(std::move(a)); o.children.push_back(std::move(b));
         stack.back().push_back(std::move(o));
         break;
       }

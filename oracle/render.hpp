@@ -21,7 +21,7 @@ struct Obj;
 typedef std::vector<Obj> Scene;
 
 struct Obj {
-  enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4 } kind = Path;
+  enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4, CPG = 5 } kind = Path;
   long id = -1;              // < 0: a fresh id per render (Id.new_ids ()), never cached
   int pretrans = -1;         // -1: Over; else PreTrans(v, Over) with delta = toint (v *. 255.)
   // Integer-pixel alias (Render.translate_renderobject -> Cache.addtranslation, render.ml:259-271,
@@ -36,6 +36,7 @@ struct Obj {
   Fill fill;
   std::vector<Edge> edges;   // sorted by sort_edgelist_maxy_rev
   Winding winding = NonZero;
+  Winding sprite_winding = NonZero;  // render.ml:1018: stroked paths take their sprite with EvenOdd
   // Primitive (render.ml:556-586): inclusive integer box; prim_null for zero-length lines
   colour prim_colour = 0;
   int prim[4] = {0, 0, 0, 0};  // x0, y0, x1, y1 inclusive
@@ -46,6 +47,8 @@ struct Obj {
   BrushStroke stroke;
   // Convolved (kernel, child geometry = children[0])
   Kernel kernel;
+  // CPG (op, a = children[0], b = children[1]), render.ml:17-18
+  int cpg_op = 0;  // 0 Union, 1 Intersection, 2 Subtraction, 3 ExclusiveOr
 };
 
 // ---- cache.ml restated: shapes and partial sprites keyed by id, integer-translation
@@ -168,6 +171,22 @@ struct Renderer {
         cache.addshape(o.id, shp, minshp);
         return;
       }
+      case Obj::CPG: {  // render.ml:508-528 (operands are rendered as dummy objects with fresh ids)
+        if (cache.getshape(o.id, shp, minshp)) return;
+        Shape as, am, bs, bm;
+        shape_of_basicshape(o.children.at(0), as, am);
+        shape_of_basicshape(o.children.at(1), bs, bm);
+        switch (o.cpg_op) {
+          case 0: shp = shape_union(as, bs); minshp = shape_union(am, bm); break;
+          case 1: shp = shape_intersection(as, bs); minshp = shape_intersection(am, bm); break;
+          case 2: shp = shape_difference(as, bm); minshp = shape_difference(am, bs); break;
+          default:
+            shp = shape_difference(shape_union(as, bs), shape_intersection(am, bm));
+            minshp = shape_union(shape_difference(bm, as), shape_difference(am, bs));
+        }
+        cache.addshape(o.id, shp, minshp);
+        return;
+      }
       case Obj::Primitive: {
         shp = Shape();
         if (!o.prim_null) shp = shape_box(o.prim[0], o.prim[1], o.prim[2] - o.prim[0] + 1, o.prim[3] - o.prim[1] + 1);
@@ -206,8 +225,9 @@ struct Renderer {
         render_scene(u, a, o.children, true);
         return a;
       }
-      case Obj::Path: return polygon_sprite_edgelist(o.fill, shp, o.edges, o.winding);
+      case Obj::Path: return polygon_sprite_edgelist(o.fill, shp, o.edges, o.sprite_winding);
       case Obj::Brush: return sprite_of_brushstroke(o.stroke, o.fill, shp);
+      case Obj::CPG: return sprite_of_cpg(o, shp);
       case Obj::Convolved: {  // render.ml:1023-1052: always the "fancy" route
         int r = radius_of_kernel(o.kernel);
         Shape shp2 = bloat(r, r, shp);
@@ -216,6 +236,68 @@ struct Renderer {
       }
       default: throw std::runtime_error("Internal inconsistency: Should already have been rendered");
     }
+  }
+
+  // render.ml:858-864
+  static int eor(int a, int b) {
+    auto inv = [](int v) { return 255 - v; };
+    if (a < 128 && b < 128) return std::max(a, b);
+    if (a >= 128 && b < 128) return inv(std::max(inv(a), b));
+    if (a < 128 && b >= 128) return inv(std::max(a, inv(b)));
+    return std::max(inv(a), inv(b));
+  }
+  // render.ml:867-981 — constructive planar geometry: both operands are rendered as black alpha
+  // mattes, the alphas are combined region by region, then the fill is dissolved by the result.
+  Sprite sprite_of_cpg(const Obj& o, const Shape& shp) {
+    Obj da = o.children.at(0), db = o.children.at(1);
+    da.fill = Fill::plain(mkcol(0, 0, 0)); db.fill = da.fill;
+    Shape shp_a, min_a, shp_b, min_b;
+    shape_of_basicshape(da, shp_a, min_a); shape_of_basicshape(db, shp_b, min_b);
+    shp_a = shape_intersection(shp_a, shp); min_a = shape_intersection(min_a, shp);
+    shp_b = shape_intersection(shp_b, shp); min_b = shape_intersection(min_b, shp);
+    Shape max_a = shape_difference(shp_a, min_a), max_b = shape_difference(shp_b, min_b);
+    Shape tor_a = shape_intersection(shp, shp_a);
+    Shape tor_b = shape_difference(shape_intersection(shp, shp_b), shape_intersection(min_a, min_b));
+    Sprite spr_a = sprite_of_basicshape(da, tor_a), spr_b = sprite_of_basicshape(db, tor_b);
+    Shape rend_a = shape_of_sprite(spr_a), rend_b = shape_of_sprite(spr_b);
+    Shape total = shape_union(rend_a, rend_b);
+    Shape mm = shape_intersection(shape_intersection(min_a, min_b), total), mM = shape_intersection(shape_intersection(min_a, max_b), total);
+    Shape Mm = shape_intersection(shape_intersection(max_a, min_b), total), MM = shape_intersection(shape_intersection(max_a, max_b), total);
+    auto invert = [](const Sprite& s) { return sprite_map([](colour c) { return colour_of_channel(255 - alpha_of_colour(c)); }, s); };
+    auto both = [&](const CompOp& f) { return caf(f, opaque, portion(spr_a, MM), portion(spr_b, MM)).first; };
+    Sprite minmin, minmax, maxmin, maxmax;
+    switch (o.cpg_op) {
+      case 0:
+        minmin = portion(spr_a, mm); minmax = portion(spr_b, mM); maxmin = portion(spr_a, Mm);
+        maxmax = both([](colour a, colour b) { int t = alpha_of_colour(a) + alpha_of_colour(b); return colour_of_rgba(0, 0, 0, t > 255 ? 255 : t); });
+        break;
+      case 2:
+        minmax = invert(portion(spr_b, mM));
+        maxmax = both([](colour a, colour b) { return colour_of_channel(std::max(0, alpha_of_colour(a) - alpha_of_colour(b))); });
+        break;
+      case 1:
+        minmin = portion(spr_a, mm); minmax = portion(spr_b, mM); maxmin = portion(spr_a, Mm);
+        maxmax = both([](colour a, colour b) { return colour_of_channel(std::min(alpha_of_colour(a), alpha_of_colour(b))); });
+        break;
+      default:
+        minmax = invert(portion(spr_b, mM)); maxmin = invert(portion(spr_a, Mm));
+        maxmax = both([](colour a, colour b) { return colour_of_rgba(0, 0, 0, eor(alpha_of_colour(a), alpha_of_colour(b))); });
+    }
+    Shape covered = shape_union(shape_union(mm, mM), shape_union(Mm, MM));
+    Sprite parts[8] = {minmin, minmax, maxmin, maxmax,
+                       portion(spr_a, shape_intersection(shape_difference(min_a, covered), rend_a)),
+                       portion(spr_b, shape_intersection(shape_difference(min_b, covered), rend_b)),
+                       portion(spr_a, shape_intersection(shape_difference(max_a, covered), rend_a)),
+                       portion(spr_b, shape_intersection(shape_difference(max_b, covered), rend_b))};
+    Sprite alpha;
+    for (auto& part : parts) alpha = caf([](colour, colour) -> colour { throw std::runtime_error("CPG caf"); }, opaque, alpha, part).first;
+    // 6. apply the fill (map_coords: per pixel fill lookup)
+    Sprite out = alpha;
+    for (auto& r : out.rows) {
+      int off = 0;
+      for (auto& sp : r.spans) { for (int k = 0; k < sp.len; k++) r.px[off + k] = dissolve(o.fill.fillsingle(sp.x + k, r.y), alpha_of_colour(r.px[off + k])); off += sp.len; }
+    }
+    return out;
   }
 
   // render.ml:1134-1242 (non-filter objects)

@@ -387,3 +387,74 @@ def test_convolve_sprite(ctx, oracle):
         ctx.shape_free(ho)
     with pytest.raises(abi.CohError):
         ctx.convolve_sprite("unit", 0, 0, np.zeros(0, np.uint32))
+
+
+def test_stroked_path_winding_quirk(ctx, oracle):
+    """Basic (fill, StrokedPath ...): shape with NonZero, sprite with EvenOdd (render.ml:510 vs 1018).  The edge
+    list here is a self-overlapping outline (what a stroker emits for a tight bend), where the rules differ."""
+    W, H = 220, 180
+    pts = [(20.0, 20.0), (200.0, 30.0), (190.0, 160.0), (30.0, 150.0), (20.0, 20.0), (110.0, 10.0), (180.0, 90.0), (100.0, 170.0), (25.0, 95.0)]
+    s = S.sub_of_float
+    edges = np.array([[s(pts[i][0]), s(pts[i][1]), s(pts[(i + 1) % len(pts)][0]), s(pts[(i + 1) % len(pts)][1])] for i in range(len(pts))], dtype=np.int32)
+    b = S.SceneBuilder()
+    b.stroked_path_edges(edges, S.Fill.plain(S.dissolve(S.rgba8(10, 10, 10), 210)))
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    b2 = S.SceneBuilder()
+    b2.path_edges(edges, S.Fill.plain(S.dissolve(S.rgba8(10, 10, 10), 210)))
+    b2.begin_background()
+    b2.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, e, p = b2.arrays()
+    assert not np.array_equal(oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H)), ref), "the quirk must be visible on this input"
+
+
+def _cpg_scene(op, W, H, fill, **kw):
+    b = S.SceneBuilder()
+    sq = [S.polygon_segments([(30.3, 30.2), (120.5, 33.9), (118.1, 110.7), (28.8, 104.4)])]
+    star = [S.polygon_segments([(80.0, 20.0), (180.4, 80.2), (90.7, 150.1), (150.2, 25.5), (60.9, 120.3)])]
+    b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+    b.cpg(op, sq, star, fill, winding_b=S.COH_EVENODD, **kw)
+    b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    return b
+
+
+@pytest.mark.parametrize("op", ["union", "intersection", "subtraction", "xor"])
+def test_cpg_objects(ctx, oracle, op):
+    """Basic (fill, CPG (op, Path a, Path b)) (render.ml:522-528 shapes, 867-981 sprite): overlapping operands
+    with different winding rules, plain and gradient fills, under an alias offset and a dissolving group."""
+    W, H = 200, 160
+    for fill in (S.Fill.plain(S.dissolve(S.rgba8(200, 30, 30), 230)),
+                 S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 0, 255), 128))):
+        b = _cpg_scene(op, W, H, fill)
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u), op
+        assert _max_lsb(got, ref) == 0, op
+    b = _cpg_scene(op, W, H, S.Fill.plain(S.rgba8(200, 30, 30)), dx=13, dy=-7, pretrans=150)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, op
+
+
+def test_cpg_object_shape(ctx, oracle):
+    """coh_scene_object_shape of a CPG object = the reference's set expressions of the operands' shapes."""
+    W, H = 200, 160
+    ctx.fb_configure(W, H)
+    for op in ("union", "intersection", "subtraction", "xor"):
+        b = _cpg_scene(op, W, H, S.Fill.plain(S.rgba8(1, 2, 3)))
+        objs, n, nbg, e, p = b.arrays()
+        sc = ctx.scene_create(objs, nbg, e, p)
+        hs, hm = ctx.scene_object_shape(sc, 1)
+        o = objs[1]
+        sa, ma = oracle.shapeminshape(e[o.first:o.first + o.count], o.winding)
+        sb, mb = oracle.shapeminshape(e[o.first2:o.first2 + o.count2], o.winding2)
+        U, D, I = (lambda x, y: oracle.shape_op("union", x, y)), (lambda x, y: oracle.shape_op("difference", x, y)), (lambda x, y: oracle.shape_op("intersection", x, y))
+        exp_s, exp_m = {"union": (U(sa, sb), U(ma, mb)), "intersection": (I(sa, sb), I(ma, mb)), "subtraction": (D(sa, mb), D(ma, sb)),
+                        "xor": (D(U(sa, sb), I(ma, mb)), U(D(mb, sa), D(ma, sb)))}[op]
+        assert np.array_equal(ctx.shape_export(hs), exp_s), op
+        assert np.array_equal(ctx.shape_export(hm), exp_m), op
+        ctx.shape_free(hs)
+        ctx.shape_free(hm)
+        ctx.scene_free(sc)
