@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COH_LIB_PATH", os.path.join(_HERE, "libcoherence_b200.so"))  # override: kernel-variant experiments
 
 COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH, COH_OBJ_CPG = 0, 1, 2, 3, 4, 5
+COH_OBJ_FILTER = 6
+COH_FILTER_HOLE, COH_FILTER_MONOCHROME, COH_FILTER_BLUR, COH_FILTER_SCENE, COH_FILTER_READING_SCENE = 1, 2, 3, 4, 100
 COH_CPG_UNION, COH_CPG_INTERSECTION, COH_CPG_SUBTRACTION, COH_CPG_EXCLUSIVEOR = 0, 1, 2, 3
 COH_NONZERO, COH_EVENODD = 0, 1
 COH_FILL_PLAIN, COH_FILL_AXIAL, COH_FILL_RADIAL = 0, 1, 2
@@ -30,6 +32,7 @@ class CohObject(C.Structure):
         ("prim", C.c_int32 * 4), ("prim_null", C.c_int32), ("convolve", C.c_int32), ("sprite_winding", C.c_int32), ("id", C.c_int64),
         ("fparam", C.c_double * 6), ("brush_opacity", C.c_double), ("brush_radius", C.c_double),
         ("first2", C.c_int32), ("count2", C.c_int32), ("winding2", C.c_int32), ("cpg_op", C.c_int32),
+        ("filter_kind", C.c_int32), ("filter_kernel", C.c_int32),
     ]
 
 

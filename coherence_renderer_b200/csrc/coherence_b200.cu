@@ -40,6 +40,13 @@ struct DevScene {
   std::vector<int64_t> ids;      // cache key (Id.idset) of every record
   std::vector<int> rec_of_abi;   // record index of every object of the ABI array (-1: GROUP_END / dropped)
   std::vector<int> group_last;   // for group records: last record index inside the group
+  // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
+  // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
+  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; };
+  std::vector<FilterRec> filters;
+  int n_scene_leaves = 0;        // ordinary leaves of the scene list
+  int n_front_leaves = 0;        // + leaves of reading-scene groups (the background list follows)
+  std::vector<int> h_leaves;
   bool has_fancy = false;    // some object has a gradient / radial fill
   bool has_brush = false;
   size_t items_total = 0;
@@ -801,18 +808,57 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
   std::vector<int> group_last;
   std::vector<int64_t> ids;
+  // filters and their reading-scene groups (include/coherence_b200.h, COH_FILTER_*)
+  std::vector<DevScene::FilterRec> filters;
+  std::vector<int> filter_read_abi;            // per filter: abi index of its reading-scene group, or -1
+  std::map<int, std::pair<int, int>> reading;  // abi index of a reading-scene GROUP_BEGIN -> leaf range
+  std::vector<int> open_reading;               // per open GROUP_BEGIN: abi index if it is a reading-scene group, else -1
+  int cur_reading = -1, n_scene_leaves = -1, n_front_leaves = -1;
   for (int i = 0; i < n_objs; i++) {
     if (i == n_objs - n_background) {
-      if (open.size() != 1) FAIL("scene: unterminated group");
+      if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
+      if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+      n_front_leaves = (int)leaves.size();
       root.flags = OF_ROOT_BACKGROUND;
       recs.push_back(root); open[0] = (int)recs.size() - 1;
     }
     const coh_object& c = objs[i];
     if (c.kind == COH_OBJ_GROUP_END) {
+      if (open_reading.empty()) FAIL("scene: GROUP_END without GROUP_BEGIN");
+      const int rd = open_reading.back(); open_reading.pop_back();
+      if (rd >= 0) { reading[rd].second = (int)leaves.size(); cur_reading = -1; continue; }
       if (open.size() <= 1) FAIL("scene: GROUP_END without GROUP_BEGIN");
       group_last.resize(recs.size(), -1);
       group_last[open.back()] = (int)recs.size() - 1;
       open.pop_back();
+      continue;
+    }
+    if (c.kind == COH_OBJ_GROUP_BEGIN && c.filter_kind == COH_FILTER_READING_SCENE) {
+      // members become direct members of the root list of their own pass (render.ml:1091 renders the list)
+      if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: reading-scene groups must be top-level members of the scene list");
+      if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+      open_reading.push_back(i); cur_reading = i;
+      reading[i] = std::make_pair((int)leaves.size(), (int)leaves.size());
+      continue;
+    }
+    if (n_scene_leaves >= 0 && cur_reading < 0 && i < n_objs - n_background) FAIL("scene: reading-scene groups must come after every ordinary scene object");
+    if (c.kind == COH_OBJ_FILTER) {
+      if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: filter objects must be top-level members of the scene list");
+      if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+      if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
+      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SCENE) FAIL("scene: bad filter kind");
+      if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
+      if (c.dx || c.dy) FAIL("scene: translated filter objects are not supported yet");
+      DevScene::FilterRec f; memset(&f, 0, sizeof f);
+      f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
+      if (c.filter_kind == COH_FILTER_BLUR) {
+        f.kernel_kind = c.filter_kernel & 255; f.r = c.filter_kernel >> 8;
+        if ((f.kernel_kind != COH_CONV_UNIT && f.kernel_kind != COH_CONV_GAUSSIAN) || f.r <= 0 || f.r > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
+      }
+      if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
+      EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+      shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
+      filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
       continue;
     }
     ObjRec o; memset(&o, 0, sizeof o);
@@ -827,7 +873,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       case COH_OBJ_GROUP_BEGIN:
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
-        recs.push_back(o); open.push_back((int)recs.size() - 1);
+        recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
         rec_of_abi[i] = (int)recs.size() - 1;
         ids.resize(recs.size(), -1); ids.back() = c.id;
         continue;
@@ -933,8 +979,17 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     ids.resize(recs.size(), -1); ids.back() = c.id;
     leaves.push_back((int)recs.size() - 1);
   }
-  if (open.size() != 1) FAIL("scene: unterminated group");
+  if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
+  if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+  if (n_front_leaves < 0) n_front_leaves = (int)leaves.size();
+  for (size_t k = 0; k < filters.size(); k++) {
+    if (filter_read_abi[k] < 0) continue;
+    auto it = reading.find(filter_read_abi[k]);
+    if (it == reading.end()) FAIL("scene: filter without its reading-scene group");
+    filters[k].read0 = it->second.first; filters[k].read1 = it->second.second;
+  }
   DevScene* s = new DevScene();
+  s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves; s->h_leaves = leaves;
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->h_objs = recs;
   group_last.resize(recs.size(), -1);
@@ -943,6 +998,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH || o.kind == K_CONV || o.kind == K_CPG) s->has_brush = true;
+    if (!filters.empty()) s->has_brush = true;  // the filter passes need the walker variant that can continue a frame
   }
   CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1062,9 +1118,23 @@ int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y
   return 0;
 }
 
-// One pass (scene or background) of render_frame over the band.
-static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh, bool write_clear, bool record_u) {
+// One walk over the leaves [l0, l1) of a scene: binning + k_walk.
+struct PassArgs {
+  int l0, l1;                 // leaf range (list order)
+  int ux, uy, uw, uh;         // update box (used when u_init is null)
+  const uint32_t* u_init;     // update set as a bit-frame, or null
+  uint32_t* u_out;            // receives `u` after the scene list, or null (may alias u_init)
+  uint32_t* fb;               // target canvas
+  bool write_clear, resume;
+};
+static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   const Frame& fr = ctx->fr;
+  const int ux = A.ux, uy = A.uy, uw = A.uw, uh = A.uh;
+  const bool write_clear = A.write_clear;
+  const int n_leaves = A.l1 - A.l0;
+  const int4* leaf_box = s->leaf_box + A.l0;
+  const int* leaves = s->leaves + A.l0;
+  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves;
   if (fr.band_y1 <= fr.band_y0 || uw <= 0 || uh <= 0) return 0;
   int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
@@ -1086,21 +1156,22 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   // K1: count, scan, fill.  Small scenes: warp per cell scanning all leaves (lists come out sorted,
   // no atomics).  Large scenes: warp per leaf over the cells it covers + per-cell sort.
-  const bool big = s->n_leaves > 1024;
+  const bool big = n_leaves > 1024;
   // capacity of the item pool: the exact total is a pure function of the object boxes and the
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
-  if (s->items_for_W != fr.W || s->items_for_H != fr.H || s->items_for_y0 != fr.band_y0 || s->items_for_y1 != fr.band_y1) {
+  size_t total = 0;
+  if (!whole || s->items_for_W != fr.W || s->items_for_H != fr.H || s->items_for_y0 != fr.band_y0 || s->items_for_y1 != fr.band_y1) {
     size_t tot = 0;
-    for (const ObjRec& o : s->h_objs) {
-      if (o.kind == K_GROUP) continue;
+    for (int li = A.l0; li < A.l1; li++) {
+      const ObjRec& o = s->h_objs[s->h_leaves[li]];
       int cx0 = std::max(o.bx0 >> 5, 0), cx1 = std::min(o.bx1 >> 5, fr.tiles_x - 1);
       int cy0 = std::max(floordiv(o.by0, CELL_H), cell_row0), cy1 = std::min(floordiv(o.by1, CELL_H), cell_row1);
       if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
     }
-    s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1;
-  }
-  const size_t total = s->items_total;
+    total = tot;
+    if (whole) { s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
+  } else total = s->items_total;
   const size_t need = big ? 2 * total : total;  // the sort of very long lists stages through the upper half
   if (need > ctx->cell_items_cap) {
     DFREE(ctx->cell_items);
@@ -1110,20 +1181,20 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   }
   if (!big) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
-    k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
+    k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
     if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr)) return 1;
-    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   } else {
-    const int obj_blocks = cdiv(s->n_leaves * 32, 256);
+    const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
-    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
+    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
     if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, nullptr)) return 1;
     if (ordered) {
       k_bin_hist<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(ctx->cell_counts, n_cells, ctx->order_hist); LAUNCHED();
       k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED();
     }
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
-    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(s->leaf_box, s->leaves, s->n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, ctx->cell_off, ctx->cell_items); LAUNCHED();
+    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, ctx->cell_off, ctx->cell_items); LAUNCHED();
     k_bin_sort<<<cdiv(n_cells * 32, 128), 128, 0, ctx->stream>>>(ctx->cell_off, ctx->cell_items, ctx->cell_items + total, n_cells, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   }
   WalkParams P;
@@ -1132,8 +1203,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
   P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
-  P.u_init = ctx->use_u_init ? ctx->u_init : nullptr; P.u_out = record_u ? ctx->u_out : nullptr; P.fb = ctx->fb; P.error_flag = ctx->d_error;
-  P.write_clear = write_clear ? 1 : 0;
+  P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
+  P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
   // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
   const int walk_h = big ? 16 : 4;
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
@@ -1168,6 +1239,125 @@ static int render_pass(coh_ctx* ctx, DevScene* s, int ux, int uy, int uw, int uh
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Frames with filter objects (render.ml:1080-1131, 1248-1265; filters.ml).  A filter splits the
+// scene list: the members in front of it are walked as usual; the filter itself renders its
+// reading scene (X) and the members below it (Z) into canvases of their own — each a recursive
+// render of the rest of the list, as in the reference — filters X, and blends the two by the
+// antialiased matte of its geometry into the accumulator; its whole shape then leaves `u`
+// (the "extra finish", render.ml:1120-1121, 1308) and the walk continues below it, the
+// accumulator carrying on from the framebuffer (WalkParams::resume).
+// ---------------------------------------------------------------------------------------
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh);
+
+static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target) {
+  const DevScene::FilterRec& F = s->filters[fi];
+  const Frame& fr = ctx->fr;
+  const int W = fr.W, H = fr.H, nw = fr.tiles_x;
+  const size_t nwords = (size_t)nw * H, npx = (size_t)W * H;
+  const int y0 = std::max(F.by0, 0), y1 = std::min(F.by1, H - 1);
+  if (y0 > y1 || F.bx1 < 0 || F.bx0 >= W) return 0;  // geometry outside the frame
+  const int h = y1 - y0 + 1;
+  const unsigned wblocks = (unsigned)((nwords + 255) / 256);
+  uint32_t *SG = nullptr, *MG = nullptr, *T = nullptr, *R = nullptr, *X = nullptr, *Z = nullptr, *tmp = nullptr;
+  uint8_t *op = nullptr, *alpha = nullptr; int* d_taps = nullptr;
+  CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&MG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
+  CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(MG, 0, 4 * nwords, ctx->stream));
+  const EdgeRec* ed = s->edges + F.first;
+  // shape / minshape of the geometry (render.ml:472-474)
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, MG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();  // MG: coverage, unused
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, U, T, nwords, 2); LAUNCHED();     // shptorender = r &&& u (render.ml:1281)
+  // reading scene -> X -> filter function -> Y (in place)
+  uint32_t* Y = nullptr;
+  if (F.kind != COH_FILTER_HOLE) {
+    CK(DMALLOC(&X, 4 * npx));
+    CK(cudaMemsetAsync(X, 0, 4 * npx, ctx->stream));
+    if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp
+      k_dilate<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(T, R, H, nw, 2 * F.r + 1, 2 * F.r + 1); LAUNCHED();
+    } else CK(cudaMemcpyAsync(R, T, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (F.kind == COH_FILTER_SCENE) {
+      PassArgs A{F.read0, F.read1, 0, 0, W, H, R, nullptr, X, true, false};
+      if (render_pass(ctx, s, A)) return 1;
+    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true)) return 1;
+    Y = X;
+    if (F.kind == COH_FILTER_MONOCHROME) {
+      k_monochrome<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(X, X, npx); LAUNCHED();
+    } else if (F.kind == COH_FILTER_BLUR) {
+      // Convolve.convolve_sprite_in_shape (convolve.ml:265-296) on the frame-sized canvas: pixels the
+      // reading scene did not render are clear, exactly like the reference's canvas outside the sprite
+      std::vector<int> taps; int total = 0;
+      if (F.kernel_kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+        for (int i = -F.r; i <= F.r; i++) {
+          double xr = (double)i / (double)F.r, yr = 0. / (double)F.r;
+          double gg = exp(-(xr * xr + yr * yr)) / 2.;
+          int v = (int)((double)(4 * F.r * F.r) * gg + 0.5);
+          taps.push_back(v); total += v;
+        }
+        CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
+        CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // `taps` is a local
+      }
+      CK(DMALLOC(&tmp, 4 * npx));
+      dim3 gp(cdiv(W, 128), H);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, tmp, W, H, F.r, F.kernel_kind, d_taps, total, 0); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X, W, H, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
+    }
+  }
+  // the geometry's matte in the update (render.ml:1099-1103)
+  CK(DMALLOC(&op, (size_t)nw * 32 * H)); CK(DMALLOC(&alpha, npx));
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, T + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op + (size_t)y0 * nw * 32, ctx->d_error); LAUNCHED();
+  k_filter_matte<<<dim3(cdiv(nw, 4), H), 128, 0, ctx->stream>>>(T, op, F.colour, W, H, nw, alpha, R); LAUNCHED();  // R := finished
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, R, R, nwords, 1); LAUNCHED();      // pixels_for_normal_scene (render.ml:1105)
+  CK(DMALLOC(&Z, 4 * npx));
+  CK(cudaMemsetAsync(Z, 0, 4 * npx, ctx->stream));
+  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true)) return 1;
+  k_filter_blend<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(T, alpha, Z, Y, target, W, H, nw); LAUNCHED();
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(U, SG, U, nwords, 1); LAUNCHED();     // u --- ef (render.ml:1308)
+  DFREE(SG); DFREE(MG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
+  return 0;
+}
+// Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh) {
+  const Frame& fr = ctx->fr;
+  auto segment = [&](int a, int b) -> int {
+    if (b > a) {
+      PassArgs A{a, b, 0, 0, fr.W, fr.H, U, U, target, fresh, !fresh};
+      if (render_pass(ctx, s, A)) return 1;
+    } else if (fresh) {
+      k_clear_in_bits<<<dim3(cdiv(fr.W, 128), fr.H), 128, 0, ctx->stream>>>(target, U, fr.W, fr.H, fr.tiles_x); LAUNCHED();
+    }
+    fresh = false;
+    return 0;
+  };
+  for (int f = f0; f < (int)s->filters.size(); f++) {
+    if (segment(l0, s->filters[f].pos)) return 1;
+    if (apply_filter(ctx, s, f, U, target)) return 1;
+    l0 = s->filters[f].pos;
+  }
+  return segment(l0, s->n_scene_leaves);
+}
+static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, int ux, int uy, int uw, int uh) {
+  const Frame& fr = ctx->fr;
+  if (fr.band_y0 != 0 || fr.band_y1 != fr.H) FAIL("render_frame: scenes with filter objects need the whole frame on one context (filters read outside their band)");
+  if (uw <= 0 || uh <= 0) return 0;
+  const int nw = fr.tiles_x;
+  const size_t nwords = (size_t)nw * fr.H;
+  uint32_t *U = ctx->u_out, *U0 = nullptr;
+  CK(DMALLOC(&U0, 4 * nwords));
+  if (u_init) CK(cudaMemcpyAsync(U0, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, ux, uy, std::min(ux + uw - 1, fr.W - 1), uy + uh - 1); LAUNCHED(); }
+  CK(cudaMemcpyAsync(U, U0, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true)) return 1;
+  if (s->n_leaves > s->n_front_leaves) {
+    // the background list shows wherever the scene pass is not opaque (render.ml:1363-1365)
+    k_not_opaque_bits<<<dim3(cdiv(nw, 4), fr.H), 128, 0, ctx->stream>>>(ctx->fb, U0, U0, fr.W, fr.H, nw); LAUNCHED();
+    PassArgs A{s->n_front_leaves, s->n_leaves, 0, 0, fr.W, fr.H, U0, nullptr, ctx->fb, false, true};
+    if (render_pass(ctx, s, A)) return 1;
+  }
+  DFREE(U0);
+  return 0;  // kernel-side failures are reported by coh_sync, as for plain frames
+}
+
 // Merge the objects of `scene` and `background` into one walk: the reference renders the two
 // lists separately over the same update and composites the results with `over`
 // (render.ml:1357-1365); a pixel of the background is only visible where the scene pass left
@@ -1179,7 +1369,13 @@ int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, in
   DevScene* s = (DevScene*)scene;
   if (!s) FAIL("coh_render_frame: null scene");
   bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
-  if (render_pass(ctx, s, ux, uy, uw, uh, true, record_u)) return 1;
+  if (!s->filters.empty()) {
+    if (render_filtered(ctx, s, nullptr, ux, uy, uw, uh)) return 1;
+    ctx->have_u = true;
+    return 0;
+  }
+  PassArgs A{0, s->n_leaves, ux, uy, uw, uh, nullptr, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
+  if (render_pass(ctx, s, A)) return 1;
   ctx->have_u = record_u;
   return 0;
 }
@@ -1389,9 +1585,13 @@ int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, 
   CK(cudaMemsetAsync(ctx->u_init, 0, sizeof(uint32_t) * (size_t)fr.tiles_x * fr.H, ctx->stream));
   k_spans_to_bits<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(us->row_ptr, us->spans, us->y0, us->n_rows, 0, fr.H, 0, fr.tiles_x, ctx->u_init); LAUNCHED();
   bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
-  ctx->use_u_init = true;
-  int rc = render_pass(ctx, s, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1, true, record_u);
-  ctx->use_u_init = false;
+  if (!s->filters.empty()) {
+    int rc = render_filtered(ctx, s, ctx->u_init, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1);
+    ctx->have_u = !rc;
+    return rc;
+  }
+  PassArgs A{0, s->n_leaves, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1, ctx->u_init, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
+  int rc = render_pass(ctx, s, A);
   ctx->have_u = record_u && !rc;
   return rc;
 }

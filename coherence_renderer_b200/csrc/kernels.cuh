@@ -279,6 +279,7 @@ struct WalkParams {
   uint32_t* fb;                // RGBA8 framebuffer, fr.W x fr.H
   int* error_flag;             // set to 1 when an object overflows COH_MAXX crossings
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
+  int resume;                  // continue a frame: the root accumulators start from what `fb` already holds
   // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
   // x of its span (polygon.ml:736) and a span may begin in a tile further left.  Every tile
   // publishes, per fancy object whose visible edge run touches its right border, where that run
@@ -516,7 +517,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
   // Fast path: the only object reaching this item is an opaque primitive that covers all of it
   // (typically the background rectangle): the rows are just that colour.
-  if (it1 - it0 == 1) {
+  if (it1 - it0 == 1 && !P.resume) {
     const ObjRec& o = P.objs[P.cell_items[it0]];
     bool simple = o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && P.objs[o.anc[0]].pretrans < 0;
     if (simple) {
@@ -572,8 +573,19 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     if ((gflags & OF_ROOT_SCENE) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = u;
   };
   auto push_group = [&](int g) {
+    // Continuing a frame (filter passes, render.ml:1080-1131): the scene list's accumulator carries on from the
+    // framebuffer (render_scene's `a`); the background list is composited under it (render.ml:1363-1365).
+    const int rflags = (BRUSH && P.resume && depth == 0) ? P.objs[g].flags : 0;
 #pragma unroll 1
-    for (int r = 0; r < WALK_H; r++) { stk_acc[depth][r] = acc_rows[r][lane]; acc_rows[r][lane] = 0u; }
+    for (int r = 0; r < WALK_H; r++) {
+      uint32_t below = acc_rows[r][lane], fresh = 0u;
+      if (BRUSH && rflags) {
+        const int py = y0 + r, px = tx0 + lane;
+        const uint32_t have = (py < P.fr.H && px < P.fr.W) ? P.fb[(size_t)py * P.fr.W + px] : 0u;
+        if (rflags & OF_ROOT_SCENE) fresh = have; else below = have;
+      }
+      stk_acc[depth][r] = below; acc_rows[r][lane] = fresh;
+    }
     stk_u[depth] = u;
     open_grp[depth] = g;
     // A group composited with PreTrans (v < 1) gives pixels back to its parent's `u` when it
@@ -692,8 +704,8 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, aa_bits, stage, s_prefix, volume, lane, ok);
             if (!ok) bad = true;
           } else if (BRUSH && okind == K_CPG) {
-            // sprite_of_cpg (render.ml:867-981): both operands become alpha mattes (255 inside the
-            // minshape, antialiased on the rest of the shape, 0 outside) and are combined per pixel
+            // sprite_of_cpg (render.ml:867-981): both operands become antialiased alpha mattes (0 outside
+            // their shape) and are combined per pixel
             const int src = cc * WALK_H + r;
             const uint32_t SA = __shfl_sync(0xFFFFFFFFu, gSA, src), MA = __shfl_sync(0xFFFFFFFFu, gMA, src);
             const uint32_t SB = __shfl_sync(0xFFFFFFFFu, gSB, src), MB = __shfl_sync(0xFFFFFFFFu, gMB, src);
@@ -712,6 +724,10 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
               b = aa_tile_nl(P.edges, P.rowedge_idx + ea, eb - ea, o.b_opw >> 8, xx0, yy, XB, aa_bits, stage, s_prefix, volume, lane, ok);
               if (!ok) bad = true;
             }
+            // Inside an operand's minshape the reference never consults that operand's matte (regions
+            // min/max and max/min take the other operand's alpha, or its inverse): 255 stands for it in
+            // cpg_alpha.  (Its sampled value could be below 255: the minshape's row band misses the top
+            // quarter of the AA window.)
             a = ((MA >> lane) & 1u) ? 255 : (((XA >> lane) & 1u) ? a : 0);
             b = ((MB >> lane) & 1u) ? 255 : (((XB >> lane) & 1u) ? b : 0);
             opacity = cpg_alpha(o.b_opw & 255, a, b);
@@ -977,6 +993,64 @@ __global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf
   o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy;
   leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
 }
+// ------------------------------------------------------------------------------------
+// Filters (render.ml:1080-1131, 1248-1265; filters.ml).  Frame-sized RGBA8 canvases and bit-frames
+// (nw words per row, bit 0 of word 0 = pixel x 0).
+// ------------------------------------------------------------------------------------
+// canvas[p] = clear for every pixel p of the bit-frame
+__global__ void k_clear_in_bits(uint32_t* __restrict__ canvas, const uint32_t* __restrict__ bits, int W, int H, int nw) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  if ((bits[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u) canvas[(size_t)y * W + x] = 0u;
+}
+// Filters.monochrome: sprite_map Colour.monochrome (colour.ml: average of r, g, b; alpha kept)
+__global__ void k_monochrome(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = in[i];
+  const uint32_t av = ((c & 255u) + ((c >> 8) & 255u) + ((c >> 16) & 255u)) / 3u;
+  out[i] = av | (av << 8) | (av << 16) | (c & 0xFF000000u);
+}
+// The filter geometry's matte inside T (render.ml:1099): alpha of `dissolve fill opacity` with the
+// antialiased opacity bytes `op` (Polygon.polygon_sprite samples every pixel it is given, minshape
+// pixels included); `finished` = its opaque pixels (1100-1103).  One word per warp.
+__global__ void k_filter_matte(const uint32_t* __restrict__ T, const uint8_t* __restrict__ op,
+                               uint32_t colour, int W, int H, int nw, uint8_t* __restrict__ alpha, uint32_t* __restrict__ finished) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = blockIdx.y, lane = threadIdx.x & 31;
+  if (w >= nw || y >= H) return;
+  const uint32_t t = T[(size_t)y * nw + w];
+  const int x = 32 * w + lane;
+  int a = 0;
+  if (((t >> lane) & 1u) && x < W) {
+    a = (int)(px_dissolve(colour, op[(size_t)y * nw * 32 + x]) >> 24);
+    alpha[(size_t)y * W + x] = (uint8_t)a;
+  }
+  const uint32_t f = __ballot_sync(0xFFFFFFFFu, a == 255);
+  if (lane == 0) finished[(size_t)y * nw + w] = f & t;
+}
+// blend' (render.ml:1248-1265) and the composite of the filter's sprite into the accumulator
+// (render.ml:1290-1291): fb = over fb (pd_plus (dissolve Z (255 - alpha)) (dissolve Y alpha)) on T.
+// Pixels a scene did not render are clear in Z / Y, which both operators treat as absent.
+__global__ void k_filter_blend(const uint32_t* __restrict__ T, const uint8_t* __restrict__ alpha, const uint32_t* __restrict__ Z,
+                               const uint32_t* __restrict__ Y, uint32_t* __restrict__ fb, int W, int H, int nw) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  if (!((T[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u)) return;
+  const size_t i = (size_t)y * W + x;
+  const int a = alpha[i];
+  const uint32_t z = px_dissolve(Z[i], 255 - a), yy = Y ? px_dissolve(Y[i], a) : 0u;
+  fb[i] = px_over(fb[i], px_plus(z, yy));
+}
+// update & ~opaque(fb): where the background list is still visible under the scene pass
+__global__ void k_not_opaque_bits(const uint32_t* __restrict__ fb, const uint32_t* __restrict__ U, uint32_t* __restrict__ out, int W, int H, int nw) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = blockIdx.y, lane = threadIdx.x & 31;
+  if (w >= nw || y >= H) return;
+  const int x = 32 * w + lane;
+  const bool opq = x < W && (fb[(size_t)y * W + x] >> 24) == 255u;
+  const uint32_t o = __ballot_sync(0xFFFFFFFFu, opq);
+  if (lane == 0) out[(size_t)y * nw + w] = U[(size_t)y * nw + w] & ~o;
+}
+
 // ------------------------------------------------------------------------------------
 // K6 convolve (convolve.ml:115-232) on dense RGBA8 canvases [h][w]; pixels outside the canvas
 // read as clear, like the 2r border of Sprite.flatten_sprite (convolve.ml:247).  One pass per

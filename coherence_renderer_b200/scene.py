@@ -319,6 +319,32 @@ class SceneBuilder:
         fill.apply(o)
         return o
 
+    def filter(self, kind, subpaths, fill=None, winding=COH_NONZERO, kernel=None, **kw):
+        """Filter {geometry = Basic (fill, Path subpaths); ...} (filters.ml): kind in "hole" | "monochrome" | "blur" |
+        "scene".  kernel = ("gaussian" | "unit", r) for blur; a "scene" filter (affine, rgb, wireframe ...: the
+        caller rewrites the objects below) gets its modified scene from reading_scene_begin(filter_obj)."""
+        from . import abi
+
+        o = self._obj(abi.COH_OBJ_FILTER, **kw)
+        e = np.concatenate([abi.host_edgelist_of_subpath(sg) for sg in subpaths]).reshape(-1, 4)
+        o.first, o.count, o.winding = self._n_edges, len(e), winding
+        self.edges.append(e)
+        self._n_edges += len(e)
+        (fill or Fill.plain(WHITE)).apply(o)
+        o.filter_kind = {"hole": 1, "monochrome": 2, "blur": 3, "scene": 4}[kind]
+        if kind == "blur":
+            o.filter_kernel = {"unit": 1, "gaussian": 2}[kernel[0]] | (int(kernel[1]) << 8)
+        return o
+
+    def reading_scene_begin(self, filter_obj):
+        """Open the reading-scene group of a "scene" filter (after every ordinary scene object); close with group_end()."""
+        from . import abi
+
+        o = self.group_begin()
+        o.filter_kind = abi.COH_FILTER_READING_SCENE
+        filter_obj.first2 = len(self.objs) - 1
+        return o
+
     def group_begin(self, **kw):
         return self._obj(COH_OBJ_GROUP_BEGIN, **kw)
 

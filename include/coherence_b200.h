@@ -40,8 +40,22 @@ enum {
   COH_OBJ_GROUP_BEGIN = 2, /* Group scene ... */
   COH_OBJ_GROUP_END = 3,   /* ... end of the innermost open group                          */
   COH_OBJ_BRUSH = 4,       /* Basic (fill, Brushstroke ((opacity, Gaussian r), path))      */
-  COH_OBJ_CPG = 5          /* Basic (fill, CPG (op, Path a, Path b)), render.ml:17-18, 522-528, 867-981 */
+  COH_OBJ_CPG = 5,         /* Basic (fill, CPG (op, Path a, Path b)), render.ml:17-18, 522-528, 867-981 */
+  COH_OBJ_FILTER = 6       /* Filter {geometry = Basic (fill, Path); reading_scene; filter} (render.ml:37-48, 1080-1131) */
 };
+/* Filters (filters.ml).  The reference passes closures; across the ABI a filter is a descriptor:
+ *   HOLE        filters.ml:216-224  reading scene = [], filter = identity
+ *   MONOCHROME  filters.ml:229-238  reading scene = the objects below, filter = sprite_map Colour.monochrome
+ *   BLUR        filters.ml:243-258  reading scene = the objects below read in bloat (2r+1) (2r+1) shape,
+ *                                   filter = Convolve.convolve_sprite_in_shape kernel (filter_kernel = COH_CONV_* | r << 8)
+ *   SCENE       affine / rgb / wireframe / swapdepth / minus (filters.ml:105-212, 271-332): the caller builds the
+ *               modified scene (a host-side rewrite of the objects below) and passes it as a reading-scene
+ *               group; filter = identity.  first2 = index (in the objs array) of that group's GROUP_BEGIN.
+ * A reading-scene group is a top-level GROUP_BEGIN of the scene section with filter_kind =
+ * COH_FILTER_READING_SCENE; such groups come after every ordinary scene object and are never drawn
+ * on their own.  Filter objects must be top-level members of the scene list. */
+enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4,
+       COH_FILTER_READING_SCENE = 100 };
 enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH_CPG_EXCLUSIVEOR = 3 };
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
 enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
@@ -76,6 +90,8 @@ typedef struct coh_object {
   int32_t count2;
   int32_t winding2;     /* CPG: winding rule of operand b */
   int32_t cpg_op;       /* CPG: COH_CPG_* */
+  int32_t filter_kind;  /* FILTER: COH_FILTER_*; GROUP_BEGIN: COH_FILTER_READING_SCENE or 0 */
+  int32_t filter_kernel;/* FILTER BLUR: COH_CONV_UNIT | COH_CONV_GAUSSIAN, radius << 8 */
 } coh_object;
 
 /* ---- lifecycle ---- */

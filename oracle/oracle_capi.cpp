@@ -4,6 +4,8 @@
 // PARITY UNPINNED (no reference tests / golden vectors exist; OCaml cannot be built here).
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <string>
 #include "../include/coherence_b200.h"
 #include "render.hpp"
@@ -38,6 +40,9 @@ static Fill fill_from(const coh_object& o) {
 static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, const int32_t* points) {
   std::vector<Scene> stack(1);
   std::vector<Obj> open;
+  std::vector<int> open_reading;                          // abi index of an open reading-scene group, or -1
+  std::map<int, std::shared_ptr<Scene>> reading;          // reading-scene groups by the index of their GROUP_BEGIN
+  std::vector<std::pair<size_t, int>> pending_reading;    // (position of the filter in the top-level list, first2)
   for (int i = 0; i < n; i++) {
     const coh_object& c = objs[i];
     Obj o;
@@ -61,6 +66,19 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
           stack.back().push_back(std::move(outer));
           break;
         }
+        stack.back().push_back(std::move(o));
+        break;
+      }
+      case COH_OBJ_FILTER: {
+        o.kind = Obj::Filter; o.filter_kind = c.filter_kind; o.has_bounds = false;
+        if (c.filter_kind == COH_FILTER_BLUR) o.kernel = (c.filter_kernel & 255) == COH_CONV_UNIT ? mkunit(c.filter_kernel >> 8) : mkgaussian(c.filter_kernel >> 8);
+        Obj g;
+        g.kind = Obj::Path; g.fill = fill_from(c); g.winding = g.sprite_winding = (Winding)c.winding;
+        g.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
+        sort_edgelist_maxy_rev(g.edges);
+        o.children.push_back(std::move(g));
+        if (stack.size() != 1) throw std::runtime_error("scene: filter objects must be top-level");
+        if (c.filter_kind == COH_FILTER_SCENE) pending_reading.push_back({stack.back().size(), c.first2});
         stack.back().push_back(std::move(o));
         break;
       }
@@ -92,6 +110,8 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
       }
       case COH_OBJ_GROUP_BEGIN: {
         o.kind = Obj::Group;
+        if (c.filter_kind == COH_FILTER_READING_SCENE && !open.empty()) throw std::runtime_error("scene: reading-scene groups must be top-level");
+        open_reading.push_back(c.filter_kind == COH_FILTER_READING_SCENE ? i : -1);
         open.push_back(std::move(o)); stack.emplace_back();
         break;
       }
@@ -99,6 +119,8 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         if (open.empty()) throw std::runtime_error("scene: GROUP_END without GROUP_BEGIN");
         Obj g = std::move(open.back()); open.pop_back();
         g.children = std::move(stack.back()); stack.pop_back();
+        const int rd = open_reading.back(); open_reading.pop_back();
+        if (rd >= 0) { reading[rd] = std::make_shared<Scene>(std::move(g.children)); break; }
         if (g.children.empty()) throw std::runtime_error("Empty groups aren't allowed");  // render.ml:317
         stack.back().push_back(std::move(g));
         break;
@@ -107,6 +129,11 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
     }
   }
   if (!open.empty()) throw std::runtime_error("scene: unterminated group");
+  for (auto& pr : pending_reading) {
+    auto it = reading.find(pr.second);
+    if (it == reading.end()) throw std::runtime_error("scene: filter without its reading-scene group");
+    stack[0].at(pr.first).reading_scene = it->second;
+  }
   return stack[0];
 }
 static void sprite_to_dense(const Sprite& s, int ux, int uy, int uw, int uh, uint32_t* out) {

@@ -21,7 +21,7 @@ struct Obj;
 typedef std::vector<Obj> Scene;
 
 struct Obj {
-  enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4, CPG = 5 } kind = Path;
+  enum Kind { Path = 0, Primitive = 1, Group = 2, Brush = 3, Convolved = 4, CPG = 5, Filter = 6 } kind = Path;
   long id = -1;              // < 0: a fresh id per render (Id.new_ids ()), never cached
   int pretrans = -1;         // -1: Over; else PreTrans(v, Over) with delta = toint (v *. 255.)
   // Integer-pixel alias (Render.translate_renderobject -> Cache.addtranslation, render.ml:259-271,
@@ -49,6 +49,11 @@ struct Obj {
   Kernel kernel;
   // CPG (op, a = children[0], b = children[1]), render.ml:17-18
   int cpg_op = 0;  // 0 Union, 1 Intersection, 2 Subtraction, 3 ExclusiveOr
+  // Filter {geometry = children[0]; reading_scene; filter} (render.ml:37-48; filters.ml).  The
+  // reference's closures are restated per filter kind: 1 hole, 2 monochrome, 3 blur (kernel),
+  // 4 identity filter over a caller-built reading scene (affine / rgb / wireframe / swapdepth / minus).
+  int filter_kind = 0;
+  std::shared_ptr<Scene> reading_scene;
 };
 
 // ---- cache.ml restated: shapes and partial sprites keyed by id, integer-translation
@@ -171,6 +176,9 @@ struct Renderer {
         cache.addshape(o.id, shp, minshp);
         return;
       }
+      case Obj::Filter:  // render.ml:472-474: the filter's geometry
+        shape_of_basicshape(o.children.at(0), shp, minshp);
+        return;
       case Obj::CPG: {  // render.ml:508-528 (operands are rendered as dummy objects with fresh ids)
         if (cache.getshape(o.id, shp, minshp)) return;
         Shape as, am, bs, bm;
@@ -228,6 +236,7 @@ struct Renderer {
       case Obj::Path: return polygon_sprite_edgelist(o.fill, shp, o.edges, o.sprite_winding);
       case Obj::Brush: return sprite_of_brushstroke(o.stroke, o.fill, shp);
       case Obj::CPG: return sprite_of_cpg(o, shp);
+      case Obj::Filter: return sprite_of_basicshape(o.children.at(0), shp);  // render.ml:986-987
       case Obj::Convolved: {  // render.ml:1023-1052: always the "fancy" route
         int r = radius_of_kernel(o.kernel);
         Shape shp2 = bloat(r, r, shp);
@@ -325,8 +334,43 @@ struct Renderer {
     return portion(newwhole, shape_intersection(shp, pshape2));
   }
 
+  // render.ml:1080-1131 — a filter object: render the reading scene, filter it, render the scene
+  // below where the filter's matte is not opaque, blend the two by the matte (blend', 1248-1265).
+  // Returns the sprite and the extra finish (the whole shape of the filter's geometry).
+  std::pair<Sprite, Shape> spriteof_filter(const Obj& o, const Scene& objs, size_t below, const Shape& shptorender) {
+    Scene tail(objs.begin() + (long)below, objs.end());
+    int r = o.filter_kind == 3 ? radius_of_kernel(o.kernel) : 0;
+    // reading_scene (filters.ml:221, 233-234, 247-250, 276-278)
+    Shape readshape = o.filter_kind == 3 ? bloat(2 * r + 1, 2 * r + 1, shptorender) : shptorender;
+    const Shape& shp2 = shptorender;
+    Scene none;
+    const Scene& scene2 = o.filter_kind == 1 ? none : (o.filter_kind == 4 ? *o.reading_scene : tail);
+    Sprite X; { Shape u = readshape; render_scene(u, X, scene2, true); }
+    Sprite Y;
+    switch (o.filter_kind) {
+      case 2: Y = sprite_map(monochrome, X); break;                                  // filters.ml:235-236
+      case 3: {                                                                        // filters.ml:251-255
+        Shape bloated = bloat(r, r, shape_of_sprite(X));
+        Y = convolve_sprite_in_shape(o.kernel, X, bloated, shape_intersection(bloated, shp2));
+        break;
+      }
+      default: Y = X;                                                                  // nullfilterfunction
+    }
+    Sprite alpha = sprite_of_basicshape(o, shp2);
+    Shape finished = caf(nocover, opaque, Sprite(), alpha).second;
+    Sprite Z; { Shape u = shape_difference(shp2, finished); if (!u.null()) render_scene(u, Z, tail, true); }
+    // blend' (render.ml:1248-1265)
+    Sprite a_in_z = portion(alpha, shape_of_sprite(Z)), a_in_y = portion(alpha, shape_of_sprite(Y));
+    Sprite z_att = caf([](colour c, colour al) { return dissolve(c, 255 - alpha_of_colour(al)); }, opaque, Z, a_in_z).first;
+    Sprite y_att = caf([](colour c, colour al) { return dissolve(c, alpha_of_colour(al)); }, opaque, Y, a_in_y).first;
+    Sprite res = caf(pd_plus, opaque, z_att, y_att).first;
+    Shape s, m; shape_of_basicshape(o, s, m);
+    return {res, s};
+  }
+
   // render.ml:1268-1308
-  void renderobj(const Obj& o, Shape& u, Sprite& a) {
+  void renderobj(const Scene& objs, size_t idx, Shape& u, Sprite& a) {
+    const Obj& o = objs[idx];
     if (bbox_reject && o.has_bounds) {
       Box ub; shape_bounds(u, ub);
       // Pdfutil.box_overlap on inclusive integer boxes
@@ -335,6 +379,12 @@ struct Renderer {
     Shape r, rm; shape_of_basicshape(o, r, rm);
     Shape r2 = shape_intersection(r, u);
     if (r2.null()) return;
+    if (o.kind == Obj::Filter) {  // render.ml:1289-1291, 1308: composited with over; only the extra finish leaves u
+      auto se = spriteof_filter(o, objs, idx + 1, r2);
+      a = caf(over, opaque, a, se.first).first;
+      u = shape_difference(u, se.second);
+      return;
+    }
     Sprite s = spriteof(o, r2);
     if (o.pretrans >= 0) {
       int d = o.pretrans;
@@ -346,9 +396,9 @@ struct Renderer {
   }
   // render.ml:1310-1335
   void render_scene(Shape& u, Sprite& a, const Scene& objs, bool nested) {
-    for (const Obj& o : objs) {
+    for (size_t i = 0; i < objs.size(); i++) {
       if (u.null()) return;
-      renderobj(o, u, a);
+      renderobj(objs, i, u, a);
       if (!nested && trace_u) trace_u->push_back(u);
     }
   }

@@ -436,6 +436,15 @@ def test_cpg_objects(ctx, oracle, op):
     b = _cpg_scene(op, W, H, S.Fill.plain(S.rgba8(200, 30, 30)), dx=13, dy=-7, pretrans=150)
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, op
+    # shallow edges: a minshape pixel of an operand need not be fully covered (the minshape's row band misses
+    # the top quarter of the AA window); the reference never consults an operand's matte inside its minshape
+    b = S.SceneBuilder()
+    b.cpg(op, [S.polygon_segments([(10.2, 40.3), (190.6, 43.1), (188.0, 100.2), (12.0, 97.7)])],
+          [S.polygon_segments([(30.0, 20.4), (170.0, 70.2), (160.0, 140.9), (25.0, 72.6)])], S.Fill.plain(S.rgba8(30, 30, 200)))
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, op
 
 
 def test_cpg_object_shape(ctx, oracle):
@@ -458,3 +467,67 @@ def test_cpg_object_shape(ctx, oracle):
         ctx.shape_free(hs)
         ctx.shape_free(hm)
         ctx.scene_free(sc)
+
+
+def _circle(cx, cy, r, n=28):
+    import math
+
+    return [S.polygon_segments([(cx + r * math.cos(2 * math.pi * i / n), cy + r * math.sin(2 * math.pi * i / n)) for i in range(n)])]
+
+
+def _filter_scene(kind, W, H, second=None, matte=None, **kw):
+    b = S.SceneBuilder()
+    b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+    f = b.filter(kind, _circle(100.3, 80.2, 50.5), fill=matte, **kw)
+    b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+    if second is not None:
+        b.filter(second[0], _circle(120.0, 100.0, 40.0), **second[1])
+    b.group_begin(pretrans=200)
+    b.polygon([(60.0, 20.0), (120.0, 140.0), (20.0, 120.0)], S.Fill.plain(S.rgba8(250, 240, 20)))
+    b.rectangle(S.rgba8(0, 0, 0), 90.0, 100.0, 170.0, 150.0)
+    b.group_end()
+    b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+    return b, f
+
+
+def _finish(b, W, H):
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    return b
+
+
+@pytest.mark.parametrize("kind,kw", [("hole", {}), ("monochrome", {}), ("blur", {"kernel": ("gaussian", 3)}), ("blur", {"kernel": ("unit", 2)})])
+def test_filters(ctx, oracle, kind, kw):
+    """Filter objects (render.ml:1080-1131, blend' 1248-1265; filters.ml hole / monochrome / blur): the scene below
+    is rendered twice (reading scene and ordinary scene), filtered and blended by the geometry's AA matte; the
+    filter's whole shape leaves u.  Opaque and translucent mattes."""
+    W, H = 200, 160
+    for matte in (None, S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 170))):
+        b, _ = _filter_scene(kind, W, H, matte=matte, **kw)
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+        assert np.array_equal(got_u, ref_u), (kind, kw)
+        assert _max_lsb(got, ref) == 0, (kind, kw)
+
+
+def test_filters_stacked_and_partial_update(ctx, oracle):
+    """A filter below another filter is rendered inside both of the upper filter's recursive renders."""
+    W, H = 200, 160
+    b, _ = _filter_scene("blur", W, H, second=("monochrome", {}), kernel=("gaussian", 2))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    b, _ = _filter_scene("monochrome", W, H, second=("hole", {}))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H, update=(70, 50, 60, 70))
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+
+
+def test_filter_with_reading_scene(ctx, oracle):
+    """Filters whose reading scene is a rewrite of the objects below (affine, rgb, wireframe, swapdepth, minus:
+    filters.ml:105-212, 271-332): the caller supplies the rewritten list as a reading-scene group."""
+    W, H = 200, 160
+    b, f = _filter_scene("scene", W, H)
+    b.reading_scene_begin(f)   # "affine": the objects below, moved and squashed
+    b.polygon([(40.3, 50.2), (160.5, 53.9), (158.1, 100.7), (38.8, 94.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+    b.polygon([(15.0, 25.0), (195.0, 28.0), (185.0, 120.0), (22.0, 110.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+    b.group_end()
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
