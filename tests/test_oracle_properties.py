@@ -161,3 +161,87 @@ def test_host_geometry_matches_oracle(oracle):
         flat = [[1.0] + [c for q in p for c in q], [0.0, p[3][0], p[3][1], p[0][0], p[0][1], 0, 0, 0, 0]]
         ref = oracle.points_on_path(flat, float(int(np.ceil(r)) * 2 + 1) / 20.0)
         assert np.array_equal(np.array(pts, dtype=np.int32).reshape(-1, 2), ref)
+
+
+def _dense_mask(flat, W, H):
+    return util.bitmap_of_flat(flat, 0, 0, W, H).astype(bool)
+
+
+def _dense_opacity(oracle, edges, winding, shape_flat, W, H):
+    out = np.zeros((H, W), dtype=np.int64)
+    vals = oracle.polygon_opacity(edges, winding, shape_flat)
+    k = 0
+    for y, spans in util.rows_of_flat(shape_flat):
+        for x, l in spans:
+            out[y, x:x + l] = vals[k:k + l]
+            k += l
+    return out
+
+
+@pytest.mark.parametrize("op", ["union", "intersection", "subtraction", "xor"])
+def test_cpg_sprite_equals_per_pixel_alpha_algebra(oracle, op):
+    """The region-by-region restatement of sprite_of_cpg (render.ml:867-981) equals one per-pixel expression of the
+    operands' mattes (a = 255 inside an operand's minshape, its antialiased opacity on the rest of its shape,
+    0 outside) — the form the CUDA walker evaluates (cpg_alpha, raster_core.cuh)."""
+    W, H = 200, 160
+    a_sub = [S.polygon_segments([(10.2, 40.3), (190.6, 43.1), (188.0, 100.2), (12.0, 97.7)])]
+    b_sub = [S.polygon_segments([(30.0, 20.4), (170.0, 70.2), (160.0, 140.9), (25.0, 72.6)])]
+    col = S.rgba8(30, 30, 200)
+    b = S.SceneBuilder()
+    o = b.cpg(op, a_sub, b_sub, S.Fill.plain(col))
+    objs, n, nbg, e, p = b.arrays()
+    img = oracle.render_frame(objs, n, 0, e, p, (0, 0, W, H))
+    ea, eb = e[o.first:o.first + o.count], e[o.first2:o.first2 + o.count2]
+    sa, ma = oracle.shapeminshape(ea, 0)
+    sb, mb = oracle.shapeminshape(eb, 0)
+    SA, MA, SB, MB = (_dense_mask(f, W, H) for f in (sa, ma, sb, mb))
+    A = np.where(MA, 255, np.where(SA, _dense_opacity(oracle, ea, 0, sa, W, H), 0))
+    B = np.where(MB, 255, np.where(SB, _dense_opacity(oracle, eb, 0, sb, W, H), 0))
+    if op == "union":
+        shp, mn, al = SA | SB, MA | MB, np.minimum(255, A + B)
+    elif op == "intersection":
+        shp, mn, al = SA & SB, MA & MB, np.minimum(A, B)
+    elif op == "subtraction":
+        shp, mn, al = SA & ~MB, MA & ~SB, np.maximum(0, A - B)
+    else:
+        shp, mn = (SA | SB) & ~(MA & MB), (MB & ~SA) | (MA & ~SB)
+        ia, ib = 255 - A, 255 - B
+        al = np.where((A < 128) & (B < 128), np.maximum(A, B), np.where((A >= 128) & (B < 128), 255 - np.maximum(ia, B),
+                      np.where((A < 128) & (B >= 128), 255 - np.maximum(A, ib), np.maximum(ia, ib))))
+    al = np.where(mn, 255, al)
+    exp = np.zeros((H, W), dtype=np.uint32)
+    for y, x in np.argwhere(shp):
+        exp[y, x] = oracle.colour_op("dissolve", col, int(al[y, x]))
+    assert np.array_equal(img, exp)
+
+
+def test_filter_limits(oracle):
+    """Filters (render.ml:1080-1131): a hole with an opaque matte shows nothing of the scene below inside the
+    geometry's opaque part; monochrome leaves grey pixels grey; a filter over an empty scene is transparent;
+    the filter's whole shape leaves u."""
+    import math
+
+    W, H = 160, 120
+    circ = [S.polygon_segments([(80.3 + 40.5 * math.cos(2 * math.pi * i / 24), 60.2 + 40.5 * math.sin(2 * math.pi * i / 24)) for i in range(24)])]
+
+    def frame(kind, below, **kw):
+        b = S.SceneBuilder()
+        f = b.filter(kind, circ, **kw)
+        for pts, c in below:
+            b.polygon(pts, S.Fill.plain(c))
+        objs, n, nbg, e, p = b.arrays()
+        img, u = oracle.render_frame(objs, n, 0, e, p, (0, 0, W, H), want_u=True)
+        shp, _ = oracle.shapeminshape(e[f.first:f.first + f.count], 0)
+        return img, _dense_mask(u, W, H), _dense_mask(shp, W, H)
+
+    quad = [(10.0, 10.0), (150.0, 12.0), (148.0, 110.0), (12.0, 108.0)]
+    red, grey = S.rgba8(200, 30, 30), S.rgba8(90, 90, 90)
+    img, u, g = frame("hole", [(quad, red)])
+    assert not (u & g).any(), "the extra finish removes the whole geometry from u"
+    assert img[60, 80] == 0 and img[60, 20] == red
+    img_m, _, _ = frame("monochrome", [(quad, grey)])
+    img_p, _, _ = frame("hole", [])
+    assert img_m[60, 80] == grey and img_m[60, 20] == grey, "monochrome of grey is the identity"
+    assert not img_p.any()
+    img_b, _, _ = frame("blur", [(quad, red)], kernel=("gaussian", 3))
+    assert img_b[60, 80] == red, "the blur of a flat colour is that colour"
