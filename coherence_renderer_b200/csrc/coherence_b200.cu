@@ -78,6 +78,7 @@ struct coh_ctx {
   bool have_u = false;
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
+  int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* h_total = nullptr;  // pinned
   // cross-tile carry for fancy fills
@@ -150,6 +151,7 @@ static void build_aa_table(AATable& t) {
     for (int i = 0; i < 32; i++) { t.prefix[j][i + 1] = t.prefix[j][i] + M[i][j]; total += M[i][j]; }
   }
   t.volume = (int)((total * 256) / 255);
+  if (t.volume != AA_VOLUME) { fprintf(stderr, "coherence_b200: AA table volume %d != %d\n", t.volume, AA_VOLUME); abort(); }
 }
 
 extern "C" {
@@ -198,7 +200,7 @@ int coh_shutdown(coh_ctx* ctx) {
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
-  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items);
+  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1139,7 +1141,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
   if (n_cells > ctx->n_cells_cap) {
-    DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_order);
+    DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_order); DFREE(ctx->cell_head);
+    CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
     CK(DMALLOC(&ctx->cell_counts, sizeof(int) * n_cells));
     CK(DMALLOC(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
     CK(DMALLOC(&ctx->cell_order, sizeof(int) * n_cells));
@@ -1183,7 +1186,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
     if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr)) return 1;
-    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head); LAUNCHED();
   } else {
     const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
@@ -1201,7 +1204,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
-  P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
+  P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;

@@ -91,7 +91,7 @@ template <bool FILL>
 __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/, const int* __restrict__ leaves, int n_leaves, Frame fr,
                       int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
                       int* __restrict__ items, int* __restrict__ hist /*[2*ORDER_BINS]: starts, cursors*/,
-                      int* __restrict__ order) {
+                      int* __restrict__ order, const ObjRec* __restrict__ objs = nullptr, int2* __restrict__ cell_head = nullptr) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_cells) return;
@@ -99,7 +99,7 @@ __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/
   int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1;
   int y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
   int base = FILL ? offsets[warp] : 0;
-  int n = 0;
+  int n = 0, first = -1;
   for (int b = 0; b < n_leaves; b += 32) {
     int li = b + lane;
     bool hit = false;
@@ -111,7 +111,22 @@ __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/
     }
     unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
     if (FILL && hit) items[base + n + __popc(m & ((1u << lane) - 1u))] = idx;
+    if (FILL && n == 0 && m) first = __shfl_sync(0xFFFFFFFFu, idx, __ffs((int)m) - 1);
     n += __popc(m);
+  }
+  if (FILL && cell_head && lane == 0) {
+    // Cell header for the walker: a cell whose only object is an opaque primitive covering all of it
+    // (typically the background rectangle) is just that colour — the walker then needs no list, object
+    // or group record at all (one load instead of a chain of four dependent ones).
+    int2 hd = make_int2(0, 0);
+    if (n == 1) {
+      const ObjRec& o = objs[first];
+      const int ex1 = x1 < fr.W - 1 ? x1 : fr.W - 1, ey1 = y1 < fr.H - 1 ? y1 : fr.H - 1;
+      if (o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && objs[o.anc[0]].pretrans < 0 &&
+          o.prim[0] + o.dx <= x0 && o.prim[2] + o.dx >= ex1 && o.prim[1] + o.dy <= y0 && o.prim[3] + o.dy >= ey1)
+        hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
+    }
+    cell_head[warp] = hd;
   }
   if (lane == 0) {
     const int bin = ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1);  // bin 0 = longest lists
@@ -270,6 +285,7 @@ struct WalkParams {
   const uint8_t* stamps;       // brush alpha stamps
   const int* cell_off;         // per cell [first, last) into cell_items
   const int* cell_items;
+  const int2* cell_head;       // per cell: {colour, 1 | 2 (scene list)} when the cell is one opaque covering primitive, else {0, 0}; may be null
   const AATable* aa;
   Frame fr;
   int cell_row0;               // first cell row covered by cell_off
@@ -495,6 +511,9 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   const size_t my_slot = (size_t)(my_y - P.fr.band_y0) * P.fr.tiles_x + tile;  // carry slot of (row, tile)
   int n_carry = 0;                                   // published carry entries of my row (mirrored)
 
+  const int cell = by * P.fr.tiles_x + tile;
+  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+  const int2 head = (P.cell_head && !P.resume) ? P.cell_head[cell] : make_int2(0, 0);
   // initial covered-so-far complement `u` of my row's word
   uint32_t u = 0u;
   if (row_in_band) {
@@ -513,29 +532,18 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   };
   if (__ballot_sync(0xFFFFFFFFu, u != 0u) == 0u) { publish_done(); return; }
 
-  const int cell = by * P.fr.tiles_x + tile;
-  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
-  // Fast path: the only object reaching this item is an opaque primitive that covers all of it
-  // (typically the background rectangle): the rows are just that colour.
-  if (it1 - it0 == 1 && !P.resume) {
-    const ObjRec& o = P.objs[P.cell_items[it0]];
-    bool simple = o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && P.objs[o.anc[0]].pretrans < 0;
-    if (simple) {
-      const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
-      const uint32_t m = (yy >= o.prim[1] && yy <= o.prim[3]) ? interval_mask32(xx0, o.prim[0], o.prim[2]) : 0u;
-      if (__all_sync(0xFFFFFFFFu, (u & ~m) == 0u)) {
-        const uint32_t c0 = o.fill.c0;
-        const bool scene_root = (P.objs[o.anc[0]].flags & OF_ROOT_SCENE) != 0;
-        if (scene_root && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = 0u;
-        publish_done();
+  // Fast path: the only object reaching this cell is an opaque primitive that covers all of it
+  // (typically the background rectangle; flagged by the binning kernel): the rows are just that colour.
+  if (head.y & 1) {
+    const uint32_t c0 = (uint32_t)head.x;
+    if ((head.y & 2) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = 0u;
+    publish_done();
 #pragma unroll 1
-        for (int r = 0; r < WALK_H; r++) {
-          const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u, r);
-          if ((uu >> lane) & 1u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = c0;
-        }
-        return;
-      }
+    for (int r = 0; r < WALK_H; r++) {
+      const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u, r);
+      if ((uu >> lane) & 1u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = c0;
     }
+    return;
   }
 
 #pragma unroll

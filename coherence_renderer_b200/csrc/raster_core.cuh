@@ -413,7 +413,12 @@ struct SinkRegs {
 // address so that one out-of-line routine serves every call site with ld/st.shared (a generic
 // pointer would cost generic loads/stores, inlining it five times cost 465 instructions of I-cache).
 #if defined(__CUDACC__)
-__device__ __noinline__ void smem_row_put(uint32_t saddr, int nwords, int wx0, int a, int b) {
+#ifdef COH_ROWPUT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void smem_row_put(uint32_t saddr, int nwords, int wx0, int a, int b) {
   a -= wx0; b -= wx0;
   const int nb = nwords * 32;
   if (b < 0 || a >= nb) return;
@@ -504,8 +509,17 @@ COH_HD int aa_row_sum(const int* prefix_row /*33 ints*/, uint32_t m) {
   }
   return sum;
 }
+// polygon.ml:646-647: volume = (sum of maintable * 256) / 255 = 42285 for the reference's table; the
+// library checks the table it builds against this constant at start-up (division by a constant is a
+// multiply-high instead of ~30 instructions)
+constexpr int AA_VOLUME = 42285;
 COH_HD int aa_opacity(int table_sum, int volume) {  // polygon.ml:650-651 with cov = 256 * sum
+#ifdef COH_RUNTIME_VOLUME
   return (256 * table_sum + volume / 2) / volume;
+#else
+  (void)volume;
+  return (256 * table_sum + AA_VOLUME / 2) / AA_VOLUME;
+#endif
 }
 
 // ---- constructive planar geometry (render.ml:522-528, 858-981) ----
