@@ -48,7 +48,7 @@ struct DevScene {
   int n_front_leaves = 0;        // + leaves of reading-scene groups (the background list follows)
   std::vector<int> h_leaves;
   bool has_fancy = false;    // some object has a gradient / radial fill
-  bool has_brush = false;
+  int extras = 0;            // walker variant: 0 polygons / primitives, 1 + brush / Convolved, 2 + CPG / filters
   size_t items_total = 0;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
 };
@@ -999,8 +999,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
-    if (o.kind == K_BRUSH || o.kind == K_CONV || o.kind == K_CPG) s->has_brush = true;
-    if (!filters.empty()) s->has_brush = true;  // the filter passes need the walker variant that can continue a frame
+    if (o.kind == K_BRUSH || o.kind == K_CONV) s->extras = std::max(s->extras, 1);
+    if (o.kind == K_CPG || !filters.empty()) s->extras = 2;  // the filter passes need the walker variant that can continue a frame
   }
   CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1211,13 +1211,15 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
   const int walk_h = big ? 16 : 4;
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
+#define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
+  do {                                                                                                             \
+    if (walk_h == 4) k_walk<CARRYV, EX, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                         \
+    else k_walk<CARRYV, EX, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                                    \
+    LAUNCHED();                                                                                                    \
+  } while (0)
 #define LAUNCH_WALK(CARRYV)                                                                                        \
   do {                                                                                                             \
-    if (walk_h == 4) { if (s->has_brush) k_walk<CARRYV, true, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);    \
-                       else k_walk<CARRYV, false, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P); }              \
-    else { if (s->has_brush) k_walk<CARRYV, true, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);               \
-           else k_walk<CARRYV, false, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P); }                         \
-    LAUNCHED();                                                                                                    \
+    if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
   P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.n_cells = n_cells;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));

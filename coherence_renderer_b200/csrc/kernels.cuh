@@ -495,12 +495,15 @@ constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 // still has pixels inside the covered-so-far complement `u` (one 32-bit word per row, held
 // by lane r and its NC-1 mirror lanes).
 // CARRY: the scene has fancy (gradient / radial) fills -> fill evaluation and the cross-tile carry
-// are compiled in.  BRUSH: the scene has brush strokes.  Plain polygon scenes get the small kernel.
-template <bool CARRY, bool BRUSH, int WALK_H>
+// are compiled in.  EXTRAS: 0 = polygons and primitives only (the small kernel), 1 = + brush strokes and
+// Convolved objects, 2 = + CPG objects and continuing a frame (filter passes).
+template <bool CARRY, int EXTRAS, int WALK_H>
 __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int sub, const int lane,
                                           uint32_t* __restrict__ aa_bits, StagedEdge* __restrict__ stage,
                                           uint32_t (*__restrict__ acc_rows)[32],
                                           const int* __restrict__ s_prefix, const int volume) {
+  constexpr bool BRUSH = EXTRAS >= 1;      // brush strokes, Convolved objects
+  constexpr bool CPGX = EXTRAS >= 2;       // CPG objects, continuing a frame (filters)
   constexpr int NC = 32 / WALK_H;          // candidate objects scan-converted per pass
   constexpr unsigned ROWMASK = (WALK_H >= 32) ? 0xFFFFFFFFu : ((1u << WALK_H) - 1u);
   const int tx0 = tile * TILE_W;
@@ -513,7 +516,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 
   const int cell = by * P.fr.tiles_x + tile;
   const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
-  const int2 head = (P.cell_head && !P.resume) ? P.cell_head[cell] : make_int2(0, 0);
+  const int2 head = (P.cell_head && !(CPGX && P.resume)) ? P.cell_head[cell] : make_int2(0, 0);
   // initial covered-so-far complement `u` of my row's word
   uint32_t u = 0u;
   if (row_in_band) {
@@ -583,11 +586,11 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   auto push_group = [&](int g) {
     // Continuing a frame (filter passes, render.ml:1080-1131): the scene list's accumulator carries on from the
     // framebuffer (render_scene's `a`); the background list is composited under it (render.ml:1363-1365).
-    const int rflags = (BRUSH && P.resume && depth == 0) ? P.objs[g].flags : 0;
+    const int rflags = (CPGX && P.resume && depth == 0) ? P.objs[g].flags : 0;
 #pragma unroll 1
     for (int r = 0; r < WALK_H; r++) {
       uint32_t below = acc_rows[r][lane], fresh = 0u;
-      if (BRUSH && rflags) {
+      if (CPGX && rflags) {
         const int py = y0 + r, px = tx0 + lane;
         const uint32_t have = (py < P.fr.H && px < P.fr.W) ? P.fb[(size_t)py * P.fr.W + px] : 0u;
         if (rflags & OF_ROOT_SCENE) fresh = have; else below = have;
@@ -607,6 +610,10 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   // the loop runs one extra, empty pass whose only effect is to close every open group
   // (keeps a single inlined copy of the group push/pop code: the kernel must fit the I-cache)
   for (int base = it0;; base += NC) {
+    const uint32_t u_hit = hit_level >= 0 ? stk_u[hit_level] : u;  // superset of every later u of my row
+    // nothing of these rows is uncovered any more: the rest of the list cannot show
+    // (render.ml:1321-1322: render_scene stops when u is null)
+    if (it1 - base > 2 * NC && __ballot_sync(0xFFFFFFFFu, u_hit != 0u) == 0u) base = it1;
     const bool closing = base >= it1;
     PH_MARK(0)  // other / loop overhead
     // ---- lane-parallel scan conversion: lane (c, r) evaluates row y0+r of candidate c ----
@@ -614,7 +621,6 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     const int idx = ci < it1 ? P.cell_items[ci] : -1;
     uint32_t S = 0u, C = 0u;
     uint32_t gSA = 0u, gMA = 0u, gSB = 0u, gMB = 0u;   // CPG operands: shape / minshape words of a and b
-    const uint32_t u_hit = hit_level >= 0 ? stk_u[hit_level] : u;  // superset of every later u of my row
     if (idx >= 0 && u_hit != 0u) {
       const ObjRec& o = P.objs[idx];
       if (!(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
@@ -630,7 +636,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             if (!ok) bad = true;
             S = sc.x; C = sc.y;
           }
-        } else if (BRUSH && o.kind == K_CPG) {
+        } else if (CPGX && o.kind == K_CPG) {
           // CPG (op, a, b): shape / minshape are set expressions of the operands' (render.ml:522-528)
           bool ok = true;
           if (yy >= o.ry0 && yy <= o.ry1) {
@@ -711,7 +717,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
             opacity = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, aa_bits, stage, s_prefix, volume, lane, ok);
             if (!ok) bad = true;
-          } else if (BRUSH && okind == K_CPG) {
+          } else if (CPGX && okind == K_CPG) {
             // sprite_of_cpg (render.ml:867-981): both operands become antialiased alpha mattes (0 outside
             // their shape) and are combined per pixel
             const int src = cc * WALK_H + r;
@@ -824,7 +830,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 
 // Persistent launch: every warp keeps taking cells from the queue (heavy cells first) until it
 // is empty; the grid is sized to fill the GPU exactly once (WALK_MIN_CTAS CTAs per SM).
-template <bool CARRY, bool BRUSH, int WALK_H>
+template <bool CARRY, int EXTRAS, int WALK_H>
 __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
   constexpr int WALK_SUB = CELL_H / WALK_H;
   __shared__ int s_prefix[32 * 33];
@@ -845,7 +851,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
 #endif
-    walk_cell<CARRY, BRUSH, WALK_H>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    walk_cell<CARRY, EXTRAS, WALK_H>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
     __syncwarp();
 #ifdef COH_PHASE_PROFILE
     if (lane == 0 && cell < (1 << 20)) g_cell_cycles[cell] = (unsigned int)(clock64() - tc0_);
