@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -44,6 +45,11 @@ struct DevScene {
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
   struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; };
   std::vector<FilterRec> filters;
+  // Group shapes (render.ml:476-496 caches them under the group's id): kept per scene, in the frame the group
+  // had when the entry was made; moving the whole group only changes the offset applied on the way out.
+  struct GroupShape { DevShape* shape; int offx, offy; };
+  std::map<int, GroupShape> group_shape;
+  std::vector<int2> group_off;   // per record: translation applied to the whole group since scene creation
   int n_scene_leaves = 0;        // ordinary leaves of the scene list
   int n_front_leaves = 0;        // + leaves of reading-scene groups (the background list follows)
   std::vector<int> h_leaves;
@@ -764,6 +770,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   if (!s) return 0;
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
   DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px);
+  for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
   delete s;
   return 0;
 }
@@ -997,6 +1004,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   group_last.resize(recs.size(), -1);
   ids.resize(recs.size(), -1);
   s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
+  s->group_off.assign(recs.size(), make_int2(0, 0));
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH || o.kind == K_CONV) s->extras = std::max(s->extras, 1);
@@ -1209,7 +1217,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
   // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
-  const int walk_h = big ? 16 : 4;
+  int walk_h = big ? 16 : 4;
+  if (const char* e = getenv("COH_WALK_H")) { int v = atoi(e); if (v == 4 || v == 16) walk_h = v; }  // experiments (1- and 2-row items measured slower at 1 and 2 GPUs)
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
 #define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
   do {                                                                                                             \
@@ -1480,7 +1489,7 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
   const int64_t id = s->ids[r];
   int32_t found = 0;
   coh_shape_t cs = 0, cm = 0;
-  if (coh_cache_getshape(ctx, id, &cs, &cm, &found)) return 1;
+  if (o.kind != K_GROUP && coh_cache_getshape(ctx, id, &cs, &cm, &found)) return 1;   // group shapes are kept per scene
   if (!found) {
     if (o.kind == K_PATH) {
       if (shapes_from_device_edges(ctx, s->edges + o.first, o.count, o.winding, o.bx0 - o.dx, o.by0 - o.dy, o.bx1 - o.dx, o.by1 - o.dy, &cs, &cm, "coh_scene_object_shape")) return 1;
@@ -1507,6 +1516,12 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
       if (coh_shape_translate(ctx, cs, 0, 0, &cm)) return 1;
     } else if (o.kind == K_GROUP) {
       // union of the members' shapes, minshape null (render.ml:476-496); members are not cached (fresh ids)
+      const int2 off = s->group_off[r];
+      auto git = ctx->usecache ? s->group_shape.find(r) : s->group_shape.end();
+      if (git != s->group_shape.end()) {
+        ctx->shphit++;
+        return coh_shape_translate(ctx, (coh_shape_t)git->second.shape, off.x - git->second.offx, off.y - git->second.offy, shape);
+      }
       for (int k = r + 1; k <= s->group_last[r]; k++) {
         if (s->h_objs[k].depth != o.depth + 1) continue;  // direct children only (nested groups recurse)
         coh_shape_t ms = 0, mm = 0, un = 0;
@@ -1515,7 +1530,12 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
         coh_shape_free(ctx, cs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
         cs = un;
       }
-      // members already carry their own alias offsets: the group's entry is stored untranslated
+      // members already carry their own alias offsets
+      if (ctx->usecache && cs) {
+        coh_shape_t keep = 0;
+        if (coh_shape_translate(ctx, cs, 0, 0, &keep)) return 1;
+        s->group_shape[r] = DevScene::GroupShape{(DevShape*)keep, off.x, off.y};
+      }
       *shape = cs; *minshape = 0;
       return 0;
     } else FAIL("coh_scene_object_shape: unsupported object kind");
@@ -1567,9 +1587,14 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
   if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_translate_object: no such object");
   const int r = s->rec_of_abi[obj_index];
   const int last = s->h_objs[r].kind == K_GROUP ? s->group_last[r] : r;
+  if (s->h_objs[r].kind != K_GROUP)   // a member moved on its own: the shapes of the groups around it are stale
+    for (int d = 0; d < s->h_objs[r].depth; d++) {
+      auto git = s->group_shape.find(s->h_objs[r].anc[d]);
+      if (git != s->group_shape.end()) { free_shape(ctx, git->second.shape); s->group_shape.erase(git); }
+    }
   for (int k = r; k <= last; k++) {
     ObjRec& o = s->h_objs[k];
-    if (o.kind == K_GROUP) continue;
+    if (o.kind == K_GROUP) { s->group_off[k].x += dx; s->group_off[k].y += dy; continue; }
     o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
   }
   s->items_for_W = -1;  // the item-pool bound depends on the boxes
@@ -1597,6 +1622,66 @@ int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, 
   }
   PassArgs A{0, s->n_leaves, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1, ctx->u_init, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
   int rc = render_pass(ctx, s, A);
+  ctx->have_u = record_u && !rc;
+  return rc;
+}
+// One drag step on device-resident data (see the header): translate, dirty region as a bit-frame, render.
+int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy, int32_t flags,
+                          int32_t dirty_bbox[4]) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_scene_drag_object: call coh_fb_configure first");
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_scene_drag_object: null scene");
+  if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_drag_object: no such object");
+  const int r = s->rec_of_abi[obj_index];
+  const ObjRec& o = s->h_objs[r];
+  // Fill.Plain objects: plaindirty; groups, fancy fills, brush strokes, Convolved objects: alldirty (render.ml:1396-1400)
+  const bool plain = (o.kind == K_PATH || o.kind == K_CPG) && o.fill.kind == 0;
+  const bool prim = o.kind == K_PRIM;
+  coh_shape_t so = 0, mo = 0;
+  if (object_shape_rec(ctx, s, r, &so, &mo)) return 1;   // served by the cache after the first step
+  if (coh_scene_translate_object(ctx, scene, obj_index, dx, dy)) return 1;
+  const Frame& fr = ctx->fr;
+  const int nw = fr.tiles_x;
+  const size_t nwords = (size_t)nw * fr.H;
+  if (!ctx->u_init) CK(DMALLOC(&ctx->u_init, sizeof(uint32_t) * nwords));
+  uint32_t* U = ctx->u_init;
+  CK(cudaMemsetAsync(U, 0, 4 * nwords, ctx->stream));
+  DevShape* S = (DevShape*)so; DevShape* M = (DevShape*)mo;
+  int bb[4] = {0, 0, -1, -1};
+  if (S) {
+    // old position: offset 0; new position: the same span set read through the offset (dx, dy)
+    auto put = [&](const DevShape* sh, uint32_t* bits, int ox, int oy) -> int {
+      k_spans_to_bits<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(sh->row_ptr, sh->spans, sh->y0 + oy, sh->n_rows, 0, fr.H, -ox, nw, bits); LAUNCHED();
+      return 0;
+    };
+    if ((plain || prim) && M) {
+      uint32_t *A = nullptr, *B = nullptr;
+      CK(DMALLOC(&A, 4 * nwords)); CK(DMALLOC(&B, 4 * nwords));
+      const unsigned wb = (unsigned)((nwords + 255) / 256);
+      CK(cudaMemsetAsync(A, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(B, 0, 4 * nwords, ctx->stream));
+      if (put(S, A, 0, 0) || put(M, B, dx, dy)) return 1;
+      k_bitop<<<wb, 256, 0, ctx->stream>>>(A, B, U, nwords, 1); LAUNCHED();            // shp_o --- minshp_n
+      CK(cudaMemsetAsync(A, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(B, 0, 4 * nwords, ctx->stream));
+      if (put(S, A, dx, dy) || put(M, B, 0, 0)) return 1;
+      k_bitop<<<wb, 256, 0, ctx->stream>>>(A, B, A, nwords, 1); LAUNCHED();            // shp_n --- minshp_o
+      k_bitop<<<wb, 256, 0, ctx->stream>>>(U, A, U, nwords, 0); LAUNCHED();
+      DFREE(A); DFREE(B);
+    } else {
+      if (put(S, U, 0, 0) || put(S, U, dx, dy)) return 1;                                // shp_o ||| shp_n
+    }
+    bb[0] = std::max(0, S->bx0 + std::min(dx, 0)); bb[1] = std::max(0, S->by0 + std::min(dy, 0));
+    bb[2] = std::min(fr.W - 1, S->bx1 + std::max(dx, 0)); bb[3] = std::min(fr.H - 1, S->by1 + std::max(dy, 0));
+  }
+  coh_shape_free(ctx, so); coh_shape_free(ctx, mo);
+  if (dirty_bbox) for (int k = 0; k < 4; k++) dirty_bbox[k] = bb[k];
+  ctx->have_u = false;
+  if (bb[2] < bb[0] || bb[3] < bb[1]) return 0;
+  const bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
+  int rc;
+  if (!s->filters.empty()) { rc = render_filtered(ctx, s, U, bb[0], bb[1], bb[2] - bb[0] + 1, bb[3] - bb[1] + 1); ctx->have_u = !rc; return rc; }
+  PassArgs A{0, s->n_leaves, bb[0], bb[1], bb[2] - bb[0] + 1, bb[3] - bb[1] + 1, U, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
+  rc = render_pass(ctx, s, A);
   ctx->have_u = record_u && !rc;
   return rc;
 }

@@ -367,33 +367,88 @@ def lion_paths():
         return json.load(f)["paths"]
 
 
-def lion_scene(width, height, scale, background=True, pretrans=None):
-    """C1/C2: the lion (examples.ml:174-180: Group (rev objs), Over) centred on a
-    width x height canvas, y flipped about its bounding box, uniformly scaled; background =
-    Primitive (lightgrey, Rectangle (0, 0, W, H)) (engine.ml:73-74)."""
+def add_lion(b, width, height, scale, pretrans=None, oid=-1, transform=None):
+    """Append the lion (examples.ml:174-180: Group (rev objs), Over), centred on a width x height canvas, y flipped
+    about its bounding box, uniformly scaled; `transform` maps device-space points (an affine filter's rewrite)."""
     paths = lion_paths()
     xs = [p[0] for q in paths for p in q["subpaths"][0]]
     ys = [p[1] for q in paths for p in q["subpaths"][0]]
     cx, cy = (min(xs) + max(xs)) / 2.0, (min(ys) + max(ys)) / 2.0
 
     def tr(p):
-        return ((p[0] - cx) * scale + width / 2.0, (cy - p[1]) * scale + height / 2.0)
+        q = ((p[0] - cx) * scale + width / 2.0, (cy - p[1]) * scale + height / 2.0)
+        return transform(q) if transform else q
 
-    b = SceneBuilder()
-    b.group_begin(pretrans=pretrans)
+    g = b.group_begin(pretrans=pretrans, oid=oid)
     for q in reversed(paths):  # head = front-most = painted last
-        r, g, bl = q["rgb"]
-        fill = Fill.plain(colour_of_rgba_float(r, g, bl, 1.0))
+        r, g8, bl = q["rgb"]
+        fill = Fill.plain(colour_of_rgba_float(r, g8, bl, 1.0))
         subs = []
         for sp in q["subpaths"]:
             pts = [tr(p) for p in sp]
             subs.append([("L", pts[i], pts[i + 1]) for i in range(len(pts) - 1)])
         b.path(subs, fill, COH_NONZERO)
     b.group_end()
+    return g
+
+
+def lion_scene(width, height, scale, background=True, pretrans=None):
+    """C1/C2: the lion over Primitive (lightgrey, Rectangle (0, 0, W, H)) (engine.ml:73-74)."""
+    b = SceneBuilder()
+    add_lion(b, width, height, scale, pretrans=pretrans)
     if background:
         b.begin_background()
         b.rectangle(LIGHTGREY, 0.0, 0.0, float(width), float(height))
     return b
+
+
+def circle_subpath(cx, cy, r, n=64):
+    return [polygon_segments([(cx + r * math.cos(2.0 * math.pi * i / n), cy + r * math.sin(2.0 * math.pi * i / n)) for i in range(n)])]
+
+
+def filter_scene(width, height, scale):
+    """C5: the lion under a blur lens (circle, mkgaussian 5), a monochrome lens (circle), an affine lens
+    (rectangle; reading scene = the lion squashed and sheared about the lens centre, filters.ml:271-285) and a page
+    shadow Convolved (mkgaussian 4, rectangle) (engine.ml:85-88), laid out like examples.ml:69-88."""
+    W, H = float(width), float(height)
+    u = min(W, H)
+    b = SceneBuilder()
+    b.filter("blur", circle_subpath(0.36 * W, 0.40 * H, 0.185 * u), kernel=("gaussian", 5))
+    b.filter("monochrome", circle_subpath(0.62 * W, 0.36 * H, 0.16 * u))
+    ax0, ay0, ax1, ay1 = 0.42 * W, 0.58 * H, 0.70 * W, 0.88 * H
+    acx, acy = (ax0 + ax1) / 2.0, (ay0 + ay1) / 2.0
+    aff = b.filter("scene", [polygon_segments([(ax0, ay0), (ax1, ay0), (ax1, ay1), (ax0, ay1)])])
+    add_lion(b, width, height, scale)
+    shadow = [polygon_segments([(0.08 * W, 0.08 * H), (0.92 * W, 0.08 * H), (0.92 * W, 0.92 * H), (0.08 * W, 0.92 * H)])]
+    b.path(shadow, Fill.plain(dissolve(rgba8(0, 0, 0), 120)), COH_NONZERO, convolve=("gaussian", 4))
+
+    def affine(p):  # Scale ((cx, cy), 1, -0.5) then ShearX ((cx, cy), -0.3)
+        x, y = p[0], acy + (p[1] - acy) * -0.5
+        return (x + (y - acy) * -0.3, y)
+
+    b.reading_scene_begin(aff)
+    add_lion(b, width, height, scale, transform=affine)
+    b.group_end()
+    b.begin_background()
+    b.rectangle(LIGHTGREY, 0.0, 0.0, W, H)
+    return b
+
+
+def drag_scene(width, height, scale, n_static=400, seed=0xD1CE):
+    """C4: n_static C3-style objects with the lion group (id 1) in front as the dragged object.
+    Returns (builder, abi index of the lion group)."""
+    b = SceneBuilder()
+    add_lion(b, width, height, scale, oid=1)
+    static = random_scene(width, height, n_static, seed=seed, brush_fraction=0.0, background=False)
+    for k, o in enumerate(static.objs):
+        o.first += b._n_edges
+        o.id = 1000 + k
+        b.objs.append(o)
+    b.edges.extend(static.edges)
+    b._n_edges += static._n_edges
+    b.begin_background()
+    b.rectangle(LIGHTGREY, 0.0, 0.0, float(width), float(height))
+    return b, 0
 
 
 class PCG32:

@@ -186,6 +186,16 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8);
 enum { COH_RENDER_RECORD_U = 1 };
 int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh,
                      int32_t flags);
+/* One step of an interactive drag (engine.ml:441-493 around render.ml:259-271, 1376-1400 and 1345-1365):
+ * the object (or group) becomes an alias of its cached self moved by (dx, dy) whole pixels, the dirty region
+ * dirty_region obj obj' = plaindirty | alldirty is formed from the cached, HBM-resident span sets, intersected
+ * with the framebuffer rectangle, and render_frame runs over exactly that region.  Nothing is synchronised or
+ * copied to the host; dirty_bbox (may be NULL) receives the pixel box x0, y0, x1, y1 (inclusive, clipped to the
+ * frame; x1 < x0 when nothing is dirty) that a front end would re-read with coh_fb_read_rgb888.
+ * Equivalent to coh_scene_object_shape + coh_scene_translate_object + coh_scene_object_shape +
+ * coh_dirty_region + coh_render_frame_shape, without materialising the region as a span set. */
+int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy, int32_t flags,
+                          int32_t dirty_bbox[4]);
 /* Render.render_frame over an arbitrary update shape — the dirty region that engine.ml:224-252
  * (force_update) passes after a change; pixels outside the shape keep their previous value. */
 int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, int32_t flags);

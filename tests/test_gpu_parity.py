@@ -531,3 +531,56 @@ def test_filter_with_reading_scene(ctx, oracle):
     b.group_end()
     got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+
+
+def test_drag_object_fused_step(ctx, oracle):
+    """coh_scene_drag_object = translate + dirty region + render of that region, on device-resident span sets: after
+    every step the framebuffer equals the oracle's full render of the moved scene — for a plain path (plaindirty),
+    a group (alldirty) and a primitive.  (Plain fills only: an antialiased pixel of a fancy fill takes the fill at
+    the start of its visible span, polygon.ml:736, so in the reference too a partial update can differ from a
+    full render.)"""
+    W, H = 400, 300
+    b = S.SceneBuilder()
+    b.polygon([(100.2, 80.1), (220.5, 100.9), (200.0, 230.3), (90.0, 200.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 220, 30), 200)), oid=7)
+    b.group_begin(oid=8)
+    b.polygon([(40.0, 40.0), (140.5, 60.5), (90.0, 160.0)], S.Fill.plain(S.rgba8(10, 200, 40)))
+    b.polygon([(60.0, 90.0), (180.0, 95.0), (150.0, 190.0)], S.Fill.plain(S.dissolve(S.rgba8(255, 0, 0), 140)))
+    b.group_end()
+    b.rectangle(S.rgba8(0, 0, 90), 250.0, 40.0, 330.0, 120.0, oid=9)
+    for i in range(12):
+        x, y = 20.0 + 28 * i, 30.0 + 17 * i
+        b.polygon([(x, y), (x + 90.5, y + 10.2), (x + 70.1, y + 95.5), (x - 5.0, y + 60.0)], S.Fill.plain(S.dissolve(S.rgba8(20 * i % 255, 200, 255 - 9 * i), 255 if i % 3 else 170)), oid=100 + i)
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, edges, points = b.arrays()
+    group_index, prim_index = 1, 5
+    ctx.cache_clear()
+    ctx.cache_configure(True, 64 << 20)
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    moves = [(0, 3, 2), (group_index, -4, 5), (prim_index, 6, -3), (0, -9, 0), (group_index, 11, 7), (prim_index, -20, 15), (0, 1, 1)]
+    for step, (idx, dx, dy) in enumerate(moves):
+        bb = ctx.scene_drag_object(sc, idx, dx, dy)
+        ctx.sync()
+        assert bb[2] >= bb[0] and bb[3] >= bb[1]
+        last = idx
+        if objs[idx].kind == abi.COH_OBJ_GROUP_BEGIN:  # the members carry the offsets
+            k, depth = idx + 1, 1
+            while depth:
+                if objs[k].kind == abi.COH_OBJ_GROUP_BEGIN:
+                    depth += 1
+                elif objs[k].kind == abi.COH_OBJ_GROUP_END:
+                    depth -= 1
+                else:
+                    objs[k].dx += dx
+                    objs[k].dy += dy
+                k += 1
+        else:
+            objs[last].dx += dx
+            objs[last].dy += dy
+        got = ctx.fb_read_rgba(0, 0, W, H)
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert _max_lsb(got, ref) == 0, f"frame differs after drag step {step}"
+    ctx.scene_free(sc)
+    ctx.cache_clear()
