@@ -1144,9 +1144,17 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   const int n_leaves = A.l1 - A.l0;
   const int4* leaf_box = s->leaf_box + A.l0;
   const int* leaves = s->leaves + A.l0;
-  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves;
   if (fr.band_y1 <= fr.band_y0 || uw <= 0 || uh <= 0) return 0;
-  int cell_row0 = fr.band_y0 / CELL_H, cell_row1 = (fr.band_y1 - 1) / CELL_H;
+  // only the cell rows the update box reaches (a dirty region is usually a small part of the frame)
+  const int ry0 = std::max(fr.band_y0, uy), ry1 = std::min(fr.band_y1, uy + uh);
+  if (ry1 <= ry0) return 0;
+  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves && ry0 == fr.band_y0 && ry1 == fr.band_y1;
+  int cell_row0 = ry0 / CELL_H, cell_row1 = (ry1 - 1) / CELL_H;
+  if (A.u_out && A.u_out != A.u_init) {  // rows the walk does not visit have nothing uncovered
+    const int wy0 = cell_row0 * CELL_H, wy1 = std::min((cell_row1 + 1) * CELL_H, fr.H);
+    if (wy0 > fr.band_y0) CK(cudaMemsetAsync(A.u_out + (size_t)fr.band_y0 * fr.tiles_x, 0, 4 * (size_t)(wy0 - fr.band_y0) * fr.tiles_x, ctx->stream));
+    if (wy1 < fr.band_y1) CK(cudaMemsetAsync(A.u_out + (size_t)wy1 * fr.tiles_x, 0, 4 * (size_t)(fr.band_y1 - wy1) * fr.tiles_x, ctx->stream));
+  }
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
   if (n_cells > ctx->n_cells_cap) {
     DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_order); DFREE(ctx->cell_head);
