@@ -1270,42 +1270,51 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
 // (the "extra finish", render.ml:1120-1121, 1308) and the walk continues below it, the
 // accumulator carrying on from the framebuffer (WalkParams::resume).
 // ---------------------------------------------------------------------------------------
-static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh);
+struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box);
 
-static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target) {
+// `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small and handled
+// whole; the RGBA8 canvases are only touched in the rows the filter reads or writes).
+static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target, PixBox box) {
   const DevScene::FilterRec& F = s->filters[fi];
   const Frame& fr = ctx->fr;
   const int W = fr.W, H = fr.H, nw = fr.tiles_x;
-  const size_t nwords = (size_t)nw * H, npx = (size_t)W * H;
-  const int y0 = std::max(F.by0, 0), y1 = std::min(F.by1, H - 1);
-  if (y0 > y1 || F.bx1 < 0 || F.bx0 >= W) return 0;  // geometry outside the frame
+  const size_t nwords = (size_t)nw * H;
+  // rows / columns of shptorender = shape(geometry) ∩ u
+  const int y0 = std::max(std::max(F.by0, 0), box.y0), y1 = std::min(std::min(F.by1, H - 1), box.y1);
+  const int x0 = std::max(std::max(F.bx0, 0), box.x0), x1 = std::min(std::min(F.bx1, W - 1), box.x1);
+  if (y0 > y1 || x0 > x1) return 0;  // the geometry cannot meet u: nothing to render, nothing leaves u
   const int h = y1 - y0 + 1;
+  const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : 0;             // reach of the reading shape
+  const int ry0 = std::max(0, y0 - m), ry1 = std::min(H - 1, y1 + m), rh = ry1 - ry0 + 1;
+  const PixBox tbox{x0, y0, x1, y1}, rbox{std::max(0, x0 - m), ry0, std::min(W - 1, x1 + m), ry1};
   const unsigned wblocks = (unsigned)((nwords + 255) / 256);
-  uint32_t *SG = nullptr, *MG = nullptr, *T = nullptr, *R = nullptr, *X = nullptr, *Z = nullptr, *tmp = nullptr;
+  const size_t po = (size_t)ry0 * W, pn = (size_t)rh * W;                 // canvas rows [ry0, ry1]
+  uint32_t *SG = nullptr, *CG = nullptr, *T = nullptr, *R = nullptr, *X = nullptr, *Z = nullptr, *tmp = nullptr;
   uint8_t *op = nullptr, *alpha = nullptr; int* d_taps = nullptr;
-  CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&MG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
-  CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(MG, 0, 4 * nwords, ctx->stream));
+  CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&CG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
+  CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(CG, 0, 4 * nwords, ctx->stream));
   const EdgeRec* ed = s->edges + F.first;
-  // shape / minshape of the geometry (render.ml:472-474)
-  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, MG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();  // MG: coverage, unused
+  // shape of the geometry (render.ml:472-474); CG receives the coverage and is not used
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, CG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, U, T, nwords, 2); LAUNCHED();     // shptorender = r &&& u (render.ml:1281)
   // reading scene -> X -> filter function -> Y (in place)
   uint32_t* Y = nullptr;
   if (F.kind != COH_FILTER_HOLE) {
-    CK(DMALLOC(&X, 4 * npx));
-    CK(cudaMemsetAsync(X, 0, 4 * npx, ctx->stream));
+    CK(DMALLOC(&X, 4 * (size_t)W * H));
+    CK(cudaMemsetAsync(X + po, 0, 4 * pn, ctx->stream));
     if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp
-      k_dilate<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(T, R, H, nw, 2 * F.r + 1, 2 * F.r + 1); LAUNCHED();
+      k_dilate<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(T, R, H, nw, m, m); LAUNCHED();
     } else CK(cudaMemcpyAsync(R, T, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
     if (F.kind == COH_FILTER_SCENE) {
-      PassArgs A{F.read0, F.read1, 0, 0, W, H, R, nullptr, X, true, false};
+      PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
-    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true)) return 1;
+    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox)) return 1;
     Y = X;
     if (F.kind == COH_FILTER_MONOCHROME) {
-      k_monochrome<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(X, X, npx); LAUNCHED();
+      k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED();
     } else if (F.kind == COH_FILTER_BLUR) {
-      // Convolve.convolve_sprite_in_shape (convolve.ml:265-296) on the frame-sized canvas: pixels the
+      // Convolve.convolve_sprite_in_shape (convolve.ml:265-296) on the canvas rows [ry0, ry1]: pixels the
       // reading scene did not render are clear, exactly like the reference's canvas outside the sprite
       std::vector<int> taps; int total = 0;
       if (F.kernel_kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
@@ -1319,41 +1328,44 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
         CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // `taps` is a local
       }
-      CK(DMALLOC(&tmp, 4 * npx));
-      dim3 gp(cdiv(W, 128), H);
-      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, tmp, W, H, F.r, F.kernel_kind, d_taps, total, 0); LAUNCHED();
-      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X, W, H, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
+      CK(DMALLOC(&tmp, 4 * pn));
+      dim3 gp(cdiv(W, 128), rh);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X + po, tmp, W, rh, F.r, F.kernel_kind, d_taps, total, 0); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X + po, W, rh, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
     }
   }
-  // the geometry's matte in the update (render.ml:1099-1103)
-  CK(DMALLOC(&op, (size_t)nw * 32 * H)); CK(DMALLOC(&alpha, npx));
-  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, T + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op + (size_t)y0 * nw * 32, ctx->d_error); LAUNCHED();
-  k_filter_matte<<<dim3(cdiv(nw, 4), H), 128, 0, ctx->stream>>>(T, op, F.colour, W, H, nw, alpha, R); LAUNCHED();  // R := finished
+  // the geometry's matte in the update (render.ml:1099-1103); Polygon.polygon_sprite samples every pixel
+  CK(DMALLOC(&op, (size_t)nw * 32 * h)); CK(DMALLOC(&alpha, (size_t)W * h));
+  CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, T + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, op, F.colour, W, h, nw, alpha, R + (size_t)y0 * nw); LAUNCHED();  // R := finished
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, R, R, nwords, 1); LAUNCHED();      // pixels_for_normal_scene (render.ml:1105)
-  CK(DMALLOC(&Z, 4 * npx));
-  CK(cudaMemsetAsync(Z, 0, 4 * npx, ctx->stream));
-  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true)) return 1;
-  k_filter_blend<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(T, alpha, Z, Y, target, W, H, nw); LAUNCHED();
+  CK(DMALLOC(&Z, 4 * (size_t)W * H));
+  CK(cudaMemsetAsync(Z + (size_t)y0 * W, 0, 4 * (size_t)h * W, ctx->stream));
+  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox)) return 1;
+  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw); LAUNCHED();
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(U, SG, U, nwords, 1); LAUNCHED();     // u --- ef (render.ml:1308)
-  DFREE(SG); DFREE(MG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
+  DFREE(SG); DFREE(CG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
   return 0;
 }
 // Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)
-static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh) {
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box) {
   const Frame& fr = ctx->fr;
+  if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
   auto segment = [&](int a, int b) -> int {
     if (b > a) {
-      PassArgs A{a, b, 0, 0, fr.W, fr.H, U, U, target, fresh, !fresh};
+      PassArgs A{a, b, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U, U, target, fresh, !fresh};
       if (render_pass(ctx, s, A)) return 1;
     } else if (fresh) {
-      k_clear_in_bits<<<dim3(cdiv(fr.W, 128), fr.H), 128, 0, ctx->stream>>>(target, U, fr.W, fr.H, fr.tiles_x); LAUNCHED();
+      const int hh = box.y1 - box.y0 + 1;
+      k_clear_in_bits<<<dim3(cdiv(fr.W, 128), hh), 128, 0, ctx->stream>>>(target + (size_t)box.y0 * fr.W, U + (size_t)box.y0 * fr.tiles_x, fr.W, hh, fr.tiles_x); LAUNCHED();
     }
     fresh = false;
     return 0;
   };
   for (int f = f0; f < (int)s->filters.size(); f++) {
     if (segment(l0, s->filters[f].pos)) return 1;
-    if (apply_filter(ctx, s, f, U, target)) return 1;
+    if (apply_filter(ctx, s, f, U, target, box)) return 1;
     l0 = s->filters[f].pos;
   }
   return segment(l0, s->n_scene_leaves);
@@ -1362,18 +1374,20 @@ static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, in
   const Frame& fr = ctx->fr;
   if (fr.band_y0 != 0 || fr.band_y1 != fr.H) FAIL("render_frame: scenes with filter objects need the whole frame on one context (filters read outside their band)");
   if (uw <= 0 || uh <= 0) return 0;
+  const PixBox box{std::max(ux, 0), std::max(uy, 0), std::min(ux + uw - 1, fr.W - 1), std::min(uy + uh - 1, fr.H - 1)};
+  if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
   const int nw = fr.tiles_x;
   const size_t nwords = (size_t)nw * fr.H;
   uint32_t *U = ctx->u_out, *U0 = nullptr;
   CK(DMALLOC(&U0, 4 * nwords));
   if (u_init) CK(cudaMemcpyAsync(U0, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
-  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, ux, uy, std::min(ux + uw - 1, fr.W - 1), uy + uh - 1); LAUNCHED(); }
+  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
   CK(cudaMemcpyAsync(U, U0, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true)) return 1;
+  if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true, box)) return 1;
   if (s->n_leaves > s->n_front_leaves) {
     // the background list shows wherever the scene pass is not opaque (render.ml:1363-1365)
     k_not_opaque_bits<<<dim3(cdiv(nw, 4), fr.H), 128, 0, ctx->stream>>>(ctx->fb, U0, U0, fr.W, fr.H, nw); LAUNCHED();
-    PassArgs A{s->n_front_leaves, s->n_leaves, 0, 0, fr.W, fr.H, U0, nullptr, ctx->fb, false, true};
+    PassArgs A{s->n_front_leaves, s->n_leaves, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U0, nullptr, ctx->fb, false, true};
     if (render_pass(ctx, s, A)) return 1;
   }
   DFREE(U0);
