@@ -48,7 +48,7 @@ SYMBOLS = [
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
-    "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_scene_object_shape", "coh_convolve_sprite",
+    "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
 ]
 
 _lib = None
@@ -275,6 +275,11 @@ class Context:
         bb = (C.c_int32 * 4)()
         self._chk(lib().coh_scene_drag_object(self._h, C.c_uint64(scene), obj_index, dx, dy, flags, bb))
         return tuple(bb)
+
+    def dirty_filter(self, scene, lmo_index, initial_dirty):
+        o = C.c_uint64()
+        self._chk(lib().coh_dirty_filter(self._h, C.c_uint64(scene), lmo_index, C.c_uint64(initial_dirty), C.byref(o)))
+        return o.value
 
     def dirty_region(self, shp_o, min_o, shp_n, min_n, u, plain):
         o = C.c_uint64()

@@ -43,7 +43,7 @@ struct DevScene {
   std::vector<int> group_last;   // for group records: last record index inside the group
   // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
-  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; };
+  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; };
   std::vector<FilterRec> filters;
   // Group shapes (render.ml:476-496 caches them under the group's id): kept per scene, in the frame the group
   // had when the entry was made; moving the whole group only changes the offset applied on the way out.
@@ -859,7 +859,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
       if (c.dx || c.dy) FAIL("scene: translated filter objects are not supported yet");
       DevScene::FilterRec f; memset(&f, 0, sizeof f);
-      f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
+      f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
       if (c.filter_kind == COH_FILTER_BLUR) {
         f.kernel_kind = c.filter_kernel & 255; f.r = c.filter_kernel >> 8;
         if ((f.kernel_kind != COH_CONV_UNIT && f.kernel_kind != COH_CONV_GAUSSIAN) || f.r <= 0 || f.r > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
@@ -1646,6 +1646,31 @@ int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, 
   int rc = render_pass(ctx, s, A);
   ctx->have_u = record_u && !rc;
   return rc;
+}
+// Render.dirty_filter (render.ml:1418-1438) with the dirty functions of filters.ml restated per filter kind.
+int coh_dirty_filter(coh_ctx* ctx, coh_scene_t scene, int32_t lmo_index, coh_shape_t initial_dirty, coh_shape_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_dirty_filter: null scene");
+  coh_shape_t cur = 0;
+  if (coh_shape_translate(ctx, initial_dirty, 0, 0, &cur)) return 1;
+  // filters above the lmo, folded from the last of them to the first (fold_left over rev filters)
+  for (int k = (int)s->filters.size() - 1; k >= 0; k--) {
+    const DevScene::FilterRec& F = s->filters[k];
+    if (lmo_index >= 0 && F.abi >= lmo_index) continue;
+    if (F.kind != COH_FILTER_BLUR || !cur) continue;  // nulldirty
+    // bloatdirty r r (filters.ml:63-75)
+    coh_shape_t fs = 0, fm = 0, bf = 0, inf = 0, outf = 0, bl = 0, bif = 0, res = 0;
+    if (shapes_from_device_edges(ctx, s->edges + F.first, F.count, F.winding, F.bx0, F.by0, F.bx1, F.by1, &fs, &fm, "coh_dirty_filter")) return 1;
+    int rc = coh_shape_bloat(ctx, fs, F.r, F.r, &bf) || coh_shape_intersection(ctx, bf, cur, &inf) || coh_shape_difference(ctx, cur, bf, &outf) ||
+             coh_shape_bloat(ctx, inf, F.r, F.r, &bl) || coh_shape_intersection(ctx, bl, bf, &bif) || coh_shape_union(ctx, bif, outf, &res);
+    for (coh_shape_t h : {fs, fm, bf, inf, outf, bl, bif, cur}) coh_shape_free(ctx, h);
+    if (rc) return 1;
+    cur = res;
+  }
+  *out = cur;
+  return 0;
 }
 // One drag step on device-resident data (see the header): translate, dirty region as a bit-frame, render.
 int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy, int32_t flags,

@@ -186,6 +186,12 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8);
 enum { COH_RENDER_RECORD_U = 1 };
 int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh,
                      int32_t flags);
+/* Render.dirty_filter lmo initial_dirty scene (render.ml:1418-1438): the dirty functions of the filters in
+ * front of the last-moved object (lmo_index, an index into the objs array; -1 = every filter), composed from the
+ * one nearest the object to the front-most: hole / monochrome / caller-built reading scenes use nulldirty
+ * (filters.ml:9-12; the shim composes the transform-based dirty functions of affine / rgb / wireframe itself with
+ * the coh_shape_* operations), blur uses bloatdirty r r (filters.ml:63-75). */
+int coh_dirty_filter(coh_ctx* ctx, coh_scene_t scene, int32_t lmo_index, coh_shape_t initial_dirty, coh_shape_t* out);
 /* One step of an interactive drag (engine.ml:441-493 around render.ml:259-271, 1376-1400 and 1345-1365):
  * the object (or group) becomes an alias of its cached self moved by (dx, dy) whole pixels, the dirty region
  * dirty_region obj obj' = plaindirty | alldirty is formed from the cached, HBM-resident span sets, intersected

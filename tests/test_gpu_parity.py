@@ -584,3 +584,33 @@ def test_drag_object_fused_step(ctx, oracle):
         assert _max_lsb(got, ref) == 0, f"frame differs after drag step {step}"
     ctx.scene_free(sc)
     ctx.cache_clear()
+
+
+def test_dirty_filter(ctx, oracle):
+    """Render.dirty_filter (render.ml:1418-1438): the dirty region of a moved object grows through every blur lens
+    in front of it (bloatdirty, filters.ml:63-75) and passes the other filters unchanged."""
+    W, H = 200, 160
+    b, _ = _filter_scene("blur", W, H, second=("monochrome", {}), kernel=("gaussian", 3))
+    objs, n, nbg, e, p = _finish(b, W, H).arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    rng = random.Random(5)
+    f = objs[1]
+    fshape, _ = oracle.shapeminshape(e[f.first:f.first + f.count], f.winding)
+    r = 3
+    for it in range(6):
+        d = util.random_shape_flat(rng, x0=10 + 20 * it, y0=5 + 12 * it, w=90, h=70, density=0.5)
+        hd = ctx.shape_import(d)
+        # lmo = the last scene object: both filters are in front of it
+        got = ctx.dirty_filter(sc, n - nbg - 1, hd)
+        bf = oracle.shape_unary("bloat", fshape, r, r)
+        inf, outf = oracle.shape_op("intersection", bf, d), oracle.shape_op("difference", d, bf)
+        exp = oracle.shape_op("union", oracle.shape_op("intersection", oracle.shape_unary("bloat", inf, r, r), bf), outf)
+        assert np.array_equal(ctx.shape_export(got), exp), it
+        ctx.shape_free(got)
+        # lmo in front of every filter: nothing applies
+        got = ctx.dirty_filter(sc, 0, hd)
+        assert np.array_equal(ctx.shape_export(got), d)
+        ctx.shape_free(got)
+        ctx.shape_free(hd)
+    ctx.scene_free(sc)
