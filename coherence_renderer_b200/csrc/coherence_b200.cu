@@ -85,6 +85,11 @@ struct coh_ctx {
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
+  // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
+  cudaStream_t copy_stream = nullptr;
+  uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  int stage_next = 0;
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* h_total = nullptr;  // pinned
   // cross-tile carry for fancy fills
@@ -202,6 +207,12 @@ int coh_shutdown(coh_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  coh_fb_read_wait(ctx);
+  DFREE(ctx->stage[0]); DFREE(ctx->stage[1]);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_ready[k]); cudaEventDestroy(ctx->ev_done[k]); }
+  }
   coh_cache_clear(ctx);
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
@@ -1034,10 +1045,16 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
     if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
     if (exclusive_scan(ctx, d_counts, s->rowedge_ptr, (int)slots, nullptr)) return 1;
-    int total = 0;
-    CK(cudaMemcpyAsync(&total, s->rowedge_ptr + slots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(DMALLOC(&s->rowedge_idx, sizeof(int) * (size_t)std::max(total, 1)));
+    // size of the lists: the same row range per edge as k_rowedges, summed on the host (no device round trip:
+    // a device-to-host read here would queue behind an asynchronous framebuffer read-back of the previous frame)
+    long long total = 0;
+    for (int e = 0; e < n_edges; e++) {
+      if (edge_obj[e] < 0) continue;
+      const int ymin = std::min(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]), ymax = std::max(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]);
+      total += floordiv(ymax + 67, 32) - floordiv(ymin - 16 + 31, 32) + 1;
+    }
+    if (total > 0x7FFFFFF0LL) FAIL("scene: row-edge table too large");
+    CK(DMALLOC(&s->rowedge_idx, sizeof(int) * (size_t)std::max<long long>(total, 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
     if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1763,6 +1780,38 @@ int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, u
   if (w == 0 || h == 0) return 0;
   CK(cudaMemcpy2DAsync(out, (size_t)w * 4, ctx->fb + (size_t)y * ctx->fr.W + x, (size_t)ctx->fr.W * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int coh_fb_read_rgba_async(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_fb_read_rgba_async: no framebuffer");
+  if (x < 0 || y < 0 || w < 0 || h < 0 || x + w > ctx->fr.W || y + h > ctx->fr.H) FAIL("coh_fb_read_rgba_async: rectangle outside the framebuffer");
+  if (w == 0 || h == 0) return 0;
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) { CK(cudaEventCreateWithFlags(&ctx->ev_ready[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming)); }
+  }
+  const int k = ctx->stage_next; ctx->stage_next ^= 1;
+  const size_t bytes = (size_t)w * h * 4;
+  if (bytes > ctx->stage_cap[k]) {
+    if (ctx->stage_busy[k]) CK(cudaEventSynchronize(ctx->ev_done[k]));
+    DFREE(ctx->stage[k]);
+    CK(DMALLOC(&ctx->stage[k], bytes));
+    ctx->stage_cap[k] = bytes;
+  }
+  if (ctx->stage_busy[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[k], 0));  // the copy of two reads ago still owns this buffer
+  CK(cudaMemcpy2DAsync(ctx->stage[k], (size_t)w * 4, ctx->fb + (size_t)y * ctx->fr.W + x, (size_t)ctx->fr.W * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_ready[k], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[k], 0));
+  CK(cudaMemcpyAsync(out, ctx->stage[k], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_done[k], ctx->copy_stream));
+  ctx->stage_busy[k] = true;
+  return 0;
+}
+int coh_fb_read_wait(coh_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  for (int k = 0; k < 2; k++)
+    if (ctx->stage_busy[k]) { CK(cudaEventSynchronize(ctx->ev_done[k])); ctx->stage_busy[k] = false; }
   return 0;
 }
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {

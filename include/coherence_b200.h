@@ -225,6 +225,13 @@ void* coh_fb_device_ptr(coh_ctx* ctx);
  * Wxgui.plot_sprite writes (wxgui.ml:417-424, premultiplied r,g,b bytes, no alpha). */
 int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+/* Asynchronous variant of coh_fb_read_rgba for a stream of frames (the refresh loop of wxgui.ml:333-367 reads
+ * frame k while the engine already works on frame k+1): the rectangle is snapshotted on the render stream into
+ * one of two staging buffers and copied to `out` (pinned host memory) on a copy stream, so the next
+ * coh_scene_create / coh_render_frame overlap the transfer.  `out` is valid after coh_fb_read_wait, which waits
+ * for every outstanding asynchronous read.  At most two reads are in flight; a third waits for the oldest. */
+int coh_fb_read_rgba_async(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+int coh_fb_read_wait(coh_ctx* ctx);
 
 /* ---- host-side geometry preparation (CPU; the step before the raster path) ----
  * A path segment record is 9 doubles: kind (0 straight, 1 cubic bezier) then up to four points.

@@ -614,3 +614,24 @@ def test_dirty_filter(ctx, oracle):
         ctx.shape_free(got)
         ctx.shape_free(hd)
     ctx.scene_free(sc)
+
+
+def test_async_readback_equals_blocking_read(ctx):
+    """coh_fb_read_rgba_async / coh_fb_read_wait: frames read back while the next one renders are the frames
+    that were rendered (two staging buffers; three reads in flight exercise the reuse path)."""
+    W, H = 320, 200
+    ctx.fb_configure(W, H)
+    frames, scenes = [], []
+    for k in range(3):
+        b = S.lion_scene(W, H, 0.6 + 0.2 * k)
+        objs, n, nbg, e, p = b.arrays()
+        scenes.append(ctx.scene_create(objs, nbg, e, p))
+    outs = [np.zeros((H, W), dtype=np.uint32) for _ in range(3)]
+    for k in range(3):
+        ctx.render_frame(scenes[k], (0, 0, W, H))
+        ctx.fb_read_rgba_async(0, 0, W, H, outs[k])
+    ctx.fb_read_wait()
+    for k in range(3):
+        ctx.render_frame(scenes[k], (0, 0, W, H))
+        assert np.array_equal(ctx.fb_read_rgba(0, 0, W, H), outs[k]), k
+        ctx.scene_free(scenes[k])
