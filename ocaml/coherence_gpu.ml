@@ -30,6 +30,14 @@ external scene_create : ctx -> u8 -> int -> i32 -> i32 -> scene_h = "coh_ml_scen
 external scene_free : ctx -> scene_h -> unit = "coh_ml_scene_free"
 external fb_configure : ctx -> int -> int -> int -> int -> unit = "coh_ml_fb_configure"
 external render_frame_rgb888 : ctx -> scene_h -> int * int * int * int -> u8 -> unit = "coh_ml_render_frame_rgb888"
+external cache_configure : ctx -> bool -> int64 -> unit = "coh_ml_cache_configure"
+external cache_clear : ctx -> unit = "coh_ml_cache_clear"
+external scene_drag_object : ctx -> scene_h -> int -> int -> int -> int * int * int * int = "coh_ml_scene_drag_object"
+external scene_object_shape : ctx -> scene_h -> int -> shape_h * shape_h = "coh_ml_scene_object_shape"
+external dirty_filter : ctx -> scene_h -> int -> shape_h -> shape_h = "coh_ml_dirty_filter"
+external render_frame_shape : ctx -> scene_h -> shape_h -> unit = "coh_ml_render_frame_shape"
+external read_rgb888 : ctx -> int * int * int * int -> u8 -> unit = "coh_ml_read_rgb888"
+external convolve_sprite : ctx -> int * int -> shape_h -> (int32, int32_elt, c_layout) Array1.t -> (int32, int32_elt, c_layout) Array1.t -> shape_h = "coh_ml_convolve_sprite"
 
 let the_ctx = lazy (init (-1))
 

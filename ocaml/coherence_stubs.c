@@ -106,3 +106,55 @@ CAMLprim value coh_ml_render_frame_rgb888(value ctx, value scene, value box, val
   check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), x, y, w, h, (uint8_t*)Caml_ba_data_val(out)));
   CAMLreturn(Val_unit);
 }
+
+/* ---- coherence across frames (engine.ml:441-493, render.ml:259-271, 1376-1438, cache.mli) ---- */
+CAMLprim value coh_ml_cache_configure(value ctx, value on, value bytes) {   /* Cache.usecache / Cache.setsize */
+  check(CTX(ctx), coh_cache_configure(CTX(ctx), Bool_val(on), Int64_val(bytes)));
+  return Val_unit;
+}
+CAMLprim value coh_ml_cache_clear(value ctx) { check(CTX(ctx), coh_cache_clear(CTX(ctx))); return Val_unit; }
+/* Render.translate_renderobject + dirty_region + render_frame over the dirty region, as one device-side step;
+ * returns the dirty pixel box (x0, y0, x1, y1) the front end re-reads with coh_ml_read_rgb888 */
+CAMLprim value coh_ml_scene_drag_object(value ctx, value scene, value index, value dx, value dy) {
+  CAMLparam5(ctx, scene, index, dx, dy);
+  CAMLlocal1(r);
+  int32_t bb[4];
+  check(CTX(ctx), coh_scene_drag_object(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(index), Int_val(dx), Int_val(dy), 0, bb));
+  r = caml_alloc_tuple(4);
+  for (int k = 0; k < 4; k++) Store_field(r, k, Val_int(bb[k]));
+  CAMLreturn(r);
+}
+CAMLprim value coh_ml_scene_object_shape(value ctx, value scene, value index) {   /* Render.shape_of_basicshape */
+  CAMLparam3(ctx, scene, index);
+  CAMLlocal1(r);
+  coh_shape_t s = 0, m = 0;
+  check(CTX(ctx), coh_scene_object_shape(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(index), &s, &m));
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, caml_copy_int64((int64_t)s));
+  Store_field(r, 1, caml_copy_int64((int64_t)m));
+  CAMLreturn(r);
+}
+CAMLprim value coh_ml_dirty_filter(value ctx, value scene, value lmo, value dirty) {   /* Render.dirty_filter */
+  CAMLparam4(ctx, scene, lmo, dirty);
+  coh_shape_t o = 0;
+  check(CTX(ctx), coh_dirty_filter(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(lmo), (coh_shape_t)Int64_val(dirty), &o));
+  CAMLreturn(caml_copy_int64((int64_t)o));
+}
+CAMLprim value coh_ml_render_frame_shape(value ctx, value scene, value update) {   /* render_frame over any update shape */
+  check(CTX(ctx), coh_render_frame_shape(CTX(ctx), (coh_scene_t)Int64_val(scene), (coh_shape_t)Int64_val(update), 0));
+  return Val_unit;
+}
+CAMLprim value coh_ml_read_rgb888(value ctx, value box, value out) {   /* Wxgui.plot_sprite's bytes for a rectangle */
+  CAMLparam3(ctx, box, out);
+  check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+/* Convolve.convolve_sprite kernel sprite: sprite = (shape handle, RGBA8 per pixel in span order) */
+CAMLprim value coh_ml_convolve_sprite(value ctx, value kind_r, value shape, value rgba_in, value rgba_out) {
+  CAMLparam5(ctx, kind_r, shape, rgba_in, rgba_out);
+  coh_shape_t o = 0;
+  int64_t n = 0;
+  check(CTX(ctx), coh_convolve_sprite(CTX(ctx), Int_val(Field(kind_r, 0)), Int_val(Field(kind_r, 1)), (coh_shape_t)Int64_val(shape),
+        (const uint32_t*)Caml_ba_data_val(rgba_in), &o, (uint32_t*)Caml_ba_data_val(rgba_out), Caml_ba_array_val(rgba_out)->dim[0], &n));
+  CAMLreturn(caml_copy_int64((int64_t)o));
+}
