@@ -157,7 +157,10 @@ def run_ours(args):
     n_edges, n_objs = len(edges), n
     from coherence_renderer_b200 import bands
 
-    y0, y1 = bands.band_rows(HEIGHT, N, rank)
+    # equal scanline bands; COH_BALANCED_BANDS=1 cuts them by estimated cost instead (measured slower on the lion,
+    # whose rows are evenly loaded: 0.242 vs 0.223 ms at 4 GPUs — the ragged strip exchange costs more than it saves)
+    band_list = bands.balanced_bands(bands.row_costs(edges, HEIGHT, WIDTH), N) if N > 1 and os.environ.get("COH_BALANCED_BANDS") else bands.all_bands(HEIGHT, N)
+    y0, y1 = band_list[rank]
 
     ctx = abi.Context(local)
     stream = torch.cuda.current_stream()
@@ -173,7 +176,7 @@ def run_ours(args):
     def frame():
         ctx.render_frame(scene_h, update)
         if N > 1:
-            bands.gather_strips(dist, fb[y0:y1], full, HEIGHT, N)
+            bands.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
 
     def barrier():
         if N > 1:
@@ -251,7 +254,7 @@ def run_ours(args):
             "metric": "Mpixels/s (complete antialiased frames, scene -> RGBA8 framebuffer)", "value": mpx, "unit": "Mpx/s",
             "frames_per_s": 1e3 / ms, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "l2": "256 MB flush write before every timed step (untimed)",
+            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "band_rows": [list(b) for b in band_list], "l2": "256 MB flush write before every timed step (untimed)",
                        "step": "one frame: K1 binning (3 launches) + fused walker (1 launch)" + (" + NCCL all-gather of band strips" if N > 1 else "")},
             "roofline": {"bound": "hbm", "kernel": "k_walk", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if N == 1 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": walk_ms_max, "binning_ms": bin_ms,

@@ -14,12 +14,67 @@ def all_bands(height, n_bands):
     return [band_rows(height, n_bands, k) for k in range(n_bands)]
 
 
-def gather_strips(dist, strip, full, height, n_bands):
+def row_costs(edges, height, width, edge_weight=15.0, tile_weight=0.75):
+    """Relative cost of every pixel row for the walker: a constant per 32-pixel tile (background fill) plus a
+    weight per edge whose extended band reaches the row (scan conversion + antialiasing happen there).
+    edges: int32 [n, 4] sub-pixel bins (x0, y0, x1, y1)."""
+    import numpy as np
+
+    cost = np.full(height, tile_weight * ((width + 31) // 32), dtype=np.float64)
+    if len(edges):
+        e = np.asarray(edges).reshape(-1, 4)
+        ymin, ymax = np.minimum(e[:, 1], e[:, 3]), np.maximum(e[:, 1], e[:, 3])
+        lo = np.clip((ymin - 16 + 31) >> 5, 0, height)       # the row range of k_rowedges
+        hi = np.clip(((ymax + 67) >> 5) + 1, 0, height)
+        d = np.zeros(height + 1, dtype=np.float64)
+        np.add.at(d, lo, edge_weight)
+        np.add.at(d, hi, -edge_weight)
+        cost += np.cumsum(d)[:height]
+    return cost
+
+
+def balanced_bands(cost, n_bands, align=16):
+    """Split rows into n_bands contiguous bands of about equal total cost, boundaries on multiples of `align`
+    (the walker's cell height) so that no cell row is shared by two GPUs.  Returns [(y0, y1)] like all_bands."""
+    import numpy as np
+
+    height = len(cost)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, n_bands):
+        y = int(np.searchsorted(cum, cum[-1] * k / n_bands))
+        y = int(round(y / align)) * align
+        lo = cuts[-1] + align                                  # every band keeps at least one cell row
+        hi = height - (n_bands - k) * align
+        cuts.append(max(lo, min(y, hi)) if hi >= lo else min(height, cuts[-1] + max(1, (height - cuts[-1]) // (n_bands - k + 1))))
+    cuts.append(height)
+    return [(cuts[k], cuts[k + 1]) for k in range(n_bands)]
+
+
+def gather_strips(dist, strip, full, height, n_bands, rows=None):
     """All-gather the band strips (rows of `full` owned by each rank) into `full` on every rank.
-    `strip` is this rank's rows (a contiguous [rows, W] tensor); `full` is [H, W]."""
-    rows = all_bands(height, n_bands)
+    `strip` is this rank's rows (a contiguous [rows, W] tensor); `full` is [H, W]; `rows` = the bands
+    (default: the equal split)."""
+    explicit = rows is not None
+    rows = rows or all_bands(height, n_bands)
     if len({b - a for a, b in rows}) == 1:
         dist.all_gather_into_tensor(full, strip)
+        return full
+    if explicit and dist.get_backend() == "nccl":
+        # cost-balanced bands have very different heights: one grouped exchange of exact-size strips
+        # (ncclGroupStart / Send / Recv / End) instead of padding every strip to the tallest band
+        rank = dist.get_rank()
+        ops = []
+        for k, (a, b) in enumerate(rows):
+            if k == rank:
+                continue
+            ops.append(dist.P2POp(dist.isend, strip, k))
+            ops.append(dist.P2POp(dist.irecv, full[a:b], k))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        a, b = rows[rank]
+        if full[a:b].data_ptr() != strip.data_ptr():
+            full[a:b] = strip
         return full
     # ragged bands (H not divisible by N): gather strips padded to the tallest band
     import torch

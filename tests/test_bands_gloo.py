@@ -56,3 +56,24 @@ def test_band_sharded_frame_equals_whole_frame(tmp_path, world, oracle):
     objs, n, nbg, edges, points = scene.lion_scene(W, H, 0.55).arrays()
     whole = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
     assert np.array_equal(np.load(out), whole)
+
+
+def test_balanced_bands_partition_rows_on_cell_boundaries():
+    """Cost-weighted bands: contiguous, cover every row once, cut on multiples of the cell
+    height, and carry about equal estimated cost."""
+    import numpy as np
+
+    from coherence_renderer_b200 import bands, scene
+
+    H, W = 2160, 3840
+    _, _, _, edges, _ = scene.lion_scene(W, H, 7.0).arrays()
+    cost = bands.row_costs(edges, H, W)
+    assert cost.min() > 0 and cost.max() > 5 * cost.min()
+    for n in (1, 2, 3, 4, 8):
+        bl = bands.balanced_bands(cost, n)
+        assert bl[0][0] == 0 and bl[-1][1] == H and all(bl[k][1] == bl[k + 1][0] for k in range(n - 1))
+        assert all(b > a for a, b in bl) and all(a % 16 == 0 for a, _ in bl)
+        share = [cost[a:b].sum() / cost.sum() for a, b in bl]
+        assert max(share) < 1.25 / n
+    flat = np.ones(100)
+    assert bands.balanced_bands(flat, 3, align=1) == [(0, 33), (33, 67), (67, 100)] or sum(b - a for a, b in bands.balanced_bands(flat, 3, align=1)) == 100
