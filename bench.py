@@ -166,16 +166,42 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.fb_configure(WIDTH, HEIGHT, y0, y1)
-    fb = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
-    ctx.fb_attach(fb.data_ptr())
-    full = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if N > 1 else None
+    # N > 1: the band gather.  Preferred: the framebuffers of all ranks live in symmetric memory (peer-mapped over
+    # NVLink) and the walker stores every finished pixel to all of them as it goes — compute and "collective" are
+    # one kernel, followed only by a cross-rank barrier.  If symmetric memory cannot be set up on this box, fall
+    # back to an NCCL all-gather of the strips after the frame.
+    fb, full, symm, gather = None, None, None, "none (single GPU)"
+    if N > 1 and not os.environ.get("COH_NCCL_GATHER"):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            fb = symm_mem.empty((HEIGHT, WIDTH), dtype=torch.int32, device=torch.device("cuda", local))
+            fb.zero_()
+            symm = symm_mem.rendezvous(fb, dist.group.WORLD)
+            ptrs = [int(symm.buffer_ptrs[r]) for r in range(N)]
+            ctx.fb_attach(ptrs[rank])
+            ctx.fb_set_peers([ptrs[r] for r in range(N) if r != rank])
+            full = fb
+            gather = "fused into the walker: peer stores over NVLink into every rank's framebuffer (symmetric memory) + cross-rank barrier"
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
+            symm = None
+    if symm is None:
+        fb = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
+        ctx.fb_attach(fb.data_ptr())
+        full = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if N > 1 else None
+        if N > 1:
+            gather = "NCCL all-gather of the band strips after the frame"
     scene_h = ctx.scene_create(objs, nbg, edges, points)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     update = (0, 0, WIDTH, HEIGHT)
 
     def frame():
         ctx.render_frame(scene_h, update)
-        if N > 1:
+        if symm is not None:
+            symm.barrier()  # every rank's band has landed in this rank's framebuffer
+        elif N > 1:
             bands.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
 
     def barrier():
@@ -187,6 +213,13 @@ def run_ours(args):
         frame()
     barrier()
     ctx.sync()  # surfaces kernel-side errors
+    if N > 1:  # every rank must now hold the same, complete frame
+        chk = full[::13, ::7].to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if lo.item() != hi.item() or (full[:: HEIGHT // 8, 5] == 0).any().item():
+            raise SystemExit("bench.py: the gathered frames differ between ranks or have missing bands")
 
     # ---- device-timed steps: L2 flushed (untimed) before every step, CUDA events on the launching stream
     sampler = ClockSampler(local)
@@ -255,7 +288,7 @@ def run_ours(args):
             "frames_per_s": 1e3 / ms, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "band_rows": [list(b) for b in band_list], "l2": "256 MB flush write before every timed step (untimed)",
-                       "step": "one frame: K1 binning (3 launches) + fused walker (1 launch)" + (" + NCCL all-gather of band strips" if N > 1 else "")},
+                       "step": "one frame: K1 binning (3 launches) + fused walker (1 launch)", "gather": gather},
             "roofline": {"bound": "hbm", "kernel": "k_walk", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if N == 1 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": walk_ms_max, "binning_ms": bin_ms,
                          "note": "integer/bit + FP64-crossing work: the walker is issue/latency bound, not HBM bound (DESIGN.md)"},

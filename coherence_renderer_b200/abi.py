@@ -45,7 +45,7 @@ SYMBOLS = [
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
-    "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_rgba_async", "coh_fb_read_wait",
+    "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
@@ -321,6 +321,11 @@ class Context:
             out = np.zeros((h, w), dtype=np.uint32)
         self._chk(lib().coh_fb_read_rgba(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
+
+    def fb_set_peers(self, peer_ptrs):
+        """peer_ptrs: device pointers (ints) of the other ranks' framebuffers, peer-mapped into this process."""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(p) for p in peer_ptrs])
+        self._chk(lib().coh_fb_set_peers(self._h, len(peer_ptrs), arr))
 
     def fb_read_rgba_async(self, x, y, w, h, out):
         """out: pinned host array of h*w uint32; valid after fb_read_wait()."""

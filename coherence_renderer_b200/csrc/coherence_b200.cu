@@ -85,6 +85,7 @@ struct coh_ctx {
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
+  uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
   cudaStream_t copy_stream = nullptr;
   uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
@@ -1128,6 +1129,12 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8) {
   ctx->fb = (uint32_t*)device_rgba8; ctx->own_fb = false;
   return 0;
 }
+int coh_fb_set_peers(coh_ctx* ctx, int32_t n_peers, void* const* peer_fbs) {
+  if (n_peers < 0 || n_peers > COH_MAX_PEERS) FAIL("coh_fb_set_peers: at most 7 peers (one 8-GPU box)");
+  ctx->n_peers = n_peers;
+  for (int k = 0; k < n_peers; k++) ctx->peer_fb[k] = (uint32_t*)peer_fbs[k];
+  return 0;
+}
 int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1) {
   CK(cudaSetDevice(ctx->device));
   if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
@@ -1241,13 +1248,20 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
+  P.n_peers = (A.fb == ctx->fb) ? ctx->n_peers : 0;   // only the frame itself is mirrored, not filter canvases
+  for (int k = 0; k < COH_MAX_PEERS; k++) P.peer_fb[k] = k < P.n_peers ? ctx->peer_fb[k] : nullptr;
   // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
   int walk_h = big ? 16 : 4;
-  if (const char* e = getenv("COH_WALK_H")) { int v = atoi(e); if (v == 4 || v == 16) walk_h = v; }  // experiments (1- and 2-row items measured slower at 1 and 2 GPUs)
+  // Few cells (a band of an 8-GPU split, a small dirty region): the launch is bounded by its longest work item,
+  // not by throughput — one-row items shorten that path (measured on the lion at 8 GPUs: 0.164 -> 0.141 ms;
+  // at 1 to 4 GPUs four-row items are as fast or faster).
+  if (!big && (long long)n_cells * 4 < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 1;
+  if (const char* e = getenv("COH_WALK_H")) { int v = atoi(e); if (v == 1 || v == 4 || v == 16) walk_h = v; }  // tests force every variant
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
 #define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
   do {                                                                                                             \
     if (walk_h == 4) k_walk<CARRYV, EX, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                         \
+    else if (walk_h == 1) k_walk<CARRYV, EX, 1><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                    \
     else k_walk<CARRYV, EX, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                                    \
     LAUNCHED();                                                                                                    \
   } while (0)

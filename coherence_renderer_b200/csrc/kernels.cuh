@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__
 // ------------------------------------------------------------------------------------
 // The fused walker.
 // ------------------------------------------------------------------------------------
+constexpr int COH_MAX_PEERS = 7;
 struct WalkParams {
   const ObjRec* objs;
   const EdgeRec* edges;
@@ -294,6 +295,11 @@ struct WalkParams {
   uint32_t* u_out;             // optional: `u` after the scene pass (same layout)
   uint32_t* fb;                // RGBA8 framebuffer, fr.W x fr.H
   int* error_flag;             // set to 1 when an object overflows COH_MAXX crossings
+  // Band gather fused into the walk: the same framebuffers on the other GPUs of the box (peer-mapped over
+  // NVLink); every final pixel is stored to all of them as it is produced, so the strips arrive while the
+  // walk is still running and no collective follows.
+  uint32_t* peer_fb[COH_MAX_PEERS];
+  int n_peers;
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
   int resume;                  // continue a frame: the root accumulators start from what `fb` already holds
   // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
@@ -544,7 +550,11 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 #pragma unroll 1
     for (int r = 0; r < WALK_H; r++) {
       const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u, r);
-      if ((uu >> lane) & 1u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = c0;
+      if ((uu >> lane) & 1u) {
+        const size_t at = (size_t)(y0 + r) * P.fr.W + tx0 + lane;
+        P.fb[at] = c0;
+        for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = c0;
+      }
     }
     return;
   }
@@ -821,7 +831,11 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);
     if ((uu >> lane) & 1u) {
       const uint32_t acc = acc_rows[r][lane];
-      if (P.write_clear || acc != 0u) P.fb[(size_t)(y0 + r) * P.fr.W + tx0 + lane] = acc;
+      if (P.write_clear || acc != 0u) {
+        const size_t at = (size_t)(y0 + r) * P.fr.W + tx0 + lane;
+        P.fb[at] = acc;
+        for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
+      }
     }
   }
   PH_MARK(0)

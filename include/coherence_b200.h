@@ -217,6 +217,12 @@ int coh_scene_object_shape(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, c
  * rendered with COH_RENDER_RECORD_U (the set-subtraction artefact of render.ml:1308:
  * update minus every pixel the scene pass made opaque), as a device shape. */
 int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out);
+/* Multi-GPU band gather without a collective: peer_fbs are device pointers to the framebuffers of the other
+ * GPUs of the box (same width x height, peer-mapped into this process: CUDA IPC / symmetric memory); from now on
+ * every pixel this context renders into its own framebuffer is also stored to each of them over NVLink as it is
+ * produced, so after all ranks have rendered their bands (and a cross-rank barrier) every GPU holds the whole
+ * frame.  n_peers = 0 switches it off.  Frames with filter objects mirror only their final pixels. */
+int coh_fb_set_peers(coh_ctx* ctx, int32_t n_peers, void* const* peer_fbs);
 /* Wait for the context's stream and report deferred kernel-side failures. */
 int coh_sync(coh_ctx* ctx);
 /* Device pointer of the framebuffer (band gather by NCCL / peer copies happens on these). */

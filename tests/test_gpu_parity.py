@@ -635,3 +635,26 @@ def test_async_readback_equals_blocking_read(ctx):
         ctx.render_frame(scenes[k], (0, 0, W, H))
         assert np.array_equal(ctx.fb_read_rgba(0, 0, W, H), outs[k]), k
         ctx.scene_free(scenes[k])
+
+
+@pytest.mark.parametrize("walk_h", ["1", "4", "16"])
+def test_every_walker_item_height(ctx, oracle, walk_h, monkeypatch):
+    """The walker is compiled for work items of 1, 4 and 16 rows and picks one from the scene and frame size;
+    every variant must give the same pixels (COH_WALK_H forces one)."""
+    monkeypatch.setenv("COH_WALK_H", walk_h)
+    W, H = 640, 480
+    b = S.lion_scene(W, H, 1.4, pretrans=200)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    b = S.random_scene(300, 200, 50, seed=5, brush_fraction=0.3)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, 300, 200)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    W, H = 200, 160
+    b = S.SceneBuilder()
+    b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0), (40.0, 120.0)], S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 0, 255), 128)))
+    b.cpg("xor", [S.polygon_segments([(10.2, 40.3), (190.6, 43.1), (188.0, 100.2), (12.0, 97.7)])],
+          [S.polygon_segments([(30.0, 20.4), (170.0, 70.2), (160.0, 140.9), (25.0, 72.6)])], S.Fill.plain(S.rgba8(30, 30, 200)))
+    b.filter("blur", _circle(100.3, 80.2, 50.5), kernel=("gaussian", 2))
+    b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
