@@ -1126,6 +1126,12 @@ int coh_fb_attach(coh_ctx* ctx, void* device_rgba8) {
   if (drain_timing(ctx)) return 1;
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->own_fb) DFREE(ctx->fb);
+  if (!device_rgba8) {  // detach: back to a framebuffer owned by the context
+    ctx->fb = nullptr; ctx->own_fb = true;
+    CK(DMALLOC(&ctx->fb, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H));
+    CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H, ctx->stream));
+    return 0;
+  }
   ctx->fb = (uint32_t*)device_rgba8; ctx->own_fb = false;
   return 0;
 }

@@ -176,7 +176,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t s);
  * [band_y0, band_y1) this context renders; rows outside the band are left untouched. */
 int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1);
 /* Render into a caller-owned device buffer of W*H RGBA8 words instead (band gather by NCCL
- * happens on buffers the collective library knows). */
+ * happens on buffers the collective library knows); NULL goes back to a buffer owned by the context. */
 int coh_fb_attach(coh_ctx* ctx, void* device_rgba8);
 /* Render.render_frame lmo view update (render.ml:1345-1365) with update = Sprite.box ux uy uw uh:
  * scene pass over (pages @ background) pass, composited front to back with hidden-surface

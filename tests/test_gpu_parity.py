@@ -658,3 +658,35 @@ def test_every_walker_item_height(ctx, oracle, walk_h, monkeypatch):
     b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
     got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+
+
+def test_peer_framebuffer_mirror(ctx, oracle):
+    """coh_fb_set_peers: every pixel rendered into the framebuffer is also stored to the peer framebuffers (on a
+    multi-GPU box: the other ranks' frames over NVLink; here a second buffer on the same GPU stands in for a
+    peer).  Two bands rendered by two passes into mirrored buffers assemble the whole frame in both."""
+    import torch
+
+    W, H = 320, 208
+    b = S.lion_scene(W, H, 0.75)
+    objs, n, nbg, e, p = b.arrays()
+    ref = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H), bbox_reject=False)
+    bufs = [torch.zeros((H, W), dtype=torch.int32, device="cuda") for _ in range(2)]
+    sc = None
+    try:
+        for k, (y0, y1) in enumerate([(0, 112), (112, H)]):  # "rank" k renders band k into buffer k, mirrored to the other
+            ctx.fb_configure(W, H, y0, y1)
+            ctx.fb_attach(bufs[k].data_ptr())
+            ctx.fb_set_peers([bufs[1 - k].data_ptr()])
+            if sc is None:
+                sc = ctx.scene_create(objs, nbg, e, p)
+            ctx.render_frame(sc, (0, 0, W, H))
+            ctx.sync()
+        for k in range(2):
+            got = bufs[k].cpu().numpy().view(np.uint32)
+            assert _max_lsb(got, ref) == 0, f"buffer {k}"
+    finally:
+        ctx.fb_set_peers([])
+        ctx.fb_configure(W, H)
+        ctx.fb_attach(0)         # back to a context-owned framebuffer for the tests that follow
+        if sc:
+            ctx.scene_free(sc)
