@@ -86,6 +86,8 @@ struct coh_ctx {
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
+  // three-phase frames: per (cell item, row) pair
+  uint2* pre_sc = nullptr; uint32_t* pre_em = nullptr; int* pre_list = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
   // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
   cudaStream_t copy_stream = nullptr;
   uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
@@ -219,6 +221,7 @@ int coh_shutdown(coh_ctx* ctx) {
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
   DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head);
+  DFREE(ctx->pre_sc); DFREE(ctx->pre_em); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -995,6 +998,11 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       default: FAIL("scene: unknown object kind");
     }
     o.bx0 += o.dx; o.bx1 += o.dx; o.by0 += o.dy; o.by1 += o.dy;
+    if ((o.kind == K_PATH || o.kind == K_PRIM) && o.fill.kind == 0 && (o.fill.c0 >> 24) == 255u && o.pretrans < 0) {
+      bool clear_path = true;
+      for (int d = 0; d < o.depth; d++) clear_path = clear_path && recs[o.anc[d]].pretrans < 0;
+      if (clear_path) o.flags |= OF_OCCLUDES;
+    }
     recs.push_back(o);
     rec_of_abi[i] = (int)recs.size() - 1;
     ids.resize(recs.size(), -1); ids.back() = c.id;
@@ -1275,8 +1283,37 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   do {                                                                                                             \
     if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
-  P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.n_cells = n_cells;
+  P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.order_starts = ctx->order_hist; P.n_cells = n_cells;
+  P.pre_sc = nullptr; P.pre_op = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
+  const bool pre = s->extras == 0 && !s->has_fancy && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) && !getenv("COH_FUSED");
+  if (pre) {
+    const size_t n_pairs = total * CELL_H;
+    if (n_pairs > ctx->pre_cap) {
+      DFREE(ctx->pre_sc); DFREE(ctx->pre_em); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
+      const size_t cap = n_pairs + n_pairs / 4 + 1024;
+      CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap)); CK(DMALLOC(&ctx->pre_em, sizeof(uint32_t) * cap));
+      CK(DMALLOC(&ctx->pre_list, sizeof(int) * (cap + 1))); CK(DMALLOC(&ctx->pre_op, 32 * cap));
+      ctx->pre_cap = cap;
+    }
+    int* list_n = ctx->pre_list + ctx->pre_cap;
+    CK(cudaMemsetAsync(list_n, 0, sizeof(int), ctx->stream));
+    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc); LAUNCHED();
+    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_em, ctx->pre_list, list_n); LAUNCHED();
+    k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_em, ctx->pre_list, list_n, ctx->pre_op); LAUNCHED();
+    P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
+    int pre_h = walk_h == 1 ? 1 : 4, pre_ctas = WALK_MIN_CTAS;
+    if (const char* e = getenv("COH_PRE_H")) pre_h = atoi(e);
+    if (const char* e = getenv("COH_PRE_CTAS")) pre_ctas = atoi(e);
+    const int pgrid = std::min(ctx->n_sms * pre_ctas, cdiv(n_cells * (CELL_H / pre_h), WALK_WARPS));
+    if (pre_h == 1) k_walk<false, 0, 1, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    else if (pre_h == 16) k_walk<false, 0, 16, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    else k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+    LAUNCHED();
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
+    return 0;
+  }
   P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
   if (s->has_fancy) {
     size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);

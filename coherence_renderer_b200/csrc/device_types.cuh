@@ -14,7 +14,8 @@ constexpr int MAX_DEPTH = 6;     // nested Group depth (incl. the implicit scene
 constexpr int AA_WORDS = 17;     // (32 + 2) * 16 scaled columns of one tile = 544 bits
 
 enum { K_PATH = 0, K_PRIM = 1, K_GROUP = 2, K_BRUSH = 4, K_CONV = 5, K_CPG = 6 };
-enum { OF_ROOT_SCENE = 1, OF_ROOT_BACKGROUND = 2 };
+enum { OF_ROOT_SCENE = 1, OF_ROOT_BACKGROUND = 2,
+       OF_OCCLUDES = 4 };  // leaf with an opaque plain fill and no dissolve on the way to the root: its minshape hides what lies behind
 
 // One record per leaf object or group, device resident (96 bytes + fill).
 struct ObjRec {

@@ -300,6 +300,10 @@ struct WalkParams {
   // walk is still running and no collective follows.
   uint32_t* peer_fb[COH_MAX_PEERS];
   int n_peers;
+  // Three-phase frames (k_walk<..., PRE = true>): scan conversion and antialiasing were done by
+  // k_pre_scan / k_pre_vis / k_pre_aa for every (cell item, row) pair; the walk only composites.
+  const uint2* pre_sc;         // per pair (item * CELL_H + row of the cell): shape / coverage words
+  const uint8_t* pre_op;       // per pair: 32 opacity bytes (valid where the pair's edge mask is set)
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
   int resume;                  // continue a frame: the root accumulators start from what `fb` already holds
   // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
@@ -310,6 +314,7 @@ struct WalkParams {
   // (decoupled look-back).
   int* queue;                  // work queue head: persistent warps take cells with atomicAdd
   const int* order;            // q-th cell to process (heavy first), or null for row-major order
+  const int* order_starts;     // with `order`: first position of every list-length bin (bin 0 = longest lists)
   int n_cells;
   int* carry_done;             // per (band row, tile): == epoch when the tile has finished
   int* carry_cnt;              // per (band row, tile): number of published entries
@@ -503,7 +508,7 @@ constexpr int WALK_WARPS = 8;            // warps (= cells) per CTA
 // CARRY: the scene has fancy (gradient / radial) fills -> fill evaluation and the cross-tile carry
 // are compiled in.  EXTRAS: 0 = polygons and primitives only (the small kernel), 1 = + brush strokes and
 // Convolved objects, 2 = + CPG objects and continuing a frame (filter passes).
-template <bool CARRY, int EXTRAS, int WALK_H>
+template <bool CARRY, int EXTRAS, int WALK_H, bool PRE>
 __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, const int by, const int sub, const int lane,
                                           uint32_t* __restrict__ aa_bits, StagedEdge* __restrict__ stage,
                                           uint32_t (*__restrict__ acc_rows)[32],
@@ -631,7 +636,12 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
     const int idx = ci < it1 ? P.cell_items[ci] : -1;
     uint32_t S = 0u, C = 0u;
     uint32_t gSA = 0u, gMA = 0u, gSB = 0u, gMB = 0u;   // CPG operands: shape / minshape words of a and b
-    if (idx >= 0 && u_hit != 0u) {
+    if (PRE) {
+      if (idx >= 0 && u_hit != 0u) {   // scan-converted by k_pre_scan: no object, row list or edge is touched here
+        const uint2 sc = P.pre_sc[(size_t)ci * CELL_H + sub * WALK_H + r_lane];
+        S = sc.x; C = sc.y;
+      }
+    } else if (idx >= 0 && u_hit != 0u) {
       const ObjRec& o = P.objs[idx];
       if (!(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
         const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
@@ -721,7 +731,9 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         int opacity = 255;
         PH_MARK(3)  // row setup
         if (edge) {
-          if (okind == K_PATH) {
+          if (PRE) {
+            if (okind == K_PATH) opacity = P.pre_op[((size_t)(base + cc) * CELL_H + sub * WALK_H + r) * 32 + lane];
+          } else if (okind == K_PATH) {
             bool ok;
             const int slot = o.row_base + yy - o.ry0;
             const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
@@ -844,7 +856,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 
 // Persistent launch: every warp keeps taking cells from the queue (heavy cells first) until it
 // is empty; the grid is sized to fill the GPU exactly once (WALK_MIN_CTAS CTAs per SM).
-template <bool CARRY, int EXTRAS, int WALK_H>
+template <bool CARRY, int EXTRAS, int WALK_H, bool PRE = false>
 __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
   constexpr int WALK_SUB = CELL_H / WALK_H;
   __shared__ int s_prefix[32 * 33];
@@ -855,17 +867,27 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
   __syncthreads();
   const int volume = P.aa->volume;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // Work items come off one atomic counter.  The heavy cells at the head of the order are taken one item at a
+  // time (balance); the long tail of cells with at most one object (mostly background) is taken in batches,
+  // or every warp of the GPU would queue up on the same counter for ~100 instructions of work per item.
+  const int n_items = P.n_cells * WALK_SUB;
+  const int heavy_items = P.order ? P.order_starts[ORDER_BINS - 2] * WALK_SUB : n_items;  // cells with >= 2 objects
+  int q_next = 0, q_end = 0;
   for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(P.queue, 1);
-    q = __shfl_sync(0xFFFFFFFFu, q, 0);
-    if (q >= P.n_cells * WALK_SUB) break;
+    if (q_next == q_end) {
+      const int batch = q_end >= heavy_items ? 8 : 1;
+      if (lane == 0) q_next = atomicAdd(P.queue, batch);
+      q_next = __shfl_sync(0xFFFFFFFFu, q_next, 0);
+      q_end = q_next + batch;
+    }
+    const int q = q_next++;
+    if (q >= n_items) break;
     const int cell = P.order ? P.order[q / WALK_SUB] : q / WALK_SUB;
     const int sub = q % WALK_SUB;
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
 #endif
-    walk_cell<CARRY, EXTRAS, WALK_H>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    walk_cell<CARRY, EXTRAS, WALK_H, PRE>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
     __syncwarp();
 #ifdef COH_PHASE_PROFILE
     if (lane == 0 && cell < (1 << 20)) g_cell_cycles[cell] = (unsigned int)(clock64() - tc0_);
@@ -877,6 +899,98 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
 // K2 stand-alone (export path): one thread per pixel row of one edge list writes the
 // shape and coverage bit-rows into global bit-frames of `nw` words per row.
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// Three-phase frames for scenes of plain-filled paths and primitives (the lion).  The fused walker's
+// longest work item is a chain of antialiasing calls that must run one after the other; here scan
+// conversion and antialiasing of every (cell item, row) pair are independent work for the whole GPU,
+// and the front-to-back walk that remains only composites:
+//   k_pre_scan  thread / pair: shape and coverage words (the walker's scan phase, for every candidate)
+//   k_pre_vis   lane / (cell, row): which edge pixels can still show — `u` pruned by the minshapes of the
+//               opaque objects in front (a superset of the exact `u`: edge pixels never count as covered
+//               here), and the list of pairs that need antialiasing
+//   k_pre_aa    warp / listed pair: opacity bytes (aa_tile)
+//   k_walk<PRE> composite with the exact `u`; every pixel it antialiases is in the superset.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_of_item(const int* __restrict__ cell_off, int n_cells, int item) {
+  int lo = 0, hi = n_cells;   // last cell with cell_off[cell] <= item
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cell_off[mid] <= item) lo = mid; else hi = mid; }
+  return lo;
+}
+__global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  const int item = pair / CELL_H, row = pair % CELL_H;
+  const int cell = cell_of_item(P.cell_off, P.n_cells, item);
+  const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
+  const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
+  const ObjRec& o = P.objs[P.cell_items[item]];
+  uint32_t S = 0u, C = 0u;
+  if (my_y >= P.fr.band_y0 && my_y < P.fr.band_y1 && !(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
+    const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
+    if (o.kind == K_PRIM) {
+      if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
+    } else if (yy >= o.ry0 && yy <= o.ry1) {
+      const int slot = o.row_base + yy - o.ry0;
+      const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+      bool ok = true;
+      const uint2 w = scan_row_word(P.edges, P.rowedge_idx + a, b - a, yy, o.winding, xx0, ok);
+      if (!ok) *P.error_flag = 1;
+      S = w.x; C = w.y;
+    }
+  }
+  sc[pair] = make_uint2(S, C);
+}
+// blockDim = 128: 8 (cell, 16 rows) groups per block
+__global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, uint32_t* __restrict__ edge_mask, int* __restrict__ list, int* __restrict__ list_n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cell = t / CELL_H, row = t % CELL_H;
+  if (cell >= P.n_cells) return;
+  const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
+  const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
+  uint32_t u = 0u;
+  if (my_y >= P.fr.band_y0 && my_y < P.fr.band_y1) {
+    if (P.u_init) u = P.u_init[(size_t)my_y * P.fr.tiles_x + tile];
+    else u = (my_y >= P.uy0 && my_y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
+    if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
+  }
+  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+  for (int it = it0; it < it1; it++) {
+    const ObjRec& o = P.objs[P.cell_items[it]];
+    const size_t pair = (size_t)it * CELL_H + row;
+    const uint2 w = sc[pair];
+    const uint32_t M = w.x & ~w.y;
+    const uint32_t e = (o.kind == K_PATH) ? (w.x & ~M & u) : 0u;
+    edge_mask[pair] = e;
+    if (e) list[atomicAdd(list_n, 1)] = (int)pair;
+    if (o.flags & OF_OCCLUDES) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
+  }
+}
+__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const uint32_t* __restrict__ edge_mask, const int* __restrict__ list, const int* __restrict__ list_n,
+                                                uint8_t* __restrict__ op) {
+  __shared__ int s_prefix[32 * 33];
+  __shared__ uint32_t s_aa[8][32 * AA_WORDS];
+  __shared__ StagedEdge s_stage[8][32];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = *list_n, n_warps = gridDim.x * 8;
+  for (int i = blockIdx.x * 8 + wid; i < n; i += n_warps) {
+    const int pair = list[i];
+    const int item = pair / CELL_H, row = pair % CELL_H;
+    const int cell = cell_of_item(P.cell_off, P.n_cells, item);
+    const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
+    const ObjRec& o = P.objs[P.cell_items[item]];
+    const int yy = (P.cell_row0 + by) * CELL_H + row - o.dy, xx0 = tile * TILE_W - o.dx;
+    const int slot = o.row_base + yy - o.ry0;
+    const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+    bool ok;
+    const int v = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge_mask[pair], s_aa[wid], s_stage[wid], s_prefix, P.aa->volume, lane, ok);
+    if (!ok) *P.error_flag = 1;
+    op[(size_t)pair * 32 + lane] = (uint8_t)v;
+    __syncwarp();
+  }
+}
+
 constexpr int SCAN_CHUNK_WORDS = 8;  // one thread scans a 256-pixel window of one row
 __global__ void k_scan_rows(const EdgeRec* __restrict__ edges, int n_edges, int winding, int y0, int n_rows,
                             int wx0, int nw, uint32_t* __restrict__ S, uint32_t* __restrict__ C, int* error_flag) {
