@@ -385,7 +385,15 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
   SinkRow fsink; fsink.wx0 = wlo; fsink.nwords = AA_WORDS; fsink.saddr = (uint32_t)__cvta_generic_to_shared(row);
 #pragma unroll
   for (int w = 0; w < AA_WORDS; w++) row[w] = 0u;
-  scan_begin(fst, 16 * yy - 32 + lane, true, wlo, whi);
+  // Only the super-sampled columns under the edge pixels are ever read back: classify and rank crossings
+  // against that narrower window (pixel b reads columns wlo + 16 b .. wlo + 16 b + 31).  Everything to
+  // its left only contributes a winding count, everything to its right only "a successor exists".
+#ifndef COH_AA_WIDE
+  const int nlo = wlo + 16 * (__ffs((int)edge) - 1), nhi = wlo + 16 * (31 - __clz((int)edge)) + 31;
+#else
+  const int nlo = wlo, nhi = whi;
+#endif
+  scan_begin(fst, 16 * yy - 32 + lane, true, nlo, nhi);
   // The candidate edges are the same for all 32 super-sampled rows: lane i fetches and scales
   // candidate i once (one parallel round trip to L2 instead of a dependent chain per lane) and
   // classifies it against the window; then every lane walks the staged copies in shared memory.
@@ -395,7 +403,7 @@ __device__ __forceinline__ int aa_tile(const EdgeRec* __restrict__ edges, const 
       const EdgeRec e = edges[idx ? idx[i] : i];
       StagedEdge se;
       se.x0 = e.x0in * 16; se.x1 = e.x1in * 16; se.ymin = e.ymin * 16; se.ymax = e.ymax * 16;
-      se.g = e.g; se.dir = e.dir; se.side = edge_side(se.x0, se.x1, wlo, whi);
+      se.g = e.g; se.dir = e.dir; se.side = edge_side(se.x0, se.x1, nlo, nhi);
       stage[lane] = se;
     }
     __syncwarp();
