@@ -87,13 +87,14 @@ struct coh_ctx {
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // three-phase frames: per (cell item, row) pair
-  uint2* pre_sc = nullptr; uint32_t* pre_em = nullptr; int* pre_list = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
+  uint2* pre_sc = nullptr; int4* pre_list = nullptr; int* pre_n = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
   // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
   cudaStream_t copy_stream = nullptr;
   uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int stage_next = 0;
   int* cell_items = nullptr; size_t cell_items_cap = 0;
+  int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)
   int* h_total = nullptr;  // pinned
   // cross-tile carry for fancy fills
   int* queue = nullptr; int* order_hist = nullptr; int* cell_order = nullptr; int n_sms = 0;
@@ -221,7 +222,7 @@ int coh_shutdown(coh_ctx* ctx) {
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
   DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head);
-  DFREE(ctx->pre_sc); DFREE(ctx->pre_em); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
+  DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->item_cell);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1231,16 +1232,17 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   } else total = s->items_total;
   const size_t need = big ? 2 * total : total;  // the sort of very long lists stages through the upper half
   if (need > ctx->cell_items_cap) {
-    DFREE(ctx->cell_items);
+    DFREE(ctx->cell_items); DFREE(ctx->item_cell);
     size_t cap = need + need / 2 + 1024;
     CK(DMALLOC(&ctx->cell_items, sizeof(int) * cap));
+    CK(DMALLOC(&ctx->item_cell, sizeof(int) * cap));
     ctx->cell_items_cap = cap;
   }
   if (!big) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
     if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr)) return 1;
-    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head); LAUNCHED();
+    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell); LAUNCHED();
   } else {
     const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
@@ -1284,24 +1286,25 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
   P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.order_starts = ctx->order_hist; P.n_cells = n_cells;
-  P.pre_sc = nullptr; P.pre_op = nullptr;
+  P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
   const bool pre = s->extras == 0 && !s->has_fancy && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) && !getenv("COH_FUSED");
   if (pre) {
     const size_t n_pairs = total * CELL_H;
     if (n_pairs > ctx->pre_cap) {
-      DFREE(ctx->pre_sc); DFREE(ctx->pre_em); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
+      DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
       const size_t cap = n_pairs + n_pairs / 4 + 1024;
-      CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap)); CK(DMALLOC(&ctx->pre_em, sizeof(uint32_t) * cap));
-      CK(DMALLOC(&ctx->pre_list, sizeof(int) * (cap + 1))); CK(DMALLOC(&ctx->pre_op, 32 * cap));
+      CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap));
+      CK(DMALLOC(&ctx->pre_list, sizeof(int4) * cap)); CK(DMALLOC(&ctx->pre_op, 32 * cap));
+      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, sizeof(int)));
       ctx->pre_cap = cap;
     }
-    int* list_n = ctx->pre_list + ctx->pre_cap;
-    CK(cudaMemsetAsync(list_n, 0, sizeof(int), ctx->stream));
+    P.item_cell = ctx->item_cell;
+    CK(cudaMemsetAsync(ctx->pre_n, 0, sizeof(int), ctx->stream));
     k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc); LAUNCHED();
-    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_em, ctx->pre_list, list_n); LAUNCHED();
-    k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_em, ctx->pre_list, list_n, ctx->pre_op); LAUNCHED();
+    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n); LAUNCHED();
+    k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     int pre_h = walk_h == 1 ? 1 : 4, pre_ctas = WALK_MIN_CTAS;
     if (const char* e = getenv("COH_PRE_H")) pre_h = atoi(e);

@@ -91,7 +91,8 @@ template <bool FILL>
 __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/, const int* __restrict__ leaves, int n_leaves, Frame fr,
                       int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
                       int* __restrict__ items, int* __restrict__ hist /*[2*ORDER_BINS]: starts, cursors*/,
-                      int* __restrict__ order, const ObjRec* __restrict__ objs = nullptr, int2* __restrict__ cell_head = nullptr) {
+                      int* __restrict__ order, const ObjRec* __restrict__ objs = nullptr, int2* __restrict__ cell_head = nullptr,
+                      int* __restrict__ item_cell = nullptr /* cell of every list entry (three-phase frames) */) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_cells) return;
@@ -110,7 +111,11 @@ __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/
       hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
     }
     unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (FILL && hit) items[base + n + __popc(m & ((1u << lane) - 1u))] = idx;
+    if (FILL && hit) {
+      const int at = base + n + __popc(m & ((1u << lane) - 1u));
+      items[at] = idx;
+      if (item_cell) item_cell[at] = warp;
+    }
     if (FILL && n == 0 && m) first = __shfl_sync(0xFFFFFFFFu, idx, __ffs((int)m) - 1);
     n += __popc(m);
   }
@@ -302,6 +307,7 @@ struct WalkParams {
   int n_peers;
   // Three-phase frames (k_walk<..., PRE = true>): scan conversion and antialiasing were done by
   // k_pre_scan / k_pre_vis / k_pre_aa for every (cell item, row) pair; the walk only composites.
+  const int* item_cell;        // cell of every entry of cell_items
   const uint2* pre_sc;         // per pair (item * CELL_H + row of the cell): shape / coverage words
   const uint8_t* pre_op;       // per pair: 32 opacity bytes (valid where the pair's edge mask is set)
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
@@ -919,16 +925,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
 //   k_pre_aa    warp / listed pair: opacity bytes (aa_tile)
 //   k_walk<PRE> composite with the exact `u`; every pixel it antialiases is in the superset.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_of_item(const int* __restrict__ cell_off, int n_cells, int item) {
-  int lo = 0, hi = n_cells;   // last cell with cell_off[cell] <= item
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cell_off[mid] <= item) lo = mid; else hi = mid; }
-  return lo;
-}
 __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= n_pairs) return;
   const int item = pair / CELL_H, row = pair % CELL_H;
-  const int cell = cell_of_item(P.cell_off, P.n_cells, item);
+  const int cell = P.item_cell[item];
   const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   const ObjRec& o = P.objs[P.cell_items[item]];
@@ -949,7 +950,7 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
   sc[pair] = make_uint2(S, C);
 }
 // blockDim = 128: 8 (cell, 16 rows) groups per block
-__global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, uint32_t* __restrict__ edge_mask, int* __restrict__ list, int* __restrict__ list_n) {
+__global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __restrict__ list /* pair, object, edge mask, (tile << 16 | row of the frame) */, int* __restrict__ list_n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
   if (cell >= P.n_cells) return;
@@ -963,18 +964,17 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, uint32_t* 
   }
   const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
   for (int it = it0; it < it1; it++) {
-    const ObjRec& o = P.objs[P.cell_items[it]];
+    const int oi = P.cell_items[it];
+    const ObjRec& o = P.objs[oi];
     const size_t pair = (size_t)it * CELL_H + row;
     const uint2 w = sc[pair];
     const uint32_t M = w.x & ~w.y;
     const uint32_t e = (o.kind == K_PATH) ? (w.x & ~M & u) : 0u;
-    edge_mask[pair] = e;
-    if (e) list[atomicAdd(list_n, 1)] = (int)pair;
+    if (e) list[atomicAdd(list_n, 1)] = make_int4((int)pair, oi, (int)e, (tile << 16) | my_y);
     if (o.flags & OF_OCCLUDES) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
   }
 }
-__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const uint32_t* __restrict__ edge_mask, const int* __restrict__ list, const int* __restrict__ list_n,
-                                                uint8_t* __restrict__ op) {
+__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n, uint8_t* __restrict__ op) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
   __shared__ StagedEdge s_stage[8][32];
@@ -983,18 +983,15 @@ __global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const uint32_t* __
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = *list_n, n_warps = gridDim.x * 8;
   for (int i = blockIdx.x * 8 + wid; i < n; i += n_warps) {
-    const int pair = list[i];
-    const int item = pair / CELL_H, row = pair % CELL_H;
-    const int cell = cell_of_item(P.cell_off, P.n_cells, item);
-    const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
-    const ObjRec& o = P.objs[P.cell_items[item]];
-    const int yy = (P.cell_row0 + by) * CELL_H + row - o.dy, xx0 = tile * TILE_W - o.dx;
+    const int4 ent = list[i];
+    const ObjRec& o = P.objs[ent.y];
+    const int yy = (ent.w & 0xFFFF) - o.dy, xx0 = (ent.w >> 16) * TILE_W - o.dx;
     const int slot = o.row_base + yy - o.ry0;
     const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
     bool ok;
-    const int v = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge_mask[pair], s_aa[wid], s_stage[wid], s_prefix, P.aa->volume, lane, ok);
+    const int v = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, (uint32_t)ent.z, s_aa[wid], s_stage[wid], s_prefix, P.aa->volume, lane, ok);
     if (!ok) *P.error_flag = 1;
-    op[(size_t)pair * 32 + lane] = (uint8_t)v;
+    op[(size_t)ent.x * 32 + lane] = (uint8_t)v;
     __syncwarp();
   }
 }
