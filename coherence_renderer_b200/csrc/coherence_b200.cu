@@ -1289,7 +1289,11 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
-  const bool pre = s->extras == 0 && !s->has_fancy && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) && !getenv("COH_FUSED");
+  // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
+  // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
+  const char* force = getenv("COH_FUSED");   // tests force either path: "1" fused, "0" three-phase
+  const bool pre = s->extras == 0 && !s->has_fancy && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+                   (force ? force[0] == '0' : walk_h != 1);
   if (pre) {
     const size_t n_pairs = total * CELL_H;
     if (n_pairs > ctx->pre_cap) {
@@ -1306,14 +1310,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n); LAUNCHED();
     k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
-    int pre_h = walk_h == 1 ? 1 : 4, pre_ctas = WALK_MIN_CTAS;
-    if (const char* e = getenv("COH_PRE_H")) pre_h = atoi(e);
-    if (const char* e = getenv("COH_PRE_CTAS")) pre_ctas = atoi(e);
-    const int pgrid = std::min(ctx->n_sms * pre_ctas, cdiv(n_cells * (CELL_H / pre_h), WALK_WARPS));
-    if (pre_h == 1) k_walk<false, 0, 1, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    else if (pre_h == 16) k_walk<false, 0, 16, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    else k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
-    LAUNCHED();
+    const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
+    k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
     return 0;
   }

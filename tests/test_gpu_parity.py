@@ -637,11 +637,13 @@ def test_async_readback_equals_blocking_read(ctx):
         ctx.scene_free(scenes[k])
 
 
-@pytest.mark.parametrize("walk_h", ["1", "4", "16"])
-def test_every_walker_item_height(ctx, oracle, walk_h, monkeypatch):
-    """The walker is compiled for work items of 1, 4 and 16 rows and picks one from the scene and frame size;
-    every variant must give the same pixels (COH_WALK_H forces one)."""
+@pytest.mark.parametrize("walk_h,fused", [("1", "1"), ("4", "1"), ("16", "1"), ("4", "0")])
+def test_every_walker_variant(ctx, oracle, walk_h, fused, monkeypatch):
+    """The walker is compiled for work items of 1, 4 and 16 rows, and plain polygon scenes have a three-phase path
+    (scan / visibility / antialiasing kernels + a compositing walk) next to the fused one; the library picks by
+    scene and frame size.  Every variant must give the same pixels (COH_WALK_H / COH_FUSED force one)."""
     monkeypatch.setenv("COH_WALK_H", walk_h)
+    monkeypatch.setenv("COH_FUSED", fused)
     W, H = 640, 480
     b = S.lion_scene(W, H, 1.4, pretrans=200)
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
