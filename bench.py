@@ -29,10 +29,11 @@ WIDTH, HEIGHT, SCALE = 3840, 2160, 7.0
 WORKLOAD = "C2: lion.pdf scene (132 AA polygons in a Group over a lightgrey background) at 3840x2160, scale 7.0, cold cache"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch on C2, from the ncu --set full capture
-# summarised in profiles/r1_ncu_k_walk_lion4k.csv (1.35 MB read + 0.86 MB written: the 33 MB frame stays in
-# the 126 MB L2 and the whole scene is L2-resident, so DRAM traffic is far below the algorithmic bytes)
-NCU_TRAFFIC_BYTES = 2208000
+# dram__bytes_read.sum + dram__bytes_write.sum of the raster phase of one C2 frame (k_pre_scan + k_pre_vis +
+# k_pre_aa + k_walk), from the ncu --set full capture summarised in profiles/r1_ncu_raster_phase_lion4k.csv:
+# 1.6 + 4.7 + 1.4 + 5.6 MB.  The 33 MB frame stays in the 126 MB L2 and the scene is L2-resident, so DRAM
+# traffic is below the algorithmic bytes.
+NCU_TRAFFIC_BYTES = 13320000
 
 
 def peaks():
@@ -288,10 +289,10 @@ def run_ours(args):
             "frames_per_s": 1e3 / ms, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "band_rows": [list(b) for b in band_list], "l2": "256 MB flush write before every timed step (untimed)",
-                       "step": "one frame: K1 binning (3 launches) + fused walker (1 launch)", "gather": gather},
-            "roofline": {"bound": "hbm", "kernel": "k_walk", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if N == 1 else None,
+                       "step": "one frame: K1 binning (3 launches) + raster phase (scan, visibility, antialiasing, compositing walk: 4 launches)", "gather": gather},
+            "roofline": {"bound": "hbm", "kernel": "raster phase: k_pre_scan + k_pre_vis + k_pre_aa (dominant) + k_walk", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if N == 1 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": walk_ms_max, "binning_ms": bin_ms,
-                         "note": "integer/bit + FP64-crossing work: the walker is issue/latency bound, not HBM bound (DESIGN.md)"},
+                         "note": "kernel_ms is the device time of the four raster-phase launches together (CUDA events on the launching stream); integer/bit + FP64-crossing work, issue bound, not HBM bound (DESIGN.md)"},
             "e2e": {"value": WIDTH * HEIGHT / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                     "path": "per frame: coh_scene_create(host arrays) + coh_render_frame + coh_fb_read_rgba_async(pinned host); the read-back of frame k overlaps frame k+1, all copies complete inside the timed region"},
             "gpu_launches": int(launches),

@@ -2,7 +2,7 @@
 //
 //   k_prep_edges      int32 edges -> EdgeRec (x0in/x1in/ymin/ymax, FP64 gradient, direction)
 //   k_bin_count/fill  K1: per-cell (32 px x 16 rows) front-to-back object lists (ballot compaction)
-//   k_walk            K2+K4+K5 fused: one warp per (pixel row, 32-pixel tile) walks its cell list
+//   k_walk            K2+K4+K5 fused: one warp per work item (32 px x 1/4/16 rows of a cell) walks the cell list
 //                     front to back; scan-converts each candidate object's row into 32-bit
 //                     shape/coverage words, prunes with the covered-so-far word `u`, evaluates the
 //                     correlated-matte AA only for still-visible edge pixels, composites with
