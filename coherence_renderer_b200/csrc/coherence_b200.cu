@@ -1053,7 +1053,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(DMALLOC(&d_counts, sizeof(int) * slots));
     CK(DMALLOC(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
-    if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
+    if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges * 32, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
     if (exclusive_scan(ctx, d_counts, s->rowedge_ptr, (int)slots, nullptr)) return 1;
     // size of the lists: the same row range per edge as k_rowedges, summed on the host (no device round trip:
     // a device-to-host read here would queue behind an asynchronous framebuffer read-back of the previous frame)
@@ -1066,7 +1066,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (total > 0x7FFFFFF0LL) FAIL("scene: row-edge table too large");
     CK(DMALLOC(&s->rowedge_idx, sizeof(int) * (size_t)std::max<long long>(total, 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
-    if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
+    if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges * 32, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
     CK(cudaStreamSynchronize(ctx->stream));
     DFREE(d_edge_obj); DFREE(d_counts);
   }

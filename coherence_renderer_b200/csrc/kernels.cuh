@@ -41,11 +41,12 @@ __global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ 
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ int floordiv32(int a) { return a >> 5; }               // floor(a / 32)
 __device__ __forceinline__ int ceildiv32(int a) { return (a + 31) >> 5; }         // ceil(a / 32)
+// One warp per edge, lanes over the rows it reaches (an edge of a page-sized rectangle reaches thousands).
 template <bool FILL>
 __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restrict__ edge_obj, int n_edges,
                            const ObjRec* __restrict__ objs, int* __restrict__ counts, const int* __restrict__ ptr,
                            int* __restrict__ idx) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= n_edges) return;
   int oi = edge_obj[e];
   if (oi < 0) return;
@@ -53,7 +54,7 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
   int row_base = objs[oi].row_base, ry0 = objs[oi].ry0;
   if (objs[oi].kind == K_CPG && e >= objs[oi].b_first) { row_base = objs[oi].b_row_base; ry0 = objs[oi].b_ry0; }  // operand b
   int ylo = ceildiv32(ed.ymin - 16), yhi = floordiv32(ed.ymax + 67);
-  for (int y = ylo; y <= yhi; y++) {
+  for (int y = ylo + lane; y <= yhi; y += 32) {
     int slot = row_base + y - ry0;
     int k = atomicAdd(&counts[slot], 1);
     if (FILL) idx[ptr[slot] + k] = e;
