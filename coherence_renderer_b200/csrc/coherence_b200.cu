@@ -85,6 +85,7 @@ struct coh_ctx {
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
+  int2* cell_rng = nullptr;   // per cell [start, end) into cell_items (one-pass binning)
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // three-phase frames: per (cell item, row) pair
   uint2* pre_sc = nullptr; int4* pre_list = nullptr; int* pre_n = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
@@ -221,7 +222,7 @@ int coh_shutdown(coh_ctx* ctx) {
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
-  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head);
+  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head); DFREE(ctx->cell_rng);
   DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->item_cell);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
@@ -1200,7 +1201,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
     CK(DMALLOC(&ctx->cell_counts, sizeof(int) * n_cells));
     CK(DMALLOC(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
-    CK(DMALLOC(&ctx->cell_order, sizeof(int) * n_cells));
+    DFREE(ctx->cell_rng);
+    CK(DMALLOC(&ctx->cell_rng, sizeof(int2) * n_cells));
+    CK(DMALLOC(&ctx->cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
     ctx->n_cells_cap = n_cells;
   }
   if (!ctx->queue) {
@@ -1239,10 +1242,10 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     ctx->cell_items_cap = cap;
   }
   if (!big) {
+    // one pass: hit masks in registers, lists carved from one cursor, length classes instead of a sort
     const int bin_blocks = cdiv(n_cells * 32, 256);
-    k_bin<false><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_counts, nullptr, nullptr, ctx->order_hist, nullptr); LAUNCHED();
-    if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, ordered ? ctx->order_hist : nullptr)) return 1;
-    k_bin<true><<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, nullptr, ctx->cell_off, ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell); LAUNCHED();
+    k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_rng, ctx->cell_items, ctx->order_hist,
+                                               ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell); LAUNCHED();
   } else {
     const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
     CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
@@ -1260,7 +1263,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
-  P.cell_off = ctx->cell_off; P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
+  P.cell_off = big ? ctx->cell_off : nullptr; P.cell_rng = big ? nullptr : ctx->cell_rng;
+  P.cls_cells = (!big && ordered) ? ctx->cell_order : nullptr; P.cls_cnt = (!big && ordered) ? ctx->order_hist + 1 : nullptr;
+  P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
@@ -1285,7 +1290,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   do {                                                                                                             \
     if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
-  P.queue = ctx->queue; P.order = ordered ? ctx->cell_order : nullptr; P.order_starts = ctx->order_hist; P.n_cells = n_cells;
+  P.queue = ctx->queue; P.order = (big && ordered) ? ctx->cell_order : nullptr; P.order_starts = ctx->order_hist; P.n_cells = n_cells;
   P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)

@@ -81,49 +81,79 @@ __global__ void k_brush_rows(const int2* __restrict__ points, const int* __restr
 }
 
 // ------------------------------------------------------------------------------------
-// K1 binning.  One warp per cell scans the leaf objects in index order (= front to back),
-// 32 at a time; ballot + popc give each overlapping object its slot, so every list comes
-// out already sorted and the two passes (count / fill) are identical apart from the store.
+// K1 cell binning for scenes of at most 1024 leaves.  One warp per cell scans the leaf objects in index
+// order (= front to back), 32 at a time; ballot + popc give each overlapping object its slot, so every
+// list comes out already sorted.  The warp of a cell keeps the hit masks of its 32-leaf chunks in
+// registers (chunk c in lane c), takes its slice of the item pool from one global cursor and writes the
+// list — no count pass, no scan.  Lists are addressed by [start, end) per cell.  The walker's heavy-first
+// order is sixteen length classes (>= 48 objects ... 2, 1, 0) filled through cursors reserved once per
+// block, so that the persistent walker warps take the heavy cells first and the tail of the launch is light.
 // ------------------------------------------------------------------------------------
-// The same kernels also build the walker's work order: cells sorted by descending list length
-// (256-bin counting sort: histogram in the count pass, scatter in the fill pass), so that the
-// persistent walker warps take the heavy cells first and the tail of the launch is light.
-template <bool FILL>
-__global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/, const int* __restrict__ leaves, int n_leaves, Frame fr,
-                      int cell_row0, int n_cells, int* __restrict__ counts, const int* __restrict__ offsets,
-                      int* __restrict__ items, int* __restrict__ hist /*[2*ORDER_BINS]: starts, cursors*/,
-                      int* __restrict__ order, const ObjRec* __restrict__ objs = nullptr, int2* __restrict__ cell_head = nullptr,
-                      int* __restrict__ item_cell = nullptr /* cell of every list entry (three-phase frames) */) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= n_cells) return;
-  int cx = warp % fr.tiles_x, cy = cell_row0 + warp / fr.tiles_x;
-  int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1;
-  int y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
-  int base = FILL ? offsets[warp] : 0;
+constexpr int BIN_CLASSES = 16;
+constexpr int BIN_HEAVY_CLASSES = 14;   // classes of cells with at least two objects
+__device__ __forceinline__ int bin_class(int n) {  // longest lists first; the last two classes: one object, none
+  if (n >= 16) return n >= 48 ? 0 : n >= 40 ? 1 : n >= 32 ? 2 : n >= 28 ? 3 : n >= 24 ? 4 : n >= 20 ? 5 : 6;
+  return n >= 12 ? 7 : n >= 8 ? 8 : n >= 6 ? 9 : n >= 5 ? 10 : n == 4 ? 11 : n == 3 ? 12 : n == 2 ? 13 : n == 1 ? 14 : 15;
+}
+// blockDim = 256 (8 cells per block); pool slices and class positions are reserved once per block
+__global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr, int cell_row0,
+                       int n_cells, int2* __restrict__ cell_rng, int* __restrict__ items, int* __restrict__ state /* [0] pool cursor, [1..] class counts */,
+                       int* __restrict__ cls_cells /* [BIN_CLASSES][n_cells] or null */, const ObjRec* __restrict__ objs, int2* __restrict__ cell_head,
+                       int* __restrict__ item_cell) {
+  __shared__ int s_n[8], s_c[8], s_base[8], s_pos[8];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 8 + wid;
+  const bool active = warp < n_cells;
+  const int cx = active ? warp % fr.tiles_x : 0, cy = active ? cell_row0 + warp / fr.tiles_x : 0;
+  const int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1, y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
+  unsigned mymask = 0u;
   int n = 0, first = -1;
-  for (int b = 0; b < n_leaves; b += 32) {
-    int li = b + lane;
-    bool hit = false;
-    int idx = -1;
-    if (li < n_leaves) {
-      idx = leaves[li];
-      const int4 bb = leaf_box[li];
-      hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
+  if (active)
+    for (int b = 0; b < n_leaves; b += 32) {
+      const int li = b + lane;
+      bool hit = false;
+      if (li < n_leaves) {
+        const int4 bb = leaf_box[li];
+        hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (lane == (b >> 5)) mymask = m;
+      if (n == 0 && m) first = leaves[b + __ffs((int)m) - 1];
+      n += __popc(m);
     }
-    unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (FILL && hit) {
-      const int at = base + n + __popc(m & ((1u << lane) - 1u));
-      items[at] = idx;
-      if (item_cell) item_cell[at] = warp;
-    }
-    if (FILL && n == 0 && m) first = __shfl_sync(0xFFFFFFFFu, idx, __ffs((int)m) - 1);
-    n += __popc(m);
+  if (lane == 0) { s_n[wid] = n; s_c[wid] = active ? bin_class(n) : -1; }
+  __syncthreads();
+  if (wid == 0 && lane < 8) {
+    // pool slice of the block, split by warp; class positions: one atomic per class present in the block
+    int tot = 0, mine = 0;
+    for (int k = 0; k < 8; k++) { if (k == lane) mine = tot; tot += s_n[k]; }
+    int blk = 0;
+    if (lane == 0 && tot) blk = atomicAdd(&state[0], tot);
+    blk = __shfl_sync(0xFFu, blk, 0);
+    s_base[lane] = blk + mine;
+    const int c = s_c[lane];
+    int rank = 0, same = 0, leader = lane;
+    for (int k = 0; k < 8; k++) if (s_c[k] == c) { if (k < lane) rank++; same++; if (k < leader) leader = k; }
+    int cb = 0;
+    if (cls_cells && c >= 0 && leader == lane) cb = atomicAdd(&state[1 + c], same);
+    cb = __shfl_sync(0xFFu, cb, leader);
+    s_pos[lane] = cb + rank;
   }
-  if (FILL && cell_head && lane == 0) {
-    // Cell header for the walker: a cell whose only object is an opaque primitive covering all of it
-    // (typically the background rectangle) is just that colour — the walker then needs no list, object
-    // or group record at all (one load instead of a chain of four dependent ones).
+  __syncthreads();
+  if (!active) return;
+  const int base = s_base[wid];
+  int at = base;
+  for (int b = 0; b < n_leaves; b += 32) {
+    const unsigned m = __shfl_sync(0xFFFFFFFFu, mymask, b >> 5);
+    if ((m >> lane) & 1u) {
+      const int dst = at + __popc(m & ((1u << lane) - 1u));
+      items[dst] = leaves[b + lane];
+      if (item_cell) item_cell[dst] = warp;
+    }
+    at += __popc(m);
+  }
+  if (lane == 0) {
+    cell_rng[warp] = make_int2(base, base + n);
     int2 hd = make_int2(0, 0);
     if (n == 1) {
       const ObjRec& o = objs[first];
@@ -133,11 +163,7 @@ __global__ void k_bin(const int4* __restrict__ leaf_box /*x0,y0,x1,y1 per leaf*/
         hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
     }
     cell_head[warp] = hd;
-  }
-  if (lane == 0) {
-    const int bin = ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1);  // bin 0 = longest lists
-    if (!FILL) { counts[warp] = n; atomicAdd(&hist[bin], 1); }
-    else if (order) order[hist[bin] + atomicAdd(&hist[ORDER_BINS + bin], 1)] = warp;
+    if (cls_cells) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
   }
 }
 // exclusive scan of the histogram in place (one warp)
@@ -290,7 +316,10 @@ struct WalkParams {
   const uint32_t* conv_bits;   // Convolved objects: shape / minshape bit-rows
   const uint32_t* conv_px;     // Convolved objects: pre-convolved RGBA8 canvases
   const uint8_t* stamps;       // brush alpha stamps
-  const int* cell_off;         // per cell [first, last) into cell_items
+  const int* cell_off;         // per cell [first, last) into cell_items (prefix array), or
+  const int2* cell_rng;        // ... [start, end) per cell (one-pass binning); exactly one of the two is set
+  const int* cls_cells;        // one-pass binning: cells by list-length class [BIN_CLASSES][n_cells] (heavy first), with
+  const int* cls_cnt;          // ... the number of cells in every class; null: `order` / row-major
   const int* cell_items;
   const int2* cell_head;       // per cell: {colour, 1 | 2 (scene list)} when the cell is one opaque covering primitive, else {0, 0}; may be null
   const AATable* aa;
@@ -541,7 +570,8 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   int n_carry = 0;                                   // published carry entries of my row (mirrored)
 
   const int cell = by * P.fr.tiles_x + tile;
-  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+  int it0, it1;
+  if (P.cell_rng) { const int2 rg = P.cell_rng[cell]; it0 = rg.x; it1 = rg.y; } else { it0 = P.cell_off[cell]; it1 = P.cell_off[cell + 1]; }
   const int2 head = (P.cell_head && !(CPGX && P.resume)) ? P.cell_head[cell] : make_int2(0, 0);
   // initial covered-so-far complement `u` of my row's word
   uint32_t u = 0u;
@@ -885,9 +915,16 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
   // Work items come off one atomic counter.  The heavy cells at the head of the order are taken one item at a
   // time (balance); the long tail of cells with at most one object (mostly background) is taken in batches,
   // or every warp of the GPU would queue up on the same counter for ~100 instructions of work per item.
+  __shared__ int s_cls[BIN_CLASSES + 1];   // first position of every length class in the heavy-first order
+  if (P.cls_cnt && threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < BIN_CLASSES; c++) { s_cls[c] = acc; acc += P.cls_cnt[c]; }
+    s_cls[BIN_CLASSES] = acc;
+  }
+  __syncthreads();
   const int n_items = P.n_cells * WALK_SUB;
-  const int heavy_items = P.order ? P.order_starts[ORDER_BINS - 2] * WALK_SUB : n_items;  // cells with >= 2 objects
-  int q_next = 0, q_end = 0;
+  const int heavy_items = P.cls_cnt ? s_cls[BIN_HEAVY_CLASSES] * WALK_SUB : P.order ? P.order_starts[ORDER_BINS - 2] * WALK_SUB : n_items;  // cells with >= 2 objects
+  int q_next = 0, q_end = 0, cur_cls = 0;
   for (;;) {
     if (q_next == q_end) {
       const int batch = q_end >= heavy_items ? 8 : 1;
@@ -897,7 +934,11 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
     }
     const int q = q_next++;
     if (q >= n_items) break;
-    const int cell = P.order ? P.order[q / WALK_SUB] : q / WALK_SUB;
+    int cell = q / WALK_SUB;
+    if (P.cls_cnt) {
+      while (cur_cls < BIN_CLASSES - 1 && cell >= s_cls[cur_cls + 1]) cur_cls++;   // a warp's queue positions only grow
+      cell = P.cls_cells[(size_t)cur_cls * P.n_cells + cell - s_cls[cur_cls]];
+    } else if (P.order) cell = P.order[cell];
     const int sub = q % WALK_SUB;
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
@@ -963,7 +1004,8 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
     else u = (my_y >= P.uy0 && my_y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
     if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
   }
-  const int it0 = P.cell_off[cell], it1 = P.cell_off[cell + 1];
+  int it0, it1;
+  if (P.cell_rng) { const int2 rg = P.cell_rng[cell]; it0 = rg.x; it1 = rg.y; } else { it0 = P.cell_off[cell]; it1 = P.cell_off[cell + 1]; }
   for (int it = it0; it < it1; it++) {
     const int oi = P.cell_items[it];
     const ObjRec& o = P.objs[oi];
