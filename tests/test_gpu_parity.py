@@ -692,3 +692,60 @@ def test_peer_framebuffer_mirror(ctx, oracle):
         ctx.fb_attach(0)         # back to a context-owned framebuffer for the tests that follow
         if sc:
             ctx.scene_free(sc)
+
+
+def test_lion_c2_full_size_frame(ctx, oracle):
+    """BASELINE.json's headline configuration at full size: the lion at 3840x2160 (scale 7), whole-frame update —
+    framebuffer and covered-so-far set bit-exact against the oracle."""
+    W, H = 3840, 2160
+    b = S.lion_scene(W, H, 7.0)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+
+
+def test_edge_cases(ctx, oracle):
+    """Empty scenes, empty and out-of-frame updates, objects outside the frame or with no area, horizontal and
+    zero-length edges, a frame narrower than one tile, the deepest allowed group nesting and one level more."""
+    W, H = 70, 37   # not multiples of the 32 x 16 cell
+    b = S.SceneBuilder()
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)          # nothing at all
+    assert not got.any() and np.array_equal(got_u, ref_u)
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)          # background only
+    assert np.array_equal(got, ref) and np.array_equal(got_u, ref_u)
+    b = S.SceneBuilder()
+    b.polygon([(-300.0, -300.0), (-200.0, -310.0), (-250.0, -200.0)], S.Fill.plain(S.rgba8(255, 0, 0)))   # outside
+    b.polygon([(10.0, 10.0), (60.0, 10.0), (35.0, 10.0)], S.Fill.plain(S.rgba8(0, 255, 0)))                 # no area
+    b.path_edges(np.array([[320, 320, 320, 320], [320, 640, 1600, 640]], dtype=np.int32), S.Fill.plain(S.rgba8(0, 0, 255)))  # degenerate
+    b.polygon([(-20.5, 5.2), (90.0, 8.0), (30.0, 60.0)], S.Fill.plain(S.dissolve(S.rgba8(200, 100, 0), 200)))  # crosses every border
+    for _ in range(5):
+        b.group_begin(pretrans=250)
+    b.polygon([(5.0, 3.0), (66.0, 4.0), (40.0, 33.0)], S.Fill.plain(S.rgba8(1, 2, 3)))
+    for _ in range(5):
+        b.group_end()
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H, update=(33, 7, 20, 11))   # a box inside
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    ctx.render_frame(sc, (0, 0, 0, 0))             # Sprite.box x y 0 0 = NullShape: nothing happens
+    ctx.render_frame(sc, (500, 500, 10, 10))       # entirely outside the frame
+    ctx.sync()
+    with pytest.raises(abi.CohError):
+        ctx.render_frame(sc, (0, 0, -1, 5))        # Sprite.box: negative argument (sprite.ml:463)
+    ctx.scene_free(sc)
+    deep = S.SceneBuilder()
+    for _ in range(6):
+        deep.group_begin()
+    deep.polygon([(5.0, 3.0), (66.0, 4.0), (40.0, 33.0)], S.Fill.plain(S.rgba8(1, 2, 3)))
+    for _ in range(6):
+        deep.group_end()
+    objs, n, nbg, e, p = deep.arrays()
+    with pytest.raises(abi.CohError):              # nesting beyond MAX_DEPTH fails loudly at scene creation
+        ctx.scene_create(objs, nbg, e, p)
