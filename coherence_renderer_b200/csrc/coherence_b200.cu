@@ -34,7 +34,7 @@ struct DevScene {
   uint8_t* stamps = nullptr;
   int* rowedge_ptr = nullptr;   // K1 edge binning (CSR over (path object, pixel row))
   int* rowedge_idx = nullptr;
-  int2* brush_ranges = nullptr; // per (stroke, row): [first, last] stamp index reaching the row
+  int2* brush_ranges = nullptr; // per (stroke, cell of its box): [first, last] stamp index reaching the cell
   uint32_t* conv_bits = nullptr; // Convolved objects: shape / minshape bit-rows
   uint32_t* conv_px = nullptr;   // Convolved objects: pre-convolved canvases
   std::vector<ObjRec> h_objs;
@@ -989,8 +989,10 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         }
         o.bx0 = x0 - o.brush_r; o.bx1 = x1 + o.brush_r; o.by0 = y0 - o.brush_r; o.by1 = y1 + o.brush_r;
         o.ry0 = o.by0; o.ry1 = o.by1;   // object-frame rows (the alias offset is added to the box below)
-        if (total_brush_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many brush rows");
-        o.row_base = (int)total_brush_rows; total_brush_rows += o.ry1 - o.ry0 + 1;
+        o.bc_x0 = floordiv(o.bx0, 32); o.bc_y0 = floordiv(o.by0, CELL_H);
+        o.bc_nx = floordiv(o.bx1, 32) - o.bc_x0 + 1; o.bc_ny = floordiv(o.by1, CELL_H) - o.bc_y0 + 1;
+        if (total_brush_rows + (long long)o.bc_nx * o.bc_ny > 0x7FFFFFF0LL) FAIL("scene: too many brush cells");
+        o.bc_base = (int)total_brush_rows; total_brush_rows += (long long)o.bc_nx * o.bc_ny;
         for (int k = 0; k < c.count; k++) {
           if (point_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share brush points");
           point_obj[(size_t)c.first + k] = (int)recs.size();
@@ -1122,7 +1124,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(DMALLOC(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
     std::vector<int2> init((size_t)total_brush_rows, make_int2(INT32_MAX, -1));
     CK(cudaMemcpyAsync(s->brush_ranges, init.data(), sizeof(int2) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
-    k_brush_rows<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
+    k_brush_cells<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
     CK(cudaStreamSynchronize(ctx->stream));
     DFREE(d_point_obj);
   }

@@ -49,6 +49,14 @@ struct ObjRec {
       int b_row_base;        // first slot of operand b in the row-edge CSR
       int b_opw;             // op (COH_CPG_*) | winding rule of b << 8
     };
+    struct {
+      // BRUSH: grid of 32 x CELL_H pixel cells (object frame) over the stroke's box; per cell the range of
+      // stamp indices (list order) whose footprint reaches it
+      int bc_x0, bc_y0;      // cell column / row of the box's top-left corner: floor(x / 32), floor(y / CELL_H)
+      int bc_nx, bc_ny;      // cells per row, rows of cells
+      int bc_base;           // first slot of this stroke in the scene's brush range table
+      int bc_pad;
+    };
   };
   int pad;
   FillRec fill;

@@ -61,23 +61,41 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
   }
 }
 
-// K1 for brush strokes: for every (stroke, pixel row) the range [imin, imax] of stamp indices (list
-// order) whose footprint reaches the row.  Stamps are sampled along the path, so the stamps that
-// reach a row are (nearly) consecutive; walking the range in order keeps the reference's stamping
-// order (brush.ml:207-212) and makes the per-row / per-pixel cost independent of the stroke length.
-__global__ void k_brush_rows(const int2* __restrict__ points, const int* __restrict__ point_obj, int n_points,
-                             const ObjRec* __restrict__ objs, int2* __restrict__ ranges) {
+// K1 for brush strokes: for every (stroke, 32 x CELL_H pixel cell of its box, object frame) the range
+// [imin, imax] of stamp indices (list order) whose footprint reaches the cell.  Stamps are sampled along the
+// path, so the stamps that reach a cell are (nearly) consecutive; walking the range in order keeps the
+// reference's stamping order (brush.ml:207-212) and makes the per-pixel cost independent of the stroke length.
+__device__ __forceinline__ int floordiv_pos(int a, int d) { return a >= 0 ? a / d : -((-a + d - 1) / d); }
+__global__ void k_brush_cells(const int2* __restrict__ points, const int* __restrict__ point_obj, int n_points,
+                              const ObjRec* __restrict__ objs, int2* __restrict__ ranges) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int oi = point_obj[i];
   if (oi < 0) return;
   const ObjRec& o = objs[oi];
-  const int k = i - o.first, py = points[i].y, r = o.brush_r;
-  for (int y = py - r; y <= py + r; y++) {
-    int2* e = ranges + o.row_base + (y - o.ry0);
-    atomicMin(&e->x, k);
-    atomicMax(&e->y, k);
+  const int k = i - o.first, r = o.brush_r;
+  const int2 p = points[i];
+  const int cx0 = floordiv_pos(p.x - r, 32) - o.bc_x0, cx1 = floordiv_pos(p.x + r, 32) - o.bc_x0;
+  const int cy0 = floordiv_pos(p.y - r, CELL_H) - o.bc_y0, cy1 = floordiv_pos(p.y + r, CELL_H) - o.bc_y0;
+  for (int cy = cy0; cy <= cy1; cy++)
+    for (int cx = cx0; cx <= cx1; cx++) {
+      int2* e = ranges + o.bc_base + cy * o.bc_nx + cx;
+      atomicMin(&e->x, k);
+      atomicMax(&e->y, k);
+    }
+}
+// stamps that may reach the 32 pixels xx0 .. xx0 + 31 of row yy (object frame): the window lies in one or two cells
+__device__ __forceinline__ int2 brush_range(const int2* __restrict__ ranges, const ObjRec& o, int xx0, int yy) {
+  const int cy = floordiv_pos(yy, CELL_H) - o.bc_y0;
+  if (cy < 0 || cy >= o.bc_ny) return make_int2(0, -1);
+  const int ca = floordiv_pos(xx0, 32) - o.bc_x0, cb = floordiv_pos(xx0 + 31, 32) - o.bc_x0;
+  int2 rg = make_int2(INT32_MAX, -1);
+  if (ca >= 0 && ca < o.bc_nx) rg = ranges[o.bc_base + cy * o.bc_nx + ca];
+  if (cb != ca && cb >= 0 && cb < o.bc_nx) {
+    const int2 r2 = ranges[o.bc_base + cy * o.bc_nx + cb];
+    rg.x = min(rg.x, r2.x); rg.y = max(rg.y, r2.y);
   }
+  return rg;
 }
 
 // ------------------------------------------------------------------------------------
@@ -312,7 +330,7 @@ struct WalkParams {
   const int* rowedge_ptr;      // K1 edge binning: per (path object, pixel row) candidate edge lists (CSR)
   const int* rowedge_idx;
   const int2* points;          // brush stamp centres (object frame), list order
-  const int2* brush_ranges;    // per (stroke, row): first / last stamp index reaching the row
+  const int2* brush_ranges;    // per (stroke, cell of its box): first / last stamp index reaching the cell
   const uint32_t* conv_bits;   // Convolved objects: shape / minshape bit-rows
   const uint32_t* conv_px;     // Convolved objects: pre-convolved RGBA8 canvases
   const uint8_t* stamps;       // brush alpha stamps
@@ -731,12 +749,10 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         } else if (BRUSH && o.kind == K_BRUSH) {
           // shape = dilation of the stamp centres by the brush box (brush.ml:143-168); minshape null
           const int br = o.brush_r;
-          if (yy >= o.ry0 && yy <= o.ry1) {
-            const int2 rg = P.brush_ranges[o.row_base + yy - o.ry0];
-            for (int k = rg.x; k <= rg.y; k++) {
-              int2 p = P.points[o.first + k];
-              if (p.y - br <= yy && yy <= p.y + br) S |= interval_mask32(xx0, p.x - br, p.x + br);
-            }
+          const int2 rg = brush_range(P.brush_ranges, o, xx0, yy);
+          for (int k = rg.x; k <= rg.y; k++) {
+            int2 p = P.points[o.first + k];
+            if (p.y - br <= yy && yy <= p.y + br) S |= interval_mask32(xx0, p.x - br, p.x + br);
           }
           C = S;
         }
@@ -818,7 +834,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
             const int px = xx0 + lane;
             uint32_t al = 0u;
             if ((edge >> lane) & 1u) {
-              const int2 rg = P.brush_ranges[o.row_base + yy - o.ry0];
+              const int2 rg = brush_range(P.brush_ranges, o, xx0, yy);
               for (int q = rg.x; q <= rg.y; q++) {
                 int2 p = P.points[o.first + q];
                 int ddx = px - p.x, ddy = yy - p.y;
