@@ -55,7 +55,7 @@ struct DevScene {
   std::vector<int> h_leaves;
   bool has_fancy = false;    // some object has a gradient / radial fill
   int extras = 0;            // walker variant: 0 polygons / primitives, 1 + brush / Convolved, 2 + CPG / filters
-  size_t items_total = 0;
+  size_t items_total = 0, coarse_total = 0; bool coarse_total_valid = false;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
 };
 
@@ -85,7 +85,9 @@ struct coh_ctx {
   // binning scratch
   int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
-  int2* cell_rng = nullptr;   // per cell [start, end) into cell_items (one-pass binning)
+  int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
+  // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
+  int* coarse_items = nullptr; int* coarse_counts = nullptr; int* coarse_off = nullptr; size_t coarse_cap = 0, coarse_cells_cap = 0;
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // three-phase frames: per (cell item, row) pair
   uint2* pre_sc = nullptr; int4* pre_list = nullptr; int* pre_n = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
@@ -223,6 +225,7 @@ int coh_shutdown(coh_ctx* ctx) {
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
   DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head); DFREE(ctx->cell_rng);
+  DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
   DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->item_cell);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
@@ -1233,9 +1236,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
     }
     total = tot;
-    if (whole) { s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
+    if (whole) { s->coarse_total_valid = false; s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
   } else total = s->items_total;
-  const size_t need = big ? 2 * total : total;  // the sort of very long lists stages through the upper half
+  const size_t need = total;
   if (need > ctx->cell_items_cap) {
     DFREE(ctx->cell_items); DFREE(ctx->item_cell);
     size_t cap = need + need / 2 + 1024;
@@ -1249,24 +1252,43 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_rng, ctx->cell_items, ctx->order_hist,
                                                ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell); LAUNCHED();
   } else {
-    const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
-    CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
-    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, nullptr, nullptr); LAUNCHED();
-    if (exclusive_scan(ctx, ctx->cell_counts, ctx->cell_off, n_cells, nullptr)) return 1;
-    if (ordered) {
-      k_bin_hist<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(ctx->cell_counts, n_cells, ctx->order_hist); LAUNCHED();
-      k_order_scan<<<1, 32, 0, ctx->stream>>>(ctx->order_hist); LAUNCHED();
+    // two levels: leaves into coarse cells (object-parallel, sorted per coarse list), then every fine cell from its coarse list
+    const int ctx_x = cdiv(fr.tiles_x, COARSE), crow0 = cell_row0 >> COARSE_SHIFT, crow1 = cell_row1 >> COARSE_SHIFT;
+    const int n_coarse = ctx_x * (crow1 - crow0 + 1);
+    size_t ctot = 0;
+    if (whole && s->coarse_total_valid) ctot = s->coarse_total;   // a pure function of the boxes and the frame geometry, like items_total
+    else {
+      for (int li = A.l0; li < A.l1; li++) {
+        const ObjRec& o = s->h_objs[s->h_leaves[li]];
+        int cx0 = std::max(floordiv(o.bx0, 32 * COARSE), 0), cx1 = std::min(floordiv(o.bx1, 32 * COARSE), ctx_x - 1);
+        int cy0 = std::max(floordiv(o.by0, CELL_H * COARSE), crow0), cy1 = std::min(floordiv(o.by1, CELL_H * COARSE), crow1);
+        if (cx1 >= cx0 && cy1 >= cy0) ctot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+      }
+      if (whole) { s->coarse_total = ctot; s->coarse_total_valid = true; }
     }
-    CK(cudaMemsetAsync(ctx->cell_counts, 0, sizeof(int) * n_cells, ctx->stream));
-    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, cell_row1, ctx->cell_counts, ctx->cell_off, ctx->cell_items); LAUNCHED();
-    k_bin_sort<<<cdiv(n_cells * 32, 128), 128, 0, ctx->stream>>>(ctx->cell_off, ctx->cell_items, ctx->cell_items + total, n_cells, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+    if (2 * ctot + 1 > ctx->coarse_cap || (size_t)n_coarse + 1 > ctx->coarse_cells_cap) {
+      DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
+      ctx->coarse_cap = 2 * ctot + ctot / 2 + 1024; ctx->coarse_cells_cap = (size_t)n_coarse + 1;
+      CK(DMALLOC(&ctx->coarse_items, sizeof(int) * ctx->coarse_cap));
+      CK(DMALLOC(&ctx->coarse_counts, sizeof(int) * ctx->coarse_cells_cap));
+      CK(DMALLOC(&ctx->coarse_off, sizeof(int) * (ctx->coarse_cells_cap + 1)));
+    }
+    const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
+    CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
+    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, n_leaves, ctx_x, crow0, crow1, ctx->coarse_counts, nullptr, nullptr); LAUNCHED();
+    if (exclusive_scan(ctx, ctx->coarse_counts, ctx->coarse_off, n_coarse, nullptr)) return 1;
+    CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
+    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, n_leaves, ctx_x, crow0, crow1, ctx->coarse_counts, ctx->coarse_off, ctx->coarse_items); LAUNCHED();
+    k_bin_sort<<<cdiv(n_coarse * 32, 128), 128, 0, ctx->stream>>>(ctx->coarse_off, ctx->coarse_items, ctx->coarse_items + ctot, n_coarse); LAUNCHED();
+    k_bin2<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(leaf_box, leaves, ctx->coarse_off, ctx->coarse_items, ctx_x, crow0, fr, cell_row0, n_cells, ctx->cell_rng,
+                                                          ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
   }
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
-  P.cell_off = big ? ctx->cell_off : nullptr; P.cell_rng = big ? nullptr : ctx->cell_rng;
-  P.cls_cells = (!big && ordered) ? ctx->cell_order : nullptr; P.cls_cnt = (!big && ordered) ? ctx->order_hist + 1 : nullptr;
+  P.cell_rng = ctx->cell_rng;
+  P.cls_cells = ordered ? ctx->cell_order : nullptr; P.cls_cnt = ordered ? ctx->order_hist + 1 : nullptr;
   P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
@@ -1292,7 +1314,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   do {                                                                                                             \
     if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
-  P.queue = ctx->queue; P.order = (big && ordered) ? ctx->cell_order : nullptr; P.order_starts = ctx->order_hist; P.n_cells = n_cells;
+  P.queue = ctx->queue; P.n_cells = n_cells;
   P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)

@@ -20,7 +20,7 @@
 
 namespace coh {
 
-constexpr int ORDER_BINS = 256;  // bins of the heavy-first cell order (counting sort by list length)
+constexpr int ORDER_BINS = 256;  // ints of binning state per pass (pool cursor, class counts, work-queue head behind them)
 
 // ------------------------------------------------------------------------------------
 __global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ out, int n) {
@@ -184,62 +184,42 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
     if (cls_cells) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
   }
 }
-// exclusive scan of the histogram in place (one warp)
-__global__ void k_order_scan(int* __restrict__ hist) {
-  int lane = threadIdx.x, carry = 0;
-  for (int base = 0; base < ORDER_BINS; base += 32) {
-    int v = hist[base + lane], x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
-    hist[base + lane] = carry + x - v;
-    carry += __shfl_sync(0xFFFFFFFFu, x, 31);
-  }
-}
-
 // ------------------------------------------------------------------------------------
-// K1 binning for large scenes (object-parallel): one warp per leaf walks the cells its box
-// covers, lanes over cells.  Pass 1 counts (atomics), pass 2 scatters with atomic cursors, then
-// k_bin_sort restores front-to-back order inside every cell (rank sort: leaf indices are unique)
-// and emits the heavy-first cell order.  Cost is O(sum of covered cells), not O(cells x leaves).
+// K1 binning for large scenes, two levels.  Level 1 is object-parallel over coarse cells of
+// COARSE x COARSE fine cells (128 x 64 pixels): one warp per leaf adds its POSITION in the leaf list to
+// every coarse cell its box covers (count with fire-and-forget atomics, scan, scatter with atomic cursors),
+// then k_bin_sort restores front-to-back order inside every coarse list (rank sort: positions are unique).
+// Level 2 is cell-parallel like k_bin1: the warp of a fine cell scans only its coarse cell's list — two
+// passes over a list of about a hundred entries instead of one scattered atomic with a return value per
+// (leaf, fine cell) pair and a sort of every fine list.  Cost: O(sum of covered coarse cells + cells x
+// coarse list length), not O(cells x leaves).
 // ------------------------------------------------------------------------------------
+constexpr int COARSE_SHIFT = 2, COARSE = 1 << COARSE_SHIFT;
 template <bool FILL>
-__global__ void k_bin_obj(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr,
-                          int cell_row0, int cell_row1, int* __restrict__ counts, const int* __restrict__ offsets,
-                          int* __restrict__ items) {
+__global__ void k_bin_obj(const int4* __restrict__ leaf_box, int n_leaves, int ctiles_x, int crow0, int crow1,
+                          int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ items) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_leaves) return;
   const int4 bb = leaf_box[warp];
-  const int cx0 = max(bb.x >> 5, 0), cx1 = min(bb.z >> 5, fr.tiles_x - 1);
-  const int cy0 = max(bb.y / CELL_H - (bb.y < 0 ? 1 : 0), cell_row0), cy1 = min(bb.w < 0 ? -1 : bb.w / CELL_H, cell_row1);
+  constexpr int CW = 32 * COARSE, CH = CELL_H * COARSE;
+  const int cx0 = max(floordiv_pos(bb.x, CW), 0), cx1 = min(floordiv_pos(bb.z, CW), ctiles_x - 1);
+  const int cy0 = max(floordiv_pos(bb.y, CH), crow0), cy1 = min(floordiv_pos(bb.w, CH), crow1);
   if (cx1 < cx0 || cy1 < cy0) return;
   const int nx = cx1 - cx0 + 1, n = nx * (cy1 - cy0 + 1);
-  const int idx = leaves[warp];
   for (int k = lane; k < n; k += 32) {
-    const int cell = (cy0 + k / nx - cell_row0) * fr.tiles_x + cx0 + k % nx;
+    const int cell = (cy0 + k / nx - crow0) * ctiles_x + cx0 + k % nx;
     const int pos = atomicAdd(&counts[cell], 1);
-    if (FILL) items[offsets[cell] + pos] = idx;
+    if (FILL) items[offsets[cell] + pos] = warp;
   }
 }
-// histogram of list lengths (for the heavy-first order), one thread per cell
-__global__ void k_bin_hist(const int* __restrict__ counts, int n_cells, int* __restrict__ hist) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cells) return;
-  int n = counts[c];
-  atomicAdd(&hist[ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1)], 1);
-}
-// one warp per cell: rank sort of its list (ascending leaf index) + heavy-first order scatter
+// Rank sort of every coarse list (ascending leaf position = front to back), one warp per list.
 constexpr int SORT_SMEM = 1024;  // list entries staged in shared memory per warp
 __global__ void __launch_bounds__(128) k_bin_sort(const int* __restrict__ offsets, int* __restrict__ items,
-                                                  int* __restrict__ tmp, int n_cells, int* __restrict__ hist,
-                                                  int* __restrict__ order) {
+                                                  int* __restrict__ tmp, int n_cells) {
   __shared__ int s_list[4][SORT_SMEM];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (warp >= n_cells) return;
   const int a = offsets[warp], n = offsets[warp + 1] - a;
-  if (lane == 0 && order) {
-    const int bin = ORDER_BINS - 1 - (n < ORDER_BINS ? n : ORDER_BINS - 1);
-    order[hist[bin] + atomicAdd(&hist[ORDER_BINS + bin], 1)] = warp;
-  }
   if (n <= 1) return;
   const bool in_smem = n <= SORT_SMEM;
   int* src = in_smem ? s_list[wid] : (tmp + a);
@@ -250,6 +230,65 @@ __global__ void __launch_bounds__(128) k_bin_sort(const int* __restrict__ offset
     int rank = 0;
     for (int j = 0; j < n; j++) rank += src[j] < v;
     items[a + rank] = v;
+  }
+}
+// Level 2: blockDim = 256 (8 fine cells per block); same outputs as k_bin1.
+__global__ void __launch_bounds__(256) k_bin2(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, const int* __restrict__ coarse_off,
+                       const int* __restrict__ coarse_items, int ctiles_x, int crow0, Frame fr, int cell_row0, int n_cells,
+                       int2* __restrict__ cell_rng, int* __restrict__ items, int* __restrict__ state, int* __restrict__ cls_cells) {
+  __shared__ int s_n[8], s_c[8], s_base[8], s_pos[8];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 8 + wid;
+  const bool active = warp < n_cells;
+  const int cx = active ? warp % fr.tiles_x : 0, cy = active ? cell_row0 + warp / fr.tiles_x : 0;
+  const int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1, y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
+  const int cc = ((cy >> COARSE_SHIFT) - crow0) * ctiles_x + (cx >> COARSE_SHIFT);
+  const int la = active ? coarse_off[cc] : 0, lb = active ? coarse_off[cc + 1] : 0;
+  int n = 0;
+  for (int b = la; b < lb; b += 32) {
+    bool hit = false;
+    if (b + lane < lb) {
+      const int4 bb = leaf_box[coarse_items[b + lane]];
+      hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
+    }
+    n += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+  }
+  if (lane == 0) { s_n[wid] = n; s_c[wid] = active ? bin_class(n) : -1; }
+  __syncthreads();
+  if (wid == 0 && lane < 8) {
+    int tot = 0, mine = 0;
+    for (int k = 0; k < 8; k++) { if (k == lane) mine = tot; tot += s_n[k]; }
+    int blk = 0;
+    if (lane == 0 && tot) blk = atomicAdd(&state[0], tot);
+    blk = __shfl_sync(0xFFu, blk, 0);
+    s_base[lane] = blk + mine;
+    const int c = s_c[lane];
+    int rank = 0, same = 0, leader = lane;
+    for (int k = 0; k < 8; k++) if (s_c[k] == c) { if (k < lane) rank++; same++; if (k < leader) leader = k; }
+    int cb = 0;
+    if (cls_cells && c >= 0 && leader == lane) cb = atomicAdd(&state[1 + c], same);
+    cb = __shfl_sync(0xFFu, cb, leader);
+    s_pos[lane] = cb + rank;
+  }
+  __syncthreads();
+  if (!active) return;
+  const int base = s_base[wid];
+  int at = base;
+  for (int b = la; b < lb; b += 32) {
+    bool hit = false;
+    int li = 0;
+    if (b + lane < lb) {
+      li = coarse_items[b + lane];
+      const int4 bb = leaf_box[li];
+      hit = !(bb.x > x1 || bb.z < x0 || bb.y > y1 || bb.w < y0);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) items[at + __popc(m & ((1u << lane) - 1u))] = leaves[li];
+    at += __popc(m);
+  }
+  if (lane == 0) {
+    cell_rng[warp] = make_int2(base, base + n);
+    if (cls_cells) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
   }
 }
 
@@ -334,15 +373,14 @@ struct WalkParams {
   const uint32_t* conv_bits;   // Convolved objects: shape / minshape bit-rows
   const uint32_t* conv_px;     // Convolved objects: pre-convolved RGBA8 canvases
   const uint8_t* stamps;       // brush alpha stamps
-  const int* cell_off;         // per cell [first, last) into cell_items (prefix array), or
-  const int2* cell_rng;        // ... [start, end) per cell (one-pass binning); exactly one of the two is set
-  const int* cls_cells;        // one-pass binning: cells by list-length class [BIN_CLASSES][n_cells] (heavy first), with
-  const int* cls_cnt;          // ... the number of cells in every class; null: `order` / row-major
+  const int2* cell_rng;        // per cell [start, end) into cell_items
+  const int* cls_cells;        // cells by list-length class [BIN_CLASSES][n_cells] (heavy first), with
+  const int* cls_cnt;          // ... the number of cells in every class; null: row-major order
   const int* cell_items;
   const int2* cell_head;       // per cell: {colour, 1 | 2 (scene list)} when the cell is one opaque covering primitive, else {0, 0}; may be null
   const AATable* aa;
   Frame fr;
-  int cell_row0;               // first cell row covered by cell_off
+  int cell_row0;               // first cell row covered by cell_rng
   int ux0, uy0, ux1, uy1;      // update box, inclusive
   const uint32_t* u_init;      // optional update set as a bit-frame (fr.H x fr.tiles_x words), else box
   uint32_t* u_out;             // optional: `u` after the scene pass (same layout)
@@ -367,8 +405,6 @@ struct WalkParams {
   // in row-major order, so the cell waited on has always been started by a resident warp
   // (decoupled look-back).
   int* queue;                  // work queue head: persistent warps take cells with atomicAdd
-  const int* order;            // q-th cell to process (heavy first), or null for row-major order
-  const int* order_starts;     // with `order`: first position of every list-length bin (bin 0 = longest lists)
   int n_cells;
   int* carry_done;             // per (band row, tile): == epoch when the tile has finished
   int* carry_cnt;              // per (band row, tile): number of published entries
@@ -588,8 +624,8 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   int n_carry = 0;                                   // published carry entries of my row (mirrored)
 
   const int cell = by * P.fr.tiles_x + tile;
-  int it0, it1;
-  if (P.cell_rng) { const int2 rg = P.cell_rng[cell]; it0 = rg.x; it1 = rg.y; } else { it0 = P.cell_off[cell]; it1 = P.cell_off[cell + 1]; }
+  const int2 cell_rg = P.cell_rng[cell];
+  const int it0 = cell_rg.x, it1 = cell_rg.y;
   const int2 head = (P.cell_head && !(CPGX && P.resume)) ? P.cell_head[cell] : make_int2(0, 0);
   // initial covered-so-far complement `u` of my row's word
   uint32_t u = 0u;
@@ -939,7 +975,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
   }
   __syncthreads();
   const int n_items = P.n_cells * WALK_SUB;
-  const int heavy_items = P.cls_cnt ? s_cls[BIN_HEAVY_CLASSES] * WALK_SUB : P.order ? P.order_starts[ORDER_BINS - 2] * WALK_SUB : n_items;  // cells with >= 2 objects
+  const int heavy_items = P.cls_cnt ? s_cls[BIN_HEAVY_CLASSES] * WALK_SUB : n_items;  // cells with >= 2 objects
   int q_next = 0, q_end = 0, cur_cls = 0;
   for (;;) {
     if (q_next == q_end) {
@@ -954,7 +990,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
     if (P.cls_cnt) {
       while (cur_cls < BIN_CLASSES - 1 && cell >= s_cls[cur_cls + 1]) cur_cls++;   // a warp's queue positions only grow
       cell = P.cls_cells[(size_t)cur_cls * P.n_cells + cell - s_cls[cur_cls]];
-    } else if (P.order) cell = P.order[cell];
+    }
     const int sub = q % WALK_SUB;
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
@@ -1020,8 +1056,8 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
     else u = (my_y >= P.uy0 && my_y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u;
     if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
   }
-  int it0, it1;
-  if (P.cell_rng) { const int2 rg = P.cell_rng[cell]; it0 = rg.x; it1 = rg.y; } else { it0 = P.cell_off[cell]; it1 = P.cell_off[cell + 1]; }
+  const int2 cell_rg = P.cell_rng[cell];
+  const int it0 = cell_rg.x, it1 = cell_rg.y;
   for (int it = it0; it < it1; it++) {
     const int oi = P.cell_items[it];
     const ObjRec& o = P.objs[oi];
