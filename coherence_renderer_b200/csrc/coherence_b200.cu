@@ -83,7 +83,7 @@ struct coh_ctx {
   bool use_u_init = false;
   bool have_u = false;
   // binning scratch
-  int* cell_counts = nullptr; int* cell_off = nullptr; int n_cells_cap = 0;
+  int n_cells_cap = 0;
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
   // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
@@ -224,7 +224,7 @@ int coh_shutdown(coh_ctx* ctx) {
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
-  DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_items); DFREE(ctx->cell_head); DFREE(ctx->cell_rng);
+  DFREE(ctx->cell_items); DFREE(ctx->cell_head); DFREE(ctx->cell_rng);
   DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
   DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->item_cell);
   DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
@@ -1202,10 +1202,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   }
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
   if (n_cells > ctx->n_cells_cap) {
-    DFREE(ctx->cell_counts); DFREE(ctx->cell_off); DFREE(ctx->cell_order); DFREE(ctx->cell_head);
+    DFREE(ctx->cell_order); DFREE(ctx->cell_head);
     CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
-    CK(DMALLOC(&ctx->cell_counts, sizeof(int) * n_cells));
-    CK(DMALLOC(&ctx->cell_off, sizeof(int) * (n_cells + 1)));
     DFREE(ctx->cell_rng);
     CK(DMALLOC(&ctx->cell_rng, sizeof(int2) * n_cells));
     CK(DMALLOC(&ctx->cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class

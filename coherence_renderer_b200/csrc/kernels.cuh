@@ -1,16 +1,23 @@
 // kernels.cuh — hand-written sm_100a kernels of the raster hot path.
 //
 //   k_prep_edges      int32 edges -> EdgeRec (x0in/x1in/ymin/ymax, FP64 gradient, direction)
-//   k_bin_count/fill  K1: per-cell (32 px x 16 rows) front-to-back object lists (ballot compaction)
-//   k_walk            K2+K4+K5 fused: one warp per work item (32 px x 1/4/16 rows of a cell) walks the cell list
-//                     front to back; scan-converts each candidate object's row into 32-bit
+//   k_rowedges        K1, once per scene: per (path object, pixel row) candidate edge lists (CSR)
+//   k_brush_cells     K1, once per scene: per (stroke, cell of its box) range of stamps reaching the cell
+//   k_bin1            K1, every frame, <= 1024 leaves: per-cell (32 px x 16 rows) front-to-back object lists in
+//                     one pass (ballot compaction, pool cursor), list-length classes for the heavy-first order
+//   k_bin_obj / k_bin_sort / k_bin2   K1, every frame, large scenes: two-level binning
+//   k_walk            K2+K4+K5 fused: one warp per work item (32 px x 1/4/16 rows of a cell) walks the cell
+//                     list front to back; scan-converts each candidate object's row into 32-bit
 //                     shape/coverage words, prunes with the covered-so-far word `u`, evaluates the
 //                     correlated-matte AA only for still-visible edge pixels, composites with
 //                     8-bit premultiplied `over`, and subtracts newly opaque pixels from `u`.
-//                     The row of RGBA8 is written once, 128 B per warp, fully coalesced.
+//                     The row of RGBA8 is written once, 128 B per warp, fully coalesced (and mirrored to
+//                     the peer framebuffers of the other GPUs when bands are gathered).
+//   k_pre_scan / k_pre_vis / k_pre_aa + k_walk<PRE>   three-phase frames for plain polygon scenes
 //   k_scan_rows       K2 stand-alone: shape + coverage bit-rows of one edge list (export path)
 //   k_aa_rows         K4 stand-alone: AA opacity bytes for the pixels of a bit-frame
-//   bit-frame kernels K3: span sets <-> bit-frames, AND/OR/ANDNOT, dilation
+//   bit-frame kernels K3: span sets <-> bit-frames, AND/OR/ANDNOT, dilation, run extraction
+//   k_conv_pass, k_monochrome, k_filter_matte, k_filter_blend   convolve.ml / filters.ml passes
 //
 // Design notes are in DESIGN.md.  No tensor cores: this is integer/bit work with a few FP64
 // crossings per (edge,row); the relevant roofline is HBM.
