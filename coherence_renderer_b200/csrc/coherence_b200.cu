@@ -1373,7 +1373,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
 // accumulator carrying on from the framebuffer (WalkParams::resume).
 // ---------------------------------------------------------------------------------------
 struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
-static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box);
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed = false);
 
 // `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small and handled
 // whole; the RGBA8 canvases are only touched in the rows the filter reads or writes).
@@ -1397,7 +1397,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&CG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
   CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(CG, 0, 4 * nwords, ctx->stream));
   const EdgeRec* ed = s->edges + F.first;
-  // shape of the geometry (render.ml:472-474); CG receives the coverage and is not used
+  // shape of the geometry (render.ml:472-474); CG receives the coverage (the minshape is needed for the matte)
   k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, CG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, U, T, nwords, 2); LAUNCHED();     // shptorender = r &&& u (render.ml:1281)
   // reading scene -> X -> filter function -> Y (in place)
@@ -1406,12 +1406,13 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
     CK(DMALLOC(&X, 4 * (size_t)W * H));
     CK(cudaMemsetAsync(X + po, 0, 4 * pn, ctx->stream));
     if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp
-      k_dilate<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(T, R, H, nw, m, m); LAUNCHED();
+      CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
+      k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED();  // T is empty outside [y0, y1]
     } else CK(cudaMemcpyAsync(R, T, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
     if (F.kind == COH_FILTER_SCENE) {
       PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
-    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox)) return 1;
+    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox, true)) return 1;
     Y = X;
     if (F.kind == COH_FILTER_MONOCHROME) {
       k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED();
@@ -1436,29 +1437,47 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
       k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X + po, W, rh, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
     }
   }
-  // the geometry's matte in the update (render.ml:1099-1103); Polygon.polygon_sprite samples every pixel
+  // The geometry's matte in the update (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is
+  // given, but a pixel whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its
+  // 2 x 2-pixel sampling window (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge
+  // pieces), so all 32 x 32 samples are inside and the opacity is 255: only the rest is super-sampled.
   CK(DMALLOC(&op, (size_t)nw * 32 * h)); CK(DMALLOC(&alpha, (size_t)W * h));
+  {
+    uint32_t* I = nullptr;   // interior = erode 2 2 minshape, clipped 2 pixels inside the rows / columns scanned here
+    CK(DMALLOC(&I, 4 * nwords));
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, CG, CG, nwords, 1); LAUNCHED();          // CG := minshape = shape - coverage
+    k_fill_words<<<wblocks, 256, 0, ctx->stream>>>(I, nwords, 0xFFFFFFFFu); LAUNCHED();
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, CG, I, nwords, 1); LAUNCHED();            // everything but the minshape
+    {  // rows y0 .. y1 only (everything outside is "not minshape" and the box mask below cuts 2 rows off each end)
+      k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(I + (size_t)y0 * nw, R + (size_t)y0 * nw, h, nw, 2, 2); LAUNCHED();
+    }
+    k_fill_box_bits<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(I, H, nw, 0, 0, 2, y0 + 2, W - 3, y1 - 2); LAUNCHED();
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, R, I, nwords, 1); LAUNCHED();             // interior
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, I, I, nwords, 1); LAUNCHED();             // to be super-sampled: T - interior
+    CK(cudaMemsetAsync(op, 255, (size_t)nw * 32 * h, ctx->stream));
+    k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, I + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+    DFREE(I);
+  }
   CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
-  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, T + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
   k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, op, F.colour, W, h, nw, alpha, R + (size_t)y0 * nw); LAUNCHED();  // R := finished
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, R, R, nwords, 1); LAUNCHED();      // pixels_for_normal_scene (render.ml:1105)
   CK(DMALLOC(&Z, 4 * (size_t)W * H));
   CK(cudaMemsetAsync(Z + (size_t)y0 * W, 0, 4 * (size_t)h * W, ctx->stream));
-  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox)) return 1;
+  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox, true)) return 1;
   k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw); LAUNCHED();
   k_bitop<<<wblocks, 256, 0, ctx->stream>>>(U, SG, U, nwords, 1); LAUNCHED();     // u --- ef (render.ml:1308)
   DFREE(SG); DFREE(CG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
   return 0;
 }
 // Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)
-static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box) {
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed) {
   const Frame& fr = ctx->fr;
   if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
   auto segment = [&](int a, int b) -> int {
     if (b > a) {
       PassArgs A{a, b, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U, U, target, fresh, !fresh};
       if (render_pass(ctx, s, A)) return 1;
-    } else if (fresh) {
+    } else if (fresh && !target_zeroed) {
       const int hh = box.y1 - box.y0 + 1;
       k_clear_in_bits<<<dim3(cdiv(fr.W, 128), hh), 128, 0, ctx->stream>>>(target + (size_t)box.y0 * fr.W, U + (size_t)box.y0 * fr.tiles_x, fr.W, hh, fr.tiles_x); LAUNCHED();
     }

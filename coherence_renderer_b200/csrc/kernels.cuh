@@ -1122,12 +1122,12 @@ __global__ void __launch_bounds__(256) k_aa_rows(const EdgeRec* __restrict__ edg
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
   __shared__ StagedEdge s_stage[8][32];
-  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&aa->prefix[0][0])[i];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int w = blockIdx.x * 8 + wid, r = blockIdx.y;
-  if (w >= nw || r >= n_rows) return;
-  uint32_t q = Q[(size_t)r * nw + w];
+  const uint32_t q = (w < nw && r < n_rows) ? Q[(size_t)r * nw + w] : 0u;
+  if (!__syncthreads_or(q != 0u)) return;   // most blocks of a sparse frame have nothing to sample: leave before loading the table
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&aa->prefix[0][0])[i];
+  __syncthreads();
   if (!q) return;
   bool ok;
   int op = aa_tile(edges, nullptr, n_edges, winding, wx0 + 32 * w, y0 + r, q, s_aa[wid], s_stage[wid], s_prefix, aa->volume, lane, ok);

@@ -749,3 +749,22 @@ def test_edge_cases(ctx, oracle):
     objs, n, nbg, e, p = deep.arrays()
     with pytest.raises(abi.CohError):              # nesting beyond MAX_DEPTH fails loudly at scene creation
         ctx.scene_create(objs, nbg, e, p)
+
+
+def test_filter_matte_interior_shortcut(ctx, oracle):
+    """The matte of a filter's geometry is super-sampled only where an edge can be near (outside the twice-eroded
+    minshape); geometries with acute spikes, thin slivers, holes (even-odd) and parts outside the frame must
+    still match the reference, which samples every pixel."""
+    W, H = 260, 200
+    spike = [S.polygon_segments([(20.0, 20.0), (240.0, 35.0), (130.0, 60.0), (250.0, 180.0), (120.0, 90.0), (15.0, 190.0), (90.0, 70.0)])]
+    ring = [S.polygon_segments([(-30.0, -20.0), (200.0, -10.0), (210.0, 170.0), (-25.0, 160.0)]),
+            S.polygon_segments([(40.0, 40.0), (150.0, 45.0), (145.0, 120.0), (45.0, 118.0)])]
+    sliver = [S.polygon_segments([(10.0, 100.0), (250.0, 101.2), (250.0, 106.9), (10.0, 104.1)])]
+    for geom, wind in ((spike, S.COH_NONZERO), (ring, S.COH_EVENODD), (sliver, S.COH_NONZERO)):
+        for kind, kw in (("monochrome", {}), ("blur", {"kernel": ("unit", 2)})):
+            b = S.SceneBuilder()
+            b.filter(kind, geom, fill=S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 240)), winding=wind, **kw)
+            b.polygon([(5.0, 5.0), (255.0, 8.0), (245.0, 190.0), (12.0, 180.0)], S.Fill.plain(S.rgba8(200, 60, 20)))
+            b.polygon([(60.0, 0.0), (200.0, 100.0), (60.0, 199.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 60, 220), 150)))
+            got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+            assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, (kind, wind)
