@@ -76,7 +76,7 @@ struct coh_ctx {
   int* d_error = nullptr;
   int* h_error = nullptr;  // pinned
   // framebuffer
-  Frame fr{0, 0, 0, 0, 0, 0};
+  Frame fr{0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t* fb = nullptr;
   uint32_t* u_out = nullptr;   // bit-frame of `u` after the scene pass
   uint32_t* u_init = nullptr;  // bit-frame of an arbitrary update shape
@@ -1169,6 +1169,7 @@ int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y
   }
   ctx->fr.W = width; ctx->fr.H = height; ctx->fr.band_y0 = band_y0; ctx->fr.band_y1 = band_y1;
   ctx->fr.tiles_x = cdiv(width, 32); ctx->fr.cells_y = cdiv(height, CELL_H);
+  ctx->fr.ctx0 = 0; ctx->fr.cntx = ctx->fr.tiles_x;
   ctx->have_u = false;
   return 0;
 }
@@ -1183,7 +1184,7 @@ struct PassArgs {
   bool write_clear, resume;
 };
 static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
-  const Frame& fr = ctx->fr;
+  Frame fr = ctx->fr;
   const int ux = A.ux, uy = A.uy, uw = A.uw, uh = A.uh;
   const bool write_clear = A.write_clear;
   const int n_leaves = A.l1 - A.l0;
@@ -1193,14 +1194,17 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // only the cell rows the update box reaches (a dirty region is usually a small part of the frame)
   const int ry0 = std::max(fr.band_y0, uy), ry1 = std::min(fr.band_y1, uy + uh);
   if (ry1 <= ry0) return 0;
-  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves && ry0 == fr.band_y0 && ry1 == fr.band_y1;
+  // ... and only the tile columns it reaches
+  fr.ctx0 = std::max(0, ux >> 5);
+  const int ctx1 = std::min(fr.tiles_x - 1, (int)(((long long)ux + uw - 1) >> 5));
+  if (ctx1 < fr.ctx0) return 0;
+  fr.cntx = ctx1 - fr.ctx0 + 1;
+  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves && ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x;
   int cell_row0 = ry0 / CELL_H, cell_row1 = (ry1 - 1) / CELL_H;
-  if (A.u_out && A.u_out != A.u_init) {  // rows the walk does not visit have nothing uncovered
-    const int wy0 = cell_row0 * CELL_H, wy1 = std::min((cell_row1 + 1) * CELL_H, fr.H);
-    if (wy0 > fr.band_y0) CK(cudaMemsetAsync(A.u_out + (size_t)fr.band_y0 * fr.tiles_x, 0, 4 * (size_t)(wy0 - fr.band_y0) * fr.tiles_x, ctx->stream));
-    if (wy1 < fr.band_y1) CK(cudaMemsetAsync(A.u_out + (size_t)wy1 * fr.tiles_x, 0, 4 * (size_t)(fr.band_y1 - wy1) * fr.tiles_x, ctx->stream));
-  }
-  int n_cells = (cell_row1 - cell_row0 + 1) * fr.tiles_x;
+  if (A.u_out && A.u_out != A.u_init && !(ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x))
+    // rows and columns the walk does not visit have nothing uncovered
+    CK(cudaMemsetAsync(A.u_out + (size_t)fr.band_y0 * fr.tiles_x, 0, 4 * (size_t)(fr.band_y1 - fr.band_y0) * fr.tiles_x, ctx->stream));
+  int n_cells = (cell_row1 - cell_row0 + 1) * fr.cntx;
   if (n_cells > ctx->n_cells_cap) {
     DFREE(ctx->cell_order); DFREE(ctx->cell_head);
     CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
@@ -1229,7 +1233,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     size_t tot = 0;
     for (int li = A.l0; li < A.l1; li++) {
       const ObjRec& o = s->h_objs[s->h_leaves[li]];
-      int cx0 = std::max(o.bx0 >> 5, 0), cx1 = std::min(o.bx1 >> 5, fr.tiles_x - 1);
+      int cx0 = std::max(o.bx0 >> 5, fr.ctx0), cx1 = std::min(o.bx1 >> 5, ctx1);
       int cy0 = std::max(floordiv(o.by0, CELL_H), cell_row0), cy1 = std::min(floordiv(o.by1, CELL_H), cell_row1);
       if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
     }

@@ -67,6 +67,8 @@ struct Frame {
   int band_y0, band_y1;  // rows rendered by this context
   int tiles_x;         // ceil(W / 32)
   int cells_y;         // ceil(H / CELL_H)
+  int ctx0, cntx;      // cell grid of the current pass: first tile column and number of tile columns (an update box
+                       // usually spans few of the frame's columns); cell = row * cntx + (tile - ctx0)
 };
 
 }  // namespace coh

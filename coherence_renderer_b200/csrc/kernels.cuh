@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + wid;
   const bool active = warp < n_cells;
-  const int cx = active ? warp % fr.tiles_x : 0, cy = active ? cell_row0 + warp / fr.tiles_x : 0;
+  const int cx = active ? fr.ctx0 + warp % fr.cntx : 0, cy = active ? cell_row0 + warp / fr.cntx : 0;
   const int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1, y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
   unsigned mymask = 0u;
   int n = 0, first = -1;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_bin2(const int4* __restrict__ leaf_box,
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + wid;
   const bool active = warp < n_cells;
-  const int cx = active ? warp % fr.tiles_x : 0, cy = active ? cell_row0 + warp / fr.tiles_x : 0;
+  const int cx = active ? fr.ctx0 + warp % fr.cntx : 0, cy = active ? cell_row0 + warp / fr.cntx : 0;
   const int x0 = cx * TILE_W, x1 = x0 + TILE_W - 1, y0 = cy * CELL_H, y1 = y0 + CELL_H - 1;
   const int cc = ((cy >> COARSE_SHIFT) - crow0) * ctiles_x + (cx >> COARSE_SHIFT);
   const int la = active ? coarse_off[cc] : 0, lb = active ? coarse_off[cc + 1] : 0;
@@ -630,7 +630,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   const size_t my_slot = (size_t)(my_y - P.fr.band_y0) * P.fr.tiles_x + tile;  // carry slot of (row, tile)
   int n_carry = 0;                                   // published carry entries of my row (mirrored)
 
-  const int cell = by * P.fr.tiles_x + tile;
+  const int cell = by * P.fr.cntx + tile - P.fr.ctx0;
   const int2 cell_rg = P.cell_rng[cell];
   const int it0 = cell_rg.x, it1 = cell_rg.y;
   const int2 head = (P.cell_head && !(CPGX && P.resume)) ? P.cell_head[cell] : make_int2(0, 0);
@@ -892,7 +892,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         int lead_start = xx0;  // object-frame x where the run containing bit 0 begins
         if (CARRY && edge && okind == K_PATH && fkind != 0) {
           const size_t slot = (size_t)(y0 + r - P.fr.band_y0) * P.fr.tiles_x + tile;
-          if ((edge & 1u) && tile > 0) {
+          if ((edge & 1u) && tile > P.fr.ctx0) {   // (nothing is visible left of the pass's first column: u is empty there)
             const volatile int* done = P.carry_done + slot - 1;
             while (*done != P.epoch) __nanosleep(32);
             __threadfence();
@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
 #ifdef COH_PHASE_PROFILE
     long long tc0_ = clock64();
 #endif
-    walk_cell<CARRY, EXTRAS, WALK_H, PRE>(P, cell % P.fr.tiles_x, cell / P.fr.tiles_x, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
+    walk_cell<CARRY, EXTRAS, WALK_H, PRE>(P, P.fr.ctx0 + cell % P.fr.cntx, cell / P.fr.cntx, sub, lane, s_aa[wid], s_stage[wid], s_acc[wid], s_prefix, volume);
     __syncwarp();
 #ifdef COH_PHASE_PROFILE
     if (lane == 0 && cell < (1 << 20)) g_cell_cycles[cell] = (unsigned int)(clock64() - tc0_);
@@ -1031,7 +1031,7 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
   if (pair >= n_pairs) return;
   const int item = pair / CELL_H, row = pair % CELL_H;
   const int cell = P.item_cell[item];
-  const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
+  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   const ObjRec& o = P.objs[P.cell_items[item]];
   uint32_t S = 0u, C = 0u;
@@ -1055,7 +1055,7 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
   if (cell >= P.n_cells) return;
-  const int tile = cell % P.fr.tiles_x, by = cell / P.fr.tiles_x;
+  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t u = 0u;
   if (my_y >= P.fr.band_y0 && my_y < P.fr.band_y1) {
