@@ -275,6 +275,16 @@ int coh_get_timing(coh_ctx* ctx, double* walk_ms_avg, double* bin_ms_avg, int64_
 }
 int64_t coh_launch_count(coh_ctx* ctx) { return ctx->launches; }
 static int check_error_flag(coh_ctx* ctx, const char* what);
+int coh_mem_in_use(coh_ctx* ctx, int64_t* bytes) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  uint64_t used = 0;
+  CK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+  *bytes = (int64_t)used;
+  return 0;
+}
 int coh_sync(coh_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   return check_error_flag(ctx, "coh_sync");  // synchronises the stream and reports deferred kernel-side failures
@@ -1685,6 +1695,21 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
       }
       *shape = cs; *minshape = 0;
       return 0;
+    } else if (o.kind == K_BRUSH) {  // Brush.shape_of_brushstroke, minshape null (render.ml:529-535)
+      const int x0 = o.bx0 - o.dx, y0 = o.by0 - o.dy, x1 = o.bx1 - o.dx, y1 = o.by1 - o.dy;
+      const int wx0 = floordiv(x0, 32) * 32, nw = (x1 - wx0) / 32 + 1, n_rows = y1 - y0 + 1;
+      uint32_t* bits = nullptr;
+      CK(DMALLOC(&bits, 4 * (size_t)nw * n_rows));
+      CK(cudaMemsetAsync(bits, 0, 4 * (size_t)nw * n_rows, ctx->stream));
+      const int side = 2 * o.brush_r + 1;
+      k_stamp_boxes_to_bits<<<cdiv(o.count * side, 256), 256, 0, ctx->stream>>>(s->points + o.first, o.count, o.brush_r, y0, n_rows, wx0, nw, bits); LAUNCHED();
+      int rc = shape_from_bits(ctx, bits, y0, n_rows, wx0, nw, &cs);
+      DFREE(bits);
+      if (rc) return 1;
+    } else if (o.kind == K_CONV) {   // bloat r r (shape g), erode r r (minshape g) (render.ml:536-555): kept as bit-rows by the scene
+      const uint32_t* S = s->conv_bits + o.cv_bits;
+      if (shape_from_bits(ctx, S, o.cv_y0, o.cv_h, o.cv_x0, o.cv_nw, &cs)) return 1;
+      if (shape_from_bits(ctx, S + (size_t)o.cv_nw * o.cv_h, o.cv_y0, o.cv_h, o.cv_x0, o.cv_nw, &cm)) return 1;
     } else FAIL("coh_scene_object_shape: unsupported object kind");
     if (coh_cache_addshape(ctx, id, cs, cm)) return 1;
   }

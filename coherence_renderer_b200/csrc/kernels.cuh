@@ -1151,6 +1151,24 @@ __global__ void k_spans_to_bits(const int* __restrict__ row_ptr, const int2* __r
     or_interval(row, 1, nw, wx0, s.x, s.x + s.y - 1);
   }
 }
+// Brush.shape_of_brushstroke (brush.ml:135-173): the union of the (2r+1)^2 boxes around the stamp centres.
+// One thread per (stamp, row of its box); rows y0 .., nw words per row starting at pixel wx0.
+__global__ void k_stamp_boxes_to_bits(const int2* __restrict__ points, int n_points, int r, int y0, int n_rows, int wx0, int nw,
+                                      uint32_t* __restrict__ bits) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, side = 2 * r + 1;
+  if (t >= n_points * side) return;
+  const int2 p = points[t / side];
+  const int row = p.y - r + t % side - y0;
+  if (row < 0 || row >= n_rows) return;
+  int a = p.x - r - wx0, b = p.x + r - wx0;
+  if (b < 0 || a >= nw * 32) return;
+  a = max(a, 0); b = min(b, nw * 32 - 1);
+  uint32_t* rowp = bits + (size_t)row * nw;
+  for (int w = a >> 5; w <= (b >> 5); w++) {
+    const int lo = max(a, w * 32) & 31, hi = min(b, w * 32 + 31) & 31;
+    atomicOr(&rowp[w], (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi)));
+  }
+}
 // op: 0 OR, 1 ANDNOT (a & ~b), 2 AND
 __global__ void k_bitop(const uint32_t* a, const uint32_t* b, uint32_t* out,
                         size_t n, int op) {

@@ -223,6 +223,10 @@ int coh_render_uncovered(coh_ctx* ctx, coh_shape_t* out);
  * produced, so after all ranks have rendered their bands (and a cross-rank barrier) every GPU holds the whole
  * frame.  n_peers = 0 switches it off.  Frames with filter objects mirror only their final pixels. */
 int coh_fb_set_peers(coh_ctx* ctx, int32_t n_peers, void* const* peer_fbs);
+/* Bytes of device memory currently allocated from the stream-ordered pool every coh_* allocation comes from
+ * (scenes, span sets, cache entries, framebuffer, scratch): for leak checks and for sizing the cache budget
+ * that cache.mli:27-28 expresses in bytes. */
+int coh_mem_in_use(coh_ctx* ctx, int64_t* bytes);
 /* Wait for the context's stream and report deferred kernel-side failures. */
 int coh_sync(coh_ctx* ctx);
 /* Device pointer of the framebuffer (band gather by NCCL / peer copies happens on these). */

@@ -768,3 +768,82 @@ def test_filter_matte_interior_shortcut(ctx, oracle):
             b.polygon([(60.0, 0.0), (200.0, 100.0), (60.0, 199.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 60, 220), 150)))
             got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
             assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, (kind, wind)
+
+
+def test_no_device_memory_leaks(ctx, oracle):
+    """Scenes, frames (plain, filtered, dragged), span-set algebra, cache entries and convolutions give back every
+    byte they allocate: device memory in use returns to its level after repeated cycles."""
+    W, H = 320, 240
+    rng = random.Random(3)
+
+    def cycle():
+        ctx.cache_clear()
+        ctx.cache_configure(True, 32 << 20)
+        ctx.fb_configure(W, H)
+        b, _ = _filter_scene("blur", W, H, second=("monochrome", {}), kernel=("gaussian", 2))
+        objs, n, nbg, e, p = _finish(b, W, H).arrays()
+        sc = ctx.scene_create(objs, nbg, e, p)
+        ctx.render_frame(sc, (0, 0, W, H), abi.COH_RENDER_RECORD_U)
+        hu = ctx.render_uncovered()
+        ctx.shape_free(hu)
+        ctx.scene_free(sc)
+        b = S.random_scene(W, H, 40, seed=rng.randint(1, 99), brush_fraction=0.3)
+        objs, n, nbg, e, p = b.arrays()
+        for o in objs:
+            if o.kind in (abi.COH_OBJ_PATH, abi.COH_OBJ_BRUSH):
+                o.id = 500 + rng.randint(0, 10000)
+        sc = ctx.scene_create(objs, nbg, e, p)
+        ctx.render_frame(sc, (0, 0, W, H))
+        for k in range(3):
+            ctx.scene_drag_object(sc, k, 2, -1)
+        hs, hm = ctx.scene_object_shape(sc, 0)
+        hb = ctx.shape_bloat(hs, 2, 2) if hs else 0
+        hd = ctx.shape_difference(hb, hm) if hb else 0
+        for h in (hs, hm, hb, hd):
+            ctx.shape_free(h)
+        ctx.scene_free(sc)
+        ctx.cache_clear()
+        ctx.sync()
+
+    for _ in range(3):
+        cycle()
+    base = ctx.mem_in_use()
+    for _ in range(10):
+        cycle()
+    assert ctx.mem_in_use() == base
+
+
+def test_object_shapes_of_brush_and_convolved(ctx, oracle):
+    """Render.shape_of_basicshape for Brushstroke (dilated stamp centres, minshape null, brush.ml:135-173) and
+    Convolved (bloat r r shape, erode r r minshape, render.ml:536-555)."""
+    W, H = 300, 200
+    b = S.SceneBuilder()
+    b.brush(0.8, 6.0, [[("C", (30.0, 40.0), (120.0, 10.0), (200.0, 190.0), (270.0, 60.0))]], S.Fill.plain(S.rgba8(10, 10, 200)))
+    quad = [(60.3, 50.2), (220.5, 63.9), (208.1, 150.7), (48.8, 134.4)]
+    b.polygon(quad, S.Fill.plain(S.rgba8(200, 30, 30)), convolve=("gaussian", 4))
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    hs, hm = ctx.scene_object_shape(sc, 0)
+    o = objs[0]
+    pts = p[o.first:o.first + o.count]
+    r = int(np.ceil(6.0))
+    rows = {}
+    for x, y in pts:
+        for yy in range(y - r, y + r + 1):
+            rows.setdefault(yy, []).append((x - r, 2 * r + 1))
+    exp = None
+    for yy in sorted(rows):
+        for x, l in rows[yy]:
+            one = util.flat_of_rows([(yy, [(x, l)])])
+            exp = one if exp is None else oracle.shape_op("union", exp, one)
+    assert np.array_equal(ctx.shape_export(hs), exp) and hm == 0
+    ctx.shape_free(hs)
+    hs, hm = ctx.scene_object_shape(sc, 1)
+    o = objs[1]
+    ss, mm = oracle.shapeminshape(e[o.first:o.first + o.count], o.winding)
+    assert np.array_equal(ctx.shape_export(hs), oracle.shape_unary("bloat", ss, 4, 4))
+    assert np.array_equal(ctx.shape_export(hm), oracle.shape_unary("erode", mm, 4, 4))
+    ctx.shape_free(hs)
+    ctx.shape_free(hm)
+    ctx.scene_free(sc)
