@@ -1261,8 +1261,14 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   if (!big) {
     // one pass: hit masks in registers, lists carved from one cursor, length classes instead of a sort
     const int bin_blocks = cdiv(n_cells * 32, 256);
+    BinPrefill pf; memset(&pf, 0, sizeof pf);
+    if (ordered && !A.u_init && !A.resume) {
+      pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1;
+      pf.n_peers = (A.fb == ctx->fb) ? ctx->n_peers : 0;
+      for (int k = 0; k < pf.n_peers; k++) pf.peer_fb[k] = ctx->peer_fb[k];
+    }
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_rng, ctx->cell_items, ctx->order_hist,
-                                               ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell); LAUNCHED();
+                                               ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell, pf); LAUNCHED();
   } else {
     // two levels: leaves into coarse cells (object-parallel, sorted per coarse list), then every fine cell from its coarse list
     const int ctx_x = cdiv(fr.tiles_x, COARSE), crow0 = cell_row0 >> COARSE_SHIFT, crow1 = cell_row1 >> COARSE_SHIFT;

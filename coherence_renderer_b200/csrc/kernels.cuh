@@ -120,11 +120,20 @@ __device__ __forceinline__ int bin_class(int n) {  // longest lists first; the l
   if (n >= 16) return n >= 48 ? 0 : n >= 40 ? 1 : n >= 32 ? 2 : n >= 28 ? 3 : n >= 24 ? 4 : n >= 20 ? 5 : 6;
   return n >= 12 ? 7 : n >= 8 ? 8 : n >= 6 ? 9 : n >= 5 ? 10 : n == 4 ? 11 : n == 3 ? 12 : n == 2 ? 13 : n == 1 ? 14 : 15;
 }
+// Cells whose only object is an opaque primitive covering all of them (the background rectangle: most cells of
+// most frames) are finished right here when the update is a box: their pixels are that colour, and they never
+// enter the walker's queue.
+struct BinPrefill {
+  uint32_t* fb;                     // null: off (arbitrary update shapes, continued frames, row-major order)
+  uint32_t* peer_fb[7]; int n_peers;
+  uint32_t* u_out;                  // optional
+  int ux0, uy0, ux1, uy1;           // update box, inclusive
+};
 // blockDim = 256 (8 cells per block); pool slices and class positions are reserved once per block
 __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr, int cell_row0,
                        int n_cells, int2* __restrict__ cell_rng, int* __restrict__ items, int* __restrict__ state /* [0] pool cursor, [1..] class counts */,
                        int* __restrict__ cls_cells /* [BIN_CLASSES][n_cells] or null */, const ObjRec* __restrict__ objs, int2* __restrict__ cell_head,
-                       int* __restrict__ item_cell) {
+                       int* __restrict__ item_cell, BinPrefill pf) {
   __shared__ int s_n[8], s_c[8], s_base[8], s_pos[8];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + wid;
@@ -146,7 +155,16 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
       if (n == 0 && m) first = leaves[b + __ffs((int)m) - 1];
       n += __popc(m);
     }
-  if (lane == 0) { s_n[wid] = n; s_c[wid] = active ? bin_class(n) : -1; }
+  int2 hd = make_int2(0, 0);
+  if (lane == 0 && n == 1) {
+    const ObjRec& o = objs[first];
+    const int ex1 = x1 < fr.W - 1 ? x1 : fr.W - 1, ey1 = y1 < fr.H - 1 ? y1 : fr.H - 1;
+    if (o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && objs[o.anc[0]].pretrans < 0 &&
+        o.prim[0] + o.dx <= x0 && o.prim[2] + o.dx >= ex1 && o.prim[1] + o.dy <= y0 && o.prim[3] + o.dy >= ey1)
+      hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
+  }
+  const bool prefill = pf.fb != nullptr && (hd.y & 1);          // (lane 0's view)
+  if (lane == 0) { s_n[wid] = n; s_c[wid] = (active && !prefill) ? bin_class(n) : -1; }
   __syncthreads();
   if (wid == 0 && lane < 8) {
     // pool slice of the block, split by warp; class positions: one atomic per class present in the block
@@ -179,16 +197,26 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
   }
   if (lane == 0) {
     cell_rng[warp] = make_int2(base, base + n);
-    int2 hd = make_int2(0, 0);
-    if (n == 1) {
-      const ObjRec& o = objs[first];
-      const int ex1 = x1 < fr.W - 1 ? x1 : fr.W - 1, ey1 = y1 < fr.H - 1 ? y1 : fr.H - 1;
-      if (o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0 && o.depth == 1 && objs[o.anc[0]].pretrans < 0 &&
-          o.prim[0] + o.dx <= x0 && o.prim[2] + o.dx >= ex1 && o.prim[1] + o.dy <= y0 && o.prim[3] + o.dy >= ey1)
-        hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
-    }
     cell_head[warp] = hd;
-    if (cls_cells) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
+    if (cls_cells && s_c[wid] >= 0) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
+  }
+  if (__shfl_sync(0xFFFFFFFFu, (int)prefill, 0)) {
+    const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, hd.x, 0);
+    const bool scene_root = (__shfl_sync(0xFFFFFFFFu, hd.y, 0) & 2) != 0;
+    uint32_t colmask = interval_mask32(x0, pf.ux0, pf.ux1);
+    if (x0 + 31 >= fr.W) colmask &= interval_mask32(x0, 0, fr.W - 1);
+#pragma unroll 1
+    for (int r = 0; r < CELL_H; r++) {
+      const int y = y0 + r;
+      if (y < fr.band_y0 || y >= fr.band_y1) continue;
+      const uint32_t u = (y >= pf.uy0 && y <= pf.uy1) ? colmask : 0u;
+      if (pf.u_out && lane == 0) pf.u_out[(size_t)y * fr.tiles_x + cx] = scene_root ? 0u : u;
+      if ((u >> lane) & 1u) {
+        const size_t at = (size_t)y * fr.W + x0 + lane;
+        pf.fb[at] = c0;
+        for (int k = 0; k < pf.n_peers; k++) pf.peer_fb[k][at] = c0;
+      }
+    }
   }
 }
 // ------------------------------------------------------------------------------------
@@ -981,7 +1009,7 @@ __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkPar
     s_cls[BIN_CLASSES] = acc;
   }
   __syncthreads();
-  const int n_items = P.n_cells * WALK_SUB;
+  const int n_items = (P.cls_cnt ? s_cls[BIN_CLASSES] : P.n_cells) * WALK_SUB;   // cells finished by the binning kernel are in no class
   const int heavy_items = P.cls_cnt ? s_cls[BIN_HEAVY_CLASSES] * WALK_SUB : n_items;  // cells with >= 2 objects
   int q_next = 0, q_end = 0, cur_cls = 0;
   for (;;) {
@@ -1031,6 +1059,7 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
   if (pair >= n_pairs) return;
   const int item = pair / CELL_H, row = pair % CELL_H;
   const int cell = P.item_cell[item];
+  if (P.cell_head[cell].y & 1) return;   // a background cell: finished by the binning kernel or the walker's fast path, nobody reads these words
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   const ObjRec& o = P.objs[P.cell_items[item]];
@@ -1054,7 +1083,7 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
 __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __restrict__ list /* pair, object, edge mask, (tile << 16 | row of the frame) */, int* __restrict__ list_n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
-  if (cell >= P.n_cells) return;
+  if (cell >= P.n_cells || (P.cell_head[cell].y & 1)) return;
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t u = 0u;
