@@ -1339,7 +1339,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
   // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
   const char* force = getenv("COH_FUSED");   // tests force either path: "1" fused, "0" three-phase
-  const bool pre = s->extras == 0 && !s->has_fancy && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+  const bool pre = s->extras == 0 && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
                    (force ? force[0] == '0' : walk_h != 1);
   if (pre) {
     const size_t n_pairs = total * CELL_H;
@@ -1358,7 +1358,22 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
-    k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+    if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
+      size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
+      if (slots > ctx->carry_slots) {
+        DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+        CK(DMALLOC(&ctx->carry_done, sizeof(int) * slots));
+        CK(DMALLOC(&ctx->carry_cnt, sizeof(int) * slots));
+        CK(DMALLOC(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
+        CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
+        ctx->carry_slots = slots;
+      }
+      P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
+      P.epoch = ++ctx->epoch;
+      k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+    } else {
+      k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+    }
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
     return 0;
   }

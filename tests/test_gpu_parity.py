@@ -150,6 +150,14 @@ def test_fancy_fills(ctx, oracle):
     assert _max_lsb(got, ref) == 0
 
 
+def test_fancy_fills_three_phase_path(ctx, oracle, monkeypatch):
+    """The three-phase frame path (forced) with gradient fills: the compositing walk keeps the cross-tile carry of
+    span starts."""
+    monkeypatch.setenv("COH_FUSED", "0")
+    test_fancy_fills(ctx, oracle)
+    test_fancy_fill_long_shallow_edges(ctx, oracle)
+
+
 def test_fancy_fill_long_shallow_edges(ctx, oracle):
     """Edge runs hundreds of pixels long (nearly horizontal edges) under a gradient whose alpha varies."""
     W, H = 700, 120
