@@ -1,0 +1,216 @@
+// host_polygon.inl — part of coherence_b200.cu (one translation unit; included in order): Polygon entry points (scan conversion, AA opacity, sprites) and Convolve.convolve_sprite.
+
+// ---------------------------------------------------------------------------------------
+// Polygon
+// ---------------------------------------------------------------------------------------
+struct EdgeBox { int xmin, xmax, ymin, ymax; };
+static EdgeBox edge_bounds(const int32_t* e, int n) {
+  EdgeBox b{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+  for (int i = 0; i < n; i++) {
+    b.xmin = std::min(b.xmin, std::min(e[4 * i], e[4 * i + 2])); b.xmax = std::max(b.xmax, std::max(e[4 * i], e[4 * i + 2]));
+    b.ymin = std::min(b.ymin, std::min(e[4 * i + 1], e[4 * i + 3])); b.ymax = std::max(b.ymax, std::max(e[4 * i + 1], e[4 * i + 3]));
+  }
+  return b;
+}
+// Conservative pixel box of the shape of an edge list: a row y is touched iff its band
+// [32y-47, 32y+16] meets [ymin, ymax]; columns from the widened coverage (polygon.ml:444-453)
+// plus two pixels of slack: band crossings are rounded by truncation toward zero and the
+// bottom crossing of a doubly clipped edge restarts from the rounded top crossing
+// (polygon.ml:365-379), so a crossing can leave the edge's x range by up to 3 sub-bins, and
+// pix_of_sub itself truncates toward zero on negative sub-bins.
+static void shape_pixel_box(const EdgeBox& b, int& px0, int& py0, int& px1, int& py1) {
+  py0 = floordiv(b.ymin - 16 + 31, 32);   // smallest y with 32y+16 >= ymin
+  py1 = floordiv(b.ymax + 47, 32);        // largest y with 32y-47 <= ymax
+  px0 = floordiv(b.xmin - 16, 32) - 2;
+  px1 = floordiv(b.xmax + 16 + 31, 32) + 2;
+}
+static int upload_edges(coh_ctx* ctx, const int32_t* edges, int n, EdgeRec** out) {
+  int4* raw = nullptr;
+  CK(DMALLOC(&raw, sizeof(int4) * std::max(n, 1)));
+  CK(DMALLOC(out, sizeof(EdgeRec) * std::max(n, 1)));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(raw, edges, sizeof(int4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_prep_edges<<<cdiv(n, 256), 256, 0, ctx->stream>>>(raw, *out, n); LAUNCHED();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(raw);
+  return 0;
+}
+static int check_error_flag(coh_ctx* ctx, const char* what) {
+  CK(cudaMemcpyAsync(ctx->h_error, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_error) {
+    cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
+    ctx->err = std::string(what) + ": an object has more than " + std::to_string(COH_MAXX) + " band crossings inside one tile window of a row (COH_MAXX), or more than " + std::to_string(CARRY_CAP) + " fancy-fill edge runs cross one tile border (CARRY_CAP)";
+    return 1;
+  }
+  return 0;
+}
+
+// scan-convert device-resident prepared edges inside a pixel box into (shape, minshape) span sets
+static int shapes_from_device_edges(coh_ctx* ctx, const EdgeRec* d_edges, int n_edges, int winding, int px0, int py0,
+                                    int px1, int py1, coh_shape_t* shape, coh_shape_t* minshape, const char* who) {
+  int wx0 = floordiv(px0, 32) * 32, nw = (px1 - wx0) / 32 + 1, n_rows = py1 - py0 + 1;
+  size_t nwords = (size_t)n_rows * nw;
+  uint32_t *S = nullptr, *C = nullptr;
+  CK(DMALLOC(&S, sizeof(uint32_t) * nwords)); CK(DMALLOC(&C, sizeof(uint32_t) * nwords));
+  CK(cudaMemsetAsync(S, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  CK(cudaMemsetAsync(C, 0, sizeof(uint32_t) * nwords, ctx->stream));
+  k_scan_rows<<<dim3(cdiv(n_rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(d_edges, n_edges, winding, py0, n_rows, wx0, nw, S, C, ctx->d_error); LAUNCHED();
+  int rc = check_error_flag(ctx, who);
+  if (!rc) rc = shape_from_bits(ctx, S, py0, n_rows, wx0, nw, shape);
+  if (!rc) { k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED(); }  // minshape = shape - C
+  if (!rc) rc = shape_from_bits(ctx, C, py0, n_rows, wx0, nw, minshape);
+  DFREE(S); DFREE(C);
+  return rc;
+}
+int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding,
+                                  coh_shape_t* shape, coh_shape_t* minshape) {
+  CK(cudaSetDevice(ctx->device));
+  *shape = 0; *minshape = 0;
+  if (n_edges <= 0) return 0;  // polygon.ml:584: NullShape, NullShape
+  if (winding != COH_NONZERO && winding != COH_EVENODD) FAIL("bad winding rule");
+  EdgeBox eb = edge_bounds(edges, n_edges);
+  int px0, py0, px1, py1; shape_pixel_box(eb, px0, py0, px1, py1);
+  EdgeRec* d_edges = nullptr;
+  if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
+  int rc = shapes_from_device_edges(ctx, d_edges, n_edges, winding, px0, py0, px1, py1, shape, minshape, "coh_shapeminshape_of_edgelist");
+  DFREE(d_edges);
+  return rc;
+}
+
+// dense AA opacity bytes over the bit-frame of `shp`, then gathered in span order
+static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges, int winding, const DevShape* s,
+                                 uint8_t** dense, int* wx0_out, int* nw_out) {
+  int wx0 = floordiv(s->bx0, 32) * 32, nw = (s->bx1 - wx0) / 32 + 1;
+  uint32_t* Q = nullptr;
+  if (bits_from_shape(ctx, s, s->y0, s->n_rows, wx0, nw, &Q)) return 1;
+  EdgeRec* d_edges = nullptr;
+  if (upload_edges(ctx, edges, n_edges, &d_edges)) return 1;
+  CK(DMALLOC(dense, (size_t)s->n_rows * nw * 32));
+  CK(cudaMemsetAsync(*dense, 0, (size_t)s->n_rows * nw * 32, ctx->stream));
+  dim3 g(cdiv(nw, 8), s->n_rows);
+  k_aa_rows<<<g, 256, 0, ctx->stream>>>(d_edges, n_edges, winding, Q, s->y0, s->n_rows, wx0, nw, ctx->d_aa, *dense, ctx->d_error); LAUNCHED();
+  int rc = check_error_flag(ctx, "coh_polygon_opacity");
+  DFREE(Q); DFREE(d_edges);
+  *wx0_out = wx0; *nw_out = nw;
+  return rc;
+}
+int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding, coh_shape_t shp,
+                        uint8_t* out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!shp) return 0;
+  DevShape* s = (DevShape*)shp;
+  if (s->card > cap) FAIL("coh_polygon_opacity: buffer too small");
+  uint8_t* dense = nullptr; int wx0, nw;
+  if (n_edges <= 0) { memset(out, 0, (size_t)s->card); *n_out = s->card; return 0; }  // empty scaled shape: coverage 0
+  if (polygon_opacity_dense(ctx, edges, n_edges, winding, s, &dense, &wx0, &nw)) return 1;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  std::vector<uint8_t> h((size_t)s->n_rows * nw * 32);
+  CK(cudaMemcpyAsync(h.data(), dense, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(dense);
+  int64_t k = 0;
+  for (int r = 0; r < s->n_rows; r++)
+    for (int q = ptr[r]; q < ptr[r + 1]; q++)
+      for (int i = 0; i < spans[q].y; i++) out[k++] = h[(size_t)r * nw * 32 + (spans[q].x + i - wx0)];
+  *n_out = k;
+  return 0;
+}
+int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edges, int32_t n_edges, int32_t winding,
+                       coh_shape_t shp, uint32_t* out, int64_t cap, int64_t* n_out) {
+  // polygon.ml:729-746: per span, colour = dissolve (fillsingle x_spanstart y) opacity.  The fill is
+  // evaluated by the same device routine as the walker through a one-object render of `shp`'s spans;
+  // here the opacity comes from the AA kernel and the (cheap, per-span) fill lookup runs on the host
+  // side of the ABI only for this export entry point.
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!shp) return 0;
+  DevShape* s = (DevShape*)shp;
+  if (s->card > cap) FAIL("coh_polygon_sprite: buffer too small");
+  std::vector<uint8_t> op((size_t)s->card);
+  int64_t n = 0;
+  if (coh_polygon_opacity(ctx, edges, n_edges, winding, shp, op.data(), s->card, &n)) return 1;
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  FillRec f; f.kind = fill->fill_kind; f.c0 = fill->colour0; f.c1 = fill->colour1; f.flags = fill->fill_flags;
+  for (int i = 0; i < 6; i++) f.p[i] = fill->fparam[i];
+  int64_t k = 0;
+  for (int r = 0; r < s->n_rows; r++)
+    for (int q = ptr[r]; q < ptr[r + 1]; q++) {
+      uint32_t c = fill_lookup(f, spans[q].x, s->y0 + r);
+      for (int i = 0; i < spans[q].y; i++, k++) out[k] = px_dissolve(c, op[k]);
+    }
+  *n_out = k;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Convolve (convolve.mli:28-40)
+// ---------------------------------------------------------------------------------------
+static int conv_taps(coh_ctx* ctx, int kind, int r, int** d_taps, int* total) {
+  *d_taps = nullptr; *total = 0;
+  if (kind != COH_CONV_GAUSSIAN) return 0;
+  std::vector<int> taps;
+  for (int i = -r; i <= r; i++) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+    double xr = (double)i / (double)r, yr = 0. / (double)r;
+    int v = (int)((double)(4 * r * r) * (exp(-(xr * xr + yr * yr)) / 2.) + 0.5);
+    taps.push_back(v); *total += v;
+  }
+  CK(DMALLOC(d_taps, sizeof(int) * taps.size()));
+  CK(cudaMemcpyAsync(*d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+static int shape_pixel_offsets(coh_ctx* ctx, const DevShape* s, std::vector<long long>& off) {
+  std::vector<int> ptr; std::vector<int2> spans;
+  if (download_shape(ctx, s, ptr, spans)) return 1;
+  off.assign(s->n_rows + 1, 0);
+  for (int r = 0; r < s->n_rows; r++) { long long n = 0; for (int q = ptr[r]; q < ptr[r + 1]; q++) n += spans[q].y; off[r + 1] = off[r] + n; }
+  return 0;
+}
+// Convolve.convolve_sprite kernel sprite (convolve.ml:239-258): the sprite is (shape, one RGBA8 per pixel in
+// span order); the result lives on bloat r r (shape) and is returned the same way.
+int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_t shape, const uint32_t* rgba_in,
+                        coh_shape_t* out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *out_shape = 0; *n_out = 0;
+  if ((kernel_kind != COH_CONV_UNIT && kernel_kind != COH_CONV_GAUSSIAN) || r <= 0) FAIL("Convolve.mkunit / Convolve.mkxy: Invalid_argument");
+  if (!shape) return 0;  // NullSprite -> NullSprite
+  DevShape* s = (DevShape*)shape;
+  coh_shape_t R = 0;
+  if (coh_shape_bloat(ctx, shape, r, r, &R)) return 1;
+  DevShape* rs = (DevShape*)R;
+  if (rs->card > cap) { coh_shape_free(ctx, R); FAIL("coh_convolve_sprite: buffer too small"); }
+  // canvas = bounding box grown by 2r (Sprite.flatten_sprite border, convolve.ml:247)
+  const int x0 = s->bx0 - 2 * r, y0 = s->by0 - 2 * r, w = s->bx1 - s->bx0 + 1 + 4 * r, h = s->by1 - s->by0 + 1 + 4 * r;
+  const size_t npx = (size_t)w * h;
+  uint32_t *A = nullptr, *X = nullptr, *d_in = nullptr, *d_out = nullptr; long long* d_off = nullptr; int* d_taps = nullptr; int total = 0;
+  std::vector<long long> off;
+  if (shape_pixel_offsets(ctx, s, off)) return 1;
+  CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx));
+  CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
+  CK(DMALLOC(&d_in, 4 * (size_t)std::max<long long>(s->card, 1))); CK(DMALLOC(&d_off, sizeof(long long) * off.size()));
+  CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_scatter_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, s->y0 - y0, x0, w, d_in, A); LAUNCHED();
+  if (conv_taps(ctx, kernel_kind, r, &d_taps, &total)) return 1;
+  dim3 gp(cdiv(w, 128), h);
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, r, kernel_kind, d_taps, total, 0); LAUNCHED();
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, A, w, h, r, kernel_kind, d_taps, total, 1); LAUNCHED();
+  // pick the result up on R (Sprite.pickup)
+  std::vector<long long> roff;
+  if (shape_pixel_offsets(ctx, rs, roff)) return 1;
+  long long* d_roff = nullptr;
+  CK(DMALLOC(&d_roff, sizeof(long long) * roff.size())); CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
+  CK(cudaMemcpyAsync(d_roff, roff.data(), sizeof(long long) * roff.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // k_gather_spans indexes dense rows from the shape's first row: pass the canvas rows starting at R's first row
+  k_gather_spans<uint32_t><<<cdiv(rs->n_rows, 128), 128, 0, ctx->stream>>>(rs->row_ptr, rs->spans, d_roff, rs->n_rows, x0, w, A + (size_t)(rs->y0 - y0) * w, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)rs->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(A); DFREE(X); DFREE(d_in); DFREE(d_out); DFREE(d_off); DFREE(d_roff); DFREE(d_taps);
+  *out_shape = R; *n_out = rs->card;
+  return 0;
+}

@@ -1,0 +1,390 @@
+// host_render.inl — part of coherence_b200.cu (one translation unit; included in order): render_pass (binning + walker launches), filter passes, coh_render_frame.
+
+// One walk over the leaves [l0, l1) of a scene: binning + k_walk.
+struct PassArgs {
+  int l0, l1;                 // leaf range (list order)
+  int ux, uy, uw, uh;         // update box (used when u_init is null)
+  const uint32_t* u_init;     // update set as a bit-frame, or null
+  uint32_t* u_out;            // receives `u` after the scene list, or null (may alias u_init)
+  uint32_t* fb;               // target canvas
+  bool write_clear, resume;
+};
+static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
+  Frame fr = ctx->fr;
+  const int ux = A.ux, uy = A.uy, uw = A.uw, uh = A.uh;
+  const bool write_clear = A.write_clear;
+  const int n_leaves = A.l1 - A.l0;
+  const int4* leaf_box = s->leaf_box + A.l0;
+  const int* leaves = s->leaves + A.l0;
+  if (fr.band_y1 <= fr.band_y0 || uw <= 0 || uh <= 0) return 0;
+  // only the cell rows the update box reaches (a dirty region is usually a small part of the frame)
+  const int ry0 = std::max(fr.band_y0, uy), ry1 = std::min(fr.band_y1, uy + uh);
+  if (ry1 <= ry0) return 0;
+  // ... and only the tile columns it reaches
+  fr.ctx0 = std::max(0, ux >> 5);
+  const int ctx1 = std::min(fr.tiles_x - 1, (int)(((long long)ux + uw - 1) >> 5));
+  if (ctx1 < fr.ctx0) return 0;
+  fr.cntx = ctx1 - fr.ctx0 + 1;
+  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves && ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x;
+  int cell_row0 = ry0 / CELL_H, cell_row1 = (ry1 - 1) / CELL_H;
+  if (A.u_out && A.u_out != A.u_init && !(ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x))
+    // rows and columns the walk does not visit have nothing uncovered
+    CK(cudaMemsetAsync(A.u_out + (size_t)fr.band_y0 * fr.tiles_x, 0, 4 * (size_t)(fr.band_y1 - fr.band_y0) * fr.tiles_x, ctx->stream));
+  int n_cells = (cell_row1 - cell_row0 + 1) * fr.cntx;
+  if (n_cells > ctx->n_cells_cap) {
+    DFREE(ctx->cell_order); DFREE(ctx->cell_head);
+    CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
+    DFREE(ctx->cell_rng);
+    CK(DMALLOC(&ctx->cell_rng, sizeof(int2) * n_cells));
+    CK(DMALLOC(&ctx->cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
+    ctx->n_cells_cap = n_cells;
+  }
+  if (!ctx->queue) {
+    CK(DMALLOC(&ctx->order_hist, sizeof(int) * (2 * ORDER_BINS + 1)));  // histogram, cursors, work-queue head
+    ctx->queue = ctx->order_hist + 2 * ORDER_BINS;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->n_sms = prop.multiProcessorCount;
+  }
+  const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
+  CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * (2 * ORDER_BINS + 1), ctx->stream));
+  if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
+  // K1: count, scan, fill.  Small scenes: warp per cell scanning all leaves (lists come out sorted,
+  // no atomics).  Large scenes: warp per leaf over the cells it covers + per-cell sort.
+  const bool big = n_leaves > 1024;
+  // capacity of the item pool: the exact total is a pure function of the object boxes and the
+  // frame geometry, so it is computed on the host (once per scene and geometry) — no device
+  // round trip inside a frame.
+  size_t total = 0;
+  if (!whole || s->items_for_W != fr.W || s->items_for_H != fr.H || s->items_for_y0 != fr.band_y0 || s->items_for_y1 != fr.band_y1) {
+    size_t tot = 0;
+    for (int li = A.l0; li < A.l1; li++) {
+      const ObjRec& o = s->h_objs[s->h_leaves[li]];
+      int cx0 = std::max(o.bx0 >> 5, fr.ctx0), cx1 = std::min(o.bx1 >> 5, ctx1);
+      int cy0 = std::max(floordiv(o.by0, CELL_H), cell_row0), cy1 = std::min(floordiv(o.by1, CELL_H), cell_row1);
+      if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+    }
+    total = tot;
+    if (whole) { s->coarse_total_valid = false; s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
+  } else total = s->items_total;
+  const size_t need = total;
+  if (need > ctx->cell_items_cap) {
+    DFREE(ctx->cell_items); DFREE(ctx->item_cell);
+    size_t cap = need + need / 2 + 1024;
+    CK(DMALLOC(&ctx->cell_items, sizeof(int) * cap));
+    CK(DMALLOC(&ctx->item_cell, sizeof(int) * cap));
+    ctx->cell_items_cap = cap;
+  }
+  if (!big) {
+    // one pass: hit masks in registers, lists carved from one cursor, length classes instead of a sort
+    const int bin_blocks = cdiv(n_cells * 32, 256);
+    BinPrefill pf; memset(&pf, 0, sizeof pf);
+    // (not with peer framebuffers: the mirrored stores of background cells are better spread over the walker's
+    // warps — measured at 2 / 4 / 8 GPUs)
+    if (ordered && !A.u_init && !A.resume && !(A.fb == ctx->fb && ctx->n_peers > 0)) {
+      pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1;
+      pf.n_peers = 0;
+    }
+    k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_rng, ctx->cell_items, ctx->order_hist,
+                                               ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell, pf); LAUNCHED();
+  } else {
+    // two levels: leaves into coarse cells (object-parallel, sorted per coarse list), then every fine cell from its coarse list
+    const int ctx_x = cdiv(fr.tiles_x, COARSE), crow0 = cell_row0 >> COARSE_SHIFT, crow1 = cell_row1 >> COARSE_SHIFT;
+    const int n_coarse = ctx_x * (crow1 - crow0 + 1);
+    size_t ctot = 0;
+    if (whole && s->coarse_total_valid) ctot = s->coarse_total;   // a pure function of the boxes and the frame geometry, like items_total
+    else {
+      for (int li = A.l0; li < A.l1; li++) {
+        const ObjRec& o = s->h_objs[s->h_leaves[li]];
+        int cx0 = std::max(floordiv(o.bx0, 32 * COARSE), 0), cx1 = std::min(floordiv(o.bx1, 32 * COARSE), ctx_x - 1);
+        int cy0 = std::max(floordiv(o.by0, CELL_H * COARSE), crow0), cy1 = std::min(floordiv(o.by1, CELL_H * COARSE), crow1);
+        if (cx1 >= cx0 && cy1 >= cy0) ctot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+      }
+      if (whole) { s->coarse_total = ctot; s->coarse_total_valid = true; }
+    }
+    if (2 * ctot + 1 > ctx->coarse_cap || (size_t)n_coarse + 1 > ctx->coarse_cells_cap) {
+      DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
+      ctx->coarse_cap = 2 * ctot + ctot / 2 + 1024; ctx->coarse_cells_cap = (size_t)n_coarse + 1;
+      CK(DMALLOC(&ctx->coarse_items, sizeof(int) * ctx->coarse_cap));
+      CK(DMALLOC(&ctx->coarse_counts, sizeof(int) * ctx->coarse_cells_cap));
+      CK(DMALLOC(&ctx->coarse_off, sizeof(int) * (ctx->coarse_cells_cap + 1)));
+    }
+    const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
+    CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
+    k_bin_obj<false><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, n_leaves, ctx_x, crow0, crow1, ctx->coarse_counts, nullptr, nullptr); LAUNCHED();
+    if (exclusive_scan(ctx, ctx->coarse_counts, ctx->coarse_off, n_coarse, nullptr)) return 1;
+    CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
+    k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, n_leaves, ctx_x, crow0, crow1, ctx->coarse_counts, ctx->coarse_off, ctx->coarse_items); LAUNCHED();
+    k_bin_sort<<<cdiv(n_coarse * 32, 128), 128, 0, ctx->stream>>>(ctx->coarse_off, ctx->coarse_items, ctx->coarse_items + ctot, n_coarse); LAUNCHED();
+    k_bin2<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(leaf_box, leaves, ctx->coarse_off, ctx->coarse_items, ctx_x, crow0, fr, cell_row0, n_cells, ctx->cell_rng,
+                                                          ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+  }
+  WalkParams P;
+  P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
+  P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
+  P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
+  P.cell_rng = ctx->cell_rng;
+  P.cls_cells = ordered ? ctx->cell_order : nullptr; P.cls_cnt = ordered ? ctx->order_hist + 1 : nullptr;
+  P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
+  P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
+  P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
+  P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
+  P.n_peers = (A.fb == ctx->fb) ? ctx->n_peers : 0;   // only the frame itself is mirrored, not filter canvases
+  for (int k = 0; k < COH_MAX_PEERS; k++) P.peer_fb[k] = k < P.n_peers ? ctx->peer_fb[k] : nullptr;
+  // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
+  int walk_h = big ? 16 : 4;
+  // Few cells (a band of an 8-GPU split, a small dirty region): the launch is bounded by its longest work item,
+  // not by throughput — one-row items shorten that path (measured on the lion at 8 GPUs: 0.164 -> 0.141 ms;
+  // at 1 to 4 GPUs four-row items are as fast or faster).
+  if (!big && (long long)n_cells * 4 < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 1;
+  if (const char* e = getenv("COH_WALK_H")) { int v = atoi(e); if (v == 1 || v == 4 || v == 16) walk_h = v; }  // tests force every variant
+  const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
+#define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
+  do {                                                                                                             \
+    if (walk_h == 4) k_walk<CARRYV, EX, 4><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                         \
+    else if (walk_h == 1) k_walk<CARRYV, EX, 1><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                    \
+    else k_walk<CARRYV, EX, 16><<<grid, WALK_WARPS * 32, 0, ctx->stream>>>(P);                                    \
+    LAUNCHED();                                                                                                    \
+  } while (0)
+#define LAUNCH_WALK(CARRYV)                                                                                        \
+  do {                                                                                                             \
+    if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
+  } while (0)
+  P.queue = ctx->queue; P.n_cells = n_cells;
+  P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
+  // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
+  // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
+  const char* force = getenv("COH_FUSED");   // tests force either path: "1" fused, "0" three-phase
+  const bool pre = s->extras == 0 && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+                   (force ? force[0] == '0' : walk_h != 1);
+  if (pre) {
+    const size_t n_pairs = total * CELL_H;
+    if (n_pairs > ctx->pre_cap) {
+      DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_op);
+      const size_t cap = n_pairs + n_pairs / 4 + 1024;
+      CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap));
+      CK(DMALLOC(&ctx->pre_list, sizeof(int4) * cap)); CK(DMALLOC(&ctx->pre_op, 32 * cap));
+      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, sizeof(int)));
+      ctx->pre_cap = cap;
+    }
+    P.item_cell = ctx->item_cell;
+    CK(cudaMemsetAsync(ctx->pre_n, 0, sizeof(int), ctx->stream));
+    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc); LAUNCHED();
+    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n); LAUNCHED();
+    k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
+    P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
+    const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
+    if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
+      size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
+      if (slots > ctx->carry_slots) {
+        DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+        CK(DMALLOC(&ctx->carry_done, sizeof(int) * slots));
+        CK(DMALLOC(&ctx->carry_cnt, sizeof(int) * slots));
+        CK(DMALLOC(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
+        CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
+        ctx->carry_slots = slots;
+      }
+      P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
+      P.epoch = ++ctx->epoch;
+      k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+    } else {
+      k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+    }
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
+    return 0;
+  }
+  P.carry_done = nullptr; P.carry_cnt = nullptr; P.carry_ent = nullptr; P.epoch = 0;
+  if (s->has_fancy) {
+    size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
+    if (slots > ctx->carry_slots) {
+      DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+      CK(DMALLOC(&ctx->carry_done, sizeof(int) * slots));
+      CK(DMALLOC(&ctx->carry_cnt, sizeof(int) * slots));
+      CK(DMALLOC(&ctx->carry_ent, sizeof(int2) * slots * CARRY_CAP));
+      CK(cudaMemsetAsync(ctx->carry_done, 0, sizeof(int) * slots, ctx->stream));
+      ctx->carry_slots = slots;
+    }
+    P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
+    P.epoch = ++ctx->epoch;
+    LAUNCH_WALK(true);
+  } else {
+    LAUNCH_WALK(false);
+  }
+  if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Frames with filter objects (render.ml:1080-1131, 1248-1265; filters.ml).  A filter splits the
+// scene list: the members in front of it are walked as usual; the filter itself renders its
+// reading scene (X) and the members below it (Z) into canvases of their own — each a recursive
+// render of the rest of the list, as in the reference — filters X, and blends the two by the
+// antialiased matte of its geometry into the accumulator; its whole shape then leaves `u`
+// (the "extra finish", render.ml:1120-1121, 1308) and the walk continues below it, the
+// accumulator carrying on from the framebuffer (WalkParams::resume).
+// ---------------------------------------------------------------------------------------
+struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed = false);
+
+// `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small and handled
+// whole; the RGBA8 canvases are only touched in the rows the filter reads or writes).
+static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target, PixBox box) {
+  const DevScene::FilterRec& F = s->filters[fi];
+  const Frame& fr = ctx->fr;
+  const int W = fr.W, H = fr.H, nw = fr.tiles_x;
+  const size_t nwords = (size_t)nw * H;
+  // rows / columns of shptorender = shape(geometry) ∩ u
+  const int y0 = std::max(std::max(F.by0, 0), box.y0), y1 = std::min(std::min(F.by1, H - 1), box.y1);
+  const int x0 = std::max(std::max(F.bx0, 0), box.x0), x1 = std::min(std::min(F.bx1, W - 1), box.x1);
+  if (y0 > y1 || x0 > x1) return 0;  // the geometry cannot meet u: nothing to render, nothing leaves u
+  const int h = y1 - y0 + 1;
+  const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : 0;             // reach of the reading shape
+  const int ry0 = std::max(0, y0 - m), ry1 = std::min(H - 1, y1 + m), rh = ry1 - ry0 + 1;
+  const PixBox tbox{x0, y0, x1, y1}, rbox{std::max(0, x0 - m), ry0, std::min(W - 1, x1 + m), ry1};
+  const unsigned wblocks = (unsigned)((nwords + 255) / 256);
+  const size_t po = (size_t)ry0 * W, pn = (size_t)rh * W;                 // canvas rows [ry0, ry1]
+  uint32_t *SG = nullptr, *CG = nullptr, *T = nullptr, *R = nullptr, *X = nullptr, *Z = nullptr, *tmp = nullptr;
+  uint8_t *op = nullptr, *alpha = nullptr; int* d_taps = nullptr;
+  CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&CG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
+  CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(CG, 0, 4 * nwords, ctx->stream));
+  const EdgeRec* ed = s->edges + F.first;
+  // shape of the geometry (render.ml:472-474); CG receives the coverage (the minshape is needed for the matte)
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, CG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, U, T, nwords, 2); LAUNCHED();     // shptorender = r &&& u (render.ml:1281)
+  // reading scene -> X -> filter function -> Y (in place)
+  uint32_t* Y = nullptr;
+  if (F.kind != COH_FILTER_HOLE) {
+    CK(DMALLOC(&X, 4 * (size_t)W * H));
+    CK(cudaMemsetAsync(X + po, 0, 4 * pn, ctx->stream));
+    if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp
+      CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
+      k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED();  // T is empty outside [y0, y1]
+    } else CK(cudaMemcpyAsync(R, T, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (F.kind == COH_FILTER_SCENE) {
+      PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
+      if (render_pass(ctx, s, A)) return 1;
+    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox, true)) return 1;
+    Y = X;
+    if (F.kind == COH_FILTER_MONOCHROME) {
+      k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED();
+    } else if (F.kind == COH_FILTER_BLUR) {
+      // Convolve.convolve_sprite_in_shape (convolve.ml:265-296) on the canvas rows [ry0, ry1]: pixels the
+      // reading scene did not render are clear, exactly like the reference's canvas outside the sprite
+      std::vector<int> taps; int total = 0;
+      if (F.kernel_kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+        for (int i = -F.r; i <= F.r; i++) {
+          double xr = (double)i / (double)F.r, yr = 0. / (double)F.r;
+          double gg = exp(-(xr * xr + yr * yr)) / 2.;
+          int v = (int)((double)(4 * F.r * F.r) * gg + 0.5);
+          taps.push_back(v); total += v;
+        }
+        CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
+        CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // `taps` is a local
+      }
+      CK(DMALLOC(&tmp, 4 * pn));
+      dim3 gp(cdiv(W, 128), rh);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X + po, tmp, W, rh, F.r, F.kernel_kind, d_taps, total, 0); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X + po, W, rh, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
+    }
+  }
+  // The geometry's matte in the update (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is
+  // given, but a pixel whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its
+  // 2 x 2-pixel sampling window (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge
+  // pieces), so all 32 x 32 samples are inside and the opacity is 255: only the rest is super-sampled.
+  CK(DMALLOC(&op, (size_t)nw * 32 * h)); CK(DMALLOC(&alpha, (size_t)W * h));
+  {
+    uint32_t* I = nullptr;   // interior = erode 2 2 minshape, clipped 2 pixels inside the rows / columns scanned here
+    CK(DMALLOC(&I, 4 * nwords));
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, CG, CG, nwords, 1); LAUNCHED();          // CG := minshape = shape - coverage
+    k_fill_words<<<wblocks, 256, 0, ctx->stream>>>(I, nwords, 0xFFFFFFFFu); LAUNCHED();
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, CG, I, nwords, 1); LAUNCHED();            // everything but the minshape
+    {  // rows y0 .. y1 only (everything outside is "not minshape" and the box mask below cuts 2 rows off each end)
+      k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(I + (size_t)y0 * nw, R + (size_t)y0 * nw, h, nw, 2, 2); LAUNCHED();
+    }
+    k_fill_box_bits<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(I, H, nw, 0, 0, 2, y0 + 2, W - 3, y1 - 2); LAUNCHED();
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, R, I, nwords, 1); LAUNCHED();             // interior
+    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, I, I, nwords, 1); LAUNCHED();             // to be super-sampled: T - interior
+    CK(cudaMemsetAsync(op, 255, (size_t)nw * 32 * h, ctx->stream));
+    k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, I + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+    DFREE(I);
+  }
+  CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
+  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, op, F.colour, W, h, nw, alpha, R + (size_t)y0 * nw); LAUNCHED();  // R := finished
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, R, R, nwords, 1); LAUNCHED();      // pixels_for_normal_scene (render.ml:1105)
+  CK(DMALLOC(&Z, 4 * (size_t)W * H));
+  CK(cudaMemsetAsync(Z + (size_t)y0 * W, 0, 4 * (size_t)h * W, ctx->stream));
+  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox, true)) return 1;
+  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw); LAUNCHED();
+  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(U, SG, U, nwords, 1); LAUNCHED();     // u --- ef (render.ml:1308)
+  DFREE(SG); DFREE(CG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
+  return 0;
+}
+// Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)
+static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed) {
+  const Frame& fr = ctx->fr;
+  if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
+  auto segment = [&](int a, int b) -> int {
+    if (b > a) {
+      PassArgs A{a, b, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U, U, target, fresh, !fresh};
+      if (render_pass(ctx, s, A)) return 1;
+    } else if (fresh && !target_zeroed) {
+      const int hh = box.y1 - box.y0 + 1;
+      k_clear_in_bits<<<dim3(cdiv(fr.W, 128), hh), 128, 0, ctx->stream>>>(target + (size_t)box.y0 * fr.W, U + (size_t)box.y0 * fr.tiles_x, fr.W, hh, fr.tiles_x); LAUNCHED();
+    }
+    fresh = false;
+    return 0;
+  };
+  for (int f = f0; f < (int)s->filters.size(); f++) {
+    if (segment(l0, s->filters[f].pos)) return 1;
+    if (apply_filter(ctx, s, f, U, target, box)) return 1;
+    l0 = s->filters[f].pos;
+  }
+  return segment(l0, s->n_scene_leaves);
+}
+static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, int ux, int uy, int uw, int uh) {
+  const Frame& fr = ctx->fr;
+  if (fr.band_y0 != 0 || fr.band_y1 != fr.H) FAIL("render_frame: scenes with filter objects need the whole frame on one context (filters read outside their band)");
+  if (uw <= 0 || uh <= 0) return 0;
+  const PixBox box{std::max(ux, 0), std::max(uy, 0), std::min(ux + uw - 1, fr.W - 1), std::min(uy + uh - 1, fr.H - 1)};
+  if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
+  const int nw = fr.tiles_x;
+  const size_t nwords = (size_t)nw * fr.H;
+  uint32_t *U = ctx->u_out, *U0 = nullptr;
+  CK(DMALLOC(&U0, 4 * nwords));
+  if (u_init) CK(cudaMemcpyAsync(U0, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
+  CK(cudaMemcpyAsync(U, U0, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true, box)) return 1;
+  if (s->n_leaves > s->n_front_leaves) {
+    // the background list shows wherever the scene pass is not opaque (render.ml:1363-1365)
+    k_not_opaque_bits<<<dim3(cdiv(nw, 4), fr.H), 128, 0, ctx->stream>>>(ctx->fb, U0, U0, fr.W, fr.H, nw); LAUNCHED();
+    PassArgs A{s->n_front_leaves, s->n_leaves, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U0, nullptr, ctx->fb, false, true};
+    if (render_pass(ctx, s, A)) return 1;
+  }
+  DFREE(U0);
+  return 0;  // kernel-side failures are reported by coh_sync, as for plain frames
+}
+
+// Merge the objects of `scene` and `background` into one walk: the reference renders the two
+// lists separately over the same update and composites the results with `over`
+// (render.ml:1357-1365); a pixel of the background is only visible where the scene pass left
+// `u`, so one front-to-back walk over [Group scene; Group background] gives the same pixels.
+int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh, int32_t flags) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fb) FAIL("coh_render_frame: call coh_fb_configure first");
+  if (uw < 0 || uh < 0) FAIL("Sprite.box: negative argument.");
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_render_frame: null scene");
+  bool record_u = (flags & COH_RENDER_RECORD_U) != 0;
+  if (!s->filters.empty()) {
+    if (render_filtered(ctx, s, nullptr, ux, uy, uw, uh)) return 1;
+    ctx->have_u = true;
+    return 0;
+  }
+  PassArgs A{0, s->n_leaves, ux, uy, uw, uh, nullptr, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
+  if (render_pass(ctx, s, A)) return 1;
+  ctx->have_u = record_u;
+  return 0;
+}

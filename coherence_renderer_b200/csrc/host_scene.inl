@@ -1,0 +1,394 @@
+// host_scene.inl — part of coherence_b200.cu (one translation unit; included in order): scene creation (flattened renderobject list -> device records, K1 edge binning, Convolved pre-pass) and the framebuffer.
+
+// ---------------------------------------------------------------------------------------
+// Scenes and rendering
+// ---------------------------------------------------------------------------------------
+int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
+  CK(cudaSetDevice(ctx->device));
+  DevScene* s = (DevScene*)h;
+  if (!s) return 0;
+  DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
+  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px);
+  for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
+  delete s;
+  return 0;
+}
+
+// brush.ml:60-92: alpha of the Gaussian stamp of white at `opacity`.
+static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out) {
+  int intopacity = (int)(opacity * 255.), intr = (int)ceil(radius);
+  int size = 2 * intr + 1;
+  r_out = intr;
+  size_t base = out.size();
+  out.resize(base + (size_t)size * size);
+  uint32_t white = 0xFFFFFFFFu;
+  uint32_t c1 = px_dissolve(white, intopacity);
+  for (int y = 0; y < size; y++)
+    for (int x = 0; x < size; x++) {
+      double xp = (double)(x - intr), yp = (double)(y - intr), rr = radius / 2.;
+      double v = 255. * exp(-((xp / rr) * (xp / rr) + (yp / rr) * (yp / rr)));
+      int vi = (int)(v * 1.);
+      out[base + (size_t)y * size + x] = (uint8_t)(px_dissolve(c1, vi) >> 24);
+    }
+}
+
+int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32_t n_background, const int32_t* edges,
+                     int32_t n_edges, const int32_t* points, int32_t n_points, coh_scene_t* out) {
+  CK(cudaSetDevice(ctx->device));
+  *out = 0;
+  if (n_objs < 0 || n_background < 0 || n_background > n_objs) FAIL("scene: bad object counts");
+  // The scene list and the (pages @ background) list are each wrapped in an implicit root group:
+  // render_frame renders them separately over the same update and composites the two results
+  // with `over` (render.ml:1357-1365), which is exactly what two sibling groups do in one walk.
+  std::vector<ObjRec> recs;
+  std::vector<int> leaves;
+  std::vector<uint8_t> stamps;
+  std::vector<int> open;  // indices (into recs) of open groups
+  std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
+  std::vector<int> point_obj((size_t)std::max(n_points, 1), -1);  // owning brush object of every point
+  struct ConvItem { int rec, kind, r; };
+  std::vector<ConvItem> conv_list;
+  size_t conv_words = 0, conv_pixels = 0;
+  long long total_rows = 0, total_brush_rows = 0;
+  ObjRec root; memset(&root, 0, sizeof root);
+  root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
+  recs.push_back(root); open.push_back(0);
+  std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
+  std::vector<int> group_last;
+  std::vector<int64_t> ids;
+  // filters and their reading-scene groups (include/coherence_b200.h, COH_FILTER_*)
+  std::vector<DevScene::FilterRec> filters;
+  std::vector<int> filter_read_abi;            // per filter: abi index of its reading-scene group, or -1
+  std::map<int, std::pair<int, int>> reading;  // abi index of a reading-scene GROUP_BEGIN -> leaf range
+  std::vector<int> open_reading;               // per open GROUP_BEGIN: abi index if it is a reading-scene group, else -1
+  int cur_reading = -1, n_scene_leaves = -1, n_front_leaves = -1;
+  for (int i = 0; i < n_objs; i++) {
+    if (i == n_objs - n_background) {
+      if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
+      if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+      n_front_leaves = (int)leaves.size();
+      root.flags = OF_ROOT_BACKGROUND;
+      recs.push_back(root); open[0] = (int)recs.size() - 1;
+    }
+    const coh_object& c = objs[i];
+    if (c.kind == COH_OBJ_GROUP_END) {
+      if (open_reading.empty()) FAIL("scene: GROUP_END without GROUP_BEGIN");
+      const int rd = open_reading.back(); open_reading.pop_back();
+      if (rd >= 0) { reading[rd].second = (int)leaves.size(); cur_reading = -1; continue; }
+      if (open.size() <= 1) FAIL("scene: GROUP_END without GROUP_BEGIN");
+      group_last.resize(recs.size(), -1);
+      group_last[open.back()] = (int)recs.size() - 1;
+      open.pop_back();
+      continue;
+    }
+    if (c.kind == COH_OBJ_GROUP_BEGIN && c.filter_kind == COH_FILTER_READING_SCENE) {
+      // members become direct members of the root list of their own pass (render.ml:1091 renders the list)
+      if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: reading-scene groups must be top-level members of the scene list");
+      if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+      open_reading.push_back(i); cur_reading = i;
+      reading[i] = std::make_pair((int)leaves.size(), (int)leaves.size());
+      continue;
+    }
+    if (n_scene_leaves >= 0 && cur_reading < 0 && i < n_objs - n_background) FAIL("scene: reading-scene groups must come after every ordinary scene object");
+    if (c.kind == COH_OBJ_FILTER) {
+      if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: filter objects must be top-level members of the scene list");
+      if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+      if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
+      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SCENE) FAIL("scene: bad filter kind");
+      if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
+      if (c.dx || c.dy) FAIL("scene: translated filter objects are not supported yet");
+      DevScene::FilterRec f; memset(&f, 0, sizeof f);
+      f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
+      if (c.filter_kind == COH_FILTER_BLUR) {
+        f.kernel_kind = c.filter_kernel & 255; f.r = c.filter_kernel >> 8;
+        if ((f.kernel_kind != COH_CONV_UNIT && f.kernel_kind != COH_CONV_GAUSSIAN) || f.r <= 0 || f.r > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
+      }
+      if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
+      EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+      shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
+      filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
+      continue;
+    }
+    ObjRec o; memset(&o, 0, sizeof o);
+    o.pretrans = c.pretrans; o.dx = c.dx; o.dy = c.dy;
+    if (c.pretrans < -1 || c.pretrans > 255) FAIL("scene: pretrans out of range");
+    o.depth = (int)open.size();
+    if (o.depth > MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
+    for (int d = 0; d < o.depth; d++) o.anc[d] = open[d];
+    o.fill.kind = c.fill_kind; o.fill.c0 = c.colour0; o.fill.c1 = c.colour1; o.fill.flags = c.fill_flags;
+    for (int k = 0; k < 6; k++) o.fill.p[k] = c.fparam[k];
+    switch (c.kind) {
+      case COH_OBJ_GROUP_BEGIN:
+        o.kind = K_GROUP;
+        if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
+        recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
+        rec_of_abi[i] = (int)recs.size() - 1;
+        ids.resize(recs.size(), -1); ids.back() = c.id;
+        continue;
+      case COH_OBJ_PATH: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
+        if (c.sprite_winding < 0 || c.sprite_winding > 2) FAIL("scene: bad sprite winding rule");
+        o.kind = K_PATH; o.winding = c.winding; o.aa_winding = c.sprite_winding ? c.sprite_winding - 1 : c.winding;
+        o.first = c.first; o.count = c.count;
+        if (c.count == 0) continue;  // NullShape: nothing to draw
+        if (c.convolve) {
+          const int ck = c.convolve & 255, cr = c.convolve >> 8;
+          if ((ck != COH_CONV_UNIT && ck != COH_CONV_GAUSSIAN) || cr <= 0 || cr > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");  // convolve.ml:37-51 Invalid_argument
+          if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: Convolved objects with fancy fills are not supported yet");
+          o.kind = K_CONV;
+          conv_list.push_back({(int)recs.size(), ck, cr});
+        }
+        EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+        shape_pixel_box(eb, o.bx0, o.by0, o.bx1, o.by1);
+        if (o.kind == K_CONV) {  // the convolved object reaches r pixels further; its canvas another r (X-pass inputs)
+          const int cr = c.convolve >> 8;
+          o.cv_x0 = floordiv(o.bx0 - 2 * cr, 32) * 32; o.cv_y0 = o.by0 - 2 * cr;
+          o.cv_nw = (o.bx1 + 2 * cr - o.cv_x0) / 32 + 1; o.cv_h = o.by1 + 2 * cr - o.cv_y0 + 1;
+          o.bx0 -= cr; o.bx1 += cr; o.by0 -= cr; o.by1 += cr;
+          o.cv_bits = (int)conv_words; conv_words += 2 * (size_t)o.cv_nw * o.cv_h;
+          o.cv_px = (int)conv_pixels; conv_pixels += (size_t)o.cv_nw * 32 * o.cv_h;
+          if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull) FAIL("scene: Convolved canvases too large");
+        }
+        // rows with a candidate edge list: extended band [32y-67, 32y+16] meets [ymin, ymax]
+        o.ry0 = floordiv(eb.ymin - 16 + 31, 32); o.ry1 = floordiv(eb.ymax + 67, 32);
+        if (total_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
+        o.row_base = (int)total_rows; total_rows += o.ry1 - o.ry0 + 1;
+        for (int k = 0; k < c.count; k++) {
+          if (edge_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share edges");
+          edge_obj[(size_t)c.first + k] = (int)recs.size();
+        }
+        break;
+      }
+      case COH_OBJ_CPG: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.first2 < 0 || c.count2 < 0 || (int64_t)c.first2 + c.count2 > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.first2 < c.first + c.count) FAIL("scene: CPG operand b's edges must follow operand a's");
+        if ((c.winding != COH_NONZERO && c.winding != COH_EVENODD) || (c.winding2 != COH_NONZERO && c.winding2 != COH_EVENODD)) FAIL("scene: bad winding rule");
+        if (c.cpg_op < COH_CPG_UNION || c.cpg_op > COH_CPG_EXCLUSIVEOR) FAIL("scene: bad CPG operator");
+        if (c.convolve) FAIL("scene: Convolved CPG objects are not supported yet");
+        o.kind = K_CPG; o.winding = o.aa_winding = c.winding;
+        o.first = c.first; o.count = c.count; o.b_first = c.first2; o.b_count = c.count2; o.b_opw = c.cpg_op | (c.winding2 << 8);
+        o.bx0 = o.by0 = INT32_MAX; o.bx1 = o.by1 = INT32_MIN;
+        o.ry0 = o.b_ry0 = 0; o.ry1 = o.b_ry1 = -1;   // operands without edges have no rows
+        for (int side = 0; side < 2; side++) {
+          const int f = side ? c.first2 : c.first, n = side ? c.count2 : c.count;
+          if (n == 0) continue;
+          EdgeBox eb = edge_bounds(edges + 4 * (size_t)f, n);
+          int x0, y0, x1, y1;
+          shape_pixel_box(eb, x0, y0, x1, y1);
+          o.bx0 = std::min(o.bx0, x0); o.by0 = std::min(o.by0, y0); o.bx1 = std::max(o.bx1, x1); o.by1 = std::max(o.by1, y1);
+          const int r0 = floordiv(eb.ymin - 16 + 31, 32), r1 = floordiv(eb.ymax + 67, 32);
+          if (total_rows + (r1 - r0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
+          if (side) { o.b_ry0 = r0; o.b_ry1 = r1; o.b_row_base = (int)total_rows; } else { o.ry0 = r0; o.ry1 = r1; o.row_base = (int)total_rows; }
+          total_rows += r1 - r0 + 1;
+          for (int k = 0; k < n; k++) {
+            if (edge_obj[(size_t)f + k] != -1) FAIL("scene: objects may not share edges");
+            edge_obj[(size_t)f + k] = (int)recs.size();
+          }
+        }
+        if (o.bx0 > o.bx1) continue;  // both operands null
+        break;
+      }
+      case COH_OBJ_PRIMITIVE:
+        o.kind = K_PRIM; o.fill.kind = 0;
+        if (c.prim_null) continue;
+        for (int k = 0; k < 4; k++) o.prim[k] = c.prim[k];
+        if (c.prim[2] < c.prim[0] || c.prim[3] < c.prim[1]) FAIL("scene: primitive with negative extent");
+        o.bx0 = c.prim[0]; o.by0 = c.prim[1]; o.bx1 = c.prim[2]; o.by1 = c.prim[3];
+        break;
+      case COH_OBJ_BRUSH: {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_points) FAIL("scene: point range out of bounds");
+        if (!(c.brush_radius >= 0.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range");
+        o.kind = K_BRUSH; o.first = c.first; o.count = c.count;
+        if (c.count == 0) continue;
+        o.stamp_off = (int)stamps.size();
+        brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r);
+        int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+        for (int k = 0; k < c.count; k++) {
+          int px = points[2 * ((size_t)c.first + k)], py = points[2 * ((size_t)c.first + k) + 1];
+          x0 = std::min(x0, px); x1 = std::max(x1, px); y0 = std::min(y0, py); y1 = std::max(y1, py);
+        }
+        o.bx0 = x0 - o.brush_r; o.bx1 = x1 + o.brush_r; o.by0 = y0 - o.brush_r; o.by1 = y1 + o.brush_r;
+        o.ry0 = o.by0; o.ry1 = o.by1;   // object-frame rows (the alias offset is added to the box below)
+        o.bc_x0 = floordiv(o.bx0, 32); o.bc_y0 = floordiv(o.by0, CELL_H);
+        o.bc_nx = floordiv(o.bx1, 32) - o.bc_x0 + 1; o.bc_ny = floordiv(o.by1, CELL_H) - o.bc_y0 + 1;
+        if (total_brush_rows + (long long)o.bc_nx * o.bc_ny > 0x7FFFFFF0LL) FAIL("scene: too many brush cells");
+        o.bc_base = (int)total_brush_rows; total_brush_rows += (long long)o.bc_nx * o.bc_ny;
+        for (int k = 0; k < c.count; k++) {
+          if (point_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share brush points");
+          point_obj[(size_t)c.first + k] = (int)recs.size();
+        }
+        break;
+      }
+      default: FAIL("scene: unknown object kind");
+    }
+    o.bx0 += o.dx; o.bx1 += o.dx; o.by0 += o.dy; o.by1 += o.dy;
+    if ((o.kind == K_PATH || o.kind == K_PRIM) && o.fill.kind == 0 && (o.fill.c0 >> 24) == 255u && o.pretrans < 0) {
+      bool clear_path = true;
+      for (int d = 0; d < o.depth; d++) clear_path = clear_path && recs[o.anc[d]].pretrans < 0;
+      if (clear_path) o.flags |= OF_OCCLUDES;
+    }
+    recs.push_back(o);
+    rec_of_abi[i] = (int)recs.size() - 1;
+    ids.resize(recs.size(), -1); ids.back() = c.id;
+    leaves.push_back((int)recs.size() - 1);
+  }
+  if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
+  if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
+  if (n_front_leaves < 0) n_front_leaves = (int)leaves.size();
+  for (size_t k = 0; k < filters.size(); k++) {
+    if (filter_read_abi[k] < 0) continue;
+    auto it = reading.find(filter_read_abi[k]);
+    if (it == reading.end()) FAIL("scene: filter without its reading-scene group");
+    filters[k].read0 = it->second.first; filters[k].read1 = it->second.second;
+  }
+  DevScene* s = new DevScene();
+  s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves; s->h_leaves = leaves;
+  s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
+  s->h_objs = recs;
+  group_last.resize(recs.size(), -1);
+  ids.resize(recs.size(), -1);
+  s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
+  s->group_off.assign(recs.size(), make_int2(0, 0));
+  for (const ObjRec& o : recs) {
+    if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
+    if (o.kind == K_BRUSH || o.kind == K_CONV) s->extras = std::max(s->extras, 1);
+    if (o.kind == K_CPG || !filters.empty()) s->extras = 2;  // the filter passes need the walker variant that can continue a frame
+  }
+  CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
+  CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(DMALLOC(&s->leaves, sizeof(int) * std::max<size_t>(leaves.size(), 1)));
+  if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaves, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int4> boxes(leaves.size());
+  for (size_t i = 0; i < leaves.size(); i++) { const ObjRec& o = recs[leaves[i]]; boxes[i] = make_int4(o.bx0, o.by0, o.bx1, o.by1); }
+  CK(DMALLOC(&s->leaf_box, sizeof(int4) * std::max<size_t>(leaves.size(), 1)));
+  if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaf_box, boxes.data(), sizeof(int4) * boxes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
+  CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
+  if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
+  CK(DMALLOC(&s->stamps, std::max<size_t>(stamps.size(), 1)));
+  if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // K1 edge binning: count -> scan -> fill
+  {
+    int* d_edge_obj = nullptr; int* d_counts = nullptr;
+    size_t slots = (size_t)std::max<long long>(total_rows, 1);
+    CK(DMALLOC(&d_edge_obj, sizeof(int) * edge_obj.size()));
+    CK(cudaMemcpyAsync(d_edge_obj, edge_obj.data(), sizeof(int) * edge_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(DMALLOC(&d_counts, sizeof(int) * slots));
+    CK(DMALLOC(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
+    if (n_edges > 0) { k_rowedges<false><<<cdiv(n_edges * 32, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, nullptr, nullptr); LAUNCHED(); }
+    if (exclusive_scan(ctx, d_counts, s->rowedge_ptr, (int)slots, nullptr)) return 1;
+    // size of the lists: the same row range per edge as k_rowedges, summed on the host (no device round trip:
+    // a device-to-host read here would queue behind an asynchronous framebuffer read-back of the previous frame)
+    long long total = 0;
+    for (int e = 0; e < n_edges; e++) {
+      if (edge_obj[e] < 0) continue;
+      const int ymin = std::min(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]), ymax = std::max(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]);
+      total += floordiv(ymax + 67, 32) - floordiv(ymin - 16 + 31, 32) + 1;
+    }
+    if (total > 0x7FFFFFF0LL) FAIL("scene: row-edge table too large");
+    CK(DMALLOC(&s->rowedge_idx, sizeof(int) * (size_t)std::max<long long>(total, 1)));
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
+    if (n_edges > 0) { k_rowedges<true><<<cdiv(n_edges * 32, 256), 256, 0, ctx->stream>>>(s->edges, d_edge_obj, n_edges, s->objs, d_counts, s->rowedge_ptr, s->rowedge_idx); LAUNCHED(); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    DFREE(d_edge_obj); DFREE(d_counts);
+  }
+  // Convolved objects (render.ml:1023-1052): AA-rasterise the whole (twice bloated) box of the child,
+  // X pass, Y pass; keep the shape / minshape bit-rows and the convolved canvas resident.
+  if (!conv_list.empty()) {
+    CK(DMALLOC(&s->conv_bits, sizeof(uint32_t) * conv_words));
+    CK(DMALLOC(&s->conv_px, sizeof(uint32_t) * conv_pixels));
+    for (const ConvItem& ci : conv_list) {
+      const ObjRec& o = recs[ci.rec];
+      const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;
+      const size_t nwords = (size_t)nw * h, npx = (size_t)w * h;
+      uint32_t *S = nullptr, *C = nullptr, *T = nullptr, *Q = nullptr, *A = nullptr, *X = nullptr; uint8_t* op = nullptr; int* d_taps = nullptr;
+      CK(DMALLOC(&S, 4 * nwords)); CK(DMALLOC(&C, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&Q, 4 * nwords));
+      CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx)); CK(DMALLOC(&op, npx));
+      CK(cudaMemsetAsync(S, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(C, 0, 4 * nwords, ctx->stream));
+      CK(cudaMemsetAsync(op, 0, npx, ctx->stream));
+      const EdgeRec* ed = s->edges + o.first;
+      k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, o.count, o.winding, o.cv_y0, h, o.cv_x0, nw, S, C, ctx->d_error); LAUNCHED();
+      uint32_t* convS = s->conv_bits + o.cv_bits; uint32_t* convM = convS + nwords;
+      dim3 g(cdiv(nw, 128), h);
+      k_dilate<<<g, 128, 0, ctx->stream>>>(S, convS, h, nw, ci.r, ci.r); LAUNCHED();                  // shape = bloat r r (shape g)
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(S, C, C, nwords, 1); LAUNCHED();  // C := minshape g
+      k_fill_words<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(Q, nwords, 0xFFFFFFFFu); LAUNCHED();
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(Q, C, T, nwords, 1); LAUNCHED();  // T := frame - minshape
+      k_dilate<<<g, 128, 0, ctx->stream>>>(T, S, h, nw, ci.r, ci.r); LAUNCHED();                       // S := bloat (frame - minshape)
+      k_bitop<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(C, S, convM, nwords, 1); LAUNCHED();  // minshape = erode r r (minshape g)
+      k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, o.count, o.aa_winding, Q, o.cv_y0, h, o.cv_x0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+      k_raster_plain<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(op, A, npx, o.fill.c0); LAUNCHED();
+      std::vector<int> taps; int total = 0;
+      if (ci.kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+        for (int i = -ci.r; i <= ci.r; i++) {
+          double xr = (double)i / (double)ci.r, yr = 0. / (double)ci.r;
+          double gg = exp(-(xr * xr + yr * yr)) / 2.;
+          int v = (int)((double)(4 * ci.r * ci.r) * gg + 0.5);
+          taps.push_back(v); total += v;
+        }
+        CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
+        CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      dim3 gp(cdiv(w, 128), h);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, ci.r, ci.kind, d_taps, total, 0); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, s->conv_px + o.cv_px, w, h, ci.r, ci.kind, d_taps, total, 1); LAUNCHED();
+      if (check_error_flag(ctx, "coh_scene_create (Convolved object)")) return 1;
+      DFREE(S); DFREE(C); DFREE(T); DFREE(Q); DFREE(A); DFREE(X); DFREE(op); DFREE(d_taps);
+    }
+  }
+  if (total_brush_rows > 0) {
+    int* d_point_obj = nullptr;
+    CK(DMALLOC(&d_point_obj, sizeof(int) * point_obj.size()));
+    CK(cudaMemcpyAsync(d_point_obj, point_obj.data(), sizeof(int) * point_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(DMALLOC(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
+    std::vector<int2> init((size_t)total_brush_rows, make_int2(INT32_MAX, -1));
+    CK(cudaMemcpyAsync(s->brush_ranges, init.data(), sizeof(int2) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_brush_cells<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    DFREE(d_point_obj);
+  }
+  *out = (coh_scene_t)s;
+  return 0;
+}
+
+int coh_fb_attach(coh_ctx* ctx, void* device_rgba8) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fr.W) FAIL("coh_fb_attach: call coh_fb_configure first");
+  if (drain_timing(ctx)) return 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_fb) DFREE(ctx->fb);
+  if (!device_rgba8) {  // detach: back to a framebuffer owned by the context
+    ctx->fb = nullptr; ctx->own_fb = true;
+    CK(DMALLOC(&ctx->fb, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H));
+    CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H, ctx->stream));
+    return 0;
+  }
+  ctx->fb = (uint32_t*)device_rgba8; ctx->own_fb = false;
+  return 0;
+}
+int coh_fb_set_peers(coh_ctx* ctx, int32_t n_peers, void* const* peer_fbs) {
+  if (n_peers < 0 || n_peers > COH_MAX_PEERS) FAIL("coh_fb_set_peers: at most 7 peers (one 8-GPU box)");
+  ctx->n_peers = n_peers;
+  for (int k = 0; k < n_peers; k++) ctx->peer_fb[k] = (uint32_t*)peer_fbs[k];
+  return 0;
+}
+int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1) {
+  CK(cudaSetDevice(ctx->device));
+  if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
+  if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
+  if (width != ctx->fr.W || height != ctx->fr.H) {
+    if (ctx->own_fb) DFREE(ctx->fb);
+    DFREE(ctx->u_out); DFREE(ctx->u_init); ctx->fb = nullptr; ctx->u_out = nullptr; ctx->u_init = nullptr; ctx->own_fb = true;
+    CK(DMALLOC(&ctx->fb, sizeof(uint32_t) * (size_t)width * height));
+    CK(cudaMemsetAsync(ctx->fb, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
+    CK(DMALLOC(&ctx->u_out, sizeof(uint32_t) * (size_t)cdiv(width, 32) * height));
+  }
+  ctx->fr.W = width; ctx->fr.H = height; ctx->fr.band_y0 = band_y0; ctx->fr.band_y1 = band_y1;
+  ctx->fr.tiles_x = cdiv(width, 32); ctx->fr.cells_y = cdiv(height, CELL_H);
+  ctx->fr.ctx0 = 0; ctx->fr.cntx = ctx->fr.tiles_x;
+  ctx->have_u = false;
+  return 0;
+}
