@@ -1,0 +1,266 @@
+// kernels_shapes.cuh — part of kernels.cuh (included inside namespace coh, in order): span-set algebra on bit-frames, filter and convolve passes, exports.
+
+// ------------------------------------------------------------------------------------
+// K3: span sets <-> bit-frames and word-wise set algebra.
+// A device span set is CSR: rows y0 .. y0+n_rows-1, row_ptr[n_rows+1], spans (x, len).
+// ------------------------------------------------------------------------------------
+__global__ void k_spans_to_bits(const int* __restrict__ row_ptr, const int2* __restrict__ spans, int src_y0,
+                                int src_rows, int y0, int n_rows, int wx0, int nw, uint32_t* __restrict__ bits) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;  // destination row
+  if (r >= n_rows) return;
+  int sr = y0 + r - src_y0;
+  if (sr < 0 || sr >= src_rows) return;
+  uint32_t* row = bits + (size_t)r * nw;
+  for (int k = row_ptr[sr]; k < row_ptr[sr + 1]; k++) {
+    int2 s = spans[k];
+    or_interval(row, 1, nw, wx0, s.x, s.x + s.y - 1);
+  }
+}
+// Brush.shape_of_brushstroke (brush.ml:135-173): the union of the (2r+1)^2 boxes around the stamp centres.
+// One thread per (stamp, row of its box); rows y0 .., nw words per row starting at pixel wx0.
+__global__ void k_stamp_boxes_to_bits(const int2* __restrict__ points, int n_points, int r, int y0, int n_rows, int wx0, int nw,
+                                      uint32_t* __restrict__ bits) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, side = 2 * r + 1;
+  if (t >= n_points * side) return;
+  const int2 p = points[t / side];
+  const int row = p.y - r + t % side - y0;
+  if (row < 0 || row >= n_rows) return;
+  int a = p.x - r - wx0, b = p.x + r - wx0;
+  if (b < 0 || a >= nw * 32) return;
+  a = max(a, 0); b = min(b, nw * 32 - 1);
+  uint32_t* rowp = bits + (size_t)row * nw;
+  for (int w = a >> 5; w <= (b >> 5); w++) {
+    const int lo = max(a, w * 32) & 31, hi = min(b, w * 32 + 31) & 31;
+    atomicOr(&rowp[w], (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi)));
+  }
+}
+// op: 0 OR, 1 ANDNOT (a & ~b), 2 AND
+__global__ void k_bitop(const uint32_t* a, const uint32_t* b, uint32_t* out,
+                        size_t n, int op) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = a[i], y = b[i];
+  out[i] = op == 0 ? (x | y) : op == 1 ? (x & ~y) : (x & y);
+}
+// Dilation by (2m+1) x (2n+1) (Sprite.bloat, sprite.ml:1749-1864) on a bit-frame that
+// already has a margin of m pixels / n rows around the set.  One thread per word.
+__global__ void k_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n_rows, int nw, int m, int n) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  uint32_t acc = 0u;
+  for (int rr = max(0, r - n); rr <= min(n_rows - 1, r + n); rr++) {
+    const uint32_t* row = in + (size_t)rr * nw;
+    // OR of the row shifted by -m..+m pixels, gathered for this word
+    for (int s = -m; s <= m; s++) {
+      // bit i of result word w comes from pixel 32w + i - s
+      int q = 32 * w - s;            // source pixel of bit 0
+      int qw = q >> 5, qb = q & 31;  // arithmetic shift: floor
+      uint32_t lo = (qw >= 0 && qw < nw) ? row[qw] : 0u;
+      uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
+      acc |= qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
+    }
+  }
+  out[(size_t)r * nw + w] = acc;
+}
+// Run extraction: count the maximal runs of every row (thread per row), then fill.
+__global__ void k_count_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int* __restrict__ counts,
+                             unsigned long long* __restrict__ card) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t* row = bits + (size_t)r * nw;
+  int n = 0; uint32_t carry = 0u; unsigned long long px = 0;
+  for (int w = 0; w < nw; w++) {
+    uint32_t v = row[w];
+    n += __popc(v & ~((v << 1) | carry));
+    px += __popc(v);
+    carry = v >> 31;
+  }
+  counts[r] = n;
+  if (card && px) atomicAdd(card, px);
+}
+__global__ void k_fill_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int wx0,
+                            const int* __restrict__ row_ptr, int2* __restrict__ spans) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t* row = bits + (size_t)r * nw;
+  int k = row_ptr[r];
+  int start = 0; bool in = false;
+  for (int w = 0; w < nw; w++) {
+    uint32_t v = row[w];
+    int base = wx0 + 32 * w;
+    int pos = 0;
+    while (pos < 32) {
+      if (!in) {
+        uint32_t rest = pos ? (v >> pos) : v;
+        if (!rest) break;
+        pos += __ffs((int)rest) - 1;
+        start = base + pos; in = true;
+      } else {
+        uint32_t rest = ~(pos ? (v >> pos) : v);
+        if (pos) rest &= (0xFFFFFFFFu >> pos);  // bits shifted in from above are not pixels
+        if (!rest) { pos = 32; break; }
+        pos += __ffs((int)rest) - 1;
+        spans[k++] = make_int2(start, base + pos - start);
+        in = false;
+      }
+    }
+  }
+  if (in) spans[k++] = make_int2(start, wx0 + 32 * nw - start);
+}
+// Sprite.translate_shape (sprite.ml:470-484) on a device span set: spans move by dx (rows move by
+// changing y0 on the host side).
+__global__ void k_translate_spans(const int2* __restrict__ in, int2* __restrict__ out, int n, int dx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { int2 s = in[i]; out[i] = make_int2(s.x + dx, s.y); }
+}
+// Per-object alias offsets changed in place (Render.translate_renderobject -> Cache.addtranslation):
+// shift the device-space boxes the binning reads.  delta = new offset - old offset.
+__global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf_box, const int* __restrict__ leaves,
+                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy) {
+  int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n_leaves) return;
+  int oi = leaves[li];
+  if (oi < first_obj || oi > last_obj) return;
+  ObjRec& o = objs[oi];
+  o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy;
+  leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
+}
+// ------------------------------------------------------------------------------------
+// Filters (render.ml:1080-1131, 1248-1265; filters.ml).  Frame-sized RGBA8 canvases and bit-frames
+// (nw words per row, bit 0 of word 0 = pixel x 0).
+// ------------------------------------------------------------------------------------
+// canvas[p] = clear for every pixel p of the bit-frame
+__global__ void k_clear_in_bits(uint32_t* __restrict__ canvas, const uint32_t* __restrict__ bits, int W, int H, int nw) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  if ((bits[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u) canvas[(size_t)y * W + x] = 0u;
+}
+// Filters.monochrome: sprite_map Colour.monochrome (colour.ml: average of r, g, b; alpha kept)
+__global__ void k_monochrome(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = in[i];
+  const uint32_t av = ((c & 255u) + ((c >> 8) & 255u) + ((c >> 16) & 255u)) / 3u;
+  out[i] = av | (av << 8) | (av << 16) | (c & 0xFF000000u);
+}
+// The filter geometry's matte inside T (render.ml:1099): alpha of `dissolve fill opacity` with the
+// antialiased opacity bytes `op` (Polygon.polygon_sprite samples every pixel it is given, minshape
+// pixels included); `finished` = its opaque pixels (1100-1103).  One word per warp.
+__global__ void k_filter_matte(const uint32_t* __restrict__ T, const uint8_t* __restrict__ op,
+                               uint32_t colour, int W, int H, int nw, uint8_t* __restrict__ alpha, uint32_t* __restrict__ finished) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = blockIdx.y, lane = threadIdx.x & 31;
+  if (w >= nw || y >= H) return;
+  const uint32_t t = T[(size_t)y * nw + w];
+  const int x = 32 * w + lane;
+  int a = 0;
+  if (((t >> lane) & 1u) && x < W) {
+    a = (int)(px_dissolve(colour, op[(size_t)y * nw * 32 + x]) >> 24);
+    alpha[(size_t)y * W + x] = (uint8_t)a;
+  }
+  const uint32_t f = __ballot_sync(0xFFFFFFFFu, a == 255);
+  if (lane == 0) finished[(size_t)y * nw + w] = f & t;
+}
+// blend' (render.ml:1248-1265) and the composite of the filter's sprite into the accumulator
+// (render.ml:1290-1291): fb = over fb (pd_plus (dissolve Z (255 - alpha)) (dissolve Y alpha)) on T.
+// Pixels a scene did not render are clear in Z / Y, which both operators treat as absent.
+__global__ void k_filter_blend(const uint32_t* __restrict__ T, const uint8_t* __restrict__ alpha, const uint32_t* __restrict__ Z,
+                               const uint32_t* __restrict__ Y, uint32_t* __restrict__ fb, int W, int H, int nw) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  if (!((T[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u)) return;
+  const size_t i = (size_t)y * W + x;
+  const int a = alpha[i];
+  const uint32_t z = px_dissolve(Z[i], 255 - a), yy = Y ? px_dissolve(Y[i], a) : 0u;
+  fb[i] = px_over(fb[i], px_plus(z, yy));
+}
+// update & ~opaque(fb): where the background list is still visible under the scene pass
+__global__ void k_not_opaque_bits(const uint32_t* __restrict__ fb, const uint32_t* __restrict__ U, uint32_t* __restrict__ out, int W, int H, int nw) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = blockIdx.y, lane = threadIdx.x & 31;
+  if (w >= nw || y >= H) return;
+  const int x = 32 * w + lane;
+  const bool opq = x < W && (fb[(size_t)y * W + x] >> 24) == 255u;
+  const uint32_t o = __ballot_sync(0xFFFFFFFFu, opq);
+  if (lane == 0) out[(size_t)y * nw + w] = U[(size_t)y * nw + w] & ~o;
+}
+
+// ------------------------------------------------------------------------------------
+// K6 convolve (convolve.ml:115-232) on dense RGBA8 canvases [h][w]; pixels outside the canvas
+// read as clear, like the 2r border of Sprite.flatten_sprite (convolve.ml:247).  One pass per
+// launch (horizontal, then vertical on the re-quantised result): integer sums, truncating
+// division, r,g clamped to alpha for XY kernels (the blue clamp of the reference is a no-op,
+// convolve.ml:118), plain division for the unit kernel (161-204).
+// ------------------------------------------------------------------------------------
+__global__ void k_conv_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int w, int h, int r,
+                            int kind /*1 unit, 2 xy*/, const int* __restrict__ taps, int total, int vertical) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  int tr = 0, tg = 0, tb = 0, ta = 0;
+  for (int q = -r; q <= r; q++) {
+    int xx = vertical ? x : x + q, yy = vertical ? y + q : y;
+    uint32_t c = (xx >= 0 && xx < w && yy >= 0 && yy < h) ? in[(size_t)yy * w + xx] : 0u;
+    int k = kind == 2 ? taps[q + r] : 1;
+    tr += (int)(c & 255u) * k; tg += (int)((c >> 8) & 255u) * k; tb += (int)((c >> 16) & 255u) * k; ta += (int)(c >> 24) * k;
+  }
+  int d = kind == 2 ? total : (2 * r + 1);
+  tr /= d; tg /= d; tb /= d; ta /= d;
+  if (kind == 2) { tr = min(ta, tr); tg = min(ta, tg); }
+  out[(size_t)y * w + x] = (uint32_t)tr | ((uint32_t)tg << 8) | ((uint32_t)tb << 16) | ((uint32_t)ta << 24);
+}
+// AA raster of a plain-filled polygon from dense opacity bytes: dissolve fill opacity (polygon.ml:733-738)
+__global__ void k_raster_plain(const uint8_t* __restrict__ opacity, uint32_t* __restrict__ out, size_t n, uint32_t colour) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = px_dissolve(colour, opacity[i]);
+}
+__global__ void k_fill_words(uint32_t* __restrict__ p, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// 32 bits of a bit-row starting at an arbitrary bit offset (zeros outside the row)
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t* __restrict__ row, int nw, int bitoff) {
+  const int qw = bitoff >> 5, qb = bitoff & 31;
+  const uint32_t lo = (qw >= 0 && qw < nw) ? row[qw] : 0u;
+  const uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? row[qw + 1] : 0u;
+  return qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
+}
+// Box-shaped bit-frame (Sprite.box) or clear.
+__global__ void k_fill_box_bits(uint32_t* __restrict__ bits, int n_rows, int nw, int wx0, int y0, int bx0, int by0,
+                                int bx1, int by1) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  int y = y0 + r;
+  bits[(size_t)r * nw + w] = (y >= by0 && y <= by1) ? interval_mask32(wx0 + 32 * w, bx0, bx1) : 0u;
+}
+// RGB888 export of a framebuffer rectangle (wxgui.ml:417-424 plot_sprite byte layout).
+__global__ void k_rgb888(const uint32_t* __restrict__ fb, int W, int x0, int y0, int w, int h, uint8_t* __restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  uint32_t c = fb[(size_t)(y0 + y) * W + x0 + x];
+  uint8_t* p = out + ((size_t)y * w + x) * 3;
+  p[0] = c & 255u; p[1] = (c >> 8) & 255u; p[2] = (c >> 16) & 255u;
+}
+// Scatter per-pixel values given in canonical span order into a dense canvas: thread per row.
+template <class T>
+__global__ void k_scatter_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,
+                                const long long* __restrict__ px_off, int n_rows, int row0, int wx0, int w,
+                                const T* __restrict__ in, T* __restrict__ dense) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  long long o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    int2 s = spans[k];
+    for (int i = 0; i < s.y; i++) dense[(size_t)(row0 + r) * w + (s.x + i - wx0)] = in[o++];
+  }
+}
+// Gather dense per-pixel values in canonical span order: thread per row.
+template <class T>
+__global__ void k_gather_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,
+                               const long long* __restrict__ px_off, int n_rows, int wx0, int pitch,
+                               const T* __restrict__ dense, T* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  long long o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    int2 s = spans[k];
+    for (int i = 0; i < s.y; i++) out[o++] = dense[(size_t)r * pitch + (s.x + i - wx0)];
+  }
+}
