@@ -156,7 +156,18 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
   // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
   const char* force = getenv("COH_FUSED");   // tests force either path: "1" fused, "0" three-phase
-  const bool pre = s->extras == 0 && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+  // eligible: every leaf of the range is a path, a primitive or a Convolved object
+  bool kinds_ok = s->extras == 0;
+  bool has_conv = false;
+  if (!kinds_ok && !A.resume && !big) {
+    kinds_ok = true;
+    for (int li = A.l0; li < A.l1 && kinds_ok; li++) {
+      const int k = s->h_objs[s->h_leaves[li]].kind;
+      kinds_ok = k == K_PATH || k == K_PRIM || k == K_CONV;
+      has_conv = has_conv || k == K_CONV;
+    }
+  }
+  const bool pre = kinds_ok && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
                    (force ? force[0] == '0' : walk_h != 1);
   if (pre) {
     const size_t n_pairs = total * CELL_H;
@@ -187,9 +198,13 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       }
       P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
       P.epoch = ++ctx->epoch;
-      k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+      if (has_conv) k_walk<true, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      else k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      LAUNCHED();
     } else {
-      k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P); LAUNCHED();
+      if (has_conv) k_walk<false, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      else k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      LAUNCHED();
     }
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
     return 0;

@@ -30,6 +30,12 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
     const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
     if (o.kind == K_PRIM) {
       if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
+    } else if (o.kind == K_CONV) {   // Convolved object: shape / minshape kept as bit-rows by the scene
+      if (yy >= o.cv_y0 && yy < o.cv_y0 + o.cv_h) {
+        const uint32_t* rowS = P.conv_bits + o.cv_bits + (size_t)(yy - o.cv_y0) * o.cv_nw;
+        S = conv_load_bits32(rowS, o.cv_nw, xx0 - o.cv_x0);
+        C = S & ~conv_load_bits32(rowS + (size_t)o.cv_h * o.cv_nw, o.cv_nw, xx0 - o.cv_x0);
+      }
     } else if (yy >= o.ry0 && yy <= o.ry1) {
       const int slot = o.row_base + yy - o.ry0;
       const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
