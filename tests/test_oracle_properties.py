@@ -245,3 +245,26 @@ def test_filter_limits(oracle):
     assert not img_p.any()
     img_b, _, _ = frame("blur", [(quad, red)], kernel=("gaussian", 3))
     assert img_b[60, 80] == red, "the blur of a flat colour is that colour"
+
+
+def test_benchmark_scene_builders_render(oracle):
+    """The C4 / C5 scene builders produce scenes the oracle accepts at a reduced size: filters with
+    their reading-scene group, a Convolved page shadow, the lion group as the dragged object."""
+    W, H = 320, 180
+    objs, n, nbg, e, p = S.filter_scene(W, H, 0.55).arrays()
+    kinds = [o.kind for o in objs]
+    assert kinds.count(6) == 3 and any(o.filter_kind == 100 for o in objs) and any(o.convolve for o in objs)
+    img = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H))
+    assert (img >> 24 == 255).all(), "the background makes every pixel opaque"
+    b, mover = S.drag_scene(W, H, 0.3, n_static=20)
+    objs, n, nbg, e, p = b.arrays()
+    assert objs[mover].kind == 2 and objs[mover].id == 1
+    base = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H))
+    k, depth = mover + 1, 1
+    while depth:
+        depth += 1 if objs[k].kind == 2 else -1 if objs[k].kind == 3 else 0
+        if objs[k].kind not in (2, 3):
+            objs[k].dx, objs[k].dy = 7, -4
+        k += 1
+    moved = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H))
+    assert not np.array_equal(base, moved)
