@@ -39,7 +39,7 @@ class CohObject(C.Structure):
 # every symbol include/coherence_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
     "coh_init", "coh_shutdown", "coh_last_error", "coh_device_name", "coh_stream", "coh_launch_count",
-    "coh_set_stream", "coh_set_timing", "coh_get_timing", "coh_fb_attach",
+    "coh_set_stream", "coh_set_timing", "coh_get_timing", "coh_fb_attach", "coh_set_option",
     "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_polygon_opacity",
     "coh_polygon_sprite", "coh_shape_box", "coh_shape_import", "coh_shape_export_size", "coh_shape_export",
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
@@ -133,6 +133,9 @@ class Context:
         w, b, n = C.c_double(), C.c_double(), C.c_int64()
         self._chk(lib().coh_get_timing(self._h, C.byref(w), C.byref(b), C.byref(n)))
         return w.value, b.value, n.value
+
+    def set_option(self, name, value):
+        self._chk(lib().coh_set_option(self._h, name.encode(), int(value)))
 
     def fb_attach(self, device_ptr):
         self._chk(lib().coh_fb_attach(self._h, C.c_void_p(device_ptr)))

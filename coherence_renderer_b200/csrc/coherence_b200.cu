@@ -24,6 +24,17 @@ struct DevShape {
   long long card = 0;           // pixels
   int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;  // tight bounds (valid if n_spans > 0)
 };
+// Output of K1 cell binning for one pass geometry: per-cell front-to-back lists and the heavy-first order.
+struct BinSet {
+  int n_cells_cap = 0;
+  int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
+  int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
+  int* cell_order = nullptr;  // cells by list-length class [BIN_CLASSES][n_cells]
+  int* cell_items = nullptr; size_t cell_items_cap = 0;
+  int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)
+  int2* item_attr = nullptr;  // compositing attributes of every list entry (small-scene binning only)
+  int* state = nullptr;       // ORDER_BINS ints: [0] pool cursor, [1 ..] class counts
+};
 struct DevScene {
   int n_objs = 0, n_leaves = 0, n_edges = 0, n_points = 0;
   ObjRec* objs = nullptr;
@@ -37,6 +48,8 @@ struct DevScene {
   int2* brush_ranges = nullptr; // per (stroke, cell of its box): [first, last] stamp index reaching the cell
   uint32_t* conv_bits = nullptr; // Convolved objects: shape / minshape bit-rows
   uint32_t* conv_px = nullptr;   // Convolved objects: pre-convolved canvases
+  int2* attr = nullptr;          // per record: {plain colour, is-path | background-list << 1 | (pretrans + 1) << 8} for the row compositor
+  bool flat_ok = false;          // every leaf a direct member of a root list, plain paths / primitives only
   std::vector<ObjRec> h_objs;
   std::vector<int64_t> ids;      // cache key (Id.idset) of every record
   std::vector<int> rec_of_abi;   // record index of every object of the ABI array (-1: GROUP_END / dropped)
@@ -57,6 +70,9 @@ struct DevScene {
   int extras = 0;            // walker variant: 0 polygons / primitives, 1 + brush / Convolved, 2 + CPG / filters
   size_t items_total = 0, coarse_total = 0; bool coarse_total_valid = false;
   int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
+  // Whole-frame binning kept with the scene (it is a pure function of the object boxes and the frame geometry,
+  // like the row-edge lists): valid until an object moves or the framebuffer geometry changes.
+  BinSet bins; bool bins_valid = false; int bins_key[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // Cache (cache.ml:57-83): entries keyed by object id hold device-resident span sets
@@ -82,25 +98,28 @@ struct coh_ctx {
   uint32_t* u_init = nullptr;  // bit-frame of an arbitrary update shape
   bool use_u_init = false;
   bool have_u = false;
-  // binning scratch
-  int n_cells_cap = 0;
-  int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
-  int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
+  // binning scratch (passes whose binning is not kept with the scene)
+  BinSet bins;
+  bool opt_bin_cache = true;  // keep whole-frame binning with the scene
+  bool opt_comp_rows = true;  // flat scenes: row compositor instead of the walker in three-phase frames
   // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
   int* coarse_items = nullptr; int* coarse_counts = nullptr; int* coarse_off = nullptr; size_t coarse_cap = 0, coarse_cells_cap = 0;
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // three-phase frames: per (cell item, row) pair
   uint2* pre_sc = nullptr; int4* pre_list = nullptr; int* pre_n = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
+  int2* pre_cplx = nullptr;    // (pair, edge pixels) the interval-form antialiasing kernel hands to the general one
+  // tuning / test options (coh_set_option; the environment is read once, in coh_init)
+  int opt_walk_h = 0;          // 0 = chosen per pass; 1 | 4 | 16 forces the walker's work-item height
+  int opt_fused = -1;          // -1 = chosen per pass; 1 fused walker, 0 three-phase frame
+  bool aa_general = false;     // every pair through the general (bit-row) antialiasing kernel
   // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
   cudaStream_t copy_stream = nullptr;
   uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int stage_next = 0;
-  int* cell_items = nullptr; size_t cell_items_cap = 0;
-  int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)
   int* h_total = nullptr;  // pinned
   // cross-tile carry for fancy fills
-  int* queue = nullptr; int* order_hist = nullptr; int* cell_order = nullptr; int n_sms = 0;
+  int* queue = nullptr; int n_sms = 0;
   int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
   size_t carry_slots = 0; int epoch = 0;
   bool own_stream = true, own_fb = true;
@@ -205,10 +224,27 @@ int coh_init(int device, coh_ctx** out) {
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("cudaStreamSynchronize", e);
   if ((e = cudaMallocHost(&ctx->h_error, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&ctx->h_total, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if (const char* e = getenv("COH_WALK_H")) coh_set_option(ctx, "walk_h", atoi(e));
+  if (const char* e = getenv("COH_FUSED")) coh_set_option(ctx, "fused", atoi(e));
+  if (const char* e = getenv("COH_AA_GENERAL")) coh_set_option(ctx, "aa_general", atoi(e));
   *out = ctx;
   return 0;
 }
+int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
+  const std::string n = name ? name : "";
+  if (n == "walk_h") { if (value != 0 && value != 1 && value != 4 && value != 16) FAIL("coh_set_option: walk_h is 0, 1, 4 or 16"); ctx->opt_walk_h = value; }
+  else if (n == "fused") { if (value < -1 || value > 1) FAIL("coh_set_option: fused is -1, 0 or 1"); ctx->opt_fused = value; }
+  else if (n == "aa_general") ctx->aa_general = value != 0;
+  else if (n == "bin_cache") ctx->opt_bin_cache = value != 0;
+  else if (n == "comp_rows") ctx->opt_comp_rows = value != 0;
+  else FAIL("coh_set_option: unknown option '" + n + "'");
+  return 0;
+}
 
+static void free_binset(coh_ctx* ctx, BinSet& b) {
+  DFREE(b.cell_head); DFREE(b.cell_rng); DFREE(b.cell_order); DFREE(b.cell_items); DFREE(b.item_cell); DFREE(b.item_attr); DFREE(b.state);
+  b = BinSet();
+}
 int coh_cache_clear(coh_ctx* ctx);
 int coh_shutdown(coh_ctx* ctx) {
   if (!ctx) return 0;
@@ -224,10 +260,10 @@ int coh_shutdown(coh_ctx* ctx) {
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
-  DFREE(ctx->cell_items); DFREE(ctx->cell_head); DFREE(ctx->cell_rng);
+  free_binset(ctx, ctx->bins); DFREE(ctx->queue);
   DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
-  DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->item_cell);
-  DFREE(ctx->order_hist); DFREE(ctx->cell_order); DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
+  DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->pre_cplx);
+  DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -220,6 +220,7 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
     o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
   }
   s->items_for_W = -1;  // the item-pool bound depends on the boxes
+  s->bins_valid = false;  // ... and so do the cell lists
   if (s->n_leaves > 0) { k_move_leaves<<<cdiv(s->n_leaves, 256), 256, 0, ctx->stream>>>(s->objs, s->leaf_box, s->leaves, s->n_leaves, r, last, dx, dy); LAUNCHED(); }
   return 0;
 }

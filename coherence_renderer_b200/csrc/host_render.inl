@@ -31,26 +31,33 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     // rows and columns the walk does not visit have nothing uncovered
     CK(cudaMemsetAsync(A.u_out + (size_t)fr.band_y0 * fr.tiles_x, 0, 4 * (size_t)(fr.band_y1 - fr.band_y0) * fr.tiles_x, ctx->stream));
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.cntx;
-  if (n_cells > ctx->n_cells_cap) {
-    DFREE(ctx->cell_order); DFREE(ctx->cell_head);
-    CK(DMALLOC(&ctx->cell_head, sizeof(int2) * n_cells));
-    DFREE(ctx->cell_rng);
-    CK(DMALLOC(&ctx->cell_rng, sizeof(int2) * n_cells));
-    CK(DMALLOC(&ctx->cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
-    ctx->n_cells_cap = n_cells;
+  const bool big = n_leaves > 1024;
+  const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
+  // Background cells of a box update are finished by k_prefill and never enter the walker's queue
+  // (not with peer framebuffers: the mirrored stores of background cells are better spread over the walker's
+  // warps — measured at 2 / 4 / 8 GPUs)
+  const bool prefill = !big && ordered && !A.u_init && !A.resume && !(A.fb == ctx->fb && ctx->n_peers > 0);
+  // Whole-frame binning of a small scene is kept with the scene; every other pass bins into the context's scratch.
+  const bool keep = whole && !big && ctx->opt_bin_cache;
+  BinSet& B = keep ? s->bins : ctx->bins;
+  const int key[6] = {fr.W, fr.H, fr.band_y0, fr.band_y1, ordered ? 1 : 0, prefill ? 1 : 0};
+  const bool hit = keep && s->bins_valid && memcmp(key, s->bins_key, sizeof key) == 0;
+  if (n_cells > B.n_cells_cap) {
+    DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng);
+    B.n_cells_cap = 0;
+    CK(DMALLOC(&B.cell_head, sizeof(int2) * n_cells));
+    CK(DMALLOC(&B.cell_rng, sizeof(int2) * n_cells));
+    CK(DMALLOC(&B.cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
+    B.n_cells_cap = n_cells;
   }
+  if (!B.state) CK(DMALLOC(&B.state, sizeof(int) * ORDER_BINS));
   if (!ctx->queue) {
-    CK(DMALLOC(&ctx->order_hist, sizeof(int) * (2 * ORDER_BINS + 1)));  // histogram, cursors, work-queue head
-    ctx->queue = ctx->order_hist + 2 * ORDER_BINS;
+    CK(DMALLOC(&ctx->queue, sizeof(int)));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->n_sms = prop.multiProcessorCount;
   }
-  const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
-  CK(cudaMemsetAsync(ctx->order_hist, 0, sizeof(int) * (2 * ORDER_BINS + 1), ctx->stream));
+  CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
   if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
-  // K1: count, scan, fill.  Small scenes: warp per cell scanning all leaves (lists come out sorted,
-  // no atomics).  Large scenes: warp per leaf over the cells it covers + per-cell sort.
-  const bool big = n_leaves > 1024;
   // capacity of the item pool: the exact total is a pure function of the object boxes and the
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
@@ -67,26 +74,28 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     if (whole) { s->coarse_total_valid = false; s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
   } else total = s->items_total;
   const size_t need = total;
-  if (need > ctx->cell_items_cap) {
-    DFREE(ctx->cell_items); DFREE(ctx->item_cell);
+  if (need > B.cell_items_cap) {
+    DFREE(B.cell_items); DFREE(B.item_cell); DFREE(B.item_attr);
+    B.cell_items_cap = 0;
     size_t cap = need + need / 2 + 1024;
-    CK(DMALLOC(&ctx->cell_items, sizeof(int) * cap));
-    CK(DMALLOC(&ctx->item_cell, sizeof(int) * cap));
-    ctx->cell_items_cap = cap;
+    CK(DMALLOC(&B.cell_items, sizeof(int) * cap));
+    CK(DMALLOC(&B.item_cell, sizeof(int) * cap));
+    CK(DMALLOC(&B.item_attr, sizeof(int2) * cap));
+    B.cell_items_cap = cap;
   }
-  if (!big) {
+  // K1.  Small scenes: warp per cell scanning all leaves (lists come out sorted, no atomics).  Large scenes:
+  // warp per leaf over the coarse cells it covers, then every fine cell from its coarse list.
+  if (hit) {
+    // nothing to do: lists, classes and cell headers of this geometry are resident
+  } else if (!big) {
+    CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
     // one pass: hit masks in registers, lists carved from one cursor, length classes instead of a sort
     const int bin_blocks = cdiv(n_cells * 32, 256);
-    BinPrefill pf; memset(&pf, 0, sizeof pf);
-    // (not with peer framebuffers: the mirrored stores of background cells are better spread over the walker's
-    // warps — measured at 2 / 4 / 8 GPUs)
-    if (ordered && !A.u_init && !A.resume && !(A.fb == ctx->fb && ctx->n_peers > 0)) {
-      pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1;
-      pf.n_peers = 0;
-    }
-    k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, ctx->cell_rng, ctx->cell_items, ctx->order_hist,
-                                               ordered ? ctx->cell_order : nullptr, s->objs, ctx->cell_head, ctx->item_cell, pf); LAUNCHED();
+    k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, B.cell_rng, B.cell_items, B.state,
+                                               ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr); LAUNCHED();
+    if (keep) { s->bins_valid = true; memcpy(s->bins_key, key, sizeof key); }
   } else {
+    CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
     // two levels: leaves into coarse cells (object-parallel, sorted per coarse list), then every fine cell from its coarse list
     const int ctx_x = cdiv(fr.tiles_x, COARSE), crow0 = cell_row0 >> COARSE_SHIFT, crow1 = cell_row1 >> COARSE_SHIFT;
     const int n_coarse = ctx_x * (crow1 - crow0 + 1);
@@ -103,10 +112,12 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     }
     if (2 * ctot + 1 > ctx->coarse_cap || (size_t)n_coarse + 1 > ctx->coarse_cells_cap) {
       DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
-      ctx->coarse_cap = 2 * ctot + ctot / 2 + 1024; ctx->coarse_cells_cap = (size_t)n_coarse + 1;
-      CK(DMALLOC(&ctx->coarse_items, sizeof(int) * ctx->coarse_cap));
-      CK(DMALLOC(&ctx->coarse_counts, sizeof(int) * ctx->coarse_cells_cap));
-      CK(DMALLOC(&ctx->coarse_off, sizeof(int) * (ctx->coarse_cells_cap + 1)));
+      ctx->coarse_cap = 0; ctx->coarse_cells_cap = 0;
+      const size_t cap = 2 * ctot + ctot / 2 + 1024, ccap = (size_t)n_coarse + 1;
+      CK(DMALLOC(&ctx->coarse_items, sizeof(int) * cap));
+      CK(DMALLOC(&ctx->coarse_counts, sizeof(int) * ccap));
+      CK(DMALLOC(&ctx->coarse_off, sizeof(int) * (ccap + 1)));
+      ctx->coarse_cap = cap; ctx->coarse_cells_cap = ccap;
     }
     const int obj_blocks = cdiv(std::max(n_leaves, 1) * 32, 256);
     CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
@@ -115,16 +126,21 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     CK(cudaMemsetAsync(ctx->coarse_counts, 0, sizeof(int) * n_coarse, ctx->stream));
     k_bin_obj<true><<<obj_blocks, 256, 0, ctx->stream>>>(leaf_box, n_leaves, ctx_x, crow0, crow1, ctx->coarse_counts, ctx->coarse_off, ctx->coarse_items); LAUNCHED();
     k_bin_sort<<<cdiv(n_coarse * 32, 128), 128, 0, ctx->stream>>>(ctx->coarse_off, ctx->coarse_items, ctx->coarse_items + ctot, n_coarse); LAUNCHED();
-    k_bin2<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(leaf_box, leaves, ctx->coarse_off, ctx->coarse_items, ctx_x, crow0, fr, cell_row0, n_cells, ctx->cell_rng,
-                                                          ctx->cell_items, ctx->order_hist, ordered ? ctx->cell_order : nullptr); LAUNCHED();
+    k_bin2<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(leaf_box, leaves, ctx->coarse_off, ctx->coarse_items, ctx_x, crow0, fr, cell_row0, n_cells, B.cell_rng,
+                                                          B.cell_items, B.state, ordered ? B.cell_order : nullptr); LAUNCHED();
+  }
+  if (prefill) {
+    BinPrefill pf; memset(&pf, 0, sizeof pf);
+    pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1; pf.n_peers = 0;
+    k_prefill<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(B.cell_head, fr, cell_row0, n_cells, pf); LAUNCHED();
   }
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
   P.rowedge_ptr = s->rowedge_ptr; P.rowedge_idx = s->rowedge_idx; P.brush_ranges = s->brush_ranges;
   P.conv_bits = s->conv_bits; P.conv_px = s->conv_px;
-  P.cell_rng = ctx->cell_rng;
-  P.cls_cells = ordered ? ctx->cell_order : nullptr; P.cls_cnt = ordered ? ctx->order_hist + 1 : nullptr;
-  P.cell_items = ctx->cell_items; P.cell_head = big ? nullptr : ctx->cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
+  P.cell_rng = B.cell_rng;
+  P.cls_cells = ordered ? B.cell_order : nullptr; P.cls_cnt = ordered ? B.state + 1 : nullptr;
+  P.cell_items = B.cell_items; P.cell_head = big ? nullptr : B.cell_head; P.aa = ctx->d_aa; P.fr = fr; P.cell_row0 = cell_row0;
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
@@ -136,7 +152,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // not by throughput — one-row items shorten that path (measured on the lion at 8 GPUs: 0.164 -> 0.141 ms;
   // at 1 to 4 GPUs four-row items are as fast or faster).
   if (!big && (long long)n_cells * 4 < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 1;
-  if (const char* e = getenv("COH_WALK_H")) { int v = atoi(e); if (v == 1 || v == 4 || v == 16) walk_h = v; }  // tests force every variant
+  if (ctx->opt_walk_h) walk_h = ctx->opt_walk_h;  // tests force every variant
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
 #define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
   do {                                                                                                             \
@@ -155,7 +171,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
   // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
   // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
-  const char* force = getenv("COH_FUSED");   // tests force either path: "1" fused, "0" three-phase
+  const int force = ctx->opt_fused;   // tests force either path: 1 fused, 0 three-phase
   // eligible: every leaf of the range is a path, a primitive or a Convolved object
   bool kinds_ok = s->extras == 0;
   bool has_conv = false;
@@ -168,7 +184,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     }
   }
   const bool pre = kinds_ok && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
-                   (force ? force[0] == '0' : walk_h != 1);
+                   (force >= 0 ? force == 0 : walk_h != 1);
   if (pre) {
     const size_t n_pairs = total * CELL_H;
     if (n_pairs > ctx->pre_cap) {
@@ -176,17 +192,27 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       const size_t cap = n_pairs + n_pairs / 4 + 1024;
       CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap));
       CK(DMALLOC(&ctx->pre_list, sizeof(int4) * cap)); CK(DMALLOC(&ctx->pre_op, 32 * cap));
-      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, sizeof(int)));
+      DFREE(ctx->pre_cplx);
+      CK(DMALLOC(&ctx->pre_cplx, sizeof(int2) * cap));
+      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, 2 * sizeof(int)));   // list length, complex-list length
       ctx->pre_cap = cap;
     }
-    P.item_cell = ctx->item_cell;
-    CK(cudaMemsetAsync(ctx->pre_n, 0, sizeof(int), ctx->stream));
+    P.item_cell = B.item_cell;
+    CK(cudaMemsetAsync(ctx->pre_n, 0, 2 * sizeof(int), ctx->stream));
     k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc); LAUNCHED();
     k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n); LAUNCHED();
-    k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
+    if (ctx->aa_general) { k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED(); }
+    else {
+      // interval form for the pairs whose super-sampled rows are single runs, bit-rows for the rest
+      k_pre_aa_runs<<<ctx->n_sms * 6, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op, ctx->pre_cplx, ctx->pre_n + 1); LAUNCHED();
+      k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n + 1, ctx->pre_op, ctx->pre_cplx); LAUNCHED();
+    }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
-    if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
+    if (s->flat_ok && ctx->opt_comp_rows) {
+      // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
+      k_comp_rows<<<n_cells, CELL_H * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
+    } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {
         DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);

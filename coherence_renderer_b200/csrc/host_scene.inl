@@ -8,8 +8,9 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
-  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px);
+  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr);
   for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
+  free_binset(ctx, s->bins);
   delete s;
   return 0;
 }
@@ -44,6 +45,16 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<int> leaves;
   std::vector<uint8_t> stamps;
   std::vector<int> open;  // indices (into recs) of open groups
+  // A Group that is the first member of its list and is composited with plain Over goes under an accumulator that is
+  // still clear, and `over clear s = s` exactly (colour.ml:314-316): its members can composite straight into the
+  // parent's accumulator — same pixels, same u — so such groups vanish from the members' ancestor chains (the lion of
+  // examples.ml:174-180 in front of a scene is one).  Not with filters in the scene: their passes continue a frame
+  // from accumulators that are not clear.
+  std::vector<int> eff_open;      // the ancestor chain the walker sees: open groups that are not dissolved into their parent
+  std::vector<int> n_children;    // per open group: members seen so far
+  std::vector<char> open_flat;    // per open group: dissolved into its parent
+  bool any_filter = false;
+  for (int i = 0; i < n_objs; i++) any_filter = any_filter || objs[i].kind == COH_OBJ_FILTER;
   std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
   std::vector<int> point_obj((size_t)std::max(n_points, 1), -1);  // owning brush object of every point
   struct ConvItem { int rec, kind, r; };
@@ -53,6 +64,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
   recs.push_back(root); open.push_back(0);
+  eff_open.push_back(0); n_children.push_back(0); open_flat.push_back(0);
   std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
   std::vector<int> group_last;
   std::vector<int64_t> ids;
@@ -69,6 +81,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       n_front_leaves = (int)leaves.size();
       root.flags = OF_ROOT_BACKGROUND;
       recs.push_back(root); open[0] = (int)recs.size() - 1;
+      eff_open[0] = open[0]; n_children[0] = 0;
     }
     const coh_object& c = objs[i];
     if (c.kind == COH_OBJ_GROUP_END) {
@@ -79,6 +92,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       group_last.resize(recs.size(), -1);
       group_last[open.back()] = (int)recs.size() - 1;
       open.pop_back();
+      if (!open_flat.back()) eff_open.pop_back();
+      open_flat.pop_back(); n_children.pop_back();
       continue;
     }
     if (c.kind == COH_OBJ_GROUP_BEGIN && c.filter_kind == COH_FILTER_READING_SCENE) {
@@ -112,9 +127,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     ObjRec o; memset(&o, 0, sizeof o);
     o.pretrans = c.pretrans; o.dx = c.dx; o.dy = c.dy;
     if (c.pretrans < -1 || c.pretrans > 255) FAIL("scene: pretrans out of range");
-    o.depth = (int)open.size();
+    o.depth = (int)eff_open.size();
     if (o.depth > MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
-    for (int d = 0; d < o.depth; d++) o.anc[d] = open[d];
+    for (int d = 0; d < o.depth; d++) o.anc[d] = eff_open[d];
     o.fill.kind = c.fill_kind; o.fill.c0 = c.colour0; o.fill.c1 = c.colour1; o.fill.flags = c.fill_flags;
     for (int k = 0; k < 6; k++) o.fill.p[k] = c.fparam[k];
     switch (c.kind) {
@@ -122,6 +137,12 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
         recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
+        {
+          const bool flat = !any_filter && o.pretrans < 0 && n_children.back() == 0;
+          n_children.back()++;
+          open_flat.push_back(flat ? 1 : 0); n_children.push_back(0);
+          if (!flat) eff_open.push_back((int)recs.size() - 1);
+        }
         rec_of_abi[i] = (int)recs.size() - 1;
         ids.resize(recs.size(), -1); ids.back() = c.id;
         continue;
@@ -230,6 +251,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (clear_path) o.flags |= OF_OCCLUDES;
     }
     recs.push_back(o);
+    n_children.back()++;
     rec_of_abi[i] = (int)recs.size() - 1;
     ids.resize(recs.size(), -1); ids.back() = c.id;
     leaves.push_back((int)recs.size() - 1);
@@ -255,6 +277,25 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH || o.kind == K_CONV) s->extras = std::max(s->extras, 1);
     if (o.kind == K_CPG || !filters.empty()) s->extras = 2;  // the filter passes need the walker variant that can continue a frame
+  }
+  // Flat scenes — every leaf a direct member of one of the two root lists, plain-filled paths and primitives only —
+  // take the row compositor (k_comp_rows) in three-phase frames.  The background list is composited as a list of
+  // its own (render.ml:1364-1365); walking it under the scene's accumulator gives the same pixels when it has one
+  // member, or only opaque primitives (the first one covering a pixel finishes it either way).
+  std::vector<int2> attr(recs.size(), make_int2(0, 0));   // (uploaded asynchronously: lives until the synchronisation below)
+  {
+    bool flat = filters.empty();
+    int n_bg = 0; bool bg_opaque_prims = true;
+    for (int li : leaves) {
+      const ObjRec& o = recs[li];
+      flat = flat && o.depth == 1 && (o.kind == K_PATH || o.kind == K_PRIM) && o.fill.kind == 0;
+      const bool bg = (recs[o.anc[0]].flags & OF_ROOT_BACKGROUND) != 0;
+      if (bg) { n_bg++; bg_opaque_prims = bg_opaque_prims && o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0; }
+      attr[li] = make_int2((int)o.fill.c0, (o.kind == K_PATH ? 1 : 0) | (bg ? 2 : 0) | ((o.pretrans + 1) << 8));
+    }
+    s->flat_ok = flat && (n_bg <= 1 || bg_opaque_prims);
+    CK(DMALLOC(&s->attr, sizeof(int2) * recs.size()));
+    CK(cudaMemcpyAsync(s->attr, attr.data(), sizeof(int2) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(DMALLOC(&s->objs, sizeof(ObjRec) * recs.size()));
   CK(cudaMemcpyAsync(s->objs, recs.data(), sizeof(ObjRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));

@@ -121,7 +121,7 @@ __device__ __forceinline__ int bin_class(int n) {  // longest lists first; the l
   return n >= 12 ? 7 : n >= 8 ? 8 : n >= 6 ? 9 : n >= 5 ? 10 : n == 4 ? 11 : n == 3 ? 12 : n == 2 ? 13 : n == 1 ? 14 : 15;
 }
 // Cells whose only object is an opaque primitive covering all of them (the background rectangle: most cells of
-// most frames) are finished right here when the update is a box: their pixels are that colour, and they never
+// most frames) are finished by k_prefill when the update is a box: their pixels are that colour, and they never
 // enter the walker's queue.
 struct BinPrefill {
   uint32_t* fb;                     // null: off (arbitrary update shapes, continued frames, row-major order)
@@ -133,7 +133,7 @@ struct BinPrefill {
 __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr, int cell_row0,
                        int n_cells, int2* __restrict__ cell_rng, int* __restrict__ items, int* __restrict__ state /* [0] pool cursor, [1..] class counts */,
                        int* __restrict__ cls_cells /* [BIN_CLASSES][n_cells] or null */, const ObjRec* __restrict__ objs, int2* __restrict__ cell_head,
-                       int* __restrict__ item_cell, BinPrefill pf) {
+                       int* __restrict__ item_cell, int prefill_on, const int2* __restrict__ attr, int2* __restrict__ item_attr) {
   __shared__ int s_n[8], s_c[8], s_base[8], s_pos[8];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + wid;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
         o.prim[0] + o.dx <= x0 && o.prim[2] + o.dx >= ex1 && o.prim[1] + o.dy <= y0 && o.prim[3] + o.dy >= ey1)
       hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
   }
-  const bool prefill = pf.fb != nullptr && (hd.y & 1);          // (lane 0's view)
+  const bool prefill = prefill_on && (hd.y & 1);          // (lane 0's view): finished by k_prefill, in no class
   if (lane == 0) { s_n[wid] = n; s_c[wid] = (active && !prefill) ? bin_class(n) : -1; }
   __syncthreads();
   if (wid == 0 && lane < 8) {
@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
     const unsigned m = __shfl_sync(0xFFFFFFFFu, mymask, b >> 5);
     if ((m >> lane) & 1u) {
       const int dst = at + __popc(m & ((1u << lane) - 1u));
-      items[dst] = leaves[b + lane];
+      const int leaf = leaves[b + lane];
+      items[dst] = leaf;
       if (item_cell) item_cell[dst] = warp;
+      if (item_attr) item_attr[dst] = attr[leaf];
     }
     at += __popc(m);
   }
@@ -200,24 +202,44 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
     cell_head[warp] = hd;
     if (cls_cells && s_c[wid] >= 0) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
   }
-  if (__shfl_sync(0xFFFFFFFFu, (int)prefill, 0)) {
-    const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, hd.x, 0);
-    const bool scene_root = (__shfl_sync(0xFFFFFFFFu, hd.y, 0) & 2) != 0;
-    uint32_t colmask = interval_mask32(x0, pf.ux0, pf.ux1);
-    if (x0 + 31 >= fr.W) colmask &= interval_mask32(x0, 0, fr.W - 1);
-#pragma unroll 1
-    for (int r = 0; r < CELL_H; r++) {
-      const int y = y0 + r;
-      if (y < fr.band_y0 || y >= fr.band_y1) continue;
-      const uint32_t u = (y >= pf.uy0 && y <= pf.uy1) ? colmask : 0u;
-      if (pf.u_out && lane == 0) pf.u_out[(size_t)y * fr.tiles_x + cx] = scene_root ? 0u : u;
-      if ((u >> lane) & 1u) {
-        const size_t at = (size_t)y * fr.W + x0 + lane;
-        pf.fb[at] = c0;
-        for (int k = 0; k < pf.n_peers; k++) pf.peer_fb[k][at] = c0;
-      }
-    }
+}
+// The background cells of a box update (flagged by k_bin1): one warp per cell streams the cell's 16 rows of one
+// colour with 128-bit stores (8 lanes per 128-byte row, 4 rows per instruction) where the cell lies inside the
+// update box, pixel by pixel at the box's rim.
+__global__ void __launch_bounds__(256) k_prefill(const int2* __restrict__ cell_head, Frame fr, int cell_row0, int n_cells, BinPrefill pf) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_cells) return;
+  const int2 hd = cell_head[warp];
+  if (!(hd.y & 1)) return;
+  const int cx = fr.ctx0 + warp % fr.cntx, cy = cell_row0 + warp / fr.cntx;
+  const int x0 = cx * TILE_W, y0 = cy * CELL_H;
+  const uint32_t c0 = (uint32_t)hd.x;
+  const bool scene_root = (hd.y & 2) != 0;
+  uint32_t colmask = interval_mask32(x0, pf.ux0, pf.ux1);
+  if (x0 + 31 >= fr.W) colmask &= interval_mask32(x0, 0, fr.W - 1);
+  const int ya = max(max(y0, fr.band_y0), pf.uy0), yb = min(min(y0 + CELL_H - 1, fr.band_y1 - 1), pf.uy1);   // rows of the cell inside band and update
+  if (pf.u_out && lane < CELL_H) {
+    const int y = y0 + lane;
+    if (y >= fr.band_y0 && y < fr.band_y1) pf.u_out[(size_t)y * fr.tiles_x + cx] = (scene_root || y < pf.uy0 || y > pf.uy1) ? 0u : colmask;
   }
+  if (yb < ya || colmask == 0u) return;
+  if (colmask == 0xFFFFFFFFu && (fr.W & 3) == 0) {
+    const uint4 v = make_uint4(c0, c0, c0, c0);
+    for (int y = ya + (lane >> 3); y <= yb; y += 4) {
+      const size_t at = (size_t)y * fr.W + x0 + 4 * (lane & 7);
+      *reinterpret_cast<uint4*>(pf.fb + at) = v;
+#pragma unroll
+      for (int k = 0; k < 7; k++) if (k < pf.n_peers) *reinterpret_cast<uint4*>(pf.peer_fb[k] + at) = v;
+    }
+    return;
+  }
+  if ((colmask >> lane) & 1u)
+    for (int y = ya; y <= yb; y++) {
+      const size_t at = (size_t)y * fr.W + x0 + lane;
+      pf.fb[at] = c0;
+#pragma unroll
+      for (int k = 0; k < 7; k++) if (k < pf.n_peers) pf.peer_fb[k][at] = c0;
+    }
 }
 // ------------------------------------------------------------------------------------
 // K1 binning for large scenes, two levels.  Level 1 is object-parallel over coarse cells of

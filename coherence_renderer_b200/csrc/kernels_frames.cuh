@@ -73,25 +73,201 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
     if (o.flags & OF_OCCLUDES) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
   }
 }
-__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n, uint8_t* __restrict__ op) {
+// General antialiasing of listed pairs (bit-rows in shared memory, any number of crossings).  With `sel` the
+// kernel runs over the entries sel[0 .. *sel_n) = (list index, edge pixels) that the interval kernel found complex.
+__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n, uint8_t* __restrict__ op,
+                                                 const int2* __restrict__ sel = nullptr) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
   __shared__ StagedEdge s_stage[8][32];
+  const int n = *list_n;
+  if (blockIdx.x * 8 >= n) return;   // (the grid is sized before the list length is known)
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = *list_n, n_warps = gridDim.x * 8;
+  const int n_warps = gridDim.x * 8;
   for (int i = blockIdx.x * 8 + wid; i < n; i += n_warps) {
-    const int4 ent = list[i];
+    const int2 pick = sel ? sel[i] : make_int2(i, 0);
+    const int4 ent = list[pick.x];
+    const uint32_t edge = sel ? (uint32_t)pick.y : (uint32_t)ent.z;
     const ObjRec& o = P.objs[ent.y];
     const int yy = (ent.w & 0xFFFF) - o.dy, xx0 = (ent.w >> 16) * TILE_W - o.dx;
     const int slot = o.row_base + yy - o.ry0;
     const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
     bool ok;
-    const int v = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, (uint32_t)ent.z, s_aa[wid], s_stage[wid], s_prefix, P.aa->volume, lane, ok);
+    const int v = aa_tile(P.edges, P.rowedge_idx + a, b - a, o.aa_winding, xx0, yy, edge, s_aa[wid], s_stage[wid], s_prefix, P.aa->volume, lane, ok);
     if (!ok) *P.error_flag = 1;
-    op[(size_t)ent.x * 32 + lane] = (uint8_t)v;
+    if ((edge >> lane) & 1u) op[(size_t)ent.x * 32 + lane] = (uint8_t)v;
     __syncwarp();
+  }
+}
+// Antialiasing of listed pairs in interval form (raster_core.cuh, AaScan): lane j evaluates super-sampled row
+// 16 y - 32 + j of the x16 edge list as a run [lo, hi] (minus at most one gap) of the columns under the pair's edge
+// pixels — no bit-row, no crossing lists — and every edge pixel is two prefix-table reads per lane plus one
+// redux.sync for two pixels.  A pair with a row that is not provably of that form (2 % on the lion) is retried
+// run by run of its edge pixels (narrower windows); what is still complex goes on the `cplx` list for k_pre_aa.
+constexpr int AA2_WARPS = 8;
+// the edge pixels `edge` (a subset of the pair's) against the staged candidates; returns false when some row is complex
+__device__ __forceinline__ bool aa_runs_pixels(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int winding,
+                                               int xx0, int yy, uint32_t edge, AaEdge* __restrict__ stage, const int* __restrict__ prow,
+                                               int lane, int& mytot) {
+  const int wlo = 16 * xx0 - 32;
+  const int nlo = wlo + 16 * (__ffs((int)edge) - 1), nhi = wlo + 16 * (31 - __clz((int)edge)) + 31;
+  AaScan sc; sc.begin(16 * yy - 32 + lane, nlo, nhi);
+  for (int base = 0; base < n_cand; base += 32) {
+    if (base + lane < n_cand) stage[lane] = make_aa_edge(edges[idx[base + lane]], nlo, nhi);
+    __syncwarp();
+    const int cnt = min(32, n_cand - base);
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) sc.edge(stage[k]);
+    __syncwarp();
+  }
+  int lo, hi, glo, ghi;
+  const bool simple = sc.finish(winding, lo, hi, glo, ghi);
+  if (!__all_sync(0xFFFFFFFFu, simple)) return false;
+  const bool any_gap = __any_sync(0xFFFFFFFFu, glo <= ghi);   // some row is two runs: the hull minus a gap
+  uint32_t e = edge;
+  // run by run of edge pixels, two pixels per warp reduction: a table sum is below 2^16, so two pixels share
+  // one register through redux.sync
+  while (e) {
+    const int b0 = __ffs((int)e) - 1;
+    const uint32_t tz = ~(e >> b0);
+    const int len = min(tz ? (__ffs((int)tz) - 1) : 32, 32 - b0);
+    e &= ~((len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0);
+#pragma unroll 1
+    for (int k = 0; k < len; k += 2) {
+      const int w0 = wlo + 16 * (b0 + k);
+      const bool two = k + 1 < len;
+      int p = aa_interval_sum(prow, lo, hi, w0);
+      int q = two ? aa_interval_sum(prow, lo, hi, w0 + 16) : 0;
+      if (any_gap) {
+        p -= aa_interval_sum(prow, glo, ghi, w0);
+        q -= two ? aa_interval_sum(prow, glo, ghi, w0 + 16) : 0;
+      }
+      const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, (unsigned)p | ((unsigned)q << 16));
+      mytot = (lane == b0 + k) ? (int)(tot & 0xFFFFu) : mytot;
+      mytot = (lane == b0 + k + 1) ? (int)(tot >> 16) : mytot;
+    }
+  }
+  return true;
+}
+__global__ void __launch_bounds__(AA2_WARPS * 32) k_pre_aa_runs(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n,
+                                                                  uint8_t* __restrict__ op, int2* __restrict__ cplx, int* __restrict__ cplx_n) {
+  __shared__ int s_prefix[32 * 33];
+  __shared__ AaEdge s_stage[AA2_WARPS][32];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = *list_n, n_warps = gridDim.x * AA2_WARPS;
+  const int* prow = s_prefix + lane * 33;
+  AaEdge* stage = s_stage[wid];
+  for (int i = blockIdx.x * AA2_WARPS + wid; i < n; i += n_warps) {
+    const int4 ent = list[i];
+    const ObjRec& o = P.objs[ent.y];
+    const int yy = (ent.w & 0xFFFF) - o.dy, xx0 = (ent.w >> 16) * TILE_W - o.dx;
+    const int slot = o.row_base + yy - o.ry0;
+    const int ea = P.rowedge_ptr[slot], n_cand = P.rowedge_ptr[slot + 1] - ea;
+    const int winding = o.aa_winding;
+    const uint32_t edge = (uint32_t)ent.z;
+    int mytot = 0;
+    uint32_t mine = edge;   // the pixels this kernel finishes
+    if (!aa_runs_pixels(P.edges, P.rowedge_idx + ea, n_cand, winding, xx0, yy, edge, stage, prow, lane, mytot)) {
+      // retry run by run of the edge pixels: each run sees only the part of the object near it
+      uint32_t e = edge, hard = 0u;
+      while (e) {
+        const int b0 = __ffs((int)e) - 1;
+        const uint32_t tz = ~(e >> b0);
+        const int len = min(tz ? (__ffs((int)tz) - 1) : 32, 32 - b0);
+        const uint32_t run = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0;
+        e &= ~run;
+        if (run == edge || !aa_runs_pixels(P.edges, P.rowedge_idx + ea, n_cand, winding, xx0, yy, run, stage, prow, lane, mytot)) hard |= run;
+      }
+      if (hard && lane == 0) cplx[atomicAdd(cplx_n, 1)] = make_int2(i, (int)hard);
+      mine &= ~hard;   // k_pre_aa writes those bytes
+    }
+    if ((mine >> lane) & 1u) op[(size_t)ent.x * 32 + lane] = (uint8_t)aa_opacity(mytot, AA_VOLUME);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Row compositor of three-phase frames for FLAT scenes (every leaf a direct member of the scene list or of the
+// background list, plain-filled paths and primitives): the front-to-back loop of render.ml:1268-1335 for one pixel
+// row of one cell per warp, lane = pixel column.  Scan conversion (k_pre_scan) and antialiasing (k_pre_aa*) are
+// done; here 32 list entries at a time are tested against the covered-so-far word `u` (lane = entry), and the entries
+// that still show are composited in list order: vis = S & u, edge pixels dissolve the fill by their opacity byte
+// (render.ml:1201-1204), PreTrans dissolves again (1295-1298), acc = over acc s, u' = u - opaque (1294, 1308).
+// One block per cell (CELL_H warps), cells in heavy-first order; background cells were finished by k_prefill.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CELL_H * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr) {
+  __shared__ int s_cell;
+  if (threadIdx.x == 0) {
+    // position blockIdx.x of the heavy-first order -> cell (classes are consecutive segments of cls_cells)
+    int q = blockIdx.x, cell = -1;
+    if (P.cls_cnt) {
+      for (int c = 0; c < BIN_CLASSES; c++) { const int n = P.cls_cnt[c]; if (q < n) { cell = P.cls_cells[(size_t)c * P.n_cells + q]; break; } q -= n; }
+    } else cell = q < P.n_cells ? q : -1;
+    s_cell = cell;
+  }
+  __syncthreads();
+  const int cell = s_cell;
+  if (cell < 0) return;
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
+  const int tx0 = tile * TILE_W, y = (P.cell_row0 + by) * CELL_H + row;
+  if (y < P.fr.band_y0 || y >= P.fr.band_y1) return;
+  uint32_t u = P.u_init ? P.u_init[(size_t)y * P.fr.tiles_x + tile] : ((y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u);
+  if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
+  const uint32_t u_update = u;
+  uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
+  if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
+  const int2 rg = P.cell_rng[cell];
+  uint32_t acc = 0u;
+  const uint32_t lbit = 1u << lane;
+  for (int base = rg.x; base < rg.y; base += 32) {
+    if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
+    const int it = base + lane;
+    uint2 sc = make_uint2(0u, 0u); int2 at = make_int2(0, 0);
+    if (it < rg.y) { sc = P.pre_sc[(size_t)it * CELL_H + row]; at = item_attr[it]; }
+    unsigned hits = __ballot_sync(0xFFFFFFFFu, (sc.x & u) != 0u);
+    const unsigned bgm = __ballot_sync(0xFFFFFFFFu, (at.y & 2) != 0);
+    if (u_rec && bgm) {   // the scene list ends inside this chunk: its hits first, then record u
+      unsigned hs = hits & ~bgm;
+      hits &= bgm;
+      while (hs) {
+        const int k = __ffs((int)hs) - 1; hs &= hs - 1;
+        const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k), C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
+        const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
+        const uint32_t vis = S & u;
+        if (vis == 0u) continue;
+        const uint32_t edge = vis & C;
+        uint32_t col = c0;
+        if ((fl & 1) && (edge & lbit)) col = px_dissolve(c0, P.pre_op[((size_t)(base + k) * CELL_H + row) * 32 + lane]);
+        if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
+        if (vis & lbit) acc = px_over(acc, col);
+        u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
+      }
+      if (lane == 0) *u_rec = u;
+      u_rec = nullptr;
+    }
+    while (hits) {
+      const int k = __ffs((int)hits) - 1; hits &= hits - 1;
+      const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k), C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
+      const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
+      const uint32_t vis = S & u;
+      if (vis == 0u) continue;
+      const uint32_t edge = vis & C;        // shptorender ∩ maxshape: S & ~(S & ~C) restricted to vis
+      uint32_t col = c0;
+      if ((fl & 1) && (edge & lbit)) col = px_dissolve(c0, P.pre_op[((size_t)(base + k) * CELL_H + row) * 32 + lane]);
+      if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
+      if (vis & lbit) acc = px_over(acc, col);
+      u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
+    }
+  }
+  if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
+  if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
+    const size_t at = (size_t)y * P.fr.W + tx0 + lane;
+    P.fb[at] = acc;
+    for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
   }
 }
 

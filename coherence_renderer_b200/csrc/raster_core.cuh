@@ -522,6 +522,122 @@ COH_HD int aa_opacity(int table_sum, int volume) {  // polygon.ml:650-651 with c
 #endif
 }
 
+// ---------------------------------------------------------------------------------
+// Antialiasing, interval form.  Inside the columns a pixel's window can read, one super-sampled row of an
+// object is nearly always ONE run (everything left of an edge, everything right of it, the strip between two
+// edges of a thin feature).  AaScan evaluates a row of the x16 edge list (polygon.ml:673-692, the `_aa` span
+// rules of 469-512) without any bit-row: crossings that touch the window are kept as the two smallest of a
+// sorted pair per band line, the coverage pieces as their hull plus at most one gap, and finish() either proves
+// that T ∪ B ∪ C is the interval [lo, hi] minus at most one gap [glo, ghi] (two disjoint parts of the object in
+// the window) or reports `complex` (more than two crossings on a band line inside the window, a second gap) — the
+// caller then takes the general bit-row path.  The proof: every winding span starts / ends at the window border
+// or at a crossing, and a crossing lies inside its own edge's coverage piece, so every span hangs on a coverage
+// piece and either stays on its side of the gap or reaches across all of it; with one coverage component
+// everything is connected, with two the union is the hull, or the hull minus the gap when no span bridges it.
+// ---------------------------------------------------------------------------------
+struct AaEdge {          // staged candidate edge, coordinates scaled by 16
+  double x0d, g, g63;    // (double) x0, gradient, g * 63.25 (the both-ends-clipped step of polygon.ml:372-379)
+  int x0, x1, ymin, ymax;
+  int dir, side;         // side: edge_side() against the window the scan is classified in
+};
+COH_HD AaEdge make_aa_edge(const EdgeRec& e, int wlo, int whi);
+COH_HD int pix_of_sub_fast(int n) { const int t = n + 31; return (t + ((t >> 31) & 31)) >> 5; }  // (n + 31) / 32, truncating
+struct AaBandLine {      // the crossings of one band line (top or bottom)
+  int nl, cl, n, v0, v1; bool hr;
+  COH_HD void init() { nl = 0; cl = 0; n = 0; v0 = 0x7FFFFFFF; v1 = 0x7FFFFFFF; hr = false; }
+  COH_HD void add(bool pred, int p, int dir, int wlo, int whi) {
+    const int px = pix_of_sub_fast(p);
+    const bool left = pred && px < wlo, right = pred && px > whi, inside = pred && !(px < wlo) && !(px > whi);
+    cl += left ? dir : 0; nl += left ? 1 : 0; hr = hr || right;
+    const int nv = inside ? ((p << 1) | (dir > 0)) : 0x7FFFFFFF;
+    const int a = imin(v0, nv), b = imax(v0, nv);
+    v0 = a; v1 = imin(v1, b);
+    n += inside ? 1 : 0;
+  }
+};
+struct AaScan {
+  int top, bot, wlo, whi;
+  AaBandLine T, B;
+  int clo, chi, glo, ghi, nc; bool gap, cplx;
+  COH_HD void begin(int y, int wlo_, int whi_) {
+    top = 32 * y - 47; bot = top + 63; wlo = wlo_; whi = whi_;
+    T.init(); B.init();
+    clo = 0x7FFFFFFF; chi = -0x7FFFFFFF; glo = 0; ghi = 0; nc = 0; gap = false; cplx = false;
+  }
+  COH_HD void edge(const AaEdge& e) {
+    const bool horiz = e.ymin == e.ymax;
+    const bool cross_top = !horiz && e.ymin < top && e.ymax >= top;      // polygon.ml:338-343 for an edge longer than the band
+    const bool cross_bot = !horiz && e.ymax > bot && e.ymin <= bot;
+    if (e.side == 1) {
+      T.cl += cross_top ? e.dir : 0; T.nl += cross_top ? 1 : 0;
+      B.cl += cross_bot ? e.dir : 0; B.nl += cross_bot ? 1 : 0;
+      return;
+    }
+    if (e.side == 2) { T.hr = T.hr || cross_top; B.hr = B.hr || cross_bot; return; }
+    const bool active = !(e.ymin > bot || e.ymax < top);
+    const int xt = (int)dadd(dadd(e.x0d, dmul(e.g, dadd((double)(top - 1 - e.ymin), 0.25))), 0.5);
+    const int xs = cross_top ? xt : e.x0;
+    const double step = cross_top ? e.g63 : dmul(e.g, dadd((double)(bot - e.ymin), 0.25));
+    const int xb = (int)dadd(dadd((double)xs, step), 0.5);
+    T.add(cross_top, xt, e.dir, wlo, whi);
+    B.add(cross_bot, xb, e.dir, wlo, whi);
+    const int pe = cross_bot ? xb : e.x1;
+    const int ca = pix_of_sub_fast(imin(xs, pe) - 16), cb = pix_of_sub_fast(imax(xs, pe) + 16);   // polygon.ml:444-453
+    if (active && cb >= wlo && ca <= whi) {
+      const bool touch = ca <= chi + 1 && cb >= clo - 1;
+      cplx = cplx || (gap && (!touch || (ca <= ghi && cb >= glo)));   // a second gap, or a piece inside the gap
+      if (nc > 0 && !touch) {
+        gap = true;
+        const bool rightof = ca > chi;
+        glo = rightof ? chi + 1 : cb + 1; ghi = rightof ? ca - 1 : clo - 1;
+      }
+      clo = imin(clo, ca); chi = imax(chi, cb); nc++;
+    }
+  }
+  // spans of one band line (polygon.ml:469-512): anything anchored on the window's left / right border, and
+  // whether a span reaches across the gap
+  COH_HD void line_spans(const AaBandLine& L, int winding, bool& left_any, bool& right_any, bool& bridged) const {
+    const int P0 = pix_of_sub_fast(L.v0 >> 1), P1 = pix_of_sub_fast(L.v1 >> 1);
+    const bool odd = (L.nl & 1) != 0;
+    const int c0 = L.cl + ((L.v0 & 1) ? 1 : -1), c1 = c0 + ((L.v1 & 1) ? 1 : -1);
+    const bool e_left = winding == 0 ? (L.cl != 0) : odd;
+    const bool e0 = winding == 0 ? (c0 != 0) : !odd;
+    const bool e1 = winding == 0 ? (c1 != 0) : odd;
+    const bool sL = L.nl > 0 && (L.n > 0 || L.hr) && e_left;    // [wlo, n > 0 ? P0 : whi]
+    const bool s0 = L.n >= 1 && e0 && (L.n >= 2 || L.hr);       // [P0, n >= 2 ? P1 : whi]
+    const bool s1 = L.n >= 2 && e1 && L.hr;                     // [P1, whi]
+    left_any = left_any || sL;
+    right_any = right_any || (sL && L.n == 0) || (s0 && L.n == 1) || s1;
+    const int bL = L.n > 0 ? P0 : whi, b0 = L.n >= 2 ? P1 : whi;
+    bridged = bridged || (sL && bL >= ghi) || (s0 && P0 <= glo && b0 >= ghi) || (s1 && P1 <= glo);
+  }
+  // true: the row's occupancy inside [wlo, whi] is exactly [lo, hi] minus [glo_, ghi_] (either may be empty: lo > hi)
+  COH_HD bool finish(int winding, int& lo, int& hi, int& glo_, int& ghi_) const {
+    bool left_any = false, right_any = false, bridged = false;
+    line_spans(T, winding, left_any, right_any, bridged);
+    line_spans(B, winding, left_any, right_any, bridged);
+    glo_ = 1; ghi_ = 0;
+    if (cplx || T.n > 2 || B.n > 2) return false;
+    if (nc == 0) { lo = (left_any || right_any) ? wlo : 1; hi = (left_any || right_any) ? whi : 0; return true; }
+    lo = left_any ? wlo : imax(clo, wlo);
+    hi = right_any ? whi : imin(chi, whi);
+    if (gap && !bridged) { glo_ = glo; ghi_ = ghi; }
+    return true;
+  }
+};
+COH_HD AaEdge make_aa_edge(const EdgeRec& e, int wlo, int whi) {
+  AaEdge a;
+  a.x0 = e.x0in * 16; a.x1 = e.x1in * 16; a.ymin = e.ymin * 16; a.ymax = e.ymax * 16;
+  a.x0d = (double)a.x0; a.g = e.g; a.g63 = dmul(e.g, 63.25);
+  a.dir = e.dir; a.side = edge_side(a.x0, a.x1, wlo, whi);
+  return a;
+}
+// table-weighted sum of the run [lo, hi] of super-sampled row j inside the 32 columns starting at w0
+COH_HD int aa_interval_sum(const int* prefix_row /*33 ints*/, int lo, int hi, int w0) {
+  const int a = imin(imax(lo - w0, 0), 32), b = imin(imax(hi - w0 + 1, 0), 32);
+  return b > a ? prefix_row[b] - prefix_row[a] : 0;
+}
+
 // ---- constructive planar geometry (render.ml:522-528, 858-981) ----
 // shape / minshape words of CPG (op, a, b) from the operands' words; op: 0 Union, 1 Intersection,
 // 2 Subtraction, 3 ExclusiveOr

@@ -140,6 +140,77 @@ int emul_opacity_word_fast(const int32_t* edges, int n, int winding, int x0, int
   }
   return 0;
 }
+// The interval form (AaScan): every super-sampled row as one run, classified against the columns under the
+// edge pixels `edge` only (as aa_tile narrows its window).  Returns 0 when every row was proven to be one
+// interval (out32 written for the pixels of `edge`), 1 when some row was complex (caller falls back), -1 on error.
+int emul_opacity_word_interval(const int32_t* edges, int n, int winding, int x0, int y, uint32_t edge, uint8_t* out32) {
+  init_aa();
+  if (!edge) return 0;
+  const int wlo = 16 * x0 - 32;
+  const int nlo = wlo + 16 * __builtin_ctz(edge), nhi = wlo + 16 * (31 - __builtin_clz(edge)) + 31;
+  std::vector<AaEdge> es;
+  for (int i = 0; i < n; i++) es.push_back(make_aa_edge(make_edge(edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]), nlo, nhi));
+  int lo[32], hi[32], glo[32], ghi[32];
+  for (int j = 0; j < 32; j++) {
+    AaScan sc; sc.begin(16 * y - 32 + j, nlo, nhi);
+    for (int i = 0; i < n; i++) sc.edge(es[i]);
+    if (!sc.finish(winding, lo[j], hi[j], glo[j], ghi[j])) return 1;
+  }
+  for (int b = 0; b < 32; b++) {
+    if (!((edge >> b) & 1u)) continue;
+    int tot = 0;
+    for (int j = 0; j < 32; j++) tot += aa_interval_sum(g_aa.prefix[j], lo[j], hi[j], wlo + 16 * b) - aa_interval_sum(g_aa.prefix[j], glo[j], ghi[j], wlo + 16 * b);
+    out32[b] = (uint8_t)aa_opacity(tot, g_aa.volume);
+  }
+  return 0;
+}
+// Statistics + self-check over every (row, 32-pixel tile) of one object at a tile grid aligned to multiples of 32
+// pixels: the interval form against the general bit-row path for the max-shape pixels (shape - minshape).
+// stats[0] += pairs, [1] += complex pairs, [2] += mismatching pixels, [3] += edge pixels
+int emul_interval_stats(const int32_t* edges, int n, int winding, int64_t* stats) {
+  init_aa();
+  std::vector<EdgeRec> es;
+  int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+  for (int i = 0; i < n; i++) {
+    es.push_back(make_edge(edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]));
+    xmin = std::min(xmin, std::min(edges[4 * i], edges[4 * i + 2])); xmax = std::max(xmax, std::max(edges[4 * i], edges[4 * i + 2]));
+    ymin = std::min(ymin, std::min(edges[4 * i + 1], edges[4 * i + 3])); ymax = std::max(ymax, std::max(edges[4 * i + 1], edges[4 * i + 3]));
+  }
+  if (n == 0) return 0;
+  const int py0 = floordiv(ymin - 16 + 31, 32), py1 = floordiv(ymax + 47, 32);
+  const int tx0 = floordiv(floordiv(xmin - 16, 32) - 2, 32), tx1 = floordiv(floordiv(xmax + 16 + 31, 32) + 2, 32);
+  for (int y = py0; y <= py1; y++)
+    for (int t = tx0; t <= tx1; t++) {
+      Sink32 sink; sink.wx0 = 32 * t; sink.S = 0u; sink.C = 0u;
+      if (!scan_row(es.data(), nullptr, n, 1, y, winding, false, 32 * t, 32 * t + 31, sink)) return 2;
+      const uint32_t edge = sink.C;   // S & ~M with M = S & ~C
+      if (!edge) continue;
+      stats[0]++; stats[3] += __builtin_popcount(edge);
+      uint8_t a[32], b[32];
+      int rc = emul_opacity_word_interval(edges, n, winding, 32 * t, y, edge, a);
+      if (rc < 0) return 3;
+      if (rc == 1) {
+        stats[1]++;
+        // retry per cluster of edge bits (runs of set bits, split at every zero bit)
+        uint32_t m = edge; bool still = false; int ncl = 0;
+        while (m) {
+          const int s0 = __builtin_ctz(m);
+          const uint32_t tz = ~(m >> s0);
+          int l = tz ? __builtin_ctz(tz) : 32;
+          if (l > 32 - s0) l = 32 - s0;
+          const uint32_t cl = (l >= 32 ? 0xFFFFFFFFu : ((1u << l) - 1u)) << s0;
+          m &= ~cl; ncl++;
+          if (emul_opacity_word_interval(edges, n, winding, 32 * t, y, cl, a) == 1) still = true;
+        }
+        if (still) stats[4]++;
+        stats[5] += ncl;
+        continue;
+      }
+      if (emul_opacity_word(edges, n, winding, 32 * t, y, b)) return 4;
+      for (int k = 0; k < 32; k++) if (((edge >> k) & 1u) && a[k] != b[k]) stats[2]++;
+    }
+  return 0;
+}
 uint32_t emul_over(uint32_t a, uint32_t b) { return px_over(a, b); }
 uint32_t emul_dissolve(uint32_t c, int d) { return px_dissolve(c, d); }
 uint32_t emul_dissolve_between(uint32_t a, uint32_t b, int alpha) { return px_dissolve_between(a, b, alpha); }

@@ -150,10 +150,18 @@ def test_fancy_fills(ctx, oracle):
     assert _max_lsb(got, ref) == 0
 
 
-def test_fancy_fills_three_phase_path(ctx, oracle, monkeypatch):
+@pytest.fixture
+def options(ctx):
+    """Force code paths through coh_set_option; everything is reset afterwards."""
+    yield ctx.set_option
+    for name, v in (("walk_h", 0), ("fused", -1), ("aa_general", 0), ("bin_cache", 1), ("comp_rows", 1)):
+        ctx.set_option(name, v)
+
+
+def test_fancy_fills_three_phase_path(ctx, oracle, options):
     """The three-phase frame path (forced) with gradient fills: the compositing walk keeps the cross-tile carry of
     span starts."""
-    monkeypatch.setenv("COH_FUSED", "0")
+    options("fused", 0)
     test_fancy_fills(ctx, oracle)
     test_fancy_fill_long_shallow_edges(ctx, oracle)
 
@@ -645,16 +653,29 @@ def test_async_readback_equals_blocking_read(ctx):
         ctx.scene_free(scenes[k])
 
 
-@pytest.mark.parametrize("walk_h,fused", [("1", "1"), ("4", "1"), ("16", "1"), ("4", "0")])
-def test_every_walker_variant(ctx, oracle, walk_h, fused, monkeypatch):
+@pytest.mark.parametrize("walk_h,fused,aa_general,comp_rows", [("1", "1", 0, 1), ("4", "1", 0, 1), ("16", "1", 0, 1), ("4", "0", 0, 1), ("4", "0", 1, 1), ("4", "0", 0, 0)])
+def test_every_walker_variant(ctx, oracle, walk_h, fused, aa_general, comp_rows, options):
     """The walker is compiled for work items of 1, 4 and 16 rows, and plain polygon scenes have a three-phase path
     (scan / visibility / antialiasing kernels + a compositing walk) next to the fused one; the library picks by
     scene and frame size.  Every variant must give the same pixels (COH_WALK_H / COH_FUSED force one)."""
-    monkeypatch.setenv("COH_WALK_H", walk_h)
-    monkeypatch.setenv("COH_FUSED", fused)
+    options("walk_h", int(walk_h))
+    options("fused", int(fused))
+    options("comp_rows", comp_rows)     # flat scenes in three-phase frames: row compositor, or the walker
+    options("aa_general", aa_general)   # antialiasing of the three-phase frame: interval form + general kernel, or all general
     W, H = 640, 480
     b = S.lion_scene(W, H, 1.4, pretrans=200)
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    # flat scenes (the lion's group is the first member of the list and dissolves into it; a plain list of
+    # translucent polygons with a PreTrans member)
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, S.lion_scene(W, H, 1.4), W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    b = S.random_scene(300, 200, 60, seed=9, brush_fraction=0.0)
+    b.objs[3].pretrans = 120
+    b.objs[7].pretrans = 0
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, 300, 200)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, 300, 200, update=(37, 21, 150, 101))
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
     b = S.random_scene(300, 200, 50, seed=5, brush_fraction=0.3)
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, 300, 200)
@@ -855,3 +876,74 @@ def test_object_shapes_of_brush_and_convolved(ctx, oracle):
     ctx.shape_free(hs)
     ctx.shape_free(hm)
     ctx.scene_free(sc)
+
+
+def test_binning_kept_with_the_scene_is_invalidated(ctx, oracle, options):
+    """Whole-frame cell binning is kept with the scene (a pure function of the object boxes and the frame geometry).
+    It must be rebuilt when an object moves or the framebuffer geometry changes, and switching it off must give the
+    same pixels."""
+    W, H = 640, 480
+    b = S.lion_scene(W, H, 1.4)
+    b.objs[0].id = 5
+    objs, n, nbg, edges, points = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    try:
+        for rep in range(3):  # the second and third frame run from the kept lists
+            ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert _max_lsb(ctx.fb_read_rgba(0, 0, W, H), ref) == 0
+        ctx.scene_translate_object(sc, 0, 37, -21)   # the whole lion group
+        for k in range(1, n - nbg - 1):
+            objs[k].dx, objs[k].dy = 37, -21
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert _max_lsb(ctx.fb_read_rgba(0, 0, W, H), ref) == 0, "stale cell lists after a move"
+        ctx.fb_configure(W, H, 100, 300)             # another band of the same frame
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        assert _max_lsb(ctx.fb_read_rgba(0, 100, W, 200), ref[100:300]) == 0, "stale cell lists after a change of band"
+        ctx.fb_configure(W, H)
+        options("bin_cache", 0)
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.sync()
+        assert _max_lsb(ctx.fb_read_rgba(0, 0, W, H), ref) == 0
+    finally:
+        ctx.set_option("bin_cache", 1)
+        ctx.scene_free(sc)
+
+
+def test_first_member_groups_dissolve_into_their_parent(ctx, oracle):
+    """A Group that is the first member of its list and is composited with plain Over lands on a clear accumulator
+    (`over clear s = s`), so the library lets its members composite straight into the parent's accumulator.  Translucent
+    fills make any regrouping of `over` visible: nested first members, a later sibling group (kept), a first member
+    with PreTrans (kept), and a group that is first only after a null object."""
+    W, H = 260, 200
+
+    def tri(b, x, y, c, a, **kw):
+        return b.polygon([(x, y), (x + 110.5, y + 14.2), (x + 40.1, y + 120.7)], S.Fill.plain(S.dissolve(c, a)), **kw)
+
+    for variant in range(3):
+        b = S.SceneBuilder()
+        if variant == 2:
+            b.path_edges(np.zeros((0, 4), np.int32), S.Fill.plain(S.WHITE))   # NullShape object in front
+        b.group_begin(pretrans=(150 if variant == 1 else None))
+        b.group_begin()
+        tri(b, 20.3, 15.1, S.rgba8(220, 40, 40), 130)
+        tri(b, 50.9, 30.4, S.rgba8(40, 220, 40), 170)
+        b.group_end()
+        tri(b, 80.2, 22.8, S.rgba8(40, 40, 220), 90)
+        b.group_end()
+        b.group_begin()
+        tri(b, 60.6, 50.5, S.rgba8(200, 200, 30), 140)
+        tri(b, 100.1, 40.9, S.rgba8(30, 200, 200), 200, pretrans=99)
+        b.group_end()
+        tri(b, 10.0, 60.0, S.rgba8(255, 255, 255), 255)
+        b.begin_background()
+        b.rectangle(S.dissolve(S.rgba8(90, 90, 90), 200), 0.0, 0.0, float(W), float(H))
+        b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u), f"variant {variant}"
+        assert _max_lsb(got, ref) == 0, f"variant {variant}"
