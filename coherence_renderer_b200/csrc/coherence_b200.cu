@@ -33,6 +33,7 @@ struct BinSet {
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)
   int2* item_attr = nullptr;  // compositing attributes of every list entry (small-scene binning only)
+  int4* item_rec = nullptr;   // scan-conversion record of every list entry, two int4 each (small-scene binning only)
   int* state = nullptr;       // ORDER_BINS ints: [0] pool cursor, [1 ..] class counts
 };
 struct DevScene {
@@ -48,12 +49,13 @@ struct DevScene {
   int2* brush_ranges = nullptr; // per (stroke, cell of its box): [first, last] stamp index reaching the cell
   uint32_t* conv_bits = nullptr; // Convolved objects: shape / minshape bit-rows
   uint32_t* conv_px = nullptr;   // Convolved objects: pre-convolved canvases
-  int2* attr = nullptr;          // per record: {plain colour, is-path | background-list << 1 | (pretrans + 1) << 8} for the row compositor
+  int2* attr = nullptr;          // per record: {plain colour, is-path | background-list << 1 | occludes << 2 | (pretrans + 1) << 8}
   bool flat_ok = false;          // every leaf a direct member of a root list, plain paths / primitives only
   std::vector<ObjRec> h_objs;
   std::vector<int64_t> ids;      // cache key (Id.idset) of every record
   std::vector<int> rec_of_abi;   // record index of every object of the ABI array (-1: GROUP_END / dropped)
   std::vector<int> group_last;   // for group records: last record index inside the group
+  std::vector<int> real_depth;   // per record: enclosing groups in the scene as given (ObjRec.depth leaves out groups dissolved into their parent)
   // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
   struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; };
@@ -107,7 +109,6 @@ struct coh_ctx {
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
   // three-phase frames: per (cell item, row) pair
   uint2* pre_sc = nullptr; int4* pre_list = nullptr; int* pre_n = nullptr; uint8_t* pre_op = nullptr; size_t pre_cap = 0;
-  int2* pre_cplx = nullptr;    // (pair, edge pixels) the interval-form antialiasing kernel hands to the general one
   // tuning / test options (coh_set_option; the environment is read once, in coh_init)
   int opt_walk_h = 0;          // 0 = chosen per pass; 1 | 4 | 16 forces the walker's work-item height
   int opt_fused = -1;          // -1 = chosen per pass; 1 fused walker, 0 three-phase frame
@@ -150,7 +151,7 @@ static std::string g_init_err;
 // Device memory comes from the stream-ordered pool (cudaMallocAsync): allocation and release are
 // ordered on the context's stream and cost microseconds instead of a device-wide synchronisation.
 #define DMALLOC(ptr, bytes) cudaMallocAsync((void**)(ptr), (bytes), ctx->stream)
-#define DFREE(ptr) do { if (ptr) cudaFreeAsync((void*)(ptr), ctx->stream); } while (0)
+#define DFREE(ptr) do { if (ptr) { cudaFreeAsync((void*)(ptr), ctx->stream); (ptr) = nullptr; } } while (0)
 #define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -242,7 +243,7 @@ int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
 }
 
 static void free_binset(coh_ctx* ctx, BinSet& b) {
-  DFREE(b.cell_head); DFREE(b.cell_rng); DFREE(b.cell_order); DFREE(b.cell_items); DFREE(b.item_cell); DFREE(b.item_attr); DFREE(b.state);
+  DFREE(b.cell_head); DFREE(b.cell_rng); DFREE(b.cell_order); DFREE(b.cell_items); DFREE(b.item_cell); DFREE(b.item_attr); DFREE(b.item_rec); DFREE(b.state);
   b = BinSet();
 }
 int coh_cache_clear(coh_ctx* ctx);
@@ -262,7 +263,7 @@ int coh_shutdown(coh_ctx* ctx) {
   DFREE(ctx->u_out); DFREE(ctx->u_init);
   free_binset(ctx, ctx->bins); DFREE(ctx->queue);
   DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
-  DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op); DFREE(ctx->pre_cplx);
+  DFREE(ctx->pre_sc); DFREE(ctx->pre_list); DFREE(ctx->pre_n); DFREE(ctx->pre_op);
   DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -395,8 +396,7 @@ int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, u
   if (x < 0 || y < 0 || w < 0 || h < 0 || x + w > ctx->fr.W || y + h > ctx->fr.H) FAIL("coh_fb_read_rgba: rectangle outside the framebuffer");
   if (w == 0 || h == 0) return 0;
   CK(cudaMemcpy2DAsync(out, (size_t)w * 4, ctx->fb + (size_t)y * ctx->fr.W + x, (size_t)ctx->fr.W * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return check_error_flag(ctx, "coh_fb_read_rgba (a frame rendered before this read)");  // synchronises; a frame that overflowed a kernel-side limit must not be handed back as good
 }
 int coh_fb_read_rgba_async(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
   CK(cudaSetDevice(ctx->device));
@@ -426,9 +426,10 @@ int coh_fb_read_rgba_async(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_
 }
 int coh_fb_read_wait(coh_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
+  bool any = false;
   for (int k = 0; k < 2; k++)
-    if (ctx->stage_busy[k]) { CK(cudaEventSynchronize(ctx->ev_done[k])); ctx->stage_busy[k] = false; }
-  return 0;
+    if (ctx->stage_busy[k]) { CK(cudaEventSynchronize(ctx->ev_done[k])); ctx->stage_busy[k] = false; any = true; }
+  return any ? check_error_flag(ctx, "coh_fb_read_wait (a frame rendered before these reads)") : 0;
 }
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
   CK(cudaSetDevice(ctx->device));
@@ -440,9 +441,9 @@ int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h,
   dim3 g(cdiv(w, 128), h);
   k_rgb888<<<g, 128, 0, ctx->stream>>>(ctx->fb, ctx->fr.W, x, y, w, h, d); LAUNCHED();
   CK(cudaMemcpyAsync(out, d, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  const int rc = check_error_flag(ctx, "coh_fb_read_rgb888 (a frame rendered before this read)");
   DFREE(d);
-  return 0;
+  return rc;
 }
 
 }  // extern "C"

@@ -130,7 +130,7 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
         return coh_shape_translate(ctx, (coh_shape_t)git->second.shape, off.x - git->second.offx, off.y - git->second.offy, shape);
       }
       for (int k = r + 1; k <= s->group_last[r]; k++) {
-        if (s->h_objs[k].depth != o.depth + 1) continue;  // direct children only (nested groups recurse)
+        if (s->real_depth[k] != s->real_depth[r] + 1) continue;  // direct children only (nested groups recurse)
         coh_shape_t ms = 0, mm = 0, un = 0;
         if (object_shape_rec(ctx, s, k, &ms, &mm)) return 1;
         if (coh_shape_union(ctx, cs, ms, &un)) return 1;
@@ -209,11 +209,13 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
   if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_translate_object: no such object");
   const int r = s->rec_of_abi[obj_index];
   const int last = s->h_objs[r].kind == K_GROUP ? s->group_last[r] : r;
-  if (s->h_objs[r].kind != K_GROUP)   // a member moved on its own: the shapes of the groups around it are stale
-    for (int d = 0; d < s->h_objs[r].depth; d++) {
-      auto git = s->group_shape.find(s->h_objs[r].anc[d]);
-      if (git != s->group_shape.end()) { free_shape(ctx, git->second.shape); s->group_shape.erase(git); }
-    }
+  // the kept shapes of every group around the moved object (or group) are stale; a moved group's own entry stays
+  // valid (it is corrected through group_off on the way out)
+  for (auto git = s->group_shape.begin(); git != s->group_shape.end();) {
+    const int g = git->first;
+    if (g < r && s->group_last[g] >= last) { free_shape(ctx, git->second.shape); git = s->group_shape.erase(git); }
+    else ++git;
+  }
   for (int k = r; k <= last; k++) {
     ObjRec& o = s->h_objs[k];
     if (o.kind == K_GROUP) { s->group_off[k].x += dx; s->group_off[k].y += dy; continue; }

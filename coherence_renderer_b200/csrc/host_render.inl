@@ -75,12 +75,13 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   } else total = s->items_total;
   const size_t need = total;
   if (need > B.cell_items_cap) {
-    DFREE(B.cell_items); DFREE(B.item_cell); DFREE(B.item_attr);
+    DFREE(B.cell_items); DFREE(B.item_cell); DFREE(B.item_attr); DFREE(B.item_rec);
     B.cell_items_cap = 0;
     size_t cap = need + need / 2 + 1024;
     CK(DMALLOC(&B.cell_items, sizeof(int) * cap));
     CK(DMALLOC(&B.item_cell, sizeof(int) * cap));
     CK(DMALLOC(&B.item_attr, sizeof(int2) * cap));
+    CK(DMALLOC(&B.item_rec, sizeof(int4) * 2 * cap));
     B.cell_items_cap = cap;
   }
   // K1.  Small scenes: warp per cell scanning all leaves (lists come out sorted, no atomics).  Large scenes:
@@ -92,7 +93,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     // one pass: hit masks in registers, lists carved from one cursor, length classes instead of a sort
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, B.cell_rng, B.cell_items, B.state,
-                                               ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr); LAUNCHED();
+                                               ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr, B.item_rec); LAUNCHED();
     if (keep) { s->bins_valid = true; memcpy(s->bins_key, key, sizeof key); }
   } else {
     CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
@@ -192,26 +193,24 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       const size_t cap = n_pairs + n_pairs / 4 + 1024;
       CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap));
       CK(DMALLOC(&ctx->pre_list, sizeof(int4) * cap)); CK(DMALLOC(&ctx->pre_op, 32 * cap));
-      DFREE(ctx->pre_cplx);
-      CK(DMALLOC(&ctx->pre_cplx, sizeof(int2) * cap));
-      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, 2 * sizeof(int)));   // list length, complex-list length
+      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, sizeof(int)));
       ctx->pre_cap = cap;
     }
     P.item_cell = B.item_cell;
-    CK(cudaMemsetAsync(ctx->pre_n, 0, 2 * sizeof(int), ctx->stream));
-    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc); LAUNCHED();
-    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n); LAUNCHED();
+    CK(cudaMemsetAsync(ctx->pre_n, 0, sizeof(int), ctx->stream));
+    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc, B.item_rec); LAUNCHED();
+    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n, B.item_attr); LAUNCHED();
     if (ctx->aa_general) { k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED(); }
     else {
-      // interval form for the pairs whose super-sampled rows are single runs, bit-rows for the rest
-      k_pre_aa_runs<<<ctx->n_sms * 6, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op, ctx->pre_cplx, ctx->pre_n + 1); LAUNCHED();
-      k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n + 1, ctx->pre_op, ctx->pre_cplx); LAUNCHED();
+      // interval form (the few pairs with rows that are not runs take the bit-row routine inside the same kernel)
+      k_pre_aa_runs<<<ctx->n_sms * 6, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
     }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
     if (s->flat_ok && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
-      k_comp_rows<<<n_cells, CELL_H * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
+      const int cgrid = std::min(ctx->n_sms * 8, n_cells * (CELL_H / COMP_WARPS));
+      k_comp_rows<<<cgrid, COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {

@@ -67,6 +67,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   eff_open.push_back(0); n_children.push_back(0); open_flat.push_back(0);
   std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
   std::vector<int> group_last;
+  std::vector<int> real_depth;   // per record: number of enclosing groups in the scene as given (roots included)
   std::vector<int64_t> ids;
   // filters and their reading-scene groups (include/coherence_b200.h, COH_FILTER_*)
   std::vector<DevScene::FilterRec> filters;
@@ -128,6 +129,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     o.pretrans = c.pretrans; o.dx = c.dx; o.dy = c.dy;
     if (c.pretrans < -1 || c.pretrans > 255) FAIL("scene: pretrans out of range");
     o.depth = (int)eff_open.size();
+    const int nesting = (int)open.size();   // the reference's nesting (group shapes, direct members), o.depth: what the walker sees
     if (o.depth > MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
     for (int d = 0; d < o.depth; d++) o.anc[d] = eff_open[d];
     o.fill.kind = c.fill_kind; o.fill.c0 = c.colour0; o.fill.c1 = c.colour1; o.fill.flags = c.fill_flags;
@@ -137,6 +139,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
         recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
+        real_depth.resize(recs.size(), 0); real_depth.back() = nesting;
         {
           const bool flat = !any_filter && o.pretrans < 0 && n_children.back() == 0;
           n_children.back()++;
@@ -251,6 +254,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (clear_path) o.flags |= OF_OCCLUDES;
     }
     recs.push_back(o);
+    real_depth.resize(recs.size(), 0); real_depth.back() = nesting;
     n_children.back()++;
     rec_of_abi[i] = (int)recs.size() - 1;
     ids.resize(recs.size(), -1); ids.back() = c.id;
@@ -271,7 +275,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   s->h_objs = recs;
   group_last.resize(recs.size(), -1);
   ids.resize(recs.size(), -1);
-  s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids;
+  real_depth.resize(recs.size(), 0);
+  s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids; s->real_depth = real_depth;
   s->group_off.assign(recs.size(), make_int2(0, 0));
   for (const ObjRec& o : recs) {
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
@@ -291,7 +296,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       flat = flat && o.depth == 1 && (o.kind == K_PATH || o.kind == K_PRIM) && o.fill.kind == 0;
       const bool bg = (recs[o.anc[0]].flags & OF_ROOT_BACKGROUND) != 0;
       if (bg) { n_bg++; bg_opaque_prims = bg_opaque_prims && o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0; }
-      attr[li] = make_int2((int)o.fill.c0, (o.kind == K_PATH ? 1 : 0) | (bg ? 2 : 0) | ((o.pretrans + 1) << 8));
+      attr[li] = make_int2((int)o.fill.c0, (o.kind == K_PATH ? 1 : 0) | (bg ? 2 : 0) | ((o.flags & OF_OCCLUDES) ? 4 : 0) | ((o.pretrans + 1) << 8));
     }
     s->flat_ok = flat && (n_bg <= 1 || bg_opaque_prims);
     CK(DMALLOC(&s->attr, sizeof(int2) * recs.size()));

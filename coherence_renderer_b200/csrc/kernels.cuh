@@ -133,7 +133,8 @@ struct BinPrefill {
 __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box, const int* __restrict__ leaves, int n_leaves, Frame fr, int cell_row0,
                        int n_cells, int2* __restrict__ cell_rng, int* __restrict__ items, int* __restrict__ state /* [0] pool cursor, [1..] class counts */,
                        int* __restrict__ cls_cells /* [BIN_CLASSES][n_cells] or null */, const ObjRec* __restrict__ objs, int2* __restrict__ cell_head,
-                       int* __restrict__ item_cell, int prefill_on, const int2* __restrict__ attr, int2* __restrict__ item_attr) {
+                       int* __restrict__ item_cell, int prefill_on, const int2* __restrict__ attr, int2* __restrict__ item_attr,
+                       int4* __restrict__ item_rec) {
   __shared__ int s_n[8], s_c[8], s_base[8], s_pos[8];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + wid;
@@ -194,6 +195,16 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
       items[dst] = leaf;
       if (item_cell) item_cell[dst] = warp;
       if (item_attr) item_attr[dst] = attr[leaf];
+      if (item_rec) {
+        // what k_pre_scan needs of the object, in device space, next to the list entry (two int4 per entry):
+        //   {object, cell, kind | winding << 8, first row-edge slot - first listed row}
+        //   paths: {first listed row, last listed row, dx, dy};  primitives: the box x0, y0, x1, y1
+        const ObjRec& o = objs[leaf];
+        int4 r0 = make_int4(leaf, warp, o.kind | (o.winding << 8), 0), r1 = make_int4(0, 0, 0, 0);
+        if (o.kind == K_PRIM) r1 = make_int4(o.prim[0] + o.dx, o.prim[1] + o.dy, o.prim[2] + o.dx, o.prim[3] + o.dy);
+        else if (o.kind == K_PATH) { r0.w = o.row_base - (o.ry0 + o.dy); r1 = make_int4(o.ry0 + o.dy, o.ry1 + o.dy, o.dx, o.dy); }
+        item_rec[2 * (size_t)dst] = r0; item_rec[2 * (size_t)dst + 1] = r1;
+      }
     }
     at += __popc(m);
   }

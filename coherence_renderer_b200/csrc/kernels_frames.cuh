@@ -16,17 +16,32 @@
 //   k_pre_aa    warp / listed pair: opacity bytes (aa_tile)
 //   k_walk<PRE> composite with the exact `u`; every pixel it antialiases is in the superset.
 // ------------------------------------------------------------------------------------
-__global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
+__global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc, const int4* __restrict__ item_rec) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= n_pairs) return;
   const int item = pair / CELL_H, row = pair % CELL_H;
-  const int cell = P.item_cell[item];
-  if (P.cell_head[cell].y & 1) return;   // a background cell: finished by the binning kernel or the walker's fast path, nobody reads these words
+  // the list entry carries what is needed of the object (written by k_bin1): no walk through ObjRec for paths and primitives
+  const int4 r0 = item_rec[2 * (size_t)item], r1 = item_rec[2 * (size_t)item + 1];
+  const int cell = r0.y, kind = r0.z & 255;
+  if (P.cell_head[cell].y & 1) return;   // a background cell: finished by k_prefill or the walker's fast path, nobody reads these words
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
-  const ObjRec& o = P.objs[P.cell_items[item]];
   uint32_t S = 0u, C = 0u;
-  if (my_y >= P.fr.band_y0 && my_y < P.fr.band_y1 && !(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
+  const bool in_band = my_y >= P.fr.band_y0 && my_y < P.fr.band_y1;
+  if (in_band && kind == K_PRIM) {
+    if (my_y >= r1.y && my_y <= r1.w) S = interval_mask32(tx0, r1.x, r1.z);
+  } else if (in_band && kind == K_PATH) {
+    if (my_y >= r1.x && my_y <= r1.y) {
+      const int slot = r0.w + my_y;
+      const int a = P.rowedge_ptr[slot], b = P.rowedge_ptr[slot + 1];
+      bool ok = true;
+      const uint2 w = scan_row_word(P.edges, P.rowedge_idx + a, b - a, my_y - r1.w, (r0.z >> 8) & 255, tx0 - r1.z, ok);
+      if (!ok) *P.error_flag = 1;
+      S = w.x; C = w.y;
+    }
+  } else if (in_band) {
+    const ObjRec& o = P.objs[r0.x];
+    if (!(o.by0 > my_y || o.by1 < my_y || o.bx0 > tx0 + 31 || o.bx1 < tx0)) {
     const int yy = my_y - o.dy, xx0 = tx0 - o.dx;
     if (o.kind == K_PRIM) {
       if (yy >= o.prim[1] && yy <= o.prim[3]) S = interval_mask32(xx0, o.prim[0], o.prim[2]);
@@ -44,11 +59,13 @@ __global__ void k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc) {
       if (!ok) *P.error_flag = 1;
       S = w.x; C = w.y;
     }
+    }
   }
   sc[pair] = make_uint2(S, C);
 }
 // blockDim = 128: 8 (cell, 16 rows) groups per block
-__global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __restrict__ list /* pair, object, edge mask, (tile << 16 | row of the frame) */, int* __restrict__ list_n) {
+__global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __restrict__ list /* pair, object, edge mask, (tile << 16 | row of the frame) */, int* __restrict__ list_n,
+                          const int2* __restrict__ item_attr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
   if (cell >= P.n_cells || (P.cell_head[cell].y & 1)) return;
@@ -62,21 +79,28 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
   }
   const int2 cell_rg = P.cell_rng[cell];
   const int it0 = cell_rg.x, it1 = cell_rg.y;
-  for (int it = it0; it < it1; it++) {
-    const int oi = P.cell_items[it];
-    const ObjRec& o = P.objs[oi];
-    const size_t pair = (size_t)it * CELL_H + row;
-    const uint2 w = sc[pair];
-    const uint32_t M = w.x & ~w.y;
-    const uint32_t e = (o.kind == K_PATH) ? (w.x & ~M & u) : 0u;
-    if (e) list[atomicAdd(list_n, 1)] = make_int4((int)pair, oi, (int)e, (tile << 16) | my_y);
-    if (o.flags & OF_OCCLUDES) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
+  // the entries' attributes ride along with the lists (k_bin1): is-path, occludes — four entries are fetched at a
+  // time so that their loads are in flight together; only u chains one entry to the next
+  for (int it = it0; it < it1 && u != 0u; it += 4) {
+    int2 at[4]; uint2 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const bool in = it + k < it1;
+      at[k] = in ? item_attr[it + k] : make_int2(0, 0);
+      w[k] = in ? sc[(size_t)(it + k) * CELL_H + row] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t M = w[k].x & ~w[k].y;
+      const uint32_t e = (at[k].y & 1) ? (w[k].x & w[k].y & u) : 0u;   // shape - minshape, still uncovered
+      if (e) list[atomicAdd(list_n, 1)] = make_int4((it + k) * CELL_H + row, P.cell_items[it + k], (int)e, (tile << 16) | my_y);
+      if (at[k].y & 4) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
+    }
   }
 }
-// General antialiasing of listed pairs (bit-rows in shared memory, any number of crossings).  With `sel` the
-// kernel runs over the entries sel[0 .. *sel_n) = (list index, edge pixels) that the interval kernel found complex.
-__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n, uint8_t* __restrict__ op,
-                                                 const int2* __restrict__ sel = nullptr) {
+// General antialiasing of listed pairs (bit-rows in shared memory, any number of crossings): the reference form of
+// k_pre_aa_runs (option "aa_general").
+__global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n, uint8_t* __restrict__ op) {
   __shared__ int s_prefix[32 * 33];
   __shared__ uint32_t s_aa[8][32 * AA_WORDS];
   __shared__ StagedEdge s_stage[8][32];
@@ -87,9 +111,8 @@ __global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __rest
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n_warps = gridDim.x * 8;
   for (int i = blockIdx.x * 8 + wid; i < n; i += n_warps) {
-    const int2 pick = sel ? sel[i] : make_int2(i, 0);
-    const int4 ent = list[pick.x];
-    const uint32_t edge = sel ? (uint32_t)pick.y : (uint32_t)ent.z;
+    const int4 ent = list[i];
+    const uint32_t edge = (uint32_t)ent.z;
     const ObjRec& o = P.objs[ent.y];
     const int yy = (ent.w & 0xFFFF) - o.dy, xx0 = (ent.w >> 16) * TILE_W - o.dx;
     const int slot = o.row_base + yy - o.ry0;
@@ -105,7 +128,8 @@ __global__ void __launch_bounds__(256) k_pre_aa(WalkParams P, const int4* __rest
 // 16 y - 32 + j of the x16 edge list as a run [lo, hi] (minus at most one gap) of the columns under the pair's edge
 // pixels — no bit-row, no crossing lists — and every edge pixel is two prefix-table reads per lane plus one
 // redux.sync for two pixels.  A pair with a row that is not provably of that form (2 % on the lion) is retried
-// run by run of its edge pixels (narrower windows); what is still complex goes on the `cplx` list for k_pre_aa.
+// run by run of its edge pixels (narrower windows); what is still complex (a few dozen pairs of a frame) takes the
+// general bit-row routine right here — a kernel of its own for them costs a launch and the latency of one pair.
 constexpr int AA2_WARPS = 8;
 // the edge pixels `edge` (a subset of the pair's) against the staged candidates; returns false when some row is complex
 __device__ __forceinline__ bool aa_runs_pixels(const EdgeRec* __restrict__ edges, const int* __restrict__ idx, int n_cand, int winding,
@@ -151,10 +175,12 @@ __device__ __forceinline__ bool aa_runs_pixels(const EdgeRec* __restrict__ edges
   }
   return true;
 }
-__global__ void __launch_bounds__(AA2_WARPS * 32) k_pre_aa_runs(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n,
-                                                                  uint8_t* __restrict__ op, int2* __restrict__ cplx, int* __restrict__ cplx_n) {
+static_assert(sizeof(AaEdge) >= sizeof(StagedEdge), "the stage of the interval scan doubles as the stage of the general scan");
+__global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n,
+                                                                  uint8_t* __restrict__ op) {
   __shared__ int s_prefix[32 * 33];
   __shared__ AaEdge s_stage[AA2_WARPS][32];
+  __shared__ uint32_t s_aa[AA2_WARPS][32 * AA_WORDS];   // bit-rows of the general routine (rarely touched)
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -182,8 +208,14 @@ __global__ void __launch_bounds__(AA2_WARPS * 32) k_pre_aa_runs(WalkParams P, co
         e &= ~run;
         if (run == edge || !aa_runs_pixels(P.edges, P.rowedge_idx + ea, n_cand, winding, xx0, yy, run, stage, prow, lane, mytot)) hard |= run;
       }
-      if (hard && lane == 0) cplx[atomicAdd(cplx_n, 1)] = make_int2(i, (int)hard);
-      mine &= ~hard;   // k_pre_aa writes those bytes
+      if (hard) {
+        bool ok;
+        const int v = aa_tile_nl(P.edges, P.rowedge_idx + ea, n_cand, winding, xx0, yy, hard, s_aa[wid], reinterpret_cast<StagedEdge*>(stage), s_prefix, AA_VOLUME, lane, ok);
+        if (!ok) *P.error_flag = 1;
+        if ((hard >> lane) & 1u) op[(size_t)ent.x * 32 + lane] = (uint8_t)v;
+        mine &= ~hard;
+        __syncwarp();
+      }
     }
     if ((mine >> lane) & 1u) op[(size_t)ent.x * 32 + lane] = (uint8_t)aa_opacity(mytot, AA_VOLUME);
   }
@@ -198,76 +230,83 @@ __global__ void __launch_bounds__(AA2_WARPS * 32) k_pre_aa_runs(WalkParams P, co
 // (render.ml:1201-1204), PreTrans dissolves again (1295-1298), acc = over acc s, u' = u - opaque (1294, 1308).
 // One block per cell (CELL_H warps), cells in heavy-first order; background cells were finished by k_prefill.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CELL_H * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr) {
-  __shared__ int s_cell;
+constexpr int COMP_WARPS = 8;   // rows of a cell per work item
+__global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr) {
+  constexpr int PARTS = CELL_H / COMP_WARPS;   // work items per cell
+  __shared__ int s_cls[BIN_CLASSES + 1];       // first position of every length class in the heavy-first order
+  __shared__ int s_q;
   if (threadIdx.x == 0) {
-    // position blockIdx.x of the heavy-first order -> cell (classes are consecutive segments of cls_cells)
-    int q = blockIdx.x, cell = -1;
-    if (P.cls_cnt) {
-      for (int c = 0; c < BIN_CLASSES; c++) { const int n = P.cls_cnt[c]; if (q < n) { cell = P.cls_cells[(size_t)c * P.n_cells + q]; break; } q -= n; }
-    } else cell = q < P.n_cells ? q : -1;
-    s_cell = cell;
+    int acc = 0;
+    for (int c = 0; c < BIN_CLASSES; c++) { s_cls[c] = acc; acc += P.cls_cnt ? P.cls_cnt[c] : 0; }
+    s_cls[BIN_CLASSES] = P.cls_cnt ? acc : P.n_cells;
   }
   __syncthreads();
-  const int cell = s_cell;
-  if (cell < 0) return;
-  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
-  const int tx0 = tile * TILE_W, y = (P.cell_row0 + by) * CELL_H + row;
-  if (y < P.fr.band_y0 || y >= P.fr.band_y1) return;
-  uint32_t u = P.u_init ? P.u_init[(size_t)y * P.fr.tiles_x + tile] : ((y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u);
-  if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
-  const uint32_t u_update = u;
-  uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
-  if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
-  const int2 rg = P.cell_rng[cell];
-  uint32_t acc = 0u;
+  const int n_items = s_cls[BIN_CLASSES] * PARTS;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lbit = 1u << lane;
-  for (int base = rg.x; base < rg.y; base += 32) {
-    if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
-    const int it = base + lane;
-    uint2 sc = make_uint2(0u, 0u); int2 at = make_int2(0, 0);
-    if (it < rg.y) { sc = P.pre_sc[(size_t)it * CELL_H + row]; at = item_attr[it]; }
-    unsigned hits = __ballot_sync(0xFFFFFFFFu, (sc.x & u) != 0u);
-    const unsigned bgm = __ballot_sync(0xFFFFFFFFu, (at.y & 2) != 0);
-    if (u_rec && bgm) {   // the scene list ends inside this chunk: its hits first, then record u
-      unsigned hs = hits & ~bgm;
-      hits &= bgm;
-      while (hs) {
-        const int k = __ffs((int)hs) - 1; hs &= hs - 1;
-        const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k), C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
-        const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
-        const uint32_t vis = S & u;
-        if (vis == 0u) continue;
-        const uint32_t edge = vis & C;
-        uint32_t col = c0;
-        if ((fl & 1) && (edge & lbit)) col = px_dissolve(c0, P.pre_op[((size_t)(base + k) * CELL_H + row) * 32 + lane]);
-        if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
-        if (vis & lbit) acc = px_over(acc, col);
-        u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
+  for (;;) {
+    // persistent blocks take work items (COMP_WARPS rows of a cell) off one counter, heavy cells first
+    if (threadIdx.x == 0) s_q = atomicAdd(P.queue, 1);
+    __syncthreads();
+    const int q = s_q;
+    __syncthreads();
+    if (q >= n_items) return;
+    int cell = q / PARTS;
+    if (P.cls_cnt) {
+      int c = 0;
+      while (c < BIN_CLASSES - 1 && cell >= s_cls[c + 1]) c++;
+      cell = P.cls_cells[(size_t)c * P.n_cells + cell - s_cls[c]];
+    }
+    const int row = (q % PARTS) * COMP_WARPS + wid;
+    const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
+    const int tx0 = tile * TILE_W, y = (P.cell_row0 + by) * CELL_H + row;
+    if (y < P.fr.band_y0 || y >= P.fr.band_y1) continue;
+    uint32_t u = P.u_init ? P.u_init[(size_t)y * P.fr.tiles_x + tile] : ((y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u);
+    if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
+    const uint32_t u_update = u;
+    uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
+    if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; continue; }
+    const int2 rg = P.cell_rng[cell];
+    const uint2* sc_row = P.pre_sc + row;
+    const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
+    uint32_t acc = 0u;
+    for (int base = rg.x; base < rg.y; base += 32) {
+      if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
+      const int it = base + lane;
+      uint2 sc = make_uint2(0u, 0u); int2 at = make_int2(0, 0);
+      if (it < rg.y) { sc = sc_row[(size_t)it * CELL_H]; at = item_attr[it]; }
+      unsigned hits = __ballot_sync(0xFFFFFFFFu, (sc.x & u) != 0u);
+      // the scene list ends where the background list begins: u is recorded between the two
+      unsigned bgm = u_rec ? __ballot_sync(0xFFFFFFFFu, (at.y & 2) != 0) : 0u;
+      unsigned later = bgm ? (hits & bgm) : 0u;
+      hits &= ~later;
+      for (;;) {
+        while (hits) {
+          const int k = __ffs((int)hits) - 1; hits &= hits - 1;
+          const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k);
+          const uint32_t vis = S & u;
+          if (vis == 0u) continue;
+          const uint32_t C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
+          const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
+          uint32_t col = c0;
+          // shptorender ∩ maxshape = vis & ~(S & ~C) = vis & C: those pixels dissolve the fill by their opacity
+          if ((fl & 1) && (vis & C & lbit)) col = px_dissolve(c0, op_row[(size_t)(base + k) * (CELL_H * 32)]);
+          if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
+          if (vis & lbit) acc = px_over(acc, col);
+          u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
+        }
+        if (!bgm) break;
+        if (lane == 0) *u_rec = u;
+        u_rec = nullptr; bgm = 0u;
+        hits = later;
       }
-      if (lane == 0) *u_rec = u;
-      u_rec = nullptr;
     }
-    while (hits) {
-      const int k = __ffs((int)hits) - 1; hits &= hits - 1;
-      const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k), C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
-      const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
-      const uint32_t vis = S & u;
-      if (vis == 0u) continue;
-      const uint32_t edge = vis & C;        // shptorender ∩ maxshape: S & ~(S & ~C) restricted to vis
-      uint32_t col = c0;
-      if ((fl & 1) && (edge & lbit)) col = px_dissolve(c0, P.pre_op[((size_t)(base + k) * CELL_H + row) * 32 + lane]);
-      if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
-      if (vis & lbit) acc = px_over(acc, col);
-      u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
+    if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
+    if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
+      const size_t at = (size_t)y * P.fr.W + tx0 + lane;
+      P.fb[at] = acc;
+      for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
     }
-  }
-  if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
-  if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
-    const size_t at = (size_t)y * P.fr.W + tx0 + lane;
-    P.fb[at] = acc;
-    for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
   }
 }
 

@@ -769,15 +769,25 @@ def test_edge_cases(ctx, oracle):
     with pytest.raises(abi.CohError):
         ctx.render_frame(sc, (0, 0, -1, 5))        # Sprite.box: negative argument (sprite.ml:463)
     ctx.scene_free(sc)
+    tri = [(5.0, 3.0), (66.0, 4.0), (40.0, 33.0)]
     deep = S.SceneBuilder()
-    for _ in range(6):
-        deep.group_begin()
-    deep.polygon([(5.0, 3.0), (66.0, 4.0), (40.0, 33.0)], S.Fill.plain(S.rgba8(1, 2, 3)))
+    for _ in range(6):                             # PreTrans groups keep their accumulators: six levels are too many
+        deep.group_begin(pretrans=200)
+    deep.polygon(tri, S.Fill.plain(S.rgba8(1, 2, 3)))
     for _ in range(6):
         deep.group_end()
     objs, n, nbg, e, p = deep.arrays()
     with pytest.raises(abi.CohError):              # nesting beyond MAX_DEPTH fails loudly at scene creation
         ctx.scene_create(objs, nbg, e, p)
+    deep = S.SceneBuilder()
+    for _ in range(12):                            # first members composited with plain Over dissolve into their parent:
+        deep.group_begin()                         # any depth of those is fine
+    deep.polygon(tri, S.Fill.plain(S.dissolve(S.rgba8(10, 200, 30), 100)))
+    for _ in range(12):
+        deep.group_end()
+    deep.polygon([(t[0] + 9.5, t[1] + 4.25) for t in tri], S.Fill.plain(S.dissolve(S.rgba8(200, 20, 30), 180)))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, deep, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
 
 
 def test_filter_matte_interior_shortcut(ctx, oracle):
