@@ -193,24 +193,23 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       const size_t cap = n_pairs + n_pairs / 4 + 1024;
       CK(DMALLOC(&ctx->pre_sc, sizeof(uint2) * cap));
       CK(DMALLOC(&ctx->pre_list, sizeof(int4) * cap)); CK(DMALLOC(&ctx->pre_op, 32 * cap));
-      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, sizeof(int)));
+      if (!ctx->pre_n) CK(DMALLOC(&ctx->pre_n, 2 * sizeof(int)));   // list length, next pair of the antialiasing kernel
       ctx->pre_cap = cap;
     }
     P.item_cell = B.item_cell;
-    CK(cudaMemsetAsync(ctx->pre_n, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pre_n, 0, 2 * sizeof(int), ctx->stream));
     k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc, B.item_rec); LAUNCHED();
     k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n, B.item_attr); LAUNCHED();
     if (ctx->aa_general) { k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED(); }
     else {
       // interval form (the few pairs with rows that are not runs take the bit-row routine inside the same kernel)
-      k_pre_aa_runs<<<ctx->n_sms * 6, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED();
+      k_pre_aa_runs<<<ctx->n_sms * 4, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op, ctx->pre_n + 1); LAUNCHED();
     }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
     if (s->flat_ok && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
-      const int cgrid = std::min(ctx->n_sms * 8, n_cells * (CELL_H / COMP_WARPS));
-      k_comp_rows<<<cgrid, COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
+      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {

@@ -177,17 +177,22 @@ __device__ __forceinline__ bool aa_runs_pixels(const EdgeRec* __restrict__ edges
 }
 static_assert(sizeof(AaEdge) >= sizeof(StagedEdge), "the stage of the interval scan doubles as the stage of the general scan");
 __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n,
-                                                                  uint8_t* __restrict__ op) {
+                                                                  uint8_t* __restrict__ op, int* __restrict__ next) {
   __shared__ int s_prefix[32 * 33];
   __shared__ AaEdge s_stage[AA2_WARPS][32];
   __shared__ uint32_t s_aa[AA2_WARPS][32 * AA_WORDS];   // bit-rows of the general routine (rarely touched)
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = *list_n, n_warps = gridDim.x * AA2_WARPS;
+  const int n = *list_n;
   const int* prow = s_prefix + lane * 33;
   AaEdge* stage = s_stage[wid];
-  for (int i = blockIdx.x * AA2_WARPS + wid; i < n; i += n_warps) {
+  // one resident wave of warps; pairs come off a counter (their cost varies with the number of candidate edges)
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(next, 1);
+    i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    if (i >= n) break;
     const int4 ent = list[i];
     const ObjRec& o = P.objs[ent.y];
     const int yy = (ent.w & 0xFFFF) - o.dy, xx0 = (ent.w >> 16) * TILE_W - o.dx;
@@ -230,83 +235,78 @@ __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P,
 // (render.ml:1201-1204), PreTrans dissolves again (1295-1298), acc = over acc s, u' = u - opaque (1294, 1308).
 // One block per cell (CELL_H warps), cells in heavy-first order; background cells were finished by k_prefill.
 // ------------------------------------------------------------------------------------
-constexpr int COMP_WARPS = 8;   // rows of a cell per work item
+constexpr int COMP_WARPS = 8;   // rows of a cell per block
 __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr) {
-  constexpr int PARTS = CELL_H / COMP_WARPS;   // work items per cell
-  __shared__ int s_cls[BIN_CLASSES + 1];       // first position of every length class in the heavy-first order
-  __shared__ int s_q;
+  constexpr int PARTS = CELL_H / COMP_WARPS;   // blocks per cell
+  // Block b takes position b / PARTS of the heavy-first order (blocks are dispatched in index order, so the long
+  // lists start first); one thread resolves it to a cell — the classes are consecutive segments of cls_cells — and
+  // the grid is sized for every cell: positions beyond the queued cells (background cells were finished by
+  // k_prefill) leave at once.
+  __shared__ int s_cell[4];   // cell, tile, first row of the block, column mask of the update box
   if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int c = 0; c < BIN_CLASSES; c++) { s_cls[c] = acc; acc += P.cls_cnt ? P.cls_cnt[c] : 0; }
-    s_cls[BIN_CLASSES] = P.cls_cnt ? acc : P.n_cells;
+    int q = blockIdx.x / PARTS, cell = -1;
+    if (P.cls_cnt) {
+      for (int c = 0; c < BIN_CLASSES; c++) { const int n = P.cls_cnt[c]; if (q < n) { cell = P.cls_cells[(size_t)c * P.n_cells + q]; break; } q -= n; }
+    } else cell = q < P.n_cells ? q : -1;
+    s_cell[0] = cell;
+    if (cell >= 0) {
+      const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
+      uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
+      if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
+      s_cell[1] = tile; s_cell[2] = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS; s_cell[3] = (int)colmask;
+    }
   }
   __syncthreads();
-  const int n_items = s_cls[BIN_CLASSES] * PARTS;
+  const int cell = s_cell[0];
+  if (cell < 0) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lbit = 1u << lane;
-  for (;;) {
-    // persistent blocks take work items (COMP_WARPS rows of a cell) off one counter, heavy cells first
-    if (threadIdx.x == 0) s_q = atomicAdd(P.queue, 1);
-    __syncthreads();
-    const int q = s_q;
-    __syncthreads();
-    if (q >= n_items) return;
-    int cell = q / PARTS;
-    if (P.cls_cnt) {
-      int c = 0;
-      while (c < BIN_CLASSES - 1 && cell >= s_cls[c + 1]) c++;
-      cell = P.cls_cells[(size_t)c * P.n_cells + cell - s_cls[c]];
-    }
-    const int row = (q % PARTS) * COMP_WARPS + wid;
-    const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
-    const int tx0 = tile * TILE_W, y = (P.cell_row0 + by) * CELL_H + row;
-    if (y < P.fr.band_y0 || y >= P.fr.band_y1) continue;
-    uint32_t u = P.u_init ? P.u_init[(size_t)y * P.fr.tiles_x + tile] : ((y >= P.uy0 && y <= P.uy1) ? interval_mask32(tx0, P.ux0, P.ux1) : 0u);
-    if (tx0 + 31 >= P.fr.W) u &= interval_mask32(tx0, 0, P.fr.W - 1);
-    const uint32_t u_update = u;
-    uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
-    if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; continue; }
-    const int2 rg = P.cell_rng[cell];
-    const uint2* sc_row = P.pre_sc + row;
-    const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
-    uint32_t acc = 0u;
-    for (int base = rg.x; base < rg.y; base += 32) {
-      if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
-      const int it = base + lane;
-      uint2 sc = make_uint2(0u, 0u); int2 at = make_int2(0, 0);
-      if (it < rg.y) { sc = sc_row[(size_t)it * CELL_H]; at = item_attr[it]; }
-      unsigned hits = __ballot_sync(0xFFFFFFFFu, (sc.x & u) != 0u);
-      // the scene list ends where the background list begins: u is recorded between the two
-      unsigned bgm = u_rec ? __ballot_sync(0xFFFFFFFFu, (at.y & 2) != 0) : 0u;
-      unsigned later = bgm ? (hits & bgm) : 0u;
-      hits &= ~later;
-      for (;;) {
-        while (hits) {
-          const int k = __ffs((int)hits) - 1; hits &= hits - 1;
-          const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k);
-          const uint32_t vis = S & u;
-          if (vis == 0u) continue;
-          const uint32_t C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
-          const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
-          uint32_t col = c0;
-          // shptorender ∩ maxshape = vis & ~(S & ~C) = vis & C: those pixels dissolve the fill by their opacity
-          if ((fl & 1) && (vis & C & lbit)) col = px_dissolve(c0, op_row[(size_t)(base + k) * (CELL_H * 32)]);
-          if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
-          if (vis & lbit) acc = px_over(acc, col);
-          u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
-        }
-        if (!bgm) break;
-        if (lane == 0) *u_rec = u;
-        u_rec = nullptr; bgm = 0u;
-        hits = later;
+  const int tile = s_cell[1], y = s_cell[2] + wid, row = y & (CELL_H - 1);
+  if (y < P.fr.band_y0 || y >= P.fr.band_y1) return;
+  uint32_t u = P.u_init ? (P.u_init[(size_t)y * P.fr.tiles_x + tile] & (uint32_t)s_cell[3]) : ((y >= P.uy0 && y <= P.uy1) ? (uint32_t)s_cell[3] : 0u);
+  const uint32_t u_update = u;
+  uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
+  if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
+  const int2 rg = P.cell_rng[cell];
+  const uint2* sc_row = P.pre_sc + row;
+  const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
+  uint32_t acc = 0u;
+  for (int base = rg.x; base < rg.y; base += 32) {
+    if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
+    const int it = base + lane;
+    uint2 sc = make_uint2(0u, 0u); int2 at = make_int2(0, 0);
+    if (it < rg.y) { sc = sc_row[(size_t)it * CELL_H]; at = item_attr[it]; }
+    unsigned hits = __ballot_sync(0xFFFFFFFFu, (sc.x & u) != 0u);
+    // the scene list ends where the background list begins: u is recorded between the two
+    unsigned bgm = u_rec ? __ballot_sync(0xFFFFFFFFu, (at.y & 2) != 0) : 0u;
+    unsigned later = bgm ? (hits & bgm) : 0u;
+    hits &= ~later;
+    for (;;) {
+      while (hits) {
+        const int k = __ffs((int)hits) - 1; hits &= hits - 1;
+        const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k);
+        const uint32_t vis = S & u;
+        if (vis == 0u) continue;
+        const uint32_t C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
+        const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
+        uint32_t col = c0;
+        // shptorender ∩ maxshape = vis & ~(S & ~C) = vis & C: those pixels dissolve the fill by their opacity
+        if ((fl & 1) && (vis & C & lbit)) col = px_dissolve(c0, op_row[(size_t)(base + k) * (CELL_H * 32)]);
+        if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
+        if (vis & lbit) acc = px_over(acc, col);
+        u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
       }
+      if (!bgm) break;
+      if (lane == 0) *u_rec = u;
+      u_rec = nullptr; bgm = 0u;
+      hits = later;
     }
-    if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
-    if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
-      const size_t at = (size_t)y * P.fr.W + tx0 + lane;
-      P.fb[at] = acc;
-      for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
-    }
+  }
+  if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
+  if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
+    const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
+    P.fb[at] = acc;
+    for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
   }
 }
 

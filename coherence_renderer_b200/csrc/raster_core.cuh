@@ -66,28 +66,29 @@ COH_HD int imax(int a, int b) { return a > b ? a : b; }
 // ---------------------------------------------------------------------------------
 COH_HD uint32_t div255(uint32_t i) { return (i + (i >> 8) + 1) >> 8; }  // colour.ml:287
 COH_HD uint32_t px_alpha(uint32_t c) { return c >> 24; }
+// Two channels per 32-bit multiply: the products of 8-bit values stay inside their 16-bit halves, and so does
+// every intermediate of div255 / prelerp, so the packed forms are exact.  div255 (c * 0) = 0 and div255 (c * 255) = c,
+// so the reference's early-outs for delta = 0 / 255 need no branch.
 COH_HD uint32_t px_dissolve(uint32_t c, int delta) {  // colour.ml:291-304
-  if (delta == 0) return 0u;
-  if (delta == 255) return c;
-  uint32_t d = (uint32_t)delta;
-  uint32_t r = div255((c & 255u) * d), g = div255(((c >> 8) & 255u) * d);
-  uint32_t b = div255(((c >> 16) & 255u) * d), a = div255((c >> 24) * d);
-  return r | (g << 8) | (b << 16) | (a << 24);
+  const uint32_t d = (uint32_t)delta;
+  uint32_t rb = (c & 0x00FF00FFu) * d, ga = ((c >> 8) & 0x00FF00FFu) * d;
+  rb = ((rb + ((rb >> 8) & 0x00FF00FFu) + 0x00010001u) >> 8) & 0x00FF00FFu;
+  ga = (ga + ((ga >> 8) & 0x00FF00FFu) + 0x00010001u) & 0xFF00FF00u;
+  return rb | ga;
 }
 COH_HD uint32_t prelerp(uint32_t p, uint32_t q, uint32_t a) {  // colour.ml:310-311
   uint32_t t = a * p + 128u;
   return p + q - (((t >> 8) + t) >> 8);
 }
-// colour.ml:314-328: `over a b`, a nearer the viewer.
+// colour.ml:314-328: `over a b`, a nearer the viewer (premultiplied colours: every channel of the result fits its byte).
 COH_HD uint32_t px_over(uint32_t a, uint32_t b) {
-  uint32_t aa = a >> 24;
-  if (aa == 0) return b;
-  if (aa == 255) return a;
-  uint32_t r = prelerp(b & 255u, a & 255u, aa);
-  uint32_t g = prelerp((b >> 8) & 255u, (a >> 8) & 255u, aa);
-  uint32_t bl = prelerp((b >> 16) & 255u, (a >> 16) & 255u, aa);
-  uint32_t al = prelerp(b >> 24, aa, aa);
-  return r | (g << 8) | (bl << 16) | (al << 24);
+  const uint32_t aa = a >> 24;
+  const uint32_t prb = b & 0x00FF00FFu, pga = (b >> 8) & 0x00FF00FFu;
+  const uint32_t trb = prb * aa + 0x00800080u, tga = pga * aa + 0x00800080u;
+  const uint32_t xrb = ((((trb >> 8) & 0x00FF00FFu) + trb) >> 8) & 0x00FF00FFu;
+  const uint32_t xga = ((((tga >> 8) & 0x00FF00FFu) + tga) >> 8) & 0x00FF00FFu;
+  const uint32_t res = (prb + (a & 0x00FF00FFu) - xrb) | ((pga + ((a >> 8) & 0x00FF00FFu) - xga) << 8);
+  return aa == 0u ? b : (aa == 255u ? a : res);
 }
 // colour.ml:332-336 on the alpha channel alone (brush stamping only reads alpha back).
 COH_HD uint32_t alpha_over(uint32_t aa, uint32_t ab) {
