@@ -29,11 +29,30 @@ WIDTH, HEIGHT, SCALE = 3840, 2160, 7.0
 WORKLOAD = "C2: lion.pdf scene (132 AA polygons in a Group over a lightgrey background) at 3840x2160, scale 7.0, cold cache"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one C2 frame (k_bin1 + k_pre_scan + k_pre_vis + k_pre_aa + k_walk),
-# from the ncu --set full capture summarised in profiles/r1_ncu_raster_phase_lion4k.csv: 4.2 + 1.7 + 3.4 + 1.4 +
-# 5.1 MB.  The 33 MB frame stays in the 126 MB L2 and the scene is L2-resident, so DRAM traffic is below the
+# Per-kernel ncu summary of one C2 frame of THIS build (ncu --set full --clock-control none; committed with the
+# code): dram__bytes_read.sum + dram__bytes_write.sum give roofline.traffic, smsp__inst_executed.sum the issue-slot
+# bound.  The 33 MB frame stays in the 126 MB L2 and the scene is L2-resident, so DRAM traffic is below the
 # algorithmic bytes.
-NCU_TRAFFIC_BYTES = 15700000
+NCU_SUMMARY = os.path.join("profiles", "r2_ncu_frame_lion4k.csv")
+
+
+def ncu_summary():
+    """(traffic bytes per frame, warp-instructions per frame) summed over the kernels of the frame, or (None, None)."""
+    import csv
+
+    path = os.path.join(ROOT, NCU_SUMMARY)
+    if not os.path.exists(path):
+        return None, None
+    traffic, inst = 0.0, 0.0
+    for row in csv.reader(open(path)):
+        if not row or row[0].startswith("#") or row[0] == "metric":
+            continue
+        vals = [float(v) for v in row[2:] if v not in ("", "-")]
+        if row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            traffic += sum(vals) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[row[1]]
+        elif row[0] == "smsp__inst_executed.sum":
+            inst += sum(vals)
+    return (int(traffic) if traffic else None), (int(inst) if inst else None)
 
 
 def peaks():
@@ -116,14 +135,14 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_frames(1, cores)
-    steps = max(1, min(args.steps, 5))  # bounded sample: each step is one full C2 frame
+    if args.warmup > 0:
+        cpu_frames(args.warmup, cores)
+    steps = max(1, args.steps)  # each step is one full C2 frame (about a quarter of a second on 16 cores)
     sec = cpu_frames(steps, cores)
     mpx = WIDTH * HEIGHT / sec / 1e6
     line = {
         "impl": "reference", "metric": "Mpixels/s (complete antialiased frames, scene -> RGBA8 framebuffer)", "value": mpx, "unit": "Mpx/s",
-        "frames_per_s": 1.0 / sec, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "frames_per_s": 1.0 / sec, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT},
         "cpu_baseline": {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port",
@@ -164,6 +183,7 @@ def run_ours(args):
     y0, y1 = band_list[rank]
 
     ctx = abi.Context(local)
+    ctx_sms = torch.cuda.get_device_properties(local).multi_processor_count
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.fb_configure(WIDTH, HEIGHT, y0, y1)
@@ -280,6 +300,8 @@ def run_ours(args):
         ms = total_ms / args.steps
         mpx = WIDTH * HEIGHT / (ms * 1e-3) / 1e6
         peak, peak_src = peaks()
+        traffic, inst = ncu_summary()
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6 if clocks else 1965.0e6
         # algorithmic bytes of ONE walker launch on this rank: one RGBA8 write per output
         # pixel of the band + one read of every prepared edge (32 B) and object record
         alg_bytes = 4 * WIDTH * (y1 - y0) + 16 * n_edges + 32 * n_objs
@@ -290,9 +312,13 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "band_rows": [list(b) for b in band_list], "l2": "256 MB flush write before every timed step (untimed)",
                        "step": "one frame: K1 binning (3 launches) + raster phase (scan, visibility, antialiasing, compositing walk: 4 launches)", "gather": gather},
-            "roofline": {"bound": "hbm", "kernel": "raster phase: k_pre_scan + k_pre_vis + k_pre_aa (dominant) + k_walk", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if N == 1 else None,
+            "roofline": {"bound": "hbm", "kernel": "raster phase: k_pre_scan + k_pre_vis + k_pre_aa_runs (dominant) + k_comp_rows", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic if N == 1 else None, "traffic_source": NCU_SUMMARY if traffic else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": walk_ms_max, "binning_ms": bin_ms,
-                         "note": "kernel_ms is the device time of the four raster-phase launches together (CUDA events on the launching stream); integer/bit + FP64-crossing work, issue bound, not HBM bound (DESIGN.md)"},
+                         # the honest second bound: the path is integer / bit work, limited by instruction issue, not by HBM
+                         "issue_frac": (inst / (ctx_sms * 4 * sm_hz * ms * 1e-3)) if (inst and N == 1) else None,
+                         "warp_instructions_per_frame": inst if N == 1 else None,
+                         "note": "kernel_ms is the device time of the raster-phase launches together (CUDA events on the launching stream); integer/bit + FP64-crossing work, issue bound, not HBM bound (DESIGN.md): issue_frac = warp-instructions of the frame (ncu, same build) / (SMs x 4 schedulers x SM clock x step time)"},
             "e2e": {"value": WIDTH * HEIGHT / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                     "path": "per frame: coh_scene_create(host arrays) + coh_render_frame + coh_fb_read_rgba_async(pinned host); the read-back of frame k overlaps frame k+1, all copies complete inside the timed region"},
             "gpu_launches": int(launches),
@@ -301,8 +327,10 @@ def run_ours(args):
         if args.cpu_baseline:
             cores = os.cpu_count() or 1
             sec = cpu_frames(2, cores)
+            sec1 = cpu_frames(1, 1)   # the reference is single-threaded: one frame on one core
             line["cpu_baseline"] = {"value": WIDTH * HEIGHT / sec / 1e6, "unit": "Mpx/s", "cores": cores, "kind": "port", "ms_per_frame": sec * 1e3,
-                                    "sample": f"2 full C2 frames, each split into {cores} horizontal bands rendered in parallel by the oracle (C++ restatement of the single-threaded OCaml reference)"}
+                                    "cores_1_ms_per_frame": sec1 * 1e3, "cores_1_value": WIDTH * HEIGHT / sec1 / 1e6,
+                                    "sample": f"2 full C2 frames, each split into {cores} horizontal bands rendered in parallel by the oracle (C++ restatement of the single-threaded OCaml reference), and 1 full frame on 1 core"}
         print(json.dumps(line))
     ctx.scene_free(scene_h)
     ctx.close()

@@ -45,7 +45,7 @@ SYMBOLS = [
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
-    "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
+    "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_sprite", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
@@ -341,6 +341,14 @@ class Context:
 
     def fb_read_wait(self):
         self._chk(lib().coh_fb_read_wait(self._h))
+
+    def fb_read_sprite(self, update_shape):
+        """The frame's pixels on `update_shape`, RGBA8 per pixel in canonical span order (Render.render_frame's sprite)."""
+        cap = self.shape_card(update_shape) if update_shape else 0
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = C.c_int64()
+        self._chk(lib().coh_fb_read_sprite(self._h, C.c_uint64(update_shape), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
 
     def fb_read_rgb888(self, x, y, w, h):
         out = np.zeros((h, w, 3), dtype=np.uint8)

@@ -431,6 +431,26 @@ int coh_fb_read_wait(coh_ctx* ctx) {
     if (ctx->stage_busy[k]) { CK(cudaEventSynchronize(ctx->ev_done[k])); ctx->stage_busy[k] = false; any = true; }
   return any ? check_error_flag(ctx, "coh_fb_read_wait (a frame rendered before these reads)") : 0;
 }
+// The result sprite of Render.render_frame over `update` (render.mli:211-217 returns a Sprite.sprite): the
+// framebuffer's pixels on the update shape, one RGBA8 word per pixel in canonical span order.
+int coh_fb_read_sprite(coh_ctx* ctx, coh_shape_t update, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  if (!ctx->fb) FAIL("coh_fb_read_sprite: no framebuffer");
+  if (!update) return 0;   // NullShape -> NullSprite
+  DevShape* s = (DevShape*)update;
+  if (s->card > cap) FAIL("coh_fb_read_sprite: buffer too small");
+  if (s->bx0 < 0 || s->by0 < 0 || s->bx1 >= ctx->fr.W || s->by1 >= ctx->fr.H) FAIL("coh_fb_read_sprite: shape outside the framebuffer");
+  int* d_off = nullptr; uint32_t* d_out = nullptr;
+  if (shape_pixel_offsets(ctx, s, &d_off)) return 1;
+  CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(s->card, 1)));
+  k_gather_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, 0, ctx->fr.W, ctx->fb + (size_t)s->y0 * ctx->fr.W, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
+  const int rc = check_error_flag(ctx, "coh_fb_read_sprite (a frame rendered before this read)");
+  DFREE(d_off); DFREE(d_out);
+  if (!rc) *n_out = s->card;
+  return rc;
+}
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->fb) FAIL("coh_fb_read_rgb888: no framebuffer");

@@ -96,6 +96,30 @@ static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges
   *wx0_out = wx0; *nw_out = nw;
   return rc;
 }
+// Offset of every row's first pixel in canonical span order (device, n_rows + 1 ints): row pixel counts + scan.
+static int shape_pixel_offsets(coh_ctx* ctx, const DevShape* s, int** d_off) {
+  int* counts = nullptr;
+  *d_off = nullptr;
+  if (s->card > 0x7FFFFFF0LL) FAIL("span set too large for a per-pixel export");
+  CK(DMALLOC(&counts, sizeof(int) * std::max(s->n_rows, 1)));
+  CK(DMALLOC(d_off, sizeof(int) * (s->n_rows + 1)));
+  k_row_pixels<<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, s->n_rows, counts); LAUNCHED();
+  if (exclusive_scan(ctx, counts, *d_off, s->n_rows, nullptr)) return 1;
+  DFREE(counts);
+  return 0;
+}
+// AA opacity of every pixel of `s` in canonical span order, device resident (card bytes)
+static int polygon_opacity_spans(coh_ctx* ctx, const int32_t* edges, int n_edges, int winding, const DevShape* s, uint8_t** d_op, int** d_off) {
+  uint8_t* dense = nullptr; int wx0, nw;
+  *d_op = nullptr;
+  if (shape_pixel_offsets(ctx, s, d_off)) return 1;
+  CK(DMALLOC(d_op, (size_t)std::max<long long>(s->card, 1)));
+  if (n_edges <= 0) { CK(cudaMemsetAsync(*d_op, 0, (size_t)s->card, ctx->stream)); return 0; }  // empty scaled shape: coverage 0
+  if (polygon_opacity_dense(ctx, edges, n_edges, winding, s, &dense, &wx0, &nw)) return 1;
+  k_gather_spans<uint8_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, *d_off, s->n_rows, wx0, nw * 32, dense, *d_op); LAUNCHED();
+  DFREE(dense);
+  return 0;
+}
 int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int32_t winding, coh_shape_t shp,
                         uint8_t* out, int64_t cap, int64_t* n_out) {
   CK(cudaSetDevice(ctx->device));
@@ -103,47 +127,34 @@ int coh_polygon_opacity(coh_ctx* ctx, const int32_t* edges, int32_t n_edges, int
   if (!shp) return 0;
   DevShape* s = (DevShape*)shp;
   if (s->card > cap) FAIL("coh_polygon_opacity: buffer too small");
-  uint8_t* dense = nullptr; int wx0, nw;
-  if (n_edges <= 0) { memset(out, 0, (size_t)s->card); *n_out = s->card; return 0; }  // empty scaled shape: coverage 0
-  if (polygon_opacity_dense(ctx, edges, n_edges, winding, s, &dense, &wx0, &nw)) return 1;
-  std::vector<int> ptr; std::vector<int2> spans;
-  if (download_shape(ctx, s, ptr, spans)) return 1;
-  std::vector<uint8_t> h((size_t)s->n_rows * nw * 32);
-  CK(cudaMemcpyAsync(h.data(), dense, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  uint8_t* d_op = nullptr; int* d_off = nullptr;
+  if (polygon_opacity_spans(ctx, edges, n_edges, winding, s, &d_op, &d_off)) return 1;
+  CK(cudaMemcpyAsync(out, d_op, (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  DFREE(dense);
-  int64_t k = 0;
-  for (int r = 0; r < s->n_rows; r++)
-    for (int q = ptr[r]; q < ptr[r + 1]; q++)
-      for (int i = 0; i < spans[q].y; i++) out[k++] = h[(size_t)r * nw * 32 + (spans[q].x + i - wx0)];
-  *n_out = k;
+  DFREE(d_op); DFREE(d_off);
+  *n_out = s->card;
   return 0;
 }
 int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edges, int32_t n_edges, int32_t winding,
                        coh_shape_t shp, uint32_t* out, int64_t cap, int64_t* n_out) {
-  // polygon.ml:729-746: per span, colour = dissolve (fillsingle x_spanstart y) opacity.  The fill is
-  // evaluated by the same device routine as the walker through a one-object render of `shp`'s spans;
-  // here the opacity comes from the AA kernel and the (cheap, per-span) fill lookup runs on the host
-  // side of the ABI only for this export entry point.
+  // polygon.ml:729-746: per span, colour = dissolve (fillsingle x_spanstart y) opacity — the opacity from the
+  // AA kernel, fill and dissolve by k_sprite_fill, all on the device; only the finished sprite crosses the ABI.
   CK(cudaSetDevice(ctx->device));
   *n_out = 0;
   if (!shp) return 0;
   DevShape* s = (DevShape*)shp;
   if (s->card > cap) FAIL("coh_polygon_sprite: buffer too small");
-  std::vector<uint8_t> op((size_t)s->card);
-  int64_t n = 0;
-  if (coh_polygon_opacity(ctx, edges, n_edges, winding, shp, op.data(), s->card, &n)) return 1;
-  std::vector<int> ptr; std::vector<int2> spans;
-  if (download_shape(ctx, s, ptr, spans)) return 1;
+  if (fill->fill_kind < COH_FILL_PLAIN || fill->fill_kind > COH_FILL_RADIAL) FAIL("coh_polygon_sprite: bad fill kind");
+  uint8_t* d_op = nullptr; int* d_off = nullptr; uint32_t* d_out = nullptr;
+  if (polygon_opacity_spans(ctx, edges, n_edges, winding, s, &d_op, &d_off)) return 1;
   FillRec f; f.kind = fill->fill_kind; f.c0 = fill->colour0; f.c1 = fill->colour1; f.flags = fill->fill_flags;
   for (int i = 0; i < 6; i++) f.p[i] = fill->fparam[i];
-  int64_t k = 0;
-  for (int r = 0; r < s->n_rows; r++)
-    for (int q = ptr[r]; q < ptr[r + 1]; q++) {
-      uint32_t c = fill_lookup(f, spans[q].x, s->y0 + r);
-      for (int i = 0; i < spans[q].y; i++, k++) out[k] = px_dissolve(c, op[k]);
-    }
-  *n_out = k;
+  CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(s->card, 1)));
+  k_sprite_fill<<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->y0, s->n_rows, f, d_op, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(out, d_out, 4 * (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(d_op); DFREE(d_off); DFREE(d_out);
+  *n_out = s->card;
   return 0;
 }
 
@@ -164,13 +175,6 @@ static int conv_taps(coh_ctx* ctx, int kind, int r, int** d_taps, int* total) {
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
-static int shape_pixel_offsets(coh_ctx* ctx, const DevShape* s, std::vector<long long>& off) {
-  std::vector<int> ptr; std::vector<int2> spans;
-  if (download_shape(ctx, s, ptr, spans)) return 1;
-  off.assign(s->n_rows + 1, 0);
-  for (int r = 0; r < s->n_rows; r++) { long long n = 0; for (int q = ptr[r]; q < ptr[r + 1]; q++) n += spans[q].y; off[r + 1] = off[r] + n; }
-  return 0;
-}
 // Convolve.convolve_sprite kernel sprite (convolve.ml:239-258): the sprite is (shape, one RGBA8 per pixel in
 // span order); the result lives on bloat r r (shape) and is returned the same way.
 int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_t shape, const uint32_t* rgba_in,
@@ -187,25 +191,21 @@ int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_
   // canvas = bounding box grown by 2r (Sprite.flatten_sprite border, convolve.ml:247)
   const int x0 = s->bx0 - 2 * r, y0 = s->by0 - 2 * r, w = s->bx1 - s->bx0 + 1 + 4 * r, h = s->by1 - s->by0 + 1 + 4 * r;
   const size_t npx = (size_t)w * h;
-  uint32_t *A = nullptr, *X = nullptr, *d_in = nullptr, *d_out = nullptr; long long* d_off = nullptr; int* d_taps = nullptr; int total = 0;
-  std::vector<long long> off;
-  if (shape_pixel_offsets(ctx, s, off)) return 1;
+  uint32_t *A = nullptr, *X = nullptr, *d_in = nullptr, *d_out = nullptr; int* d_off = nullptr; int* d_taps = nullptr; int total = 0;
+  if (shape_pixel_offsets(ctx, s, &d_off)) return 1;
   CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx));
   CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
-  CK(DMALLOC(&d_in, 4 * (size_t)std::max<long long>(s->card, 1))); CK(DMALLOC(&d_off, sizeof(long long) * off.size()));
+  CK(DMALLOC(&d_in, 4 * (size_t)std::max<long long>(s->card, 1)));
   CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
   k_scatter_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, s->y0 - y0, x0, w, d_in, A); LAUNCHED();
   if (conv_taps(ctx, kernel_kind, r, &d_taps, &total)) return 1;
   dim3 gp(cdiv(w, 128), h);
   k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, r, kernel_kind, d_taps, total, 0); LAUNCHED();
   k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, A, w, h, r, kernel_kind, d_taps, total, 1); LAUNCHED();
   // pick the result up on R (Sprite.pickup)
-  std::vector<long long> roff;
-  if (shape_pixel_offsets(ctx, rs, roff)) return 1;
-  long long* d_roff = nullptr;
-  CK(DMALLOC(&d_roff, sizeof(long long) * roff.size())); CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
-  CK(cudaMemcpyAsync(d_roff, roff.data(), sizeof(long long) * roff.size(), cudaMemcpyHostToDevice, ctx->stream));
+  int* d_roff = nullptr;
+  if (shape_pixel_offsets(ctx, rs, &d_roff)) return 1;
+  CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(rs->card, 1)));
   // k_gather_spans indexes dense rows from the shape's first row: pass the canvas rows starting at R's first row
   k_gather_spans<uint32_t><<<cdiv(rs->n_rows, 128), 128, 0, ctx->stream>>>(rs->row_ptr, rs->spans, d_roff, rs->n_rows, x0, w, A + (size_t)(rs->y0 - y0) * w, d_out); LAUNCHED();
   CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)rs->card, cudaMemcpyDeviceToHost, ctx->stream));

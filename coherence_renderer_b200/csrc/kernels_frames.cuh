@@ -243,17 +243,31 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   // the grid is sized for every cell: positions beyond the queued cells (background cells were finished by
   // k_prefill) leave at once.
   __shared__ int s_cell[4];   // cell, tile, first row of the block, column mask of the update box
-  if (threadIdx.x == 0) {
-    int q = blockIdx.x / PARTS, cell = -1;
+  if (threadIdx.x < 32) {
+    // warp 0: lane c holds the size of class c; an inclusive scan finds the class of position q with one load
+    const int lane0 = threadIdx.x;
+    const int q = blockIdx.x / PARTS;
+    int cell = -1;
     if (P.cls_cnt) {
-      for (int c = 0; c < BIN_CLASSES; c++) { const int n = P.cls_cnt[c]; if (q < n) { cell = P.cls_cells[(size_t)c * P.n_cells + q]; break; } q -= n; }
-    } else cell = q < P.n_cells ? q : -1;
-    s_cell[0] = cell;
-    if (cell >= 0) {
-      const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
-      uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
-      if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
-      s_cell[1] = tile; s_cell[2] = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS; s_cell[3] = (int)colmask;
+      const int n = lane0 < BIN_CLASSES ? P.cls_cnt[lane0] : 0;
+      int incl = n;
+#pragma unroll
+      for (int d = 1; d < BIN_CLASSES; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane0 >= d) incl += t; }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, lane0 < BIN_CLASSES && q < incl);
+      if (m) {
+        const int c = __ffs((int)m) - 1;
+        const int before = __shfl_sync(0xFFFFFFFFu, incl - n, c);
+        if (lane0 == 0) cell = P.cls_cells[(size_t)c * P.n_cells + q - before];
+      }
+    } else if (lane0 == 0) cell = q < P.n_cells ? q : -1;
+    if (lane0 == 0) {
+      s_cell[0] = cell;
+      if (cell >= 0) {
+        const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
+        uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
+        if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
+        s_cell[1] = tile; s_cell[2] = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS; s_cell[3] = (int)colmask;
+      }
     }
   }
   __syncthreads();

@@ -238,14 +238,35 @@ __global__ void k_rgb888(const uint32_t* __restrict__ fb, int W, int x0, int y0,
   uint8_t* p = out + ((size_t)y * w + x) * 3;
   p[0] = c & 255u; p[1] = (c >> 8) & 255u; p[2] = (c >> 16) & 255u;
 }
+// Pixels per row of a span set (input of the exclusive scan that gives every row its offset in span order).
+__global__ void k_row_pixels(const int* __restrict__ row_ptr, const int2* __restrict__ spans, int n_rows, int* __restrict__ counts) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int n = 0;
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) n += spans[k].y;
+  counts[r] = n;
+}
+// Polygon.polygon_sprite_edgelist's colouring (polygon.ml:733-738): every pixel of a span takes the fill at the
+// span's FIRST x, dissolved by the pixel's opacity.  Thread per row, values in canonical span order.
+__global__ void k_sprite_fill(const int* __restrict__ row_ptr, const int2* __restrict__ spans, const int* __restrict__ px_off,
+                              int y0, int n_rows, FillRec fill, const uint8_t* __restrict__ opacity, uint32_t* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    const int2 s = spans[k];
+    const uint32_t c = fill_lookup(fill, s.x, y0 + r);
+    for (int i = 0; i < s.y; i++, o++) out[o] = px_dissolve(c, opacity[o]);
+  }
+}
 // Scatter per-pixel values given in canonical span order into a dense canvas: thread per row.
 template <class T>
 __global__ void k_scatter_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,
-                                const long long* __restrict__ px_off, int n_rows, int row0, int wx0, int w,
+                                const int* __restrict__ px_off, int n_rows, int row0, int wx0, int w,
                                 const T* __restrict__ in, T* __restrict__ dense) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
-  long long o = px_off[r];
+  int o = px_off[r];
   for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
     int2 s = spans[k];
     for (int i = 0; i < s.y; i++) dense[(size_t)(row0 + r) * w + (s.x + i - wx0)] = in[o++];
@@ -254,11 +275,11 @@ __global__ void k_scatter_spans(const int* __restrict__ row_ptr, const int2* __r
 // Gather dense per-pixel values in canonical span order: thread per row.
 template <class T>
 __global__ void k_gather_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,
-                               const long long* __restrict__ px_off, int n_rows, int wx0, int pitch,
+                               const int* __restrict__ px_off, int n_rows, int wx0, int pitch,
                                const T* __restrict__ dense, T* __restrict__ out) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
-  long long o = px_off[r];
+  int o = px_off[r];
   for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
     int2 s = spans[k];
     for (int i = 0; i < s.y; i++) out[o++] = dense[(size_t)r * pitch + (s.x + i - wx0)];

@@ -242,6 +242,10 @@ void* coh_fb_device_ptr(coh_ctx* ctx);
  * Wxgui.plot_sprite writes (wxgui.ml:417-424, premultiplied r,g,b bytes, no alpha). */
 int coh_fb_read_rgba(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
 int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+/* The value of Render.render_frame (render.mli:211-217: a Sprite.sprite on the update shape): the framebuffer's
+ * pixels on `update`, one RGBA8 word per pixel in canonical span order — with coh_shape_export (update) the OCaml
+ * shim rebuilds the sprite (spans of Fill.Samples).  The shape must lie inside the framebuffer. */
+int coh_fb_read_sprite(coh_ctx* ctx, coh_shape_t update, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
 /* Asynchronous variant of coh_fb_read_rgba for a stream of frames (the refresh loop of wxgui.ml:333-367 reads
  * frame k while the engine already works on frame k+1): the rectangle is snapshotted on the render stream into
  * one of two staging buffers and copied to `out` (pinned host memory) on a copy stream, so the next

@@ -1,16 +1,20 @@
-/* coherence_stubs.c — OCaml externals over the C ABI (include/coherence_b200.h).
+/* coherence_stubs.c — OCaml externals over the C ABI (include/coherence_b200.h): one stub per exported symbol.
  *
  * NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no OCaml toolchain here (no ocamlfind,
- * no caml/mlvalues.h).  Delivered as reviewed source; build with
+ * no caml/mlvalues.h; probed on the GPU box as well).  Delivered as reviewed source; build with
  *   ocamlfind ocamlopt -package bigarray -I include -c ocaml/coherence_stubs.c
  * and link with -cclib -lcoherence_b200.
  *
- * Conventions: bulk data arrives in Bigarray.Array1 (c_layout, int32 / int8_unsigned); handles
+ * Conventions: bulk data arrives in Bigarray.Array1 (c_layout, int32 / int8_unsigned / float64); handles
  * are boxed int64 (Int64.t); a non-zero status raises Failure (coh_last_error), which is the
  * reference's own error convention (failwith).  The stubs never retain OCaml pointers across
  * calls, so the GC may move values freely; device objects are freed by explicit calls wired to
  * Gc.finalise in coherence_gpu.ml.  The caller is the single OCaml thread; calls block until the
  * requested host bytes are ready, so the runtime lock is not released.
+ *
+ * GC discipline: every value that is allocated here is bound to a CAMLlocal root BEFORE it is stored into another
+ * block (Store_field (t, i, caml_copy_int64 (..)) would compute the field address before the allocation can move
+ * the tuple); Bigarray arguments are checked against the sizes the C ABI is going to write.
  */
 #include <caml/alloc.h>
 #include <caml/bigarray.h>
@@ -21,8 +25,31 @@
 #include "coherence_b200.h"
 
 #define CTX(v) ((coh_ctx*)Nativeint_val(v))
+#define SHAPE(v) ((coh_shape_t)Int64_val(v))
+#define SCENE(v) ((coh_scene_t)Int64_val(v))
+#define BA_LEN(v) ((int64_t)Caml_ba_array_val(v)->dim[0])
 static void check(coh_ctx* c, int rc) { if (rc) caml_failwith(coh_last_error(c)); }
+static void need(value ba, int64_t n, const char* what) { if (BA_LEN(ba) < n) caml_invalid_argument(what); }
+/* (int64, int64) tuple of two handles */
+static value pair_of_handles(coh_shape_t a, coh_shape_t b) {
+  CAMLparam0();
+  CAMLlocal3(pair, va, vb);
+  va = caml_copy_int64((int64_t)a);
+  vb = caml_copy_int64((int64_t)b);
+  pair = caml_alloc_tuple(2);
+  Store_field(pair, 0, va);
+  Store_field(pair, 1, vb);
+  CAMLreturn(pair);
+}
+static value tuple_of_ints(const int32_t* v, int n) {
+  CAMLparam0();
+  CAMLlocal1(r);
+  r = caml_alloc_tuple(n);
+  for (int k = 0; k < n; k++) Store_field(r, k, Val_int(v[k]));   /* immediates: no allocation */
+  CAMLreturn(r);
+}
 
+/* ---- lifecycle ---- */
 CAMLprim value coh_ml_init(value device) {
   CAMLparam1(device);
   coh_ctx* c = NULL;
@@ -30,131 +57,313 @@ CAMLprim value coh_ml_init(value device) {
   CAMLreturn(caml_copy_nativeint((intnat)c));
 }
 CAMLprim value coh_ml_shutdown(value ctx) { coh_shutdown(CTX(ctx)); return Val_unit; }
+CAMLprim value coh_ml_device_name(value ctx) {
+  CAMLparam1(ctx);
+  char buf[256];
+  check(CTX(ctx), coh_device_name(CTX(ctx), buf, sizeof buf));
+  CAMLreturn(caml_copy_string(buf));
+}
+CAMLprim value coh_ml_stream(value ctx) { return caml_copy_nativeint((intnat)coh_stream(CTX(ctx))); }
+CAMLprim value coh_ml_set_stream(value ctx, value s) { check(CTX(ctx), coh_set_stream(CTX(ctx), (void*)Nativeint_val(s))); return Val_unit; }
+CAMLprim value coh_ml_launch_count(value ctx) { return caml_copy_int64(coh_launch_count(CTX(ctx))); }
+CAMLprim value coh_ml_set_timing(value ctx, value on) { check(CTX(ctx), coh_set_timing(CTX(ctx), Bool_val(on))); return Val_unit; }
+CAMLprim value coh_ml_get_timing(value ctx) {   /* (raster ms, binning ms, frames) */
+  CAMLparam1(ctx);
+  CAMLlocal3(r, a, b);
+  double w = 0, bn = 0; int64_t n = 0;
+  check(CTX(ctx), coh_get_timing(CTX(ctx), &w, &bn, &n));
+  a = caml_copy_double(w); b = caml_copy_double(bn);
+  r = caml_alloc_tuple(3);
+  Store_field(r, 0, a); Store_field(r, 1, b); Store_field(r, 2, Val_long((long)n));
+  CAMLreturn(r);
+}
+CAMLprim value coh_ml_set_option(value ctx, value name, value v) { check(CTX(ctx), coh_set_option(CTX(ctx), String_val(name), Int_val(v))); return Val_unit; }
+CAMLprim value coh_ml_mem_in_use(value ctx) { int64_t n = 0; check(CTX(ctx), coh_mem_in_use(CTX(ctx), &n)); return caml_copy_int64(n); }
+CAMLprim value coh_ml_sync(value ctx) { check(CTX(ctx), coh_sync(CTX(ctx))); return Val_unit; }
 
-/* Colour.colour (31-bit int) <-> RGBA8 word */
+/* ---- Colour.colour (31-bit int) <-> RGBA8 word ---- */
 CAMLprim value coh_ml_rgba8_of_colour(value c) { return caml_copy_int32((int32_t)coh_rgba8_of_colour((int32_t)Long_val(c))); }
 CAMLprim value coh_ml_colour_of_rgba8(value w) { return Val_long(coh_colour_of_rgba8((uint32_t)Int32_val(w))); }
 
+/* ---- Polygon ---- */
 /* Polygon.shapeminshape_of_unsorted_edgelist: edges : (int32, c_layout) Array1 of 4*n */
 CAMLprim value coh_ml_shapeminshape(value ctx, value edges, value winding) {
   CAMLparam3(ctx, edges, winding);
-  CAMLlocal1(pair);
   coh_shape_t s = 0, m = 0;
-  check(CTX(ctx), coh_shapeminshape_of_edgelist(CTX(ctx), (const int32_t*)Caml_ba_data_val(edges),
-        (int32_t)(Caml_ba_array_val(edges)->dim[0] / 4), Int_val(winding), &s, &m));
-  pair = caml_alloc_tuple(2);
-  Store_field(pair, 0, caml_copy_int64((int64_t)s));
-  Store_field(pair, 1, caml_copy_int64((int64_t)m));
-  CAMLreturn(pair);
+  check(CTX(ctx), coh_shapeminshape_of_edgelist(CTX(ctx), (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), Int_val(winding), &s, &m));
+  CAMLreturn(pair_of_handles(s, m));
+}
+/* opacity bytes of every pixel of `shape`, span order; out : (int, int8_unsigned) Array1 of Sprite.shape_card shape */
+CAMLprim value coh_ml_polygon_opacity(value ctx, value edges, value winding, value shape, value out) {
+  CAMLparam5(ctx, edges, winding, shape, out);
+  int64_t n = 0;
+  check(CTX(ctx), coh_polygon_opacity(CTX(ctx), (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), Int_val(winding), SHAPE(shape),
+        (uint8_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+/* Polygon.polygon_sprite_edgelist: fill = one packed coh_object record (coh_ml_pack_object); out : int32 Array1 */
+CAMLprim value coh_ml_polygon_sprite(value ctx, value fill, value edges, value winding, value shape, value out) {
+  CAMLparam5(ctx, fill, edges, winding, shape);
+  CAMLxparam1(out);
+  int64_t n = 0;
+  need(fill, (int64_t)sizeof(coh_object), "coh_polygon_sprite: fill record too short");
+  check(CTX(ctx), coh_polygon_sprite(CTX(ctx), (const coh_object*)Caml_ba_data_val(fill), (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4),
+        Int_val(winding), SHAPE(shape), (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+CAMLprim value coh_ml_polygon_sprite_bc(value* a, int n) { (void)n; return coh_ml_polygon_sprite(a[0], a[1], a[2], a[3], a[4], a[5]); }
+
+/* ---- Sprite.shape ---- */
+CAMLprim value coh_ml_shape_box(value ctx, value x, value y, value w, value h) {
+  CAMLparam5(ctx, x, y, w, h);
+  coh_shape_t o = 0;
+  check(CTX(ctx), coh_shape_box(CTX(ctx), Int_val(x), Int_val(y), Int_val(w), Int_val(h), &o));
+  CAMLreturn(caml_copy_int64((int64_t)o));
 }
 /* Sprite.shape export: returns the flat (y, nspans, (x,len)...) records in a fresh Bigarray */
 CAMLprim value coh_ml_shape_export(value ctx, value shape) {
   CAMLparam2(ctx, shape);
+  CAMLlocal1(ba);
   int64_t n = 0, got = 0;
-  check(CTX(ctx), coh_shape_export_size(CTX(ctx), (coh_shape_t)Int64_val(shape), &n));
+  check(CTX(ctx), coh_shape_export_size(CTX(ctx), SHAPE(shape), &n));
   intnat dim = (intnat)n;
-  value ba = caml_ba_alloc(CAML_BA_INT32 | CAML_BA_C_LAYOUT, 1, NULL, &dim);
-  check(CTX(ctx), coh_shape_export(CTX(ctx), (coh_shape_t)Int64_val(shape), (int32_t*)Caml_ba_data_val(ba), n, &got));
+  ba = caml_ba_alloc(CAML_BA_INT32 | CAML_BA_C_LAYOUT, 1, NULL, &dim);
+  check(CTX(ctx), coh_shape_export(CTX(ctx), SHAPE(shape), (int32_t*)Caml_ba_data_val(ba), n, &got));
   CAMLreturn(ba);
 }
 CAMLprim value coh_ml_shape_import(value ctx, value flat) {
   CAMLparam2(ctx, flat);
   coh_shape_t s = 0;
-  check(CTX(ctx), coh_shape_import(CTX(ctx), (const int32_t*)Caml_ba_data_val(flat), Caml_ba_array_val(flat)->dim[0], &s));
+  check(CTX(ctx), coh_shape_import(CTX(ctx), (const int32_t*)Caml_ba_data_val(flat), BA_LEN(flat), &s));
   CAMLreturn(caml_copy_int64((int64_t)s));
 }
-CAMLprim value coh_ml_shape_free(value ctx, value s) { coh_shape_free(CTX(ctx), (coh_shape_t)Int64_val(s)); return Val_unit; }
+CAMLprim value coh_ml_shape_bounds(value ctx, value s) {   /* (x0, y0, x1, y1) option */
+  CAMLparam2(ctx, s);
+  CAMLlocal2(t, some);
+  int32_t box[4], isnull = 0;
+  check(CTX(ctx), coh_shape_bounds(CTX(ctx), SHAPE(s), box, &isnull));
+  if (isnull) CAMLreturn(Val_int(0));   /* None */
+  t = tuple_of_ints(box, 4);
+  some = caml_alloc(1, 0);
+  Store_field(some, 0, t);
+  CAMLreturn(some);
+}
+CAMLprim value coh_ml_shape_card(value ctx, value s) { int64_t n = 0; check(CTX(ctx), coh_shape_card(CTX(ctx), SHAPE(s), &n)); return Val_long((long)n); }
+CAMLprim value coh_ml_shape_free(value ctx, value s) { coh_shape_free(CTX(ctx), SHAPE(s)); return Val_unit; }
 #define BINOP(name, fn)                                                              \
   CAMLprim value name(value ctx, value a, value b) {                                 \
     CAMLparam3(ctx, a, b);                                                           \
     coh_shape_t o = 0;                                                               \
-    check(CTX(ctx), fn(CTX(ctx), (coh_shape_t)Int64_val(a), (coh_shape_t)Int64_val(b), &o)); \
+    check(CTX(ctx), fn(CTX(ctx), SHAPE(a), SHAPE(b), &o));                           \
     CAMLreturn(caml_copy_int64((int64_t)o));                                         \
   }
 BINOP(coh_ml_shape_union, coh_shape_union)              /* Sprite.( ||| ) */
 BINOP(coh_ml_shape_difference, coh_shape_difference)    /* Sprite.( --- ) */
 BINOP(coh_ml_shape_intersection, coh_shape_intersection)/* Sprite.( &&& ) */
-CAMLprim value coh_ml_shape_bloat(value ctx, value a, value m, value n) {
-  CAMLparam4(ctx, a, m, n);
+#define UNOP(name, fn)                                                               \
+  CAMLprim value name(value ctx, value a, value m, value n) {                        \
+    CAMLparam4(ctx, a, m, n);                                                        \
+    coh_shape_t o = 0;                                                               \
+    check(CTX(ctx), fn(CTX(ctx), SHAPE(a), Int_val(m), Int_val(n), &o));             \
+    CAMLreturn(caml_copy_int64((int64_t)o));                                         \
+  }
+UNOP(coh_ml_shape_translate, coh_shape_translate)       /* Sprite.translate_shape */
+UNOP(coh_ml_shape_bloat, coh_shape_bloat)               /* Sprite.bloat */
+UNOP(coh_ml_shape_erode, coh_shape_erode)               /* Sprite.erode */
+
+/* ---- Convolve.convolve_sprite kernel sprite: sprite = (shape handle, RGBA8 per pixel in span order) ---- */
+CAMLprim value coh_ml_convolve_sprite(value ctx, value kind_r, value shape, value rgba_in, value rgba_out) {
+  CAMLparam5(ctx, kind_r, shape, rgba_in, rgba_out);
   coh_shape_t o = 0;
-  check(CTX(ctx), coh_shape_bloat(CTX(ctx), (coh_shape_t)Int64_val(a), Int_val(m), Int_val(n), &o));
+  int64_t n = 0;
+  check(CTX(ctx), coh_convolve_sprite(CTX(ctx), Int_val(Field(kind_r, 0)), Int_val(Field(kind_r, 1)), SHAPE(shape),
+        (const uint32_t*)Caml_ba_data_val(rgba_in), &o, (uint32_t*)Caml_ba_data_val(rgba_out), BA_LEN(rgba_out), &n));
   CAMLreturn(caml_copy_int64((int64_t)o));
 }
 
-/* Render: objs is a Bigarray of bytes holding n packed coh_object records built by
- * Coherence_gpu.flatten_scene (closures -> descriptors happens on the OCaml side). */
-CAMLprim value coh_ml_scene_create(value ctx, value objs, value n_background, value edges, value points) {
-  CAMLparam5(ctx, objs, n_background, edges, points);
-  coh_scene_t s = 0;
-  check(CTX(ctx), coh_scene_create(CTX(ctx), (const coh_object*)Caml_ba_data_val(objs),
-        (int32_t)(Caml_ba_array_val(objs)->dim[0] / sizeof(coh_object)), Int_val(n_background),
-        (const int32_t*)Caml_ba_data_val(edges), (int32_t)(Caml_ba_array_val(edges)->dim[0] / 4),
-        (const int32_t*)Caml_ba_data_val(points), (int32_t)(Caml_ba_array_val(points)->dim[0] / 2), &s));
-  CAMLreturn(caml_copy_int64((int64_t)s));
-}
-CAMLprim value coh_ml_scene_free(value ctx, value s) { coh_scene_free(CTX(ctx), (coh_scene_t)Int64_val(s)); return Val_unit; }
-CAMLprim value coh_ml_fb_configure(value ctx, value w, value h, value y0, value y1) {
-  check(CTX(ctx), coh_fb_configure(CTX(ctx), Int_val(w), Int_val(h), Int_val(y0), Int_val(y1)));
-  return Val_unit;
-}
-/* Render.render_frame over update = Sprite.box x y w h, then plot_sprite's RGB888 bytes of the
- * same rectangle straight into the caller's canvas slice (wxgui.ml:254-262, 417-424). */
-CAMLprim value coh_ml_render_frame_rgb888(value ctx, value scene, value box, value out) {
-  CAMLparam4(ctx, scene, box, out);
-  int x = Int_val(Field(box, 0)), y = Int_val(Field(box, 1)), w = Int_val(Field(box, 2)), h = Int_val(Field(box, 3));
-  check(CTX(ctx), coh_render_frame(CTX(ctx), (coh_scene_t)Int64_val(scene), x, y, w, h, 0));
-  check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), x, y, w, h, (uint8_t*)Caml_ba_data_val(out)));
-  CAMLreturn(Val_unit);
-}
-
-/* ---- coherence across frames (engine.ml:441-493, render.ml:259-271, 1376-1438, cache.mli) ---- */
+/* ---- Cache ---- */
 CAMLprim value coh_ml_cache_configure(value ctx, value on, value bytes) {   /* Cache.usecache / Cache.setsize */
   check(CTX(ctx), coh_cache_configure(CTX(ctx), Bool_val(on), Int64_val(bytes)));
   return Val_unit;
 }
 CAMLprim value coh_ml_cache_clear(value ctx) { check(CTX(ctx), coh_cache_clear(CTX(ctx))); return Val_unit; }
+CAMLprim value coh_ml_cache_stats(value ctx) {   /* (hits, misses, bytes, entries, sprite hits, sprite bytes) */
+  CAMLparam1(ctx);
+  CAMLlocal1(r);
+  int64_t st[6] = {0, 0, 0, 0, 0, 0};
+  check(CTX(ctx), coh_cache_stats(CTX(ctx), st));
+  r = caml_alloc_tuple(4);
+  for (int k = 0; k < 4; k++) Store_field(r, k, Val_long((long)st[k]));
+  CAMLreturn(r);
+}
+CAMLprim value coh_ml_cache_addshape(value ctx, value id, value s, value m) {
+  check(CTX(ctx), coh_cache_addshape(CTX(ctx), Int64_val(id), SHAPE(s), SHAPE(m)));
+  return Val_unit;
+}
+CAMLprim value coh_ml_cache_getshape(value ctx, value id) {   /* (shape_h * shape_h) option */
+  CAMLparam2(ctx, id);
+  CAMLlocal2(p, some);
+  coh_shape_t s = 0, m = 0; int32_t found = 0;
+  check(CTX(ctx), coh_cache_getshape(CTX(ctx), Int64_val(id), &s, &m, &found));
+  if (!found) CAMLreturn(Val_int(0));
+  p = pair_of_handles(s, m);
+  some = caml_alloc(1, 0);
+  Store_field(some, 0, p);
+  CAMLreturn(some);
+}
+CAMLprim value coh_ml_cache_addtranslation(value ctx, value id, value target, value dx, value dy) {
+  check(CTX(ctx), coh_cache_addtranslation(CTX(ctx), Int64_val(id), Int64_val(target), Int_val(dx), Int_val(dy)));
+  return Val_unit;
+}
+/* Render.plaindirty (plain = true) / alldirty */
+CAMLprim value coh_ml_dirty_region(value ctx, value shapes, value u, value plain) {
+  CAMLparam4(ctx, shapes, u, plain);
+  coh_shape_t o = 0;
+  check(CTX(ctx), coh_dirty_region(CTX(ctx), SHAPE(Field(shapes, 0)), SHAPE(Field(shapes, 1)), SHAPE(Field(shapes, 2)), SHAPE(Field(shapes, 3)),
+        SHAPE(u), Bool_val(plain), &o));
+  CAMLreturn(caml_copy_int64((int64_t)o));
+}
+
+/* ---- Render ---- */
+/* One coh_object record from its fields, in the order of the header: ints = [| kind; winding; first; count; fill_kind;
+ * colour0; colour1; fill_flags; pretrans; dx; dy; b0; b1; b2; b3; p0; p1; p2; p3; prim_null; convolve; sprite_winding;
+ * first2; count2; winding2; cpg_op; filter_kind; filter_kernel |], floats = [| fparam (6); brush_opacity; brush_radius |].
+ * The struct layout stays on the C side. */
+CAMLprim value coh_ml_pack_object(value objs, value index, value ints, value floats, value id) {
+  CAMLparam5(objs, index, ints, floats, id);
+  const int64_t i = Long_val(index);
+  need(objs, (i + 1) * (int64_t)sizeof(coh_object), "coh_ml_pack_object: record outside the buffer");
+  if (Wosize_val(ints) < 28 || Wosize_val(floats) / Double_wosize < 8) caml_invalid_argument("coh_ml_pack_object: field arrays too short");
+  coh_object o;
+  memset(&o, 0, sizeof o);
+#define I(k) ((int32_t)Long_val(Field(ints, k)))
+  o.kind = I(0); o.winding = I(1); o.first = I(2); o.count = I(3); o.fill_kind = I(4);
+  o.colour0 = (uint32_t)I(5); o.colour1 = (uint32_t)I(6); o.fill_flags = I(7); o.pretrans = I(8); o.dx = I(9); o.dy = I(10);
+  for (int k = 0; k < 4; k++) { o.bounds[k] = I(11 + k); o.prim[k] = I(15 + k); }
+  o.prim_null = I(19); o.convolve = I(20); o.sprite_winding = I(21);
+  o.first2 = I(22); o.count2 = I(23); o.winding2 = I(24); o.cpg_op = I(25); o.filter_kind = I(26); o.filter_kernel = I(27);
+#undef I
+  for (int k = 0; k < 6; k++) o.fparam[k] = Double_flat_field(floats, k);
+  o.brush_opacity = Double_flat_field(floats, 6); o.brush_radius = Double_flat_field(floats, 7);
+  o.id = Int64_val(id);
+  memcpy((char*)Caml_ba_data_val(objs) + i * sizeof(coh_object), &o, sizeof o);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_sizeof_object(value unit) { (void)unit; return Val_long((long)sizeof(coh_object)); }
+/* objs is a Bigarray of bytes holding n packed coh_object records built by Coherence_gpu.flatten_scene */
+CAMLprim value coh_ml_scene_create(value ctx, value objs, value n_background, value edges, value points) {
+  CAMLparam5(ctx, objs, n_background, edges, points);
+  coh_scene_t s = 0;
+  check(CTX(ctx), coh_scene_create(CTX(ctx), (const coh_object*)Caml_ba_data_val(objs), (int32_t)(BA_LEN(objs) / (int64_t)sizeof(coh_object)), Int_val(n_background),
+        (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), (const int32_t*)Caml_ba_data_val(points), (int32_t)(BA_LEN(points) / 2), &s));
+  CAMLreturn(caml_copy_int64((int64_t)s));
+}
+CAMLprim value coh_ml_scene_free(value ctx, value s) { coh_scene_free(CTX(ctx), SCENE(s)); return Val_unit; }
+CAMLprim value coh_ml_fb_configure(value ctx, value w, value h, value y0, value y1) {
+  check(CTX(ctx), coh_fb_configure(CTX(ctx), Int_val(w), Int_val(h), Int_val(y0), Int_val(y1)));
+  return Val_unit;
+}
+CAMLprim value coh_ml_fb_attach(value ctx, value p) { check(CTX(ctx), coh_fb_attach(CTX(ctx), (void*)Nativeint_val(p))); return Val_unit; }
+CAMLprim value coh_ml_fb_device_ptr(value ctx) { return caml_copy_nativeint((intnat)coh_fb_device_ptr(CTX(ctx))); }
+CAMLprim value coh_ml_fb_set_peers(value ctx, value peers) {   /* nativeint array */
+  CAMLparam2(ctx, peers);
+  void* p[8];
+  const int n = (int)Wosize_val(peers);
+  if (n > 7) caml_invalid_argument("coh_fb_set_peers: at most 7 peers");
+  for (int k = 0; k < n; k++) p[k] = (void*)Nativeint_val(Field(peers, k));
+  check(CTX(ctx), coh_fb_set_peers(CTX(ctx), n, p));
+  CAMLreturn(Val_unit);
+}
+/* Render.render_frame over update = Sprite.box x y w h (flags: 1 = keep the covered-so-far set) */
+CAMLprim value coh_ml_render_frame(value ctx, value scene, value box, value flags) {
+  CAMLparam4(ctx, scene, box, flags);
+  check(CTX(ctx), coh_render_frame(CTX(ctx), SCENE(scene), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), Int_val(flags)));
+  CAMLreturn(Val_unit);
+}
+/* ... then plot_sprite's RGB888 bytes of the same rectangle straight into the caller's canvas slice (wxgui.ml:254-262, 417-424) */
+CAMLprim value coh_ml_render_frame_rgb888(value ctx, value scene, value box, value out) {
+  CAMLparam4(ctx, scene, box, out);
+  int x = Int_val(Field(box, 0)), y = Int_val(Field(box, 1)), w = Int_val(Field(box, 2)), h = Int_val(Field(box, 3));
+  if (w < 0 || h < 0) caml_failwith("Sprite.box: negative argument.");
+  need(out, (int64_t)w * h * 3, "render_frame_rgb888: canvas slice too small");
+  check(CTX(ctx), coh_render_frame(CTX(ctx), SCENE(scene), x, y, w, h, 0));
+  check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), x, y, w, h, (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_render_frame_shape(value ctx, value scene, value update, value flags) {   /* render_frame over any update shape */
+  check(CTX(ctx), coh_render_frame_shape(CTX(ctx), SCENE(scene), SHAPE(update), Int_val(flags)));
+  return Val_unit;
+}
+CAMLprim value coh_ml_render_uncovered(value ctx) {
+  CAMLparam1(ctx);
+  coh_shape_t o = 0;
+  check(CTX(ctx), coh_render_uncovered(CTX(ctx), &o));
+  CAMLreturn(caml_copy_int64((int64_t)o));
+}
+/* the Sprite.sprite render_frame returns: RGBA8 per pixel of `update` in span order, in a fresh int32 Bigarray */
+CAMLprim value coh_ml_fb_read_sprite(value ctx, value update) {
+  CAMLparam2(ctx, update);
+  CAMLlocal1(ba);
+  int64_t card = 0, got = 0;
+  check(CTX(ctx), coh_shape_card(CTX(ctx), SHAPE(update), &card));
+  intnat dim = (intnat)card;
+  ba = caml_ba_alloc(CAML_BA_INT32 | CAML_BA_C_LAYOUT, 1, NULL, &dim);
+  check(CTX(ctx), coh_fb_read_sprite(CTX(ctx), SHAPE(update), (uint32_t*)Caml_ba_data_val(ba), card, &got));
+  CAMLreturn(ba);
+}
+CAMLprim value coh_ml_read_rgba(value ctx, value box, value out) {
+  CAMLparam3(ctx, box, out);
+  need(out, (int64_t)Int_val(Field(box, 2)) * Int_val(Field(box, 3)) * 4, "read_rgba: buffer too small");
+  check(CTX(ctx), coh_fb_read_rgba(CTX(ctx), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+/* asynchronous variant: `out` must stay alive (and is not moved: Bigarray data lives outside the OCaml heap) until read_wait */
+CAMLprim value coh_ml_read_rgba_async(value ctx, value box, value out) {
+  CAMLparam3(ctx, box, out);
+  need(out, (int64_t)Int_val(Field(box, 2)) * Int_val(Field(box, 3)) * 4, "read_rgba_async: buffer too small");
+  check(CTX(ctx), coh_fb_read_rgba_async(CTX(ctx), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_read_wait(value ctx) { check(CTX(ctx), coh_fb_read_wait(CTX(ctx))); return Val_unit; }
+CAMLprim value coh_ml_read_rgb888(value ctx, value box, value out) {   /* Wxgui.plot_sprite's bytes for a rectangle */
+  CAMLparam3(ctx, box, out);
+  need(out, (int64_t)Int_val(Field(box, 2)) * Int_val(Field(box, 3)) * 3, "read_rgb888: canvas slice too small");
+  check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+
+/* ---- coherence across frames (engine.ml:441-493, render.ml:259-271, 1376-1438) ---- */
+CAMLprim value coh_ml_scene_translate_object(value ctx, value scene, value index, value dx, value dy) {   /* Render.translate_renderobject */
+  check(CTX(ctx), coh_scene_translate_object(CTX(ctx), SCENE(scene), Int_val(index), Int_val(dx), Int_val(dy)));
+  return Val_unit;
+}
 /* Render.translate_renderobject + dirty_region + render_frame over the dirty region, as one device-side step;
  * returns the dirty pixel box (x0, y0, x1, y1) the front end re-reads with coh_ml_read_rgb888 */
 CAMLprim value coh_ml_scene_drag_object(value ctx, value scene, value index, value dx, value dy) {
   CAMLparam5(ctx, scene, index, dx, dy);
-  CAMLlocal1(r);
   int32_t bb[4];
-  check(CTX(ctx), coh_scene_drag_object(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(index), Int_val(dx), Int_val(dy), 0, bb));
-  r = caml_alloc_tuple(4);
-  for (int k = 0; k < 4; k++) Store_field(r, k, Val_int(bb[k]));
-  CAMLreturn(r);
+  check(CTX(ctx), coh_scene_drag_object(CTX(ctx), SCENE(scene), Int_val(index), Int_val(dx), Int_val(dy), 0, bb));
+  CAMLreturn(tuple_of_ints(bb, 4));
 }
 CAMLprim value coh_ml_scene_object_shape(value ctx, value scene, value index) {   /* Render.shape_of_basicshape */
   CAMLparam3(ctx, scene, index);
-  CAMLlocal1(r);
   coh_shape_t s = 0, m = 0;
-  check(CTX(ctx), coh_scene_object_shape(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(index), &s, &m));
-  r = caml_alloc_tuple(2);
-  Store_field(r, 0, caml_copy_int64((int64_t)s));
-  Store_field(r, 1, caml_copy_int64((int64_t)m));
-  CAMLreturn(r);
+  check(CTX(ctx), coh_scene_object_shape(CTX(ctx), SCENE(scene), Int_val(index), &s, &m));
+  CAMLreturn(pair_of_handles(s, m));
 }
 CAMLprim value coh_ml_dirty_filter(value ctx, value scene, value lmo, value dirty) {   /* Render.dirty_filter */
   CAMLparam4(ctx, scene, lmo, dirty);
   coh_shape_t o = 0;
-  check(CTX(ctx), coh_dirty_filter(CTX(ctx), (coh_scene_t)Int64_val(scene), Int_val(lmo), (coh_shape_t)Int64_val(dirty), &o));
+  check(CTX(ctx), coh_dirty_filter(CTX(ctx), SCENE(scene), Int_val(lmo), SHAPE(dirty), &o));
   CAMLreturn(caml_copy_int64((int64_t)o));
 }
-CAMLprim value coh_ml_render_frame_shape(value ctx, value scene, value update) {   /* render_frame over any update shape */
-  check(CTX(ctx), coh_render_frame_shape(CTX(ctx), (coh_scene_t)Int64_val(scene), (coh_shape_t)Int64_val(update), 0));
-  return Val_unit;
+
+/* ---- host-side geometry (Polygon.edgelist_of_path / Brush.points_of_brushstroke for one subpath) ---- */
+CAMLprim value coh_ml_host_edgelist_of_subpath(value segs, value out) {   /* segs : float64 Array1 of 9*n; returns the edge count */
+  int64_t n = coh_host_edgelist_of_subpath((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4);
+  return Val_long((long)n);
 }
-CAMLprim value coh_ml_read_rgb888(value ctx, value box, value out) {   /* Wxgui.plot_sprite's bytes for a rectangle */
-  CAMLparam3(ctx, box, out);
-  check(CTX(ctx), coh_fb_read_rgb888(CTX(ctx), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
-  CAMLreturn(Val_unit);
-}
-/* Convolve.convolve_sprite kernel sprite: sprite = (shape handle, RGBA8 per pixel in span order) */
-CAMLprim value coh_ml_convolve_sprite(value ctx, value kind_r, value shape, value rgba_in, value rgba_out) {
-  CAMLparam5(ctx, kind_r, shape, rgba_in, rgba_out);
-  coh_shape_t o = 0;
-  int64_t n = 0;
-  check(CTX(ctx), coh_convolve_sprite(CTX(ctx), Int_val(Field(kind_r, 0)), Int_val(Field(kind_r, 1)), (coh_shape_t)Int64_val(shape),
-        (const uint32_t*)Caml_ba_data_val(rgba_in), &o, (uint32_t*)Caml_ba_data_val(rgba_out), Caml_ba_array_val(rgba_out)->dim[0], &n));
-  CAMLreturn(caml_copy_int64((int64_t)o));
+CAMLprim value coh_ml_host_brush_points(value segs, value radius, value out) {
+  int64_t n = coh_host_brush_points((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), Double_val(radius), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 2);
+  return Val_long((long)n);
 }

@@ -1,0 +1,164 @@
+/* Plain C (C99) against include/coherence_b200.h: calls EVERY exported entry point with plain host buffers, and every
+ * error path that is reachable without breaking the device.  Prints "ok <name>" per check and "ABI-EVERY-SYMBOL PASS n"
+ * at the end; any unexpected status prints "FAIL ..." and exits 1.  Without a CUDA device it checks that coh_init
+ * fails loudly (there is no CPU path) and exits 0.  tests/test_abi_c.py builds and runs it. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "coherence_b200.h"
+
+static coh_ctx* C = NULL;
+static int n_ok = 0;
+#define OK(call) do { if ((call) != 0) { printf("FAIL %s: %s\n", #call, coh_last_error(C)); exit(1); } n_ok++; } while (0)
+#define ERR(call, what) do { if ((call) == 0) { printf("FAIL expected an error: %s\n", #call); exit(1); } \
+  if (!strstr(coh_last_error(C), what)) { printf("FAIL wrong message for %s: %s\n", #call, coh_last_error(C)); exit(1); } n_ok++; } while (0)
+#define CHECK(cond) do { if (!(cond)) { printf("FAIL %s (line %d)\n", #cond, __LINE__); exit(1); } n_ok++; } while (0)
+
+static int sub_of_float(double f) { return (int)ceil(f * 32.0 - 16.0); }
+static void tri_edges(int32_t* e, double ax, double ay, double bx, double by, double cx, double cy) {
+  double p[4][2] = {{ax, ay}, {bx, by}, {cx, cy}, {ax, ay}};
+  for (int i = 0; i < 3; i++) { e[4 * i] = sub_of_float(p[i][0]); e[4 * i + 1] = sub_of_float(p[i][1]); e[4 * i + 2] = sub_of_float(p[i + 1][0]); e[4 * i + 3] = sub_of_float(p[i + 1][1]); }
+}
+static coh_object blank(int kind) { coh_object o; memset(&o, 0, sizeof o); o.kind = kind; o.pretrans = -1; o.id = -1; return o; }
+
+int main(int argc, char** argv) {
+  (void)argc; (void)argv;
+  if (coh_init(-1, &C) != 0) {
+    const char* m = coh_last_error(NULL);
+    if (!strstr(m, "no CPU fallback")) { printf("FAIL init message: %s\n", m); return 1; }
+    printf("no device: %s\nABI-EVERY-SYMBOL NO-DEVICE\n", m);
+    return 0;
+  }
+  char name[128];
+  OK(coh_device_name(C, name, sizeof name));
+  CHECK(coh_stream(C) != NULL);
+  CHECK(coh_launch_count(C) >= 0);
+  OK(coh_set_option(C, "walk_h", 0));
+  ERR(coh_set_option(C, "walk_h", 3), "walk_h");
+  ERR(coh_set_option(C, "no_such_option", 1), "unknown option");
+  OK(coh_set_timing(C, 1));
+  /* colour codec: Colour.clear = 0x43800000, white = 0x7F9FFFFF */
+  CHECK(coh_colour_of_rgba8(0u) == 0x43800000); CHECK(coh_colour_of_rgba8(0xFFFFFFFFu) == 0x7F9FFFFF);
+  CHECK(coh_rgba8_of_colour(0x7F9FFFFF) == 0xFFFFFFFFu);
+  /* Polygon */
+  int32_t e[12]; tri_edges(e, 20.3, 20.1, 120.7, 30.2, 60.2, 150.9);
+  coh_shape_t s = 0, m = 0, mx = 0, t = 0, u = 0;
+  OK(coh_shapeminshape_of_edgelist(C, e, 3, COH_NONZERO, &s, &m));
+  ERR(coh_shapeminshape_of_edgelist(C, e, 3, 7, &t, &u), "winding");
+  OK(coh_shapeminshape_of_edgelist(C, e, 0, COH_NONZERO, &t, &u)); CHECK(t == 0 && u == 0);   /* NullShape, NullShape */
+  int64_t card = 0, n = 0, sz = 0;
+  OK(coh_shape_card(C, s, &card)); CHECK(card > 0);
+  OK(coh_shape_difference(C, s, m, &mx));
+  OK(coh_shape_card(C, mx, &card));
+  uint8_t* op = (uint8_t*)malloc((size_t)card);
+  OK(coh_polygon_opacity(C, e, 3, COH_NONZERO, mx, op, card, &n)); CHECK(n == card);
+  ERR(coh_polygon_opacity(C, e, 3, COH_NONZERO, mx, op, card - 1, &n), "buffer too small");
+  coh_object fill = blank(COH_OBJ_PATH); fill.fill_kind = COH_FILL_PLAIN; fill.colour0 = 0xFF2030C8u;
+  uint32_t* px = (uint32_t*)malloc(4 * (size_t)card);
+  OK(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, card, &n)); CHECK(n == card);
+  ERR(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, 1, &n), "buffer too small");
+  fill.fill_kind = 9; ERR(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, card, &n), "fill kind"); fill.fill_kind = 0;
+  /* Sprite span-set algebra */
+  coh_shape_t bx = 0, un = 0, in = 0, tr = 0, bl = 0, er = 0, imp = 0;
+  OK(coh_shape_box(C, 10, 10, 50, 40, &bx));
+  ERR(coh_shape_box(C, 0, 0, -1, 3, &t), "negative");
+  OK(coh_shape_box(C, 0, 0, 0, 0, &t)); CHECK(t == 0);
+  OK(coh_shape_union(C, s, bx, &un)); OK(coh_shape_intersection(C, s, bx, &in));
+  OK(coh_shape_translate(C, bx, 3, -4, &tr)); OK(coh_shape_bloat(C, bx, 2, 1, &bl)); OK(coh_shape_erode(C, bx, 2, 1, &er));
+  int32_t box[4], isnull = 0;
+  OK(coh_shape_bounds(C, bl, box, &isnull)); CHECK(!isnull && box[0] == 8 && box[1] == 9 && box[2] == 61 && box[3] == 50);
+  OK(coh_shape_bounds(C, 0, box, &isnull)); CHECK(isnull);
+  OK(coh_shape_export_size(C, bx, &sz)); CHECK(sz == 40 * 4);
+  int32_t* flat = (int32_t*)malloc(4 * (size_t)sz);
+  OK(coh_shape_export(C, bx, flat, sz, &n)); CHECK(n == sz && flat[0] == 10 && flat[1] == 1 && flat[2] == 10 && flat[3] == 50);
+  ERR(coh_shape_export(C, bx, flat, sz - 1, &n), "too small");
+  OK(coh_shape_import(C, flat, sz, &imp));
+  flat[3] = 0; ERR(coh_shape_import(C, flat, sz, &t), "malformed shape"); flat[3] = 50;   /* empty span: not canonical (sprite.ml:201-239) */
+  /* Convolve */
+  OK(coh_shape_card(C, bx, &card));
+  uint32_t* spr = (uint32_t*)malloc(4 * (size_t)card);
+  for (int64_t i = 0; i < card; i++) spr[i] = 0xFF0000FFu;
+  coh_shape_t cs = 0; int64_t bcard = 0;
+  OK(coh_shape_card(C, bl, &bcard));
+  uint32_t* cout = (uint32_t*)malloc(4 * (size_t)(bcard + 4096));
+  OK(coh_convolve_sprite(C, COH_CONV_UNIT, 1, bx, spr, &cs, cout, bcard + 4096, &n)); CHECK(cs != 0 && n > card);
+  ERR(coh_convolve_sprite(C, 7, 1, bx, spr, &t, cout, bcard, &n), "Invalid_argument");
+  ERR(coh_convolve_sprite(C, COH_CONV_UNIT, 0, bx, spr, &t, cout, bcard, &n), "Invalid_argument");
+  /* Cache */
+  int64_t st[4]; int32_t found = 0;
+  OK(coh_cache_clear(C)); OK(coh_cache_configure(C, 1, 32 << 20));
+  OK(coh_cache_addshape(C, 41, s, m));
+  OK(coh_cache_getshape(C, 41, &t, &u, &found)); CHECK(found && t && u); OK(coh_shape_free(C, t)); OK(coh_shape_free(C, u));
+  OK(coh_cache_getshape(C, 42, &t, &u, &found)); CHECK(!found);
+  OK(coh_cache_addtranslation(C, 42, 41, 5, 6));
+  OK(coh_cache_getshape(C, 42, &t, &u, &found)); CHECK(found); OK(coh_shape_free(C, t)); OK(coh_shape_free(C, u));
+  OK(coh_cache_stats(C, st)); CHECK(st[0] == 2 && st[1] == 1 && st[3] >= 1);
+  coh_shape_t dirty = 0;
+  OK(coh_dirty_region(C, s, m, tr, er, bl, 1, &dirty)); OK(coh_shape_free(C, dirty));
+  OK(coh_dirty_region(C, s, 0, tr, 0, bl, 0, &dirty));
+  /* Render */
+  const int W = 200, H = 160;
+  coh_object objs[5];
+  objs[0] = blank(COH_OBJ_GROUP_BEGIN); objs[0].id = 7;
+  objs[1] = blank(COH_OBJ_PATH); objs[1].first = 0; objs[1].count = 3; objs[1].colour0 = 0xB4141487u;   /* premultiplied, alpha 180 */
+  objs[2] = blank(COH_OBJ_GROUP_END);
+  objs[3] = blank(COH_OBJ_PRIMITIVE); objs[3].colour0 = 0xFF00FF00u; objs[3].prim[0] = 100; objs[3].prim[1] = 20; objs[3].prim[2] = 150; objs[3].prim[3] = 60; objs[3].id = 9;
+  objs[4] = blank(COH_OBJ_PRIMITIVE); objs[4].colour0 = 0xFFD3D3D3u; objs[4].prim[2] = W; objs[4].prim[3] = H;
+  coh_scene_t sc = 0, bad = 0;
+  ERR(coh_render_frame(C, 0, 0, 0, W, H, 0), "coh_fb_configure");
+  ERR(coh_fb_configure(C, 0, 10, 0, 10), "bad size"); ERR(coh_fb_configure(C, W, H, 10, H + 1), "bad band");
+  OK(coh_fb_configure(C, W, H, 0, H));
+  OK(coh_scene_create(C, objs, 5, 1, e, 3, NULL, 0, &sc));
+  ERR(coh_scene_create(C, objs, 2, 0, e, 3, NULL, 0, &bad), "unterminated");
+  objs[1].count = 9; ERR(coh_scene_create(C, objs, 5, 1, e, 3, NULL, 0, &bad), "out of bounds"); objs[1].count = 3;
+  objs[1].kind = 77; ERR(coh_scene_create(C, objs, 5, 1, e, 3, NULL, 0, &bad), "unknown object kind"); objs[1].kind = COH_OBJ_PATH;
+  OK(coh_render_frame(C, sc, 0, 0, W, H, COH_RENDER_RECORD_U));
+  ERR(coh_render_frame(C, sc, 0, 0, -1, 5, 0), "negative");
+  ERR(coh_render_frame(C, 0, 0, 0, W, H, 0), "null scene");
+  OK(coh_sync(C));
+  coh_shape_t unc = 0; OK(coh_render_uncovered(C, &unc)); CHECK(unc != 0);   /* u after the scene pass: the update minus what the triangle's interior and the green rectangle made opaque */
+  OK(coh_shape_card(C, unc, &card)); CHECK(card > 0 && card < (int64_t)W * H); OK(coh_shape_free(C, unc));
+  ERR(coh_shape_bloat(C, bx, -1, 0, &t), "negative radius");
+  uint32_t* img = (uint32_t*)malloc(4 * (size_t)W * H);
+  uint8_t* rgb = (uint8_t*)malloc(3 * (size_t)W * H);
+  OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img)); CHECK(img[0] == 0xFFD3D3D3u && img[30 * W + 120] == 0xFF00FF00u);
+  ERR(coh_fb_read_rgba(C, 0, 0, W + 1, H, (uint8_t*)img), "outside");
+  OK(coh_fb_read_rgb888(C, 0, 0, W, H, rgb)); CHECK(rgb[0] == 0xD3 && rgb[3 * (30 * W + 120) + 1] == 0xFF);
+  ERR(coh_fb_read_rgb888(C, -1, 0, 4, 4, rgb), "outside");
+  OK(coh_fb_read_rgba_async(C, 0, 0, W, H, (uint8_t*)img)); OK(coh_fb_read_wait(C));
+  OK(coh_shape_card(C, bx, &card));
+  OK(coh_fb_read_sprite(C, bx, px, card, &n)); CHECK(n == card);
+  ERR(coh_fb_read_sprite(C, bx, px, 3, &n), "too small");
+  OK(coh_render_frame_shape(C, sc, bx, 0));
+  coh_shape_t os = 0, om = 0;
+  OK(coh_scene_object_shape(C, sc, 0, &os, &om)); CHECK(os != 0 && om == 0);   /* a Group: minshape null (render.ml:494) */
+  ERR(coh_scene_object_shape(C, sc, 99, &t, &u), "no such object");
+  OK(coh_scene_translate_object(C, sc, 3, 4, 5));
+  ERR(coh_scene_translate_object(C, sc, 2, 1, 1), "no such object");   /* a GROUP_END is not an object */
+  int32_t bb[4];
+  OK(coh_scene_drag_object(C, sc, 0, 3, 2, 0, bb)); CHECK(bb[2] >= bb[0] && bb[3] >= bb[1]);
+  coh_shape_t df = 0;
+  OK(coh_dirty_filter(C, sc, -1, dirty, &df));
+  double walk = 0, bin = 0; int64_t frames = 0;
+  OK(coh_get_timing(C, &walk, &bin, &frames)); CHECK(frames >= 1); OK(coh_set_timing(C, 0));
+  /* caller-owned framebuffer, peers (a second pointer into the same buffer stands in for a peer GPU) */
+  void* own = coh_fb_device_ptr(C); CHECK(own != NULL);
+  void* peers[1] = {own};
+  OK(coh_fb_set_peers(C, 1, peers)); OK(coh_render_frame(C, sc, 0, 0, W, H, 0)); OK(coh_fb_set_peers(C, 0, NULL));
+  ERR(coh_fb_set_peers(C, 9, peers), "at most 7");
+  OK(coh_fb_attach(C, NULL));
+  int64_t mem = 0; OK(coh_mem_in_use(C, &mem)); CHECK(mem > 0);
+  OK(coh_set_stream(C, coh_stream(C)));
+  /* host-side geometry */
+  double segs[9] = {0, 10.0, 10.0, 90.0, 20.0, 0, 0, 0, 0};
+  int32_t he[8]; CHECK(coh_host_edgelist_of_subpath(segs, 1, he, 2) == 1 && he[0] == sub_of_float(10.0));
+  int32_t hp[64]; CHECK(coh_host_brush_points(segs, 1, 4.0, hp, 32) > 0);
+  /* release */
+  coh_shape_t all[] = {s, m, mx, bx, un, in, tr, bl, er, imp, cs, dirty, os, om, df};
+  for (unsigned i = 0; i < sizeof all / sizeof all[0]; i++) OK(coh_shape_free(C, all[i]));
+  OK(coh_scene_free(C, sc)); OK(coh_cache_clear(C));
+  OK(coh_shutdown(C));
+  printf("ABI-EVERY-SYMBOL PASS %d\n", n_ok);
+  return 0;
+}

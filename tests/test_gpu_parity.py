@@ -957,3 +957,100 @@ def test_first_member_groups_dissolve_into_their_parent(ctx, oracle):
         got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
         assert np.array_equal(got_u, ref_u), f"variant {variant}"
         assert _max_lsb(got, ref) == 0, f"variant {variant}"
+
+
+def test_polygon_sprite_entry_point(ctx, oracle):
+    """coh_polygon_sprite = Polygon.polygon_sprite_edgelist (polygon.ml:729-746): RGBA8 per pixel of the given shape in
+    span order — plain, axial and radial fills (the fill is taken at every span's first x, polygon.ml:736)."""
+    rng = random.Random(77)
+    fills = [S.Fill.plain(S.dissolve(S.rgba8(200, 40, 90), 170)),
+             S.Fill.gradient((10.0, 20.0), (150.0, 90.0), True, False, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 0, 255), 128)),
+             S.Fill.radial((80.0, 60.0), (90.0, 60.0), (150.0, 60.0), True, True, S.rgba8(255, 255, 0), S.rgba8(0, 90, 30))]
+    checked = 0
+    for it in range(24):
+        edges = util.random_polygon_edges(rng, lo=-10, hi=180, rmax=70, kmax=8)
+        w = rng.randint(0, 1)
+        ref_s, ref_m = oracle.shapeminshape(edges, w)
+        if len(ref_s) == 0:
+            continue
+        o = abi.CohObject()
+        fills[it % 3].apply(o)
+        for shp_flat in (ref_s, oracle.shape_op("difference", ref_s, ref_m)):   # the whole shape; only its max-shape
+            if len(shp_flat) == 0:
+                continue
+            h = ctx.shape_import(shp_flat)
+            got = ctx.polygon_sprite(o, edges, w, h)
+            ref = oracle.polygon_sprite(o, edges, w, shp_flat)
+            assert np.array_equal(got, ref), f"sprite differs (case {it}, fill {it % 3})"
+            checked += len(ref)
+            ctx.shape_free(h)
+    assert checked > 10000
+
+
+def test_rgb888_and_sprite_export_against_oracle(ctx, oracle):
+    """coh_fb_read_rgb888 = what Wxgui.plot_sprite writes (wxgui.ml:417-424: the premultiplied r, g, b bytes of every
+    pixel), coh_fb_read_sprite = the Sprite.sprite Render.render_frame returns (pixels of the update shape in span
+    order) — both against the oracle's frame."""
+    W, H = 320, 240
+    b = S.lion_scene(W, H, 0.7)
+    b.polygon([(30.5, 20.2), (290.1, 60.7), (120.9, 220.3)], S.Fill.plain(S.dissolve(S.rgba8(30, 60, 220), 120)))
+    objs, n, nbg, edges, points = b.arrays()
+    ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    x, y, w, h = 37, 21, 201, 150
+    rgb = ctx.fb_read_rgb888(x, y, w, h)
+    want = ref[y : y + h, x : x + w]
+    assert np.array_equal(rgb[:, :, 0], (want & 255).astype(np.uint8)) and np.array_equal(rgb[:, :, 1], ((want >> 8) & 255).astype(np.uint8))
+    assert np.array_equal(rgb[:, :, 2], ((want >> 16) & 255).astype(np.uint8))
+    # a sprite on an update shape with several spans per row
+    rng = random.Random(5)
+    flat = util.random_shape_flat(rng, x0=5, y0=8, w=300, h=220)
+    hs = ctx.shape_import(flat)
+    got = ctx.fb_read_sprite(hs)
+    want = np.concatenate([ref[yy, xx : xx + l] for yy, spans in util.rows_of_flat(flat) for xx, l in spans])
+    assert np.array_equal(got, want)
+    assert len(ctx.fb_read_sprite(0)) == 0
+    outside = ctx.shape_box(W - 5, 3, 10, 4)
+    with pytest.raises(abi.CohError):
+        ctx.fb_read_sprite(outside)
+    for s_ in (hs, outside):
+        ctx.shape_free(s_)
+    ctx.scene_free(sc)
+
+
+def test_cache_entry_points(ctx, oracle):
+    """Cache.addshape / getshape / addtranslation through the ABI (cache.ml:280-324, 370-388, 423-436): copies are kept,
+    an alias serves the target's shapes translated, aliases of aliases collapse, statistics count."""
+    rng = random.Random(3)
+    ctx.cache_clear()
+    ctx.cache_configure(True, 8 << 20)
+    a, m = util.random_shape_flat(rng), util.random_shape_flat(rng, density=0.15)
+    ha, hm = ctx.shape_import(a), ctx.shape_import(m)
+    assert ctx.cache_getshape(41) is None
+    ctx.cache_addshape(41, ha, hm)
+    ctx.shape_free(ha)
+    ctx.shape_free(hm)                       # the cache keeps copies of its own
+    got = ctx.cache_getshape(41)
+    assert got is not None
+    assert np.array_equal(ctx.shape_export(got[0]), a) and np.array_equal(ctx.shape_export(got[1]), m)
+    for h in got:
+        ctx.shape_free(h)
+    ctx.cache_addtranslation(42, 41, 7, -3)
+    ctx.cache_addtranslation(43, 42, 10, 10)  # alias of an alias: (17, 7) from 41 (cache.ml:434-436)
+    for oid, (dx, dy) in ((42, (7, -3)), (43, (17, 7))):
+        got = ctx.cache_getshape(oid)
+        assert got is not None
+        assert np.array_equal(ctx.shape_export(got[0]), oracle.shape_unary("translate", a, dx, dy))
+        assert np.array_equal(ctx.shape_export(got[1]), oracle.shape_unary("translate", m, dx, dy))
+        for h in got:
+            ctx.shape_free(h)
+    st = ctx.cache_stats()
+    assert st["shape_hits"] == 3 and st["shape_misses"] == 1 and st["entries"] >= 1 and st["bytes"] > 0
+    ctx.cache_configure(False, 8 << 20)       # Cache.usecache := false: nothing is served
+    assert ctx.cache_getshape(41) is None
+    ctx.cache_configure(True, 50 << 20)
+    ctx.cache_clear()
+    assert ctx.cache_stats()["entries"] == 0
