@@ -187,43 +187,43 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.fb_configure(WIDTH, HEIGHT, y0, y1)
-    # N > 1: the band gather.  Preferred: the framebuffers of all ranks live in symmetric memory (peer-mapped over
-    # NVLink) and the walker stores every finished pixel to all of them as it goes — compute and "collective" are
-    # one kernel, followed only by a cross-rank barrier.  If symmetric memory cannot be set up on this box, fall
-    # back to an NCCL all-gather of the strips after the frame.
-    fb, full, symm, gather = None, None, None, "none (single GPU)"
+    # N > 1: the band gather.  Preferred: every rank's framebuffer is allocated by the LIBRARY for export
+    # (coh_fb_alloc_shared), the 64-byte CUDA IPC handles are exchanged over the process group, every rank maps the
+    # others' framebuffers (coh_fb_open_peer -> coh_fb_set_peers) and the rendering kernels store every finished pixel
+    # to all of them over NVLink as they go — compute and "collective" are one kernel, followed only by a cross-rank
+    # barrier.  If the mapping cannot be set up on this box, fall back to an NCCL all-gather of the strips.
+    fb, full, fused, gather = None, None, False, "none (single GPU)"
     if N > 1 and not os.environ.get("COH_NCCL_GATHER"):
         try:
-            import torch.distributed._symmetric_memory as symm_mem
+            from coherence_renderer_b200 import torch_plumbing
 
-            fb = symm_mem.empty((HEIGHT, WIDTH), dtype=torch.int32, device=torch.device("cuda", local))
-            fb.zero_()
-            symm = symm_mem.rendezvous(fb, dist.group.WORLD)
-            ptrs = [int(symm.buffer_ptrs[r]) for r in range(N)]
-            ctx.fb_attach(ptrs[rank])
-            ctx.fb_set_peers([ptrs[r] for r in range(N) if r != rank])
-            full = fb
-            gather = "fused into the walker: peer stores over NVLink into every rank's framebuffer (symmetric memory) + cross-rank barrier"
+            handles = torch_plumbing.exchange_ipc_handles(dist, ctx.fb_alloc_shared())
+            ctx.fb_set_peers([ctx.fb_open_peer(handles[r]) for r in range(N) if r != rank])
+            fused = True
+            gather = "fused into the rendering kernels: peer stores over NVLink into every rank's framebuffer (CUDA IPC mappings made by the library) + cross-rank barrier"
         except Exception as exc:  # noqa: BLE001
             if rank == 0:
-                print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
-            symm = None
-    if symm is None:
+                print(f"bench.py: peer framebuffers unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
+            fused = False
+    if not fused and N > 1:
+        from coherence_renderer_b200 import torch_plumbing
+
         fb = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
         ctx.fb_attach(fb.data_ptr())
-        full = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if N > 1 else None
-        if N > 1:
-            gather = "NCCL all-gather of the band strips after the frame"
+        full = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
+        gather = "NCCL all-gather of the band strips after the frame"
     scene_h = ctx.scene_create(objs, nbg, edges, points)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     update = (0, 0, WIDTH, HEIGHT)
 
+    sync_t = torch.zeros(1, dtype=torch.int32, device="cuda")
+
     def frame():
         ctx.render_frame(scene_h, update)
-        if symm is not None:
-            symm.barrier()  # every rank's band has landed in this rank's framebuffer
+        if fused:
+            dist.all_reduce(sync_t)  # cross-rank barrier on the stream: every rank's band has landed in this rank's framebuffer
         elif N > 1:
-            bands.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
+            torch_plumbing.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
 
     def barrier():
         if N > 1:
@@ -235,12 +235,14 @@ def run_ours(args):
     barrier()
     ctx.sync()  # surfaces kernel-side errors
     if N > 1:  # every rank must now hold the same, complete frame
-        chk = full[::13, ::7].to(torch.int64).sum().reshape(1)
+        whole = torch.from_numpy(ctx.fb_read_rgba(0, 0, WIDTH, HEIGHT).view(np.int32)).cuda() if fused else full
+        chk = whole[::13, ::7].to(torch.int64).sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if lo.item() != hi.item() or (full[:: HEIGHT // 8, 5] == 0).any().item():
+        if lo.item() != hi.item() or (whole[:: HEIGHT // 8, 5] == 0).any().item():
             raise SystemExit("bench.py: the gathered frames differ between ranks or have missing bands")
+        del whole
 
     # ---- device-timed steps: L2 flushed (untimed) before every step, CUDA events on the launching stream
     sampler = ClockSampler(local)
@@ -250,10 +252,16 @@ def run_ours(args):
     l0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    ev_mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]   # after this rank's own kernels, before the barrier
     for s in range(args.steps):
         flush.zero_()
         ev[s][0].record(stream)
-        frame()
+        ctx.render_frame(scene_h, update)
+        ev_mid[s].record(stream)
+        if fused:
+            dist.all_reduce(sync_t)
+        elif N > 1:
+            torch_plumbing.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
         ev[s][1].record(stream)
     barrier()
     launches = ctx.launch_count() - l0
@@ -261,27 +269,40 @@ def run_ours(args):
     walk_ms, bin_ms, timed = ctx.get_timing()
     ctx.set_timing(False)
     total_ms = sum(step_ms)
+    own_ms = sum(a.elapsed_time(m) for (a, _), m in zip(ev, ev_mid)) / args.steps        # this rank's kernels
+    wait_ms = sum(m.elapsed_time(b) for (_, b), m in zip(ev, ev_mid)) / args.steps       # barrier / gather: waiting for the slowest rank
     t = torch.tensor([total_ms, walk_ms], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros((N, 4), dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([bin_ms, walk_ms, own_ms, wait_ms], dtype=torch.float64)
     if N > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank)
     total_ms, walk_ms_max = t.tolist()
+    per_rank = per_rank.tolist()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public C-ABI call with HOST buffers: per step the scene is uploaded
     # from host arrays (H2D), rendered, and the band strip read back to pinned host memory (D2H)
     # (frame k's read-back overlaps frame k+1's upload and rendering: two pinned host buffers, the
     # library's asynchronous read; every copy has completed before the clock stops)
-    hosts = [torch.empty((y1 - y0, WIDTH), dtype=torch.int32).pin_memory() for _ in range(2)]
+    # N > 1: the WHOLE frame ends up in one pinned host buffer on rank 0 (every framebuffer holds every band after the
+    # barrier); the other ranks upload their scene and render, and read nothing back
+    reader = rank == 0
+    ry0, ry1 = (0, HEIGHT) if (N > 1 and fused) else (y0, y1)
+    hosts = [torch.empty((ry1 - ry0, WIDTH), dtype=torch.int32).pin_memory() for _ in range(2)] if (reader or not fused) else []
     hosts_np = [h.numpy().view(np.uint32) for h in hosts]
     e2e_steps = max(3, min(args.steps, 20))
     h2d = objs._length_ * abi.C.sizeof(abi.CohObject) + edges.nbytes + points.nbytes
-    d2h = hosts_np[0].nbytes
+    d2h = hosts_np[0].nbytes if hosts_np else 0
 
     def e2e_run(k):
         for i in range(k):
             sh = ctx.scene_create(objs, nbg, edges, points)
             ctx.render_frame(sh, update)
-            ctx.fb_read_rgba_async(0, y0, WIDTH, y1 - y0, hosts_np[i & 1])
+            if fused:
+                dist.all_reduce(sync_t)   # (stream-ordered: the read-back below is queued behind it)
+            if hosts_np:
+                ctx.fb_read_rgba_async(0, ry0, WIDTH, ry1 - ry0, hosts_np[i & 1])
             ctx.scene_free(sh)
         ctx.fb_read_wait()
 
@@ -324,6 +345,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if N > 1:
+            # where a step goes on every rank (ms, averaged over the timed steps): K1 binning and raster phase from the
+            # library's own CUDA events, this rank's kernels end to end, and the wait at the cross-rank barrier
+            line["per_rank"] = [{"rank": r, "band_rows": list(band_list[r]), "binning_ms": v[0], "raster_ms": v[1], "own_kernels_ms": v[2], "barrier_wait_ms": v[3]} for r, v in enumerate(per_rank)]
+            line["e2e"]["path"] = ("per frame: every rank uploads the scene (coh_scene_create) and renders its band; after the cross-rank barrier rank 0 reads the WHOLE frame "
+                                   "(every framebuffer holds every band) into pinned host memory with coh_fb_read_rgba_async; the read-back of frame k overlaps frame k+1")
         if args.cpu_baseline:
             cores = os.cpu_count() or 1
             sec = cpu_frames(2, cores)

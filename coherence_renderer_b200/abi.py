@@ -49,6 +49,9 @@ SYMBOLS = [
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
+    "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
+    "coh_multi_scene_create", "coh_multi_scene_free", "coh_multi_scene_translate_object", "coh_multi_render_frame", "coh_multi_sync",
+    "coh_multi_fb_read_rgba", "coh_multi_fb_read_rgb888", "coh_fb_alloc_shared", "coh_fb_open_peer",
 ]
 
 _lib = None
@@ -79,6 +82,10 @@ def lib():
         L.coh_colour_of_rgba8.restype = C.c_int32
         L.coh_host_edgelist_of_subpath.restype = C.c_int64
         L.coh_host_brush_points.restype = C.c_int64
+        L.coh_multi_last_error.restype = C.c_char_p
+        L.coh_multi_last_error.argtypes = [C.c_void_p]
+        L.coh_multi_ctx.restype = C.c_void_p
+        L.coh_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 
@@ -90,16 +97,20 @@ def _i32p(a):
 class Context:
     """One GPU, one scanline band (coh_init / coh_shutdown)."""
 
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, _borrowed=None):
         self._h = C.c_void_p()
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)   # a device's context of a MultiContext
+            return
         rc = lib().coh_init(device, C.byref(self._h))
         if rc != 0:
             raise CohError(lib().coh_last_error(None).decode())
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             lib().coh_shutdown(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __enter__(self):
         return self
@@ -335,6 +346,19 @@ class Context:
         arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(p) for p in peer_ptrs])
         self._chk(lib().coh_fb_set_peers(self._h, len(peer_ptrs), arr))
 
+    def fb_alloc_shared(self):
+        """A framebuffer that other processes can map: returns its 64-byte CUDA IPC handle."""
+        h = (C.c_uint8 * 64)()
+        self._chk(lib().coh_fb_alloc_shared(self._h, h))
+        return bytes(h)
+
+    def fb_open_peer(self, handle):
+        """Map another process's shared framebuffer; returns the device pointer for fb_set_peers."""
+        buf = (C.c_uint8 * 64)(*handle)
+        p = C.c_void_p()
+        self._chk(lib().coh_fb_open_peer(self._h, buf, C.byref(p)))
+        return p.value
+
     def fb_read_rgba_async(self, x, y, w, h, out):
         """out: pinned host array of h*w uint32; valid after fb_read_wait()."""
         self._chk(lib().coh_fb_read_rgba_async(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
@@ -353,6 +377,72 @@ class Context:
     def fb_read_rgb888(self, x, y, w, h):
         out = np.zeros((h, w, 3), dtype=np.uint8)
         self._chk(lib().coh_fb_read_rgb888(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+
+class MultiContext:
+    """Several GPUs of one box from one process (coh_multi_*): every device renders its band of scanlines and stores
+    its pixels into every framebuffer over NVLink."""
+
+    def __init__(self, n_devices, device_ids=None):
+        self._h = C.c_void_p()
+        ids = (C.c_int32 * n_devices)(*device_ids) if device_ids else None
+        if lib().coh_multi_init(n_devices, ids, C.byref(self._h)) != 0:
+            raise CohError(lib().coh_multi_last_error(None).decode())
+        self.n = n_devices
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise CohError(lib().coh_multi_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().coh_multi_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def ctx(self, i):
+        return Context(_borrowed=lib().coh_multi_ctx(self._h, i))
+
+    def configure(self, width, height, cuts=None):
+        arr = (C.c_int32 * (self.n + 1))(*cuts) if cuts is not None else None
+        self._chk(lib().coh_multi_configure(self._h, width, height, arr))
+
+    def scene_create(self, objs, n_background, edges, points):
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
+        p = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+        h = C.c_uint64()
+        self._chk(lib().coh_multi_scene_create(self._h, objs, len(objs), n_background, _i32p(e), len(e), _i32p(p), len(p), C.byref(h)))
+        return h.value
+
+    def scene_free(self, h):
+        if h:
+            self._chk(lib().coh_multi_scene_free(self._h, C.c_uint64(h)))
+
+    def scene_translate_object(self, scene, obj_index, dx, dy):
+        self._chk(lib().coh_multi_scene_translate_object(self._h, C.c_uint64(scene), obj_index, dx, dy))
+
+    def render_frame(self, scene, update, flags=0):
+        ux, uy, uw, uh = update
+        self._chk(lib().coh_multi_render_frame(self._h, C.c_uint64(scene), ux, uy, uw, uh, flags))
+
+    def sync(self):
+        self._chk(lib().coh_multi_sync(self._h))
+
+    def fb_read_rgba(self, x, y, w, h, out=None):
+        if out is None:
+            out = np.zeros((h, w), dtype=np.uint32)
+        self._chk(lib().coh_multi_fb_read_rgba(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def fb_read_rgb888(self, x, y, w, h):
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        self._chk(lib().coh_multi_fb_read_rgb888(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
 
 

@@ -2,8 +2,9 @@
 
 Every stage of the raster path is a pure function of (edge lists, row), so band k of N
 owns rows [floor(k*H/N), floor((k+1)*H/N)) and renders them with no halo and no exchange;
-the only collective is the gather of the RGBA8 strips into the output framebuffer.
-torch.distributed is plumbing (process group + NCCL/gloo transport)."""
+the only exchange is the gather of the RGBA8 strips, which the library fuses into the rendering
+kernels (peer stores over NVLink: coh_multi_* for one host process, coh_fb_alloc_shared / coh_fb_open_peer for one
+process per GPU).  This module is the band arithmetic only; it imports nothing but numpy."""
 
 
 def band_rows(height, n_bands, k):
@@ -49,41 +50,3 @@ def balanced_bands(cost, n_bands, align=16):
         cuts.append(max(lo, min(y, hi)) if hi >= lo else min(height, cuts[-1] + max(1, (height - cuts[-1]) // (n_bands - k + 1))))
     cuts.append(height)
     return [(cuts[k], cuts[k + 1]) for k in range(n_bands)]
-
-
-def gather_strips(dist, strip, full, height, n_bands, rows=None):
-    """All-gather the band strips (rows of `full` owned by each rank) into `full` on every rank.
-    `strip` is this rank's rows (a contiguous [rows, W] tensor); `full` is [H, W]; `rows` = the bands
-    (default: the equal split)."""
-    explicit = rows is not None
-    rows = rows or all_bands(height, n_bands)
-    if len({b - a for a, b in rows}) == 1:
-        dist.all_gather_into_tensor(full, strip)
-        return full
-    if explicit and dist.get_backend() == "nccl":
-        # cost-balanced bands have very different heights: one grouped exchange of exact-size strips
-        # (ncclGroupStart / Send / Recv / End) instead of padding every strip to the tallest band
-        rank = dist.get_rank()
-        ops = []
-        for k, (a, b) in enumerate(rows):
-            if k == rank:
-                continue
-            ops.append(dist.P2POp(dist.isend, strip, k))
-            ops.append(dist.P2POp(dist.irecv, full[a:b], k))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        a, b = rows[rank]
-        if full[a:b].data_ptr() != strip.data_ptr():
-            full[a:b] = strip
-        return full
-    # ragged bands (H not divisible by N): gather strips padded to the tallest band
-    import torch
-
-    tallest = max(b - a for a, b in rows)
-    padded = torch.zeros((tallest, full.shape[1]), dtype=full.dtype, device=full.device)
-    padded[: strip.shape[0]] = strip
-    tmp = torch.empty((n_bands * tallest, full.shape[1]), dtype=full.dtype, device=full.device)
-    dist.all_gather_into_tensor(tmp, padded)
-    for k, (a, b) in enumerate(rows):
-        full[a:b] = tmp[k * tallest : k * tallest + (b - a)]
-    return full

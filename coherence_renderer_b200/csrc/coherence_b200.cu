@@ -124,6 +124,8 @@ struct coh_ctx {
   int* carry_done = nullptr; int* carry_cnt = nullptr; int2* carry_ent = nullptr;
   size_t carry_slots = 0; int epoch = 0;
   bool own_stream = true, own_fb = true;
+  uint32_t* shared_fb = nullptr;            // coh_fb_alloc_shared: cudaMalloc'ed, exported by CUDA IPC
+  std::vector<void*> opened_peers;          // coh_fb_open_peer: mappings to close at shutdown
   // coherence cache (HBM-resident span sets)
   std::map<int64_t, CacheEntry> cache;
   bool usecache = true; size_t cache_max = 50u * 1024u * 1024u, cache_size = 0; uint64_t cache_timer = 0;  // cache.ml:72-73
@@ -258,6 +260,8 @@ int coh_shutdown(coh_ctx* ctx) {
     for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_ready[k]); cudaEventDestroy(ctx->ev_done[k]); }
   }
   coh_cache_clear(ctx);
+  for (void* p : ctx->opened_peers) cudaIpcCloseMemHandle(p);
+  if (ctx->shared_fb) { if (ctx->fb == ctx->shared_fb) { ctx->fb = nullptr; ctx->own_fb = true; } cudaFree(ctx->shared_fb); ctx->shared_fb = nullptr; }
   DFREE(ctx->d_aa); DFREE(ctx->d_error); cudaFreeHost(ctx->h_error); cudaFreeHost(ctx->h_total);
   if (ctx->own_fb) DFREE(ctx->fb);
   DFREE(ctx->u_out); DFREE(ctx->u_init);
@@ -467,3 +471,4 @@ int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h,
 }
 
 }  // extern "C"
+#include "host_multi.inl"

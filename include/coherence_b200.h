@@ -254,6 +254,37 @@ int coh_fb_read_sprite(coh_ctx* ctx, coh_shape_t update, uint32_t* rgba_out, int
 int coh_fb_read_rgba_async(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
 int coh_fb_read_wait(coh_ctx* ctx);
 
+/* ---- several GPUs of one box ----
+ * A frame shards by horizontal scanline bands (every stage is a pure function of the edge lists and the row): every
+ * device holds the whole scene and renders its band; the gather of the RGBA8 strips is fused into the rendering
+ * kernels — framebuffers are peer-mapped over NVLink and every finished pixel is stored to all of them
+ * (coh_fb_set_peers) — so after a frame every device holds the whole picture and no collective follows.
+ *
+ * (1) ONE host process (the OCaml engine is one): coh_multi_* owns one context per device, enables peer access, and
+ *     issues every device's launches from a worker thread of its own. */
+typedef struct coh_multi coh_multi;
+int coh_multi_init(int32_t n_devices, const int32_t* device_ids /* NULL: 0 .. n-1 */, coh_multi** out);
+int coh_multi_shutdown(coh_multi* m);
+const char* coh_multi_last_error(coh_multi* m);   /* m may be NULL for init errors */
+int coh_multi_device_count(coh_multi* m);
+coh_ctx* coh_multi_ctx(coh_multi* m, int32_t i);  /* the i-th device's context, for every other coh_* call */
+/* framebuffer of width x height on every device; band k = rows [cuts[k], cuts[k+1]) (cuts = NULL: equal bands) */
+int coh_multi_configure(coh_multi* m, int32_t width, int32_t height, const int32_t* cuts /* n_devices + 1, or NULL */);
+int coh_multi_scene_create(coh_multi* m, const coh_object* objs, int32_t n_objs, int32_t n_background,
+                           const int32_t* edges, int32_t n_edges, const int32_t* points, int32_t n_points, coh_scene_t* out);
+int coh_multi_scene_free(coh_multi* m, coh_scene_t scene);
+int coh_multi_scene_translate_object(coh_multi* m, coh_scene_t scene, int32_t obj_index, int32_t dx, int32_t dy);
+/* Render.render_frame, every device its band; returns when the launches are issued */
+int coh_multi_render_frame(coh_multi* m, coh_scene_t scene, int32_t ux, int32_t uy, int32_t uw, int32_t uh, int32_t flags);
+int coh_multi_sync(coh_multi* m);   /* every device done: each framebuffer now holds the whole frame */
+int coh_multi_fb_read_rgba(coh_multi* m, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);   /* from device 0 */
+int coh_multi_fb_read_rgb888(coh_multi* m, int32_t x, int32_t y, int32_t w, int32_t h, uint8_t* out);
+/* (2) one process per GPU (MPI / torchrun style hosts): the framebuffer is allocated for export, its 64-byte CUDA IPC
+ *     handle travels through whatever channel the host has, and every other process maps it and passes the pointers
+ *     to coh_fb_set_peers.  The host provides the cross-process barrier after a frame. */
+int coh_fb_alloc_shared(coh_ctx* ctx, uint8_t handle_out[64]);   /* after coh_fb_configure; replaces the framebuffer */
+int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_out);
+
 /* ---- host-side geometry preparation (CPU; the step before the raster path) ----
  * A path segment record is 9 doubles: kind (0 straight, 1 cubic bezier) then up to four points.
  * Polygon.edgelist_of_path for one subpath (polygon.ml:119-127, 262-287; Coord.sub_of_float):

@@ -79,6 +79,21 @@ external scene_translate_object : ctx -> scene_h -> int -> int -> int -> unit = 
 external scene_drag_object : ctx -> scene_h -> int -> int -> int -> int * int * int * int = "coh_ml_scene_drag_object"
 external scene_object_shape : ctx -> scene_h -> int -> shape_h * shape_h = "coh_ml_scene_object_shape"
 external dirty_filter : ctx -> scene_h -> int -> shape_h -> shape_h = "coh_ml_dirty_filter"
+type multi = nativeint
+external multi_init : int array -> multi = "coh_ml_multi_init"
+external multi_shutdown : multi -> unit = "coh_ml_multi_shutdown"
+external multi_device_count : multi -> int = "coh_ml_multi_device_count"
+external multi_ctx : multi -> int -> ctx = "coh_ml_multi_ctx"
+external multi_configure : multi -> int -> int -> unit = "coh_ml_multi_configure"
+external multi_scene_create : multi -> u8 -> int -> i32 -> i32 -> scene_h = "coh_ml_multi_scene_create"
+external multi_scene_free : multi -> scene_h -> unit = "coh_ml_multi_scene_free"
+external multi_scene_translate_object : multi -> scene_h -> int -> int -> int -> unit = "coh_ml_multi_scene_translate_object"
+external multi_render_frame : multi -> scene_h -> int * int * int * int -> int -> unit = "coh_ml_multi_render_frame"
+external multi_sync : multi -> unit = "coh_ml_multi_sync"
+external multi_read_rgba : multi -> int * int * int * int -> u8 -> unit = "coh_ml_multi_read_rgba"
+external multi_read_rgb888 : multi -> int * int * int * int -> u8 -> unit = "coh_ml_multi_read_rgb888"
+external fb_alloc_shared : ctx -> u8 -> unit = "coh_ml_fb_alloc_shared"
+external fb_open_peer : ctx -> u8 -> nativeint = "coh_ml_fb_open_peer"
 external host_edgelist_of_subpath : f64 -> i32 -> int = "coh_ml_host_edgelist_of_subpath"
 external host_brush_points : f64 -> float -> i32 -> int = "coh_ml_host_brush_points"
 
@@ -432,6 +447,17 @@ let render_frame ?(display_selection = true) ?(topobjects = []) (_lmo : Id.idset
 let render_simple_scene (scene : Render.scene) (update : Sprite.shape) : Sprite.sprite =
   ensure_canvas ();
   with_scene scene [] (fun h -> with_shape update (fun u -> render_frame_shape (ctx ()) h u 0; sprite_of_frame u))
+
+(* The same frame on every GPU of the box (engine start-up: [let gpus = multi_init [|0; 1; 2; 3|]]): the scene goes to
+   every device, each renders its band of scanlines, the canvas bytes come from device 0 *)
+let render_rect_rgb888_multi (gpus : multi) (view : Render.view) (x, y, w, h) (canvas_slice : u8) =
+  let cw, ch = !canvas in
+  multi_configure gpus cw ch;
+  let (objs, nbg, edges, points) = flatten_scene view.Render.scene (view.Render.pages @ view.Render.background) in
+  let s = multi_scene_create gpus objs nbg edges points in
+  (try multi_render_frame gpus s (x, y, w, h) 0; multi_read_rgb888 gpus (x, y, w, h) canvas_slice
+   with e -> multi_scene_free gpus s; raise e);
+  multi_scene_free gpus s
 
 (* engine.ml:208-221 render_rect: update = Sprite.box x y w h, result straight into the RGB888 canvas of wxgui.ml *)
 let render_rect_rgb888 (view : Render.view) (x, y, w, h) (canvas_slice : u8) =

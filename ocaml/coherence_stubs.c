@@ -358,6 +358,68 @@ CAMLprim value coh_ml_dirty_filter(value ctx, value scene, value lmo, value dirt
   CAMLreturn(caml_copy_int64((int64_t)o));
 }
 
+/* ---- several GPUs ---- */
+#define MULTI(v) ((coh_multi*)Nativeint_val(v))
+static void mcheck(coh_multi* m, int rc) { if (rc) caml_failwith(coh_multi_last_error(m)); }
+CAMLprim value coh_ml_multi_init(value devices) {   /* int array of device ids */
+  CAMLparam1(devices);
+  int32_t ids[8];
+  const int n = (int)Wosize_val(devices);
+  if (n < 1 || n > 8) caml_invalid_argument("coh_multi_init: 1 .. 8 devices");
+  for (int k = 0; k < n; k++) ids[k] = Int_val(Field(devices, k));
+  coh_multi* m = NULL;
+  if (coh_multi_init(n, ids, &m)) caml_failwith(coh_multi_last_error(NULL));
+  CAMLreturn(caml_copy_nativeint((intnat)m));
+}
+CAMLprim value coh_ml_multi_shutdown(value m) { coh_multi_shutdown(MULTI(m)); return Val_unit; }
+CAMLprim value coh_ml_multi_device_count(value m) { return Val_int(coh_multi_device_count(MULTI(m))); }
+CAMLprim value coh_ml_multi_ctx(value m, value i) { return caml_copy_nativeint((intnat)coh_multi_ctx(MULTI(m), Int_val(i))); }
+CAMLprim value coh_ml_multi_configure(value m, value w, value h) { mcheck(MULTI(m), coh_multi_configure(MULTI(m), Int_val(w), Int_val(h), NULL)); return Val_unit; }
+CAMLprim value coh_ml_multi_scene_create(value m, value objs, value n_background, value edges, value points) {
+  CAMLparam5(m, objs, n_background, edges, points);
+  coh_scene_t s = 0;
+  mcheck(MULTI(m), coh_multi_scene_create(MULTI(m), (const coh_object*)Caml_ba_data_val(objs), (int32_t)(BA_LEN(objs) / (int64_t)sizeof(coh_object)), Int_val(n_background),
+         (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), (const int32_t*)Caml_ba_data_val(points), (int32_t)(BA_LEN(points) / 2), &s));
+  CAMLreturn(caml_copy_int64((int64_t)s));
+}
+CAMLprim value coh_ml_multi_scene_free(value m, value s) { mcheck(MULTI(m), coh_multi_scene_free(MULTI(m), SCENE(s))); return Val_unit; }
+CAMLprim value coh_ml_multi_scene_translate_object(value m, value s, value index, value dx, value dy) {
+  mcheck(MULTI(m), coh_multi_scene_translate_object(MULTI(m), SCENE(s), Int_val(index), Int_val(dx), Int_val(dy)));
+  return Val_unit;
+}
+CAMLprim value coh_ml_multi_render_frame(value m, value s, value box, value flags) {
+  CAMLparam4(m, s, box, flags);
+  mcheck(MULTI(m), coh_multi_render_frame(MULTI(m), SCENE(s), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), Int_val(flags)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_multi_sync(value m) { mcheck(MULTI(m), coh_multi_sync(MULTI(m))); return Val_unit; }
+CAMLprim value coh_ml_multi_read_rgba(value m, value box, value out) {
+  CAMLparam3(m, box, out);
+  need(out, (int64_t)Int_val(Field(box, 2)) * Int_val(Field(box, 3)) * 4, "multi_read_rgba: buffer too small");
+  mcheck(MULTI(m), coh_multi_fb_read_rgba(MULTI(m), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_multi_read_rgb888(value m, value box, value out) {
+  CAMLparam3(m, box, out);
+  need(out, (int64_t)Int_val(Field(box, 2)) * Int_val(Field(box, 3)) * 3, "multi_read_rgb888: canvas slice too small");
+  mcheck(MULTI(m), coh_multi_fb_read_rgb888(MULTI(m), Int_val(Field(box, 0)), Int_val(Field(box, 1)), Int_val(Field(box, 2)), Int_val(Field(box, 3)), (uint8_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+/* one process per GPU: the 64-byte CUDA IPC handle of a framebuffer allocated for export, as a Bigarray of bytes */
+CAMLprim value coh_ml_fb_alloc_shared(value ctx, value handle) {
+  CAMLparam2(ctx, handle);
+  need(handle, 64, "fb_alloc_shared: the handle buffer holds 64 bytes");
+  check(CTX(ctx), coh_fb_alloc_shared(CTX(ctx), (uint8_t*)Caml_ba_data_val(handle)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_fb_open_peer(value ctx, value handle) {
+  CAMLparam2(ctx, handle);
+  void* p = NULL;
+  need(handle, 64, "fb_open_peer: the handle buffer holds 64 bytes");
+  check(CTX(ctx), coh_fb_open_peer(CTX(ctx), (const uint8_t*)Caml_ba_data_val(handle), &p));
+  CAMLreturn(caml_copy_nativeint((intnat)p));
+}
+
 /* ---- host-side geometry (Polygon.edgelist_of_path / Brush.points_of_brushstroke for one subpath) ---- */
 CAMLprim value coh_ml_host_edgelist_of_subpath(value segs, value out) {   /* segs : float64 Array1 of 9*n; returns the edge count */
   int64_t n = coh_host_edgelist_of_subpath((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4);

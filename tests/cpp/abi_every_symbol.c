@@ -122,9 +122,9 @@ int main(int argc, char** argv) {
   ERR(coh_shape_bloat(C, bx, -1, 0, &t), "negative radius");
   uint32_t* img = (uint32_t*)malloc(4 * (size_t)W * H);
   uint8_t* rgb = (uint8_t*)malloc(3 * (size_t)W * H);
-  OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img)); CHECK(img[0] == 0xFFD3D3D3u && img[30 * W + 120] == 0xFF00FF00u);
+  OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img)); CHECK(img[0] == 0xFFD3D3D3u && img[40 * W + 140] == 0xFF00FF00u);
   ERR(coh_fb_read_rgba(C, 0, 0, W + 1, H, (uint8_t*)img), "outside");
-  OK(coh_fb_read_rgb888(C, 0, 0, W, H, rgb)); CHECK(rgb[0] == 0xD3 && rgb[3 * (30 * W + 120) + 1] == 0xFF);
+  OK(coh_fb_read_rgb888(C, 0, 0, W, H, rgb)); CHECK(rgb[0] == 0xD3 && rgb[3 * (40 * W + 140) + 1] == 0xFF);
   ERR(coh_fb_read_rgb888(C, -1, 0, 4, 4, rgb), "outside");
   OK(coh_fb_read_rgba_async(C, 0, 0, W, H, (uint8_t*)img)); OK(coh_fb_read_wait(C));
   OK(coh_shape_card(C, bx, &card));
@@ -150,6 +150,39 @@ int main(int argc, char** argv) {
   OK(coh_fb_attach(C, NULL));
   int64_t mem = 0; OK(coh_mem_in_use(C, &mem)); CHECK(mem > 0);
   OK(coh_set_stream(C, coh_stream(C)));
+  /* one process per GPU: a framebuffer allocated for export; mapping it back into the SAME process is refused by CUDA */
+  uint8_t ipc[64]; void* mapped = NULL;
+  OK(coh_fb_alloc_shared(C, ipc));
+  ERR(coh_fb_open_peer(C, ipc, &mapped), "cudaIpcOpenMemHandle");
+  OK(coh_render_frame(C, sc, 0, 0, W, H, 0)); OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img)); CHECK(img[0] == 0xFFD3D3D3u);
+  OK(coh_fb_attach(C, NULL));
+  /* one process, several devices (here: as many as are visible, at most 2) */
+  {
+    coh_multi* M = NULL;
+    int nd = 0;
+    if (coh_multi_init(99, NULL, &M) == 0) { printf("FAIL coh_multi_init accepted 99 devices\n"); return 1; }
+    CHECK(strstr(coh_multi_last_error(NULL), "devices") != NULL);
+    for (nd = 2; nd >= 1; nd--) if (coh_multi_init(nd, NULL, &M) == 0) break;
+    CHECK(M != NULL && coh_multi_device_count(M) == nd && coh_multi_ctx(M, 0) != NULL && coh_multi_ctx(M, nd) == NULL);
+    if (coh_multi_configure(M, W, H, NULL)) { printf("FAIL coh_multi_configure: %s\n", coh_multi_last_error(M)); return 1; }
+    int32_t badcuts[3] = {0, 50, 90};
+    CHECK(coh_multi_configure(M, W, H, badcuts) != 0 || nd != 2);
+    if (coh_multi_configure(M, W, H, NULL)) return 1;
+    coh_scene_t msc = 0;
+    if (coh_multi_scene_create(M, objs, 5, 1, e, 3, NULL, 0, &msc)) { printf("FAIL coh_multi_scene_create: %s\n", coh_multi_last_error(M)); return 1; }
+    if (coh_multi_render_frame(M, msc, 0, 0, W, H, 0) || coh_multi_sync(M)) { printf("FAIL coh_multi_render_frame: %s\n", coh_multi_last_error(M)); return 1; }
+    uint32_t* img2 = (uint32_t*)malloc(4 * (size_t)W * H);
+    if (coh_multi_fb_read_rgba(M, 0, 0, W, H, (uint8_t*)img2)) return 1;
+    OK(coh_fb_configure(C, W, H, 0, H)); OK(coh_render_frame(C, sc, 0, 0, W, H, 0)); OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img));
+    CHECK(memcmp(img, img2, 4 * (size_t)W * H) == 0);   /* the banded frame of nd devices = the single-device frame */
+    if (coh_multi_fb_read_rgb888(M, 0, 0, W, H, rgb)) return 1;
+    CHECK(rgb[0] == 0xD3);
+    if (coh_multi_scene_translate_object(M, msc, 3, 2, 2) || coh_multi_render_frame(M, msc, 0, 0, W, H, 0) || coh_multi_sync(M)) return 1;
+    CHECK(coh_multi_render_frame(M, 0, 0, 0, W, H, 0) != 0 && strstr(coh_multi_last_error(M), "null scene") != NULL);
+    if (coh_multi_scene_free(M, msc) || coh_multi_shutdown(M)) return 1;
+    printf("ok coh_multi on %d device(s)\n", nd);
+    free(img2);
+  }
   /* host-side geometry */
   double segs[9] = {0, 10.0, 10.0, 90.0, 20.0, 0, 0, 0, 0};
   int32_t he[8]; CHECK(coh_host_edgelist_of_subpath(segs, 1, he, 2) == 1 && he[0] == sub_of_float(10.0));

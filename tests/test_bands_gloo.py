@@ -17,7 +17,7 @@ W, H = 256, 190  # 190 rows: ragged for 3 bands
 
 def _worker(rank, world, port, out_path):
     sys.path.insert(0, ROOT)
-    from coherence_renderer_b200 import bands, scene
+    from coherence_renderer_b200 import bands, scene, torch_plumbing
     from oracle import pyoracle
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -30,7 +30,7 @@ def _worker(rank, world, port, out_path):
     # differently from the same rows of a whole frame (render.ml:1270-1279; DESIGN.md "known divergences").
     strip = pyoracle.render_frame(objs, n - nbg, nbg, edges, points, (0, y0, W, y1 - y0), bbox_reject=False)
     full = torch.zeros((H, W), dtype=torch.int32)
-    bands.gather_strips(dist, torch.from_numpy(strip.view(np.int32)).contiguous(), full, H, world)
+    torch_plumbing.gather_strips(dist, torch.from_numpy(strip.view(np.int32)).contiguous(), full, H, world)
     if rank == 0:
         np.save(out_path, full.numpy().view(np.uint32))
     dist.barrier()
