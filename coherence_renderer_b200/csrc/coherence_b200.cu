@@ -146,6 +146,7 @@ static std::string g_init_err;
       char b_[512];                                                                           \
       snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
       ctx->err = b_;                                                                          \
+      cudaGetLastError(); /* a refused call must not be blamed on the next launch */          \
       return 1;                                                                               \
     }                                                                                         \
   } while (0)
@@ -284,6 +285,7 @@ int coh_device_name(coh_ctx* ctx, char* buf, int cap) {
 void* coh_stream(coh_ctx* ctx) { return (void*)ctx->stream; }
 int coh_set_stream(coh_ctx* ctx, void* stream) {
   CK(cudaSetDevice(ctx->device));
+  if ((cudaStream_t)stream == ctx->stream) return 0;   // already running on it
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)stream; ctx->own_stream = false;

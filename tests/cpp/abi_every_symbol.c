@@ -10,7 +10,7 @@
 
 static coh_ctx* C = NULL;
 static int n_ok = 0;
-#define OK(call) do { if ((call) != 0) { printf("FAIL %s: %s\n", #call, coh_last_error(C)); exit(1); } n_ok++; } while (0)
+#define OK(call) do { if (getenv("ABI_TRACE")) printf("> %s\n", #call); if ((call) != 0) { printf("FAIL %s: %s\n", #call, coh_last_error(C)); exit(1); } n_ok++; } while (0)
 #define ERR(call, what) do { if ((call) == 0) { printf("FAIL expected an error: %s\n", #call); exit(1); } \
   if (!strstr(coh_last_error(C), what)) { printf("FAIL wrong message for %s: %s\n", #call, coh_last_error(C)); exit(1); } n_ok++; } while (0)
 #define CHECK(cond) do { if (!(cond)) { printf("FAIL %s (line %d)\n", #cond, __LINE__); exit(1); } n_ok++; } while (0)
@@ -24,6 +24,7 @@ static coh_object blank(int kind) { coh_object o; memset(&o, 0, sizeof o); o.kin
 
 int main(int argc, char** argv) {
   (void)argc; (void)argv;
+  setvbuf(stdout, NULL, _IONBF, 0);
   if (coh_init(-1, &C) != 0) {
     const char* m = coh_last_error(NULL);
     if (!strstr(m, "no CPU fallback")) { printf("FAIL init message: %s\n", m); return 1; }
@@ -55,7 +56,7 @@ int main(int argc, char** argv) {
   OK(coh_polygon_opacity(C, e, 3, COH_NONZERO, mx, op, card, &n)); CHECK(n == card);
   ERR(coh_polygon_opacity(C, e, 3, COH_NONZERO, mx, op, card - 1, &n), "buffer too small");
   coh_object fill = blank(COH_OBJ_PATH); fill.fill_kind = COH_FILL_PLAIN; fill.colour0 = 0xFF2030C8u;
-  uint32_t* px = (uint32_t*)malloc(4 * (size_t)card);
+  uint32_t* px = (uint32_t*)malloc(4 * (size_t)200 * 160);   /* large enough for every sprite read below */
   OK(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, card, &n)); CHECK(n == card);
   ERR(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, 1, &n), "buffer too small");
   fill.fill_kind = 9; ERR(coh_polygon_sprite(C, &fill, e, 3, COH_NONZERO, mx, px, card, &n), "fill kind"); fill.fill_kind = 0;
@@ -173,7 +174,10 @@ int main(int argc, char** argv) {
     if (coh_multi_render_frame(M, msc, 0, 0, W, H, 0) || coh_multi_sync(M)) { printf("FAIL coh_multi_render_frame: %s\n", coh_multi_last_error(M)); return 1; }
     uint32_t* img2 = (uint32_t*)malloc(4 * (size_t)W * H);
     if (coh_multi_fb_read_rgba(M, 0, 0, W, H, (uint8_t*)img2)) return 1;
-    OK(coh_fb_configure(C, W, H, 0, H)); OK(coh_render_frame(C, sc, 0, 0, W, H, 0)); OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img));
+    coh_scene_t sc2 = 0;   /* (sc has had objects moved since) */
+    OK(coh_scene_create(C, objs, 5, 1, e, 3, NULL, 0, &sc2));
+    OK(coh_fb_configure(C, W, H, 0, H)); OK(coh_render_frame(C, sc2, 0, 0, W, H, 0)); OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img));
+    OK(coh_scene_free(C, sc2));
     CHECK(memcmp(img, img2, 4 * (size_t)W * H) == 0);   /* the banded frame of nd devices = the single-device frame */
     if (coh_multi_fb_read_rgb888(M, 0, 0, W, H, rgb)) return 1;
     CHECK(rgb[0] == 0xD3);

@@ -1029,6 +1029,7 @@ def test_cache_entry_points(ctx, oracle):
     ctx.cache_configure(True, 8 << 20)
     a, m = util.random_shape_flat(rng), util.random_shape_flat(rng, density=0.15)
     ha, hm = ctx.shape_import(a), ctx.shape_import(m)
+    st0 = ctx.cache_stats()                   # the counters run for the life of the context (cache.ml:24-38)
     assert ctx.cache_getshape(41) is None
     ctx.cache_addshape(41, ha, hm)
     ctx.shape_free(ha)
@@ -1048,7 +1049,7 @@ def test_cache_entry_points(ctx, oracle):
         for h in got:
             ctx.shape_free(h)
     st = ctx.cache_stats()
-    assert st["shape_hits"] == 3 and st["shape_misses"] == 1 and st["entries"] >= 1 and st["bytes"] > 0
+    assert st["shape_hits"] - st0["shape_hits"] == 3 and st["shape_misses"] - st0["shape_misses"] == 1 and st["entries"] >= 1 and st["bytes"] > 0
     ctx.cache_configure(False, 8 << 20)       # Cache.usecache := false: nothing is served
     assert ctx.cache_getshape(41) is None
     ctx.cache_configure(True, 50 << 20)
