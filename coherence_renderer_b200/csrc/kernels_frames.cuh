@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   // lists start first); one thread resolves it to a cell — the classes are consecutive segments of cls_cells — and
   // the grid is sized for every cell: positions beyond the queued cells (background cells were finished by
   // k_prefill) leave at once.
-  __shared__ int s_cell[4];   // cell, tile, first row of the block, column mask of the update box
+  __shared__ int s_cell[6];   // cell, tile, first row of the block, column mask of the update box, cell header
   if (threadIdx.x < 32) {
     // warp 0: lane c holds the size of class c; an inclusive scan finds the class of position q with one load
     const int lane0 = threadIdx.x;
@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
         uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
         if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
         s_cell[1] = tile; s_cell[2] = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS; s_cell[3] = (int)colmask;
+        const int2 hd = P.cell_head ? P.cell_head[cell] : make_int2(0, 0);
+        s_cell[4] = hd.x; s_cell[5] = hd.y;
       }
     }
   }
@@ -281,6 +283,17 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   const uint32_t u_update = u;
   uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
   if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
+  if (s_cell[5] & 1) {
+    // a background cell that k_prefill did not take (frames mirrored to peer framebuffers spread these stores over
+    // the compositor's blocks): one opaque primitive covers the cell, nothing was scan-converted for it
+    if (u_rec && lane == 0) *u_rec = (s_cell[5] & 2) ? 0u : u;
+    if (u & lbit) {
+      const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
+      P.fb[at] = (uint32_t)s_cell[4];
+      for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = (uint32_t)s_cell[4];
+    }
+    return;
+  }
   const int2 rg = P.cell_rng[cell];
   const uint2* sc_row = P.pre_sc + row;
   const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;

@@ -691,11 +691,16 @@ def test_every_walker_variant(ctx, oracle, walk_h, fused, aa_general, comp_rows,
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
 
 
-def test_peer_framebuffer_mirror(ctx, oracle):
+@pytest.mark.parametrize("fused", [-1, 0, 1])
+def test_peer_framebuffer_mirror(ctx, oracle, options, fused):
     """coh_fb_set_peers: every pixel rendered into the framebuffer is also stored to the peer framebuffers (on a
     multi-GPU box: the other ranks' frames over NVLink; here a second buffer on the same GPU stands in for a
-    peer).  Two bands rendered by two passes into mirrored buffers assemble the whole frame in both."""
+    peer).  Two bands rendered by two passes into mirrored buffers assemble the whole frame in both — through the
+    fused walker and through the three-phase frame with the row compositor (whose blocks then also finish the
+    background cells: k_prefill is off with peers)."""
     import torch
+
+    options("fused", fused)
 
     W, H = 320, 208
     b = S.lion_scene(W, H, 0.75)
