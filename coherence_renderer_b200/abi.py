@@ -47,7 +47,7 @@ SYMBOLS = [
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_sprite", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points",
-    "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_addshape", "coh_cache_getshape",
+    "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_sprite_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
     "coh_multi_scene_create", "coh_multi_scene_free", "coh_multi_scene_translate_object", "coh_multi_render_frame", "coh_multi_sync",
@@ -315,6 +315,11 @@ class Context:
         out = (C.c_int64 * 4)()
         self._chk(lib().coh_cache_stats(self._h, out))
         return {"shape_hits": out[0], "shape_misses": out[1], "bytes": out[2], "entries": out[3]}
+
+    def cache_sprite_stats(self, scene):
+        out = (C.c_int64 * 4)()
+        self._chk(lib().coh_cache_sprite_stats(self._h, C.c_uint64(scene), out))
+        return {"sprite_hits": out[0], "sprite_fills": out[1], "bytes": out[2], "entries": out[3]}
 
     def cache_addshape(self, oid, shape, minshape):
         self._chk(lib().coh_cache_addshape(self._h, C.c_int64(oid), C.c_uint64(shape), C.c_uint64(minshape)))

@@ -36,11 +36,41 @@ struct BinSet {
   int4* item_rec = nullptr;   // scan-conversion record of every list entry, two int4 each (small-scene binning only)
   int* state = nullptr;       // ORDER_BINS ints: [0] pool cursor, [1 ..] class counts
 };
-struct DevScene {
-  int n_objs = 0, n_leaves = 0, n_edges = 0, n_points = 0;
-  ObjRec* objs = nullptr;
+// A leaf list of a scene (front to back) with what the binning derives from it.  A scene has two: every leaf, and
+// the list in which every object with a cached sprite is ONE leaf (its members collapsed).
+struct LeafView {
+  int n = 0;
   int* leaves = nullptr;
   int4* leaf_box = nullptr;     // conservative device-space pixel box per leaf (binning reads these, coalesced)
+  std::vector<int> h_leaves;
+  size_t items_total = 0, coarse_total = 0; bool coarse_total_valid = false;
+  int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
+  // Whole-frame binning kept with the scene (it is a pure function of the object boxes and the frame geometry,
+  // like the row-edge lists): valid until an object moves or the framebuffer geometry changes.
+  BinSet bins; bool bins_valid = false; int bins_key[6] = {0, 0, 0, 0, 0, 0};
+};
+// Partial-sprite cache entry (render.ml:1169-1242; cache.ml:328-367): a top-level Group with an id, as one sprite.
+struct SpriteEntry {
+  int grp = 0;                 // record of the group
+  int l0 = 0, l1 = 0;          // its member leaves in the full list
+  int leaf_rec = 0;            // record of the sprite leaf (K_CONV layout: shape planes + RGBA8 canvas in the object's frame)
+  uint32_t* valid = nullptr;   // pshape: pixels whose value is in the canvas
+  size_t plane_words = 0, bytes = 0;
+  bool complete = false;       // pshape = shape: nothing left to render, ever
+  bool dead = false;           // a member moved on its own: the entry is not used any more
+  int* h_missing = nullptr;    // pinned: pixels of the shape not yet in pshape (read back asynchronously)
+  int* d_missing = nullptr;
+  cudaEvent_t ev = nullptr; bool ev_pending = false;
+};
+struct DevScene {
+  int n_objs = 0, n_edges = 0, n_points = 0;
+  ObjRec* objs = nullptr;
+  LeafView full, sp;            // every leaf / cached objects collapsed into their sprite leaves
+  int& n_leaves = full.n;
+  int*& leaves = full.leaves;
+  int4*& leaf_box = full.leaf_box;
+  std::vector<SpriteEntry> sprites;
+  int64_t sprite_hits = 0, sprite_fills = 0;
   EdgeRec* edges = nullptr;
   int2* points = nullptr;
   uint8_t* stamps = nullptr;
@@ -67,14 +97,9 @@ struct DevScene {
   std::vector<int2> group_off;   // per record: translation applied to the whole group since scene creation
   int n_scene_leaves = 0;        // ordinary leaves of the scene list
   int n_front_leaves = 0;        // + leaves of reading-scene groups (the background list follows)
-  std::vector<int> h_leaves;
+  std::vector<int>& h_leaves = full.h_leaves;
   bool has_fancy = false;    // some object has a gradient / radial fill
   int extras = 0;            // walker variant: 0 polygons / primitives, 1 + brush / Convolved, 2 + CPG / filters
-  size_t items_total = 0, coarse_total = 0; bool coarse_total_valid = false;
-  int items_for_W = -1, items_for_H = -1, items_for_y0 = -1, items_for_y1 = -1;
-  // Whole-frame binning kept with the scene (it is a pure function of the object boxes and the frame geometry,
-  // like the row-edge lists): valid until an object moves or the framebuffer geometry changes.
-  BinSet bins; bool bins_valid = false; int bins_key[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // Cache (cache.ml:57-83): entries keyed by object id hold device-resident span sets

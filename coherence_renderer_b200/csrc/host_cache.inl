@@ -43,6 +43,16 @@ int coh_cache_stats(coh_ctx* ctx, int64_t out[4]) {  // cache.ml:24-38
   out[0] = ctx->shphit; out[1] = ctx->shpmis; out[2] = (int64_t)ctx->cache_size; out[3] = (int64_t)ctx->cache.size();
   return 0;
 }
+// The partial-sprite side of the cache (cache.ml:328-367) for one scene: frames served entirely from cached sprites,
+// frames that had to render into them, bytes of sprite canvases and planes resident in HBM, cached objects.
+int coh_cache_sprite_stats(coh_ctx* ctx, coh_scene_t scene, int64_t out[4]) {
+  DevScene* s = (DevScene*)scene;
+  if (!s) FAIL("coh_cache_sprite_stats: null scene");
+  size_t bytes = 0; int64_t n = 0;
+  for (const SpriteEntry& e : s->sprites) if (!e.dead) { bytes += e.bytes; n++; }
+  out[0] = s->sprite_hits; out[1] = s->sprite_fills; out[2] = (int64_t)bytes; out[3] = n;
+  return 0;
+}
 // Cache.addshape idset shp minshp (cache.ml:280-324): copies are kept; an existing shape is not replaced
 int coh_cache_addshape(coh_ctx* ctx, int64_t id, coh_shape_t shape, coh_shape_t minshape) {
   CK(cudaSetDevice(ctx->device));
@@ -221,9 +231,22 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
     if (o.kind == K_GROUP) { s->group_off[k].x += dx; s->group_off[k].y += dy; continue; }
     o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
   }
-  s->items_for_W = -1;  // the item-pool bound depends on the boxes
-  s->bins_valid = false;  // ... and so do the cell lists
-  if (s->n_leaves > 0) { k_move_leaves<<<cdiv(s->n_leaves, 256), 256, 0, ctx->stream>>>(s->objs, s->leaf_box, s->leaves, s->n_leaves, r, last, dx, dy); LAUNCHED(); }
+  s->full.items_for_W = -1; s->sp.items_for_W = -1;    // the item-pool bounds depend on the boxes
+  s->full.bins_valid = false; s->sp.bins_valid = false;  // ... and so do the cell lists
+  if (s->n_leaves > 0) { k_move_leaves<<<cdiv(s->n_leaves, 256), 256, 0, ctx->stream>>>(s->objs, s->leaf_box, s->leaves, s->n_leaves, r, last, dx, dy, 1); LAUNCHED(); }
+  if (s->sp.n > 0) {
+    // the list with cached objects collapsed: boxes of the leaves it shares follow the records; a cached object moved as
+    // a whole takes its sprite leaf along (the alias reads the cached sprite translated, cache.ml:400-405); one whose
+    // member moved on its own is no longer the object that was cached
+    k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, r, last, dx, dy, 0); LAUNCHED();
+    for (SpriteEntry& e : s->sprites) {
+      if (e.grp >= r && e.grp <= last) {
+        ObjRec& o = s->h_objs[e.leaf_rec];
+        o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
+        k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, e.leaf_rec, e.leaf_rec, dx, dy, 1); LAUNCHED();
+      } else if (r > e.grp && r <= s->group_last[e.grp]) e.dead = true;
+    }
+  }
   return 0;
 }
 // Render.render_frame over an arbitrary update shape (the dirty region of engine.ml:224-252).
@@ -246,7 +269,7 @@ int coh_render_frame_shape(coh_ctx* ctx, coh_scene_t scene, coh_shape_t update, 
     return rc;
   }
   PassArgs A{0, s->n_leaves, us->bx0, us->by0, us->bx1 - us->bx0 + 1, us->by1 - us->by0 + 1, ctx->u_init, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
-  int rc = render_pass(ctx, s, A);
+  int rc = render_frame_passes(ctx, s, A);
   ctx->have_u = record_u && !rc;
   return rc;
 }
@@ -331,7 +354,7 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
   int rc;
   if (!s->filters.empty()) { rc = render_filtered(ctx, s, U, bb[0], bb[1], bb[2] - bb[0] + 1, bb[3] - bb[1] + 1); ctx->have_u = !rc; return rc; }
   PassArgs A{0, s->n_leaves, bb[0], bb[1], bb[2] - bb[0] + 1, bb[3] - bb[1] + 1, U, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
-  rc = render_pass(ctx, s, A);
+  rc = render_frame_passes(ctx, s, A);
   ctx->have_u = record_u && !rc;
   return rc;
 }

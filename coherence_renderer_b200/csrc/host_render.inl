@@ -8,14 +8,17 @@ struct PassArgs {
   uint32_t* u_out;            // receives `u` after the scene list, or null (may alias u_init)
   uint32_t* fb;               // target canvas
   bool write_clear, resume;
+  bool collapsed = false;     // walk the leaf list in which cached objects are one sprite leaf each (l0 / l1 index that list)
 };
 static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   Frame fr = ctx->fr;
   const int ux = A.ux, uy = A.uy, uw = A.uw, uh = A.uh;
   const bool write_clear = A.write_clear;
+  LeafView& V = A.collapsed ? s->sp : s->full;
+  const int extras = A.collapsed ? std::max(s->extras, 1) : s->extras;   // sprite leaves are read like Convolved objects' canvases
   const int n_leaves = A.l1 - A.l0;
-  const int4* leaf_box = s->leaf_box + A.l0;
-  const int* leaves = s->leaves + A.l0;
+  const int4* leaf_box = V.leaf_box + A.l0;
+  const int* leaves = V.leaves + A.l0;
   if (fr.band_y1 <= fr.band_y0 || uw <= 0 || uh <= 0) return 0;
   // only the cell rows the update box reaches (a dirty region is usually a small part of the frame)
   const int ry0 = std::max(fr.band_y0, uy), ry1 = std::min(fr.band_y1, uy + uh);
@@ -25,7 +28,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   const int ctx1 = std::min(fr.tiles_x - 1, (int)(((long long)ux + uw - 1) >> 5));
   if (ctx1 < fr.ctx0) return 0;
   fr.cntx = ctx1 - fr.ctx0 + 1;
-  const bool whole = A.l0 == 0 && A.l1 == s->n_leaves && ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x;
+  const bool whole = A.l0 == 0 && A.l1 == V.n && ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x;
   int cell_row0 = ry0 / CELL_H, cell_row1 = (ry1 - 1) / CELL_H;
   if (A.u_out && A.u_out != A.u_init && !(ry0 == fr.band_y0 && ry1 == fr.band_y1 && fr.cntx == fr.tiles_x))
     // rows and columns the walk does not visit have nothing uncovered
@@ -39,9 +42,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   const bool prefill = !big && ordered && !A.u_init && !A.resume && !(A.fb == ctx->fb && ctx->n_peers > 0);
   // Whole-frame binning of a small scene is kept with the scene; every other pass bins into the context's scratch.
   const bool keep = whole && !big && ctx->opt_bin_cache;
-  BinSet& B = keep ? s->bins : ctx->bins;
+  BinSet& B = keep ? V.bins : ctx->bins;
   const int key[6] = {fr.W, fr.H, fr.band_y0, fr.band_y1, ordered ? 1 : 0, prefill ? 1 : 0};
-  const bool hit = keep && s->bins_valid && memcmp(key, s->bins_key, sizeof key) == 0;
+  const bool hit = keep && V.bins_valid && memcmp(key, V.bins_key, sizeof key) == 0;
   if (n_cells > B.n_cells_cap) {
     DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng);
     B.n_cells_cap = 0;
@@ -62,17 +65,17 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
   size_t total = 0;
-  if (!whole || s->items_for_W != fr.W || s->items_for_H != fr.H || s->items_for_y0 != fr.band_y0 || s->items_for_y1 != fr.band_y1) {
+  if (!whole || V.items_for_W != fr.W || V.items_for_H != fr.H || V.items_for_y0 != fr.band_y0 || V.items_for_y1 != fr.band_y1) {
     size_t tot = 0;
     for (int li = A.l0; li < A.l1; li++) {
-      const ObjRec& o = s->h_objs[s->h_leaves[li]];
+      const ObjRec& o = s->h_objs[V.h_leaves[li]];
       int cx0 = std::max(o.bx0 >> 5, fr.ctx0), cx1 = std::min(o.bx1 >> 5, ctx1);
       int cy0 = std::max(floordiv(o.by0, CELL_H), cell_row0), cy1 = std::min(floordiv(o.by1, CELL_H), cell_row1);
       if (cx1 >= cx0 && cy1 >= cy0) tot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
     }
     total = tot;
-    if (whole) { s->coarse_total_valid = false; s->items_total = tot; s->items_for_W = fr.W; s->items_for_H = fr.H; s->items_for_y0 = fr.band_y0; s->items_for_y1 = fr.band_y1; }
-  } else total = s->items_total;
+    if (whole) { V.coarse_total_valid = false; V.items_total = tot; V.items_for_W = fr.W; V.items_for_H = fr.H; V.items_for_y0 = fr.band_y0; V.items_for_y1 = fr.band_y1; }
+  } else total = V.items_total;
   const size_t need = total;
   if (need > B.cell_items_cap) {
     DFREE(B.cell_items); DFREE(B.item_cell); DFREE(B.item_attr); DFREE(B.item_rec);
@@ -94,22 +97,22 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, B.cell_rng, B.cell_items, B.state,
                                                ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr, B.item_rec); LAUNCHED();
-    if (keep) { s->bins_valid = true; memcpy(s->bins_key, key, sizeof key); }
+    if (keep) { V.bins_valid = true; memcpy(V.bins_key, key, sizeof key); }
   } else {
     CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
     // two levels: leaves into coarse cells (object-parallel, sorted per coarse list), then every fine cell from its coarse list
     const int ctx_x = cdiv(fr.tiles_x, COARSE), crow0 = cell_row0 >> COARSE_SHIFT, crow1 = cell_row1 >> COARSE_SHIFT;
     const int n_coarse = ctx_x * (crow1 - crow0 + 1);
     size_t ctot = 0;
-    if (whole && s->coarse_total_valid) ctot = s->coarse_total;   // a pure function of the boxes and the frame geometry, like items_total
+    if (whole && V.coarse_total_valid) ctot = V.coarse_total;   // a pure function of the boxes and the frame geometry, like items_total
     else {
       for (int li = A.l0; li < A.l1; li++) {
-        const ObjRec& o = s->h_objs[s->h_leaves[li]];
+        const ObjRec& o = s->h_objs[V.h_leaves[li]];
         int cx0 = std::max(floordiv(o.bx0, 32 * COARSE), 0), cx1 = std::min(floordiv(o.bx1, 32 * COARSE), ctx_x - 1);
         int cy0 = std::max(floordiv(o.by0, CELL_H * COARSE), crow0), cy1 = std::min(floordiv(o.by1, CELL_H * COARSE), crow1);
         if (cx1 >= cx0 && cy1 >= cy0) ctot += (size_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
       }
-      if (whole) { s->coarse_total = ctot; s->coarse_total_valid = true; }
+      if (whole) { V.coarse_total = ctot; V.coarse_total_valid = true; }
     }
     if (2 * ctot + 1 > ctx->coarse_cap || (size_t)n_coarse + 1 > ctx->coarse_cells_cap) {
       DFREE(ctx->coarse_items); DFREE(ctx->coarse_counts); DFREE(ctx->coarse_off);
@@ -164,7 +167,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   } while (0)
 #define LAUNCH_WALK(CARRYV)                                                                                        \
   do {                                                                                                             \
-    if (s->extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (s->extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
+    if (extras == 0) LAUNCH_WALK_E(CARRYV, 0); else if (extras == 1) LAUNCH_WALK_E(CARRYV, 1); else LAUNCH_WALK_E(CARRYV, 2); \
   } while (0)
   P.queue = ctx->queue; P.n_cells = n_cells;
   P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
@@ -174,12 +177,12 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
   const int force = ctx->opt_fused;   // tests force either path: 1 fused, 0 three-phase
   // eligible: every leaf of the range is a path, a primitive or a Convolved object
-  bool kinds_ok = s->extras == 0;
+  bool kinds_ok = extras == 0;
   bool has_conv = false;
   if (!kinds_ok && !A.resume && !big) {
     kinds_ok = true;
     for (int li = A.l0; li < A.l1 && kinds_ok; li++) {
-      const int k = s->h_objs[s->h_leaves[li]].kind;
+      const int k = s->h_objs[V.h_leaves[li]].kind;
       kinds_ok = k == K_PATH || k == K_PRIM || k == K_CONV;
       has_conv = has_conv || k == K_CONV;
     }
@@ -207,7 +210,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
-    if (s->flat_ok && ctx->opt_comp_rows) {
+    if (s->flat_ok && !A.collapsed && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
       k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
@@ -252,6 +255,57 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   }
   if (ctx->timing) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_pending = true; }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Frames of scenes with cached sprites (render.ml:1169-1242 spriteof; cache.ml:328-367, 390-407).  For every cached
+// object: shptorender = r' - pshape — here update ∩ shape - pshape, a superset of the reference's (it intersects with
+// the exact u; rendering more pixels of a plain-filled group into the cache changes no value) — is rendered from
+// the object's members alone into a scratch canvas and merged into the object's canvas and pshape
+// (Cache.addsprite); then the frame is walked over the list in which the object is one sprite leaf.  Once pshape has
+// reached the shape (one asynchronous counter read-back) the object costs one leaf per frame, wherever it is moved.
+// ---------------------------------------------------------------------------------------
+static bool sprites_usable(coh_ctx* ctx, DevScene* s) {
+  if (!ctx->usecache || s->sprites.empty() || !s->filters.empty()) return false;
+  if (ctx->fr.band_y0 != 0 || ctx->fr.band_y1 != ctx->fr.H) return false;   // a band never completes a sprite that straddles it
+  for (const SpriteEntry& e : s->sprites) if (e.dead) return false;
+  return true;
+}
+static int render_frame_passes(coh_ctx* ctx, DevScene* s, PassArgs A) {
+  if (!sprites_usable(ctx, s)) return render_pass(ctx, s, A);
+  const Frame& fr = ctx->fr;
+  const int nw = fr.tiles_x;
+  bool filled = false;
+  for (SpriteEntry& e : s->sprites) {
+    if (e.ev_pending && cudaEventQuery(e.ev) == cudaSuccess) { e.ev_pending = false; if (*e.h_missing == 0) e.complete = true; }
+    if (e.complete) continue;
+    const ObjRec& o = s->h_objs[e.leaf_rec];
+    const int x0 = std::max(std::max(A.ux, o.bx0), 0), x1 = std::min(std::min(A.ux + A.uw - 1, o.bx1), fr.W - 1);
+    const int y0 = std::max(std::max(A.uy, o.by0), 0), y1 = std::min(std::min(A.uy + A.uh - 1, o.by1), fr.H - 1);
+    if (x1 < x0 || y1 < y0) continue;
+    const int rows = y1 - y0 + 1;
+    uint32_t *T = nullptr, *tmp = nullptr;
+    CK(DMALLOC(&T, 4 * (size_t)nw * fr.H));
+    CK(DMALLOC(&tmp, 4 * (size_t)fr.W * fr.H));
+    const uint32_t* S = s->conv_bits + o.cv_bits;
+    k_sprite_todo<<<dim3(cdiv(nw, 128), rows), 128, 0, ctx->stream>>>(A.u_init, A.ux, A.uy, A.ux + A.uw - 1, A.uy + A.uh - 1, S, e.valid, o.cv_x0, o.cv_y0, o.cv_nw, o.cv_h,
+                                                                      o.dx, o.dy, fr.W, nw, y0, rows, T, nullptr); LAUNCHED();
+    PassArgs F{e.l0, e.l1, x0, y0, x1 - x0 + 1, rows, T, nullptr, tmp, true, false};
+    if (render_pass(ctx, s, F)) return 1;
+    k_sprite_store<<<dim3(cdiv(fr.W, 256), rows), 256, 0, ctx->stream>>>(tmp, T, s->conv_px + o.cv_px, e.valid, o.cv_x0, o.cv_y0, o.cv_nw, o.cv_h, o.dx, o.dy, fr.W, nw, y0, rows); LAUNCHED();
+    if (!e.ev_pending) {   // has pshape reached the shape?  (answered a few frames later, without a wait)
+      CK(cudaMemsetAsync(e.d_missing, 0, sizeof(int), ctx->stream));
+      k_sprite_missing<<<(unsigned)((e.plane_words + 255) / 256), 256, 0, ctx->stream>>>(S, e.valid, e.plane_words, e.d_missing); LAUNCHED();
+      CK(cudaMemcpyAsync(e.h_missing, e.d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(e.ev, ctx->stream));
+      e.ev_pending = true;
+    }
+    DFREE(T); DFREE(tmp);
+    filled = true;
+  }
+  if (filled) s->sprite_fills++; else s->sprite_hits++;
+  A.collapsed = true; A.l0 = 0; A.l1 = s->sp.n;
+  return render_pass(ctx, s, A);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -423,7 +477,7 @@ int coh_render_frame(coh_ctx* ctx, coh_scene_t scene, int32_t ux, int32_t uy, in
     return 0;
   }
   PassArgs A{0, s->n_leaves, ux, uy, uw, uh, nullptr, record_u ? ctx->u_out : nullptr, ctx->fb, true, false};
-  if (render_pass(ctx, s, A)) return 1;
+  if (render_frame_passes(ctx, s, A)) return 1;
   ctx->have_u = record_u;
   return 0;
 }

@@ -10,7 +10,14 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
   DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr);
   for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
-  free_binset(ctx, s->bins);
+  free_binset(ctx, s->full.bins); free_binset(ctx, s->sp.bins);
+  DFREE(s->sp.leaves); DFREE(s->sp.leaf_box);
+  for (SpriteEntry& e : s->sprites) {
+    if (e.ev_pending) cudaEventSynchronize(e.ev);
+    DFREE(e.valid); DFREE(e.d_missing);
+    if (e.h_missing) cudaFreeHost(e.h_missing);
+    if (e.ev) cudaEventDestroy(e.ev);
+  }
   delete s;
   return 0;
 }
@@ -269,16 +276,65 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (it == reading.end()) FAIL("scene: filter without its reading-scene group");
     filters[k].read0 = it->second.first; filters[k].read1 = it->second.second;
   }
+  group_last.resize(recs.size(), -1);
+  ids.resize(recs.size(), -1);
+  real_depth.resize(recs.size(), 0);
+  // Partial-sprite cache (render.ml:1169-1242): a top-level Group of the scene list that carries an id (the only
+  // kind of object whose sprite the reference ever finds again: members get fresh ids on every render, render.ml:993)
+  // is given a sprite leaf — shape planes and an RGBA8 canvas in its own frame, laid out like a Convolved object's —
+  // and a second leaf list in which that leaf stands for all its members.
+  std::vector<SpriteEntry> sprites;
+  const int n_real_recs = (int)recs.size();
+  if (filters.empty())
+    for (int g = 0; g < n_real_recs; g++) {
+      if (recs[g].kind != K_GROUP || real_depth[g] != 1 || ids[g] < 0 || recs[g].pretrans >= 0) continue;
+      if (!(recs[recs[g].anc[0]].flags & OF_ROOT_SCENE)) continue;
+      int l0 = -1, l1 = -1;
+      for (int li = 0; li < (int)leaves.size(); li++)
+        if (leaves[li] > g && leaves[li] <= group_last[g]) { if (l0 < 0) l0 = li; l1 = li + 1; }
+      if (l0 < 0 || l1 - l0 < 2) continue;
+      bool ok = true;
+      int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = INT32_MIN, by1 = INT32_MIN;
+      for (int li = l0; li < l1 && ok; li++) {
+        const ObjRec& m = recs[leaves[li]];
+        ok = (m.kind == K_PATH || m.kind == K_PRIM) && m.fill.kind == 0 && m.dx == 0 && m.dy == 0;
+        bx0 = std::min(bx0, m.bx0); by0 = std::min(by0, m.by0); bx1 = std::max(bx1, m.bx1); by1 = std::max(by1, m.by1);
+      }
+      if (!ok) continue;
+      ObjRec o; memset(&o, 0, sizeof o);
+      o.kind = K_CONV; o.pretrans = -1; o.depth = 1; o.anc[0] = recs[g].anc[0];
+      o.bx0 = bx0; o.by0 = by0; o.bx1 = bx1; o.by1 = by1;
+      o.cv_x0 = floordiv(bx0, 32) * 32; o.cv_y0 = by0; o.cv_nw = (bx1 - o.cv_x0) / 32 + 1; o.cv_h = by1 - by0 + 1;
+      const size_t words = (size_t)o.cv_nw * o.cv_h, bytes = words * 4 * 3 + words * 32 * 4;   // S, M, V planes + canvas
+      if (bytes > ctx->cache_max / 2) continue;                      // cache.ml: an item larger than half the cache is not kept
+      if (conv_words + 2 * words > 0x7FFFFFF0ull || conv_pixels + words * 32 > 0x7FFFFFF0ull) continue;
+      o.cv_bits = (int)conv_words; conv_words += 2 * words;
+      o.cv_px = (int)conv_pixels; conv_pixels += words * 32;
+      SpriteEntry e; e.grp = g; e.l0 = l0; e.l1 = l1; e.leaf_rec = (int)recs.size(); e.plane_words = words; e.bytes = bytes;
+      recs.push_back(o);
+      sprites.push_back(e);
+    }
+  group_last.resize(recs.size(), -1);
+  ids.resize(recs.size(), -1);
+  real_depth.resize(recs.size(), 0);
   DevScene* s = new DevScene();
   s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves; s->h_leaves = leaves;
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->h_objs = recs;
-  group_last.resize(recs.size(), -1);
-  ids.resize(recs.size(), -1);
-  real_depth.resize(recs.size(), 0);
+  s->sprites = sprites;
+  if (!sprites.empty()) {   // the collapsed leaf list
+    size_t k = 0;
+    for (int li = 0; li < (int)leaves.size(); li++) {
+      while (k < sprites.size() && li >= sprites[k].l1) k++;
+      if (k < sprites.size() && li >= sprites[k].l0) { if (li == sprites[k].l0) s->sp.h_leaves.push_back(sprites[k].leaf_rec); continue; }
+      s->sp.h_leaves.push_back(leaves[li]);
+    }
+    s->sp.n = (int)s->sp.h_leaves.size();
+  }
   s->rec_of_abi = rec_of_abi; s->group_last = group_last; s->ids = ids; s->real_depth = real_depth;
   s->group_off.assign(recs.size(), make_int2(0, 0));
-  for (const ObjRec& o : recs) {
+  for (int ri = 0; ri < n_real_recs; ri++) {
+    const ObjRec& o = recs[ri];
     if (o.kind != K_GROUP && o.kind != K_PRIM && o.fill.kind != 0) s->has_fancy = true;
     if (o.kind == K_BRUSH || o.kind == K_CONV) s->extras = std::max(s->extras, 1);
     if (o.kind == K_CPG || !filters.empty()) s->extras = 2;  // the filter passes need the walker variant that can continue a frame
@@ -310,6 +366,14 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   for (size_t i = 0; i < leaves.size(); i++) { const ObjRec& o = recs[leaves[i]]; boxes[i] = make_int4(o.bx0, o.by0, o.bx1, o.by1); }
   CK(DMALLOC(&s->leaf_box, sizeof(int4) * std::max<size_t>(leaves.size(), 1)));
   if (!leaves.empty()) CK(cudaMemcpyAsync(s->leaf_box, boxes.data(), sizeof(int4) * boxes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int4> sp_boxes(s->sp.h_leaves.size());
+  if (s->sp.n > 0) {
+    for (size_t i = 0; i < sp_boxes.size(); i++) { const ObjRec& o = recs[s->sp.h_leaves[i]]; sp_boxes[i] = make_int4(o.bx0, o.by0, o.bx1, o.by1); }
+    CK(DMALLOC(&s->sp.leaves, sizeof(int) * s->sp.n));
+    CK(DMALLOC(&s->sp.leaf_box, sizeof(int4) * s->sp.n));
+    CK(cudaMemcpyAsync(s->sp.leaves, s->sp.h_leaves.data(), sizeof(int) * s->sp.n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s->sp.leaf_box, sp_boxes.data(), sizeof(int4) * s->sp.n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
   CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
   if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
@@ -343,9 +407,37 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   }
   // Convolved objects (render.ml:1023-1052): AA-rasterise the whole (twice bloated) box of the child,
   // X pass, Y pass; keep the shape / minshape bit-rows and the convolved canvas resident.
-  if (!conv_list.empty()) {
+  if (conv_words > 0) {
     CK(DMALLOC(&s->conv_bits, sizeof(uint32_t) * conv_words));
     CK(DMALLOC(&s->conv_px, sizeof(uint32_t) * conv_pixels));
+  }
+  // sprite leaves: shape plane = union of the members' shapes (render.ml:476-496), minshape plane null, pshape empty
+  for (SpriteEntry& e : s->sprites) {
+    const ObjRec& o = recs[e.leaf_rec];
+    const int nw = o.cv_nw, h = o.cv_h;
+    uint32_t* S = s->conv_bits + o.cv_bits;
+    uint32_t *Cs = nullptr;
+    CK(DMALLOC(&Cs, 4 * e.plane_words));
+    CK(cudaMemsetAsync(S, 0, 4 * 2 * e.plane_words, ctx->stream));
+    CK(DMALLOC(&e.valid, 4 * e.plane_words));
+    CK(cudaMemsetAsync(e.valid, 0, 4 * e.plane_words, ctx->stream));
+    for (int li = e.l0; li < e.l1; li++) {
+      const ObjRec& m = recs[leaves[li]];
+      const int r0 = m.by0 - o.cv_y0, rows = m.by1 - m.by0 + 1;   // the member's rows of the planes
+      if (m.kind == K_PATH) {
+        k_scan_rows<<<dim3(cdiv(rows, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(s->edges + m.first, m.count, m.winding, m.by0, rows, o.cv_x0, nw,
+                                                                                                 S + (size_t)r0 * nw, Cs + (size_t)r0 * nw, ctx->d_error); LAUNCHED();
+      } else {
+        k_fill_box_bits<<<dim3(cdiv(nw, 128), rows), 128, 0, ctx->stream>>>(Cs + (size_t)r0 * nw, rows, nw, o.cv_x0, m.by0, m.prim[0], m.prim[1], m.prim[2], m.prim[3]); LAUNCHED();
+        k_bitop<<<(unsigned)(((size_t)rows * nw + 255) / 256), 256, 0, ctx->stream>>>(S + (size_t)r0 * nw, Cs + (size_t)r0 * nw, S + (size_t)r0 * nw, (size_t)rows * nw, 0); LAUNCHED();
+      }
+    }
+    DFREE(Cs);
+    CK(DMALLOC(&e.d_missing, sizeof(int)));
+    CK(cudaMallocHost(&e.h_missing, sizeof(int)));
+    CK(cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming));
+  }
+  if (!conv_list.empty()) {
     for (const ConvItem& ci : conv_list) {
       const ObjRec& o = recs[ci.rec];
       const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;

@@ -18,45 +18,31 @@ int coh_shape_free(coh_ctx* ctx, coh_shape_t h) {
 static int shape_from_bits(coh_ctx* ctx, const uint32_t* bits, int y0, int n_rows, int wx0, int nw, coh_shape_t* out) {
   *out = 0;
   if (n_rows <= 0 || nw <= 0) return 0;
-  int* counts = nullptr; int* ptr = nullptr; unsigned long long* d_card = nullptr;
+  int* counts = nullptr; int* ptr = nullptr; ShapeMeta* d_meta = nullptr;
   CK(DMALLOC(&counts, sizeof(int) * n_rows));
   CK(DMALLOC(&ptr, sizeof(int) * (n_rows + 1)));
-  CK(DMALLOC(&d_card, sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_card, 0, sizeof(unsigned long long), ctx->stream));
-  k_count_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, counts, d_card); LAUNCHED();
+  CK(DMALLOC(&d_meta, sizeof(ShapeMeta)));
+  const ShapeMeta init{0ull, 0, 0x7FFFFFFF, -1, 0x7FFFFFFF, -1, 0};
+  CK(cudaMemcpyAsync(d_meta, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  k_count_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, counts, d_meta); LAUNCHED();
   if (exclusive_scan(ctx, counts, ptr, n_rows, nullptr)) return 1;
-  std::vector<int> h_ptr(n_rows + 1);
-  unsigned long long card = 0;
-  CK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int) * (n_rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(&card, d_card, sizeof card, cudaMemcpyDeviceToHost, ctx->stream));
+  // one small read-back: the host keeps cardinality, span count and tight bounds of every span set (they size the
+  // bit-frames of later operations and answer coh_shape_bounds / coh_shape_card); the spans stay on the device
+  ShapeMeta m;
+  CK(cudaMemcpyAsync(&m, d_meta, sizeof m, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  DFREE(counts); DFREE(d_card);
-  int total = h_ptr[n_rows];
-  if (total == 0) { DFREE(ptr); return 0; }
-  // trim empty rows at both ends so that y0 / n_rows are tight
-  int first = 0, last = n_rows - 1;
-  while (h_ptr[first + 1] == h_ptr[first]) first++;
-  while (h_ptr[last + 1] == h_ptr[last]) last--;
+  DFREE(counts); DFREE(d_meta);
+  if (m.n_spans == 0) { DFREE(ptr); return 0; }
+  const int first = m.first_row, last = m.last_row;   // empty rows at both ends are trimmed: y0 / n_rows are tight
   DevShape* s = new DevShape();
-  s->n_spans = total; s->card = (long long)card;
-  CK(DMALLOC(&s->spans, sizeof(int2) * total));
+  s->n_spans = m.n_spans; s->card = (long long)m.card;
+  CK(DMALLOC(&s->spans, sizeof(int2) * m.n_spans));
   k_fill_runs<<<cdiv(n_rows, 128), 128, 0, ctx->stream>>>(bits, n_rows, nw, wx0, ptr, s->spans); LAUNCHED();
   s->y0 = y0 + first; s->n_rows = last - first + 1;
   CK(DMALLOC(&s->row_ptr, sizeof(int) * (s->n_rows + 1)));
   CK(cudaMemcpyAsync(s->row_ptr, ptr + first, sizeof(int) * (s->n_rows + 1), cudaMemcpyDeviceToDevice, ctx->stream));
-  // bounds: x extremes need the spans; take them from a host copy (export path, not hot)
-  std::vector<int2> h_spans(total);
-  CK(cudaMemcpyAsync(h_spans.data(), s->spans, sizeof(int2) * total, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
   DFREE(ptr);
-  s->by0 = s->y0; s->by1 = s->y0 + s->n_rows - 1; s->bx0 = INT32_MAX; s->bx1 = INT32_MIN;
-  for (int r = first; r <= last; r++) {
-    if (h_ptr[r + 1] > h_ptr[r]) {
-      s->bx0 = std::min(s->bx0, h_spans[h_ptr[r]].x);
-      const int2& l = h_spans[h_ptr[r + 1] - 1];
-      s->bx1 = std::max(s->bx1, l.x + l.y - 1);
-    }
-  }
+  s->by0 = s->y0; s->by1 = s->y0 + s->n_rows - 1; s->bx0 = wx0 + m.bit_lo; s->bx1 = wx0 + m.bit_hi;
   *out = (coh_shape_t)s;
   return 0;
 }
@@ -79,9 +65,15 @@ int coh_shape_box(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h, coh_
   if (w == 0 && h == 0) return 0;                       // sprite.ml:463
   if (w < 0 || h < 0) FAIL("Sprite.box: negative argument.");  // sprite.ml:464
   if (w == 0 || h == 0) return 0;
-  std::vector<int> flat;
-  for (int r = 0; r < h; r++) { flat.push_back(y + r); flat.push_back(1); flat.push_back(x); flat.push_back(w); }
-  return coh_shape_import(ctx, flat.data(), (int64_t)flat.size(), out);
+  // Sprite.box: h rows of one span (x, w), written by a kernel — nothing is built on the host
+  DevShape* s = new DevShape();
+  s->y0 = y; s->n_rows = h; s->n_spans = h; s->card = (long long)w * h;
+  s->bx0 = x; s->bx1 = x + w - 1; s->by0 = y; s->by1 = y + h - 1;
+  CK(DMALLOC(&s->row_ptr, sizeof(int) * (h + 1)));
+  CK(DMALLOC(&s->spans, sizeof(int2) * h));
+  k_box_spans<<<cdiv(h + 1, 256), 256, 0, ctx->stream>>>(s->row_ptr, s->spans, h, x, w); LAUNCHED();
+  *out = (coh_shape_t)s;
+  return 0;
 }
 int coh_shape_import(coh_ctx* ctx, const int32_t* flat, int64_t n, coh_shape_t* out) {
   CK(cudaSetDevice(ctx->device));

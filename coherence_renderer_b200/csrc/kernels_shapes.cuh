@@ -62,21 +62,37 @@ __global__ void k_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__
   }
   out[(size_t)r * nw + w] = acc;
 }
-// Run extraction: count the maximal runs of every row (thread per row), then fill.
+// Sprite.box x y w h (sprite.ml:462-465) as a device span set: every row one span
+__global__ void k_box_spans(int* __restrict__ row_ptr, int2* __restrict__ spans, int h, int x, int w) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > h) return;
+  row_ptr[r] = r;
+  if (r < h) spans[r] = make_int2(x, w);
+}
+// What the host needs to know of a span set, reduced on the device (one small read-back instead of the spans):
+struct ShapeMeta { unsigned long long card; int n_spans, first_row, last_row, bit_lo, bit_hi, pad; };
+// Run extraction: count the maximal runs of every row (thread per row), then fill.  `meta` (optional) receives the
+// cardinality, the number of runs, the first / last non-empty row and the lowest / highest set bit of any row.
 __global__ void k_count_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int* __restrict__ counts,
-                             unsigned long long* __restrict__ card) {
+                             ShapeMeta* __restrict__ meta) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const uint32_t* row = bits + (size_t)r * nw;
   int n = 0; uint32_t carry = 0u; unsigned long long px = 0;
+  int lo = 0x7FFFFFFF, hi = -1;
   for (int w = 0; w < nw; w++) {
     uint32_t v = row[w];
     n += __popc(v & ~((v << 1) | carry));
     px += __popc(v);
     carry = v >> 31;
+    if (v) { if (hi < 0) lo = 32 * w + __ffs((int)v) - 1; hi = 32 * w + 31 - __clz((int)v); }
   }
   counts[r] = n;
-  if (card && px) atomicAdd(card, px);
+  if (meta && px) {
+    atomicAdd(&meta->card, px); atomicAdd(&meta->n_spans, n);
+    atomicMin(&meta->first_row, r); atomicMax(&meta->last_row, r);
+    atomicMin(&meta->bit_lo, lo); atomicMax(&meta->bit_hi, hi);
+  }
 }
 __global__ void k_fill_runs(const uint32_t* __restrict__ bits, int n_rows, int nw, int wx0,
                             const int* __restrict__ row_ptr, int2* __restrict__ spans) {
@@ -115,15 +131,67 @@ __global__ void k_translate_spans(const int2* __restrict__ in, int2* __restrict_
 }
 // Per-object alias offsets changed in place (Render.translate_renderobject -> Cache.addtranslation):
 // shift the device-space boxes the binning reads.  delta = new offset - old offset.
+// (update_objs = 0: a second leaf list over the same records only refreshes its boxes)
 __global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf_box, const int* __restrict__ leaves,
-                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy) {
+                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy, int update_objs) {
   int li = blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= n_leaves) return;
   int oi = leaves[li];
   if (oi < first_obj || oi > last_obj) return;
   ObjRec& o = objs[oi];
-  o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy;
+  if (update_objs) { o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy; }
   leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
+}
+// ------------------------------------------------------------------------------------
+// Partial-sprite cache (render.ml:1169-1242, cache.ml:328-367, 390-407).  The sprite of a cached object lives in an
+// RGBA8 canvas in the object's own frame, next to two bit planes over the same box: S = its shape, V = pshape, the
+// pixels whose value is in the canvas.  A frame renders only shptorender = r' - pshape (here: update ∩ S - V, a
+// superset) and merges it into the canvas; everything else is served from it.  Planes are [cv_h][cv_nw] words, bit 0
+// of word 0 = pixel cv_x0 of the object's frame; (dx, dy) is the object's alias offset (cache.ml:400-405).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t plane_bits32(const uint32_t* __restrict__ plane, int nw, int h, int row, int bitoff) {
+  if (row < 0 || row >= h) return 0u;
+  const uint32_t* r = plane + (size_t)row * nw;
+  const int qw = bitoff >> 5, qb = bitoff & 31;
+  const uint32_t lo = (qw >= 0 && qw < nw) ? r[qw] : 0u;
+  const uint32_t hi = (qw + 1 >= 0 && qw + 1 < nw) ? r[qw + 1] : 0u;
+  return qb ? ((lo >> qb) | (hi << (32 - qb))) : lo;
+}
+// T = update ∩ S - V as a bit-frame (frame coordinates), rows [y0, y0 + n_rows); `missing` counts its pixels
+__global__ void k_sprite_todo(const uint32_t* __restrict__ U /* update bit-frame or null */, int ux0, int uy0, int ux1, int uy1,
+                              const uint32_t* __restrict__ S, const uint32_t* __restrict__ V, int cv_x0, int cv_y0, int cv_nw, int cv_h,
+                              int dx, int dy, int W, int nw, int y0, int n_rows, uint32_t* __restrict__ T, int* __restrict__ missing) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  const int y = y0 + r, x0 = 32 * w;
+  uint32_t u = U ? U[(size_t)y * nw + w] : ((y >= uy0 && y <= uy1) ? interval_mask32(x0, ux0, ux1) : 0u);
+  if (x0 + 31 >= W) u &= interval_mask32(x0, 0, W - 1);
+  uint32_t t = 0u;
+  if (u) {
+    const int row = y - dy - cv_y0, bit = x0 - dx - cv_x0;
+    t = u & plane_bits32(S, cv_nw, cv_h, row, bit) & ~plane_bits32(V, cv_nw, cv_h, row, bit);
+  }
+  T[(size_t)y * nw + w] = t;
+  if (t && missing) atomicAdd(missing, __popc(t));
+}
+// merge the freshly rendered pixels (frame-sized canvas `tmp`, pixels of T) into the sprite's canvas and pshape
+__global__ void k_sprite_store(const uint32_t* __restrict__ tmp, const uint32_t* __restrict__ T, uint32_t* __restrict__ canvas,
+                               uint32_t* __restrict__ V, int cv_x0, int cv_y0, int cv_nw, int cv_h, int dx, int dy, int W, int nw, int y0, int n_rows) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (x >= W || r >= n_rows) return;
+  const int y = y0 + r;
+  if (!((T[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u)) return;
+  const int cx = x - dx - cv_x0, cy = y - dy - cv_y0;
+  if (cx < 0 || cy < 0 || cx >= cv_nw * 32 || cy >= cv_h) return;
+  canvas[(size_t)cy * (cv_nw * 32) + cx] = tmp[(size_t)y * W + x];
+  atomicOr(&V[(size_t)cy * cv_nw + (cx >> 5)], 1u << (cx & 31));
+}
+// pixels of the shape that are not in pshape yet
+__global__ void k_sprite_missing(const uint32_t* __restrict__ S, const uint32_t* __restrict__ V, size_t n, int* __restrict__ missing) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t m = S[i] & ~V[i];
+  if (m) atomicAdd(missing, __popc(m));
 }
 // ------------------------------------------------------------------------------------
 // Filters (render.ml:1080-1131, 1248-1265; filters.ml).  Frame-sized RGBA8 canvases and bit-frames

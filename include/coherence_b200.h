@@ -163,6 +163,11 @@ int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_
 int coh_cache_configure(coh_ctx* ctx, int32_t usecache, int64_t max_bytes); /* Cache.usecache / setsize (default 50 MiB, cache.ml:73) */
 int coh_cache_clear(coh_ctx* ctx);                                           /* Cache.clear */
 int coh_cache_stats(coh_ctx* ctx, int64_t out[4]);                           /* shape hits, misses, bytes, entries (cache.ml:24-38) */
+/* Partial sprites (Cache.addsprite / getsprite, cache.ml:328-367, 390-407; render.ml:1169-1242) are kept per scene: a
+ * top-level Group with an id >= 0 (plain-filled paths and primitives inside) owns an RGBA8 canvas and a pshape plane in
+ * HBM; a frame renders only what of it is not cached yet, and a drag reads the cached sprite translated.
+ * out = frames served from the sprites alone, frames that rendered into them, bytes resident, cached objects. */
+int coh_cache_sprite_stats(coh_ctx* ctx, coh_scene_t scene, int64_t out[4]);
 int coh_cache_addshape(coh_ctx* ctx, int64_t id, coh_shape_t shape, coh_shape_t minshape); /* Cache.addshape: copies kept, cache.ml:280 */
 int coh_cache_getshape(coh_ctx* ctx, int64_t id, coh_shape_t* shape, coh_shape_t* minshape, int32_t* found); /* Cache.getshape, cache.ml:370 */
 int coh_cache_addtranslation(coh_ctx* ctx, int64_t id, int64_t target, int32_t dx, int32_t dy); /* cache.ml:423 */

@@ -54,6 +54,7 @@ external convolve_sprite_raw : ctx -> int * int -> shape_h -> i32 -> i32 -> shap
 external cache_configure : ctx -> bool -> int64 -> unit = "coh_ml_cache_configure"
 external cache_clear : ctx -> unit = "coh_ml_cache_clear"
 external cache_stats : ctx -> int * int * int * int = "coh_ml_cache_stats"
+external cache_sprite_stats : ctx -> scene_h -> int * int * int * int = "coh_ml_cache_sprite_stats"
 external cache_addshape : ctx -> int64 -> shape_h -> shape_h -> unit = "coh_ml_cache_addshape"
 external cache_getshape : ctx -> int64 -> (shape_h * shape_h) option = "coh_ml_cache_getshape"
 external cache_addtranslation : ctx -> int64 -> int64 -> int -> int -> unit = "coh_ml_cache_addtranslation"

@@ -196,6 +196,14 @@ CAMLprim value coh_ml_cache_stats(value ctx) {   /* (hits, misses, bytes, entrie
   for (int k = 0; k < 4; k++) Store_field(r, k, Val_long((long)st[k]));
   CAMLreturn(r);
 }
+CAMLprim value coh_ml_cache_sprite_stats(value ctx, value scene) {   /* (frames from sprites, frames that filled, bytes, objects) */
+  CAMLparam2(ctx, scene);
+  int64_t st[4] = {0, 0, 0, 0};
+  int32_t v[4];
+  check(CTX(ctx), coh_cache_sprite_stats(CTX(ctx), SCENE(scene), st));
+  for (int k = 0; k < 4; k++) v[k] = (int32_t)st[k];
+  CAMLreturn(tuple_of_ints(v, 4));
+}
 CAMLprim value coh_ml_cache_addshape(value ctx, value id, value s, value m) {
   check(CTX(ctx), coh_cache_addshape(CTX(ctx), Int64_val(id), SHAPE(s), SHAPE(m)));
   return Val_unit;

@@ -202,3 +202,35 @@ def brush_stamp(radius, opacity):
     _chk(lib().orc_brush_stamp(C.c_double(radius), C.c_double(opacity), _ptr(out, C.c_uint8), len(out), C.byref(size)))
     s = size.value
     return out[: s * s].reshape(s, s)
+
+
+class Renderer:
+    """A persistent oracle renderer: Cache (shapes, partial sprites, aliases) survives between frames, as the
+    reference's does between calls of Render.render_frame (cache.ml).  usecache = Cache.usecache."""
+
+    def __init__(self, usecache=True):
+        self._h = C.c_void_p(lib().orc_renderer_new(1 if usecache else 0))
+
+    def close(self):
+        if self._h:
+            lib().orc_renderer_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def addtranslation(self, oid, target, dx, dy):
+        _chk(lib().orc_renderer_addtranslation(self._h, C.c_int64(oid), C.c_int64(target), dx, dy))
+
+    def frame(self, objs, n_scene, n_background, edges, points, update_flat, out_box):
+        """Render.render_frame over the update shape (flat records); returns the dense RGBA8 image of out_box."""
+        ox, oy, ow, oh = out_box
+        e = _i32(edges).reshape(-1, 4)
+        p = _i32(points).reshape(-1, 2)
+        u = _i32(update_flat)
+        out = np.zeros((oh, ow), dtype=np.uint32)
+        _chk(lib().orc_renderer_frame(self._h, objs, n_scene, n_background, _ptr(e), _ptr(p), _ptr(u), C.c_int64(len(u)), ox, oy, ow, oh, _ptr(out, C.c_uint32)))
+        return out

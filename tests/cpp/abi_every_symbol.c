@@ -141,6 +141,9 @@ int main(int argc, char** argv) {
   OK(coh_scene_drag_object(C, sc, 0, 3, 2, 0, bb)); CHECK(bb[2] >= bb[0] && bb[3] >= bb[1]);
   coh_shape_t df = 0;
   OK(coh_dirty_filter(C, sc, -1, dirty, &df));
+  int64_t sst[4];
+  OK(coh_cache_sprite_stats(C, sc, sst)); CHECK(sst[3] == 0);   /* the group has a single member: nothing worth a sprite */
+  ERR(coh_cache_sprite_stats(C, 0, sst), "null scene");
   double walk = 0, bin = 0; int64_t frames = 0;
   OK(coh_get_timing(C, &walk, &bin, &frames)); CHECK(frames >= 1); OK(coh_set_timing(C, 0));
   /* caller-owned framebuffer, peers (a second pointer into the same buffer stands in for a peer GPU) */

@@ -1060,3 +1060,75 @@ def test_cache_entry_points(ctx, oracle):
     ctx.cache_configure(True, 50 << 20)
     ctx.cache_clear()
     assert ctx.cache_stats()["entries"] == 0
+
+
+def test_partial_sprite_cache(ctx, oracle):
+    """The partial-sprite cache (render.ml:1169-1242; cache.ml:328-367, 390-407): a top-level Group with an id keeps a
+    sprite that GROWS as more of it is exposed — three different update shapes, each rendering only what is not cached
+    yet — and then follows the group through a drag as an alias (the cached sprite is read translated).  Against the
+    oracle with Cache.usecache = true and a persistent cache; and the same frames with the cache off."""
+    W, H = 400, 300
+
+    def tri(b, x, y, c, a):
+        return b.polygon([(x, y), (x + 130.5, y + 24.2), (x + 50.1, y + 140.7)], S.Fill.plain(S.dissolve(c, a)))
+
+    b = S.SceneBuilder()
+    b.polygon([(150.2, 20.1), (260.5, 60.9), (170.0, 130.3)], S.Fill.plain(S.dissolve(S.rgba8(250, 220, 30), 150)), oid=5)   # in front of the group
+    g = b.group_begin(oid=8)
+    tri(b, 40.3, 35.1, S.rgba8(220, 40, 40), 255)
+    tri(b, 90.9, 60.4, S.rgba8(40, 220, 40), 170)
+    b.rectangle(S.rgba8(30, 30, 160), 120.0, 100.0, 200.0, 170.0)
+    tri(b, 60.2, 82.8, S.rgba8(40, 40, 220), 90)
+    b.group_end()
+    for i in range(6):   # behind it
+        x, y = 20.0 + 55 * i, 30.0 + 31 * i
+        b.polygon([(x, y), (x + 90.5, y + 10.2), (x + 70.1, y + 95.5), (x - 5.0, y + 60.0)], S.Fill.plain(S.dissolve(S.rgba8(20 * i % 255, 200, 255 - 9 * i), 255 if i % 2 else 170)), oid=100 + i)
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, edges, points = b.arrays()
+    group_index = 1
+    updates = [util.flat_of_rows([(y, [(30, 90)]) for y in range(40, 120)]),
+               util.flat_of_rows([(y, [(60, 50), (150, 120)]) for y in range(90, 200)]),
+               util.flat_of_rows([(y, [(0, W)]) for y in range(H)])]
+    for usecache in (True, False):
+        ctx.cache_clear()
+        ctx.cache_configure(usecache, 64 << 20)
+        ctx.fb_configure(W, H)
+        objs[group_index].dx = objs[group_index].dy = 0
+        sc = ctx.scene_create(objs, nbg, edges, points)
+        with oracle.Renderer(usecache=usecache) as ref_r:
+            try:
+                ref_fb = np.zeros((H, W), dtype=np.uint32)
+                for k, flat in enumerate(updates):   # the cached sprite grows: 1st partial, 2nd overlapping the 1st, 3rd everything
+                    hu = ctx.shape_import(flat)
+                    ctx.render_frame_shape(sc, hu)
+                    got = ctx.fb_read_sprite(hu)
+                    ctx.shape_free(hu)
+                    img = ref_r.frame(objs, n - nbg, nbg, edges, points, flat, (0, 0, W, H))
+                    want = np.concatenate([img[yy, xx : xx + l] for yy, spans in util.rows_of_flat(flat) for xx, l in spans])
+                    assert np.array_equal(got, want), f"update {k} (usecache={usecache})"
+                    for yy, spans in util.rows_of_flat(flat):
+                        for xx, l in spans:
+                            ref_fb[yy, xx : xx + l] = img[yy, xx : xx + l]
+                st = ctx.cache_sprite_stats(sc)
+                if usecache:
+                    assert st["entries"] == 1 and st["bytes"] > 0 and st["sprite_fills"] >= 1
+                else:
+                    assert st["sprite_fills"] == 0 and st["sprite_hits"] == 0
+                tx = ty = 0
+                for step, (dx, dy) in enumerate([(5, 3), (-9, 7), (20, -6), (3, 3), (-30, 15)]):   # the group follows the pointer as an alias
+                    ctx.scene_drag_object(sc, group_index, dx, dy)
+                    tx, ty = tx + dx, ty + dy
+                    objs[group_index].dx, objs[group_index].dy = tx, ty
+                    full = util.flat_of_rows([(y, [(0, W)]) for y in range(H)])
+                    ref = ref_r.frame(objs, n - nbg, nbg, edges, points, full, (0, 0, W, H))
+                    got = ctx.fb_read_rgba(0, 0, W, H)
+                    assert _max_lsb(got, ref) == 0, f"drag step {step} (usecache={usecache})"
+                if usecache:
+                    st2 = ctx.cache_sprite_stats(sc)
+                    assert st2["sprite_hits"] >= 1, "once the sprite is complete, drag frames are served from it"
+            finally:
+                ctx.scene_free(sc)
+    objs[group_index].dx = objs[group_index].dy = 0
+    ctx.cache_configure(True, 50 << 20)
+    ctx.cache_clear()
