@@ -127,6 +127,7 @@ struct coh_ctx {
   bool have_u = false;
   // binning scratch (passes whose binning is not kept with the scene)
   BinSet bins;
+  int opt_pre_min_pairs = 4096;  // passes with fewer (list entry, row) pairs stay on the fused walker: four dependent launches cost more than they gain
   bool opt_bin_cache = true;  // keep whole-frame binning with the scene
   bool opt_comp_rows = true;  // flat scenes: row compositor instead of the walker in three-phase frames
   // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
@@ -265,6 +266,7 @@ int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
   else if (n == "fused") { if (value < -1 || value > 1) FAIL("coh_set_option: fused is -1, 0 or 1"); ctx->opt_fused = value; }
   else if (n == "aa_general") ctx->aa_general = value != 0;
   else if (n == "bin_cache") ctx->opt_bin_cache = value != 0;
+  else if (n == "pre_min_pairs") ctx->opt_pre_min_pairs = value;
   else if (n == "comp_rows") ctx->opt_comp_rows = value != 0;
   else FAIL("coh_set_option: unknown option '" + n + "'");
   return 0;

@@ -98,6 +98,8 @@ def test_c4_full_size_drag(ctx, oracle):
                     objs[m].dx, objs[m].dy = tx, ty
                 ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
                 assert _max_lsb(got, ref) == 0, f"frame {f} of the drag differs from the oracle's full render"
+        st = ctx.cache_sprite_stats(sc)
+        assert st["entries"] == 1 and st["bytes"] > 0 and st["sprite_hits"] > 900, "the drag must run from the lion's cached sprite"
     finally:
         ctx.scene_free(sc)
         ctx.cache_clear()

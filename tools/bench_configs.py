@@ -87,6 +87,7 @@ def c4(ctx, frames):
         ctx.scene_drag_object(sc, mover, round(3 * math.cos(2 * math.pi * f / 250)), round(2 * math.sin(2 * math.pi * f / 250)))
 
     fused_ms = timed_frames(ctx, step_fused, frames, warm=5)
+    sprite = ctx.cache_sprite_stats(sc)
     # the incrementally maintained framebuffer equals a fresh full render of the final scene
     inc = ctx.fb_read_rgba(0, 0, W, H)
     ctx.render_frame(sc, (0, 0, W, H))
@@ -96,7 +97,7 @@ def c4(ctx, frames):
     ctx.shape_free(master)
     ctx.scene_free(sc)
     return {"config": "C4", "workload": f"{frames}-frame drag of the lion group (alias path) over 400 static polygons, {W}x{H}, dirty region = alldirty from cached span sets",
-            "ms_per_frame": fused_ms, "ms_per_frame_stepwise_api": ms, "first_frame_ms": first_ms, "full_frame_ms": full_ms, "mean_dirty_pixels": float(np.mean(dirty_px)), "cache": st,
+            "ms_per_frame": fused_ms, "ms_per_frame_stepwise_api": ms, "first_frame_ms": first_ms, "full_frame_ms": full_ms, "mean_dirty_pixels": float(np.mean(dirty_px)), "cache": st, "sprite_cache": sprite,
             "incremental_equals_full_render": same}
 
 
