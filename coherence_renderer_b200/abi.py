@@ -52,6 +52,7 @@ SYMBOLS = [
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
     "coh_multi_scene_create", "coh_multi_scene_free", "coh_multi_scene_translate_object", "coh_multi_render_frame", "coh_multi_sync",
     "coh_multi_fb_read_rgba", "coh_multi_fb_read_rgb888", "coh_fb_alloc_shared", "coh_fb_open_peer",
+    "coh_shape_intersects", "coh_sprite_portion", "coh_sprite_fillshape", "coh_sprite_map", "coh_sprite_map_coords_fill",
 ]
 
 _lib = None
@@ -243,6 +244,40 @@ class Context:
         out = np.zeros(max(cap, 1), dtype=np.uint32)
         n = C.c_int64()
         self._chk(lib().coh_polygon_sprite(self._h, C.byref(fill_obj), _i32p(e), len(e), winding, C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    # -- sprites: (shape handle, RGBA8 per pixel in span order)
+    def shape_intersects(self, a, b):
+        y = C.c_int32()
+        self._chk(lib().coh_shape_intersects(self._h, C.c_uint64(a), C.c_uint64(b), C.byref(y)))
+        return bool(y.value)
+
+    def _sprite_out(self, shape):
+        cap = self.shape_card(shape) if shape else 0
+        return cap, np.zeros(max(cap, 1), dtype=np.uint32), C.c_int64()
+
+    def sprite_portion(self, shape, rgba, sub):
+        src = np.ascontiguousarray(rgba, dtype=np.uint32)
+        cap, out, n = self._sprite_out(sub)
+        self._chk(lib().coh_sprite_portion(self._h, C.c_uint64(shape), src.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(sub), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    def sprite_fillshape(self, shape, fill_obj):
+        cap, out, n = self._sprite_out(shape)
+        self._chk(lib().coh_sprite_fillshape(self._h, C.c_uint64(shape), C.byref(fill_obj), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    def sprite_map(self, op, rgba, arg=0):
+        src = np.ascontiguousarray(rgba, dtype=np.uint32)
+        out = np.zeros(max(len(src), 1), dtype=np.uint32)
+        code = {"monochrome": 0, "dissolve": 1, "red_channel": 2, "green_channel": 3, "blue_channel": 4}[op]
+        self._chk(lib().coh_sprite_map(self._h, code, arg, src.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(len(src)), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out[: len(src)]
+
+    def sprite_map_coords_fill(self, shape, fill_obj, rgba):
+        src = np.ascontiguousarray(rgba, dtype=np.uint32)
+        cap, out, n = self._sprite_out(shape)
+        self._chk(lib().coh_sprite_map_coords_fill(self._h, C.c_uint64(shape), C.byref(fill_obj), src.ctypes.data_as(C.POINTER(C.c_uint32)), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
         return out[: n.value]
 
     def convolve_sprite(self, kernel, r, shape, rgba):

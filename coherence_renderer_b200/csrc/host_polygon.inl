@@ -159,6 +159,101 @@ int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edge
 }
 
 // ---------------------------------------------------------------------------------------
+// Sprite operations on whole sprites (sprite.mli:96-125).  A sprite crosses the boundary as its shape (a device span
+// set) and one RGBA8 word per pixel in canonical span order.  Sprite.translate_sprite moves only the shape
+// (coh_shape_translate): the pixel array is unchanged.
+// ---------------------------------------------------------------------------------------
+static FillRec fillrec_of(const coh_object* fill) {
+  FillRec f; f.kind = fill->fill_kind; f.c0 = fill->colour0; f.c1 = fill->colour1; f.flags = fill->fill_flags;
+  for (int i = 0; i < 6; i++) f.p[i] = fill->fparam[i];
+  return f;
+}
+int coh_shape_intersects(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, int32_t* yes) {   // sprite.ml:1661-1662
+  coh_shape_t t = 0;
+  *yes = 0;
+  if (coh_shape_intersection(ctx, a, b, &t)) return 1;
+  *yes = t != 0;
+  return coh_shape_free(ctx, t);
+}
+// Sprite.portion spr shp (sprite.ml:642-721): the pixels of the sprite on `sub`, which must lie inside its shape
+int coh_sprite_portion(coh_ctx* ctx, coh_shape_t shape, const uint32_t* rgba, coh_shape_t sub, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  DevShape* a = (DevShape*)shape; DevShape* b = (DevShape*)sub;
+  if (!b) return 0;
+  if (!a) FAIL("portion: malformed input (sprite null, shape not)");
+  if (b->card > cap) FAIL("coh_sprite_portion: buffer too small");
+  coh_shape_t outside = 0;
+  if (coh_shape_difference(ctx, sub, shape, &outside)) return 1;
+  if (outside) { coh_shape_free(ctx, outside); FAIL("portion_spanline: bad input"); }   // shp is not a subset of the sprite's shape
+  const int wx0 = floordiv(a->bx0, 32) * 32, w = a->bx1 - wx0 + 1, h = a->n_rows;
+  uint32_t *canvas = nullptr, *d_in = nullptr, *d_out = nullptr; int *offa = nullptr, *offb = nullptr;
+  if (shape_pixel_offsets(ctx, a, &offa) || shape_pixel_offsets(ctx, b, &offb)) return 1;
+  CK(DMALLOC(&canvas, 4 * (size_t)w * h)); CK(DMALLOC(&d_in, 4 * (size_t)a->card)); CK(DMALLOC(&d_out, 4 * (size_t)b->card));
+  CK(cudaMemcpyAsync(d_in, rgba, 4 * (size_t)a->card, cudaMemcpyHostToDevice, ctx->stream));
+  k_scatter_spans<uint32_t><<<cdiv(a->n_rows, 128), 128, 0, ctx->stream>>>(a->row_ptr, a->spans, offa, a->n_rows, 0, wx0, w, d_in, canvas); LAUNCHED();
+  k_gather_spans<uint32_t><<<cdiv(b->n_rows, 128), 128, 0, ctx->stream>>>(b->row_ptr, b->spans, offb, b->n_rows, wx0, w, canvas + (size_t)(b->y0 - a->y0) * w, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)b->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(canvas); DFREE(d_in); DFREE(d_out); DFREE(offa); DFREE(offb);
+  *n_out = b->card;
+  return 0;
+}
+// Sprite.fillshape shp fill (sprite.ml:158-175)
+int coh_sprite_fillshape(coh_ctx* ctx, coh_shape_t shape, const coh_object* fill, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  DevShape* s = (DevShape*)shape;
+  if (!s) return 0;
+  if (s->card > cap) FAIL("coh_sprite_fillshape: buffer too small");
+  if (fill->fill_kind < COH_FILL_PLAIN || fill->fill_kind > COH_FILL_RADIAL) FAIL("coh_sprite_fillshape: bad fill kind");
+  int* off = nullptr; uint32_t* d_out = nullptr;
+  if (shape_pixel_offsets(ctx, s, &off)) return 1;
+  CK(DMALLOC(&d_out, 4 * (size_t)s->card));
+  k_sprite_fillshape<<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, off, s->y0, s->n_rows, fillrec_of(fill), d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(off); DFREE(d_out);
+  *n_out = s->card;
+  return 0;
+}
+// Sprite.sprite_map f spr with f = Colour.monochrome | dissolve ~delta:arg | red / green / blue_channel
+int coh_sprite_map(coh_ctx* ctx, int32_t op, int32_t arg, const uint32_t* rgba_in, int64_t n, uint32_t* rgba_out) {
+  CK(cudaSetDevice(ctx->device));
+  if (op < COH_MAP_MONOCHROME || op > COH_MAP_BLUE_CHANNEL) FAIL("coh_sprite_map: unknown colour function");
+  if (op == COH_MAP_DISSOLVE && (arg < 0 || arg > 255)) FAIL("Colour.dissolve: delta out of range");   // colour.ml:292 assert
+  if (n <= 0) return 0;
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  CK(DMALLOC(&d_in, 4 * (size_t)n)); CK(DMALLOC(&d_out, 4 * (size_t)n));
+  CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  k_sprite_map<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, arg, d_in, d_out, (size_t)n); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(d_in); DFREE(d_out);
+  return 0;
+}
+// Sprite.map_coords (fun x y c -> Colour.dissolve (fill x y) ~delta:(alpha c)) spr: a fill applied to an alpha matte,
+// the closing step of Render.sprite_of_cpg (render.ml:976-981)
+int coh_sprite_map_coords_fill(coh_ctx* ctx, coh_shape_t shape, const coh_object* fill, const uint32_t* rgba_in, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  DevShape* s = (DevShape*)shape;
+  if (!s) return 0;
+  if (s->card > cap) FAIL("coh_sprite_map_coords_fill: buffer too small");
+  if (fill->fill_kind < COH_FILL_PLAIN || fill->fill_kind > COH_FILL_RADIAL) FAIL("coh_sprite_map_coords_fill: bad fill kind");
+  int* off = nullptr; uint32_t *d_in = nullptr, *d_out = nullptr;
+  if (shape_pixel_offsets(ctx, s, &off)) return 1;
+  CK(DMALLOC(&d_in, 4 * (size_t)s->card)); CK(DMALLOC(&d_out, 4 * (size_t)s->card));
+  CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
+  k_sprite_fill_alpha<<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, off, s->y0, s->n_rows, fillrec_of(fill), d_in, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(off); DFREE(d_in); DFREE(d_out);
+  *n_out = s->card;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Convolve (convolve.mli:28-40)
 // ---------------------------------------------------------------------------------------
 static int conv_taps(coh_ctx* ctx, int kind, int r, int** d_taps, int* total) {

@@ -51,6 +51,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<ObjRec> recs;
   std::vector<int> leaves;
   std::vector<uint8_t> stamps;
+  std::map<std::pair<uint64_t, int>, std::pair<int, int>> stamp_cache;   // (radius, integer opacity) -> (offset, r)
   std::vector<int> open;  // indices (into recs) of open groups
   // A Group that is the first member of its list and is composited with plain Over goes under an accumulator that is
   // still clear, and `over clear s = s` exactly (colour.ml:314-316): its members can composite straight into the
@@ -233,8 +234,18 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         if (!(c.brush_radius >= 0.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range");
         o.kind = K_BRUSH; o.first = c.first; o.count = c.count;
         if (c.count == 0) continue;
-        o.stamp_off = (int)stamps.size();
-        brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r);
+        {
+          // the stamp is a function of (radius, toint (opacity *. 255.)) alone (brush.ml:60-92): strokes share it
+          // (10^4 strokes of a scene use a few hundred distinct stamps; the exponentials are the cost of this loop)
+          uint64_t rbits; memcpy(&rbits, &c.brush_radius, sizeof rbits);
+          const std::pair<uint64_t, int> key(rbits, (int)(c.brush_opacity * 255.));
+          auto it = stamp_cache.find(key);
+          if (it == stamp_cache.end()) {
+            o.stamp_off = (int)stamps.size();
+            brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r);
+            stamp_cache[key] = std::make_pair(o.stamp_off, o.brush_r);
+          } else { o.stamp_off = it->second.first; o.brush_r = it->second.second; }
+        }
         int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
         for (int k = 0; k < c.count; k++) {
           int px = points[2 * ((size_t)c.first + k)], py = points[2 * ((size_t)c.first + k) + 1];

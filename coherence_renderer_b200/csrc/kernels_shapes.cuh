@@ -327,6 +327,43 @@ __global__ void k_sprite_fill(const int* __restrict__ row_ptr, const int2* __res
     for (int i = 0; i < s.y; i++, o++) out[o] = px_dissolve(c, opacity[o]);
   }
 }
+// Sprite.fillshape shp fill (sprite.ml:158-175): every pixel the fill at its own coordinates (a Plain fill is one colour)
+__global__ void k_sprite_fillshape(const int* __restrict__ row_ptr, const int2* __restrict__ spans, const int* __restrict__ px_off,
+                                   int y0, int n_rows, FillRec fill, uint32_t* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    const int2 s = spans[k];
+    for (int i = 0; i < s.y; i++, o++) out[o] = fill_lookup(fill, s.x + i, y0 + r);
+  }
+}
+// Sprite.map_coords (fun x y c -> dissolve (fill x y) (alpha c)) (render.ml:976-981): the fill applied to an alpha matte
+__global__ void k_sprite_fill_alpha(const int* __restrict__ row_ptr, const int2* __restrict__ spans, const int* __restrict__ px_off,
+                                    int y0, int n_rows, FillRec fill, const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    const int2 s = spans[k];
+    for (int i = 0; i < s.y; i++, o++) out[o] = px_dissolve(fill_lookup(fill, s.x + i, y0 + r), (int)(in[o] >> 24));
+  }
+}
+// Sprite.sprite_map f (sprite.ml:358-374), f one of the colour functions of colour.ml:266-304
+__global__ void k_sprite_map(int op, int arg, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = in[i];
+  uint32_t r;
+  switch (op) {
+    case 0: { const uint32_t av = ((c & 255u) + ((c >> 8) & 255u) + ((c >> 16) & 255u)) / 3u; r = av | (av << 8) | (av << 16) | (c & 0xFF000000u); break; }  // monochrome
+    case 1: r = px_dissolve(c, arg); break;
+    case 2: r = c & 0xFF0000FFu; break;   // red_channel
+    case 3: r = c & 0xFF00FF00u; break;   // green_channel
+    default: r = c & 0xFFFF0000u; break;  // blue_channel
+  }
+  out[i] = r;
+}
 // Scatter per-pixel values given in canonical span order into a dense canvas: thread per row.
 template <class T>
 __global__ void k_scatter_spans(const int* __restrict__ row_ptr, const int2* __restrict__ spans,

@@ -152,6 +152,20 @@ int coh_shape_translate(coh_ctx* ctx, coh_shape_t a, int32_t dx, int32_t dy, coh
 int coh_shape_bloat(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1857 */
 int coh_shape_erode(coh_ctx* ctx, coh_shape_t a, int32_t m, int32_t n, coh_shape_t* out); /* sprite.ml:1867 */
 
+/* ---- Sprite operations on whole sprites (sprite.mli:96-125) ----
+ * A sprite crosses the boundary as its shape (a device span set) plus one RGBA8 word per pixel in canonical span
+ * order.  Sprite.translate_sprite (sprite.mli:106) is coh_shape_translate on the shape: the pixels do not change. */
+int coh_shape_intersects(coh_ctx* ctx, coh_shape_t a, coh_shape_t b, int32_t* yes);   /* Sprite.shape_intersects, sprite.ml:1661 */
+/* Sprite.portion spr shp (sprite.ml:642-721): fails ("portion_spanline: bad input") unless shp lies inside the sprite's shape */
+int coh_sprite_portion(coh_ctx* ctx, coh_shape_t shape, const uint32_t* rgba, coh_shape_t sub, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+/* Sprite.fillshape shp fill (sprite.ml:158-175); `fill` uses the fill_* / colour* / fparam fields */
+int coh_sprite_fillshape(coh_ctx* ctx, coh_shape_t shape, const coh_object* fill, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+/* Sprite.sprite_map f spr (sprite.ml:358-374); the closure becomes an enumerated colour function (colour.ml:266-304) */
+enum { COH_MAP_MONOCHROME = 0, COH_MAP_DISSOLVE = 1 /* ~delta:arg */, COH_MAP_RED_CHANNEL = 2, COH_MAP_GREEN_CHANNEL = 3, COH_MAP_BLUE_CHANNEL = 4 };
+int coh_sprite_map(coh_ctx* ctx, int32_t op, int32_t arg, const uint32_t* rgba_in, int64_t n, uint32_t* rgba_out);
+/* Sprite.map_coords (fun x y c -> dissolve (fill x y) ~delta:(alpha c)) spr (sprite.ml:307-356; render.ml:976-981) */
+int coh_sprite_map_coords_fill(coh_ctx* ctx, coh_shape_t shape, const coh_object* fill, const uint32_t* rgba_in, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+
 /* ---- Convolve (convolve.mli:28-40) ----
  * Convolve.convolve_sprite kernel sprite (convolve.ml:239-258) with kernel = mkunit r / mkgaussian r.  A sprite
  * crosses the boundary as its shape plus one RGBA8 word per pixel in canonical span order; the result

@@ -50,6 +50,11 @@ external shape_intersection : ctx -> shape_h -> shape_h -> shape_h = "coh_ml_sha
 external shape_translate : ctx -> shape_h -> int -> int -> shape_h = "coh_ml_shape_translate"
 external shape_bloat : ctx -> shape_h -> int -> int -> shape_h = "coh_ml_shape_bloat"
 external shape_erode : ctx -> shape_h -> int -> int -> shape_h = "coh_ml_shape_erode"
+external shape_intersects_raw : ctx -> shape_h -> shape_h -> bool = "coh_ml_shape_intersects"
+external sprite_portion_raw : ctx -> shape_h -> i32 -> shape_h -> i32 -> int = "coh_ml_sprite_portion"
+external sprite_fillshape_raw : ctx -> shape_h -> u8 -> i32 -> int = "coh_ml_sprite_fillshape"
+external sprite_map_raw : ctx -> int * int -> i32 -> i32 -> unit = "coh_ml_sprite_map"
+external sprite_map_coords_fill_raw : ctx -> shape_h -> u8 -> i32 -> i32 -> int = "coh_ml_sprite_map_coords_fill"
 external convolve_sprite_raw : ctx -> int * int -> shape_h -> i32 -> i32 -> shape_h = "coh_ml_convolve_sprite"
 external cache_configure : ctx -> bool -> int64 -> unit = "coh_ml_cache_configure"
 external cache_clear : ctx -> unit = "coh_ml_cache_clear"
@@ -480,6 +485,42 @@ let box x y w h = take_shape (shape_box (ctx ()) x y w h)
 let dirty_region ~plain (so, mo, sn, mn) u =
   with_shape so (fun a -> with_shape mo (fun b -> with_shape sn (fun c -> with_shape mn (fun d -> with_shape u (fun hu ->
     take_shape (dirty_region_raw (ctx ()) (a, b, c, d) hu plain))))))
+
+(* a Sprite.sprite as (device shape handle, pixels in span order); the handle is the caller's to free *)
+let pixels_of_sprite (spr : Sprite.sprite) : i32 =
+  let n = Sprite.sprite_card spr in
+  let px = Array1.create int32 c_layout n in
+  let i = ref 0 in
+  Sprite.sprite_iter (fun _ _ c -> px.{!i} <- rgba8_of_colour c; incr i) spr;
+  px
+
+let fill_record (fill : Fill.fill) : u8 =
+  let r = blank k_path in
+  set_fill r (desc_of_fill fill);
+  let (ints, floats, id) = r in
+  let rec_ = Array1.create int8_unsigned c_layout (sizeof_object ()) in
+  Array1.fill rec_ 0;
+  pack_object rec_ 0 ints floats id;
+  rec_
+
+(* sprite.mli:96-125 *)
+let shape_intersects a b = with_shape a (fun ha -> with_shape b (fun hb -> shape_intersects_raw (ctx ()) ha hb))
+let portion (spr : Sprite.sprite) (shp : Sprite.shape) : Sprite.sprite =
+  with_shape (Sprite.shape_of_sprite spr) (fun ha -> with_shape shp (fun hb ->
+    let out = Array1.create int32 c_layout (shape_card (ctx ()) hb) in
+    ignore (sprite_portion_raw (ctx ()) ha (pixels_of_sprite spr) hb out);
+    sprite_of_pixels (shape_export (ctx ()) hb) out))
+let fillshape (shp : Sprite.shape) (fill : Fill.fill) : Sprite.sprite =
+  with_shape shp (fun h ->
+    let out = Array1.create int32 c_layout (shape_card (ctx ()) h) in
+    ignore (sprite_fillshape_raw (ctx ()) h (fill_record fill) out);
+    sprite_of_pixels (shape_export (ctx ()) h) out)
+type colour_map = Monochrome | Dissolve of int | Red_channel | Green_channel | Blue_channel   (* Sprite.sprite_map's closures, enumerated *)
+let sprite_map (f : colour_map) (spr : Sprite.sprite) : Sprite.sprite =
+  let px = pixels_of_sprite spr in
+  let out = Array1.create int32 c_layout (Array1.dim px) in
+  sprite_map_raw (ctx ()) (match f with Monochrome -> (0, 0) | Dissolve d -> (1, d) | Red_channel -> (2, 0) | Green_channel -> (3, 0) | Blue_channel -> (4, 0)) px out;
+  sprite_of_pixels (flat_of_shape (Sprite.shape_of_sprite spr)) out
 
 (* Polygon.polygon_sprite_edgelist fill shp edges winding (polygon.mli:58-59) *)
 let polygon_sprite_edgelist (fill : Fill.fill) (shp : Sprite.shape) (edges : Polygon.edge list) winding : Sprite.sprite =

@@ -171,6 +171,39 @@ UNOP(coh_ml_shape_translate, coh_shape_translate)       /* Sprite.translate_shap
 UNOP(coh_ml_shape_bloat, coh_shape_bloat)               /* Sprite.bloat */
 UNOP(coh_ml_shape_erode, coh_shape_erode)               /* Sprite.erode */
 
+/* ---- whole sprites: (shape handle, RGBA8 per pixel in span order as an int32 Bigarray) ---- */
+CAMLprim value coh_ml_shape_intersects(value ctx, value a, value b) {
+  int32_t yes = 0;
+  check(CTX(ctx), coh_shape_intersects(CTX(ctx), SHAPE(a), SHAPE(b), &yes));
+  return Val_bool(yes);
+}
+CAMLprim value coh_ml_sprite_portion(value ctx, value shape, value rgba, value sub, value out) {
+  CAMLparam5(ctx, shape, rgba, sub, out);
+  int64_t n = 0;
+  check(CTX(ctx), coh_sprite_portion(CTX(ctx), SHAPE(shape), (const uint32_t*)Caml_ba_data_val(rgba), SHAPE(sub), (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+CAMLprim value coh_ml_sprite_fillshape(value ctx, value shape, value fill, value out) {
+  CAMLparam4(ctx, shape, fill, out);
+  int64_t n = 0;
+  need(fill, (int64_t)sizeof(coh_object), "sprite_fillshape: fill record too short");
+  check(CTX(ctx), coh_sprite_fillshape(CTX(ctx), SHAPE(shape), (const coh_object*)Caml_ba_data_val(fill), (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+CAMLprim value coh_ml_sprite_map(value ctx, value op_arg, value rgba, value out) {
+  CAMLparam4(ctx, op_arg, rgba, out);
+  need(out, BA_LEN(rgba), "sprite_map: output shorter than input");
+  check(CTX(ctx), coh_sprite_map(CTX(ctx), Int_val(Field(op_arg, 0)), Int_val(Field(op_arg, 1)), (const uint32_t*)Caml_ba_data_val(rgba), BA_LEN(rgba), (uint32_t*)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_sprite_map_coords_fill(value ctx, value shape, value fill, value rgba, value out) {
+  CAMLparam5(ctx, shape, fill, rgba, out);
+  int64_t n = 0;
+  need(fill, (int64_t)sizeof(coh_object), "sprite_map_coords_fill: fill record too short");
+  check(CTX(ctx), coh_sprite_map_coords_fill(CTX(ctx), SHAPE(shape), (const coh_object*)Caml_ba_data_val(fill), (const uint32_t*)Caml_ba_data_val(rgba), (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+
 /* ---- Convolve.convolve_sprite kernel sprite: sprite = (shape handle, RGBA8 per pixel in span order) ---- */
 CAMLprim value coh_ml_convolve_sprite(value ctx, value kind_r, value shape, value rgba_in, value rgba_out) {
   CAMLparam5(ctx, kind_r, shape, rgba_in, rgba_out);

@@ -296,6 +296,57 @@ int orc_convolve_sprite(int kind, int r, const int32_t* shape, int64_t nshape, c
   ORC_CATCH
 }
 
+// Sprite operations on (flat shape, RGBA8 per pixel in span order) sprites.
+static Sprite sprite_from(const int32_t* shape, int64_t nshape, const uint32_t* rgba) {
+  Shape shp = shape_from_flat(shape, (int)nshape);
+  Sprite spr; int64_t k = 0;
+  for (auto& row : shp.rows) {
+    SpriteRow sr; sr.y = row.y; sr.spans = row.spans;
+    for (auto& sp : row.spans) for (int i = 0; i < sp.len; i++) sr.px.push_back(colour_of_rgba8(rgba[k++]));
+    spr.rows.push_back(std::move(sr));
+  }
+  return spr;
+}
+static int64_t sprite_out(const Sprite& s, uint32_t* out, int64_t cap) {
+  int64_t n = 0;
+  for (auto& row : s.rows) for (colour c : row.px) { if (n >= cap) throw std::runtime_error("sprite buffer too small"); out[n++] = rgba8_of_colour(c); }
+  return n;
+}
+// Sprite.portion spr shp (sprite.ml:642-721)
+int orc_sprite_portion(const int32_t* shape, int64_t nshape, const uint32_t* rgba, const int32_t* sub, int64_t nsub, uint32_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  *nout = sprite_out(portion(sprite_from(shape, nshape, rgba), shape_from_flat(sub, (int)nsub)), out, cap);
+  ORC_CATCH
+}
+// Sprite.fillshape shp fill (sprite.ml:158-175)
+int orc_sprite_fillshape(const coh_object* fill, const int32_t* shape, int64_t nshape, uint32_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  *nout = sprite_out(fillshape(shape_from_flat(shape, (int)nshape), fill_from(*fill)), out, cap);
+  ORC_CATCH
+}
+// Sprite.sprite_map f (sprite.ml:358-374) with f = 0 Colour.monochrome | 1 dissolve ~delta:arg | 2 / 3 / 4 red / green / blue_channel
+int orc_sprite_map(int op, int arg, const uint32_t* rgba, int64_t n, uint32_t* out) {
+  ORC_TRY
+  for (int64_t i = 0; i < n; i++) {
+    colour c = colour_of_rgba8(rgba[i]);
+    colour r = op == 0 ? monochrome(c) : op == 1 ? dissolve(c, arg) : op == 2 ? red_channel(c) : op == 3 ? green_channel(c) : blue_channel(c);
+    out[i] = rgba8_of_colour(r);
+  }
+  ORC_CATCH
+}
+// Sprite.map_coords (fun x y c -> dissolve (fill x y) (alpha c)) (render.ml:976-981, the last step of sprite_of_cpg)
+int orc_sprite_map_coords_fill(const coh_object* fill, const int32_t* shape, int64_t nshape, const uint32_t* rgba, uint32_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  Sprite s = sprite_from(shape, nshape, rgba);
+  Fill f = fill_from(*fill);
+  for (auto& r : s.rows) {
+    int off = 0;
+    for (auto& sp : r.spans) { for (int k = 0; k < sp.len; k++) r.px[off + k] = dissolve(f.fillsingle(sp.x + k, r.y), alpha_of_colour(r.px[off + k])); off += sp.len; }
+  }
+  *nout = sprite_out(s, out, cap);
+  ORC_CATCH
+}
+
 // Persistent renderer for the cached / animated configurations (C4): keeps Cache between frames.
 void* orc_renderer_new(int usecache) { Renderer* r = new Renderer(); r->cache.usecache = usecache != 0; return r; }
 void orc_renderer_free(void* r) { delete (Renderer*)r; }

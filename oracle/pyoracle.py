@@ -234,3 +234,40 @@ class Renderer:
         out = np.zeros((oh, ow), dtype=np.uint32)
         _chk(lib().orc_renderer_frame(self._h, objs, n_scene, n_background, _ptr(e), _ptr(p), _ptr(u), C.c_int64(len(u)), ox, oy, ow, oh, _ptr(out, C.c_uint32)))
         return out
+
+
+def sprite_portion(shape_flat, rgba, sub_flat):
+    s, b = _i32(shape_flat), _i32(sub_flat)
+    src = np.ascontiguousarray(rgba, dtype=np.uint32)
+    cap = shape_card(b)
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_int64()
+    _chk(lib().orc_sprite_portion(_ptr(s), C.c_int64(len(s)), _ptr(src, C.c_uint32), _ptr(b), C.c_int64(len(b)), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]
+
+
+def sprite_fillshape(fill_obj, shape_flat):
+    s = _i32(shape_flat)
+    cap = shape_card(s)
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_int64()
+    _chk(lib().orc_sprite_fillshape(C.byref(fill_obj), _ptr(s), C.c_int64(len(s)), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]
+
+
+def sprite_map(op, rgba, arg=0):
+    src = np.ascontiguousarray(rgba, dtype=np.uint32)
+    out = np.zeros(max(len(src), 1), dtype=np.uint32)
+    code = {"monochrome": 0, "dissolve": 1, "red_channel": 2, "green_channel": 3, "blue_channel": 4}[op]
+    _chk(lib().orc_sprite_map(code, arg, _ptr(src, C.c_uint32), C.c_int64(len(src)), _ptr(out, C.c_uint32)))
+    return out[: len(src)]
+
+
+def sprite_map_coords_fill(fill_obj, shape_flat, rgba):
+    s = _i32(shape_flat)
+    src = np.ascontiguousarray(rgba, dtype=np.uint32)
+    cap = shape_card(s)
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_int64()
+    _chk(lib().orc_sprite_map_coords_fill(C.byref(fill_obj), _ptr(s), C.c_int64(len(s)), _ptr(src, C.c_uint32), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]

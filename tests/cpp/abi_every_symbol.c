@@ -76,6 +76,24 @@ int main(int argc, char** argv) {
   ERR(coh_shape_export(C, bx, flat, sz - 1, &n), "too small");
   OK(coh_shape_import(C, flat, sz, &imp));
   flat[3] = 0; ERR(coh_shape_import(C, flat, sz, &t), "malformed shape"); flat[3] = 50;   /* empty span: not canonical (sprite.ml:201-239) */
+  /* whole-sprite operations */
+  {
+    int32_t yes = 0;
+    OK(coh_shape_intersects(C, s, bx, &yes)); CHECK(yes == 1);
+    OK(coh_shape_card(C, bx, &card));
+    uint32_t* whole = (uint32_t*)malloc(4 * (size_t)card);
+    OK(coh_sprite_fillshape(C, bx, &fill, whole, card, &n)); CHECK(n == card && whole[0] == 0xFF2030C8u);
+    ERR(coh_sprite_fillshape(C, bx, &fill, whole, 2, &n), "buffer too small");
+    int64_t ecard = 0; OK(coh_shape_card(C, er, &ecard));
+    OK(coh_sprite_portion(C, bx, whole, er, px, ecard, &n)); CHECK(n == ecard && px[0] == 0xFF2030C8u);
+    ERR(coh_sprite_portion(C, er, whole, bx, px, card, &n), "bad input");   /* the shape is not inside the sprite's */
+    OK(coh_sprite_map(C, COH_MAP_DISSOLVE, 128, whole, card, px)); CHECK((px[0] >> 24) == 128);
+    OK(coh_sprite_map(C, COH_MAP_RED_CHANNEL, 0, whole, card, px)); CHECK(px[0] == 0xFF0000C8u);
+    ERR(coh_sprite_map(C, 9, 0, whole, card, px), "unknown colour function");
+    ERR(coh_sprite_map(C, COH_MAP_DISSOLVE, 300, whole, card, px), "delta");
+    OK(coh_sprite_map_coords_fill(C, bx, &fill, whole, px, card, &n)); CHECK(n == card && px[0] == 0xFF2030C8u);
+    free(whole);
+  }
   /* Convolve */
   OK(coh_shape_card(C, bx, &card));
   uint32_t* spr = (uint32_t*)malloc(4 * (size_t)card);

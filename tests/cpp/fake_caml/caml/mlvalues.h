@@ -11,6 +11,7 @@ typedef intptr_t value; typedef intptr_t intnat;
 #define Int_val(v) ((int)(v))
 #define Long_val(v) ((long)(v))
 #define Bool_val(v) ((int)(v))
+#define Val_bool(x) ((value)((x) != 0))
 #define Field(v,i) (((value*)(v))[i])
 #define Store_field(b,i,v) (((value*)(b))[i]=(v))
 #define Wosize_val(v) ((size_t)((value*)(v))[-1])

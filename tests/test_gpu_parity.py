@@ -1132,3 +1132,38 @@ def test_partial_sprite_cache(ctx, oracle):
     objs[group_index].dx = objs[group_index].dy = 0
     ctx.cache_configure(True, 50 << 20)
     ctx.cache_clear()
+
+
+def _random_premultiplied(rng, n):
+    a = np.array([rng.choice([0, 1, 127, 128, 254, 255, rng.randint(0, 255)]) for _ in range(n)], dtype=np.uint32)
+    ch = [np.array([rng.randint(0, int(v)) for v in a], dtype=np.uint32) for _ in range(3)]
+    return ch[0] | (ch[1] << 8) | (ch[2] << 16) | (a << 24)
+
+
+def test_sprite_operations(ctx, oracle):
+    """Sprite.portion / fillshape / sprite_map / map_coords / shape_intersects across the ABI (sprite.mli:96-125), a
+    sprite being (shape, RGBA8 per pixel in span order), against the oracle's restatement of sprite.ml."""
+    rng = random.Random(21)
+    fills = [S.Fill.plain(S.dissolve(S.rgba8(200, 40, 90), 170)),
+             S.Fill.gradient((10.0, 20.0), (250.0, 150.0), True, False, S.rgba8(255, 0, 0), S.dissolve(S.rgba8(0, 0, 255), 128)),
+             S.Fill.radial((120.0, 80.0), (130.0, 80.0), (220.0, 80.0), False, True, S.rgba8(255, 255, 0), S.rgba8(0, 90, 30))]
+    for it in range(6):
+        a = util.random_shape_flat(rng)
+        b = util.random_shape_flat(rng, x0=20, y0=-10)
+        sub = oracle.shape_op("intersection", a, b)
+        ha, hb, hsub = ctx.shape_import(a), ctx.shape_import(b), ctx.shape_import(sub)
+        assert ctx.shape_intersects(ha, hb) == (len(sub) > 0)
+        px = _random_premultiplied(rng, oracle.shape_card(a))
+        assert np.array_equal(ctx.sprite_portion(ha, px, hsub), oracle.sprite_portion(a, px, sub))
+        if len(oracle.shape_op("difference", b, a)):
+            with pytest.raises(abi.CohError):            # Sprite.portion fails unless the shape lies inside the sprite's
+                ctx.sprite_portion(ha, px, hb)
+        o = abi.CohObject()
+        fills[it % 3].apply(o)
+        assert np.array_equal(ctx.sprite_fillshape(ha, o), oracle.sprite_fillshape(o, a)), f"fillshape (fill {it % 3})"
+        assert np.array_equal(ctx.sprite_map_coords_fill(ha, o, px), oracle.sprite_map_coords_fill(o, a, px)), f"map_coords (fill {it % 3})"
+        for op, arg in (("monochrome", 0), ("dissolve", rng.randint(0, 255)), ("dissolve", 0), ("dissolve", 255), ("red_channel", 0), ("green_channel", 0), ("blue_channel", 0)):
+            assert np.array_equal(ctx.sprite_map(op, px, arg), oracle.sprite_map(op, px, arg)), op
+        for h in (ha, hb, hsub):
+            ctx.shape_free(h)
+    assert not ctx.shape_intersects(0, 0) and len(ctx.sprite_portion(0, np.zeros(0, np.uint32), 0)) == 0

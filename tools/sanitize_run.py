@@ -12,6 +12,17 @@ def run(b, W, H):
     u = ctx.render_uncovered(); ctx.shape_export(u); ctx.shape_free(u)
     img = ctx.fb_read_rgba(0, 0, W, H); ctx.scene_free(sc); return img
 run(S.lion_scene(333, 257, 0.7), 333, 257)
+for opts in ({"fused": 0}, {"fused": 0, "comp_rows": 0}, {"fused": 0, "aa_general": 1}, {"fused": 1, "walk_h": 4}):   # three-phase frame (interval AA + row compositor), its other variants, the fused walker
+    for k, v in opts.items(): ctx.set_option(k, v)
+    run(S.lion_scene(333, 257, 0.7), 333, 257)
+    for k in opts: ctx.set_option(k, {"fused": -1, "comp_rows": 1, "aa_general": 0, "walk_h": 0}[k])
+# partial-sprite cache: a group with an id, a partial update, a drag
+b = S.SceneBuilder(); S.add_lion(b, 333, 257, 0.7, oid=4); b.begin_background(); b.rectangle(S.LIGHTGREY, 0.0, 0.0, 333.0, 257.0)
+objs, n, nbg, e, p = b.arrays()
+ctx.fb_configure(333, 257); sc = ctx.scene_create(objs, nbg, e, p)
+ctx.render_frame(sc, (40, 30, 120, 90)); ctx.render_frame(sc, (0, 0, 333, 257))
+for d in ((3, 2), (-5, 4)): ctx.scene_drag_object(sc, 0, *d)
+ctx.sync(); ctx.scene_free(sc)
 run(S.random_scene(300, 200, 1200, seed=3), 300, 200)
 b = S.SceneBuilder()
 b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0), (40.0, 120.0)], S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.rgba8(0, 0, 255)))
