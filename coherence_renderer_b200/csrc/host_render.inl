@@ -179,7 +179,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   // eligible: every leaf of the range is a path, a primitive or a Convolved object
   bool kinds_ok = extras == 0;
   bool has_conv = false;
-  if (!kinds_ok && !A.resume && !big) {
+  if (!kinds_ok && !big) {
     kinds_ok = true;
     for (int li = A.l0; li < A.l1 && kinds_ok; li++) {
       const int k = s->h_objs[V.h_leaves[li]].kind;
@@ -187,7 +187,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       has_conv = has_conv || k == K_CONV;
     }
   }
-  const bool pre = kinds_ok && !A.resume && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+  // (a pass that continues a frame — after a filter — takes the three-phase path too: its compositing walk is the
+  // variant that starts the root accumulators from the framebuffer)
+  const bool pre = kinds_ok && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
                    // flat scenes have the row compositor: worth it from a few thousand pairs on (measured on bands of the
                    // lion: 1/8 of the frame 0.069 -> 0.053 ms, 1/2 0.155 -> 0.098 ms); other scenes composite with the
                    // walker, and their small passes (a drag's dirty region: 0.088 vs 0.103 ms) stay fused
@@ -228,11 +230,13 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       }
       P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
       P.epoch = ++ctx->epoch;
-      if (has_conv) k_walk<true, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      if (A.resume) k_walk<true, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      else if (has_conv) k_walk<true, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       LAUNCHED();
     } else {
-      if (has_conv) k_walk<false, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      if (A.resume) k_walk<false, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      else if (has_conv) k_walk<false, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       LAUNCHED();
     }

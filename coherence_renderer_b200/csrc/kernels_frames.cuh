@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uin
   // the list entry carries what is needed of the object (written by k_bin1): no walk through ObjRec for paths and primitives
   const int4 r0 = item_rec[2 * (size_t)item], r1 = item_rec[2 * (size_t)item + 1];
   const int cell = r0.y, kind = r0.z & 255;
-  if (P.cell_head[cell].y & 1) return;   // a background cell: finished by k_prefill or the walker's fast path, nobody reads these words
+  if (!P.resume && (P.cell_head[cell].y & 1)) return;   // a background cell: finished by k_prefill or the walker's fast path, nobody reads these words (a continued frame has no such shortcut)
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t S = 0u, C = 0u;
@@ -68,7 +68,7 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
                           const int2* __restrict__ item_attr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
-  if (cell >= P.n_cells || (P.cell_head[cell].y & 1)) return;
+  if (cell >= P.n_cells || (!P.resume && (P.cell_head[cell].y & 1))) return;
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t u = 0u;
