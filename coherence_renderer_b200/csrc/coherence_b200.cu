@@ -10,6 +10,10 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <memory>
+#include <atomic>
+#include <thread>
 #include "../../include/coherence_b200.h"
 #include "kernels.cuh"
 
@@ -30,6 +34,7 @@ struct BinSet {
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
   int* cell_order = nullptr;  // cells by list-length class [BIN_CLASSES][n_cells]
+  int4* comp_order = nullptr; // the same order, flattened for the row compositor: {cell, list start, list end, header flags}, cell -1 past the end
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)
   int2* item_attr = nullptr;  // compositing attributes of every list entry (small-scene binning only)
@@ -129,6 +134,8 @@ struct coh_ctx {
   BinSet bins;
   int opt_pre_min_pairs = 4096;  // passes with fewer (list entry, row) pairs stay on the fused walker: four dependent launches cost more than they gain
   bool opt_bin_cache = true;  // keep whole-frame binning with the scene
+  bool opt_fork_prefill = true;  // three-phase frames: background prefill on a second stream beside the scan kernels
+  int opt_ab = 0;   // scratch switch for A/B measurements
   bool opt_comp_rows = true;  // flat scenes: row compositor instead of the walker in three-phase frames
   // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
   int* coarse_items = nullptr; int* coarse_counts = nullptr; int* coarse_off = nullptr; size_t coarse_cap = 0, coarse_cells_cap = 0;
@@ -141,6 +148,8 @@ struct coh_ctx {
   bool aa_general = false;     // every pair through the general (bit-row) antialiasing kernel
   // asynchronous read-back (coh_fb_read_rgba_async): two staging buffers, a copy stream
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;            // background prefill of a three-phase frame runs beside its scan kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; bool stage_busy[2] = {false, false};
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int stage_next = 0;
@@ -268,12 +277,14 @@ int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
   else if (n == "bin_cache") ctx->opt_bin_cache = value != 0;
   else if (n == "pre_min_pairs") ctx->opt_pre_min_pairs = value;
   else if (n == "comp_rows") ctx->opt_comp_rows = value != 0;
+  else if (n == "ab") ctx->opt_ab = value;
+  else if (n == "fork_prefill") ctx->opt_fork_prefill = value != 0;
   else FAIL("coh_set_option: unknown option '" + n + "'");
   return 0;
 }
 
 static void free_binset(coh_ctx* ctx, BinSet& b) {
-  DFREE(b.cell_head); DFREE(b.cell_rng); DFREE(b.cell_order); DFREE(b.cell_items); DFREE(b.item_cell); DFREE(b.item_attr); DFREE(b.item_rec); DFREE(b.state);
+  DFREE(b.cell_head); DFREE(b.cell_rng); DFREE(b.cell_order); DFREE(b.comp_order); DFREE(b.cell_items); DFREE(b.item_cell); DFREE(b.item_attr); DFREE(b.item_rec); DFREE(b.state);
   b = BinSet();
 }
 int coh_cache_clear(coh_ctx* ctx);
@@ -287,6 +298,7 @@ int coh_shutdown(coh_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_ready[k]); cudaEventDestroy(ctx->ev_done[k]); }
   }
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
   coh_cache_clear(ctx);
   for (void* p : ctx->opened_peers) cudaIpcCloseMemHandle(p);
   if (ctx->shared_fb) { if (ctx->fb == ctx->shared_fb) { ctx->fb = nullptr; ctx->own_fb = true; } cudaFree(ctx->shared_fb); ctx->shared_fb = nullptr; }

@@ -46,11 +46,12 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   const int key[6] = {fr.W, fr.H, fr.band_y0, fr.band_y1, ordered ? 1 : 0, prefill ? 1 : 0};
   const bool hit = keep && V.bins_valid && memcmp(key, V.bins_key, sizeof key) == 0;
   if (n_cells > B.n_cells_cap) {
-    DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng);
+    DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng); DFREE(B.comp_order);
     B.n_cells_cap = 0;
     CK(DMALLOC(&B.cell_head, sizeof(int2) * n_cells));
     CK(DMALLOC(&B.cell_rng, sizeof(int2) * n_cells));
     CK(DMALLOC(&B.cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
+    CK(DMALLOC(&B.comp_order, sizeof(int4) * (size_t)n_cells));
     B.n_cells_cap = n_cells;
   }
   if (!B.state) CK(DMALLOC(&B.state, sizeof(int) * ORDER_BINS));
@@ -97,6 +98,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, B.cell_rng, B.cell_items, B.state,
                                                ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr, B.item_rec); LAUNCHED();
+    if (ordered) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); }
     if (keep) { V.bins_valid = true; memcpy(V.bins_key, key, sizeof key); }
   } else {
     CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
@@ -132,11 +134,6 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     k_bin_sort<<<cdiv(n_coarse * 32, 128), 128, 0, ctx->stream>>>(ctx->coarse_off, ctx->coarse_items, ctx->coarse_items + ctot, n_coarse); LAUNCHED();
     k_bin2<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(leaf_box, leaves, ctx->coarse_off, ctx->coarse_items, ctx_x, crow0, fr, cell_row0, n_cells, B.cell_rng,
                                                           B.cell_items, B.state, ordered ? B.cell_order : nullptr); LAUNCHED();
-  }
-  if (prefill) {
-    BinPrefill pf; memset(&pf, 0, sizeof pf);
-    pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1; pf.n_peers = 0;
-    k_prefill<<<cdiv(n_cells * 32, 256), 256, 0, ctx->stream>>>(B.cell_head, fr, cell_row0, n_cells, pf); LAUNCHED();
   }
   WalkParams P;
   P.objs = s->objs; P.edges = s->edges; P.points = s->points; P.stamps = s->stamps;
@@ -194,6 +191,24 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
                    // lion: 1/8 of the frame 0.069 -> 0.053 ms, 1/2 0.155 -> 0.098 ms); other scenes composite with the
                    // walker, and their small passes (a drag's dirty region: 0.088 vs 0.103 ms) stay fused
                    (force >= 0 ? force == 0 : ((s->flat_ok && !A.collapsed) ? (long long)total * CELL_H >= ctx->opt_pre_min_pairs : walk_h != 1));
+  // background cells: cleared to the background colour by their own kernel.  In a three-phase frame it touches nothing
+  // the scan kernels read, so it runs beside them on a second stream and joins before the compositor.
+  bool prefill_forked = false;
+  if (prefill) {
+    BinPrefill pf; memset(&pf, 0, sizeof pf);
+    pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1; pf.n_peers = 0;
+    cudaStream_t st = ctx->stream;
+    if (pre && ctx->opt_fork_prefill) {
+      if (!ctx->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+      st = ctx->aux_stream; prefill_forked = true;
+    }
+    k_prefill<<<cdiv(n_cells * 32, 256), 256, 0, st>>>(B.cell_head, fr, cell_row0, n_cells, pf); LAUNCHED();
+    if (prefill_forked) CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+  }
   if (pre) {
     const size_t n_pairs = total * CELL_H;
     if (n_pairs > ctx->pre_cap) {
@@ -214,10 +229,11 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       k_pre_aa_runs<<<ctx->n_sms * 4, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op, ctx->pre_n + 1); LAUNCHED();
     }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
+    if (prefill_forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
     if (s->flat_ok && !A.collapsed && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
-      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr); LAUNCHED();
+      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, (ordered && !(ctx->opt_ab & 1)) ? B.comp_order : nullptr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {

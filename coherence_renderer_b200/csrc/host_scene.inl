@@ -40,16 +40,96 @@ static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out
     }
 }
 
+// Ownership of edges / brush points by objects, as ranges (see coh_scene_create).
+struct OwnerRanges {
+  std::vector<int4> ranges;   // first, count, record, -
+  bool monotone = true; long long last_end = 0;
+  void add(int first, int count, int rec) {
+    if (count <= 0) return;
+    if (first < last_end) monotone = false;
+    last_end = std::max(last_end, (long long)first + count);
+    ranges.push_back(make_int4(first, count, rec, 0));
+  }
+  bool overlapping() const {
+    if (monotone) return false;   // every range began at or after the end of all earlier ones
+    std::vector<int4> r(ranges);
+    std::sort(r.begin(), r.end(), [](const int4& a, const int4& b) { return a.x < b.x; });
+    for (size_t k = 1; k < r.size(); k++) if ((long long)r[k - 1].x + r[k - 1].y > r[k].x) return true;
+    return false;
+  }
+};
+// per-element owner array on the device (-1: no owner) from the ranges
+static int expand_owners(coh_ctx* ctx, const OwnerRanges& own, int n_elems, int** d_owner) {
+  CK(DMALLOC(d_owner, sizeof(int) * (size_t)std::max(n_elems, 1)));
+  CK(cudaMemsetAsync(*d_owner, 0xFF, sizeof(int) * (size_t)std::max(n_elems, 1), ctx->stream));
+  if (own.ranges.empty()) return 0;
+  int4* d_rg = nullptr;
+  CK(DMALLOC(&d_rg, sizeof(int4) * own.ranges.size()));
+  CK(cudaMemcpyAsync(d_rg, own.ranges.data(), sizeof(int4) * own.ranges.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_fill_owner<<<cdiv((int)own.ranges.size() * 32, 256), 256, 0, ctx->stream>>>(d_rg, (int)own.ranges.size(), *d_owner); LAUNCHED();
+  CK(cudaStreamSynchronize(ctx->stream));   // (the range list is a local of the caller's frame)
+  DFREE(d_rg);
+  return 0;
+}
+// Bounds of the elements of every object: a / b = the edge lists of a path, a filter's geometry or the operands of a
+// CPG; for a brush stroke a = the box of its points.  Ranges that are out of bounds are skipped here — the object
+// loop rejects them before it looks at the result.
+struct ElemBounds { EdgeBox a, b; };
+static void element_bounds(const coh_object* objs, int n_objs, const int32_t* edges, int n_edges, const int32_t* points, int n_points,
+                           std::vector<ElemBounds>& out) {
+  out.resize((size_t)std::max(n_objs, 1));
+  auto in_range = [](int first, int count, int n) { return first >= 0 && count >= 0 && (int64_t)first + count <= n; };
+  auto one = [&](int i) {
+    const coh_object& c = objs[i];
+    ElemBounds& r = out[i];
+    if (c.kind == COH_OBJ_BRUSH) {
+      if (!in_range(c.first, c.count, n_points)) return;
+      EdgeBox b{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+      const int32_t* p = points + 2 * (size_t)c.first;
+      for (int k = 0; k < c.count; k++) {
+        b.xmin = std::min(b.xmin, p[2 * k]); b.xmax = std::max(b.xmax, p[2 * k]);
+        b.ymin = std::min(b.ymin, p[2 * k + 1]); b.ymax = std::max(b.ymax, p[2 * k + 1]);
+      }
+      r.a = b;
+    } else if (c.kind == COH_OBJ_PATH || c.kind == COH_OBJ_CPG || c.kind == COH_OBJ_FILTER) {
+      if (in_range(c.first, c.count, n_edges)) r.a = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+      if (c.kind == COH_OBJ_CPG && in_range(c.first2, c.count2, n_edges)) r.b = edge_bounds(edges + 4 * (size_t)c.first2, c.count2);
+    }
+  };
+  const long long work = (long long)n_edges + n_points;
+  unsigned nt = work > 400000 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  if (nt <= 1) { for (int i = 0; i < n_objs; i++) one(i); return; }
+  std::atomic<int> next(0);
+  const int chunk = 256;
+  auto worker = [&]() { for (;;) { const int i0 = next.fetch_add(chunk); if (i0 >= n_objs) return; for (int i = i0; i < std::min(n_objs, i0 + chunk); i++) one(i); } };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+}
+
 int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32_t n_background, const int32_t* edges,
                      int32_t n_edges, const int32_t* points, int32_t n_points, coh_scene_t* out) {
   CK(cudaSetDevice(ctx->device));
   *out = 0;
+  // option "trace_create": phase times of this call on stderr (synchronises at every mark)
+  auto t_last = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!(ctx->opt_ab & 2)) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "coh_scene_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   if (n_objs < 0 || n_background < 0 || n_background > n_objs) FAIL("scene: bad object counts");
   // The scene list and the (pages @ background) list are each wrapped in an implicit root group:
   // render_frame renders them separately over the same update and composites the two results
   // with `over` (render.ml:1357-1365), which is exactly what two sibling groups do in one walk.
-  std::vector<ObjRec> recs;
-  std::vector<int> leaves;
+  // the scene is built in place: records and leaf list are the scene's own vectors (no copy of 10^5 records at the end)
+  std::unique_ptr<DevScene> holder(new DevScene());
+  DevScene* s = holder.get();
+  std::vector<ObjRec>& recs = s->h_objs;
+  std::vector<int>& leaves = s->h_leaves;
   std::vector<uint8_t> stamps;
   std::map<std::pair<uint64_t, int>, std::pair<int, int>> stamp_cache;   // (radius, integer opacity) -> (offset, r)
   std::vector<int> open;  // indices (into recs) of open groups
@@ -63,14 +143,21 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   std::vector<char> open_flat;    // per open group: dissolved into its parent
   bool any_filter = false;
   for (int i = 0; i < n_objs; i++) any_filter = any_filter || objs[i].kind == COH_OBJ_FILTER;
-  std::vector<int> edge_obj((size_t)std::max(n_edges, 1), -1);  // owning path object of every edge
-  std::vector<int> point_obj((size_t)std::max(n_points, 1), -1);  // owning brush object of every point
+  // Owning object of every edge / brush point: kept as (first, count, record) ranges here and expanded on the device
+  // (k_fill_owner); ranges of different objects may not overlap.
+  OwnerRanges edge_own, point_own;
+  // Bounds of every object's elements (edge lists, brush points) are independent of everything else in the scene:
+  // computed up front by a few host threads when the scene is large.
+  std::vector<ElemBounds> pre_bounds;
+  element_bounds(objs, n_objs, edges, n_edges, points, n_points, pre_bounds);
+  mark("element bounds");
   struct ConvItem { int rec, kind, r; };
   std::vector<ConvItem> conv_list;
   size_t conv_words = 0, conv_pixels = 0;
   long long total_rows = 0, total_brush_rows = 0;
   ObjRec root; memset(&root, 0, sizeof root);
   root.kind = K_GROUP; root.pretrans = -1; root.depth = 0; root.flags = OF_ROOT_SCENE;
+  recs.reserve((size_t)n_objs + 4); leaves.reserve((size_t)n_objs);
   recs.push_back(root); open.push_back(0);
   eff_open.push_back(0); n_children.push_back(0); open_flat.push_back(0);
   std::vector<int> rec_of_abi((size_t)std::max(n_objs, 1), -1);
@@ -171,7 +258,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           o.kind = K_CONV;
           conv_list.push_back({(int)recs.size(), ck, cr});
         }
-        EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+        const EdgeBox eb = pre_bounds[i].a;
         shape_pixel_box(eb, o.bx0, o.by0, o.bx1, o.by1);
         if (o.kind == K_CONV) {  // the convolved object reaches r pixels further; its canvas another r (X-pass inputs)
           const int cr = c.convolve >> 8;
@@ -186,10 +273,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         o.ry0 = floordiv(eb.ymin - 16 + 31, 32); o.ry1 = floordiv(eb.ymax + 67, 32);
         if (total_rows + (o.ry1 - o.ry0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
         o.row_base = (int)total_rows; total_rows += o.ry1 - o.ry0 + 1;
-        for (int k = 0; k < c.count; k++) {
-          if (edge_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share edges");
-          edge_obj[(size_t)c.first + k] = (int)recs.size();
-        }
+        edge_own.add(c.first, c.count, (int)recs.size());
         break;
       }
       case COH_OBJ_CPG: {
@@ -206,7 +290,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         for (int side = 0; side < 2; side++) {
           const int f = side ? c.first2 : c.first, n = side ? c.count2 : c.count;
           if (n == 0) continue;
-          EdgeBox eb = edge_bounds(edges + 4 * (size_t)f, n);
+          const EdgeBox eb = side ? pre_bounds[i].b : pre_bounds[i].a;
           int x0, y0, x1, y1;
           shape_pixel_box(eb, x0, y0, x1, y1);
           o.bx0 = std::min(o.bx0, x0); o.by0 = std::min(o.by0, y0); o.bx1 = std::max(o.bx1, x1); o.by1 = std::max(o.by1, y1);
@@ -214,10 +298,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           if (total_rows + (r1 - r0 + 1) > 0x7FFFFFF0LL) FAIL("scene: too many object rows for the row-edge table");
           if (side) { o.b_ry0 = r0; o.b_ry1 = r1; o.b_row_base = (int)total_rows; } else { o.ry0 = r0; o.ry1 = r1; o.row_base = (int)total_rows; }
           total_rows += r1 - r0 + 1;
-          for (int k = 0; k < n; k++) {
-            if (edge_obj[(size_t)f + k] != -1) FAIL("scene: objects may not share edges");
-            edge_obj[(size_t)f + k] = (int)recs.size();
-          }
+          edge_own.add(f, n, (int)recs.size());
         }
         if (o.bx0 > o.bx1) continue;  // both operands null
         break;
@@ -246,21 +327,14 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
             stamp_cache[key] = std::make_pair(o.stamp_off, o.brush_r);
           } else { o.stamp_off = it->second.first; o.brush_r = it->second.second; }
         }
-        int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
-        for (int k = 0; k < c.count; k++) {
-          int px = points[2 * ((size_t)c.first + k)], py = points[2 * ((size_t)c.first + k) + 1];
-          x0 = std::min(x0, px); x1 = std::max(x1, px); y0 = std::min(y0, py); y1 = std::max(y1, py);
-        }
+        const int x0 = pre_bounds[i].a.xmin, x1 = pre_bounds[i].a.xmax, y0 = pre_bounds[i].a.ymin, y1 = pre_bounds[i].a.ymax;
         o.bx0 = x0 - o.brush_r; o.bx1 = x1 + o.brush_r; o.by0 = y0 - o.brush_r; o.by1 = y1 + o.brush_r;
         o.ry0 = o.by0; o.ry1 = o.by1;   // object-frame rows (the alias offset is added to the box below)
         o.bc_x0 = floordiv(o.bx0, 32); o.bc_y0 = floordiv(o.by0, CELL_H);
         o.bc_nx = floordiv(o.bx1, 32) - o.bc_x0 + 1; o.bc_ny = floordiv(o.by1, CELL_H) - o.bc_y0 + 1;
         if (total_brush_rows + (long long)o.bc_nx * o.bc_ny > 0x7FFFFFF0LL) FAIL("scene: too many brush cells");
         o.bc_base = (int)total_brush_rows; total_brush_rows += (long long)o.bc_nx * o.bc_ny;
-        for (int k = 0; k < c.count; k++) {
-          if (point_obj[(size_t)c.first + k] != -1) FAIL("scene: objects may not share brush points");
-          point_obj[(size_t)c.first + k] = (int)recs.size();
-        }
+        point_own.add(c.first, c.count, (int)recs.size());
         break;
       }
       default: FAIL("scene: unknown object kind");
@@ -278,6 +352,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     ids.resize(recs.size(), -1); ids.back() = c.id;
     leaves.push_back((int)recs.size() - 1);
   }
+  mark("object loop");
+  if (edge_own.overlapping()) FAIL("scene: objects may not share edges");
+  if (point_own.overlapping()) FAIL("scene: objects may not share brush points");
   if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
   if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
   if (n_front_leaves < 0) n_front_leaves = (int)leaves.size();
@@ -328,10 +405,9 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   group_last.resize(recs.size(), -1);
   ids.resize(recs.size(), -1);
   real_depth.resize(recs.size(), 0);
-  DevScene* s = new DevScene();
-  s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves; s->h_leaves = leaves;
+  mark("sprite entries");
+  s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves;
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
-  s->h_objs = recs;
   s->sprites = sprites;
   if (!sprites.empty()) {   // the collapsed leaf list
     size_t k = 0;
@@ -385,17 +461,18 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(cudaMemcpyAsync(s->sp.leaves, s->sp.h_leaves.data(), sizeof(int) * s->sp.n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(s->sp.leaf_box, sp_boxes.data(), sizeof(int4) * s->sp.n, cudaMemcpyHostToDevice, ctx->stream));
   }
+  mark("records, leaves, boxes");
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
   CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
   if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
   CK(DMALLOC(&s->stamps, std::max<size_t>(stamps.size(), 1)));
   if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  mark("edges, points, stamps");
   // K1 edge binning: count -> scan -> fill
   {
     int* d_edge_obj = nullptr; int* d_counts = nullptr;
     size_t slots = (size_t)std::max<long long>(total_rows, 1);
-    CK(DMALLOC(&d_edge_obj, sizeof(int) * edge_obj.size()));
-    CK(cudaMemcpyAsync(d_edge_obj, edge_obj.data(), sizeof(int) * edge_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (expand_owners(ctx, edge_own, n_edges, &d_edge_obj)) return 1;
     CK(DMALLOC(&d_counts, sizeof(int) * slots));
     CK(DMALLOC(&s->rowedge_ptr, sizeof(int) * (slots + 1)));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * slots, ctx->stream));
@@ -404,8 +481,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     // size of the lists: the same row range per edge as k_rowedges, summed on the host (no device round trip:
     // a device-to-host read here would queue behind an asynchronous framebuffer read-back of the previous frame)
     long long total = 0;
-    for (int e = 0; e < n_edges; e++) {
-      if (edge_obj[e] < 0) continue;
+    for (const int4& rg : edge_own.ranges)
+     for (int e = rg.x; e < rg.x + rg.y; e++) {
       const int ymin = std::min(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]), ymax = std::max(edges[4 * (size_t)e + 1], edges[4 * (size_t)e + 3]);
       total += floordiv(ymax + 67, 32) - floordiv(ymin - 16 + 31, 32) + 1;
     }
@@ -416,6 +493,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     CK(cudaStreamSynchronize(ctx->stream));
     DFREE(d_edge_obj); DFREE(d_counts);
   }
+  mark("row-edge lists");
   // Convolved objects (render.ml:1023-1052): AA-rasterise the whole (twice bloated) box of the child,
   // X pass, Y pass; keep the shape / minshape bit-rows and the convolved canvas resident.
   if (conv_words > 0) {
@@ -488,18 +566,18 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       DFREE(S); DFREE(C); DFREE(T); DFREE(Q); DFREE(A); DFREE(X); DFREE(op); DFREE(d_taps);
     }
   }
+  mark("sprites, Convolved");
   if (total_brush_rows > 0) {
     int* d_point_obj = nullptr;
-    CK(DMALLOC(&d_point_obj, sizeof(int) * point_obj.size()));
-    CK(cudaMemcpyAsync(d_point_obj, point_obj.data(), sizeof(int) * point_obj.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (expand_owners(ctx, point_own, n_points, &d_point_obj)) return 1;
     CK(DMALLOC(&s->brush_ranges, sizeof(int2) * (size_t)total_brush_rows));
-    std::vector<int2> init((size_t)total_brush_rows, make_int2(INT32_MAX, -1));
-    CK(cudaMemcpyAsync(s->brush_ranges, init.data(), sizeof(int2) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_int2<<<cdiv((int)total_brush_rows, 256), 256, 0, ctx->stream>>>(s->brush_ranges, (int)total_brush_rows, make_int2(INT32_MAX, -1)); LAUNCHED();
     k_brush_cells<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(s->points, d_point_obj, n_points, s->objs, s->brush_ranges); LAUNCHED();
     CK(cudaStreamSynchronize(ctx->stream));
     DFREE(d_point_obj);
   }
-  *out = (coh_scene_t)s;
+  mark("brush cells");
+  *out = (coh_scene_t)holder.release();
   return 0;
 }
 

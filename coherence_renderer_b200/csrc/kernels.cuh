@@ -68,6 +68,17 @@ __global__ void k_rowedges(const EdgeRec* __restrict__ edges, const int* __restr
   }
 }
 
+// Owner arrays from ranges: one warp per (first, count, record) range.
+__global__ void k_fill_owner(const int4* __restrict__ ranges, int n_ranges, int* __restrict__ owner) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n_ranges) return;
+  const int4 rg = ranges[r];
+  for (int k = lane; k < rg.y; k += 32) owner[rg.x + k] = rg.z;
+}
+__global__ void k_fill_int2(int2* __restrict__ dst, int n, int2 v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
 // K1 for brush strokes: for every (stroke, 32 x CELL_H pixel cell of its box, object frame) the range
 // [imin, imax] of stamp indices (list order) whose footprint reaches the cell.  Stamps are sampled along the
 // path, so the stamps that reach a cell are (nearly) consecutive; walking the range in order keeps the
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
       hd = make_int2((int)o.fill.c0, 1 | ((objs[o.anc[0]].flags & OF_ROOT_SCENE) ? 2 : 0));
   }
   const bool prefill = prefill_on && (hd.y & 1);          // (lane 0's view): finished by k_prefill, in no class
+  const int head_bit = __shfl_sync(0xFFFFFFFFu, hd.y & 1, 0);   // a background cell: its entries are never scan-converted
   if (lane == 0) { s_n[wid] = n; s_c[wid] = (active && !prefill) ? bin_class(n) : -1; }
   __syncthreads();
   if (wid == 0 && lane < 8) {
@@ -197,10 +209,10 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
       if (item_attr) item_attr[dst] = attr[leaf];
       if (item_rec) {
         // what k_pre_scan needs of the object, in device space, next to the list entry (two int4 per entry):
-        //   {object, cell, kind | winding << 8, first row-edge slot - first listed row}
+        //   {object, cell, kind | winding << 8 | background cell << 16, first row-edge slot - first listed row}
         //   paths: {first listed row, last listed row, dx, dy};  primitives: the box x0, y0, x1, y1
         const ObjRec& o = objs[leaf];
-        int4 r0 = make_int4(leaf, warp, o.kind | (o.winding << 8), 0), r1 = make_int4(0, 0, 0, 0);
+        int4 r0 = make_int4(leaf, warp, o.kind | (o.winding << 8) | (head_bit << 16), 0), r1 = make_int4(0, 0, 0, 0);
         if (o.kind == K_PRIM) r1 = make_int4(o.prim[0] + o.dx, o.prim[1] + o.dy, o.prim[2] + o.dx, o.prim[3] + o.dy);
         else if (o.kind == K_PATH) { r0.w = o.row_base - (o.ry0 + o.dy); r1 = make_int4(o.ry0 + o.dy, o.ry1 + o.dy, o.dx, o.dy); }
         item_rec[2 * (size_t)dst] = r0; item_rec[2 * (size_t)dst + 1] = r1;
@@ -213,6 +225,22 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
     cell_head[warp] = hd;
     if (cls_cells && s_c[wid] >= 0) cls_cells[(size_t)s_c[wid] * n_cells + s_pos[wid]] = warp;
   }
+}
+// The heavy-first order of k_bin1 flattened for the row compositor: position q -> {cell, list start, list end, header
+// flags}; positions past the queued cells hold cell -1.  One thread per position; runs when the binning does.
+__global__ void k_comp_order(const int* __restrict__ cls_cnt, const int* __restrict__ cls_cells, const int2* __restrict__ cell_rng, const int2* __restrict__ cell_head,
+                             int n_cells, int4* __restrict__ order) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_cells) return;
+  int before = 0, cell = -1;
+  for (int c = 0; c < BIN_CLASSES; c++) {
+    const int n = cls_cnt[c];
+    if (q < before + n) { cell = cls_cells[(size_t)c * n_cells + q - before]; break; }
+    before += n;
+  }
+  int4 r = make_int4(-1, 0, 0, 0);
+  if (cell >= 0) { const int2 rg = cell_rng[cell]; r = make_int4(cell, rg.x, rg.y, cell_head[cell].y); }
+  order[q] = r;
 }
 // The background cells of a box update (flagged by k_bin1): one warp per cell streams the cell's 16 rows of one
 // colour with 128-bit stores (8 lanes per 128-byte row, 4 rows per instruction) where the cell lies inside the

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uin
   // the list entry carries what is needed of the object (written by k_bin1): no walk through ObjRec for paths and primitives
   const int4 r0 = item_rec[2 * (size_t)item], r1 = item_rec[2 * (size_t)item + 1];
   const int cell = r0.y, kind = r0.z & 255;
-  if (!P.resume && (P.cell_head[cell].y & 1)) return;   // a background cell: finished by k_prefill or the walker's fast path, nobody reads these words (a continued frame has no such shortcut)
+  if (!P.resume && ((r0.z >> 16) & 1)) return;   // a background cell: finished by k_prefill or the walker's fast path, nobody reads these words (a continued frame has no such shortcut)
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t S = 0u, C = 0u;
@@ -93,7 +93,15 @@ __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __re
     for (int k = 0; k < 4; k++) {
       const uint32_t M = w[k].x & ~w[k].y;
       const uint32_t e = (at[k].y & 1) ? (w[k].x & w[k].y & u) : 0u;   // shape - minshape, still uncovered
-      if (e) list[atomicAdd(list_n, 1)] = make_int4((it + k) * CELL_H + row, P.cell_items[it + k], (int)e, (tile << 16) | my_y);
+      if (e) {
+        // one atomic per group of lanes that arrive here together
+        const uint32_t m = __activemask();
+        const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(list_n, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        list[base + __popc(m & ((1u << lane) - 1u))] = make_int4((it + k) * CELL_H + row, P.cell_items[it + k], (int)e, (tile << 16) | my_y);
+      }
       if (at[k].y & 4) u &= ~M;   // opaque fill, no dissolve on the way up: its interior hides what is behind
     }
   }
@@ -236,65 +244,42 @@ __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P,
 // One block per cell (CELL_H warps), cells in heavy-first order; background cells were finished by k_prefill.
 // ------------------------------------------------------------------------------------
 constexpr int COMP_WARPS = 8;   // rows of a cell per block
-__global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr) {
+__global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr, const int4* __restrict__ order) {
   constexpr int PARTS = CELL_H / COMP_WARPS;   // blocks per cell
   // Block b takes position b / PARTS of the heavy-first order (blocks are dispatched in index order, so the long
-  // lists start first); one thread resolves it to a cell — the classes are consecutive segments of cls_cells — and
-  // the grid is sized for every cell: positions beyond the queued cells (background cells were finished by
-  // k_prefill) leave at once.
-  __shared__ int s_cell[6];   // cell, tile, first row of the block, column mask of the update box, cell header
-  if (threadIdx.x < 32) {
-    // warp 0: lane c holds the size of class c; an inclusive scan finds the class of position q with one load
-    const int lane0 = threadIdx.x;
-    const int q = blockIdx.x / PARTS;
-    int cell = -1;
-    if (P.cls_cnt) {
-      const int n = lane0 < BIN_CLASSES ? P.cls_cnt[lane0] : 0;
-      int incl = n;
-#pragma unroll
-      for (int d = 1; d < BIN_CLASSES; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane0 >= d) incl += t; }
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, lane0 < BIN_CLASSES && q < incl);
-      if (m) {
-        const int c = __ffs((int)m) - 1;
-        const int before = __shfl_sync(0xFFFFFFFFu, incl - n, c);
-        if (lane0 == 0) cell = P.cls_cells[(size_t)c * P.n_cells + q - before];
-      }
-    } else if (lane0 == 0) cell = q < P.n_cells ? q : -1;
-    if (lane0 == 0) {
-      s_cell[0] = cell;
-      if (cell >= 0) {
-        const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
-        uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
-        if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
-        s_cell[1] = tile; s_cell[2] = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS; s_cell[3] = (int)colmask;
-        const int2 hd = P.cell_head ? P.cell_head[cell] : make_int2(0, 0);
-        s_cell[4] = hd.x; s_cell[5] = hd.y;
-      }
-    }
-  }
-  __syncthreads();
-  const int cell = s_cell[0];
+  // lists start first).  The order was flattened by k_comp_order when the cells were binned: one load gives the
+  // cell, its list and its header flags — every warp fetches it for itself, no barrier; the grid is sized for
+  // every cell, and positions beyond the queued cells (background cells were finished by k_prefill) leave at once.
+  const int q = blockIdx.x / PARTS;
+  int4 oc;
+  if (order) oc = order[q];
+  else { oc = make_int4(q < P.n_cells ? q : -1, 0, 0, 0); if (oc.x >= 0) { const int2 rg0 = P.cell_rng[q]; oc.y = rg0.x; oc.z = rg0.y; oc.w = P.cell_head ? P.cell_head[q].y : 0; } }
+  const int cell = oc.x;
   if (cell < 0) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lbit = 1u << lane;
-  const int tile = s_cell[1], y = s_cell[2] + wid, row = y & (CELL_H - 1);
+  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
+  const int y = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS + wid, row = y & (CELL_H - 1);
   if (y < P.fr.band_y0 || y >= P.fr.band_y1) return;
-  uint32_t u = P.u_init ? (P.u_init[(size_t)y * P.fr.tiles_x + tile] & (uint32_t)s_cell[3]) : ((y >= P.uy0 && y <= P.uy1) ? (uint32_t)s_cell[3] : 0u);
+  uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
+  if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
+  uint32_t u = P.u_init ? (P.u_init[(size_t)y * P.fr.tiles_x + tile] & colmask) : ((y >= P.uy0 && y <= P.uy1) ? colmask : 0u);
   const uint32_t u_update = u;
   uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
   if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
-  if (s_cell[5] & 1) {
+  if (oc.w & 1) {
     // a background cell that k_prefill did not take (frames mirrored to peer framebuffers spread these stores over
     // the compositor's blocks): one opaque primitive covers the cell, nothing was scan-converted for it
-    if (u_rec && lane == 0) *u_rec = (s_cell[5] & 2) ? 0u : u;
+    if (u_rec && lane == 0) *u_rec = (oc.w & 2) ? 0u : u;
     if (u & lbit) {
       const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
-      P.fb[at] = (uint32_t)s_cell[4];
-      for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = (uint32_t)s_cell[4];
+      const uint32_t bg = (uint32_t)P.cell_head[cell].x;
+      P.fb[at] = bg;
+      for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = bg;
     }
     return;
   }
-  const int2 rg = P.cell_rng[cell];
+  const int2 rg = make_int2(oc.y, oc.z);
   const uint2* sc_row = P.pre_sc + row;
   const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
   uint32_t acc = 0u;

@@ -116,7 +116,8 @@ int coh_get_timing(coh_ctx* ctx, double* walk_ms_avg, double* bin_ms_avg, int64_
  * pass); "fused" -1 | 0 | 1 — force the three-phase frame (0) or the fused walker (1); "aa_general" 0 | 1 — every
  * antialiased pair through the general bit-row kernel instead of the interval form; "bin_cache" 0 | 1 — keep the
  * whole-frame cell binning with the scene; "comp_rows" 0 | 1 — flat scenes composite three-phase frames with the row
- * compositor instead of the walker.  coh_init reads COH_WALK_H, COH_FUSED, COH_AA_GENERAL from the environment once. */
+ * compositor instead of the walker; "fork_prefill" 0 | 1 — the background prefill of a three-phase frame runs on a
+ * second stream beside the scan kernels.  coh_init reads COH_WALK_H, COH_FUSED, COH_AA_GENERAL from the environment once. */
 int coh_set_option(coh_ctx* ctx, const char* name, int32_t value);
 
 /* ---- colour codec (colour.ml:99-172 colour_of_rgba / rgba_of_colour) ---- */

@@ -154,7 +154,7 @@ def test_fancy_fills(ctx, oracle):
 def options(ctx):
     """Force code paths through coh_set_option; everything is reset afterwards."""
     yield ctx.set_option
-    for name, v in (("walk_h", 0), ("fused", -1), ("aa_general", 0), ("bin_cache", 1), ("comp_rows", 1)):
+    for name, v in (("walk_h", 0), ("fused", -1), ("aa_general", 0), ("bin_cache", 1), ("comp_rows", 1), ("fork_prefill", 1)):
         ctx.set_option(name, v)
 
 

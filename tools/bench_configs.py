@@ -34,7 +34,14 @@ def c3(ctx, frames):
     t = time.perf_counter()
     sc = ctx.scene_create(objs, nbg, e, p)
     ctx.sync()
-    create_ms = (time.perf_counter() - t) * 1e3
+    create_ms = (time.perf_counter() - t) * 1e3   # the first creation also grows the device memory pool
+    again = []
+    for _ in range(3):
+        ctx.scene_free(sc)
+        t = time.perf_counter()
+        sc = ctx.scene_create(objs, nbg, e, p)
+        ctx.sync()
+        again.append((time.perf_counter() - t) * 1e3)
     ms = timed_frames(ctx, lambda: ctx.render_frame(sc, (0, 0, W, H)), frames)
     ctx.set_timing(True)
     ctx.render_frame(sc, (0, 0, W, H))
@@ -44,7 +51,7 @@ def c3(ctx, frames):
     img = ctx.fb_read_rgba(0, 0, W, H)
     ctx.scene_free(sc)
     return {"config": "C3", "workload": f"{N} random layered polygons / brush strokes, {W}x{H}, seed 0xC0FFEE", "ms_per_frame": ms, "Mpx_per_s": W * H / ms / 1e3,
-            "walker_ms": walk, "binning_ms": binning, "scene_create_ms": create_ms, "edges": int(len(e)), "stamp_points": int(len(p)),
+            "walker_ms": walk, "binning_ms": binning, "scene_create_ms": create_ms, "scene_recreate_ms": sorted(again)[1], "edges": int(len(e)), "stamp_points": int(len(p)),
             "checksum": int(img[::7, ::5].astype("uint64").sum())}
 
 
