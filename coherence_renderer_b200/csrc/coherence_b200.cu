@@ -34,6 +34,7 @@ struct BinSet {
   int2* cell_head = nullptr;  // per cell: colour + flags when the cell is one opaque covering primitive
   int2* cell_rng = nullptr;   // per cell [start, end) into cell_items
   int* cell_order = nullptr;  // cells by list-length class [BIN_CLASSES][n_cells]
+  bool comp_valid = false;
   int4* comp_order = nullptr; // the same order, flattened for the row compositor: {cell, list start, list end, header flags}, cell -1 past the end
   int* cell_items = nullptr; size_t cell_items_cap = 0;
   int* item_cell = nullptr;   // cell of every list entry (small-scene binning only)

@@ -358,3 +358,73 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
   ctx->have_u = record_u && !rc;
   return rc;
 }
+
+// Convolved (kernel, Group members): shape = bloat r r (union of the members' shapes), minshape null (render.ml:536-555);
+// sprite = convolve_sprite kernel (the group's sprite) (render.ml:1023-1052).  The members' scene is rendered once
+// over the whole twice-bloated box into a canvas whose origin is moved to the frame origin by aliasing the members.
+static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, ConvGroup& cg) {
+  DevScene* ss = cg.sub;
+  const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;
+  const size_t nwords = (size_t)nw * h, npx = (size_t)w * h;
+  uint32_t *S = nullptr, *A = nullptr, *X = nullptr; int* d_taps = nullptr;
+  CK(DMALLOC(&S, 4 * nwords)); CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx));
+  CK(cudaMemsetAsync(S, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
+  // (1) the group's shape, with the cache switched off as the reference does while it computes it
+  {
+    const bool saved = ctx->usecache; ctx->usecache = false;
+    coh_shape_t gs = 0; int rc = 0;
+    for (int k = 1; k < (int)ss->real_depth.size() && !rc; k++) {
+      if (ss->real_depth[k] != 1) continue;   // direct members of the group
+      coh_shape_t ms = 0, mm = 0, un = 0;
+      rc = object_shape_rec(ctx, ss, k, &ms, &mm) || coh_shape_union(ctx, gs, ms, &un);
+      coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
+      gs = un;
+    }
+    ctx->usecache = saved;
+    if (rc) return 1;
+    if (gs) {
+      const DevShape* G = (const DevShape*)gs;
+      k_spans_to_bits<<<cdiv(h, 128), 128, 0, ctx->stream>>>(G->row_ptr, G->spans, G->y0, G->n_rows, o.cv_y0, h, o.cv_x0, nw, S); LAUNCHED();
+      coh_shape_free(ctx, gs);
+    }
+  }
+  uint32_t* convS = s->conv_bits + o.cv_bits;
+  k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(S, convS, h, nw, cg.r, cg.r); LAUNCHED();
+  CK(cudaMemsetAsync(convS + nwords, 0, 4 * nwords, ctx->stream));
+  // (2) the group's sprite: the members' scene rendered with the canvas as its frame
+  {
+    int depth = 0;
+    for (int t = 0; t < cg.n_members; t++) {
+      const int kind = cg.members[t].kind;
+      if (kind == COH_OBJ_GROUP_END) { depth--; continue; }
+      if (depth == 0 && t < (int)ss->rec_of_abi.size() && ss->rec_of_abi[t] >= 0)
+        if (coh_scene_translate_object(ctx, (coh_scene_t)ss, t, -o.cv_x0, -o.cv_y0)) return 1;
+      if (kind == COH_OBJ_GROUP_BEGIN && !cg.members[t].convolve) depth++;
+    }
+    const Frame saved = ctx->fr;
+    ctx->fr.W = w; ctx->fr.H = h; ctx->fr.band_y0 = 0; ctx->fr.band_y1 = h; ctx->fr.tiles_x = nw; ctx->fr.cells_y = cdiv(h, CELL_H); ctx->fr.ctx0 = 0; ctx->fr.cntx = nw;
+    PassArgs pa{0, ss->n_leaves, 0, 0, w, h, nullptr, nullptr, A, true, false};
+    const int rc = render_pass(ctx, ss, pa);
+    ctx->fr = saved;
+    if (rc) return 1;
+  }
+  // (3) Convolve.convolve_sprite on the canvas: X pass, Y pass
+  std::vector<int> taps; int total = 0;
+  if (cg.kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
+    for (int i = -cg.r; i <= cg.r; i++) {
+      double xr = (double)i / (double)cg.r, yr = 0. / (double)cg.r;
+      double gg = exp(-(xr * xr + yr * yr)) / 2.;
+      int v = (int)((double)(4 * cg.r * cg.r) * gg + 0.5);
+      taps.push_back(v); total += v;
+    }
+    CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
+    CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  dim3 gp(cdiv(w, 128), h);
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(A, X, w, h, cg.r, cg.kind, d_taps, total, 0); LAUNCHED();
+  k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X, s->conv_px + o.cv_px, w, h, cg.r, cg.kind, d_taps, total, 1); LAUNCHED();
+  if (check_error_flag(ctx, "coh_scene_create (Convolved group)")) return 1;
+  DFREE(S); DFREE(A); DFREE(X); DFREE(d_taps);
+  coh_scene_free(ctx, (coh_scene_t)ss); cg.sub = nullptr;
+  return 0;
+}

@@ -98,7 +98,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     const int bin_blocks = cdiv(n_cells * 32, 256);
     k_bin1<<<bin_blocks, 256, 0, ctx->stream>>>(leaf_box, leaves, n_leaves, fr, cell_row0, n_cells, B.cell_rng, B.cell_items, B.state,
                                                ordered ? B.cell_order : nullptr, s->objs, B.cell_head, B.item_cell, prefill ? 1 : 0, s->attr, B.item_attr, B.item_rec); LAUNCHED();
-    if (ordered) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); }
+    B.comp_valid = false;
     if (keep) { V.bins_valid = true; memcpy(V.bins_key, key, sizeof key); }
   } else {
     CK(cudaMemsetAsync(B.state, 0, sizeof(int) * ORDER_BINS, ctx->stream));
@@ -233,7 +233,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
     if (s->flat_ok && !A.collapsed && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
-      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, (ordered && !(ctx->opt_ab & 1)) ? B.comp_order : nullptr); LAUNCHED();
+      // (the heavy-first order flattened for this kernel: made when the cells were binned, kept with cached lists)
+      if (ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); B.comp_valid = true; }
+      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, ordered ? B.comp_order : nullptr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {

@@ -40,6 +40,10 @@ static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out
     }
 }
 
+// Convolved (kernel, Group members): the members are a scene of their own (realised in host_cache.inl, after the
+// render passes and the shape functions it needs)
+struct ConvGroup { int rec, kind, r; DevScene* sub; const coh_object* members; int n_members; };
+static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, ConvGroup& cg);
 // Ownership of edges / brush points by objects, as ranges (see coh_scene_create).
 struct OwnerRanges {
   std::vector<int4> ranges;   // first, count, record, -
@@ -153,6 +157,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   mark("element bounds");
   struct ConvItem { int rec, kind, r; };
   std::vector<ConvItem> conv_list;
+  std::vector<ConvGroup> conv_groups;   // Convolved (kernel, Group members): the members are a scene of their own
+  struct SubScenes { coh_ctx* ctx; std::vector<ConvGroup>* v; ~SubScenes() { for (ConvGroup& g : *v) if (g.sub) coh_scene_free(ctx, (coh_scene_t)g.sub); } } sub_guard{ctx, &conv_groups};
   size_t conv_words = 0, conv_pixels = 0;
   long long total_rows = 0, total_brush_rows = 0;
   ObjRec root; memset(&root, 0, sizeof root);
@@ -180,6 +186,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       eff_open[0] = open[0]; n_children[0] = 0;
     }
     const coh_object& c = objs[i];
+    int skip_to = -1;
     if (c.kind == COH_OBJ_GROUP_END) {
       if (open_reading.empty()) FAIL("scene: GROUP_END without GROUP_BEGIN");
       const int rd = open_reading.back(); open_reading.pop_back();
@@ -231,6 +238,45 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     for (int k = 0; k < 6; k++) o.fill.p[k] = c.fparam[k];
     switch (c.kind) {
       case COH_OBJ_GROUP_BEGIN:
+        if (c.convolve) {
+          // Convolved (kernel, Group members) (render.ml:63, 1023-1052 with a Group child; shapes render.ml:536-555, where
+          // findfill of a Group is "fancy": minshape null).  The members become a scene of their own, rendered once into
+          // the object's canvas and convolved there (below); the object itself is one leaf, like Convolved (Basic Path).
+          const int ck = c.convolve & 255, cr = c.convolve >> 8;
+          if ((ck != COH_CONV_UNIT && ck != COH_CONV_GAUSSIAN) || cr <= 0 || cr > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
+          if (c.filter_kind == COH_FILTER_READING_SCENE) FAIL("scene: a reading-scene group cannot be Convolved");
+          int j = i + 1, nest = 1;
+          for (; j < n_objs; j++) {
+            const coh_object& m = objs[j];
+            if (j == n_objs - n_background) break;   // (a group may not straddle the two lists)
+            if (m.kind == COH_OBJ_GROUP_BEGIN) nest++;
+            else if (m.kind == COH_OBJ_GROUP_END) { if (--nest == 0) break; }
+            else if (m.kind == COH_OBJ_FILTER) FAIL("scene: filter objects inside a Convolved group are not supported");
+            else if (m.kind != COH_OBJ_PRIMITIVE && m.fill_kind != COH_FILL_PLAIN)
+              // the span-start fill quirk (polygon.ml:736) makes a fancy-filled member depend on the region requested at
+              // render time, which a canvas rendered once cannot follow
+              FAIL("scene: Convolved groups with fancy-filled members are not supported yet");
+          }
+          if (j >= n_objs || nest != 0) FAIL("scene: unterminated group");
+          if (j == i + 1) FAIL("Empty groups aren't allowed");   // render.ml:317
+          coh_scene_t sub = 0;
+          if (coh_scene_create(ctx, objs + i + 1, j - i - 1, 0, edges, n_edges, points, n_points, &sub)) return 1;
+          DevScene* ss = (DevScene*)sub;
+          conv_groups.push_back({(int)recs.size(), ck, cr, ss, objs + i + 1, j - i - 1});
+          skip_to = j;   // the members belong to the Convolved object
+          int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+          for (int li : ss->h_leaves) { const ObjRec& m = ss->h_objs[li]; x0 = std::min(x0, m.bx0); y0 = std::min(y0, m.by0); x1 = std::max(x1, m.bx1); y1 = std::max(y1, m.by1); }
+          if (x0 > x1) { rec_of_abi[i] = -1; i = j; conv_groups.back().rec = -1; continue; }   // nothing to draw
+          o.kind = K_CONV; o.fill.kind = 0; o.fill.c0 = 0;
+          o.bx0 = x0; o.by0 = y0; o.bx1 = x1; o.by1 = y1;
+          o.cv_x0 = floordiv(o.bx0 - 2 * cr, 32) * 32; o.cv_y0 = o.by0 - 2 * cr;
+          o.cv_nw = (o.bx1 + 2 * cr - o.cv_x0) / 32 + 1; o.cv_h = o.by1 + 2 * cr - o.cv_y0 + 1;
+          o.bx0 -= cr; o.bx1 += cr; o.by0 -= cr; o.by1 += cr;
+          o.cv_bits = (int)conv_words; conv_words += 2 * (size_t)o.cv_nw * o.cv_h;
+          o.cv_px = (int)conv_pixels; conv_pixels += (size_t)o.cv_nw * 32 * o.cv_h;
+          if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull) FAIL("scene: Convolved canvases too large");
+          break;
+        }
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");
         recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
@@ -351,6 +397,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     rec_of_abi[i] = (int)recs.size() - 1;
     ids.resize(recs.size(), -1); ids.back() = c.id;
     leaves.push_back((int)recs.size() - 1);
+    if (skip_to >= 0) i = skip_to;
   }
   mark("object loop");
   if (edge_own.overlapping()) FAIL("scene: objects may not share edges");
@@ -566,6 +613,8 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       DFREE(S); DFREE(C); DFREE(T); DFREE(Q); DFREE(A); DFREE(X); DFREE(op); DFREE(d_taps);
     }
   }
+  for (ConvGroup& cg : conv_groups)
+    if (cg.rec >= 0 && realize_convolved_group(ctx, s, recs[cg.rec], cg)) return 1;
   mark("sprites, Convolved");
   if (total_brush_rows > 0) {
     int* d_point_obj = nullptr;

@@ -207,11 +207,12 @@ class SceneBuilder:
         self._in_background = False
 
     def _obj(self, kind, pretrans=None, oid=-1, dx=0, dy=0, convolve=None):
-        """convolve = ("unit" | "gaussian", r): Convolved (Convolve.mkunit r | mkgaussian r, this geometry)."""
+        """convolve = ("unit" | "gaussian", r): Convolved (Convolve.mkunit r | mkgaussian r, this geometry) — a path, or a
+        group (group_begin(convolve=...): Convolved (kernel, Group members))."""
         o = CohObject()
         o.kind, o.pretrans, o.id, o.dx, o.dy = kind, (-1 if pretrans is None else pretrans), oid, dx, dy
         if convolve is not None:
-            assert kind == COH_OBJ_PATH and convolve[1] > 0
+            assert kind in (COH_OBJ_PATH, COH_OBJ_GROUP_BEGIN) and convolve[1] > 0
             o.convolve = {"unit": 1, "gaussian": 2}[convolve[0]] | (int(convolve[1]) << 8)
         self.objs.append(o)
         if self._in_background:

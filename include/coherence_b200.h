@@ -78,7 +78,9 @@ typedef struct coh_object {
   int32_t prim[4];     /* PRIMITIVE: inclusive pixel box x0,y0,x1,y1 (toint of the float rectangle) */
   int32_t prim_null;   /* PRIMITIVE: 1 for a zero-length HLine/VLine (NullShape) */
   int32_t convolve;    /* PATH: 0, or Convolved (kernel, Basic (fill, Path p)) (render.ml:63, 1023-1052):
-                          COH_CONV_UNIT | r << 8  = Convolve.mkunit r,  COH_CONV_GAUSSIAN | r << 8 = Convolve.mkgaussian r */
+                          COH_CONV_UNIT | r << 8  = Convolve.mkunit r,  COH_CONV_GAUSSIAN | r << 8 = Convolve.mkgaussian r.
+                          GROUP_BEGIN: 0, or Convolved (kernel, Group members) — the members up to the matching GROUP_END
+                          (plain fills only; no filters) are rendered once into the object's canvas and convolved there */
   int32_t sprite_winding; /* PATH: 0 = the AA sprite uses `winding`; 1 + rule otherwise.  Basic (fill, StrokedPath (p, spec)),
                           with edges = Shapes.strokepath spec p, takes its shape with NonZero (render.ml:510) but
                           its sprite with EvenOdd (render.ml:1018): winding = COH_NONZERO, sprite_winding = 1 + COH_EVENODD */

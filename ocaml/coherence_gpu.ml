@@ -309,13 +309,14 @@ let edges_of_basic tr sk =
     (Shapes.strokepath spec p, 0, 1 + 1)
   | _ -> failwith "Coherence_gpu: CPG operands must be paths"
 
-let rec flatten_obj fl ?(cached = true) (Render.Obj (ids, geom, tr, compop)) =
+let rec flatten_obj fl ?(cached = true) ?(conv = 0) (Render.Obj (ids, geom, tr, compop)) =
   let id = if cached then key_of_idset ids else -1L in
   match geom with
   | Render.Group objs ->
-    (* render.ml:988-1001: the group's transform is appended onto its members; members get fresh ids (never cached) *)
+    (* render.ml:988-1001: the group's transform is appended onto its members; members get fresh ids (never cached).
+       conv <> 0: Convolved (k, Group objs) — the GROUP_BEGIN record carries the kernel (coh_object.convolve) *)
     let (ints, floats, _) = blank k_group_begin in
-    ints.(8) <- pretrans_of_compop compop;
+    ints.(8) <- pretrans_of_compop compop; ints.(20) <- conv;
     push fl (ints, floats, id);
     List.iter (fun (Render.Obj (i, g, tr', c)) -> flatten_obj fl ~cached:false (Render.Obj (i, g, Pdftransform.append tr tr', c))) objs;
     push fl (blank k_group_end)
@@ -337,7 +338,10 @@ let rec flatten_obj fl ?(cached = true) (Render.Obj (ids, geom, tr, compop)) =
   | Render.Basic (fill, shapekind) -> flatten_basic fl id compop tr (transform_desc tr (desc_of_fill fill)) shapekind 0
   | Render.Convolved (k, Render.Basic (fill, shapekind)) ->
     flatten_basic fl id compop tr (transform_desc tr (desc_of_fill fill)) shapekind (kernel_code k (Convolve.radius_of_kernel k))
-  | Render.Convolved (_, _) -> failwith "Coherence_gpu: Convolved (k, Group _) is rendered by the reference path for now"
+  | Render.Convolved (k, (Render.Group _ as g)) ->
+    (* render.ml:1023-1052 with a Group child: members with fancy fills are refused by coh_scene_create (DESIGN.md) *)
+    flatten_obj fl ~cached ~conv:(kernel_code k (Convolve.radius_of_kernel k)) (Render.Obj (ids, g, tr, compop))
+  | Render.Convolved (_, _) -> failwith "Coherence_gpu: Convolved of this geometry (Convolved, Filter, Primitive) is not handled by the device path"
   | Render.Filter f ->
     let d = try List.assq f !filter_table with Not_found -> failwith "Coherence_gpu: a filter that was not registered (register_filter)" in
     (match f.Render.geometry with

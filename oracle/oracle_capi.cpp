@@ -41,6 +41,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
   std::vector<Scene> stack(1);
   std::vector<Obj> open;
   std::vector<int> open_reading;                          // abi index of an open reading-scene group, or -1
+  std::vector<int> open_conv;                             // per open group: its `convolve` word (Convolved (kernel, Group members))
   std::map<int, std::shared_ptr<Scene>> reading;          // reading-scene groups by the index of their GROUP_BEGIN
   std::vector<std::pair<size_t, int>> pending_reading;    // (position of the filter in the top-level list, first2)
   for (int i = 0; i < n; i++) {
@@ -112,7 +113,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         o.kind = Obj::Group;
         if (c.filter_kind == COH_FILTER_READING_SCENE && !open.empty()) throw std::runtime_error("scene: reading-scene groups must be top-level");
         open_reading.push_back(c.filter_kind == COH_FILTER_READING_SCENE ? i : -1);
-        open.push_back(std::move(o)); stack.emplace_back();
+        open.push_back(std::move(o)); stack.emplace_back(); open_conv.push_back(c.convolve);
         break;
       }
       case COH_OBJ_GROUP_END: {
@@ -120,8 +121,19 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         Obj g = std::move(open.back()); open.pop_back();
         g.children = std::move(stack.back()); stack.pop_back();
         const int rd = open_reading.back(); open_reading.pop_back();
+        const int conv = open_conv.back(); open_conv.pop_back();
         if (rd >= 0) { reading[rd] = std::make_shared<Scene>(std::move(g.children)); break; }
         if (g.children.empty()) throw std::runtime_error("Empty groups aren't allowed");  // render.ml:317
+        if (conv) {  // Convolved (kernel, Group members) (render.ml:63, 1023-1052): the group becomes the child
+          Obj outer;
+          outer.kind = Obj::Convolved; outer.id = g.id; outer.pretrans = g.pretrans; outer.dx = g.dx; outer.dy = g.dy;
+          const int r = conv >> 8;
+          outer.kernel = (conv & 255) == COH_CONV_UNIT ? mkunit(r) : mkgaussian(r);
+          g.id = -1; g.pretrans = -1; g.dx = g.dy = 0; g.has_bounds = false;
+          outer.children.push_back(std::move(g));
+          stack.back().push_back(std::move(outer));
+          break;
+        }
         stack.back().push_back(std::move(g));
         break;
       }

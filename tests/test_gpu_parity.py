@@ -386,6 +386,66 @@ def test_convolved_objects(ctx, oracle):
         assert _max_lsb(got, ref) == 0, kern
 
 
+def test_convolved_groups(ctx, oracle):
+    """Convolved (kernel, Group members) (render.ml:63, 1023-1052 with a Group child): shape = bloat r r of the union of
+    the members' shapes, minshape null (a Group's fill is "fancy", render.ml:536-555), sprite = convolve_sprite of the
+    group's sprite.  Members: translucent and opaque paths, a primitive, a brush stroke, a CPG, a nested PreTrans group,
+    a nested Convolved path; the Convolved group itself under PreTrans, translated, partly hidden and partly off-frame."""
+    W, H = 360, 260
+    for kern in (("gaussian", 3), ("unit", 2)):
+        b = S.SceneBuilder()
+        b.polygon([(200.3, 10.2), (340.9, 60.1), (250.0, 120.7)], S.Fill.plain(S.rgba8(250, 180, 20)))   # opaque, in front
+        b.group_begin(convolve=kern, pretrans=240, oid=11)
+        b.polygon([(60.0, 40.0), (230.0, 45.5), (210.5, 170.0), (70.0, 150.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 40, 200), 180)))
+        b.rectangle(S.rgba8(200, 30, 30), 100.0, 90.0, 160.0, 140.0)
+        b.group_begin(pretrans=128)
+        b.polygon([(150.0, 60.0), (300.0, 80.0), (280.0, 200.0)], S.Fill.plain(S.rgba8(30, 160, 60)))
+        b.polygon([(160.0, 100.0), (260.0, 110.0), (200.0, 190.0)], S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 90)), convolve=("unit", 2))
+        b.group_end()
+        b.brush(0.8, 6.0, [[("C", (80.0, 200.0), (140.0, 120.0), (220.0, 230.0), (300.0, 150.0))]], S.Fill.plain(S.rgba8(10, 10, 10)))
+        b.group_end()
+        b.group_begin(convolve=("gaussian", 5), dx=-40, dy=30)   # reaches out of the frame on the left / bottom
+        b.polygon([(10.0, 150.0), (120.0, 160.0), (90.0, 250.0), (20.0, 240.0)], S.Fill.plain(S.rgba8(120, 0, 160)))
+        b.polygon([(40.0, 170.0), (150.0, 200.0), (60.0, 230.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 200, 200), 200)))
+        b.group_end()
+        b.begin_background()
+        b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+        assert np.array_equal(got_u, ref_u), kern
+        assert _max_lsb(got, ref) == 0, kern
+        # partial update, and the object's shape through the cache entry points
+        objs, n, nbg, e, p = b.arrays()
+        ctx.fb_configure(W, H)
+        sc = ctx.scene_create(objs, nbg, e, p)
+        ctx.render_frame(sc, (90, 70, 150, 120))
+        sub = ctx.fb_read_rgba(90, 70, 150, 120)
+        assert np.array_equal(sub, ref[70:190, 90:240]), kern
+        ctx.scene_free(sc)
+    # Render.shape_of_basicshape of the object: bloat r r (union of the members' shapes), minshape null
+    b = S.SceneBuilder()
+    b.group_begin(convolve=("gaussian", 5))
+    b.polygon([(10.0, 150.0), (120.0, 160.0), (90.0, 250.0), (20.0, 240.0)], S.Fill.plain(S.rgba8(120, 0, 160)))
+    b.polygon([(140.0, 170.0), (250.0, 200.0), (160.0, 230.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 200, 200), 200)))
+    b.group_end()
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    gs, gm = ctx.scene_object_shape(sc, 0)
+    sa, _ = oracle.shapeminshape(e[objs[1].first:objs[1].first + objs[1].count], objs[1].winding)
+    sb, _ = oracle.shapeminshape(e[objs[2].first:objs[2].first + objs[2].count], objs[2].winding)
+    assert np.array_equal(ctx.shape_export(gs), oracle.shape_unary("bloat", oracle.shape_op("union", sa, sb), 5, 5)) and gm == 0
+    ctx.shape_free(gs)
+    ctx.scene_free(sc)
+    # what is refused, loudly
+    b = S.SceneBuilder()
+    b.group_begin(convolve=("gaussian", 3))
+    b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0)], S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.rgba8(0, 0, 255)))
+    b.group_end()
+    objs, n, nbg, e, p = b.arrays()
+    with pytest.raises(abi.CohError):
+        ctx.scene_create(objs, nbg, e, p)
+
+
 def test_convolve_sprite(ctx, oracle):
     """Convolve.convolve_sprite on arbitrary sprites (random canonical shapes, random premultiplied colours)."""
     rng = random.Random(41)

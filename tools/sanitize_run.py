@@ -27,6 +27,10 @@ run(S.random_scene(300, 200, 1200, seed=3), 300, 200)
 b = S.SceneBuilder()
 b.polygon([(30.5, 30.5), (170.2, 40.1), (150.0, 140.0), (40.0, 120.0)], S.Fill.gradient((20.0, 20.0), (150.0, 120.0), True, False, S.rgba8(255, 0, 0), S.rgba8(0, 0, 255)))
 b.polygon([(50.0, 40.0), (150.0, 45.5), (140.5, 120.0)], S.Fill.plain(S.rgba8(0, 0, 0)), convolve=("gaussian", 4))
+b.group_begin(convolve=("unit", 2), pretrans=200)   # Convolved (kernel, Group members)
+b.polygon([(20.0, 90.0), (120.0, 95.5), (110.5, 150.0)], S.Fill.plain(S.rgba8(0, 90, 0)))
+b.rectangle(S.rgba8(200, 30, 30), 60.0, 100.0, 90.0, 130.0)
+b.group_end()
 b.begin_background(); b.rectangle(S.WHITE, 0.0, 0.0, 200.0, 160.0)
 run(b, 200, 160)
 a = ctx.shape_box(5, 5, 100, 50); c = ctx.shape_box(50, 20, 100, 70)
