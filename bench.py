@@ -332,7 +332,7 @@ def run_ours(args):
             "frames_per_s": 1e3 / ms, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 crossings)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "bands": N, "band_rows": [list(b) for b in band_list], "l2": "256 MB flush write before every timed step (untimed)",
-                       "step": "one frame: K1 binning (3 launches) + raster phase (scan, visibility, antialiasing, compositing walk: 4 launches)", "gather": gather},
+                       "step": "one frame = 5 launches: background prefill (second stream) beside scan conversion, visibility and antialiasing of every (cell entry, row) pair, then the row compositor; the cell lists are kept with the scene (binned once)", "gather": gather},
             "roofline": {"bound": "hbm", "kernel": "raster phase: k_pre_scan + k_pre_vis + k_pre_aa_runs (dominant) + k_comp_rows", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic if N == 1 else None, "traffic_source": NCU_SUMMARY if traffic else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": walk_ms_max, "binning_ms": bin_ms,

@@ -1,6 +1,7 @@
 """C3 (10^5 objects at 7680x4320) split into scanline bands over the GPUs of one box: torchrun --nproc-per-node N
-tools/c3_bands.py.  Every rank renders its band into the symmetric-memory framebuffers of all ranks (fused gather);
-prints the per-frame time (max over ranks, CUDA events) on rank 0."""
+tools/c3_bands.py.  Every rank renders its band into the framebuffers of all ranks (the library's CUDA IPC mappings:
+coh_fb_alloc_shared / coh_fb_open_peer / coh_fb_set_peers — the gather is fused into the rendering kernels), followed
+by a cross-rank barrier on the stream; prints the per-frame time (max over ranks, CUDA events) on rank 0."""
 import json
 import os
 import sys
@@ -23,26 +24,20 @@ ctx = abi.Context(local)
 stream = torch.cuda.current_stream()
 ctx.set_stream(stream.cuda_stream)
 ctx.fb_configure(W, H, y0, y1)
-symm = None
-if world > 1:
-    import torch.distributed._symmetric_memory as symm_mem
+fused = world > 1
+sync_t = torch.zeros(1, dtype=torch.int32, device="cuda")
+if fused:
+    from coherence_renderer_b200 import torch_plumbing
 
-    fb = symm_mem.empty((H, W), dtype=torch.int32, device=torch.device("cuda", local))
-    fb.zero_()
-    symm = symm_mem.rendezvous(fb, dist.group.WORLD)
-    ptrs = [int(symm.buffer_ptrs[r]) for r in range(world)]
-    ctx.fb_attach(ptrs[rank])
-    ctx.fb_set_peers([ptrs[r] for r in range(world) if r != rank])
-else:
-    fb = torch.zeros((H, W), dtype=torch.int32, device="cuda")
-    ctx.fb_attach(fb.data_ptr())
+    handles = torch_plumbing.exchange_ipc_handles(dist, ctx.fb_alloc_shared())
+    ctx.fb_set_peers([ctx.fb_open_peer(handles[r]) for r in range(world) if r != rank])
 sc = ctx.scene_create(objs, nbg, e, p)
 
 
 def frame():
     ctx.render_frame(sc, (0, 0, W, H))
-    if symm is not None:
-        symm.barrier()
+    if fused:
+        dist.all_reduce(sync_t)   # every rank's band has landed in this rank's framebuffer
 
 
 for _ in range(3):
@@ -58,7 +53,9 @@ for a, b in ev:
     b.record(stream)
 torch.cuda.synchronize()
 t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / K], dtype=torch.float64, device="cuda")
-chk = fb[::7, ::5].to(torch.int64).sum().reshape(1)
+import numpy as np  # noqa: E402
+
+chk = torch.tensor([int(ctx.fb_read_rgba(0, 0, W, H)[::7, ::5].astype(np.uint64).sum()) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     lo, hi = chk.clone(), chk.clone()
