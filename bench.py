@@ -193,14 +193,21 @@ def run_ours(args):
     # to all of them over NVLink as they go — compute and "collective" are one kernel, followed only by a cross-rank
     # barrier.  If the mapping cannot be set up on this box, fall back to an NCCL all-gather of the strips.
     fb, full, fused, gather = None, None, False, "none (single GPU)"
+    display_only = os.environ.get("COH_GATHER", "display") != "all"
     if N > 1 and not os.environ.get("COH_NCCL_GATHER"):
         try:
             from coherence_renderer_b200 import torch_plumbing
 
             handles = torch_plumbing.exchange_ipc_handles(dist, ctx.fb_alloc_shared())
-            ctx.fb_set_peers([ctx.fb_open_peer(handles[r]) for r in range(N) if r != rank])
+            if display_only:
+                # strips go to the display rank.  Rank r > 0 mirrors its band into rank 0's framebuffer
+                # only (H/N rows over NVLink per rank instead of (N-1) H/N); rank 0 ends up with the whole frame.
+                ctx.fb_set_peers([ctx.fb_open_peer(handles[0])] if rank else [])
+                gather = "fused into the rendering kernels: every rank stores its band into the display rank's (rank 0) framebuffer over NVLink (CUDA IPC mapping made by the library) + cross-rank barrier; COH_GATHER=all mirrors into every rank"
+            else:
+                ctx.fb_set_peers([ctx.fb_open_peer(handles[r]) for r in range(N) if r != rank])
+                gather = "fused into the rendering kernels: peer stores over NVLink into every rank's framebuffer (CUDA IPC mappings made by the library) + cross-rank barrier"
             fused = True
-            gather = "fused into the rendering kernels: peer stores over NVLink into every rank's framebuffer (CUDA IPC mappings made by the library) + cross-rank barrier"
         except Exception as exc:  # noqa: BLE001
             if rank == 0:
                 print(f"bench.py: peer framebuffers unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
@@ -234,7 +241,23 @@ def run_ours(args):
         frame()
     barrier()
     ctx.sync()  # surfaces kernel-side errors
-    if N > 1:  # every rank must now hold the same, complete frame
+    if N > 1 and fused and display_only:
+        # the display rank must hold every band exactly as the rank that rendered it holds it
+        mine = torch.from_numpy(ctx.fb_read_rgba(0, y0, WIDTH, y1 - y0).view(np.int32)).cuda()
+        sums = torch.zeros(N, dtype=torch.int64, device="cuda")
+        sums[rank] = mine[::5, ::7].to(torch.int64).sum()
+        dist.all_reduce(sums)
+        bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            whole = torch.from_numpy(ctx.fb_read_rgba(0, 0, WIDTH, HEIGHT).view(np.int32)).cuda()
+            for k, (a, b) in enumerate(band_list):
+                if whole[a:b][::5, ::7].to(torch.int64).sum().item() != sums[k].item() or (whole[a:b][:: max((b - a) // 4, 1), 5] == 0).any().item():
+                    bad += 1
+            del whole
+        dist.all_reduce(bad)
+        if bad.item():
+            raise SystemExit("bench.py: the display rank's frame differs from the bands the ranks rendered")
+    elif N > 1:  # every rank must now hold the same, complete frame
         whole = torch.from_numpy(ctx.fb_read_rgba(0, 0, WIDTH, HEIGHT).view(np.int32)).cuda() if fused else full
         chk = whole[::13, ::7].to(torch.int64).sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()

@@ -266,6 +266,7 @@ int coh_init(int device, coh_ctx** out) {
   if ((e = cudaMallocHost(&ctx->h_total, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
   if (const char* e = getenv("COH_WALK_H")) coh_set_option(ctx, "walk_h", atoi(e));
   if (const char* e = getenv("COH_FUSED")) coh_set_option(ctx, "fused", atoi(e));
+  if (const char* e = getenv("COH_AB")) coh_set_option(ctx, "ab", atoi(e));
   if (const char* e = getenv("COH_AA_GENERAL")) coh_set_option(ctx, "aa_general", atoi(e));
   *out = ctx;
   return 0;

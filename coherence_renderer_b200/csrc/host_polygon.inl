@@ -277,6 +277,7 @@ int coh_convolve_sprite(coh_ctx* ctx, int32_t kernel_kind, int32_t r, coh_shape_
   CK(cudaSetDevice(ctx->device));
   *out_shape = 0; *n_out = 0;
   if ((kernel_kind != COH_CONV_UNIT && kernel_kind != COH_CONV_GAUSSIAN) || r <= 0) FAIL("Convolve.mkunit / Convolve.mkxy: Invalid_argument");
+  if (r > 64) FAIL("coh_convolve_sprite: kernel radius above 64 (the 32-bit tap sums of k_conv_pass are sized for it)");
   if (!shape) return 0;  // NullSprite -> NullSprite
   DevShape* s = (DevShape*)shape;
   coh_shape_t R = 0;

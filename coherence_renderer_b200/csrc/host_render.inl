@@ -36,32 +36,11 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   int n_cells = (cell_row1 - cell_row0 + 1) * fr.cntx;
   const bool big = n_leaves > 1024;
   const bool ordered = !s->has_fancy;  // with fancy fills the queue must stay row-major (carry look-back)
-  // Background cells of a box update are finished by k_prefill and never enter the walker's queue
-  // (not with peer framebuffers: the mirrored stores of background cells are better spread over the walker's
-  // warps — measured at 2 / 4 / 8 GPUs)
-  const bool prefill = !big && ordered && !A.u_init && !A.resume && !(A.fb == ctx->fb && ctx->n_peers > 0);
-  // Whole-frame binning of a small scene is kept with the scene; every other pass bins into the context's scratch.
-  const bool keep = whole && !big && ctx->opt_bin_cache;
-  BinSet& B = keep ? V.bins : ctx->bins;
-  const int key[6] = {fr.W, fr.H, fr.band_y0, fr.band_y1, ordered ? 1 : 0, prefill ? 1 : 0};
-  const bool hit = keep && V.bins_valid && memcmp(key, V.bins_key, sizeof key) == 0;
-  if (n_cells > B.n_cells_cap) {
-    DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng); DFREE(B.comp_order);
-    B.n_cells_cap = 0;
-    CK(DMALLOC(&B.cell_head, sizeof(int2) * n_cells));
-    CK(DMALLOC(&B.cell_rng, sizeof(int2) * n_cells));
-    CK(DMALLOC(&B.cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
-    CK(DMALLOC(&B.comp_order, sizeof(int4) * (size_t)n_cells));
-    B.n_cells_cap = n_cells;
-  }
-  if (!B.state) CK(DMALLOC(&B.state, sizeof(int) * ORDER_BINS));
   if (!ctx->queue) {
     CK(DMALLOC(&ctx->queue, sizeof(int)));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->n_sms = prop.multiProcessorCount;
   }
-  CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
-  if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   // capacity of the item pool: the exact total is a pure function of the object boxes and the
   // frame geometry, so it is computed on the host (once per scene and geometry) — no device
   // round trip inside a frame.
@@ -78,6 +57,62 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     if (whole) { V.coarse_total_valid = false; V.items_total = tot; V.items_for_W = fr.W; V.items_for_H = fr.H; V.items_for_y0 = fr.band_y0; V.items_for_y1 = fr.band_y1; }
   } else total = V.items_total;
   const size_t need = total;
+  // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
+  int walk_h = big ? 16 : 4;
+  // Few cells (a band of an 8-GPU split, a small dirty region): the launch is bounded by its longest work item,
+  // not by throughput — one-row items shorten that path (measured on the lion at 8 GPUs: 0.164 -> 0.141 ms;
+  // at 1 to 4 GPUs four-row items are as fast or faster).
+  if (!big && (long long)n_cells * 4 < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 1;
+  // ... and a band of a very large scene with fewer than three 16-row items per resident warp is bounded by its heaviest
+  // cells: four-row items cost more work in total (C3 whole frame: 4.3 vs 3.0 ms) but quarter the critical path
+  // (C3, slowest 1/8 band: 0.98 -> 0.73 ms; at 1/4 the two are equal)
+  if (big && (long long)n_cells < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 4;
+  if (ctx->opt_walk_h) walk_h = ctx->opt_walk_h;  // tests force every variant
+  // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
+  // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
+  // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
+  const int force = ctx->opt_fused;   // tests force either path: 1 fused, 0 three-phase
+  // eligible: every leaf of the range is a path, a primitive or a Convolved object
+  bool kinds_ok = extras == 0;
+  bool has_conv = false;
+  if (!kinds_ok && !big) {
+    kinds_ok = true;
+    for (int li = A.l0; li < A.l1 && kinds_ok; li++) {
+      const int k = s->h_objs[V.h_leaves[li]].kind;
+      kinds_ok = k == K_PATH || k == K_PRIM || k == K_CONV;
+      has_conv = has_conv || k == K_CONV;
+    }
+  }
+  // (a pass that continues a frame — after a filter — takes the three-phase path too: its compositing walk is the
+  // variant that starts the root accumulators from the framebuffer)
+  const bool pre = kinds_ok && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
+                   // flat scenes have the row compositor: worth it from a few thousand pairs on (measured on bands of the
+                   // lion: 1/8 of the frame 0.069 -> 0.053 ms, 1/2 0.155 -> 0.098 ms); other scenes composite with the
+                   // walker, and their small passes (a drag's dirty region: 0.088 vs 0.103 ms) stay fused
+                   (force >= 0 ? force == 0 : ((s->flat_ok && !A.collapsed) ? (long long)total * CELL_H >= ctx->opt_pre_min_pairs : walk_h != 1));
+  // Background cells of a box update are finished by k_prefill and never enter the walker's queue.  With peer
+  // framebuffers only in three-phase frames, where the prefill — and its mirrored stores over NVLink — runs beside the
+  // scan kernels (in a fused walk the mirrored stores of background cells are better spread over the walker's warps:
+  // measured at 2 / 4 / 8 GPUs)
+  const bool mirrored = A.fb == ctx->fb && ctx->n_peers > 0;
+  const bool prefill = !big && ordered && !A.u_init && !A.resume && (!mirrored || (pre && ctx->opt_fork_prefill && !(ctx->opt_ab & 4)));
+  // Whole-frame binning of a small scene is kept with the scene; every other pass bins into the context's scratch.
+  const bool keep = whole && !big && ctx->opt_bin_cache;
+  BinSet& B = keep ? V.bins : ctx->bins;
+  const int key[6] = {fr.W, fr.H, fr.band_y0, fr.band_y1, ordered ? 1 : 0, prefill ? 1 : 0};
+  const bool hit = keep && V.bins_valid && memcmp(key, V.bins_key, sizeof key) == 0;
+  if (n_cells > B.n_cells_cap) {
+    DFREE(B.cell_order); DFREE(B.cell_head); DFREE(B.cell_rng); DFREE(B.comp_order);
+    B.n_cells_cap = 0;
+    CK(DMALLOC(&B.cell_head, sizeof(int2) * n_cells));
+    CK(DMALLOC(&B.cell_rng, sizeof(int2) * n_cells));
+    CK(DMALLOC(&B.cell_order, sizeof(int) * (size_t)n_cells * BIN_CLASSES));  // one-pass binning keeps one segment per length class
+    CK(DMALLOC(&B.comp_order, sizeof(int4) * (size_t)n_cells));
+    B.n_cells_cap = n_cells;
+  }
+  if (!B.state) CK(DMALLOC(&B.state, sizeof(int) * ORDER_BINS));
+  CK(cudaMemsetAsync(ctx->queue, 0, sizeof(int), ctx->stream));
+  if (ctx->timing) { if (drain_timing(ctx)) return 1; CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
   if (need > B.cell_items_cap) {
     DFREE(B.cell_items); DFREE(B.item_cell); DFREE(B.item_attr); DFREE(B.item_rec);
     B.cell_items_cap = 0;
@@ -147,13 +182,6 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
   P.n_peers = (A.fb == ctx->fb) ? ctx->n_peers : 0;   // only the frame itself is mirrored, not filter canvases
   for (int k = 0; k < COH_MAX_PEERS; k++) P.peer_fb[k] = k < P.n_peers ? ctx->peer_fb[k] : nullptr;
-  // persistent grid: exactly one resident wave.  Work items are 4 rows high, or 16 for very large scenes.
-  int walk_h = big ? 16 : 4;
-  // Few cells (a band of an 8-GPU split, a small dirty region): the launch is bounded by its longest work item,
-  // not by throughput — one-row items shorten that path (measured on the lion at 8 GPUs: 0.164 -> 0.141 ms;
-  // at 1 to 4 GPUs four-row items are as fast or faster).
-  if (!big && (long long)n_cells * 4 < 3LL * ctx->n_sms * WALK_MIN_CTAS * WALK_WARPS) walk_h = 1;
-  if (ctx->opt_walk_h) walk_h = ctx->opt_walk_h;  // tests force every variant
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
 #define LAUNCH_WALK_E(CARRYV, EX)                                                                                  \
   do {                                                                                                             \
@@ -169,34 +197,14 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.queue = ctx->queue; P.n_cells = n_cells;
   P.pre_sc = nullptr; P.pre_op = nullptr; P.item_cell = nullptr;
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  // Plain-filled paths and primitives only, a list pool of moderate size: three-phase frame (kernels.cuh)
-  // (small launches — a band of an 8-GPU split, a dirty region — stay fused: four dependent launches cost more
-  // than the parallelism gains there; measured on 1/8 bands of the lion: 0.051 vs 0.059 ms)
-  const int force = ctx->opt_fused;   // tests force either path: 1 fused, 0 three-phase
-  // eligible: every leaf of the range is a path, a primitive or a Convolved object
-  bool kinds_ok = extras == 0;
-  bool has_conv = false;
-  if (!kinds_ok && !big) {
-    kinds_ok = true;
-    for (int li = A.l0; li < A.l1 && kinds_ok; li++) {
-      const int k = s->h_objs[V.h_leaves[li]].kind;
-      kinds_ok = k == K_PATH || k == K_PRIM || k == K_CONV;
-      has_conv = has_conv || k == K_CONV;
-    }
-  }
-  // (a pass that continues a frame — after a filter — takes the three-phase path too: its compositing walk is the
-  // variant that starts the root accumulators from the framebuffer)
-  const bool pre = kinds_ok && !big && total > 0 && total * CELL_H <= (size_t)(1 << 23) &&
-                   // flat scenes have the row compositor: worth it from a few thousand pairs on (measured on bands of the
-                   // lion: 1/8 of the frame 0.069 -> 0.053 ms, 1/2 0.155 -> 0.098 ms); other scenes composite with the
-                   // walker, and their small passes (a drag's dirty region: 0.088 vs 0.103 ms) stay fused
-                   (force >= 0 ? force == 0 : ((s->flat_ok && !A.collapsed) ? (long long)total * CELL_H >= ctx->opt_pre_min_pairs : walk_h != 1));
   // background cells: cleared to the background colour by their own kernel.  In a three-phase frame it touches nothing
   // the scan kernels read, so it runs beside them on a second stream and joins before the compositor.
   bool prefill_forked = false;
   if (prefill) {
     BinPrefill pf; memset(&pf, 0, sizeof pf);
-    pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1; pf.n_peers = 0;
+    pf.fb = A.fb; pf.u_out = A.u_out; pf.ux0 = ux; pf.uy0 = uy; pf.ux1 = ux + uw - 1; pf.uy1 = uy + uh - 1;
+    pf.n_peers = mirrored ? ctx->n_peers : 0;
+    for (int k = 0; k < pf.n_peers; k++) pf.peer_fb[k] = ctx->peer_fb[k];
     cudaStream_t st = ctx->stream;
     if (pre && ctx->opt_fork_prefill) {
       if (!ctx->aux_stream) {

@@ -274,7 +274,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           o.bx0 -= cr; o.bx1 += cr; o.by0 -= cr; o.by1 += cr;
           o.cv_bits = (int)conv_words; conv_words += 2 * (size_t)o.cv_nw * o.cv_h;
           o.cv_px = (int)conv_pixels; conv_pixels += (size_t)o.cv_nw * 32 * o.cv_h;
-          if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull) FAIL("scene: Convolved canvases too large");
+          if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull || o.cv_h > 65535 || o.cv_nw > 32767) FAIL("scene: Convolved canvases too large");
           break;
         }
         o.kind = K_GROUP;
@@ -654,6 +654,8 @@ int coh_fb_set_peers(coh_ctx* ctx, int32_t n_peers, void* const* peer_fbs) {
 int coh_fb_configure(coh_ctx* ctx, int32_t width, int32_t height, int32_t band_y0, int32_t band_y1) {
   CK(cudaSetDevice(ctx->device));
   if (width <= 0 || height <= 0) FAIL("coh_fb_configure: bad size");
+  // the pair list of three-phase frames packs (tile column << 16 | row) into one word
+  if (height > 65535 || width > 32 * 32767) FAIL("coh_fb_configure: framebuffer larger than 1048544 x 65535 pixels");
   if (band_y0 < 0 || band_y1 > height || band_y0 > band_y1) FAIL("coh_fb_configure: bad band");
   if (width != ctx->fr.W || height != ctx->fr.H) {
     if (ctx->own_fb) DFREE(ctx->fb);

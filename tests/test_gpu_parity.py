@@ -853,6 +853,12 @@ def test_edge_cases(ctx, oracle):
     deep.polygon([(t[0] + 9.5, t[1] + 4.25) for t in tri], S.Fill.plain(S.dissolve(S.rgba8(200, 20, 30), 180)))
     got, ref, got_u, ref_u = _render_both(ctx, oracle, deep, W, H)
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+    # size limits of the packed (tile, row) words and of the 32-bit tap sums fail loudly
+    with pytest.raises(abi.CohError):
+        ctx.fb_configure(64, 70000)
+    ctx.fb_configure(W, H)
+    with pytest.raises(abi.CohError):
+        ctx.convolve_sprite("gaussian", 65, ctx.shape_box(0, 0, 4, 4), np.zeros(16, np.uint32))
 
 
 def test_filter_matte_interior_shortcut(ctx, oracle):
