@@ -133,6 +133,7 @@ struct coh_ctx {
   bool have_u = false;
   // binning scratch (passes whose binning is not kept with the scene)
   BinSet bins;
+  int opt_pre_min_pairs_walk = 1 << 30;  // the same threshold for passes that composite with the walker when their cells are few (one-row items)
   int opt_pre_min_pairs = 4096;  // passes with fewer (list entry, row) pairs stay on the fused walker: four dependent launches cost more than they gain
   bool opt_bin_cache = true;  // keep whole-frame binning with the scene
   bool opt_fork_prefill = true;  // three-phase frames: background prefill on a second stream beside the scan kernels
@@ -278,6 +279,7 @@ int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
   else if (n == "aa_general") ctx->aa_general = value != 0;
   else if (n == "bin_cache") ctx->opt_bin_cache = value != 0;
   else if (n == "pre_min_pairs") ctx->opt_pre_min_pairs = value;
+  else if (n == "pre_min_pairs_walk") ctx->opt_pre_min_pairs_walk = value;
   else if (n == "comp_rows") ctx->opt_comp_rows = value != 0;
   else if (n == "ab") ctx->opt_ab = value;
   else if (n == "fork_prefill") ctx->opt_fork_prefill = value != 0;

@@ -89,7 +89,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
                    // flat scenes have the row compositor: worth it from a few thousand pairs on (measured on bands of the
                    // lion: 1/8 of the frame 0.069 -> 0.053 ms, 1/2 0.155 -> 0.098 ms); other scenes composite with the
                    // walker, and their small passes (a drag's dirty region: 0.088 vs 0.103 ms) stay fused
-                   (force >= 0 ? force == 0 : ((s->flat_ok && !A.collapsed) ? (long long)total * CELL_H >= ctx->opt_pre_min_pairs : walk_h != 1));
+                   (force >= 0 ? force == 0 : ((s->flat_ok && !A.collapsed) ? (long long)total * CELL_H >= ctx->opt_pre_min_pairs : (walk_h != 1 || (long long)total * CELL_H >= ctx->opt_pre_min_pairs_walk)));
   // Background cells of a box update are finished by k_prefill and never enter the walker's queue.  With peer
   // framebuffers only in three-phase frames, where the prefill — and its mirrored stores over NVLink — runs beside the
   // scan kernels (in a fused walk the mirrored stores of background cells are better spread over the walker's warps:

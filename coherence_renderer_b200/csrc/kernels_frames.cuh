@@ -331,8 +331,14 @@ __global__ void k_scan_rows(const EdgeRec* __restrict__ edges, int n_edges, int 
   SinkMem sink;
   sink.wx0 = wx0 + 32 * w0; sink.nwords = min(SCAN_CHUNK_WORDS, nw - w0); sink.stride = 1;
   sink.S = S + (size_t)r * nw + w0; sink.C = C + (size_t)r * nw + w0;
-  if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink))
-    *error_flag = 1;
+  if (scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink)) return;
+  // more crossings touch the 256-pixel window than a list holds (a line of small text as one compound path): word by word
+  const int words = sink.nwords, x0 = sink.wx0;
+  for (int w = 0; w < words; w++) {
+    sink.wx0 = x0 + 32 * w; sink.nwords = 1;
+    sink.S = S + (size_t)r * nw + w0 + w; sink.C = C + (size_t)r * nw + w0 + w;
+    if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 31, sink)) *error_flag = 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------

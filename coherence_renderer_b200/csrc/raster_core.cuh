@@ -195,7 +195,7 @@ COH_HD uint32_t interval_mask32(int wx0, int a, int b) {
 // the caller reports the object as too complex for the window (loudly).
 // ---------------------------------------------------------------------------------
 #ifndef COH_MAXX
-#define COH_MAXX 16
+#define COH_MAXX 64
 #endif
 
 // CAP = COH_MAXX: general list (dynamically indexed, lives in local memory).

@@ -31,6 +31,58 @@ def test_shapeminshape_random_polygons(ctx, oracle):
         ctx.shape_free(hm)
 
 
+def _comb_edges(x0, y0, teeth, pitch, width, height):
+    """A comb as ONE compound path: `teeth` thin rectangles `width` wide every `pitch` pixels (a line of small text has
+    this crossing density)."""
+    segs = []
+    for k in range(teeth):
+        xa = x0 + k * pitch
+        segs.append(S.polygon_segments([(xa, y0), (xa + width, y0 + 0.3), (xa + width + 0.4, y0 + height), (xa + 0.2, y0 + height - 0.2)]))
+    return np.concatenate([abi.host_edgelist_of_subpath(sg) for sg in segs]).reshape(-1, 4)
+
+
+def test_many_crossings_per_window(ctx, oracle):
+    """Dense compound paths: ~40 band crossings touch one 32-pixel window of a row (the crossing lists hold 64; the
+    stand-alone scan falls back from its 256-pixel windows to single words) — stand-alone scan conversion, the matte,
+    and whole frames through the three-phase path and the fused walker."""
+    edges = _comb_edges(10.3, 8.1, 150, 1.55, 0.8, 22.0)    # ~20 teeth = 40 crossings per 32 pixels, 165 per 256
+    for w in (0, 1):
+        ref_s, ref_m = oracle.shapeminshape(edges, w)
+        hs, hm = ctx.shapeminshape_of_edgelist(edges, w)
+        assert np.array_equal(ctx.shape_export(hs), ref_s) and np.array_equal(ctx.shape_export(hm), ref_m)
+        ctx.shape_free(hs)
+        ctx.shape_free(hm)
+        maxshape = oracle.shape_op("difference", ref_s, ref_m)
+        hx = ctx.shape_import(maxshape)
+        assert np.array_equal(ctx.polygon_opacity(edges, w, hx), oracle.polygon_opacity(edges, w, maxshape))
+        ctx.shape_free(hx)
+    W, H = 300, 48
+    for fused in (0, 1):
+        ctx.set_option("fused", fused)
+        try:
+            b = S.SceneBuilder()
+            b.path_edges(edges, S.Fill.plain(S.dissolve(S.rgba8(20, 20, 20), 230)))
+            b.path_edges(_comb_edges(5.0, 20.0, 120, 2.1, 1.0, 20.0), S.Fill.plain(S.rgba8(200, 40, 40)), winding=S.COH_EVENODD)
+            b.begin_background()
+            b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+            got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+            assert np.array_equal(got_u, ref_u), fused
+            assert _max_lsb(got, ref) == 0, fused
+        finally:
+            ctx.set_option("fused", -1)
+    # beyond the lists' capacity the frame still fails loudly (never a wrong picture)
+    dense = _comb_edges(10.0, 4.0, 400, 0.4, 0.2, 12.0)     # ~160 crossings per 32 pixels
+    b = S.SceneBuilder()
+    b.path_edges(dense, S.Fill.plain(S.rgba8(0, 0, 0)))
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    with pytest.raises(abi.CohError):
+        ctx.render_frame(sc, (0, 0, W, H))
+        ctx.fb_read_rgba(0, 0, W, H)
+    ctx.scene_free(sc)
+
+
 def test_polygon_opacity_random(ctx, oracle):
     rng = random.Random(12)
     for it in range(40):
