@@ -94,7 +94,8 @@ struct DevScene {
   std::vector<int> real_depth;   // per record: enclosing groups in the scene as given (ObjRec.depth leaves out groups dissolved into their parent)
   // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
-  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; };
+  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total; };
+  int* filter_taps = nullptr;    // blur filters: Convolve.mkgaussian taps (convolve.ml:60-70), made once per scene
   std::vector<FilterRec> filters;
   // Group shapes (render.ml:476-496 caches them under the group's id): kept per scene, in the frame the group
   // had when the entry was made; moving the whole group only changes the offset applied on the way out.

@@ -352,10 +352,19 @@ static int render_frame_passes(coh_ctx* ctx, DevScene* s, PassArgs A) {
 // ---------------------------------------------------------------------------------------
 struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
 static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed = false);
+// temporaries of one filter application: released on every way out
+struct StreamTemps {
+  coh_ctx* ctx; std::vector<void*> v;
+  explicit StreamTemps(coh_ctx* c) : ctx(c) {}
+  ~StreamTemps() { for (void* p : v) cudaFreeAsync(p, ctx->stream); }
+  cudaError_t get_(void** p, size_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream); if (e == cudaSuccess) v.push_back(*p); return e; }
+#define TMPGET(tmp, p, bytes) (tmp).get_((void**)(p), (bytes))
+};
 
-// `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small and handled
-// whole; the RGBA8 canvases are only touched in the rows the filter reads or writes).
-static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target, PixBox box) {
+// `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small; the RGBA8 canvases are only
+// touched in the rows and columns the filter reads or writes).  `fresh`: nothing but filters has been composited into
+// `target` so far — every pixel still in U has a clear accumulator there (a filter finishes the whole of its shape).
+static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target, PixBox box, bool fresh) {
   const DevScene::FilterRec& F = s->filters[fi];
   const Frame& fr = ctx->fr;
   const int W = fr.W, H = fr.H, nw = fr.tiles_x;
@@ -368,106 +377,100 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : 0;             // reach of the reading shape
   const int ry0 = std::max(0, y0 - m), ry1 = std::min(H - 1, y1 + m), rh = ry1 - ry0 + 1;
   const PixBox tbox{x0, y0, x1, y1}, rbox{std::max(0, x0 - m), ry0, std::min(W - 1, x1 + m), ry1};
-  const unsigned wblocks = (unsigned)((nwords + 255) / 256);
   const size_t po = (size_t)ry0 * W, pn = (size_t)rh * W;                 // canvas rows [ry0, ry1]
-  uint32_t *SG = nullptr, *CG = nullptr, *T = nullptr, *R = nullptr, *X = nullptr, *Z = nullptr, *tmp = nullptr;
-  uint8_t *op = nullptr, *alpha = nullptr; int* d_taps = nullptr;
-  CK(DMALLOC(&SG, 4 * nwords)); CK(DMALLOC(&CG, 4 * nwords)); CK(DMALLOC(&T, 4 * nwords)); CK(DMALLOC(&R, 4 * nwords));
-  CK(cudaMemsetAsync(SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(CG, 0, 4 * nwords, ctx->stream));
+  const size_t r0 = (size_t)y0 * nw;                                      // first word of row y0 in a bit-frame
+  StreamTemps tmp(ctx);
+  // bit-frames: SG / CG = shape / coverage of the geometry (rows y0 .. y1 are used), T = shptorender, R = reading shape,
+  // then the pixels the scene below shows through; Q = pixels the matte super-samples (rows y0 .. y1)
+  uint32_t* planes = nullptr;
+  CK(TMPGET(tmp, &planes, 4 * nwords * 5));
+  uint32_t *SG = planes, *CG = planes + nwords, *T = planes + 2 * nwords, *R = planes + 3 * nwords, *Q = planes + 4 * nwords;
+  CK(cudaMemsetAsync(planes, 0, 4 * nwords * 4, ctx->stream));
   const EdgeRec* ed = s->edges + F.first;
-  // shape of the geometry (render.ml:472-474); CG receives the coverage (the minshape is needed for the matte)
-  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + (size_t)y0 * nw, CG + (size_t)y0 * nw, ctx->d_error); LAUNCHED();
-  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, U, T, nwords, 2); LAUNCHED();     // shptorender = r &&& u (render.ml:1281)
-  // reading scene -> X -> filter function -> Y (in place)
-  uint32_t* Y = nullptr;
+  // shape of the geometry (render.ml:472-474), its coverage (the minshape is needed for the matte), and
+  // shptorender = r &&& u (render.ml:1281)
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + r0, CG + r0, ctx->d_error, U + r0, T + r0); LAUNCHED();
+  // The scene below renders the same pixels whatever region it is asked for (plain fills: no span-start quirk,
+  // polygon.ml:736), so where the reading scene IS the scene below (monochrome, blur: filters.ml:229-258) the pixels
+  // that show through the matte (render.ml:1105-1110) are taken from the reading scene's render before its filter function.
+  const bool z_is_x = (F.kind == COH_FILTER_MONOCHROME || F.kind == COH_FILTER_BLUR) && !s->has_fancy;
+  // reading scene -> X -> filter function -> Y
+  uint32_t *X = nullptr, *Y = nullptr, *Z = nullptr;
+  int blend_flags = fresh ? 1 : 0;
   if (F.kind != COH_FILTER_HOLE) {
-    CK(DMALLOC(&X, 4 * (size_t)W * H));
-    CK(cudaMemsetAsync(X + po, 0, 4 * pn, ctx->stream));
-    if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp
-      CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
-      k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED();  // T is empty outside [y0, y1]
-    } else CK(cudaMemcpyAsync(R, T, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(TMPGET(tmp, &X, 4 * (size_t)W * H));
+    CK(cudaMemset2DAsync(X + po + rbox.x0, 4 * (size_t)W, 0, 4 * (size_t)(rbox.x1 - rbox.x0 + 1), rh, ctx->stream));
+    if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp (T is empty outside [y0, y1])
+      if (m <= 32) { k_dilate32<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
+      else { k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
+    } else CK(cudaMemcpyAsync(R + r0, T + r0, 4 * (size_t)h * nw, cudaMemcpyDeviceToDevice, ctx->stream));
     if (F.kind == COH_FILTER_SCENE) {
       PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
     } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox, true)) return 1;
     Y = X;
     if (F.kind == COH_FILTER_MONOCHROME) {
-      k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED();
+      if (z_is_x) blend_flags |= 2;   // Y = monochrome of Z, taken on the fly
+      else { k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED(); }
     } else if (F.kind == COH_FILTER_BLUR) {
       // Convolve.convolve_sprite_in_shape (convolve.ml:265-296) on the canvas rows [ry0, ry1]: pixels the
-      // reading scene did not render are clear, exactly like the reference's canvas outside the sprite
-      std::vector<int> taps; int total = 0;
-      if (F.kernel_kind == COH_CONV_GAUSSIAN) {  // Convolve.mkgaussian r (convolve.ml:60-70)
-        for (int i = -F.r; i <= F.r; i++) {
-          double xr = (double)i / (double)F.r, yr = 0. / (double)F.r;
-          double gg = exp(-(xr * xr + yr * yr)) / 2.;
-          int v = (int)((double)(4 * F.r * F.r) * gg + 0.5);
-          taps.push_back(v); total += v;
-        }
-        CK(DMALLOC(&d_taps, sizeof(int) * taps.size()));
-        CK(cudaMemcpyAsync(d_taps, taps.data(), sizeof(int) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));  // `taps` is a local
-      }
-      CK(DMALLOC(&tmp, 4 * pn));
-      dim3 gp(cdiv(W, 128), rh);
-      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X + po, tmp, W, rh, F.r, F.kernel_kind, d_taps, total, 0); LAUNCHED();
-      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(tmp, X + po, W, rh, F.r, F.kernel_kind, d_taps, total, 1); LAUNCHED();
+      // reading scene did not render are clear, exactly like the reference's canvas outside the sprite.
+      // Only the columns of shptorender are needed of the result.
+      uint32_t* t1 = nullptr;
+      CK(TMPGET(tmp, &t1, 4 * pn));
+      if (z_is_x) { CK(TMPGET(tmp, &Y, 4 * (size_t)W * H)); }
+      const int* taps = F.kernel_kind == COH_CONV_GAUSSIAN ? s->filter_taps + F.taps_off : nullptr;
+      dim3 gp(cdiv(x1 - x0 + 1, 128), rh);
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(X + po, t1, W, rh, F.r, F.kernel_kind, taps, F.taps_total, 0, x0, x1); LAUNCHED();
+      k_conv_pass<<<gp, 128, 0, ctx->stream>>>(t1, Y + po, W, rh, F.r, F.kernel_kind, taps, F.taps_total, 1, x0, x1); LAUNCHED();
     }
   }
   // The geometry's matte in the update (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is
   // given, but a pixel whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its
   // 2 x 2-pixel sampling window (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge
-  // pieces), so all 32 x 32 samples are inside and the opacity is 255: only the rest is super-sampled.
-  CK(DMALLOC(&op, (size_t)nw * 32 * h)); CK(DMALLOC(&alpha, (size_t)W * h));
-  {
-    uint32_t* I = nullptr;   // interior = erode 2 2 minshape, clipped 2 pixels inside the rows / columns scanned here
-    CK(DMALLOC(&I, 4 * nwords));
-    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(SG, CG, CG, nwords, 1); LAUNCHED();          // CG := minshape = shape - coverage
-    k_fill_words<<<wblocks, 256, 0, ctx->stream>>>(I, nwords, 0xFFFFFFFFu); LAUNCHED();
-    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, CG, I, nwords, 1); LAUNCHED();            // everything but the minshape
-    {  // rows y0 .. y1 only (everything outside is "not minshape" and the box mask below cuts 2 rows off each end)
-      k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(I + (size_t)y0 * nw, R + (size_t)y0 * nw, h, nw, 2, 2); LAUNCHED();
-    }
-    k_fill_box_bits<<<dim3(cdiv(nw, 128), H), 128, 0, ctx->stream>>>(I, H, nw, 0, 0, 2, y0 + 2, W - 3, y1 - 2); LAUNCHED();
-    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(I, R, I, nwords, 1); LAUNCHED();             // interior
-    k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, I, I, nwords, 1); LAUNCHED();             // to be super-sampled: T - interior
-    CK(cudaMemsetAsync(op, 255, (size_t)nw * 32 * h, ctx->stream));
-    k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, I + (size_t)y0 * nw, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
-    DFREE(I);
+  // pieces), so all 32 x 32 samples are inside and the opacity is 255: only the rest is super-sampled
+  // (interior = erode 2 2 minshape, clipped 2 pixels inside the rows / columns scanned here).
+  uint8_t *op = nullptr, *alpha = nullptr;
+  CK(TMPGET(tmp, &op, (size_t)nw * 32 * h)); CK(TMPGET(tmp, &alpha, (size_t)W * h));
+  k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(SG + r0, CG + r0, T + r0, Q + r0, h, nw, W); LAUNCHED();
+  CK(cudaMemsetAsync(op, 255, (size_t)nw * 32 * h, ctx->stream));
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q + r0, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+  if (m > 0) CK(cudaMemsetAsync(R + (size_t)ry0 * nw, 0, 4 * (size_t)rh * nw, ctx->stream));   // what the reading scene left of its (bloated) update
+  // R := pixels_for_normal_scene = shptorender' --- pixels_finished (render.ml:1100-1105)
+  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + r0, op, F.colour, W, h, nw, alpha, R + r0); LAUNCHED();
+  if (z_is_x) Z = X;
+  else {
+    CK(TMPGET(tmp, &Z, 4 * (size_t)W * H));
+    CK(cudaMemset2DAsync(Z + (size_t)y0 * W + x0, 4 * (size_t)W, 0, 4 * (size_t)(x1 - x0 + 1), h, ctx->stream));
+    if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox, true)) return 1;
   }
-  CK(cudaMemsetAsync(R, 0, 4 * nwords, ctx->stream));
-  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, op, F.colour, W, h, nw, alpha, R + (size_t)y0 * nw); LAUNCHED();  // R := finished
-  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(T, R, R, nwords, 1); LAUNCHED();      // pixels_for_normal_scene (render.ml:1105)
-  CK(DMALLOC(&Z, 4 * (size_t)W * H));
-  CK(cudaMemsetAsync(Z + (size_t)y0 * W, 0, 4 * (size_t)h * W, ctx->stream));
-  if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox, true)) return 1;
-  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + (size_t)y0 * nw, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw); LAUNCHED();
-  k_bitop<<<wblocks, 256, 0, ctx->stream>>>(U, SG, U, nwords, 1); LAUNCHED();     // u --- ef (render.ml:1308)
-  DFREE(SG); DFREE(CG); DFREE(T); DFREE(R); DFREE(X); DFREE(Z); DFREE(tmp); DFREE(op); DFREE(alpha); DFREE(d_taps);
+  // blend' and the composite into the accumulator; u --- ef (render.ml:1308)
+  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + r0, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw, blend_flags, SG + r0, U + r0); LAUNCHED();
   return 0;
 }
 // Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)
 static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed) {
   const Frame& fr = ctx->fr;
   if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
+  // `fresh` holds until the first leaves are composited: filters alone leave the accumulator clear on what is left of U
   auto segment = [&](int a, int b) -> int {
-    if (b > a) {
-      PassArgs A{a, b, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U, U, target, fresh, !fresh};
-      if (render_pass(ctx, s, A)) return 1;
-    } else if (fresh && !target_zeroed) {
-      const int hh = box.y1 - box.y0 + 1;
-      k_clear_in_bits<<<dim3(cdiv(fr.W, 128), hh), 128, 0, ctx->stream>>>(target + (size_t)box.y0 * fr.W, U + (size_t)box.y0 * fr.tiles_x, fr.W, hh, fr.tiles_x); LAUNCHED();
-    }
+    if (b <= a) return 0;
+    PassArgs A{a, b, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U, U, target, fresh, !fresh};
+    if (render_pass(ctx, s, A)) return 1;
     fresh = false;
     return 0;
   };
   for (int f = f0; f < (int)s->filters.size(); f++) {
     if (segment(l0, s->filters[f].pos)) return 1;
-    if (apply_filter(ctx, s, f, U, target, box)) return 1;
+    if (apply_filter(ctx, s, f, U, target, box, fresh)) return 1;
     l0 = s->filters[f].pos;
   }
-  return segment(l0, s->n_scene_leaves);
+  if (segment(l0, s->n_scene_leaves)) return 1;
+  if (fresh && !target_zeroed) {   // no leaves at all: what is left of U shows nothing
+    const int hh = box.y1 - box.y0 + 1;
+    k_clear_in_bits<<<dim3(cdiv(fr.W, 128), hh), 128, 0, ctx->stream>>>(target + (size_t)box.y0 * fr.W, U + (size_t)box.y0 * fr.tiles_x, fr.W, hh, fr.tiles_x); LAUNCHED();
+  }
+  return 0;
 }
 static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, int ux, int uy, int uw, int uh) {
   const Frame& fr = ctx->fr;
@@ -477,19 +480,38 @@ static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, in
   if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
   const int nw = fr.tiles_x;
   const size_t nwords = (size_t)nw * fr.H;
-  uint32_t *U = ctx->u_out, *U0 = nullptr;
-  CK(DMALLOC(&U0, 4 * nwords));
-  if (u_init) CK(cudaMemcpyAsync(U0, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
-  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
-  CK(cudaMemcpyAsync(U, U0, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  uint32_t* U = ctx->u_out;
+  if (u_init) CK(cudaMemcpyAsync(U, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
   if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true, box)) return 1;
   if (s->n_leaves > s->n_front_leaves) {
     // the background list shows wherever the scene pass is not opaque (render.ml:1363-1365)
-    k_not_opaque_bits<<<dim3(cdiv(nw, 4), fr.H), 128, 0, ctx->stream>>>(ctx->fb, U0, U0, fr.W, fr.H, nw); LAUNCHED();
-    PassArgs A{s->n_front_leaves, s->n_leaves, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U0, nullptr, ctx->fb, false, true};
-    if (render_pass(ctx, s, A)) return 1;
+    BgPrims B; memset(&B, 0, sizeof B);
+    bool prims = s->n_leaves - s->n_front_leaves <= 8;
+    for (int li = s->n_front_leaves; li < s->n_leaves && prims; li++) {
+      const ObjRec& o = s->h_objs[s->full.h_leaves[li]];
+      prims = o.kind == K_PRIM && o.depth == 1 && o.fill.kind == 0;
+      if (!prims) break;
+      B.x0[B.n] = o.prim[0] + o.dx; B.y0[B.n] = o.prim[1] + o.dy; B.x1[B.n] = o.prim[2] + o.dx; B.y1[B.n] = o.prim[3] + o.dy;
+      B.col[B.n] = o.fill.c0; B.pretrans[B.n] = o.pretrans; B.n++;
+    }
+    if (prims) {
+      // plain primitives (the page, the window background): one pass over the update
+      PeerFbs peers; memset(&peers, 0, sizeof peers);
+      for (int k = 0; k < ctx->n_peers; k++) peers.p[k] = ctx->peer_fb[k];
+      k_bg_over<<<dim3(cdiv(cdiv(fr.W, 4), 128), box.y1 - box.y0 + 1), 128, 0, ctx->stream>>>(ctx->fb, u_init, fr.W, nw, box.x0, box.y0, box.x1, box.y1, B, ctx->n_peers, peers); LAUNCHED();
+    } else {
+      uint32_t* U0 = nullptr;
+      CK(DMALLOC(&U0, 4 * nwords));
+      if (u_init) CK(cudaMemcpyAsync(U0, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+      else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U0, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
+      k_not_opaque_bits<<<dim3(cdiv(nw, 4), fr.H), 128, 0, ctx->stream>>>(ctx->fb, U0, U0, fr.W, fr.H, nw); LAUNCHED();
+      PassArgs A{s->n_front_leaves, s->n_leaves, box.x0, box.y0, box.x1 - box.x0 + 1, box.y1 - box.y0 + 1, U0, nullptr, ctx->fb, false, true};
+      const int rc = render_pass(ctx, s, A);
+      DFREE(U0);
+      if (rc) return 1;
+    }
   }
-  DFREE(U0);
   return 0;  // kernel-side failures are reported by coh_sync, as for plain frames
 }
 

@@ -8,7 +8,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   DevScene* s = (DevScene*)h;
   if (!s) return 0;
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
-  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr);
+  DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr); DFREE(s->filter_taps);
   for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
   free_binset(ctx, s->full.bins); free_binset(ctx, s->sp.bins);
   DFREE(s->sp.leaves); DFREE(s->sp.leaf_box);
@@ -140,13 +140,12 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   // A Group that is the first member of its list and is composited with plain Over goes under an accumulator that is
   // still clear, and `over clear s = s` exactly (colour.ml:314-316): its members can composite straight into the
   // parent's accumulator — same pixels, same u — so such groups vanish from the members' ancestor chains (the lion of
-  // examples.ml:174-180 in front of a scene is one).  Not with filters in the scene: their passes continue a frame
-  // from accumulators that are not clear.
+  // examples.ml:174-180 in front of a scene is one).  Filter objects do not count as members here: a filter finishes
+  // the whole of its shape (render.ml:1120-1121), so every pixel still in `u` after it has a clear accumulator, and the
+  // pass that follows filters alone starts fresh (render_suffix).
   std::vector<int> eff_open;      // the ancestor chain the walker sees: open groups that are not dissolved into their parent
   std::vector<int> n_children;    // per open group: members seen so far
   std::vector<char> open_flat;    // per open group: dissolved into its parent
-  bool any_filter = false;
-  for (int i = 0; i < n_objs; i++) any_filter = any_filter || objs[i].kind == COH_OBJ_FILTER;
   // Owning object of every edge / brush point: kept as (first, count, record) ranges here and expanded on the device
   // (k_fill_owner); ranges of different objects may not overlap.
   OwnerRanges edge_own, point_own;
@@ -204,6 +203,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: reading-scene groups must be top-level members of the scene list");
       if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
       open_reading.push_back(i); cur_reading = i;
+      n_children[0] = 0;   // a list of its own, rendered from a clear accumulator (render.ml:1091)
       reading[i] = std::make_pair((int)leaves.size(), (int)leaves.size());
       continue;
     }
@@ -282,7 +282,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         recs.push_back(o); open.push_back((int)recs.size() - 1); open_reading.push_back(-1);
         real_depth.resize(recs.size(), 0); real_depth.back() = nesting;
         {
-          const bool flat = !any_filter && o.pretrans < 0 && n_children.back() == 0;
+          const bool flat = o.pretrans < 0 && n_children.back() == 0;
           n_children.back()++;
           open_flat.push_back(flat ? 1 : 0); n_children.push_back(0);
           if (!flat) eff_open.push_back((int)recs.size() - 1);
@@ -453,6 +453,22 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   ids.resize(recs.size(), -1);
   real_depth.resize(recs.size(), 0);
   mark("sprite entries");
+  std::vector<int> filter_taps;
+  for (DevScene::FilterRec& f : filters) {
+    f.taps_off = (int)filter_taps.size(); f.taps_total = 0;
+    if (f.kind != COH_FILTER_BLUR || f.kernel_kind != COH_CONV_GAUSSIAN) continue;
+    for (int i = -f.r; i <= f.r; i++) {   // Convolve.mkgaussian r (convolve.ml:60-70)
+      double xr = (double)i / (double)f.r, yr = 0. / (double)f.r;
+      double gg = exp(-(xr * xr + yr * yr)) / 2.;
+      int v = (int)((double)(4 * f.r * f.r) * gg + 0.5);
+      filter_taps.push_back(v); f.taps_total += v;
+    }
+  }
+  if (!filter_taps.empty()) {
+    CK(DMALLOC(&s->filter_taps, sizeof(int) * filter_taps.size()));
+    CK(cudaMemcpyAsync(s->filter_taps, filter_taps.data(), sizeof(int) * filter_taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   s->filters = filters; s->n_scene_leaves = n_scene_leaves; s->n_front_leaves = n_front_leaves;
   s->n_objs = (int)recs.size(); s->n_leaves = (int)leaves.size(); s->n_edges = n_edges; s->n_points = n_points;
   s->sprites = sprites;
@@ -479,14 +495,14 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   // member, or only opaque primitives (the first one covering a pixel finishes it either way).
   std::vector<int2> attr(recs.size(), make_int2(0, 0));   // (uploaded asynchronously: lives until the synchronisation below)
   {
-    bool flat = filters.empty();
+    bool flat = true;
     int n_bg = 0; bool bg_opaque_prims = true;
     for (int li : leaves) {
       const ObjRec& o = recs[li];
-      flat = flat && o.depth == 1 && (o.kind == K_PATH || o.kind == K_PRIM) && o.fill.kind == 0;
+      flat = flat && o.depth == 1 && (o.kind == K_PATH || o.kind == K_PRIM || o.kind == K_CONV) && o.fill.kind == 0;
       const bool bg = (recs[o.anc[0]].flags & OF_ROOT_BACKGROUND) != 0;
       if (bg) { n_bg++; bg_opaque_prims = bg_opaque_prims && o.kind == K_PRIM && (o.fill.c0 >> 24) == 255u && o.pretrans < 0; }
-      attr[li] = make_int2((int)o.fill.c0, (o.kind == K_PATH ? 1 : 0) | (bg ? 2 : 0) | ((o.flags & OF_OCCLUDES) ? 4 : 0) | ((o.pretrans + 1) << 8));
+      attr[li] = make_int2((int)o.fill.c0, (o.kind == K_PATH ? 1 : 0) | (bg ? 2 : 0) | ((o.flags & OF_OCCLUDES) ? 4 : 0) | (o.kind == K_CONV ? 8 : 0) | ((o.pretrans + 1) << 8));
     }
     s->flat_ok = flat && (n_bg <= 1 || bg_opaque_prims);
     CK(DMALLOC(&s->attr, sizeof(int2) * recs.size()));

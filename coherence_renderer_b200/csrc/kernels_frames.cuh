@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   const uint32_t u_update = u;
   uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
   if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
-  if (oc.w & 1) {
+  if ((oc.w & 1) && !P.resume) {
     // a background cell that k_prefill did not take (frames mirrored to peer framebuffers spread these stores over
     // the compositor's blocks): one opaque primitive covers the cell, nothing was scan-converted for it
     if (u_rec && lane == 0) *u_rec = (oc.w & 2) ? 0u : u;
@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   const uint2* sc_row = P.pre_sc + row;
   const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
   uint32_t acc = 0u;
+  // a pass that continues a frame (after a filter, render.ml:1080-1131): the accumulator carries on from the framebuffer
+  if (P.resume && (u & lbit)) acc = P.fb[(size_t)y * P.fr.W + tile * TILE_W + lane];
   for (int base = rg.x; base < rg.y; base += 32) {
     if (u == 0u) break;   // nothing of this row is uncovered any more (render.ml:1321-1322)
     const int it = base + lane;
@@ -304,6 +306,11 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
         uint32_t col = c0;
         // shptorender ∩ maxshape = vis & ~(S & ~C) = vis & C: those pixels dissolve the fill by their opacity
         if ((fl & 1) && (vis & C & lbit)) col = px_dissolve(c0, op_row[(size_t)(base + k) * (CELL_H * 32)]);
+        if (fl & 8) {
+          // a Convolved object: the pre-convolved sprite, cropped to the visible max-shape (render.ml:1052)
+          const ObjRec& o = P.objs[P.cell_items[base + k]];
+          if (vis & C & lbit) col = P.conv_px[(size_t)o.cv_px + (size_t)(y - o.dy - o.cv_y0) * (o.cv_nw * 32) + (tile * TILE_W + lane - o.dx - o.cv_x0)];
+        }
         if (fl >> 8) col = px_dissolve(col, (fl >> 8) - 1);
         if (vis & lbit) acc = px_over(acc, col);
         u &= ~__ballot_sync(0xFFFFFFFFu, (vis & lbit) && (acc >> 24) == 255u);
@@ -323,22 +330,26 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
 }
 
 constexpr int SCAN_CHUNK_WORDS = 8;  // one thread scans a 256-pixel window of one row
+// With `U` and `T` (planes laid out like S): T = S & U, the part of the shape inside an update set (render.ml:1281).
 __global__ void k_scan_rows(const EdgeRec* __restrict__ edges, int n_edges, int winding, int y0, int n_rows,
-                            int wx0, int nw, uint32_t* __restrict__ S, uint32_t* __restrict__ C, int* error_flag) {
+                            int wx0, int nw, uint32_t* __restrict__ S, uint32_t* __restrict__ C, int* error_flag,
+                            const uint32_t* __restrict__ U = nullptr, uint32_t* __restrict__ T = nullptr) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   int w0 = blockIdx.y * SCAN_CHUNK_WORDS;
   if (r >= n_rows || w0 >= nw) return;
   SinkMem sink;
   sink.wx0 = wx0 + 32 * w0; sink.nwords = min(SCAN_CHUNK_WORDS, nw - w0); sink.stride = 1;
   sink.S = S + (size_t)r * nw + w0; sink.C = C + (size_t)r * nw + w0;
-  if (scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink)) return;
-  // more crossings touch the 256-pixel window than a list holds (a line of small text as one compound path): word by word
   const int words = sink.nwords, x0 = sink.wx0;
-  for (int w = 0; w < words; w++) {
-    sink.wx0 = x0 + 32 * w; sink.nwords = 1;
-    sink.S = S + (size_t)r * nw + w0 + w; sink.C = C + (size_t)r * nw + w0 + w;
-    if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 31, sink)) *error_flag = 1;
+  if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 32 * sink.nwords - 1, sink)) {
+    // more crossings touch the 256-pixel window than a list holds (a line of small text as one compound path): word by word
+    for (int w = 0; w < words; w++) {
+      sink.wx0 = x0 + 32 * w; sink.nwords = 1;
+      sink.S = S + (size_t)r * nw + w0 + w; sink.C = C + (size_t)r * nw + w0 + w;
+      if (!scan_row(edges, nullptr, n_edges, 1, y0 + r, winding, false, sink.wx0, sink.wx0 + 31, sink)) *error_flag = 1;
+    }
   }
+  if (T) for (int w = 0; w < words; w++) { const size_t i = (size_t)r * nw + w0 + w; T[i] = S[i] & U[i]; }
 }
 
 // ------------------------------------------------------------------------------------

@@ -62,6 +62,29 @@ __global__ void k_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__
   }
   out[(size_t)r * nw + w] = acc;
 }
+// The same dilation for m <= 32: a row's horizontal part comes from three words by shift doubling, so a word costs
+// O((2n+1) log m) operations instead of O((2n+1)(2m+1)) (the blur filter's reading shape, filters.ml:247: m = n = 2r+1).
+__device__ __forceinline__ uint32_t hdilate_word(uint32_t a, uint32_t b, uint32_t c, int m) {
+  // bits of b's word: pixel i set when any of pixels i-m .. i+m is (a = the word to the left, c = to the right)
+  unsigned long long lo = ((unsigned long long)b << 32) | a;   // smear towards higher pixels, read the high half
+  unsigned long long hi = ((unsigned long long)c << 32) | b;   // smear towards lower pixels, read the low half
+  for (int cover = 0; cover < m;) {
+    const int step = min(cover + 1, m - cover);
+    lo |= lo << step; hi |= hi >> step;
+    cover += step;
+  }
+  return (uint32_t)(lo >> 32) | (uint32_t)hi;
+}
+__global__ void k_dilate32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n_rows, int nw, int m, int n) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= n_rows) return;
+  uint32_t acc = 0u;
+  for (int rr = max(0, r - n); rr <= min(n_rows - 1, r + n); rr++) {
+    const uint32_t* row = in + (size_t)rr * nw;
+    acc |= hdilate_word(w > 0 ? row[w - 1] : 0u, row[w], w + 1 < nw ? row[w + 1] : 0u, m);
+  }
+  out[(size_t)r * nw + w] = acc;
+}
 // Sprite.box x y w h (sprite.ml:462-465) as a device span set: every row one span
 __global__ void k_box_spans(int* __restrict__ row_ptr, int2* __restrict__ spans, int h, int x, int w) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,7 +238,7 @@ __global__ void k_monochrome(const uint32_t* __restrict__ in, uint32_t* __restri
 // antialiased opacity bytes `op` (Polygon.polygon_sprite samples every pixel it is given, minshape
 // pixels included); `finished` = its opaque pixels (1100-1103).  One word per warp.
 __global__ void k_filter_matte(const uint32_t* __restrict__ T, const uint8_t* __restrict__ op,
-                               uint32_t colour, int W, int H, int nw, uint8_t* __restrict__ alpha, uint32_t* __restrict__ finished) {
+                               uint32_t colour, int W, int H, int nw, uint8_t* __restrict__ alpha, uint32_t* __restrict__ unfinished) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = blockIdx.y, lane = threadIdx.x & 31;
   if (w >= nw || y >= H) return;
   const uint32_t t = T[(size_t)y * nw + w];
@@ -226,20 +249,89 @@ __global__ void k_filter_matte(const uint32_t* __restrict__ T, const uint8_t* __
     alpha[(size_t)y * W + x] = (uint8_t)a;
   }
   const uint32_t f = __ballot_sync(0xFFFFFFFFu, a == 255);
-  if (lane == 0) finished[(size_t)y * nw + w] = f & t;
+  if (lane == 0) unfinished[(size_t)y * nw + w] = t & ~f;   // pixels_for_normal_scene = shptorender' --- pixels_finished (render.ml:1105)
+}
+// Which pixels of T the matte has to super-sample: all but those whose 5 x 5 neighbourhood lies in the geometry's
+// minshape M = S & ~C (see apply_filter): todo = T - (box - dilate 2 2 (not M)), rows [0, h) of the planes given,
+// box = columns [2, W-3] of rows [2, h-3].
+__global__ void k_matte_todo(const uint32_t* __restrict__ S, const uint32_t* __restrict__ C, const uint32_t* __restrict__ T,
+                             uint32_t* __restrict__ todo, int h, int nw, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= h) return;
+  uint32_t dil = 0u;
+  for (int rr = max(0, r - 2); rr <= min(h - 1, r + 2); rr++) {
+    const uint32_t* s = S + (size_t)rr * nw; const uint32_t* c = C + (size_t)rr * nw;
+    const uint32_t a = w > 0 ? ~(s[w - 1] & ~c[w - 1]) : 0u, b = ~(s[w] & ~c[w]), d = w + 1 < nw ? ~(s[w + 1] & ~c[w + 1]) : 0u;
+    dil |= hdilate_word(a, b, d, 2);
+  }
+  const uint32_t box = (r >= 2 && r <= h - 3) ? interval_mask32(32 * w, 2, W - 3) : 0u;
+  todo[(size_t)r * nw + w] = T[(size_t)r * nw + w] & ~(box & ~dil);
 }
 // blend' (render.ml:1248-1265) and the composite of the filter's sprite into the accumulator
 // (render.ml:1290-1291): fb = over fb (pd_plus (dissolve Z (255 - alpha)) (dissolve Y alpha)) on T.
 // Pixels a scene did not render are clear in Z / Y, which both operators treat as absent.
+__device__ __forceinline__ uint32_t px_monochrome(uint32_t c) {
+  const uint32_t av = ((c & 255u) + ((c >> 8) & 255u) + ((c >> 16) & 255u)) / 3u;
+  return av | (av << 8) | (av << 16) | (c & 0xFF000000u);
+}
+// flags: 1 = the accumulator is clear on every pixel of T (nothing but filters composited so far: over clear s = s);
+// 2 = Y is Colour.monochrome of Z (filters.ml:229-238, where reading scene and scene below are the same list).
+// The filter's whole shape S then leaves u (the extra finish, render.ml:1120-1121, 1308).
 __global__ void k_filter_blend(const uint32_t* __restrict__ T, const uint8_t* __restrict__ alpha, const uint32_t* __restrict__ Z,
-                               const uint32_t* __restrict__ Y, uint32_t* __restrict__ fb, int W, int H, int nw) {
+                               const uint32_t* __restrict__ Y, uint32_t* __restrict__ fb, int W, int H, int nw, int flags,
+                               const uint32_t* __restrict__ S, uint32_t* __restrict__ U) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W || y >= H) return;
-  if (!((T[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 1u)) return;
+  const size_t wi = (size_t)y * nw + (x >> 5);
+  const uint32_t t = T[wi];
+  if ((x & 31) == 0 && U) U[wi] &= ~S[wi];
+  if (!((t >> (x & 31)) & 1u)) return;
   const size_t i = (size_t)y * W + x;
   const int a = alpha[i];
-  const uint32_t z = px_dissolve(Z[i], 255 - a), yy = Y ? px_dissolve(Y[i], a) : 0u;
-  fb[i] = px_over(fb[i], px_plus(z, yy));
+  const uint32_t zz = Z[i];
+  const uint32_t z = px_dissolve(zz, 255 - a), yy = (flags & 2) ? px_dissolve(px_monochrome(zz), a) : (Y ? px_dissolve(Y[i], a) : 0u);
+  const uint32_t res = px_plus(z, yy);
+  fb[i] = (flags & 1) ? res : px_over(fb[i], res);
+}
+// The background list of a frame whose scene pass is finished (render.ml:1363-1365): frame = scene over background,
+// for a background of plain primitives (the page, the window background): per pixel of the update that the scene
+// pass left not opaque, the front-to-back fold of the primitives covering it goes under the framebuffer's colour.
+struct PeerFbs { uint32_t* p[7]; };
+struct BgPrims { int n; int x0[8], y0[8], x1[8], y1[8]; uint32_t col[8]; int pretrans[8]; };
+__global__ void k_bg_over(uint32_t* __restrict__ fb, const uint32_t* __restrict__ u_init, int W, int nw, int ux0, int uy0, int ux1, int uy1,
+                          BgPrims B, int n_peers, PeerFbs peers) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = uy0 + blockIdx.y;
+  if (x > ux1 || x + 3 < ux0 || y > uy1) return;
+  uint32_t m = 0u;
+  for (int k = 0; k < 4; k++) if (x + k >= ux0 && x + k <= ux1 && x + k < W) m |= 1u << k;
+  if (u_init) m &= (u_init[(size_t)y * nw + (x >> 5)] >> (x & 31)) & 15u;
+  if (!m) return;
+  const size_t at = (size_t)y * W + x;
+  const bool vec = x + 3 < W && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(fb) & 15) == 0;
+  uint32_t px[4];
+  if (vec) { const uint4 v = *reinterpret_cast<const uint4*>(fb + at); px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w; }
+  else for (int k = 0; k < 4; k++) px[k] = (x + k < W) ? fb[at + k] : 0u;
+  bool changed = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (!((m >> k) & 1u) || (px[k] >> 24) == 255u) continue;
+    uint32_t acc = 0u;
+    for (int j = 0; j < B.n; j++) {
+      if (x + k < B.x0[j] || x + k > B.x1[j] || y < B.y0[j] || y > B.y1[j]) continue;
+      uint32_t c = B.col[j];
+      if (B.pretrans[j] >= 0) c = px_dissolve(c, B.pretrans[j]);
+      acc = px_over(acc, c);
+      if ((acc >> 24) == 255u) break;
+    }
+    if (acc != 0u) { px[k] = px_over(px[k], acc); changed = true; }
+  }
+  if (!changed) return;
+  if (vec) {
+    const uint4 v = make_uint4(px[0], px[1], px[2], px[3]);
+    *reinterpret_cast<uint4*>(fb + at) = v;
+    for (int p = 0; p < n_peers; p++) *reinterpret_cast<uint4*>(peers.p[p] + at) = v;
+  } else
+    for (int k = 0; k < 4; k++) if (x + k < W) { fb[at + k] = px[k]; for (int p = 0; p < n_peers; p++) peers.p[p][at + k] = px[k]; }
 }
 // update & ~opaque(fb): where the background list is still visible under the scene pass
 __global__ void k_not_opaque_bits(const uint32_t* __restrict__ fb, const uint32_t* __restrict__ U, uint32_t* __restrict__ out, int W, int H, int nw) {
@@ -259,9 +351,9 @@ __global__ void k_not_opaque_bits(const uint32_t* __restrict__ fb, const uint32_
 // convolve.ml:118), plain division for the unit kernel (161-204).
 // ------------------------------------------------------------------------------------
 __global__ void k_conv_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int w, int h, int r,
-                            int kind /*1 unit, 2 xy*/, const int* __restrict__ taps, int total, int vertical) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w || y >= h) return;
+                            int kind /*1 unit, 2 xy*/, const int* __restrict__ taps, int total, int vertical, int cx0 = 0, int cx1 = 0x7FFFFFFF) {
+  int x = cx0 + blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;   // only columns [cx0, cx1] are written
+  if (x >= w || x > cx1 || y >= h) return;
   int tr = 0, tg = 0, tb = 0, ta = 0;
   for (int q = -r; q <= r; q++) {
     int xx = vertical ? x : x + q, yy = vertical ? y + q : y;
