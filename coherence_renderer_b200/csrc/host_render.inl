@@ -242,8 +242,10 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
     if (s->flat_ok && !A.collapsed && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
       // (the heavy-first order flattened for this kernel: made when the cells were binned, kept with cached lists)
-      if (ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); B.comp_valid = true; }
-      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, ordered ? B.comp_order : nullptr); LAUNCHED();
+      // (a small pass — a filter's lens — gains nothing from the heavy-first order: one dependent launch less)
+      const bool comp_ordered = ordered && n_cells > 2048;
+      if (comp_ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); B.comp_valid = true; }
+      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, comp_ordered ? B.comp_order : nullptr); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {
@@ -364,8 +366,39 @@ struct StreamTemps {
 // `box` bounds the set bits of U: all work is confined to its rows (bit-frames are small; the RGBA8 canvases are only
 // touched in the rows and columns the filter reads or writes).  `fresh`: nothing but filters has been composited into
 // `target` so far — every pixel still in U has a clear accumulator there (a filter finishes the whole of its shape).
+// Shape / coverage bit-rows of a filter's geometry and the antialiased opacity of all its pixels: computed at the first
+// frame that needs them and kept with the scene (per frame geometry).
+static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
+  const Frame& fr = ctx->fr;
+  const int W = fr.W, H = fr.H, nw = fr.tiles_x;
+  if (F.SG && F.gW == W && F.gH == H) return 0;
+  DFREE(F.SG); DFREE(F.CG); DFREE(F.op);
+  F.gW = W; F.gH = H;
+  F.gy0 = std::max(F.by0, 0);
+  F.gh = std::min(F.by1, H - 1) - F.gy0 + 1;
+  if (F.gh <= 0) { F.gh = 0; return 0; }
+  const int h = F.gh;
+  const size_t nwords = (size_t)nw * h;
+  CK(DMALLOC(&F.SG, 4 * nwords)); CK(DMALLOC(&F.CG, 4 * nwords)); CK(DMALLOC(&F.op, (size_t)nw * 32 * h));
+  CK(cudaMemsetAsync(F.SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(F.CG, 0, 4 * nwords, ctx->stream));
+  const EdgeRec* ed = s->edges + F.first;
+  // shape of the geometry (render.ml:472-474) and its coverage (minshape = shape - coverage, needed for the matte)
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, F.gy0, h, 0, nw, F.SG, F.CG, ctx->d_error); LAUNCHED();
+  // The geometry's matte (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is given, but a pixel
+  // whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its 2 x 2-pixel sampling window
+  // (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge pieces), so all 32 x 32 samples
+  // are inside and the opacity is 255: only the rest is super-sampled (interior = erode 2 2 minshape, clipped 2 pixels
+  // inside the rows / columns scanned here).
+  uint32_t* Q = nullptr;
+  CK(DMALLOC(&Q, 4 * nwords));
+  k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(F.SG, F.CG, F.SG, Q, h, nw, W); LAUNCHED();
+  CK(cudaMemsetAsync(F.op, 255, (size_t)nw * 32 * h, ctx->stream));
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q, F.gy0, h, 0, nw, ctx->d_aa, F.op, ctx->d_error); LAUNCHED();
+  DFREE(Q);
+  return 0;
+}
 static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t* target, PixBox box, bool fresh) {
-  const DevScene::FilterRec& F = s->filters[fi];
+  DevScene::FilterRec& F = s->filters[fi];
   const Frame& fr = ctx->fr;
   const int W = fr.W, H = fr.H, nw = fr.tiles_x;
   const size_t nwords = (size_t)nw * H;
@@ -373,23 +406,23 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   const int y0 = std::max(std::max(F.by0, 0), box.y0), y1 = std::min(std::min(F.by1, H - 1), box.y1);
   const int x0 = std::max(std::max(F.bx0, 0), box.x0), x1 = std::min(std::min(F.bx1, W - 1), box.x1);
   if (y0 > y1 || x0 > x1) return 0;  // the geometry cannot meet u: nothing to render, nothing leaves u
+  if (filter_geometry(ctx, s, F)) return 1;
   const int h = y1 - y0 + 1;
   const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : 0;             // reach of the reading shape
   const int ry0 = std::max(0, y0 - m), ry1 = std::min(H - 1, y1 + m), rh = ry1 - ry0 + 1;
   const PixBox tbox{x0, y0, x1, y1}, rbox{std::max(0, x0 - m), ry0, std::min(W - 1, x1 + m), ry1};
   const size_t po = (size_t)ry0 * W, pn = (size_t)rh * W;                 // canvas rows [ry0, ry1]
   const size_t r0 = (size_t)y0 * nw;                                      // first word of row y0 in a bit-frame
+  const size_t g0 = (size_t)(y0 - F.gy0) * nw;                            // ... and in the geometry's own planes
+  const uint32_t* SG = F.SG + g0;
   StreamTemps tmp(ctx);
-  // bit-frames: SG / CG = shape / coverage of the geometry (rows y0 .. y1 are used), T = shptorender, R = reading shape,
-  // then the pixels the scene below shows through; Q = pixels the matte super-samples (rows y0 .. y1)
+  // bit-frames: T = shptorender, R = the reading shape, then the pixels the scene below shows through
   uint32_t* planes = nullptr;
-  CK(TMPGET(tmp, &planes, 4 * nwords * 5));
-  uint32_t *SG = planes, *CG = planes + nwords, *T = planes + 2 * nwords, *R = planes + 3 * nwords, *Q = planes + 4 * nwords;
-  CK(cudaMemsetAsync(planes, 0, 4 * nwords * 4, ctx->stream));
-  const EdgeRec* ed = s->edges + F.first;
-  // shape of the geometry (render.ml:472-474), its coverage (the minshape is needed for the matte), and
-  // shptorender = r &&& u (render.ml:1281)
-  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, y0, h, 0, nw, SG + r0, CG + r0, ctx->d_error, U + r0, T + r0); LAUNCHED();
+  CK(TMPGET(tmp, &planes, 4 * nwords * 2));
+  uint32_t *T = planes, *R = planes + nwords;
+  CK(cudaMemsetAsync(planes, 0, 4 * nwords * 2, ctx->stream));
+  // shptorender = r &&& u (render.ml:1281); a filter other than blur reads where it writes
+  k_and_rows<<<(unsigned)(((size_t)h * nw + 255) / 256), 256, 0, ctx->stream>>>(SG, U + r0, T + r0, m > 0 ? nullptr : R + r0, (size_t)h * nw); LAUNCHED();
   // The scene below renders the same pixels whatever region it is asked for (plain fills: no span-start quirk,
   // polygon.ml:736), so where the reading scene IS the scene below (monochrome, blur: filters.ml:229-258) the pixels
   // that show through the matte (render.ml:1105-1110) are taken from the reading scene's render before its filter function.
@@ -403,7 +436,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
     if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp (T is empty outside [y0, y1])
       if (m <= 32) { k_dilate32<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
       else { k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
-    } else CK(cudaMemcpyAsync(R + r0, T + r0, 4 * (size_t)h * nw, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     if (F.kind == COH_FILTER_SCENE) {
       PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
@@ -425,19 +458,11 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
       k_conv_pass<<<gp, 128, 0, ctx->stream>>>(t1, Y + po, W, rh, F.r, F.kernel_kind, taps, F.taps_total, 1, x0, x1); LAUNCHED();
     }
   }
-  // The geometry's matte in the update (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is
-  // given, but a pixel whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its
-  // 2 x 2-pixel sampling window (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge
-  // pieces), so all 32 x 32 samples are inside and the opacity is 255: only the rest is super-sampled
-  // (interior = erode 2 2 minshape, clipped 2 pixels inside the rows / columns scanned here).
-  uint8_t *op = nullptr, *alpha = nullptr;
-  CK(TMPGET(tmp, &op, (size_t)nw * 32 * h)); CK(TMPGET(tmp, &alpha, (size_t)W * h));
-  k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(SG + r0, CG + r0, T + r0, Q + r0, h, nw, W); LAUNCHED();
-  CK(cudaMemsetAsync(op, 255, (size_t)nw * 32 * h, ctx->stream));
-  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q + r0, y0, h, 0, nw, ctx->d_aa, op, ctx->d_error); LAUNCHED();
+  uint8_t* alpha = nullptr;
+  CK(TMPGET(tmp, &alpha, (size_t)W * h));
   if (m > 0) CK(cudaMemsetAsync(R + (size_t)ry0 * nw, 0, 4 * (size_t)rh * nw, ctx->stream));   // what the reading scene left of its (bloated) update
   // R := pixels_for_normal_scene = shptorender' --- pixels_finished (render.ml:1100-1105)
-  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + r0, op, F.colour, W, h, nw, alpha, R + r0); LAUNCHED();
+  k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + r0, F.op + g0 * 32, F.colour, W, h, nw, alpha, R + r0); LAUNCHED();
   if (z_is_x) Z = X;
   else {
     CK(TMPGET(tmp, &Z, 4 * (size_t)W * H));
@@ -445,7 +470,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
     if (render_suffix(ctx, s, F.pos, fi + 1, R, Z, true, tbox, true)) return 1;
   }
   // blend' and the composite into the accumulator; u --- ef (render.ml:1308)
-  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + r0, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw, blend_flags, SG + r0, U + r0); LAUNCHED();
+  k_filter_blend<<<dim3(cdiv(W, 128), h), 128, 0, ctx->stream>>>(T + r0, alpha, Z + (size_t)y0 * W, Y ? Y + (size_t)y0 * W : nullptr, target + (size_t)y0 * W, W, h, nw, blend_flags, SG, U + r0); LAUNCHED();
   return 0;
 }
 // Render the scene list from leaf l0 / filter f0 to its end inside U (updated to the `u` left over)

@@ -9,6 +9,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   if (!s) return 0;
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
   DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr); DFREE(s->filter_taps);
+  for (DevScene::FilterRec& f : s->filters) { DFREE(f.SG); DFREE(f.CG); DFREE(f.op); }
   for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
   free_binset(ctx, s->full.bins); free_binset(ctx, s->sp.bins);
   DFREE(s->sp.leaves); DFREE(s->sp.leaf_box);

@@ -251,6 +251,14 @@ __global__ void k_filter_matte(const uint32_t* __restrict__ T, const uint8_t* __
   const uint32_t f = __ballot_sync(0xFFFFFFFFu, a == 255);
   if (lane == 0) unfinished[(size_t)y * nw + w] = t & ~f;   // pixels_for_normal_scene = shptorender' --- pixels_finished (render.ml:1105)
 }
+// T = S & U, and optionally a copy R of it (shptorender = r &&& u, render.ml:1281; the reading shape of a filter that reads where it writes)
+__global__ void k_and_rows(const uint32_t* __restrict__ S, const uint32_t* __restrict__ U, uint32_t* __restrict__ T, uint32_t* __restrict__ R, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = S[i] & U[i];
+  T[i] = t;
+  if (R) R[i] = t;
+}
 // Which pixels of T the matte has to super-sample: all but those whose 5 x 5 neighbourhood lies in the geometry's
 // minshape M = S & ~C (see apply_filter): todo = T - (box - dilate 2 2 (not M)), rows [0, h) of the planes given,
 // box = columns [2, W-3] of rows [2, h-3].
@@ -316,12 +324,13 @@ __global__ void k_bg_over(uint32_t* __restrict__ fb, const uint32_t* __restrict_
   for (int k = 0; k < 4; k++) {
     if (!((m >> k) & 1u) || (px[k] >> 24) == 255u) continue;
     uint32_t acc = 0u;
-    for (int j = 0; j < B.n; j++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {   // (constant indices: the parameter arrays stay in the constant bank)
+      if (j >= B.n || (acc >> 24) == 255u) continue;
       if (x + k < B.x0[j] || x + k > B.x1[j] || y < B.y0[j] || y > B.y1[j]) continue;
       uint32_t c = B.col[j];
       if (B.pretrans[j] >= 0) c = px_dissolve(c, B.pretrans[j]);
       acc = px_over(acc, c);
-      if ((acc >> 24) == 255u) break;
     }
     if (acc != 0u) { px[k] = px_over(px[k], acc); changed = true; }
   }
