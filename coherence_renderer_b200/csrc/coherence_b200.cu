@@ -95,10 +95,11 @@ struct DevScene {
   // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
   struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total;
+                     int dx, dy;   // alias translation in whole pixels (render.ml:259-271); bx0 .. by1 include it
                      // kept with the scene once computed (the reference finds a filter geometry's shape in its cache by id,
                      // render.ml:472-474): shape / coverage bit-rows and the antialiased opacity of every shape pixel, for the
                      // geometry's rows gy0 .. gy0 + gh - 1 of a frame gW x gH
-                     uint32_t *SG, *CG; uint8_t* op; int gy0, gh, gW, gH; };
+                     uint32_t *SG, *CG; uint8_t* op; int gy0, gh, gW, gH, gdx, gdy; };
   int* filter_taps = nullptr;    // blur filters: Convolve.mkgaussian taps (convolve.ml:60-70), made once per scene
   std::vector<FilterRec> filters;
   // Group shapes (render.ml:476-496 caches them under the group's id): kept per scene, in the frame the group

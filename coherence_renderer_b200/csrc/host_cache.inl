@@ -183,10 +183,24 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
   *shape = cs; *minshape = cm;
   return 0;
 }
+// shapeonly_of_basicshape of a filter object = the shape of its geometry (render.ml:472-474), moved with its alias
+static int filter_shapes(coh_ctx* ctx, DevScene* s, const DevScene::FilterRec& F, coh_shape_t* shape, coh_shape_t* minshape, const char* who) {
+  coh_shape_t fs = 0, fm = 0;
+  if (shapes_from_device_edges(ctx, s->edges + F.first, F.count, F.winding, F.bx0 - F.dx, F.by0 - F.dy, F.bx1 - F.dx, F.by1 - F.dy, &fs, &fm, who)) return 1;
+  if (!F.dx && !F.dy) { *shape = fs; *minshape = fm; return 0; }
+  int rc = coh_shape_translate(ctx, fs, F.dx, F.dy, shape) || coh_shape_translate(ctx, fm, F.dx, F.dy, minshape);
+  coh_shape_free(ctx, fs); coh_shape_free(ctx, fm);
+  return rc;
+}
+static DevScene::FilterRec* filter_of_abi(DevScene* s, int obj_index) {
+  for (DevScene::FilterRec& F : s->filters) if (F.abi == obj_index) return &F;
+  return nullptr;
+}
 int coh_scene_object_shape(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, coh_shape_t* shape, coh_shape_t* minshape) {
   CK(cudaSetDevice(ctx->device));
   DevScene* s = (DevScene*)scene;
   if (!s) FAIL("coh_scene_object_shape: null scene");
+  if (const DevScene::FilterRec* F = filter_of_abi(s, obj_index)) return filter_shapes(ctx, s, *F, shape, minshape, "coh_scene_object_shape");
   if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_object_shape: no such object");
   return object_shape_rec(ctx, s, s->rec_of_abi[obj_index], shape, minshape);
 }
@@ -216,6 +230,11 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
   CK(cudaSetDevice(ctx->device));
   DevScene* s = (DevScene*)scene;
   if (!s) FAIL("coh_scene_translate_object: null scene");
+  if (DevScene::FilterRec* F = filter_of_abi(s, obj_index)) {
+    // a lens moves: its kept planes are re-made at the next frame (the key holds the offset)
+    F->dx += dx; F->dy += dy; F->bx0 += dx; F->bx1 += dx; F->by0 += dy; F->by1 += dy;
+    return 0;
+  }
   if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_translate_object: no such object");
   const int r = s->rec_of_abi[obj_index];
   const int last = s->h_objs[r].kind == K_GROUP ? s->group_last[r] : r;
@@ -288,7 +307,7 @@ int coh_dirty_filter(coh_ctx* ctx, coh_scene_t scene, int32_t lmo_index, coh_sha
     if (F.kind != COH_FILTER_BLUR || !cur) continue;  // nulldirty
     // bloatdirty r r (filters.ml:63-75)
     coh_shape_t fs = 0, fm = 0, bf = 0, inf = 0, outf = 0, bl = 0, bif = 0, res = 0;
-    if (shapes_from_device_edges(ctx, s->edges + F.first, F.count, F.winding, F.bx0, F.by0, F.bx1, F.by1, &fs, &fm, "coh_dirty_filter")) return 1;
+    if (filter_shapes(ctx, s, F, &fs, &fm, "coh_dirty_filter")) return 1;
     int rc = coh_shape_bloat(ctx, fs, F.r, F.r, &bf) || coh_shape_intersection(ctx, bf, cur, &inf) || coh_shape_difference(ctx, cur, bf, &outf) ||
              coh_shape_bloat(ctx, inf, F.r, F.r, &bl) || coh_shape_intersection(ctx, bl, bf, &bif) || coh_shape_union(ctx, bif, outf, &res);
     for (coh_shape_t h : {fs, fm, bf, inf, outf, bl, bif, cur}) coh_shape_free(ctx, h);
@@ -305,14 +324,19 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
   if (!ctx->fb) FAIL("coh_scene_drag_object: call coh_fb_configure first");
   DevScene* s = (DevScene*)scene;
   if (!s) FAIL("coh_scene_drag_object: null scene");
-  if (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0) FAIL("coh_scene_drag_object: no such object");
-  const int r = s->rec_of_abi[obj_index];
-  const ObjRec& o = s->h_objs[r];
-  // Fill.Plain objects: plaindirty; groups, fancy fills, brush strokes, Convolved objects: alldirty (render.ml:1396-1400)
-  const bool plain = (o.kind == K_PATH || o.kind == K_CPG) && o.fill.kind == 0;
-  const bool prim = o.kind == K_PRIM;
+  const DevScene::FilterRec* Fm = filter_of_abi(s, obj_index);
+  if (!Fm && (obj_index < 0 || obj_index >= (int)s->rec_of_abi.size() || s->rec_of_abi[obj_index] < 0)) FAIL("coh_scene_drag_object: no such object");
+  // Fill.Plain objects: plaindirty; groups, fancy fills, brush strokes, Convolved objects, filters: alldirty (render.ml:1396-1400)
+  bool plain = false, prim = false;
   coh_shape_t so = 0, mo = 0;
-  if (object_shape_rec(ctx, s, r, &so, &mo)) return 1;   // served by the cache after the first step
+  if (Fm) { if (filter_shapes(ctx, s, *Fm, &so, &mo, "coh_scene_drag_object")) return 1; }
+  else {
+    const int r = s->rec_of_abi[obj_index];
+    const ObjRec& o = s->h_objs[r];
+    plain = (o.kind == K_PATH || o.kind == K_CPG) && o.fill.kind == 0;
+    prim = o.kind == K_PRIM;
+    if (object_shape_rec(ctx, s, r, &so, &mo)) return 1;   // served by the cache after the first step
+  }
   if (coh_scene_translate_object(ctx, scene, obj_index, dx, dy)) return 1;
   const Frame& fr = ctx->fr;
   const int nw = fr.tiles_x;

@@ -371,9 +371,9 @@ struct StreamTemps {
 static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   const Frame& fr = ctx->fr;
   const int W = fr.W, H = fr.H, nw = fr.tiles_x;
-  if (F.SG && F.gW == W && F.gH == H) return 0;
+  if (F.SG && F.gW == W && F.gH == H && F.gdx == F.dx && F.gdy == F.dy) return 0;
   DFREE(F.SG); DFREE(F.CG); DFREE(F.op);
-  F.gW = W; F.gH = H;
+  F.gW = W; F.gH = H; F.gdx = F.dx; F.gdy = F.dy;
   F.gy0 = std::max(F.by0, 0);
   F.gh = std::min(F.by1, H - 1) - F.gy0 + 1;
   if (F.gh <= 0) { F.gh = 0; return 0; }
@@ -383,7 +383,7 @@ static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   CK(cudaMemsetAsync(F.SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(F.CG, 0, 4 * nwords, ctx->stream));
   const EdgeRec* ed = s->edges + F.first;
   // shape of the geometry (render.ml:472-474) and its coverage (minshape = shape - coverage, needed for the matte)
-  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, F.gy0, h, 0, nw, F.SG, F.CG, ctx->d_error); LAUNCHED();
+  k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, F.gy0 - F.dy, h, -F.dx, nw, F.SG, F.CG, ctx->d_error); LAUNCHED();   // (an alias reads the geometry's own frame moved by whole pixels)
   // The geometry's matte (render.ml:1099-1103).  Polygon.polygon_sprite samples every pixel it is given, but a pixel
   // whose 5 x 5 neighbourhood lies in the geometry's minshape has no edge anywhere near its 2 x 2-pixel sampling window
   // (a minshape pixel's row band [32y-47, 32y+16] and its columns are free of edge pieces), so all 32 x 32 samples
@@ -393,7 +393,7 @@ static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   CK(DMALLOC(&Q, 4 * nwords));
   k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(F.SG, F.CG, F.SG, Q, h, nw, W); LAUNCHED();
   CK(cudaMemsetAsync(F.op, 255, (size_t)nw * 32 * h, ctx->stream));
-  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q, F.gy0, h, 0, nw, ctx->d_aa, F.op, ctx->d_error); LAUNCHED();
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q, F.gy0 - F.dy, h, -F.dx, nw, ctx->d_aa, F.op, ctx->d_error); LAUNCHED();
   DFREE(Q);
   return 0;
 }

@@ -215,7 +215,6 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
       if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SCENE) FAIL("scene: bad filter kind");
       if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
-      if (c.dx || c.dy) FAIL("scene: translated filter objects are not supported yet");
       DevScene::FilterRec f; memset(&f, 0, sizeof f);
       f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
       if (c.filter_kind == COH_FILTER_BLUR) {
@@ -225,6 +224,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
       EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
       shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
+      f.dx = c.dx; f.dy = c.dy; f.bx0 += c.dx; f.bx1 += c.dx; f.by0 += c.dy; f.by1 += c.dy;
       filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
       continue;
     }

@@ -661,6 +661,42 @@ def test_filter_with_reading_scene(ctx, oracle):
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
 
 
+def test_translated_and_dragged_lenses(ctx, oracle):
+    """A filter object with an alias offset (render.ml:259-271) reads its geometry moved by whole pixels; dragging a
+    lens (coh_scene_drag_object: alldirty of its shape at both places) re-renders exactly what a full frame of the
+    moved scene shows."""
+    W, H = 200, 160
+    for kind, kw in (("monochrome", {}), ("blur", {"kernel": ("gaussian", 2)})):
+        b, f = _filter_scene(kind, W, H, **kw)
+        f.dx, f.dy = 23, -11
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+        assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, kind
+    b, f = _filter_scene("monochrome", W, H)
+    _finish(b, W, H)
+    objs, n, nbg, edges, points = b.arrays()
+    fi = [k for k, o in enumerate(objs) if o.kind == abi.COH_OBJ_FILTER][0]
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    for step, (dx, dy) in enumerate([(5, 3), (-12, 7), (30, -20), (1, 0)]):
+        bb = ctx.scene_drag_object(sc, fi, dx, dy)
+        ctx.sync()
+        assert bb[2] >= bb[0] and bb[3] >= bb[1]
+        objs[fi].dx += dx
+        objs[fi].dy += dy
+        got = ctx.fb_read_rgba(0, 0, W, H)
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert _max_lsb(got, ref) == 0, f"frame differs after lens drag step {step}"
+    # shapeonly_of_basicshape of the filter = its geometry's shape, where the alias has taken it
+    hs, hm = ctx.scene_object_shape(sc, fi)
+    g0, g1 = ctx.shapeminshape_of_edgelist(np.asarray(edges).reshape(-1, 4)[objs[fi].first:objs[fi].first + objs[fi].count], objs[fi].winding)
+    gt = ctx.shape_translate(g0, objs[fi].dx, objs[fi].dy)
+    assert np.array_equal(ctx.shape_export(hs), ctx.shape_export(gt))
+    for h in (hs, hm, g0, g1, gt):
+        ctx.shape_free(h)
+    ctx.scene_free(sc)
+
+
 def test_drag_object_fused_step(ctx, oracle):
     """coh_scene_drag_object = translate + dirty region + render of that region, on device-resident span sets: after
     every step the framebuffer equals the oracle's full render of the moved scene — for a plain path (plaindirty),
