@@ -404,6 +404,13 @@ static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, C
       coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
       gs = un;
     }
+    for (const DevScene::FilterRec& F : ss->filters) {   // a filter member's shape is its geometry's (render.ml:472-474)
+      if (rc) break;
+      coh_shape_t ms = 0, mm = 0, un = 0;
+      rc = filter_shapes(ctx, ss, F, &ms, &mm, "coh_scene_create (group)") || coh_shape_union(ctx, gs, ms, &un);
+      coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
+      gs = un;
+    }
     ctx->usecache = saved;
     if (rc) return 1;
     if (gs) {
@@ -413,7 +420,8 @@ static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, C
     }
   }
   uint32_t* convS = s->conv_bits + o.cv_bits;
-  k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(S, convS, h, nw, cg.r, cg.r); LAUNCHED();
+  if (cg.r > 0) { k_dilate<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(S, convS, h, nw, cg.r, cg.r); LAUNCHED(); }
+  else CK(cudaMemcpyAsync(convS, S, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemsetAsync(convS + nwords, 0, 4 * nwords, ctx->stream));
   // (2) the group's sprite: the members' scene rendered with the canvas as its frame
   {
@@ -421,16 +429,35 @@ static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, C
     for (int t = 0; t < cg.n_members; t++) {
       const int kind = cg.members[t].kind;
       if (kind == COH_OBJ_GROUP_END) { depth--; continue; }
-      if (depth == 0 && t < (int)ss->rec_of_abi.size() && ss->rec_of_abi[t] >= 0)
+      if (depth == 0 && ((t < (int)ss->rec_of_abi.size() && ss->rec_of_abi[t] >= 0) || filter_of_abi(ss, t)))
         if (coh_scene_translate_object(ctx, (coh_scene_t)ss, t, -o.cv_x0, -o.cv_y0)) return 1;
       if (kind == COH_OBJ_GROUP_BEGIN && !cg.members[t].convolve) depth++;
     }
     const Frame saved = ctx->fr;
     ctx->fr.W = w; ctx->fr.H = h; ctx->fr.band_y0 = 0; ctx->fr.band_y1 = h; ctx->fr.tiles_x = nw; ctx->fr.cells_y = cdiv(h, CELL_H); ctx->fr.ctx0 = 0; ctx->fr.cntx = nw;
-    PassArgs pa{0, ss->n_leaves, 0, 0, w, h, nullptr, nullptr, A, true, false};
-    const int rc = render_pass(ctx, ss, pa);
+    int rc;
+    if (ss->filters.empty()) {
+      PassArgs pa{0, ss->n_leaves, 0, 0, w, h, nullptr, nullptr, A, true, false};
+      rc = render_pass(ctx, ss, pa);
+    } else {
+      // filter passes work on the context's frame: the canvas stands in for it
+      uint32_t* saved_fb = ctx->fb; uint32_t* saved_u = ctx->u_out; const int saved_peers = ctx->n_peers;
+      uint32_t* Uc = nullptr;
+      CK(DMALLOC(&Uc, 4 * nwords));
+      ctx->fb = A; ctx->u_out = Uc; ctx->n_peers = 0;
+      rc = render_filtered(ctx, ss, nullptr, 0, 0, w, h);
+      ctx->fb = saved_fb; ctx->u_out = saved_u; ctx->n_peers = saved_peers;
+      DFREE(Uc);
+    }
     ctx->fr = saved;
     if (rc) return 1;
+  }
+  if (cg.r == 0) {   // no kernel: the canvas is the sprite
+    CK(cudaMemcpyAsync(s->conv_px + o.cv_px, A, 4 * npx, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (check_error_flag(ctx, "coh_scene_create (group holding filters)")) return 1;
+    DFREE(S); DFREE(A); DFREE(X);
+    coh_scene_free(ctx, (coh_scene_t)ss); cg.sub = nullptr;
+    return 0;
   }
   // (3) Convolve.convolve_sprite on the canvas: X pass, Y pass
   std::vector<int> taps; int total = 0;

@@ -238,13 +238,23 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     o.fill.kind = c.fill_kind; o.fill.c0 = c.colour0; o.fill.c1 = c.colour1; o.fill.flags = c.fill_flags;
     for (int k = 0; k < 6; k++) o.fill.p[k] = c.fparam[k];
     switch (c.kind) {
-      case COH_OBJ_GROUP_BEGIN:
-        if (c.convolve) {
+      case COH_OBJ_GROUP_BEGIN: {
+        // A Group with a filter object among its members (render.ml:988-1001: the members are rendered as a scene of
+        // their own, so the filter's "objects below" are the rest of THIS list) is realised like a Convolved group with
+        // no kernel: its members become a scene of their own, rendered once into the group's canvas.
+        bool holds_filter = false;
+        if (!c.convolve && c.filter_kind != COH_FILTER_READING_SCENE)
+          for (int j = i + 1, nest = 1; j < n_objs && nest > 0; j++) {
+            if (objs[j].kind == COH_OBJ_GROUP_BEGIN) nest++;
+            else if (objs[j].kind == COH_OBJ_GROUP_END) nest--;
+            else if (objs[j].kind == COH_OBJ_FILTER) { holds_filter = true; break; }
+          }
+        if (c.convolve || holds_filter) {
           // Convolved (kernel, Group members) (render.ml:63, 1023-1052 with a Group child; shapes render.ml:536-555, where
           // findfill of a Group is "fancy": minshape null).  The members become a scene of their own, rendered once into
           // the object's canvas and convolved there (below); the object itself is one leaf, like Convolved (Basic Path).
           const int ck = c.convolve & 255, cr = c.convolve >> 8;
-          if ((ck != COH_CONV_UNIT && ck != COH_CONV_GAUSSIAN) || cr <= 0 || cr > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
+          if (c.convolve && ((ck != COH_CONV_UNIT && ck != COH_CONV_GAUSSIAN) || cr <= 0 || cr > 64)) FAIL("Convolve.mkunit / mkxy: bad kernel");
           if (c.filter_kind == COH_FILTER_READING_SCENE) FAIL("scene: a reading-scene group cannot be Convolved");
           int j = i + 1, nest = 1;
           for (; j < n_objs; j++) {
@@ -252,11 +262,12 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
             if (j == n_objs - n_background) break;   // (a group may not straddle the two lists)
             if (m.kind == COH_OBJ_GROUP_BEGIN) nest++;
             else if (m.kind == COH_OBJ_GROUP_END) { if (--nest == 0) break; }
-            else if (m.kind == COH_OBJ_FILTER) FAIL("scene: filter objects inside a Convolved group are not supported");
-            else if (m.kind != COH_OBJ_PRIMITIVE && m.fill_kind != COH_FILL_PLAIN)
+            else if (m.kind == COH_OBJ_FILTER) {
+              if (m.filter_kind == COH_FILTER_SCENE) FAIL("scene: a filter with a caller-built reading scene must be a top-level member of the scene list");
+            } else if (m.kind != COH_OBJ_PRIMITIVE && m.fill_kind != COH_FILL_PLAIN)
               // the span-start fill quirk (polygon.ml:736) makes a fancy-filled member depend on the region requested at
               // render time, which a canvas rendered once cannot follow
-              FAIL("scene: Convolved groups with fancy-filled members are not supported yet");
+              FAIL("scene: Convolved groups (and groups holding filters) with fancy-filled members are not supported yet");
           }
           if (j >= n_objs || nest != 0) FAIL("scene: unterminated group");
           if (j == i + 1) FAIL("Empty groups aren't allowed");   // render.ml:317
@@ -267,6 +278,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           skip_to = j;   // the members belong to the Convolved object
           int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
           for (int li : ss->h_leaves) { const ObjRec& m = ss->h_objs[li]; x0 = std::min(x0, m.bx0); y0 = std::min(y0, m.by0); x1 = std::max(x1, m.bx1); y1 = std::max(y1, m.by1); }
+          for (const DevScene::FilterRec& m : ss->filters) { x0 = std::min(x0, m.bx0); y0 = std::min(y0, m.by0); x1 = std::max(x1, m.bx1); y1 = std::max(y1, m.by1); }   // a filter's shape is its geometry's (render.ml:472-474)
           if (x0 > x1) { rec_of_abi[i] = -1; i = j; conv_groups.back().rec = -1; continue; }   // nothing to draw
           o.kind = K_CONV; o.fill.kind = 0; o.fill.c0 = 0;
           o.bx0 = x0; o.by0 = y0; o.bx1 = x1; o.by1 = y1;
@@ -277,6 +289,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           o.cv_px = (int)conv_pixels; conv_pixels += (size_t)o.cv_nw * 32 * o.cv_h;
           if (conv_words > 0x7FFFFFF0ull || conv_pixels > 0x7FFFFFF0ull || o.cv_h > 65535 || o.cv_nw > 32767) FAIL("scene: Convolved canvases too large");
           break;
+        }
         }
         o.kind = K_GROUP;
         if (o.depth >= MAX_DEPTH) FAIL("scene: groups nested too deeply (MAX_DEPTH)");

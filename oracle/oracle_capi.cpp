@@ -78,8 +78,11 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         g.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
         sort_edgelist_maxy_rev(g.edges);
         o.children.push_back(std::move(g));
-        if (stack.size() != 1) throw std::runtime_error("scene: filter objects must be top-level");
-        if (c.filter_kind == COH_FILTER_SCENE) pending_reading.push_back({stack.back().size(), c.first2});
+        // (a filter inside a Group sees the rest of that group's list as its objects below, render.ml:988-1001)
+        if (c.filter_kind == COH_FILTER_SCENE) {
+          if (stack.size() != 1) throw std::runtime_error("scene: a filter with a caller-built reading scene must be top-level");
+          pending_reading.push_back({stack.back().size(), c.first2});
+        }
         stack.back().push_back(std::move(o));
         break;
       }

@@ -661,6 +661,30 @@ def test_filter_with_reading_scene(ctx, oracle):
     assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
 
 
+def test_filters_inside_groups(ctx, oracle):
+    """A filter object that is a member of a Group (render.ml:988-1001): its objects below are the rest of the group's
+    own list; the group (PreTrans or not, nested or not) is composited as one sprite."""
+    W, H = 200, 160
+    for kind, kw, pt in (("monochrome", {}, -1), ("blur", {"kernel": ("gaussian", 2)}, 180), ("hole", {}, -1)):
+        b = S.SceneBuilder()
+        b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+        b.group_begin(pretrans=pt)
+        b.polygon([(50.3, 20.2), (90.5, 23.9), (88.1, 60.7), (48.8, 54.4)], S.Fill.plain(S.rgba8(30, 30, 220)))
+        b.filter(kind, _circle(100.3, 80.2, 40.5), **kw)
+        b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+        b.group_begin()
+        b.filter("monochrome", _circle(70.0, 100.0, 25.0))
+        b.polygon([(60.0, 20.0), (120.0, 140.0), (20.0, 120.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 240, 20), 200)))
+        b.group_end()
+        b.group_end()
+        b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+        assert np.array_equal(got_u, ref_u), kind
+        assert _max_lsb(got, ref) == 0, kind
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H, update=(40, 30, 90, 100))
+        assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, kind
+
+
 def test_translated_and_dragged_lenses(ctx, oracle):
     """A filter object with an alias offset (render.ml:259-271) reads its geometry moved by whole pixels; dragging a
     lens (coh_scene_drag_object: alldirty of its shape at both places) re-renders exactly what a full frame of the
