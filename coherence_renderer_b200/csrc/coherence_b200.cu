@@ -96,6 +96,7 @@ struct DevScene {
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
   struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total;
                      int dx, dy;   // alias translation in whole pixels (render.ml:259-271); bx0 .. by1 include it
+                     int head_abi, head_l1;   // MINUS: the object that follows the filter, the leaf index where the list continues after it
                      // kept with the scene once computed (the reference finds a filter geometry's shape in its cache by id,
                      // render.ml:472-474): shape / coverage bit-rows and the antialiased opacity of every shape pixel, for the
                      // geometry's rows gy0 .. gy0 + gh - 1 of a frame gW x gH

@@ -354,6 +354,7 @@ static int render_frame_passes(coh_ctx* ctx, DevScene* s, PassArgs A) {
 // ---------------------------------------------------------------------------------------
 struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
 static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed = false);
+static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape, coh_shape_t* minshape);
 // temporaries of one filter application: released on every way out
 struct StreamTemps {
   coh_ctx* ctx; std::vector<void*> v;
@@ -423,6 +424,22 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   CK(cudaMemsetAsync(planes, 0, 4 * nwords * 2, ctx->stream));
   // shptorender = r &&& u (render.ml:1281); a filter other than blur reads where it writes
   k_and_rows<<<(unsigned)(((size_t)h * nw + 255) / 256), 256, 0, ctx->stream>>>(SG, U + r0, T + r0, m > 0 ? nullptr : R + r0, (size_t)h * nw); LAUNCHED();
+  if (F.kind == COH_FILTER_MINUS) {
+    // filters.ml:291-303: the filter reads, and acts, only in shape (filter) ∩ shape (hd scene) ∩ shp
+    const int hr = s->rec_of_abi[F.head_abi];
+    coh_shape_t hs = 0, hm = 0;
+    if (hr >= 0 && object_shape_rec(ctx, s, hr, &hs, &hm)) return 1;
+    const DevShape* Hs = (const DevShape*)hs;
+    if (Hs) {
+      uint32_t* Hb = nullptr;
+      CK(TMPGET(tmp, &Hb, 4 * (size_t)h * nw));
+      CK(cudaMemsetAsync(Hb, 0, 4 * (size_t)h * nw, ctx->stream));
+      k_spans_to_bits<<<cdiv(h, 128), 128, 0, ctx->stream>>>(Hs->row_ptr, Hs->spans, Hs->y0, Hs->n_rows, y0, h, 0, nw, Hb); LAUNCHED();
+      k_bitop<<<(unsigned)(((size_t)h * nw + 255) / 256), 256, 0, ctx->stream>>>(T + r0, Hb, T + r0, (size_t)h * nw, 2); LAUNCHED();
+    } else CK(cudaMemsetAsync(T + r0, 0, 4 * (size_t)h * nw, ctx->stream));
+    CK(cudaMemcpyAsync(R + r0, T + r0, 4 * (size_t)h * nw, cudaMemcpyDeviceToDevice, ctx->stream));
+    coh_shape_free(ctx, hs); coh_shape_free(ctx, hm);
+  }
   // The scene below renders the same pixels whatever region it is asked for (plain fills: no span-start quirk,
   // polygon.ml:736), so where the reading scene IS the scene below (monochrome, blur: filters.ml:229-258) the pixels
   // that show through the matte (render.ml:1105-1110) are taken from the reading scene's render before its filter function.
@@ -440,7 +457,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
     if (F.kind == COH_FILTER_SCENE) {
       PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
-    } else if (render_suffix(ctx, s, F.pos, fi + 1, R, X, true, rbox, true)) return 1;
+    } else if (render_suffix(ctx, s, F.kind == COH_FILTER_MINUS ? F.head_l1 : F.pos, fi + 1, R, X, true, rbox, true)) return 1;   // MINUS: tl scene
     Y = X;
     if (F.kind == COH_FILTER_MONOCHROME) {
       if (z_is_x) blend_flags |= 2;   // Y = monochrome of Z, taken on the fly

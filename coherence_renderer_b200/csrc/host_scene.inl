@@ -213,13 +213,19 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: filter objects must be top-level members of the scene list");
       if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
       if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
-      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SCENE) FAIL("scene: bad filter kind");
+      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_MINUS) FAIL("scene: bad filter kind");
       if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
       DevScene::FilterRec f; memset(&f, 0, sizeof f);
       f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
       if (c.filter_kind == COH_FILTER_BLUR) {
         f.kernel_kind = c.filter_kernel & 255; f.r = c.filter_kernel >> 8;
         if ((f.kernel_kind != COH_CONV_UNIT && f.kernel_kind != COH_CONV_GAUSSIAN) || f.r <= 0 || f.r > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
+      }
+      if (c.filter_kind == COH_FILTER_MINUS) {   // filters.ml:295: hd scene
+        f.head_abi = i + 1;
+        if (i + 1 >= n_objs - n_background || objs[i + 1].kind == COH_OBJ_GROUP_END || objs[i + 1].kind == COH_OBJ_FILTER ||
+            (objs[i + 1].kind == COH_OBJ_GROUP_BEGIN && objs[i + 1].filter_kind == COH_FILTER_READING_SCENE))
+          FAIL("Filters.minus: no object below the filter (hd)");
       }
       if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
       EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
@@ -419,6 +425,18 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   if (open.size() != 1 || cur_reading >= 0) FAIL("scene: unterminated group");
   if (n_scene_leaves < 0) n_scene_leaves = (int)leaves.size();
   if (n_front_leaves < 0) n_front_leaves = (int)leaves.size();
+  for (DevScene::FilterRec& f : filters) {
+    if (f.kind != COH_FILTER_MINUS) continue;
+    // the list continues after the head object's last leaf (records and leaves are made in list order)
+    const int hr = rec_of_abi[f.head_abi];
+    f.head_l1 = f.pos;
+    if (hr >= 0) {
+      group_last.resize(recs.size(), -1);
+      const int last = recs[hr].kind == K_GROUP ? group_last[hr] : hr;
+      const int end = n_scene_leaves;
+      while (f.head_l1 < end && leaves[f.head_l1] <= last) f.head_l1++;
+    }
+  }
   for (size_t k = 0; k < filters.size(); k++) {
     if (filter_read_abi[k] < 0) continue;
     auto it = reading.find(filter_read_abi[k]);

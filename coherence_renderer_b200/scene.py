@@ -332,7 +332,7 @@ class SceneBuilder:
         self.edges.append(e)
         self._n_edges += len(e)
         (fill or Fill.plain(WHITE)).apply(o)
-        o.filter_kind = {"hole": 1, "monochrome": 2, "blur": 3, "scene": 4}[kind]
+        o.filter_kind = {"hole": 1, "monochrome": 2, "blur": 3, "scene": 4, "minus": 5}[kind]
         if kind == "blur":
             o.filter_kernel = {"unit": 1, "gaussian": 2}[kernel[0]] | (int(kernel[1]) << 8)
         return o

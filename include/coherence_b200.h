@@ -48,13 +48,19 @@ enum {
  *   MONOCHROME  filters.ml:229-238  reading scene = the objects below, filter = sprite_map Colour.monochrome
  *   BLUR        filters.ml:243-258  reading scene = the objects below read in bloat (2r+1) (2r+1) shape,
  *                                   filter = Convolve.convolve_sprite_in_shape kernel (filter_kernel = COH_CONV_* | r << 8)
- *   SCENE       affine / rgb / wireframe / swapdepth / minus (filters.ml:105-212, 271-332): the caller builds the
+ *   SCENE       affine / rgb / wireframe / swapdepth (filters.ml:105-212, 271-285, 305-332): the caller builds the
  *               modified scene (a host-side rewrite of the objects below) and passes it as a reading-scene
  *               group; filter = identity.  first2 = index (in the objs array) of that group's GROUP_BEGIN.
+ *   MINUS       filters.ml:289-303  a single-object hole: the object that follows the filter in its list is cut away
+ *                                   inside the filter — reading scene = the objects below but that first one, read (and the
+ *                                   filter applied) only in shape (filter) ∩ shape (first object below); filter = identity
  * A reading-scene group is a top-level GROUP_BEGIN of the scene section with filter_kind =
  * COH_FILTER_READING_SCENE; such groups come after every ordinary scene object and are never drawn
- * on their own.  Filter objects must be top-level members of the scene list. */
-enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4,
+ * on their own.  A filter object may carry an alias offset (dx, dy) and may be a member of a group: such a group's members
+ * are rendered once, as a scene of their own, into the group's canvas (like Convolved (kernel, Group members)), so they
+ * take plain fills only; SCENE filters must be top-level members of the scene list.  The geometry of a filter is a path
+ * with a plain fill. */
+enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4, COH_FILTER_MINUS = 5,
        COH_FILTER_READING_SCENE = 100 };
 enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH_CPG_EXCLUSIVEOR = 3 };
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */

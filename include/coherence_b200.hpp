@@ -249,7 +249,7 @@ inline compop PreTrans(double v) { compop c; c.pretrans = (int)(v * 255.); retur
 struct renderobject;
 typedef std::vector<renderobject> scene;  // head = front-most
 enum cpgop { Union = COH_CPG_UNION, Intersection = COH_CPG_INTERSECTION, Subtraction = COH_CPG_SUBTRACTION, ExclusiveOr = COH_CPG_EXCLUSIVEOR };
-enum filterkind { Hole = COH_FILTER_HOLE, Monochrome = COH_FILTER_MONOCHROME, Blur = COH_FILTER_BLUR, ReadingScene = COH_FILTER_SCENE };
+enum filterkind { Hole = COH_FILTER_HOLE, Monochrome = COH_FILTER_MONOCHROME, Blur = COH_FILTER_BLUR, ReadingScene = COH_FILTER_SCENE, Minus = COH_FILTER_MINUS };
 
 // Obj (idset, geometry, transform, compop) with the transform already applied (render.ml:19-75)
 struct renderobject {

@@ -342,9 +342,16 @@ struct Renderer {
     int r = o.filter_kind == 3 ? radius_of_kernel(o.kernel) : 0;
     // reading_scene (filters.ml:221, 233-234, 247-250, 276-278)
     Shape readshape = o.filter_kind == 3 ? bloat(2 * r + 1, 2 * r + 1, shptorender) : shptorender;
-    const Shape& shp2 = shptorender;
-    Scene none;
-    const Scene& scene2 = o.filter_kind == 1 ? none : (o.filter_kind == 4 ? *o.reading_scene : tail);
+    Shape shp2 = shptorender;
+    Scene none, tl;
+    if (o.filter_kind == 5) {  // Filters.minus (filters.ml:289-303): hd scene is cut away inside the filter
+      if (tail.empty()) throw std::runtime_error("hd");
+      Shape fs, fm, hs, hm; shape_of_basicshape(o, fs, fm); shape_of_basicshape(tail[0], hs, hm);
+      shp2 = shape_intersection(shape_intersection(fs, hs), shptorender);
+      readshape = shp2;
+      tl = Scene(tail.begin() + 1, tail.end());
+    }
+    const Scene& scene2 = o.filter_kind == 1 ? none : (o.filter_kind == 4 ? *o.reading_scene : (o.filter_kind == 5 ? tl : tail));
     Sprite X; { Shape u = readshape; render_scene(u, X, scene2, true); }
     Sprite Y;
     switch (o.filter_kind) {

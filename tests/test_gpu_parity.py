@@ -685,6 +685,31 @@ def test_filters_inside_groups(ctx, oracle):
         assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, kind
 
 
+def test_filter_minus(ctx, oracle):
+    """Filters.minus (filters.ml:289-303), a single-object hole: inside shape (filter) ∩ shape (object below) the
+    scene is read without that object; the rest of the filter's shape is finished with nothing in it.  Head object a
+    path, a group, and an object the filter does not meet."""
+    W, H = 200, 160
+    for variant in range(3):
+        b = S.SceneBuilder()
+        b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+        b.filter("minus", _circle(100.3, 80.2, 45.5), fill=S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 255 if variant != 1 else 150)))
+        if variant == 0:
+            b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+        elif variant == 1:
+            b.group_begin(pretrans=220)
+            b.polygon([(30.3, 30.2), (120.5, 33.9), (118.1, 100.7), (28.8, 94.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+            b.polygon([(80.0, 70.0), (170.0, 75.0), (160.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(30, 30, 200), 180)))
+            b.group_end()
+        else:
+            b.polygon([(2.0, 2.0), (30.0, 3.0), (20.0, 25.0)], S.Fill.plain(S.rgba8(200, 30, 30)))
+        b.polygon([(60.0, 20.0), (120.0, 140.0), (20.0, 120.0)], S.Fill.plain(S.rgba8(250, 240, 20)))
+        b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+        assert np.array_equal(got_u, ref_u), variant
+        assert _max_lsb(got, ref) == 0, variant
+
+
 def test_translated_and_dragged_lenses(ctx, oracle):
     """A filter object with an alias offset (render.ml:259-271) reads its geometry moved by whole pixels; dragging a
     lens (coh_scene_drag_object: alldirty of its shape at both places) re-renders exactly what a full frame of the
