@@ -379,9 +379,21 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       case COH_OBJ_BRUSH: {
         if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_points) FAIL("scene: point range out of bounds");
         if (!(c.brush_radius >= 0.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range");
+        if (c.winding != COH_BRUSH_GAUSSIAN && c.winding != COH_BRUSH_DUMMY) FAIL("scene: bad brush kind");
         o.kind = K_BRUSH; o.first = c.first; o.count = c.count;
         if (c.count == 0) continue;
-        {
+        if (c.winding == COH_BRUSH_DUMMY) {
+          // Dummy (r, r) (brush.ml:14-22, 178-181): every pixel of the stroke's shape in opaque white — a stamp of 255s
+          if (c.brush_radius > 4096. || c.brush_radius != (double)(int)c.brush_radius) FAIL("scene: the radius of a dummy brush is a small integer");
+          o.fill.kind = 0; o.fill.c0 = 0xFFFFFFFFu;
+          const std::pair<uint64_t, int> key((uint64_t)c.brush_radius, -1);
+          auto it = stamp_cache.find(key);
+          if (it == stamp_cache.end()) {
+            o.stamp_off = (int)stamps.size(); o.brush_r = (int)c.brush_radius;
+            stamps.resize(stamps.size() + (size_t)(2 * o.brush_r + 1) * (2 * o.brush_r + 1), (uint8_t)255);
+            stamp_cache[key] = std::make_pair(o.stamp_off, o.brush_r);
+          } else { o.stamp_off = it->second.first; o.brush_r = it->second.second; }
+        } else {
           // the stamp is a function of (radius, toint (opacity *. 255.)) alone (brush.ml:60-92): strokes share it
           // (10^4 strokes of a scene use a few hundred distinct stamps; the exponentials are the cost of this loop)
           uint64_t rbits; memcpy(&rbits, &c.brush_radius, sizeof rbits);

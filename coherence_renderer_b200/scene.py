@@ -305,6 +305,18 @@ class SceneBuilder:
         fill.apply(o)
         return o
 
+    def dummy_brush(self, radius, subpaths, **kw):
+        """Basic (_, Brushstroke (Brush.mkdummy ((opacity, Gaussian radius), path))) (brush.ml:70-73): the stroke's whole
+        shape in white."""
+        import math
+
+        from . import abi
+
+        o = self.brush(1.0, radius, subpaths, Fill.plain(WHITE), **kw)
+        o.winding = abi.COH_BRUSH_DUMMY
+        o.brush_radius = float(math.ceil(radius))   # ((2 ceil r + 1) - 1) / 2
+        return o
+
     def cpg(self, op, subpaths_a, subpaths_b, fill, winding_a=COH_NONZERO, winding_b=COH_NONZERO, **kw):
         """Basic (fill, CPG (op, Path a, Path b)); op in "union" | "intersection" | "subtraction" | "xor"."""
         from . import abi

@@ -66,11 +66,14 @@ enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
 enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
 enum { COH_FILL_EXT_S = 1, COH_FILL_EXT_E = 2 };
+enum { COH_BRUSH_GAUSSIAN = 0, COH_BRUSH_DUMMY = 1 };  /* Brush.brushkind (brush.ml:14-16); BRUSH objects carry it in `winding` */
 enum { COH_CONV_UNIT = 1, COH_CONV_GAUSSIAN = 2 };  /* convolve.ml:19-22,37-70 (UnitKernel r / XYKernel from mkgaussian r) */
 
 typedef struct coh_object {
   int32_t kind;        /* COH_OBJ_* */
-  int32_t winding;     /* COH_NONZERO / COH_EVENODD (PATH) */
+  int32_t winding;     /* COH_NONZERO / COH_EVENODD (PATH); BRUSH: COH_BRUSH_GAUSSIAN, or COH_BRUSH_DUMMY = Dummy (r, r) with
+                          r = brush_radius (an integer): the whole shape of the stroke in white, whatever the fill
+                          (brush.ml:178-181; Brush.mkdummy) */
   int32_t first;       /* PATH: first edge; BRUSH: first point */
   int32_t count;       /* PATH: number of edges; BRUSH: number of points */
   int32_t fill_kind;   /* COH_FILL_* */

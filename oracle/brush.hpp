@@ -62,8 +62,9 @@ inline std::vector<Pt> points_on_path(double sep, const Path& path) {
 
 struct BrushStroke {
   double opacity = 1.0, radius = 1.0;       // (opacity, Gaussian radius)
+  bool dummy = false; int rx = 0;           // Dummy (rx, ry), rx = ry (brush.ml:14-16; Brush.mkdummy always makes them equal)
   std::vector<std::pair<int, int>> points;  // toint(x+0.5), toint(y+0.5), in list order (brush.ml:172,196-199)
-  int bw() const { return (int)std::ceil(radius) * 2 + 1; }  // brush.ml:25-28
+  int bw() const { return dummy ? rx * 2 + 1 : (int)std::ceil(radius) * 2 + 1; }  // brush.ml:25-28
 };
 inline std::vector<std::pair<int, int>> round_points(const std::vector<Pt>& pts) {
   std::vector<std::pair<int, int>> o;
@@ -108,6 +109,8 @@ inline Shape shape_of_brushstroke(const BrushStroke& b) {
 }
 // brush.ml:176-222
 inline Sprite sprite_of_brushstroke(const BrushStroke& b, const Fill& fill, const Shape& shp) {
+  // brush.ml:178-181: a dummy brush is the WHOLE shape of the stroke in white, whatever fill and region are asked for
+  if (b.dummy) return fillshape(shape_of_brushstroke(b), Fill::plain(mkcol(255, 255, 255)));
   Sprite none;
   if (shp.null()) return none;
   int r = (b.bw() - 1) / 2;

@@ -107,6 +107,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
       case COH_OBJ_BRUSH: {
         o.kind = Obj::Brush; o.fill = fill_from(c);
         o.stroke.opacity = c.brush_opacity; o.stroke.radius = c.brush_radius;
+        if (c.winding == COH_BRUSH_DUMMY) { o.stroke.dummy = true; o.stroke.rx = (int)c.brush_radius; }
         for (int k = 0; k < c.count; k++)
           o.stroke.points.push_back({points[2 * ((size_t)c.first + k)], points[2 * ((size_t)c.first + k) + 1]});
         stack.back().push_back(std::move(o));

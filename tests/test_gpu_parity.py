@@ -247,6 +247,23 @@ def test_brush_strokes(ctx, oracle):
     assert _max_lsb(got, ref) == 0
 
 
+def test_dummy_brush(ctx, oracle):
+    """Brushstroke with a Dummy brush (brush.ml:14-22, 70-73, 178-181): the whole shape of the stroke — the boxes around
+    its stamp points — in opaque white, whatever fill it was given; minshape null."""
+    W, H = 320, 240
+    b = S.SceneBuilder()
+    b.brush(0.8, 6.0, [[("C", (30.0, 200.0), (100.0, 10.0), (220.0, 230.0), (290.0, 40.0))]], S.Fill.plain(S.rgba8(20, 20, 120)))
+    b.dummy_brush(4.5, [[("C", (20.0, 30.0), (120.0, 220.0), (200.0, 20.0), (300.0, 200.0))]], pretrans=170)
+    b.dummy_brush(9.0, [[("L", (10.0, 10.0), (300.0, 60.0))]])
+    b.polygon([(60.0, 60.0), (260.0, 80.0), (160.0, 220.0)], S.Fill.plain(S.rgba8(240, 200, 60)))
+    b.begin_background()
+    b.rectangle(S.LIGHTGREY, 0.0, 0.0, float(W), float(H))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+    assert np.array_equal(got_u, ref_u)
+    assert _max_lsb(got, ref) == 0
+    assert (got == 0xFFFFFFFF).sum() > 2000   # the opaque white stroke shows
+
+
 def test_rgb888_export(ctx):
     W, H = 96, 64
     b = S.SceneBuilder()
