@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("COH_LIB_PATH", os.path.join(_HERE, "libcoherence_b200
 COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH, COH_OBJ_CPG = 0, 1, 2, 3, 4, 5
 COH_OBJ_FILTER = 6
 COH_BRUSH_GAUSSIAN, COH_BRUSH_DUMMY = 0, 1
-COH_FILTER_HOLE, COH_FILTER_MONOCHROME, COH_FILTER_BLUR, COH_FILTER_SCENE, COH_FILTER_MINUS, COH_FILTER_READING_SCENE = 1, 2, 3, 4, 5, 100
+COH_FILTER_HOLE, COH_FILTER_MONOCHROME, COH_FILTER_BLUR, COH_FILTER_SCENE, COH_FILTER_MINUS, COH_FILTER_SMEAR, COH_FILTER_READING_SCENE = 1, 2, 3, 4, 5, 6, 100
 COH_CPG_UNION, COH_CPG_INTERSECTION, COH_CPG_SUBTRACTION, COH_CPG_EXCLUSIVEOR = 0, 1, 2, 3
 COH_NONZERO, COH_EVENODD = 0, 1
 COH_FILL_PLAIN, COH_FILL_AXIAL, COH_FILL_RADIAL = 0, 1, 2
@@ -47,7 +47,7 @@ SYMBOLS = [
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_sprite", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
-    "coh_host_edgelist_of_subpath", "coh_host_brush_points",
+    "coh_host_edgelist_of_subpath", "coh_host_brush_points", "coh_host_smear_points",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_sprite_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
@@ -84,6 +84,7 @@ def lib():
         L.coh_colour_of_rgba8.restype = C.c_int32
         L.coh_host_edgelist_of_subpath.restype = C.c_int64
         L.coh_host_brush_points.restype = C.c_int64
+        L.coh_host_smear_points.restype = C.c_int64
         L.coh_multi_last_error.restype = C.c_char_p
         L.coh_multi_last_error.argtypes = [C.c_void_p]
         L.coh_multi_ctx.restype = C.c_void_p
@@ -503,6 +504,18 @@ def host_edgelist_of_subpath(segs):
     while True:
         out = np.zeros((cap, 4), dtype=np.int32)
         n = lib().coh_host_edgelist_of_subpath(rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), _i32p(out), C.c_int64(cap))
+        if n <= cap:
+            return out[:n]
+        cap = int(n)
+
+
+def host_smear_points(segs):
+    """Integer points of Brush.find_smear_directions (brush.ml:239-283) for all the segments of a path in order."""
+    rec = _seg_records(segs)
+    cap = 4096
+    while True:
+        out = np.zeros((cap, 2), dtype=np.int32)
+        n = lib().coh_host_smear_points(rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), _i32p(out), C.c_int64(cap))
         if n <= cap:
             return out[:n]
         cap = int(n)

@@ -97,6 +97,7 @@ struct DevScene {
   struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total;
                      int dx, dy;   // alias translation in whole pixels (render.ml:259-271); bx0 .. by1 include it
                      int head_abi, head_l1;   // MINUS: the object that follows the filter, the leaf index where the list continues after it
+                     int first2, count2, stamp_off, brush_r;   // SMEAR: smear points (in the points array), the brush's stamp (alpha bytes), its radius
                      // kept with the scene once computed (the reference finds a filter geometry's shape in its cache by id,
                      // render.ml:472-474): shape / coverage bit-rows and the antialiased opacity of every shape pixel, for the
                      // geometry's rows gy0 .. gy0 + gh - 1 of a frame gW x gH
@@ -136,6 +137,7 @@ struct coh_ctx {
   uint32_t* fb = nullptr;
   uint32_t* u_out = nullptr;   // bit-frame of `u` after the scene pass
   uint32_t* u_init = nullptr;  // bit-frame of an arbitrary update shape
+  uint32_t* touched = nullptr; // while a smear filter renders its reading scene: the bit-frame that receives the shape of that render
   bool use_u_init = false;
   bool have_u = false;
   // binning scratch (passes whose binning is not kept with the scene)

@@ -53,6 +53,35 @@ int64_t coh_host_edgelist_of_subpath(const double* segs, int32_t n_segs, int32_t
   }
   return (int64_t)f.size();
 }
+// Brush.points_of_brushstroke_smear (brush.ml:239-257) + the integer points of find_smear_directions (259-283).
+namespace {
+void subdivide_adjacent(Pt p1, Pt p2, Pt p3, Pt p4, std::vector<Pt>& starts) {
+  const double d = sqrt((p1.first - p4.first) * (p1.first - p4.first) + (p1.second - p4.second) * (p1.second - p4.second));
+  if (d <= 2.) { starts.push_back(p1); return; }
+  auto half = [](Pt a, Pt b) { return Pt((a.first + b.first) / 2., (a.second + b.second) / 2.); };
+  Pt l2 = half(p1, p2), h = half(p2, p3), l3 = half(l2, h), r3 = half(p3, p4), r2 = half(h, r3), l4 = half(l3, r2);
+  subdivide_adjacent(p1, l2, l3, l4, starts);
+  subdivide_adjacent(l4, r2, r3, p4, starts);
+}
+}  // namespace
+int64_t coh_host_smear_points(const double* segs, int32_t n_segs, int32_t* points_out, int64_t cap) {
+  std::vector<Pt> pts;
+  for (int i = 0; i < n_segs; i++) {
+    const double* s = segs + 9 * i;
+    if (s[0] == 0.) {
+      Pt a(s[1], s[2]), b(s[3], s[4]), m((a.first + b.first) / 2., (a.second + b.second) / 2.);   // Pdfutil.between
+      subdivide_adjacent(a, m, m, b, pts);
+    } else subdivide_adjacent(Pt(s[1], s[2]), Pt(s[3], s[4]), Pt(s[5], s[6]), Pt(s[7], s[8]), pts);
+  }
+  int64_t n = 0; int lx = 0, ly = 0;
+  for (const Pt& p : pts) {
+    const int x = (int)p.first, y = (int)p.second;   // toint: truncation
+    if (n && x == lx && y == ly) continue;            // drop_duplicates
+    if (n < cap) { points_out[2 * n] = x; points_out[2 * n + 1] = y; }
+    lx = x; ly = y; n++;
+  }
+  return n;
+}
 // Brush.points_of_brushstroke rounded as in brush.ml:172, one subpath: returns the number of points.
 int64_t coh_host_brush_points(const double* segs, int32_t n_segs, double radius, int32_t* points_out, int64_t cap) {
   const int w = (int)ceil(radius) * 2 + 1;       // brush.ml:25-28

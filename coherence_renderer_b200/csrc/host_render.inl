@@ -180,6 +180,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   P.ux0 = ux; P.uy0 = uy; P.ux1 = ux + uw - 1; P.uy1 = uy + uh - 1;
   P.u_init = A.u_init; P.u_out = A.u_out; P.fb = A.fb; P.error_flag = ctx->d_error;
   P.write_clear = write_clear ? 1 : 0; P.resume = A.resume ? 1 : 0;
+  P.touched = ctx->touched;
   P.n_peers = (A.fb == ctx->fb) ? ctx->n_peers : 0;   // only the frame itself is mirrored, not filter canvases
   for (int k = 0; k < COH_MAX_PEERS; k++) P.peer_fb[k] = k < P.n_peers ? ctx->peer_fb[k] : nullptr;
   const int grid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / walk_h), WALK_WARPS));
@@ -382,6 +383,13 @@ static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   const size_t nwords = (size_t)nw * h;
   CK(DMALLOC(&F.SG, 4 * nwords)); CK(DMALLOC(&F.CG, 4 * nwords)); CK(DMALLOC(&F.op, (size_t)nw * 32 * h));
   CK(cudaMemsetAsync(F.SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(F.CG, 0, 4 * nwords, ctx->stream));
+  if (F.kind == COH_FILTER_SMEAR) {
+    // geometry = the stroke's dummy brush (filters.ml:205-207): the boxes around its stamp points, opaque white all over
+    const int side = 2 * F.brush_r + 1;
+    k_stamp_boxes_to_bits<<<cdiv(F.count * side, 256), 256, 0, ctx->stream>>>(s->points + F.first, F.count, F.brush_r, F.gy0 - F.dy, h, -F.dx, nw, F.SG); LAUNCHED();
+    CK(cudaMemsetAsync(F.op, 255, (size_t)nw * 32 * h, ctx->stream));
+    return 0;
+  }
   const EdgeRec* ed = s->edges + F.first;
   // shape of the geometry (render.ml:472-474) and its coverage (minshape = shape - coverage, needed for the matte)
   k_scan_rows<<<dim3(cdiv(h, 64), cdiv(nw, SCAN_CHUNK_WORDS)), 64, 0, ctx->stream>>>(ed, F.count, F.winding, F.gy0 - F.dy, h, -F.dx, nw, F.SG, F.CG, ctx->d_error); LAUNCHED();   // (an alias reads the geometry's own frame moved by whole pixels)
@@ -409,7 +417,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   if (y0 > y1 || x0 > x1) return 0;  // the geometry cannot meet u: nothing to render, nothing leaves u
   if (filter_geometry(ctx, s, F)) return 1;
   const int h = y1 - y0 + 1;
-  const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : 0;             // reach of the reading shape
+  const int m = F.kind == COH_FILTER_BLUR ? 2 * F.r + 1 : (F.kind == COH_FILTER_SMEAR ? F.brush_r : 0);   // reach of the reading shape
   const int ry0 = std::max(0, y0 - m), ry1 = std::min(H - 1, y1 + m), rh = ry1 - ry0 + 1;
   const PixBox tbox{x0, y0, x1, y1}, rbox{std::max(0, x0 - m), ry0, std::min(W - 1, x1 + m), ry1};
   const size_t po = (size_t)ry0 * W, pn = (size_t)rh * W;                 // canvas rows [ry0, ry1]
@@ -440,6 +448,9 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
     CK(cudaMemcpyAsync(R + r0, T + r0, 4 * (size_t)h * nw, cudaMemcpyDeviceToDevice, ctx->stream));
     coh_shape_free(ctx, hs); coh_shape_free(ctx, hm);
   }
+  if (ctx->touched) {   // an enclosing smear filter wants the shape of what is rendered here: this filter's sprite covers T
+    k_bitop<<<(unsigned)(((size_t)h * nw + 255) / 256), 256, 0, ctx->stream>>>(ctx->touched + r0, T + r0, ctx->touched + r0, (size_t)h * nw, 0); LAUNCHED();
+  }
   // The scene below renders the same pixels whatever region it is asked for (plain fills: no span-start quirk,
   // polygon.ml:736), so where the reading scene IS the scene below (monochrome, blur: filters.ml:229-258) the pixels
   // that show through the matte (render.ml:1105-1110) are taken from the reading scene's render before its filter function.
@@ -450,15 +461,36 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   if (F.kind != COH_FILTER_HOLE) {
     CK(TMPGET(tmp, &X, 4 * (size_t)W * H));
     CK(cudaMemset2DAsync(X + po + rbox.x0, 4 * (size_t)W, 0, 4 * (size_t)(rbox.x1 - rbox.x0 + 1), rh, ctx->stream));
-    if (F.kind == COH_FILTER_BLUR) {  // filters.ml:247-250: read in bloat (2r+1) (2r+1) shp (T is empty outside [y0, y1])
+    if (m > 0) {  // blur: read in bloat (2r+1) (2r+1) shp (filters.ml:247-250); smear: bloat rx ry shp (filters.ml:209) (T is empty outside [y0, y1])
       if (m <= 32) { k_dilate32<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
       else { k_dilate<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(T + (size_t)ry0 * nw, R + (size_t)ry0 * nw, rh, nw, m, m); LAUNCHED(); }
     }
+    uint32_t* touched = nullptr; int* d_bb = nullptr;
+    uint32_t* const outer_touched = ctx->touched;
+    if (F.kind == COH_FILTER_SMEAR) {   // the shape of the reading scene's sprite is needed, not only its pixels
+      CK(TMPGET(tmp, &touched, 4 * (size_t)rh * nw)); CK(TMPGET(tmp, &d_bb, 4 * sizeof(int)));
+      CK(cudaMemsetAsync(touched, 0, 4 * (size_t)rh * nw, ctx->stream));
+      ctx->touched = touched - (size_t)ry0 * nw;   // (indexed by frame row; only rows ry0 .. ry1 are visited)
+    } else ctx->touched = nullptr;
+    struct Restore { coh_ctx* c; uint32_t* t; ~Restore() { c->touched = t; } } restore{ctx, outer_touched};
     if (F.kind == COH_FILTER_SCENE) {
       PassArgs A{F.read0, F.read1, rbox.x0, rbox.y0, rbox.x1 - rbox.x0 + 1, rbox.y1 - rbox.y0 + 1, R, nullptr, X, true, false};
       if (render_pass(ctx, s, A)) return 1;
     } else if (render_suffix(ctx, s, F.kind == COH_FILTER_MINUS ? F.head_l1 : F.pos, fi + 1, R, X, true, rbox, true)) return 1;   // MINUS: tl scene
     Y = X;
+    ctx->touched = nullptr;
+    if (F.kind == COH_FILTER_SMEAR) {
+      // Brush.smear (brush.ml:286-331) on a canvas around the stroke: box of bloat r r (stroke shape), one pixel of border
+      const int init[4] = {INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN};
+      CK(cudaMemcpyAsync(d_bb, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));   // (pageable: staged before the call returns)
+      k_bits_bbox<<<dim3(cdiv(nw, 128), rh), 128, 0, ctx->stream>>>(touched, rh, nw, ry0, d_bb); LAUNCHED();
+      const int cx0 = F.bx0 - F.brush_r - 2, cy0 = F.by0 - F.brush_r - 2, cw = F.bx1 - F.bx0 + 1 + 2 * F.brush_r + 4, ch = F.by1 - F.by0 + 1 + 2 * F.brush_r + 4;
+      uint32_t* Cv = nullptr;
+      CK(TMPGET(tmp, &Cv, 4 * (size_t)cw * ch));
+      CK(TMPGET(tmp, &Y, 4 * (size_t)W * H));
+      k_smear<<<1, SMEAR_THREADS, 0, ctx->stream>>>(X, Y, W, H, Cv, cx0, cy0, cw, ch, d_bb, F.bx0, F.by0, F.bx1, F.by1,
+                                                  s->points + F.first2, F.count2, F.dx, F.dy, s->stamps + F.stamp_off, F.brush_r, rbox.x0, rbox.y0, rbox.x1, rbox.y1); LAUNCHED();
+    }
     if (F.kind == COH_FILTER_MONOCHROME) {
       if (z_is_x) blend_flags |= 2;   // Y = monochrome of Z, taken on the fly
       else { k_monochrome<<<(unsigned)((pn + 255) / 256), 256, 0, ctx->stream>>>(X + po, X + po, pn); LAUNCHED(); }
@@ -480,7 +512,7 @@ static int apply_filter(coh_ctx* ctx, DevScene* s, int fi, uint32_t* U, uint32_t
   if (m > 0) CK(cudaMemsetAsync(R + (size_t)ry0 * nw, 0, 4 * (size_t)rh * nw, ctx->stream));   // what the reading scene left of its (bloated) update
   // R := pixels_for_normal_scene = shptorender' --- pixels_finished (render.ml:1100-1105)
   k_filter_matte<<<dim3(cdiv(nw, 4), h), 128, 0, ctx->stream>>>(T + r0, F.op + g0 * 32, F.colour, W, h, nw, alpha, R + r0); LAUNCHED();
-  if (z_is_x) Z = X;
+  if (z_is_x || F.kind == COH_FILTER_SMEAR) Z = X;   // (a smear's matte is opaque all over: nothing shows through)
   else {
     CK(TMPGET(tmp, &Z, 4 * (size_t)W * H));
     CK(cudaMemset2DAsync(Z + (size_t)y0 * W + x0, 4 * (size_t)W, 0, 4 * (size_t)(x1 - x0 + 1), h, ctx->stream));

@@ -211,10 +211,16 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
     if (n_scene_leaves >= 0 && cur_reading < 0 && i < n_objs - n_background) FAIL("scene: reading-scene groups must come after every ordinary scene object");
     if (c.kind == COH_OBJ_FILTER) {
       if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: filter objects must be top-level members of the scene list");
-      if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
-      if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
-      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_MINUS) FAIL("scene: bad filter kind");
-      if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
+      if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SMEAR) FAIL("scene: bad filter kind");
+      const bool smear = c.filter_kind == COH_FILTER_SMEAR;
+      if (smear) {   // geometry = the stroke's dummy: stamp points; smear points beside them (both in the points array)
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_points || c.first2 < 0 || c.count2 < 0 || (int64_t)c.first2 + c.count2 > n_points) FAIL("scene: point range out of bounds");
+        if (!(c.brush_radius >= 0. && c.brush_radius <= 64.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range (a smear brush has a radius of at most 64)");
+      } else {
+        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
+        if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
+        if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
+      }
       DevScene::FilterRec f; memset(&f, 0, sizeof f);
       f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
       if (c.filter_kind == COH_FILTER_BLUR) {
@@ -228,8 +234,26 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           FAIL("Filters.minus: no object below the filter (hd)");
       }
       if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
-      EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
-      shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
+      if (smear) {
+        uint64_t rbits; memcpy(&rbits, &c.brush_radius, sizeof rbits);
+        const std::pair<uint64_t, int> key(rbits, (int)(c.brush_opacity * 255.));
+        auto it = stamp_cache.find(key);
+        if (it == stamp_cache.end()) {
+          f.stamp_off = (int)stamps.size();
+          brush_stamp(c.brush_radius, c.brush_opacity, stamps, f.brush_r);
+          stamp_cache[key] = std::make_pair(f.stamp_off, f.brush_r);
+        } else { f.stamp_off = it->second.first; f.brush_r = it->second.second; }
+        f.first2 = c.first2; f.count2 = c.count2; f.colour = 0xFFFFFFFFu;
+        int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+        for (int k = 0; k < c.count; k++) {
+          const int32_t* p = points + 2 * ((size_t)c.first + k);
+          x0 = std::min(x0, p[0]); x1 = std::max(x1, p[0]); y0 = std::min(y0, p[1]); y1 = std::max(y1, p[1]);
+        }
+        f.bx0 = x0 - f.brush_r; f.bx1 = x1 + f.brush_r; f.by0 = y0 - f.brush_r; f.by1 = y1 + f.brush_r;
+      } else {
+        EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+        shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
+      }
       f.dx = c.dx; f.dy = c.dy; f.bx0 += c.dx; f.bx1 += c.dx; f.by0 += c.dy; f.by1 += c.dy;
       filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
       continue;

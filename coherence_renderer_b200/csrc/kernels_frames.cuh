@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
     // a background cell that k_prefill did not take (frames mirrored to peer framebuffers spread these stores over
     // the compositor's blocks): one opaque primitive covers the cell, nothing was scan-converted for it
     if (u_rec && lane == 0) *u_rec = (oc.w & 2) ? 0u : u;
+    if (P.touched && lane == 0) P.touched[(size_t)y * P.fr.tiles_x + tile] |= u;
     if (u & lbit) {
       const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
       const uint32_t bg = (uint32_t)P.cell_head[cell].x;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   const int2 rg = make_int2(oc.y, oc.z);
   const uint2* sc_row = P.pre_sc + row;
   const uint8_t* op_row = P.pre_op + (size_t)row * 32 + lane;
-  uint32_t acc = 0u;
+  uint32_t acc = 0u, touched_w = 0u;
   // a pass that continues a frame (after a filter, render.ml:1080-1131): the accumulator carries on from the framebuffer
   if (P.resume && (u & lbit)) acc = P.fb[(size_t)y * P.fr.W + tile * TILE_W + lane];
   for (int base = rg.x; base < rg.y; base += 32) {
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
         const uint32_t S = __shfl_sync(0xFFFFFFFFu, sc.x, k);
         const uint32_t vis = S & u;
         if (vis == 0u) continue;
+        touched_w |= vis;
         const uint32_t C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
         const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
         uint32_t col = c0;
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
     }
   }
   if (u_rec && lane == 0) *u_rec = u;   // the scene list ran out (or u did) before any member of the background list
+  if (P.touched && touched_w && lane == 0) P.touched[(size_t)y * P.fr.tiles_x + tile] |= touched_w;
   if ((u_update & lbit) && (P.write_clear || acc != 0u)) {
     const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
     P.fb[at] = acc;

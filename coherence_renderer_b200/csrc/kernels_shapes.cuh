@@ -301,6 +301,72 @@ __global__ void k_filter_blend(const uint32_t* __restrict__ T, const uint8_t* __
   const uint32_t res = px_plus(z, yy);
   fb[i] = (flags & 1) ? res : px_over(fb[i], res);
 }
+// Bounding box of the set bits of a bit-frame's rows [0, h): bb = {x0, y0, x1, y1} by atomic min / max (start from
+// {INT_MAX, INT_MAX, INT_MIN, INT_MIN}); y counts from `ybase`.
+__global__ void k_bits_bbox(const uint32_t* __restrict__ bits, int h, int nw, int ybase, int* __restrict__ bb) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (w >= nw || r >= h) return;
+  const uint32_t v = bits[(size_t)r * nw + w];
+  if (!v) return;
+  atomicMin(&bb[0], 32 * w + __ffs((int)v) - 1); atomicMax(&bb[2], 32 * w + 31 - __clz((int)v));
+  atomicMin(&bb[1], ybase + r); atomicMax(&bb[3], ybase + r);
+}
+// Brush.smear (brush.ml:286-331) on a canvas: for every smear point in order, twice over, the brush-sized block one
+// step against the direction of travel is read, then blended into the block at the point by the brush's alpha
+// (Colour.dissolve_between).  Each step reads what the steps before it wrote: one block walks the points; its threads
+// share the pixels of the brush.  The reference's canvas is the bounding box of (the reading scene's sprite ∪ the stroke's
+// shape) with a border of one pixel, and a step whose source or destination block leaves it is skipped (its exception is
+// swallowed): `bb` holds the sprite's box (k_bits_bbox over the touched plane), sb the stroke's.
+// X: frame-sized source canvas (W x H); C: working canvas covering [cx0, cx0 + cw) x [cy0, cy0 + ch) (clear outside the
+// frame); the result goes to Y (frame-sized) wherever C overlaps the frame.
+constexpr int SMEAR_THREADS = 1024;
+constexpr int SMEAR_MAX_PER_THREAD = 17;   // (2 * 64 + 1)^2 / 1024
+__global__ void __launch_bounds__(SMEAR_THREADS) k_smear(const uint32_t* __restrict__ X, uint32_t* __restrict__ Y, int W, int H,
+                                                         uint32_t* __restrict__ C, int cx0, int cy0, int cw, int ch,
+                                                         const int* __restrict__ bb, int sbx0, int sby0, int sbx1, int sby1,
+                                                         const int2* __restrict__ pts, int n_pts, int odx, int ody,
+                                                         const uint8_t* __restrict__ stamp, int rad,
+                                                         int rx0, int ry0, int rx1, int ry1 /* the part of X that was rendered into */) {
+  const int tid = threadIdx.x, bw = 2 * rad + 1, n_px = bw * bw;
+  // the canvas of the reference: box of (sprite ∪ stroke shape), one pixel of border
+  const int vx0 = min(bb[0], sbx0) - 1, vy0 = min(bb[1], sby0) - 1, vx1 = max(bb[2], sbx1) + 1, vy1 = max(bb[3], sby1) + 1;
+  for (int i = tid; i < cw * ch; i += SMEAR_THREADS) {
+    const int x = cx0 + i % cw, y = cy0 + i / cw;
+    C[i] = (x >= rx0 && x <= rx1 && y >= ry0 && y <= ry1) ? X[(size_t)y * W + x] : 0u;
+  }
+  __syncthreads();
+  uint32_t v[SMEAR_MAX_PER_THREAD];
+  for (int pass = 0; pass < 2; pass++)
+    for (int i = 0; i < n_pts; i++) {
+      const int2 p = pts[i];
+      int dx = 0, dy = 0;
+      if (i) { const int2 q = pts[i - 1]; dx = p.x > q.x ? -1 : (p.x < q.x ? 1 : 0); dy = p.y > q.y ? -1 : (p.y < q.y ? 1 : 0); }   // (sic: brush.ml:268-272)
+      const int px = p.x + odx, py = p.y + ody;
+      // source block: centred one step away; destination block: centred at the point (both uniform over the block)
+      const int sx0 = px - dx - rad, sy0 = py - dy - rad, dx0 = px - rad, dy0 = py - rad;
+      if (sx0 < vx0 || sy0 < vy0 || sx0 + bw - 1 > vx1 || sy0 + bw - 1 > vy1) continue;    // Failure "subcopy"
+      if (dx0 < vx0 || dy0 < vy0 || dx0 + bw - 1 > vx1 || dy0 + bw - 1 > vy1) continue;    // Failure "Brush.stamp"
+#pragma unroll
+      for (int k = 0; k < SMEAR_MAX_PER_THREAD; k++) {
+        const int j = tid + k * SMEAR_THREADS;
+        if (j < n_px) v[k] = C[(size_t)(sy0 + j / bw - cy0) * cw + (sx0 + j % bw - cx0)];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SMEAR_MAX_PER_THREAD; k++) {
+        const int j = tid + k * SMEAR_THREADS;
+        if (j < n_px) {
+          uint32_t* d = C + (size_t)(dy0 + j / bw - cy0) * cw + (dx0 + j % bw - cx0);
+          *d = px_dissolve_between(v[k], *d, stamp[j]);
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < cw * ch; i += SMEAR_THREADS) {
+    const int x = cx0 + i % cw, y = cy0 + i / cw;
+    if (x >= 0 && x < W && y >= 0 && y < H) Y[(size_t)y * W + x] = C[i];
+  }
+}
 // The background list of a frame whose scene pass is finished (render.ml:1363-1365): frame = scene over background,
 // for a background of plain primitives (the page, the window background): per pixel of the update that the scene
 // pass left not opaque, the front-to-back fold of the primitives covering it goes under the framebuffer's colour.

@@ -39,6 +39,8 @@ struct WalkParams {
   const uint8_t* pre_op;       // per pair: 32 opacity bytes (valid where the pair's edge mask is set)
   int write_clear;             // write clear pixels of the update too (1) or only touched pixels
   int resume;                  // continue a frame: the root accumulators start from what `fb` already holds
+  uint32_t* touched;           // optional bit-frame: receives every pixel some object of the pass was composited at (the
+                               // shape of the pass's sprite, which is more than its non-clear pixels; Brush.smear needs it)
   // Cross-tile carry for fancy fills (k_walk<true> only): an AA pixel takes the fill at the first
   // x of its span (polygon.ml:736) and a span may begin in a tile further left.  Every tile
   // publishes, per fancy object whose visible edge run touches its right border, where that run
@@ -290,6 +292,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   // (typically the background rectangle; flagged by the binning kernel): the rows are just that colour.
   if (head.y & 1) {
     const uint32_t c0 = (uint32_t)head.x;
+    if (P.touched && row_in_band && c_lane == 0 && u) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= u;
     if ((head.y & 2) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = 0u;
     publish_done();
 #pragma unroll 1
@@ -307,6 +310,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 #pragma unroll
   for (int r = 0; r < WALK_H; r++) acc_rows[r][lane] = 0u;   // accumulator of the current nesting level
   __syncwarp();
+  uint32_t touched_w = 0u;             // pixels of my row some object was composited at
   int depth = 0;                       // open groups
   int hit_level = -1;                  // outermost open group that dissolves its sprite (PreTrans), or -1
   int open_grp[MAX_DEPTH];
@@ -463,6 +467,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         const uint32_t ur = __shfl_sync(0xFFFFFFFFu, u, r);
         const uint32_t vis = Sk & ur;
         if (vis == 0u) continue;
+        if (r_lane == r) touched_w |= vis;
         const uint32_t M = Sk & ~Ck;          // minshape word (polygon.ml:526)
         const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
         const int yy = y0 + r - ody, xx0 = tx0 - odx;
@@ -576,6 +581,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   PH_MARK(2)
   publish_done();
   if (bad) *P.error_flag = 1;
+  if (P.touched && row_in_band && c_lane == 0 && touched_w) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= touched_w;
 #pragma unroll 1
   for (int r = 0; r < WALK_H; r++) {
     const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);

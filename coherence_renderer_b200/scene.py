@@ -349,6 +349,26 @@ class SceneBuilder:
             o.filter_kernel = {"unit": 1, "gaussian": 2}[kernel[0]] | (int(kernel[1]) << 8)
         return o
 
+    def smear_filter(self, opacity, radius, subpaths, **kw):
+        """Filters.smear ((opacity, Gaussian radius), path) (filters.ml:201-217): geometry = the stroke's dummy brush
+        (its stamp points), plus the integer smear points of Brush.find_smear_directions; both in the points array."""
+        from . import abi
+
+        o = self._obj(abi.COH_OBJ_FILTER, **kw)
+        parts = [abi.host_brush_points(segs, radius) for segs in subpaths]
+        pts = np.concatenate(parts) if parts else np.zeros((0, 2), np.int32)
+        o.first, o.count = self._n_points, len(pts)
+        self.points.append(pts)
+        self._n_points += len(pts)
+        sm = abi.host_smear_points([sg for segs in subpaths for sg in segs])
+        o.first2, o.count2 = self._n_points, len(sm)
+        self.points.append(sm)
+        self._n_points += len(sm)
+        o.brush_opacity, o.brush_radius = float(opacity), float(radius)
+        Fill.plain(WHITE).apply(o)
+        o.filter_kind = abi.COH_FILTER_SMEAR
+        return o
+
     def reading_scene_begin(self, filter_obj):
         """Open the reading-scene group of a "scene" filter (after every ordinary scene object); close with group_end()."""
         from . import abi

@@ -54,13 +54,18 @@ enum {
  *   MINUS       filters.ml:289-303  a single-object hole: the object that follows the filter in its list is cut away
  *                                   inside the filter — reading scene = the objects below but that first one, read (and the
  *                                   filter applied) only in shape (filter) ∩ shape (first object below); filter = identity
+ *   SMEAR       filters.ml:201-217  smear along a brush stroke (Brush.smear, brush.ml:235-331): the geometry is the
+ *                                   stroke's dummy (first / count = its stamp points in the points array, brush_radius,
+ *                                   brush_opacity = the brush), the scene below is read in bloat r r shape, and
+ *                                   first2 / count2 = the integer points of Brush.find_smear_directions, consecutive
+ *                                   duplicates dropped (coh_host_smear_points), in the points array
  * A reading-scene group is a top-level GROUP_BEGIN of the scene section with filter_kind =
  * COH_FILTER_READING_SCENE; such groups come after every ordinary scene object and are never drawn
  * on their own.  A filter object may carry an alias offset (dx, dy) and may be a member of a group: such a group's members
  * are rendered once, as a scene of their own, into the group's canvas (like Convolved (kernel, Group members)), so they
  * take plain fills only; SCENE filters must be top-level members of the scene list.  The geometry of a filter is a path
  * with a plain fill. */
-enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4, COH_FILTER_MINUS = 5,
+enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4, COH_FILTER_MINUS = 5, COH_FILTER_SMEAR = 6,
        COH_FILTER_READING_SCENE = 100 };
 enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH_CPG_EXCLUSIVEOR = 3 };
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
@@ -323,6 +328,9 @@ int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_o
 int64_t coh_host_edgelist_of_subpath(const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap);
 /* Brush.points_of_brushstroke for one subpath, rounded as in brush.ml:172 (polygon.ml:143-218):
  * returns the number of stamp centres and writes min(n, cap) of them as int32 x,y in list order. */
+/* Brush.points_of_brushstroke_smear and the integer points of Brush.find_smear_directions (brush.ml:239-283) for all the
+ * segments of a path in order: pieces at most 2 apart, start points truncated, consecutive duplicates dropped. */
+int64_t coh_host_smear_points(const double* segs, int32_t n_segs, int32_t* points_out, int64_t cap);
 int64_t coh_host_brush_points(const double* segs, int32_t n_segs, double radius, int32_t* points_out, int64_t cap);
 
 #ifdef __cplusplus

@@ -102,6 +102,7 @@ external fb_alloc_shared : ctx -> u8 -> unit = "coh_ml_fb_alloc_shared"
 external fb_open_peer : ctx -> u8 -> nativeint = "coh_ml_fb_open_peer"
 external host_edgelist_of_subpath : f64 -> i32 -> int = "coh_ml_host_edgelist_of_subpath"
 external host_brush_points : f64 -> float -> i32 -> int = "coh_ml_host_brush_points"
+external host_smear_points : f64 -> i32 -> int = "coh_ml_host_smear_points"
 
 let the_ctx = lazy (init (-1))
 let ctx () = Lazy.force the_ctx

@@ -466,6 +466,10 @@ CAMLprim value coh_ml_host_edgelist_of_subpath(value segs, value out) {   /* seg
   int64_t n = coh_host_edgelist_of_subpath((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4);
   return Val_long((long)n);
 }
+CAMLprim value coh_ml_host_smear_points(value segs, value out) {   /* all the segments of a path; returns the point count */
+  int64_t n = coh_host_smear_points((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 2);
+  return Val_long((long)n);
+}
 CAMLprim value coh_ml_host_brush_points(value segs, value radius, value out) {
   int64_t n = coh_host_brush_points((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), Double_val(radius), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 2);
   return Val_long((long)n);

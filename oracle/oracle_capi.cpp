@@ -74,9 +74,18 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         o.kind = Obj::Filter; o.filter_kind = c.filter_kind; o.has_bounds = false;
         if (c.filter_kind == COH_FILTER_BLUR) o.kernel = (c.filter_kernel & 255) == COH_CONV_UNIT ? mkunit(c.filter_kernel >> 8) : mkgaussian(c.filter_kernel >> 8);
         Obj g;
-        g.kind = Obj::Path; g.fill = fill_from(c); g.winding = g.sprite_winding = (Winding)c.winding;
-        g.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
-        sort_edgelist_maxy_rev(g.edges);
+        if (c.filter_kind == COH_FILTER_SMEAR) {
+          // geometry = Basic (white, Brushstroke (Brush.mkdummy brushstroke)) (filters.ml:205-207)
+          o.stroke.opacity = c.brush_opacity; o.stroke.radius = c.brush_radius;
+          for (int k = 0; k < c.count; k++) o.stroke.points.push_back({points[2 * ((size_t)c.first + k)], points[2 * ((size_t)c.first + k) + 1]});
+          for (int k = 0; k < c.count2; k++) o.smear_pts.push_back({points[2 * ((size_t)c.first2 + k)], points[2 * ((size_t)c.first2 + k) + 1]});
+          g.kind = Obj::Brush; g.fill = Fill::plain(mkcol(255, 255, 255));
+          g.stroke = o.stroke; g.stroke.dummy = true; g.stroke.rx = (o.stroke.bw() - 1) / 2; g.stroke.opacity = 1.;
+        } else {
+          g.kind = Obj::Path; g.fill = fill_from(c); g.winding = g.sprite_winding = (Winding)c.winding;
+          g.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
+          sort_edgelist_maxy_rev(g.edges);
+        }
         o.children.push_back(std::move(g));
         // (a filter inside a Group sees the rest of that group's list as its objects below, render.ml:988-1001)
         if (c.filter_kind == COH_FILTER_SCENE) {
@@ -167,6 +176,20 @@ static void sprite_to_dense(const Sprite& s, int ux, int uy, int uw, int uh, uin
 }
 
 extern "C" {
+// Brush.points_of_brushstroke_smear + the integer points of find_smear_directions (brush.ml:239-283); segs = records of
+// 9 doubles (kind 0 straight / 1 bezier, then up to 4 points), all segments of the path in order
+int64_t orc_smear_points(const double* segs, int32_t n_segs, int32_t* out, int64_t cap) {
+  Path path(1);
+  for (int i = 0; i < n_segs; i++) {
+    const double* q = segs + 9 * i;
+    Segment sg; sg.bezier = q[0] != 0.;
+    for (int k = 0; k < 4; k++) sg.p[k] = Pt(q[1 + 2 * k], q[2 + 2 * k]);
+    path[0].push_back(sg);
+  }
+  auto ip = smear_int_points(points_of_brushstroke_smear(path));
+  for (size_t i = 0; i < ip.size() && (int64_t)i < cap; i++) { out[2 * i] = ip[i].first; out[2 * i + 1] = ip[i].second; }
+  return (int64_t)ip.size();
+}
 const char* orc_last_error() { return g_err.c_str(); }
 void orc_free(void* p) { std::free(p); }
 

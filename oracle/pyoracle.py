@@ -54,6 +54,16 @@ def _take(p, n):
     return out
 
 
+def smear_points(seg_records):
+    """Brush.points_of_brushstroke_smear + integer points of find_smear_directions; seg_records: float64 [n][9]."""
+    rec = np.ascontiguousarray(seg_records, dtype=np.float64).reshape(-1, 9)
+    lib().orc_smear_points.restype = C.c_int64
+    cap = 1 << 16
+    out = np.zeros((cap, 2), dtype=np.int32)
+    n = lib().orc_smear_points(rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(cap))
+    return out[:n]
+
+
 def colour_of_rgba8(w):
     return lib().orc_colour_of_rgba8(C.c_uint32(w))
 

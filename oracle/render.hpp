@@ -52,8 +52,11 @@ struct Obj {
   // Filter {geometry = children[0]; reading_scene; filter} (render.ml:37-48; filters.ml).  The
   // reference's closures are restated per filter kind: 1 hole, 2 monochrome, 3 blur (kernel),
   // 4 identity filter over a caller-built reading scene (affine / rgb / wireframe / swapdepth / minus).
+  // 5 minus; 6 smear: `stroke` is the (transformed) brush stroke, the geometry children[0] its dummy (filters.ml:201-217),
+  // smear_pts the deduplicated integer points of Brush.find_smear_directions (brush.ml:266-283)
   int filter_kind = 0;
   std::shared_ptr<Scene> reading_scene;
+  std::vector<std::pair<int, int>> smear_pts;
 };
 
 // ---- cache.ml restated: shapes and partial sprites keyed by id, integer-translation
@@ -351,6 +354,10 @@ struct Renderer {
       readshape = shp2;
       tl = Scene(tail.begin() + 1, tail.end());
     }
+    if (o.filter_kind == 6) {  // Filters.smear (filters.ml:201-217): read in bloat rx ry shp
+      const int rr = (o.stroke.bw() - 1) / 2;
+      readshape = bloat(rr, rr, shptorender);
+    }
     const Scene& scene2 = o.filter_kind == 1 ? none : (o.filter_kind == 4 ? *o.reading_scene : (o.filter_kind == 5 ? tl : tail));
     Sprite X; { Shape u = readshape; render_scene(u, X, scene2, true); }
     Sprite Y;
@@ -359,6 +366,11 @@ struct Renderer {
       case 3: {                                                                        // filters.ml:251-255
         Shape bloated = bloat(r, r, shape_of_sprite(X));
         Y = convolve_sprite_in_shape(o.kernel, X, bloated, shape_intersection(bloated, shp2));
+        break;
+      }
+      case 6: {                                                                        // filters.ml:211-214
+        Sprite sm = smear(X, o.stroke, o.smear_pts);
+        Y = portion(sm, shape_intersection(shp2, shape_of_sprite(sm)));
         break;
       }
       default: Y = X;                                                                  // nullfilterfunction

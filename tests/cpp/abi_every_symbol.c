@@ -212,6 +212,7 @@ int main(int argc, char** argv) {
   double segs[9] = {0, 10.0, 10.0, 90.0, 20.0, 0, 0, 0, 0};
   int32_t he[8]; CHECK(coh_host_edgelist_of_subpath(segs, 1, he, 2) == 1 && he[0] == sub_of_float(10.0));
   int32_t hp[64]; CHECK(coh_host_brush_points(segs, 1, 4.0, hp, 32) > 0);
+  int32_t hs[256]; CHECK(coh_host_smear_points(segs, 1, hs, 128) > 30 && hs[0] == 10 && hs[1] == 10);
   /* release */
   coh_shape_t all[] = {s, m, mx, bx, un, in, tr, bl, er, imp, cs, dirty, os, om, df};
   for (unsigned i = 0; i < sizeof all / sizeof all[0]; i++) OK(coh_shape_free(C, all[i]));

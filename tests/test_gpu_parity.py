@@ -727,6 +727,42 @@ def test_filter_minus(ctx, oracle):
         assert _max_lsb(got, ref) == 0, variant
 
 
+def test_smear_filter(ctx, oracle):
+    """Filters.smear (filters.ml:201-217) = Brush.smear (brush.ml:235-331) along a brush stroke over the scene below:
+    the sequential read-block / blend-block walk over the smear points, twice, on the reference's canvas (steps whose
+    blocks leave it are skipped, as its swallowed exceptions do)."""
+    W, H = 240, 200
+    strokes = [
+        (1.0, 7.0, [[("C", (40.0, 150.0), (90.0, 30.0), (150.0, 170.0), (200.0, 50.0))]]),
+        (0.7, 4.0, [[("L", (30.0, 40.0), (200.0, 60.0)), ("L", (200.0, 60.0), (120.0, 160.0))]]),
+        (1.0, 3.0, [[("L", (205.5, 12.0), (232.0, 17.5)), ("C", (232.0, 17.5), (236.0, 40.0), (200.0, 30.0), (215.0, 60.0))]]),   # mostly over nothing
+    ]
+    for opacity, radius, path in strokes:
+        b = S.SceneBuilder()
+        b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+        b.smear_filter(opacity, radius, path)
+        b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+        b.polygon([(100.0, 20.0), (220.0, 150.0), (60.0, 180.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 240, 20), 200)))
+        b.rectangle(S.rgba8(0, 0, 0), 150.0, 100.0, 230.0, 190.0)
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
+        assert np.array_equal(got_u, ref_u), radius
+        assert _max_lsb(got, ref) == 0, radius
+        got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H, update=(60, 40, 120, 90))
+        assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0, radius
+        if radius == 7.0:
+            first = b
+    b = first
+    # the filter does something: without it the frame differs
+    b2 = S.SceneBuilder()
+    b2.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+    b2.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+    b2.polygon([(100.0, 20.0), (220.0, 150.0), (60.0, 180.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 240, 20), 200)))
+    b2.rectangle(S.rgba8(0, 0, 0), 150.0, 100.0, 230.0, 190.0)
+    plain, _, _, _ = _render_both(ctx, oracle, _finish(b2, W, H), W, H)
+    full, _, _, _ = _render_both(ctx, oracle, b, W, H)
+    assert (plain != full).sum() > 200
+
+
 def test_translated_and_dragged_lenses(ctx, oracle):
     """A filter object with an alias offset (render.ml:259-271) reads its geometry moved by whole pixels; dragging a
     lens (coh_scene_drag_object: alldirty of its shape at both places) re-renders exactly what a full frame of the

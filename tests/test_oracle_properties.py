@@ -268,3 +268,24 @@ def test_benchmark_scene_builders_render(oracle):
         k += 1
     moved = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H))
     assert not np.array_equal(base, moved)
+
+
+def test_smear_points_product_vs_oracle():
+    """coh_host_smear_points (host geometry of the product) against the oracle's restatement of
+    Brush.points_of_brushstroke_smear / find_smear_directions (brush.ml:239-283): pieces at most 2 apart, start points
+    truncated, consecutive duplicates dropped."""
+    from coherence_renderer_b200 import abi
+    from oracle import pyoracle
+
+    paths = [
+        [("C", (40.0, 150.0), (90.0, 30.0), (150.0, 170.0), (200.0, 50.0))],
+        [("L", (30.5, 40.25), (200.0, 60.0)), ("L", (200.0, 60.0), (120.75, 160.0)), ("C", (120.75, 160.0), (10.0, 10.0), (300.0, 5.0), (12.0, 90.0))],
+        [("L", (5.0, 5.0), (6.0, 5.5))],
+    ]
+    for segs in paths:
+        got = abi.host_smear_points(segs)
+        ref = pyoracle.smear_points(abi._seg_records(segs))
+        assert np.array_equal(got, ref)
+        assert len(got) >= 1
+        d = np.abs(np.diff(got.astype(int), axis=0))
+        assert len(d) == 0 or (d.max() <= 2 and d.sum(axis=1).min() >= 1)   # adjacent pixels, no duplicates
