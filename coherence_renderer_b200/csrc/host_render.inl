@@ -12,6 +12,9 @@ struct PassArgs {
 };
 static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
   Frame fr = ctx->fr;
+  // the band is the context's share of the FRAME: a pass into a canvas of its own (a filter's reading scene, which
+  // reaches rows outside the band — halo rows are recomputed, not exchanged) covers whatever it is asked for
+  if (A.fb != ctx->fb) { fr.band_y0 = 0; fr.band_y1 = fr.H; }
   const int ux = A.ux, uy = A.uy, uw = A.uw, uh = A.uh;
   const bool write_clear = A.write_clear;
   LeafView& V = A.collapsed ? s->sp : s->full;
@@ -548,15 +551,22 @@ static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U,
 }
 static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, int ux, int uy, int uw, int uh) {
   const Frame& fr = ctx->fr;
-  if (fr.band_y0 != 0 || fr.band_y1 != fr.H) FAIL("render_frame: scenes with filter objects need the whole frame on one context (filters read outside their band)");
   if (uw <= 0 || uh <= 0) return 0;
-  const PixBox box{std::max(ux, 0), std::max(uy, 0), std::min(ux + uw - 1, fr.W - 1), std::min(uy + uh - 1, fr.H - 1)};
+  // a band renders its own rows of the update; what its filters read above and below them is rendered again into the
+  // filters' canvases on this context (render_pass)
+  const PixBox box{std::max(ux, 0), std::max(std::max(uy, 0), fr.band_y0), std::min(ux + uw - 1, fr.W - 1), std::min(std::min(uy + uh - 1, fr.H - 1), fr.band_y1 - 1)};
   if (box.x1 < box.x0 || box.y1 < box.y0) return 0;
   const int nw = fr.tiles_x;
   const size_t nwords = (size_t)nw * fr.H;
   uint32_t* U = ctx->u_out;
-  if (u_init) CK(cudaMemcpyAsync(U, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
-  else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
+  if (u_init) {
+    CK(cudaMemcpyAsync(U, u_init, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (box.y0 > 0) CK(cudaMemsetAsync(U, 0, 4 * (size_t)box.y0 * nw, ctx->stream));
+    if (box.y1 + 1 < fr.H) CK(cudaMemsetAsync(U + (size_t)(box.y1 + 1) * nw, 0, 4 * (size_t)(fr.H - 1 - box.y1) * nw, ctx->stream));
+  } else { k_fill_box_bits<<<dim3(cdiv(nw, 128), fr.H), 128, 0, ctx->stream>>>(U, fr.H, nw, 0, 0, box.x0, box.y0, box.x1, box.y1); LAUNCHED(); }
+  // peer framebuffers receive the finished rows in one strip copy at the end (the filter kernels do not mirror their stores)
+  struct Peers { coh_ctx* c; int n; ~Peers() { c->n_peers = n; } } peers_guard{ctx, ctx->n_peers};
+  ctx->n_peers = 0;
   if (render_suffix(ctx, s, 0, 0, U, ctx->fb, true, box)) return 1;
   if (s->n_leaves > s->n_front_leaves) {
     // the background list shows wherever the scene pass is not opaque (render.ml:1363-1365)
@@ -572,8 +582,7 @@ static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, in
     if (prims) {
       // plain primitives (the page, the window background): one pass over the update
       PeerFbs peers; memset(&peers, 0, sizeof peers);
-      for (int k = 0; k < ctx->n_peers; k++) peers.p[k] = ctx->peer_fb[k];
-      k_bg_over<<<dim3(cdiv(cdiv(fr.W, 4), 128), box.y1 - box.y0 + 1), 128, 0, ctx->stream>>>(ctx->fb, u_init, fr.W, nw, box.x0, box.y0, box.x1, box.y1, B, ctx->n_peers, peers); LAUNCHED();
+      k_bg_over<<<dim3(cdiv(cdiv(fr.W, 4), 128), box.y1 - box.y0 + 1), 128, 0, ctx->stream>>>(ctx->fb, u_init, fr.W, nw, box.x0, box.y0, box.x1, box.y1, B, 0, peers); LAUNCHED();
     } else {
       uint32_t* U0 = nullptr;
       CK(DMALLOC(&U0, 4 * nwords));
@@ -586,6 +595,9 @@ static int render_filtered(coh_ctx* ctx, DevScene* s, const uint32_t* u_init, in
       if (rc) return 1;
     }
   }
+  for (int k = 0; k < peers_guard.n; k++)
+    CK(cudaMemcpy2DAsync(ctx->peer_fb[k] + (size_t)box.y0 * fr.W + box.x0, 4 * (size_t)fr.W, ctx->fb + (size_t)box.y0 * fr.W + box.x0, 4 * (size_t)fr.W,
+                         4 * (size_t)(box.x1 - box.x0 + 1), box.y1 - box.y0 + 1, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;  // kernel-side failures are reported by coh_sync, as for plain frames
 }
 

@@ -299,6 +299,40 @@ def test_band_partition_equals_whole_frame(ctx, oracle):
     ctx.scene_free(sc)
 
 
+def test_band_partition_of_filter_scenes(ctx, oracle):
+    """§8e for scenes with filter objects: a band renders its own rows; what its lenses read above and below the band
+    (a blur's reading shape, a smear's) is rendered again on that band's context — halo rows are recomputed, not
+    exchanged.  Bands cut through every lens; the assembled strips equal the whole frame and the oracle."""
+    W, H = 200, 160
+    b, _ = _filter_scene("blur", W, H, second=("monochrome", {}), kernel=("gaussian", 3))
+    b.smear_filter(1.0, 5.0, [[("L", (20.0, 30.0), (180.0, 130.0))]])
+    b.polygon([(15.0, 20.0), (190.0, 25.0), (180.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(90, 20, 160), 210)))
+    _finish(b, W, H)
+    objs, n, nbg, edges, points = b.arrays()
+    ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, points)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    whole = ctx.fb_read_rgba(0, 0, W, H).copy()
+    assert _max_lsb(whole, ref) == 0
+    for cuts in ([0, 53, 107, 160], [0, 80, 81, 97, 160]):
+        parts = []
+        for y0, y1 in zip(cuts[:-1], cuts[1:]):
+            ctx.fb_configure(W, H, y0, y1)
+            ctx.render_frame(sc, (0, 0, W, H))
+            ctx.sync()
+            parts.append(ctx.fb_read_rgba(0, y0, W, y1 - y0).copy())
+        assert np.array_equal(np.concatenate(parts, axis=0), whole), cuts
+    # a partial update inside a band
+    ctx.fb_configure(W, H, 40, 120)
+    ctx.render_frame(sc, (30, 20, 140, 130))
+    ctx.sync()
+    assert np.array_equal(ctx.fb_read_rgba(30, 40, 140, 80), whole[40:120, 30:170])
+    ctx.fb_configure(W, H)
+    ctx.scene_free(sc)
+
+
 def test_pretrans_group_returns_pixels_to_u(ctx, oracle):
     """A PreTrans group with opaque members gives its pixels back to the parent's u when it closes;
     many objects follow so that several scan passes start while the group is open."""
@@ -974,6 +1008,38 @@ def test_peer_framebuffer_mirror(ctx, oracle, options, fused):
         ctx.fb_set_peers([])
         ctx.fb_configure(W, H)
         ctx.fb_attach(0)         # back to a context-owned framebuffer for the tests that follow
+        if sc:
+            ctx.scene_free(sc)
+
+
+def test_peer_framebuffer_mirror_of_filter_frames(ctx, oracle):
+    """Bands of a scene with filter objects, gathered through peer framebuffers: the filter kernels do not mirror their
+    stores, every band sends its finished rows to the peers in one strip copy."""
+    import torch
+
+    W, H = 200, 160
+    b, _ = _filter_scene("blur", W, H, second=("monochrome", {}), kernel=("gaussian", 2))
+    _finish(b, W, H)
+    objs, n, nbg, e, p = b.arrays()
+    ref = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H))
+    bufs = [torch.zeros((H, W), dtype=torch.int32, device="cuda") for _ in range(2)]
+    sc = None
+    try:
+        for k, (y0, y1) in enumerate([(0, 90), (90, H)]):
+            ctx.fb_configure(W, H, y0, y1)
+            ctx.fb_attach(bufs[k].data_ptr())
+            ctx.fb_set_peers([bufs[1 - k].data_ptr()])
+            if sc is None:
+                sc = ctx.scene_create(objs, nbg, e, p)
+            ctx.render_frame(sc, (0, 0, W, H))
+            ctx.sync()
+        for k in range(2):
+            got = bufs[k].cpu().numpy().view(np.uint32)
+            assert _max_lsb(got, ref) == 0, f"buffer {k}"
+    finally:
+        ctx.fb_set_peers([])
+        ctx.fb_configure(W, H)
+        ctx.fb_attach(0)
         if sc:
             ctx.scene_free(sc)
 
