@@ -41,7 +41,7 @@ class CohObject(C.Structure):
 SYMBOLS = [
     "coh_init", "coh_shutdown", "coh_last_error", "coh_device_name", "coh_stream", "coh_launch_count",
     "coh_set_stream", "coh_set_timing", "coh_get_timing", "coh_fb_attach", "coh_set_option",
-    "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_polygon_opacity",
+    "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_edgelist_of_path", "coh_shapeminshape_of_path", "coh_polygon_opacity",
     "coh_polygon_sprite", "coh_shape_box", "coh_shape_import", "coh_shape_export_size", "coh_shape_export",
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
@@ -230,6 +230,25 @@ class Context:
         e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 4)
         s, m = C.c_uint64(), C.c_uint64()
         self._chk(lib().coh_shapeminshape_of_edgelist(self._h, _i32p(e), len(e), winding, C.byref(s), C.byref(m)))
+        return s.value, m.value
+
+    def edgelist_of_path(self, segs):
+        """Polygon.edgelist_of_path on the device for the segments of a path (N2)."""
+        rec = _seg_records(segs)
+        cap = 64 * len(rec) + 64
+        while True:
+            out = np.zeros((cap, 4), dtype=np.int32)
+            n = C.c_int64()
+            self._chk(lib().coh_edgelist_of_path(self._h, rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), _i32p(out), C.c_int64(cap), C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value]
+            cap = int(n.value)
+
+    def shapeminshape_of_path(self, segs, winding):
+        """Polygon.shapeminshape_polygon: flattening and scan conversion both on the device."""
+        rec = _seg_records(segs)
+        s, m = C.c_uint64(), C.c_uint64()
+        self._chk(lib().coh_shapeminshape_of_path(self._h, rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), winding, C.byref(s), C.byref(m)))
         return s.value, m.value
 
     def polygon_opacity(self, edges, winding, shp):

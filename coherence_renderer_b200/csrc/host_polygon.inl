@@ -79,6 +79,67 @@ int coh_shapeminshape_of_edgelist(coh_ctx* ctx, const int32_t* edges, int32_t n_
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------
+// N2: Polygon.edgelist_of_path on the device.  The flattened edges stay in HBM; `box` (host, 4 ints:
+// sub-bin x min / y min / x max / y max) and the edge count come back in one small read.
+// ---------------------------------------------------------------------------------------
+static int flatten_on_device(coh_ctx* ctx, const double* segs, int n_segs, int4** d_edges, int* n_edges, int box[4]) {
+  *d_edges = nullptr; *n_edges = 0;
+  if (n_segs <= 0) return 0;
+  double* d_segs = nullptr; int *counts = nullptr, *offs = nullptr, *d_box = nullptr;
+  CK(DMALLOC(&d_segs, sizeof(double) * 9 * (size_t)n_segs));
+  CK(DMALLOC(&counts, sizeof(int) * n_segs)); CK(DMALLOC(&offs, sizeof(int) * ((size_t)n_segs + 1))); CK(DMALLOC(&d_box, 4 * sizeof(int)));
+  CK(cudaMemcpyAsync(d_segs, segs, sizeof(double) * 9 * (size_t)n_segs, cudaMemcpyHostToDevice, ctx->stream));
+  const int init[4] = {INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN};
+  CK(cudaMemcpyAsync(d_box, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  k_flatten<false><<<cdiv(n_segs, 128), 128, 0, ctx->stream>>>(d_segs, n_segs, counts, nullptr, nullptr, nullptr, ctx->d_error); LAUNCHED();
+  if (exclusive_scan(ctx, counts, offs, n_segs, nullptr)) return 1;
+  int total = 0;
+  CK(cudaMemcpyAsync(&total, offs + n_segs, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(DMALLOC(d_edges, sizeof(int4) * (size_t)std::max(total, 1)));
+  k_flatten<true><<<cdiv(n_segs, 128), 128, 0, ctx->stream>>>(d_segs, n_segs, nullptr, offs, *d_edges, d_box, ctx->d_error); LAUNCHED();
+  CK(cudaMemcpyAsync(box, d_box, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_error, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(d_segs); DFREE(counts); DFREE(offs); DFREE(d_box);
+  if (*ctx->h_error) {
+    cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
+    DFREE(*d_edges);
+    FAIL("coh_edgelist_of_path: a curve needs more than 40 levels of subdivision");
+  }
+  *n_edges = total;
+  return 0;
+}
+int coh_edgelist_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  int4* d_edges = nullptr; int n = 0, box[4];
+  if (flatten_on_device(ctx, segs, n_segs, &d_edges, &n, box)) return 1;
+  *n_out = n;
+  if (n > 0 && cap > 0) {
+    CK(cudaMemcpyAsync(edges_out, d_edges, sizeof(int4) * (size_t)std::min<int64_t>(n, cap), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  DFREE(d_edges);
+  return 0;
+}
+int coh_shapeminshape_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t winding, coh_shape_t* shape, coh_shape_t* minshape) {
+  CK(cudaSetDevice(ctx->device));
+  *shape = 0; *minshape = 0;
+  if (winding != COH_NONZERO && winding != COH_EVENODD) FAIL("bad winding rule");
+  int4* raw = nullptr; int n = 0, box[4];
+  if (flatten_on_device(ctx, segs, n_segs, &raw, &n, box)) return 1;
+  if (n <= 0) { DFREE(raw); return 0; }
+  EdgeRec* d_edges = nullptr;
+  CK(DMALLOC(&d_edges, sizeof(EdgeRec) * (size_t)n));
+  k_prep_edges<<<cdiv(n, 256), 256, 0, ctx->stream>>>(raw, d_edges, n); LAUNCHED();
+  int px0, py0, px1, py1; shape_pixel_box(EdgeBox{box[0], box[2], box[1], box[3]}, px0, py0, px1, py1);
+  int rc = shapes_from_device_edges(ctx, d_edges, n, winding, px0, py0, px1, py1, shape, minshape, "coh_shapeminshape_of_path");
+  DFREE(raw); DFREE(d_edges);
+  return rc;
+}
+
 // dense AA opacity bytes over the bit-frame of `shp`, then gathered in span order
 static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges, int winding, const DevShape* s,
                                  uint8_t** dense, int* wx0_out, int* nw_out) {

@@ -557,3 +557,68 @@ __global__ void k_gather_spans(const int* __restrict__ row_ptr, const int2* __re
     for (int i = 0; i < s.y; i++) out[o++] = dense[(size_t)r * pitch + (s.x + i - wx0)];
   }
 }
+
+// ------------------------------------------------------------------------------------
+// N2: Polygon.edgelist_of_path on the device (polygon.ml:83-127, 262-287; coord.ml:47).  One thread per
+// path segment: de Casteljau subdivision until Polygon.bezier_epsilon holds (curve_accuracy = 0.2), depth first,
+// left half first — the pieces come out in the reference's order.  FP64 with one rounding per operation
+// (__dadd_rn / __dmul_rn / __ddiv_rn / __dsqrt_rn) like OCaml.  EMIT = false counts the pieces of every segment,
+// EMIT = true writes them as int32 sub-bin edges at the segment's offset (exclusive scan of the counts).
+// segs: records of 9 doubles (kind 0 straight / 1 bezier, then up to 4 points).  box: x min / y min / x max / y max of
+// the emitted coordinates by atomics.
+// ------------------------------------------------------------------------------------
+constexpr int FLATTEN_MAX_DEPTH = 40;
+struct Pt2 { double x, y; };
+__device__ __forceinline__ Pt2 pt_half(Pt2 a, Pt2 b) { return Pt2{__ddiv_rn(__dadd_rn(a.x, b.x), 2.), __ddiv_rn(__dadd_rn(a.y, b.y), 2.)}; }
+__device__ __forceinline__ double dist_point_line(Pt2 c, Pt2 a, Pt2 b) {   // polygon.ml:83-90
+  const double ex = __dadd_rn(b.x, -a.x), ey = __dadd_rn(b.y, -a.y);
+  const double l = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+  const double num = __dadd_rn(__dmul_rn(__dadd_rn(a.y, -c.y), ex), -__dmul_rn(__dadd_rn(a.x, -c.x), ey));
+  return __dmul_rn(fabs(__ddiv_rn(num, __dmul_rn(l, l))), l);
+}
+__device__ __forceinline__ bool fp_normal(double d) { return isfinite(d) && fabs(d) >= 2.2250738585072014e-308; }   // classify_float = FP_normal
+__device__ __forceinline__ bool flat_enough(Pt2 p1, Pt2 p2, Pt2 p3, Pt2 p4) {   // polygon.ml:107-116
+  const double d1 = dist_point_line(p2, p1, p4), d2 = dist_point_line(p3, p1, p4);
+  if (fp_normal(d1) && fp_normal(d2)) return d1 < 0.2 && d2 < 0.2;
+  return true;
+}
+__device__ __forceinline__ int sub_of_float_dev(double f) { return (int)ceil(__dadd_rn(__dmul_rn(f, 32.0), -16.0)); }   // coord.ml:47
+template <bool EMIT>
+__global__ void k_flatten(const double* __restrict__ segs, int n_segs, int* __restrict__ counts, const int* __restrict__ offs,
+                          int4* __restrict__ edges, int* __restrict__ box, int* __restrict__ error_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_segs) return;
+  const double* q = segs + 9 * (size_t)i;
+  int n = 0;
+  int4* out = EMIT ? edges + offs[i] : nullptr;
+  int bx0 = INT32_MAX, by0 = INT32_MAX, bx1 = INT32_MIN, by1 = INT32_MIN;
+  auto emit = [&](Pt2 a, Pt2 b) {
+    if (EMIT) {
+      const int4 e = make_int4(sub_of_float_dev(a.x), sub_of_float_dev(a.y), sub_of_float_dev(b.x), sub_of_float_dev(b.y));
+      out[n] = e;
+      bx0 = min(bx0, min(e.x, e.z)); bx1 = max(bx1, max(e.x, e.z)); by0 = min(by0, min(e.y, e.w)); by1 = max(by1, max(e.y, e.w));
+    }
+    n++;
+  };
+  if (q[0] == 0.) emit(Pt2{q[1], q[2]}, Pt2{q[3], q[4]});
+  else {
+    // explicit stack of the right halves still to visit (the left half is always taken next)
+    Pt2 st[FLATTEN_MAX_DEPTH][4];
+    int sp = 0;
+    Pt2 p1{q[1], q[2]}, p2{q[3], q[4]}, p3{q[5], q[6]}, p4{q[7], q[8]};
+    for (;;) {
+      if (flat_enough(p1, p2, p3, p4)) {
+        emit(p1, p4);
+        if (sp == 0) break;
+        sp--; p1 = st[sp][0]; p2 = st[sp][1]; p3 = st[sp][2]; p4 = st[sp][3];
+        continue;
+      }
+      const Pt2 l2 = pt_half(p1, p2), h = pt_half(p2, p3), l3 = pt_half(l2, h), r3 = pt_half(p3, p4), r2 = pt_half(h, r3), l4 = pt_half(l3, r2);
+      if (sp >= FLATTEN_MAX_DEPTH) { *error_flag = 2; break; }
+      st[sp][0] = l4; st[sp][1] = r2; st[sp][2] = r3; st[sp][3] = p4; sp++;
+      p2 = l2; p3 = l3; p4 = l4;
+    }
+  }
+  if (!EMIT) counts[i] = n;
+  else if (n > 0 && box) { atomicMin(&box[0], bx0); atomicMin(&box[1], by0); atomicMax(&box[2], bx1); atomicMax(&box[3], by1); }
+}

@@ -328,6 +328,13 @@ int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_o
 int64_t coh_host_edgelist_of_subpath(const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap);
 /* Brush.points_of_brushstroke for one subpath, rounded as in brush.ml:172 (polygon.ml:143-218):
  * returns the number of stamp centres and writes min(n, cap) of them as int32 x,y in list order. */
+/* N2 — the step in front of the raster path on the device: Polygon.edgelist_of_path (polygon.ml:83-127, 262-287;
+ * coord.ml:47) for the segments of a path (records of 9 doubles: kind 0 straight / 1 bezier, then up to 4 points, already
+ * transformed to device space): de Casteljau subdivision to curve_accuracy, sub-bin edges in the reference's order.
+ * coh_edgelist_of_path copies the edges back (n_out = their number, whatever cap is); coh_shapeminshape_of_path keeps them
+ * in HBM and scan-converts them there (= Polygon.shapeminshape_polygon of the path, polygon.ml:605). */
+int coh_edgelist_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap, int64_t* n_out);
+int coh_shapeminshape_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t winding, coh_shape_t* shape, coh_shape_t* minshape);
 /* Brush.points_of_brushstroke_smear and the integer points of Brush.find_smear_directions (brush.ml:239-283) for all the
  * segments of a path in order: pieces at most 2 apart, start points truncated, consecutive duplicates dropped. */
 int64_t coh_host_smear_points(const double* segs, int32_t n_segs, int32_t* points_out, int64_t cap);

@@ -36,6 +36,9 @@ external sync : ctx -> unit = "coh_ml_sync"
 external rgba8_of_colour : Colour.colour -> int32 = "coh_ml_rgba8_of_colour"
 external colour_of_rgba8 : int32 -> Colour.colour = "coh_ml_colour_of_rgba8"
 external shapeminshape : ctx -> i32 -> int -> shape_h * shape_h = "coh_ml_shapeminshape"
+(* N2: Polygon.edgelist_of_path / shapeminshape_polygon with the flattening on the device (segments as 9 floats each) *)
+external edgelist_of_path : ctx -> f64 -> i32 -> int = "coh_ml_edgelist_of_path"
+external shapeminshape_of_path : ctx -> f64 -> int -> shape_h * shape_h = "coh_ml_shapeminshape_of_path"
 external polygon_opacity : ctx -> i32 -> int -> shape_h -> u8 -> int = "coh_ml_polygon_opacity"
 external polygon_sprite_raw : ctx -> u8 -> i32 -> int -> shape_h -> i32 -> int = "coh_ml_polygon_sprite_bc" "coh_ml_polygon_sprite"
 external shape_box : ctx -> int -> int -> int -> int -> shape_h = "coh_ml_shape_box"

@@ -93,6 +93,20 @@ CAMLprim value coh_ml_shapeminshape(value ctx, value edges, value winding) {
   check(CTX(ctx), coh_shapeminshape_of_edgelist(CTX(ctx), (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), Int_val(winding), &s, &m));
   CAMLreturn(pair_of_handles(s, m));
 }
+/* N2: Polygon.edgelist_of_path on the device; segs : float64 Array1 of 9*n, out : int32 Array1 of 4*cap; returns the edge count */
+CAMLprim value coh_ml_edgelist_of_path(value ctx, value segs, value out) {
+  CAMLparam3(ctx, segs, out);
+  int64_t n = 0;
+  check(CTX(ctx), coh_edgelist_of_path(CTX(ctx), (const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4, &n));
+  CAMLreturn(Val_long((long)n));
+}
+/* Polygon.shapeminshape_polygon with the flattened edges kept in HBM */
+CAMLprim value coh_ml_shapeminshape_of_path(value ctx, value segs, value winding) {
+  CAMLparam3(ctx, segs, winding);
+  coh_shape_t s = 0, m = 0;
+  check(CTX(ctx), coh_shapeminshape_of_path(CTX(ctx), (const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), Int_val(winding), &s, &m));
+  CAMLreturn(pair_of_handles(s, m));
+}
 /* opacity bytes of every pixel of `shape`, span order; out : (int, int8_unsigned) Array1 of Sprite.shape_card shape */
 CAMLprim value coh_ml_polygon_opacity(value ctx, value edges, value winding, value shape, value out) {
   CAMLparam5(ctx, edges, winding, shape, out);

@@ -213,6 +213,20 @@ int main(int argc, char** argv) {
   int32_t he[8]; CHECK(coh_host_edgelist_of_subpath(segs, 1, he, 2) == 1 && he[0] == sub_of_float(10.0));
   int32_t hp[64]; CHECK(coh_host_brush_points(segs, 1, 4.0, hp, 32) > 0);
   int32_t hs[256]; CHECK(coh_host_smear_points(segs, 1, hs, 128) > 30 && hs[0] == 10 && hs[1] == 10);
+  /* N2: the same flattening on the device */
+  {
+    double tri[27] = {0, 10.0, 10.0, 90.0, 20.0, 0, 0, 0, 0,   1, 90.0, 20.0, 120.0, 60.0, 40.0, 90.0, 30.0, 70.0,   0, 30.0, 70.0, 10.0, 10.0, 0, 0, 0, 0};
+    int32_t de[4 * 64], he2[4 * 64]; int64_t dn = 0;
+    OK(coh_edgelist_of_path(C, tri, 3, de, 64, &dn));
+    int64_t hn = coh_host_edgelist_of_subpath(tri, 3, he2, 64);
+    CHECK(dn == hn && dn > 3 && memcmp(de, he2, sizeof(int32_t) * 4 * (size_t)dn) == 0);
+    coh_shape_t ps = 0, pm = 0, es = 0, em = 0;
+    OK(coh_shapeminshape_of_path(C, tri, 3, COH_NONZERO, &ps, &pm));
+    OK(coh_shapeminshape_of_edgelist(C, he2, (int32_t)hn, COH_NONZERO, &es, &em));
+    int64_t c1 = 0, c2 = 0; OK(coh_shape_card(C, ps, &c1)); OK(coh_shape_card(C, es, &c2)); CHECK(c1 == c2 && c1 > 1000);
+    ERR(coh_shapeminshape_of_path(C, tri, 3, 9, &ps, &pm), "winding");
+    OK(coh_shape_free(C, ps)); OK(coh_shape_free(C, pm)); OK(coh_shape_free(C, es)); OK(coh_shape_free(C, em));
+  }
   /* release */
   coh_shape_t all[] = {s, m, mx, bx, un, in, tr, bl, er, imp, cs, dirty, os, om, df};
   for (unsigned i = 0; i < sizeof all / sizeof all[0]; i++) OK(coh_shape_free(C, all[i]));

@@ -247,6 +247,40 @@ def test_brush_strokes(ctx, oracle):
     assert _max_lsb(got, ref) == 0
 
 
+def test_path_flattening_on_device(ctx, oracle):
+    """N2: Polygon.edgelist_of_path (polygon.ml:83-127, 262-287; coord.ml:47) on the device — de Casteljau subdivision
+    in FP64, one rounding per operation — gives the edges of the host-side geometry, in the same order; scan conversion
+    of the resident edges gives the oracle's shape and minshape."""
+    import random
+
+    rnd = random.Random(77)
+    for trial in range(12):
+        segs, p0 = [], (rnd.uniform(20, 600), rnd.uniform(20, 400))
+        start = p0
+        for k in range(rnd.randint(2, 9)):
+            if rnd.random() < 0.6:
+                c = [(rnd.uniform(-50, 700), rnd.uniform(-50, 500)) for _ in range(3)]
+                segs.append(("C", p0, c[0], c[1], c[2]))
+                p0 = c[2]
+            else:
+                p1 = (rnd.uniform(0, 640), rnd.uniform(0, 480))
+                segs.append(("L", p0, p1))
+                p0 = p1
+        segs.append(("L", p0, start))
+        host = abi.host_edgelist_of_subpath(segs)
+        dev = ctx.edgelist_of_path(segs)
+        assert np.array_equal(dev, host), trial
+        for w in (abi.COH_NONZERO, abi.COH_EVENODD):
+            hs, hm = ctx.shapeminshape_of_path(segs, w)
+            rs, rm = oracle.shapeminshape(host, w)
+            assert np.array_equal(ctx.shape_export(hs), rs) and np.array_equal(ctx.shape_export(hm), rm), (trial, w)
+            ctx.shape_free(hs)
+            ctx.shape_free(hm)
+    # degenerate curves (coincident control points: distances that are not FP_normal count as flat)
+    flat = [("C", (10.0, 10.0), (10.0, 10.0), (10.0, 10.0), (10.0, 10.0)), ("C", (10.0, 10.0), (50.0, 10.0), (90.0, 10.0), (130.0, 10.0))]
+    assert np.array_equal(ctx.edgelist_of_path(flat), abi.host_edgelist_of_subpath(flat))
+
+
 def test_dummy_brush(ctx, oracle):
     """Brushstroke with a Dummy brush (brush.ml:14-22, 70-73, 178-181): the whole shape of the stroke — the boxes around
     its stamp points — in opaque white, whatever fill it was given; minshape null."""
