@@ -248,8 +248,9 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       // (the heavy-first order flattened for this kernel: made when the cells were binned, kept with cached lists)
       // (a small pass — a filter's lens — gains nothing from the heavy-first order: one dependent launch less)
       const bool comp_ordered = ordered && n_cells > 2048;
-      if (comp_ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order); LAUNCHED(); B.comp_valid = true; }
-      k_comp_rows<<<n_cells * (CELL_H / COMP_WARPS), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, comp_ordered ? B.comp_order : nullptr); LAUNCHED();
+      if (comp_ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order, fr.cntx); LAUNCHED(); B.comp_valid = true; }
+      const int comp_blocks = n_cells * (CELL_H / COMP_WARPS);
+      k_comp_rows<<<std::min(comp_blocks, ctx->n_sms * (2048 / (COMP_WARPS * 32))), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, comp_ordered ? B.comp_order : nullptr, comp_blocks); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {

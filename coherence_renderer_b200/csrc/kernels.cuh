@@ -228,8 +228,9 @@ __global__ void __launch_bounds__(256) k_bin1(const int4* __restrict__ leaf_box,
 }
 // The heavy-first order of k_bin1 flattened for the row compositor: position q -> {cell, list start, list end, header
 // flags}; positions past the queued cells hold cell -1.  One thread per position; runs when the binning does.
+// (w: bits 0-3 header flags, 4-18 tile column of the cell inside the pass, 19-30 its cell row: no division per pixel row)
 __global__ void k_comp_order(const int* __restrict__ cls_cnt, const int* __restrict__ cls_cells, const int2* __restrict__ cell_rng, const int2* __restrict__ cell_head,
-                             int n_cells, int4* __restrict__ order) {
+                             int n_cells, int4* __restrict__ order, int cntx) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_cells) return;
   int before = 0, cell = -1;
@@ -239,7 +240,7 @@ __global__ void k_comp_order(const int* __restrict__ cls_cnt, const int* __restr
     before += n;
   }
   int4 r = make_int4(-1, 0, 0, 0);
-  if (cell >= 0) { const int2 rg = cell_rng[cell]; r = make_int4(cell, rg.x, rg.y, cell_head[cell].y); }
+  if (cell >= 0) { const int2 rg = cell_rng[cell]; r = make_int4(cell, rg.x, rg.y, (cell_head[cell].y & 15) | ((cell % cntx) << 4) | ((cell / cntx) << 19)); }
   order[q] = r;
 }
 // The background cells of a box update (flagged by k_bin1): one warp per cell streams the cell's 16 rows of one

@@ -244,29 +244,32 @@ __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P,
 // One block per cell (CELL_H warps), cells in heavy-first order; background cells were finished by k_prefill.
 // ------------------------------------------------------------------------------------
 constexpr int COMP_WARPS = 8;   // rows of a cell per block
-__global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr, const int4* __restrict__ order) {
+__global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, const int2* __restrict__ item_attr, const int4* __restrict__ order, int n_blocks) {
   constexpr int PARTS = CELL_H / COMP_WARPS;   // blocks per cell
   // Block b takes position b / PARTS of the heavy-first order (blocks are dispatched in index order, so the long
   // lists start first).  The order was flattened by k_comp_order when the cells were binned: one load gives the
   // cell, its list and its header flags — every warp fetches it for itself, no barrier; the grid is sized for
   // every cell, and positions beyond the queued cells (background cells were finished by k_prefill) leave at once.
-  const int q = blockIdx.x / PARTS;
+  // A resident grid walks the positions (n_blocks = cells x PARTS of them, most of them background cells that leave at
+  // once: one block per position would spend the launch on block dispatch).
+  for (int bq = blockIdx.x; bq < n_blocks; bq += gridDim.x) {
+  const int q = bq / PARTS;
   int4 oc;
   if (order) oc = order[q];
-  else { oc = make_int4(q < P.n_cells ? q : -1, 0, 0, 0); if (oc.x >= 0) { const int2 rg0 = P.cell_rng[q]; oc.y = rg0.x; oc.z = rg0.y; oc.w = P.cell_head ? P.cell_head[q].y : 0; } }
+  else { oc = make_int4(q < P.n_cells ? q : -1, 0, 0, 0); if (oc.x >= 0) { const int2 rg0 = P.cell_rng[q]; oc.y = rg0.x; oc.z = rg0.y; oc.w = ((P.cell_head ? P.cell_head[q].y : 0) & 15) | ((q % P.fr.cntx) << 4) | ((q / P.fr.cntx) << 19); } }
   const int cell = oc.x;
-  if (cell < 0) return;
+  if (cell < 0) { if (order) break; continue; }   // (ordered: every later position is empty too)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lbit = 1u << lane;
-  const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
-  const int y = (P.cell_row0 + by) * CELL_H + (blockIdx.x % PARTS) * COMP_WARPS + wid, row = y & (CELL_H - 1);
-  if (y < P.fr.band_y0 || y >= P.fr.band_y1) return;
+  const int tile = P.fr.ctx0 + ((oc.w >> 4) & 0x7FFF), by = (oc.w >> 19) & 0xFFF;
+  const int y = (P.cell_row0 + by) * CELL_H + (bq % PARTS) * COMP_WARPS + wid, row = y & (CELL_H - 1);
+  if (y < P.fr.band_y0 || y >= P.fr.band_y1) continue;
   uint32_t colmask = interval_mask32(tile * TILE_W, P.ux0, P.ux1);
   if (tile * TILE_W + 31 >= P.fr.W) colmask &= interval_mask32(tile * TILE_W, 0, P.fr.W - 1);
   uint32_t u = P.u_init ? (P.u_init[(size_t)y * P.fr.tiles_x + tile] & colmask) : ((y >= P.uy0 && y <= P.uy1) ? colmask : 0u);
   const uint32_t u_update = u;
   uint32_t* u_rec = P.u_out ? P.u_out + (size_t)y * P.fr.tiles_x + tile : nullptr;   // receives u after the scene list
-  if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; return; }
+  if (u == 0u) { if (u_rec && lane == 0) *u_rec = 0u; continue; }
   if ((oc.w & 1) && !P.resume) {
     // a background cell that k_prefill did not take (frames mirrored to peer framebuffers spread these stores over
     // the compositor's blocks): one opaque primitive covers the cell, nothing was scan-converted for it
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
       P.fb[at] = bg;
       for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = bg;
     }
-    return;
+    continue;
   }
   const int2 rg = make_int2(oc.y, oc.z);
   const uint2* sc_row = P.pre_sc + row;
@@ -305,6 +308,16 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
         touched_w |= vis;
         const uint32_t C = __shfl_sync(0xFFFFFFFFu, sc.y, k);
         const uint32_t c0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, at.x, k); const int fl = __shfl_sync(0xFFFFFFFFu, at.y, k);
+        // the common case — an opaque plain fill seen through its interior only (no edge pixel of this row still shows,
+        // no dissolve): every visible pixel takes the colour under what is already there and is finished
+        // (over a b with b opaque is opaque; over clear b = b, colour.ml:314-316) — no opacity bytes, no vote
+        if ((c0 >> 24) == 255u && (fl & ~7) == 0 && !((fl & 1) && (vis & C))) {
+          const bool under = (vis & lbit) && acc != 0u;
+          if (__any_sync(0xFFFFFFFFu, under)) { if (vis & lbit) acc = px_over(acc, c0); }
+          else if (vis & lbit) acc = c0;
+          u &= ~vis;
+          continue;
+        }
         uint32_t col = c0;
         // shptorender ∩ maxshape = vis & ~(S & ~C) = vis & C: those pixels dissolve the fill by their opacity
         if ((fl & 1) && (vis & C & lbit)) col = px_dissolve(c0, op_row[(size_t)(base + k) * (CELL_H * 32)]);
@@ -329,6 +342,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
     const size_t at = (size_t)y * P.fr.W + tile * TILE_W + lane;
     P.fb[at] = acc;
     for (int k = 0; k < P.n_peers; k++) P.peer_fb[k][at] = acc;
+  }
   }
 }
 
