@@ -30,6 +30,29 @@ namespace coh {
 constexpr int ORDER_BINS = 256;  // ints of binning state per pass (pool cursor, class counts, work-queue head behind them)
 
 // ------------------------------------------------------------------------------------
+// The AA prefix table (4224 bytes, polygon.ml:616-671) into shared memory by one TMA bulk copy (cp.async.bulk,
+// completion counted on an mbarrier): one elected thread issues it, the copy engine moves the bytes while the block's
+// threads set themselves up, everybody waits on the barrier's phase.  `table` and `s_prefix` are 16-byte aligned and
+// the size is a multiple of 16 (the copy unit).  Call from all threads of the block, once, before the table is read.
+__device__ __forceinline__ void stage_aa_table(int* s_prefix, unsigned long long* s_bar, const AATable* __restrict__ table) {
+  constexpr unsigned BYTES = 32 * 33 * sizeof(int);
+  static_assert(BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar), dst = (unsigned)__cvta_generic_to_shared(s_prefix);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(&table->prefix[0][0]), "r"(BYTES), "r"(bar) : "memory");
+  }
+  __syncthreads();   // the barrier is initialised (and armed) before anybody polls it
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar) : "memory");
+  }
+}
+
 __global__ void k_prep_edges(const int4* __restrict__ in, EdgeRec* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -186,11 +186,11 @@ __device__ __forceinline__ bool aa_runs_pixels(const EdgeRec* __restrict__ edges
 static_assert(sizeof(AaEdge) >= sizeof(StagedEdge), "the stage of the interval scan doubles as the stage of the general scan");
 __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P, const int4* __restrict__ list, const int* __restrict__ list_n,
                                                                   uint8_t* __restrict__ op, int* __restrict__ next) {
-  __shared__ int s_prefix[32 * 33];
+  __shared__ __align__(16) int s_prefix[32 * 33];
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ AaEdge s_stage[AA2_WARPS][32];
   __shared__ uint32_t s_aa[AA2_WARPS][32 * AA_WORDS];   // bit-rows of the general routine (rarely touched)
-  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
-  __syncthreads();
+  stage_aa_table(s_prefix, &s_bar, P.aa);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = *list_n;
   const int* prow = s_prefix + lane * 33;

@@ -603,12 +603,12 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
 template <bool CARRY, int EXTRAS, int WALK_H, bool PRE = false>
 __global__ void __launch_bounds__(WALK_WARPS * 32, WALK_MIN_CTAS) k_walk(WalkParams P) {
   constexpr int WALK_SUB = CELL_H / WALK_H;
-  __shared__ int s_prefix[32 * 33];
+  __shared__ __align__(16) int s_prefix[32 * 33];
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_aa[WALK_WARPS][32 * AA_WORDS];
   __shared__ uint32_t s_acc[WALK_WARPS][WALK_H][32];
   __shared__ StagedEdge s_stage[WALK_WARPS][32];
-  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) s_prefix[i] = (&P.aa->prefix[0][0])[i];
-  __syncthreads();
+  stage_aa_table(s_prefix, &s_bar, P.aa);
   const int volume = P.aa->volume;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // Work items come off one atomic counter.  The heavy cells at the head of the order are taken one item at a
