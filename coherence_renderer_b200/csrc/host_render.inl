@@ -252,6 +252,7 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       const int comp_blocks = n_cells * (CELL_H / COMP_WARPS);
       k_comp_rows<<<std::min(comp_blocks, ctx->n_sms * (2048 / (COMP_WARPS * 32))), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, comp_ordered ? B.comp_order : nullptr, comp_blocks); LAUNCHED();
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
+      // (the touched plane of a smear filter is compiled into the EXTRAS = 2 variants only)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);
       if (slots > ctx->carry_slots) {
         DFREE(ctx->carry_done); DFREE(ctx->carry_cnt); DFREE(ctx->carry_ent);
@@ -263,12 +264,12 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       }
       P.carry_done = ctx->carry_done; P.carry_cnt = ctx->carry_cnt; P.carry_ent = ctx->carry_ent;
       P.epoch = ++ctx->epoch;
-      if (A.resume) k_walk<true, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      if (A.resume || ctx->touched) k_walk<true, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else if (has_conv) k_walk<true, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else k_walk<true, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       LAUNCHED();
     } else {
-      if (A.resume) k_walk<false, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
+      if (A.resume || ctx->touched) k_walk<false, 2, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else if (has_conv) k_walk<false, 1, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       else k_walk<false, 0, 4, true><<<pgrid, WALK_WARPS * 32, 0, ctx->stream>>>(P);
       LAUNCHED();

@@ -292,7 +292,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   // (typically the background rectangle; flagged by the binning kernel): the rows are just that colour.
   if (head.y & 1) {
     const uint32_t c0 = (uint32_t)head.x;
-    if (P.touched && row_in_band && c_lane == 0 && u) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= u;
+    if (CPGX && P.touched && row_in_band && c_lane == 0 && u) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= u;   // (filter scenes only: they walk with EXTRAS = 2)
     if ((head.y & 2) && P.u_out && row_in_band && c_lane == 0) P.u_out[(size_t)my_y * P.fr.tiles_x + tile] = 0u;
     publish_done();
 #pragma unroll 1
@@ -467,7 +467,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
         const uint32_t ur = __shfl_sync(0xFFFFFFFFu, u, r);
         const uint32_t vis = Sk & ur;
         if (vis == 0u) continue;
-        if (r_lane == r) touched_w |= vis;
+        if (CPGX && r_lane == r) touched_w |= vis;
         const uint32_t M = Sk & ~Ck;          // minshape word (polygon.ml:526)
         const uint32_t edge = vis & ~M;       // shptorender ∩ maxshape (render.ml:1201-1204)
         const int yy = y0 + r - ody, xx0 = tx0 - odx;
@@ -581,7 +581,7 @@ __device__ __forceinline__ void walk_cell(const WalkParams& P, const int tile, c
   PH_MARK(2)
   publish_done();
   if (bad) *P.error_flag = 1;
-  if (P.touched && row_in_band && c_lane == 0 && touched_w) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= touched_w;
+  if (CPGX && P.touched && row_in_band && c_lane == 0 && touched_w) P.touched[(size_t)my_y * P.fr.tiles_x + tile] |= touched_w;
 #pragma unroll 1
   for (int r = 0; r < WALK_H; r++) {
     const uint32_t uu = __shfl_sync(0xFFFFFFFFu, u_update, r);

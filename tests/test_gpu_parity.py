@@ -812,6 +812,11 @@ def test_smear_filter(ctx, oracle):
         b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
         b.polygon([(100.0, 20.0), (220.0, 150.0), (60.0, 180.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 240, 20), 200)))
         b.rectangle(S.rgba8(0, 0, 0), 150.0, 100.0, 230.0, 190.0)
+        if radius == 4.0:   # a scene that is not flat: the compositing walker, fused and three-phase
+            b.group_begin(pretrans=200)
+            b.polygon([(20.0, 100.0), (120.0, 110.0), (60.0, 190.0)], S.Fill.plain(S.rgba8(10, 200, 90)))
+            b.polygon([(40.0, 20.0), (230.0, 40.0), (200.0, 90.0)], S.Fill.plain(S.dissolve(S.rgba8(90, 10, 200), 140)))
+            b.group_end()
         got, ref, got_u, ref_u = _render_both(ctx, oracle, _finish(b, W, H), W, H)
         assert np.array_equal(got_u, ref_u), radius
         assert _max_lsb(got, ref) == 0, radius
