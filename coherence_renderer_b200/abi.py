@@ -41,7 +41,7 @@ class CohObject(C.Structure):
 SYMBOLS = [
     "coh_init", "coh_shutdown", "coh_last_error", "coh_device_name", "coh_stream", "coh_launch_count",
     "coh_set_stream", "coh_set_timing", "coh_get_timing", "coh_fb_attach", "coh_set_option",
-    "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_edgelist_of_path", "coh_shapeminshape_of_path", "coh_polygon_opacity",
+    "coh_colour_of_rgba8", "coh_rgba8_of_colour", "coh_shapeminshape_of_edgelist", "coh_edgelist_of_path", "coh_shapeminshape_of_path", "coh_brush_shape", "coh_brush_sprite", "coh_brush_smear", "coh_polygon_opacity",
     "coh_polygon_sprite", "coh_shape_box", "coh_shape_import", "coh_shape_export_size", "coh_shape_export",
     "coh_shape_bounds", "coh_shape_card", "coh_shape_free", "coh_shape_union", "coh_shape_difference",
     "coh_shape_intersection", "coh_shape_translate", "coh_shape_bloat", "coh_shape_erode", "coh_scene_create",
@@ -266,6 +266,37 @@ class Context:
         n = C.c_int64()
         self._chk(lib().coh_polygon_sprite(self._h, C.byref(fill_obj), _i32p(e), len(e), winding, C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
         return out[: n.value]
+
+    # -- brush strokes outside a scene (brush.mli:20-27): brush_obj = a BRUSH CohObject, points = rounded stamp points
+    def brush_shape(self, brush_obj, points):
+        p = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+        h = C.c_uint64()
+        self._chk(lib().coh_brush_shape(self._h, C.byref(brush_obj), _i32p(p), len(p), C.byref(h)))
+        return h.value
+
+    def brush_sprite(self, brush_obj, points, shp):
+        p = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+        cap = self.shape_card(shp)
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = C.c_int64()
+        self._chk(lib().coh_brush_sprite(self._h, C.byref(brush_obj), _i32p(p), len(p), C.c_uint64(shp), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return out[: n.value]
+
+    def brush_smear(self, shape, rgba, brush_obj, points, smear_points):
+        """Brush.smear: returns (shape handle of the result, rgba per pixel)."""
+        p = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+        q = np.ascontiguousarray(smear_points, dtype=np.int32).reshape(-1, 2)
+        src = np.ascontiguousarray(rgba, dtype=np.uint32)
+        bs = self.brush_shape(brush_obj, p)
+        un = self.shape_union(shape, bs)
+        cap = self.shape_card(un)
+        self.shape_free(bs)
+        self.shape_free(un)
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        o, n = C.c_uint64(), C.c_int64()
+        self._chk(lib().coh_brush_smear(self._h, C.c_uint64(shape), src.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(brush_obj), _i32p(p), len(p), _i32p(q), len(q),
+                                        C.byref(o), out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(cap), C.byref(n)))
+        return o.value, out[: n.value]
 
     # -- sprites: (shape handle, RGBA8 per pixel in span order)
     def shape_intersects(self, a, b):

@@ -220,6 +220,124 @@ int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edge
 }
 
 // ---------------------------------------------------------------------------------------
+// Brush strokes outside a scene (brush.mli:20-27): shape_of_brushstroke, sprite_of_brushstroke, smear.  The stroke
+// crosses the boundary as its rounded stamp points (Brush.points_of_brushstroke, brush.ml:126-130, 172) and a BRUSH
+// object record (brush_radius, brush_opacity, winding = COH_BRUSH_*, fill).
+// ---------------------------------------------------------------------------------------
+static FillRec fillrec_of(const coh_object* fill);
+static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out);   // host_scene.inl
+static int brush_radius_of(coh_ctx* ctx, const coh_object* b, int* r) {
+  if (!(b->brush_radius >= 0. && b->brush_radius <= 4096.) || !(b->brush_opacity >= 0. && b->brush_opacity <= 1.)) FAIL("brush radius / opacity out of range");
+  if (b->winding != COH_BRUSH_GAUSSIAN && b->winding != COH_BRUSH_DUMMY) FAIL("bad brush kind");
+  *r = b->winding == COH_BRUSH_DUMMY ? (int)b->brush_radius : (int)ceil(b->brush_radius);   // ((2 r + 1) - 1) / 2 of sizeof_brush (brush.ml:25-28)
+  return 0;
+}
+int coh_brush_shape(coh_ctx* ctx, const coh_object* brush, const int32_t* points, int32_t n_points, coh_shape_t* shape) {
+  CK(cudaSetDevice(ctx->device));
+  *shape = 0;
+  int r;
+  if (brush_radius_of(ctx, brush, &r)) return 1;
+  if (n_points <= 0) return 0;   // NullShape (brush.ml:155)
+  int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+  for (int k = 0; k < n_points; k++) { x0 = std::min(x0, points[2 * k]); x1 = std::max(x1, points[2 * k]); y0 = std::min(y0, points[2 * k + 1]); y1 = std::max(y1, points[2 * k + 1]); }
+  x0 -= r; y0 -= r; x1 += r; y1 += r;
+  const int wx0 = floordiv(x0, 32) * 32, nw = (x1 - wx0) / 32 + 1, n_rows = y1 - y0 + 1;
+  int2* d_pts = nullptr; uint32_t* bits = nullptr;
+  CK(DMALLOC(&d_pts, sizeof(int2) * (size_t)n_points)); CK(DMALLOC(&bits, 4 * (size_t)nw * n_rows));
+  CK(cudaMemcpyAsync(d_pts, points, sizeof(int2) * (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(bits, 0, 4 * (size_t)nw * n_rows, ctx->stream));
+  const int side = 2 * r + 1;
+  k_stamp_boxes_to_bits<<<cdiv(n_points * side, 256), 256, 0, ctx->stream>>>(d_pts, n_points, r, y0, n_rows, wx0, nw, bits); LAUNCHED();
+  int rc = shape_from_bits(ctx, bits, y0, n_rows, wx0, nw, shape);
+  CK(cudaStreamSynchronize(ctx->stream));   // (`points` is the caller's)
+  DFREE(d_pts); DFREE(bits);
+  return rc;
+}
+// device copy of a brush's stamp (alpha bytes of Brush.drawbrush brush white, brush.ml:75-92)
+static int upload_stamp(coh_ctx* ctx, const coh_object* brush, int r, uint8_t** d_stamp) {
+  std::vector<uint8_t> st; int rr = r;
+  if (brush->winding == COH_BRUSH_DUMMY) st.assign((size_t)(2 * r + 1) * (2 * r + 1), (uint8_t)255);
+  else brush_stamp(brush->brush_radius, brush->brush_opacity, st, rr);
+  CK(DMALLOC(d_stamp, st.size()));
+  CK(cudaMemcpyAsync(*d_stamp, st.data(), st.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int coh_brush_sprite(coh_ctx* ctx, const coh_object* brush, const int32_t* points, int32_t n_points, coh_shape_t shp,
+                     uint32_t* out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  int r;
+  if (brush_radius_of(ctx, brush, &r)) return 1;
+  if (brush->fill_kind < COH_FILL_PLAIN || brush->fill_kind > COH_FILL_RADIAL) FAIL("coh_brush_sprite: bad fill kind");
+  if (!shp) return 0;   // NullShape -> NullSprite (brush.ml:184)
+  DevShape* s = (DevShape*)shp;
+  if (s->card > cap) FAIL("coh_brush_sprite: buffer too small");
+  int2* d_pts = nullptr; uint8_t* d_stamp = nullptr; int* d_off = nullptr; uint32_t* d_out = nullptr;
+  CK(DMALLOC(&d_pts, sizeof(int2) * (size_t)std::max(n_points, 1)));
+  if (n_points > 0) CK(cudaMemcpyAsync(d_pts, points, sizeof(int2) * (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
+  if (upload_stamp(ctx, brush, r, &d_stamp)) return 1;
+  if (shape_pixel_offsets(ctx, s, &d_off)) return 1;
+  CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(s->card, 1)));
+  FillRec f = fillrec_of(brush);
+  if (brush->winding == COH_BRUSH_DUMMY) { f.kind = 0; f.c0 = 0xFFFFFFFFu; }   // white, whatever the fill (brush.ml:178-181)
+  k_brush_sprite<<<cdiv(s->n_rows, 4), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->y0, s->n_rows, d_pts, n_points, r, d_stamp, f, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(out, d_out, 4 * (size_t)s->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(d_pts); DFREE(d_stamp); DFREE(d_off); DFREE(d_out);
+  *n_out = s->card;
+  return 0;
+}
+// Brush.smear spr brushstroke (brush.ml:286-331): the sprite fleshed out to the stroke's shape, smeared along the smear
+// points (coh_host_smear_points) on a canvas of its box plus one pixel; result = a sprite on shape(spr) ∪ shape(stroke).
+int coh_brush_smear(coh_ctx* ctx, coh_shape_t shape, const uint32_t* rgba_in, const coh_object* brush, const int32_t* points, int32_t n_points,
+                    const int32_t* smear_points, int32_t n_smear, coh_shape_t* out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  CK(cudaSetDevice(ctx->device));
+  *out_shape = 0; *n_out = 0;
+  int r;
+  if (brush_radius_of(ctx, brush, &r)) return 1;
+  if (brush->winding != COH_BRUSH_GAUSSIAN) FAIL("Brush.drawbrush : One cannot draw a dummy brush");   // brush.ml:98-99
+  if (r > 64) FAIL("coh_brush_smear: brush radius above 64");
+  coh_shape_t bs = 0, U = 0;
+  if (coh_brush_shape(ctx, brush, points, n_points, &bs)) return 1;
+  if (coh_shape_union(ctx, shape, bs, &U)) return 1;
+  DevShape* s = (DevShape*)shape; DevShape* us = (DevShape*)U; DevShape* bsh = (DevShape*)bs;
+  if (!us) { coh_shape_free(ctx, bs); return 0; }   // NullSprite
+  if (us->card > cap) { coh_shape_free(ctx, bs); coh_shape_free(ctx, U); FAIL("coh_brush_smear: buffer too small"); }
+  // canvas coordinates: the box of the fleshed-out sprite with a border of one pixel (Sprite.flatten_sprite 1)
+  const int ax0 = us->bx0 - 1, ay0 = us->by0 - 1, cw = us->bx1 - us->bx0 + 3, ch = us->by1 - us->by0 + 3;
+  const size_t npx = (size_t)cw * ch;
+  uint32_t *A = nullptr, *Cv = nullptr, *Y = nullptr, *d_in = nullptr, *d_out = nullptr; int *d_off = nullptr, *d_uoff = nullptr, *d_bb = nullptr;
+  int2* d_sm = nullptr; uint8_t* d_stamp = nullptr;
+  CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&Cv, 4 * npx)); CK(DMALLOC(&Y, 4 * npx)); CK(DMALLOC(&d_bb, 4 * sizeof(int)));
+  CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
+  if (s) {
+    if (shape_pixel_offsets(ctx, s, &d_off)) return 1;
+    CK(DMALLOC(&d_in, 4 * (size_t)std::max<long long>(s->card, 1)));
+    CK(cudaMemcpyAsync(d_in, rgba_in, 4 * (size_t)s->card, cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter_spans<uint32_t><<<cdiv(s->n_rows, 128), 128, 0, ctx->stream>>>(s->row_ptr, s->spans, d_off, s->n_rows, s->y0 - ay0, ax0, cw, d_in, A); LAUNCHED();
+  }
+  // the box of the fleshed-out sprite is the box of the union: k_smear takes it as (sprite box, stroke box)
+  const int bb[4] = {us->bx0 - ax0, us->by0 - ay0, us->bx1 - ax0, us->by1 - ay0};
+  CK(cudaMemcpyAsync(d_bb, bb, sizeof bb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(DMALLOC(&d_sm, sizeof(int2) * (size_t)std::max(n_smear, 1)));
+  if (n_smear > 0) CK(cudaMemcpyAsync(d_sm, smear_points, sizeof(int2) * (size_t)n_smear, cudaMemcpyHostToDevice, ctx->stream));
+  if (upload_stamp(ctx, brush, r, &d_stamp)) return 1;
+  k_smear<<<1, SMEAR_THREADS, 0, ctx->stream>>>(A, Y, cw, ch, Cv, 0, 0, cw, ch, d_bb, bb[0], bb[1], bb[2], bb[3], d_sm, n_smear, -ax0, -ay0, d_stamp, r, 0, 0, cw - 1, ch - 1); LAUNCHED();
+  // Sprite.pickup on the fleshed-out shape
+  if (shape_pixel_offsets(ctx, us, &d_uoff)) return 1;
+  CK(DMALLOC(&d_out, 4 * (size_t)std::max<long long>(us->card, 1)));
+  k_gather_spans<uint32_t><<<cdiv(us->n_rows, 128), 128, 0, ctx->stream>>>(us->row_ptr, us->spans, d_uoff, us->n_rows, ax0, cw, Y + (size_t)(us->y0 - ay0) * cw, d_out); LAUNCHED();
+  CK(cudaMemcpyAsync(rgba_out, d_out, 4 * (size_t)us->card, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DFREE(A); DFREE(Cv); DFREE(Y); DFREE(d_in); DFREE(d_out); DFREE(d_off); DFREE(d_uoff); DFREE(d_bb); DFREE(d_sm); DFREE(d_stamp);
+  (void)bsh;
+  coh_shape_free(ctx, bs);
+  *out_shape = U; *n_out = us->card;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Sprite operations on whole sprites (sprite.mli:96-125).  A sprite crosses the boundary as its shape (a device span
 // set) and one RGBA8 word per pixel in canonical span order.  Sprite.translate_sprite moves only the shape
 // (coh_shape_translate): the pixel array is unchanged.

@@ -301,6 +301,33 @@ __global__ void k_filter_blend(const uint32_t* __restrict__ T, const uint8_t* __
   const uint32_t res = px_plus(z, yy);
   fb[i] = (flags & 1) ? res : px_over(fb[i], res);
 }
+// Brush.sprite_of_brushstroke (brush.ml:176-222) for the pixels of a span set in canonical span order: the ordered
+// alpha_over of every stamp that covers a pixel (207-212), then dissolve (fill x y) by that alpha (214-220).  One warp
+// per row of the shape, lanes over the pixels of its spans, the stamp points walked by the whole warp.
+__global__ void __launch_bounds__(128) k_brush_sprite(const int* __restrict__ row_ptr, const int2* __restrict__ spans, const int* __restrict__ px_off,
+                                                      int y0, int n_rows, const int2* __restrict__ points, int n_points, int br,
+                                                      const uint8_t* __restrict__ stamp, FillRec fill, uint32_t* __restrict__ out) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int y = y0 + r, w = 2 * br + 1;
+  int o = px_off[r];
+  for (int k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+    const int2 sp = spans[k];
+    for (int i0 = 0; i0 < sp.y; i0 += 32) {
+      const int x = sp.x + i0 + lane;
+      const bool in = i0 + lane < sp.y;
+      uint32_t al = 0u;
+      for (int q = 0; q < n_points; q++) {
+        const int2 p = points[q];
+        const int ddx = x - p.x, ddy = y - p.y;
+        if (ddy < -br || ddy > br) continue;   // (uniform over the warp)
+        if (in && ddx >= -br && ddx <= br) al = alpha_over(al, stamp[(ddy + br) * w + (ddx + br)]);
+      }
+      if (in) out[o + i0 + lane] = px_dissolve(fill_lookup(fill, x, y), (int)al);
+    }
+    o += sp.y;
+  }
+}
 // Bounding box of the set bits of a bit-frame's rows [0, h): bb = {x0, y0, x1, y1} by atomic min / max (start from
 // {INT_MAX, INT_MAX, INT_MIN, INT_MIN}); y counts from `ybase`.
 __global__ void k_bits_bbox(const uint32_t* __restrict__ bits, int h, int nw, int ybase, int* __restrict__ bb) {

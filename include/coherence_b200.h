@@ -328,6 +328,21 @@ int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_o
 int64_t coh_host_edgelist_of_subpath(const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap);
 /* Brush.points_of_brushstroke for one subpath, rounded as in brush.ml:172 (polygon.ml:143-218):
  * returns the number of stamp centres and writes min(n, cap) of them as int32 x,y in list order. */
+/* ---- brush strokes outside a scene (brush.mli:20-27) ----
+ * `brush`: a BRUSH object record (brush_radius, brush_opacity, winding = COH_BRUSH_*, fill); points: the stroke's rounded
+ * stamp points (Brush.points_of_brushstroke, brush.ml:126-130, 172; coh_host_brush_points), x, y pairs.
+ * coh_brush_shape   Brush.shape_of_brushstroke (brush.ml:135-173): the boxes around the stamp points (the minshape is null).
+ * coh_brush_sprite  Brush.sprite_of_brushstroke stroke fill shape (brush.ml:176-222): RGBA8 of every pixel of `shape` in span
+ *                   order.  A dummy brush gives white (the reference returns the white sprite of the stroke's WHOLE shape
+ *                   whatever shape it is asked for: pass coh_brush_shape's result).
+ * coh_brush_smear   Brush.smear sprite stroke (brush.ml:286-331): the sprite (shape + RGBA8 in span order; shape 0 = NullSprite)
+ *                   fleshed out to the stroke's shape and smeared along smear_points (Brush.find_smear_directions' integer
+ *                   points, coh_host_smear_points); the result is a sprite on *out_shape = shape ∪ coh_brush_shape. */
+int coh_brush_shape(coh_ctx* ctx, const coh_object* brush, const int32_t* points, int32_t n_points, coh_shape_t* shape);
+int coh_brush_sprite(coh_ctx* ctx, const coh_object* brush, const int32_t* points, int32_t n_points, coh_shape_t shape,
+                     uint32_t* rgba_out, int64_t cap, int64_t* n_out);
+int coh_brush_smear(coh_ctx* ctx, coh_shape_t shape, const uint32_t* rgba_in, const coh_object* brush, const int32_t* points, int32_t n_points,
+                    const int32_t* smear_points, int32_t n_smear, coh_shape_t* out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out);
 /* N2 — the step in front of the raster path on the device: Polygon.edgelist_of_path (polygon.ml:83-127, 262-287;
  * coord.ml:47) for the segments of a path (records of 9 doubles: kind 0 straight / 1 bezier, then up to 4 points, already
  * transformed to device space): de Casteljau subdivision to curve_accuracy, sub-bin edges in the reference's order.

@@ -36,6 +36,11 @@ external sync : ctx -> unit = "coh_ml_sync"
 external rgba8_of_colour : Colour.colour -> int32 = "coh_ml_rgba8_of_colour"
 external colour_of_rgba8 : int32 -> Colour.colour = "coh_ml_colour_of_rgba8"
 external shapeminshape : ctx -> i32 -> int -> shape_h * shape_h = "coh_ml_shapeminshape"
+(* Brush.shape_of_brushstroke / sprite_of_brushstroke / smear outside a scene (brush.mli:20-27): the brush as a packed BRUSH
+   record, the stroke as its rounded stamp points *)
+external brush_shape : ctx -> u8 -> i32 -> shape_h = "coh_ml_brush_shape"
+external brush_sprite : ctx -> u8 -> i32 -> shape_h -> i32 -> int = "coh_ml_brush_sprite"
+external brush_smear : ctx -> shape_h -> i32 -> u8 -> i32 -> i32 -> i32 -> shape_h * int = "coh_ml_brush_smear_bc" "coh_ml_brush_smear"
 (* N2: Polygon.edgelist_of_path / shapeminshape_polygon with the flattening on the device (segments as 9 floats each) *)
 external edgelist_of_path : ctx -> f64 -> i32 -> int = "coh_ml_edgelist_of_path"
 external shapeminshape_of_path : ctx -> f64 -> int -> shape_h * shape_h = "coh_ml_shapeminshape_of_path"

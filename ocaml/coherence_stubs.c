@@ -93,6 +93,35 @@ CAMLprim value coh_ml_shapeminshape(value ctx, value edges, value winding) {
   check(CTX(ctx), coh_shapeminshape_of_edgelist(CTX(ctx), (const int32_t*)Caml_ba_data_val(edges), (int32_t)(BA_LEN(edges) / 4), Int_val(winding), &s, &m));
   CAMLreturn(pair_of_handles(s, m));
 }
+/* ---- brush strokes outside a scene (brush.mli:20-27); brush = one packed BRUSH coh_object record (coh_ml_pack_object) ---- */
+CAMLprim value coh_ml_brush_shape(value ctx, value brush, value points) {
+  CAMLparam3(ctx, brush, points);
+  coh_shape_t s = 0;
+  check(CTX(ctx), coh_brush_shape(CTX(ctx), (const coh_object*)Caml_ba_data_val(brush), (const int32_t*)Caml_ba_data_val(points), (int32_t)(BA_LEN(points) / 2), &s));
+  CAMLreturn(caml_copy_int64((int64_t)s));
+}
+CAMLprim value coh_ml_brush_sprite(value ctx, value brush, value points, value shape, value out) {
+  CAMLparam5(ctx, brush, points, shape, out);
+  int64_t n = 0;
+  check(CTX(ctx), coh_brush_sprite(CTX(ctx), (const coh_object*)Caml_ba_data_val(brush), (const int32_t*)Caml_ba_data_val(points), (int32_t)(BA_LEN(points) / 2), SHAPE(shape),
+        (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  CAMLreturn(Val_long((long)n));
+}
+/* returns (handle of the result's shape, number of pixels written to out) */
+CAMLprim value coh_ml_brush_smear(value ctx, value shape, value rgba, value brush, value points, value smear_points, value out) {
+  CAMLparam5(ctx, shape, rgba, brush, points);
+  CAMLxparam2(smear_points, out);
+  CAMLlocal2(pair, h);
+  coh_shape_t so = 0; int64_t n = 0;
+  check(CTX(ctx), coh_brush_smear(CTX(ctx), SHAPE(shape), (const uint32_t*)Caml_ba_data_val(rgba), (const coh_object*)Caml_ba_data_val(brush),
+        (const int32_t*)Caml_ba_data_val(points), (int32_t)(BA_LEN(points) / 2), (const int32_t*)Caml_ba_data_val(smear_points), (int32_t)(BA_LEN(smear_points) / 2),
+        &so, (uint32_t*)Caml_ba_data_val(out), BA_LEN(out), &n));
+  h = caml_copy_int64((int64_t)so);
+  pair = caml_alloc_tuple(2);
+  Store_field(pair, 0, h); Store_field(pair, 1, Val_long((long)n));
+  CAMLreturn(pair);
+}
+CAMLprim value coh_ml_brush_smear_bc(value* argv, int argn) { (void)argn; return coh_ml_brush_smear(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]); }
 /* N2: Polygon.edgelist_of_path on the device; segs : float64 Array1 of 9*n, out : int32 Array1 of 4*cap; returns the edge count */
 CAMLprim value coh_ml_edgelist_of_path(value ctx, value segs, value out) {
   CAMLparam3(ctx, segs, out);

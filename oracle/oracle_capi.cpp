@@ -351,6 +351,36 @@ static int64_t sprite_out(const Sprite& s, uint32_t* out, int64_t cap) {
   for (auto& row : s.rows) for (colour c : row.px) { if (n >= cap) throw std::runtime_error("sprite buffer too small"); out[n++] = rgba8_of_colour(c); }
   return n;
 }
+// Brush strokes outside a scene (brush.mli:20-27).  brush: a BRUSH object record; points: rounded stamp points.
+static BrushStroke stroke_from(const coh_object* b, const int32_t* points, int n) {
+  BrushStroke st; st.opacity = b->brush_opacity; st.radius = b->brush_radius;
+  if (b->winding == COH_BRUSH_DUMMY) { st.dummy = true; st.rx = (int)b->brush_radius; }
+  for (int k = 0; k < n; k++) st.points.push_back({points[2 * k], points[2 * k + 1]});
+  return st;
+}
+int orc_brush_shape(const coh_object* brush, const int32_t* points, int n, int32_t** out, int64_t* nout) {
+  ORC_TRY
+  auto f = shape_to_flat(shape_of_brushstroke(stroke_from(brush, points, n)));
+  *out = dup_ints(f); *nout = (int64_t)f.size();
+  ORC_CATCH
+}
+int orc_brush_sprite(const coh_object* brush, const int32_t* points, int n, const int32_t* shape, int64_t nshape, uint32_t* out, int64_t cap, int64_t* nout) {
+  ORC_TRY
+  *nout = sprite_out(sprite_of_brushstroke(stroke_from(brush, points, n), fill_from(*brush), shape_from_flat(shape, (int)nshape)), out, cap);
+  ORC_CATCH
+}
+int orc_brush_smear(const int32_t* shape, int64_t nshape, const uint32_t* rgba, const coh_object* brush, const int32_t* points, int n,
+                    const int32_t* smear_points, int n_smear, int32_t** out_shape, int64_t* n_out_shape, uint32_t* rgba_out, int64_t cap, int64_t* n_out) {
+  ORC_TRY
+  std::vector<std::pair<int, int>> sp;
+  for (int k = 0; k < n_smear; k++) sp.push_back({smear_points[2 * k], smear_points[2 * k + 1]});
+  Sprite in = nshape ? sprite_from(shape, nshape, rgba) : Sprite();
+  Sprite res = smear(in, stroke_from(brush, points, n), sp);
+  auto f = shape_to_flat(shape_of_sprite(res));
+  *out_shape = dup_ints(f); *n_out_shape = (int64_t)f.size();
+  *n_out = sprite_out(res, rgba_out, cap);
+  ORC_CATCH
+}
 // Sprite.portion spr shp (sprite.ml:642-721)
 int orc_sprite_portion(const int32_t* shape, int64_t nshape, const uint32_t* rgba, const int32_t* sub, int64_t nsub, uint32_t* out, int64_t cap, int64_t* nout) {
   ORC_TRY

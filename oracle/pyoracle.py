@@ -190,6 +190,37 @@ def convolve_sprite(kernel, r, shape_flat, rgba):
     return _take(ps, ns.value), out[: n.value]
 
 
+def brush_shape(brush_obj, points):
+    p = _i32(points).reshape(-1, 2)
+    ps, ns = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_brush_shape(C.byref(brush_obj), _ptr(p), len(p), C.byref(ps), C.byref(ns)))
+    return _take(ps, ns.value)
+
+
+def brush_sprite(brush_obj, points, shape_flat):
+    p = _i32(points).reshape(-1, 2)
+    s = _i32(shape_flat)
+    cap = shape_card(s)
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_int64()
+    _chk(lib().orc_brush_sprite(C.byref(brush_obj), _ptr(p), len(p), _ptr(s), C.c_int64(len(s)), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return out[: n.value]
+
+
+def brush_smear(shape_flat, rgba, brush_obj, points, smear_pts):
+    """Brush.smear: returns (flat shape of the result, rgba per pixel)."""
+    s = _i32(shape_flat)
+    src = np.ascontiguousarray(rgba, dtype=np.uint32)
+    p = _i32(points).reshape(-1, 2)
+    q = _i32(smear_pts).reshape(-1, 2)
+    cap = shape_card(shape_op("union", s, brush_shape(brush_obj, p))) if len(s) else shape_card(brush_shape(brush_obj, p))
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    ps, ns, n = C.POINTER(C.c_int32)(), C.c_int64(), C.c_int64()
+    _chk(lib().orc_brush_smear(_ptr(s), C.c_int64(len(s)), _ptr(src, C.c_uint32), C.byref(brush_obj), _ptr(p), len(p), _ptr(q), len(q), C.byref(ps), C.byref(ns),
+                               _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
+    return _take(ps, ns.value), out[: n.value]
+
+
 def flatten_bezier(p8, eps=0.2):
     a = np.ascontiguousarray(p8, dtype=np.float64).reshape(8)
     p, n = C.POINTER(C.c_double)(), C.c_int64()

@@ -213,6 +213,23 @@ int main(int argc, char** argv) {
   int32_t he[8]; CHECK(coh_host_edgelist_of_subpath(segs, 1, he, 2) == 1 && he[0] == sub_of_float(10.0));
   int32_t hp[64]; CHECK(coh_host_brush_points(segs, 1, 4.0, hp, 32) > 0);
   int32_t hs[256]; CHECK(coh_host_smear_points(segs, 1, hs, 128) > 30 && hs[0] == 10 && hs[1] == 10);
+  /* brush strokes outside a scene */
+  {
+    coh_object bo; memset(&bo, 0, sizeof bo);
+    bo.kind = COH_OBJ_BRUSH; bo.brush_radius = 4.0; bo.brush_opacity = 0.9; bo.pretrans = -1; bo.id = -1; bo.colour0 = 0xFF2080F0u;
+    int32_t np = (int32_t)coh_host_brush_points(segs, 1, 4.0, hp, 32); if (np > 32) np = 32;   /* (the count is returned whatever cap is) */
+    coh_shape_t bsh = 0, so = 0; int64_t bc = 0, bn = 0;
+    OK(coh_brush_shape(C, &bo, hp, np, &bsh)); OK(coh_shape_card(C, bsh, &bc)); CHECK(bc > 100);
+    uint32_t* bpx = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)bc * 2 + 16);
+    OK(coh_brush_sprite(C, &bo, hp, np, bsh, bpx, bc, &bn)); CHECK(bn == bc);
+    ERR(coh_brush_sprite(C, &bo, hp, np, bsh, bpx, 1, &bn), "buffer too small");
+    int32_t ns = (int32_t)coh_host_smear_points(segs, 1, hs, 128); if (ns > 128) ns = 128;
+    OK(coh_brush_smear(C, bsh, bpx, &bo, hp, np, hs, ns, &so, bpx, bc * 2, &bn)); CHECK(so != 0 && bn == bc);
+    bo.winding = COH_BRUSH_DUMMY;
+    ERR(coh_brush_smear(C, bsh, bpx, &bo, hp, np, hs, ns, &so, bpx, bc * 2, &bn), "dummy brush");
+    bo.winding = 7; ERR(coh_brush_shape(C, &bo, hp, np, &bsh), "brush kind");
+    free(bpx); OK(coh_shape_free(C, bsh)); OK(coh_shape_free(C, so));
+  }
   /* N2: the same flattening on the device */
   {
     double tri[27] = {0, 10.0, 10.0, 90.0, 20.0, 0, 0, 0, 0,   1, 90.0, 20.0, 120.0, 60.0, 40.0, 90.0, 30.0, 70.0,   0, 30.0, 70.0, 10.0, 10.0, 0, 0, 0, 0};

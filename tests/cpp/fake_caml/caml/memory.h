@@ -6,6 +6,7 @@
 #define CAMLparam4(a,b,c,d)
 #define CAMLparam5(a,b,c,d,e)
 #define CAMLxparam1(a)
+#define CAMLxparam2(a,b)
 #define CAMLlocal1(a) value a = 0
 #define CAMLlocal2(a,b) value a = 0, b = 0
 #define CAMLlocal3(a,b,c) value a = 0, b = 0, c = 0

@@ -281,6 +281,65 @@ def test_path_flattening_on_device(ctx, oracle):
     assert np.array_equal(ctx.edgelist_of_path(flat), abi.host_edgelist_of_subpath(flat))
 
 
+def _brush_obj(opacity, radius, fill, kind=0):
+    o = abi.CohObject()
+    o.kind = abi.COH_OBJ_BRUSH
+    o.winding = kind
+    o.brush_opacity, o.brush_radius = float(opacity), float(radius)
+    o.pretrans = -1
+    o.id = -1
+    fill.apply(o)
+    return o
+
+
+def test_brush_entry_points(ctx, oracle):
+    """brush.mli:20-27 outside a scene: Brush.shape_of_brushstroke, sprite_of_brushstroke (plain and gradient fills, in
+    the stroke's own shape and in another one) and Brush.smear of a sprite, against the oracle."""
+    segs = [("C", (40.0, 150.0), (90.0, 30.0), (150.0, 170.0), (200.0, 50.0)), ("L", (200.0, 50.0), (230.0, 120.0))]
+    for opacity, radius in ((0.8, 6.0), (1.0, 3.5)):
+        pts = abi.host_brush_points(segs, radius)
+        for fill in (S.Fill.plain(S.dissolve(S.rgba8(20, 200, 120), 220)), S.Fill.gradient((30.0, 30.0), (220.0, 160.0), True, True, S.rgba8(255, 0, 0), S.rgba8(0, 0, 255))):
+            bo = _brush_obj(opacity, radius, fill)
+            hs = ctx.brush_shape(bo, pts)
+            ref_s = oracle.brush_shape(bo, pts)
+            assert np.array_equal(ctx.shape_export(hs), ref_s)
+            got = ctx.brush_sprite(bo, pts, hs)
+            assert np.array_equal(got, oracle.brush_sprite(bo, pts, ref_s))
+            box = ctx.shape_box(60, 40, 120, 90)
+            part = ctx.shape_intersection(hs, box)
+            assert np.array_equal(ctx.brush_sprite(bo, pts, part), oracle.brush_sprite(bo, pts, ctx.shape_export(part)))
+            for h in (hs, box, part):
+                ctx.shape_free(h)
+    # dummy brush: white all over its shape
+    bo = _brush_obj(1.0, 6.0, S.Fill.plain(S.rgba8(1, 2, 3)), kind=abi.COH_BRUSH_DUMMY)
+    pts = abi.host_brush_points(segs, 6.0)
+    hs = ctx.brush_shape(bo, pts)
+    assert np.array_equal(ctx.shape_export(hs), oracle.brush_shape(bo, pts))
+    got = ctx.brush_sprite(bo, pts, hs)
+    assert np.array_equal(got, oracle.brush_sprite(bo, pts, ctx.shape_export(hs))) and (got == 0xFFFFFFFF).all()
+    ctx.shape_free(hs)
+    # Brush.smear of a sprite: a gradient-filled polygon's sprite, smeared along the stroke
+    sm = abi.host_smear_points(segs)
+    poly = abi.host_edgelist_of_subpath(S.polygon_segments([(30.3, 30.2), (210.5, 43.9), (188.1, 150.7), (28.8, 134.4)]))
+    ps, pm = ctx.shapeminshape_of_edgelist(poly, abi.COH_NONZERO)
+    fo = _brush_obj(1.0, 1.0, S.Fill.gradient((30.0, 30.0), (220.0, 160.0), True, True, S.rgba8(255, 200, 0), S.dissolve(S.rgba8(0, 0, 255), 150)))
+    spr = ctx.polygon_sprite(fo, poly, abi.COH_NONZERO, ps)
+    for opacity, radius in ((1.0, 7.0), (0.6, 3.0)):
+        bo = _brush_obj(opacity, radius, S.Fill.plain(S.WHITE))
+        pts = abi.host_brush_points(segs, radius)
+        ho, got = ctx.brush_smear(ps, spr, bo, pts, sm)
+        ref_shape, ref = oracle.brush_smear(ctx.shape_export(ps), spr, bo, pts, sm)
+        assert np.array_equal(ctx.shape_export(ho), ref_shape)
+        assert np.array_equal(got, ref)
+        ctx.shape_free(ho)
+    # NullSprite: only the stroke's shape, clear
+    ho, got = ctx.brush_smear(0, np.zeros(0, np.uint32), bo, pts, sm)
+    ref_shape, ref = oracle.brush_smear(np.zeros(0, np.int32), np.zeros(0, np.uint32), bo, pts, sm)
+    assert np.array_equal(ctx.shape_export(ho), ref_shape) and np.array_equal(got, ref) and not got.any()
+    for h in (ho, ps, pm):
+        ctx.shape_free(h)
+
+
 def test_dummy_brush(ctx, oracle):
     """Brushstroke with a Dummy brush (brush.ml:14-22, 70-73, 178-181): the whole shape of the stroke — the boxes around
     its stamp points — in opaque white, whatever fill it was given; minshape null."""
