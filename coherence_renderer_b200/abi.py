@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("COH_LIB_PATH", os.path.join(_HERE, "libcoherence_b200
 COH_OBJ_PATH, COH_OBJ_PRIMITIVE, COH_OBJ_GROUP_BEGIN, COH_OBJ_GROUP_END, COH_OBJ_BRUSH, COH_OBJ_CPG = 0, 1, 2, 3, 4, 5
 COH_OBJ_FILTER = 6
 COH_BRUSH_GAUSSIAN, COH_BRUSH_DUMMY = 0, 1
+COH_GEOM_PATH, COH_GEOM_NEXT = 0, 1
 COH_FILTER_HOLE, COH_FILTER_MONOCHROME, COH_FILTER_BLUR, COH_FILTER_SCENE, COH_FILTER_MINUS, COH_FILTER_SMEAR, COH_FILTER_READING_SCENE = 1, 2, 3, 4, 5, 6, 100
 COH_CPG_UNION, COH_CPG_INTERSECTION, COH_CPG_SUBTRACTION, COH_CPG_EXCLUSIVEOR = 0, 1, 2, 3
 COH_NONZERO, COH_EVENODD = 0, 1

@@ -94,9 +94,10 @@ struct DevScene {
   std::vector<int> real_depth;   // per record: enclosing groups in the scene as given (ObjRec.depth leaves out groups dissolved into their parent)
   // Filters (render.ml:37-48): top-level members of the scene list that are not leaves.  `pos` = number of
   // ordinary scene leaves in front of the filter; the leaves are ordered [scene | reading scenes | background].
-  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total;
+  struct FilterRec { int pos, kind, kernel_kind, r, first, count, winding, aa_winding; uint32_t colour; int read0, read1; int bx0, by0, bx1, by1; int abi; int taps_off, taps_total;
                      int dx, dy;   // alias translation in whole pixels (render.ml:259-271); bx0 .. by1 include it
                      int head_abi, head_l1;   // MINUS: the object that follows the filter, the leaf index where the list continues after it
+                     DevScene* geom_sub; int gcx0, gcy0, gcnw, gch;   // COH_GEOM_NEXT: the geometry object as a scene of its own, aliased into a canvas at (gcx0, gcy0) of gcnw words x gch rows
                      int first2, count2, stamp_off, brush_r;   // SMEAR: smear points (in the points array), the brush's stamp (alpha bytes), its radius
                      // kept with the scene once computed (the reference finds a filter geometry's shape in its cache by id,
                      // render.ml:472-474): shape / coverage bit-rows and the antialiased opacity of every shape pixel, for the

@@ -186,6 +186,28 @@ static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape
 // shapeonly_of_basicshape of a filter object = the shape of its geometry (render.ml:472-474), moved with its alias
 static int filter_shapes(coh_ctx* ctx, DevScene* s, const DevScene::FilterRec& F, coh_shape_t* shape, coh_shape_t* minshape, const char* who) {
   coh_shape_t fs = 0, fm = 0;
+  if (F.geom_sub) {   // the geometry is an object of its own, kept as a scene in canvas coordinates; the minshape is not kept
+    *shape = 0; *minshape = 0;
+    if (subscene_shape(ctx, F.geom_sub, &fs)) return 1;
+    int rc = coh_shape_translate(ctx, fs, F.gcx0 + F.dx, F.gcy0 + F.dy, shape);
+    coh_shape_free(ctx, fs);
+    return rc;
+  }
+  if (F.kind == COH_FILTER_SMEAR) {   // the stroke's dummy brush: boxes around its stamp points
+    *shape = 0; *minshape = 0;
+    const int x0 = F.bx0 - F.dx, y0 = F.by0 - F.dy, x1 = F.bx1 - F.dx, y1 = F.by1 - F.dy;
+    const int wx0 = floordiv(x0, 32) * 32, nw = (x1 - wx0) / 32 + 1, n_rows = y1 - y0 + 1;
+    uint32_t* bits = nullptr;
+    CK(DMALLOC(&bits, 4 * (size_t)nw * n_rows));
+    CK(cudaMemsetAsync(bits, 0, 4 * (size_t)nw * n_rows, ctx->stream));
+    const int side = 2 * F.brush_r + 1;
+    k_stamp_boxes_to_bits<<<cdiv(F.count * side, 256), 256, 0, ctx->stream>>>(s->points + F.first, F.count, F.brush_r, y0, n_rows, wx0, nw, bits); LAUNCHED();
+    int rc = shape_from_bits(ctx, bits, y0, n_rows, wx0, nw, &fs);
+    DFREE(bits);
+    if (!rc) rc = coh_shape_translate(ctx, fs, F.dx, F.dy, shape);
+    coh_shape_free(ctx, fs);
+    return rc;
+  }
   if (shapes_from_device_edges(ctx, s->edges + F.first, F.count, F.winding, F.bx0 - F.dx, F.by0 - F.dy, F.bx1 - F.dx, F.by1 - F.dy, &fs, &fm, who)) return 1;
   if (!F.dx && !F.dy) { *shape = fs; *minshape = fm; return 0; }
   int rc = coh_shape_translate(ctx, fs, F.dx, F.dy, shape) || coh_shape_translate(ctx, fm, F.dx, F.dy, minshape);
@@ -386,6 +408,63 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
 // Convolved (kernel, Group members): shape = bloat r r (union of the members' shapes), minshape null (render.ml:536-555);
 // sprite = convolve_sprite kernel (the group's sprite) (render.ml:1023-1052).  The members' scene is rendered once
 // over the whole twice-bloated box into a canvas whose origin is moved to the frame origin by aliasing the members.
+// Union of the shapes of a sub-scene's direct members (filters count with their geometry's shape, render.ml:472-474), with the
+// cache switched off as the reference does while it computes a group's shape (render.ml:476-496)
+static int subscene_shape(coh_ctx* ctx, DevScene* ss, coh_shape_t* out) {
+  const bool saved = ctx->usecache; ctx->usecache = false;
+  coh_shape_t gs = 0; int rc = 0;
+  for (int k = 1; k < (int)ss->real_depth.size() && !rc; k++) {
+    if (ss->real_depth[k] != 1) continue;   // direct members
+    coh_shape_t ms = 0, mm = 0, un = 0;
+    rc = object_shape_rec(ctx, ss, k, &ms, &mm) || coh_shape_union(ctx, gs, ms, &un);
+    coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
+    gs = un;
+  }
+  for (const DevScene::FilterRec& F : ss->filters) {
+    if (rc) break;
+    coh_shape_t ms = 0, mm = 0, un = 0;
+    rc = filter_shapes(ctx, ss, F, &ms, &mm, "coh_scene_create (group)") || coh_shape_union(ctx, gs, ms, &un);
+    coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
+    gs = un;
+  }
+  ctx->usecache = saved;
+  *out = gs;
+  return rc;
+}
+// Alias the direct members of a sub-scene (objs: the records it was created from) by (dx, dy)
+static int subscene_translate(coh_ctx* ctx, DevScene* ss, const coh_object* objs, int n, int dx, int dy) {
+  int depth = 0;
+  for (int t = 0; t < n; t++) {
+    const int kind = objs[t].kind;
+    if (kind == COH_OBJ_GROUP_END) { depth--; continue; }
+    if (depth == 0 && ((t < (int)ss->rec_of_abi.size() && ss->rec_of_abi[t] >= 0) || filter_of_abi(ss, t)))
+      if (coh_scene_translate_object(ctx, (coh_scene_t)ss, t, dx, dy)) return 1;
+    if (kind == COH_OBJ_GROUP_BEGIN && !objs[t].convolve) depth++;
+  }
+  return 0;
+}
+// Render a sub-scene, whose frame is a canvas of nw words x h rows, into `A` (cleared by the caller)
+static int subscene_render(coh_ctx* ctx, DevScene* ss, int nw, int h, uint32_t* A) {
+  const int w = nw * 32;
+  const Frame saved = ctx->fr;
+  ctx->fr.W = w; ctx->fr.H = h; ctx->fr.band_y0 = 0; ctx->fr.band_y1 = h; ctx->fr.tiles_x = nw; ctx->fr.cells_y = cdiv(h, CELL_H); ctx->fr.ctx0 = 0; ctx->fr.cntx = nw;
+  int rc;
+  if (ss->filters.empty()) {
+    PassArgs pa{0, ss->n_leaves, 0, 0, w, h, nullptr, nullptr, A, true, false};
+    rc = render_pass(ctx, ss, pa);
+  } else {
+    // filter passes work on the context's frame: the canvas stands in for it
+    uint32_t* saved_fb = ctx->fb; uint32_t* saved_u = ctx->u_out; const int saved_peers = ctx->n_peers;
+    uint32_t* Uc = nullptr;
+    if (DMALLOC(&Uc, 4 * (size_t)nw * h) != cudaSuccess) { ctx->fr = saved; FAIL("sub-scene render: out of memory"); }
+    ctx->fb = A; ctx->u_out = Uc; ctx->n_peers = 0;
+    rc = render_filtered(ctx, ss, nullptr, 0, 0, w, h);
+    ctx->fb = saved_fb; ctx->u_out = saved_u; ctx->n_peers = saved_peers;
+    DFREE(Uc);
+  }
+  ctx->fr = saved;
+  return rc;
+}
 static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, ConvGroup& cg) {
   DevScene* ss = cg.sub;
   const int nw = o.cv_nw, h = o.cv_h, w = nw * 32;
@@ -393,26 +472,10 @@ static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, C
   uint32_t *S = nullptr, *A = nullptr, *X = nullptr; int* d_taps = nullptr;
   CK(DMALLOC(&S, 4 * nwords)); CK(DMALLOC(&A, 4 * npx)); CK(DMALLOC(&X, 4 * npx));
   CK(cudaMemsetAsync(S, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(A, 0, 4 * npx, ctx->stream));
-  // (1) the group's shape, with the cache switched off as the reference does while it computes it
+  // (1) the group's shape
   {
-    const bool saved = ctx->usecache; ctx->usecache = false;
-    coh_shape_t gs = 0; int rc = 0;
-    for (int k = 1; k < (int)ss->real_depth.size() && !rc; k++) {
-      if (ss->real_depth[k] != 1) continue;   // direct members of the group
-      coh_shape_t ms = 0, mm = 0, un = 0;
-      rc = object_shape_rec(ctx, ss, k, &ms, &mm) || coh_shape_union(ctx, gs, ms, &un);
-      coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
-      gs = un;
-    }
-    for (const DevScene::FilterRec& F : ss->filters) {   // a filter member's shape is its geometry's (render.ml:472-474)
-      if (rc) break;
-      coh_shape_t ms = 0, mm = 0, un = 0;
-      rc = filter_shapes(ctx, ss, F, &ms, &mm, "coh_scene_create (group)") || coh_shape_union(ctx, gs, ms, &un);
-      coh_shape_free(ctx, gs); coh_shape_free(ctx, ms); coh_shape_free(ctx, mm);
-      gs = un;
-    }
-    ctx->usecache = saved;
-    if (rc) return 1;
+    coh_shape_t gs = 0;
+    if (subscene_shape(ctx, ss, &gs)) return 1;
     if (gs) {
       const DevShape* G = (const DevShape*)gs;
       k_spans_to_bits<<<cdiv(h, 128), 128, 0, ctx->stream>>>(G->row_ptr, G->spans, G->y0, G->n_rows, o.cv_y0, h, o.cv_x0, nw, S); LAUNCHED();
@@ -424,34 +487,8 @@ static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, C
   else CK(cudaMemcpyAsync(convS, S, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemsetAsync(convS + nwords, 0, 4 * nwords, ctx->stream));
   // (2) the group's sprite: the members' scene rendered with the canvas as its frame
-  {
-    int depth = 0;
-    for (int t = 0; t < cg.n_members; t++) {
-      const int kind = cg.members[t].kind;
-      if (kind == COH_OBJ_GROUP_END) { depth--; continue; }
-      if (depth == 0 && ((t < (int)ss->rec_of_abi.size() && ss->rec_of_abi[t] >= 0) || filter_of_abi(ss, t)))
-        if (coh_scene_translate_object(ctx, (coh_scene_t)ss, t, -o.cv_x0, -o.cv_y0)) return 1;
-      if (kind == COH_OBJ_GROUP_BEGIN && !cg.members[t].convolve) depth++;
-    }
-    const Frame saved = ctx->fr;
-    ctx->fr.W = w; ctx->fr.H = h; ctx->fr.band_y0 = 0; ctx->fr.band_y1 = h; ctx->fr.tiles_x = nw; ctx->fr.cells_y = cdiv(h, CELL_H); ctx->fr.ctx0 = 0; ctx->fr.cntx = nw;
-    int rc;
-    if (ss->filters.empty()) {
-      PassArgs pa{0, ss->n_leaves, 0, 0, w, h, nullptr, nullptr, A, true, false};
-      rc = render_pass(ctx, ss, pa);
-    } else {
-      // filter passes work on the context's frame: the canvas stands in for it
-      uint32_t* saved_fb = ctx->fb; uint32_t* saved_u = ctx->u_out; const int saved_peers = ctx->n_peers;
-      uint32_t* Uc = nullptr;
-      CK(DMALLOC(&Uc, 4 * nwords));
-      ctx->fb = A; ctx->u_out = Uc; ctx->n_peers = 0;
-      rc = render_filtered(ctx, ss, nullptr, 0, 0, w, h);
-      ctx->fb = saved_fb; ctx->u_out = saved_u; ctx->n_peers = saved_peers;
-      DFREE(Uc);
-    }
-    ctx->fr = saved;
-    if (rc) return 1;
-  }
+  if (subscene_translate(ctx, ss, cg.members, cg.n_members, -o.cv_x0, -o.cv_y0)) return 1;
+  if (subscene_render(ctx, ss, nw, h, A)) return 1;
   if (cg.r == 0) {   // no kernel: the canvas is the sprite
     CK(cudaMemcpyAsync(s->conv_px + o.cv_px, A, 4 * npx, cudaMemcpyDeviceToDevice, ctx->stream));
     if (check_error_flag(ctx, "coh_scene_create (group holding filters)")) return 1;

@@ -361,6 +361,8 @@ static int render_frame_passes(coh_ctx* ctx, DevScene* s, PassArgs A) {
 struct PixBox { int x0, y0, x1, y1; };   // inclusive pixel box; empty when x1 < x0 or y1 < y0
 static int render_suffix(coh_ctx* ctx, DevScene* s, int l0, int f0, uint32_t* U, uint32_t* target, bool fresh, PixBox box, bool target_zeroed = false);
 static int object_shape_rec(coh_ctx* ctx, DevScene* s, int r, coh_shape_t* shape, coh_shape_t* minshape);
+static int subscene_shape(coh_ctx* ctx, DevScene* ss, coh_shape_t* out);
+static int subscene_render(coh_ctx* ctx, DevScene* ss, int nw, int h, uint32_t* A);
 // temporaries of one filter application: released on every way out
 struct StreamTemps {
   coh_ctx* ctx; std::vector<void*> v;
@@ -388,6 +390,26 @@ static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   const size_t nwords = (size_t)nw * h;
   CK(DMALLOC(&F.SG, 4 * nwords)); CK(DMALLOC(&F.CG, 4 * nwords)); CK(DMALLOC(&F.op, (size_t)nw * 32 * h));
   CK(cudaMemsetAsync(F.SG, 0, 4 * nwords, ctx->stream)); CK(cudaMemsetAsync(F.CG, 0, 4 * nwords, ctx->stream));
+  if (F.geom_sub) {
+    // COH_GEOM_NEXT: shape = the geometry object's (render.ml:472-474), matte = the alpha of its sprite (render.ml:1099)
+    // — the object rendered as a scene of its own into a canvas (its members were aliased into canvas coordinates)
+    DevScene* ss = F.geom_sub;
+    coh_shape_t gs = 0;
+    if (subscene_shape(ctx, ss, &gs)) return 1;
+    if (gs) {
+      const DevShape* G = (const DevShape*)gs;
+      k_spans_to_bits<<<cdiv(h, 128), 128, 0, ctx->stream>>>(G->row_ptr, G->spans, G->y0 + F.gcy0 + F.dy, G->n_rows, F.gy0, h, -(F.gcx0 + F.dx), nw, F.SG); LAUNCHED();
+      coh_shape_free(ctx, gs);
+    }
+    uint32_t* A = nullptr;
+    const size_t cpx = (size_t)F.gcnw * 32 * F.gch;
+    CK(DMALLOC(&A, 4 * cpx));
+    CK(cudaMemsetAsync(A, 0, 4 * cpx, ctx->stream));
+    if (subscene_render(ctx, ss, F.gcnw, F.gch, A)) return 1;
+    k_canvas_alpha<<<dim3(cdiv(nw * 32, 256), h), 256, 0, ctx->stream>>>(A, F.gcnw * 32, F.gch, F.gcx0 + F.dx, F.gcy0 + F.dy, F.gy0, h, nw * 32, F.op); LAUNCHED();
+    DFREE(A);
+    return 0;
+  }
   if (F.kind == COH_FILTER_SMEAR) {
     // geometry = the stroke's dummy brush (filters.ml:205-207): the boxes around its stamp points, opaque white all over
     const int side = 2 * F.brush_r + 1;
@@ -405,9 +427,10 @@ static int filter_geometry(coh_ctx* ctx, DevScene* s, DevScene::FilterRec& F) {
   // inside the rows / columns scanned here).
   uint32_t* Q = nullptr;
   CK(DMALLOC(&Q, 4 * nwords));
-  k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(F.SG, F.CG, F.SG, Q, h, nw, W); LAUNCHED();
+  if (F.aa_winding == F.winding) { k_matte_todo<<<dim3(cdiv(nw, 128), h), 128, 0, ctx->stream>>>(F.SG, F.CG, F.SG, Q, h, nw, W); LAUNCHED(); }
+  else CK(cudaMemcpyAsync(Q, F.SG, 4 * nwords, cudaMemcpyDeviceToDevice, ctx->stream));   // a stroked path's sprite (EvenOdd) is not its shape's interior (NonZero): sample everything
   CK(cudaMemsetAsync(F.op, 255, (size_t)nw * 32 * h, ctx->stream));
-  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.winding, Q, F.gy0 - F.dy, h, -F.dx, nw, ctx->d_aa, F.op, ctx->d_error); LAUNCHED();
+  k_aa_rows<<<dim3(cdiv(nw, 8), h), 256, 0, ctx->stream>>>(ed, F.count, F.aa_winding, Q, F.gy0 - F.dy, h, -F.dx, nw, ctx->d_aa, F.op, ctx->d_error); LAUNCHED();
   DFREE(Q);
   return 0;
 }

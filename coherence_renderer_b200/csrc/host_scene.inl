@@ -9,7 +9,7 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
   if (!s) return 0;
   DFREE(s->objs); DFREE(s->leaves); DFREE(s->leaf_box); DFREE(s->edges); DFREE(s->points); DFREE(s->stamps);
   DFREE(s->rowedge_ptr); DFREE(s->rowedge_idx); DFREE(s->brush_ranges); DFREE(s->conv_bits); DFREE(s->conv_px); DFREE(s->attr); DFREE(s->filter_taps);
-  for (DevScene::FilterRec& f : s->filters) { DFREE(f.SG); DFREE(f.CG); DFREE(f.op); }
+  for (DevScene::FilterRec& f : s->filters) { DFREE(f.SG); DFREE(f.CG); DFREE(f.op); if (f.geom_sub) coh_scene_free(ctx, (coh_scene_t)f.geom_sub); }
   for (auto& g : s->group_shape) free_shape(ctx, g.second.shape);
   free_binset(ctx, s->full.bins); free_binset(ctx, s->sp.bins);
   DFREE(s->sp.leaves); DFREE(s->sp.leaf_box);
@@ -45,6 +45,7 @@ static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out
 // render passes and the shape functions it needs)
 struct ConvGroup { int rec, kind, r; DevScene* sub; const coh_object* members; int n_members; };
 static int realize_convolved_group(coh_ctx* ctx, DevScene* s, const ObjRec& o, ConvGroup& cg);
+static int subscene_translate(coh_ctx* ctx, DevScene* ss, const coh_object* objs, int n, int dx, int dy);
 // Ownership of edges / brush points by objects, as ranges (see coh_scene_create).
 struct OwnerRanges {
   std::vector<int4> ranges;   // first, count, record, -
@@ -213,27 +214,87 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
       if (open.size() != 1 || cur_reading >= 0 || i >= n_objs - n_background) FAIL("scene: filter objects must be top-level members of the scene list");
       if (c.filter_kind < COH_FILTER_HOLE || c.filter_kind > COH_FILTER_SMEAR) FAIL("scene: bad filter kind");
       const bool smear = c.filter_kind == COH_FILTER_SMEAR;
-      if (smear) {   // geometry = the stroke's dummy: stamp points; smear points beside them (both in the points array)
+      bool geom_next = !smear && c.cpg_op == COH_GEOM_NEXT;
+      int gj = i;   // last record of the geometry object, when it follows the filter
+      const coh_object* own = &c;   // the record that describes a path geometry
+      if (geom_next && i + 1 < n_objs - n_background && objs[i + 1].kind == COH_OBJ_PATH && !objs[i + 1].convolve) {
+        // a plain path (or stroked-path outline) as the following object is the same thing as the filter's own path:
+        // Polygon.polygon_sprite samples EVERY pixel it is given (render.ml:1018, polygon.ml:729-746), which the path
+        // route reproduces and a scene render (interior pixels filled, not sampled) would not
+        own = &objs[i + 1]; geom_next = false; gj = i + 1;
+      }
+      if (geom_next) {
+        if (i + 1 >= n_objs - n_background || objs[i + 1].kind == COH_OBJ_GROUP_END || objs[i + 1].kind == COH_OBJ_FILTER ||
+            (objs[i + 1].kind == COH_OBJ_GROUP_BEGIN && objs[i + 1].filter_kind == COH_FILTER_READING_SCENE))
+          FAIL("scene: a filter with COH_GEOM_NEXT is followed by its geometry object");
+        gj = i + 1;
+        // sprite_of_cpg asked for ALL the pixels of the object combines the operands' SAMPLED alphas also inside their
+        // minshapes (render.ml:867-981), where a scene render takes the fill: wrap the CPG in a group to get the latter
+        if (objs[gj].kind == COH_OBJ_CPG) FAIL("scene: a CPG as a filter's geometry itself is not supported (make it the member of a group)");
+        if (objs[gj].kind == COH_OBJ_GROUP_BEGIN) {
+          int nest = 1;
+          for (gj = i + 2; gj < n_objs - n_background; gj++) {
+            if (objs[gj].kind == COH_OBJ_GROUP_BEGIN) nest++;
+            else if (objs[gj].kind == COH_OBJ_GROUP_END && --nest == 0) break;
+          }
+          if (gj >= n_objs - n_background) FAIL("scene: unterminated group");
+        }
+        for (int k = i + 1; k <= gj; k++) {
+          const coh_object& m = objs[k];
+          if (m.kind == COH_OBJ_FILTER) FAIL("scene: a filter's geometry may not hold filters");
+          if (m.kind != COH_OBJ_GROUP_BEGIN && m.kind != COH_OBJ_GROUP_END && m.kind != COH_OBJ_PRIMITIVE && m.fill_kind != COH_FILL_PLAIN)
+            FAIL("scene: filter geometry with a fancy fill is not supported yet");
+        }
+      } else if (smear) {   // geometry = the stroke's dummy: stamp points; smear points beside them (both in the points array)
         if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_points || c.first2 < 0 || c.count2 < 0 || (int64_t)c.first2 + c.count2 > n_points) FAIL("scene: point range out of bounds");
         if (!(c.brush_radius >= 0. && c.brush_radius <= 64.) || !(c.brush_opacity >= 0. && c.brush_opacity <= 1.)) FAIL("scene: brush radius/opacity out of range (a smear brush has a radius of at most 64)");
       } else {
-        if (c.first < 0 || c.count < 0 || (int64_t)c.first + c.count > n_edges) FAIL("scene: edge range out of bounds");
-        if (c.winding != COH_NONZERO && c.winding != COH_EVENODD) FAIL("scene: bad winding rule");
-        if (c.fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
+        if (own->first < 0 || own->count < 0 || (int64_t)own->first + own->count > n_edges) FAIL("scene: edge range out of bounds");
+        if (own->winding != COH_NONZERO && own->winding != COH_EVENODD) FAIL("scene: bad winding rule");
+        if (own->sprite_winding < 0 || own->sprite_winding > 2) FAIL("scene: bad sprite winding rule");
+        if (own->fill_kind != COH_FILL_PLAIN) FAIL("scene: filter geometry with a fancy fill is not supported yet");
       }
       DevScene::FilterRec f; memset(&f, 0, sizeof f);
-      f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = c.first; f.count = c.count; f.winding = c.winding; f.colour = c.colour0;
+      f.abi = i; f.pos = (int)leaves.size(); f.kind = c.filter_kind; f.first = own->first; f.count = own->count; f.winding = own->winding; f.colour = own->colour0;
+      f.aa_winding = own->sprite_winding ? own->sprite_winding - 1 : own->winding;   // a stroked path takes its sprite with EvenOdd (render.ml:1018)
       if (c.filter_kind == COH_FILTER_BLUR) {
         f.kernel_kind = c.filter_kernel & 255; f.r = c.filter_kernel >> 8;
         if ((f.kernel_kind != COH_CONV_UNIT && f.kernel_kind != COH_CONV_GAUSSIAN) || f.r <= 0 || f.r > 64) FAIL("Convolve.mkunit / mkxy: bad kernel");
       }
       if (c.filter_kind == COH_FILTER_MINUS) {   // filters.ml:295: hd scene
-        f.head_abi = i + 1;
-        if (i + 1 >= n_objs - n_background || objs[i + 1].kind == COH_OBJ_GROUP_END || objs[i + 1].kind == COH_OBJ_FILTER ||
-            (objs[i + 1].kind == COH_OBJ_GROUP_BEGIN && objs[i + 1].filter_kind == COH_FILTER_READING_SCENE))
+        f.head_abi = gj + 1;
+        if (gj + 1 >= n_objs - n_background || objs[gj + 1].kind == COH_OBJ_GROUP_END || objs[gj + 1].kind == COH_OBJ_FILTER ||
+            (objs[gj + 1].kind == COH_OBJ_GROUP_BEGIN && objs[gj + 1].filter_kind == COH_FILTER_READING_SCENE))
           FAIL("Filters.minus: no object below the filter (hd)");
       }
-      if (c.count == 0) continue;  // NullShape geometry: the filter touches nothing
+      if (geom_next) {
+        // the geometry object as a scene of its own: its shape is the filter's, the alpha of its sprite the matte
+        coh_scene_t sub = 0;
+        if (coh_scene_create(ctx, objs + i + 1, gj - i, 0, edges, n_edges, points, n_points, &sub)) return 1;
+        DevScene* ss = (DevScene*)sub;
+        int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+        for (int li : ss->h_leaves) { const ObjRec& m = ss->h_objs[li]; x0 = std::min(x0, m.bx0); y0 = std::min(y0, m.by0); x1 = std::max(x1, m.bx1); y1 = std::max(y1, m.by1); }
+        const int skip = gj;
+        if (x0 > x1) { coh_scene_free(ctx, sub); i = skip; continue; }   // NullShape geometry
+        f.bx0 = x0; f.by0 = y0; f.bx1 = x1; f.by1 = y1;
+        f.gcx0 = floordiv(x0, 32) * 32; f.gcy0 = y0; f.gcnw = (x1 - f.gcx0) / 32 + 1; f.gch = y1 - y0 + 1;
+        if (f.gch > 65535 || f.gcnw > 32767) { coh_scene_free(ctx, sub); FAIL("scene: filter geometry too large"); }
+        if (subscene_translate(ctx, ss, objs + i + 1, gj - i, -f.gcx0, -f.gcy0)) { coh_scene_free(ctx, sub); return 1; }   // canvas coordinates from here on
+        if (ss->n_leaves == 1 && ss->h_objs[ss->h_leaves[0]].kind == K_CONV) {
+          // Convolved (k, g) as the geometry itself: sprite_of_basicshape convolves everywhere (render.ml:1023-1052), it
+          // does not fill the eroded minshape like spriteof (1201-1204) — and the convolution of a raster whose interior
+          // samples are not all 255 is not the fill there.  The canvas holds the convolution of the whole box: read all of it.
+          const ObjRec& co = ss->h_objs[ss->h_leaves[0]];
+          const size_t cw = (size_t)co.cv_nw * co.cv_h;
+          CK(cudaMemsetAsync(ss->conv_bits + co.cv_bits + cw, 0, 4 * cw, ctx->stream));
+        }
+        f.geom_sub = ss; f.colour = 0xFFFFFFFFu;
+        f.dx = c.dx; f.dy = c.dy; f.bx0 += c.dx; f.bx1 += c.dx; f.by0 += c.dy; f.by1 += c.dy;
+        filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
+        i = skip;
+        continue;
+      }
+      if (own->count == 0) { i = gj; continue; }  // NullShape geometry: the filter touches nothing
       if (smear) {
         uint64_t rbits; memcpy(&rbits, &c.brush_radius, sizeof rbits);
         const std::pair<uint64_t, int> key(rbits, (int)(c.brush_opacity * 255.));
@@ -251,11 +312,14 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         }
         f.bx0 = x0 - f.brush_r; f.bx1 = x1 + f.brush_r; f.by0 = y0 - f.brush_r; f.by1 = y1 + f.brush_r;
       } else {
-        EdgeBox eb = edge_bounds(edges + 4 * (size_t)c.first, c.count);
+        EdgeBox eb = edge_bounds(edges + 4 * (size_t)own->first, own->count);
         shape_pixel_box(eb, f.bx0, f.by0, f.bx1, f.by1);
       }
-      f.dx = c.dx; f.dy = c.dy; f.bx0 += c.dx; f.bx1 += c.dx; f.by0 += c.dy; f.by1 += c.dy;
+      f.dx = c.dx; f.dy = c.dy;
+      if (own != &c) { f.dx += own->dx; f.dy += own->dy; }
+      f.bx0 += f.dx; f.bx1 += f.dx; f.by0 += f.dy; f.by1 += f.dy;
       filters.push_back(f); filter_read_abi.push_back(c.filter_kind == COH_FILTER_SCENE ? c.first2 : -1);
+      i = gj;
       continue;
     }
     ObjRec o; memset(&o, 0, sizeof o);

@@ -328,6 +328,14 @@ __global__ void __launch_bounds__(128) k_brush_sprite(const int* __restrict__ ro
     o += sp.y;
   }
 }
+// Alpha bytes of a canvas (cw x ch pixels with its origin at (ox, oy) of the frame) into rows [y0, y0 + h) of a dense
+// byte plane `pitch` wide: the matte of a filter whose geometry is an object of its own (render.ml:1099).
+__global__ void k_canvas_alpha(const uint32_t* __restrict__ canvas, int cw, int ch, int ox, int oy, int y0, int h, int pitch, uint8_t* __restrict__ op) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (x >= pitch || r >= h) return;
+  const int cx = x - ox, cy = y0 + r - oy;
+  op[(size_t)r * pitch + x] = (cx >= 0 && cx < cw && cy >= 0 && cy < ch) ? (uint8_t)(canvas[(size_t)cy * cw + cx] >> 24) : (uint8_t)0;
+}
 // Bounding box of the set bits of a bit-frame's rows [0, h): bb = {x0, y0, x1, y1} by atomic min / max (start from
 // {INT_MAX, INT_MAX, INT_MIN, INT_MIN}); y counts from `ybase`.
 __global__ void k_bits_bbox(const uint32_t* __restrict__ bits, int h, int nw, int ybase, int* __restrict__ bb) {

@@ -349,6 +349,19 @@ class SceneBuilder:
             o.filter_kernel = {"unit": 1, "gaussian": 2}[kernel[0]] | (int(kernel[1]) << 8)
         return o
 
+    def filter_with_geometry(self, kind, kernel=None, **kw):
+        """A filter whose geometry is the OBJECT ADDED NEXT (a brush stroke, a Convolved path, a CPG, a group ...): that
+        object is consumed by the filter, its shape is the filter's and the alpha of its sprite the matte."""
+        from . import abi
+
+        o = self._obj(abi.COH_OBJ_FILTER, **kw)
+        o.cpg_op = abi.COH_GEOM_NEXT
+        Fill.plain(WHITE).apply(o)
+        o.filter_kind = {"hole": 1, "monochrome": 2, "blur": 3, "scene": 4, "minus": 5}[kind]
+        if kind == "blur":
+            o.filter_kernel = {"unit": 1, "gaussian": 2}[kernel[0]] | (int(kernel[1]) << 8)
+        return o
+
     def smear_filter(self, opacity, radius, subpaths, **kw):
         """Filters.smear ((opacity, Gaussian radius), path) (filters.ml:201-217): geometry = the stroke's dummy brush
         (its stamp points), plus the integer smear points of Brush.find_smear_directions; both in the points array."""

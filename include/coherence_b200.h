@@ -63,14 +63,19 @@ enum {
  * COH_FILTER_READING_SCENE; such groups come after every ordinary scene object and are never drawn
  * on their own.  A filter object may carry an alias offset (dx, dy) and may be a member of a group: such a group's members
  * are rendered once, as a scene of their own, into the group's canvas (like Convolved (kernel, Group members)), so they
- * take plain fills only; SCENE filters must be top-level members of the scene list.  The geometry of a filter is a path
- * with a plain fill. */
+ * take plain fills only; SCENE filters must be top-level members of the scene list.  The geometry of a filter is the path
+ * with a plain fill described by the filter's own record (first / count / winding / colour0), or — cpg_op = COH_GEOM_NEXT —
+ * the OBJECT THAT FOLLOWS the filter in the list (one record, or a whole GROUP_BEGIN .. GROUP_END): a brush stroke
+ * (examples.ml:279-300), a Convolved path (engine.ml:33-36: soft-edged lenses), a CPG, a stroked path, a group; plain
+ * fills.  That object is consumed by the filter: it is not drawn, and the filter's "objects below" begin after it.  Its
+ * shape is the filter's shape and the alpha of its sprite the filter's matte (render.ml:1099). */
 enum { COH_FILTER_NONE = 0, COH_FILTER_HOLE = 1, COH_FILTER_MONOCHROME = 2, COH_FILTER_BLUR = 3, COH_FILTER_SCENE = 4, COH_FILTER_MINUS = 5, COH_FILTER_SMEAR = 6,
        COH_FILTER_READING_SCENE = 100 };
 enum { COH_CPG_UNION = 0, COH_CPG_INTERSECTION = 1, COH_CPG_SUBTRACTION = 2, COH_CPG_EXCLUSIVEOR = 3 };
 enum { COH_NONZERO = 0, COH_EVENODD = 1 };              /* Pdfgraphics.winding_rule */
 enum { COH_FILL_PLAIN = 0, COH_FILL_AXIAL = 1, COH_FILL_RADIAL = 2 }; /* fill.ml:62,77,112 */
 enum { COH_FILL_EXT_S = 1, COH_FILL_EXT_E = 2 };
+enum { COH_GEOM_PATH = 0, COH_GEOM_NEXT = 1 };  /* FILTER objects carry it in `cpg_op`: the geometry is the filter record's own path, or the object that follows */
 enum { COH_BRUSH_GAUSSIAN = 0, COH_BRUSH_DUMMY = 1 };  /* Brush.brushkind (brush.ml:14-16); BRUSH objects carry it in `winding` */
 enum { COH_CONV_UNIT = 1, COH_CONV_GAUSSIAN = 2 };  /* convolve.ml:19-22,37-70 (UnitKernel r / XYKernel from mkgaussian r) */
 

@@ -44,6 +44,17 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
   std::vector<int> open_conv;                             // per open group: its `convolve` word (Convolved (kernel, Group members))
   std::map<int, std::shared_ptr<Scene>> reading;          // reading-scene groups by the index of their GROUP_BEGIN
   std::vector<std::pair<size_t, int>> pending_reading;    // (position of the filter in the top-level list, first2)
+  std::vector<std::pair<int, size_t>> awaiting_geom;      // COH_GEOM_NEXT filters: (stack depth, position in that list) waiting for the next object
+  // the object just appended to the list at this depth is the geometry of the filter in front of it
+  auto take_geometry = [&]() {
+    if (awaiting_geom.empty() || awaiting_geom.back().first != (int)stack.size()) return;
+    Scene& l = stack.back();
+    const size_t fp = awaiting_geom.back().second;
+    if (l.size() != fp + 2) return;
+    Obj g = std::move(l.back()); l.pop_back();
+    l[fp].children.push_back(std::move(g));
+    awaiting_geom.pop_back();
+  };
   for (int i = 0; i < n; i++) {
     const coh_object& c = objs[i];
     Obj o;
@@ -74,7 +85,9 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
         o.kind = Obj::Filter; o.filter_kind = c.filter_kind; o.has_bounds = false;
         if (c.filter_kind == COH_FILTER_BLUR) o.kernel = (c.filter_kernel & 255) == COH_CONV_UNIT ? mkunit(c.filter_kernel >> 8) : mkgaussian(c.filter_kernel >> 8);
         Obj g;
-        if (c.filter_kind == COH_FILTER_SMEAR) {
+        if (c.filter_kind != COH_FILTER_SMEAR && c.cpg_op == COH_GEOM_NEXT) {
+          awaiting_geom.push_back({(int)stack.size(), stack.back().size()});   // the object that follows becomes children[0]
+        } else if (c.filter_kind == COH_FILTER_SMEAR) {
           // geometry = Basic (white, Brushstroke (Brush.mkdummy brushstroke)) (filters.ml:205-207)
           o.stroke.opacity = c.brush_opacity; o.stroke.radius = c.brush_radius;
           for (int k = 0; k < c.count; k++) o.stroke.points.push_back({points[2 * ((size_t)c.first + k)], points[2 * ((size_t)c.first + k) + 1]});
@@ -86,7 +99,7 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
           g.edges = edges_from(edges + 4 * (size_t)c.first, c.count);
           sort_edgelist_maxy_rev(g.edges);
         }
-        o.children.push_back(std::move(g));
+        if (!(c.filter_kind != COH_FILTER_SMEAR && c.cpg_op == COH_GEOM_NEXT)) o.children.push_back(std::move(g));
         // (a filter inside a Group sees the rest of that group's list as its objects below, render.ml:988-1001)
         if (c.filter_kind == COH_FILTER_SCENE) {
           if (stack.size() != 1) throw std::runtime_error("scene: a filter with a caller-built reading scene must be top-level");
@@ -152,7 +165,9 @@ static Scene build_scene(const coh_object* objs, int n, const int32_t* edges, co
       }
       default: throw std::runtime_error("scene: unknown object kind");
     }
+    take_geometry();
   }
+  if (!awaiting_geom.empty()) throw std::runtime_error("scene: a filter with COH_GEOM_NEXT is followed by its geometry object");
   if (!open.empty()) throw std::runtime_error("scene: unterminated group");
   for (auto& pr : pending_reading) {
     auto it = reading.find(pr.second);

@@ -895,6 +895,44 @@ def test_smear_filter(ctx, oracle):
     assert (plain != full).sum() > 200
 
 
+def test_filters_with_object_geometry(ctx, oracle):
+    """Filter geometry other than a path (COH_GEOM_NEXT): a brush stroke (examples.ml:279-300 monobrush: the matte is the
+    stroke's Gaussian alpha), a Convolved path (engine.ml:33-36: a soft-edged lens), a CPG and a group — the object that
+    follows the filter is its geometry, its sprite's alpha the matte (render.ml:1099)."""
+    W, H = 200, 160
+
+    def scene(kind, geometry, kw):
+        b = S.SceneBuilder()
+        b.polygon([(10.0, 60.0), (190.0, 70.0), (100.0, 95.0)], S.Fill.plain(S.dissolve(S.rgba8(0, 90, 200), 120)))
+        f = b.filter_with_geometry(kind, **kw)
+        geometry(b)
+        b.polygon([(30.3, 30.2), (150.5, 33.9), (148.1, 130.7), (28.8, 124.4)], S.Fill.plain(S.rgba8(200, 30, 30)))
+        b.polygon([(60.0, 20.0), (120.0, 140.0), (20.0, 120.0)], S.Fill.plain(S.dissolve(S.rgba8(250, 240, 20), 200)))
+        b.polygon([(5.0, 5.0), (195.0, 8.0), (185.0, 150.0), (12.0, 140.0)], S.Fill.plain(S.dissolve(S.rgba8(20, 160, 20), 90)))
+        return _finish(b, W, H), f
+
+    white = S.Fill.plain(S.WHITE)
+    geometries = {
+        "brush": lambda b: b.brush(0.9, 9.0, [[("C", (30.0, 130.0), (80.0, 20.0), (130.0, 150.0), (180.0, 40.0))]], white),
+        "convolved": lambda b: b.path(_circle(100.3, 80.2, 40.5), white, abi.COH_NONZERO, convolve=("gaussian", 4)),
+        "cpg": lambda b: (b.group_begin(), b.cpg("xor", _circle(80.0, 80.0, 40.0), _circle(120.0, 85.0, 35.0), S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 200))), b.group_end()),
+        "path": lambda b: b.path(_circle(100.3, 80.2, 40.5), S.Fill.plain(S.dissolve(S.rgba8(255, 255, 255), 190)), abi.COH_NONZERO),
+        "group": lambda b: (b.group_begin(), b.polygon([(40.0, 40.0), (90.0, 45.0), (85.0, 110.0)], white),
+                            b.brush(1.0, 5.0, [[("L", (100.0, 30.0), (170.0, 120.0))]], white), b.group_end()),
+    }
+    for gname, geometry in geometries.items():
+        for kind, kw in (("monochrome", {}), ("blur", {"kernel": ("gaussian", 2)}), ("minus", {})):
+            b, f = scene(kind, geometry, kw)
+            got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)
+            assert np.array_equal(got_u, ref_u), (gname, kind)
+            assert _max_lsb(got, ref) == 0, (gname, kind)
+    # translated, and a partial update
+    b, f = scene("monochrome", geometries["brush"], {})
+    f.dx, f.dy = -14, 9
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H, update=(40, 30, 120, 100))
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
+
+
 def test_translated_and_dragged_lenses(ctx, oracle):
     """A filter object with an alias offset (render.ml:259-271) reads its geometry moved by whole pixels; dragging a
     lens (coh_scene_drag_object: alldirty of its shape at both places) re-renders exactly what a full frame of the
