@@ -343,7 +343,10 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
             else if (objs[j].kind == COH_OBJ_GROUP_END) nest--;
             else if (objs[j].kind == COH_OBJ_FILTER) { holds_filter = true; break; }
           }
-        if (c.convolve || holds_filter) {
+        // ... and so is a group that would be nested more deeply than the walker's accumulator stack (MAX_DEPTH levels,
+        // counted after first-member groups have dissolved): the reference has no nesting limit
+        const bool too_deep = !c.convolve && c.filter_kind != COH_FILTER_READING_SCENE && o.depth >= MAX_DEPTH && !(o.pretrans < 0 && n_children.back() == 0);
+        if (c.convolve || holds_filter || too_deep) {
           // Convolved (kernel, Group members) (render.ml:63, 1023-1052 with a Group child; shapes render.ml:536-555, where
           // findfill of a Group is "fancy": minshape null).  The members become a scene of their own, rendered once into
           // the object's canvas and convolved there (below); the object itself is one leaf, like Convolved (Basic Path).

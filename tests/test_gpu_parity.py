@@ -1192,7 +1192,7 @@ def test_lion_c2_full_size_frame(ctx, oracle):
 
 def test_edge_cases(ctx, oracle):
     """Empty scenes, empty and out-of-frame updates, objects outside the frame or with no area, horizontal and
-    zero-length edges, a frame narrower than one tile, the deepest allowed group nesting and one level more."""
+    zero-length edges, a frame narrower than one tile, group nesting up to and beyond the walker's accumulator stack."""
     W, H = 70, 37   # not multiples of the 32 x 16 cell
     b = S.SceneBuilder()
     got, ref, got_u, ref_u = _render_both(ctx, oracle, b, W, H)          # nothing at all
@@ -1228,14 +1228,15 @@ def test_edge_cases(ctx, oracle):
     ctx.scene_free(sc)
     tri = [(5.0, 3.0), (66.0, 4.0), (40.0, 33.0)]
     deep = S.SceneBuilder()
-    for _ in range(6):                             # PreTrans groups keep their accumulators: six levels are too many
-        deep.group_begin(pretrans=200)
-    deep.polygon(tri, S.Fill.plain(S.rgba8(1, 2, 3)))
-    for _ in range(6):
+    for _ in range(9):                             # PreTrans groups keep their accumulators; beyond the walker's stack
+        deep.group_begin(pretrans=200)             # (MAX_DEPTH) the inner groups become canvases rendered once —
+    deep.polygon(tri, S.Fill.plain(S.rgba8(1, 2, 3)))   # the reference has no nesting limit
+    deep.polygon([(t[0] - 3.0, t[1] + 2.5) for t in tri], S.Fill.plain(S.dissolve(S.rgba8(90, 20, 200), 120)))
+    for _ in range(9):
         deep.group_end()
-    objs, n, nbg, e, p = deep.arrays()
-    with pytest.raises(abi.CohError):              # nesting beyond MAX_DEPTH fails loudly at scene creation
-        ctx.scene_create(objs, nbg, e, p)
+    deep.polygon([(t[0] + 4.0, t[1] - 1.5) for t in tri], S.Fill.plain(S.dissolve(S.rgba8(20, 90, 30), 77)))
+    got, ref, got_u, ref_u = _render_both(ctx, oracle, deep, W, H)
+    assert np.array_equal(got_u, ref_u) and _max_lsb(got, ref) == 0
     deep = S.SceneBuilder()
     for _ in range(12):                            # first members composited with plain Over dissolve into their parent:
         deep.group_begin()                         # any depth of those is fine
