@@ -110,6 +110,9 @@ class Context:
         rc = lib().coh_init(device, C.byref(self._h))
         if rc != 0:
             raise CohError(lib().coh_last_error(None).decode())
+        for kv in filter(None, os.environ.get("COH_OPTIONS", "").split(",")):   # A/B measurements: COH_OPTIONS=pdl=0,ab=1
+            name, _, value = kv.partition("=")
+            self.set_option(name.strip(), int(value))
 
     def close(self):
         if self._h and self._owned:

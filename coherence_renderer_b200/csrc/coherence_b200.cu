@@ -149,6 +149,7 @@ struct coh_ctx {
   bool opt_fork_prefill = true;  // three-phase frames: background prefill on a second stream beside the scan kernels
   int opt_ab = 0;   // scratch switch for A/B measurements
   bool opt_comp_rows = true;  // flat scenes: row compositor instead of the walker in three-phase frames
+  bool opt_pdl = true;  // three-phase frames: the chain of kernels launched with programmatic stream serialization
   // large scenes: coarse level of the two-level binning (leaf positions per coarse cell)
   int* coarse_items = nullptr; int* coarse_counts = nullptr; int* coarse_off = nullptr; size_t coarse_cap = 0, coarse_cells_cap = 0;
   uint32_t* peer_fb[COH_MAX_PEERS] = {nullptr}; int n_peers = 0;  // coh_fb_set_peers
@@ -242,6 +243,18 @@ static void build_aa_table(AATable& t) {
   if (t.volume != AA_VOLUME) { fprintf(stderr, "coherence_b200: AA table volume %d != %d\n", t.volume, AA_VOLUME); abort(); }
 }
 
+// Launch with (or without) the programmatic-stream-serialization attribute: the kernel may be scheduled before the kernel
+// ahead of it in the stream has completed and waits for it in cudaGridDependencySynchronize ().
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st;
+  cudaLaunchAttribute at[1]; memset(at, 0, sizeof at);
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 extern "C" {
 
 const char* coh_last_error(coh_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
@@ -293,6 +306,7 @@ int coh_set_option(coh_ctx* ctx, const char* name, int32_t value) {
   else if (n == "comp_rows") ctx->opt_comp_rows = value != 0;
   else if (n == "ab") ctx->opt_ab = value;
   else if (n == "fork_prefill") ctx->opt_fork_prefill = value != 0;
+  else if (n == "pdl") ctx->opt_pdl = value != 0;
   else FAIL("coh_set_option: unknown option '" + n + "'");
   return 0;
 }

@@ -232,16 +232,24 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       ctx->pre_cap = cap;
     }
     P.item_cell = B.item_cell;
-    CK(cudaMemsetAsync(ctx->pre_n, 0, 2 * sizeof(int), ctx->stream));
-    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc, B.item_rec); LAUNCHED();
-    k_pre_vis<<<cdiv(n_cells * CELL_H, 128), 128, 0, ctx->stream>>>(P, ctx->pre_sc, ctx->pre_list, ctx->pre_n, B.item_attr); LAUNCHED();
+    // The four kernels of the chain are launched with programmatic stream serialization (PDL): every producer signals at
+    // its start that its dependents may be scheduled, every consumer does what does not depend on the producer (staging
+    // the AA table, its own indices) and waits in cudaGridDependencySynchronize () for the producer's grid to complete —
+    // the consumer's blocks fill the SMs as the producer's last blocks leave, instead of after the grid has drained.
+    const bool pdl = ctx->opt_pdl;
+    k_pre_scan<<<cdiv((int)n_pairs, 128), 128, 0, ctx->stream>>>(P, (int)n_pairs, ctx->pre_sc, B.item_rec, ctx->pre_n); LAUNCHED();
+    CK(launch_chain(k_pre_vis, cdiv(n_cells * CELL_H, 128), 128, ctx->stream, pdl && !(ctx->opt_ab & 64), P, (const uint2*)ctx->pre_sc, ctx->pre_list, ctx->pre_n, (const int2*)B.item_attr)); LAUNCHED();
     if (ctx->aa_general) { k_pre_aa<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op); LAUNCHED(); }
     else {
       // interval form (the few pairs with rows that are not runs take the bit-row routine inside the same kernel)
-      k_pre_aa_runs<<<ctx->n_sms * 4, AA2_WARPS * 32, 0, ctx->stream>>>(P, ctx->pre_list, ctx->pre_n, ctx->pre_op, ctx->pre_n + 1); LAUNCHED();
+      CK(launch_chain(k_pre_aa_runs, ctx->n_sms * 4, AA2_WARPS * 32, ctx->stream, pdl && !(ctx->opt_ab & 32), P, (const int4*)ctx->pre_list, (const int*)ctx->pre_n, ctx->pre_op, ctx->pre_n + 1)); LAUNCHED();
     }
     P.pre_sc = ctx->pre_sc; P.pre_op = ctx->pre_op;
-    if (prefill_forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    // the row compositor touches no cell that k_prefill finishes (and the other way round): with PDL the join moves behind it,
+    // so that no event wait stands between the antialiasing kernel and its dependent
+    const bool pdl_comp = pdl && !(ctx->opt_ab & 16);
+    const bool join_late = prefill_forked && pdl_comp && !(ctx->opt_ab & 8) && !ctx->aa_general && s->flat_ok && !A.collapsed && ctx->opt_comp_rows;
+    if (prefill_forked && !join_late) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     const int pgrid = std::min(ctx->n_sms * WALK_MIN_CTAS, cdiv(n_cells * (CELL_H / 4), WALK_WARPS));
     if (s->flat_ok && !A.collapsed && ctx->opt_comp_rows) {
       // flat scene: one warp per pixel row of a cell composites the pre-scanned, pre-antialiased list entries
@@ -250,7 +258,8 @@ static int render_pass(coh_ctx* ctx, DevScene* s, const PassArgs& A) {
       const bool comp_ordered = ordered && n_cells > 2048;
       if (comp_ordered && !B.comp_valid) { k_comp_order<<<cdiv(n_cells, 256), 256, 0, ctx->stream>>>(B.state + 1, B.cell_order, B.cell_rng, B.cell_head, n_cells, B.comp_order, fr.cntx); LAUNCHED(); B.comp_valid = true; }
       const int comp_blocks = n_cells * (CELL_H / COMP_WARPS);
-      k_comp_rows<<<std::min(comp_blocks, ctx->n_sms * (2048 / (COMP_WARPS * 32))), COMP_WARPS * 32, 0, ctx->stream>>>(P, B.item_attr, comp_ordered ? B.comp_order : nullptr, comp_blocks); LAUNCHED();
+      CK(launch_chain(k_comp_rows, std::min(comp_blocks, ctx->n_sms * (2048 / (COMP_WARPS * 32))), COMP_WARPS * 32, ctx->stream, pdl_comp && (join_late || !prefill_forked), P, (const int2*)B.item_attr, (const int4*)(comp_ordered ? B.comp_order : nullptr), comp_blocks)); LAUNCHED();
+      if (join_late) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else if (s->has_fancy) {  // fancy fills: the compositing walk keeps the cross-tile carry (row-major queue order)
       // (the touched plane of a smear filter is compiled into the EXTRAS = 2 variants only)
       size_t slots = (size_t)fr.tiles_x * (fr.band_y1 - fr.band_y0);

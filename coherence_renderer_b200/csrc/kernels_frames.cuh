@@ -16,8 +16,10 @@
 //   k_pre_aa    warp / listed pair: opacity bytes (aa_tile)
 //   k_walk<PRE> composite with the exact `u`; every pixel it antialiases is in the superset.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc, const int4* __restrict__ item_rec) {
+__global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uint2* __restrict__ sc, const int4* __restrict__ item_rec, int* __restrict__ counters) {
+  cudaTriggerProgrammaticLaunchCompletion();   // (PDL: the visibility kernel's blocks may be scheduled as this grid's last blocks start)
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair < 2) counters[pair] = 0;   // list length and next pair of the kernels behind (they wait for this grid): no memset node in front of the frame
   if (pair >= n_pairs) return;
   const int item = pair / CELL_H, row = pair % CELL_H;
   // the list entry carries what is needed of the object (written by k_bin1): no walk through ObjRec for paths and primitives
@@ -66,9 +68,12 @@ __global__ void __launch_bounds__(128) k_pre_scan(WalkParams P, int n_pairs, uin
 // blockDim = 128: 8 (cell, 16 rows) groups per block
 __global__ void k_pre_vis(WalkParams P, const uint2* __restrict__ sc, int4* __restrict__ list /* pair, object, edge mask, (tile << 16 | row of the frame) */, int* __restrict__ list_n,
                           const int2* __restrict__ item_attr) {
+  cudaTriggerProgrammaticLaunchCompletion();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int cell = t / CELL_H, row = t % CELL_H;
-  if (cell >= P.n_cells || (!P.resume && (P.cell_head[cell].y & 1))) return;
+  if (cell >= P.n_cells || (!P.resume && (P.cell_head[cell].y & 1))) return;   // (cell_head: written when the cells were binned)
+  cudaGridDependencySynchronize();   // the scan words of k_pre_scan
+  asm volatile("" : "+l"(sc));         // (`sc` is const __restrict__: nothing read through it may be hoisted above the wait)
   const int tile = P.fr.ctx0 + cell % P.fr.cntx, by = cell / P.fr.cntx;
   const int tx0 = tile * TILE_W, my_y = (P.cell_row0 + by) * CELL_H + row;
   uint32_t u = 0u;
@@ -190,9 +195,12 @@ __global__ void __launch_bounds__(AA2_WARPS * 32, 4) k_pre_aa_runs(WalkParams P,
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ AaEdge s_stage[AA2_WARPS][32];
   __shared__ uint32_t s_aa[AA2_WARPS][32 * AA_WORDS];   // bit-rows of the general routine (rarely touched)
-  stage_aa_table(s_prefix, &s_bar, P.aa);
+  cudaTriggerProgrammaticLaunchCompletion();
+  stage_aa_table(s_prefix, &s_bar, P.aa);   // (the table is a constant of the context: staged while k_pre_vis finishes)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = *list_n;
+  cudaGridDependencySynchronize();   // the list of k_pre_vis
+  asm volatile("" : "+l"(list), "+l"(list_n));   // (const __restrict__ pointers: a load through them is invariant to the compiler and
+  const int n = *list_n;                          //  may otherwise be hoisted above the wait — the list length was)
   const int* prow = s_prefix + lane * 33;
   AaEdge* stage = s_stage[wid];
   // one resident wave of warps; pairs come off a counter (their cost varies with the number of candidate edges)
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) k_comp_rows(WalkParams P, con
   // every cell, and positions beyond the queued cells (background cells were finished by k_prefill) leave at once.
   // A resident grid walks the positions (n_blocks = cells x PARTS of them, most of them background cells that leave at
   // once: one block per position would spend the launch on block dispatch).
+  cudaGridDependencySynchronize();   // the opacities of the antialiasing kernel
   for (int bq = blockIdx.x; bq < n_blocks; bq += gridDim.x) {
   const int q = bq / PARTS;
   int4 oc;
