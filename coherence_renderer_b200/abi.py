@@ -49,6 +49,7 @@ SYMBOLS = [
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_sprite", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points", "coh_host_smear_points",
+    "coh_host_strokepath", "coh_strokepath", "coh_shapeminshape_of_stroke",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_sprite_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
@@ -86,6 +87,7 @@ def lib():
         L.coh_host_edgelist_of_subpath.restype = C.c_int64
         L.coh_host_brush_points.restype = C.c_int64
         L.coh_host_smear_points.restype = C.c_int64
+        L.coh_host_strokepath.restype = C.c_int64
         L.coh_multi_last_error.restype = C.c_char_p
         L.coh_multi_last_error.argtypes = [C.c_void_p]
         L.coh_multi_ctx.restype = C.c_void_p
@@ -253,6 +255,27 @@ class Context:
         rec = _seg_records(segs)
         s, m = C.c_uint64(), C.c_uint64()
         self._chk(lib().coh_shapeminshape_of_path(self._h, rec.ctypes.data_as(C.POINTER(C.c_double)), len(rec), winding, C.byref(s), C.byref(m)))
+        return s.value, m.value
+
+    def strokepath(self, spec, subpaths):
+        """Shapes.strokepath: the stroke's outline (host stroker) flattened on the device, edges sorted by maximum y.
+        Returns (edges, winding rule of the outline)."""
+        rec, cnt = _path_records(subpaths)
+        cap = 256 * len(rec) + 256
+        while True:
+            out = np.zeros((cap, 4), dtype=np.int32)
+            n, w = C.c_int64(), C.c_int32()
+            self._chk(lib().coh_strokepath(self._h, C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt),
+                                           _i32p(out), C.c_int64(cap), C.byref(n), C.byref(w)))
+            if n.value <= cap:
+                return out[:n.value], w.value
+            cap = int(n.value)
+
+    def shapeminshape_of_stroke(self, spec, subpaths):
+        """Shape and minshape of a stroked path: stroker on the host, flattening and scan conversion on the device."""
+        rec, cnt = _path_records(subpaths)
+        s, m = C.c_uint64(), C.c_uint64()
+        self._chk(lib().coh_shapeminshape_of_stroke(self._h, C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt), C.byref(s), C.byref(m)))
         return s.value, m.value
 
     def polygon_opacity(self, edges, winding, shp):
@@ -549,6 +572,43 @@ def _seg_records(segs):
         for k, p in enumerate(s[1:]):
             rec[i, 1 + 2 * k], rec[i, 2 + 2 * k] = p
     return rec
+
+
+def _path_records(subpaths):
+    """Segment records of all the subpaths of a path in order + the number of segments of each."""
+    cnt = np.array([len(sp) for sp in subpaths], dtype=np.int32)
+    rec = _seg_records([s for sp in subpaths for s in sp])
+    return rec, cnt
+
+
+CAP_BUTT, CAP_ROUND, CAP_PROJECTING = 0, 1, 2
+JOIN_ROUND, JOIN_MITRED, JOIN_BEVEL = 0, 1, 2
+
+
+class StrokeSpec(C.Structure):
+    """coh_strokespec (shapes.ml:166-171)."""
+    _fields_ = [("startcap", C.c_int32), ("join", C.c_int32), ("endcap", C.c_int32), ("reserved", C.c_int32),
+                ("mitrelimit", C.c_double), ("linewidth", C.c_double)]
+
+
+def strokespec(startcap, join, endcap, mitrelimit, linewidth):
+    return StrokeSpec(startcap, join, endcap, 0, mitrelimit, linewidth)
+
+
+def host_strokepath(spec, subpaths):
+    """Shapes.strokepath_polygon through the library's host stroker: (outline records (n, 9), segments per outline
+    subpath, winding rule)."""
+    rec, cnt = _path_records(subpaths)
+    m, w = C.c_int32(), C.c_int32()
+    counts = np.zeros(max(len(cnt), 1), dtype=np.int32)
+    n = lib().coh_host_strokepath(C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt),
+                                  None, C.c_int64(0), _i32p(counts), 0, C.byref(m), C.byref(w))
+    if n < 0:
+        raise CohError("Shapes.joinsegments: a rail that ends in a curve cannot be joined")
+    out = np.zeros((max(int(n), 1), 9), dtype=np.float64)
+    lib().coh_host_strokepath(C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt),
+                              out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n), _i32p(counts), len(counts), C.byref(m), C.byref(w))
+    return out[:n], counts[: m.value], w.value
 
 
 def host_edgelist_of_subpath(segs):

@@ -140,6 +140,48 @@ int coh_shapeminshape_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, 
   return rc;
 }
 
+// Shapes.strokepath (shapes.ml:529-530): the outline from the host stroker (host_stroke.cpp), flattened by k_flatten
+static int stroke_outline(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                          std::vector<double>& outline, int32_t* winding) {
+  if (!spec || n_subpaths < 0) FAIL("strokepath: bad arguments");
+  if (spec->startcap < 0 || spec->startcap > 2 || spec->endcap < 0 || spec->endcap > 2 || spec->join < 0 || spec->join > 2) FAIL("strokepath: bad cap or join");
+  std::vector<int32_t> counts((size_t)std::max(n_subpaths, 1));
+  int32_t m = 0;
+  int64_t n = coh_host_strokepath(spec, segs, subpath_segs, n_subpaths, nullptr, 0, counts.data(), 0, &m, winding);
+  if (n < 0) FAIL("Shapes.joinsegments: a rail that ends in a curve cannot be joined");
+  outline.resize((size_t)std::max<int64_t>(n, 1) * 9);
+  if (coh_host_strokepath(spec, segs, subpath_segs, n_subpaths, outline.data(), n, counts.data(), 0, &m, winding) != n) FAIL("strokepath: inconsistent outline");
+  outline.resize((size_t)n * 9);
+  return 0;
+}
+int coh_strokepath(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                   int32_t* edges_out, int64_t cap, int64_t* n_out, int32_t* winding_out) {
+  *n_out = 0;
+  std::vector<double> outline; int32_t winding = COH_EVENODD;
+  if (stroke_outline(ctx, spec, segs, subpath_segs, n_subpaths, outline, &winding)) return 1;
+  if (winding_out) *winding_out = winding;
+  CK(cudaSetDevice(ctx->device));
+  int4* d_edges = nullptr; int n = 0, box[4];
+  if (flatten_on_device(ctx, outline.data(), (int)(outline.size() / 9), &d_edges, &n, box)) return 1;
+  *n_out = n;
+  if (n > 0) {
+    std::vector<int4> e((size_t)n);
+    CK(cudaMemcpyAsync(e.data(), d_edges, sizeof(int4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::stable_sort(e.begin(), e.end(), [](const int4& a, const int4& b) { return std::max(a.y, a.w) > std::max(b.y, b.w); });   // polygon.ml:243-244
+    if (cap > 0) memcpy(edges_out, e.data(), sizeof(int4) * (size_t)std::min<int64_t>(n, cap));
+  }
+  DFREE(d_edges);
+  return 0;
+}
+int coh_shapeminshape_of_stroke(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                                coh_shape_t* shape, coh_shape_t* minshape) {
+  *shape = 0; *minshape = 0;
+  std::vector<double> outline; int32_t winding = COH_EVENODD;
+  if (stroke_outline(ctx, spec, segs, subpath_segs, n_subpaths, outline, &winding)) return 1;
+  return coh_shapeminshape_of_path(ctx, outline.data(), (int32_t)(outline.size() / 9), winding, shape, minshape);
+}
+
 // dense AA opacity bytes over the bit-frame of `shp`, then gathered in span order
 static int polygon_opacity_dense(coh_ctx* ctx, const int32_t* edges, int n_edges, int winding, const DevShape* s,
                                  uint8_t** dense, int* wx0_out, int* nw_out) {

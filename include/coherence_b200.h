@@ -355,6 +355,33 @@ int coh_brush_smear(coh_ctx* ctx, coh_shape_t shape, const uint32_t* rgba_in, co
  * in HBM and scan-converts them there (= Polygon.shapeminshape_polygon of the path, polygon.ml:605). */
 int coh_edgelist_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t* edges_out, int64_t cap, int64_t* n_out);
 int coh_shapeminshape_of_path(coh_ctx* ctx, const double* segs, int32_t n_segs, int32_t winding, coh_shape_t* shape, coh_shape_t* minshape);
+/* N2 — the stroker: Shapes.strokepath (shapes.ml:203-530; shapes.mli:30-41).  A stroke specification is the reference's
+ * record (shapes.ml:166-171).  The path: 9-double segment records of all its subpaths in order, subpath_segs[k] of them in
+ * subpath k (closed subpaths are stroked like open ones, as in the reference, which reads the segments only).
+ * coh_host_strokepath           Shapes.strokepath_polygon on the host: the outline as closed subpaths of straight and bezier
+ *                               segments (rails, joins, caps; the circle of a degenerate path with round caps) and its
+ *                               winding rule.  Returns the number of outline segments (whatever the caps are), -1 where
+ *                               the reference fails.  The joins are made in Pdfutil.pair_reduce's order.
+ * coh_strokepath                Shapes.strokepath: that outline flattened on the device (k_flatten) and sorted by
+ *                               Polygon.sort_edgelist_maxy_rev (stable): the edge list a StrokedPath object carries.
+ * coh_shapeminshape_of_stroke   the same edges kept in HBM and scan-converted there with the outline's winding rule. */
+#define COH_CAP_BUTT 0
+#define COH_CAP_ROUND 1
+#define COH_CAP_PROJECTING 2
+#define COH_JOIN_ROUND 0
+#define COH_JOIN_MITRED 1
+#define COH_JOIN_BEVEL 2
+typedef struct coh_strokespec {
+  int32_t startcap, join, endcap, reserved;   /* COH_CAP_*, COH_JOIN_*, COH_CAP_* */
+  double mitrelimit, linewidth;
+} coh_strokespec;
+int64_t coh_host_strokepath(const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                            double* segs_out, int64_t cap_segs, int32_t* subpath_segs_out, int32_t cap_subpaths,
+                            int32_t* n_subpaths_out, int32_t* winding_out);
+int coh_strokepath(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                   int32_t* edges_out, int64_t cap, int64_t* n_out, int32_t* winding_out);
+int coh_shapeminshape_of_stroke(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
+                                coh_shape_t* shape, coh_shape_t* minshape);
 /* Brush.points_of_brushstroke_smear and the integer points of Brush.find_smear_directions (brush.ml:239-283) for all the
  * segments of a path in order: pieces at most 2 apart, start points truncated, consecutive duplicates dropped. */
 int64_t coh_host_smear_points(const double* segs, int32_t n_segs, int32_t* points_out, int64_t cap);

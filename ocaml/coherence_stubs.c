@@ -136,6 +136,48 @@ CAMLprim value coh_ml_shapeminshape_of_path(value ctx, value segs, value winding
   check(CTX(ctx), coh_shapeminshape_of_path(CTX(ctx), (const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), Int_val(winding), &s, &m));
   CAMLreturn(pair_of_handles(s, m));
 }
+/* N2: Shapes.strokepath.  spec : float64 Array1 [| startcap; join; endcap; mitrelimit; linewidth |] (caps Butt 0 / Round 1 /
+ * Projecting 2, joins Round 0 / Mitred 1 / Bevel 2); counts : int32 Array1, the segments of each subpath. */
+static coh_strokespec strokespec_of(value spec) {
+  const double* d = (const double*)Caml_ba_data_val(spec);
+  coh_strokespec sp; memset(&sp, 0, sizeof sp);
+  need(spec, 5, "strokespec: startcap, join, endcap, mitrelimit, linewidth");
+  sp.startcap = (int32_t)d[0]; sp.join = (int32_t)d[1]; sp.endcap = (int32_t)d[2]; sp.mitrelimit = d[3]; sp.linewidth = d[4];
+  return sp;
+}
+/* returns (edge count, winding rule of the outline); out : int32 Array1 of 4 * cap */
+CAMLprim value coh_ml_strokepath(value ctx, value spec, value segs, value counts, value out) {
+  CAMLparam5(ctx, spec, segs, counts, out);
+  CAMLlocal1(r);
+  coh_strokespec sp = strokespec_of(spec);
+  int64_t n = 0; int32_t w = 0;
+  check(CTX(ctx), coh_strokepath(CTX(ctx), &sp, (const double*)Caml_ba_data_val(segs), (const int32_t*)Caml_ba_data_val(counts), (int32_t)BA_LEN(counts),
+                                 (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4, &n, &w));
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, Val_long((long)n)); Store_field(r, 1, Val_int(w));
+  CAMLreturn(r);
+}
+CAMLprim value coh_ml_shapeminshape_of_stroke(value ctx, value spec, value segs, value counts) {
+  CAMLparam4(ctx, spec, segs, counts);
+  coh_strokespec sp = strokespec_of(spec);
+  coh_shape_t s = 0, m = 0;
+  check(CTX(ctx), coh_shapeminshape_of_stroke(CTX(ctx), &sp, (const double*)Caml_ba_data_val(segs), (const int32_t*)Caml_ba_data_val(counts), (int32_t)BA_LEN(counts), &s, &m));
+  CAMLreturn(pair_of_handles(s, m));
+}
+/* Shapes.strokepath_polygon on the host: returns (outline segments, outline subpaths, winding); out : float64 Array1 of
+ * 9 * cap, out_counts : int32 Array1 */
+CAMLprim value coh_ml_host_strokepath(value spec, value segs, value counts, value out, value out_counts) {
+  CAMLparam5(spec, segs, counts, out, out_counts);
+  CAMLlocal1(r);
+  coh_strokespec sp = strokespec_of(spec);
+  int32_t m = 0, w = 0;
+  int64_t n = coh_host_strokepath(&sp, (const double*)Caml_ba_data_val(segs), (const int32_t*)Caml_ba_data_val(counts), (int32_t)BA_LEN(counts),
+                                  (double*)Caml_ba_data_val(out), BA_LEN(out) / 9, (int32_t*)Caml_ba_data_val(out_counts), (int32_t)BA_LEN(out_counts), &m, &w);
+  if (n < 0) caml_failwith("Shapes.joinsegments: Not implemented");
+  r = caml_alloc_tuple(3);
+  Store_field(r, 0, Val_long((long)n)); Store_field(r, 1, Val_int(m)); Store_field(r, 2, Val_int(w));
+  CAMLreturn(r);
+}
 /* opacity bytes of every pixel of `shape`, span order; out : (int, int8_unsigned) Array1 of Sprite.shape_card shape */
 CAMLprim value coh_ml_polygon_opacity(value ctx, value edges, value winding, value shape, value out) {
   CAMLparam5(ctx, edges, winding, shape, out);

@@ -9,6 +9,7 @@
 #include <string>
 #include "../include/coherence_b200.h"
 #include "render.hpp"
+#include "shapes.hpp"
 
 using namespace oracle;
 
@@ -474,6 +475,44 @@ int orc_points_on_path(const double* segs, int nseg, double sep, int32_t** out, 
   std::vector<int> f;
   for (auto& p : pts) { f.push_back(p.first); f.push_back(p.second); }
   *out = dup_ints(f); *npts = (int64_t)pts.size();
+  ORC_CATCH
+}
+// Shapes.strokepath_polygon / Shapes.strokepath (shapes.ml:203-530).  spec5: startcap, join, endcap (oracle enums: caps
+// Butt 0 / Round 1 / Projecting 2, joins Round 0 / Mitred 1 / Bevel 2), mitrelimit, linewidth.  subpath_n: segments per
+// subpath.  Returns the outline (9-double records, segments per outline subpath), its winding rule and the sorted edges.
+int orc_strokepath(const double* spec5, const double* segs, const int32_t* subpath_n, int n_subpaths, double** segs_out, int64_t* n_segs_out,
+                   int32_t** subpath_n_out, int64_t* n_subpaths_out, int* winding_out, int32_t** edges_out, int64_t* n_edges_out) {
+  ORC_TRY
+  StrokeSpec spec{(Cap)(int)spec5[0], (Join)(int)spec5[1], (Cap)(int)spec5[2], spec5[3], spec5[4]};
+  Path path;
+  int at = 0;
+  for (int k = 0; k < n_subpaths; k++) {
+    Subpath sub;
+    for (int i = 0; i < subpath_n[k]; i++, at++) {
+      Segment s; s.bezier = segs[9 * at] != 0.;
+      for (int q = 0; q < 4; q++) s.p[q] = Pt(segs[9 * at + 1 + 2 * q], segs[9 * at + 2 + 2 * q]);
+      sub.push_back(s);
+    }
+    path.push_back(sub);
+  }
+  Path outline;
+  *winding_out = (int)strokepath_polygon(spec, path, outline);
+  std::vector<double> f; std::vector<int> cnt;
+  for (const Subpath& sp : outline) {
+    cnt.push_back((int)sp.size());
+    for (const Segment& s : sp) {
+      f.push_back(s.bezier ? 1. : 0.);
+      for (int q = 0; q < 4; q++) { f.push_back(s.bezier || q < 2 ? s.p[q].first : 0.); f.push_back(s.bezier || q < 2 ? s.p[q].second : 0.); }
+    }
+  }
+  double* o = (double*)std::malloc(sizeof(double) * (f.size() + 1));
+  std::copy(f.begin(), f.end(), o);
+  *segs_out = o; *n_segs_out = (int64_t)(f.size() / 9);
+  *subpath_n_out = dup_ints(cnt); *n_subpaths_out = (int64_t)cnt.size();
+  std::vector<Edge> es = strokepath(spec, path);
+  std::vector<int> e;
+  for (const Edge& d : es) { e.push_back(d.x0); e.push_back(d.y0); e.push_back(d.x1); e.push_back(d.y1); }
+  *edges_out = dup_ints(e); *n_edges_out = (int64_t)es.size();
   ORC_CATCH
 }
 int orc_brush_stamp(double radius, double opacity, uint8_t* alpha_out, int cap, int* size_out) {

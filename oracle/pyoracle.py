@@ -237,6 +237,22 @@ def points_on_path(segs, sep):
     return _take(p, n.value * 2).reshape(-1, 2)
 
 
+def strokepath(spec, segs, subpath_n):
+    """Shapes.strokepath_polygon + Shapes.strokepath.  spec = (startcap, join, endcap, mitrelimit, linewidth) with the
+    oracle's enums (caps Butt 0 / Round 1 / Projecting 2; joins Round 0 / Mitred 1 / Bevel 2).
+    Returns (outline segments (n, 9), segments per outline subpath, winding, sorted edges (m, 4))."""
+    a = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 9)
+    cnt = np.ascontiguousarray(subpath_n, dtype=np.int32)
+    sp = np.ascontiguousarray(spec, dtype=np.float64)
+    so, ns, co, nc, w = C.POINTER(C.c_double)(), C.c_int64(), C.POINTER(C.c_int32)(), C.c_int64(), C.c_int()
+    eo, ne = C.POINTER(C.c_int32)(), C.c_int64()
+    _chk(lib().orc_strokepath(_ptr(sp, C.c_double), _ptr(a, C.c_double), _ptr(cnt, C.c_int32), len(cnt), C.byref(so), C.byref(ns),
+                              C.byref(co), C.byref(nc), C.byref(w), C.byref(eo), C.byref(ne)))
+    out = np.ctypeslib.as_array(so, shape=(max(ns.value * 9, 1),))[: ns.value * 9].copy().reshape(-1, 9)
+    lib().orc_free(so)
+    return out, _take(co, nc.value), w.value, _take(eo, ne.value * 4).reshape(-1, 4)
+
+
 def brush_stamp(radius, opacity):
     out = np.zeros(101 * 101, dtype=np.uint8)
     size = C.c_int()

@@ -244,6 +244,27 @@ int main(int argc, char** argv) {
     ERR(coh_shapeminshape_of_path(C, tri, 3, 9, &ps, &pm), "winding");
     OK(coh_shape_free(C, ps)); OK(coh_shape_free(C, pm)); OK(coh_shape_free(C, es)); OK(coh_shape_free(C, em));
   }
+  /* N2: the stroker — outline on the host, flattening and scan conversion on the device */
+  {
+    double path[27] = {0, 20.0, 20.0, 120.0, 20.0, 0, 0, 0, 0,   0, 120.0, 20.0, 120.0, 90.0, 0, 0, 0, 0,   1, 120.0, 90.0, 100.0, 130.0, 60.0, 130.0, 40.0, 90.0};
+    int32_t counts[1] = {3}, oc[4], om_ = 0, ow = -1;
+    coh_strokespec sp; memset(&sp, 0, sizeof sp);
+    sp.startcap = COH_CAP_ROUND; sp.join = COH_JOIN_MITRED; sp.endcap = COH_CAP_PROJECTING; sp.mitrelimit = 10.0; sp.linewidth = 8.0;
+    int64_t on = coh_host_strokepath(&sp, path, counts, 1, NULL, 0, oc, 4, &om_, &ow);
+    CHECK(on > 12 && om_ == 1 && oc[0] == on && ow == COH_EVENODD);
+    double* outl = (double*)malloc(sizeof(double) * 9 * (size_t)on);
+    CHECK(coh_host_strokepath(&sp, path, counts, 1, outl, on, oc, 4, &om_, &ow) == on && outl[0] == 1.0);   /* a round cap comes first */
+    int32_t* se = (int32_t*)malloc(sizeof(int32_t) * 4 * 4096); int64_t sn = 0; int32_t sw = -1;
+    OK(coh_strokepath(C, &sp, path, counts, 1, se, 4096, &sn, &sw)); CHECK(sn >= on && sn <= 4096 && sw == COH_EVENODD);
+    for (int64_t i = 1; i < sn; i++) CHECK((se[4 * i + 1] > se[4 * i + 3] ? se[4 * i + 1] : se[4 * i + 3]) <= (se[4 * i - 3] > se[4 * i - 1] ? se[4 * i - 3] : se[4 * i - 1]));   /* sort_edgelist_maxy_rev */
+    coh_shape_t ss = 0, sm = 0, es2 = 0, em2 = 0; int64_t c1 = 0, c2 = 0;
+    OK(coh_shapeminshape_of_stroke(C, &sp, path, counts, 1, &ss, &sm));
+    OK(coh_shapeminshape_of_edgelist(C, se, (int32_t)sn, sw, &es2, &em2));
+    OK(coh_shape_card(C, ss, &c1)); OK(coh_shape_card(C, es2, &c2)); CHECK(c1 == c2 && c1 > 8 * 200);
+    sp.join = 9; ERR(coh_strokepath(C, &sp, path, counts, 1, se, 4096, &sn, &sw), "cap or join");
+    OK(coh_shape_free(C, ss)); OK(coh_shape_free(C, sm)); OK(coh_shape_free(C, es2)); OK(coh_shape_free(C, em2));
+    free(outl); free(se);
+  }
   /* release */
   coh_shape_t all[] = {s, m, mx, bx, un, in, tr, bl, er, imp, cs, dirty, os, om, df};
   for (unsigned i = 0; i < sizeof all / sizeof all[0]; i++) OK(coh_shape_free(C, all[i]));
