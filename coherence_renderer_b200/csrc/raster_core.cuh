@@ -382,34 +382,6 @@ struct Sink32 {
   COH_HD void span(int a, int b) { S |= interval_mask32(wx0, a, b); }
   COH_HD void cover(int a, int b) { uint32_t m = interval_mask32(wx0, a, b); S |= m; C |= m; }
 };
-// A handful of intervals kept in registers (AA fast path): intervals are clipped to the
-// window on insertion; `over` is set when more than K were produced.
-template <int K>
-struct SinkRegs {
-  int wlo, whi;
-  int a[K], b[K];
-  int n;
-  bool over;
-  COH_HD void init(int lo, int hi) { wlo = lo; whi = hi; n = 0; over = false; }
-  COH_HD void put(int x, int y) {
-    if (x < wlo) x = wlo;
-    if (y > whi) y = whi;
-    if (x > y) return;
-#pragma unroll
-    for (int k = 0; k < K; k++) if (n == k) { a[k] = x; b[k] = y; }
-    if (n >= K) over = true;
-    n++;
-  }
-  COH_HD void span(int x, int y) { put(x, y); }
-  COH_HD void cover(int x, int y) { put(x, y); }
-  // occupancy of the 32 pixels starting at wx0
-  COH_HD uint32_t mask32(int wx0) const {
-    uint32_t m = 0u;
-#pragma unroll
-    for (int k = 0; k < K; k++) if (k < n) m |= interval_mask32(wx0, a[k], b[k]);
-    return m;
-  }
-};
 // Multi-word row in SHARED memory (the AA rows of the walker), addressed by its 32-bit shared-window
 // address so that one out-of-line routine serves every call site with ld/st.shared (a generic
 // pointer would cost generic loads/stores, inlining it five times cost 465 instructions of I-cache).

@@ -36,4 +36,8 @@ run(b, 200, 160)
 a = ctx.shape_box(5, 5, 100, 50); c = ctx.shape_box(50, 20, 100, 70)
 for f in (ctx.shape_union, ctx.shape_difference, ctx.shape_intersection): ctx.shape_free(f(a, c))
 ctx.shape_free(ctx.shape_bloat(a, 3, 2)); ctx.shape_free(ctx.shape_erode(a, 3, 2))
+spec = abi.strokespec(abi.CAP_ROUND, abi.JOIN_ROUND, abi.CAP_PROJECTING, 10.0, 7.5)   # the stroker: outline -> k_flatten -> scan conversion
+path = [[("L", (20.0, 20.0), (120.0, 30.0)), ("C", (120.0, 30.0), (160.0, 90.0), (60.0, 130.0), (30.0, 80.0))]]
+ctx.strokepath(spec, path)
+for h in ctx.shapeminshape_of_stroke(spec, path): ctx.shape_free(h)
 print("sanitize run OK")
