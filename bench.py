@@ -193,6 +193,7 @@ def run_ours(args):
     # to all of them over NVLink as they go — compute and "collective" are one kernel, followed only by a cross-rank
     # barrier.  If the mapping cannot be set up on this box, fall back to an NCCL all-gather of the strips.
     fb, full, fused, gather = None, None, False, "none (single GPU)"
+    signals, epoch = None, [0]
     display_only = os.environ.get("COH_GATHER", "display") != "all"
     if N > 1 and not os.environ.get("COH_NCCL_GATHER"):
         try:
@@ -202,8 +203,15 @@ def run_ours(args):
             if display_only:
                 # strips go to the display rank.  Rank r > 0 mirrors its band into rank 0's framebuffer
                 # only (H/N rows over NVLink per rank instead of (N-1) H/N); rank 0 ends up with the whole frame.
-                ctx.fb_set_peers([ctx.fb_open_peer(handles[0])] if rank else [])
-                gather = "fused into the rendering kernels: every rank stores its band into the display rank's (rank 0) framebuffer over NVLink (CUDA IPC mapping made by the library) + cross-rank barrier; COH_GATHER=all mirrors into every rank"
+                fb0 = ctx.fb_open_peer(handles[0]) if rank else None
+                ctx.fb_set_peers([fb0] if rank else [])
+                if not os.environ.get("COH_NCCL_BARRIER"):
+                    # frame signals through the shared framebuffers (coh_frame_signal / coh_frame_wait) instead of a
+                    # collective: rank r sets counter r of rank 0's framebuffer behind its frame ("band landed"), rank 0
+                    # waits for counters 1 .. N-1 and then sets counter 0 of every other framebuffer ("frame consumed"),
+                    # which rank r awaits before it stores the next frame
+                    signals = {"fb0": fb0, "others": [ctx.fb_open_peer(handles[r]) for r in range(1, N)] if rank == 0 else []}
+                gather = "fused into the rendering kernels: every rank stores its band into the display rank's (rank 0) framebuffer over NVLink (CUDA IPC mapping made by the library); frame signals through counters in the shared framebuffers (coh_frame_signal / coh_frame_wait; COH_NCCL_BARRIER=1: an NCCL all-reduce instead); COH_GATHER=all mirrors into every rank"
             else:
                 ctx.fb_set_peers([ctx.fb_open_peer(handles[r]) for r in range(N) if r != rank])
                 gather = "fused into the rendering kernels: peer stores over NVLink into every rank's framebuffer (CUDA IPC mappings made by the library) + cross-rank barrier"
@@ -225,12 +233,30 @@ def run_ours(args):
 
     sync_t = torch.zeros(1, dtype=torch.int32, device="cuda")
 
-    def frame():
-        ctx.render_frame(scene_h, update)
-        if fused:
+    def frame_done():
+        """Behind the frame's kernels: the cross-rank step that makes the display rank's framebuffer complete."""
+        if signals is not None:
+            e = epoch[0]
+            if rank:
+                ctx.frame_signal([signals["fb0"]], rank, e)            # my band has landed in rank 0's framebuffer
+            else:
+                ctx.frame_wait(list(range(1, N)), e)                   # every band has landed
+                ctx.frame_signal(signals["others"], 0, e)              # the frame is complete: the next one may be stored
+        elif fused:
             dist.all_reduce(sync_t)  # cross-rank barrier on the stream: every rank's band has landed in this rank's framebuffer
         elif N > 1:
             torch_plumbing.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
+
+    def frame_begin():
+        if signals is not None:
+            epoch[0] += 1
+            if rank and epoch[0] > 1:
+                ctx.frame_wait([0], epoch[0] - 1)                      # rank 0 is done with the frame before
+
+    def frame():
+        frame_begin()
+        ctx.render_frame(scene_h, update)
+        frame_done()
 
     def barrier():
         if N > 1:
@@ -279,12 +305,10 @@ def run_ours(args):
     for s in range(args.steps):
         flush.zero_()
         ev[s][0].record(stream)
+        frame_begin()
         ctx.render_frame(scene_h, update)
         ev_mid[s].record(stream)
-        if fused:
-            dist.all_reduce(sync_t)
-        elif N > 1:
-            torch_plumbing.gather_strips(dist, fb[y0:y1], full, HEIGHT, N, rows=band_list)
+        frame_done()
         ev[s][1].record(stream)
     barrier()
     launches = ctx.launch_count() - l0

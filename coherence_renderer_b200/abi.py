@@ -54,7 +54,7 @@ SYMBOLS = [
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
     "coh_multi_scene_create", "coh_multi_scene_free", "coh_multi_scene_translate_object", "coh_multi_render_frame", "coh_multi_sync",
-    "coh_multi_fb_read_rgba", "coh_multi_fb_read_rgb888", "coh_fb_alloc_shared", "coh_fb_open_peer",
+    "coh_multi_fb_read_rgba", "coh_multi_fb_read_rgb888", "coh_fb_alloc_shared", "coh_fb_open_peer", "coh_frame_signal", "coh_frame_wait",
     "coh_shape_intersects", "coh_sprite_portion", "coh_sprite_fillshape", "coh_sprite_map", "coh_sprite_map_coords_fill",
 ]
 
@@ -159,6 +159,17 @@ class Context:
 
     def fb_attach(self, device_ptr):
         self._chk(lib().coh_fb_attach(self._h, C.c_void_p(device_ptr)))
+
+    def frame_signal(self, target_fbs, slot, epoch):
+        """Counter `slot` of every target framebuffer (fb_open_peer pointers / own fb_device_ptr) becomes `epoch` behind the
+        work issued so far on the stream."""
+        arr = (C.c_void_p * max(len(target_fbs), 1))(*[C.c_void_p(int(p)) for p in target_fbs])
+        self._chk(lib().coh_frame_signal(self._h, len(target_fbs), arr, int(slot), int(epoch)))
+
+    def frame_wait(self, slots, epoch):
+        """The stream waits on the device until the listed counters of the own shared framebuffer have reached `epoch`."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        self._chk(lib().coh_frame_wait(self._h, len(sl), _i32p(sl), int(epoch)))
 
     def mem_in_use(self):
         n = C.c_int64()

@@ -186,12 +186,15 @@ int coh_multi_fb_read_rgb888(coh_multi* m, int32_t x, int32_t y, int32_t w, int3
 // ---- one process per GPU: framebuffers cross process boundaries as CUDA IPC handles (64 bytes each) ----
 // The framebuffer must be one this library allocated with cudaMalloc for the purpose (coh_fb_alloc_shared); the pool
 // allocations behind coh_fb_configure cannot be exported.
+// Behind its W x H pixels a shared framebuffer carries COH_SIGNAL_SLOTS 32-bit frame counters: the cross-process
+// "this band has landed" / "this frame is consumed" signals of coh_frame_signal / coh_frame_wait.
+static size_t shared_fb_bytes(const coh_ctx* ctx) { return sizeof(uint32_t) * ((size_t)ctx->fr.W * ctx->fr.H + COH_SIGNAL_SLOTS); }
 int coh_fb_alloc_shared(coh_ctx* ctx, uint8_t handle_out[64]) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->fr.W) FAIL("coh_fb_alloc_shared: call coh_fb_configure first");
   uint32_t* p = nullptr;
-  CK(cudaMalloc(&p, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H));
-  CK(cudaMemset(p, 0, sizeof(uint32_t) * (size_t)ctx->fr.W * ctx->fr.H));
+  CK(cudaMalloc(&p, shared_fb_bytes(ctx)));
+  CK(cudaMemset(p, 0, shared_fb_bytes(ctx)));
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, p));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
@@ -206,6 +209,64 @@ int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_o
   memcpy(&h, handle, 64);
   CK(cudaIpcOpenMemHandle(device_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
   ctx->opened_peers.push_back(*device_ptr_out);
+  return 0;
+}
+}  // extern "C"
+
+// ---- frame signals between processes (one per GPU): counters in the shared framebuffers, written over NVLink ----
+struct SignalTargets { int* flag[COH_MAX_PEERS + 1]; int n; };
+struct SignalSlots { int slot[COH_SIGNAL_SLOTS]; int n; };
+// Runs behind the frame's kernels in the stream: their stores (local and peer) are complete; the fence orders them
+// before the counter for observers on other devices, the counter is released at system scope.
+__global__ void k_frame_signal(SignalTargets T, int epoch) {
+  if (threadIdx.x < T.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(T.flag[threadIdx.x]), "r"(epoch) : "memory");
+  }
+}
+// One thread per awaited counter; gives up after ~4 s (a peer that died must not hang the GPU) and raises the error flag.
+__global__ void k_frame_wait(const int* flags, SignalSlots L, int epoch, int* error_flag) {
+  if (threadIdx.x < L.n) {
+    const int* f = flags + L.slot[threadIdx.x];
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v - epoch >= 0) break;   // (counters may wrap)
+      __nanosleep(200);
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 4000000000ull) { *error_flag = 5; break; }
+    }
+  }
+}
+extern "C" {
+// coh_frame_signal: after everything issued so far on the context's stream, counter `slot` of every target framebuffer
+// (this context's own shared framebuffer, or pointers from coh_fb_open_peer) becomes `epoch`.
+int coh_frame_signal(coh_ctx* ctx, int32_t n_targets, void* const* target_fbs, int32_t slot, int32_t epoch) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->fr.W) FAIL("coh_frame_signal: call coh_fb_configure first");
+  if (slot < 0 || slot >= COH_SIGNAL_SLOTS) FAIL("coh_frame_signal: slot out of range");
+  if (n_targets < 0 || n_targets > COH_MAX_PEERS + 1) FAIL("coh_frame_signal: too many targets");
+  if (n_targets == 0) return 0;
+  SignalTargets T; memset(&T, 0, sizeof T); T.n = n_targets;
+  for (int k = 0; k < n_targets; k++) {
+    void* p = target_fbs[k];
+    const bool known = (p && p == (void*)ctx->shared_fb) || std::find(ctx->opened_peers.begin(), ctx->opened_peers.end(), p) != ctx->opened_peers.end();
+    if (!known) FAIL("coh_frame_signal: a target is neither this context's shared framebuffer nor a pointer from coh_fb_open_peer");
+    T.flag[k] = (int*)((uint32_t*)p + (size_t)ctx->fr.W * ctx->fr.H) + slot;
+  }
+  k_frame_signal<<<1, 32, 0, ctx->stream>>>(T, epoch); LAUNCHED();
+  return 0;
+}
+// coh_frame_wait: the context's stream waits (on the device, no host round trip) until the listed counters of its own shared
+// framebuffer have reached `epoch`.
+int coh_frame_wait(coh_ctx* ctx, int32_t n_slots, const int32_t* slots, int32_t epoch) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->shared_fb || ctx->fb != ctx->shared_fb) FAIL("coh_frame_wait: the framebuffer is not a shared one (coh_fb_alloc_shared)");
+  if (n_slots < 0 || n_slots > COH_SIGNAL_SLOTS) FAIL("coh_frame_wait: too many slots");
+  if (n_slots == 0) return 0;
+  SignalSlots L; memset(&L, 0, sizeof L); L.n = n_slots;
+  for (int k = 0; k < n_slots; k++) { if (slots[k] < 0 || slots[k] >= COH_SIGNAL_SLOTS) FAIL("coh_frame_wait: slot out of range"); L.slot[k] = slots[k]; }
+  k_frame_wait<<<1, 32, 0, ctx->stream>>>((const int*)(ctx->shared_fb + (size_t)ctx->fr.W * ctx->fr.H), L, epoch, ctx->d_error); LAUNCHED();
   return 0;
 }
 }  // extern "C"

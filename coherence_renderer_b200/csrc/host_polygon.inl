@@ -41,6 +41,7 @@ static int check_error_flag(coh_ctx* ctx, const char* what) {
   CK(cudaStreamSynchronize(ctx->stream));
   if (*ctx->h_error) {
     cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->stream);
+    if (*ctx->h_error == 5) { ctx->err = std::string(what) + ": coh_frame_wait gave up after 4 s (a peer never signalled its frame)"; return 1; }
     ctx->err = std::string(what) + ": an object has more than " + std::to_string(COH_MAXX) + " band crossings inside one tile window of a row (COH_MAXX), or more than " + std::to_string(CARRY_CAP) + " fancy-fill edge runs cross one tile border (CARRY_CAP)";
     return 1;
   }

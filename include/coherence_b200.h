@@ -325,6 +325,16 @@ int coh_multi_fb_read_rgb888(coh_multi* m, int32_t x, int32_t y, int32_t w, int3
  *     to coh_fb_set_peers.  The host provides the cross-process barrier after a frame. */
 int coh_fb_alloc_shared(coh_ctx* ctx, uint8_t handle_out[64]);   /* after coh_fb_configure; replaces the framebuffer */
 int coh_fb_open_peer(coh_ctx* ctx, const uint8_t handle[64], void** device_ptr_out);
+/*     Frame signals for such hosts (no collective library in the data path): a shared framebuffer carries COH_SIGNAL_SLOTS
+ *     frame counters behind its pixels.  coh_frame_signal sets counter `slot` of every target framebuffer (pointers from
+ *     coh_fb_open_peer, or this context's own coh_fb_device_ptr) to `epoch` once everything issued so far on the context's
+ *     stream — the frame's kernels with their peer stores — is complete; coh_frame_wait makes the context's stream wait, on
+ *     the device, until the listed counters of its own shared framebuffer have reached `epoch` (it gives up after ~4 s and
+ *     the next coh_sync reports it).  The display rank waits for its peers' "band landed" counters; the peers wait for its
+ *     "frame consumed" counter before they store the next frame (bench.py). */
+#define COH_SIGNAL_SLOTS 16
+int coh_frame_signal(coh_ctx* ctx, int32_t n_targets, void* const* target_fbs, int32_t slot, int32_t epoch);
+int coh_frame_wait(coh_ctx* ctx, int32_t n_slots, const int32_t* slots, int32_t epoch);
 
 /* ---- host-side geometry preparation (CPU; the step before the raster path) ----
  * A path segment record is 9 doubles: kind (0 straight, 1 cubic bezier) then up to four points.

@@ -113,6 +113,9 @@ external multi_read_rgba : multi -> int * int * int * int -> u8 -> unit = "coh_m
 external multi_read_rgb888 : multi -> int * int * int * int -> u8 -> unit = "coh_ml_multi_read_rgb888"
 external fb_alloc_shared : ctx -> u8 -> unit = "coh_ml_fb_alloc_shared"
 external fb_open_peer : ctx -> u8 -> nativeint = "coh_ml_fb_open_peer"
+(* frame counters behind the pixels of a shared framebuffer: "band landed" / "frame consumed" between processes *)
+external frame_signal : ctx -> nativeint array -> int -> int -> unit = "coh_ml_frame_signal"
+external frame_wait : ctx -> i32 -> int -> unit = "coh_ml_frame_wait"
 external host_edgelist_of_subpath : f64 -> i32 -> int = "coh_ml_host_edgelist_of_subpath"
 external host_brush_points : f64 -> float -> i32 -> int = "coh_ml_host_brush_points"
 external host_smear_points : f64 -> i32 -> int = "coh_ml_host_smear_points"

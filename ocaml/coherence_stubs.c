@@ -546,6 +546,22 @@ CAMLprim value coh_ml_fb_open_peer(value ctx, value handle) {
   CAMLreturn(caml_copy_nativeint((intnat)p));
 }
 
+/* frame signals between processes: targets : nativeint array (pointers from fb_open_peer / fb_device_ptr) */
+CAMLprim value coh_ml_frame_signal(value ctx, value targets, value slot, value epoch) {
+  CAMLparam4(ctx, targets, slot, epoch);
+  void* t[16];
+  const long n = (long)Wosize_val(targets);
+  if (n > 16) caml_invalid_argument("frame_signal: too many targets");
+  for (long i = 0; i < n; i++) t[i] = (void*)Nativeint_val(Field(targets, i));
+  check(CTX(ctx), coh_frame_signal(CTX(ctx), (int32_t)n, t, Int_val(slot), Int_val(epoch)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value coh_ml_frame_wait(value ctx, value slots, value epoch) {   /* slots : int32 Array1 */
+  CAMLparam3(ctx, slots, epoch);
+  check(CTX(ctx), coh_frame_wait(CTX(ctx), (int32_t)BA_LEN(slots), (const int32_t*)Caml_ba_data_val(slots), Int_val(epoch)));
+  CAMLreturn(Val_unit);
+}
+
 /* ---- host-side geometry (Polygon.edgelist_of_path / Brush.points_of_brushstroke for one subpath) ---- */
 CAMLprim value coh_ml_host_edgelist_of_subpath(value segs, value out) {   /* segs : float64 Array1 of 9*n; returns the edge count */
   int64_t n = coh_host_edgelist_of_subpath((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 4);

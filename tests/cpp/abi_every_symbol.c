@@ -177,7 +177,17 @@ int main(int argc, char** argv) {
   OK(coh_fb_alloc_shared(C, ipc));
   ERR(coh_fb_open_peer(C, ipc, &mapped), "cudaIpcOpenMemHandle");
   OK(coh_render_frame(C, sc, 0, 0, W, H, 0)); OK(coh_fb_read_rgba(C, 0, 0, W, H, (uint8_t*)img)); CHECK(img[0] == 0xFFD3D3D3u);
+  /* frame signals: counters behind the pixels of a shared framebuffer (here the context signals itself) */
+  {
+    void* self_fb[1] = {coh_fb_device_ptr(C)}; int32_t slots[2] = {3, 3}; int dummy;
+    void* stranger[1] = {(void*)&dummy};
+    OK(coh_frame_signal(C, 1, self_fb, 3, 7)); OK(coh_frame_wait(C, 2, slots, 7)); OK(coh_frame_wait(C, 1, slots, 6)); OK(coh_sync(C));
+    ERR(coh_frame_signal(C, 1, stranger, 3, 8), "coh_fb_open_peer");
+    ERR(coh_frame_signal(C, 1, self_fb, 99, 8), "slot");
+    slots[0] = -1; ERR(coh_frame_wait(C, 1, slots, 7), "slot");
+  }
   OK(coh_fb_attach(C, NULL));
+  { int32_t s0 = 0; ERR(coh_frame_wait(C, 1, &s0, 1), "shared"); }
   /* one process, several devices (here: as many as are visible, at most 2) */
   {
     coh_multi* M = NULL;

@@ -157,3 +157,52 @@ def test_strokepath_on_device(ctx, oracle):
         ctx.shape_free(m)
     with pytest.raises(abi.CohError):
         ctx.strokepath(abi.strokespec(7, 0, 0, 10.0, 2.0), [[("L", (0.0, 0.0), (5.0, 5.0))]])
+
+
+@pytest.mark.gpu
+def test_stroked_path_objects_in_a_scene(ctx, oracle):
+    """Basic (fill, StrokedPath (spec, path)) end to end: the product's stroker gives the object's edges (coh_strokepath),
+    the frame renders them with the StrokedPath winding quirk (shape NonZero, sprite EvenOdd: render.ml:510, 1018); the
+    oracle strokes the same paths with its own restatement and renders its own edges.  Tight bends and a self-crossing
+    path make the outline overlap itself, where the two rules differ."""
+    from coherence_renderer_b200 import scene as S
+
+    W, H = 320, 240
+    strokes = [
+        (abi.strokespec(abi.CAP_ROUND, abi.JOIN_ROUND, abi.CAP_ROUND, 10.0, 14.0),
+         [[("L", (30.0, 200.0), (150.0, 40.0)), ("L", (150.0, 40.0), (170.0, 200.0)), ("C", (170.0, 200.0), (300.0, 220.0), (310.0, 20.0), (200.0, 60.0))]],
+         S.Fill.plain(S.dissolve(S.rgba8(200, 40, 20), 200))),
+        (abi.strokespec(abi.CAP_PROJECTING, abi.JOIN_MITRED, abi.CAP_BUTT, 4.0, 9.5),
+         [[("L", (20.0, 30.0), (280.0, 120.0)), ("L", (280.0, 120.0), (40.0, 150.0)), ("L", (40.0, 150.0), (260.0, 35.0))],
+          [("C", (60.0, 220.0), (100.0, 160.0), (200.0, 230.0), (250.0, 170.0))]],
+         S.Fill.plain(S.rgba8(20, 60, 160))),
+        (abi.strokespec(abi.CAP_BUTT, abi.JOIN_BEVEL, abi.CAP_ROUND, 10.0, 3.0),
+         [[("C", (10.0, 120.0), (100.0, 10.0), (220.0, 230.0), (310.0, 110.0)), ("L", (310.0, 110.0), (160.0, 118.0))]],
+         S.Fill.plain(S.dissolve(S.rgba8(10, 10, 10), 230))),
+    ]
+    b, bo = S.SceneBuilder(), S.SceneBuilder()
+    for spec, path, fill in strokes:
+        edges, w = ctx.strokepath(spec, path)
+        rec, cnt = abi._path_records(path)
+        _, _, ref_w, ref_edges = oracle.strokepath((spec.startcap, spec.join, spec.endcap, spec.mitrelimit, spec.linewidth), rec, cnt)
+        assert w == ref_w == abi.COH_EVENODD
+        b.stroked_path_edges(edges, fill)
+        bo.stroked_path_edges(ref_edges, fill)
+    for x in (b, bo):
+        x.begin_background()
+        x.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, e, p = b.arrays()
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, e, p)
+    ctx.render_frame(sc, (0, 0, W, H), abi.COH_RENDER_RECORD_U)
+    ctx.sync()
+    got = ctx.fb_read_rgba(0, 0, W, H)
+    u = ctx.render_uncovered()
+    got_u = ctx.shape_export(u)
+    ctx.shape_free(u)
+    ctx.scene_free(sc)
+    objs, n, nbg, e, p = bo.arrays()
+    ref, ref_u = oracle.render_frame(objs, n - nbg, nbg, e, p, (0, 0, W, H), want_u=True)
+    assert np.array_equal(got_u, ref_u)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert len(np.unique(got)) > 50   # strokes, their antialiased borders and the overlaps are all there
