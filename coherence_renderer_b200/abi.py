@@ -49,7 +49,7 @@ SYMBOLS = [
     "coh_scene_free", "coh_fb_configure", "coh_render_frame", "coh_render_frame_shape", "coh_scene_translate_object", "coh_render_uncovered", "coh_sync",
     "coh_fb_device_ptr", "coh_fb_read_rgba", "coh_fb_read_rgb888", "coh_fb_read_sprite", "coh_fb_read_rgba_async", "coh_fb_read_wait", "coh_fb_set_peers", "coh_mem_in_use",
     "coh_host_edgelist_of_subpath", "coh_host_brush_points", "coh_host_smear_points",
-    "coh_host_strokepath", "coh_strokepath", "coh_shapeminshape_of_stroke",
+    "coh_host_strokepath", "coh_host_bounds_stroke", "coh_strokepath", "coh_shapeminshape_of_stroke",
     "coh_cache_configure", "coh_cache_clear", "coh_cache_stats", "coh_cache_sprite_stats", "coh_cache_addshape", "coh_cache_getshape",
     "coh_cache_addtranslation", "coh_dirty_region", "coh_scene_drag_object", "coh_dirty_filter", "coh_scene_object_shape", "coh_convolve_sprite",
     "coh_multi_init", "coh_multi_shutdown", "coh_multi_last_error", "coh_multi_device_count", "coh_multi_ctx", "coh_multi_configure",
@@ -620,6 +620,15 @@ def host_strokepath(spec, subpaths):
     lib().coh_host_strokepath(C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt),
                               out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n), _i32p(counts), len(counts), C.byref(m), C.byref(w))
     return out[:n], counts[: m.value], w.value
+
+
+def host_bounds_stroke(spec, subpaths):
+    """Shapes.bounds_stroke: (xmin, xmax, ymin, ymax) of the stroke in pixels."""
+    rec, cnt = _path_records(subpaths)
+    out = np.zeros(4, dtype=np.int32)
+    if lib().coh_host_bounds_stroke(C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt), _i32p(out)) != 0:
+        raise CohError("Polygon2.bounds_polygon: Malformed (empty) path")
+    return tuple(int(v) for v in out)
 
 
 def host_edgelist_of_subpath(segs):

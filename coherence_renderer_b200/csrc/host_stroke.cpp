@@ -215,6 +215,27 @@ bool stroke_subpath(const coh_strokespec& spec, const std::vector<Seg>& segs, Ra
     outline.push_back(it->curve ? curve(it->p[3], it->p[2], it->p[1], it->p[0]) : line(it->p[1], it->p[0]));
   return true;
 }
+// Polygon.bounds_polygon (polygon.ml:404-438): pixel box of the segments' end points; a curve counts through its pieces at
+// a flatness of 1, grown by one pixel.
+inline int pix_of(double f) { const int sub = (int)ceil(f * 32.0 - 16.0); return (sub + 31) / 32; }   // coord.ml:44-50
+struct PixBounds {
+  int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+  void point(V p, int grow) {
+    const int x = pix_of(p.x), y = pix_of(p.y);
+    if (x - grow < x0) x0 = x - grow;
+    if (x + grow > x1) x1 = x + grow;
+    if (y - grow < y0) y0 = y - grow;
+    if (y + grow > y1) y1 = y + grow;
+  }
+};
+void chop_coarse(V p1, V p2, V p3, V p4, PixBounds& b) {   // bezier_subdivide (bezier_epsilon 1.): both ends of every piece
+  const double d1 = dist_from_chord(p2, p1, p4), d2 = dist_from_chord(p3, p1, p4);
+  const bool flat = (fpclassify(d1) == FP_NORMAL && fpclassify(d2) == FP_NORMAL) ? (d1 < 1. && d2 < 1.) : true;
+  if (flat) { b.point(p1, 1); b.point(p4, 1); return; }
+  const V l2 = mid(p1, p2), h = mid(p2, p3), l3 = mid(l2, h), r3 = mid(p3, p4), r2 = mid(h, r3), l4 = mid(l3, r2);
+  chop_coarse(p1, l2, l3, l4, b);
+  chop_coarse(l4, r2, r3, p4, b);
+}
 }  // namespace
 
 extern "C" {
@@ -277,5 +298,23 @@ int64_t coh_host_strokepath(const coh_strokespec* spec, const double* segs, cons
   }
   *n_subpaths_out = m; *winding_out = winding;
   return n;
+}
+// Shapes.bounds_stroke (shapes.ml:522-540): xmin, xmax, ymin, ymax of the path in pixels, grown by the stroke's reach.
+// Returns -1 for a path without subpaths (the reference fails).
+int32_t coh_host_bounds_stroke(const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths, int32_t bounds_out[4]) {
+  if (n_subpaths <= 0) return -1;
+  PixBounds b;
+  int64_t at = 0;
+  for (int k = 0; k < n_subpaths; k++)
+    for (int i = 0; i < subpath_segs[k]; i++, at++) {
+      const double* s = segs + 9 * at;
+      if (s[0] == 0.) { b.point(V{s[1], s[2]}, 0); b.point(V{s[3], s[4]}, 0); }
+      else chop_coarse(V{s[1], s[2]}, V{s[3], s[4]}, V{s[5], s[6]}, V{s[7], s[8]}, b);
+    }
+  double reach = (spec->startcap == COH_CAP_PROJECTING || spec->endcap == COH_CAP_PROJECTING) ? spec->linewidth : spec->linewidth / 2.;
+  if (spec->join == COH_JOIN_MITRED) { const double m = spec->mitrelimit * spec->linewidth; if (!(reach > m)) reach = m; }
+  const int grow = (int)ceil(reach);
+  bounds_out[0] = b.x0 - grow; bounds_out[1] = b.x1 + grow; bounds_out[2] = b.y0 - grow; bounds_out[3] = b.y1 + grow;
+  return 0;
 }
 }

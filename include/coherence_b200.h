@@ -388,6 +388,9 @@ typedef struct coh_strokespec {
 int64_t coh_host_strokepath(const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
                             double* segs_out, int64_t cap_segs, int32_t* subpath_segs_out, int32_t cap_subpaths,
                             int32_t* n_subpaths_out, int32_t* winding_out);
+/* Shapes.bounds_stroke (shapes.ml:522-540; Polygon.bounds_polygon, polygon.ml:404-438): xmin, xmax, ymin, ymax of the stroke in
+ * pixels — the path's pixel box grown by the reach of its caps and joins.  Returns -1 for a path without subpaths. */
+int32_t coh_host_bounds_stroke(const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths, int32_t bounds_out[4]);
 int coh_strokepath(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,
                    int32_t* edges_out, int64_t cap, int64_t* n_out, int32_t* winding_out);
 int coh_shapeminshape_of_stroke(coh_ctx* ctx, const coh_strokespec* spec, const double* segs, const int32_t* subpath_segs, int32_t n_subpaths,

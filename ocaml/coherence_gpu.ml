@@ -49,6 +49,7 @@ external shapeminshape_of_path : ctx -> f64 -> int -> shape_h * shape_h = "coh_m
 external strokepath_raw : ctx -> f64 -> f64 -> i32 -> i32 -> int * int = "coh_ml_strokepath"
 external shapeminshape_of_stroke : ctx -> f64 -> f64 -> i32 -> shape_h * shape_h = "coh_ml_shapeminshape_of_stroke"
 external host_strokepath : f64 -> f64 -> i32 -> f64 -> i32 -> int * int * int = "coh_ml_host_strokepath"
+external host_bounds_stroke : f64 -> f64 -> i32 -> int * int * int * int = "coh_ml_host_bounds_stroke"
 external polygon_opacity : ctx -> i32 -> int -> shape_h -> u8 -> int = "coh_ml_polygon_opacity"
 external polygon_sprite_raw : ctx -> u8 -> i32 -> int -> shape_h -> i32 -> int = "coh_ml_polygon_sprite_bc" "coh_ml_polygon_sprite"
 external shape_box : ctx -> int -> int -> int -> int -> shape_h = "coh_ml_shape_box"

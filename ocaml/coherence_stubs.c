@@ -164,6 +164,18 @@ CAMLprim value coh_ml_shapeminshape_of_stroke(value ctx, value spec, value segs,
   check(CTX(ctx), coh_shapeminshape_of_stroke(CTX(ctx), &sp, (const double*)Caml_ba_data_val(segs), (const int32_t*)Caml_ba_data_val(counts), (int32_t)BA_LEN(counts), &s, &m));
   CAMLreturn(pair_of_handles(s, m));
 }
+/* Shapes.bounds_stroke: (xmin, xmax, ymin, ymax) */
+CAMLprim value coh_ml_host_bounds_stroke(value spec, value segs, value counts) {
+  CAMLparam3(spec, segs, counts);
+  CAMLlocal1(r);
+  coh_strokespec sp = strokespec_of(spec);
+  int32_t b[4];
+  if (coh_host_bounds_stroke(&sp, (const double*)Caml_ba_data_val(segs), (const int32_t*)Caml_ba_data_val(counts), (int32_t)BA_LEN(counts), b) != 0)
+    caml_failwith("Polygon2.bounds_polygon: Malformed (empty) path");
+  r = caml_alloc_tuple(4);
+  for (int k = 0; k < 4; k++) Store_field(r, k, Val_int(b[k]));
+  CAMLreturn(r);
+}
 /* Shapes.strokepath_polygon on the host: returns (outline segments, outline subpaths, winding); out : float64 Array1 of
  * 9 * cap, out_counts : int32 Array1 */
 CAMLprim value coh_ml_host_strokepath(value spec, value segs, value counts, value out, value out_counts) {

@@ -515,6 +515,25 @@ int orc_strokepath(const double* spec5, const double* segs, const int32_t* subpa
   *edges_out = dup_ints(e); *n_edges_out = (int64_t)es.size();
   ORC_CATCH
 }
+int orc_bounds_stroke(const double* spec5, const double* segs, const int32_t* subpath_n, int n_subpaths, int32_t* bounds4) {
+  ORC_TRY
+  StrokeSpec spec{(Cap)(int)spec5[0], (Join)(int)spec5[1], (Cap)(int)spec5[2], spec5[3], spec5[4]};
+  Path path;
+  int at = 0;
+  for (int k = 0; k < n_subpaths; k++) {
+    Subpath sub;
+    for (int i = 0; i < subpath_n[k]; i++, at++) {
+      Segment s; s.bezier = segs[9 * at] != 0.;
+      for (int q = 0; q < 4; q++) s.p[q] = Pt(segs[9 * at + 1 + 2 * q], segs[9 * at + 2 + 2 * q]);
+      sub.push_back(s);
+    }
+    path.push_back(sub);
+  }
+  int b[4];
+  bounds_stroke(path, spec, b);
+  for (int k = 0; k < 4; k++) bounds4[k] = b[k];
+  ORC_CATCH
+}
 int orc_brush_stamp(double radius, double opacity, uint8_t* alpha_out, int cap, int* size_out) {
   ORC_TRY
   int size; auto b = drawround(radius, opacity, mkcol(255, 255, 255), size);

@@ -253,6 +253,16 @@ def strokepath(spec, segs, subpath_n):
     return out, _take(co, nc.value), w.value, _take(eo, ne.value * 4).reshape(-1, 4)
 
 
+def bounds_stroke(spec, segs, subpath_n):
+    """Shapes.bounds_stroke: (xmin, xmax, ymin, ymax) in pixels."""
+    a = np.ascontiguousarray(segs, dtype=np.float64).reshape(-1, 9)
+    cnt = np.ascontiguousarray(subpath_n, dtype=np.int32)
+    sp = np.ascontiguousarray(spec, dtype=np.float64)
+    out = np.zeros(4, dtype=np.int32)
+    _chk(lib().orc_bounds_stroke(_ptr(sp, C.c_double), _ptr(a, C.c_double), _ptr(cnt, C.c_int32), len(cnt), _ptr(out)))
+    return tuple(int(v) for v in out)
+
+
 def brush_stamp(radius, opacity):
     out = np.zeros(101 * 101, dtype=np.uint8)
     size = C.c_int()

@@ -325,4 +325,36 @@ inline std::vector<Edge> strokepath(const StrokeSpec& spec, const Path& path) {
   return es;
 }
 
+// polygon.ml:404-438 (bounds_polygon) and shapes.ml:522-540 (bounds_stroke): xmin, xmax, ymin, ymax
+inline void bounds_polygon(const Path& subpaths, int b[4]) {
+  ORACLE_ASSERT(!subpaths.empty(), "Polygon2.bounds_polygon: Malformed (empty) path");
+  int minx = INT32_MAX, maxx = INT32_MIN, miny = INT32_MAX, maxy = INT32_MIN;   // (max_int / min_int of the reference: never met by data)
+  for (const Subpath& sp : subpaths)
+    for (const Segment& s : sp) {
+      if (!s.bezier) {
+        int x0 = pix_of_float(s.p[0].first), x1 = pix_of_float(s.p[1].first), y0 = pix_of_float(s.p[0].second), y1 = pix_of_float(s.p[1].second);
+        minx = std::min(minx, std::min(x0, x1)); maxx = std::max(maxx, std::max(x0, x1));
+        miny = std::min(miny, std::min(y0, y1)); maxy = std::max(maxy, std::max(y0, y1));
+      } else {
+        std::vector<std::pair<Pt, Pt>> e;
+        bezier_subdivide(1., s.p[0], s.p[1], s.p[2], s.p[3], e);
+        Subpath segs;
+        for (auto& pe : e) segs.push_back(Straight(pe.first, pe.second));
+        int bb[4];
+        bounds_polygon(Path{segs}, bb);
+        minx = std::min(minx, bb[0] - 1); maxx = std::max(maxx, bb[1] + 1);
+        miny = std::min(miny, bb[2] - 1); maxy = std::max(maxy, bb[3] + 1);
+      }
+    }
+  b[0] = minx; b[1] = maxx; b[2] = miny; b[3] = maxy;
+}
+inline void bounds_stroke(const Path& path, const StrokeSpec& spec, int b[4]) {
+  double oversize = (spec.startcap == ProjectingCap || spec.endcap == ProjectingCap) ? spec.linewidth : spec.linewidth / 2.;
+  double oversize2 = oversize;
+  if (spec.join == MitredJoin) { double m = spec.mitrelimit * spec.linewidth; oversize2 = oversize > m ? oversize : m; }   // Pdfutil.fmax
+  int oi = (int)std::ceil(oversize2);
+  bounds_polygon(path, b);
+  b[0] -= oi; b[1] += oi; b[2] -= oi; b[3] += oi;
+}
+
 }  // namespace oracle

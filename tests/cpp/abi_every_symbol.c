@@ -262,6 +262,8 @@ int main(int argc, char** argv) {
     sp.startcap = COH_CAP_ROUND; sp.join = COH_JOIN_MITRED; sp.endcap = COH_CAP_PROJECTING; sp.mitrelimit = 10.0; sp.linewidth = 8.0;
     int64_t on = coh_host_strokepath(&sp, path, counts, 1, NULL, 0, oc, 4, &om_, &ow);
     CHECK(on > 12 && om_ == 1 && oc[0] == on && ow == COH_EVENODD);
+    int32_t sb[4]; CHECK(coh_host_bounds_stroke(&sp, path, counts, 1, sb) == 0 && sb[0] <= 20 - 80 && sb[1] >= 120 + 80 && sb[2] <= 20 - 80 && sb[3] >= 120 + 80);   /* mitre limit 10 x width 8 */
+    CHECK(coh_host_bounds_stroke(&sp, path, counts, 0, sb) == -1);
     double* outl = (double*)malloc(sizeof(double) * 9 * (size_t)on);
     CHECK(coh_host_strokepath(&sp, path, counts, 1, outl, on, oc, 4, &om_, &ow) == on && outl[0] == 1.0);   /* a round cap comes first */
     int32_t* se = (int32_t*)malloc(sizeof(int32_t) * 4 * 4096); int64_t sn = 0; int32_t sw = -1;

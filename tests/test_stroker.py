@@ -121,6 +121,30 @@ def test_join_areas_are_ordered_and_mitre_limit_bevels(oracle):
     assert _area(oracle, edges, wd)[0] == area[abi.JOIN_BEVEL]
 
 
+def test_bounds_stroke(oracle):
+    """Shapes.bounds_stroke (shapes.ml:522-540): product = oracle, and the box holds the stroke's shape (to within the few pixels of the reference's estimate)."""
+    rng = np.random.default_rng(31)
+    for trial in range(60):
+        subpaths = _random_path(rng, degenerate=False)
+        rec, cnt = abi._path_records(subpaths)
+        sc, jn, ec = int(rng.integers(0, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        ml, lw = float(rng.choice([1.0, 2.5, 10.0])), float(rng.choice([0.5, 3.0, 11.5]))
+        got = abi.host_bounds_stroke(abi.strokespec(sc, jn, ec, ml, lw), subpaths)
+        assert got == oracle.bounds_stroke((sc, jn, ec, ml, lw), rec, cnt), trial
+        _, _, wd, edges = oracle.strokepath((sc, jn, ec, ml, lw), rec, cnt)
+        shape, _ = oracle.shapeminshape(edges, wd)
+        rows = list(_rows(shape))
+        if jn == abi.JOIN_MITRED:
+            continue   # (a sharp mitre under a small limit is bevelled, under a large one it may still reach beyond: shapes.ml:520-521)
+        # the box is the reference's estimate, not a proof: the soft matte and the flaring of offset curves at tight bends
+        # (shapes.ml:155-158) reach a few pixels beyond the stroke's half width
+        slack = 6
+        assert min(int(r[0]) for r in rows) >= got[2] - slack and max(int(r[0]) for r in rows) <= got[3] + slack, trial
+        assert min(int(r[1]) for r in rows) >= got[0] - slack and max(int(r[-2] + r[-1] - 1) for r in rows) <= got[1] + slack, trial
+    with pytest.raises(abi.CohError):
+        abi.host_bounds_stroke(abi.strokespec(0, 0, 0, 10.0, 1.0), [])
+
+
 def test_degenerate_path_with_round_caps_is_a_circle(oracle):
     rec, cnt = abi._path_records([[("L", (50.0, 60.0), (50.0, 60.0))]])
     out, c, wd, edges = oracle.strokepath((abi.CAP_ROUND, abi.JOIN_BEVEL, abi.CAP_ROUND, 10.0, 30.0), rec, cnt)
