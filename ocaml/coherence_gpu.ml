@@ -222,6 +222,50 @@ let shapeminshape_of_unsorted_edgelist (edges : Polygon.edge list) winding =
 let shapeminshape_polygon (path : Pdfgraphics.path) =
   shapeminshape_of_unsorted_edgelist (Polygon.edgelist_of_path path) (fst path)
 
+(* ---- shapes.mli:38-41: Shapes.strokepath / bounds_stroke through the library (N2) ---- *)
+let f64_of_strokespec (sp : Shapes.strokespec) : f64 =
+  let cap = function Shapes.ButtCap -> 0. | Shapes.RoundCap -> 1. | Shapes.ProjectingCap -> 2.
+  and join = function Shapes.RoundJoin -> 0. | Shapes.MitredJoin -> 1. | Shapes.BevelJoin -> 2. in
+  let a = Array1.create float64 c_layout 5 in
+  a.{0} <- cap sp.Shapes.startcap; a.{1} <- join sp.Shapes.join; a.{2} <- cap sp.Shapes.endcap;
+  a.{3} <- sp.Shapes.mitrelimit; a.{4} <- sp.Shapes.linewidth;
+  a
+
+(* the segments of every subpath as 9-float records (kind, then up to four points) + the segments per subpath *)
+let records_of_path ((_, subpaths) : Pdfgraphics.path) : f64 * i32 =
+  let segs = List.concat (List.map (fun (_, _, s) -> s) subpaths) in
+  let rec_ = Array1.create float64 c_layout (9 * max 1 (List.length segs)) in
+  Array1.fill rec_ 0.;
+  List.iteri
+    (fun i seg ->
+       let put k (x, y) = rec_.{9 * i + 1 + 2 * k} <- x; rec_.{9 * i + 2 + 2 * k} <- y in
+       match seg with
+       | Pdfgraphics.Straight (a, b) -> rec_.{9 * i} <- 0.; put 0 a; put 1 b
+       | Pdfgraphics.Bezier (a, b, c, d) -> rec_.{9 * i} <- 1.; put 0 a; put 1 b; put 2 c; put 3 d)
+    segs;
+  let counts = Array1.create int32 c_layout (List.length subpaths) in
+  List.iteri (fun k (_, _, s) -> counts.{k} <- Int32.of_int (List.length s)) subpaths;
+  (Array1.sub rec_ 0 (9 * List.length segs), counts)
+
+(* val strokepath : strokespec -> Pdfgraphics.path -> Polygon.edge list — the outline by the library's host stroker,
+   flattened on the device, sorted by Polygon.sort_edgelist_maxy_rev *)
+let strokepath (sp : Shapes.strokespec) (path : Pdfgraphics.path) : Polygon.edge list =
+  let spec = f64_of_strokespec sp and segs, counts = records_of_path path in
+  let rec go cap =
+    let out = Array1.create int32 c_layout (4 * cap) in
+    let n, _ = strokepath_raw (ctx ()) spec segs counts out in
+    if n > cap then go n
+    else List.init n (fun i ->
+        { Polygon.x0 = Int32.to_int out.{4 * i}; Polygon.y0 = Int32.to_int out.{4 * i + 1};
+          Polygon.x1 = Int32.to_int out.{4 * i + 2}; Polygon.y1 = Int32.to_int out.{4 * i + 3} })
+  in
+  go (256 * (Array1.dim segs / 9) + 256)
+
+(* val bounds_stroke : Pdfgraphics.path -> strokespec -> int * int * int * int *)
+let bounds_stroke (path : Pdfgraphics.path) (sp : Shapes.strokespec) =
+  let segs, counts = records_of_path path in
+  host_bounds_stroke (f64_of_strokespec sp) segs counts
+
 (* ---- fills: descriptors for the records of closures (fill.mli) ---- *)
 type fill_desc =
   | FPlain of Colour.colour
