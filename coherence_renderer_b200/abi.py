@@ -56,6 +56,7 @@ SYMBOLS = [
     "coh_multi_scene_create", "coh_multi_scene_free", "coh_multi_scene_translate_object", "coh_multi_render_frame", "coh_multi_sync",
     "coh_multi_fb_read_rgba", "coh_multi_fb_read_rgb888", "coh_fb_alloc_shared", "coh_fb_open_peer", "coh_frame_signal", "coh_frame_wait",
     "coh_shape_intersects", "coh_sprite_portion", "coh_sprite_fillshape", "coh_sprite_map", "coh_sprite_map_coords_fill",
+    "coh_host_wire_marshal", "coh_host_wire_unmarshal", "coh_host_wire_refresh_window", "coh_wire_refresh_window",
 ]
 
 _lib = None
@@ -88,6 +89,8 @@ def lib():
         L.coh_host_brush_points.restype = C.c_int64
         L.coh_host_smear_points.restype = C.c_int64
         L.coh_host_strokepath.restype = C.c_int64
+        L.coh_host_wire_marshal.restype = C.c_int64
+        L.coh_host_wire_refresh_window.restype = C.c_int64
         L.coh_multi_last_error.restype = C.c_char_p
         L.coh_multi_last_error.argtypes = [C.c_void_p]
         L.coh_multi_ctx.restype = C.c_void_p
@@ -509,6 +512,17 @@ class Context:
         self._chk(lib().coh_fb_read_rgb888(self._h, x, y, w, h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
 
+    def wire_refresh_window(self, window, xmin, ymin, xmax, ymax):
+        """Wxgui.refresh_window's marshalled message (wxgui.ml:352-366) with the pixels of the framebuffer; b"" where the
+        reference sends nothing."""
+        n = C.c_int64()
+        self._chk(lib().coh_wire_refresh_window(self._h, window, xmin, ymin, xmax, ymax, None, C.c_int64(0), C.byref(n)))
+        if n.value == 0:
+            return b""
+        out = np.zeros(n.value, dtype=np.uint8)
+        self._chk(lib().coh_wire_refresh_window(self._h, window, xmin, ymin, xmax, ymax, out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n.value), C.byref(n)))
+        return out.tobytes()
+
 
 class MultiContext:
     """Several GPUs of one box from one process (coh_multi_*): every device renders its band of scanlines and stores
@@ -629,6 +643,93 @@ def host_bounds_stroke(spec, subpaths):
     if lib().coh_host_bounds_stroke(C.byref(spec), rec.ctypes.data_as(C.POINTER(C.c_double)), _i32p(cnt), len(cnt), _i32p(out)) != 0:
         raise CohError("Polygon2.bounds_polygon: Malformed (empty) path")
     return tuple(int(v) for v in out)
+
+
+# ---- the front end's socket format (camlpy.mli): Python values <-> Camlpy.marshallable as pycaml.py maps them
+# (None = Unit, bool = Bool, int = Int, bytes / str = String, list / tuple = Tuple)
+WIRE_TUPLE, WIRE_UNIT, WIRE_INT, WIRE_STRING, WIRE_BOOL = 0, 1, 2, 3, 4
+
+
+def _wire_tokens(m, kinds, values, offsets, blob):
+    if m is None:
+        kinds.append(WIRE_UNIT), values.append(0), offsets.append(0)
+    elif isinstance(m, bool):
+        kinds.append(WIRE_BOOL), values.append(int(m)), offsets.append(0)
+    elif isinstance(m, int):
+        kinds.append(WIRE_INT), values.append(m), offsets.append(0)
+    elif isinstance(m, (bytes, bytearray, str)):
+        b = m.encode("latin-1") if isinstance(m, str) else bytes(m)
+        kinds.append(WIRE_STRING), values.append(len(b)), offsets.append(len(blob))
+        blob.extend(b)
+    elif isinstance(m, (list, tuple)):
+        kinds.append(WIRE_TUPLE), values.append(len(m)), offsets.append(0)
+        for e in m:
+            _wire_tokens(e, kinds, values, offsets, blob)
+    else:
+        raise CohError("Invalid Data")
+
+
+def _i64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def host_wire_marshal_tokens(kinds, values, offsets, blob=b""):
+    """coh_host_wire_marshal on a raw token list (None when the list is not exactly one value)."""
+    k, v, o = np.asarray(kinds, dtype=np.int32), np.asarray(values, dtype=np.int64), np.asarray(offsets, dtype=np.int64)
+    sb = np.frombuffer(bytes(blob) + b"\0", dtype=np.uint8)
+    n = lib().coh_host_wire_marshal(_i32p(k), _i64p(v), _i64p(o), len(k), sb.ctypes.data_as(C.POINTER(C.c_uint8)), None, C.c_int64(0))
+    if n < 0:
+        return None
+    out = np.zeros(n, dtype=np.uint8)
+    lib().coh_host_wire_marshal(_i32p(k), _i64p(v), _i64p(o), len(k), sb.ctypes.data_as(C.POINTER(C.c_uint8)), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n))
+    return out.tobytes()
+
+
+def host_wire_marshal(m):
+    """Camlpy.marshall (camlpy.ml:77-82) of a Python value."""
+    kinds, values, offsets, blob = [], [], [], bytearray()
+    _wire_tokens(m, kinds, values, offsets, blob)
+    return host_wire_marshal_tokens(kinds, values, offsets, blob)
+
+
+def host_wire_unmarshal(data):
+    """Camlpy.unmarshall (camlpy.ml:106-124): None while the message is incomplete, else (bytes taken, value); CohError for
+    Invalid_data.  Strings come back as bytes."""
+    buf = np.frombuffer(bytes(data) + b"\0", dtype=np.uint8)
+    nt, taken = C.c_int32(), C.c_int64()
+    bp = buf.ctypes.data_as(C.POINTER(C.c_uint8))
+    if lib().coh_host_wire_unmarshal(bp, C.c_int64(len(data)), None, None, None, 0, C.byref(nt), C.byref(taken)) != 0:
+        raise CohError("Invalid_data")
+    if taken.value == 0:
+        return None
+    k, v, o = np.zeros(nt.value, dtype=np.int32), np.zeros(nt.value, dtype=np.int64), np.zeros(nt.value, dtype=np.int64)
+    lib().coh_host_wire_unmarshal(bp, C.c_int64(len(data)), _i32p(k), _i64p(v), _i64p(o), nt.value, C.byref(nt), C.byref(taken))
+    pos = [0]
+
+    def build():
+        i = pos[0]
+        pos[0] += 1
+        if k[i] == WIRE_UNIT:
+            return None
+        if k[i] == WIRE_BOOL:
+            return bool(v[i])
+        if k[i] == WIRE_INT:
+            return int(v[i])
+        if k[i] == WIRE_STRING:
+            return bytes(data[int(o[i]) : int(o[i]) + int(v[i])])
+        return [build() for _ in range(int(v[i]))]
+
+    return taken.value, build()
+
+
+def host_wire_refresh_window(window, xmin, ymin, xmax, ymax):
+    """(size of the whole RefreshWindow message, the bytes in front of its pixels); (0, b"") where nothing is sent."""
+    hdr = np.zeros(64, dtype=np.uint8)
+    hl = C.c_int32()
+    n = lib().coh_host_wire_refresh_window(window, xmin, ymin, xmax, ymax, hdr.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(hl))
+    if n < 0:
+        raise CohError("refresh_window: not a rectangle (wxgui.ml:335)")
+    return int(n), hdr[: hl.value].tobytes()
 
 
 def host_edgelist_of_subpath(segs):

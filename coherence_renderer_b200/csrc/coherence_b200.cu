@@ -538,6 +538,21 @@ int coh_fb_read_rgb888(coh_ctx* ctx, int32_t x, int32_t y, int32_t w, int32_t h,
   DFREE(d);
   return rc;
 }
+// Wxgui.refresh_window (wxgui.ml:333-366) without the canvas walk: the marshalled "RefreshWindow" message of a dirty
+// rectangle, its pixel string filled from the framebuffer by coh_fb_read_rgb888's kernel and copy.
+int coh_wire_refresh_window(coh_ctx* ctx, int32_t window, int32_t xmin, int32_t ymin, int32_t xmax, int32_t ymax, uint8_t* out, int64_t cap, int64_t* len) {
+  if (!len) FAIL("coh_wire_refresh_window: len is NULL");
+  *len = 0;
+  uint8_t hdr[64]; int32_t hl = 0;
+  const int64_t total = coh_host_wire_refresh_window(window, xmin, ymin, xmax, ymax, hdr, &hl);
+  if (total < 0) FAIL("coh_wire_refresh_window: not a rectangle (wxgui.ml:335)");
+  if (total == 0) return 0;                       // zero-width or zero-height rectangles just do nothing (wxgui.ml:354-357)
+  *len = total;
+  if (!out || cap < total) return 0;              // the size is reported; nothing is written
+  if (coh_fb_read_rgb888(ctx, xmin, ymin, xmax - xmin + 1, ymax - ymin + 1, out + hl)) { *len = 0; return 1; }
+  memcpy(out, hdr, (size_t)hl);
+  return 0;
+}
 
 }  // extern "C"
 #include "host_multi.inl"

@@ -400,6 +400,36 @@ int coh_shapeminshape_of_stroke(coh_ctx* ctx, const coh_strokespec* spec, const 
 int64_t coh_host_smear_points(const double* segs, int32_t n_segs, int32_t* points_out, int64_t cap);
 int64_t coh_host_brush_points(const double* segs, int32_t n_segs, double radius, int32_t* points_out, int64_t cap);
 
+/* ---- N4 meeting N1 — the front end's socket format (camlpy.mli; camlpy.ml:18-124, Python side pycaml.py:30-98) ----
+ * A Camlpy.marshallable crosses the ABI as its pre-order token list: kinds[i] = COH_WIRE_* (the format's own tags,
+ * camlpy.ml:26-30); values[i] = the Int (written as its low 32 bits, read back as 0 .. 2^32 - 1 without sign extension,
+ * camlpy.ml:33-37, 85-86), the Bool (0 / 1; any non-zero byte reads as 1), the String's length, or the number of members of
+ * the Tuple; offsets[i] = where a String's bytes lie — in `strings` for marshal, in the message for unmarshal.
+ * coh_host_wire_marshal     Camlpy.marshall: 4 bytes of size + the flattened value.  Returns the message size (written only
+ *                           when out != NULL and cap suffices), -1 for a token list that is not exactly one value.
+ * coh_host_wire_unmarshal   Camlpy.unmarshall: *taken = 0 while the message is incomplete (None), else the bytes taken
+ *                           (Some (len + 4, v)); returns -1 for Invalid_data (malformed, or not exactly one value).
+ *                           *n_tokens is the number of tokens whatever cap_tokens is.
+ * coh_host_wire_refresh_window   the bytes in front of the pixels of Wxgui.refresh_window's message (wxgui.ml:352-366):
+ *                           Tuple [String "RefreshWindow"; Int window; Int xmin; Int ymin; Int w; Int h; String rgb888].
+ *                           Returns the size of the whole message, 0 where the reference sends nothing (xmin = xmax or
+ *                           ymin = ymax), -1 where its assertion fails (wxgui.ml:335).
+ * coh_wire_refresh_window   the whole message, its pixel string (string_of_canvas_portion, wxgui.ml:334-350: rows ymin ..
+ *                           ymax, columns xmin .. xmax INCLUSIVE, r, g, b) copied out of the GPU framebuffer; *len = its
+ *                           size (0: nothing to send); nothing is written when cap < *len.  The reference's canvas is
+ *                           1280 x 1024 "for now" (wxgui.ml:336); here the rectangle must lie inside the framebuffer. */
+#define COH_WIRE_TUPLE 0
+#define COH_WIRE_UNIT 1
+#define COH_WIRE_INT 2
+#define COH_WIRE_STRING 3
+#define COH_WIRE_BOOL 4
+int64_t coh_host_wire_marshal(const int32_t* kinds, const int64_t* values, const int64_t* offsets, int32_t n_tokens,
+                              const uint8_t* strings, uint8_t* out, int64_t cap);
+int32_t coh_host_wire_unmarshal(const uint8_t* buf, int64_t n, int32_t* kinds, int64_t* values, int64_t* offsets, int32_t cap_tokens,
+                                int32_t* n_tokens, int64_t* taken);
+int64_t coh_host_wire_refresh_window(int32_t window, int32_t xmin, int32_t ymin, int32_t xmax, int32_t ymax, uint8_t header_out[64], int32_t* header_len);
+int coh_wire_refresh_window(coh_ctx* ctx, int32_t window, int32_t xmin, int32_t ymin, int32_t xmax, int32_t ymax, uint8_t* out, int64_t cap, int64_t* len);
+
 #ifdef __cplusplus
 }
 #endif

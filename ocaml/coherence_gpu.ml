@@ -20,6 +20,7 @@ type scene_h = int64
 type i32 = (int32, int32_elt, c_layout) Array1.t
 type u8 = (int, int8_unsigned_elt, c_layout) Array1.t
 type f64 = (float, float64_elt, c_layout) Array1.t
+type i64 = (int64, int64_elt, c_layout) Array1.t
 
 (* ---- one external per exported symbol (ocaml/coherence_stubs.c) ---- *)
 external init : int -> ctx = "coh_ml_init"
@@ -50,6 +51,10 @@ external strokepath_raw : ctx -> f64 -> f64 -> i32 -> i32 -> int * int = "coh_ml
 external shapeminshape_of_stroke : ctx -> f64 -> f64 -> i32 -> shape_h * shape_h = "coh_ml_shapeminshape_of_stroke"
 external host_strokepath : f64 -> f64 -> i32 -> f64 -> i32 -> int * int * int = "coh_ml_host_strokepath"
 external host_bounds_stroke : f64 -> f64 -> i32 -> int * int * int * int = "coh_ml_host_bounds_stroke"
+external host_wire_marshal : i32 -> i64 -> i64 -> string -> string = "coh_ml_host_wire_marshal"
+external host_wire_unmarshal : string -> i32 -> i64 -> i64 -> int * int = "coh_ml_host_wire_unmarshal"
+external host_wire_refresh_window : int -> int * int * int * int -> string * int = "coh_ml_host_wire_refresh_window"
+external wire_refresh_window : ctx -> int -> int * int * int * int -> string = "coh_ml_wire_refresh_window"
 external polygon_opacity : ctx -> i32 -> int -> shape_h -> u8 -> int = "coh_ml_polygon_opacity"
 external polygon_sprite_raw : ctx -> u8 -> i32 -> int -> shape_h -> i32 -> int = "coh_ml_polygon_sprite_bc" "coh_ml_polygon_sprite"
 external shape_box : ctx -> int -> int -> int -> int -> shape_h = "coh_ml_shape_box"
@@ -617,3 +622,56 @@ let convolve_sprite (k : Convolve.kernel) (spr : Sprite.sprite) : Sprite.sprite 
     let rs = convolve_sprite_raw (ctx ()) (kind_of_kernel k, r) h px out in
     let s = sprite_of_pixels (shape_export (ctx ()) rs) out in
     shape_free (ctx ()) rs; s)
+
+(* ---- N4 / N1: camlpy.mli through the library, and Wxgui.refresh_window without the canvas walk ---- *)
+let wire_tuple = 0 and wire_unit = 1 and wire_int = 2 and wire_string = 3 and wire_bool = 4   (* camlpy.ml:26-30 *)
+
+(* val marshall : marshallable -> string (camlpy.mli) *)
+let marshall (m : Camlpy.marshallable) : string =
+  let toks = ref [] and blob = Buffer.create 64 in
+  let rec go = function
+    | Camlpy.Unit -> toks := (wire_unit, 0L, 0L) :: !toks
+    | Camlpy.Int i -> toks := (wire_int, Int64.of_int i, 0L) :: !toks
+    | Camlpy.Bool b -> toks := (wire_bool, (if b then 1L else 0L), 0L) :: !toks
+    | Camlpy.String st ->
+        toks := (wire_string, Int64.of_int (String.length st), Int64.of_int (Buffer.length blob)) :: !toks;
+        Buffer.add_string blob st
+    | Camlpy.Tuple ls -> toks := (wire_tuple, Int64.of_int (List.length ls), 0L) :: !toks; List.iter go ls
+  in
+  go m;
+  let toks = Array.of_list (List.rev !toks) in
+  let n = Array.length toks in
+  let kinds = Array1.create int32 c_layout n and values = Array1.create int64 c_layout n and offsets = Array1.create int64 c_layout n in
+  Array.iteri (fun i (k, v, o) -> kinds.{i} <- Int32.of_int k; values.{i} <- v; offsets.{i} <- o) toks;
+  host_wire_marshal kinds values offsets (Buffer.contents blob)
+
+(* val unmarshall : string -> (int * marshallable) option (camlpy.mli); raises Camlpy.Invalid_data *)
+let unmarshall (str : string) : (int * Camlpy.marshallable) option =
+  let cap = max 1 (String.length str) in   (* every token takes at least one byte *)
+  let kinds = Array1.create int32 c_layout cap and values = Array1.create int64 c_layout cap and offsets = Array1.create int64 c_layout cap in
+  let (taken, _) = try host_wire_unmarshal str kinds values offsets with Failure _ -> raise Camlpy.Invalid_data in
+  if taken = 0 then None else begin
+    let pos = ref 0 in
+    let rec build () =
+      let i = !pos in
+      incr pos;
+      let k = Int32.to_int kinds.{i} and v = Int64.to_int values.{i} in
+      if k = wire_unit then Camlpy.Unit
+      else if k = wire_int then Camlpy.Int v
+      else if k = wire_bool then Camlpy.Bool (v <> 0)
+      else if k = wire_string then Camlpy.String (String.sub str (Int64.to_int offsets.{i}) v)
+      else begin
+        let members = ref [] in
+        for _ = 1 to v do members := build () :: !members done;
+        Camlpy.Tuple (List.rev !members)
+      end
+    in
+    Some (taken, build ())
+  end
+
+(* Wxgui.refresh_window window (xmin, ymin, xmax, ymax) (wxgui.ml:352-366) for a framebuffer kept on the GPU: the
+   marshalled message, ready for Pytalk's send; "" for the rectangles the reference sends nothing for.  After
+   Render.render_frame has run on the device (render_frame_box / scene_drag_object), this replaces plot_sprite +
+   string_of_canvas_portion + Camlpy.marshall: no sprite is rebuilt, no canvas is walked. *)
+let refresh_window_message (window : int) (rect : int * int * int * int) : string =
+  wire_refresh_window (ctx ()) window rect

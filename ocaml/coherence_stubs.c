@@ -587,3 +587,55 @@ CAMLprim value coh_ml_host_brush_points(value segs, value radius, value out) {
   int64_t n = coh_host_brush_points((const double*)Caml_ba_data_val(segs), (int32_t)(BA_LEN(segs) / 9), Double_val(radius), (int32_t*)Caml_ba_data_val(out), BA_LEN(out) / 2);
   return Val_long((long)n);
 }
+
+/* ---- N4 / N1: the front end's socket format (camlpy.mli) and Wxgui.refresh_window's message ----
+ * kinds : int32 Array1; values, offsets : int64 Array1 (pre-order tokens, include/coherence_b200.h); strings : string */
+CAMLprim value coh_ml_host_wire_marshal(value kinds, value values, value offsets, value strings) {   /* Camlpy.marshall */
+  CAMLparam4(kinds, values, offsets, strings);
+  CAMLlocal1(s);
+  const int32_t n = (int32_t)BA_LEN(kinds);
+  if (BA_LEN(values) < n || BA_LEN(offsets) < n) caml_invalid_argument("wire_marshal: token arrays of different lengths");
+  const int64_t size = coh_host_wire_marshal((const int32_t*)Caml_ba_data_val(kinds), (const int64_t*)Caml_ba_data_val(values), (const int64_t*)Caml_ba_data_val(offsets), n,
+                                             (const uint8_t*)String_val(strings), NULL, 0);
+  if (size < 0) caml_invalid_argument("wire_marshal: not one marshallable");
+  s = caml_alloc_string((size_t)size);   /* (allocation: String_val (strings) is taken again below) */
+  coh_host_wire_marshal((const int32_t*)Caml_ba_data_val(kinds), (const int64_t*)Caml_ba_data_val(values), (const int64_t*)Caml_ba_data_val(offsets), n,
+                        (const uint8_t*)String_val(strings), (uint8_t*)Bytes_val(s), size);
+  CAMLreturn(s);
+}
+/* Camlpy.unmarshall: (bytes taken, tokens); taken = 0: the message is not complete yet; Failure "Invalid_data" */
+CAMLprim value coh_ml_host_wire_unmarshal(value str, value kinds, value values, value offsets) {
+  CAMLparam4(str, kinds, values, offsets);
+  int32_t nt = 0, cap = (int32_t)BA_LEN(kinds);
+  int64_t taken = 0;
+  if (BA_LEN(values) < cap || BA_LEN(offsets) < cap) caml_invalid_argument("wire_unmarshal: token arrays of different lengths");
+  if (coh_host_wire_unmarshal((const uint8_t*)String_val(str), (int64_t)caml_string_length(str), (int32_t*)Caml_ba_data_val(kinds), (int64_t*)Caml_ba_data_val(values),
+                              (int64_t*)Caml_ba_data_val(offsets), cap, &nt, &taken) != 0) caml_failwith("Invalid_data");
+  int32_t r[2] = {(int32_t)taken, nt};
+  CAMLreturn(tuple_of_ints(r, 2));
+}
+/* the bytes in front of the pixels of a RefreshWindow message and the size of the whole message; ("", 0): nothing to send */
+CAMLprim value coh_ml_host_wire_refresh_window(value window, value rect) {   /* rect = (xmin, ymin, xmax, ymax), inclusive */
+  CAMLparam2(window, rect);
+  CAMLlocal2(h, r);
+  uint8_t hdr[64]; int32_t hl = 0;
+  const int64_t total = coh_host_wire_refresh_window(Int_val(window), Int_val(Field(rect, 0)), Int_val(Field(rect, 1)), Int_val(Field(rect, 2)), Int_val(Field(rect, 3)), hdr, &hl);
+  if (total < 0) caml_invalid_argument("refresh_window: not a rectangle");
+  h = caml_alloc_string((size_t)hl);
+  memcpy(Bytes_val(h), hdr, (size_t)hl);
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, h);
+  Store_field(r, 1, Val_long((long)total));
+  CAMLreturn(r);
+}
+/* Wxgui.refresh_window's whole message for a dirty rectangle, pixels from the GPU framebuffer ("" = nothing to send) */
+CAMLprim value coh_ml_wire_refresh_window(value ctx, value window, value rect) {
+  CAMLparam3(ctx, window, rect);
+  CAMLlocal1(s);
+  const int32_t w = Int_val(window), x0 = Int_val(Field(rect, 0)), y0 = Int_val(Field(rect, 1)), x1 = Int_val(Field(rect, 2)), y1 = Int_val(Field(rect, 3));
+  int64_t len = 0;
+  check(CTX(ctx), coh_wire_refresh_window(CTX(ctx), w, x0, y0, x1, y1, NULL, 0, &len));
+  s = caml_alloc_string((size_t)len);
+  if (len > 0) check(CTX(ctx), coh_wire_refresh_window(CTX(ctx), w, x0, y0, x1, y1, (uint8_t*)Bytes_val(s), len, &len));   /* (blocks; the runtime lock is held: s does not move) */
+  CAMLreturn(s);
+}

@@ -145,6 +145,30 @@ int main(int argc, char** argv) {
   ERR(coh_fb_read_rgba(C, 0, 0, W + 1, H, (uint8_t*)img), "outside");
   OK(coh_fb_read_rgb888(C, 0, 0, W, H, rgb)); CHECK(rgb[0] == 0xD3 && rgb[3 * (40 * W + 140) + 1] == 0xFF);
   ERR(coh_fb_read_rgb888(C, -1, 0, 4, 4, rgb), "outside");
+  /* N4 / N1: the socket format and the RefreshWindow message of a dirty rectangle */
+  {
+    const int32_t kinds[4] = {COH_WIRE_TUPLE, COH_WIRE_STRING, COH_WIRE_INT, COH_WIRE_BOOL};
+    const int64_t vals[4] = {3, 8, 7, 1}, offs[4] = {0, 0, 0, 0};
+    uint8_t wm[64]; int32_t k2[8], nt = 0; int64_t v2[8], o2[8], taken = -1;
+    int64_t wl = coh_host_wire_marshal(kinds, vals, offs, 4, (const uint8_t*)"MouseNow", wm, sizeof wm);
+    CHECK(wl == 4 + 5 + 13 + 5 + 2 && wm[3] == wl - 4 && wm[4] == COH_WIRE_TUPLE && wm[8] == wl - 9 && !memcmp(wm + 14, "MouseNow", 8));
+    CHECK(coh_host_wire_marshal(kinds, vals, offs, 3, (const uint8_t*)"MouseNow", wm, sizeof wm) == -1);   /* a member missing */
+    CHECK(coh_host_wire_unmarshal(wm, wl - 1, k2, v2, o2, 8, &nt, &taken) == 0 && taken == 0);            /* None: incomplete */
+    CHECK(coh_host_wire_unmarshal(wm, wl, k2, v2, o2, 8, &nt, &taken) == 0 && taken == wl && nt == 4 && k2[0] == COH_WIRE_TUPLE && v2[0] == 3 &&
+          k2[1] == COH_WIRE_STRING && v2[1] == 8 && o2[1] == 14 && v2[2] == 7 && k2[3] == COH_WIRE_BOOL && v2[3] == 1);
+    wm[9] = 9; CHECK(coh_host_wire_unmarshal(wm, wl, k2, v2, o2, 8, &nt, &taken) == -1);                    /* Invalid_data */
+    uint8_t hdr[64]; int32_t hl = 0;
+    CHECK(coh_host_wire_refresh_window(1, 130, 30, 149, 49, hdr, &hl) == 57 + 20 * 20 * 3 && hl == 57 && !memcmp(hdr + 14, "RefreshWindow", 13));
+    CHECK(coh_host_wire_refresh_window(1, 130, 30, 130, 49, hdr, &hl) == 0 && coh_host_wire_refresh_window(1, 131, 30, 130, 49, hdr, &hl) == -1);
+    uint8_t* msg = (uint8_t*)malloc(57 + 20 * 20 * 3); int64_t ml = -1;
+    OK(coh_wire_refresh_window(C, 1, 130, 30, 149, 49, NULL, 0, &ml)); CHECK(ml == 57 + 20 * 20 * 3);
+    OK(coh_wire_refresh_window(C, 1, 130, 30, 149, 49, msg, ml, &ml));
+    CHECK(!memcmp(msg, hdr, 57) && msg[4] == COH_WIRE_TUPLE && !memcmp(msg + 57, rgb + 3 * (30 * W + 130), 60) && !memcmp(msg + 57 + 60 * 10, rgb + 3 * (40 * W + 130), 60));
+    OK(coh_wire_refresh_window(C, 1, 130, 30, 130, 49, msg, ml, &ml)); CHECK(ml == 0);
+    ERR(coh_wire_refresh_window(C, 1, 130, 30, W, 49, msg, 1 << 20, &ml), "outside");
+    ERR(coh_wire_refresh_window(C, 1, 131, 30, 130, 49, msg, 1 << 20, &ml), "not a rectangle");
+    free(msg);
+  }
   OK(coh_fb_read_rgba_async(C, 0, 0, W, H, (uint8_t*)img)); OK(coh_fb_read_wait(C));
   OK(coh_shape_card(C, bx, &card));
   OK(coh_fb_read_sprite(C, bx, px, card, &n)); CHECK(n == card);

@@ -22,3 +22,5 @@ typedef intptr_t value; typedef intptr_t intnat;
 #define Nativeint_val(v) (*(intnat*)(v))
 #define Int64_val(v) (*(int64_t*)(v))
 #define Int32_val(v) (*(int32_t*)(v))
+#define Bytes_val(v) ((unsigned char*)(v))
+size_t caml_string_length(value);
