@@ -440,4 +440,15 @@ inline std::vector<uint8_t> read_rgb888(int x, int y, int w, int h) {
   return out;
 }
 }  // namespace Render
+// Wxgui.refresh_window window (xmin, ymin, xmax, ymax) (wxgui.ml:352-366): the marshalled "RefreshWindow" message of a
+// dirty rectangle with the framebuffer's pixels, ready for the socket; empty where the reference sends nothing.
+namespace Wxgui {
+inline std::string refresh_window_message(int window, int xmin, int ymin, int xmax, int ymax) {
+  int64_t n = 0;
+  ck(coh_wire_refresh_window(Context::get().raw(), window, xmin, ymin, xmax, ymax, nullptr, 0, &n));
+  std::string out((size_t)n, '\0');
+  if (n > 0) ck(coh_wire_refresh_window(Context::get().raw(), window, xmin, ymin, xmax, ymax, (uint8_t*)&out[0], n, &n));
+  return out;
+}
+}  // namespace Wxgui
 }  // namespace coherence
