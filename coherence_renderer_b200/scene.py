@@ -438,6 +438,28 @@ def add_lion(b, width, height, scale, pretrans=None, oid=-1, transform=None):
     return g
 
 
+def add_text_page(b, scale, origin=(0.0, 0.0), name="mintext1", **group_kw):
+    """Append a text page of the reference (examples.ml:158-165 load_text: Group (rev objs)) from its committed geometry
+    (scenes/<name>.json, written by tools/make_text_fixture.py through pdf_import): glyph outlines as filled paths of
+    lines and curves.  x' = ox + scale x, y' = oy + scale (page height - y)."""
+    with open(os.path.join(_SCENES, name + ".json")) as f:
+        page = json.load(f)
+    ox, oy = origin
+    ph = page["mediabox"][3]
+
+    def tr(x, y):
+        return (ox + scale * x, oy + scale * (ph - y))
+
+    g = b.group_begin(**group_kw)
+    for q in reversed(page["paths"]):
+        subs = []
+        for sp in q["subpaths"]:
+            subs.append([(("L" if len(s) == 4 else "C"),) + tuple(tr(s[i], s[i + 1]) for i in range(0, len(s), 2)) for s in sp])
+        b.path(subs, Fill.plain(q["colour"]), COH_NONZERO if q["winding"] == "NonZero" else COH_EVENODD)
+    b.group_end()
+    return g
+
+
 def lion_scene(width, height, scale, background=True, pretrans=None):
     """C1/C2: the lion over Primitive (lightgrey, Rectangle (0, 0, W, H)) (engine.ml:73-74)."""
     b = SceneBuilder()
