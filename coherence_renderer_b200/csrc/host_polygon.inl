@@ -268,7 +268,8 @@ int coh_polygon_sprite(coh_ctx* ctx, const coh_object* fill, const int32_t* edge
 // object record (brush_radius, brush_opacity, winding = COH_BRUSH_*, fill).
 // ---------------------------------------------------------------------------------------
 static FillRec fillrec_of(const coh_object* fill);
-static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out);   // host_scene.inl
+typedef std::map<uint64_t, std::vector<uint8_t>> StampGauss;
+static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out, StampGauss* gauss);   // host_scene.inl
 static int brush_radius_of(coh_ctx* ctx, const coh_object* b, int* r) {
   if (!(b->brush_radius >= 0. && b->brush_radius <= 4096.) || !(b->brush_opacity >= 0. && b->brush_opacity <= 1.)) FAIL("brush radius / opacity out of range");
   if (b->winding != COH_BRUSH_GAUSSIAN && b->winding != COH_BRUSH_DUMMY) FAIL("bad brush kind");
@@ -300,7 +301,7 @@ int coh_brush_shape(coh_ctx* ctx, const coh_object* brush, const int32_t* points
 static int upload_stamp(coh_ctx* ctx, const coh_object* brush, int r, uint8_t** d_stamp) {
   std::vector<uint8_t> st; int rr = r;
   if (brush->winding == COH_BRUSH_DUMMY) st.assign((size_t)(2 * r + 1) * (2 * r + 1), (uint8_t)255);
-  else brush_stamp(brush->brush_radius, brush->brush_opacity, st, rr);
+  else brush_stamp(brush->brush_radius, brush->brush_opacity, st, rr, nullptr);
   CK(DMALLOC(d_stamp, st.size()));
   CK(cudaMemcpyAsync(*d_stamp, st.data(), st.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

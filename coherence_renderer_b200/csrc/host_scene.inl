@@ -24,7 +24,11 @@ int coh_scene_free(coh_ctx* ctx, coh_scene_t h) {
 }
 
 // brush.ml:60-92: alpha of the Gaussian stamp of white at `opacity`.
-static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out) {
+// The Gaussian of a stamp (brush.ml:60-92) is a function of the radius alone; the opacity only dissolves it.  Scenes use
+// few radii and many opacities (C3: 18 radii, ~2300 stamps), so the exponentials are kept per radius for the duration
+// of a call (`gauss`, keyed by the bits of the radius): same expression, same roundings, computed once.
+typedef std::map<uint64_t, std::vector<uint8_t>> StampGauss;
+static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out, int& r_out, StampGauss* gauss = nullptr) {
   int intopacity = (int)(opacity * 255.), intr = (int)ceil(radius);
   int size = 2 * intr + 1;
   r_out = intr;
@@ -32,13 +36,21 @@ static void brush_stamp(double radius, double opacity, std::vector<uint8_t>& out
   out.resize(base + (size_t)size * size);
   uint32_t white = 0xFFFFFFFFu;
   uint32_t c1 = px_dissolve(white, intopacity);
-  for (int y = 0; y < size; y++)
-    for (int x = 0; x < size; x++) {
-      double xp = (double)(x - intr), yp = (double)(y - intr), rr = radius / 2.;
-      double v = 255. * exp(-((xp / rr) * (xp / rr) + (yp / rr) * (yp / rr)));
-      int vi = (int)(v * 1.);
-      out[base + (size_t)y * size + x] = (uint8_t)(px_dissolve(c1, vi) >> 24);
-    }
+  StampGauss local;
+  uint64_t rbits; memcpy(&rbits, &radius, sizeof rbits);
+  std::vector<uint8_t>& g = (gauss ? *gauss : local)[rbits];
+  if (g.empty()) {
+    g.resize((size_t)size * size);
+    for (int y = 0; y < size; y++)
+      for (int x = 0; x < size; x++) {
+        double xp = (double)(x - intr), yp = (double)(y - intr), rr = radius / 2.;
+        double v = 255. * exp(-((xp / rr) * (xp / rr) + (yp / rr) * (yp / rr)));
+        g[(size_t)y * size + x] = (uint8_t)(int)(v * 1.);   // 0 .. 255
+      }
+  }
+  uint8_t of_v[256];   // px_dissolve (c1, vi) >> 24 for every vi
+  for (int vi = 0; vi < 256; vi++) of_v[vi] = (uint8_t)(px_dissolve(c1, vi) >> 24);
+  for (size_t k = 0; k < (size_t)size * size; k++) out[base + k] = of_v[g[k]];
 }
 
 // Convolved (kernel, Group members): the members are a scene of their own (realised in host_cache.inl, after the
@@ -136,8 +148,29 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   DevScene* s = holder.get();
   std::vector<ObjRec>& recs = s->h_objs;
   std::vector<int>& leaves = s->h_leaves;
+  // The brush points of a large scene (C3: 88 MB of pageable host memory, 9 ms) go up on a stream of their own from a helper
+  // thread while this thread walks the objects.  (Declared after `holder`: joined before the scene can go away.)
+  struct PointUpload {
+    std::thread th; cudaStream_t st = nullptr; cudaEvent_t ev = nullptr; cudaError_t err = cudaSuccess;
+    ~PointUpload() { if (th.joinable()) th.join(); if (ev) cudaEventDestroy(ev); if (st) cudaStreamDestroy(st); }
+  } up;
+  if (n_points >= (1 << 20)) {
+    const size_t bytes = sizeof(int2) * (size_t)n_points;
+    CK(DMALLOC(&s->points, bytes));
+    CK(cudaStreamCreateWithFlags(&up.st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&up.ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(up.ev, ctx->stream));   // the allocation is ordered on the context's stream
+    CK(cudaStreamWaitEvent(up.st, up.ev, 0));
+    PointUpload* u = &up; const int dev = ctx->device; int2* dst = s->points;
+    up.th = std::thread([u, dev, dst, points, bytes] {
+      u->err = cudaSetDevice(dev);
+      if (u->err == cudaSuccess) u->err = cudaMemcpyAsync(dst, points, bytes, cudaMemcpyHostToDevice, u->st);
+      if (u->err == cudaSuccess) u->err = cudaStreamSynchronize(u->st);   // resident before this thread is joined
+    });
+  }
   std::vector<uint8_t> stamps;
   std::map<std::pair<uint64_t, int>, std::pair<int, int>> stamp_cache;   // (radius, integer opacity) -> (offset, r)
+  StampGauss stamp_gauss;
   std::vector<int> open;  // indices (into recs) of open groups
   // A Group that is the first member of its list and is composited with plain Over goes under an accumulator that is
   // still clear, and `over clear s = s` exactly (colour.ml:314-316): its members can composite straight into the
@@ -301,7 +334,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
         auto it = stamp_cache.find(key);
         if (it == stamp_cache.end()) {
           f.stamp_off = (int)stamps.size();
-          brush_stamp(c.brush_radius, c.brush_opacity, stamps, f.brush_r);
+          brush_stamp(c.brush_radius, c.brush_opacity, stamps, f.brush_r, &stamp_gauss);
           stamp_cache[key] = std::make_pair(f.stamp_off, f.brush_r);
         } else { f.stamp_off = it->second.first; f.brush_r = it->second.second; }
         f.first2 = c.first2; f.count2 = c.count2; f.colour = 0xFFFFFFFFu;
@@ -492,7 +525,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
           auto it = stamp_cache.find(key);
           if (it == stamp_cache.end()) {
             o.stamp_off = (int)stamps.size();
-            brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r);
+            brush_stamp(c.brush_radius, c.brush_opacity, stamps, o.brush_r, &stamp_gauss);
             stamp_cache[key] = std::make_pair(o.stamp_off, o.brush_r);
           } else { o.stamp_off = it->second.first; o.brush_r = it->second.second; }
         }
@@ -661,8 +694,11 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   }
   mark("records, leaves, boxes");
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
-  CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
-  if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
+  if (up.th.joinable()) { up.th.join(); CK(up.err); }   // uploaded meanwhile
+  else {
+    CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
+    if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));
+  }
   CK(DMALLOC(&s->stamps, std::max<size_t>(stamps.size(), 1)));
   if (!stamps.empty()) CK(cudaMemcpyAsync(s->stamps, stamps.data(), stamps.size(), cudaMemcpyHostToDevice, ctx->stream));
   mark("edges, points, stamps");
