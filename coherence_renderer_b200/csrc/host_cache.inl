@@ -279,12 +279,15 @@ int coh_scene_translate_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_inde
     // the list with cached objects collapsed: boxes of the leaves it shares follow the records; a cached object moved as
     // a whole takes its sprite leaf along (the alias reads the cached sprite translated, cache.ml:400-405); one whose
     // member moved on its own is no longer the object that was cached
-    k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, r, last, dx, dy, 0); LAUNCHED();
+    // (the first sprite leaf that moves along rides in the same launch: its record lies outside [r, last])
+    int along = -1;
+    for (const SpriteEntry& e : s->sprites) if (e.grp >= r && e.grp <= last && (e.leaf_rec < r || e.leaf_rec > last)) { along = e.leaf_rec; break; }
+    k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, r, last, dx, dy, 0, along); LAUNCHED();
     for (SpriteEntry& e : s->sprites) {
       if (e.grp >= r && e.grp <= last) {
         ObjRec& o = s->h_objs[e.leaf_rec];
         o.dx += dx; o.dy += dy; o.bx0 += dx; o.bx1 += dx; o.by0 += dy; o.by1 += dy;
-        k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, e.leaf_rec, e.leaf_rec, dx, dy, 1); LAUNCHED();
+        if (e.leaf_rec != along) { k_move_leaves<<<cdiv(s->sp.n, 256), 256, 0, ctx->stream>>>(s->objs, s->sp.leaf_box, s->sp.leaves, s->sp.n, e.leaf_rec, e.leaf_rec, dx, dy, 1); LAUNCHED(); }
       } else if (r > e.grp && r <= s->group_last[e.grp]) e.dead = true;
     }
   }
@@ -387,7 +390,8 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
       k_bitop<<<wb, 256, 0, ctx->stream>>>(U, A, U, nwords, 0); LAUNCHED();
       DFREE(A); DFREE(B);
     } else {
-      if (put(S, U, 0, 0) || put(S, U, dx, dy)) return 1;                                // shp_o ||| shp_n
+      // shp_o ||| shp_n: the old position (offset 0) and the new one (the same span set read through (dx, dy)) in one launch
+      k_spans_to_bits2<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(S->row_ptr, S->spans, S->y0, 0, S->y0 + dy, -dx, S->n_rows, fr.H, nw, U); LAUNCHED();
     }
     bb[0] = std::max(0, S->bx0 + std::min(dx, 0)); bb[1] = std::max(0, S->by0 + std::min(dy, 0));
     bb[2] = std::min(fr.W - 1, S->bx1 + std::max(dx, 0)); bb[3] = std::min(fr.H - 1, S->by1 + std::max(dy, 0));

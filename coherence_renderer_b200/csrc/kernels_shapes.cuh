@@ -16,6 +16,23 @@ __global__ void k_spans_to_bits(const int* __restrict__ row_ptr, const int2* __r
     or_interval(row, 1, nw, wx0, s.x, s.x + s.y - 1);
   }
 }
+// The same span set at two positions into one bit-frame (shp_o ||| shp_n of a drag step, render.ml:1396-1400): one thread
+// per destination row ORs the source row of either position, so one launch does what two did.
+__global__ void k_spans_to_bits2(const int* __restrict__ row_ptr, const int2* __restrict__ spans, int src_y0a, int wx0a, int src_y0b, int wx0b,
+                                 int src_rows, int n_rows, int nw, uint32_t* __restrict__ bits) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;  // destination row
+  if (r >= n_rows) return;
+  uint32_t* row = bits + (size_t)r * nw;
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int sr = r - (pass ? src_y0b : src_y0a), wx0 = pass ? wx0b : wx0a;
+    if (sr < 0 || sr >= src_rows) continue;
+    for (int k = row_ptr[sr]; k < row_ptr[sr + 1]; k++) {
+      int2 s = spans[k];
+      or_interval(row, 1, nw, wx0, s.x, s.x + s.y - 1);
+    }
+  }
+}
 // Brush.shape_of_brushstroke (brush.ml:135-173): the union of the (2r+1)^2 boxes around the stamp centres.
 // One thread per (stamp, row of its box); rows y0 .., nw words per row starting at pixel wx0.
 __global__ void k_stamp_boxes_to_bits(const int2* __restrict__ points, int n_points, int r, int y0, int n_rows, int wx0, int nw,
@@ -156,13 +173,14 @@ __global__ void k_translate_spans(const int2* __restrict__ in, int2* __restrict_
 // shift the device-space boxes the binning reads.  delta = new offset - old offset.
 // (update_objs = 0: a second leaf list over the same records only refreshes its boxes)
 __global__ void k_move_leaves(ObjRec* __restrict__ objs, int4* __restrict__ leaf_box, const int* __restrict__ leaves,
-                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy, int update_objs) {
+                              int n_leaves, int first_obj, int last_obj, int ddx, int ddy, int update_objs, int also_obj = -1) {
   int li = blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= n_leaves) return;
   int oi = leaves[li];
-  if (oi < first_obj || oi > last_obj) return;
+  const bool also = oi == also_obj;   // (a record outside the range that moves along: the sprite leaf of a cached group)
+  if ((oi < first_obj || oi > last_obj) && !also) return;
   ObjRec& o = objs[oi];
-  if (update_objs) { o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy; }
+  if (update_objs || also) { o.dx += ddx; o.dy += ddy; o.bx0 += ddx; o.bx1 += ddx; o.by0 += ddy; o.by1 += ddy; }
   leaf_box[li] = make_int4(o.bx0, o.by0, o.bx1, o.by1);
 }
 // ------------------------------------------------------------------------------------
