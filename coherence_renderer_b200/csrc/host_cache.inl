@@ -354,13 +354,23 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
   // Fill.Plain objects: plaindirty; groups, fancy fills, brush strokes, Convolved objects, filters: alldirty (render.ml:1396-1400)
   bool plain = false, prim = false;
   coh_shape_t so = 0, mo = 0;
+  const DevShape* kept = nullptr; int kox = 0, koy = 0;
   if (Fm) { if (filter_shapes(ctx, s, *Fm, &so, &mo, "coh_scene_drag_object")) return 1; }
   else {
     const int r = s->rec_of_abi[obj_index];
     const ObjRec& o = s->h_objs[r];
     plain = (o.kind == K_PATH || o.kind == K_CPG) && o.fill.kind == 0;
     prim = o.kind == K_PRIM;
-    if (object_shape_rec(ctx, s, r, &so, &mo)) return 1;   // served by the cache after the first step
+    // a group whose shape is kept with the scene: the span set is read in place through the group's offset (what
+    // object_shape_rec would hand out as a translated copy: two allocations, a copy and a launch per step)
+    if (o.kind == K_GROUP && ctx->usecache) {
+      auto git = s->group_shape.find(r);
+      if (git != s->group_shape.end() && git->second.shape) {
+        kept = git->second.shape; kox = s->group_off[r].x - git->second.offx; koy = s->group_off[r].y - git->second.offy;
+        ctx->shphit++;
+      }
+    }
+    if (!kept && object_shape_rec(ctx, s, r, &so, &mo)) return 1;   // served by the cache after the first step
   }
   if (coh_scene_translate_object(ctx, scene, obj_index, dx, dy)) return 1;
   const Frame& fr = ctx->fr;
@@ -369,7 +379,7 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
   if (!ctx->u_init) CK(DMALLOC(&ctx->u_init, sizeof(uint32_t) * nwords));
   uint32_t* U = ctx->u_init;
   CK(cudaMemsetAsync(U, 0, 4 * nwords, ctx->stream));
-  DevShape* S = (DevShape*)so; DevShape* M = (DevShape*)mo;
+  const DevShape* S = kept ? kept : (const DevShape*)so; DevShape* M = (DevShape*)mo;
   int bb[4] = {0, 0, -1, -1};
   if (S) {
     // old position: offset 0; new position: the same span set read through the offset (dx, dy)
@@ -391,10 +401,10 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
       DFREE(A); DFREE(B);
     } else {
       // shp_o ||| shp_n: the old position (offset 0) and the new one (the same span set read through (dx, dy)) in one launch
-      k_spans_to_bits2<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(S->row_ptr, S->spans, S->y0, 0, S->y0 + dy, -dx, S->n_rows, fr.H, nw, U); LAUNCHED();
+      k_spans_to_bits2<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(S->row_ptr, S->spans, S->y0 + koy, -kox, S->y0 + koy + dy, -(kox + dx), S->n_rows, fr.H, nw, U); LAUNCHED();
     }
-    bb[0] = std::max(0, S->bx0 + std::min(dx, 0)); bb[1] = std::max(0, S->by0 + std::min(dy, 0));
-    bb[2] = std::min(fr.W - 1, S->bx1 + std::max(dx, 0)); bb[3] = std::min(fr.H - 1, S->by1 + std::max(dy, 0));
+    bb[0] = std::max(0, S->bx0 + kox + std::min(dx, 0)); bb[1] = std::max(0, S->by0 + koy + std::min(dy, 0));
+    bb[2] = std::min(fr.W - 1, S->bx1 + kox + std::max(dx, 0)); bb[3] = std::min(fr.H - 1, S->by1 + koy + std::max(dy, 0));
   }
   coh_shape_free(ctx, so); coh_shape_free(ctx, mo);
   if (dirty_bbox) for (int k = 0; k < 4; k++) dirty_bbox[k] = bb[k];
