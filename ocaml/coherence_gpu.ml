@@ -645,11 +645,13 @@ let marshall (m : Camlpy.marshallable) : string =
   Array.iteri (fun i (k, v, o) -> kinds.{i} <- Int32.of_int k; values.{i} <- v; offsets.{i} <- o) toks;
   host_wire_marshal kinds values offsets (Buffer.contents blob)
 
-(* val unmarshall : string -> (int * marshallable) option (camlpy.mli); raises Camlpy.Invalid_data *)
+(* val unmarshall : string -> (int * marshallable) option (camlpy.mli).  Malformed data raises Invalid_data like
+   camlpy.ml:84, 119-123 — a local exception there too (camlpy.mli does not export it), so this module has its own *)
+exception Invalid_data
 let unmarshall (str : string) : (int * Camlpy.marshallable) option =
   let cap = max 1 (String.length str) in   (* every token takes at least one byte *)
   let kinds = Array1.create int32 c_layout cap and values = Array1.create int64 c_layout cap and offsets = Array1.create int64 c_layout cap in
-  let (taken, _) = try host_wire_unmarshal str kinds values offsets with Failure _ -> raise Camlpy.Invalid_data in
+  let (taken, _) = try host_wire_unmarshal str kinds values offsets with Failure _ -> raise Invalid_data in
   if taken = 0 then None else begin
     let pos = ref 0 in
     let rec build () =
