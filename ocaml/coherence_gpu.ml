@@ -664,7 +664,7 @@ let unmarshall (str : string) : (int * Camlpy.marshallable) option =
       else if k = wire_string then Camlpy.String (String.sub str (Int64.to_int offsets.{i}) v)
       else begin
         let members = ref [] in
-        for _ = 1 to v do members := build () :: !members done;
+        for _k = 1 to v do members := build () :: !members done;
         Camlpy.Tuple (List.rev !members)
       end
     in
