@@ -401,7 +401,7 @@ int coh_scene_drag_object(coh_ctx* ctx, coh_scene_t scene, int32_t obj_index, in
       DFREE(A); DFREE(B);
     } else {
       // shp_o ||| shp_n: the old position (offset 0) and the new one (the same span set read through (dx, dy)) in one launch
-      k_spans_to_bits2<<<cdiv(fr.H, 128), 128, 0, ctx->stream>>>(S->row_ptr, S->spans, S->y0 + koy, -kox, S->y0 + koy + dy, -(kox + dx), S->n_rows, fr.H, nw, U); LAUNCHED();
+      k_spans_to_bits2<<<cdiv(fr.H * 32, 256), 256, 0, ctx->stream>>>(S->row_ptr, S->spans, S->y0 + koy, -kox, S->y0 + koy + dy, -(kox + dx), S->n_rows, fr.H, nw, U); LAUNCHED();
     }
     bb[0] = std::max(0, S->bx0 + kox + std::min(dx, 0)); bb[1] = std::max(0, S->by0 + koy + std::min(dy, 0));
     bb[2] = std::min(fr.W - 1, S->bx1 + kox + std::max(dx, 0)); bb[3] = std::min(fr.H - 1, S->by1 + koy + std::max(dy, 0));
