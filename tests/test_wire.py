@@ -143,3 +143,39 @@ def test_wire_refresh_window_against_oracle(ctx, oracle):
     with pytest.raises(abi.CohError):
         ctx.wire_refresh_window(3, 10, 10, W, 50)                              # outside the framebuffer
     ctx.scene_free(sc)
+
+
+def _camlpy_marshall(m):
+    """camlpy.ml:39-82 restated in the test (big-endian low 32 bits, tags 0..4), independent of the library."""
+    def flat(v):
+        if v is None:
+            return b"\x01"
+        if isinstance(v, bool):
+            return b"\x04" + (b"\x01" if v else b"\x00")
+        if isinstance(v, int):
+            return b"\x02" + (v & 0xFFFFFFFF).to_bytes(4, "big")
+        if isinstance(v, bytes):
+            return b"\x03" + len(v).to_bytes(4, "big") + v
+        inner = b"".join(flat(e) for e in v)
+        return b"\x00" + len(inner).to_bytes(4, "big") + inner
+    body = flat(m)
+    return len(body).to_bytes(4, "big") + body
+
+
+def test_round_trips_of_random_values():
+    from hypothesis import given, settings, strategies as st
+
+    leaves = st.one_of(st.none(), st.booleans(), st.integers(min_value=0, max_value=2**32 - 1), st.binary(max_size=60))
+    values = st.recursive(leaves, lambda inner: st.lists(inner, max_size=6), max_leaves=40)
+
+    @settings(max_examples=300, deadline=None)
+    @given(values)
+    def check(v):
+        msg = abi.host_wire_marshal(v)
+        assert msg == _camlpy_marshall(v)
+        taken, back = abi.host_wire_unmarshal(msg)
+        assert taken == len(msg) and back == v
+        for cut in (1, len(msg) // 2, len(msg) - 1):
+            assert abi.host_wire_unmarshal(msg[:cut]) is None
+
+    check()
