@@ -152,11 +152,18 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   // thread while this thread walks the objects.  (Declared after `holder`: joined before the scene can go away.)
   struct PointUpload {
     std::thread th; cudaStream_t st = nullptr; cudaEvent_t ev = nullptr; cudaError_t err = cudaSuccess;
-    ~PointUpload() { if (th.joinable()) th.join(); if (ev) cudaEventDestroy(ev); if (st) cudaStreamDestroy(st); }
+    int2** slot = nullptr; cudaStream_t main = nullptr; bool taken = false;   // a call that fails gives the early allocation back
+    ~PointUpload() {
+      if (th.joinable()) th.join();
+      if (!taken && slot && *slot) { cudaFreeAsync(*slot, main); *slot = nullptr; }
+      if (ev) cudaEventDestroy(ev);
+      if (st) cudaStreamDestroy(st);
+    }
   } up;
   if (n_points >= (1 << 20)) {
     const size_t bytes = sizeof(int2) * (size_t)n_points;
     CK(DMALLOC(&s->points, bytes));
+    up.slot = &s->points; up.main = ctx->stream;
     CK(cudaStreamCreateWithFlags(&up.st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&up.ev, cudaEventDisableTiming));
     CK(cudaEventRecord(up.ev, ctx->stream));   // the allocation is ordered on the context's stream
@@ -694,7 +701,7 @@ int coh_scene_create(coh_ctx* ctx, const coh_object* objs, int32_t n_objs, int32
   }
   mark("records, leaves, boxes");
   if (upload_edges(ctx, edges, n_edges, &s->edges)) return 1;
-  if (up.th.joinable()) { up.th.join(); CK(up.err); }   // uploaded meanwhile
+  if (up.th.joinable()) { up.th.join(); CK(up.err); up.taken = true; }   // uploaded meanwhile
   else {
     CK(DMALLOC(&s->points, sizeof(int2) * std::max(n_points, 1)));
     if (n_points > 0) CK(cudaMemcpyAsync(s->points, points, sizeof(int2) * n_points, cudaMemcpyHostToDevice, ctx->stream));

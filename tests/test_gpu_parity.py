@@ -1626,3 +1626,33 @@ def test_sprite_operations(ctx, oracle):
         for h in (ha, hb, hsub):
             ctx.shape_free(h)
     assert not ctx.shape_intersects(0, 0) and len(ctx.sprite_portion(0, np.zeros(0, np.uint32), 0)) == 0
+
+
+@pytest.mark.gpu
+def test_large_point_arrays_upload_beside_the_object_walk(ctx, oracle):
+    """Scenes with 2^20 brush points or more send the points up from a helper thread while coh_scene_create walks the
+    objects (host_scene.inl): the frame is the oracle's, and a call that fails gives the early allocation back."""
+    W, H = 256, 192
+    b = S.SceneBuilder()
+    b.brush(0.8, 6.0, [[("C", (20.0, 30.0), (90.0, 170.0), (160.0, 10.0), (230.0, 150.0))]], S.Fill.plain(S.rgba8(200, 40, 40)))
+    b.polygon([(30.5, 20.2), (220.1, 60.7), (120.9, 180.3)], S.Fill.plain(S.dissolve(S.rgba8(30, 60, 220), 120)))
+    b.begin_background()
+    b.rectangle(S.WHITE, 0.0, 0.0, float(W), float(H))
+    objs, n, nbg, edges, points = b.arrays()
+    pad = np.zeros(((1 << 20) + 7, 2), dtype=np.int32)               # points no object owns, behind the stroke's
+    big = np.ascontiguousarray(np.concatenate([np.asarray(points, dtype=np.int32).reshape(-1, 2), pad]))
+    ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+    ctx.fb_configure(W, H)
+    sc = ctx.scene_create(objs, nbg, edges, big)
+    ctx.render_frame(sc, (0, 0, W, H))
+    ctx.sync()
+    got = np.asarray(ctx.fb_read_rgba(0, 0, W, H)).view(np.uint32).reshape(H, W)
+    assert np.array_equal(got, ref)
+    ctx.scene_free(sc)
+    ctx.sync()
+    m0 = ctx.mem_in_use()                                            # (the context's own frame buffers are in place now)
+    objs[1].winding = 7                                              # the polygon: no such winding rule
+    with pytest.raises(abi.CohError):
+        ctx.scene_create(objs, nbg, edges, big)
+    ctx.sync()
+    assert ctx.mem_in_use() <= m0 + (1 << 20)                        # the 8 MB of points did not stay behind
