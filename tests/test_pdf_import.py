@@ -155,6 +155,26 @@ def test_stroke_edges_on_the_host_equal_the_oracle(oracle):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's fixture PDFs exist in the build container only")
+def test_reference_fixture_pdfs_render_through_the_oracle(oracle):
+    """Every fixture PDF of the reference: importer -> stroker -> flattening -> the oracle's render_frame (the icons are
+    stroked and filled paths, the text pages glyph outlines); something other than the background comes out."""
+    for f in sorted(glob.glob(os.path.join(REF, "*.pdf"))):
+        pdf = P.PdfFile.open(f)
+        elts, box = P.graphic_of_page(pdf)
+        pts = [p for e in P.scene_of_graphic(elts) for sp in e[3] for s in sp for p in s[1:]]
+        xs, ys = [p[0] for p in pts], [p[1] for p in pts]
+        sc = min(300.0 / max(max(xs) - min(xs), 1e-9), 200.0 / max(max(ys) - min(ys), 1e-9))
+        W, H = int((max(xs) - min(xs)) * sc) + 20, int((max(ys) - min(ys)) * sc) + 20
+        b = S.SceneBuilder()
+        P.add_pdf_page(b, pdf, scale=sc, origin=(10 - sc * min(xs), 10 - sc * (box[3] - max(ys))), flip_height=box[3])
+        b.begin_background()
+        b.rectangle(S.rgba8(200, 220, 240), 0.0, 0.0, float(W), float(H))
+        objs, n, nbg, edges, points = b.arrays()
+        ref = oracle.render_frame(objs, n - nbg, nbg, edges, points, (0, 0, W, H))
+        assert (ref != ref[0, 0]).sum() > 50, os.path.basename(f)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's fixture PDFs exist in the build container only")
 def test_reference_fixture_pdfs():
     import json
 
