@@ -2,6 +2,8 @@
 // of the reference.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may load this library; the product library never does.
 // PARITY UNPINNED (no reference tests / golden vectors exist; OCaml cannot be built here).
+// One exception: camlpy.hpp (the socket format) IS pinned — by vectors the reference's own pycaml.py produced here
+// (tools/make_wire_golden.py -> tests/golden/wire_pycaml.json -> tests/test_wire.py).
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -10,6 +12,7 @@
 #include "../include/coherence_b200.h"
 #include "render.hpp"
 #include "shapes.hpp"
+#include "camlpy.hpp"
 
 using namespace oracle;
 
@@ -540,6 +543,60 @@ int orc_brush_stamp(double radius, double opacity, uint8_t* alpha_out, int cap, 
   if (size * size > cap) throw std::runtime_error("orc_brush_stamp: buffer too small");
   for (int i = 0; i < size * size; i++) alpha_out[i] = (uint8_t)alpha_of_colour(b[i]);
   *size_out = size;
+  ORC_CATCH
+}
+// ---- camlpy.ml (oracle/camlpy.hpp): a marshallable crosses as the pre-order token list of include/coherence_b200.h ----
+static bool tree_of_tokens(const int32_t* kinds, const int64_t* values, const int64_t* offsets, int n, const uint8_t* strings, int& at, camlpy::Marshallable& m) {
+  if (at >= n) return false;
+  const int i = at++;
+  switch (kinds[i]) {
+    case 1: m.kind = camlpy::Marshallable::Unit; return true;
+    case 2: m.kind = camlpy::Marshallable::Int; m.i = values[i]; return true;
+    case 4: m.kind = camlpy::Marshallable::Bool; m.i = values[i] != 0; return true;
+    case 3: m.kind = camlpy::Marshallable::String; if (values[i] < 0) return false; m.s.assign((const char*)strings + offsets[i], (size_t)values[i]); return true;
+    case 0:
+      m.kind = camlpy::Marshallable::Tuple;
+      if (values[i] < 0) return false;
+      for (int64_t k = 0; k < values[i]; k++) { camlpy::Marshallable c; if (!tree_of_tokens(kinds, values, offsets, n, strings, at, c)) return false; m.members.push_back(c); }
+      return true;
+    default: return false;
+  }
+}
+static void tokens_of_tree(const camlpy::Marshallable& m, int64_t& pos, std::vector<int32_t>& kinds, std::vector<int64_t>& values, std::vector<int64_t>& offsets) {
+  kinds.push_back((int32_t)m.kind);
+  switch (m.kind) {
+    case camlpy::Marshallable::Unit: values.push_back(0); offsets.push_back(0); pos += 1; break;
+    case camlpy::Marshallable::Int: values.push_back(m.i); offsets.push_back(0); pos += 5; break;
+    case camlpy::Marshallable::Bool: values.push_back(m.i); offsets.push_back(0); pos += 2; break;
+    case camlpy::Marshallable::String: values.push_back((int64_t)m.s.size()); offsets.push_back(pos + 5); pos += 5 + (int64_t)m.s.size(); break;
+    default:
+      values.push_back((int64_t)m.members.size()); offsets.push_back(0); pos += 5;
+      for (const camlpy::Marshallable& c : m.members) tokens_of_tree(c, pos, kinds, values, offsets);
+  }
+}
+// Camlpy.marshall: *size_out = -1 when the tokens are not exactly one value
+int orc_wire_marshal(const int32_t* kinds, const int64_t* values, const int64_t* offsets, int n, const uint8_t* strings, uint8_t* out, int64_t cap, int64_t* size_out) {
+  ORC_TRY
+  camlpy::Marshallable m; int at = 0;
+  if (n <= 0 || !tree_of_tokens(kinds, values, offsets, n, strings, at, m) || at != n) { *size_out = -1; return 0; }
+  const std::string s = camlpy::marshall(m);
+  *size_out = (int64_t)s.size();
+  if (out && cap >= (int64_t)s.size()) std::memcpy(out, s.data(), s.size());
+  ORC_CATCH
+}
+// Camlpy.unmarshall: *status = 0 None, 1 Some (taken, value), -1 Invalid_data; tokens up to cap, *n_tokens whatever cap is
+int orc_wire_unmarshal(const uint8_t* buf, int64_t n, int32_t* kinds, int64_t* values, int64_t* offsets, int cap, int* n_tokens, int64_t* taken, int* status) {
+  ORC_TRY
+  *n_tokens = 0; *taken = 0; *status = 0;
+  camlpy::Marshallable m; long long tk = 0;
+  bool some;
+  try { some = camlpy::unmarshall(std::string((const char*)buf, (size_t)n), tk, m); }
+  catch (const camlpy::Invalid_data&) { *status = -1; return 0; }
+  if (!some) return 0;
+  std::vector<int32_t> k; std::vector<int64_t> v, o; int64_t pos = 4;
+  tokens_of_tree(m, pos, k, v, o);
+  *n_tokens = (int)k.size(); *taken = tk; *status = 1;
+  for (int i = 0; i < (int)k.size() && i < cap; i++) { kinds[i] = k[i]; values[i] = v[i]; offsets[i] = o[i]; }
   ORC_CATCH
 }
 }  // extern "C"

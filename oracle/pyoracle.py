@@ -338,3 +338,64 @@ def sprite_map_coords_fill(fill_obj, shape_flat, rgba):
     n = C.c_int64()
     _chk(lib().orc_sprite_map_coords_fill(C.byref(fill_obj), _ptr(s), C.c_int64(len(s)), _ptr(src, C.c_uint32), _ptr(out, C.c_uint32), C.c_int64(cap), C.byref(n)))
     return out[: n.value]
+
+
+# ---- camlpy.ml (oracle/camlpy.hpp): Python values as pycaml.py maps them (None, bool, int, bytes / str, list) ----
+def _wire_tokens(m, kinds, values, offsets, blob):
+    if m is None:
+        kinds.append(1), values.append(0), offsets.append(0)
+    elif isinstance(m, bool):
+        kinds.append(4), values.append(int(m)), offsets.append(0)
+    elif isinstance(m, int):
+        kinds.append(2), values.append(m), offsets.append(0)
+    elif isinstance(m, (bytes, bytearray, str)):
+        b = m.encode("latin-1") if isinstance(m, str) else bytes(m)
+        kinds.append(3), values.append(len(b)), offsets.append(len(blob))
+        blob.extend(b)
+    else:
+        kinds.append(0), values.append(len(m)), offsets.append(0)
+        for e in m:
+            _wire_tokens(e, kinds, values, offsets, blob)
+
+
+def wire_marshal(m):
+    """Camlpy.marshall (camlpy.ml:77-82)."""
+    kinds, values, offsets, blob = [], [], [], bytearray()
+    _wire_tokens(m, kinds, values, offsets, blob)
+    k, v, o = np.asarray(kinds, dtype=np.int32), np.asarray(values, dtype=np.int64), np.asarray(offsets, dtype=np.int64)
+    sb = np.frombuffer(bytes(blob) + b"\0", dtype=np.uint8)
+    size = C.c_int64()
+    _chk(lib().orc_wire_marshal(_ptr(k), _ptr(v, C.c_int64), _ptr(o, C.c_int64), len(k), _ptr(sb, C.c_uint8), None, C.c_int64(0), C.byref(size)))
+    out = np.zeros(max(size.value, 1), dtype=np.uint8)
+    _chk(lib().orc_wire_marshal(_ptr(k), _ptr(v, C.c_int64), _ptr(o, C.c_int64), len(k), _ptr(sb, C.c_uint8), _ptr(out, C.c_uint8), C.c_int64(size.value), C.byref(size)))
+    return out[: size.value].tobytes()
+
+
+def wire_unmarshal(data):
+    """Camlpy.unmarshall (camlpy.ml:106-124): None, (taken, value) or OracleError("Invalid_data")."""
+    buf = np.frombuffer(bytes(data) + b"\0", dtype=np.uint8)
+    cap = len(data) + 1
+    k, v, o = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+    nt, taken, status = C.c_int(), C.c_int64(), C.c_int()
+    _chk(lib().orc_wire_unmarshal(_ptr(buf, C.c_uint8), C.c_int64(len(data)), _ptr(k), _ptr(v, C.c_int64), _ptr(o, C.c_int64), cap,
+                                  C.byref(nt), C.byref(taken), C.byref(status)))
+    if status.value < 0:
+        raise OracleError("Invalid_data")
+    if status.value == 0:
+        return None
+    pos = [0]
+
+    def build():
+        i = pos[0]
+        pos[0] += 1
+        if k[i] == 1:
+            return None
+        if k[i] == 4:
+            return bool(v[i])
+        if k[i] == 2:
+            return int(v[i])
+        if k[i] == 3:
+            return bytes(data[int(o[i]) : int(o[i]) + int(v[i])])
+        return [build() for _ in range(int(v[i]))]
+
+    return taken.value, build()

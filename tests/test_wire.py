@@ -30,6 +30,16 @@ def _bytes_form(v):
     return v
 
 
+def test_oracle_is_pinned_by_the_reference_python_side(oracle):
+    """oracle/camlpy.hpp (the list-based restatement of camlpy.ml) against the vectors pycaml.py produced: this part of the
+    oracle is pinned by the reference's own code before it checks the product."""
+    for c in _cases():
+        msg = bytes.fromhex(c["hex"])
+        assert oracle.wire_marshal(c["value"]) == msg, c["value"]
+        assert oracle.wire_unmarshal(msg) == (len(msg), _bytes_form(c["unmarshalled"]))
+        assert oracle.wire_unmarshal(msg[:-1]) is None
+
+
 def test_marshal_equals_the_reference_python_side():
     cases = _cases()
     assert len(cases) >= 80
@@ -74,9 +84,11 @@ def _framed(body):
     b"\x00\x00\x00\x00\x07\x03\x00\x00\x00\x09ab",     # String inside a Tuple longer than the Tuple
     b"\x00\x00\x00",                          # Tuple header cut short
 ])
-def test_unmarshal_invalid_data(body):
+def test_unmarshal_invalid_data(body, oracle):
     with pytest.raises(abi.CohError):
         abi.host_wire_unmarshal(_framed(body))
+    with pytest.raises(oracle.OracleError):                   # the oracle's list-based unmarshall_inner agrees
+        oracle.wire_unmarshal(_framed(body))
 
 
 def test_unmarshal_bool_and_nesting():
@@ -162,8 +174,10 @@ def _camlpy_marshall(m):
     return len(body).to_bytes(4, "big") + body
 
 
-def test_round_trips_of_random_values():
+def test_round_trips_of_random_values(oracle):
     from hypothesis import given, settings, strategies as st
+
+    pyoracle = oracle
 
     leaves = st.one_of(st.none(), st.booleans(), st.integers(min_value=0, max_value=2**32 - 1), st.binary(max_size=60))
     values = st.recursive(leaves, lambda inner: st.lists(inner, max_size=6), max_leaves=40)
@@ -172,7 +186,8 @@ def test_round_trips_of_random_values():
     @given(values)
     def check(v):
         msg = abi.host_wire_marshal(v)
-        assert msg == _camlpy_marshall(v)
+        assert msg == _camlpy_marshall(v) == pyoracle.wire_marshal(v)
+        assert pyoracle.wire_unmarshal(msg) == (len(msg), v)
         taken, back = abi.host_wire_unmarshal(msg)
         assert taken == len(msg) and back == v
         for cut in (1, len(msg) // 2, len(msg) - 1):
