@@ -17,8 +17,9 @@ Three layers, as in the reference:
     - ``K`` / ``k`` store c, y, m, k (pdfgraphics.ml:851, 855); ``CS`` sets the NON-stroking colour space (826);
     - an ExtGState's /LC sets cap AND join, /LJ is not read (pdfgraphics.ml:547-556); /CA and /ca count only as reals.
 * ``scene_of_graphic`` — ``Render.scene_of_graphic`` (render.ml:1476-1565): per painted path a StrokedPath object (the stroker
-  of N2) in front of ... no: LISTED BEFORE the filled Path object; MCSections and Clips are descended into; everything else is
-  dropped.  ``add_pdf_page`` appends ``Group (rev objs)`` (examples.ml:158-165, 174-180) to a SceneBuilder.
+  of N2) listed BEFORE the filled Path object (``line @ fill``, render.ml:1553 — after load_text's ``rev`` the fill ends up in
+  front of its own stroke, which is the reference's order, not PDF's); MCSections and Clips are descended into; everything
+  else is dropped.  ``add_pdf_page`` appends ``Group (rev objs)`` (examples.ml:158-165, 174-180) to a SceneBuilder.
 
 Text objects, images, shadings and patterns produce nothing in Render.scene_of_graphic and are skipped here as well.
 """
